@@ -1,0 +1,115 @@
+"""Synthetic benchmark systems of the sizes BASELINE.json names.
+
+The reference builds its benchmark boxes by tiling 1000 equilibrated SPC/E molecules
+(src/gromacs/nbnxm/benchmark/bench_system.cpp:90-151, box 3.10736 nm per 3000 atoms).  We cannot ship
+those coordinates, so we generate boxes of the SAME density, composition, force-field parameters
+(bench_system.cpp:63-82) and exclusion topology (:192-195) from a seeded lattice with random molecular
+orientations: molecule centres on a simple-cubic lattice of spacing 3.10736/10 nm, jittered.
+"""
+import numpy as np
+
+SPACING = 3.10736 / 10.0  # 1000 molecules per 3.10736^3 nm^3
+Q_O, Q_H = -0.8476, 0.4238
+C6_O, C12_O = 0.0026173456, 2.634129e-06
+ONE_4PI_EPS0 = 138.935458  # src/gromacs/math/units.h
+
+
+class System:
+    """Plain container: x[n,3] f32, box[3], types[n] i32, q[n] f32, nbfp[ntypes,ntypes,2] (6*C6, 12*C12),
+    exclusions as CSR (excl_off[n+1], excl_idx) with self included, mol_id[n]."""
+
+    def __init__(self, x, box, types, q, nbfp, excl_off, excl_idx, mol_id, name):
+        self.x, self.box, self.types, self.q, self.nbfp = x, box, types, q, nbfp
+        self.excl_off, self.excl_idx, self.mol_id, self.name = excl_off, excl_idx, mol_id, name
+        self.n = x.shape[0]
+
+
+def water_box(nx, ny, nz, seed=20261017, jitter=0.02):
+    """SPC/E-like water: nx*ny*nz molecules, 3 atoms each, box = SPACING*(nx,ny,nz)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nmol = nx * ny * nz
+    g = np.stack(np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij"), -1).reshape(-1, 3)
+    centre = (g + 0.5) * SPACING + rng.uniform(-jitter, jitter, size=(nmol, 3))
+    # random rotation per molecule from a random unit quaternion
+    qt = rng.normal(size=(nmol, 4))
+    qt /= np.linalg.norm(qt, axis=1, keepdims=True)
+    w, a, b, c = qt.T
+    R = np.stack([1 - 2 * (b * b + c * c), 2 * (a * b - c * w), 2 * (a * c + b * w),
+                  2 * (a * b + c * w), 1 - 2 * (a * a + c * c), 2 * (b * c - a * w),
+                  2 * (a * c - b * w), 2 * (b * c + a * w), 1 - 2 * (a * a + b * b)], -1).reshape(nmol, 3, 3)
+    half = np.deg2rad(109.47) / 2
+    local = np.array([[0.0, 0.0, 0.0],
+                      [0.1 * np.sin(half), 0.0, 0.1 * np.cos(half)],
+                      [-0.1 * np.sin(half), 0.0, 0.1 * np.cos(half)]])
+    x = centre[:, None, :] + np.einsum("mij,aj->mai", R, local)
+    box = np.array([nx, ny, nz], np.float64) * SPACING
+    x = np.mod(x.reshape(-1, 3), box)  # put_atoms_in_box, bench_system.cpp:157
+    x = x.astype(np.float32)
+    box32 = box.astype(np.float32)
+    x = np.where(x >= box32, x - box32, x).astype(np.float32)  # float rounding can land exactly on the edge
+    n = 3 * nmol
+    types = np.tile(np.array([0, 1, 1], np.int32), nmol)
+    q = np.tile(np.array([Q_O, Q_H, Q_H], np.float32), nmol)
+    nbfp = np.zeros((2, 2, 2), np.float32)
+    nbfp[0, 0] = (6.0 * C6_O, 12.0 * C12_O)
+    first = (np.arange(n) // 3) * 3
+    excl_idx = (first[:, None] + np.arange(3)[None, :]).astype(np.int32).ravel()
+    excl_off = (np.arange(n + 1) * 3).astype(np.int32)
+    mol_id = (np.arange(n) // 3).astype(np.int32)
+    return System(x, box32, types, q, nbfp, excl_off, excl_idx, mol_id, "water_%dx%dx%d" % (nx, ny, nz))
+
+
+NAMED = {
+    "water_3k": (10, 10, 10),
+    "water_24k": (20, 20, 20),      # BASELINE.json configs[1]
+    "water_96k": (40, 40, 20),      # configs[2]
+    "water_192k": (40, 40, 40),
+    "water_1M": (70, 70, 70),       # configs[3]: 1.029 M atoms, 21.75 nm
+    "water_1.5M": (80, 80, 80),     # configs[4] per-GPU tile: 1.536 M atoms
+}
+
+
+def named(name, seed=20261017):
+    return water_box(*NAMED[name], seed=seed)
+
+
+def argon12():
+    """The nblib argon sample: api/nblib/samples/argon-forces-integration.cpp:52-57,86-88,103."""
+    x = np.array([[0.794, 1.439, 0.610], [1.397, 0.673, 1.916], [0.659, 1.080, 0.573],
+                  [1.105, 0.090, 3.431], [1.741, 1.291, 3.432], [1.936, 1.441, 5.873],
+                  [0.960, 2.246, 1.659], [0.382, 3.023, 2.793], [0.053, 4.857, 4.242],
+                  [2.655, 5.057, 2.211], [4.114, 0.737, 0.614], [5.977, 5.104, 5.217]], np.float32)
+    n = 12
+    nbfp = np.array([[[6 * 0.0062647225, 12 * 9.847044e-06]]], np.float32)
+    return System(x, np.array([6.05449] * 3, np.float32), np.zeros(n, np.int32), np.zeros(n, np.float32), nbfp,
+                  np.arange(n + 1, dtype=np.int32), np.arange(n, dtype=np.int32), np.arange(n, dtype=np.int32),
+                  "argon12")
+
+
+def ewald_beta(rc, rtol=1e-5):
+    """calc_ewaldcoeff_q (src/gromacs/ewald/ewald_utils.cpp:46-74): bisection on erfc(beta*rc) = rtol."""
+    from math import erfc
+    beta = 5.0
+    i = 0
+    while erfc(beta * rc) > rtol:
+        i += 1
+        beta *= 2
+    n = i + 60
+    low, high = 0.0, beta
+    for _ in range(n):
+        beta = (low + high) / 2
+        if erfc(beta * rc) > rtol:
+            low = beta
+        else:
+            high = beta
+    return beta
+
+
+def rf_constants(rc, eps_rf=0.0, eps_r=1.0):
+    """calc_rffac (src/gromacs/mdlib/rf_util.cpp); eps_rf = 0 means infinity as in
+    benchmark/bench_setup.cpp:152-155 (k_rf = 0.5/rc^3, c_rf = 1/rc + k_rf rc^2)."""
+    if eps_rf == 0:
+        k = 1.0 / (2 * rc ** 3)
+    else:
+        k = (eps_rf - eps_r) / ((2 * eps_rf + eps_r) * rc ** 3)
+    return k, 1.0 / rc + k * rc * rc

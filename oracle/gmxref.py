@@ -1,0 +1,177 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of oracle/_ref/libgmxref_nbnxm.so.
+
+The .so is the UNMODIFIED reference nbnxm CPU path (grid, pair search, plain-C / SIMD /
+GPU-emulation kernels) compiled by oracle/build_ref.sh from /root/reference plus the C-ABI
+harness oracle/ref_harness.cpp.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libgmxref_nbnxm.so")
+
+KERNEL_PLAINC, KERNEL_SIMD_4XN, KERNEL_SIMD_2XNN, KERNEL_GPUREF = 0, 1, 2, 3
+EEL_CUT, EEL_RF, EEL_EWALD_ANA, EEL_EWALD_TAB = 0, 1, 2, 3
+
+
+class _System(C.Structure):
+    _fields_ = [("natoms", C.c_int), ("x", C.c_void_p), ("box", C.c_float * 3), ("ntypes", C.c_int),
+                ("nbfp", C.c_void_p), ("type", C.c_void_p), ("q", C.c_void_p),
+                ("excl_off", C.c_void_p), ("excl_idx", C.c_void_p)]
+
+
+class _Params(C.Structure):
+    _fields_ = [("rc", C.c_float), ("rlist", C.c_float), ("rlist_inner", C.c_float),
+                ("nstlist_prune", C.c_int), ("eeltype", C.c_int), ("epsfac", C.c_float),
+                ("k_rf", C.c_float), ("c_rf", C.c_float), ("ewaldcoeff", C.c_float),
+                ("sh_ewald", C.c_float), ("disp_cpot", C.c_float), ("rep_cpot", C.c_float),
+                ("kernel", C.c_int), ("comb_rule", C.c_int), ("nthreads", C.c_int),
+                ("exact_atom_flags", C.c_int), ("put_in_box", C.c_int), ("min_ilist_count", C.c_int)]
+
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        # bind OpenMP threads before libgomp initialises (unbound threads are >3x slower)
+        os.environ.setdefault("OMP_PROC_BIND", "spread")
+        os.environ.setdefault("OMP_PLACES", "cores")
+        L = C.CDLL(LIB_PATH)
+        L.gmxref_create.restype = C.c_void_p
+        L.gmxref_create.argtypes = [C.POINTER(_System), C.POINTER(_Params)]
+        L.gmxref_destroy.argtypes = [C.c_void_p]
+        L.gmxref_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gmxref_time_kernel.restype = C.c_double
+        L.gmxref_time_kernel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.gmxref_time_step.restype = C.c_double
+        L.gmxref_time_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.gmxref_grid_order.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.gmxref_grid_dims.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.gmxref_list_stats.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.gmxref_pair_set.restype = C.c_longlong
+        L.gmxref_pair_set.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_longlong]
+        L.gmxref_regrid_research.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gmxref_setup_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gmxref_ewald_coeff.restype = C.c_float
+        L.gmxref_ewald_coeff.argtypes = [C.c_float, C.c_float]
+        L.gmxref_simd_rsq.restype = C.c_float
+        L.gmxref_simd_rsq.argtypes = [C.c_float] * 6
+        _lib = L
+    return _lib
+
+
+def ewald_coeff(rc, rtol=1e-5):
+    return float(lib().gmxref_ewald_coeff(rc, rtol))
+
+
+def default_simd_kernel():
+    return int(lib().gmxref_default_simd_kernel())
+
+
+class RefNbnxm:
+    """One reference nonbonded_verlet_t instance: gridded, searched, ready to compute."""
+
+    def __init__(self, x, box, types, q, nbfp, excl_off, excl_idx, rc, rlist=None, eeltype=EEL_CUT,
+                 epsfac=138.935458, k_rf=0.0, c_rf=0.0, ewaldcoeff=0.0, sh_ewald=0.0,
+                 disp_cpot=None, rep_cpot=None, kernel=None, comb_rule=0, nthreads=1,
+                 exact_atom_flags=0, put_in_box=0, rlist_inner=0.0, min_ilist_count=0):
+        L = lib()
+        self.n = int(len(types))
+        self._x = np.ascontiguousarray(x, dtype=np.float32).reshape(self.n, 3)
+        self._types = np.ascontiguousarray(types, dtype=np.int32)
+        self._q = np.ascontiguousarray(q, dtype=np.float32)
+        self._nbfp = np.ascontiguousarray(nbfp, dtype=np.float32).ravel()
+        ntypes = int(round((self._nbfp.size // 2) ** 0.5))
+        self._eo = np.ascontiguousarray(excl_off, dtype=np.int32)
+        self._ei = np.ascontiguousarray(excl_idx, dtype=np.int32)
+        s = _System(self.n, self._x.ctypes.data, (C.c_float * 3)(*[float(b) for b in box]), ntypes,
+                    self._nbfp.ctypes.data, self._types.ctypes.data, self._q.ctypes.data,
+                    self._eo.ctypes.data, self._ei.ctypes.data)
+        if kernel is None:
+            kernel = default_simd_kernel()
+        if disp_cpot is None:
+            disp_cpot = -1.0 / rc ** 6
+        if rep_cpot is None:
+            rep_cpot = -1.0 / rc ** 12
+        p = _Params(rc, rlist if rlist else rc, rlist_inner, 0, eeltype, epsfac, k_rf, c_rf, ewaldcoeff,
+                    sh_ewald, disp_cpot, rep_cpot, kernel, comb_rule, nthreads, exact_atom_flags,
+                    put_in_box, min_ilist_count)
+        self.rc = rc
+        self.h = L.gmxref_create(C.byref(s), C.byref(p))
+        if not self.h:
+            raise RuntimeError("gmxref_create failed (kernel type unavailable in this build?)")
+
+    def close(self):
+        if self.h:
+            lib().gmxref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compute(self, x=None, energy=True, virial=True):
+        f = np.zeros((self.n, 3), np.float32)
+        fs = np.zeros((45, 3), np.float32)
+        e = np.zeros(2, np.float32)
+        xp = None
+        if x is not None:
+            xx = np.ascontiguousarray(x, dtype=np.float32)
+            xp = xx.ctypes.data
+        lib().gmxref_compute(self.h, xp, int(energy), int(virial), f.ctypes.data, fs.ctypes.data, e.ctypes.data)
+        return f, fs, float(e[0]), float(e[1])
+
+    def time_kernel(self, energy=False, nwarm=1, niter=5):
+        return float(lib().gmxref_time_kernel(self.h, int(energy), nwarm, niter))
+
+    def time_step(self, energy=False, nwarm=1, niter=5):
+        return float(lib().gmxref_time_step(self.h, int(energy), nwarm, niter))
+
+    def regrid_research(self):
+        tg, ts = C.c_double(), C.c_double()
+        lib().gmxref_regrid_research(self.h, C.byref(tg), C.byref(ts))
+        return tg.value, ts.value
+
+    def setup_times(self):
+        tg, ts = C.c_double(), C.c_double()
+        lib().gmxref_setup_times(self.h, C.byref(tg), C.byref(ts))
+        return tg.value, ts.value
+
+    def grid_order(self):
+        cap = self.n * 2 + 4096
+        out = np.zeros(cap, np.int32)
+        n = lib().gmxref_grid_order(self.h, out.ctypes.data, cap)
+        return out[:n].copy()
+
+    def grid_dims(self):
+        ncx, ncy, npad = C.c_int(), C.c_int(), C.c_int()
+        cx, cy = C.c_float(), C.c_float()
+        lib().gmxref_grid_dims(self.h, C.byref(ncx), C.byref(ncy), C.byref(cx), C.byref(cy), C.byref(npad))
+        return ncx.value, ncy.value, cx.value, cy.value, npad.value
+
+    def list_stats(self):
+        a, b = C.c_longlong(), C.c_longlong()
+        ci, cj = C.c_int(), C.c_int()
+        lib().gmxref_list_stats(self.h, C.byref(a), C.byref(b), C.byref(ci), C.byref(cj))
+        return dict(cluster_pairs=a.value, atom_pairs_computed=b.value, na_ci=ci.value, na_cj=cj.value)
+
+    def pair_count(self, rc=None):
+        return int(lib().gmxref_pair_set(self.h, rc or self.rc, None, 0))
+
+    def pair_set(self, rc=None):
+        """(npairs, 3) int32 array of (i_atom [shifted], j_atom, shift index)."""
+        n = self.pair_count(rc)
+        out = np.zeros((max(n, 1), 3), np.int32)
+        lib().gmxref_pair_set(self.h, rc or self.rc, out.ctypes.data, n)
+        return out[:n]

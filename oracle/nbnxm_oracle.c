@@ -1,0 +1,678 @@
+/* TEST INFRASTRUCTURE ONLY -- never linked into, imported by or executed from the product path.
+ *
+ * Plain-C CPU restatement of the reference short-range nonbonded (nbnxm) hot path of
+ * kassonlab/gmxapi (GROMACS 2021), written from scratch as the parity oracle for the CUDA
+ * implementation under gmxapi_b200/csrc.  Each function cites the reference file:line whose
+ * behaviour it restates (paths relative to /root/reference/src/gromacs).
+ *
+ * PARITY PINNING: this oracle is checked (tests/test_oracle_vs_reference.py, tests/golden/) against
+ *  (a) the reference's own golden vectors api/nblib/tests/refdata/NBlibTest_ArgonForcesAreCorrect.xml
+ *      and NBlibTest_SpcMethanolForcesAreCorrect.xml, and
+ *  (b) the UNMODIFIED reference code compiled here by oracle/build_ref.sh (oracle/_ref): grid atom
+ *      order, in-range pair set (bit-exact), forces / shift forces / energies of the CPU SIMD kernels.
+ *
+ * Conventions restated:
+ *  - shift vectors: pbcutil/ishift.h:40-54 (D_BOX 2,1,1 -> 45 shifts, CENTRAL 22), pbcutil/pbc.cpp:1187
+ *  - only shifts <= CENTRAL are listed for an intra-grid search and the i-atom is the shifted one
+ *    (nbnxm/pairlist.cpp:3339-3342, kernels_simd_2xmm/kernel_outer.h:482-489)
+ *  - r^2 = fma(dz,dz,fma(dx,dx,dy*dy)) with dx = (xi+shift) - xj: simd/vector_operations.h:106-115
+ *    (norm2: ax*ax, ay*ay+ret, az*az+ret) AS COMPILED by gcc 13 -O3 -mfma for the 2xMM kernels: the
+ *    disassembly of kernels_simd_2xmm/kernel_ElecEw_VdwLJCombGeom_F.cpp shows vmulps(dy,dy),
+ *    vfmadd231ps(dx,dx), vfmadd231ps(dz,dz).  Verified bit-for-bit against oracle/_ref by
+ *    tests/test_oracle_vs_reference.py::test_rsq_formula.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_CENTRAL 22
+#define ORC_SHIFTS 45
+#define ORC_CL 8        /* atoms per cluster, nbnxm/pairlistparams.h:66 */
+#define ORC_CELL 64     /* atoms per grid cell (super-cluster), pairlistparams.h:69-77 */
+
+enum { ORC_EEL_CUT = 0, ORC_EEL_RF = 1, ORC_EEL_EWALD = 2 };
+
+typedef struct
+{
+    float rc;         /* rvdw = rcoulomb */
+    int   eeltype;    /* ORC_EEL_*; CUT is evaluated as RF with k_rf=0 (nbnxm/kerneldispatch.cpp:168-171) */
+    float epsfac;     /* interaction_const_t::epsfac */
+    float k_rf, c_rf;
+    float beta;       /* ewaldcoeff_q */
+    float sh_ewald;
+    float disp_cpot;  /* dispersion_shift.cpot */
+    float rep_cpot;   /* repulsion_shift.cpot */
+    int   ntypes;
+    const float* nbfp; /* ntypes*ntypes*2: 6*C6, 12*C12 (nbnxm/atomdata.cpp:498-506) */
+} orc_params;
+
+static int shift_index(int tx, int ty, int tz)
+{
+    return 5 * (3 * (tz + 1) + (ty + 1)) + tx + 2; /* pbcutil/ishift.h:50 XYZ2IS */
+}
+
+static void shift_from_index(int is, int* tx, int* ty, int* tz)
+{
+    *tx = is % 5 - 2;
+    *ty = (is / 5) % 3 - 1;
+    *tz = is / 15 - 1;
+}
+
+/* pbcutil/pbc.cpp:1187-1202 calc_shifts for a rectangular box */
+void orc_shift_vectors(const float box[3], float* shift_vec /* 45*3 */)
+{
+    int n = 0;
+    for (int m = -1; m <= 1; m++)
+        for (int l = -1; l <= 1; l++)
+            for (int k = -2; k <= 2; k++, n++)
+            {
+                shift_vec[3 * n + 0] = k * box[0];
+                shift_vec[3 * n + 1] = l * box[1];
+                shift_vec[3 * n + 2] = m * box[2];
+            }
+}
+
+/* r^2 with the reference's operand roles and operation order (see header). */
+float orc_rsq(float xi, float yi, float zi, float sx, float sy, float sz, float xj, float yj, float zj)
+{
+    float dx = (xi + sx) - xj;
+    float dy = (yi + sy) - yj;
+    float dz = (zi + sz) - zj;
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Gridding and sorting
+ * ------------------------------------------------------------------------------------------------ */
+
+/* nbnxm/grid.cpp:103-262 Grid::setDimensions, GPU (hierarchical 8x8x8) geometry, home zone. */
+void orc_grid_dims(int natoms, const float lower[3], const float upper[3], float density, int* ncx, int* ncy,
+                   float cell_size[2], float inv_cell_size[2])
+{
+    float size[3];
+    for (int d = 0; d < 3; d++) size[d] = upper[d] - lower[d];
+    if (density <= 0) density = (float)natoms / (size[0] * size[1] * size[2]);
+    if (natoms > ORC_CELL)
+    {
+        float tlen   = cbrtf((float)ORC_CL / density);
+        float tlen_x = tlen * 2, tlen_y = tlen * 2;
+        int   nx = (int)(size[0] / tlen_x), ny = (int)(size[1] / tlen_y);
+        *ncx = nx > 1 ? nx : 1;
+        *ncy = ny > 1 ? ny : 1;
+    }
+    else
+    {
+        *ncx = 1;
+        *ncy = 1;
+    }
+    cell_size[0]     = size[0] / *ncx;
+    cell_size[1]     = size[1] / *ncy;
+    inv_cell_size[0] = 1 / cell_size[0];
+    inv_cell_size[1] = 1 / cell_size[1];
+}
+
+typedef struct
+{
+    float key;
+    int   idx;
+} sort_item;
+
+/* nbnxm/grid.cpp:292-427 sort_atoms: the pigeonhole + insertion procedure yields the exact order by
+ * (coordinate, atom index) ascending; "Backwards" emits the same sequence reversed. */
+static int cmp_item(const void* a, const void* b)
+{
+    const sort_item *p = (const sort_item*)a, *q = (const sort_item*)b;
+    if (p->key < q->key) return -1;
+    if (p->key > q->key) return 1;
+    return (p->idx > q->idx) - (p->idx < q->idx);
+}
+
+static void sort_atoms(int dim, int backwards, int* a, int n, const float* x)
+{
+    if (n <= 1) return;
+    sort_item* it = (sort_item*)malloc(sizeof(sort_item) * (size_t)n);
+    for (int i = 0; i < n; i++)
+    {
+        it[i].key = x[3 * a[i] + dim];
+        it[i].idx = a[i];
+    }
+    qsort(it, (size_t)n, sizeof(sort_item), cmp_item);
+    for (int i = 0; i < n; i++) a[i] = backwards ? it[n - 1 - i].idx : it[i].idx;
+    free(it);
+}
+
+/* nbnxm/grid.cpp:1173-1268 calcColumnIndices (home zone), :1287-1445 setCellIndices,
+ * :1051-1164 sortColumnsGpuGeometry.  Outputs:
+ *   col_cell0[ncol+1]  first cell of each column (cxy_ind_)
+ *   atom_index[npad]   original atom at each grid slot, -1 for fillers (gridSetData.atomIndices)
+ *   slot_of_atom[n]    grid slot of each atom (gridSetData.cells)
+ * Returns npad (= 64 * number of cells) or -1 if cap is too small. */
+int orc_put_on_grid(int natoms, const float* x, const float lower[3], const float upper[3], float density,
+                    int* ncx_out, int* ncy_out, int* col_cell0, int col_cap, int* atom_index, int cap,
+                    int* slot_of_atom)
+{
+    int   ncx, ncy;
+    float cs[2], ics[2];
+    orc_grid_dims(natoms, lower, upper, density, &ncx, &ncy, cs, ics);
+    *ncx_out = ncx;
+    *ncy_out = ncy;
+    const int ncol = ncx * ncy;
+    if (ncol + 1 > col_cap) return -1;
+    int* col_of = (int*)malloc(sizeof(int) * (size_t)natoms);
+    int* cnt    = (int*)calloc((size_t)ncol + 1, sizeof(int));
+    for (int i = 0; i < natoms; i++)
+    {
+        int cx = (int)((x[3 * i + 0] - lower[0]) * ics[0]);
+        int cy = (int)((x[3 * i + 1] - lower[1]) * ics[1]);
+        if (cx > ncx - 1) cx = ncx - 1;
+        if (cy > ncy - 1) cy = ncy - 1;
+        if (cx < 0) cx = 0; /* atoms a few bits below the lower bound, grid.cpp:1207-1213 */
+        if (cy < 0) cy = 0;
+        col_of[i] = cx * ncy + cy;
+        cnt[col_of[i]]++;
+    }
+    col_cell0[0] = 0;
+    for (int c = 0; c < ncol; c++) col_cell0[c + 1] = col_cell0[c] + (cnt[c] + ORC_CELL - 1) / ORC_CELL;
+    const int npad = col_cell0[ncol] * ORC_CELL;
+    if (npad > cap)
+    {
+        free(col_of);
+        free(cnt);
+        return -1;
+    }
+    for (int s = 0; s < npad; s++) atom_index[s] = -1;
+    int* fill = (int*)calloc((size_t)ncol, sizeof(int));
+    for (int i = 0; i < natoms; i++) /* grid.cpp:1390-1400: atoms enter their column in index order */
+    {
+        int c                                          = col_of[i];
+        atom_index[col_cell0[c] * ORC_CELL + fill[c]++] = i;
+    }
+    for (int c = 0; c < ncol; c++)
+    {
+        const int n   = cnt[c];
+        int*      a   = atom_index + col_cell0[c] * ORC_CELL;
+        const int ncz = col_cell0[c + 1] - col_cell0[c];
+        sort_atoms(2, 0, a, n, x);
+        for (int sub_z = 0; sub_z < ncz * 2; sub_z++)
+        {
+            const int offz = sub_z * 32;
+            int       nz   = n - offz < 32 ? n - offz : 32;
+            sort_atoms(1, (sub_z & 1) != 0, a + offz, nz, x);
+            for (int sub_y = 0; sub_y < 2; sub_y++)
+            {
+                const int offy = offz + sub_y * 16;
+                int       ny   = n - offy < 16 ? n - offy : 16;
+                /* grid.cpp:1133: direction ((cz*2+sub_y)&1), cz=-1 on odd sub_z: parity of sub_y */
+                sort_atoms(0, (sub_y & 1) != 0, a + offy, ny, x);
+            }
+        }
+    }
+    for (int s = 0; s < npad; s++)
+        if (atom_index[s] >= 0) slot_of_atom[atom_index[s]] = s;
+    free(col_of);
+    free(cnt);
+    free(fill);
+    return npad;
+}
+
+/* Bounding boxes of 8-atom clusters (nbnxm/grid.cpp:454-520 calc_bounding_box*, fillers ignored;
+ * all-filler clusters get the filler coordinate, atomdata.cpp:136-146). bb[c*6] = lx,ly,lz,ux,uy,uz. */
+void orc_bounding_boxes(int npad, const int* atom_index, const float* x, float* bb)
+{
+    for (int c = 0; c < npad / ORC_CL; c++)
+    {
+        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        int   any   = 0;
+        for (int k = 0; k < ORC_CL; k++)
+        {
+            int a = atom_index[c * ORC_CL + k];
+            if (a < 0) continue;
+            any = 1;
+            for (int d = 0; d < 3; d++)
+            {
+                if (x[3 * a + d] < lo[d]) lo[d] = x[3 * a + d];
+                if (x[3 * a + d] > hi[d]) hi[d] = x[3 * a + d];
+            }
+        }
+        for (int d = 0; d < 3; d++)
+        {
+            bb[6 * c + d]     = any ? lo[d] : -1000000.0f;
+            bb[6 * c + 3 + d] = any ? hi[d] : -1000000.0f;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * In-range atom pairs (the observable of search + prune) via a uniform cell list
+ * ------------------------------------------------------------------------------------------------ */
+
+typedef struct
+{
+    int* head;
+    int* next;
+    int  nc[3];
+    float inv[3];
+} cell_list;
+
+static void cl_build(cell_list* cl, int n, const float* x, const float box[3], float r)
+{
+    for (int d = 0; d < 3; d++)
+    {
+        cl->nc[d] = (int)(box[d] / r);
+        if (cl->nc[d] < 1) cl->nc[d] = 1;
+        if (cl->nc[d] > 256) cl->nc[d] = 256;
+        cl->inv[d] = cl->nc[d] / box[d];
+    }
+    size_t ncell = (size_t)cl->nc[0] * cl->nc[1] * cl->nc[2];
+    cl->head     = (int*)malloc(sizeof(int) * ncell);
+    cl->next     = (int*)malloc(sizeof(int) * (size_t)n);
+    for (size_t c = 0; c < ncell; c++) cl->head[c] = -1;
+    for (int i = n - 1; i >= 0; i--)
+    {
+        int c[3];
+        for (int d = 0; d < 3; d++)
+        {
+            double f = (double)x[3 * i + d] * cl->inv[d];
+            c[d]     = (int)floor(f);
+            c[d]     = ((c[d] % cl->nc[d]) + cl->nc[d]) % cl->nc[d];
+        }
+        size_t ci    = ((size_t)c[0] * cl->nc[1] + c[1]) * cl->nc[2] + c[2];
+        cl->next[i]  = cl->head[ci];
+        cl->head[ci] = i;
+    }
+}
+
+static void cl_free(cell_list* cl)
+{
+    free(cl->head);
+    free(cl->next);
+}
+
+typedef void (*pair_cb)(void* ctx, int ai, int aj, int shift, float rsq);
+
+/* Enumerates every unordered atom pair {a,b}, a != b, whose minimum-image distance evaluated with the
+ * reference's roles (i = the atom shifted by a shift vector with index <= CENTRAL,
+ * nbnxm/pairlist.cpp:3339-3342) satisfies r^2 < r2max.  For the CENTRAL shift i<j by atom index. */
+static void for_each_pair(int n, const float* x, const float box[3], float rmax, pair_cb cb, void* ctx)
+{
+    float sv[ORC_SHIFTS * 3];
+    orc_shift_vectors(box, sv);
+    cell_list cl;
+    /* cells at least rmax*(1+eps) wide so that +-1 neighbour cells suffice */
+    cl_build(&cl, n, x, box, rmax * 1.0001f + 1e-6f);
+    const float r2max = rmax * rmax;
+    for (int a = 0; a < n; a++)
+    {
+        int c[3];
+        for (int d = 0; d < 3; d++)
+        {
+            c[d] = (int)floor((double)x[3 * a + d] * cl.inv[d]);
+            c[d] = ((c[d] % cl.nc[d]) + cl.nc[d]) % cl.nc[d];
+        }
+        int lo[3], hi[3];
+        for (int d = 0; d < 3; d++)
+        {
+            if (cl.nc[d] >= 3)
+            {
+                lo[d] = -1;
+                hi[d] = 1;
+            }
+            else
+            {
+                lo[d] = 0;
+                hi[d] = cl.nc[d] - 1; /* visit every cell once */
+            }
+        }
+        for (int ox = lo[0]; ox <= hi[0]; ox++)
+            for (int oy = lo[1]; oy <= hi[1]; oy++)
+                for (int oz = lo[2]; oz <= hi[2]; oz++)
+                {
+                    int cc[3] = { cl.nc[0] >= 3 ? (c[0] + ox + cl.nc[0]) % cl.nc[0] : ox,
+                                  cl.nc[1] >= 3 ? (c[1] + oy + cl.nc[1]) % cl.nc[1] : oy,
+                                  cl.nc[2] >= 3 ? (c[2] + oz + cl.nc[2]) % cl.nc[2] : oz };
+                    size_t ci = ((size_t)cc[0] * cl.nc[1] + cc[1]) * cl.nc[2] + cc[2];
+                    for (int b = cl.head[ci]; b >= 0; b = cl.next[b])
+                    {
+                        if (b <= a) continue;
+                        /* minimum image shift of a relative to b, in double to choose the image */
+                        int t[3];
+                        for (int d = 0; d < 3; d++)
+                        {
+                            double dd = (double)x[3 * a + d] - (double)x[3 * b + d];
+                            t[d]      = -(int)lrint(dd / box[d]);
+                        }
+                        if (abs(t[0]) > 2 || abs(t[1]) > 1 || abs(t[2]) > 1) continue;
+                        int is = shift_index(t[0], t[1], t[2]);
+                        int ai = a, aj = b;
+                        if (is > ORC_CENTRAL)
+                        {
+                            /* the other atom carries the (negated) shift */
+                            is = shift_index(-t[0], -t[1], -t[2]);
+                            ai = b;
+                            aj = a;
+                        }
+                        float r2 = orc_rsq(x[3 * ai], x[3 * ai + 1], x[3 * ai + 2], sv[3 * is], sv[3 * is + 1],
+                                           sv[3 * is + 2], x[3 * aj], x[3 * aj + 1], x[3 * aj + 2]);
+                        if (r2 < r2max) cb(ctx, ai, aj, is, r2);
+                    }
+                }
+    }
+    cl_free(&cl);
+}
+
+/* exclusion lookup in the CSR topology exclusions (utility/listoflists.h as used by
+ * nbnxm/pairlist.cpp:1874-1972 setExclusionsForIEntry) */
+static int is_excluded(const int* excl_off, const int* excl_idx, int a, int b)
+{
+    if (!excl_off) return 0;
+    for (int k = excl_off[a]; k < excl_off[a + 1]; k++)
+        if (excl_idx[k] == b) return 1;
+    return 0;
+}
+
+typedef struct
+{
+    int*        out;
+    long long   cap, n;
+    const int * excl_off, *excl_idx;
+    int         include_excluded;
+} pairset_ctx;
+
+static void pairset_cb(void* vctx, int ai, int aj, int shift, float rsq)
+{
+    (void)rsq;
+    pairset_ctx* c = (pairset_ctx*)vctx;
+    if (!c->include_excluded && is_excluded(c->excl_off, c->excl_idx, ai, aj)) return;
+    if (c->out && c->n < c->cap)
+    {
+        c->out[3 * c->n]     = ai;
+        c->out[3 * c->n + 1] = aj;
+        c->out[3 * c->n + 2] = shift;
+    }
+    c->n++;
+}
+
+/* The set of interacting atom pairs after search and prune at radius r: every non-excluded pair with
+ * r^2 < r*r, as (i, j, shift) with the reference's roles. Returns the count (writes at most cap). */
+long long orc_pair_set(int n, const float* x, const float box[3], float r, const int* excl_off,
+                       const int* excl_idx, int* pairs, long long cap)
+{
+    pairset_ctx c = { pairs, cap, 0, excl_off, excl_idx, 0 };
+    for_each_pair(n, x, box, r, pairset_cb, &c);
+    return c.n;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Cluster-pair (tile) list: every (ci, cj, shift) of 8-atom clusters of the grid with at least one
+ * atom pair within rlist -- what the reference list converges to after dynamic pruning
+ * (kernels_reference/kernel_ref_prune.cpp:45-143: keep a cluster pair iff any r^2 < rlist^2;
+ * cuda/nbnxm_cuda_kernel_pruneonly.cuh:104-277), with the half-list rules of
+ * nbnxm/pairlist.cpp:3339-3342,3365-3372 (shift <= CENTRAL; cj >= ci for CENTRAL).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct
+{
+    uint64_t* keys;
+    long long cap, n;
+    const int* slot;
+} tile_ctx;
+
+static void tile_cb(void* vctx, int ai, int aj, int shift, float rsq)
+{
+    (void)rsq;
+    tile_ctx* c  = (tile_ctx*)vctx;
+    int       ci = c->slot[ai] / ORC_CL, cj = c->slot[aj] / ORC_CL;
+    if (shift == ORC_CENTRAL && cj < ci)
+    {
+        int t = ci;
+        ci    = cj;
+        cj    = t;
+    }
+    if (c->n < c->cap) c->keys[c->n] = ((uint64_t)ci << 38) | ((uint64_t)shift << 32) | (uint64_t)cj;
+    c->n++;
+}
+
+static int cmp_u64(const void* a, const void* b)
+{
+    uint64_t p = *(const uint64_t*)a, q = *(const uint64_t*)b;
+    return (p > q) - (p < q);
+}
+
+/* tiles[3*k] = ci, shift, cj sorted by (ci, shift, cj). Returns count or -1 on overflow. */
+long long orc_tile_list(int n, const float* x, const float box[3], float rlist, const int* slot_of_atom,
+                        int* tiles, long long cap)
+{
+    long long kcap = 1 << 20;
+    for (;;)
+    {
+        tile_ctx c = { (uint64_t*)malloc(sizeof(uint64_t) * (size_t)kcap), kcap, 0, slot_of_atom };
+        for_each_pair(n, x, box, rlist, tile_cb, &c);
+        if (c.n > kcap)
+        {
+            free(c.keys);
+            kcap = c.n + 16;
+            continue;
+        }
+        qsort(c.keys, (size_t)c.n, sizeof(uint64_t), cmp_u64);
+        long long m = 0;
+        for (long long k = 0; k < c.n; k++)
+        {
+            if (k > 0 && c.keys[k] == c.keys[k - 1]) continue;
+            if (m < cap)
+            {
+                tiles[3 * m]     = (int)(c.keys[k] >> 38);
+                tiles[3 * m + 1] = (int)((c.keys[k] >> 32) & 63);
+                tiles[3 * m + 2] = (int)(c.keys[k] & 0xffffffffu);
+            }
+            m++;
+        }
+        free(c.keys);
+        return m <= cap ? m : -1;
+    }
+}
+
+/* kernels_reference/kernel_ref_prune.cpp:45-143 restated for 8x8 tiles in grid order: keep[k]=1 iff any
+ * atom pair of tile k has r^2 < rlist_inner^2. x in ORIGINAL atom order, atom_index maps slot->atom. */
+void orc_prune_tiles(long long ntiles, const int* tiles, const int* atom_index, const float* x,
+                     const float box[3], float rlist_inner, unsigned char* keep)
+{
+    float sv[ORC_SHIFTS * 3];
+    orc_shift_vectors(box, sv);
+    const float r2 = rlist_inner * rlist_inner;
+    for (long long k = 0; k < ntiles; k++)
+    {
+        int ci = tiles[3 * k], is = tiles[3 * k + 1], cj = tiles[3 * k + 2];
+        int in = 0;
+        for (int i = 0; i < ORC_CL && !in; i++)
+        {
+            int a = atom_index[ci * ORC_CL + i];
+            if (a < 0) continue;
+            for (int j = 0; j < ORC_CL; j++)
+            {
+                int b = atom_index[cj * ORC_CL + j];
+                if (b < 0) continue;
+                if (is == ORC_CENTRAL && ci == cj && j <= i) continue;
+                if (orc_rsq(x[3 * a], x[3 * a + 1], x[3 * a + 2], sv[3 * is], sv[3 * is + 1], sv[3 * is + 2],
+                            x[3 * b], x[3 * b + 1], x[3 * b + 2])
+                    < r2)
+                {
+                    in = 1;
+                    break;
+                }
+            }
+        }
+        keep[k] = (unsigned char)in;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Pair interactions
+ * ------------------------------------------------------------------------------------------------ */
+
+/* simd/simd_math.h:1609-1650 pmeForceCorrection (single precision rational minimax), scalar */
+static float pme_force_correction(float z2)
+{
+    const float FN6 = -1.7357322914161492954e-8f, FN5 = 1.4703624142580877519e-6f,
+                FN4 = -0.000053401640219807709149f, FN3 = 0.0010054721316683106153f,
+                FN2 = -0.019278317264888380590f, FN1 = 0.069670166153766424023f,
+                FN0 = -0.75225204789749321333f;
+    const float FD4 = 0.0011193462567257629232f, FD3 = 0.014866955030185295499f,
+                FD2 = 0.11583842382862377919f, FD1 = 0.50736591960530292870f, FD0 = 1.0f;
+    float z4 = z2 * z2;
+    float d0 = fmaf(FD4, z4, FD2), d1 = fmaf(FD3, z4, FD1);
+    d0       = fmaf(d0, z4, FD0);
+    d0       = fmaf(d1, z2, d0);
+    d0       = 1.0f / d0;
+    float n0 = fmaf(FN6, z4, FN4), n1 = fmaf(FN5, z4, FN3);
+    n0       = fmaf(n0, z4, FN2);
+    n1       = fmaf(n1, z4, FN1);
+    n0       = fmaf(n0, z4, FN0);
+    n0       = fmaf(n1, z2, n0);
+    return n0 * d0;
+}
+
+/* simd/simd_math.h:1687-1722 pmePotentialCorrection */
+static float pme_potential_correction(float z2)
+{
+    const float VN6 = 1.9296833005951166339e-8f, VN5 = -1.4213390571557850962e-6f,
+                VN4 = 0.000041603292906656984871f, VN3 = -0.00013134036773265025626f,
+                VN2 = 0.038657983986041781264f, VN1 = 0.11285044772717598220f, VN0 = 1.1283802385263030286f;
+    const float VD3 = 0.0066752224023576045451f, VD2 = 0.078647795836373922256f,
+                VD1 = 0.43336185284710920150f, VD0 = 1.0f;
+    float z4 = z2 * z2;
+    float d1 = fmaf(VD3, z4, VD1), d0 = fmaf(VD2, z4, VD0);
+    d0       = fmaf(d1, z2, d0);
+    d0       = 1.0f / d0;
+    float n0 = fmaf(VN6, z4, VN4), n1 = fmaf(VN5, z4, VN3);
+    n0       = fmaf(n0, z4, VN2);
+    n1       = fmaf(n1, z4, VN1);
+    n0       = fmaf(n0, z4, VN0);
+    n0       = fmaf(n1, z2, n0);
+    return n0 * d0;
+}
+
+typedef struct
+{
+    const orc_params* p;
+    const float*      x;
+    const float*      q;
+    const int*        type;
+    const int *       excl_off, *excl_idx;
+    float             sv[ORC_SHIFTS * 3];
+    double*           f;      /* 3n */
+    double*           fshift; /* 45*3 */
+    double            evdw, ecoul;
+    long long         npairs; /* non-excluded pairs within the cut-off */
+    int               want_energy;
+} force_ctx;
+
+/* One atom pair, the arithmetic of kernels_simd_2xmm/kernel_inner.h:226-880 (LJ cut-off with potential
+ * shift; reaction-field / plain cut-off :376-383; analytical Ewald :386-400,462-474) evaluated in
+ * single precision; excluded pairs within the cut-off keep only the reaction-field / Ewald exclusion
+ * correction (EXCL_FORCES, :358-366,520-523).  Contributions are accumulated in double. */
+static void force_cb(void* vctx, int ai, int aj, int is, float rsq)
+{
+    force_ctx*        c = (force_ctx*)vctx;
+    const orc_params* p = c->p;
+    const int   excluded = is_excluded(c->excl_off, c->excl_idx, ai, aj);
+    const float interact = excluded ? 0.0f : 1.0f;
+    if (!excluded) c->npairs++;
+
+    const float dx = (c->x[3 * ai] + c->sv[3 * is]) - c->x[3 * aj];
+    const float dy = (c->x[3 * ai + 1] + c->sv[3 * is + 1]) - c->x[3 * aj + 1];
+    const float dz = (c->x[3 * ai + 2] + c->sv[3 * is + 2]) - c->x[3 * aj + 2];
+
+    if (rsq < 3.82e-07f) rsq = 3.82e-07f; /* nbnxm/pairlist.h:146 c_nbnxnMinDistanceSquared */
+    const float rinv    = 1.0f / sqrtf(rsq);
+    const float rinvsq  = rinv * rinv;
+    const float rinv_ex = rinv * interact;
+
+    const float qq = (p->epsfac * c->q[ai]) * c->q[aj];
+    float       frcoul, vcoul = 0;
+    if (p->eeltype == ORC_EEL_EWALD)
+    {
+        const float brsq   = p->beta * p->beta * rsq;
+        const float ewcorr = p->beta * pme_force_correction(brsq);
+        frcoul             = qq * fmaf(ewcorr, brsq, rinv_ex);
+        if (c->want_energy)
+        {
+            float vc_sub = p->beta * pme_potential_correction(brsq) + p->sh_ewald * interact;
+            vcoul        = qq * (rinv_ex - vc_sub);
+        }
+    }
+    else
+    {
+        const float k_rf = (p->eeltype == ORC_EEL_RF) ? p->k_rf : 0.0f;
+        frcoul           = qq * fmaf(rsq, -2.0f * k_rf, rinv_ex);
+        if (c->want_energy) vcoul = qq * (rinv_ex + fmaf(rsq, k_rf, -p->c_rf));
+    }
+
+    const int   ti = c->type[ai], tj = c->type[aj];
+    const float c6 = p->nbfp[(ti * p->ntypes + tj) * 2], c12 = p->nbfp[(ti * p->ntypes + tj) * 2 + 1];
+    const float rinvsix = rinvsq * rinvsq * rinvsq * interact;
+    const float frlj6 = c6 * rinvsix, frlj12 = c12 * rinvsix * rinvsix;
+    const float frlj  = frlj12 - frlj6;
+    if (c->want_energy)
+    {
+        float v6  = (1.0f / 6.0f) * fmaf(c6, p->disp_cpot, frlj6);
+        float v12 = (1.0f / 12.0f) * fmaf(c12, p->rep_cpot, frlj12);
+        c->evdw += (double)((v12 - v6) * interact);
+        c->ecoul += (double)vcoul;
+    }
+    const float fscal = rinvsq * (frcoul + frlj);
+    const float tx = fscal * dx, ty = fscal * dy, tz = fscal * dz;
+    c->f[3 * ai] += tx;
+    c->f[3 * ai + 1] += ty;
+    c->f[3 * ai + 2] += tz;
+    c->f[3 * aj] -= tx;
+    c->f[3 * aj + 1] -= ty;
+    c->f[3 * aj + 2] -= tz;
+    c->fshift[3 * is] += tx; /* kernels_simd_2xmm/kernel_outer.h:620-640: i-forces summed per shift */
+    c->fshift[3 * is + 1] += ty;
+    c->fshift[3 * is + 2] += tz;
+}
+
+/* Forces (original atom order), shift forces [45*3], energies {Vvdw, Vcoul}, pair count.
+ * Self terms: kernels_simd_2xmm/kernel_outer.h:408-452 (RF: -0.5*c_rf*facel*q^2, Ewald:
+ * -facel*q^2*beta/sqrt(pi)). Returns the number of non-excluded pairs within the cut-off. */
+long long orc_forces(int n, const float* x, const float box[3], const float* q, const int* type,
+                     const int* excl_off, const int* excl_idx, const orc_params* p, int want_energy,
+                     double* f, double* fshift, double* energies)
+{
+    force_ctx c;
+    memset(&c, 0, sizeof(c));
+    c.p = p;
+    c.x = x;
+    c.q = q;
+    c.type = type;
+    c.excl_off = excl_off;
+    c.excl_idx = excl_idx;
+    c.f = f;
+    c.fshift = fshift;
+    c.want_energy = want_energy;
+    orc_shift_vectors(box, c.sv);
+    memset(f, 0, sizeof(double) * 3 * (size_t)n);
+    memset(fshift, 0, sizeof(double) * 3 * ORC_SHIFTS);
+    for_each_pair(n, x, box, p->rc, force_cb, &c);
+    if (want_energy)
+    {
+        double sub = (p->eeltype == ORC_EEL_EWALD) ? 0.5 * p->beta * 1.12837916709551257390 /* M_2_SQRTPI */
+                                                   : 0.5 * p->c_rf;
+        for (int a = 0; a < n; a++) c.ecoul -= (double)p->epsfac * q[a] * q[a] * sub;
+    }
+    energies[0] = c.evdw;
+    energies[1] = c.ecoul;
+    return c.npairs;
+}
+
+/* mdlib/sim_util.cpp:157-183 calc_virial's shift-force part: vir = -0.5 * sum_s shift_vec[s] (x) fshift[s]
+ * (mdlib/calcvir.cpp calc_vir); returned as 9 doubles row-major. */
+void orc_virial_from_fshift(const float box[3], const double* fshift, double* vir)
+{
+    float sv[ORC_SHIFTS * 3];
+    orc_shift_vectors(box, sv);
+    for (int k = 0; k < 9; k++) vir[k] = 0;
+    for (int s = 0; s < ORC_SHIFTS; s++)
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) vir[3 * a + b] += -0.5 * (double)sv[3 * s + a] * fshift[3 * s + b];
+}

@@ -1,0 +1,174 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of the plain-C oracle (oracle/nbnxm_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product (gmxapi_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libnbnxm_oracle.so")
+EEL_CUT, EEL_RF, EEL_EWALD = 0, 1, 2
+CENTRAL, SHIFTS = 22, 45
+
+
+class _Params(C.Structure):
+    _fields_ = [("rc", C.c_float), ("eeltype", C.c_int), ("epsfac", C.c_float), ("k_rf", C.c_float),
+                ("c_rf", C.c_float), ("beta", C.c_float), ("sh_ewald", C.c_float),
+                ("disp_cpot", C.c_float), ("rep_cpot", C.c_float), ("ntypes", C.c_int), ("nbfp", C.c_void_p)]
+
+
+_lib = None
+
+
+def build():
+    src = os.path.join(_HERE, "nbnxm_oracle.c")
+    if (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "_build/libnbnxm_oracle.so"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        L.orc_rsq.restype = C.c_float
+        L.orc_rsq.argtypes = [C.c_float] * 9
+        L.orc_put_on_grid.restype = C.c_int
+        L.orc_pair_set.restype = C.c_longlong
+        L.orc_tile_list.restype = C.c_longlong
+        L.orc_forces.restype = C.c_longlong
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+def rsq(xi, shift, xj):
+    return float(lib().orc_rsq(*[C.c_float(float(v)) for v in (*xi, *shift, *xj)]))
+
+
+def shift_vectors(box):
+    sv = np.zeros((SHIFTS, 3), np.float32)
+    b = (C.c_float * 3)(*[float(v) for v in box])
+    lib().orc_shift_vectors(b, _p(sv))
+    return sv
+
+
+def put_on_grid(x, box, density=None):
+    """Returns dict(ncx, ncy, col_cell0, atom_index, slot_of_atom)."""
+    x = _f32(x)
+    n = x.shape[0]
+    lower = (C.c_float * 3)(0, 0, 0)
+    upper = (C.c_float * 3)(*[float(v) for v in box])
+    if density is None:
+        density = np.float32(n) / (np.float32(box[0]) * np.float32(box[1]) * np.float32(box[2]))
+    cap = n + 64 * 70000 + 64
+    colcap = 70002
+    atom_index = np.zeros(cap, np.int32)
+    col_cell0 = np.zeros(colcap, np.int32)
+    slot = np.zeros(n, np.int32)
+    ncx, ncy = C.c_int(), C.c_int()
+    npad = lib().orc_put_on_grid(C.c_int(n), _p(x), lower, upper, C.c_float(float(density)), C.byref(ncx),
+                                 C.byref(ncy), _p(col_cell0), C.c_int(colcap), _p(atom_index), C.c_int(cap),
+                                 _p(slot))
+    if npad < 0:
+        raise RuntimeError("orc_put_on_grid: capacity exceeded")
+    ncol = ncx.value * ncy.value
+    return dict(ncx=ncx.value, ncy=ncy.value, col_cell0=col_cell0[:ncol + 1].copy(),
+                atom_index=atom_index[:npad].copy(), slot_of_atom=slot, npad=npad)
+
+
+def pair_set(x, box, r, excl_off=None, excl_idx=None):
+    """(npairs,3) int32: (i [the shifted atom], j, shift index), unsorted."""
+    x = _f32(x)
+    n = x.shape[0]
+    b = (C.c_float * 3)(*[float(v) for v in box])
+    eo = _i32(excl_off) if excl_off is not None else None
+    ei = _i32(excl_idx) if excl_idx is not None else None
+    cnt = lib().orc_pair_set(C.c_int(n), _p(x), b, C.c_float(r), _p(eo), _p(ei), C.c_void_p(0), C.c_longlong(0))
+    out = np.zeros((max(cnt, 1), 3), np.int32)
+    lib().orc_pair_set(C.c_int(n), _p(x), b, C.c_float(r), _p(eo), _p(ei), _p(out), C.c_longlong(cnt))
+    return out[:cnt]
+
+
+def canonical_pairs(pairs):
+    """Sort (i,j,shift) triples into a canonical order; CENTRAL pairs get i<j."""
+    p = np.array(pairs, dtype=np.int64, copy=True).reshape(-1, 3)
+    cen = p[:, 2] == CENTRAL
+    lo = np.minimum(p[:, 0], p[:, 1])
+    hi = np.maximum(p[:, 0], p[:, 1])
+    p[cen, 0] = lo[cen]
+    p[cen, 1] = hi[cen]
+    key = (p[:, 0] << 34) | (p[:, 1] << 6) | p[:, 2]
+    return np.sort(key)
+
+
+def tile_list(x, box, rlist, slot_of_atom):
+    x = _f32(x)
+    n = x.shape[0]
+    b = (C.c_float * 3)(*[float(v) for v in box])
+    slot = _i32(slot_of_atom)
+    cap = max(1 << 16, n * 24)
+    while True:
+        out = np.zeros((cap, 3), np.int32)
+        m = lib().orc_tile_list(C.c_int(n), _p(x), b, C.c_float(rlist), _p(slot), _p(out), C.c_longlong(cap))
+        if m >= 0:
+            return out[:m]
+        cap *= 4
+
+
+def prune_tiles(tiles, atom_index, x, box, rlist_inner):
+    tiles = _i32(tiles)
+    x = _f32(x)
+    ai = _i32(atom_index)
+    b = (C.c_float * 3)(*[float(v) for v in box])
+    keep = np.zeros(len(tiles), np.uint8)
+    lib().orc_prune_tiles(C.c_longlong(len(tiles)), _p(tiles), _p(ai), _p(x), b, C.c_float(rlist_inner), _p(keep))
+    return keep.astype(bool)
+
+
+def forces(x, box, q, types, nbfp, rc, excl_off=None, excl_idx=None, eeltype=EEL_CUT, epsfac=138.935458,
+           k_rf=0.0, c_rf=0.0, beta=0.0, sh_ewald=0.0, disp_cpot=None, rep_cpot=None, energy=True):
+    """Returns (f[n,3] float64, fshift[45,3] float64, evdw, ecoul, npairs)."""
+    x = _f32(x)
+    n = x.shape[0]
+    q = _f32(q)
+    types = _i32(types)
+    nbfp = _f32(nbfp).ravel()
+    ntypes = int(round((nbfp.size // 2) ** 0.5))
+    if disp_cpot is None:
+        disp_cpot = -1.0 / rc ** 6
+    if rep_cpot is None:
+        rep_cpot = -1.0 / rc ** 12
+    p = _Params(rc, eeltype, epsfac, k_rf, c_rf, beta, sh_ewald, disp_cpot, rep_cpot, ntypes, nbfp.ctypes.data)
+    b = (C.c_float * 3)(*[float(v) for v in box])
+    eo = _i32(excl_off) if excl_off is not None else None
+    ei = _i32(excl_idx) if excl_idx is not None else None
+    f = np.zeros((n, 3), np.float64)
+    fs = np.zeros((SHIFTS, 3), np.float64)
+    e = np.zeros(2, np.float64)
+    npairs = lib().orc_forces(C.c_int(n), _p(x), b, _p(q), _p(types), _p(eo), _p(ei), C.byref(p),
+                              C.c_int(int(energy)), _p(f), _p(fs), _p(e))
+    return f, fs, float(e[0]), float(e[1]), int(npairs)
+
+
+def virial_from_fshift(box, fshift):
+    b = (C.c_float * 3)(*[float(v) for v in box])
+    fs = np.ascontiguousarray(fshift, dtype=np.float64)
+    vir = np.zeros(9, np.float64)
+    lib().orc_virial_from_fshift(b, _p(fs), _p(vir))
+    return vir.reshape(3, 3)

@@ -1,0 +1,617 @@
+/* TEST INFRASTRUCTURE ONLY -- never linked into the product library.
+ *
+ * C-ABI harness around the UNMODIFIED reference nbnxm CPU path, compiled from the
+ * sources where they lie under /root/reference by oracle/build_ref.sh into
+ * oracle/_ref/libgmxref_nbnxm.so.  It assembles a nonbonded_verlet_t by hand the way
+ * the reference's own benchmark does (src/gromacs/nbnxm/benchmark/bench_setup.cpp:170-232
+ * setupNbnxmForBenchInstance; api/nblib/gmxsetup.cpp:175-208 setupNbnxmInstance) and
+ * exposes: forces / shift forces / energies from the plain-C 4x4, SIMD 4xN/2xNN or
+ * GPU-emulation 8x8x8 kernels, the grid atom order, the in-range atom-pair set of the
+ * reference list, and wall-clock timings of grid / search / kernel.
+ *
+ * Used by: tests/ (validation of oracle/nbnxm_oracle.c), bench.py cpu_baseline and
+ * `bench.py --impl reference`.
+ */
+#include "gmxpre.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "gromacs/ewald/ewald_utils.h"
+#include "gromacs/gmxlib/nrnb.h"
+#include "gromacs/gpu_utils/hostallocator.h"
+#include "gromacs/math/units.h"
+#include "gromacs/math/vec.h"
+#include "gromacs/mdlib/gmx_omp_nthreads.h"
+#include "gromacs/mdtypes/enerdata.h"
+#include "gromacs/mdtypes/forcerec.h"
+#include "gromacs/mdtypes/interaction_const.h"
+#include "gromacs/mdtypes/simulation_workload.h"
+#include "gromacs/nbnxm/atomdata.h"
+#include "gromacs/nbnxm/gridset.h"
+#include "gromacs/nbnxm/nbnxm.h"
+#include "gromacs/nbnxm/nbnxm_simd.h"
+#include "gromacs/nbnxm/pairlist.h"
+#include "gromacs/nbnxm/pairlistset.h"
+#include "gromacs/nbnxm/pairlistsets.h"
+#include "gromacs/nbnxm/pairsearch.h"
+#include "gromacs/pbcutil/ishift.h"
+#include "gromacs/pbcutil/pbc.h"
+#include "gromacs/simd/simd.h"
+#include "gromacs/simd/vector_operations.h"
+#include "gromacs/tables/forcetable.h"
+#include "gromacs/utility/listoflists.h"
+#include "gromacs/utility/logger.h"
+
+#include "ref_harness.h"
+
+namespace
+{
+
+double nowSeconds()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+/* r^2 exactly as the reference SIMD kernels evaluate it: gmx::norm2 on SimdReal
+ * (simd/vector_operations.h:106-115), compiled here with the same flags as the kernels,
+ * i-atom shifted first (kernels_simd_2xmm/kernel_outer.h:482-489), dx = xi - xj. */
+float simdRsq(float xi, float yi, float zi, float xj, float yj, float zj)
+{
+#if GMX_SIMD_HAVE_REAL
+    using gmx::SimdReal;
+    SimdReal                                   dx = SimdReal(xi) - SimdReal(xj);
+    SimdReal                                   dy = SimdReal(yi) - SimdReal(yj);
+    SimdReal                                   dz = SimdReal(zi) - SimdReal(zj);
+    SimdReal                                   r2 = gmx::norm2(dx, dy, dz);
+    alignas(GMX_SIMD_ALIGNMENT) float          tmp[GMX_SIMD_REAL_WIDTH];
+    gmx::store(tmp, r2);
+    return tmp[0];
+#else
+    float dx = xi - xj, dy = yi - yj, dz = zi - zj;
+    return dx * dx + dy * dy + dz * dz;
+#endif
+}
+
+struct Instance
+{
+    std::unique_ptr<nonbonded_verlet_t> nbv;
+    interaction_const_t                 ic;
+    std::vector<gmx::RVec>              x;
+    std::vector<int>                    atomInfo;
+    gmx::ListOfLists<int>               excls;
+    matrix                              box;
+    rvec                                shiftVec[SHIFTS];
+    t_forcerec*                         fr = nullptr; // zero-filled, only shift_vec / bBHAM are read
+    int                                 natoms   = 0;
+    int                                 nthreads = 1;
+    Nbnxm::KernelType                   kernelType;
+    double                              tGrid = 0, tSearch = 0;
+};
+
+Nbnxm::KernelType kernelTypeFromInt(int k)
+{
+    switch (k)
+    {
+        case GMXREF_KERNEL_PLAINC_4X4: return Nbnxm::KernelType::Cpu4x4_PlainC;
+        case GMXREF_KERNEL_SIMD_4XN: return Nbnxm::KernelType::Cpu4xN_Simd_4xN;
+        case GMXREF_KERNEL_SIMD_2XNN: return Nbnxm::KernelType::Cpu4xN_Simd_2xNN;
+        case GMXREF_KERNEL_GPUREF_8X8X8: return Nbnxm::KernelType::Cpu8x8x8_PlainC;
+        default: return Nbnxm::KernelType::NotSet;
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int gmxref_simd_width(void)
+{
+#if GMX_SIMD_HAVE_REAL
+    return GMX_SIMD_REAL_WIDTH;
+#else
+    return 0;
+#endif
+}
+
+int gmxref_default_simd_kernel(void)
+{
+#if defined GMX_NBNXN_SIMD_2XNN && !defined GMX_NBNXN_SIMD_4XN
+    return GMXREF_KERNEL_SIMD_2XNN;
+#elif defined GMX_NBNXN_SIMD_4XN
+    return GMXREF_KERNEL_SIMD_4XN;
+#else
+    return GMXREF_KERNEL_PLAINC_4X4;
+#endif
+}
+
+float gmxref_ewald_coeff(float rc, float rtol)
+{
+    return calc_ewaldcoeff_q(rc, rtol);
+}
+
+float gmxref_simd_rsq(float xi, float yi, float zi, float xj, float yj, float zj)
+{
+    return simdRsq(xi, yi, zi, xj, yj, zj);
+}
+
+void* gmxref_create(const gmxref_system* s, const gmxref_params* p)
+{
+    Nbnxm::KernelType kernelType = kernelTypeFromInt(p->kernel);
+    if (kernelType == Nbnxm::KernelType::NotSet)
+    {
+        return nullptr;
+    }
+#ifndef GMX_NBNXN_SIMD_4XN
+    if (kernelType == Nbnxm::KernelType::Cpu4xN_Simd_4xN)
+    {
+        return nullptr;
+    }
+#endif
+#ifndef GMX_NBNXN_SIMD_2XNN
+    if (kernelType == Nbnxm::KernelType::Cpu4xN_Simd_2xNN)
+    {
+        return nullptr;
+    }
+#endif
+    auto* inst       = new Instance;
+    inst->natoms     = s->natoms;
+    inst->nthreads   = p->nthreads > 0 ? p->nthreads : 1;
+    inst->kernelType = kernelType;
+    const int nth    = inst->nthreads;
+    gmx_omp_nthreads_set(emntPairsearch, nth);
+    gmx_omp_nthreads_set(emntNonbonded, nth);
+    gmx_omp_nthreads_set(emntDefault, nth);
+
+    /* interaction constants (bench_setup.cpp:134-166, api/nblib/gmxsetup.cpp:226-284) */
+    interaction_const_t& ic = inst->ic;
+    ic.vdwtype               = evdwCUT;
+    ic.vdw_modifier          = eintmodPOTSHIFT;
+    ic.rvdw                  = p->rc;
+    ic.coulomb_modifier      = eintmodPOTSHIFT;
+    ic.rcoulomb              = p->rc;
+    ic.dispersion_shift.cpot = p->disp_cpot;
+    ic.repulsion_shift.cpot  = p->rep_cpot;
+    ic.epsilon_r             = 1;
+    ic.epsfac                = p->epsfac;
+    ic.k_rf                  = p->k_rf;
+    ic.c_rf                  = p->c_rf;
+    ic.sh_ewald              = p->sh_ewald;
+    switch (p->eeltype)
+    {
+        case GMXREF_EEL_CUT: ic.eeltype = eelCUT; break;
+        case GMXREF_EEL_RF: ic.eeltype = eelRF; break;
+        default: ic.eeltype = eelPME; break;
+    }
+    Nbnxm::KernelSetup kernelSetup;
+    kernelSetup.kernelType = kernelType;
+    const bool simdKernel  = (kernelType == Nbnxm::KernelType::Cpu4xN_Simd_4xN
+                             || kernelType == Nbnxm::KernelType::Cpu4xN_Simd_2xNN);
+    kernelSetup.ewaldExclusionType = (simdKernel && p->eeltype == GMXREF_EEL_EWALD_ANA)
+                                             ? Nbnxm::EwaldExclusionType::Analytical
+                                             : Nbnxm::EwaldExclusionType::Table;
+    if (ic.eeltype == eelPME)
+    {
+        ic.ewaldcoeff_q       = p->ewaldcoeff;
+        ic.coulombEwaldTables = std::make_unique<EwaldCorrectionTables>();
+        /* mdlib/forcerec.cpp:724-763 init_ewald_f_table, Coulomb only */
+        const real tableScale = ewald_spline3_table_scale(ic, true, false);
+        const int  tableSize  = static_cast<int>(ic.rcoulomb * tableScale) + 2;
+        *ic.coulombEwaldTables =
+                generateEwaldCorrectionTables(tableSize, tableScale, ic.ewaldcoeff_q, v_q_ewald_lr);
+    }
+
+    clear_mat(inst->box);
+    inst->box[XX][XX] = s->box[0];
+    inst->box[YY][YY] = s->box[1];
+    inst->box[ZZ][ZZ] = s->box[2];
+    calc_shifts(inst->box, inst->shiftVec);
+    inst->fr            = static_cast<t_forcerec*>(std::calloc(1, sizeof(t_forcerec)));
+    inst->fr->shift_vec = inst->shiftVec;
+
+    inst->x.resize(s->natoms);
+    inst->atomInfo.assign(s->natoms, 0);
+    std::vector<int>  types(s->type, s->type + s->natoms);
+    std::vector<real> charges(s->q, s->q + s->natoms);
+    for (int a = 0; a < s->natoms; a++)
+    {
+        inst->x[a] = { s->x[3 * a], s->x[3 * a + 1], s->x[3 * a + 2] };
+        /* bench_system.cpp:176-189: all atoms flagged VdW + Q unless the caller asks for
+         * the exact per-atom flags (half-LJ optimisation). */
+        bool hasVdw = true, hasQ = true;
+        if (p->exact_atom_flags)
+        {
+            const int t = s->type[a];
+            hasVdw      = false;
+            for (int t2 = 0; t2 < s->ntypes; t2++)
+            {
+                if (s->nbfp[(t * s->ntypes + t2) * 2] != 0 || s->nbfp[(t * s->ntypes + t2) * 2 + 1] != 0)
+                {
+                    hasVdw = true;
+                }
+            }
+            hasQ = (s->q[a] != 0);
+        }
+        if (hasVdw)
+        {
+            SET_CGINFO_HAS_VDW(inst->atomInfo[a]);
+        }
+        if (hasQ)
+        {
+            SET_CGINFO_HAS_Q(inst->atomInfo[a]);
+        }
+        const int n0 = s->excl_off[a], n1 = s->excl_off[a + 1];
+        inst->excls.pushBackListOfSize(n1 - n0);
+        gmx::ArrayRef<int> e = inst->excls.back();
+        for (int k = n0; k < n1; k++)
+        {
+            e[k - n0] = s->excl_idx[k];
+        }
+    }
+    if (p->put_in_box)
+    {
+        put_atoms_in_box(PbcType::Xyz, inst->box, inst->x);
+    }
+
+    const auto pin = gmx::PinningPolicy::CannotBePinned;
+    PairlistParams pairlistParams(kernelType, false, p->rlist, false);
+    if (p->rlist_inner > 0 && p->rlist_inner < p->rlist)
+    {
+        /* dynamic pruning set up as pairlist_tuning.cpp:506-572 would */
+        pairlistParams.useDynamicPruning      = true;
+        pairlistParams.rlistInner             = p->rlist_inner;
+        pairlistParams.nstlistPrune           = p->nstlist_prune > 0 ? p->nstlist_prune : 4;
+        pairlistParams.numRollingPruningParts = 1;
+        pairlistParams.lifetime               = 100;
+    }
+    auto pairlistSets = std::make_unique<PairlistSets>(pairlistParams, false, p->min_ilist_count);
+    auto pairSearch   = std::make_unique<PairSearch>(PbcType::Xyz, false, nullptr, nullptr,
+                                                   pairlistParams.pairlistType, false, nth, pin);
+    auto atomData     = std::make_unique<nbnxn_atomdata_t>(pin);
+    inst->nbv = std::make_unique<nonbonded_verlet_t>(std::move(pairlistSets), std::move(pairSearch),
+                                                     std::move(atomData), kernelSetup, nullptr, nullptr);
+    std::vector<real> nbfp(s->nbfp, s->nbfp + 2 * s->ntypes * s->ntypes);
+    nbnxn_atomdata_init(gmx::MDLogger(), inst->nbv->nbat.get(), kernelType, p->comb_rule, s->ntypes,
+                        nbfp, 1, nth);
+
+    const rvec lower   = { 0, 0, 0 };
+    const rvec upper   = { inst->box[XX][XX], inst->box[YY][YY], inst->box[ZZ][ZZ] };
+    const real density = s->natoms / det(inst->box);
+    t_nrnb     nrnb;
+    double     t0 = nowSeconds();
+    nbnxn_put_on_grid(inst->nbv.get(), inst->box, 0, lower, upper, nullptr, { 0, s->natoms }, density,
+                      inst->atomInfo, inst->x, 0, nullptr);
+    double t1 = nowSeconds();
+    inst->nbv->constructPairlist(gmx::InteractionLocality::Local, inst->excls, 0, &nrnb);
+    double t2     = nowSeconds();
+    inst->tGrid   = t1 - t0;
+    inst->tSearch = t2 - t1;
+    inst->nbv->setAtomProperties(types, charges, inst->atomInfo);
+    return inst;
+}
+
+void gmxref_destroy(void* h)
+{
+    auto* inst = static_cast<Instance*>(h);
+    if (inst)
+    {
+        std::free(inst->fr);
+        delete inst;
+    }
+}
+
+/* Re-grid + re-search with timing (for the CPU baseline of the search stage). */
+int gmxref_regrid_research(void* h, double* tGrid, double* tSearch)
+{
+    auto*      inst    = static_cast<Instance*>(h);
+    const rvec lower   = { 0, 0, 0 };
+    const rvec upper   = { inst->box[XX][XX], inst->box[YY][YY], inst->box[ZZ][ZZ] };
+    const real density = inst->natoms / det(inst->box);
+    t_nrnb     nrnb;
+    double     t0 = nowSeconds();
+    nbnxn_put_on_grid(inst->nbv.get(), inst->box, 0, lower, upper, nullptr, { 0, inst->natoms },
+                      density, inst->atomInfo, inst->x, 0, nullptr);
+    double t1 = nowSeconds();
+    inst->nbv->constructPairlist(gmx::InteractionLocality::Local, inst->excls, 0, &nrnb);
+    double t2 = nowSeconds();
+    *tGrid    = t1 - t0;
+    *tSearch  = t2 - t1;
+    return 0;
+}
+
+void gmxref_setup_times(void* h, double* tGrid, double* tSearch)
+{
+    auto* inst = static_cast<Instance*>(h);
+    *tGrid     = inst->tGrid;
+    *tSearch   = inst->tSearch;
+}
+
+/* Full force evaluation as GmxForceCalculator::compute does (api/nblib/gmxcalculator.cpp:70-83):
+ * convertCoordinates -> dispatchNonbondedKernel(clearF) -> atomdata_add_nbat_f_to_f.
+ * x may be NULL (use the coordinates given at create). f[3N] is overwritten, fshift[135]
+ * overwritten (zeros unless want_virial), energies[2] = {Vvdw, Vcoul}. */
+int gmxref_compute(void* h, const float* x, int want_energy, int want_virial, float* f, float* fshift,
+                   float* energies)
+{
+    auto* inst = static_cast<Instance*>(h);
+    if (x)
+    {
+        for (int a = 0; a < inst->natoms; a++)
+        {
+            inst->x[a] = { x[3 * a], x[3 * a + 1], x[3 * a + 2] };
+        }
+    }
+    inst->nbv->convertCoordinates(gmx::AtomLocality::Local, false, inst->x);
+    gmx::StepWorkload stepWork;
+    stepWork.computeForces = true;
+    stepWork.computeEnergy = want_energy != 0;
+    stepWork.computeVirial = want_virial != 0 || want_energy != 0;
+    gmx_enerdata_t enerd(1, 0);
+    t_nrnb         nrnb = { 0 };
+    inst->nbv->dispatchNonbondedKernel(gmx::InteractionLocality::Local, inst->ic, stepWork,
+                                       enbvClearFYes, *inst->fr, &enerd, &nrnb);
+    std::vector<gmx::RVec> force(inst->natoms, { 0, 0, 0 });
+    if (inst->kernelType == Nbnxm::KernelType::Cpu8x8x8_PlainC)
+    {
+        /* nbnxm.cpp:167-171 skips the reduction for GPU-layout lists without a physical GPU;
+         * call the same reduction (atomdata.cpp:1425) directly. */
+        reduceForces(inst->nbv->nbat.get(), gmx::AtomLocality::All, inst->nbv->pairSearch_->gridSet(),
+                     as_rvec_array(force.data()));
+    }
+    else
+    {
+        inst->nbv->atomdata_add_nbat_f_to_f(gmx::AtomLocality::All, force);
+    }
+    for (int a = 0; a < inst->natoms; a++)
+    {
+        f[3 * a]     = force[a][XX];
+        f[3 * a + 1] = force[a][YY];
+        f[3 * a + 2] = force[a][ZZ];
+    }
+    if (fshift)
+    {
+        std::vector<gmx::RVec> fs(SHIFTS, { 0, 0, 0 });
+        if (stepWork.computeVirial)
+        {
+            nbnxn_atomdata_add_nbat_fshift_to_fshift(*inst->nbv->nbat, fs);
+        }
+        for (int sIdx = 0; sIdx < SHIFTS; sIdx++)
+        {
+            for (int d = 0; d < DIM; d++)
+            {
+                fshift[3 * sIdx + d] = fs[sIdx][d];
+            }
+        }
+    }
+    if (energies)
+    {
+        energies[0] = enerd.grpp.ener[egLJSR][0];
+        energies[1] = enerd.grpp.ener[egCOULSR][0];
+    }
+    return 0;
+}
+
+/* Kernel-only timing, the protocol of bench_setup.cpp:303-326: one pre-iteration with
+ * force clearing, then niter iterations without clearing. Returns seconds per iteration. */
+double gmxref_time_kernel(void* h, int want_energy, int nwarm, int niter)
+{
+    auto* inst = static_cast<Instance*>(h);
+    inst->nbv->convertCoordinates(gmx::AtomLocality::Local, false, inst->x);
+    gmx::StepWorkload stepWork;
+    stepWork.computeForces = true;
+    stepWork.computeEnergy = want_energy != 0;
+    stepWork.computeVirial = want_energy != 0;
+    gmx_enerdata_t enerd(1, 0);
+    t_nrnb         nrnb = { 0 };
+    for (int i = 0; i < (nwarm > 0 ? nwarm : 1); i++)
+    {
+        inst->nbv->dispatchNonbondedKernel(gmx::InteractionLocality::Local, inst->ic, stepWork,
+                                           enbvClearFYes, *inst->fr, &enerd, &nrnb);
+    }
+    double t0 = nowSeconds();
+    for (int i = 0; i < niter; i++)
+    {
+        inst->nbv->dispatchNonbondedKernel(gmx::InteractionLocality::Local, inst->ic, stepWork,
+                                           enbvClearFNo, *inst->fr, &enerd, &nrnb);
+    }
+    return (nowSeconds() - t0) / (niter > 0 ? niter : 1);
+}
+
+/* Whole-step timing: x convert + kernel (clearing f) + force un-sort, per iteration. */
+double gmxref_time_step(void* h, int want_energy, int nwarm, int niter)
+{
+    auto*              inst = static_cast<Instance*>(h);
+    std::vector<float> f(3 * size_t(inst->natoms));
+    std::vector<float> fs(3 * SHIFTS);
+    float              e[2];
+    for (int i = 0; i < nwarm; i++)
+    {
+        gmxref_compute(h, nullptr, want_energy, 0, f.data(), fs.data(), e);
+    }
+    double t0 = nowSeconds();
+    for (int i = 0; i < niter; i++)
+    {
+        gmxref_compute(h, nullptr, want_energy, 0, f.data(), fs.data(), e);
+    }
+    return (nowSeconds() - t0) / (niter > 0 ? niter : 1);
+}
+
+/* Order of atoms on the reference grid: out[k] = original atom index at grid slot k or -1
+ * for a filler. Returns the number of slots (<= cap written). */
+int gmxref_grid_order(void* h, int* out, int cap)
+{
+    auto* inst    = static_cast<Instance*>(h);
+    auto  indices = inst->nbv->pairSearch_->gridSet().atomIndices();
+    int   n       = inst->nbv->pairSearch_->gridSet().numGridAtomsTotal();
+    for (int k = 0; k < n && k < cap; k++)
+    {
+        out[k] = indices[k];
+    }
+    return n;
+}
+
+void gmxref_grid_dims(void* h, int* ncx, int* ncy, float* cellx, float* celly, int* natomsPadded)
+{
+    auto*       inst = static_cast<Instance*>(h);
+    const auto& g    = inst->nbv->pairSearch_->gridSet().grids()[0];
+    *ncx             = g.dimensions().numCells[XX];
+    *ncy             = g.dimensions().numCells[YY];
+    *cellx           = g.dimensions().cellSize[XX];
+    *celly           = g.dimensions().cellSize[YY];
+    *natomsPadded    = inst->nbv->pairSearch_->gridSet().numGridAtomsTotal();
+}
+
+/* List statistics: number of cluster pairs in the list (na_ci x na_cj tiles) and the number of
+ * atom pairs the kernel evaluates ("total" pairs of bench_setup.cpp:316). */
+void gmxref_list_stats(void* h, long long* nClusterPairs, long long* nAtomPairsComputed, int* na_ci,
+                       int* na_cj)
+{
+    auto*       inst = static_cast<Instance*>(h);
+    const auto& set  = inst->nbv->pairlistSets().pairlistSet(gmx::InteractionLocality::Local);
+    long long   ncp  = 0;
+    if (inst->kernelType == Nbnxm::KernelType::Cpu8x8x8_PlainC)
+    {
+        const NbnxnPairlistGpu* l = set.gpuList();
+        *na_ci                    = l->na_ci;
+        *na_cj                    = l->na_cj;
+        for (const auto& cj4 : l->cj4)
+        {
+            for (int jm = 0; jm < c_nbnxnGpuJgroupSize; jm++)
+            {
+                for (int ic = 0; ic < c_nbnxnGpuNumClusterPerSupercluster; ic++)
+                {
+                    ncp += (cj4.imei[0].imask >> (jm * c_nbnxnGpuNumClusterPerSupercluster + ic)) & 1;
+                }
+            }
+        }
+    }
+    else
+    {
+        for (const auto& l : set.cpuLists())
+        {
+            *na_ci = l.na_ci;
+            *na_cj = l.na_cj;
+            for (const auto& ci : l.ci)
+            {
+                ncp += ci.cj_ind_end - ci.cj_ind_start;
+            }
+        }
+    }
+    *nClusterPairs      = ncp;
+    *nAtomPairsComputed = ncp * (*na_ci) * (*na_cj);
+}
+
+/* The in-range atom-pair set of the reference list: every list entry x interaction mask bit
+ * whose r^2 (simdRsq above, i-atom shifted) is < rc^2, excluding filler atoms and
+ * pairs where both... (nothing else: masks already contain topology and half-list exclusions).
+ * Pairs are returned in ORIGINAL atom indices as (i, j, shift) triples with i the shifted atom.
+ * Pass pairs == NULL to only count. Returns the number of pairs (may exceed cap; only cap
+ * are written). */
+long long gmxref_pair_set(void* h, float rc, int* pairs, long long cap)
+{
+    auto*       inst    = static_cast<Instance*>(h);
+    const auto& gridSet = inst->nbv->pairSearch_->gridSet();
+    auto        indices = gridSet.atomIndices();
+    const auto& set     = inst->nbv->pairlistSets().pairlistSet(gmx::InteractionLocality::Local);
+    const float rc2     = rc * rc;
+    long long   n       = 0;
+
+    auto testPair = [&](int gi, int gj, int shift) {
+        const int ai = indices[gi], aj = indices[gj];
+        if (ai < 0 || aj < 0)
+        {
+            return;
+        }
+        const float xi = inst->x[ai][XX] + inst->shiftVec[shift][XX];
+        const float yi = inst->x[ai][YY] + inst->shiftVec[shift][YY];
+        const float zi = inst->x[ai][ZZ] + inst->shiftVec[shift][ZZ];
+        const float r2 = simdRsq(xi, yi, zi, inst->x[aj][XX], inst->x[aj][YY], inst->x[aj][ZZ]);
+        if (r2 < rc2)
+        {
+            if (pairs && n < cap)
+            {
+                pairs[3 * n]     = ai;
+                pairs[3 * n + 1] = aj;
+                pairs[3 * n + 2] = shift;
+            }
+            n++;
+        }
+    };
+
+    if (inst->kernelType == Nbnxm::KernelType::Cpu8x8x8_PlainC)
+    {
+        /* layout walk as kernels_reference/kernel_gpu_ref.cpp:127-250 */
+        const NbnxnPairlistGpu* l = set.gpuList();
+        constexpr int           cs = c_nbnxnGpuClusterSize;
+        for (const nbnxn_sci_t& sci : l->sci)
+        {
+            for (int cj4Ind = sci.cj4_ind_start; cj4Ind < sci.cj4_ind_end; cj4Ind++)
+            {
+                const nbnxn_cj4_t& cj4 = l->cj4[cj4Ind];
+                const auto&        e0  = l->excl[cj4.imei[0].excl_ind];
+                const auto&        e1  = l->excl[cj4.imei[1].excl_ind];
+                for (int jm = 0; jm < c_nbnxnGpuJgroupSize; jm++)
+                {
+                    const int cj = cj4.cj[jm];
+                    for (int im = 0; im < c_nbnxnGpuNumClusterPerSupercluster; im++)
+                    {
+                        if (!((cj4.imei[0].imask >> (jm * c_nbnxnGpuNumClusterPerSupercluster + im)) & 1))
+                        {
+                            continue;
+                        }
+                        const int ci = sci.sci * c_nbnxnGpuNumClusterPerSupercluster + im;
+                        for (int ii = 0; ii < cs; ii++)
+                        {
+                            for (int jj = 0; jj < cs; jj++)
+                            {
+                                const auto& ex = (jj < cs / 2) ? e0 : e1;
+                                const int   bit = jm * c_nbnxnGpuNumClusterPerSupercluster + im;
+                                /* kernel_gpu_ref.cpp:223-226: explicit half-list skip on the diagonal */
+                                if ((sci.shift & NBNXN_CI_SHIFT) == CENTRAL && ci == cj
+                                    && cj * cs + jj <= ci * cs + ii)
+                                {
+                                    continue;
+                                }
+                                if ((ex.pair[(jj & (cs / 2 - 1)) * cs + ii] >> bit) & 1)
+                                {
+                                    testPair(ci * cs + ii, cj * cs + jj, sci.shift & NBNXN_CI_SHIFT);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    else
+    {
+        for (const auto& l : set.cpuLists())
+        {
+            for (const nbnxn_ci_t& ci : l.ci)
+            {
+                const int shift = ci.shift & NBNXN_CI_SHIFT;
+                for (int k = ci.cj_ind_start; k < ci.cj_ind_end; k++)
+                {
+                    const nbnxn_cj_t& cj = l.cj[k];
+                    for (int ii = 0; ii < l.na_ci; ii++)
+                    {
+                        for (int jj = 0; jj < l.na_cj; jj++)
+                        {
+                            if ((cj.excl >> (ii * l.na_cj + jj)) & 1)
+                            {
+                                testPair(ci.ci * l.na_ci + ii, cj.cj * l.na_cj + jj, shift);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return n;
+}
+
+} // extern "C"

@@ -1,0 +1,60 @@
+/* TEST INFRASTRUCTURE ONLY. C ABI of oracle/_ref/libgmxref_nbnxm.so (see ref_harness.cpp). */
+#ifndef B200NB_ORACLE_REF_HARNESS_H
+#define B200NB_ORACLE_REF_HARNESS_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { GMXREF_KERNEL_PLAINC_4X4 = 0, GMXREF_KERNEL_SIMD_4XN = 1, GMXREF_KERNEL_SIMD_2XNN = 2, GMXREF_KERNEL_GPUREF_8X8X8 = 3 };
+enum { GMXREF_EEL_CUT = 0, GMXREF_EEL_RF = 1, GMXREF_EEL_EWALD_ANA = 2, GMXREF_EEL_EWALD_TAB = 3 };
+
+typedef struct
+{
+    int          natoms;
+    const float* x;        /* 3*natoms */
+    float        box[3];   /* rectangular */
+    int          ntypes;
+    const float* nbfp;     /* ntypes*ntypes*2: 6*C6, 12*C12 (the fr->nbfp convention) */
+    const int*   type;     /* natoms */
+    const float* q;        /* natoms */
+    const int*   excl_off; /* natoms+1, CSR; each atom's list includes itself */
+    const int*   excl_idx;
+} gmxref_system;
+
+typedef struct
+{
+    float rc;           /* rvdw = rcoulomb */
+    float rlist;        /* outer list radius */
+    float rlist_inner;  /* <=0: no dynamic pruning */
+    int   nstlist_prune;
+    int   eeltype;      /* GMXREF_EEL_* */
+    float epsfac, k_rf, c_rf, ewaldcoeff, sh_ewald;
+    float disp_cpot, rep_cpot; /* potential-shift constants: -rc^-6, -rc^-12 or 0 */
+    int   kernel;       /* GMXREF_KERNEL_* */
+    int   comb_rule;    /* enbnxninitcombrule: 0 detect, 1 geom, 2 LB, 3 none */
+    int   nthreads;
+    int   exact_atom_flags; /* 0: all atoms flagged VdW+Q (bench default) */
+    int   put_in_box;
+    int   min_ilist_count;  /* GPU list balancing target, 0 = none */
+} gmxref_params;
+
+int    gmxref_simd_width(void);
+int    gmxref_default_simd_kernel(void);
+float  gmxref_ewald_coeff(float rc, float rtol);
+float  gmxref_simd_rsq(float xi, float yi, float zi, float xj, float yj, float zj);
+void*  gmxref_create(const gmxref_system* s, const gmxref_params* p);
+void   gmxref_destroy(void* h);
+int    gmxref_regrid_research(void* h, double* tGrid, double* tSearch);
+void   gmxref_setup_times(void* h, double* tGrid, double* tSearch);
+int    gmxref_compute(void* h, const float* x, int want_energy, int want_virial, float* f, float* fshift, float* energies);
+double gmxref_time_kernel(void* h, int want_energy, int nwarm, int niter);
+double gmxref_time_step(void* h, int want_energy, int nwarm, int niter);
+int    gmxref_grid_order(void* h, int* out, int cap);
+void   gmxref_grid_dims(void* h, int* ncx, int* ncy, float* cellx, float* celly, int* natomsPadded);
+void   gmxref_list_stats(void* h, long long* nClusterPairs, long long* nAtomPairsComputed, int* na_ci, int* na_cj);
+long long gmxref_pair_set(void* h, float rc, int* pairs, long long cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
