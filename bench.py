@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- nonbonded pair-interactions/s and ms/step of the B200 nbnxm path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A step = one pass of the hot path over one set of coordinates: coordinates -> grid-ordered device layout,
+output clear, cluster-pair force kernel (LJ + Ewald real space, force only), force un-sort.
+  value  : useful pair interactions (non-excluded, r < rc; counted exactly on the device) per second with
+           coordinates already resident in HBM, L2 flushed between steps, CUDA-event timed on the stream the
+           kernels run on, max over ranks;
+  e2e    : the same metric through the public nblib-style call ForceCalculator.compute(x_host) -> f_host with
+           pinned HOST buffers (H2D of x and D2H of f inside the timed region);
+  roofline: the force kernel alone against the FP32 FMA roofline (the path is FP32-bound), with
+           the HBM view beside it;
+  cpu_baseline: the reference's own CPU SIMD nbnxm path (oracle/_ref, compiled from the reference sources)
+           on this host's cores, bounded sample.
+N > 1: atoms are split into N slabs along x (spatial domain decomposition), one rank per GPU, halo
+coordinates / forces exchanged every step over NCCL (see gmxapi_b200/domdec.py); weak scaling: every rank
+holds one copy of the N=1 workload box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "nonbonded pair-interactions/s"
+FLOPS_PER_PAIR = {"ewald": 66, "rf": 38}  # src/gromacs/gmxlib/nrnb.cpp:101,105 (force only)
+RC = 0.9
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 9 for k in range(4) if r[5 + k].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def workload_system(name):
+    import gmxapi_b200 as g
+    return g.systems.named(name)
+
+
+def ref_instance(s, eel, nthreads):
+    from oracle import gmxref
+    import gmxapi_b200 as g
+    if eel == "ewald":
+        kw = dict(eeltype=gmxref.EEL_EWALD_ANA, ewaldcoeff=float(np.float32(g.systems.ewald_beta(RC))))
+    else:
+        k, c = g.systems.rf_constants(RC)
+        kw = dict(eeltype=gmxref.EEL_RF, k_rf=k, c_rf=c)
+    return gmxref.RefNbnxm(s.x, s.box, s.types, s.q, s.nbfp, s.excl_off, s.excl_idx, rc=RC, kernel=None,
+                           nthreads=nthreads, **kw)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def time_reference(s, eel, nthreads, steps, warmup, budget_s=20.0):
+    """Times the reference CPU step (x convert + SIMD kernel + force reduction) per iteration."""
+    r = ref_instance(s, eel, nthreads)
+    t1 = r.time_step(False, max(warmup, 1), 1)
+    n = int(max(1, min(steps, budget_s / max(t1, 1e-6))))
+    t = r.time_step(False, 1, n)
+    tk = r.time_kernel(False, 1, max(1, min(n, 50)))
+    r.close()
+    return t, tk, n
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU SIMD nbnxm path on the host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import gmxref, oracle
+    s = workload_system(args.workload)
+    cores = host_cores()
+    npairs = len(oracle.pair_set(s.x, s.box, RC, s.excl_off, s.excl_idx))
+    kind = "reference" if gmxref.available() else "port"
+    if not gmxref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgmxref_nbnxm.so missing"}))
+        return
+    t, tk, n = time_reference(s, args.eel, cores, args.steps, args.warmup, budget_s=60.0)
+    val = npairs / t
+    out = {"metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
+           "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "impl": "reference",
+           "config": {"workload": args.workload, "atoms": int(s.n), "useful_pairs_per_step": npairs, "rc": RC,
+                      "interaction": "LJ + " + ("Ewald real space (analytical)" if args.eel == "ewald" else "reaction field"),
+                      "flavor": "force only"},
+           "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": kind,
+                            "sample": "%d full steps (x convert + 2xMM SIMD kernel + f reduce) of %s, %d OpenMP threads; "
+                                      "kernel-only %.3f ms" % (n, args.workload, cores, tk * 1e3)},
+           "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def run_gpu(args):
+    import torch
+    import gmxapi_b200 as g
+    from gmxapi_b200 import lib as nb
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from gmxapi_b200 import domdec
+        return domdec.bench_multi_gpu(args, METRIC, FLOPS_PER_PAIR, ClockSampler, measured_peaks, time_reference, host_cores)
+
+    peaks = measured_peaks()
+    s = workload_system(args.workload)
+    coul = g.CoulombType.Pme if args.eel == "ewald" else g.CoulombType.ReactionField
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coul, computeVirialAndEnergy=False, device=local_rank)
+    t0 = time.perf_counter()
+    fc = g.ForceCalculator(g.SimulationState.from_system(s), opt)
+    fc.nb.synchronize()
+    t_setup = time.perf_counter() - t0
+    h = fc.nb
+    npairs = h.pair_count(RC)
+    st = h.stats()
+    stream = torch.cuda.ExternalStream(h.stream, device=torch.device("cuda", local_rank))
+
+    # ---- device-resident step ------------------------------------------------------------------------------
+    x_dev = torch.from_numpy(s.x).to("cuda", non_blocking=False).contiguous()
+    f_dev = torch.zeros_like(x_dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if not args.no_flush else None
+    torch.cuda.synchronize()
+
+    def step():
+        h.set_x(x_dev.data_ptr(), on_device=True)
+        h.clear_outputs()
+        h.launch_force(-1, 0)
+        h.get_f(f_dev.data_ptr(), on_device=True)
+
+    for _ in range(args.warmup):
+        step()
+    h.synchronize()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = h.stats()["nlaunches"]
+    for k in range(args.steps):
+        if flush is not None:
+            with torch.cuda.stream(stream):
+                flush.fill_(k & 0xff)
+        ev[k][0].record(stream)
+        step()
+        ev[k][1].record(stream)
+    h.synchronize()
+    torch.cuda.synchronize()
+    launches = h.stats()["nlaunches"] - l0
+    step_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+    # ---- force kernel alone (roofline) ----------------------------------------------------------------------
+    k_ms = h.time_force_kernel(-1, 0, 3, max(10, min(args.steps, 50)), flush_l2=not args.no_flush)
+    clocks = sampler.stop()
+
+    # ---- end to end through the public API with pinned host buffers -----------------------------------------
+    x_pin = torch.from_numpy(s.x.copy()).pin_memory()
+    f_pin = torch.empty_like(x_pin).pin_memory()
+    xh, fh = x_pin.numpy(), f_pin.numpy()
+    for _ in range(args.warmup):
+        fc.compute(xh, fh)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fc.compute(xh, fh)  # synchronous: returns after the D2H of the forces completed
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    f_host = fh.copy()
+
+    # ---- parity spot-check of what was timed (cheap, not in any timed region) -------------------------------
+    assert np.allclose(f_dev.cpu().numpy(), f_host, rtol=1e-3, atol=1e-2 * np.abs(f_host).mean())
+
+    # ---- CPU baseline: the reference's own SIMD path on this host --------------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        try:
+            cores = host_cores()
+            t, tk, n = time_reference(s, args.eel, cores, 2000, 3, budget_s=15.0)
+            cpu = {"value": npairs / t, "unit": "pairs/s", "cores": cores, "kind": "reference",
+                   "sample": "%d full steps of %s on %d OpenMP threads (x convert + 2xMM SIMD kernel + f reduce), "
+                             "%.3f ms/step; kernel alone %.3f ms" % (n, args.workload, cores, t * 1e3, tk * 1e3)}
+        except Exception as e:  # the checker library is optional for the GPU numbers
+            cpu = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
+
+    flops = FLOPS_PER_PAIR[args.eel]
+    fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    achieved = npairs * flops / (k_ms * 1e-3) / 1e12
+    npad, ntiles = st["natoms_padded"], st["ntiles_inner"]
+    alg_bytes = npad * (16 + 8 + 32) + ntiles * 4 + st["nentries"] * 16
+    out = {
+        "metric": METRIC, "value": npairs / (step_ms * 1e-3), "unit": "pairs/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "atoms": int(s.n), "useful_pairs_per_step": int(npairs),
+                   "computed_pairs_per_step": int(ntiles * 64), "rc": RC, "rlist": RC,
+                   "interaction": "LJ + " + ("Ewald real space (analytical)" if args.eel == "ewald" else "reaction field"),
+                   "flavor": "force only", "l2": "inputs < L2; L2 flushed (256 MiB write) between timed steps"
+                   if not args.no_flush else "not flushed", "setup_s": t_setup, "parallelism": "1 GPU"},
+        "roofline": {"bound": "fp32", "kernel": "k_force<Ewald,geometric LJ,F>" if args.eel == "ewald" else "k_force<RF,geometric LJ,F>",
+                     "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                     "kernel_ms": k_ms, "flops_per_useful_pair": flops,
+                     "peak_note": "148 SMs x 128 FP32 lanes x 2 x %.0f MHz (clocks.max.sm, MEASURED_PEAKS.json %s)"
+                                  % (peaks["sm_max_mhz"], peaks["source"]),
+                     "useful_pairs_per_s_kernel": npairs / (k_ms * 1e-3),
+                     "computed_pairs_per_s_kernel": ntiles * 64 / (k_ms * 1e-3),
+                     "traffic": None,
+                     "hbm": {"algorithmic_bytes": int(alg_bytes), "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
+                             "peak_gbs": peaks["hbm_gbs"], "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}},
+        "cpu_baseline": cpu,
+        "e2e": {"value": npairs / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(s.n * 12), "d2h_bytes_per_step": int(s.n * 12)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="water_24k")
+    ap.add_argument("--eel", default="ewald", choices=["ewald", "rf"])
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1550 @@
+/* b200nb: context management, device gridding/sorting, device pair search with exclusion masks,
+ * dynamic pruning, coordinate / force buffer ops, halo pack/unpack, introspection.
+ * The force kernels live in force.cu.  Hand-written for sm_100a; no CPU fallback anywhere.
+ *
+ * Reference behaviour replaced (paths relative to /root/reference/src/gromacs):
+ *   gridding      nbnxm/grid.cpp:103-262 (setDimensions), :1173-1268 (calcColumnIndices),
+ *                 :1287-1445 (setCellIndices), :292-427 (sort_atoms), :1051-1164 (sortColumnsGpuGeometry),
+ *                 :860-986 (fillCell), :454-660 (bounding boxes)
+ *   search        nbnxm/pairlist.cpp:3076-3582 (nbnxn_make_pairlist_part), :1090-1244 (make_cluster_list_supersub),
+ *                 :1874-1972 (setExclusionsForIEntry), :2077-2194 (split_sci_entry / closeIEntry)
+ *   prune         nbnxm/cuda/nbnxm_cuda_kernel_pruneonly.cuh:104-277, kernels_reference/kernel_ref_prune.cpp:45-143
+ *   buffer ops    nbnxm/cuda/nbnxm_buffer_ops_kernels.cuh:65-114, mdlib/gpuforcereduction_impl.cu:70-104
+ *   halo          domdec/gpuhaloexchange_impl.cu:77-131
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "b200nb_internal.h"
+
+int nb_fail(b200nb_context* h, int code, const std::string& msg)
+{
+    if (h) h->err = msg;
+    return code;
+}
+
+#define LAUNCH_CHECK(h)                 \
+    do                                  \
+    {                                   \
+        (h)->nlaunches++;               \
+        NB_CUDA(h, cudaGetLastError()); \
+    } while (0)
+
+template<typename T>
+static int ensure(b200nb_context* h, T** p, size_t* cap, size_t need, double slack = 1.2)
+{
+    if (need <= *cap && *p) return 0;
+    if (*p) NB_CUDA(h, cudaFree(*p));
+    *p        = nullptr;
+    size_t nc = (size_t)(need * slack) + 64;
+    NB_CUDA(h, cudaMalloc((void**)p, nc * sizeof(T)));
+    *cap = nc;
+    return 0;
+}
+
+template<typename T>
+static int alloc_exact(b200nb_context* h, T** p, size_t n)
+{
+    if (*p) NB_CUDA(h, cudaFree(*p));
+    *p = nullptr;
+    NB_CUDA(h, cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* lifetime                                                                                                */
+/* ------------------------------------------------------------------------------------------------------ */
+extern "C" int b200nb_create(b200nb_t** out, int device)
+{
+    if (!out) return B200NB_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
+    {
+        return B200NB_ERR_CUDA; /* no CUDA device: the product path fails loudly, there is no fallback */
+    }
+    b200nb_context* h = new b200nb_context;
+    h->device         = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+        delete h;
+        return B200NB_ERR_CUDA;
+    }
+    cudaMalloc((void**)&h->d_shift_vec, sizeof(float) * B200NB_SHIFTS * 3);
+    cudaMalloc((void**)&h->d_fshift, sizeof(float) * B200NB_SHIFTS * 3);
+    cudaMalloc((void**)&h->d_energy, sizeof(double) * 2);
+    cudaMalloc((void**)&h->d_scratch, sizeof(int) * 64);
+    cudaMalloc((void**)&h->d_counter, sizeof(long long) * 8);
+    cudaMemsetAsync(h->d_fshift, 0, sizeof(float) * B200NB_SHIFTS * 3, h->stream);
+    cudaMemsetAsync(h->d_energy, 0, sizeof(double) * 2, h->stream);
+    *out = h;
+    return B200NB_OK;
+}
+
+static void free_list(PairList& l)
+{
+    cudaFree(l.entries);
+    cudaFree(l.cj);
+    cudaFree(l.mask);
+    l = PairList();
+}
+
+extern "C" void b200nb_destroy(b200nb_t* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    void* ptrs[] = { h->d_nbfp,       h->d_type,     h->d_q,        h->d_excl_off,     h->d_excl_idx,  h->d_shift_vec,
+                     h->d_x,          h->d_fout,     h->d_col_of_atom, h->d_col_count, h->d_col_cell0, h->d_col_fill,
+                     h->d_atom_index, h->d_slot_of_atom, h->d_xq,   h->d_lj,           h->d_atype,     h->d_bb,
+                     h->d_cellz,      h->d_f,        h->d_fshift,   h->d_energy,       h->d_scratch,   h->d_counter,
+                     h->d_cnt_tiles,  h->d_cnt_entries, h->d_flush };
+    for (void* p : ptrs) cudaFree(p);
+    for (int l = 0; l < 2; l++)
+    {
+        if (!h->inner_is_outer) free_list(h->inner[l]);
+        free_list(h->outer[l]);
+    }
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char* b200nb_last_error(const b200nb_t* h)
+{
+    return h ? h->err.c_str() : "null context";
+}
+
+extern "C" void* b200nb_stream(b200nb_t* h)
+{
+    return h ? (void*)h->stream : nullptr;
+}
+
+extern "C" int b200nb_synchronize(b200nb_t* h)
+{
+    if (!h) return B200NB_ERR_ARG;
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int ensure_pinned(b200nb_context* h, size_t bytes)
+{
+    if (bytes <= h->pinned_bytes) return 0;
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    h->h_pinned = nullptr;
+    NB_CUDA(h, cudaMallocHost((void**)&h->h_pinned, bytes * 2));
+    h->pinned_bytes = bytes * 2;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* parameters                                                                                              */
+/* ------------------------------------------------------------------------------------------------------ */
+extern "C" int b200nb_set_params(b200nb_t* h, const b200nb_params_t* p)
+{
+    if (!h || !p || p->ntypes < 1 || !p->nbfp_host || p->rc <= 0) return nb_fail(h, B200NB_ERR_ARG, "set_params: bad argument");
+    if (p->rlist_outer < p->rc) return nb_fail(h, B200NB_ERR_ARG, "set_params: rlist_outer < rc");
+    cudaSetDevice(h->device);
+    h->hp           = *p;
+    const int nt    = p->ntypes;
+    const int ntf   = nt + 1; /* + filler type with zero parameters: atomdata.cpp:456,526-534 */
+    h->nbfp_host.assign((size_t)ntf * ntf * 2, 0.0f);
+    for (int i = 0; i < nt; i++)
+        for (int j = 0; j < nt; j++)
+        {
+            h->nbfp_host[(i * ntf + j) * 2]     = p->nbfp_host[(i * nt + j) * 2];
+            h->nbfp_host[(i * ntf + j) * 2 + 1] = p->nbfp_host[(i * nt + j) * 2 + 1];
+        }
+    h->hp.nbfp_host = nullptr;
+    /* geometric combination rule detection, tolerance 1e-5 (atomdata.cpp:462-525, gmx_within_tol) */
+    bool geom = true;
+    for (int i = 0; i < nt && geom; i++)
+        for (int j = 0; j < nt && geom; j++)
+        {
+            double c6 = p->nbfp_host[(i * nt + j) * 2], c12 = p->nbfp_host[(i * nt + j) * 2 + 1];
+            double c6ii = p->nbfp_host[(i * nt + i) * 2], c6jj = p->nbfp_host[(j * nt + j) * 2];
+            double c12ii = p->nbfp_host[(i * nt + i) * 2 + 1], c12jj = p->nbfp_host[(j * nt + j) * 2 + 1];
+            auto   within = [](double a, double b) { return std::fabs(a - b) <= 1e-5 * 0.5 * (std::fabs(a) + std::fabs(b)); };
+            geom          = within(c6 * c6, c6ii * c6jj) && within(c12 * c12, c12ii * c12jj);
+        }
+    h->comb_geom = (p->comb_rule == 1) || (p->comb_rule == 0 && geom);
+    h->max_tiles = p->max_tiles_per_entry > 0 ? p->max_tiles_per_entry : 16;
+    if (alloc_exact(h, &h->d_nbfp, (size_t)ntf * ntf * 2)) return B200NB_ERR_CUDA;
+    NB_CUDA(h, cudaMemcpyAsync(h->d_nbfp, h->nbfp_host.data(), sizeof(float) * ntf * ntf * 2, cudaMemcpyHostToDevice, h->stream));
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+
+    NbParamsDev& d  = h->dp;
+    d.rc2           = p->rc * p->rc;
+    d.rlist_outer2  = p->rlist_outer * p->rlist_outer;
+    float rin       = (p->rlist_inner > 0 && p->rlist_inner < p->rlist_outer) ? p->rlist_inner : p->rlist_outer;
+    d.rlist_inner2  = rin * rin;
+    d.epsfac        = p->epsfac;
+    d.k_rf          = (p->eeltype == B200NB_EEL_RF) ? p->k_rf : 0.0f;
+    d.two_k_rf      = 2.0f * d.k_rf;
+    d.c_rf          = p->c_rf;
+    d.beta          = p->ewald_beta;
+    d.beta2         = p->ewald_beta * p->ewald_beta;
+    d.beta3         = d.beta2 * p->ewald_beta;
+    d.sh_ewald      = p->sh_ewald;
+    d.disp_cpot     = p->disp_cpot;
+    d.rep_cpot      = p->rep_cpot;
+    d.self_sub      = (p->eeltype == B200NB_EEL_EWALD) ? (float)(0.5 * p->ewald_beta * 1.12837916709551257390) : 0.5f * p->c_rf;
+    d.ntypes        = ntf;
+    d.eeltype       = p->eeltype;
+    h->have_params  = true;
+    h->have_list    = false;
+    return 0;
+}
+
+extern "C" int b200nb_set_atoms(b200nb_t* h, int natoms, const int* type_host, const float* q_host,
+                                const int* excl_off_host, const int* excl_idx_host)
+{
+    if (!h || natoms < 1 || !type_host || !q_host) return nb_fail(h, B200NB_ERR_ARG, "set_atoms: bad argument");
+    if (!h->have_params) return nb_fail(h, B200NB_ERR_STATE, "set_atoms: set_params first");
+    cudaSetDevice(h->device);
+    for (int a = 0; a < natoms; a++)
+        if (type_host[a] < 0 || type_host[a] >= h->hp.ntypes) return nb_fail(h, B200NB_ERR_ARG, "set_atoms: atom type out of range");
+    h->natoms = natoms;
+    h->h_type.assign(type_host, type_host + natoms);
+    h->h_q.assign(q_host, q_host + natoms);
+    if (alloc_exact(h, &h->d_type, (size_t)natoms) || alloc_exact(h, &h->d_q, (size_t)natoms)) return B200NB_ERR_CUDA;
+    NB_CUDA(h, cudaMemcpy(h->d_type, type_host, sizeof(int) * natoms, cudaMemcpyHostToDevice));
+    NB_CUDA(h, cudaMemcpy(h->d_q, q_host, sizeof(float) * natoms, cudaMemcpyHostToDevice));
+    std::vector<int> off(natoms + 1, 0);
+    const int*       idx  = nullptr;
+    int              nidx = 0;
+    if (excl_off_host)
+    {
+        if (excl_off_host[0] != 0) return nb_fail(h, B200NB_ERR_ARG, "set_atoms: excl_off[0] != 0");
+        off.assign(excl_off_host, excl_off_host + natoms + 1);
+        nidx = off[natoms];
+        idx  = excl_idx_host;
+        for (int k = 0; k < nidx; k++)
+            if (idx[k] < 0 || idx[k] >= natoms) return nb_fail(h, B200NB_ERR_ARG, "set_atoms: exclusion index out of range");
+    }
+    if (alloc_exact(h, &h->d_excl_off, (size_t)natoms + 1) || alloc_exact(h, &h->d_excl_idx, (size_t)nidx)) return B200NB_ERR_CUDA;
+    NB_CUDA(h, cudaMemcpy(h->d_excl_off, off.data(), sizeof(int) * (natoms + 1), cudaMemcpyHostToDevice));
+    if (nidx) NB_CUDA(h, cudaMemcpy(h->d_excl_idx, idx, sizeof(int) * nidx, cudaMemcpyHostToDevice));
+    if (alloc_exact(h, &h->d_x, (size_t)natoms * 3) || alloc_exact(h, &h->d_fout, (size_t)natoms * 3)
+        || alloc_exact(h, &h->d_col_of_atom, (size_t)natoms) || alloc_exact(h, &h->d_slot_of_atom, (size_t)natoms))
+        return B200NB_ERR_CUDA;
+    h->grid[0].valid = h->grid[1].valid = 0;
+    h->have_list                        = false;
+    return 0;
+}
+
+extern "C" int b200nb_set_box(b200nb_t* h, const float box[3], const int pbc_dims[3])
+{
+    if (!h || !box) return nb_fail(h, B200NB_ERR_ARG, "set_box: bad argument");
+    cudaSetDevice(h->device);
+    for (int d = 0; d < 3; d++)
+    {
+        h->box[d] = box[d];
+        h->pbc[d] = pbc_dims ? pbc_dims[d] : 1;
+    }
+    /* pbcutil/pbc.cpp:1187-1202 calc_shifts, rectangular box */
+    int n = 0;
+    for (int m = -1; m <= 1; m++)
+        for (int l = -1; l <= 1; l++)
+            for (int k = -2; k <= 2; k++, n++)
+            {
+                h->h_shift_vec[3 * n]     = k * box[0];
+                h->h_shift_vec[3 * n + 1] = l * box[1];
+                h->h_shift_vec[3 * n + 2] = m * box[2];
+            }
+    NB_CUDA(h, cudaMemcpy(h->d_shift_vec, h->h_shift_vec, sizeof(h->h_shift_vec), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* gridding kernels                                                                                        */
+/* ------------------------------------------------------------------------------------------------------ */
+
+/* grid.cpp:1173-1268 calcColumnIndices: cx = int((x - x0) * invCell), clamped */
+__global__ void k_column_index(const float* __restrict__ x, GridDesc g, int* __restrict__ col_of_atom, int* __restrict__ col_count)
+{
+    int a = g.atom_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= g.atom_end) return;
+    int cx = (int)((x[3 * a] - g.lower[0]) * g.inv_cell[0]);
+    int cy = (int)((x[3 * a + 1] - g.lower[1]) * g.inv_cell[1]);
+    cx     = max(0, min(cx, g.ncx - 1));
+    cy     = max(0, min(cy, g.ncy - 1));
+    int c  = cx * g.ncy + cy;
+    col_of_atom[a] = c;
+    atomicAdd(&col_count[g.col0 + c], 1);
+}
+
+/* grid.cpp:1287-1445 setCellIndices: cells per column = ceil(n/64), prefix sum -> cxy_ind_.
+ * totals[0] = number of cells of this grid, totals[1] = max atoms in a column. */
+__global__ void k_column_scan(GridDesc g, const int* __restrict__ col_count, int* __restrict__ col_cell0, int* __restrict__ totals)
+{
+    __shared__ int s_part[1024];
+    __shared__ int s_max[1024];
+    const int      t   = threadIdx.x;
+    const int      per = (g.ncol + blockDim.x - 1) / blockDim.x;
+    int            sum = 0, mx = 0;
+    for (int k = 0; k < per; k++)
+    {
+        int c = t * per + k;
+        if (c < g.ncol)
+        {
+            int n = col_count[g.col0 + c];
+            sum += (n + NB_CELL - 1) / NB_CELL;
+            mx = max(mx, n);
+        }
+    }
+    s_part[t] = sum;
+    s_max[t]  = mx;
+    __syncthreads();
+    if (t == 0)
+    {
+        int run = 0, m = 0;
+        for (int i = 0; i < (int)blockDim.x; i++)
+        {
+            int v     = s_part[i];
+            s_part[i] = run;
+            run += v;
+            m = max(m, s_max[i]);
+        }
+        totals[0] = run;
+        totals[1] = m;
+    }
+    __syncthreads();
+    int run = s_part[t] + g.cell0;
+    for (int k = 0; k < per; k++)
+    {
+        int c = t * per + k;
+        if (c < g.ncol)
+        {
+            col_cell0[g.col0 + c] = run;
+            run += (col_count[g.col0 + c] + NB_CELL - 1) / NB_CELL;
+            if (c == g.ncol - 1) col_cell0[g.col0 + g.ncol] = run;
+        }
+    }
+}
+
+__global__ void k_column_scatter(GridDesc g, const int* __restrict__ col_of_atom, const int* __restrict__ col_cell0,
+                                 int* __restrict__ col_fill, int* __restrict__ atom_index)
+{
+    int a = g.atom_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= g.atom_end) return;
+    int c   = g.col0 + col_of_atom[a];
+    int pos = atomicAdd(&col_fill[c], 1);
+    atom_index[col_cell0[c] * NB_CELL + pos] = a;
+}
+
+__device__ __forceinline__ uint32_t orderable(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+/* In-shared-memory bitonic sort of independent aligned segments of length seg (power of two), ascending. */
+__device__ void bitonic_segments(uint64_t* s, int P, int seg)
+{
+    for (int k = 2; k <= seg; k <<= 1)
+    {
+        for (int j = k >> 1; j > 0; j >>= 1)
+        {
+            for (int i = threadIdx.x; i < P; i += blockDim.x)
+            {
+                int ixj = i ^ j;
+                if (ixj > i)
+                {
+                    bool     asc = (k == seg) ? true : ((i & k) == 0);
+                    uint64_t a = s[i], b = s[ixj];
+                    if ((a > b) == asc)
+                    {
+                        s[i]   = b;
+                        s[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+/* One CTA per grid column: the exact (coordinate, atom index) sorts of sort_atoms (grid.cpp:292-427; its
+ * pigeonhole+insertion procedure yields exactly that order) in the sequence of sortColumnsGpuGeometry
+ * (grid.cpp:1051-1164): whole column on z; 32-atom slabs on y, direction alternating with the slab
+ * parity; 16-atom halves on x, backwards on the odd half; then fills the device atom data in the
+ * pair-interleaved cluster layout (fillCell, grid.cpp:860-986) and the cluster bounding boxes. */
+__global__ void k_column_sort(GridDesc g, const float* __restrict__ x, const float* __restrict__ q, const int* __restrict__ type,
+                              const float* __restrict__ nbfp, int ntypes, const int* __restrict__ col_count,
+                              const int* __restrict__ col_cell0, int* __restrict__ atom_index, int* __restrict__ slot_of_atom,
+                              float* __restrict__ xq, float* __restrict__ lj, int* __restrict__ atype, float* __restrict__ bb,
+                              float* __restrict__ cellz)
+{
+    extern __shared__ uint64_t s_key[];
+    const int c     = g.col0 + blockIdx.x;
+    const int n     = col_count[c];
+    const int cell0 = col_cell0[c];
+    const int ncz   = col_cell0[c + 1] - cell0;
+    if (ncz == 0) return;
+    const int base = cell0 * NB_CELL;
+    const int npos = ncz * NB_CELL;
+    int       P    = 64;
+    while (P < npos) P <<= 1;
+    const uint64_t FILL = ~0ull;
+
+    /* z sort of the whole column */
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+    {
+        uint64_t k = FILL;
+        if (i < n)
+        {
+            int a = atom_index[base + i];
+            k     = ((uint64_t)orderable(x[3 * a + 2]) << 32) | (uint32_t)a;
+        }
+        s_key[i] = k;
+    }
+    __syncthreads();
+    bitonic_segments(s_key, P, P);
+    /* y sort within 32-atom slabs, backwards on odd slabs (complemented keys sort descending) */
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+    {
+        uint64_t k = s_key[i];
+        if (k != FILL)
+        {
+            int a = (int)(uint32_t)k;
+            k     = ((uint64_t)orderable(x[3 * a + 1]) << 32) | (uint32_t)a;
+            if ((i >> 5) & 1) k = ~k;
+        }
+        s_key[i] = k;
+    }
+    __syncthreads();
+    bitonic_segments(s_key, P, 32);
+    /* x sort within 16-atom halves, backwards on the odd half */
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+    {
+        uint64_t k = s_key[i];
+        if (k != FILL)
+        {
+            int a = ((i >> 5) & 1) ? (int)(uint32_t)(~k) : (int)(uint32_t)k;
+            k     = ((uint64_t)orderable(x[3 * a]) << 32) | (uint32_t)a;
+            if ((i >> 4) & 1) k = ~k;
+        }
+        s_key[i] = k;
+    }
+    __syncthreads();
+    bitonic_segments(s_key, P, 16);
+
+    /* fill atom data */
+    for (int i = threadIdx.x; i < npos; i += blockDim.x)
+    {
+        uint64_t  k    = s_key[i];
+        const int slot = base + i;
+        const int cl = slot >> 3, kk = slot & 7, pp = nb_pairpos(kk);
+        float*    xb = xq + (size_t)cl * NB_XQ_STRIDE;
+        if (k != FILL)
+        {
+            int a = ((i >> 4) & 1) ? (int)(uint32_t)(~k) : (int)(uint32_t)k;
+            atom_index[slot] = a;
+            slot_of_atom[a]  = slot;
+            xb[pp]           = x[3 * a];
+            xb[8 + pp]       = x[3 * a + 1];
+            xb[16 + pp]      = x[3 * a + 2];
+            xb[24 + pp]      = q[a];
+            int t            = type[a];
+            atype[cl * 8 + pp] = t;
+            /* sqrt(6 C6_ii), sqrt(12 C12_ii): nbfp_comb for the geometric rule (atomdata.cpp:253-330) */
+            lj[(size_t)cl * NB_LJ_STRIDE + pp]     = sqrtf(nbfp[(t * ntypes + t) * 2]);
+            lj[(size_t)cl * NB_LJ_STRIDE + 8 + pp] = sqrtf(nbfp[(t * ntypes + t) * 2 + 1]);
+        }
+        else
+        {
+            /* filler: no charge, zero-LJ filler type, parked far away at a unique position so that no
+             * two fillers are ever in range of each other (reference: -1e6, atomdata.cpp:146) */
+            atom_index[slot] = -1;
+            xb[pp]           = -1.0e6f - 8.0f * (float)slot;
+            xb[8 + pp]       = -1.0e6f;
+            xb[16 + pp]      = -1.0e6f;
+            xb[24 + pp]      = 0.0f;
+            atype[cl * 8 + pp] = ntypes - 1;
+            lj[(size_t)cl * NB_LJ_STRIDE + pp]     = 0.0f;
+            lj[(size_t)cl * NB_LJ_STRIDE + 8 + pp] = 0.0f;
+        }
+    }
+    __syncthreads();
+    /* bounding boxes of real atoms per cluster; bb[cl*6+0] > bb[cl*6+3] marks an all-filler cluster */
+    for (int cl = threadIdx.x; cl < ncz * 8; cl += blockDim.x)
+    {
+        float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
+        for (int kk = 0; kk < 8; kk++)
+        {
+            uint64_t k = s_key[cl * 8 + kk];
+            if (k == FILL) continue;
+            int i = cl * 8 + kk;
+            int a = ((i >> 4) & 1) ? (int)(uint32_t)(~k) : (int)(uint32_t)k;
+            for (int d = 0; d < 3; d++)
+            {
+                float v = x[3 * a + d];
+                lo[d]   = fminf(lo[d], v);
+                hi[d]   = fmaxf(hi[d], v);
+            }
+        }
+        float* b = bb + (size_t)(cell0 * 8 + cl) * 6;
+        for (int d = 0; d < 3; d++)
+        {
+            b[d]     = lo[d];
+            b[3 + d] = hi[d];
+        }
+    }
+    __syncthreads();
+    /* z range per cell (bbcz_, grid.cpp:1100-1102) */
+    for (int cz = threadIdx.x; cz < ncz; cz += blockDim.x)
+    {
+        float lo = 3.0e38f, hi = -3.0e38f;
+        for (int cl = 0; cl < 8; cl++)
+        {
+            const float* b = bb + (size_t)((cell0 + cz) * 8 + cl) * 6;
+            lo             = fminf(lo, b[2]);
+            hi             = fmaxf(hi, b[5]);
+        }
+        cellz[2 * (cell0 + cz)]     = lo;
+        cellz[2 * (cell0 + cz) + 1] = hi;
+    }
+}
+
+/* grid.cpp:103-262 Grid::setDimensions, GPU geometry */
+static void grid_dimensions(GridDesc& g, int natoms, const float lower[3], const float upper[3], float density, int ddZone)
+{
+    float size[3];
+    for (int d = 0; d < 3; d++)
+    {
+        g.lower[d] = lower[d];
+        g.upper[d] = upper[d];
+        size[d]    = upper[d] - lower[d];
+    }
+    if (natoms > NB_CELL)
+    {
+        float tlen   = cbrtf((float)NB_CL / density);
+        float tlen_x = tlen * 2, tlen_y = tlen * 2;
+        g.ncx = std::max(1, (int)(size[0] / tlen_x));
+        g.ncy = std::max(1, (int)(size[1] / tlen_y));
+    }
+    else
+    {
+        g.ncx = g.ncy = 1;
+    }
+    for (int d = 0; d < 2; d++)
+    {
+        g.cell[d]     = size[d] / (d == 0 ? g.ncx : g.ncy);
+        g.inv_cell[d] = 1 / g.cell[d];
+    }
+    if (ddZone > 0)
+    {
+        g.ncx++; /* grid.cpp:199-209: extra row for atoms beyond the cut-off range */
+        g.ncy++;
+    }
+    g.ncol = g.ncx * g.ncy;
+}
+
+extern "C" int b200nb_put_on_grid(b200nb_t* h, int gi, const float lower[3], const float upper[3], int atom_begin, int atom_end,
+                                  float density, const float* x, int x_on_device)
+{
+    if (!h || gi < 0 || gi > 1 || !lower || !upper || !x) return nb_fail(h, B200NB_ERR_ARG, "put_on_grid: bad argument");
+    if (!h->natoms) return nb_fail(h, B200NB_ERR_STATE, "put_on_grid: set_atoms first");
+    if (atom_begin < 0 || atom_end > h->natoms || atom_begin > atom_end) return nb_fail(h, B200NB_ERR_ARG, "put_on_grid: bad atom range");
+    if (gi == 1 && !h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "put_on_grid: grid 0 must be set before grid 1");
+    cudaSetDevice(h->device);
+    const int n = atom_end - atom_begin;
+    for (int d = 0; d < 3; d++)
+        if (!(upper[d] > lower[d])) return nb_fail(h, B200NB_ERR_ARG, "put_on_grid: upper <= lower");
+    GridDesc& g = h->grid[gi];
+    if (gi == 0)
+    {
+        if (density <= 0) density = (float)n / ((upper[0] - lower[0]) * (upper[1] - lower[1]) * (upper[2] - lower[2]));
+        h->grid[1].valid = 0;
+    }
+    else if (density <= 0)
+    {
+        const GridDesc& g0 = h->grid[0];
+        density = (float)(g0.atom_end - g0.atom_begin)
+                  / ((g0.upper[0] - g0.lower[0]) * (g0.upper[1] - g0.lower[1]) * (g0.upper[2] - g0.lower[2]));
+    }
+    grid_dimensions(g, n, lower, upper, density, gi);
+    g.atom_begin = atom_begin;
+    g.atom_end   = atom_end;
+    g.col0       = (gi == 0) ? 0 : h->grid[0].ncol + 1;
+    g.cell0      = (gi == 0) ? 0 : h->grid[0].ncells;
+    g.valid      = 0;
+
+    /* upload coordinates of this atom range */
+    if (n > 0)
+    {
+        if (x_on_device)
+            NB_CUDA(h, cudaMemcpyAsync(h->d_x + 3 * (size_t)atom_begin, x + 3 * (size_t)atom_begin, sizeof(float) * 3 * n, cudaMemcpyDeviceToDevice, h->stream));
+        else
+            NB_CUDA(h, cudaMemcpyAsync(h->d_x + 3 * (size_t)atom_begin, x + 3 * (size_t)atom_begin, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    }
+    /* column arrays */
+    size_t ncols_need = (size_t)g.col0 + g.ncol + 2;
+    if (ncols_need > h->cap_cols)
+    {
+        /* preserve grid 0's columns when growing for grid 1 */
+        int *nc = nullptr, *n0 = nullptr, *nf = nullptr;
+        size_t cap = ncols_need * 2 + 64;
+        NB_CUDA(h, cudaMalloc((void**)&nc, cap * sizeof(int)));
+        NB_CUDA(h, cudaMalloc((void**)&n0, cap * sizeof(int)));
+        NB_CUDA(h, cudaMalloc((void**)&nf, cap * sizeof(int)));
+        if (h->d_col_count && g.col0 > 0)
+        {
+            NB_CUDA(h, cudaMemcpyAsync(nc, h->d_col_count, sizeof(int) * g.col0, cudaMemcpyDeviceToDevice, h->stream));
+            NB_CUDA(h, cudaMemcpyAsync(n0, h->d_col_cell0, sizeof(int) * g.col0, cudaMemcpyDeviceToDevice, h->stream));
+            NB_CUDA(h, cudaStreamSynchronize(h->stream));
+        }
+        cudaFree(h->d_col_count);
+        cudaFree(h->d_col_cell0);
+        cudaFree(h->d_col_fill);
+        h->d_col_count = nc;
+        h->d_col_cell0 = n0;
+        h->d_col_fill  = nf;
+        h->cap_cols    = cap;
+    }
+    NB_CUDA(h, cudaMemsetAsync(h->d_col_count + g.col0, 0, sizeof(int) * (g.ncol + 1), h->stream));
+    NB_CUDA(h, cudaMemsetAsync(h->d_col_fill + g.col0, 0, sizeof(int) * (g.ncol + 1), h->stream));
+    int totals[2] = { 0, 0 };
+    if (n > 0)
+    {
+        k_column_index<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_x, g, h->d_col_of_atom, h->d_col_count);
+        LAUNCH_CHECK(h);
+    }
+    k_column_scan<<<1, 1024, 0, h->stream>>>(g, h->d_col_count, h->d_col_cell0, h->d_scratch);
+    LAUNCH_CHECK(h);
+    NB_CUDA(h, cudaMemcpyAsync(totals, h->d_scratch, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    g.ncells = totals[0];
+    if (totals[1] > 8192) return nb_fail(h, B200NB_ERR_CAPACITY, "put_on_grid: more than 8192 atoms in one grid column");
+    const int ncells_total = g.cell0 + g.ncells;
+    const size_t npad      = (size_t)ncells_total * NB_CELL;
+    if (npad > h->cap_pad)
+    {
+        /* grow all slot-indexed arrays, preserving grid 0's part when adding grid 1 */
+        size_t cap  = (size_t)(npad * 1.15) + 1024;
+        cap         = (cap + 63) / 64 * 64;
+        size_t keep = (gi == 1) ? (size_t)g.cell0 * NB_CELL : 0;
+        auto grow   = [&](void** p, size_t elem) -> int {
+            void* np = nullptr;
+            if (cudaMalloc(&np, cap * elem) != cudaSuccess) return 1;
+            if (*p && keep) cudaMemcpy(np, *p, keep * elem, cudaMemcpyDeviceToDevice);
+            cudaFree(*p);
+            *p = np;
+            return 0;
+        };
+        int bad = 0;
+        bad |= grow((void**)&h->d_atom_index, sizeof(int));
+        bad |= grow((void**)&h->d_xq, sizeof(float) * 4);
+        bad |= grow((void**)&h->d_lj, sizeof(float) * 2);
+        bad |= grow((void**)&h->d_atype, sizeof(int));
+        bad |= grow((void**)&h->d_f, sizeof(float4));
+        {
+            /* per-cluster / per-cell arrays sized from the slot capacity */
+            void* np = nullptr;
+            if (cudaMalloc(&np, cap / 8 * 6 * sizeof(float)) != cudaSuccess) bad = 1;
+            else
+            {
+                if (h->d_bb && keep) cudaMemcpy(np, h->d_bb, keep / 8 * 6 * sizeof(float), cudaMemcpyDeviceToDevice);
+                cudaFree(h->d_bb);
+                h->d_bb = (float*)np;
+            }
+            np = nullptr;
+            if (cudaMalloc(&np, cap / 64 * 2 * sizeof(float)) != cudaSuccess) bad = 1;
+            else
+            {
+                if (h->d_cellz && keep) cudaMemcpy(np, h->d_cellz, keep / 64 * 2 * sizeof(float), cudaMemcpyDeviceToDevice);
+                cudaFree(h->d_cellz);
+                h->d_cellz = (float*)np;
+            }
+        }
+        if (bad) return nb_fail(h, B200NB_ERR_CUDA, "put_on_grid: device allocation failed");
+        h->cap_pad = cap;
+        NB_CUDA(h, cudaMemsetAsync(h->d_f, 0, cap * sizeof(float4), h->stream));
+    }
+    if (n > 0)
+    {
+        k_column_scatter<<<(n + 255) / 256, 256, 0, h->stream>>>(g, h->d_col_of_atom, h->d_col_cell0, h->d_col_fill, h->d_atom_index);
+        LAUNCH_CHECK(h);
+    }
+    {
+        int    P    = 64;
+        int    need = ((totals[1] + NB_CELL - 1) / NB_CELL) * NB_CELL;
+        while (P < need) P <<= 1;
+        size_t smem = (size_t)P * sizeof(uint64_t);
+        NB_CUDA(h, cudaFuncSetAttribute(k_column_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        k_column_sort<<<g.ncol, 512, smem, h->stream>>>(g, h->d_x, h->d_q, h->d_type, h->d_nbfp, h->dp.ntypes, h->d_col_count,
+                                                        h->d_col_cell0, h->d_atom_index, h->d_slot_of_atom, h->d_xq, h->d_lj,
+                                                        h->d_atype, h->d_bb, h->d_cellz);
+        LAUNCH_CHECK(h);
+    }
+    g.valid         = 1;
+    h->ncells_total = ncells_total;
+    h->npad         = (int)npad;
+    h->ncol_total   = g.col0 + g.ncol + 1;
+    h->have_list    = false;
+    if (gi == 0)
+    {
+        double s = 0;
+        for (int a = atom_begin; a < atom_end; a++) s += (double)h->h_q[a] * h->h_q[a];
+        h->sum_q2 = s;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* pair search                                                                                             */
+/* ------------------------------------------------------------------------------------------------------ */
+
+struct SearchArgs
+{
+    GridDesc gi, gj;
+    int      intra;      /* i and j grid identical: half list */
+    int      shp[3];     /* shift range per dimension (pairlist.cpp:3168-3190) */
+    float    box[3];
+    float    rlist2, rlist;
+    int      max_tiles;
+    int      pass;       /* 0 count, 1 fill */
+};
+
+__device__ __forceinline__ float bb_dist2(const float* ilo, const float* ihi, const float* jb)
+{
+    /* pairlist.cpp:326-347 clusterBoundingBoxDistance2 */
+    float d2 = 0;
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+    {
+        float dl = ilo[d] - jb[3 + d];
+        float dh = jb[d] - ihi[d];
+        float dm = fmaxf(fmaxf(dl, dh), 0.0f);
+        d2 += dm * dm;
+    }
+    return d2;
+}
+
+/* One warp per i-cluster. Lane = il + 8*jq handles atom pairs (il, jq) and (il, jq+4) of a candidate tile.
+ * A cluster pair enters the list iff at least one atom pair has r^2 < rlist^2 (the converged result of
+ * the reference's bounding-box search, pairlist.cpp:1090-1244, followed by its list pruning,
+ * nbnxm_cuda_kernel_pruneonly.cuh), so the list is the tightest superset of the in-range pairs.
+ * Exclusion masks (pairlist.cpp:1874-1972): bit j*8+i of a tile's mask is 1 when atoms i,j interact. */
+__global__ void __launch_bounds__(128)
+k_search(SearchArgs A, const float* __restrict__ xq, const float* __restrict__ bb, const float* __restrict__ cellz,
+         const int* __restrict__ col_cell0, const int* __restrict__ atom_index, const int* __restrict__ excl_off,
+         const int* __restrict__ excl_idx, const float* __restrict__ shift_vec, int* __restrict__ cnt_tiles,
+         int* __restrict__ cnt_entries, Entry* __restrict__ entries, int* __restrict__ tile_cj, uint64_t* __restrict__ tile_mask,
+         int* __restrict__ err_flag)
+{
+    __shared__ int      s_cj[4][NB_MAX_GROUP_TILES];
+    __shared__ uint64_t s_mask[4][NB_MAX_GROUP_TILES];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncl_i = A.gi.ncells * 8;
+    const int cil   = blockIdx.x * 4 + w; /* grid-local i-cluster */
+    if (cil >= ncl_i) return;
+    const int ci = A.gi.cell0 * 8 + cil;
+    const float* ib = bb + (size_t)ci * 6;
+    const bool   i_empty = ib[0] > ib[3];
+    int tile_cursor = 0, entry_cursor = 0;
+    if (A.pass == 1)
+    {
+        tile_cursor  = cnt_tiles[cil];
+        entry_cursor = cnt_entries[cil];
+    }
+    int ntiles_total = 0, nentries_total = 0;
+    if (!i_empty)
+    {
+        const int il = lane & 7, jq = lane >> 3;
+        const float* xb = xq + (size_t)ci * NB_XQ_STRIDE;
+        const int    ip = nb_pairpos(il);
+        const float  xi0 = xb[ip], yi0 = xb[8 + ip], zi0 = xb[16 + ip];
+        const int    ai = atom_index[ci * 8 + il];
+        int e0 = 0, e1 = 0;
+        if (ai >= 0 && excl_off)
+        {
+            e0 = excl_off[ai];
+            e1 = excl_off[ai + 1];
+        }
+        const float jzlo = A.gj.lower[2], jzhi = A.gj.upper[2];
+        (void)jzlo;
+        (void)jzhi;
+        for (int tz = -A.shp[2]; tz <= A.shp[2]; tz++)
+            for (int ty = -A.shp[1]; ty <= A.shp[1]; ty++)
+                for (int tx = -A.shp[0]; tx <= A.shp[0]; tx++)
+                {
+                    const int shift = 5 * (3 * (tz + 1) + (ty + 1)) + tx + 2; /* pbcutil/ishift.h:50 */
+                    if (A.intra && shift > B200NB_CENTRAL) continue;           /* pairlist.cpp:3339-3342 */
+                    const float sx = shift_vec[3 * shift], sy = shift_vec[3 * shift + 1], sz = shift_vec[3 * shift + 2];
+                    float ilo[3] = { ib[0] + sx, ib[1] + sy, ib[2] + sz };
+                    float ihi[3] = { ib[3] + sx, ib[4] + sy, ib[5] + sz };
+                    /* column range reachable within rlist; edge columns also hold atoms beyond the grid bounds */
+                    int cx0 = (int)floorf((ilo[0] - A.rlist - A.gj.lower[0]) * A.gj.inv_cell[0]);
+                    int cx1 = (int)floorf((ihi[0] + A.rlist - A.gj.lower[0]) * A.gj.inv_cell[0]);
+                    int cy0 = (int)floorf((ilo[1] - A.rlist - A.gj.lower[1]) * A.gj.inv_cell[1]);
+                    int cy1 = (int)floorf((ihi[1] + A.rlist - A.gj.lower[1]) * A.gj.inv_cell[1]);
+                    if (cx1 < 0 || cy1 < 0 || cx0 > A.gj.ncx - 1 || cy0 > A.gj.ncy - 1)
+                    {
+                        /* entirely outside: only the clamped edge columns could hold stray atoms; they are
+                         * covered because the bounding-box test below uses real atom extents */
+                    }
+                    cx0 = max(cx0, 0);
+                    cy0 = max(cy0, 0);
+                    cx1 = min(cx1, A.gj.ncx - 1);
+                    cy1 = min(cy1, A.gj.ncy - 1);
+                    const float xi = xi0 + sx, yi = yi0 + sy, zi = zi0 + sz; /* the shifted i-atom, as in the kernels */
+                    int n_mask = 0, n_plain = 0; /* masked tiles grow from the front, plain ones from the back */
+                    for (int cx = cx0; cx <= cx1; cx++)
+                        for (int cy = cy0; cy <= cy1; cy++)
+                        {
+                            const int col = A.gj.col0 + cx * A.gj.ncy + cy;
+                            const int c0 = col_cell0[col], c1 = col_cell0[col + 1];
+                            if (c1 <= c0) continue;
+                            /* cells whose z range can be within rlist: cells are z-ordered (grid.cpp:1092-1103) */
+                            int first = c1, last = c0 - 1;
+                            for (int cb = c0; cb < c1; cb += 32)
+                            {
+                                int  c  = cb + lane;
+                                bool ok = false;
+                                if (c < c1) ok = (cellz[2 * c + 1] >= ilo[2] - A.rlist) && (cellz[2 * c] <= ihi[2] + A.rlist);
+                                unsigned m = __ballot_sync(0xffffffffu, ok);
+                                if (m)
+                                {
+                                    first = min(first, cb + __ffs(m) - 1);
+                                    last  = max(last, cb + 31 - __clz(m));
+                                }
+                            }
+                            if (last < first) continue;
+                            int cj_begin = first * 8, cj_end = (last + 1) * 8;
+                            if (A.intra && shift == B200NB_CENTRAL) cj_begin = max(cj_begin, ci); /* pairlist.cpp:3365-3372: j >= i */
+                            for (int cjb = cj_begin; cjb < cj_end; cjb += 32)
+                            {
+                                const int cjc = cjb + lane;
+                                bool      cand = false;
+                                if (cjc < cj_end)
+                                {
+                                    const float* jb = bb + (size_t)cjc * 6;
+                                    cand            = (jb[0] <= jb[3]) && bb_dist2(ilo, ihi, jb) < A.rlist2;
+                                }
+                                unsigned cm = __ballot_sync(0xffffffffu, cand);
+                                while (cm)
+                                {
+                                    const int b = __ffs(cm) - 1;
+                                    cm &= cm - 1;
+                                    const int    cj = cjb + b;
+                                    const float* jx = xq + (size_t)cj * NB_XQ_STRIDE;
+                                    const float2 xj = *(const float2*)(jx + 2 * jq);
+                                    const float2 yj = *(const float2*)(jx + 8 + 2 * jq);
+                                    const float2 zj = *(const float2*)(jx + 16 + 2 * jq);
+                                    const float  r2a = nb_rsq(xi, yi, zi, xj.x, yj.x, zj.x);
+                                    const float  r2b = nb_rsq(xi, yi, zi, xj.y, yj.y, zj.y);
+                                    const bool   in  = (r2a < A.rlist2) || (r2b < A.rlist2);
+                                    if (!__any_sync(0xffffffffu, in)) continue;
+                                    /* interaction bits from the topology exclusions of atom ai */
+                                    bool ia = true, ibit = true;
+                                    if (e1 > e0)
+                                    {
+                                        const int aja = atom_index[cj * 8 + jq], ajb = atom_index[cj * 8 + jq + 4];
+                                        for (int e = e0; e < e1; e++)
+                                        {
+                                            const int ex = excl_idx[e];
+                                            ia           = ia && (ex != aja);
+                                            ibit         = ibit && (ex != ajb);
+                                        }
+                                    }
+                                    const unsigned ma = __ballot_sync(0xffffffffu, ia);
+                                    const unsigned mb = __ballot_sync(0xffffffffu, ibit);
+                                    const uint64_t mask = ((uint64_t)mb << 32) | ma;
+                                    const bool     masked = (mask != ~0ull) || (A.intra && shift == B200NB_CENTRAL && cj == ci);
+                                    if (n_mask + n_plain >= NB_MAX_GROUP_TILES)
+                                    {
+                                        if (lane == 0) atomicExch(err_flag, 1);
+                                        continue;
+                                    }
+                                    if (lane == 0)
+                                    {
+                                        int pos = masked ? n_mask : NB_MAX_GROUP_TILES - 1 - n_plain;
+                                        s_cj[w][pos]   = cj;
+                                        s_mask[w][pos] = mask;
+                                    }
+                                    if (masked) n_mask++;
+                                    else n_plain++;
+                                }
+                            }
+                        }
+                    /* close this (ci, shift) group: pairlist.cpp:2167-2194 closeIEntry + split_sci_entry */
+                    const int n = n_mask + n_plain;
+                    if (n == 0) continue;
+                    const int nchunks = (n + A.max_tiles - 1) / A.max_tiles;
+                    if (A.pass == 1)
+                    {
+                        __syncwarp();
+                        for (int k = lane; k < n; k += 32)
+                        {
+                            /* masked tiles first, then the plain ones in discovery order */
+                            int src = (k < n_mask) ? k : NB_MAX_GROUP_TILES - 1 - (k - n_mask);
+                            tile_cj[tile_cursor + k]   = s_cj[w][src];
+                            tile_mask[tile_cursor + k] = s_mask[w][src];
+                        }
+                        for (int k = lane; k < nchunks; k += 32)
+                        {
+                            Entry e;
+                            e.ci          = ci;
+                            int nm        = min(max(n_mask - k * A.max_tiles, 0), A.max_tiles);
+                            e.shift_nmask = shift | (nm << 8);
+                            e.start       = tile_cursor + k * A.max_tiles;
+                            e.end         = tile_cursor + min((k + 1) * A.max_tiles, n);
+                            entries[entry_cursor + k] = e;
+                        }
+                        __syncwarp();
+                    }
+                    tile_cursor += n;
+                    entry_cursor += nchunks;
+                    ntiles_total += n;
+                    nentries_total += nchunks;
+                }
+    }
+    if (A.pass == 0 && lane == 0)
+    {
+        cnt_tiles[cil]   = ntiles_total;
+        cnt_entries[cil] = nentries_total;
+    }
+}
+
+/* exclusive scan of two int arrays of length n (single CTA); totals -> out_tot[0..1] as long long */
+__global__ void k_scan2(int* a, int* b, int n, long long* out_tot)
+{
+    __shared__ long long sa[1024], sb[1024];
+    const int t = threadIdx.x, per = (n + blockDim.x - 1) / blockDim.x;
+    long long s1 = 0, s2 = 0;
+    for (int k = 0; k < per; k++)
+    {
+        int i = t * per + k;
+        if (i < n)
+        {
+            s1 += a[i];
+            s2 += b[i];
+        }
+    }
+    sa[t] = s1;
+    sb[t] = s2;
+    __syncthreads();
+    if (t == 0)
+    {
+        long long r1 = 0, r2 = 0;
+        for (int i = 0; i < (int)blockDim.x; i++)
+        {
+            long long v1 = sa[i], v2 = sb[i];
+            sa[i] = r1;
+            sb[i] = r2;
+            r1 += v1;
+            r2 += v2;
+        }
+        out_tot[0] = r1;
+        out_tot[1] = r2;
+    }
+    __syncthreads();
+    long long r1 = sa[t], r2 = sb[t];
+    for (int k = 0; k < per; k++)
+    {
+        int i = t * per + k;
+        if (i < n)
+        {
+            int v1 = a[i], v2 = b[i];
+            a[i] = (int)r1;
+            b[i] = (int)r2;
+            r1 += v1;
+            r2 += v2;
+        }
+    }
+}
+
+/* Dynamic pruning (cuda/nbnxm_cuda_kernel_pruneonly.cuh:104-277; kernel_ref_prune.cpp:45-143): one warp per
+ * entry of the outer list; a tile stays iff any atom pair has r^2 < rlist_inner^2. The inner list reuses the
+ * outer list's segment layout, compacted in place per entry (masked tiles stay in front). */
+__global__ void __launch_bounds__(128)
+k_prune(const Entry* __restrict__ oe, const int* __restrict__ ocj, const uint64_t* __restrict__ omask, long long nentries,
+        int part, int nparts, const float* __restrict__ xq, const float* __restrict__ shift_vec, float rlist2,
+        Entry* __restrict__ ie, int* __restrict__ icj, uint64_t* __restrict__ imask)
+{
+    const long long wid = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const long long e   = wid * nparts + part; /* rolling parts interleave entries: pruneonly.cuh:165-166 */
+    if (e >= nentries) return;
+    const int   lane = threadIdx.x & 31, il = lane & 7, jq = lane >> 3;
+    const Entry en   = oe[e];
+    const int   shift = en.shift_nmask & 255, nmask = en.shift_nmask >> 8;
+    const float* xb  = xq + (size_t)en.ci * NB_XQ_STRIDE;
+    const int    ip  = nb_pairpos(il);
+    const float  xi = xb[ip] + shift_vec[3 * shift], yi = xb[8 + ip] + shift_vec[3 * shift + 1],
+                zi = xb[16 + ip] + shift_vec[3 * shift + 2];
+    int kept = 0, kept_mask = 0;
+    for (int t = en.start; t < en.end; t++)
+    {
+        const int    cj = ocj[t];
+        const float* jx = xq + (size_t)cj * NB_XQ_STRIDE;
+        const float2 xj = *(const float2*)(jx + 2 * jq);
+        const float2 yj = *(const float2*)(jx + 8 + 2 * jq);
+        const float2 zj = *(const float2*)(jx + 16 + 2 * jq);
+        const bool   in = (nb_rsq(xi, yi, zi, xj.x, yj.x, zj.x) < rlist2) || (nb_rsq(xi, yi, zi, xj.y, yj.y, zj.y) < rlist2);
+        if (__any_sync(0xffffffffu, in))
+        {
+            if (lane == 0)
+            {
+                icj[en.start + kept]   = cj;
+                imask[en.start + kept] = omask[t];
+            }
+            if (t - en.start < nmask) kept_mask++;
+            kept++;
+        }
+    }
+    if (lane == 0)
+    {
+        Entry o;
+        o.ci          = en.ci;
+        o.shift_nmask = shift | (kept_mask << 8);
+        o.start       = en.start;
+        o.end         = en.start + kept;
+        ie[e]         = o;
+    }
+}
+
+static int ensure_list(b200nb_context* h, PairList& l, size_t ntiles, size_t nentries)
+{
+    if (ntiles > l.cap_tiles || !l.cj)
+    {
+        cudaFree(l.cj);
+        cudaFree(l.mask);
+        l.cj = nullptr;
+        l.mask = nullptr;
+        size_t cap = (size_t)(ntiles * 1.1) + 1024;
+        NB_CUDA(h, cudaMalloc((void**)&l.cj, cap * sizeof(int)));
+        NB_CUDA(h, cudaMalloc((void**)&l.mask, cap * sizeof(uint64_t)));
+        l.cap_tiles = cap;
+    }
+    if (nentries > l.cap_entries || !l.entries)
+    {
+        cudaFree(l.entries);
+        l.entries = nullptr;
+        size_t cap = (size_t)(nentries * 1.1) + 1024;
+        NB_CUDA(h, cudaMalloc((void**)&l.entries, cap * sizeof(Entry)));
+        l.cap_entries = cap;
+    }
+    return 0;
+}
+
+static int launch_prune(b200nb_context* h, int loc, int part, int nparts)
+{
+    if (h->inner_is_outer) return 0;
+    PairList& o = h->outer[loc];
+    PairList& i = h->inner[loc];
+    if (o.nentries == 0) return 0;
+    long long nw = (o.nentries - part + nparts - 1) / nparts;
+    if (nw <= 0) return 0;
+    k_prune<<<(unsigned)((nw + 3) / 4), 128, 0, h->stream>>>(o.entries, o.cj, o.mask, o.nentries, part, nparts, h->d_xq, h->d_shift_vec,
+                                                             h->dp.rlist_inner2, i.entries, i.cj, i.mask);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+extern "C" int b200nb_build_pairlist(b200nb_t* h)
+{
+    if (!h) return B200NB_ERR_ARG;
+    if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "build_pairlist: put_on_grid first");
+    cudaSetDevice(h->device);
+    const float rl = h->hp.rlist_outer;
+    /* a periodic dimension must hold at least two list radii, else one pair has several images in range
+     * (the reference handles that with shp[XX]=2, pairlist.cpp:3185-3188; outside our scope) */
+    for (int d = 0; d < 3; d++)
+        if (h->pbc[d] && h->box[d] < 2 * rl) return nb_fail(h, B200NB_ERR_ARG, "build_pairlist: box smaller than 2*rlist along a periodic dimension");
+    const bool want_inner = h->dp.rlist_inner2 < h->dp.rlist_outer2;
+    if (!want_inner && !h->inner_is_outer)
+    {
+        for (int l = 0; l < 2; l++) free_list(h->inner[l]);
+    }
+    if (want_inner && h->inner_is_outer)
+    {
+        for (int l = 0; l < 2; l++) h->inner[l] = PairList();
+    }
+    h->inner_is_outer = !want_inner;
+
+    const int ncl_i = h->grid[0].ncells * 8;
+    if ((size_t)ncl_i > h->cap_clusters)
+    {
+        cudaFree(h->d_cnt_tiles);
+        cudaFree(h->d_cnt_entries);
+        h->cap_clusters = (size_t)(ncl_i * 1.2) + 64;
+        NB_CUDA(h, cudaMalloc((void**)&h->d_cnt_tiles, h->cap_clusters * sizeof(int)));
+        NB_CUDA(h, cudaMalloc((void**)&h->d_cnt_entries, h->cap_clusters * sizeof(int)));
+    }
+    for (int loc = 0; loc < 2; loc++)
+    {
+        PairList& L = h->outer[loc];
+        L.ntiles = L.nentries = 0;
+        if (loc == 1 && !h->grid[1].valid)
+        {
+            if (want_inner) h->inner[1].ntiles = h->inner[1].nentries = 0;
+            continue;
+        }
+        SearchArgs A;
+        A.gi    = h->grid[0];
+        A.gj    = h->grid[loc];
+        A.intra = (loc == 0);
+        for (int d = 0; d < 3; d++)
+        {
+            A.shp[d] = h->pbc[d] ? 1 : 0;
+            A.box[d] = h->box[d];
+        }
+        A.rlist     = rl;
+        A.rlist2    = h->dp.rlist_outer2;
+        A.max_tiles = h->max_tiles;
+        NB_CUDA(h, cudaMemsetAsync(h->d_scratch + 8, 0, sizeof(int), h->stream));
+        const unsigned nblk = (unsigned)((ncl_i + 3) / 4);
+        A.pass              = 0;
+        k_search<<<nblk, 128, 0, h->stream>>>(A, h->d_xq, h->d_bb, h->d_cellz, h->d_col_cell0, h->d_atom_index, h->d_excl_off,
+                                              h->d_excl_idx, h->d_shift_vec, h->d_cnt_tiles, h->d_cnt_entries, nullptr, nullptr,
+                                              nullptr, h->d_scratch + 8);
+        LAUNCH_CHECK(h);
+        k_scan2<<<1, 1024, 0, h->stream>>>(h->d_cnt_tiles, h->d_cnt_entries, ncl_i, h->d_counter);
+        LAUNCH_CHECK(h);
+        long long tot[2];
+        int       flag = 0;
+        NB_CUDA(h, cudaMemcpyAsync(tot, h->d_counter, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+        NB_CUDA(h, cudaMemcpyAsync(&flag, h->d_scratch + 8, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        NB_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (flag) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: more than 512 cluster pairs for one i-cluster and shift");
+        if (tot[0] > 2000000000LL) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: pair list exceeds 2^31 cluster pairs");
+        if (ensure_list(h, L, (size_t)tot[0], (size_t)tot[1])) return B200NB_ERR_CUDA;
+        L.ntiles   = tot[0];
+        L.nentries = tot[1];
+        if (tot[0] > 0)
+        {
+            A.pass = 1;
+            k_search<<<nblk, 128, 0, h->stream>>>(A, h->d_xq, h->d_bb, h->d_cellz, h->d_col_cell0, h->d_atom_index, h->d_excl_off,
+                                                  h->d_excl_idx, h->d_shift_vec, h->d_cnt_tiles, h->d_cnt_entries, L.entries, L.cj,
+                                                  L.mask, h->d_scratch + 8);
+            LAUNCH_CHECK(h);
+        }
+        if (want_inner)
+        {
+            PairList& I = h->inner[loc];
+            if (ensure_list(h, I, (size_t)tot[0], (size_t)tot[1])) return B200NB_ERR_CUDA;
+            I.ntiles   = tot[0]; /* upper bound; exact count via get_stats */
+            I.nentries = tot[1];
+            /* fresh-list prune of the whole list (cuda/nbnxm_cuda.cu:510-517) */
+            if (launch_prune(h, loc, 0, 1)) return B200NB_ERR_CUDA;
+        }
+        else
+        {
+            h->inner[loc] = L;
+        }
+    }
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->have_list = true;
+    return 0;
+}
+
+extern "C" int b200nb_launch_prune(b200nb_t* h, int locality, int part, int num_parts)
+{
+    if (!h || num_parts < 1 || part < 0 || part >= num_parts) return nb_fail(h, B200NB_ERR_ARG, "launch_prune: bad argument");
+    if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "launch_prune: no pair list");
+    cudaSetDevice(h->device);
+    for (int loc = 0; loc < 2; loc++)
+        if (locality < 0 || locality == loc)
+            if (launch_prune(h, loc, part, num_parts)) return B200NB_ERR_CUDA;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* per-step buffer ops                                                                                     */
+/* ------------------------------------------------------------------------------------------------------ */
+
+/* nbnxn_gpu_x_to_nbat_x_kernel (cuda/nbnxm_buffer_ops_kernels.cuh:65-114): x (atom order) -> grid layout */
+__global__ void k_x_to_grid(const float* __restrict__ x, const int* __restrict__ slot_of_atom, int a0, int a1, float* __restrict__ xq)
+{
+    int a = a0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= a1) return;
+    const int slot = slot_of_atom[a];
+    float*    xb   = xq + (size_t)(slot >> 3) * NB_XQ_STRIDE + nb_pairpos(slot & 7);
+    xb[0]          = x[3 * a];
+    xb[8]          = x[3 * a + 1];
+    xb[16]         = x[3 * a + 2];
+}
+
+/* reduceKernel (mdlib/gpuforcereduction_impl.cu:70-104): f[a] (+)= f_nb[cell[a]] */
+__global__ void k_f_from_grid(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom, int a0, int a1, int accumulate,
+                              float* __restrict__ f)
+{
+    int a = a0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= a1) return;
+    const float4 v = fg[slot_of_atom[a]];
+    if (accumulate)
+    {
+        f[3 * a] += v.x;
+        f[3 * a + 1] += v.y;
+        f[3 * a + 2] += v.z;
+    }
+    else
+    {
+        f[3 * a]     = v.x;
+        f[3 * a + 1] = v.y;
+        f[3 * a + 2] = v.z;
+    }
+}
+
+extern "C" int b200nb_set_x(b200nb_t* h, const float* x, int x_on_device, int a0, int a1)
+{
+    if (!h || !x) return nb_fail(h, B200NB_ERR_ARG, "set_x: bad argument");
+    if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "set_x: put_on_grid first");
+    if (a0 < 0 || a1 > h->natoms || a0 > a1) return nb_fail(h, B200NB_ERR_ARG, "set_x: bad atom range");
+    if (a1 == a0) return 0;
+    cudaSetDevice(h->device);
+    const int n = a1 - a0;
+    const float* src = x + 3 * (size_t)a0;
+    if (x_on_device)
+    {
+        k_x_to_grid<<<(n + 255) / 256, 256, 0, h->stream>>>(x, h->d_slot_of_atom, a0, a1, h->d_xq);
+    }
+    else
+    {
+        NB_CUDA(h, cudaMemcpyAsync(h->d_x + 3 * (size_t)a0, src, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+        k_x_to_grid<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_x, h->d_slot_of_atom, a0, a1, h->d_xq);
+    }
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+extern "C" int b200nb_clear_outputs(b200nb_t* h)
+{
+    if (!h) return B200NB_ERR_ARG;
+    if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "clear_outputs: put_on_grid first");
+    cudaSetDevice(h->device);
+    NB_CUDA(h, cudaMemsetAsync(h->d_f, 0, sizeof(float4) * (size_t)h->npad, h->stream));
+    NB_CUDA(h, cudaMemsetAsync(h->d_fshift, 0, sizeof(float) * B200NB_SHIFTS * 3, h->stream));
+    NB_CUDA(h, cudaMemsetAsync(h->d_energy, 0, sizeof(double) * 2, h->stream));
+    return 0;
+}
+
+extern "C" int b200nb_launch_force(b200nb_t* h, int locality, int flags)
+{
+    if (!h) return B200NB_ERR_ARG;
+    if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "launch_force: no pair list");
+    cudaSetDevice(h->device);
+    for (int loc = 0; loc < 2; loc++)
+        if (locality < 0 || locality == loc)
+        {
+            int rc = nb_launch_force_kernel(h, loc, flags);
+            if (rc) return rc;
+        }
+    return 0;
+}
+
+extern "C" int b200nb_get_f(b200nb_t* h, float* f, int f_on_device, int accumulate, int a0, int a1)
+{
+    if (!h || !f) return nb_fail(h, B200NB_ERR_ARG, "get_f: bad argument");
+    if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "get_f: put_on_grid first");
+    if (a0 < 0 || a1 > h->natoms || a0 > a1) return nb_fail(h, B200NB_ERR_ARG, "get_f: bad atom range");
+    if (a1 == a0) return 0;
+    cudaSetDevice(h->device);
+    const int n = a1 - a0;
+    if (f_on_device)
+    {
+        k_f_from_grid<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, a0, a1, accumulate, f);
+        LAUNCH_CHECK(h);
+    }
+    else
+    {
+        if (accumulate) return nb_fail(h, B200NB_ERR_ARG, "get_f: accumulate needs a device buffer");
+        k_f_from_grid<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, a0, a1, 0, h->d_fout);
+        LAUNCH_CHECK(h);
+        NB_CUDA(h, cudaMemcpyAsync(f + 3 * (size_t)a0, h->d_fout + 3 * (size_t)a0, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+        NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+extern "C" int b200nb_get_outputs(b200nb_t* h, float* fshift_host, double* energies_host)
+{
+    if (!h) return B200NB_ERR_ARG;
+    cudaSetDevice(h->device);
+    float  fs[B200NB_SHIFTS * 3];
+    double e[2];
+    NB_CUDA(h, cudaMemcpyAsync(fs, h->d_fshift, sizeof(fs), cudaMemcpyDeviceToHost, h->stream));
+    NB_CUDA(h, cudaMemcpyAsync(e, h->d_energy, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (fshift_host)
+        for (int k = 0; k < B200NB_SHIFTS * 3; k++) fshift_host[k] += fs[k]; /* gpu_common.h:259-275 accumulates */
+    if (energies_host)
+    {
+        energies_host[0] += e[0];
+        energies_host[1] += e[1];
+    }
+    return 0;
+}
+
+extern "C" int b200nb_compute(b200nb_t* h, const float* x_host, int flags, float* f_host, float* fshift_host, double* energies_host)
+{
+    if (!h || !x_host || !f_host) return nb_fail(h, B200NB_ERR_ARG, "compute: bad argument");
+    if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "compute: no pair list");
+    int rc;
+    if ((rc = b200nb_set_x(h, x_host, 0, 0, h->natoms))) return rc;
+    if ((rc = b200nb_clear_outputs(h))) return rc;
+    if ((rc = b200nb_launch_force(h, -1, flags))) return rc;
+    if ((rc = b200nb_get_f(h, f_host, 0, 0, 0, h->natoms))) return rc;
+    if (fshift_host || energies_host)
+    {
+        if (fshift_host) memset(fshift_host, 0, sizeof(float) * B200NB_SHIFTS * 3);
+        if (energies_host) energies_host[0] = energies_host[1] = 0;
+        if ((rc = b200nb_get_outputs(h, fshift_host, energies_host))) return rc;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* halo pack / unpack                                                                                      */
+/* ------------------------------------------------------------------------------------------------------ */
+/* packSendBufKernel<usePBC> (domdec/gpuhaloexchange_impl.cu:77-100) */
+__global__ void k_halo_pack(const float* __restrict__ x, const int* __restrict__ index, int n, float sx, float sy, float sz,
+                            float* __restrict__ out)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int a          = index[k];
+    out[3 * k]     = x[3 * a] + sx;
+    out[3 * k + 1] = x[3 * a + 1] + sy;
+    out[3 * k + 2] = x[3 * a + 2] + sz;
+}
+/* unpackRecvBufKernel<accumulate=true> (domdec/gpuhaloexchange_impl.cu:108-131) */
+__global__ void k_halo_unpack(float* __restrict__ f, const int* __restrict__ index, int n, const float* __restrict__ in)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int a = index[k];
+    f[3 * a] += in[3 * k];
+    f[3 * a + 1] += in[3 * k + 1];
+    f[3 * a + 2] += in[3 * k + 2];
+}
+
+extern "C" int b200nb_halo_pack_x(b200nb_t* h, const float* x_dev, const int* index_dev, int n, const float shift[3], float* out_dev)
+{
+    if (!h || !x_dev || !index_dev || !out_dev || n < 0) return nb_fail(h, B200NB_ERR_ARG, "halo_pack_x: bad argument");
+    if (n == 0) return 0;
+    cudaSetDevice(h->device);
+    k_halo_pack<<<(n + 255) / 256, 256, 0, h->stream>>>(x_dev, index_dev, n, shift ? shift[0] : 0.f, shift ? shift[1] : 0.f,
+                                                       shift ? shift[2] : 0.f, out_dev);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+extern "C" int b200nb_halo_unpack_f(b200nb_t* h, float* f_dev, const int* index_dev, int n, const float* in_dev)
+{
+    if (!h || !f_dev || !index_dev || !in_dev || n < 0) return nb_fail(h, B200NB_ERR_ARG, "halo_unpack_f: bad argument");
+    if (n == 0) return 0;
+    cudaSetDevice(h->device);
+    k_halo_unpack<<<(n + 255) / 256, 256, 0, h->stream>>>(f_dev, index_dev, n, in_dev);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* introspection                                                                                           */
+/* ------------------------------------------------------------------------------------------------------ */
+__global__ void k_count_tiles(const Entry* __restrict__ e, long long n, long long* out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long v = 0;
+    if (i < n) v = e[i].end - e[i].start;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd((unsigned long long*)out, (unsigned long long)v);
+}
+
+extern "C" int b200nb_get_stats(b200nb_t* h, b200nb_stats_t* out)
+{
+    if (!h || !out) return B200NB_ERR_ARG;
+    cudaSetDevice(h->device);
+    memset(out, 0, sizeof(*out));
+    out->natoms         = h->natoms;
+    out->natoms_padded  = h->npad;
+    out->nclusters      = h->npad / 8;
+    out->ncx            = h->grid[0].ncx;
+    out->ncy            = h->grid[0].ncy;
+    out->comb_geometric = h->comb_geom ? 1 : 0;
+    if (h->have_list)
+    {
+        for (int l = 0; l < 2; l++)
+        {
+            out->ntiles_outer += h->outer[l].ntiles;
+            out->nentries += h->outer[l].nentries;
+            if (h->inner_is_outer) out->ntiles_inner += h->outer[l].ntiles;
+            else if (h->inner[l].nentries)
+            {
+                long long v = 0;
+                NB_CUDA(h, cudaMemsetAsync(h->d_counter + 4, 0, sizeof(long long), h->stream));
+                k_count_tiles<<<(unsigned)((h->inner[l].nentries + 255) / 256), 256, 0, h->stream>>>(h->inner[l].entries, h->inner[l].nentries,
+                                                                                                   h->d_counter + 4);
+                LAUNCH_CHECK(h);
+                NB_CUDA(h, cudaMemcpyAsync(&v, h->d_counter + 4, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+                NB_CUDA(h, cudaStreamSynchronize(h->stream));
+                out->ntiles_inner += v;
+            }
+        }
+    }
+    out->nlaunches = h->nlaunches;
+    return 0;
+}
+
+extern "C" int b200nb_get_grid_order(b200nb_t* h, int* atom_index_host, int cap)
+{
+    if (!h || !atom_index_host) return B200NB_ERR_ARG;
+    if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "get_grid_order: put_on_grid first");
+    if (cap < h->npad) return nb_fail(h, B200NB_ERR_CAPACITY, "get_grid_order: buffer too small");
+    cudaSetDevice(h->device);
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    NB_CUDA(h, cudaMemcpy(atom_index_host, h->d_atom_index, sizeof(int) * (size_t)h->npad, cudaMemcpyDeviceToHost));
+    return h->npad;
+}
+
+extern "C" long long b200nb_get_tiles(b200nb_t* h, int outer, int* tiles_host, long long cap)
+{
+    if (!h) return B200NB_ERR_ARG;
+    if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "get_tiles: no pair list");
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    long long n = 0;
+    for (int l = 0; l < 2; l++)
+    {
+        const PairList& L = (outer || h->inner_is_outer) ? h->outer[l] : h->inner[l];
+        if (L.nentries == 0) continue;
+        std::vector<Entry> e((size_t)L.nentries);
+        std::vector<int>   cj((size_t)h->outer[l].ntiles);
+        cudaMemcpy(e.data(), L.entries, sizeof(Entry) * e.size(), cudaMemcpyDeviceToHost);
+        cudaMemcpy(cj.data(), L.cj, sizeof(int) * cj.size(), cudaMemcpyDeviceToHost);
+        for (const Entry& en : e)
+            for (int t = en.start; t < en.end; t++)
+            {
+                if (tiles_host && n < cap)
+                {
+                    tiles_host[3 * n]     = en.ci;
+                    tiles_host[3 * n + 1] = en.shift_nmask & 255;
+                    tiles_host[3 * n + 2] = cj[t];
+                }
+                n++;
+            }
+    }
+    return n;
+}
+
+/* every interacting atom pair of the list: mask bit set, not on/below the diagonal of a self tile, both
+ * atoms real, r^2 < r2 -- the same predicate the force kernel applies */
+__global__ void __launch_bounds__(128)
+k_pairs(const Entry* __restrict__ ent, const int* __restrict__ tcj, const uint64_t* __restrict__ tmask, long long nentries,
+        const float* __restrict__ xq, const float* __restrict__ shift_vec, const int* __restrict__ atom_index, float r2, int intra,
+        int* __restrict__ out, long long cap, unsigned long long* __restrict__ counter)
+{
+    const long long e = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (e >= nentries) return;
+    const int   lane = threadIdx.x & 31, il = lane & 7, jq = lane >> 3;
+    const Entry en   = ent[e];
+    const int   shift = en.shift_nmask & 255, nmask = en.shift_nmask >> 8;
+    const float* xb  = xq + (size_t)en.ci * NB_XQ_STRIDE;
+    const int    ip  = nb_pairpos(il);
+    const float  xi = xb[ip] + shift_vec[3 * shift], yi = xb[8 + ip] + shift_vec[3 * shift + 1],
+                zi = xb[16 + ip] + shift_vec[3 * shift + 2];
+    const int ai = atom_index[en.ci * 8 + il];
+    for (int t = en.start; t < en.end; t++)
+    {
+        const int      cj   = tcj[t];
+        const uint64_t mask = (t - en.start < nmask) ? tmask[t] : ~0ull;
+        const bool     diag = intra && shift == B200NB_CENTRAL && cj == en.ci;
+        const float*   jx   = xq + (size_t)cj * NB_XQ_STRIDE;
+        const float2   xj = *(const float2*)(jx + 2 * jq), yj = *(const float2*)(jx + 8 + 2 * jq), zj = *(const float2*)(jx + 16 + 2 * jq);
+        for (int half = 0; half < 2; half++)
+        {
+            const int   j  = jq + 4 * half;
+            const float r  = half ? nb_rsq(xi, yi, zi, xj.y, yj.y, zj.y) : nb_rsq(xi, yi, zi, xj.x, yj.x, zj.x);
+            const int   aj = atom_index[cj * 8 + j];
+            bool ok = (r < r2) && ((mask >> (j * 8 + il)) & 1ull) && ai >= 0 && aj >= 0 && !(diag && j <= il);
+            if (ok)
+            {
+                unsigned long long pos = atomicAdd(counter, 1ull);
+                if ((long long)pos < cap)
+                {
+                    out[3 * pos]     = ai;
+                    out[3 * pos + 1] = aj;
+                    out[3 * pos + 2] = shift;
+                }
+            }
+        }
+    }
+}
+
+extern "C" long long b200nb_get_pairs(b200nb_t* h, float r, int* pairs_host, long long cap)
+{
+    if (!h) return B200NB_ERR_ARG;
+    if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "get_pairs: no pair list");
+    cudaSetDevice(h->device);
+    int* d_out = nullptr;
+    if (pairs_host && cap > 0)
+        if (cudaMalloc((void**)&d_out, sizeof(int) * 3 * (size_t)cap) != cudaSuccess) return nb_fail(h, B200NB_ERR_CUDA, "get_pairs: cudaMalloc");
+    cudaMemsetAsync(h->d_counter + 5, 0, sizeof(long long), h->stream);
+    for (int l = 0; l < 2; l++)
+    {
+        const PairList& L = h->inner[l];
+        if (L.nentries == 0) continue;
+        k_pairs<<<(unsigned)((L.nentries + 3) / 4), 128, 0, h->stream>>>(L.entries, L.cj, L.mask, L.nentries, h->d_xq, h->d_shift_vec,
+                                                                         h->d_atom_index, r * r, l == 0, d_out, d_out ? cap : 0,
+                                                                         (unsigned long long*)(h->d_counter + 5));
+        h->nlaunches++;
+    }
+    long long n = 0;
+    cudaMemcpyAsync(&n, h->d_counter + 5, sizeof(n), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    if (d_out)
+    {
+        cudaMemcpy(pairs_host, d_out, sizeof(int) * 3 * (size_t)std::min(n, cap), cudaMemcpyDeviceToHost);
+        cudaFree(d_out);
+    }
+    if (cudaGetLastError() != cudaSuccess) return nb_fail(h, B200NB_ERR_CUDA, "get_pairs: kernel failed");
+    return n;
+}
+
+__global__ void k_flush(float* p, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 1.0f;
+}
+
+extern "C" int b200nb_time_force_kernel(b200nb_t* h, int locality, int flags, int nwarm, int niter, int flush_l2, float* ms_avg)
+{
+    if (!h || !ms_avg || niter < 1) return nb_fail(h, B200NB_ERR_ARG, "time_force_kernel: bad argument");
+    if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "time_force_kernel: no pair list");
+    cudaSetDevice(h->device);
+    if (flush_l2 && !h->d_flush)
+    {
+        h->flush_bytes = (size_t)256 << 20; /* > 126 MB L2 */
+        NB_CUDA(h, cudaMalloc((void**)&h->d_flush, h->flush_bytes));
+    }
+    cudaEvent_t e0, e1;
+    NB_CUDA(h, cudaEventCreate(&e0));
+    NB_CUDA(h, cudaEventCreate(&e1));
+    int rc;
+    for (int i = 0; i < nwarm; i++)
+        if ((rc = b200nb_launch_force(h, locality, flags))) return rc;
+    double total = 0;
+    for (int i = 0; i < niter; i++)
+    {
+        if (flush_l2)
+        {
+            k_flush<<<148 * 8, 256, 0, h->stream>>>(h->d_flush, h->flush_bytes / sizeof(float));
+        }
+        NB_CUDA(h, cudaEventRecord(e0, h->stream));
+        if ((rc = b200nb_launch_force(h, locality, flags))) return rc;
+        NB_CUDA(h, cudaEventRecord(e1, h->stream));
+        NB_CUDA(h, cudaEventSynchronize(e1));
+        float ms = 0;
+        NB_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        total += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_avg = (float)(total / niter);
+    return 0;
+}

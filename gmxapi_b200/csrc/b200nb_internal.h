@@ -1,0 +1,160 @@
+/* Internal definitions shared by the b200nb translation units (not part of the C ABI). */
+#ifndef B200NB_INTERNAL_H
+#define B200NB_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "b200nb.h"
+
+#define NB_CL 8      /* atoms per cluster */
+#define NB_CELL 64   /* atoms per grid cell = 8 clusters (nbnxm/pairlistparams.h:69-77) */
+#define NB_XQ_STRIDE 32 /* floats per cluster in the xq layout */
+#define NB_LJ_STRIDE 16 /* floats per cluster in the lj layout */
+#define NB_MIN_RSQ 3.82e-07f /* nbnxm/pairlist.h:146 c_nbnxnMinDistanceSquared */
+#define NB_MAX_GROUP_TILES 512 /* staging capacity of one (i-cluster, shift) group in the search */
+
+/* Device coordinate layout ("c8 pair-interleaved SoA"): per 8-atom cluster 32 floats
+ *   [x-pairs | y-pairs | z-pairs | q-pairs], each 8 floats ordered a0,a4,a1,a5,a2,a6,a3,a7
+ * so that ONE 8-byte load yields component c of atoms (k, k+4) in an aligned register pair -- the operand
+ * form of the sm_100 packed FP32 instructions (fma.rn.f32x2) the force kernel is written around.
+ * LJ data: per cluster 16 floats [c6s-pairs | c12s-pairs] (sqrt(6 C6_ii), sqrt(12 C12_ii)) for the
+ * geometric rule, or 8 ints of atom types in the same pair order for the table path. */
+__host__ __device__ inline int nb_pairpos(int k)
+{
+    return ((k & 3) << 1) | (k >> 2);
+}
+
+struct GridDesc
+{
+    int   ncx, ncy, ncol;
+    float lower[3], upper[3];
+    float cell[2], inv_cell[2];
+    int   atom_begin, atom_end;
+    int   cell0;  /* first 64-atom cell of this grid in the global numbering */
+    int   ncells;
+    int   col0;   /* offset of this grid's columns in the column arrays */
+    int   valid;
+};
+
+/* One unit of work of the force kernel: a run of cluster pairs sharing the i-cluster and the shift
+ * (the role nbnxn_sci_t plays in the reference, nbnxm/pairlist.h:174-188, at cluster granularity). */
+struct Entry
+{
+    int ci;
+    int shift_nmask; /* bits 0-7 shift index, bits 8.. number of leading tiles that carry a mask */
+    int start, end;  /* tile range */
+};
+
+struct NbParamsDev
+{
+    float rc2, rlist_outer2, rlist_inner2;
+    float epsfac, k_rf, two_k_rf, c_rf;
+    float beta, beta2, beta3, sh_ewald;
+    float disp_cpot, rep_cpot;
+    float self_sub; /* 0.5*c_rf or beta/sqrt(pi): kernels_simd_2xmm/kernel_outer.h:418-440 */
+    int   ntypes;   /* including the filler type */
+    int   eeltype;
+};
+
+struct PairList
+{
+    Entry*    entries = nullptr;
+    int*      cj      = nullptr;
+    uint64_t* mask    = nullptr;
+    long long ntiles = 0, nentries = 0;
+    size_t    cap_tiles = 0, cap_entries = 0;
+};
+
+struct b200nb_context
+{
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    std::string  err;
+    long long    nlaunches = 0;
+
+    bool              have_params = false;
+    b200nb_params_t   hp{};
+    NbParamsDev       dp{};
+    std::vector<float> nbfp_host; /* (ntypes+1)^2 * 2 incl. filler */
+    bool              comb_geom = false;
+    int               max_tiles = 16;
+    float*            d_nbfp = nullptr; /* float2 per type pair */
+
+    int    natoms = 0;
+    int*   d_type = nullptr;
+    float* d_q = nullptr;
+    int *  d_excl_off = nullptr, *d_excl_idx = nullptr;
+    std::vector<int>   h_type;
+    std::vector<float> h_q;
+    double             sum_q2 = 0;
+
+    float box[3] = { 0, 0, 0 };
+    int   pbc[3] = { 1, 1, 1 };
+    float* d_shift_vec = nullptr; /* 45*3 */
+    float  h_shift_vec[B200NB_SHIFTS * 3];
+
+    GridDesc grid[2]{};
+    int      ncol_total = 0, ncells_total = 0, npad = 0;
+    size_t   cap_atoms = 0, cap_pad = 0, cap_cols = 0;
+    float*   d_x = nullptr;          /* natoms*3, original order (staging) */
+    float*   d_fout = nullptr;       /* natoms*3 staging for D2H */
+    int*     d_col_of_atom = nullptr;
+    int*     d_col_count = nullptr;
+    int*     d_col_cell0 = nullptr;
+    int*     d_col_fill = nullptr;
+    int*     d_atom_index = nullptr; /* slot -> atom */
+    int*     d_slot_of_atom = nullptr;
+    float*   d_xq = nullptr;
+    float*   d_lj = nullptr;
+    int*     d_atype = nullptr;
+    float*   d_bb = nullptr;     /* 6 floats per cluster */
+    float*   d_cellz = nullptr;  /* 2 floats per cell */
+    float4*  d_f = nullptr;      /* per slot */
+    float*   d_fshift = nullptr; /* 45*3 */
+    double*  d_energy = nullptr; /* 2 */
+    int*     d_scratch = nullptr; /* small ints: totals, flags, counters */
+    long long* d_counter = nullptr;
+
+    int*  d_cnt_tiles = nullptr; /* per i-cluster counts / offsets for the two-pass search */
+    int*  d_cnt_entries = nullptr;
+    size_t cap_clusters = 0;
+
+    PairList outer[2], inner[2];
+    bool     inner_is_outer = true;
+    bool     have_list = false;
+
+    float* d_flush = nullptr;
+    size_t flush_bytes = 0;
+
+    float* h_pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+int nb_fail(b200nb_context* h, int code, const std::string& msg);
+#define NB_CUDA(h, call)                                                                         \
+    do                                                                                           \
+    {                                                                                            \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return nb_fail(h, B200NB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+/* force.cu */
+int nb_launch_force_kernel(b200nb_context* h, int locality, int flags);
+
+/* ---- device helpers shared by search / prune / pair extraction ---- */
+#ifdef __CUDACC__
+/* r^2 with the reference's operand roles and operation order: i-atom already shifted,
+ * fma(dz,dz,fma(dx,dx,dy*dy)) -- see oracle/nbnxm_oracle.c header for the derivation. */
+__device__ __forceinline__ float nb_rsq(float xi, float yi, float zi, float xj, float yj, float zj)
+{
+    float dx = __fsub_rn(xi, xj), dy = __fsub_rn(yi, yj), dz = __fsub_rn(zi, zj);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+#endif
+
+#endif

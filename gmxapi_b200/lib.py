@@ -1,0 +1,273 @@
+"""ctypes binding of the C ABI declared in include/b200nb.h (libb200nb.so).
+
+`NbnxmGpu` is the host-side handle corresponding to the reference's `NbnxmGpu*` / `nonbonded_verlet_t::gpu_nbv`
+(src/gromacs/nbnxm/nbnxm.h:406, cuda/nbnxm_cuda_types.h:150-225); its methods are 1:1 with the C entry points.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SHIFTS, CENTRAL = 45, 22
+EEL_CUT, EEL_RF, EEL_EWALD = 0, 1, 2
+FLAG_ENERGY, FLAG_VIRIAL = 1, 2
+
+EXPORTS = [
+    "b200nb_create", "b200nb_destroy", "b200nb_last_error", "b200nb_stream", "b200nb_synchronize",
+    "b200nb_set_params", "b200nb_set_atoms", "b200nb_set_box", "b200nb_put_on_grid", "b200nb_build_pairlist",
+    "b200nb_set_x", "b200nb_clear_outputs", "b200nb_launch_force", "b200nb_launch_prune", "b200nb_get_f",
+    "b200nb_get_outputs", "b200nb_compute", "b200nb_halo_pack_x", "b200nb_halo_unpack_f", "b200nb_get_stats",
+    "b200nb_get_grid_order", "b200nb_get_tiles", "b200nb_get_pairs", "b200nb_time_force_kernel",
+]
+
+
+class B200NBError(RuntimeError):
+    pass
+
+
+class _Params(C.Structure):
+    _fields_ = [("ntypes", C.c_int), ("nbfp_host", C.c_void_p), ("rc", C.c_float), ("rlist_outer", C.c_float),
+                ("rlist_inner", C.c_float), ("eeltype", C.c_int), ("epsfac", C.c_float), ("k_rf", C.c_float),
+                ("c_rf", C.c_float), ("ewald_beta", C.c_float), ("sh_ewald", C.c_float), ("disp_cpot", C.c_float),
+                ("rep_cpot", C.c_float), ("comb_rule", C.c_int), ("max_tiles_per_entry", C.c_int)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("natoms", C.c_int), ("natoms_padded", C.c_int), ("nclusters", C.c_int), ("ncx", C.c_int),
+                ("ncy", C.c_int), ("ntiles_outer", C.c_longlong), ("ntiles_inner", C.c_longlong),
+                ("nentries", C.c_longlong), ("comb_geometric", C.c_int), ("nlaunches", C.c_longlong)]
+
+
+_lib = None
+
+
+def library_path():
+    return os.path.join(_HERE, "libb200nb.so")
+
+
+def load_library():
+    """Loads libb200nb.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise B200NBError("libb200nb.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(or make -C gmxapi_b200/csrc); there is no CPU fallback")
+    L = C.CDLL(path)
+    vp, ci, cf, cll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+    L.b200nb_create.argtypes = [C.POINTER(vp), ci]
+    L.b200nb_destroy.argtypes = [vp]
+    L.b200nb_destroy.restype = None
+    L.b200nb_last_error.argtypes = [vp]
+    L.b200nb_last_error.restype = C.c_char_p
+    L.b200nb_stream.argtypes = [vp]
+    L.b200nb_stream.restype = vp
+    L.b200nb_synchronize.argtypes = [vp]
+    L.b200nb_set_params.argtypes = [vp, C.POINTER(_Params)]
+    L.b200nb_set_atoms.argtypes = [vp, ci, vp, vp, vp, vp]
+    L.b200nb_set_box.argtypes = [vp, vp, vp]
+    L.b200nb_put_on_grid.argtypes = [vp, ci, vp, vp, ci, ci, cf, vp, ci]
+    L.b200nb_build_pairlist.argtypes = [vp]
+    L.b200nb_set_x.argtypes = [vp, vp, ci, ci, ci]
+    L.b200nb_clear_outputs.argtypes = [vp]
+    L.b200nb_launch_force.argtypes = [vp, ci, ci]
+    L.b200nb_launch_prune.argtypes = [vp, ci, ci, ci]
+    L.b200nb_get_f.argtypes = [vp, vp, ci, ci, ci, ci]
+    L.b200nb_get_outputs.argtypes = [vp, vp, vp]
+    L.b200nb_compute.argtypes = [vp, vp, ci, vp, vp, vp]
+    L.b200nb_halo_pack_x.argtypes = [vp, vp, vp, ci, vp, vp]
+    L.b200nb_halo_unpack_f.argtypes = [vp, vp, vp, ci, vp]
+    L.b200nb_get_stats.argtypes = [vp, C.POINTER(_Stats)]
+    L.b200nb_get_grid_order.argtypes = [vp, vp, ci]
+    L.b200nb_get_tiles.argtypes = [vp, ci, vp, cll]
+    L.b200nb_get_tiles.restype = cll
+    L.b200nb_get_pairs.argtypes = [vp, cf, vp, cll]
+    L.b200nb_get_pairs.restype = cll
+    L.b200nb_time_force_kernel.argtypes = [vp, ci, ci, ci, ci, ci, C.POINTER(cf)]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.ctypes.data)
+
+
+class NbnxmGpu:
+    """One nonbonded context on one GPU (the reference's NbnxmGpu, created by Nbnxm::gpu_init)."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.b200nb_create(C.byref(h), int(device))
+        if rc != 0:
+            raise B200NBError("b200nb_create failed (rc=%d): no usable CUDA device %d -- this path has no CPU "
+                              "fallback" % (rc, device))
+        self._h = h
+        self.natoms = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200nb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._L.b200nb_last_error(self._h)
+            raise B200NBError("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+    @property
+    def stream(self):
+        return self._L.b200nb_stream(self._h)
+
+    def synchronize(self):
+        self._check(self._L.b200nb_synchronize(self._h), "synchronize")
+
+    def set_params(self, nbfp, rc, rlist_outer=None, rlist_inner=None, eeltype=EEL_CUT, epsfac=138.935458, k_rf=0.0,
+                   c_rf=0.0, ewald_beta=0.0, sh_ewald=0.0, disp_cpot=None, rep_cpot=None, comb_rule=0,
+                   max_tiles_per_entry=0):
+        nbfp = np.ascontiguousarray(nbfp, dtype=np.float32).ravel()
+        ntypes = int(round((nbfp.size // 2) ** 0.5))
+        if ntypes * ntypes * 2 != nbfp.size:
+            raise B200NBError("nbfp must hold ntypes*ntypes*2 values")
+        rlo = float(rlist_outer) if rlist_outer else float(rc)
+        rli = float(rlist_inner) if rlist_inner else rlo
+        p = _Params(ntypes, nbfp.ctypes.data, rc, rlo, rli, eeltype, epsfac, k_rf, c_rf, ewald_beta, sh_ewald,
+                    -1.0 / rc ** 6 if disp_cpot is None else disp_cpot,
+                    -1.0 / rc ** 12 if rep_cpot is None else rep_cpot, comb_rule, max_tiles_per_entry)
+        self._check(self._L.b200nb_set_params(self._h, C.byref(p)), "set_params")
+
+    def set_atoms(self, types, q, excl_off=None, excl_idx=None):
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        eo = np.ascontiguousarray(excl_off, dtype=np.int32) if excl_off is not None else None
+        ei = np.ascontiguousarray(excl_idx, dtype=np.int32) if excl_idx is not None else None
+        self.natoms = int(types.shape[0])
+        self._check(self._L.b200nb_set_atoms(self._h, self.natoms, _ptr(types), _ptr(q), _ptr(eo), _ptr(ei)),
+                    "set_atoms")
+
+    def set_box(self, box, pbc=(1, 1, 1)):
+        b = np.ascontiguousarray(box, dtype=np.float32)
+        p = np.ascontiguousarray(pbc, dtype=np.int32)
+        self._check(self._L.b200nb_set_box(self._h, _ptr(b), _ptr(p)), "set_box")
+
+    def put_on_grid(self, x, lower, upper, grid_index=0, atom_begin=0, atom_end=None, density=0.0, on_device=False):
+        lo = np.ascontiguousarray(lower, dtype=np.float32)
+        up = np.ascontiguousarray(upper, dtype=np.float32)
+        if atom_end is None:
+            atom_end = self.natoms
+        if not on_device:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+        self._check(self._L.b200nb_put_on_grid(self._h, grid_index, _ptr(lo), _ptr(up), atom_begin, atom_end,
+                                               float(density), _ptr(x), int(on_device)), "put_on_grid")
+
+    def build_pairlist(self):
+        self._check(self._L.b200nb_build_pairlist(self._h), "build_pairlist")
+
+    def set_x(self, x, on_device=False, atom_begin=0, atom_end=None):
+        if atom_end is None:
+            atom_end = self.natoms
+        if not on_device:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+        self._check(self._L.b200nb_set_x(self._h, _ptr(x), int(on_device), atom_begin, atom_end), "set_x")
+
+    def clear_outputs(self):
+        self._check(self._L.b200nb_clear_outputs(self._h), "clear_outputs")
+
+    def launch_force(self, locality=-1, flags=0):
+        self._check(self._L.b200nb_launch_force(self._h, locality, flags), "launch_force")
+
+    def launch_prune(self, locality=-1, part=0, num_parts=1):
+        self._check(self._L.b200nb_launch_prune(self._h, locality, part, num_parts), "launch_prune")
+
+    def get_f(self, f=None, on_device=False, accumulate=False, atom_begin=0, atom_end=None):
+        if atom_end is None:
+            atom_end = self.natoms
+        if not on_device:
+            if f is None:
+                f = np.zeros((self.natoms, 3), np.float32)
+            assert f.dtype == np.float32 and f.flags.c_contiguous
+        self._check(self._L.b200nb_get_f(self._h, _ptr(f), int(on_device), int(accumulate), atom_begin, atom_end),
+                    "get_f")
+        return f
+
+    def get_outputs(self):
+        fs = np.zeros((SHIFTS, 3), np.float32)
+        e = np.zeros(2, np.float64)
+        self._check(self._L.b200nb_get_outputs(self._h, _ptr(fs), _ptr(e)), "get_outputs")
+        return fs, float(e[0]), float(e[1])
+
+    def compute(self, x, flags=0, f=None):
+        """GmxForceCalculator::compute: returns (f, fshift, e_lj, e_el)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if f is None:
+            f = np.empty((self.natoms, 3), np.float32)
+        fs = np.zeros((SHIFTS, 3), np.float32)
+        e = np.zeros(2, np.float64)
+        want = flags != 0
+        self._check(self._L.b200nb_compute(self._h, _ptr(x), flags, _ptr(f), _ptr(fs) if want else _ptr(None),
+                                           _ptr(e) if want else _ptr(None)), "compute")
+        return f, fs, float(e[0]), float(e[1])
+
+    def halo_pack_x(self, x_dev, index_dev, n, shift, out_dev):
+        s = np.ascontiguousarray(shift, dtype=np.float32)
+        self._check(self._L.b200nb_halo_pack_x(self._h, _ptr(x_dev), _ptr(index_dev), n, _ptr(s), _ptr(out_dev)),
+                    "halo_pack_x")
+
+    def halo_unpack_f(self, f_dev, index_dev, n, in_dev):
+        self._check(self._L.b200nb_halo_unpack_f(self._h, _ptr(f_dev), _ptr(index_dev), n, _ptr(in_dev)),
+                    "halo_unpack_f")
+
+    def stats(self):
+        s = _Stats()
+        self._check(self._L.b200nb_get_stats(self._h, C.byref(s)), "get_stats")
+        return {k: getattr(s, k) for k, _ in _Stats._fields_}
+
+    def grid_order(self):
+        n = self.stats()["natoms_padded"]
+        out = np.zeros(n, np.int32)
+        rc = self._L.b200nb_get_grid_order(self._h, _ptr(out), n)
+        if rc < 0:
+            self._check(rc, "get_grid_order")
+        return out
+
+    def tiles(self, outer=False):
+        n = self._L.b200nb_get_tiles(self._h, int(outer), _ptr(None), 0)
+        if n < 0:
+            self._check(int(n), "get_tiles")
+        out = np.zeros((max(n, 1), 3), np.int32)
+        self._L.b200nb_get_tiles(self._h, int(outer), _ptr(out), n)
+        return out[:n]
+
+    def pairs(self, r):
+        n = self._L.b200nb_get_pairs(self._h, float(r), _ptr(None), 0)
+        if n < 0:
+            self._check(int(n), "get_pairs")
+        out = np.zeros((max(n, 1), 3), np.int32)
+        m = self._L.b200nb_get_pairs(self._h, float(r), _ptr(out), n)
+        assert m == n
+        return out[:n]
+
+    def pair_count(self, r):
+        n = self._L.b200nb_get_pairs(self._h, float(r), _ptr(None), 0)
+        if n < 0:
+            self._check(int(n), "get_pairs")
+        return int(n)
+
+    def time_force_kernel(self, locality=-1, flags=0, nwarm=3, niter=20, flush_l2=True):
+        ms = C.c_float()
+        self._check(self._L.b200nb_time_force_kernel(self._h, locality, flags, nwarm, niter, int(flush_l2),
+                                                     C.byref(ms)), "time_force_kernel")
+        return ms.value

@@ -1,0 +1,114 @@
+"""Host-side mirror of the nblib operator interface for the nonbonded path.
+
+Same names, argument meaning and error behaviour as the reference's C++ API so that tests read like
+api/nblib/tests/nbkernelsystem.cpp:
+  NBKernelOptions   api/nblib/kerneloptions.h:86-112
+  SimulationState   api/nblib/simulationstate.h (coordinates, box, topology: types / charges / nonbonded
+                    parameters / exclusions)
+  ForceCalculator   api/nblib/forcecalculator.h: ForceCalculator(SimulationState, NBKernelOptions),
+                    compute(coordinates, forces), updatePairList(coordinates, box)
+Setup follows GmxSetupDirector::setupGmxForceCalculator (api/nblib/gmxsetup.cpp:306-325).
+`useGpu` is real here -- and mandatory: the reference notes "currently GPUs are not supported"
+(kerneloptions.h:88-89); this implementation has no CPU path at all.
+"""
+import enum
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import lib as _lib
+from .systems import ONE_4PI_EPS0, ewald_beta, rf_constants
+
+
+class CoulombType(enum.Enum):  # api/nblib/kerneloptions.h:72-79
+    Pme = 0
+    Cutoff = 1
+    ReactionField = 2
+
+
+@dataclass
+class NBKernelOptions:
+    useGpu: bool = True
+    pairlistCutoff: float = 1.0
+    computeVirialAndEnergy: bool = False
+    coulombType: CoulombType = CoulombType.Pme
+    # extensions beyond the reference's options: dynamic pruning radii (PairlistParams, pairlistparams.h:105-131)
+    rlistOuter: float = 0.0
+    rlistInner: float = 0.0
+    device: int = 0
+
+
+class InputException(ValueError):  # nblib::InputException (api/nblib/exception.h)
+    pass
+
+
+class SimulationState:
+    def __init__(self, coordinates, box, types, charges, nonbondedParameters, excl_off=None, excl_idx=None):
+        self.coordinates = np.ascontiguousarray(coordinates, dtype=np.float32).reshape(-1, 3)
+        self.box = np.ascontiguousarray(box, dtype=np.float32).reshape(3)
+        self.types = np.ascontiguousarray(types, dtype=np.int32)
+        self.charges = np.ascontiguousarray(charges, dtype=np.float32)
+        self.nonbondedParameters = np.ascontiguousarray(nonbondedParameters, dtype=np.float32)
+        n = self.types.shape[0]
+        if self.coordinates.shape[0] != n or self.charges.shape[0] != n:
+            raise InputException("coordinates, types and charges must have the same length")
+        if not np.all(np.isfinite(self.coordinates)):
+            raise InputException("non-finite coordinates")  # simulationstate.cpp checks isRealValued
+        if excl_off is None:
+            excl_off = np.arange(n + 1, dtype=np.int32)
+            excl_idx = np.arange(n, dtype=np.int32)
+        self.excl_off = np.ascontiguousarray(excl_off, dtype=np.int32)
+        self.excl_idx = np.ascontiguousarray(excl_idx, dtype=np.int32)
+
+    @classmethod
+    def from_system(cls, s):
+        return cls(s.x, s.box, s.types, s.q, s.nbfp, s.excl_off, s.excl_idx)
+
+
+class ForceCalculator:
+    def __init__(self, state, options):
+        if not options.useGpu:
+            raise InputException("gmxapi_b200 only provides the GPU nonbonded path (useGpu must be true)")
+        self.options = options
+        self.state = state
+        rc = float(options.pairlistCutoff)
+        self.nb = _lib.NbnxmGpu(options.device)
+        # setupInteractionConst: api/nblib/gmxsetup.cpp:226-284
+        kw = dict(epsfac=ONE_4PI_EPS0)
+        if options.coulombType == CoulombType.Pme:
+            kw.update(eeltype=_lib.EEL_EWALD, ewald_beta=float(np.float32(ewald_beta(rc, 1e-5))))
+        elif options.coulombType == CoulombType.Cutoff:
+            k, c = rf_constants(rc, eps_rf=1.0)
+            kw.update(eeltype=_lib.EEL_CUT, k_rf=k, c_rf=c)
+        elif options.coulombType == CoulombType.ReactionField:
+            k, c = rf_constants(rc, eps_rf=1.0)  # epsilon_rf = 1 as gmxsetup.cpp:251-253 leaves it
+            kw.update(eeltype=_lib.EEL_RF, k_rf=k, c_rf=c)
+        else:
+            raise InputException("Unsupported electrostatic interaction")
+        self.nb.set_params(state.nonbondedParameters, rc, rlist_outer=options.rlistOuter or rc,
+                           rlist_inner=options.rlistInner or 0.0, **kw)
+        self.nb.set_atoms(state.types, state.charges, state.excl_off, state.excl_idx)
+        self._set_particles_on_grid(state.coordinates, state.box)
+        self.nb.build_pairlist()  # constructPairList, gmxsetup.cpp:299-303
+
+    def _set_particles_on_grid(self, coordinates, box):
+        # GmxForceCalculator::setParticlesOnGrid, api/nblib/gmxcalculator.cpp:85-103
+        box = np.ascontiguousarray(box, dtype=np.float32).reshape(3)
+        if not np.all(box > 0):
+            raise InputException("box must be positive")
+        self.nb.set_box(box)
+        self.nb.put_on_grid(coordinates, np.zeros(3, np.float32), box)
+
+    def compute(self, coordinates=None, forces=None):
+        """Returns forces[n,3] (float32). With computeVirialAndEnergy also keeps .energies / .shiftForces."""
+        x = self.state.coordinates if coordinates is None else coordinates
+        flags = (_lib.FLAG_ENERGY | _lib.FLAG_VIRIAL) if self.options.computeVirialAndEnergy else 0
+        f, fs, elj, eel = self.nb.compute(x, flags, forces)
+        self.shiftForces, self.energies = fs, (elj, eel)
+        return f
+
+    def updatePairList(self, coordinates, box):
+        # ForceCalculator::updatePairList (forcecalculator.cpp:62-67) re-grids; unlike the reference (which
+        # leaves the old list in place) we also rebuild the list so it stays valid.
+        self._set_particles_on_grid(coordinates, box)
+        self.nb.build_pairlist()

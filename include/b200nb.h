@@ -1,0 +1,169 @@
+/* b200nb -- B200-native (sm_100a) short-range nonbonded path, C ABI.
+ *
+ * Drop-in boundary for the nbnxm hot path of kassonlab/gmxapi (GROMACS 2021): everything below is what a
+ * thin C++ shim implementing the reference's GPU sub-interface (src/gromacs/nbnxm/nbnxm_gpu.h:138-355,
+ * gpu_data_mgmt.h:72-138) and nblib's GmxForceCalculator (api/nblib/gmxcalculator.cpp:70-103) binds to.
+ * Plain C types only; every function returns 0 on success or a negative B200NB_ERR_* code, and
+ * b200nb_last_error() gives the message (the reference aborts via gmx_fatal / exceptions instead,
+ * e.g. grid.cpp:425 "Lost particles while sorting", cuda/nbnxm_cuda.cu:142-149 grid-size overflow).
+ *
+ * All paths run on the GPU; there is no CPU fallback.  Pointers named *_host are host memory, *_dev
+ * device memory; functions taking `on_device` accept either.
+ *
+ * Reference paths below are relative to /root/reference/src/gromacs unless they start with api/.
+ */
+#ifndef B200NB_H
+#define B200NB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NB_VERSION 1
+#define B200NB_SHIFTS 45  /* pbcutil/ishift.h:40-48 */
+#define B200NB_CENTRAL 22 /* pbcutil/ishift.h:47 */
+#define B200NB_CLUSTER 8  /* nbnxm/pairlistparams.h:66 c_nbnxnGpuClusterSize */
+
+enum
+{
+    B200NB_OK            = 0,
+    B200NB_ERR_ARG       = -1,
+    B200NB_ERR_CUDA      = -2,
+    B200NB_ERR_STATE     = -3,
+    B200NB_ERR_CAPACITY  = -4,
+    B200NB_ERR_LOSTATOMS = -5
+};
+
+enum
+{
+    B200NB_EEL_CUT   = 0, /* eelCUT: evaluated as reaction-field with k_rf = 0 (nbnxm/kerneldispatch.cpp:168-171) */
+    B200NB_EEL_RF    = 1, /* eelRF */
+    B200NB_EEL_EWALD = 2  /* eelPME/eelEWALD real space, analytical correction (cuda/nbnxm_cuda_kernel.cuh:573-594) */
+};
+
+enum
+{
+    B200NB_FLAG_ENERGY = 1, /* StepWorkload::computeEnergy */
+    B200NB_FLAG_VIRIAL = 2  /* StepWorkload::computeVirial: accumulate the 45 shift forces */
+};
+
+/* Interaction parameters: mdtypes/interaction_const.h:107-172 -> NBParamGpu (nbnxm/gpu_types_common.h:63-124),
+ * filled the way set_cutoff_parameters / init_nbparam do (nbnxm_gpu_data_mgmt.cpp:166-186,
+ * cuda/nbnxm_cuda_data_mgmt.cu:121-227) plus PairlistParams (nbnxm/pairlistparams.h:105-131). */
+typedef struct
+{
+    int          ntypes;      /* atom types, without the filler type the library appends (atomdata.cpp:456) */
+    const float* nbfp_host;   /* ntypes*ntypes*2 floats {6*C6, 12*C12}: the fr->nbfp convention (atomdata.cpp:498-506) */
+    float        rc;          /* rvdw == rcoulomb */
+    float        rlist_outer; /* PairlistParams::rlistOuter: search radius */
+    float        rlist_inner; /* PairlistParams::rlistInner: dynamic-pruning radius; >= rlist_outer disables pruning */
+    int          eeltype;     /* B200NB_EEL_* */
+    float        epsfac;      /* interaction_const_t::epsfac */
+    float        k_rf, c_rf;
+    float        ewald_beta;  /* ewaldcoeff_q */
+    float        sh_ewald;
+    float        disp_cpot;   /* dispersion_shift.cpot (-rc^-6 with potential shift) */
+    float        rep_cpot;    /* repulsion_shift.cpot  (-rc^-12) */
+    int          comb_rule;   /* 0 = detect geometric rule with tol 1e-5 (atomdata.cpp:462-525), 1 = force geometric, 2 = type table */
+    int          max_tiles_per_entry; /* list balancing granularity (pairlist.cpp:2077-2194 split_sci_entry); 0 = default */
+} b200nb_params_t;
+
+typedef struct b200nb_context b200nb_t;
+
+/* ---- lifetime: Nbnxm::gpu_init / gpu_free (cuda/nbnxm_cuda_data_mgmt.cu:242,395) ------------------------ */
+int         b200nb_create(b200nb_t** out, int device);
+void        b200nb_destroy(b200nb_t* h);
+const char* b200nb_last_error(const b200nb_t* h);
+/* The CUDA stream (cudaStream_t) all work of this context is issued on; callers that bring their own
+ * device buffers order against it (the reference exposes DeviceStream objects the same way). */
+void* b200nb_stream(b200nb_t* h);
+int   b200nb_synchronize(b200nb_t* h);
+
+/* ---- parameters: init_nbparam / gpu_pme_loadbal_update_param (nbnxm_gpu_data_mgmt.cpp:225) -------------- */
+int b200nb_set_params(b200nb_t* h, const b200nb_params_t* p);
+
+/* ---- atoms: nbnxn_atomdata_set (atomdata.cpp:955-977) + the exclusion ListOfLists handed to
+ * constructPairlist (nbnxm.h:263).  Exclusions are CSR over LOCAL atom indices, each atom's list contains
+ * itself (bench_system.cpp:192-195).  natoms counts every atom this rank holds (home + halo). */
+int b200nb_set_atoms(b200nb_t* h, int natoms, const int* type_host, const float* q_host,
+                     const int* excl_off_host, const int* excl_idx_host);
+
+/* ---- box: forcerec shift_vec = calc_shifts(box) (api/nblib/gmxsetup.cpp:286-292, pbcutil/pbc.cpp:1187).
+ * pbc_dims[d] = 0 switches periodic images off along d (a dimension decomposed over ranks,
+ * pairlist.cpp:3168-3176). */
+int b200nb_set_box(b200nb_t* h, const float box[3], const int pbc_dims[3]);
+
+/* ---- gridding: nbnxn_put_on_grid (nbnxm.cpp:58-75 -> gridset.cpp:135-241 -> grid.cpp:103-1445).
+ * Grid 0 = home atoms, grid 1 = halo atoms (nbnxn_put_on_grid_nonlocal, nbnxm.cpp:77-95).  Atoms
+ * [atom_begin, atom_end) of x (natoms*3 floats, original order) are binned on 2-D columns between
+ * lower/upper, sorted into 8-atom clusters, and their bounding boxes computed, all on the device.
+ * density <= 0: computed from the home grid (grid.cpp:138-141). */
+int b200nb_put_on_grid(b200nb_t* h, int grid_index, const float lower[3], const float upper[3], int atom_begin,
+                       int atom_end, float density, const float* x, int x_on_device);
+
+/* ---- pair search: nonbonded_verlet_t::constructPairlist (pairlist.cpp:3921-4199) + gpu_init_pairlist
+ * (nbnxm_gpu_data_mgmt.cpp:251-311): device-built cluster-pair list at rlist_outer with exclusion masks,
+ * split into balanced entries, followed by the fresh-list prune to rlist_inner
+ * (cuda/nbnxm_cuda.cu:510-517).  Grid 0 x grid 0 is a half list, grid 0 x grid 1 a full list. */
+int b200nb_build_pairlist(b200nb_t* h);
+
+/* ---- per step ------------------------------------------------------------------------------------------- */
+/* gpu_copy_xq_to_gpu + nbnxn_gpu_x_to_nbat_x (cuda/nbnxm_cuda.cu:395,829): new coordinates (original
+ * order, natoms*3) -> grid-ordered device layout.  atom range [atom_begin, atom_end) lets the caller
+ * update home and halo atoms separately. */
+int b200nb_set_x(b200nb_t* h, const float* x, int x_on_device, int atom_begin, int atom_end);
+/* gpu_clear_outputs (cuda/nbnxm_cuda_data_mgmt.cu:350-377) */
+int b200nb_clear_outputs(b200nb_t* h);
+/* gpu_launch_kernel (cuda/nbnxm_cuda.cu:484-591). locality: 0 = local (home-home), 1 = non-local (home-halo),
+ * -1 = both. */
+int b200nb_launch_force(b200nb_t* h, int locality, int flags);
+/* gpu_launch_kernel_pruneonly (cuda/nbnxm_cuda.cu:593-718): rolling prune of part `part` of `num_parts`. */
+int b200nb_launch_prune(b200nb_t* h, int locality, int part, int num_parts);
+/* gpu_launch_cpyback + atomdata_add_nbat_f_to_f (cuda/nbnxm_cuda.cu:720-814, atomdata.cpp:1425-1468,
+ * mdlib/gpuforcereduction_impl.cu:70-104): f_out[a] (+)= f_grid[cell[a]] for atoms [atom_begin, atom_end). */
+int b200nb_get_f(b200nb_t* h, float* f, int f_on_device, int accumulate, int atom_begin, int atom_end);
+/* gpu_wait_finish_task's staged outputs (gpu_common.h:249-277): shift forces [45*3] and {E_lj, E_el};
+ * values are ADDED to the caller's buffers like the reference does.  Either pointer may be NULL. */
+int b200nb_get_outputs(b200nb_t* h, float* fshift_host, double* energies_host);
+
+/* ---- the nblib call: GmxForceCalculator::compute (api/nblib/gmxcalculator.cpp:70-83):
+ * x_host (natoms*3) in, f_host (natoms*3) overwritten; fshift_host[135]/energies_host[2] overwritten when
+ * not NULL.  Synchronous. */
+int b200nb_compute(b200nb_t* h, const float* x_host, int flags, float* f_host, float* fshift_host,
+                   double* energies_host);
+
+/* ---- halo exchange helpers: packSendBufKernel / unpackRecvBufKernel (domdec/gpuhaloexchange_impl.cu:77-131).
+ * index_dev: n local atom indices. pack: out[k] = x[index[k]] + shift; unpack: f[index[k]] += in[k]. */
+int b200nb_halo_pack_x(b200nb_t* h, const float* x_dev, const int* index_dev, int n, const float shift[3],
+                       float* out_dev);
+int b200nb_halo_unpack_f(b200nb_t* h, float* f_dev, const int* index_dev, int n, const float* in_dev);
+
+/* ---- introspection used by the parity tests and the bench ------------------------------------------------ */
+typedef struct
+{
+    int       natoms, natoms_padded, nclusters;
+    int       ncx, ncy;        /* home grid columns */
+    long long ntiles_outer;    /* cluster pairs in the search list */
+    long long ntiles_inner;    /* cluster pairs the force kernel evaluates (after pruning) */
+    long long nentries;        /* work units */
+    int       comb_geometric;  /* 1 if the geometric-rule kernel is used */
+    long long nlaunches;       /* kernels launched by this context so far */
+} b200nb_stats_t;
+int b200nb_get_stats(b200nb_t* h, b200nb_stats_t* out);
+/* slot -> original atom (-1 filler), natoms_padded ints: GridSet::atomIndices() */
+int b200nb_get_grid_order(b200nb_t* h, int* atom_index_host, int cap);
+/* the cluster pairs of the inner (or outer) list as (ci, shift, cj) triples */
+long long b200nb_get_tiles(b200nb_t* h, int outer, int* tiles_host, long long cap);
+/* the interacting atom pairs of the current inner list at radius r: non-excluded, r^2 < r*r, as
+ * (i, j, shift) in ORIGINAL atom indices, i the shifted atom.  Returns the count; writes at most cap. */
+long long b200nb_get_pairs(b200nb_t* h, float r, int* pairs_host, long long cap);
+/* average duration in ms of the force kernel alone over niter launches (CUDA events on this context's
+ * stream; flush_l2 != 0 writes a >L2 buffer between launches). */
+int b200nb_time_force_kernel(b200nb_t* h, int locality, int flags, int nwarm, int niter, int flush_l2, float* ms_avg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -52,13 +52,6 @@ static int shift_index(int tx, int ty, int tz)
     return 5 * (3 * (tz + 1) + (ty + 1)) + tx + 2; /* pbcutil/ishift.h:50 XYZ2IS */
 }
 
-static void shift_from_index(int is, int* tx, int* ty, int* tz)
-{
-    *tx = is % 5 - 2;
-    *ty = (is / 5) % 3 - 1;
-    *tz = is / 15 - 1;
-}
-
 /* pbcutil/pbc.cpp:1187-1202 calc_shifts for a rectangular box */
 void orc_shift_vectors(const float box[3], float* shift_vec /* 45*3 */)
 {
@@ -442,10 +435,13 @@ static int cmp_u64(const void* a, const void* b)
 long long orc_tile_list(int n, const float* x, const float box[3], float rlist, const int* slot_of_atom,
                         int* tiles, long long cap)
 {
-    long long kcap = 1 << 20;
+    long long kcap = (1 << 20) + n;
     for (;;)
     {
         tile_ctx c = { (uint64_t*)malloc(sizeof(uint64_t) * (size_t)kcap), kcap, 0, slot_of_atom };
+        /* every non-empty cluster pairs with itself (distance 0): the reference always lists the diagonal
+         * cluster pair, which also carries the self-energy term (kernel_outer.h:408-452) */
+        for (int a = 0; a < n; a++) tile_cb(&c, a, a, ORC_CENTRAL, 0.0f);
         for_each_pair(n, x, box, rlist, tile_cb, &c);
         if (c.n > kcap)
         {
@@ -491,7 +487,6 @@ void orc_prune_tiles(long long ntiles, const int* tiles, const int* atom_index, 
             {
                 int b = atom_index[cj * ORC_CL + j];
                 if (b < 0) continue;
-                if (is == ORC_CENTRAL && ci == cj && j <= i) continue;
                 if (orc_rsq(x[3 * a], x[3 * a + 1], x[3 * a + 2], sv[3 * is], sv[3 * is + 1], sv[3 * is + 2],
                             x[3 * b], x[3 * b + 1], x[3 * b + 2])
                     < r2)

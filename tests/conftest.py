@@ -1,0 +1,23 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Make sure the native pieces exist (cheap no-op when up to date)."""
+    import __graft_entry__ as ge
+    lib = os.path.join(ROOT, "gmxapi_b200", "libb200nb.so")
+    orc = os.path.join(ROOT, "oracle", "_build", "libnbnxm_oracle.so")
+    if not (os.path.exists(lib) and os.path.exists(orc)):
+        ge.build()
+    return True
