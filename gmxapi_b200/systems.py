@@ -113,3 +113,25 @@ def rf_constants(rc, eps_rf=0.0, eps_r=1.0):
     else:
         k = (eps_rf - eps_r) / ((2 * eps_rf + eps_r) * rc ** 3)
     return k, 1.0 / rc + k * rc * rc
+
+
+def spc_methanol():
+    """The nblib SPC-water + methanol test system: api/nblib/tests/testsystems.cpp:56-86 (parameters),
+    :107-153 (charges, exclusions), :313-326 (coordinates, box 3.01).  nblib combines C6/C12 with the
+    geometric rule (api/nblib/gmxsetup.cpp:143-166)."""
+    x = np.array([[1.970, 1.460, 1.209], [1.978, 1.415, 1.082], [1.905, 1.460, 1.030],
+                  [1.555, 1.511, 0.703], [1.498, 1.495, 0.784], [1.496, 1.521, 0.623]], np.float32)
+    # types: 0 Ow, 1 H, 2 OMet, 3 CMet
+    c6 = np.array([0.0026173456, 0.0, 0.0022619536, 0.0088755241])
+    c12 = np.array([2.634129e-06, 0.0, 1.505529e-06, 2.0852922e-05])
+    nbfp = np.zeros((4, 4, 2), np.float32)
+    nbfp[..., 0] = 6.0 * np.sqrt(np.outer(c6, c6))
+    nbfp[..., 1] = 12.0 * np.sqrt(np.outer(c12, c12))
+    types = np.array([3, 2, 1, 0, 1, 1], np.int32)
+    q = np.array([0.176, -0.574, 0.398, -0.82, 0.41, 0.41], np.float32)
+    n = 6
+    first = (np.arange(n) // 3) * 3
+    excl_idx = (first[:, None] + np.arange(3)[None, :]).astype(np.int32).ravel()
+    excl_off = (np.arange(n + 1) * 3).astype(np.int32)
+    return System(x, np.array([3.01] * 3, np.float32), types, q, nbfp, excl_off, excl_idx,
+                  (np.arange(n) // 3).astype(np.int32), "spc_methanol")

@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Generates the committed golden fixtures of tests/golden/ (run in the dev container, where /root/reference
+and oracle/_ref exist; the fixtures then travel to the GPU box, the reference tree does not).
+
+ 1. argon12_forces.json / spc_methanol_forces.json: the reference's own golden XMLs
+    (api/nblib/tests/refdata/NBlibTest_{Argon,SpcMethanol}ForcesAreCorrect.xml) transcribed to JSON.
+ 2. ref_<system>_<eel>.npz: outputs of the UNMODIFIED reference code (oracle/_ref, built by
+    oracle/build_ref.sh from the sources under /root/reference) on our seeded synthetic inputs:
+      f (n,3) f32, fshift (45,3) f32, e_lj, e_el   -- CPU SIMD kernel (2xMM on AVX-512), the parity target
+      npairs, pairs_sha256                           -- in-range non-excluded pair set at rc (canonical keys)
+      grid_sha256, grid_dims                         -- GPU-geometry (8x8x8) grid atom order
+"""
+import hashlib
+import json
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference/api/nblib/tests/refdata"
+RC = 0.9
+
+
+def xml_vectors(path):
+    xml = open(path).read()
+    return np.array([float(v) for v in re.findall(r'<Real Name="[XYZ]">([^<]+)</Real>', xml)]).reshape(-1, 3)
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main():
+    import gmxapi_b200.systems as S
+    from oracle import gmxref, oracle
+    for name, xml in (("argon12", "NBlibTest_ArgonForcesAreCorrect.xml"), ("spc_methanol", "NBlibTest_SpcMethanolForcesAreCorrect.xml")):
+        f = xml_vectors(os.path.join(REF, xml))
+        json.dump({"source": "api/nblib/tests/refdata/" + xml, "forces": f.tolist()},
+                  open(os.path.join(HERE, name + "_forces.json"), "w"), indent=1)
+    beta = float(np.float32(S.ewald_beta(RC)))
+    k_rf, c_rf = S.rf_constants(RC)
+    for sysname in ("water_3k", "water_24k"):
+        s = S.named(sysname)
+        for eel, kw in (("ewald", dict(eeltype=gmxref.EEL_EWALD_ANA, ewaldcoeff=beta)),
+                        ("rf", dict(eeltype=gmxref.EEL_RF, k_rf=k_rf, c_rf=c_rf))):
+            r = gmxref.RefNbnxm(s.x, s.box, s.types, s.q, s.nbfp, s.excl_off, s.excl_idx, rc=RC, nthreads=4, **kw)
+            f, fs, elj, eel_ = r.compute()
+            keys = oracle.canonical_pairs(r.pair_set())
+            r.close()
+            g = gmxref.RefNbnxm(s.x, s.box, s.types, s.q, s.nbfp, s.excl_off, s.excl_idx, rc=RC, nthreads=1,
+                                kernel=gmxref.KERNEL_GPUREF, **kw)
+            order = g.grid_order()
+            dims = g.grid_dims()
+            g.close()
+            out = dict(fshift=fs, e_lj=np.float64(elj), e_el=np.float64(eel_), npairs=np.int64(len(keys)),
+                       pairs_sha256=np.array(sha(keys)), grid_sha256=np.array(sha(order.astype(np.int32))),
+                       grid_dims=np.array(dims[:2] + (dims[4],), np.int64), beta=np.float64(beta),
+                       seed=np.int64(20261017))
+            if sysname == "water_3k":
+                out["f"] = f  # 36 kB; the 24k system keeps only checksums + a strided sample
+            else:
+                out["f_sample"] = f[::16].copy()
+                out["f_sumsq"] = np.float64((f.astype(np.float64) ** 2).sum())
+            np.savez_compressed(os.path.join(HERE, "ref_%s_%s.npz" % (sysname, eel)), **out)
+            print(sysname, eel, len(keys), elj, eel_)
+
+
+if __name__ == "__main__":
+    main()
