@@ -15,8 +15,8 @@ output clear, cluster-pair force kernel (LJ + Ewald real space, force only), for
   cpu_baseline: the reference's own CPU SIMD nbnxm path (oracle/_ref, compiled from the reference sources)
            on this host's cores, bounded sample.
 N > 1: atoms are split into N slabs along x (spatial domain decomposition), one rank per GPU, halo
-coordinates / forces exchanged every step over NCCL (see gmxapi_b200/domdec.py); weak scaling: every rank
-holds one copy of the N=1 workload box.
+coordinates / forces exchanged every step over NCCL (see gmxapi_b200/domdec.py); weak scaling: the box holds
+N copies of the N=1 workload along x, one slab per rank.
 """
 import argparse
 import json
@@ -126,7 +126,9 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import gmxref, oracle
-    s = workload_system(args.workload)
+    import gmxapi_b200 as g
+    nx, ny, nz = g.systems.NAMED[args.workload]
+    s = g.systems.water_box(nx * max(args.gpus, 1), ny, nz)  # the same box the GPU arm decomposes over args.gpus ranks
     cores = host_cores()
     npairs = len(oracle.pair_set(s.x, s.box, RC, s.excl_off, s.excl_idx))
     kind = "reference" if gmxref.available() else "port"
@@ -138,7 +140,8 @@ def run_reference(args):
     out = {"metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "impl": "reference",
-           "config": {"workload": args.workload, "atoms": int(s.n), "useful_pairs_per_step": npairs, "rc": RC,
+           "config": {"workload": args.workload if args.gpus <= 1 else "%d x %s along x" % (args.gpus, args.workload),
+                      "atoms": int(s.n), "useful_pairs_per_step": npairs, "rc": RC,
                       "interaction": "LJ + " + ("Ewald real space (analytical)" if args.eel == "ewald" else "reaction field"),
                       "flavor": "force only"},
            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": kind,
@@ -160,15 +163,12 @@ def run_gpu(args):
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        from gmxapi_b200 import domdec
-        return domdec.bench_multi_gpu(args, METRIC, FLOPS_PER_PAIR, ClockSampler, measured_peaks, time_reference, host_cores)
+        return run_multi_gpu(args, rank, world, local_rank)
 
     peaks = measured_peaks()
     s = workload_system(args.workload)
     coul = g.CoulombType.Pme if args.eel == "ewald" else g.CoulombType.ReactionField
-    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coul, computeVirialAndEnergy=False, device=local_rank)
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coul, computeVirialAndEnergy=False, device=local_rank, epsilonRf=0.0)
     t0 = time.perf_counter()
     fc = g.ForceCalculator(g.SimulationState.from_system(s), opt)
     fc.nb.synchronize()
@@ -176,7 +176,8 @@ def run_gpu(args):
     h = fc.nb
     npairs = h.pair_count(RC)
     st = h.stats()
-    stream = torch.cuda.ExternalStream(h.stream, device=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream(device=torch.device("cuda", local_rank))
+    h.set_stream(stream.cuda_stream)  # torch-owned stream: events and the L2 flush order against the kernels
 
     # ---- device-resident step ------------------------------------------------------------------------------
     x_dev = torch.from_numpy(s.x).to("cuda", non_blocking=False).contiguous()
@@ -274,6 +275,105 @@ def run_gpu(args):
         "clocks": clocks,
     }
     print(json.dumps(out))
+
+
+def run_multi_gpu(args, rank, world, local_rank):
+    """N ranks, one per GPU: slab decomposition along x of a box holding N copies of the N=1 workload (weak
+    scaling), halo coordinates / forces exchanged every step over NCCL (gmxapi_b200/domdec.py)."""
+    import torch
+    import torch.distributed as dist
+    import gmxapi_b200 as g
+    from gmxapi_b200 import domdec
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peaks = measured_peaks()
+    nx, ny, nz = g.systems.NAMED[args.workload]
+    s = g.systems.water_box(nx * world, ny, nz)
+    coul = g.CoulombType.Pme if args.eel == "ewald" else g.CoulombType.ReactionField
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coul, computeVirialAndEnergy=False, device=local_rank, epsilonRf=0.0)
+    d = domdec.DomainRank(s, opt, domdec.TorchDistTransport(), device=local_rank)
+    h, stream = d.nb, d.stream
+    dev = torch.device("cuda", local_rank)
+    cnt = torch.tensor([d.pair_count(RC), d.plan.nhome, d.plan.nhalo, h.stats()["ntiles_inner"]], dtype=torch.float64, device=dev)
+    dist.all_reduce(cnt)
+    npairs, natoms, nhalo_tot, ntiles = (int(v) for v in cnt.tolist())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if not args.no_flush else None
+
+    for _ in range(args.warmup):
+        d.step(0)
+    h.synchronize()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = h.stats()["nlaunches"]
+    for k in range(args.steps):
+        if flush is not None:
+            with torch.cuda.stream(stream):
+                flush.fill_(k & 0xff)
+        ev[k][0].record(stream)
+        d.step(0)
+        ev[k][1].record(stream)
+    h.synchronize()
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = h.stats()["nlaunches"] - l0
+    t = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in ev]))], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms = float(t.item())
+    k_ms = h.time_force_kernel(-1, 0, 3, max(10, min(args.steps, 50)), flush_l2=not args.no_flush)
+    kt = torch.tensor([k_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+    k_ms = float(kt.item())
+    clocks = sampler.stop()
+
+    # end to end: pinned host coordinates of the home atoms in, pinned host forces out, every step
+    x_pin = torch.from_numpy(np.ascontiguousarray(s.x[d.plan.home])).pin_memory()
+    f_pin = torch.empty_like(x_pin).pin_memory()
+    for _ in range(args.warmup):
+        d.compute(x_pin, 0, f_pin)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d.compute(x_pin, 0, f_pin)
+    torch.cuda.synchronize()
+    dist.barrier()
+    te = torch.tensor([(time.perf_counter() - t0) / args.steps * 1e3], dtype=torch.float64, device=dev)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+    lt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    dist.all_reduce(lt)
+    if rank == 0:
+        flops = FLOPS_PER_PAIR[args.eel]
+        fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12 * world
+        achieved = npairs * flops / (k_ms * 1e-3) / 1e12
+        halo_bytes = nhalo_tot * 12
+        out = {
+            "metric": METRIC, "value": npairs / (step_ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%d x %s along x" % (world, args.workload), "atoms": int(natoms),
+                       "useful_pairs_per_step": int(npairs), "computed_pairs_per_step": int(ntiles * 64), "rc": RC, "rlist": RC,
+                       "interaction": "LJ + " + ("Ewald real space (analytical)" if args.eel == "ewald" else "reaction field"),
+                       "flavor": "force only", "l2": "L2 flushed (256 MiB write) between timed steps" if not args.no_flush else "not flushed",
+                       "parallelism": "dd%dx1x1" % world, "halo_atoms_total": int(nhalo_tot),
+                       "halo_bytes_per_step_each_way": int(halo_bytes)},
+            "roofline": {"bound": "fp32", "kernel": "k_force (local + non-local), slowest rank", "achieved": achieved, "peak": fp32_peak,
+                         "unit": "TFLOP/s", "frac": achieved / fp32_peak, "kernel_ms": k_ms, "flops_per_useful_pair": flops,
+                         "peak_note": "%d GPUs x 148 SMs x 128 FP32 lanes x 2 x %.0f MHz" % (world, peaks["sm_max_mhz"]), "traffic": None},
+            "cpu_baseline": None,
+            "e2e": {"value": npairs / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(natoms * 12), "d2h_bytes_per_step": int(natoms * 12)},
+            "gpu_launches": int(lt.item()),
+            "clocks": clocks,
+        }
+        print(json.dumps(out), flush=True)
+    dist.barrier()
+    d.close()
+    del flush, x_pin, f_pin
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
 
 
 def main():

@@ -108,7 +108,7 @@ extern "C" void b200nb_destroy(b200nb_t* h)
         free_list(h->outer[l]);
     }
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
-    cudaStreamDestroy(h->stream);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
@@ -120,6 +120,27 @@ extern "C" const char* b200nb_last_error(const b200nb_t* h)
 extern "C" void* b200nb_stream(b200nb_t* h)
 {
     return h ? (void*)h->stream : nullptr;
+}
+
+/* Nbnxm::gpu_init receives its streams from the caller's DeviceStreamManager (cuda/nbnxm_cuda_data_mgmt.cu:242-291);
+ * here the caller may hand over a stream it owns. All later work of the context is issued on it. */
+extern "C" int b200nb_set_stream(b200nb_t* h, void* cuda_stream)
+{
+    if (!h) return B200NB_ERR_ARG;
+    cudaSetDevice(h->device);
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    if (cuda_stream)
+    {
+        h->stream     = (cudaStream_t)cuda_stream;
+        h->own_stream = false;
+    }
+    else
+    {
+        NB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    return 0;
 }
 
 extern "C" int b200nb_synchronize(b200nb_t* h)

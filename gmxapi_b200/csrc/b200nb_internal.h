@@ -73,6 +73,7 @@ struct b200nb_context
 {
     int          device = 0;
     cudaStream_t stream = nullptr;
+    bool         own_stream = true;
     std::string  err;
     long long    nlaunches = 0;
 

@@ -1,0 +1,314 @@
+"""Spatial domain decomposition of the nonbonded path over the GPUs of one box: one rank per GPU, atoms
+partitioned into slabs along x, halo coordinates sent before and halo forces returned after the non-local
+kernel, every step.
+
+Reference behaviour mirrored (paths relative to /root/reference/src/gromacs):
+  zones / eighth shell      domdec/domdec.cpp:133-146: with one decomposed dimension there are two zones, home (0)
+                            and the +x neighbour's atoms within the list radius of my upper face (1); i-zone 0
+                            interacts with j-zones 0 (half list) and 1 (full list): pairlist.cpp:3876-3916
+  dd_move_x                 domdec/domdec.cpp:260-356: send home atoms within rlist of my LOWER face to the -x
+                            neighbour, shifted by +box on the periodic edge (:300-318); the receiver appends
+                            them after its home atoms
+  dd_move_f                 domdec/domdec.cpp:358-460: the forces on those atoms travel back and are ADDED to
+                            the sender's home forces; on the periodic edge their sum also goes into the shift
+                            force of the +x shift (:426-458)
+  GPU halo                  domdec/gpuhaloexchange_impl.cu:77-131 pack / unpack kernels (ours: b200nb_halo_pack_x,
+                            b200nb_halo_unpack_f), :403-444 the transfer (ours: NCCL send/recv over NVLink)
+  non-local gridding        nbnxm.cpp:77-95 nbnxn_put_on_grid_nonlocal (ours: grid 1 of the C ABI)
+
+The decomposition PLAN (who owns which atom, which atoms are sent) is a pure function of the coordinates at
+the pair-search step and is computed by every rank for itself and its two neighbours with the same numpy
+code; the per-step coordinate / force halo traffic is real communication.  The transport is pluggable:
+torch.distributed (NCCL on GPUs; gloo for the CPU tests of the plan and the exchange pattern) or an
+in-process loopback used by the single-GPU parity tests.
+"""
+import numpy as np
+
+from . import lib as _lib
+from .nblib import InputException, interaction_kwargs
+
+SHIFT_PLUS_X = 5 * (3 * 1 + 1) + 1 + 2  # XYZ2IS(+1, 0, 0), pbcutil/ishift.h:50
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the plan: pure host logic, no device, no communication
+# ---------------------------------------------------------------------------------------------------------
+class DomainPlan:
+    """Slab `rank` of `nranks` along x.
+
+    home        global indices of the atoms this rank owns, ascending
+    send_local  positions in `home` of the atoms sent to the -x neighbour (x - lo < rlist)
+    send_shift  vector added to them (+box_x on rank 0: they appear beyond the last rank's upper face)
+    halo        global indices of the atoms received from the +x neighbour, in arrival order
+    """
+
+    def __init__(self, x, box, nranks, rank, rlist):
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 3)
+        box = np.asarray(box, dtype=np.float32).reshape(3)
+        if nranks < 1 or not (0 <= rank < nranks):
+            raise InputException("bad rank / nranks")
+        width = float(box[0]) / nranks
+        if nranks > 1 and width < rlist:
+            # one pulse only: the halo must come from the nearest neighbour alone (the reference would add
+            # pulses, domdec/domdec.cpp:274; outside this implementation's scope)
+            raise InputException("domain width %.3f < list radius %.3f: more than one halo pulse needed" % (width, rlist))
+        self.nranks, self.rank, self.rlist, self.box = nranks, rank, float(rlist), box
+        self.bounds = self.boundaries(box, nranks)
+        owner = self.owner_of(x, box, nranks)
+        self.lo, self.hi = float(self.bounds[rank]), float(self.bounds[rank + 1])
+        self.home = np.nonzero(owner == rank)[0].astype(np.int32)
+        self.left, self.right = (rank - 1) % nranks, (rank + 1) % nranks
+        if nranks == 1:
+            self.send_local = np.zeros(0, np.int32)
+            self.halo = np.zeros(0, np.int32)
+            self.send_shift = np.zeros(3, np.float32)
+            self.recv_from_periodic = False
+        else:
+            self.send_local = self._send_list(x, self.home, self.bounds[rank], rlist)
+            rhome = np.nonzero(owner == self.right)[0].astype(np.int32)
+            self.halo = rhome[self._send_list(x, rhome, self.bounds[self.right], rlist)]
+            self.send_shift = np.array([box[0] if rank == 0 else 0.0, 0.0, 0.0], np.float32)
+            self.recv_from_periodic = (self.right == 0)
+        self.nhome, self.nhalo = len(self.home), len(self.halo)
+        self.local = np.concatenate([self.home, self.halo]).astype(np.int32)
+
+    @staticmethod
+    def boundaries(box, nranks):
+        return (np.arange(nranks + 1, dtype=np.float64) * (float(box[0]) / nranks)).astype(np.float32)
+
+    @staticmethod
+    def owner_of(x, box, nranks):
+        b = DomainPlan.boundaries(box, nranks)
+        o = np.searchsorted(b, x[:, 0], side="right") - 1
+        return np.clip(o, 0, nranks - 1).astype(np.int32)
+
+    @staticmethod
+    def _send_list(x, home, lo, rlist):
+        return np.nonzero(x[home, 0] - np.float32(lo) < np.float32(rlist))[0].astype(np.int32)
+
+    def local_topology(self, types, q, excl_off, excl_idx):
+        """types / charges / exclusions of home + halo atoms with exclusions renumbered to LOCAL indices
+        (partners that are neither home nor halo on this rank are dropped: they cannot be in range here)."""
+        types = np.asarray(types)
+        q = np.asarray(q)
+        n = len(types)
+        g2l = np.full(n, -1, np.int64)
+        g2l[self.local] = np.arange(len(self.local))
+        cnt = (np.asarray(excl_off[1:]) - np.asarray(excl_off[:-1]))[self.local]
+        starts = np.asarray(excl_off)[self.local]
+        tot = int(cnt.sum())
+        # gather the CSR rows of the local atoms
+        row = np.repeat(np.arange(len(self.local)), cnt)
+        pos = np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt) + np.repeat(starts, cnt)
+        partner = g2l[np.asarray(excl_idx)[pos]]
+        keep = partner >= 0
+        row, partner = row[keep], partner[keep]
+        off = np.zeros(len(self.local) + 1, np.int64)
+        np.add.at(off, row + 1, 1)
+        off = np.cumsum(off)
+        return (types[self.local].astype(np.int32), q[self.local].astype(np.float32), off.astype(np.int32),
+                partner.astype(np.int32))
+
+    def halo_x(self, x):
+        """What the halo coordinates must be after dd_move_x (used by the tests as the expected value)."""
+        h = np.asarray(x, np.float32)[self.halo].copy()
+        if self.recv_from_periodic:
+            h[:, 0] += self.box[0]
+        return h
+
+
+# ---------------------------------------------------------------------------------------------------------
+# transports
+# ---------------------------------------------------------------------------------------------------------
+class TorchDistTransport:
+    """Halo transfers over torch.distributed: NCCL send/recv on NVLink for CUDA tensors (one group per exchange,
+    issued on the context's stream), gloo for the CPU tests."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.nranks = dist.get_rank(group), dist.get_world_size(group)
+
+    def sendrecv(self, send, dst, recv, src):
+        dist = self.dist
+        ops = []
+        if send is not None and send.numel():
+            ops.append(dist.P2POp(dist.isend, send, dst, self.group))
+        if recv is not None and recv.numel():
+            ops.append(dist.P2POp(dist.irecv, recv, src, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()  # CUDA: orders the current stream after the transfer, does not block the host
+
+    def allreduce_sum(self, t):
+        self.dist.all_reduce(t, group=self.group)
+        return t
+
+    def barrier(self):
+        self.dist.barrier(self.group)
+
+
+class LoopbackTransport:
+    """All ranks live in one process as threads (single-GPU parity tests): a queue per (src, dst) pair."""
+
+    def __init__(self, nranks):
+        import queue
+        self.nranks = nranks
+        self.q = {(s, d): queue.Queue() for s in range(nranks) for d in range(nranks)}
+        import threading
+        self._bar = threading.Barrier(nranks)
+
+    def endpoint(self, rank):
+        return _LoopbackEndpoint(self, rank)
+
+
+class _LoopbackEndpoint:
+    def __init__(self, hub, rank):
+        self.hub, self.rank, self.nranks = hub, rank, hub.nranks
+        self.sync = None  # set by DomainRank: synchronises the sender's stream before handing a buffer over
+
+    def sendrecv(self, send, dst, recv, src):
+        if send is not None and send.numel():
+            if self.sync:
+                self.sync()
+            self.hub.q[(self.rank, dst)].put(send.clone())
+            if self.sync:
+                self.sync()
+        if recv is not None and recv.numel():
+            recv.copy_(self.hub.q[(src, self.rank)].get(timeout=120))
+
+    def allreduce_sum(self, t):
+        raise NotImplementedError
+
+    def barrier(self):
+        self.hub._bar.wait()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# one rank of the decomposed calculation
+# ---------------------------------------------------------------------------------------------------------
+class DomainRank:
+    """The nonbonded calculation of one rank: its NbnxmGpu context with a home grid (0) and a halo grid (1), the
+    device buffers of the halo exchange, and the per-step schedule of do_force() (mdlib/sim_util.cpp:1388-1902
+    restricted to the nonbonded path):
+
+        x home -> grid order | pack halo x -> send/recv -> halo x -> grid order | clear | local kernel |
+        non-local kernel | forces -> atom order | halo f send/recv -> unpack-add (+ shift force on the edge)
+    """
+
+    def __init__(self, system, options, transport, rank=None, nranks=None, device=0):
+        import torch
+        self.torch = torch
+        self.t = transport
+        self.rank = transport.rank if rank is None else rank
+        self.nranks = transport.nranks if nranks is None else nranks
+        self.options = options
+        rc = float(options.pairlistCutoff)
+        self.rlist = float(options.rlistOuter or rc)
+        self.plan = DomainPlan(system.x, system.box, self.nranks, self.rank, self.rlist)
+        p = self.plan
+        self.nb = _lib.NbnxmGpu(device)
+        self.device = torch.device("cuda", device)
+        self.stream = torch.cuda.Stream(device=self.device)  # torch owns it: its allocator's per-stream pools outlive nb
+        self.nb.set_stream(self.stream.cuda_stream)
+        if hasattr(transport, "sync"):
+            transport.sync = self.nb.synchronize
+        self.nb.set_params(system.nbfp, rc, rlist_outer=self.rlist, rlist_inner=options.rlistInner or 0.0,
+                           **interaction_kwargs(options))
+        types, q, eo, ei = p.local_topology(system.types, system.q, system.excl_off, system.excl_idx)
+        self.nb.set_atoms(types, q, eo, ei)
+        self.nb.set_box(system.box, pbc=(0 if self.nranks > 1 else 1, 1, 1))
+        self.nlocal = p.nhome + p.nhalo
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self.x = torch.zeros((self.nlocal, 3), dtype=torch.float32, device=self.device)
+            self.f = torch.zeros((self.nlocal, 3), dtype=torch.float32, device=self.device)
+            self.send_idx = torch.from_numpy(p.send_local).to(self.device)
+            self.send_buf = torch.zeros((len(p.send_local), 3), dtype=torch.float32, device=self.device)
+            self.recv_f = torch.zeros((len(p.send_local), 3), dtype=torch.float32, device=self.device)
+            self.x[:p.nhome].copy_(torch.from_numpy(np.ascontiguousarray(system.x[p.home])))
+        self.nb.synchronize()
+        self.fshift_halo = np.zeros(3, np.float64)
+        self.search(first=True)
+
+    # -- pair search step: put_on_grid (home, then halo) + constructPairlist: mdlib/sim_util.cpp:1316-1366, 1454 ------
+    def search(self, first=False):
+        p = self.plan
+        box = p.box
+        self._halo_x()
+        self.nb.synchronize()
+        lower = np.array([p.lo if self.nranks > 1 else 0.0, 0, 0], np.float32)
+        upper = np.array([p.hi if self.nranks > 1 else box[0], box[1], box[2]], np.float32)
+        self.nb.put_on_grid(self.x.data_ptr(), lower, upper, 0, 0, p.nhome, on_device=True)
+        if p.nhalo:
+            hl = np.array([upper[0], 0, 0], np.float32)
+            hu = np.array([upper[0] + self.rlist, box[1], box[2]], np.float32)
+            self.nb.put_on_grid(self.x.data_ptr(), hl, hu, 1, p.nhome, self.nlocal, on_device=True)
+        self.nb.build_pairlist()
+
+    # -- dd_move_x ------------------------------------------------------------------------------------------------------
+    def _halo_x(self):
+        p = self.plan
+        if self.nranks == 1:
+            return
+        torch = self.torch
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self.nb.halo_pack_x(self.x.data_ptr(), self.send_idx.data_ptr(), len(p.send_local), p.send_shift,
+                                self.send_buf.data_ptr())
+            self.t.sendrecv(self.send_buf, p.left, self.x[p.nhome:], p.right)
+
+    # -- dd_move_f ------------------------------------------------------------------------------------------------------
+    def _halo_f(self, virial):
+        p = self.plan
+        if self.nranks == 1:
+            return
+        torch = self.torch
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self.t.sendrecv(self.f[p.nhome:], p.right, self.recv_f, p.left)
+            self.nb.halo_unpack_f(self.f.data_ptr(), self.send_idx.data_ptr(), len(p.send_local), self.recv_f.data_ptr())
+            if virial and self.rank == 0:
+                # domdec/domdec.cpp:426-458: forces that crossed the periodic edge also enter the shift forces
+                self.fshift_halo = self.recv_f.sum(0, dtype=torch.float64).cpu().numpy()
+
+    def step(self, flags=0):
+        """One nonbonded step on coordinates already in self.x[:nhome] (device). Leaves forces in self.f[:nhome]."""
+        p = self.plan
+        self.nb.set_x(self.x.data_ptr(), on_device=True, atom_begin=0, atom_end=p.nhome)
+        self.nb.clear_outputs()
+        self.nb.launch_force(0, flags)
+        if p.nhalo or self.nranks > 1:
+            self._halo_x()
+            if p.nhalo:
+                self.nb.set_x(self.x.data_ptr(), on_device=True, atom_begin=p.nhome, atom_end=self.nlocal)
+                self.nb.launch_force(1, flags)
+        self.nb.get_f(self.f.data_ptr(), on_device=True)
+        self._halo_f(bool(flags & _lib.FLAG_VIRIAL))
+
+    def compute(self, x_home_host, flags=0, f_home_host=None):
+        """The public per-rank call: host coordinates of the home atoms in, host forces of the home atoms out
+        (H2D and D2H inside). Returns (f_home, fshift[45,3], e_lj, e_el) with this rank's share of the sums."""
+        torch = self.torch
+        p = self.plan
+        xh = x_home_host if isinstance(x_home_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_home_host, np.float32))
+        if f_home_host is None:
+            f_home_host = torch.empty((p.nhome, 3), dtype=torch.float32).pin_memory()
+        fh = f_home_host if isinstance(f_home_host, torch.Tensor) else torch.from_numpy(f_home_host)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self.x[:p.nhome].copy_(xh, non_blocking=True)
+            self.step(flags)
+            fh.copy_(self.f[:p.nhome], non_blocking=True)
+        self.nb.synchronize()
+        fs = np.zeros((_lib.SHIFTS, 3), np.float32)
+        elj = eel = 0.0
+        if flags:
+            fs, elj, eel = self.nb.get_outputs()
+            if self.rank == 0 and self.nranks > 1:
+                fs[SHIFT_PLUS_X] += self.fshift_halo.astype(np.float32)
+        return fh, fs, elj, eel
+
+    def pair_count(self, r):
+        return self.nb.pair_count(r)
+
+    def close(self):
+        self.nb.synchronize()
+        self.nb.close()
+        self.x = self.f = self.send_idx = self.send_buf = self.recv_f = None

@@ -14,7 +14,7 @@ EEL_CUT, EEL_RF, EEL_EWALD = 0, 1, 2
 FLAG_ENERGY, FLAG_VIRIAL = 1, 2
 
 EXPORTS = [
-    "b200nb_create", "b200nb_destroy", "b200nb_last_error", "b200nb_stream", "b200nb_synchronize",
+    "b200nb_create", "b200nb_destroy", "b200nb_last_error", "b200nb_stream", "b200nb_set_stream", "b200nb_synchronize",
     "b200nb_set_params", "b200nb_set_atoms", "b200nb_set_box", "b200nb_put_on_grid", "b200nb_build_pairlist",
     "b200nb_set_x", "b200nb_clear_outputs", "b200nb_launch_force", "b200nb_launch_prune", "b200nb_get_f",
     "b200nb_get_outputs", "b200nb_compute", "b200nb_halo_pack_x", "b200nb_halo_unpack_f", "b200nb_get_stats",
@@ -65,6 +65,7 @@ def load_library():
     L.b200nb_stream.argtypes = [vp]
     L.b200nb_stream.restype = vp
     L.b200nb_synchronize.argtypes = [vp]
+    L.b200nb_set_stream.argtypes = [vp, vp]
     L.b200nb_set_params.argtypes = [vp, C.POINTER(_Params)]
     L.b200nb_set_atoms.argtypes = [vp, ci, vp, vp, vp, vp]
     L.b200nb_set_box.argtypes = [vp, vp, vp]
@@ -131,6 +132,10 @@ class NbnxmGpu:
     @property
     def stream(self):
         return self._L.b200nb_stream(self._h)
+
+    def set_stream(self, cuda_stream):
+        """Issue all work on the caller's CUDA stream (an integer handle, e.g. torch.cuda.Stream().cuda_stream)."""
+        self._check(self._L.b200nb_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)), "set_stream")
 
     def synchronize(self):
         self._check(self._L.b200nb_synchronize(self._h), "synchronize")

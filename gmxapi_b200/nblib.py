@@ -35,11 +35,29 @@ class NBKernelOptions:
     # extensions beyond the reference's options: dynamic pruning radii (PairlistParams, pairlistparams.h:105-131)
     rlistOuter: float = 0.0
     rlistInner: float = 0.0
+    epsilonRf: float = 1.0  # interaction_const_t::epsilon_rf as gmxsetup.cpp:251-253 leaves it; 0 = infinity
     device: int = 0
 
 
 class InputException(ValueError):  # nblib::InputException (api/nblib/exception.h)
     pass
+
+
+def interaction_kwargs(options):
+    """setupInteractionConst (api/nblib/gmxsetup.cpp:226-284) -> b200nb_set_params keywords."""
+    rc = float(options.pairlistCutoff)
+    kw = dict(epsfac=ONE_4PI_EPS0)
+    if options.coulombType == CoulombType.Pme:
+        kw.update(eeltype=_lib.EEL_EWALD, ewald_beta=float(np.float32(ewald_beta(rc, 1e-5))))
+    elif options.coulombType == CoulombType.Cutoff:
+        k, c = rf_constants(rc, eps_rf=1.0)
+        kw.update(eeltype=_lib.EEL_CUT, k_rf=k, c_rf=c)
+    elif options.coulombType == CoulombType.ReactionField:
+        k, c = rf_constants(rc, eps_rf=options.epsilonRf)
+        kw.update(eeltype=_lib.EEL_RF, k_rf=k, c_rf=c)
+    else:
+        raise InputException("Unsupported electrostatic interaction")
+    return kw
 
 
 class SimulationState:
@@ -73,18 +91,7 @@ class ForceCalculator:
         self.state = state
         rc = float(options.pairlistCutoff)
         self.nb = _lib.NbnxmGpu(options.device)
-        # setupInteractionConst: api/nblib/gmxsetup.cpp:226-284
-        kw = dict(epsfac=ONE_4PI_EPS0)
-        if options.coulombType == CoulombType.Pme:
-            kw.update(eeltype=_lib.EEL_EWALD, ewald_beta=float(np.float32(ewald_beta(rc, 1e-5))))
-        elif options.coulombType == CoulombType.Cutoff:
-            k, c = rf_constants(rc, eps_rf=1.0)
-            kw.update(eeltype=_lib.EEL_CUT, k_rf=k, c_rf=c)
-        elif options.coulombType == CoulombType.ReactionField:
-            k, c = rf_constants(rc, eps_rf=1.0)  # epsilon_rf = 1 as gmxsetup.cpp:251-253 leaves it
-            kw.update(eeltype=_lib.EEL_RF, k_rf=k, c_rf=c)
-        else:
-            raise InputException("Unsupported electrostatic interaction")
+        kw = interaction_kwargs(options)
         self.nb.set_params(state.nonbondedParameters, rc, rlist_outer=options.rlistOuter or rc,
                            rlist_inner=options.rlistInner or 0.0, **kw)
         self.nb.set_atoms(state.types, state.charges, state.excl_off, state.excl_idx)

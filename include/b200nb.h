@@ -79,6 +79,9 @@ const char* b200nb_last_error(const b200nb_t* h);
 /* The CUDA stream (cudaStream_t) all work of this context is issued on; callers that bring their own
  * device buffers order against it (the reference exposes DeviceStream objects the same way). */
 void* b200nb_stream(b200nb_t* h);
+/* Use the caller's stream instead (the reference hands its DeviceStreamManager streams to gpu_init the same way,
+ * cuda/nbnxm_cuda_data_mgmt.cu:242-291). NULL returns to a private stream. The caller keeps ownership. */
+int   b200nb_set_stream(b200nb_t* h, void* cuda_stream);
 int   b200nb_synchronize(b200nb_t* h);
 
 /* ---- parameters: init_nbparam / gpu_pme_loadbal_update_param (nbnxm_gpu_data_mgmt.cpp:225) -------------- */

@@ -1,0 +1,144 @@
+"""CPU tests of the domain-decomposition host logic: the plan (who owns / sends / receives which atom) and
+the halo exchange pattern over torch.distributed with the gloo backend, world_size 2 and 3 (no GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gmxapi_b200 import systems as S
+from gmxapi_b200.domdec import DomainPlan, TorchDistTransport
+
+RLIST = 0.9
+
+
+def _pairs_bruteforce(xi, xj, r, same):
+    """index pairs (a, b) with |xi[a] - xj[b]| < r (no PBC: the caller has applied the shifts)."""
+    out = []
+    for a0 in range(0, len(xi), 512):
+        d = xi[a0:a0 + 512, None, :].astype(np.float64) - xj[None, :, :].astype(np.float64)
+        m = (d ** 2).sum(-1) < r * r
+        a, b = np.nonzero(m)
+        a = a + a0
+        if same:
+            k = a < b
+            a, b = a[k], b[k]
+        out.append(np.stack([a, b], 1))
+    return np.concatenate(out) if out else np.zeros((0, 2), np.int64)
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+def test_plan_partitions_atoms_and_pairs(nranks):
+    """Every atom has exactly one owner; the union over ranks of home-home and home-halo pairs within rlist along
+    the decomposed dimension is every pair of the periodic system exactly once (eighth-shell rule,
+    domdec/domdec.cpp:133-146)."""
+    s = S.water_box(10, 6, 6, seed=3)  # 3.1 x 1.86 x 1.86 nm: x is the only dimension with > 2 rlist... y,z not periodic here
+    x = s.x
+    box = s.box
+    plans = [DomainPlan(x, box, nranks, r, RLIST) for r in range(nranks)]
+    owned = np.concatenate([p.home for p in plans])
+    assert np.array_equal(np.sort(owned), np.arange(s.n))
+    if nranks == 1:
+        assert plans[0].nhalo == 0
+        return
+    # reference: all pairs within rlist with periodicity along x only (minimum image in x)
+    d = x[:, None, :].astype(np.float64) - x[None, :, :].astype(np.float64)
+    d[..., 0] -= np.round(d[..., 0] / box[0]) * box[0]
+    ref = np.argwhere(np.triu((d ** 2).sum(-1) < RLIST ** 2, 1))
+    ref_keys = np.sort(ref[:, 0].astype(np.int64) * s.n + ref[:, 1])
+    got = []
+    for p in plans:
+        xh = x[p.home]
+        hh = _pairs_bruteforce(xh, xh, RLIST, True)
+        got.append(np.stack([p.home[hh[:, 0]], p.home[hh[:, 1]]], 1))
+        if p.nhalo:
+            hx = p.halo_x(x)
+            hj = _pairs_bruteforce(xh, hx, RLIST, False)
+            got.append(np.stack([p.home[hj[:, 0]], p.halo[hj[:, 1]]], 1))
+    got = np.concatenate(got)
+    lo, hi = np.minimum(got[:, 0], got[:, 1]), np.maximum(got[:, 0], got[:, 1])
+    keys = np.sort(lo.astype(np.int64) * s.n + hi)
+    if nranks == 2:
+        # with two ranks a pair can be in range both directly and through the periodic image only if box < 2 rlist
+        assert box[0] >= 2 * RLIST
+    assert len(keys) == len(np.unique(keys)), "a pair is computed on two ranks"
+    assert np.array_equal(keys, ref_keys)
+
+
+def test_plan_local_topology():
+    s = S.named("water_3k")
+    p = DomainPlan(s.x, s.box, 2, 0, RLIST)
+    t, q, off, idx = p.local_topology(s.types, s.q, s.excl_off, s.excl_idx)
+    n = p.nhome + p.nhalo
+    assert len(t) == len(q) == n and len(off) == n + 1 and off[-1] == len(idx)
+    assert np.array_equal(t, s.types[p.local]) and np.array_equal(q, s.q[p.local])
+    # every local exclusion maps back to a global exclusion of the same atom, self included
+    for a in (0, 1, p.nhome - 1, p.nhome, n - 1):
+        ga = p.local[a]
+        glob = set(s.excl_idx[s.excl_off[ga]:s.excl_off[ga + 1]].tolist())
+        loc = set(p.local[idx[off[a]:off[a + 1]]].tolist())
+        assert ga in loc and loc <= glob
+        assert loc == {g for g in glob if g in set(p.local.tolist())}
+
+
+def test_plan_rejects_thin_domains():
+    s = S.named("water_3k")  # 3.1 nm box
+    from gmxapi_b200.nblib import InputException
+    with pytest.raises(InputException):
+        DomainPlan(s.x, s.box, 4, 0, RLIST)  # 0.78 nm slabs < rlist
+
+
+def _free_port():
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        s = S.water_box(12, 6, 6, seed=5)
+        plan = DomainPlan(s.x, s.box, world, rank, RLIST)
+        t = TorchDistTransport()
+        assert (t.rank, t.nranks) == (rank, world)
+        # dd_move_x: pack on the sender (the CUDA pack kernel's arithmetic, restated with torch on the CPU for this
+        # host-logic test only), transfer, compare with what the plan says the halo must hold
+        x = torch.from_numpy(s.x[plan.local].copy())
+        x[plan.nhome:] = float("nan")
+        send = x[:plan.nhome][torch.from_numpy(plan.send_local).long()] + torch.from_numpy(plan.send_shift)
+        t.sendrecv(send.contiguous(), plan.left, x[plan.nhome:], plan.right)
+        ok_x = bool(np.array_equal(x[plan.nhome:].numpy(), plan.halo_x(s.x)))
+        # dd_move_f: each halo atom carries f = its global index; after the return trip the owner must have received
+        # exactly one contribution per sent atom, equal to that atom's global index
+        f = torch.zeros((plan.nhome + plan.nhalo, 3))
+        f[plan.nhome:] = torch.from_numpy(plan.halo.astype(np.float32))[:, None]
+        recv = torch.zeros((len(plan.send_local), 3))
+        t.sendrecv(f[plan.nhome:].contiguous(), plan.right, recv, plan.left)
+        f[:plan.nhome].index_add_(0, torch.from_numpy(plan.send_local).long(), recv)
+        exp = np.zeros(plan.nhome, np.float32)
+        exp[plan.send_local] = plan.home[plan.send_local]
+        ok_f = bool(np.array_equal(f[:plan.nhome, 0].numpy(), exp))
+        tot = t.allreduce_sum(torch.tensor([float(plan.nhome)]))
+        q.put((rank, ok_x, ok_f, int(tot.item()) == s.n, plan.nhalo))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_x, ok_f, ok_n, nhalo in res:
+        assert ok_x and ok_f and ok_n and nhalo > 0, (rank, ok_x, ok_f, ok_n, nhalo)

@@ -1,0 +1,119 @@
+"""GPU parity of the domain-decomposed path on ONE GPU: the ranks are threads of this process, each with its own
+NbnxmGpu context, exchanging halos through the in-process loopback transport (the multi-GPU run uses the same
+DomainRank code over NCCL).  Global forces / pair set / energies / virial must equal the single-domain oracle."""
+import threading
+
+import numpy as np
+import pytest
+
+import gmxapi_b200 as g
+from gmxapi_b200 import lib as nb
+from gmxapi_b200.domdec import DomainRank, LoopbackTransport
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+RC = 0.9
+CENTRAL = 22
+
+
+def shift_index(t):
+    return 5 * (3 * (t[2] + 1) + (t[1] + 1)) + t[0] + 2
+
+
+def canonical(pairs_global, tx_dd):
+    """(i, j, shift) with the DD x-shift folded in, then brought to the half-list convention (shift <= CENTRAL,
+    central pairs i < j) so that sets from different decompositions compare equal."""
+    p = np.asarray(pairs_global, np.int64).reshape(-1, 3)
+    s = p[:, 2]
+    t = np.stack([(s % 5) - 2 + tx_dd, (s // 5) % 3 - 1, s // 15 - 1], 1)
+    idx = 5 * (3 * (t[:, 2] + 1) + (t[:, 1] + 1)) + t[:, 0] + 2
+    swap = (idx > CENTRAL) | ((idx == CENTRAL) & (p[:, 0] > p[:, 1]))
+    i = np.where(swap, p[:, 1], p[:, 0])
+    j = np.where(swap, p[:, 0], p[:, 1])
+    t = np.where(swap[:, None], -t, t)
+    idx = 5 * (3 * (t[:, 2] + 1) + (t[:, 1] + 1)) + t[:, 0] + 2
+    return (i << 34) | (j << 6) | idx
+
+
+def run_ranks(s, opt, nranks, flags):
+    hub = LoopbackTransport(nranks)
+    out = [None] * nranks
+    err = []
+
+    def work(r):
+        try:
+            d = DomainRank(s, opt, hub.endpoint(r), rank=r, nranks=nranks, device=0)
+            f, fs, elj, eel = d.compute(np.ascontiguousarray(s.x[d.plan.home]), flags)
+            pr = d.nb.pairs(RC)
+            p = d.plan
+            loc = p.local
+            halo_periodic = p.recv_from_periodic
+            is_halo = pr[:, 1] >= p.nhome
+            gl = np.stack([loc[pr[:, 0]], loc[pr[:, 1]], pr[:, 2]], 1)
+            keys = np.concatenate([canonical(gl[~is_halo], 0), canonical(gl[is_halo], -1 if halo_periodic else 0)])
+            out[r] = dict(home=p.home, f=f.numpy().copy(), fs=fs, elj=elj, eel=eel, keys=keys, nhalo=p.nhalo)
+            hub.endpoint(r).barrier()
+            d.close()
+        except Exception as e:  # noqa: BLE001
+            err.append((r, repr(e)))
+            try:
+                hub._bar.abort()
+            except Exception:
+                pass
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert not err, err
+    return out
+
+
+@pytest.mark.parametrize("name,nranks,coulomb", [("water_24k", 2, g.CoulombType.Pme), ("water_24k", 3, g.CoulombType.ReactionField),
+                                                 ("water_24k", 6, g.CoulombType.Pme), ("water_96k", 4, g.CoulombType.Pme)])
+def test_domain_decomposition_matches_single_domain(built, name, nranks, coulomb):
+    s = g.systems.named(name)
+    # reaction field with epsilon_rf = infinity (benchmark/bench_setup.cpp:152-155): the force vanishes at the cut-off, so
+    # a pair flipped by the rounding of the periodic-edge shift (below) cannot show up in the forces
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coulomb, computeVirialAndEnergy=True, epsilonRf=0.0)
+    flags = nb.FLAG_ENERGY | nb.FLAG_VIRIAL
+    res = run_ranks(s, opt, nranks, flags)
+    if coulomb == g.CoulombType.Pme:
+        kw = dict(eeltype=oracle.EEL_EWALD, beta=float(np.float32(g.systems.ewald_beta(RC))))
+    else:
+        k, c = g.systems.rf_constants(RC, eps_rf=0.0)
+        kw = dict(eeltype=oracle.EEL_RF, k_rf=k, c_rf=c)
+    fo, fso, evo, eco, npairs = oracle.forces(s.x, s.box, s.q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx, **kw)
+    # pair set: every pair exactly once over all ranks, identical to the single-domain set
+    keys = np.sort(np.concatenate([r["keys"] for r in res]))
+    ok = oracle.canonical_pairs(oracle.pair_set(s.x, s.box, RC, s.excl_off, s.excl_idx))
+    # Interior halos carry unshifted coordinates, so their pairs are bit-exact. On the periodic edge dd_move_x sends
+    # x_j + box (rounded to float32, domdec/domdec.cpp:300-318) where the single-domain kernel evaluates
+    # (x_i - box) - x_j, so a pair whose r^2 sits within rounding of rc^2 may flip -- the reference's own DD runs
+    # differ from its single-rank runs in exactly this way. Any difference must be such a pair.
+    diff = np.setxor1d(keys, ok)
+    assert len(diff) <= max(2, npairs // 500000)
+    sv = oracle.shift_vectors(s.box).astype(np.float64)
+    for k in diff:
+        i, j, sh = int(k >> 34), int((k >> 6) & ((1 << 28) - 1)), int(k & 63)
+        assert (sh % 5) - 2 != 0, "a pair that does not cross the periodic x edge differs"
+        r2 = ((s.x[i].astype(np.float64) + sv[sh] - s.x[j].astype(np.float64)) ** 2).sum()
+        assert abs(r2 - RC * RC) < 5e-6
+    assert abs(len(keys) - npairs) <= len(diff)
+    # forces
+    f = np.zeros((s.n, 3), np.float64)
+    for r in res:
+        assert r["nhalo"] > 0
+        f[r["home"]] = r["f"]
+    assert np.sqrt(((f - fo) ** 2).sum() / (fo ** 2).sum()) < 1e-5
+    # energies
+    elj, eel = sum(r["elj"] for r in res), sum(r["eel"] for r in res)
+    assert abs(elj - evo) <= 2e-4 * abs(evo)
+    assert abs(eel - eco) <= 2e-4 * abs(eco)
+    # virial: -1/2 [ sum_a x_a (x) f_a + sum_s shift_vec[s] (x) fshift[s] ], decomposition-invariant
+    fs = sum(r["fs"].astype(np.float64) for r in res)
+    x = s.x.astype(np.float64)
+    vir_g = -0.5 * (x.T @ f + sv.T @ fs)
+    vir_o = -0.5 * (x.T @ fo + sv.T @ fso)
+    assert np.abs(vir_g - vir_o).max() <= 1e-5 * np.abs(vir_o).max()
