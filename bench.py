@@ -168,7 +168,8 @@ def run_gpu(args):
     peaks = measured_peaks()
     s = workload_system(args.workload)
     coul = g.CoulombType.Pme if args.eel == "ewald" else g.CoulombType.ReactionField
-    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coul, computeVirialAndEnergy=False, device=local_rank, epsilonRf=0.0)
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coul, computeVirialAndEnergy=False, device=local_rank, epsilonRf=0.0,
+                            maxTilesPerEntry=args.max_tiles)
     t0 = time.perf_counter()
     fc = g.ForceCalculator(g.SimulationState.from_system(s), opt)
     fc.nb.synchronize()
@@ -289,7 +290,8 @@ def run_multi_gpu(args, rank, world, local_rank):
     nx, ny, nz = g.systems.NAMED[args.workload]
     s = g.systems.water_box(nx * world, ny, nz)
     coul = g.CoulombType.Pme if args.eel == "ewald" else g.CoulombType.ReactionField
-    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coul, computeVirialAndEnergy=False, device=local_rank, epsilonRf=0.0)
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coul, computeVirialAndEnergy=False, device=local_rank, epsilonRf=0.0,
+                            maxTilesPerEntry=args.max_tiles)
     d = domdec.DomainRank(s, opt, domdec.TorchDistTransport(), device=local_rank)
     h, stream = d.nb, d.stream
     dev = torch.device("cuda", local_rank)
@@ -384,6 +386,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="water_24k")
     ap.add_argument("--eel", default="ewald", choices=["ewald", "rf"])
+    ap.add_argument("--max-tiles", type=int, default=0, help="cluster pairs per list entry (0 = library default)")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -76,6 +76,7 @@ extern "C" int b200nb_create(b200nb_t** out, int device)
     cudaMalloc((void**)&h->d_fshift, sizeof(float) * B200NB_SHIFTS * 3);
     cudaMalloc((void**)&h->d_energy, sizeof(double) * 2);
     cudaMalloc((void**)&h->d_scratch, sizeof(int) * 64);
+    cudaMalloc((void**)&h->d_kconst, sizeof(float) * 8);
     cudaMalloc((void**)&h->d_counter, sizeof(long long) * 8);
     cudaMemsetAsync(h->d_fshift, 0, sizeof(float) * B200NB_SHIFTS * 3, h->stream);
     cudaMemsetAsync(h->d_energy, 0, sizeof(double) * 2, h->stream);
@@ -96,7 +97,7 @@ extern "C" void b200nb_destroy(b200nb_t* h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    void* ptrs[] = { h->d_nbfp,       h->d_type,     h->d_q,        h->d_excl_off,     h->d_excl_idx,  h->d_shift_vec,
+    void* ptrs[] = { h->d_kconst, h->d_nbfp,       h->d_type,     h->d_q,        h->d_excl_off,     h->d_excl_idx,  h->d_shift_vec,
                      h->d_x,          h->d_fout,     h->d_col_of_atom, h->d_col_count, h->d_col_cell0, h->d_col_fill,
                      h->d_atom_index, h->d_slot_of_atom, h->d_xq,   h->d_lj,           h->d_atype,     h->d_bb,
                      h->d_cellz,      h->d_f,        h->d_fshift,   h->d_energy,       h->d_scratch,   h->d_counter,
@@ -191,7 +192,7 @@ extern "C" int b200nb_set_params(b200nb_t* h, const b200nb_params_t* p)
             geom          = within(c6 * c6, c6ii * c6jj) && within(c12 * c12, c12ii * c12jj);
         }
     h->comb_geom = (p->comb_rule == 1) || (p->comb_rule == 0 && geom);
-    h->max_tiles = p->max_tiles_per_entry > 0 ? p->max_tiles_per_entry : 16;
+    h->max_tiles = p->max_tiles_per_entry > 0 ? std::min(p->max_tiles_per_entry, 32) : 16; /* <= 32: force.cu keeps an entry's j indices in one warp register */
     if (alloc_exact(h, &h->d_nbfp, (size_t)ntf * ntf * 2)) return B200NB_ERR_CUDA;
     NB_CUDA(h, cudaMemcpyAsync(h->d_nbfp, h->nbfp_host.data(), sizeof(float) * ntf * ntf * 2, cudaMemcpyHostToDevice, h->stream));
     NB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -212,6 +213,13 @@ extern "C" int b200nb_set_params(b200nb_t* h, const b200nb_params_t* p)
     d.disp_cpot     = p->disp_cpot;
     d.rep_cpot      = p->rep_cpot;
     d.self_sub      = (p->eeltype == B200NB_EEL_EWALD) ? (float)(0.5 * p->ewald_beta * 1.12837916709551257390) : 0.5f * p->c_rf;
+    d.self_q2       = (p->epsfac != 0.0f) ? d.self_sub / p->epsfac : 0.0f;
+    {
+        /* leading coefficients of pmeForceCorrection (simd/simd_math.h:1609-1650) and the loop-invariant scalars */
+        const float kc[8] = { d.rc2, d.beta, d.beta2, 0.0011193462567257629232f, 0.014866955030185295499f,
+                              -1.7357322914161492954e-8f, 1.4703624142580877519e-6f, 0.0f };
+        NB_CUDA(h, cudaMemcpy(h->d_kconst, kc, sizeof(kc), cudaMemcpyHostToDevice));
+    }
     d.ntypes        = ntf;
     d.eeltype       = p->eeltype;
     h->have_params  = true;
@@ -458,36 +466,31 @@ __global__ void k_column_sort(GridDesc g, const float* __restrict__ x, const flo
     {
         uint64_t  k    = s_key[i];
         const int slot = base + i;
-        const int cl = slot >> 3, kk = slot & 7, pp = nb_pairpos(kk);
-        float*    xb = xq + (size_t)cl * NB_XQ_STRIDE;
+        float4    v;
+        float2    l;
+        int       t;
         if (k != FILL)
         {
             int a = ((i >> 4) & 1) ? (int)(uint32_t)(~k) : (int)(uint32_t)k;
             atom_index[slot] = a;
             slot_of_atom[a]  = slot;
-            xb[pp]           = x[3 * a];
-            xb[8 + pp]       = x[3 * a + 1];
-            xb[16 + pp]      = x[3 * a + 2];
-            xb[24 + pp]      = q[a];
-            int t            = type[a];
-            atype[cl * 8 + pp] = t;
+            v                = make_float4(x[3 * a], x[3 * a + 1], x[3 * a + 2], q[a]);
+            t                = type[a];
             /* sqrt(6 C6_ii), sqrt(12 C12_ii): nbfp_comb for the geometric rule (atomdata.cpp:253-330) */
-            lj[(size_t)cl * NB_LJ_STRIDE + pp]     = sqrtf(nbfp[(t * ntypes + t) * 2]);
-            lj[(size_t)cl * NB_LJ_STRIDE + 8 + pp] = sqrtf(nbfp[(t * ntypes + t) * 2 + 1]);
+            l = make_float2(sqrtf(nbfp[(t * ntypes + t) * 2]), sqrtf(nbfp[(t * ntypes + t) * 2 + 1]));
         }
         else
         {
-            /* filler: no charge, zero-LJ filler type, parked far away at a unique position so that no
-             * two fillers are ever in range of each other (reference: -1e6, atomdata.cpp:146) */
+            /* filler: no charge, zero-LJ filler type, parked far away at a unique position so that no two fillers
+             * are ever at zero distance of each other (reference: -1e6, atomdata.cpp:146) */
             atom_index[slot] = -1;
-            xb[pp]           = -1.0e6f - 8.0f * (float)slot;
-            xb[8 + pp]       = -1.0e6f;
-            xb[16 + pp]      = -1.0e6f;
-            xb[24 + pp]      = 0.0f;
-            atype[cl * 8 + pp] = ntypes - 1;
-            lj[(size_t)cl * NB_LJ_STRIDE + pp]     = 0.0f;
-            lj[(size_t)cl * NB_LJ_STRIDE + 8 + pp] = 0.0f;
+            v                = make_float4(-1.0e6f - 8.0f * (float)(slot & 0xfffff), -1.0e6f - 64.0f * (float)(slot >> 20), -1.0e6f, 0.0f);
+            t                = ntypes - 1;
+            l                = make_float2(0.0f, 0.0f);
         }
+        reinterpret_cast<float4*>(xq)[slot] = v;
+        reinterpret_cast<float2*>(lj)[slot] = l;
+        atype[slot]                         = t;
     }
     __syncthreads();
     /* bounding boxes of real atoms per cluster; bb[cl*6+0] > bb[cl*6+3] marks an all-filler cluster */
@@ -745,11 +748,11 @@ __device__ __forceinline__ float bb_dist2(const float* ilo, const float* ihi, co
     return d2;
 }
 
-/* One warp per i-cluster. Lane = il + 8*jq handles atom pairs (il, jq) and (il, jq+4) of a candidate tile.
+/* One warp per i-cluster. Lane = jl + 8*ih handles atom pairs (2*ih, jl) and (2*ih+1, jl) of a candidate tile.
  * A cluster pair enters the list iff at least one atom pair has r^2 < rlist^2 (the converged result of
  * the reference's bounding-box search, pairlist.cpp:1090-1244, followed by its list pruning,
  * nbnxm_cuda_kernel_pruneonly.cuh), so the list is the tightest superset of the in-range pairs.
- * Exclusion masks (pairlist.cpp:1874-1972): bit j*8+i of a tile's mask is 1 when atoms i,j interact. */
+ * Exclusion masks (pairlist.cpp:1874-1972): bit `lane` of mask word w is 1 when atoms (2*ih+w, jl) interact. */
 __global__ void __launch_bounds__(128)
 k_search(SearchArgs A, const float* __restrict__ xq, const float* __restrict__ bb, const float* __restrict__ cellz,
          const int* __restrict__ col_cell0, const int* __restrict__ atom_index, const int* __restrict__ excl_off,
@@ -775,16 +778,23 @@ k_search(SearchArgs A, const float* __restrict__ xq, const float* __restrict__ b
     int ntiles_total = 0, nentries_total = 0;
     if (!i_empty)
     {
-        const int il = lane & 7, jq = lane >> 3;
-        const float* xb = xq + (size_t)ci * NB_XQ_STRIDE;
-        const int    ip = nb_pairpos(il);
-        const float  xi0 = xb[ip], yi0 = xb[8 + ip], zi0 = xb[16 + ip];
-        const int    ai = atom_index[ci * 8 + il];
-        int e0 = 0, e1 = 0;
-        if (ai >= 0 && excl_off)
+        const int    jl = lane & 7, ih = lane >> 3;
+        const float4 xa = reinterpret_cast<const float4*>(xq)[(size_t)ci * 8 + 2 * ih];
+        const float4 xb = reinterpret_cast<const float4*>(xq)[(size_t)ci * 8 + 2 * ih + 1];
+        const int    ai0 = atom_index[ci * 8 + 2 * ih], ai1 = atom_index[ci * 8 + 2 * ih + 1];
+        int e00 = 0, e01 = 0, e10 = 0, e11 = 0;
+        if (excl_off)
         {
-            e0 = excl_off[ai];
-            e1 = excl_off[ai + 1];
+            if (ai0 >= 0)
+            {
+                e00 = excl_off[ai0];
+                e01 = excl_off[ai0 + 1];
+            }
+            if (ai1 >= 0)
+            {
+                e10 = excl_off[ai1];
+                e11 = excl_off[ai1 + 1];
+            }
         }
         const float jzlo = A.gj.lower[2], jzhi = A.gj.upper[2];
         (void)jzlo;
@@ -812,7 +822,8 @@ k_search(SearchArgs A, const float* __restrict__ xq, const float* __restrict__ b
                     cy0 = max(cy0, 0);
                     cx1 = min(cx1, A.gj.ncx - 1);
                     cy1 = min(cy1, A.gj.ncy - 1);
-                    const float xi = xi0 + sx, yi = yi0 + sy, zi = zi0 + sz; /* the shifted i-atom, as in the kernels */
+                    /* the shifted i-atoms, as in the kernels */
+                    const float xi0 = xa.x + sx, yi0 = xa.y + sy, zi0 = xa.z + sz, xi1 = xb.x + sx, yi1 = xb.y + sy, zi1 = xb.z + sz;
                     int n_mask = 0, n_plain = 0; /* masked tiles grow from the front, plain ones from the back */
                     for (int cx = cx0; cx <= cx1; cx++)
                         for (int cy = cy0; cy <= cy1; cy++)
@@ -852,25 +863,18 @@ k_search(SearchArgs A, const float* __restrict__ xq, const float* __restrict__ b
                                     const int b = __ffs(cm) - 1;
                                     cm &= cm - 1;
                                     const int    cj = cjb + b;
-                                    const float* jx = xq + (size_t)cj * NB_XQ_STRIDE;
-                                    const float2 xj = *(const float2*)(jx + 2 * jq);
-                                    const float2 yj = *(const float2*)(jx + 8 + 2 * jq);
-                                    const float2 zj = *(const float2*)(jx + 16 + 2 * jq);
-                                    const float  r2a = nb_rsq(xi, yi, zi, xj.x, yj.x, zj.x);
-                                    const float  r2b = nb_rsq(xi, yi, zi, xj.y, yj.y, zj.y);
+                                    const float4 xj  = reinterpret_cast<const float4*>(xq)[(size_t)cj * 8 + jl];
+                                    const float  r2a = nb_rsq(xi0, yi0, zi0, xj.x, xj.y, xj.z);
+                                    const float  r2b = nb_rsq(xi1, yi1, zi1, xj.x, xj.y, xj.z);
                                     const bool   in  = (r2a < A.rlist2) || (r2b < A.rlist2);
                                     if (!__any_sync(0xffffffffu, in)) continue;
-                                    /* interaction bits from the topology exclusions of atom ai */
+                                    /* interaction bits from the topology exclusions of the two i-atoms */
                                     bool ia = true, ibit = true;
-                                    if (e1 > e0)
+                                    if (e01 > e00 || e11 > e10)
                                     {
-                                        const int aja = atom_index[cj * 8 + jq], ajb = atom_index[cj * 8 + jq + 4];
-                                        for (int e = e0; e < e1; e++)
-                                        {
-                                            const int ex = excl_idx[e];
-                                            ia           = ia && (ex != aja);
-                                            ibit         = ibit && (ex != ajb);
-                                        }
+                                        const int aj = atom_index[cj * 8 + jl];
+                                        for (int e = e00; e < e01; e++) ia = ia && (excl_idx[e] != aj);
+                                        for (int e = e10; e < e11; e++) ibit = ibit && (excl_idx[e] != aj);
                                     }
                                     const unsigned ma = __ballot_sync(0xffffffffu, ia);
                                     const unsigned mb = __ballot_sync(0xffffffffu, ibit);
@@ -990,22 +994,19 @@ k_prune(const Entry* __restrict__ oe, const int* __restrict__ ocj, const uint64_
     const long long wid = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     const long long e   = wid * nparts + part; /* rolling parts interleave entries: pruneonly.cuh:165-166 */
     if (e >= nentries) return;
-    const int   lane = threadIdx.x & 31, il = lane & 7, jq = lane >> 3;
+    const int   lane = threadIdx.x & 31, jl = lane & 7, ih = lane >> 3;
     const Entry en   = oe[e];
     const int   shift = en.shift_nmask & 255, nmask = en.shift_nmask >> 8;
-    const float* xb  = xq + (size_t)en.ci * NB_XQ_STRIDE;
-    const int    ip  = nb_pairpos(il);
-    const float  xi = xb[ip] + shift_vec[3 * shift], yi = xb[8 + ip] + shift_vec[3 * shift + 1],
-                zi = xb[16 + ip] + shift_vec[3 * shift + 2];
+    const float4 xa = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + 2 * ih];
+    const float4 xb = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + 2 * ih + 1];
+    const float  sx = shift_vec[3 * shift], sy = shift_vec[3 * shift + 1], sz = shift_vec[3 * shift + 2];
+    const float  xi0 = xa.x + sx, yi0 = xa.y + sy, zi0 = xa.z + sz, xi1 = xb.x + sx, yi1 = xb.y + sy, zi1 = xb.z + sz;
     int kept = 0, kept_mask = 0;
     for (int t = en.start; t < en.end; t++)
     {
         const int    cj = ocj[t];
-        const float* jx = xq + (size_t)cj * NB_XQ_STRIDE;
-        const float2 xj = *(const float2*)(jx + 2 * jq);
-        const float2 yj = *(const float2*)(jx + 8 + 2 * jq);
-        const float2 zj = *(const float2*)(jx + 16 + 2 * jq);
-        const bool   in = (nb_rsq(xi, yi, zi, xj.x, yj.x, zj.x) < rlist2) || (nb_rsq(xi, yi, zi, xj.y, yj.y, zj.y) < rlist2);
+        const float4 xj = reinterpret_cast<const float4*>(xq)[(size_t)cj * 8 + jl];
+        const bool   in = (nb_rsq(xi0, yi0, zi0, xj.x, xj.y, xj.z) < rlist2) || (nb_rsq(xi1, yi1, zi1, xj.x, xj.y, xj.z) < rlist2);
         if (__any_sync(0xffffffffu, in))
         {
             if (lane == 0)
@@ -1183,11 +1184,10 @@ __global__ void k_x_to_grid(const float* __restrict__ x, const int* __restrict__
 {
     int a = a0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= a1) return;
-    const int slot = slot_of_atom[a];
-    float*    xb   = xq + (size_t)(slot >> 3) * NB_XQ_STRIDE + nb_pairpos(slot & 7);
-    xb[0]          = x[3 * a];
-    xb[8]          = x[3 * a + 1];
-    xb[16]         = x[3 * a + 2];
+    float* xb = xq + 4 * (size_t)slot_of_atom[a];
+    xb[0]     = x[3 * a];
+    xb[1]     = x[3 * a + 1];
+    xb[2]     = x[3 * a + 2];
 }
 
 /* reduceKernel (mdlib/gpuforcereduction_impl.cu:70-104): f[a] (+)= f_nb[cell[a]] */
@@ -1462,27 +1462,24 @@ k_pairs(const Entry* __restrict__ ent, const int* __restrict__ tcj, const uint64
 {
     const long long e = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (e >= nentries) return;
-    const int   lane = threadIdx.x & 31, il = lane & 7, jq = lane >> 3;
+    const int   lane = threadIdx.x & 31, jl = lane & 7, ih = lane >> 3;
     const Entry en   = ent[e];
     const int   shift = en.shift_nmask & 255, nmask = en.shift_nmask >> 8;
-    const float* xb  = xq + (size_t)en.ci * NB_XQ_STRIDE;
-    const int    ip  = nb_pairpos(il);
-    const float  xi = xb[ip] + shift_vec[3 * shift], yi = xb[8 + ip] + shift_vec[3 * shift + 1],
-                zi = xb[16 + ip] + shift_vec[3 * shift + 2];
-    const int ai = atom_index[en.ci * 8 + il];
+    const float sx = shift_vec[3 * shift], sy = shift_vec[3 * shift + 1], sz = shift_vec[3 * shift + 2];
     for (int t = en.start; t < en.end; t++)
     {
         const int      cj   = tcj[t];
         const uint64_t mask = (t - en.start < nmask) ? tmask[t] : ~0ull;
         const bool     diag = intra && shift == B200NB_CENTRAL && cj == en.ci;
-        const float*   jx   = xq + (size_t)cj * NB_XQ_STRIDE;
-        const float2   xj = *(const float2*)(jx + 2 * jq), yj = *(const float2*)(jx + 8 + 2 * jq), zj = *(const float2*)(jx + 16 + 2 * jq);
-        for (int half = 0; half < 2; half++)
+        const float4   xj   = reinterpret_cast<const float4*>(xq)[(size_t)cj * 8 + jl];
+        const int      aj   = atom_index[cj * 8 + jl];
+        for (int w = 0; w < 2; w++)
         {
-            const int   j  = jq + 4 * half;
-            const float r  = half ? nb_rsq(xi, yi, zi, xj.y, yj.y, zj.y) : nb_rsq(xi, yi, zi, xj.x, yj.x, zj.x);
-            const int   aj = atom_index[cj * 8 + j];
-            bool ok = (r < r2) && ((mask >> (j * 8 + il)) & 1ull) && ai >= 0 && aj >= 0 && !(diag && j <= il);
+            const int    i  = 2 * ih + w;
+            const float4 xi = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + i];
+            const float  r  = nb_rsq(xi.x + sx, xi.y + sy, xi.z + sz, xj.x, xj.y, xj.z);
+            const int    ai = atom_index[en.ci * 8 + i];
+            bool ok = (r < r2) && ((mask >> (32 * w + lane)) & 1ull) && ai >= 0 && aj >= 0 && !(diag && jl <= i);
             if (ok)
             {
                 unsigned long long pos = atomicAdd(counter, 1ull);

@@ -12,21 +12,16 @@
 
 #define NB_CL 8      /* atoms per cluster */
 #define NB_CELL 64   /* atoms per grid cell = 8 clusters (nbnxm/pairlistparams.h:69-77) */
-#define NB_XQ_STRIDE 32 /* floats per cluster in the xq layout */
-#define NB_LJ_STRIDE 16 /* floats per cluster in the lj layout */
 #define NB_MIN_RSQ 3.82e-07f /* nbnxm/pairlist.h:146 c_nbnxnMinDistanceSquared */
 #define NB_MAX_GROUP_TILES 512 /* staging capacity of one (i-cluster, shift) group in the search */
 
-/* Device coordinate layout ("c8 pair-interleaved SoA"): per 8-atom cluster 32 floats
- *   [x-pairs | y-pairs | z-pairs | q-pairs], each 8 floats ordered a0,a4,a1,a5,a2,a6,a3,a7
- * so that ONE 8-byte load yields component c of atoms (k, k+4) in an aligned register pair -- the operand
- * form of the sm_100 packed FP32 instructions (fma.rn.f32x2) the force kernel is written around.
- * LJ data: per cluster 16 floats [c6s-pairs | c12s-pairs] (sqrt(6 C6_ii), sqrt(12 C12_ii)) for the
- * geometric rule, or 8 ints of atom types in the same pair order for the table path. */
-__host__ __device__ inline int nb_pairpos(int k)
-{
-    return ((k & 3) << 1) | (k >> 2);
-}
+/* Device atom layout, grid (slot) order, slot = cluster*8 + k:
+ *   xq     float4 {x, y, z, q} per slot  -- the reference's nbatXYZQ (nbnxm/atomdata.cpp:659-662); one 16-byte load per atom
+ *   lj     float2 {sqrt(6 C6_ii), sqrt(12 C12_ii)} per slot (geometric rule), atype int per slot (type table)
+ *   f      float4 per slot (16-byte vector reductions; one 128-byte line per cluster)
+ * Lane mapping shared by the search, prune, pair-extraction and force kernels: lane = jl + 8*ih handles j-atom jl of the
+ * j-cluster and the i-atoms 2*ih and 2*ih+1 of the i-cluster.  A tile's 64-bit mask is two 32-bit words: bit `lane` of
+ * word w says pair (i-atom 2*ih + w, j-atom jl) interacts (nbnxn_excl_t, nbnxm/pairlist.h:208-225, re-indexed to our lanes). */
 
 struct GridDesc
 {
@@ -56,6 +51,7 @@ struct NbParamsDev
     float beta, beta2, beta3, sh_ewald;
     float disp_cpot, rep_cpot;
     float self_sub; /* 0.5*c_rf or beta/sqrt(pi): kernels_simd_2xmm/kernel_outer.h:418-440 */
+    float self_q2;  /* self_sub / epsfac (0 when epsfac is 0) */
     int   ntypes;   /* including the filler type */
     int   eeltype;
 };
@@ -84,6 +80,7 @@ struct b200nb_context
     bool              comb_geom = false;
     int               max_tiles = 16;
     float*            d_nbfp = nullptr; /* float2 per type pair */
+    float*            d_kconst = nullptr; /* 8 floats: rc2, beta, beta2, FD4, FD3, FN6, FN5, 0 (force.cu KConst) */
 
     int    natoms = 0;
     int*   d_type = nullptr;

@@ -6,62 +6,43 @@
  *   arithmetic parity target = the CPU SIMD kernels nbnxm/kernels_simd_2xmm/kernel_inner.h:226-880 and
  *   kernel_outer.h:395-452 (self terms), simd/simd_math.h:1609-1722 (Ewald correction polynomials).
  *
- * Design (not a port of the reference CUDA kernel):
- *  - one warp per list entry = one 8-atom i-cluster + shift vs a run of 8-atom j-clusters;
- *    the i-atom lives in registers for the whole entry: no shared memory, no per-tile i reloads;
- *  - lane = il + 8*jq evaluates the two atom pairs (il, jq) and (il, jq+4) of a tile at once, held as
- *    float2 register pairs, so the arithmetic maps onto Blackwell's packed FP32 pipe instructions
- *    (fma.rn.f32x2 / mul / add -> SASS FFMA2/FMUL2/FADD2) which need half the issue slots per flop;
- *  - the pair-interleaved coordinate layout (b200nb_internal.h) makes every j operand ONE 8-byte,
- *    broadcast-friendly read-only load straight into an aligned register pair;
- *  - j-forces: transposed butterfly over the 8 lanes sharing a j atom (7 shuffles per tile instead of
- *    18), then scalar red.global; i-forces: registers, 6 shuffles + one vector atomic per entry;
+ * Design (not a port of the reference CUDA kernel), sized with profiles/tools/microbench.cu: on sm_100 the FP32
+ * pipe retires 128 lane-FMAs/clk/SM whether issued as scalar FFMA or packed FFMA2, but a packed instruction takes
+ * ONE issue slot for two lanes' work; ALU-pipe instructions (FSEL, FMNMX, LOP3, IADD3) run at half that rate, SHFL
+ * at ~0.44 warp-instructions/clk/SMSP, MUFU at 16 lanes/clk/SM.  So the kernel is written to be FMA-pipe-bound:
+ *  - one warp per list entry = one 8-atom i-cluster + shift against a run of 8-atom j-clusters;
+ *  - lane = jl + 8*ih holds j-atom jl and the TWO i-atoms (2*ih, 2*ih+1) as packed float2 registers for the whole
+ *    entry: all pair arithmetic is packed (fma.rn.f32x2 -> FFMA2/FMUL2/FADD2), the j operands enter as the
+ *    scalar-broadcast operand form of those instructions, so a tile costs two loads (one 16-byte xyzq, one 8-byte
+ *    LJ pair; the 4 lanes sharing a j-atom hit the same address) and no register shuffling;
+ *  - j-forces: in-lane add of the two pairs, 2-stage reduce-scatter (3 shuffles) over the 4 lanes sharing the j-atom,
+ *    then one scalar red.global.add.f32 per lane: 32 lanes cover the 8 float4 force slots of the j-cluster's 128-byte line;
+ *  - i-forces stay in registers; per entry one transposed butterfly over the 8 j-lanes and one 16-byte red per atom;
+ *  - tiles that carry exclusion masks are sorted to the front of an entry (b200nb.cu k_search) and run through a
+ *    separate code path; the unmasked path has no mask logic and no r^2 clamp;
+ *  - LJ is evaluated as (c12*r^-6 - c6)*r^-6, the Ewald correction polynomials keep their coefficients as
+ *    instruction immediates (folding beta^3 into them would cost seven registers); out-of-range lanes are discarded by select, so garbage there cannot poison a sum;
  *  - r^2 is evaluated with the reference's operand roles and operation order so the in-range pair set is
- *    bit-identical (see nb_rsq in b200nb_internal.h).
+ *    bit-identical (see nb_rsq in b200nb_internal.h);
+ *  - the j-atom data of a whole entry (<= 32 tiles x 192 B) is staged in shared memory with cp.async (LDGSTS), all 32
+ *    lanes copying 16 B each per instruction, before the pair loop starts: the first version loaded j data with LDG one
+ *    tile ahead and spent its time in long-scoreboard stalls (L1 hit rate 35 %: consecutive entries belong to the same
+ *    i-cluster and share no j data; profiles/r1).  The i-cluster lives in registers, which beats shared memory.
+ *    TMA (cp.async.bulk) was considered and not used: the stream is a gather of 128-byte lines by cluster index, so a
+ *    bulk copy would move one line per instruction issued by one elected lane plus mbarrier traffic, while LDGSTS moves
+ *    512 B per warp instruction with per-lane addresses and needs only wait_group + syncwarp.
  */
 #include <cstdio>
 
 #include "b200nb_internal.h"
 
-#ifndef B200NB_USE_F32X2
-#define B200NB_USE_F32X2 1
-#endif
-
 namespace
 {
 
-__device__ __forceinline__ float2 mul2(float2 a, float2 b)
-{
-#if B200NB_USE_F32X2
-    return __fmul2_rn(a, b);
-#else
-    return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
-#endif
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b)
-{
-#if B200NB_USE_F32X2
-    return __fadd2_rn(a, b);
-#else
-    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
-#endif
-}
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
-{
-#if B200NB_USE_F32X2
-    return __ffma2_rn(a, b, c);
-#else
-    return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y));
-#endif
-}
-__device__ __forceinline__ float2 dup(float a)
-{
-    return make_float2(a, a);
-}
-__device__ __forceinline__ float2 ldg2(const float* p)
-{
-    return __ldg(reinterpret_cast<const float2*>(p));
-}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
 
 __device__ __forceinline__ float rcp_approx(float x)
 {
@@ -76,57 +57,47 @@ __device__ __forceinline__ float rsqrt_approx(float x)
     return r;
 }
 
-struct JData
+struct JAtom
 {
-    float2 x, y, z, q, c6, c12;
-    int    cj;
+    float4 xq;
+    float2 lj; /* GEOM: sqrt(6 C6), sqrt(12 C12); table: atom type in lj.x (as int bits) */
 };
 
-template<bool GEOM>
-__device__ __forceinline__ void load_j(JData& d, int cj, int jq, const float* __restrict__ xq, const float* __restrict__ lj,
-                                       const int* __restrict__ atype, const float2* __restrict__ nbfp, int tioff)
+/* The j-atom data of a whole entry is staged in shared memory with cp.async (LDGSTS) before the pair loop, so the
+ * loop itself never waits on L2: per warp [ntile x 128 B xyzq][ntile x 64 B LJ (or 32 B types)]. */
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr)
 {
-    const float* jb = xq + (size_t)cj * NB_XQ_STRIDE + 2 * jq;
-    d.cj            = cj;
-    d.x             = ldg2(jb);
-    d.y             = ldg2(jb + 8);
-    d.z             = ldg2(jb + 16);
-    d.q             = ldg2(jb + 24);
-    if (GEOM)
-    {
-        const float* lb = lj + (size_t)cj * NB_LJ_STRIDE + 2 * jq;
-        d.c6            = ldg2(lb);
-        d.c12           = ldg2(lb + 8);
-    }
-    else
-    {
-        const int2   t  = __ldg(reinterpret_cast<const int2*>(atype + (size_t)cj * 8 + 2 * jq));
-        const float2 pa = __ldg(nbfp + tioff + t.x), pb = __ldg(nbfp + tioff + t.y);
-        d.c6            = make_float2(pa.x, pb.x);
-        d.c12           = make_float2(pa.y, pb.y);
-    }
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
 
-/* simd/simd_math.h:1609-1650 pmeForceCorrection, two arguments at once */
-__device__ __forceinline__ float2 pme_force_corr2(float2 z2)
+template<bool GEOM>
+__device__ __forceinline__ void load_j(JAtom& J, const unsigned char* sxq_lane, const unsigned char* slj_lane, int t)
 {
-    const float2 FN6 = dup(-1.7357322914161492954e-8f), FN5 = dup(1.4703624142580877519e-6f),
+    J.xq = *reinterpret_cast<const float4*>(sxq_lane + t * 128);
+    if (GEOM) J.lj = *reinterpret_cast<const float2*>(slj_lane + t * 64);
+    else J.lj.x = __int_as_float(*reinterpret_cast<const int*>(slj_lane + t * 32));
+}
+
+/* simd/simd_math.h:1609-1650 pmeForceCorrection: denominator and numerator */
+__device__ __forceinline__ float2 pme_force_den(float2 z2, float2 z4, float fd4, float fd3)
+{
+    const float2 FD4 = dup(fd4), FD3 = dup(fd3),
+                 FD2 = dup(0.11583842382862377919f), FD1 = dup(0.50736591960530292870f), FD0 = dup(1.0f);
+    float2 d0 = fma2(FD4, z4, FD2), d1 = fma2(FD3, z4, FD1);
+    d0        = fma2(d0, z4, FD0);
+    return fma2(d1, z2, d0);
+}
+__device__ __forceinline__ float2 pme_force_num(float2 z2, float2 z4, float fn6, float fn5)
+{
+    const float2 FN6 = dup(fn6), FN5 = dup(fn5),
                  FN4 = dup(-0.000053401640219807709149f), FN3 = dup(0.0010054721316683106153f),
                  FN2 = dup(-0.019278317264888380590f), FN1 = dup(0.069670166153766424023f),
                  FN0 = dup(-0.75225204789749321333f);
-    const float2 FD4 = dup(0.0011193462567257629232f), FD3 = dup(0.014866955030185295499f),
-                 FD2 = dup(0.11583842382862377919f), FD1 = dup(0.50736591960530292870f), FD0 = dup(1.0f);
-    const float2 z4 = mul2(z2, z2);
-    float2       d0 = fma2(FD4, z4, FD2), d1 = fma2(FD3, z4, FD1);
-    d0              = fma2(d0, z4, FD0);
-    d0              = fma2(d1, z2, d0);
     float2 n0 = fma2(FN6, z4, FN4), n1 = fma2(FN5, z4, FN3);
-    n0 = fma2(n0, z4, FN2);
-    n1 = fma2(n1, z4, FN1);
-    n0 = fma2(n0, z4, FN0);
-    n0 = fma2(n1, z2, n0);
-    const float2 r = make_float2(rcp_approx(d0.x), rcp_approx(d0.y));
-    return mul2(n0, r);
+    n0        = fma2(n0, z4, FN2);
+    n1        = fma2(n1, z4, FN1);
+    n0        = fma2(n0, z4, FN0);
+    return fma2(n1, z2, n0);
 }
 
 /* simd/simd_math.h:1687-1722 pmePotentialCorrection */
@@ -150,72 +121,97 @@ __device__ __forceinline__ float2 pme_pot_corr2(float2 z2)
     return mul2(n0, r);
 }
 
+/* Loop-invariant scalars. They are read from a small global array (b200nb_context::d_kconst) rather than from kernel
+ * parameters or literals: a loaded value must stay in its register, whereas ptxas rematerialises constant-bank values and
+ * immediates inside the pair loop (7 issue slots per tile in the first version). */
+struct KConst
+{
+    float rc2, beta, beta2, fd4, fd3, fn6, fn5;
+};
 struct IData
 {
-    float2 x, y, z, q, c6, c12; /* duplicated i-atom values */
-    float  qraw;
-    int    il, jq, ci, shift;
+    float2 x, y, z;  /* the two i-atoms of this lane, shift already added */
+    float2 q;        /* epsfac * q_i */
+    float2 c6n, c12; /* GEOM: -sqrt(6 C6_i), sqrt(12 C12_i) */
+    int    t0, t1;   /* table path: type_i * ntypes */
 };
 
-/* One tile: lane computes pairs (il, jq) [.x] and (il, jq+4) [.y].  Returns the force on the i-atom in
- * (tx,ty,tz) (both pairs, packed) and accumulates energies. */
-template<int EEL, bool VF, bool MASKED>
-__device__ __forceinline__ void tile_pairs(const IData& I, const JData& J, const NbParamsDev& P, uint64_t mask, bool diag, float2& tx,
-                                           float2& ty, float2& tz, float& evdw, float& ecoul)
+/* One tile: lane computes pairs (i0, jl) [.x] and (i1, jl) [.y].  Returns the force ON THE i-ATOMS in (tx,ty,tz). */
+template<int EEL, bool GEOM, bool VF, bool MASKED>
+__device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const NbParamsDev& P, const KConst& K, const float2* __restrict__ nbfp,
+                                           float inter0, float inter1, bool ok0, bool ok1, float2& tx, float2& ty, float2& tz,
+                                           float& evdw, float& ecoul)
 {
     const float2 m1 = dup(-1.0f);
-    const float2 dx = fma2(J.x, m1, I.x); /* xi - xj, exact product */
-    const float2 dy = fma2(J.y, m1, I.y);
-    const float2 dz = fma2(J.z, m1, I.z);
-    const float2 r2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
-    bool wa = r2.x < P.rc2, wb = r2.y < P.rc2;
-    float2 inter = dup(1.0f);
+    const float2 dx = fma2(dup(J.xq.x), m1, I.x); /* xi - xj: the product is exact */
+    const float2 dy = fma2(dup(J.xq.y), m1, I.y);
+    const float2 dz = fma2(dup(J.xq.z), m1, I.z);
+    float2       r2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+    bool         wa = r2.x < K.rc2, wb = r2.y < K.rc2;
+    float2       inter;
     if (MASKED)
     {
-        inter.x = (float)((mask >> (I.jq * 8 + I.il)) & 1ull);
-        inter.y = (float)((mask >> ((I.jq + 4) * 8 + I.il)) & 1ull);
-        if (diag)
-        {
-            /* self tile: only j > i (nbnxm/pairlist.cpp:880-904, kernel_gpu_ref.cpp:223-226) */
-            wa = wa && (I.jq > I.il);
-            wb = wb && (I.jq + 4 > I.il);
-        }
+        wa    = wa && ok0;
+        wb    = wb && ok1;
+        inter = make_float2(inter0, inter1);
+        r2    = make_float2(fmaxf(r2.x, NB_MIN_RSQ), fmaxf(r2.y, NB_MIN_RSQ));
     }
-    const float2 r2c  = make_float2(fmaxf(r2.x, NB_MIN_RSQ), fmaxf(r2.y, NB_MIN_RSQ));
-    const float2 rinv = make_float2(rsqrt_approx(r2c.x), rsqrt_approx(r2c.y));
+    const float2 rinv   = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
     const float2 rinvsq = mul2(rinv, rinv);
-    float2 rinv_ex = rinv;
+    float2       rinv_ex = rinv;
     if (MASKED) rinv_ex = mul2(rinv, inter);
 
-    /* Lennard-Jones: F*r = 12 C12 r^-12 - 6 C6 r^-6 with the 6/12 folded into the parameters */
-    const float2 c6 = mul2(I.c6, J.c6), c12 = mul2(I.c12, J.c12);
-    float2       rinv6 = mul2(mul2(rinvsq, rinvsq), rinvsq);
+    float2 c6n, c12;
+    if (GEOM)
+    {
+        c6n = mul2(I.c6n, dup(J.lj.x));
+        c12 = mul2(I.c12, dup(J.lj.y));
+    }
+    else
+    {
+        const int    tj = __float_as_int(J.lj.x);
+        const float2 pa = __ldg(nbfp + I.t0 + tj), pb = __ldg(nbfp + I.t1 + tj);
+        c6n             = make_float2(-pa.x, -pb.x);
+        c12             = make_float2(pa.y, pb.y);
+    }
+    float2 rinv6 = mul2(mul2(rinvsq, rinvsq), rinvsq);
     if (MASKED) rinv6 = mul2(rinv6, inter);
-    const float2 frlj6 = mul2(c6, rinv6);
-    const float2 frlj12 = mul2(mul2(c12, rinv6), rinv6);
-    const float2 frlj   = fma2(frlj6, m1, frlj12);
-
-    const float2 qq = mul2(I.q, J.q);
-    float2       frcoul;
+    float2 fsum; /* F*r summed over LJ and Coulomb */
+    float2 frlj6, frlj12;
+    if (VF)
+    {
+        frlj6  = mul2(c6n, rinv6);               /* -6 C6 r^-6 */
+        frlj12 = mul2(mul2(c12, rinv6), rinv6);  /* 12 C12 r^-12 */
+        fsum   = add2(frlj12, frlj6);
+    }
+    else
+    {
+        fsum = mul2(fma2(c12, rinv6, c6n), rinv6);
+    }
+    const float2 qq = mul2(I.q, dup(J.xq.w));
     float2       vcoul = dup(0.0f);
     if (EEL == 1)
     {
-        const float2 brsq   = mul2(dup(P.beta2), r2c);
-        const float2 ewcorr = mul2(dup(P.beta), pme_force_corr2(brsq));
-        frcoul              = mul2(qq, fma2(ewcorr, brsq, rinv_ex));
+        const float2 z2 = mul2(dup(K.beta2), r2);
+        const float2 z4 = mul2(z2, z2);
+        const float2 den = pme_force_den(z2, z4, K.fd4, K.fd3);
+        const float2 num = pme_force_num(z2, z4, K.fn6, K.fn5);
+        const float2 t   = mul2(mul2(num, dup(K.beta)), make_float2(rcp_approx(den.x), rcp_approx(den.y))); /* beta * pmecorrF(z2) */
+        fsum             = fma2(qq, fma2(t, z2, rinv_ex), fsum);
         if (VF)
         {
-            float2 vsub = mul2(dup(P.beta), pme_pot_corr2(brsq));
-            vsub        = fma2(dup(P.sh_ewald), inter, vsub);
-            vcoul       = mul2(qq, fma2(vsub, m1, rinv_ex));
+            float2 vsub = mul2(dup(P.beta), pme_pot_corr2(z2));
+            if (MASKED) vsub = fma2(dup(P.sh_ewald), inter, vsub);
+            else vsub = add2(vsub, dup(P.sh_ewald));
+            vcoul = mul2(qq, fma2(vsub, m1, rinv_ex));
         }
     }
     else
     {
-        frcoul = mul2(qq, fma2(r2c, dup(-P.two_k_rf), rinv_ex));
-        if (VF) vcoul = mul2(qq, add2(rinv_ex, fma2(r2c, dup(P.k_rf), dup(-P.c_rf))));
+        fsum = fma2(qq, fma2(r2, dup(-P.two_k_rf), rinv_ex), fsum);
+        if (VF) vcoul = mul2(qq, add2(rinv_ex, fma2(r2, dup(P.k_rf), dup(-P.c_rf))));
     }
-    float2 fscal = mul2(rinvsq, add2(frcoul, frlj));
+    float2 fscal = mul2(rinvsq, fsum);
     fscal.x      = wa ? fscal.x : 0.0f;
     fscal.y      = wb ? fscal.y : 0.0f;
     tx           = mul2(fscal, dx);
@@ -224,141 +220,356 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JData& J, const
     if (VF)
     {
         /* kernels_simd_2xmm/kernel_inner.h:612-626: V = (FrLJ12 + c12*cpot12)/12 - (FrLJ6 + c6*cpot6)/6 */
-        float2 v6  = mul2(dup(1.0f / 6.0f), fma2(c6, dup(P.disp_cpot), frlj6));
+        float2 v6  = mul2(dup(1.0f / 6.0f), fma2(c6n, dup(P.disp_cpot), frlj6)); /* = -(FrLJ6 + c6 cpot6)/6 */
         float2 v12 = mul2(dup(1.0f / 12.0f), fma2(c12, dup(P.rep_cpot), frlj12));
-        float2 vlj = fma2(v6, m1, v12);
+        float2 vlj = add2(v12, v6);
         if (MASKED) vlj = mul2(vlj, inter);
         evdw += (wa ? vlj.x : 0.0f) + (wb ? vlj.y : 0.0f);
         ecoul += (wa ? vcoul.x : 0.0f) + (wb ? vcoul.y : 0.0f);
     }
 }
 
-/* Transposed butterfly over the 8 lanes (lane bits 0-2) that share the same two j atoms: 7 shuffles leave
- * every lane with one fully reduced x-or-y component and the z component of one of the two atoms. */
-__device__ __forceinline__ void reduce_store_j(const float2 tx, const float2 ty, const float2 tz, int il, int jq, int cj,
-                                               float4* __restrict__ f)
+/* Two plain (unmasked, force-only) tiles evaluated in lock step: every step of the arithmetic is written for both tiles
+ * before the next step, so the instruction stream carries two independent dependency chains and the 4-cycle FMA, MUFU and
+ * shuffle latencies of one tile are covered by the other (ncu: "wait"/"short scoreboard" stalls dominated the one-tile loop). */
+#ifndef B200NB_TILE_ILP
+#define B200NB_TILE_ILP 2
+#endif
+template<int EEL, bool GEOM, int NT>
+__device__ __forceinline__ void tile_pairs_multi(const IData& I, const JAtom (&J)[NT], const NbParamsDev& P, const KConst& K,
+                                                 const float2* __restrict__ nbfp, float2 (&tx)[NT], float2 (&ty)[NT], float2 (&tz)[NT])
 {
-    const unsigned full = 0xffffffffu;
-    const bool     b0 = il & 1, b1 = il & 2;
-    float kx = b0 ? tx.y : tx.x, ky = b0 ? ty.y : ty.x, kz = b0 ? tz.y : tz.x;
-    float sx = b0 ? tx.x : tx.y, sy = b0 ? ty.x : ty.y, sz = b0 ? tz.x : tz.y;
-    kx += __shfl_xor_sync(full, sx, 1);
-    ky += __shfl_xor_sync(full, sy, 1);
-    kz += __shfl_xor_sync(full, sz, 1);
-    float v = b1 ? ky : kx, s = b1 ? kx : ky;
-    v += __shfl_xor_sync(full, s, 2);
-    kz += __shfl_xor_sync(full, kz, 2);
-    v += __shfl_xor_sync(full, v, 4);
-    kz += __shfl_xor_sync(full, kz, 4);
-    float* fa = reinterpret_cast<float*>(f + ((size_t)cj * 8 + jq + (b0 ? 4 : 0)));
-    if (il < 4) atomicAdd(fa + (b1 ? 1 : 0), -v);
-    if (il < 2) atomicAdd(fa + 2, -kz);
+    const float2 m1 = dup(-1.0f);
+    float2       dx[NT], dy[NT], dz[NT], r2[NT], rinv[NT], rinvsq[NT], rinv6[NT], c6n[NT], c12[NT], fsum[NT], qq[NT];
+#pragma unroll
+    for (int u = 0; u < NT; u++) dx[u] = fma2(dup(J[u].xq.x), m1, I.x);
+#pragma unroll
+    for (int u = 0; u < NT; u++) dy[u] = fma2(dup(J[u].xq.y), m1, I.y);
+#pragma unroll
+    for (int u = 0; u < NT; u++) dz[u] = fma2(dup(J[u].xq.z), m1, I.z);
+#pragma unroll
+    for (int u = 0; u < NT; u++) r2[u] = mul2(dy[u], dy[u]);
+#pragma unroll
+    for (int u = 0; u < NT; u++) r2[u] = fma2(dx[u], dx[u], r2[u]);
+#pragma unroll
+    for (int u = 0; u < NT; u++) r2[u] = fma2(dz[u], dz[u], r2[u]);
+#pragma unroll
+    for (int u = 0; u < NT; u++) rinv[u] = make_float2(rsqrt_approx(r2[u].x), rsqrt_approx(r2[u].y));
+#pragma unroll
+    for (int u = 0; u < NT; u++)
+    {
+        if (GEOM)
+        {
+            c6n[u] = mul2(I.c6n, dup(J[u].lj.x));
+            c12[u] = mul2(I.c12, dup(J[u].lj.y));
+        }
+        else
+        {
+            const int    tj = __float_as_int(J[u].lj.x);
+            const float2 pa = __ldg(nbfp + I.t0 + tj), pb = __ldg(nbfp + I.t1 + tj);
+            c6n[u]          = make_float2(-pa.x, -pb.x);
+            c12[u]          = make_float2(pa.y, pb.y);
+        }
+        qq[u] = mul2(I.q, dup(J[u].xq.w));
+    }
+    float2 z2[NT], z4[NT], den[NT], num[NT];
+    if (EEL == 1)
+    {
+#pragma unroll
+        for (int u = 0; u < NT; u++) z2[u] = mul2(dup(K.beta2), r2[u]);
+#pragma unroll
+        for (int u = 0; u < NT; u++) z4[u] = mul2(z2[u], z2[u]);
+#pragma unroll
+        for (int u = 0; u < NT; u++) den[u] = pme_force_den(z2[u], z4[u], K.fd4, K.fd3);
+#pragma unroll
+        for (int u = 0; u < NT; u++) den[u] = make_float2(rcp_approx(den[u].x), rcp_approx(den[u].y));
+#pragma unroll
+        for (int u = 0; u < NT; u++) num[u] = mul2(pme_force_num(z2[u], z4[u], K.fn6, K.fn5), dup(K.beta));
+    }
+#pragma unroll
+    for (int u = 0; u < NT; u++) rinvsq[u] = mul2(rinv[u], rinv[u]);
+#pragma unroll
+    for (int u = 0; u < NT; u++) rinv6[u] = mul2(mul2(rinvsq[u], rinvsq[u]), rinvsq[u]);
+#pragma unroll
+    for (int u = 0; u < NT; u++) fsum[u] = mul2(fma2(c12[u], rinv6[u], c6n[u]), rinv6[u]);
+#pragma unroll
+    for (int u = 0; u < NT; u++)
+    {
+        if (EEL == 1) fsum[u] = fma2(qq[u], fma2(mul2(num[u], den[u]), z2[u], rinv[u]), fsum[u]);
+        else fsum[u] = fma2(qq[u], fma2(r2[u], dup(-P.two_k_rf), rinv[u]), fsum[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < NT; u++)
+    {
+        float2 fscal = mul2(rinvsq[u], fsum[u]);
+        fscal.x      = (r2[u].x < K.rc2) ? fscal.x : 0.0f;
+        fscal.y      = (r2[u].y < K.rc2) ? fscal.y : 0.0f;
+        tx[u]        = mul2(fscal, dx[u]);
+        ty[u]        = mul2(fscal, dy[u]);
+        tz[u]        = mul2(fscal, dz[u]);
+    }
 }
 
+/* j-force: both pairs of the lane act on the same j-atom: sum them (negated: the force on j is minus the force on i), then
+ * a 2-stage reduce-scatter over the 4 lanes (bits 4 and 3) that share the j-atom leaves lane class (b4,b3) = (0,0) with the
+ * x total, (0,1) y, (1,0) z and (1,1) a second copy of z; every lane then issues ONE scalar red.global.add.f32 to float
+ * slot 2*b4+b3 of f[cj*8+jl] -- the copy lands in the float4's pad slot, which nothing reads.  3 shuffles, 4 selects, no
+ * divergent branch (a predicated 16-byte red by 8 lanes compiled to BSSY/BRA/BSYNC plus a convergence check before the
+ * next shuffle: 7 more instructions per tile). */
+struct LaneClass
+{
+    bool  b4, b3, b3or4, b3only;
+    char* f_lane; /* f + jl (float4) + slot * 4 bytes */
+};
+__device__ __forceinline__ void reduce_store_j(const float2 tx, const float2 ty, const float2 tz, const LaneClass& C, int cj)
+{
+    const unsigned full = 0xffffffffu;
+    const float sx = -tx.x - tx.y, sy = -ty.x - ty.y, sz = -tz.x - tz.y;
+    float k0 = C.b4 ? sz : sx;
+    k0 += __shfl_xor_sync(full, C.b4 ? sx : sz, 16);   /* b4=0: x of both halves, b4=1: z of both halves */
+    const float k1 = sy + __shfl_xor_sync(full, sy, 16); /* y of both halves (used by the b4=0 lanes) */
+    float v = C.b3only ? k1 : k0;
+    v += __shfl_xor_sync(full, C.b3or4 ? k0 : k1, 8);
+    atomicAdd(reinterpret_cast<float*>(C.f_lane + (size_t)(unsigned)cj * 128u), v);
+}
+
+template<int NT>
+__device__ __forceinline__ void reduce_store_j_multi(const float2 (&tx)[NT], const float2 (&ty)[NT], const float2 (&tz)[NT], const LaneClass& C,
+                                                     const int (&cj)[NT])
+{
+    const unsigned full = 0xffffffffu;
+    float          sx[NT], sy[NT], sz[NT], k0[NT], k1[NT], v[NT];
+#pragma unroll
+    for (int u = 0; u < NT; u++) sx[u] = -tx[u].x - tx[u].y, sy[u] = -ty[u].x - ty[u].y, sz[u] = -tz[u].x - tz[u].y;
+#pragma unroll
+    for (int u = 0; u < NT; u++) k0[u] = __shfl_xor_sync(full, C.b4 ? sx[u] : sz[u], 16);
+#pragma unroll
+    for (int u = 0; u < NT; u++) k1[u] = __shfl_xor_sync(full, sy[u], 16);
+#pragma unroll
+    for (int u = 0; u < NT; u++) k0[u] += C.b4 ? sz[u] : sx[u], k1[u] += sy[u];
+#pragma unroll
+    for (int u = 0; u < NT; u++) v[u] = __shfl_xor_sync(full, C.b3or4 ? k0[u] : k1[u], 8);
+#pragma unroll
+    for (int u = 0; u < NT; u++) v[u] += C.b3only ? k1[u] : k0[u];
+#pragma unroll
+    for (int u = 0; u < NT; u++)
+    {
+#ifdef B200NB_DIAG_NO_RED /* diagnostic build only: drops the j-force scatter (wrong results) to measure its cost */
+        if (v[u] == 12345.678f)
+#endif
+            atomicAdd(reinterpret_cast<float*>(C.f_lane + (size_t)(unsigned)cj[u] * 128u), v[u]);
+    }
+}
+
+#ifndef B200NB_FORCE_MIN_BLOCKS
+#define B200NB_FORCE_MIN_BLOCKS 4
+#endif
 template<int EEL, bool GEOM, bool VF>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, B200NB_FORCE_MIN_BLOCKS)
 k_force(const Entry* __restrict__ entries, long long nentries, const int* __restrict__ tcj, const uint64_t* __restrict__ tmask,
-        const float* __restrict__ xq, const float* __restrict__ lj, const int* __restrict__ atype, const float2* __restrict__ nbfp,
+        const float4* __restrict__ xq, const float2* __restrict__ lj, const int* __restrict__ atype, const float2* __restrict__ nbfp,
         const float* __restrict__ shift_vec, float4* __restrict__ f, float* __restrict__ fshift, double* __restrict__ energy,
-        const NbParamsDev P, const int intra)
+        const __grid_constant__ NbParamsDev P, const int intra, const int maxt, const float* __restrict__ kconst)
 {
     const long long e = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (e >= nentries) return;
-    const int4 ev = __ldg(reinterpret_cast<const int4*>(entries) + e);
+    const int4 ev    = __ldg(reinterpret_cast<const int4*>(entries) + e);
     const int  start = ev.z, end = ev.w;
     if (start >= end) return;
     const int lane = threadIdx.x & 31;
-    IData     I;
-    I.il    = lane & 7;
-    I.jq    = lane >> 3;
-    I.ci    = ev.x;
-    I.shift = ev.y & 255;
-    const int nmask = ev.y >> 8;
+    const int jl = lane & 7, ih = lane >> 3;
+    const int ci = ev.x, shift = ev.y & 255, nmask = ev.y >> 8;
+    LaneClass C;
+    C.b4     = (lane & 16) != 0;
+    C.b3     = (lane & 8) != 0;
+    C.b3or4  = C.b3 || C.b4;
+    C.b3only = C.b3 && !C.b4;
+    C.f_lane = reinterpret_cast<char*>(f + jl) + 4 * (2 * (int)C.b4 + (int)C.b3);
+    KConst K;
     {
-        const float* xb = xq + (size_t)I.ci * NB_XQ_STRIDE + nb_pairpos(I.il);
-        /* the reference adds the shift to the i-atom before the subtraction: kernel_outer.h:482-489 */
-        I.x    = dup(__fadd_rn(__ldg(xb), __ldg(shift_vec + 3 * I.shift)));
-        I.y    = dup(__fadd_rn(__ldg(xb + 8), __ldg(shift_vec + 3 * I.shift + 1)));
-        I.z    = dup(__fadd_rn(__ldg(xb + 16), __ldg(shift_vec + 3 * I.shift + 2)));
-        I.qraw = __ldg(xb + 24);
-        I.q    = dup(P.epsfac * I.qraw);
+        const float4 k0 = __ldg(reinterpret_cast<const float4*>(kconst)), k1 = __ldg(reinterpret_cast<const float4*>(kconst) + 1);
+        K.rc2 = k0.x, K.beta = k0.y, K.beta2 = k0.z, K.fd4 = k0.w, K.fd3 = k1.x, K.fn6 = k1.y, K.fn5 = k1.z;
     }
-    int tioff = 0;
-    if (GEOM)
-    {
-        const float* lb = lj + (size_t)I.ci * NB_LJ_STRIDE + nb_pairpos(I.il);
-        I.c6            = dup(__ldg(lb));
-        I.c12           = dup(__ldg(lb + 8));
-    }
-    else
-    {
-        tioff = __ldg(atype + (size_t)I.ci * 8 + nb_pairpos(I.il)) * P.ntypes;
-        I.c6 = I.c12 = dup(1.0f);
-    }
-    float2 fix = dup(0.f), fiy = dup(0.f), fiz = dup(0.f);
-    float  evdw = 0.f, ecoul = 0.f;
+    /* the entry's j-cluster indices and exclusion masks (<= 32 tiles, b200nb_set_params clamps max_tiles_per_entry):
+     * lane k holds tile k's, each tile fetches them with a shuffle */
+    const int ntile = end - start;
+    const int cjreg = __ldg(tcj + start + min(lane, ntile - 1));
+    uint2     mreg  = make_uint2(~0u, ~0u);
+    if (lane < nmask) mreg = __ldg(reinterpret_cast<const uint2*>(tmask) + start + lane);
+    const unsigned full = 0xffffffffu;
 
-    /* software pipeline: j data one tile ahead, j-cluster index two tiles ahead */
-    JData cur, nxt;
-    load_j<GEOM>(cur, __ldg(tcj + start), I.jq, xq, lj, atype, nbfp, tioff);
-    int cj_next = (start + 1 < end) ? __ldg(tcj + start + 1) : cur.cj;
-    for (int t = start; t < end; t++)
+    /* ---- stage the j data of all tiles: every lane copies 16 bytes per instruction ---- */
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char* const sxq = smem_raw + (threadIdx.x >> 5) * (maxt * 192);
+    unsigned char* const slj = sxq + maxt * 128;
     {
-        const int cj_next2 = (t + 2 < end) ? __ldg(tcj + t + 2) : cj_next;
-        load_j<GEOM>(nxt, cj_next, I.jq, xq, lj, atype, nbfp, tioff);
-        float2 tx, ty, tz;
-        if (t - start < nmask)
+        const unsigned sx0 = (unsigned)__cvta_generic_to_shared(sxq), sl0 = (unsigned)__cvta_generic_to_shared(slj);
+        const char*    gx = reinterpret_cast<const char*>(xq);
+        for (int c0 = 0; c0 < ntile * 8; c0 += 32)
         {
-            const uint64_t mask = __ldg(reinterpret_cast<const unsigned long long*>(tmask) + t);
-            const bool     diag = intra && I.shift == B200NB_CENTRAL && cur.cj == I.ci;
-            tile_pairs<EEL, VF, true>(I, cur, P, mask, diag, tx, ty, tz, evdw, ecoul);
-            if (VF && diag && I.jq == 0)
+            const int c  = c0 + lane;
+            const int cj = __shfl_sync(full, cjreg, (c >> 3) & 31);
+            if (c < ntile * 8) cp_async16(sx0 + c * 16, gx + (size_t)(unsigned)cj * 128u + (c & 7) * 16);
+        }
+        if (GEOM)
+        {
+            const char* gl = reinterpret_cast<const char*>(lj);
+            for (int c0 = 0; c0 < ntile * 4; c0 += 32)
             {
-                /* self term, once per atom: kernel_outer.h:408-452 */
-                ecoul -= P.epsfac * I.qraw * I.qraw * P.self_sub;
+                const int c  = c0 + lane;
+                const int cj = __shfl_sync(full, cjreg, (c >> 2) & 31);
+                if (c < ntile * 4) cp_async16(sl0 + c * 16, gl + (size_t)(unsigned)cj * 64u + (c & 3) * 16);
             }
         }
         else
         {
-            tile_pairs<EEL, VF, false>(I, cur, P, ~0ull, false, tx, ty, tz, evdw, ecoul);
+            const char* gt = reinterpret_cast<const char*>(atype);
+            for (int c0 = 0; c0 < ntile * 2; c0 += 32)
+            {
+                const int c  = c0 + lane;
+                const int cj = __shfl_sync(full, cjreg, (c >> 1) & 31);
+                if (c < ntile * 2) cp_async16(sl0 + c * 16, gt + (size_t)(unsigned)cj * 32u + (c & 1) * 16);
+            }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    IData I;
+    {
+        const float4 a = __ldg(xq + (size_t)ci * 8 + 2 * ih), b = __ldg(xq + (size_t)ci * 8 + 2 * ih + 1);
+        const float  sx = __ldg(shift_vec + 3 * shift), sy = __ldg(shift_vec + 3 * shift + 1), sz = __ldg(shift_vec + 3 * shift + 2);
+        /* the reference adds the shift to the i-atom before the subtraction: kernel_outer.h:482-489 */
+        I.x = make_float2(__fadd_rn(a.x, sx), __fadd_rn(b.x, sx));
+        I.y = make_float2(__fadd_rn(a.y, sy), __fadd_rn(b.y, sy));
+        I.z = make_float2(__fadd_rn(a.z, sz), __fadd_rn(b.z, sz));
+        I.q = make_float2(P.epsfac * a.w, P.epsfac * b.w);
+        if (GEOM)
+        {
+            const float4 l = __ldg(reinterpret_cast<const float4*>(lj + (size_t)ci * 8 + 2 * ih));
+            I.c6n          = make_float2(-l.x, -l.z);
+            I.c12          = make_float2(l.y, l.w);
+            I.t0 = I.t1 = 0;
+        }
+        else
+        {
+            const int2 t = __ldg(reinterpret_cast<const int2*>(atype + (size_t)ci * 8 + 2 * ih));
+            I.t0         = t.x * P.ntypes;
+            I.t1         = t.y * P.ntypes;
+            I.c6n = I.c12 = dup(0.0f);
+        }
+    }
+    float2 fix = dup(0.f), fiy = dup(0.f), fiz = dup(0.f);
+    float  evdw = 0.f, ecoul = 0.f;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const unsigned char* const sxq_lane = sxq + jl * 16;
+    const unsigned char* const slj_lane = slj + jl * (GEOM ? 8 : 4);
+    int t = 0;
+
+    /* ---- tiles with exclusion masks (sorted to the front of the entry) ---- */
+    for (; t < nmask; t++)
+    {
+        const int cj = __shfl_sync(full, cjreg, t);
+        JAtom     J;
+        load_j<GEOM>(J, sxq_lane, slj_lane, t);
+        const unsigned mx = __shfl_sync(full, mreg.x, t), my = __shfl_sync(full, mreg.y, t);
+        /* mask word w, bit `lane`: pair (i-atom 2*ih + w, j-atom jl) interacts */
+        const float in0 = (float)((mx >> lane) & 1u), in1 = (float)((my >> lane) & 1u);
+        bool        ok0 = true, ok1 = true;
+        const bool  diag = intra && shift == B200NB_CENTRAL && cj == ci;
+        if (diag)
+        {
+            /* self tile: only j > i (nbnxm/pairlist.cpp:880-904, kernel_gpu_ref.cpp:223-226) */
+            ok0 = jl > 2 * ih;
+            ok1 = jl > 2 * ih + 1;
+            if (VF && jl < 2)
+            {
+                /* self term, once per atom: kernel_outer.h:408-452 */
+                const float qi = (jl == 0 ? I.q.x : I.q.y);
+                ecoul -= qi * qi * P.self_q2;
+            }
+        }
+        float2 tx, ty, tz;
+        tile_pairs<EEL, GEOM, VF, true>(I, J, P, K, nbfp, in0, in1, ok0, ok1, tx, ty, tz, evdw, ecoul);
         fix = add2(fix, tx);
         fiy = add2(fiy, ty);
         fiz = add2(fiz, tz);
-        reduce_store_j(tx, ty, tz, I.il, I.jq, cur.cj, f);
-        cur     = nxt;
-        cj_next = cj_next2;
+        reduce_store_j(tx, ty, tz, C, cj);
     }
-    /* i-force: sum the two packed halves, then over the 4 jq groups (lane bits 3-4) */
-    const unsigned full = 0xffffffffu;
-    float          fx = fix.x + fix.y, fy = fiy.x + fiy.y, fz = fiz.x + fiz.y;
-    fx += __shfl_xor_sync(full, fx, 8);
-    fy += __shfl_xor_sync(full, fy, 8);
-    fz += __shfl_xor_sync(full, fz, 8);
-    fx += __shfl_xor_sync(full, fx, 16);
-    fy += __shfl_xor_sync(full, fy, 16);
-    fz += __shfl_xor_sync(full, fz, 16);
-    if (I.jq == 0) atomicAdd(f + ((size_t)I.ci * 8 + I.il), make_float4(fx, fy, fz, 0.f));
+
+    /* ---- plain tiles ---- */
+    if (!VF)
+    {
+        constexpr int NT = B200NB_TILE_ILP;
+        for (; t + NT <= ntile; t += NT)
+        {
+            JAtom  J[NT];
+            int    cj[NT];
+            float2 tx[NT], ty[NT], tz[NT];
+#pragma unroll
+            for (int u = 0; u < NT; u++)
+            {
+                cj[u] = __shfl_sync(full, cjreg, t + u);
+                load_j<GEOM>(J[u], sxq_lane, slj_lane, t + u);
+            }
+            tile_pairs_multi<EEL, GEOM, NT>(I, J, P, K, nbfp, tx, ty, tz);
+#pragma unroll
+            for (int u = 0; u < NT; u++)
+            {
+                fix = add2(fix, tx[u]);
+                fiy = add2(fiy, ty[u]);
+                fiz = add2(fiz, tz[u]);
+            }
+            reduce_store_j_multi<NT>(tx, ty, tz, C, cj);
+        }
+    }
+    for (; t < ntile; t++)
+    {
+        const int cj = __shfl_sync(full, cjreg, t);
+        JAtom     J;
+        load_j<GEOM>(J, sxq_lane, slj_lane, t);
+        float2 tx, ty, tz;
+        tile_pairs<EEL, GEOM, VF, false>(I, J, P, K, nbfp, 1.f, 1.f, true, true, tx, ty, tz, evdw, ecoul);
+        fix = add2(fix, tx);
+        fiy = add2(fiy, ty);
+        fiz = add2(fiz, tz);
+        reduce_store_j(tx, ty, tz, C, cj);
+    }
+
+    /* ---- i-forces: reduce over the 8 j-lanes (bits 0-2). Stage 1 is transposed: even lanes keep atom i0, odd lanes i1. */
+    const bool     odd  = lane & 1;
+    float          kx = odd ? fix.y : fix.x, ky = odd ? fiy.y : fiy.x, kz = odd ? fiz.y : fiz.x;
+    const float    sx = odd ? fix.x : fix.y, sy = odd ? fiy.x : fiy.y, sz = odd ? fiz.x : fiz.y;
+    kx += __shfl_xor_sync(full, sx, 1);
+    ky += __shfl_xor_sync(full, sy, 1);
+    kz += __shfl_xor_sync(full, sz, 1);
+    kx += __shfl_xor_sync(full, kx, 2);
+    ky += __shfl_xor_sync(full, ky, 2);
+    kz += __shfl_xor_sync(full, kz, 2);
+    kx += __shfl_xor_sync(full, kx, 4);
+    ky += __shfl_xor_sync(full, ky, 4);
+    kz += __shfl_xor_sync(full, kz, 4);
+    /* lanes with jl in {0,1} hold the total force on i-atom 2*ih + jl */
+    if (jl < 2) atomicAdd(f + ((size_t)ci * 8 + 2 * ih + jl), make_float4(kx, ky, kz, 0.f));
     if (VF)
     {
-        /* shift force = sum of the i-forces of this entry (kernel_outer.h:620-640; the CUDA kernel skips
-         * the central shift, nbnxm_cuda_kernel.cuh:624-628) */
-        if (I.shift != B200NB_CENTRAL)
+        /* shift force = sum of the i-forces of this entry (kernel_outer.h:620-640; the CUDA kernel skips the central
+         * shift, nbnxm_cuda_kernel.cuh:624-628) */
+        if (shift != B200NB_CENTRAL)
         {
-            fx += __shfl_xor_sync(full, fx, 1);
-            fy += __shfl_xor_sync(full, fy, 1);
-            fz += __shfl_xor_sync(full, fz, 1);
-            fx += __shfl_xor_sync(full, fx, 2);
-            fy += __shfl_xor_sync(full, fy, 2);
-            fz += __shfl_xor_sync(full, fz, 2);
-            fx += __shfl_xor_sync(full, fx, 4);
-            fy += __shfl_xor_sync(full, fy, 4);
-            fz += __shfl_xor_sync(full, fz, 4);
+            kx += __shfl_xor_sync(full, kx, 1);
+            ky += __shfl_xor_sync(full, ky, 1);
+            kz += __shfl_xor_sync(full, kz, 1);
+            kx += __shfl_xor_sync(full, kx, 8);
+            ky += __shfl_xor_sync(full, ky, 8);
+            kz += __shfl_xor_sync(full, kz, 8);
+            kx += __shfl_xor_sync(full, kx, 16);
+            ky += __shfl_xor_sync(full, ky, 16);
+            kz += __shfl_xor_sync(full, kz, 16);
             if (lane == 0)
             {
-                atomicAdd(fshift + 3 * I.shift, fx);
-                atomicAdd(fshift + 3 * I.shift + 1, fy);
-                atomicAdd(fshift + 3 * I.shift + 2, fz);
+                atomicAdd(fshift + 3 * shift, kx);
+                atomicAdd(fshift + 3 * shift + 1, ky);
+                atomicAdd(fshift + 3 * shift + 2, kz);
             }
         }
         for (int o = 16; o > 0; o >>= 1)
@@ -378,9 +589,12 @@ template<int EEL, bool GEOM, bool VF>
 int launch(b200nb_context* h, const PairList& L, int intra)
 {
     const unsigned nblk = (unsigned)((L.nentries + 3) / 4);
-    k_force<EEL, GEOM, VF><<<nblk, 128, 0, h->stream>>>(L.entries, L.nentries, L.cj, L.mask, h->d_xq, h->d_lj, h->d_atype,
+    const int    maxt = h->max_tiles;
+    const size_t smem = (size_t)4 * maxt * 192;
+    k_force<EEL, GEOM, VF><<<nblk, 128, smem, h->stream>>>(L.entries, L.nentries, L.cj, L.mask, reinterpret_cast<const float4*>(h->d_xq),
+                                                        reinterpret_cast<const float2*>(h->d_lj), h->d_atype,
                                                         reinterpret_cast<const float2*>(h->d_nbfp), h->d_shift_vec, h->d_f, h->d_fshift,
-                                                        h->d_energy, h->dp, intra);
+                                                        h->d_energy, h->dp, intra, maxt, h->d_kconst);
     h->nlaunches++;
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return nb_fail(h, B200NB_ERR_CUDA, std::string("force kernel launch: ") + cudaGetErrorString(err));

@@ -214,7 +214,7 @@ class DomainRank:
         if hasattr(transport, "sync"):
             transport.sync = self.nb.synchronize
         self.nb.set_params(system.nbfp, rc, rlist_outer=self.rlist, rlist_inner=options.rlistInner or 0.0,
-                           **interaction_kwargs(options))
+                           max_tiles_per_entry=options.maxTilesPerEntry, **interaction_kwargs(options))
         types, q, eo, ei = p.local_topology(system.types, system.q, system.excl_off, system.excl_idx)
         self.nb.set_atoms(types, q, eo, ei)
         self.nb.set_box(system.box, pbc=(0 if self.nranks > 1 else 1, 1, 1))

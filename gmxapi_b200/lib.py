@@ -43,7 +43,8 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(_HERE, "libb200nb.so")
+    # B200NB_LIBRARY: alternative build of the same C ABI (kernel tuning experiments under profiles/tools)
+    return os.environ.get("B200NB_LIBRARY") or os.path.join(_HERE, "libb200nb.so")
 
 
 def load_library():

@@ -35,6 +35,7 @@ class NBKernelOptions:
     # extensions beyond the reference's options: dynamic pruning radii (PairlistParams, pairlistparams.h:105-131)
     rlistOuter: float = 0.0
     rlistInner: float = 0.0
+    maxTilesPerEntry: int = 0  # list balancing granularity (split_sci_entry, pairlist.cpp:2077-2194); 0 = library default
     epsilonRf: float = 1.0  # interaction_const_t::epsilon_rf as gmxsetup.cpp:251-253 leaves it; 0 = infinity
     device: int = 0
 
@@ -93,7 +94,7 @@ class ForceCalculator:
         self.nb = _lib.NbnxmGpu(options.device)
         kw = interaction_kwargs(options)
         self.nb.set_params(state.nonbondedParameters, rc, rlist_outer=options.rlistOuter or rc,
-                           rlist_inner=options.rlistInner or 0.0, **kw)
+                           rlist_inner=options.rlistInner or 0.0, max_tiles_per_entry=options.maxTilesPerEntry, **kw)
         self.nb.set_atoms(state.types, state.charges, state.excl_off, state.excl_idx)
         self._set_particles_on_grid(state.coordinates, state.box)
         self.nb.build_pairlist()  # constructPairList, gmxsetup.cpp:299-303
