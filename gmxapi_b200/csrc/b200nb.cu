@@ -73,13 +73,15 @@ extern "C" int b200nb_create(b200nb_t** out, int device)
         return B200NB_ERR_CUDA;
     }
     cudaMalloc((void**)&h->d_shift_vec, sizeof(float) * B200NB_SHIFTS * 3);
-    cudaMalloc((void**)&h->d_fshift, sizeof(float) * B200NB_SHIFTS * 3);
-    cudaMalloc((void**)&h->d_energy, sizeof(double) * 2);
+    cudaMalloc((void**)&h->d_fshift, sizeof(float) * NB_OUT_COPIES * NB_FSHIFT_PITCH);
+    cudaMalloc((void**)&h->d_energy, sizeof(double) * NB_OUT_COPIES * 2);
+    cudaMalloc((void**)&h->d_fshift_sum, sizeof(float) * NB_FSHIFT_PITCH);
+    cudaMalloc((void**)&h->d_energy_sum, sizeof(double) * 2);
     cudaMalloc((void**)&h->d_scratch, sizeof(int) * 64);
     cudaMalloc((void**)&h->d_kconst, sizeof(float) * 8);
     cudaMalloc((void**)&h->d_counter, sizeof(long long) * 8);
-    cudaMemsetAsync(h->d_fshift, 0, sizeof(float) * B200NB_SHIFTS * 3, h->stream);
-    cudaMemsetAsync(h->d_energy, 0, sizeof(double) * 2, h->stream);
+    cudaMemsetAsync(h->d_fshift, 0, sizeof(float) * NB_OUT_COPIES * NB_FSHIFT_PITCH, h->stream);
+    cudaMemsetAsync(h->d_energy, 0, sizeof(double) * NB_OUT_COPIES * 2, h->stream);
     *out = h;
     return B200NB_OK;
 }
@@ -101,12 +103,16 @@ extern "C" void b200nb_destroy(b200nb_t* h)
                      h->d_x,          h->d_fout,     h->d_col_of_atom, h->d_col_count, h->d_col_cell0, h->d_col_fill,
                      h->d_atom_index, h->d_slot_of_atom, h->d_xq,   h->d_lj,           h->d_atype,     h->d_bb,
                      h->d_cellz,      h->d_f,        h->d_fshift,   h->d_energy,       h->d_scratch,   h->d_counter,
+                     h->d_fshift_sum, h->d_energy_sum,
                      h->d_cnt_tiles,  h->d_cnt_entries, h->d_flush };
     for (void* p : ptrs) cudaFree(p);
     for (int l = 0; l < 2; l++)
     {
         if (!h->inner_is_outer) free_list(h->inner[l]);
         free_list(h->outer[l]);
+        cudaFree(h->packed[l].entries);
+        cudaFree(h->packed[l].ja);
+        cudaFree(h->packed[l].mask);
     }
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -156,7 +162,7 @@ static int ensure_pinned(b200nb_context* h, size_t bytes)
     if (bytes <= h->pinned_bytes) return 0;
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     h->h_pinned = nullptr;
-    NB_CUDA(h, cudaMallocHost((void**)&h->h_pinned, bytes * 2));
+    NB_CUDA(h, cudaHostAlloc((void**)&h->h_pinned, bytes * 2, cudaHostAllocMapped));
     h->pinned_bytes = bytes * 2;
     return 0;
 }
@@ -996,7 +1002,7 @@ k_prune(const Entry* __restrict__ oe, const int* __restrict__ ocj, const uint64_
     if (e >= nentries) return;
     const int   lane = threadIdx.x & 31, jl = lane & 7, ih = lane >> 3;
     const Entry en   = oe[e];
-    const int   shift = en.shift_nmask & 255, nmask = en.shift_nmask >> 8;
+    const int   shift = NB_ENTRY_SHIFT(en.shift_nmask), nmask = NB_ENTRY_NMASK(en.shift_nmask);
     const float4 xa = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + 2 * ih];
     const float4 xb = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + 2 * ih + 1];
     const float  sx = shift_vec[3 * shift], sy = shift_vec[3 * shift + 1], sz = shift_vec[3 * shift + 2];
@@ -1027,6 +1033,124 @@ k_prune(const Entry* __restrict__ oe, const int* __restrict__ ocj, const uint64_
         o.end         = en.start + kept;
         ie[e]         = o;
     }
+}
+
+/* Re-pack entries of the cluster-pair list at j-atom granularity for the force kernel (PackedList, b200nb_internal.h).
+ * One warp per entry, lane = jl + 8*ih as everywhere.  A j-atom is kept iff one of its pairs with the entry's 8 i-atoms has
+ * r^2 < rlist2 and is not removed by the j > i rule of the self tile; kept j-atoms that have an excluded pair (or belong to
+ * the self tile) are placed first so that only the leading tiles need masks.  Excluded pairs inside the cut-off must stay:
+ * the kernels evaluate their Ewald / reaction-field exclusion correction (kernel_inner.h:330-360).
+ * The reference has no such step: its GPU list stays at 8x8 cluster-pair granularity with per-pair masks
+ * (nbnxm/pairlist.h:190-225); this is the same pruning idea as nbnxn_kernel_prune_cuda taken down to single j-atoms. */
+__global__ void __launch_bounds__(128)
+k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t* __restrict__ imask, long long nentries, int part,
+       int nparts, const float* __restrict__ xq, const float* __restrict__ shift_vec, float rlist2, int intra, int dummy_slot, int pitch,
+       Entry* __restrict__ pe, int* __restrict__ pja, uint64_t* __restrict__ pmask)
+{
+    __shared__ int      s_ja[4][32 * 8];
+    __shared__ unsigned s_m0[4][32], s_m1[4][32];
+    const int       w   = threadIdx.x >> 5;
+    const long long wid = (long long)blockIdx.x * 4 + w;
+    const long long e   = wid * nparts + part;
+    if (e >= nentries) return;
+    const int   lane = threadIdx.x & 31, jl = lane & 7, ih = lane >> 3;
+    const Entry en   = ie[e];
+    const int   shift = NB_ENTRY_SHIFT(en.shift_nmask), nmask = NB_ENTRY_NMASK(en.shift_nmask);
+    const int   ntile = min(en.end - en.start, 32);
+    for (int k = lane; k < ntile * 8; k += 32) s_ja[w][k] = dummy_slot + (int)(e & (NB_DUMMY_SLOTS / 8 - 1)) * 8 + (k & 7);
+    s_m0[w][lane] = 0u;
+    s_m1[w][lane] = 0u;
+    __syncwarp();
+    const float4 xa = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + 2 * ih];
+    const float4 xb = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + 2 * ih + 1];
+    const float  sx = shift_vec[3 * shift], sy = shift_vec[3 * shift + 1], sz = shift_vec[3 * shift + 2];
+    const float  xi0 = xa.x + sx, yi0 = xa.y + sy, zi0 = xa.z + sz, xi1 = xb.x + sx, yi1 = xb.y + sy, zi1 = xb.z + sz;
+    int n = 0, nm = 0, has_self = 0;
+    for (int pass = 0; pass < 2; pass++)
+    {
+        const int tend = pass == 0 ? nmask : ntile;
+        for (int t = 0; t < tend; t++)
+        {
+            const int      cj   = icj[en.start + t];
+            const uint64_t m    = (t < nmask) ? imask[en.start + t] : ~0ull;
+            const bool     diag = intra && shift == B200NB_CENTRAL && cj == en.ci;
+            if (diag) has_self = 1;
+            const float4   xj   = reinterpret_cast<const float4*>(xq)[(size_t)cj * 8 + jl];
+            const bool     ina  = nb_rsq(xi0, yi0, zi0, xj.x, xj.y, xj.z) < rlist2 && !(diag && jl <= 2 * ih);
+            const bool     inb  = nb_rsq(xi1, yi1, zi1, xj.x, xj.y, xj.z) < rlist2 && !(diag && jl <= 2 * ih + 1);
+            const unsigned ba = (unsigned)(m >> lane) & 1u, bb = (unsigned)(m >> (32 + lane)) & 1u;
+            unsigned       kb = __ballot_sync(0xffffffffu, ina || inb);
+            unsigned       sb = __ballot_sync(0xffffffffu, !(ba && bb) || diag);
+            kb                = (kb | (kb >> 8) | (kb >> 16) | (kb >> 24)) & 0xffu;
+            sb                = (sb | (sb >> 8) | (sb >> 16) | (sb >> 24)) & 0xffu;
+            const unsigned sel = pass == 0 ? (kb & sb) : (kb & ~sb);
+            if ((sel >> jl) & 1u)
+            {
+                const int pos = n + __popc(sel & ((1u << jl) - 1u));
+                if (ih == 0) s_ja[w][pos] = cj * 8 + jl;
+                const int dl = (pos & 7) + 8 * ih;
+                atomicOr(&s_m0[w][pos >> 3], ba << dl);
+                atomicOr(&s_m1[w][pos >> 3], bb << dl);
+            }
+            n += __popc(sel);
+        }
+        if (pass == 0) nm = n;
+    }
+    __syncwarp();
+    const int       ntp = (n + 7) >> 3, nmt = (nm + 7) >> 3;
+    const long long t0  = e * pitch; /* entry e owns packed tiles [e*pitch, (e+1)*pitch) */
+    for (int k = lane; k < ntp * 8; k += 32) pja[(size_t)t0 * 8 + k] = s_ja[w][k];
+    if (lane < ntp) pmask[t0 + lane] = lane < nmt ? (((uint64_t)s_m1[w][lane] << 32) | s_m0[w][lane]) : ~0ull;
+    if (lane == 0)
+    {
+        Entry o;
+        o.ci          = en.ci;
+        o.shift_nmask = shift | (nmt << 8) | (has_self << 24);
+        o.start       = (int)t0;
+        o.end         = (int)t0 + ntp;
+        pe[e]         = o;
+    }
+}
+
+static int ensure_packed(b200nb_context* h, PackedList& P, size_t cap_tiles, size_t cap_entries)
+{
+    if (cap_tiles > P.cap_tiles || !P.ja)
+    {
+        cudaFree(P.ja);
+        cudaFree(P.mask);
+        P.ja = nullptr;
+        P.mask = nullptr;
+        NB_CUDA(h, cudaMalloc((void**)&P.ja, std::max<size_t>(cap_tiles, 1) * 8 * sizeof(int)));
+        NB_CUDA(h, cudaMalloc((void**)&P.mask, std::max<size_t>(cap_tiles, 1) * sizeof(uint64_t)));
+        P.cap_tiles = cap_tiles;
+    }
+    if (cap_entries > P.cap_entries || !P.entries)
+    {
+        cudaFree(P.entries);
+        P.entries = nullptr;
+        NB_CUDA(h, cudaMalloc((void**)&P.entries, std::max<size_t>(cap_entries, 1) * sizeof(Entry)));
+        P.cap_entries = cap_entries;
+    }
+    return 0;
+}
+
+/* packs part `part` of `nparts` of the inner list of locality loc */
+static int launch_pack(b200nb_context* h, int loc, int part, int nparts)
+{
+    const PairList& I = h->inner[loc];
+    PackedList&     P = h->packed[loc];
+    P.nentries        = I.nentries;
+    P.pitch           = h->max_tiles;
+    if (I.nentries == 0) return 0;
+    if ((size_t)I.nentries * P.pitch > 2000000000ull) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: packed list exceeds 2^31 tiles");
+    if (ensure_packed(h, P, I.cap_entries * P.pitch, I.cap_entries)) return B200NB_ERR_CUDA;
+    long long nw = (I.nentries - part + nparts - 1) / nparts;
+    if (nw <= 0) return 0;
+    const float r2 = h->inner_is_outer ? h->dp.rlist_outer2 : h->dp.rlist_inner2;
+    k_pack<<<(unsigned)((nw + 3) / 4), 128, 0, h->stream>>>(I.entries, I.cj, I.mask, I.nentries, part, nparts, h->d_xq, h->d_shift_vec, r2,
+                                                           loc == 0, h->dummy_slot, P.pitch, P.entries, P.ja, P.mask);
+    LAUNCH_CHECK(h);
+    return 0;
 }
 
 static int ensure_list(b200nb_context* h, PairList& l, size_t ntiles, size_t nentries)
@@ -1159,6 +1283,25 @@ extern "C" int b200nb_build_pairlist(b200nb_t* h)
             h->inner[loc] = L;
         }
     }
+    {
+        /* the far-away dummy atoms the packed list pads its last tiles with: NB_DUMMY_SLOTS slots past the grids */
+        if ((size_t)h->npad + NB_DUMMY_SLOTS > h->cap_pad) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: no room for the dummy atoms");
+        h->dummy_slot = h->npad;
+        std::vector<float> dxq(4 * NB_DUMMY_SLOTS), dlj(2 * NB_DUMMY_SLOTS, 0.0f);
+        std::vector<int>   dty(NB_DUMMY_SLOTS, h->dp.ntypes - 1);
+        for (int k = 0; k < NB_DUMMY_SLOTS; k++)
+        {
+            dxq[4 * k] = dxq[4 * k + 1] = -3.0e6f;
+            dxq[4 * k + 2]              = -3.0e6f - 64.0f * k;
+            dxq[4 * k + 3]              = 0.0f;
+        }
+        NB_CUDA(h, cudaMemcpyAsync(h->d_xq + 4 * (size_t)h->npad, dxq.data(), sizeof(float) * dxq.size(), cudaMemcpyHostToDevice, h->stream));
+        NB_CUDA(h, cudaMemcpyAsync(h->d_lj + 2 * (size_t)h->npad, dlj.data(), sizeof(float) * dlj.size(), cudaMemcpyHostToDevice, h->stream));
+        NB_CUDA(h, cudaMemcpyAsync(h->d_atype + (size_t)h->npad, dty.data(), sizeof(int) * dty.size(), cudaMemcpyHostToDevice, h->stream));
+        NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    for (int loc = 0; loc < 2; loc++)
+        if (launch_pack(h, loc, 0, 1)) return B200NB_ERR_CUDA;
     NB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->have_list = true;
     return 0;
@@ -1171,7 +1314,10 @@ extern "C" int b200nb_launch_prune(b200nb_t* h, int locality, int part, int num_
     cudaSetDevice(h->device);
     for (int loc = 0; loc < 2; loc++)
         if (locality < 0 || locality == loc)
+        {
             if (launch_prune(h, loc, part, num_parts)) return B200NB_ERR_CUDA;
+            if (!h->inner_is_outer && launch_pack(h, loc, part, num_parts)) return B200NB_ERR_CUDA;
+        }
     return 0;
 }
 
@@ -1239,8 +1385,8 @@ extern "C" int b200nb_clear_outputs(b200nb_t* h)
     if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "clear_outputs: put_on_grid first");
     cudaSetDevice(h->device);
     NB_CUDA(h, cudaMemsetAsync(h->d_f, 0, sizeof(float4) * (size_t)h->npad, h->stream));
-    NB_CUDA(h, cudaMemsetAsync(h->d_fshift, 0, sizeof(float) * B200NB_SHIFTS * 3, h->stream));
-    NB_CUDA(h, cudaMemsetAsync(h->d_energy, 0, sizeof(double) * 2, h->stream));
+    NB_CUDA(h, cudaMemsetAsync(h->d_fshift, 0, sizeof(float) * NB_OUT_COPIES * NB_FSHIFT_PITCH, h->stream));
+    NB_CUDA(h, cudaMemsetAsync(h->d_energy, 0, sizeof(double) * NB_OUT_COPIES * 2, h->stream));
     return 0;
 }
 
@@ -1282,14 +1428,37 @@ extern "C" int b200nb_get_f(b200nb_t* h, float* f, int f_on_device, int accumula
     return 0;
 }
 
+/* The force kernel spreads its per-entry shift-force and energy atomics over NB_OUT_COPIES replicas (thousands of
+ * entries adding to the same 2 + 132 addresses serialise in L2); this sums the replicas: the device half of
+ * gpu_reduce_staged_outputs (gpu_common.h:249-277). */
+__global__ void k_reduce_outputs(const float* __restrict__ fshift, const double* __restrict__ energy, float* __restrict__ fshift_sum,
+                                 double* __restrict__ energy_sum)
+{
+    const int t = threadIdx.x;
+    if (t < B200NB_SHIFTS * 3)
+    {
+        float s = 0.f;
+        for (int c = 0; c < NB_OUT_COPIES; c++) s += fshift[c * NB_FSHIFT_PITCH + t];
+        fshift_sum[t] = s;
+    }
+    else if (t < B200NB_SHIFTS * 3 + 2)
+    {
+        double s = 0.0;
+        for (int c = 0; c < NB_OUT_COPIES; c++) s += energy[2 * c + (t - B200NB_SHIFTS * 3)];
+        energy_sum[t - B200NB_SHIFTS * 3] = s;
+    }
+}
+
 extern "C" int b200nb_get_outputs(b200nb_t* h, float* fshift_host, double* energies_host)
 {
     if (!h) return B200NB_ERR_ARG;
     cudaSetDevice(h->device);
     float  fs[B200NB_SHIFTS * 3];
     double e[2];
-    NB_CUDA(h, cudaMemcpyAsync(fs, h->d_fshift, sizeof(fs), cudaMemcpyDeviceToHost, h->stream));
-    NB_CUDA(h, cudaMemcpyAsync(e, h->d_energy, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
+    k_reduce_outputs<<<1, 160, 0, h->stream>>>(h->d_fshift, h->d_energy, h->d_fshift_sum, h->d_energy_sum);
+    LAUNCH_CHECK(h);
+    NB_CUDA(h, cudaMemcpyAsync(fs, h->d_fshift_sum, sizeof(fs), cudaMemcpyDeviceToHost, h->stream));
+    NB_CUDA(h, cudaMemcpyAsync(e, h->d_energy_sum, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
     NB_CUDA(h, cudaStreamSynchronize(h->stream));
     if (fshift_host)
         for (int k = 0; k < B200NB_SHIFTS * 3; k++) fshift_host[k] += fs[k]; /* gpu_common.h:259-275 accumulates */
@@ -1301,20 +1470,233 @@ extern "C" int b200nb_get_outputs(b200nb_t* h, float* fshift_host, double* energ
     return 0;
 }
 
+__global__ void k_flush(float* p, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 1.0f;
+}
+
+/* ---- one whole step in three launches -------------------------------------------------------------------
+ * k_step_begin: coordinates (atom order) -> grid layout (nbnxn_gpu_x_to_nbat_x_kernel) fused with the clearing of f,
+ *               fshift and the energies (gpu_clear_outputs, cuda/nbnxm_cuda_data_mgmt.cu:350-377);
+ * k_force;
+ * k_step_end:   grid-ordered f -> atom order (reduceKernel, mdlib/gpuforcereduction_impl.cu:70-104).
+ * Both buffer kernels move the atom-order arrays as coalesced 16-byte vectors through shared memory, so x / f may be
+ * device memory or PINNED HOST memory mapped into the device address space: in the host case the kernels read and write
+ * it over PCIe themselves (no separate cudaMemcpyAsync, no staging buffer, two fewer dependent launches per step). */
+struct PrefetchRange
+{
+    const char* p[4];
+    size_t      bytes[4];
+};
+template<bool VEC>
+__global__ void __launch_bounds__(256)
+k_step_begin(const float* __restrict__ x, const int* __restrict__ slot_of_atom, int a0, int a1, float* __restrict__ xq,
+             float4* __restrict__ f, int nclear, float* __restrict__ fshift, double* __restrict__ energy, PrefetchRange pf)
+{
+    __shared__ __align__(16) float sx[768];
+    const int tid = threadIdx.x, t = blockIdx.x * 256 + tid;
+    /* pull the read-only inputs of the force kernel that is about to run (packed list, LJ parameters) into L2 while this
+     * kernel streams the coordinates: its prologue is a chain of dependent loads, ~3x shorter on L2 hits than from HBM */
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        for (size_t o = (size_t)t * 128; o < pf.bytes[r]; o += (size_t)gridDim.x * 256 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf.p[r] + o));
+    if (t < nclear) f[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < NB_OUT_COPIES * NB_FSHIFT_PITCH) fshift[t] = 0.f;
+    if (t < NB_OUT_COPIES * 2) energy[t] = 0.0;
+    const int base = a0 + blockIdx.x * 256;
+    const int nb   = min(256, a1 - base);
+    if (nb <= 0) return;
+    const float* src = x + 3 * (size_t)base;
+    const int    nfl = nb * 3;
+    if (VEC)
+    {
+        if (tid * 4 + 3 < nfl) *reinterpret_cast<float4*>(&sx[tid * 4]) = reinterpret_cast<const float4*>(src)[tid];
+        else
+            for (int k = tid * 4; k < nfl && k < tid * 4 + 4; k++) sx[k] = src[k];
+    }
+    else
+        for (int k = tid; k < nfl; k += 256) sx[k] = src[k];
+    __syncthreads();
+    if (tid < nb)
+    {
+        float* xb = xq + 4 * (size_t)slot_of_atom[base + tid];
+        xb[0]     = sx[3 * tid];
+        xb[1]     = sx[3 * tid + 1];
+        xb[2]     = sx[3 * tid + 2];
+    }
+}
+
+template<bool VEC>
+__global__ void __launch_bounds__(256)
+k_step_end(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom, int a0, int a1, float* __restrict__ f)
+{
+    __shared__ __align__(16) float sf[768];
+    const int tid  = threadIdx.x;
+    const int base = a0 + blockIdx.x * 256;
+    const int nb   = min(256, a1 - base);
+    if (nb <= 0) return;
+    if (tid < nb)
+    {
+        const float4 v  = fg[slot_of_atom[base + tid]];
+        sf[3 * tid]     = v.x;
+        sf[3 * tid + 1] = v.y;
+        sf[3 * tid + 2] = v.z;
+    }
+    __syncthreads();
+    float*    dst = f + 3 * (size_t)base;
+    const int nfl = nb * 3;
+    if (VEC)
+    {
+        if (tid * 4 + 3 < nfl) reinterpret_cast<float4*>(dst)[tid] = *reinterpret_cast<const float4*>(&sf[tid * 4]);
+        else
+            for (int k = tid * 4; k < nfl && k < tid * 4 + 4; k++) dst[k] = sf[k];
+    }
+    else
+        for (int k = tid; k < nfl; k += 256) dst[k] = sf[k];
+}
+
+static int launch_step(b200nb_context* h, const float* x_dev, int flags, float* f_dev, cudaEvent_t ev_force0 = nullptr,
+                       cudaEvent_t ev_force1 = nullptr)
+{
+    const int n      = h->natoms;
+    const int nclear = h->npad + NB_DUMMY_SLOTS; /* + the dummy atoms of the packed list */
+    const unsigned nb0 = (unsigned)((std::max(std::max(n, nclear), NB_OUT_COPIES * NB_FSHIFT_PITCH) + 255) / 256), nb1 = (unsigned)((n + 255) / 256);
+    PrefetchRange pf{};
+    {
+        const PackedList& P = h->packed[0];
+        pf.p[0]     = reinterpret_cast<const char*>(P.entries);
+        pf.bytes[0] = sizeof(Entry) * (size_t)P.nentries;
+        pf.p[1]     = reinterpret_cast<const char*>(P.ja);
+        pf.bytes[1] = sizeof(int) * 8 * (size_t)P.nentries * P.pitch;
+        pf.p[2]     = reinterpret_cast<const char*>(P.mask);
+        pf.bytes[2] = sizeof(uint64_t) * (size_t)P.nentries * P.pitch;
+        pf.p[3]     = reinterpret_cast<const char*>(h->comb_geom ? (const void*)h->d_lj : (const void*)h->d_atype);
+        pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
+    }
+    if ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0)
+        k_step_begin<true><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf);
+    else
+        k_step_begin<false><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf);
+    LAUNCH_CHECK(h);
+    int rc;
+    if (ev_force0) NB_CUDA(h, cudaEventRecord(ev_force0, h->stream));
+    if ((rc = b200nb_launch_force(h, -1, flags))) return rc;
+    if (ev_force1) NB_CUDA(h, cudaEventRecord(ev_force1, h->stream));
+    if ((reinterpret_cast<uintptr_t>(f_dev) & 15) == 0) k_step_end<true><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, 0, n, f_dev);
+    else k_step_end<false><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, 0, n, f_dev);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+/* device-resident step (the reference's GPU buffer-ops path, mdlib/sim_util.cpp:1043-1108): asynchronous on the stream */
+extern "C" int b200nb_step(b200nb_t* h, const float* x_dev, int flags, float* f_dev)
+{
+    if (!h || !x_dev || !f_dev) return nb_fail(h, B200NB_ERR_ARG, "step: bad argument");
+    if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "step: no pair list");
+    if (h->grid[1].valid) return nb_fail(h, B200NB_ERR_STATE, "step: single-domain call on a context with a halo grid");
+    cudaSetDevice(h->device);
+    return launch_step(h, x_dev, flags, f_dev);
+}
+
+/* Times `niter` device-resident steps with CUDA events on the context's stream: the whole step and, inside it, the
+ * force kernel alone (events recorded right before and after its launch), optionally with L2 flushed before each step. */
+extern "C" int b200nb_time_step(b200nb_t* h, const float* x_dev, float* f_dev, int flags, int nwarm, int niter, int flush_l2,
+                                float* ms_step_avg, float* ms_force_avg)
+{
+    if (!h || !x_dev || !f_dev || niter < 1) return nb_fail(h, B200NB_ERR_ARG, "time_step: bad argument");
+    if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "time_step: no pair list");
+    cudaSetDevice(h->device);
+    if (flush_l2 && !h->d_flush)
+    {
+        h->flush_bytes = (size_t)256 << 20; /* > 126 MB L2 */
+        NB_CUDA(h, cudaMalloc((void**)&h->d_flush, h->flush_bytes));
+    }
+    cudaEvent_t ev[4];
+    for (auto& e : ev) NB_CUDA(h, cudaEventCreate(&e));
+    int rc;
+    for (int i = 0; i < nwarm; i++)
+        if ((rc = launch_step(h, x_dev, flags, f_dev))) return rc;
+    double tstep = 0, tforce = 0;
+    for (int i = 0; i < niter; i++)
+    {
+        if (flush_l2) k_flush<<<148 * 8, 256, 0, h->stream>>>(h->d_flush, h->flush_bytes / sizeof(float));
+        NB_CUDA(h, cudaEventRecord(ev[0], h->stream));
+        if ((rc = launch_step(h, x_dev, flags, f_dev, ev[1], ev[2]))) return rc;
+        NB_CUDA(h, cudaEventRecord(ev[3], h->stream));
+        NB_CUDA(h, cudaEventSynchronize(ev[3]));
+        float a = 0, b = 0;
+        NB_CUDA(h, cudaEventElapsedTime(&a, ev[0], ev[3]));
+        NB_CUDA(h, cudaEventElapsedTime(&b, ev[1], ev[2]));
+        tstep += a;
+        tforce += b;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (ms_step_avg) *ms_step_avg = (float)(tstep / niter);
+    if (ms_force_avg) *ms_force_avg = (float)(tforce / niter);
+    return 0;
+}
+
+/* device-visible address of a host buffer: pinned (cudaHostAlloc / cudaHostRegister) memory is used in place */
+static float* mapped_host_pointer(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type == cudaMemoryTypeHost && at.devicePointer) return static_cast<float*>(at.devicePointer);
+    return nullptr;
+}
+
 extern "C" int b200nb_compute(b200nb_t* h, const float* x_host, int flags, float* f_host, float* fshift_host, double* energies_host)
 {
     if (!h || !x_host || !f_host) return nb_fail(h, B200NB_ERR_ARG, "compute: bad argument");
     if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "compute: no pair list");
-    int rc;
-    if ((rc = b200nb_set_x(h, x_host, 0, 0, h->natoms))) return rc;
-    if ((rc = b200nb_clear_outputs(h))) return rc;
-    if ((rc = b200nb_launch_force(h, -1, flags))) return rc;
-    if ((rc = b200nb_get_f(h, f_host, 0, 0, 0, h->natoms))) return rc;
-    if (fshift_host || energies_host)
+    if (h->grid[1].valid) return nb_fail(h, B200NB_ERR_STATE, "compute: single-domain call on a context with a halo grid");
+    cudaSetDevice(h->device);
+    const size_t bytes = sizeof(float) * 3 * (size_t)h->natoms;
+    if (h->map_x_host != x_host || h->map_f_host != f_host)
     {
-        if (fshift_host) memset(fshift_host, 0, sizeof(float) * B200NB_SHIFTS * 3);
-        if (energies_host) energies_host[0] = energies_host[1] = 0;
-        if ((rc = b200nb_get_outputs(h, fshift_host, energies_host))) return rc;
+        h->map_x_host = x_host;
+        h->map_f_host = f_host;
+        h->map_x_dev  = mapped_host_pointer(x_host);
+        h->map_f_dev  = mapped_host_pointer(f_host);
+    }
+    const bool want_out = fshift_host || energies_host;
+    /* pinned scratch: [x staging][f staging][fshift 135 floats][energies 2 doubles] */
+    const size_t off_out = 2 * ((bytes + 255) & ~(size_t)255);
+    if ((!h->map_x_dev || !h->map_f_dev || want_out) && ensure_pinned(h, off_out + 1024)) return B200NB_ERR_CUDA;
+    const float* xd = h->map_x_dev;
+    float*       fd = h->map_f_dev;
+    if (!xd)
+    {
+        /* pageable coordinates: one CPU copy into our own pinned buffer, which the kernel then reads in place */
+        memcpy(h->h_pinned, x_host, bytes);
+        xd = mapped_host_pointer(h->h_pinned);
+    }
+    if (!fd) fd = mapped_host_pointer(h->h_pinned + off_out / 2);
+    if (!xd || !fd) return nb_fail(h, B200NB_ERR_CUDA, "compute: pinned host memory is not mapped into the device address space");
+    int rc;
+    if ((rc = launch_step(h, xd, flags, fd))) return rc;
+    float*  fs_pin = reinterpret_cast<float*>(h->h_pinned + off_out);
+    double* e_pin  = reinterpret_cast<double*>(h->h_pinned + off_out + 640);
+    if (want_out)
+    {
+        k_reduce_outputs<<<1, 160, 0, h->stream>>>(h->d_fshift, h->d_energy, h->d_fshift_sum, h->d_energy_sum);
+        LAUNCH_CHECK(h);
+        NB_CUDA(h, cudaMemcpyAsync(fs_pin, h->d_fshift_sum, sizeof(float) * B200NB_SHIFTS * 3, cudaMemcpyDeviceToHost, h->stream));
+        NB_CUDA(h, cudaMemcpyAsync(e_pin, h->d_energy_sum, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->stream));
+    }
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (!h->map_f_dev) memcpy(f_host, h->h_pinned + off_out / 2, bytes);
+    if (fshift_host) memcpy(fshift_host, fs_pin, sizeof(float) * B200NB_SHIFTS * 3);
+    if (energies_host)
+    {
+        energies_host[0] = e_pin[0];
+        energies_host[1] = e_pin[1];
     }
     return 0;
 }
@@ -1408,6 +1790,19 @@ extern "C" int b200nb_get_stats(b200nb_t* h, b200nb_stats_t* out)
             }
         }
     }
+    if (h->have_list)
+        for (int l = 0; l < 2; l++)
+            if (h->packed[l].nentries)
+            {
+                long long v = 0;
+                NB_CUDA(h, cudaMemsetAsync(h->d_counter + 4, 0, sizeof(long long), h->stream));
+                k_count_tiles<<<(unsigned)((h->packed[l].nentries + 255) / 256), 256, 0, h->stream>>>(h->packed[l].entries,
+                                                                                                    h->packed[l].nentries, h->d_counter + 4);
+                LAUNCH_CHECK(h);
+                NB_CUDA(h, cudaMemcpyAsync(&v, h->d_counter + 4, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+                NB_CUDA(h, cudaStreamSynchronize(h->stream));
+                out->ntiles_packed += v;
+            }
     out->nlaunches = h->nlaunches;
     return 0;
 }
@@ -1453,33 +1848,33 @@ extern "C" long long b200nb_get_tiles(b200nb_t* h, int outer, int* tiles_host, l
     return n;
 }
 
-/* every interacting atom pair of the list: mask bit set, not on/below the diagonal of a self tile, both
- * atoms real, r^2 < r2 -- the same predicate the force kernel applies */
+/* every interacting atom pair of the PACKED list (what the force kernel consumes): mask bit set, not on/below the
+ * diagonal of the i-cluster's own atoms, both atoms real, r^2 < r2 -- the same predicate the force kernel applies */
 __global__ void __launch_bounds__(128)
-k_pairs(const Entry* __restrict__ ent, const int* __restrict__ tcj, const uint64_t* __restrict__ tmask, long long nentries,
-        const float* __restrict__ xq, const float* __restrict__ shift_vec, const int* __restrict__ atom_index, float r2, int intra,
-        int* __restrict__ out, long long cap, unsigned long long* __restrict__ counter)
+k_pairs(const Entry* __restrict__ ent, const int* __restrict__ pja, const uint64_t* __restrict__ tmask, long long nentries,
+        const float* __restrict__ xq, const float* __restrict__ shift_vec, const int* __restrict__ atom_index, int nslots, float r2,
+        int intra, int* __restrict__ out, long long cap, unsigned long long* __restrict__ counter)
 {
     const long long e = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (e >= nentries) return;
     const int   lane = threadIdx.x & 31, jl = lane & 7, ih = lane >> 3;
     const Entry en   = ent[e];
-    const int   shift = en.shift_nmask & 255, nmask = en.shift_nmask >> 8;
+    const int   shift = NB_ENTRY_SHIFT(en.shift_nmask), nmask = NB_ENTRY_NMASK(en.shift_nmask);
     const float sx = shift_vec[3 * shift], sy = shift_vec[3 * shift + 1], sz = shift_vec[3 * shift + 2];
     for (int t = en.start; t < en.end; t++)
     {
-        const int      cj   = tcj[t];
+        const int      js   = pja[(size_t)t * 8 + jl];
         const uint64_t mask = (t - en.start < nmask) ? tmask[t] : ~0ull;
-        const bool     diag = intra && shift == B200NB_CENTRAL && cj == en.ci;
-        const float4   xj   = reinterpret_cast<const float4*>(xq)[(size_t)cj * 8 + jl];
-        const int      aj   = atom_index[cj * 8 + jl];
+        const bool     diag = intra && shift == B200NB_CENTRAL && (js >> 3) == en.ci;
+        const float4   xj   = reinterpret_cast<const float4*>(xq)[js];
+        const int      aj   = js < nslots ? atom_index[js] : -1;
         for (int w = 0; w < 2; w++)
         {
             const int    i  = 2 * ih + w;
             const float4 xi = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + i];
             const float  r  = nb_rsq(xi.x + sx, xi.y + sy, xi.z + sz, xj.x, xj.y, xj.z);
             const int    ai = atom_index[en.ci * 8 + i];
-            bool ok = (r < r2) && ((mask >> (32 * w + lane)) & 1ull) && ai >= 0 && aj >= 0 && !(diag && jl <= i);
+            bool ok = (r < r2) && ((mask >> (32 * w + lane)) & 1ull) && ai >= 0 && aj >= 0 && !(diag && (js & 7) <= i);
             if (ok)
             {
                 unsigned long long pos = atomicAdd(counter, 1ull);
@@ -1505,10 +1900,10 @@ extern "C" long long b200nb_get_pairs(b200nb_t* h, float r, int* pairs_host, lon
     cudaMemsetAsync(h->d_counter + 5, 0, sizeof(long long), h->stream);
     for (int l = 0; l < 2; l++)
     {
-        const PairList& L = h->inner[l];
+        const PackedList& L = h->packed[l];
         if (L.nentries == 0) continue;
-        k_pairs<<<(unsigned)((L.nentries + 3) / 4), 128, 0, h->stream>>>(L.entries, L.cj, L.mask, L.nentries, h->d_xq, h->d_shift_vec,
-                                                                         h->d_atom_index, r * r, l == 0, d_out, d_out ? cap : 0,
+        k_pairs<<<(unsigned)((L.nentries + 3) / 4), 128, 0, h->stream>>>(L.entries, L.ja, L.mask, L.nentries, h->d_xq, h->d_shift_vec,
+                                                                         h->d_atom_index, h->npad, r * r, l == 0, d_out, d_out ? cap : 0,
                                                                          (unsigned long long*)(h->d_counter + 5));
         h->nlaunches++;
     }
@@ -1522,12 +1917,6 @@ extern "C" long long b200nb_get_pairs(b200nb_t* h, float r, int* pairs_host, lon
     }
     if (cudaGetLastError() != cudaSuccess) return nb_fail(h, B200NB_ERR_CUDA, "get_pairs: kernel failed");
     return n;
-}
-
-__global__ void k_flush(float* p, size_t n)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 1.0f;
 }
 
 extern "C" int b200nb_time_force_kernel(b200nb_t* h, int locality, int flags, int nwarm, int niter, int flush_l2, float* ms_avg)

@@ -14,6 +14,9 @@
 #define NB_CELL 64   /* atoms per grid cell = 8 clusters (nbnxm/pairlistparams.h:69-77) */
 #define NB_MIN_RSQ 3.82e-07f /* nbnxm/pairlist.h:146 c_nbnxnMinDistanceSquared */
 #define NB_MAX_GROUP_TILES 512 /* staging capacity of one (i-cluster, shift) group in the search */
+#define NB_OUT_COPIES 32   /* replicas of the shift-force / energy accumulators: per-entry atomics spread over them */
+#define NB_FSHIFT_PITCH 136 /* floats per shift-force replica (45*3 rounded up) */
+#define NB_DUMMY_SLOTS 512 /* far-away filler atoms appended after the grids: padding targets of the packed list */
 
 /* Device atom layout, grid (slot) order, slot = cluster*8 + k:
  *   xq     float4 {x, y, z, q} per slot  -- the reference's nbatXYZQ (nbnxm/atomdata.cpp:659-662); one 16-byte load per atom
@@ -40,9 +43,13 @@ struct GridDesc
 struct Entry
 {
     int ci;
-    int shift_nmask; /* bits 0-7 shift index, bits 8.. number of leading tiles that carry a mask */
+    int shift_nmask; /* bits 0-7 shift index, bits 8-23 number of leading tiles that carry a mask, bit 24 (packed list
+                        only): the entry holds the i-cluster's self tile (Coulomb self term, kernel_outer.h:408-452) */
     int start, end;  /* tile range */
 };
+#define NB_ENTRY_SHIFT(v) ((v)&255)
+#define NB_ENTRY_NMASK(v) (((v) >> 8) & 0xffff)
+#define NB_ENTRY_SELF(v) (((v) >> 24) & 1)
 
 struct NbParamsDev
 {
@@ -62,6 +69,24 @@ struct PairList
     int*      cj      = nullptr;
     uint64_t* mask    = nullptr;
     long long ntiles = 0, nentries = 0;
+    size_t    cap_tiles = 0, cap_entries = 0;
+};
+
+/* The list the force kernel consumes: every entry of the (pruned) cluster-pair list re-packed at j-ATOM granularity.
+ * A packed tile is 8 j-atom slots (any clusters) against the entry's 8-atom i-cluster; a j-atom is kept only when at
+ * least one of its 8 pairs is inside the list radius, which raises the share of in-range lanes from 35 % (8x8 cluster
+ * pairs) to 55 % at rlist = rc = 0.9 nm.  j-atoms with an excluded / self pair come first (`nmask` leading tiles carry
+ * masks in the same two-word lane format as the cluster-pair list); the tail of the last tile points at far-away
+ * dummy atoms, NB_DUMMY_SLOTS of them shared round-robin by the entries (the kernel's zero-valued force reductions
+ * for padding lanes then never pile up on one address: same-address reductions serialise in L2). */
+struct PackedList
+{
+    Entry*    entries = nullptr;
+    int*      ja      = nullptr; /* 8 slots per packed tile */
+    uint64_t* mask    = nullptr;
+    long long nentries = 0;
+    int       pitch = 0; /* tiles reserved per entry (= max_tiles_per_entry): entry e owns tiles [e*pitch, (e+1)*pitch), so
+                            the force kernel can fetch an entry's j indices without first reading the entry itself */
     size_t    cap_tiles = 0, cap_entries = 0;
 };
 
@@ -112,8 +137,10 @@ struct b200nb_context
     float*   d_bb = nullptr;     /* 6 floats per cluster */
     float*   d_cellz = nullptr;  /* 2 floats per cell */
     float4*  d_f = nullptr;      /* per slot */
-    float*   d_fshift = nullptr; /* 45*3 */
-    double*  d_energy = nullptr; /* 2 */
+    float*   d_fshift = nullptr; /* NB_OUT_COPIES x NB_FSHIFT_PITCH accumulators */
+    double*  d_energy = nullptr; /* NB_OUT_COPIES x 2 accumulators */
+    float*   d_fshift_sum = nullptr; /* 45*3: replicas summed by k_reduce_outputs */
+    double*  d_energy_sum = nullptr; /* 2 */
     int*     d_scratch = nullptr; /* small ints: totals, flags, counters */
     long long* d_counter = nullptr;
 
@@ -124,12 +151,16 @@ struct b200nb_context
     PairList outer[2], inner[2];
     bool     inner_is_outer = true;
     bool     have_list = false;
+    PackedList packed[2];
+    int        dummy_slot = 0; /* first of the NB_DUMMY_SLOTS far-away filler slots appended after the grids */
 
     float* d_flush = nullptr;
     size_t flush_bytes = 0;
 
-    float* h_pinned = nullptr;
-    size_t pinned_bytes = 0;
+    unsigned char* h_pinned = nullptr; /* mapped pinned scratch of b200nb_compute */
+    size_t         pinned_bytes = 0;
+    const void *   map_x_host = nullptr, *map_f_host = nullptr; /* last host buffers b200nb_compute resolved */
+    float *        map_x_dev = nullptr, *map_f_dev = nullptr;   /* their device-visible addresses (null: pageable) */
 };
 
 int nb_fail(b200nb_context* h, int code, const std::string& msg);
@@ -143,6 +174,7 @@ int nb_fail(b200nb_context* h, int code, const std::string& msg);
 
 /* force.cu */
 int nb_launch_force_kernel(b200nb_context* h, int locality, int flags);
+
 
 /* ---- device helpers shared by search / prune / pair extraction ---- */
 #ifdef __CUDACC__

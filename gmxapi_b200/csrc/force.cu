@@ -10,13 +10,14 @@
  * pipe retires 128 lane-FMAs/clk/SM whether issued as scalar FFMA or packed FFMA2, but a packed instruction takes
  * ONE issue slot for two lanes' work; ALU-pipe instructions (FSEL, FMNMX, LOP3, IADD3) run at half that rate, SHFL
  * at ~0.44 warp-instructions/clk/SMSP, MUFU at 16 lanes/clk/SM.  So the kernel is written to be FMA-pipe-bound:
- *  - one warp per list entry = one 8-atom i-cluster + shift against a run of 8-atom j-clusters;
- *  - lane = jl + 8*ih holds j-atom jl and the TWO i-atoms (2*ih, 2*ih+1) as packed float2 registers for the whole
+ *  - one warp per list entry = one 8-atom i-cluster + shift against a run of PACKED tiles of 8 j-atom slots each
+ *    (PackedList, b200nb_internal.h: j-atoms with no pair inside the list radius were dropped when the list was packed);
+ *  - lane = jl + 8*ih holds the j-atom in slot jl of the tile and the TWO i-atoms (2*ih, 2*ih+1) as packed float2 registers for the whole
  *    entry: all pair arithmetic is packed (fma.rn.f32x2 -> FFMA2/FMUL2/FADD2), the j operands enter as the
- *    scalar-broadcast operand form of those instructions, so a tile costs two loads (one 16-byte xyzq, one 8-byte
- *    LJ pair; the 4 lanes sharing a j-atom hit the same address) and no register shuffling;
+ *    scalar-broadcast operand form of those instructions, so a tile costs two 16-byte shared-memory loads (xyzq;
+ *    LJ pair + the j-atom's slot index; the 4 lanes sharing a j-atom hit the same address) and no register shuffling;
  *  - j-forces: in-lane add of the two pairs, 2-stage reduce-scatter (3 shuffles) over the 4 lanes sharing the j-atom,
- *    then one scalar red.global.add.f32 per lane: 32 lanes cover the 8 float4 force slots of the j-cluster's 128-byte line;
+ *    then one scalar red.global.add.f32 per lane: 32 lanes cover the float4 force slots of the tile's 8 j-atoms;
  *  - i-forces stay in registers; per entry one transposed butterfly over the 8 j-lanes and one 16-byte red per atom;
  *  - tiles that carry exclusion masks are sorted to the front of an entry (b200nb.cu k_search) and run through a
  *    separate code path; the unmasked path has no mask logic and no r^2 clamp;
@@ -24,8 +25,9 @@
  *    instruction immediates (folding beta^3 into them would cost seven registers); out-of-range lanes are discarded by select, so garbage there cannot poison a sum;
  *  - r^2 is evaluated with the reference's operand roles and operation order so the in-range pair set is
  *    bit-identical (see nb_rsq in b200nb_internal.h);
- *  - the j-atom data of a whole entry (<= 32 tiles x 192 B) is staged in shared memory with cp.async (LDGSTS), all 32
- *    lanes copying 16 B each per instruction, before the pair loop starts: the first version loaded j data with LDG one
+ *  - the j-atom data of a whole entry (<= 32 tiles x 256 B) is staged in shared memory with cp.async (LDGSTS): each lane
+ *    reads one j-slot index of the entry (coalesced) and gathers that atom's 16-byte xyzq and 8-byte LJ pair,
+ *    before the pair loop starts: the first version loaded j data with LDG one
  *    tile ahead and spent its time in long-scoreboard stalls (L1 hit rate 35 %: consecutive entries belong to the same
  *    i-cluster and share no j data; profiles/r1).  The i-cluster lives in registers, which beats shared memory.
  *    TMA (cp.async.bulk) was considered and not used: the stream is a gather of 128-byte lines by cluster index, so a
@@ -61,21 +63,33 @@ struct JAtom
 {
     float4 xq;
     float2 lj; /* GEOM: sqrt(6 C6), sqrt(12 C12); table: atom type in lj.x (as int bits) */
+    int    slot; /* grid slot of the j-atom: index into xq / f */
 };
 
 /* The j-atom data of a whole entry is staged in shared memory with cp.async (LDGSTS) before the pair loop, so the
- * loop itself never waits on L2: per warp [ntile x 128 B xyzq][ntile x 64 B LJ (or 32 B types)]. */
+ * loop itself never waits on L2.  Per warp and packed tile 256 B: [8 x float4 xyzq][8 x {lj.x, lj.y, slot, -}]; the 8
+ * lanes of a quarter-warp read 128 contiguous bytes (no bank conflicts), the 4 quarter-warps the same ones (broadcast). */
+#define NB_TILE_SMEM 256
 __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
-
-template<bool GEOM>
-__device__ __forceinline__ void load_j(JAtom& J, const unsigned char* sxq_lane, const unsigned char* slj_lane, int t)
+__device__ __forceinline__ void cp_async8(unsigned smem_addr, const void* gptr)
 {
-    J.xq = *reinterpret_cast<const float4*>(sxq_lane + t * 128);
-    if (GEOM) J.lj = *reinterpret_cast<const float2*>(slj_lane + t * 64);
-    else J.lj.x = __int_as_float(*reinterpret_cast<const int*>(slj_lane + t * 32));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned smem_addr, const void* gptr)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+
+/* s_lane = this warp's staging area + jl*16 */
+__device__ __forceinline__ void load_j(JAtom& J, const unsigned char* s_lane, int t)
+{
+    J.xq           = *reinterpret_cast<const float4*>(s_lane + t * NB_TILE_SMEM);
+    const float4 a = *reinterpret_cast<const float4*>(s_lane + t * NB_TILE_SMEM + 128);
+    J.lj           = make_float2(a.x, a.y);
+    J.slot         = __float_as_int(a.z);
 }
 
 /* simd/simd_math.h:1609-1650 pmeForceCorrection: denominator and numerator */
@@ -319,9 +333,9 @@ __device__ __forceinline__ void tile_pairs_multi(const IData& I, const JAtom (&J
 struct LaneClass
 {
     bool  b4, b3, b3or4, b3only;
-    char* f_lane; /* f + jl (float4) + slot * 4 bytes */
+    char* f_lane; /* f + component slot (2*b4+b3) * 4 bytes */
 };
-__device__ __forceinline__ void reduce_store_j(const float2 tx, const float2 ty, const float2 tz, const LaneClass& C, int cj)
+__device__ __forceinline__ void reduce_store_j(const float2 tx, const float2 ty, const float2 tz, const LaneClass& C, int jslot)
 {
     const unsigned full = 0xffffffffu;
     const float sx = -tx.x - tx.y, sy = -ty.x - ty.y, sz = -tz.x - tz.y;
@@ -330,12 +344,12 @@ __device__ __forceinline__ void reduce_store_j(const float2 tx, const float2 ty,
     const float k1 = sy + __shfl_xor_sync(full, sy, 16); /* y of both halves (used by the b4=0 lanes) */
     float v = C.b3only ? k1 : k0;
     v += __shfl_xor_sync(full, C.b3or4 ? k0 : k1, 8);
-    atomicAdd(reinterpret_cast<float*>(C.f_lane + (size_t)(unsigned)cj * 128u), v);
+    atomicAdd(reinterpret_cast<float*>(C.f_lane + (size_t)(unsigned)jslot * 16u), v);
 }
 
 template<int NT>
 __device__ __forceinline__ void reduce_store_j_multi(const float2 (&tx)[NT], const float2 (&ty)[NT], const float2 (&tz)[NT], const LaneClass& C,
-                                                     const int (&cj)[NT])
+                                                     const int (&jslot)[NT])
 {
     const unsigned full = 0xffffffffu;
     float          sx[NT], sy[NT], sz[NT], k0[NT], k1[NT], v[NT];
@@ -357,82 +371,73 @@ __device__ __forceinline__ void reduce_store_j_multi(const float2 (&tx)[NT], con
 #ifdef B200NB_DIAG_NO_RED /* diagnostic build only: drops the j-force scatter (wrong results) to measure its cost */
         if (v[u] == 12345.678f)
 #endif
-            atomicAdd(reinterpret_cast<float*>(C.f_lane + (size_t)(unsigned)cj[u] * 128u), v[u]);
+            atomicAdd(reinterpret_cast<float*>(C.f_lane + (size_t)(unsigned)jslot[u] * 16u), v[u]);
     }
 }
 
+#ifndef B200NB_FORCE_WARPS
+#define B200NB_FORCE_WARPS 1 /* warps (= list entries) per CTA: small CTAs refill an SM's warp slots at entry granularity */
+#endif
 #ifndef B200NB_FORCE_MIN_BLOCKS
-#define B200NB_FORCE_MIN_BLOCKS 4
+#define B200NB_FORCE_MIN_BLOCKS (20 / B200NB_FORCE_WARPS) /* 20 resident warps per SM = 96 registers per thread */
 #endif
 template<int EEL, bool GEOM, bool VF>
-__global__ void __launch_bounds__(128, B200NB_FORCE_MIN_BLOCKS)
-k_force(const Entry* __restrict__ entries, long long nentries, const int* __restrict__ tcj, const uint64_t* __restrict__ tmask,
+__global__ void __launch_bounds__(32 * B200NB_FORCE_WARPS, B200NB_FORCE_MIN_BLOCKS)
+k_force(const Entry* __restrict__ entries, long long nentries, const int* __restrict__ pja, const uint64_t* __restrict__ tmask,
         const float4* __restrict__ xq, const float2* __restrict__ lj, const int* __restrict__ atype, const float2* __restrict__ nbfp,
         const float* __restrict__ shift_vec, float4* __restrict__ f, float* __restrict__ fshift, double* __restrict__ energy,
         const __grid_constant__ NbParamsDev P, const int intra, const int maxt, const float* __restrict__ kconst)
 {
-    const long long e = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const long long e = (long long)blockIdx.x * B200NB_FORCE_WARPS + (threadIdx.x >> 5);
     if (e >= nentries) return;
-    const int4 ev    = __ldg(reinterpret_cast<const int4*>(entries) + e);
-    const int  start = ev.z, end = ev.w;
-    if (start >= end) return;
     const int lane = threadIdx.x & 31;
-    const int jl = lane & 7, ih = lane >> 3;
-    const int ci = ev.x, shift = ev.y & 255, nmask = ev.y >> 8;
-    LaneClass C;
-    C.b4     = (lane & 16) != 0;
-    C.b3     = (lane & 8) != 0;
-    C.b3or4  = C.b3 || C.b4;
-    C.b3only = C.b3 && !C.b4;
-    C.f_lane = reinterpret_cast<char*>(f + jl) + 4 * (2 * (int)C.b4 + (int)C.b3);
+    /* Level-1 loads, all independent: entry e owns the packed tiles [e*maxt, (e+1)*maxt), so its first 64 j-slot indices and
+     * its masks are fetched together with the entry itself (values beyond the entry's tile count are never used). */
+    const int* const ja   = pja + (size_t)e * maxt * 8;
+    const int        jsp0 = __ldg(ja + min(lane, maxt * 8 - 1)), jsp1 = __ldg(ja + min(lane + 32, maxt * 8 - 1));
+    uint2            mreg = make_uint2(~0u, ~0u);
+    if (lane < maxt) mreg = __ldg(reinterpret_cast<const uint2*>(tmask) + e * maxt + lane);
+    const int4 ev    = __ldg(reinterpret_cast<const int4*>(entries) + e);
     KConst K;
     {
         const float4 k0 = __ldg(reinterpret_cast<const float4*>(kconst)), k1 = __ldg(reinterpret_cast<const float4*>(kconst) + 1);
         K.rc2 = k0.x, K.beta = k0.y, K.beta2 = k0.z, K.fd4 = k0.w, K.fd3 = k1.x, K.fn6 = k1.y, K.fn5 = k1.z;
     }
-    /* the entry's j-cluster indices and exclusion masks (<= 32 tiles, b200nb_set_params clamps max_tiles_per_entry):
-     * lane k holds tile k's, each tile fetches them with a shuffle */
+    const int  start = ev.z, end = ev.w;
+    const bool self  = VF && NB_ENTRY_SELF(ev.y);
+    if (start >= end && !self) return;
+    const int jl = lane & 7, ih = lane >> 3;
+    const int ci = ev.x, shift = NB_ENTRY_SHIFT(ev.y), nmask = NB_ENTRY_NMASK(ev.y);
     const int ntile = end - start;
-    const int cjreg = __ldg(tcj + start + min(lane, ntile - 1));
-    uint2     mreg  = make_uint2(~0u, ~0u);
-    if (lane < nmask) mreg = __ldg(reinterpret_cast<const uint2*>(tmask) + start + lane);
     const unsigned full = 0xffffffffu;
+    if (lane >= nmask) mreg = make_uint2(~0u, ~0u);
 
-    /* ---- stage the j data of all tiles: every lane copies 16 bytes per instruction ---- */
+    /* ---- level 2: stage the j data of all tiles: each lane gathers one j-atom per round ---- */
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char* const sxq = smem_raw + (threadIdx.x >> 5) * (maxt * 192);
-    unsigned char* const slj = sxq + maxt * 128;
+    unsigned char* const sj = smem_raw + (threadIdx.x >> 5) * (maxt * NB_TILE_SMEM);
     {
-        const unsigned sx0 = (unsigned)__cvta_generic_to_shared(sxq), sl0 = (unsigned)__cvta_generic_to_shared(slj);
-        const char*    gx = reinterpret_cast<const char*>(xq);
-        for (int c0 = 0; c0 < ntile * 8; c0 += 32)
+        const unsigned s0 = (unsigned)__cvta_generic_to_shared(sj);
+        for (int a0 = 0; a0 < ntile * 8; a0 += 32)
         {
-            const int c  = c0 + lane;
-            const int cj = __shfl_sync(full, cjreg, (c >> 3) & 31);
-            if (c < ntile * 8) cp_async16(sx0 + c * 16, gx + (size_t)(unsigned)cj * 128u + (c & 7) * 16);
-        }
-        if (GEOM)
-        {
-            const char* gl = reinterpret_cast<const char*>(lj);
-            for (int c0 = 0; c0 < ntile * 4; c0 += 32)
+            const int a = a0 + lane;
+            if (a < ntile * 8)
             {
-                const int c  = c0 + lane;
-                const int cj = __shfl_sync(full, cjreg, (c >> 2) & 31);
-                if (c < ntile * 4) cp_async16(sl0 + c * 16, gl + (size_t)(unsigned)cj * 64u + (c & 3) * 16);
-            }
-        }
-        else
-        {
-            const char* gt = reinterpret_cast<const char*>(atype);
-            for (int c0 = 0; c0 < ntile * 2; c0 += 32)
-            {
-                const int c  = c0 + lane;
-                const int cj = __shfl_sync(full, cjreg, (c >> 1) & 31);
-                if (c < ntile * 2) cp_async16(sl0 + c * 16, gt + (size_t)(unsigned)cj * 32u + (c & 1) * 16);
+                const int      slot = a0 == 0 ? jsp0 : (a0 == 32 ? jsp1 : __ldg(ja + a));
+                const unsigned dx   = s0 + (a >> 3) * NB_TILE_SMEM + (a & 7) * 16;
+                cp_async16(dx, xq + slot);
+                if (GEOM) cp_async8(dx + 128, lj + slot);
+                else cp_async4(dx + 128, atype + slot);
+                asm volatile("st.shared.s32 [%0], %1;" ::"r"(dx + 136), "r"(slot) : "memory");
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    LaneClass C;
+    C.b4     = (lane & 16) != 0;
+    C.b3     = (lane & 8) != 0;
+    C.b3or4  = C.b3 || C.b4;
+    C.b3only = C.b3 && !C.b4;
+    C.f_lane = reinterpret_cast<char*>(f) + 4 * (2 * (int)C.b4 + (int)C.b3);
     IData I;
     {
         const float4 a = __ldg(xq + (size_t)ci * 8 + 2 * ih), b = __ldg(xq + (size_t)ci * 8 + 2 * ih + 1);
@@ -459,41 +464,38 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
     }
     float2 fix = dup(0.f), fiy = dup(0.f), fiz = dup(0.f);
     float  evdw = 0.f, ecoul = 0.f;
+    if (self && jl < 2)
+    {
+        /* Coulomb self term, once per i-atom: kernel_outer.h:408-452 (fillers carry q = 0) */
+        const float qi = (jl == 0 ? I.q.x : I.q.y);
+        ecoul -= qi * qi * P.self_q2;
+    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    const unsigned char* const sxq_lane = sxq + jl * 16;
-    const unsigned char* const slj_lane = slj + jl * (GEOM ? 8 : 4);
+    const unsigned char* const s_lane = sj + jl * 16;
     int t = 0;
 
     /* ---- tiles with exclusion masks (sorted to the front of the entry) ---- */
     for (; t < nmask; t++)
     {
-        const int cj = __shfl_sync(full, cjreg, t);
-        JAtom     J;
-        load_j<GEOM>(J, sxq_lane, slj_lane, t);
+        JAtom J;
+        load_j(J, s_lane, t);
         const unsigned mx = __shfl_sync(full, mreg.x, t), my = __shfl_sync(full, mreg.y, t);
-        /* mask word w, bit `lane`: pair (i-atom 2*ih + w, j-atom jl) interacts */
+        /* mask word w, bit `lane`: pair (i-atom 2*ih + w, j-slot jl) interacts */
         const float in0 = (float)((mx >> lane) & 1u), in1 = (float)((my >> lane) & 1u);
         bool        ok0 = true, ok1 = true;
-        const bool  diag = intra && shift == B200NB_CENTRAL && cj == ci;
-        if (diag)
+        if (intra && shift == B200NB_CENTRAL && (J.slot >> 3) == ci)
         {
-            /* self tile: only j > i (nbnxm/pairlist.cpp:880-904, kernel_gpu_ref.cpp:223-226) */
-            ok0 = jl > 2 * ih;
-            ok1 = jl > 2 * ih + 1;
-            if (VF && jl < 2)
-            {
-                /* self term, once per atom: kernel_outer.h:408-452 */
-                const float qi = (jl == 0 ? I.q.x : I.q.y);
-                ecoul -= qi * qi * P.self_q2;
-            }
+            /* j-atom of the i-cluster itself: only j > i (nbnxm/pairlist.cpp:880-904, kernel_gpu_ref.cpp:223-226) */
+            ok0 = (J.slot & 7) > 2 * ih;
+            ok1 = (J.slot & 7) > 2 * ih + 1;
         }
         float2 tx, ty, tz;
         tile_pairs<EEL, GEOM, VF, true>(I, J, P, K, nbfp, in0, in1, ok0, ok1, tx, ty, tz, evdw, ecoul);
         fix = add2(fix, tx);
         fiy = add2(fiy, ty);
         fiz = add2(fiz, tz);
-        reduce_store_j(tx, ty, tz, C, cj);
+        reduce_store_j(tx, ty, tz, C, J.slot);
     }
 
     /* ---- plain tiles ---- */
@@ -503,13 +505,13 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
         for (; t + NT <= ntile; t += NT)
         {
             JAtom  J[NT];
-            int    cj[NT];
+            int    js[NT];
             float2 tx[NT], ty[NT], tz[NT];
 #pragma unroll
             for (int u = 0; u < NT; u++)
             {
-                cj[u] = __shfl_sync(full, cjreg, t + u);
-                load_j<GEOM>(J[u], sxq_lane, slj_lane, t + u);
+                load_j(J[u], s_lane, t + u);
+                js[u] = J[u].slot;
             }
             tile_pairs_multi<EEL, GEOM, NT>(I, J, P, K, nbfp, tx, ty, tz);
 #pragma unroll
@@ -519,20 +521,19 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
                 fiy = add2(fiy, ty[u]);
                 fiz = add2(fiz, tz[u]);
             }
-            reduce_store_j_multi<NT>(tx, ty, tz, C, cj);
+            reduce_store_j_multi<NT>(tx, ty, tz, C, js);
         }
     }
     for (; t < ntile; t++)
     {
-        const int cj = __shfl_sync(full, cjreg, t);
-        JAtom     J;
-        load_j<GEOM>(J, sxq_lane, slj_lane, t);
+        JAtom J;
+        load_j(J, s_lane, t);
         float2 tx, ty, tz;
         tile_pairs<EEL, GEOM, VF, false>(I, J, P, K, nbfp, 1.f, 1.f, true, true, tx, ty, tz, evdw, ecoul);
         fix = add2(fix, tx);
         fiy = add2(fiy, ty);
         fiz = add2(fiz, tz);
-        reduce_store_j(tx, ty, tz, C, cj);
+        reduce_store_j(tx, ty, tz, C, J.slot);
     }
 
     /* ---- i-forces: reduce over the 8 j-lanes (bits 0-2). Stage 1 is transposed: even lanes keep atom i0, odd lanes i1. */
@@ -549,7 +550,7 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
     ky += __shfl_xor_sync(full, ky, 4);
     kz += __shfl_xor_sync(full, kz, 4);
     /* lanes with jl in {0,1} hold the total force on i-atom 2*ih + jl */
-    if (jl < 2) atomicAdd(f + ((size_t)ci * 8 + 2 * ih + jl), make_float4(kx, ky, kz, 0.f));
+    if (jl < 2 && ntile > 0) atomicAdd(f + ((size_t)ci * 8 + 2 * ih + jl), make_float4(kx, ky, kz, 0.f));
     if (VF)
     {
         /* shift force = sum of the i-forces of this entry (kernel_outer.h:620-640; the CUDA kernel skips the central
@@ -567,9 +568,10 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
             kz += __shfl_xor_sync(full, kz, 16);
             if (lane == 0)
             {
-                atomicAdd(fshift + 3 * shift, kx);
-                atomicAdd(fshift + 3 * shift + 1, ky);
-                atomicAdd(fshift + 3 * shift + 2, kz);
+                float* fs = fshift + (int)(e & (NB_OUT_COPIES - 1)) * NB_FSHIFT_PITCH + 3 * shift;
+                atomicAdd(fs, kx);
+                atomicAdd(fs + 1, ky);
+                atomicAdd(fs + 2, kz);
             }
         }
         for (int o = 16; o > 0; o >>= 1)
@@ -579,22 +581,23 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
         }
         if (lane == 0)
         {
-            atomicAdd(energy, (double)evdw);
-            atomicAdd(energy + 1, (double)ecoul);
+            double* en = energy + 2 * (int)(e & (NB_OUT_COPIES - 1));
+            atomicAdd(en, (double)evdw);
+            atomicAdd(en + 1, (double)ecoul);
         }
     }
 }
 
 template<int EEL, bool GEOM, bool VF>
-int launch(b200nb_context* h, const PairList& L, int intra)
+int launch(b200nb_context* h, const PackedList& L, int intra)
 {
-    const unsigned nblk = (unsigned)((L.nentries + 3) / 4);
-    const int    maxt = h->max_tiles;
-    const size_t smem = (size_t)4 * maxt * 192;
-    k_force<EEL, GEOM, VF><<<nblk, 128, smem, h->stream>>>(L.entries, L.nentries, L.cj, L.mask, reinterpret_cast<const float4*>(h->d_xq),
-                                                        reinterpret_cast<const float2*>(h->d_lj), h->d_atype,
-                                                        reinterpret_cast<const float2*>(h->d_nbfp), h->d_shift_vec, h->d_f, h->d_fshift,
-                                                        h->d_energy, h->dp, intra, maxt, h->d_kconst);
+    const unsigned nblk = (unsigned)((L.nentries + B200NB_FORCE_WARPS - 1) / B200NB_FORCE_WARPS);
+    const int      maxt = h->max_tiles;
+    const size_t   smem = (size_t)B200NB_FORCE_WARPS * maxt * NB_TILE_SMEM;
+    k_force<EEL, GEOM, VF><<<nblk, 32 * B200NB_FORCE_WARPS, smem, h->stream>>>(
+            L.entries, L.nentries, L.ja, L.mask, reinterpret_cast<const float4*>(h->d_xq), reinterpret_cast<const float2*>(h->d_lj),
+            h->d_atype, reinterpret_cast<const float2*>(h->d_nbfp), h->d_shift_vec, h->d_f, h->d_fshift, h->d_energy, h->dp, intra, maxt,
+            h->d_kconst);
     h->nlaunches++;
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return nb_fail(h, B200NB_ERR_CUDA, std::string("force kernel launch: ") + cudaGetErrorString(err));
@@ -605,7 +608,7 @@ int launch(b200nb_context* h, const PairList& L, int intra)
 
 int nb_launch_force_kernel(b200nb_context* h, int loc, int flags)
 {
-    const PairList& L = h->inner[loc];
+    const PackedList& L = h->packed[loc];
     if (L.nentries == 0) return 0;
     const bool vf    = (flags & (B200NB_FLAG_ENERGY | B200NB_FLAG_VIRIAL)) != 0;
     const bool ewald = h->dp.eeltype == B200NB_EEL_EWALD;

@@ -175,7 +175,11 @@ class _LoopbackEndpoint:
             if self.sync:
                 self.sync()
         if recv is not None and recv.numel():
-            recv.copy_(self.hub.q[(src, self.rank)].get(timeout=120))
+            buf = self.hub.q[(src, self.rank)].get(timeout=120)
+            recv.copy_(buf)
+            if self.sync:
+                self.sync()  # the copy must have run before `buf` returns to the sender's stream pool and is rewritten
+            del buf
 
     def allreduce_sum(self, t):
         raise NotImplementedError

@@ -17,8 +17,8 @@ EXPORTS = [
     "b200nb_create", "b200nb_destroy", "b200nb_last_error", "b200nb_stream", "b200nb_set_stream", "b200nb_synchronize",
     "b200nb_set_params", "b200nb_set_atoms", "b200nb_set_box", "b200nb_put_on_grid", "b200nb_build_pairlist",
     "b200nb_set_x", "b200nb_clear_outputs", "b200nb_launch_force", "b200nb_launch_prune", "b200nb_get_f",
-    "b200nb_get_outputs", "b200nb_compute", "b200nb_halo_pack_x", "b200nb_halo_unpack_f", "b200nb_get_stats",
-    "b200nb_get_grid_order", "b200nb_get_tiles", "b200nb_get_pairs", "b200nb_time_force_kernel",
+    "b200nb_get_outputs", "b200nb_compute", "b200nb_step", "b200nb_halo_pack_x", "b200nb_halo_unpack_f", "b200nb_get_stats",
+    "b200nb_get_grid_order", "b200nb_get_tiles", "b200nb_get_pairs", "b200nb_time_force_kernel", "b200nb_time_step",
 ]
 
 
@@ -36,7 +36,7 @@ class _Params(C.Structure):
 class _Stats(C.Structure):
     _fields_ = [("natoms", C.c_int), ("natoms_padded", C.c_int), ("nclusters", C.c_int), ("ncx", C.c_int),
                 ("ncy", C.c_int), ("ntiles_outer", C.c_longlong), ("ntiles_inner", C.c_longlong),
-                ("nentries", C.c_longlong), ("comb_geometric", C.c_int), ("nlaunches", C.c_longlong)]
+                ("nentries", C.c_longlong), ("comb_geometric", C.c_int), ("nlaunches", C.c_longlong), ("ntiles_packed", C.c_longlong)]
 
 
 _lib = None
@@ -79,6 +79,7 @@ def load_library():
     L.b200nb_get_f.argtypes = [vp, vp, ci, ci, ci, ci]
     L.b200nb_get_outputs.argtypes = [vp, vp, vp]
     L.b200nb_compute.argtypes = [vp, vp, ci, vp, vp, vp]
+    L.b200nb_step.argtypes = [vp, vp, ci, vp]
     L.b200nb_halo_pack_x.argtypes = [vp, vp, vp, ci, vp, vp]
     L.b200nb_halo_unpack_f.argtypes = [vp, vp, vp, ci, vp]
     L.b200nb_get_stats.argtypes = [vp, C.POINTER(_Stats)]
@@ -88,6 +89,7 @@ def load_library():
     L.b200nb_get_pairs.argtypes = [vp, cf, vp, cll]
     L.b200nb_get_pairs.restype = cll
     L.b200nb_time_force_kernel.argtypes = [vp, ci, ci, ci, ci, ci, C.POINTER(cf)]
+    L.b200nb_time_step.argtypes = [vp, vp, vp, ci, ci, ci, ci, C.POINTER(cf), C.POINTER(cf)]
     _lib = L
     return L
 
@@ -216,16 +218,30 @@ class NbnxmGpu:
         return fs, float(e[0]), float(e[1])
 
     def compute(self, x, flags=0, f=None):
-        """GmxForceCalculator::compute: returns (f, fshift, e_lj, e_el)."""
-        x = np.ascontiguousarray(x, dtype=np.float32)
+        """GmxForceCalculator::compute: returns (f, fshift, e_lj, e_el).  x / f that live in pinned host memory
+        (e.g. torch pin_memory, cudaHostRegister) are read / written in place by the kernels."""
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float32 and x.flags.c_contiguous):
+            x = np.ascontiguousarray(x, dtype=np.float32)
         if f is None:
             f = np.empty((self.natoms, 3), np.float32)
-        fs = np.zeros((SHIFTS, 3), np.float32)
-        e = np.zeros(2, np.float64)
-        want = flags != 0
-        self._check(self._L.b200nb_compute(self._h, _ptr(x), flags, _ptr(f), _ptr(fs) if want else _ptr(None),
-                                           _ptr(e) if want else _ptr(None)), "compute")
+        elif not (f.dtype == np.float32 and f.flags.c_contiguous and f.size == 3 * self.natoms):
+            raise B200NBError("compute: forces must be a C-contiguous float32 array of natoms*3")
+        if x.size != 3 * self.natoms:
+            raise B200NBError("compute: coordinates must hold natoms*3 values")
+        if flags:
+            fs = np.zeros((SHIFTS, 3), np.float32)
+            e = np.zeros(2, np.float64)
+            rc = self._L.b200nb_compute(self._h, x.ctypes.data, flags, f.ctypes.data, fs.ctypes.data, e.ctypes.data)
+        else:
+            fs, e = None, (0.0, 0.0)
+            rc = self._L.b200nb_compute(self._h, x.ctypes.data, 0, f.ctypes.data, None, None)
+        if rc != 0:
+            self._check(rc, "compute")
         return f, fs, float(e[0]), float(e[1])
+
+    def step(self, x_dev, f_dev, flags=0):
+        """Device-resident step (x_dev, f_dev: device addresses of natoms*3 floats); asynchronous."""
+        self._check(self._L.b200nb_step(self._h, _ptr(x_dev), flags, _ptr(f_dev)), "step")
 
     def halo_pack_x(self, x_dev, index_dev, n, shift, out_dev):
         s = np.ascontiguousarray(shift, dtype=np.float32)
@@ -271,6 +287,13 @@ class NbnxmGpu:
         if n < 0:
             self._check(int(n), "get_pairs")
         return int(n)
+
+    def time_step(self, x_dev, f_dev, flags=0, nwarm=3, niter=20, flush_l2=True):
+        """(ms per device-resident step, ms of the force kernel inside it), CUDA-event timed on the context's stream."""
+        a, b = C.c_float(), C.c_float()
+        self._check(self._L.b200nb_time_step(self._h, _ptr(x_dev), _ptr(f_dev), flags, nwarm, niter, int(flush_l2),
+                                             C.byref(a), C.byref(b)), "time_step")
+        return a.value, b.value
 
     def time_force_kernel(self, locality=-1, flags=0, nwarm=3, niter=20, flush_l2=True):
         ms = C.c_float()

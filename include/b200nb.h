@@ -133,9 +133,16 @@ int b200nb_get_outputs(b200nb_t* h, float* fshift_host, double* energies_host);
 
 /* ---- the nblib call: GmxForceCalculator::compute (api/nblib/gmxcalculator.cpp:70-83):
  * x_host (natoms*3) in, f_host (natoms*3) overwritten; fshift_host[135]/energies_host[2] overwritten when
- * not NULL.  Synchronous. */
+ * not NULL.  Synchronous.  Pinned host buffers (cudaHostAlloc / cudaHostRegister: what gmx::HostVector gives the
+ * reference's GPU path, nbnxm_setup.cpp:417-418) are read and written in place by the kernels over PCIe; pageable
+ * buffers are staged through the context's own pinned scratch. */
 int b200nb_compute(b200nb_t* h, const float* x_host, int flags, float* f_host, float* fshift_host,
                    double* energies_host);
+/* The same step with coordinates and forces resident on the device (the reference's GPU buffer-ops path:
+ * nbnxn_gpu_x_to_nbat_x + gpu_launch_kernel + GpuForceReduction, mdlib/sim_util.cpp:1043-1108): three launches
+ * (x -> grid layout fused with gpu_clear_outputs; force kernel; grid-ordered f -> atom order), asynchronous on the
+ * context's stream.  f_dev is overwritten. */
+int b200nb_step(b200nb_t* h, const float* x_dev, int flags, float* f_dev);
 
 /* ---- halo exchange helpers: packSendBufKernel / unpackRecvBufKernel (domdec/gpuhaloexchange_impl.cu:77-131).
  * index_dev: n local atom indices. pack: out[k] = x[index[k]] + shift; unpack: f[index[k]] += in[k]. */
@@ -149,10 +156,11 @@ typedef struct
     int       natoms, natoms_padded, nclusters;
     int       ncx, ncy;        /* home grid columns */
     long long ntiles_outer;    /* cluster pairs in the search list */
-    long long ntiles_inner;    /* cluster pairs the force kernel evaluates (after pruning) */
+    long long ntiles_inner;    /* cluster pairs of the pruned list */
     long long nentries;        /* work units */
     int       comb_geometric;  /* 1 if the geometric-rule kernel is used */
     long long nlaunches;       /* kernels launched by this context so far */
+    long long ntiles_packed;   /* 8-j-atom x 8-i-atom tiles the force kernel evaluates (the pruned list re-packed per j-atom) */
 } b200nb_stats_t;
 int b200nb_get_stats(b200nb_t* h, b200nb_stats_t* out);
 /* slot -> original atom (-1 filler), natoms_padded ints: GridSet::atomIndices() */
@@ -165,6 +173,10 @@ long long b200nb_get_pairs(b200nb_t* h, float r, int* pairs_host, long long cap)
 /* average duration in ms of the force kernel alone over niter launches (CUDA events on this context's
  * stream; flush_l2 != 0 writes a >L2 buffer between launches). */
 int b200nb_time_force_kernel(b200nb_t* h, int locality, int flags, int nwarm, int niter, int flush_l2, float* ms_avg);
+/* `niter` device-resident steps (b200nb_step) timed with CUDA events on the context's stream: average duration of the whole
+ * step and of the force kernel inside it (events around its launch), L2 optionally flushed before each step. */
+int b200nb_time_step(b200nb_t* h, const float* x_dev, float* f_dev, int flags, int nwarm, int niter, int flush_l2,
+                     float* ms_step_avg, float* ms_force_avg);
 
 #ifdef __cplusplus
 }

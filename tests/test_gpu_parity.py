@@ -203,3 +203,37 @@ def test_full_size_properties(built):
     n_gpu = fc.nb.pair_count(RC)
     n_orc = len(oracle.pair_set(s.x, s.box, RC, s.excl_off, s.excl_idx))
     assert n_gpu == n_orc
+
+
+def test_packed_list_and_device_step(built):
+    """The force kernel consumes the pruned list re-packed per j-atom (PackedList): fewer lanes than the 8x8 cluster-pair
+    list, same pair set (test_pairs_forces_energies extracts the pairs from the packed list).  The device-resident
+    step (b200nb_step) and the host call (b200nb_compute) with pinned and with pageable buffers give the same forces."""
+    import torch
+    s = g.systems.named("water_24k")
+    fc = make(s, g.CoulombType.Pme, energy=False)
+    st = fc.nb.stats()
+    assert 0 < st["ntiles_packed"] < 0.75 * st["ntiles_inner"]
+    fo = oracle.forces(s.x, s.box, s.q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx, energy=False,
+                       **oracle_kwargs(g.CoulombType.Pme))[0]
+    f_pageable = fc.compute(s.x.copy())
+    assert relrms(f_pageable, fo) < FORCE_TOL
+    x_pin = torch.from_numpy(s.x.copy()).pin_memory()
+    f_pin = torch.zeros_like(x_pin).pin_memory()
+    fc.compute(x_pin.numpy(), f_pin.numpy())
+    assert relrms(f_pin.numpy(), fo) < FORCE_TOL
+    x_dev = torch.from_numpy(s.x).cuda()
+    f_dev = torch.zeros_like(x_dev)
+    torch.cuda.synchronize()
+    for _ in range(2):  # twice: the step clears its own outputs
+        fc.nb.step(x_dev.data_ptr(), f_dev.data_ptr(), 0)
+    fc.nb.synchronize()
+    assert relrms(f_dev.cpu().numpy(), fo) < FORCE_TOL
+    # misaligned atom-order buffers take the scalar copy path
+    xm = torch.zeros(3 * s.n + 1, dtype=torch.float32, device="cuda")
+    xm[1:] = x_dev.reshape(-1)
+    fm = torch.zeros(3 * s.n + 1, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    fc.nb.step(xm.data_ptr() + 4, fm.data_ptr() + 4, 0)
+    fc.nb.synchronize()
+    assert relrms(fm[1:].reshape(-1, 3).cpu().numpy(), fo) < FORCE_TOL
