@@ -114,6 +114,12 @@ extern "C" void b200nb_destroy(b200nb_t* h)
         cudaFree(h->packed[l].ja);
         cudaFree(h->packed[l].mask);
     }
+    for (int side = 0; side < 2; side++)
+        if (h->dd.peer[side] && h->dd.peer_is_ipc[side]) cudaIpcCloseMemHandle(h->dd.peer[side]);
+    cudaFree(h->dd.window);
+    cudaFree(h->dd.d_count);
+    cudaFree(h->dd.d_send_idx);
+    cudaFree(h->dd.d_send_pos);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -198,7 +204,8 @@ extern "C" int b200nb_set_params(b200nb_t* h, const b200nb_params_t* p)
             geom          = within(c6 * c6, c6ii * c6jj) && within(c12 * c12, c12ii * c12jj);
         }
     h->comb_geom = (p->comb_rule == 1) || (p->comb_rule == 0 && geom);
-    h->max_tiles = p->max_tiles_per_entry > 0 ? std::min(p->max_tiles_per_entry, 32) : 16; /* <= 32: force.cu keeps an entry's j indices in one warp register */
+    /* <= 32: force.cu keeps an entry's masks in one warp register; 0 = chosen from the system size in build_pairlist */
+    h->max_tiles = p->max_tiles_per_entry > 0 ? std::min(p->max_tiles_per_entry, 32) : 16;
     if (alloc_exact(h, &h->d_nbfp, (size_t)ntf * ntf * 2)) return B200NB_ERR_CUDA;
     NB_CUDA(h, cudaMemcpyAsync(h->d_nbfp, h->nbfp_host.data(), sizeof(float) * ntf * ntf * 2, cudaMemcpyHostToDevice, h->stream));
     NB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1201,6 +1208,10 @@ extern "C" int b200nb_build_pairlist(b200nb_t* h)
      * (the reference handles that with shp[XX]=2, pairlist.cpp:3185-3188; outside our scope) */
     for (int d = 0; d < 3; d++)
         if (h->pbc[d] && h->box[d] < 2 * rl) return nb_fail(h, B200NB_ERR_ARG, "build_pairlist: box smaller than 2*rlist along a periodic dimension");
+    /* list balancing granularity (the role of get_nsubpair_target, pairlist.cpp:2485-2587): small systems need many short
+     * entries to fill 148 SMs x 32 warps, large ones amortise the per-entry prologue over more tiles
+     * (profiles/r1/g_sweep_one_entry_per_warp.txt: 24 k atoms best at 16, 192 k atoms at 24) */
+    if (h->hp.max_tiles_per_entry <= 0) h->max_tiles = (h->grid[0].atom_end - h->grid[0].atom_begin) >= 100000 ? 24 : 16;
     const bool want_inner = h->dp.rlist_inner2 < h->dp.rlist_outer2;
     if (!want_inner && !h->inner_is_outer)
     {
@@ -1744,6 +1755,360 @@ extern "C" int b200nb_halo_unpack_f(b200nb_t* h, float* f_dev, const int* index_
     cudaSetDevice(h->device);
     k_halo_unpack<<<(n + 255) / 256, 256, 0, h->stream>>>(f_dev, index_dev, n, in_dev);
     LAUNCH_CHECK(h);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* domain-decomposed step over peer-memory halo windows (DdState, b200nb_internal.h)                      */
+/* ------------------------------------------------------------------------------------------------------ */
+#define NB_DD_SPIN_LIMIT_NS 10000000000ll /* a flag that does not arrive within 10 s raises the window's err word */
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ long long globaltimer_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+/* Waits until *flag >= seq: a one-thread kernel, so that a late peer costs one idle warp slot and never SM capacity the
+ * peer's own kernels might need when several ranks share a GPU (the single-GPU parity tests); the kernel boundary orders the
+ * consumer's loads after the flag. */
+__global__ void k_dd_wait(const int* __restrict__ flag, int seq, int* __restrict__ err)
+{
+    const long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(flag) < seq)
+    {
+        __nanosleep(100);
+        if (globaltimer_ns() - t0 > NB_DD_SPIN_LIMIT_NS)
+        {
+            atomicExch(err, 1);
+            break;
+        }
+    }
+}
+/* after this CTA's stores to the peer: the last CTA of the grid publishes the flag */
+__device__ __forceinline__ void publish_flag(int* counter, int* peer_flag, int seq)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        if (atomicAdd(counter, 1) == (int)gridDim.x - 1)
+        {
+            *counter = 0;
+            __threadfence_system();
+            st_release_sys(peer_flag, seq);
+        }
+    }
+}
+
+/* dd_move_x, sending side: packSendBufKernel (gpuhaloexchange_impl.cu:77-100) fused with the transfer: the coordinates of
+ * the atoms within rlist of our lower face (+ box shift on the periodic edge) go straight into the -x neighbour's window */
+__global__ void __launch_bounds__(256)
+k_dd_push_x(const float4* __restrict__ xq, const int* __restrict__ slot_of_atom, const int* __restrict__ send_idx, int nsend, float sx,
+            float sy, float sz, float* __restrict__ peer_recv_x, int* __restrict__ peer_flag, int seq, int* __restrict__ counter)
+{
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k < nsend)
+    {
+        const float4 v      = xq[slot_of_atom[send_idx[k]]];
+        peer_recv_x[3 * k]     = v.x + sx;
+        peer_recv_x[3 * k + 1] = v.y + sy;
+        peer_recv_x[3 * k + 2] = v.z + sz;
+    }
+    publish_flag(counter, peer_flag, seq);
+}
+
+/* dd_move_x, receiving side, fused with nbnxn_gpu_x_to_nbat_x for the halo grid: window -> grid layout */
+__global__ void __launch_bounds__(256)
+k_dd_recv_x(const float* __restrict__ recv_x, const int* __restrict__ slot_of_atom, int nhome, int nhalo, float* __restrict__ xq)
+{
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= nhalo) return;
+    float* xb = xq + 4 * (size_t)slot_of_atom[nhome + k];
+    xb[0]     = __ldcg(recv_x + 3 * k); /* written by the peer: read at L2, never from a stale L1 line */
+    xb[1]     = __ldcg(recv_x + 3 * k + 1);
+    xb[2]     = __ldcg(recv_x + 3 * k + 2);
+}
+
+/* dd_move_f, sending side: the forces we computed on the halo atoms go into their owner's (+x neighbour's) window */
+__global__ void __launch_bounds__(256)
+k_dd_push_f(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom, int nhome, int nhalo, float* __restrict__ peer_recv_f,
+            int* __restrict__ peer_flag, int seq, int* __restrict__ counter)
+{
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k < nhalo)
+    {
+        const float4 v      = fg[slot_of_atom[nhome + k]];
+        peer_recv_f[3 * k]     = v.x;
+        peer_recv_f[3 * k + 1] = v.y;
+        peer_recv_f[3 * k + 2] = v.z;
+    }
+    publish_flag(counter, peer_flag, seq);
+}
+
+/* dd_move_f, receiving side (unpackRecvBufKernel<accumulate>, gpuhaloexchange_impl.cu:108-131) fused with the force
+ * un-sort (reduceKernel): f_home[a] = f_grid[slot[a]] + returned halo force of a; on the periodic edge the returned forces
+ * also enter the shift forces (domdec/domdec.cpp:426-458) */
+template<bool VEC>
+__global__ void __launch_bounds__(256)
+k_dd_step_end(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom, int nhome, const int* __restrict__ send_pos,
+              const float* __restrict__ recv_f, float* __restrict__ f, float* __restrict__ fshift_edge)
+{
+    __shared__ __align__(16) float sf[768];
+    const int tid  = threadIdx.x;
+    const int base = blockIdx.x * 256;
+    const int nb   = min(256, nhome - base);
+    if (nb <= 0) return;
+    float ex = 0.f, ey = 0.f, ez = 0.f;
+    if (tid < nb)
+    {
+        float4    v = fg[slot_of_atom[base + tid]];
+        const int p = send_pos ? send_pos[base + tid] : -1;
+        if (p >= 0)
+        {
+            ex = __ldcg(recv_f + 3 * p);
+            ey = __ldcg(recv_f + 3 * p + 1);
+            ez = __ldcg(recv_f + 3 * p + 2);
+            v.x += ex;
+            v.y += ey;
+            v.z += ez;
+        }
+        sf[3 * tid]     = v.x;
+        sf[3 * tid + 1] = v.y;
+        sf[3 * tid + 2] = v.z;
+    }
+    if (fshift_edge)
+    {
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            ex += __shfl_xor_sync(0xffffffffu, ex, o);
+            ey += __shfl_xor_sync(0xffffffffu, ey, o);
+            ez += __shfl_xor_sync(0xffffffffu, ez, o);
+        }
+        if ((tid & 31) == 0 && (ex != 0.f || ey != 0.f || ez != 0.f))
+        {
+            float* fs = fshift_edge + (blockIdx.x & (NB_OUT_COPIES - 1)) * NB_FSHIFT_PITCH;
+            atomicAdd(fs, ex);
+            atomicAdd(fs + 1, ey);
+            atomicAdd(fs + 2, ez);
+        }
+    }
+    __syncthreads();
+    float*    dst = f + 3 * (size_t)base;
+    const int nfl = nb * 3;
+    if (VEC)
+    {
+        if (tid * 4 + 3 < nfl) reinterpret_cast<float4*>(dst)[tid] = *reinterpret_cast<const float4*>(&sf[tid * 4]);
+        else
+            for (int k = tid * 4; k < nfl && k < tid * 4 + 4; k++) dst[k] = sf[k];
+    }
+    else
+        for (int k = tid; k < nfl; k += 256) dst[k] = sf[k];
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" int b200nb_dd_create_window(b200nb_t* h, int max_halo, int max_send, void* ipc_handle_out, void** window_dev_out)
+{
+    if (!h || max_halo < 0 || max_send < 0) return nb_fail(h, B200NB_ERR_ARG, "dd_create_window: bad argument");
+    cudaSetDevice(h->device);
+    DdState& D = h->dd;
+    if (D.window) return nb_fail(h, B200NB_ERR_STATE, "dd_create_window: window exists (peers hold its handle)");
+    D.max_halo     = max_halo;
+    D.max_send     = max_send;
+    D.off_recv_x   = 256;
+    D.off_recv_f   = 256 + align256(sizeof(float) * 3 * (size_t)max_halo);
+    D.window_bytes = D.off_recv_f + align256(sizeof(float) * 3 * (size_t)max_send);
+    NB_CUDA(h, cudaMalloc((void**)&D.window, D.window_bytes));
+    NB_CUDA(h, cudaMemset(D.window, 0, D.window_bytes));
+    NB_CUDA(h, cudaMalloc((void**)&D.d_count, sizeof(int) * 2));
+    NB_CUDA(h, cudaMemset(D.d_count, 0, sizeof(int) * 2));
+    if (ipc_handle_out)
+    {
+        cudaIpcMemHandle_t hd;
+        NB_CUDA(h, cudaIpcGetMemHandle(&hd, D.window));
+        memcpy(ipc_handle_out, &hd, sizeof(hd));
+    }
+    if (window_dev_out) *window_dev_out = D.window;
+    return 0;
+}
+
+/* side 0: the -x neighbour (receives our halo coordinates), side 1: the +x neighbour (receives the forces on its atoms).
+ * Either an IPC handle from another process, or the window's device pointer when the peer lives in this process.
+ * peer_max_halo: the max_halo the peer created its window with (fixes where its recv_f block starts). */
+extern "C" int b200nb_dd_open_peer(b200nb_t* h, int side, const void* ipc_handle, void* same_process_window, int peer_max_halo)
+{
+    if (!h || side < 0 || side > 1 || (!ipc_handle && !same_process_window) || peer_max_halo < 0)
+        return nb_fail(h, B200NB_ERR_ARG, "dd_open_peer: bad argument");
+    cudaSetDevice(h->device);
+    DdState& D = h->dd;
+    if (D.peer[side] && D.peer_is_ipc[side]) cudaIpcCloseMemHandle(D.peer[side]);
+    D.peer[side] = nullptr;
+    if (same_process_window)
+    {
+        D.peer[side]        = static_cast<unsigned char*>(same_process_window);
+        D.peer_is_ipc[side] = false;
+    }
+    else
+    {
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, ipc_handle, sizeof(hd));
+        void* p = nullptr;
+        NB_CUDA(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        D.peer[side]        = static_cast<unsigned char*>(p);
+        D.peer_is_ipc[side] = true;
+    }
+    D.peer_off_recv_f[side] = 256 + align256(sizeof(float) * 3 * (size_t)peer_max_halo);
+    return 0;
+}
+
+/* The halo plan of the current pair-search interval: local atoms [0, nhome) are home, [nhome, nhome + nhalo) halo (in the
+ * order the +x neighbour sends them); send_idx_host: the nsend home atoms we send to the -x neighbour, shift added to them;
+ * edge_shift_index: shift-force slot the returned forces also count for when they crossed the periodic edge, else -1. */
+extern "C" int b200nb_dd_set_plan(b200nb_t* h, int nhome, int nhalo, const int* send_idx_host, int nsend, const float shift[3],
+                                  int edge_shift_index)
+{
+    if (!h || nhome < 0 || nhalo < 0 || nsend < 0 || (nsend && !send_idx_host)) return nb_fail(h, B200NB_ERR_ARG, "dd_set_plan: bad argument");
+    cudaSetDevice(h->device);
+    DdState& D = h->dd;
+    if (!D.window) return nb_fail(h, B200NB_ERR_STATE, "dd_set_plan: create the window first");
+    if (nhalo > D.max_halo || nsend > D.max_send) return nb_fail(h, B200NB_ERR_CAPACITY, "dd_set_plan: halo larger than the window");
+    if (nhome + nhalo != h->natoms) return nb_fail(h, B200NB_ERR_ARG, "dd_set_plan: nhome + nhalo != natoms");
+    if (ensure(h, &D.d_send_idx, &D.cap_send, (size_t)std::max(nsend, 1)) || ensure(h, &D.d_send_pos, &D.cap_home, (size_t)std::max(nhome, 1)))
+        return B200NB_ERR_CUDA;
+    std::vector<int> pos((size_t)std::max(nhome, 1), -1);
+    for (int k = 0; k < nsend; k++)
+    {
+        const int a = send_idx_host[k];
+        if (a < 0 || a >= nhome || pos[a] >= 0) return nb_fail(h, B200NB_ERR_ARG, "dd_set_plan: send index out of range or repeated");
+        pos[a] = k;
+    }
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (nsend) NB_CUDA(h, cudaMemcpy(D.d_send_idx, send_idx_host, sizeof(int) * nsend, cudaMemcpyHostToDevice));
+    NB_CUDA(h, cudaMemcpy(D.d_send_pos, pos.data(), sizeof(int) * std::max(nhome, 1), cudaMemcpyHostToDevice));
+    D.nhome = nhome;
+    D.nhalo = nhalo;
+    D.nsend = nsend;
+    for (int d = 0; d < 3; d++) D.shift[d] = shift ? shift[d] : 0.f;
+    D.edge_shift = edge_shift_index;
+    D.have_plan  = true;
+    return 0;
+}
+
+/* One step of the decomposed calculation, asynchronous on the context's stream (the nonbonded part of do_force,
+ * mdlib/sim_util.cpp:1388-1902): home x -> grid layout + clear | push halo x to the -x neighbour | local kernel |
+ * wait for our halo x, -> grid layout | non-local kernel | push halo forces to the +x neighbour | wait for the forces on
+ * the atoms we sent, add, un-sort.  x_home / f_home: nhome*3 floats, device or pinned host memory. */
+extern "C" int b200nb_dd_step(b200nb_t* h, const float* x_home, float* f_home, int flags)
+{
+    if (!h || !x_home || !f_home) return nb_fail(h, B200NB_ERR_ARG, "dd_step: bad argument");
+    DdState& D = h->dd;
+    if (!h->have_list || !D.have_plan) return nb_fail(h, B200NB_ERR_STATE, "dd_step: needs a pair list and a halo plan");
+    if ((D.nsend && !D.peer[0]) || (D.nhalo && !D.peer[1])) return nb_fail(h, B200NB_ERR_STATE, "dd_step: peer windows not opened");
+    cudaSetDevice(h->device);
+    if (h->map_x_host != x_home || h->map_f_host != f_home)
+    {
+        /* pinned host buffers are used in place through their device-visible address; device pointers pass through */
+        cudaPointerAttributes ax, af;
+        if (cudaPointerGetAttributes(&ax, x_home) != cudaSuccess || cudaPointerGetAttributes(&af, f_home) != cudaSuccess
+            || !ax.devicePointer || !af.devicePointer)
+        {
+            cudaGetLastError();
+            return nb_fail(h, B200NB_ERR_ARG, "dd_step: x_home / f_home must be device or pinned host memory");
+        }
+        h->map_x_host = x_home;
+        h->map_f_host = f_home;
+        h->map_x_dev  = static_cast<float*>(ax.devicePointer);
+        h->map_f_dev  = static_cast<float*>(af.devicePointer);
+    }
+    x_home = h->map_x_dev;
+    f_home = h->map_f_dev;
+    const int seq = ++D.seq;
+    int*      flag_x = reinterpret_cast<int*>(D.window);
+    int*      flag_f = reinterpret_cast<int*>(D.window + 64);
+    int*      err    = reinterpret_cast<int*>(D.window + 128);
+    const int n = D.nhome, nclear = h->npad + NB_DUMMY_SLOTS;
+    const unsigned nb0 = (unsigned)((std::max(std::max(n, nclear), NB_OUT_COPIES * NB_FSHIFT_PITCH) + 255) / 256);
+    PrefetchRange pf{};
+    {
+        const PackedList& P = h->packed[0];
+        pf.p[0]     = reinterpret_cast<const char*>(P.entries);
+        pf.bytes[0] = sizeof(Entry) * (size_t)P.nentries;
+        pf.p[1]     = reinterpret_cast<const char*>(P.ja);
+        pf.bytes[1] = sizeof(int) * 8 * (size_t)P.nentries * P.pitch;
+        pf.p[2]     = reinterpret_cast<const char*>(P.mask);
+        pf.bytes[2] = sizeof(uint64_t) * (size_t)P.nentries * P.pitch;
+        pf.p[3]     = reinterpret_cast<const char*>(h->comb_geom ? (const void*)h->d_lj : (const void*)h->d_atype);
+        pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
+    }
+    if ((reinterpret_cast<uintptr_t>(x_home) & 15) == 0)
+        k_step_begin<true><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf);
+    else
+        k_step_begin<false><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf);
+    LAUNCH_CHECK(h);
+    if (D.peer[0])
+    {
+        k_dd_push_x<<<(unsigned)std::max(1, (D.nsend + 255) / 256), 256, 0, h->stream>>>(
+                reinterpret_cast<const float4*>(h->d_xq), h->d_slot_of_atom, D.d_send_idx, D.nsend, D.shift[0], D.shift[1], D.shift[2],
+                reinterpret_cast<float*>(D.peer[0] + 256), reinterpret_cast<int*>(D.peer[0]), seq, D.d_count);
+        LAUNCH_CHECK(h);
+    }
+    int rc;
+    if ((rc = nb_launch_force_kernel(h, 0, flags))) return rc;
+    if (D.peer[1])
+    {
+        k_dd_wait<<<1, 1, 0, h->stream>>>(flag_x, seq, err);
+        LAUNCH_CHECK(h);
+        k_dd_recv_x<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, h->stream>>>(reinterpret_cast<const float*>(D.window + D.off_recv_x),
+                                                                                       h->d_slot_of_atom, D.nhome, D.nhalo, h->d_xq);
+        LAUNCH_CHECK(h);
+        if ((rc = nb_launch_force_kernel(h, 1, flags))) return rc;
+        k_dd_push_f<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, h->stream>>>(
+                h->d_f, h->d_slot_of_atom, D.nhome, D.nhalo, reinterpret_cast<float*>(D.peer[1] + D.peer_off_recv_f[1]),
+                reinterpret_cast<int*>(D.peer[1] + 64), seq, D.d_count + 1);
+        LAUNCH_CHECK(h);
+    }
+    const unsigned nb1 = (unsigned)std::max(1, (n + 255) / 256);
+    if (D.peer[0])
+    {
+        k_dd_wait<<<1, 1, 0, h->stream>>>(flag_f, seq, err);
+        LAUNCH_CHECK(h);
+    }
+    float* fse = (D.edge_shift >= 0 && (flags & B200NB_FLAG_VIRIAL)) ? h->d_fshift + 3 * D.edge_shift : nullptr;
+    if ((reinterpret_cast<uintptr_t>(f_home) & 15) == 0)
+        k_dd_step_end<true><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.peer[0] ? D.d_send_pos : nullptr,
+                                                       reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, fse);
+    else
+        k_dd_step_end<false><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.peer[0] ? D.d_send_pos : nullptr,
+                                                        reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, fse);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+/* after synchronising: B200NB_ERR_STATE when a halo flag did not arrive in time during any step since the last call */
+extern "C" int b200nb_dd_status(b200nb_t* h)
+{
+    if (!h) return B200NB_ERR_ARG;
+    DdState& D = h->dd;
+    if (!D.window) return 0;
+    cudaSetDevice(h->device);
+    int e = 0;
+    NB_CUDA(h, cudaMemcpy(&e, D.window + 128, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e)
+    {
+        cudaMemset(D.window + 128, 0, sizeof(int));
+        return nb_fail(h, B200NB_ERR_STATE, "dd_step: a halo exchange flag did not arrive within 2 s (peer stalled or not stepping)");
+    }
     return 0;
 }
 

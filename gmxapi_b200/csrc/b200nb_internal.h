@@ -90,6 +90,33 @@ struct PackedList
     size_t    cap_tiles = 0, cap_entries = 0;
 };
 
+/* Peer-memory halo exchange of the domain-decomposed step (b200nb_dd_*): each rank owns a WINDOW in its device memory,
+ *   [flag_x @0][flag_f @64][err @128] ... [recv_x: 3 floats per halo atom @256][recv_f: 3 floats per sent atom],
+ * that its neighbours write directly over NVLink (CUDA IPC mapping, or the plain device pointer inside one process):
+ * the rank that owns the halo atoms stores their coordinates into recv_x and then raises flag_x to the step number; the
+ * rank that computed forces on them stores those into the owner's recv_f and raises flag_f.  Consumer kernels spin on the
+ * flag in their own memory (bounded; a time-out raises err).  One exchange each way per step, no host involvement, no NCCL
+ * call on the per-step path (the reference pushes with cudaMemcpyAsync + event handshakes, gpuhaloexchange_impl.cu:403-444). */
+struct DdState
+{
+    unsigned char* window = nullptr;
+    size_t         window_bytes = 0;
+    int            max_halo = 0, max_send = 0;
+    size_t         off_recv_x = 256, off_recv_f = 0;
+    unsigned char* peer[2] = { nullptr, nullptr }; /* [0]: -x neighbour's window (we push x there), [1]: +x neighbour's (we push f) */
+    bool           peer_is_ipc[2] = { false, false };
+    size_t         peer_off_recv_f[2] = { 0, 0 };
+    int            nhome = 0, nhalo = 0, nsend = 0;
+    int*           d_send_idx = nullptr; /* home atoms we send, local indices */
+    int*           d_send_pos = nullptr; /* per home atom: its position in the send list or -1 */
+    size_t         cap_send = 0, cap_home = 0;
+    float          shift[3] = { 0, 0, 0 };
+    int            edge_shift = -1; /* shift index the returned forces also count for (periodic edge), or -1 */
+    int            seq = 0;
+    int*           d_count = nullptr; /* 2 last-block counters */
+    bool           have_plan = false;
+};
+
 struct b200nb_context
 {
     int          device = 0;
@@ -152,6 +179,7 @@ struct b200nb_context
     bool     inner_is_outer = true;
     bool     have_list = false;
     PackedList packed[2];
+    DdState    dd;
     int        dummy_slot = 0; /* first of the NB_DUMMY_SLOTS far-away filler slots appended after the grids */
 
     float* d_flush = nullptr;

@@ -247,7 +247,7 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
  * before the next step, so the instruction stream carries two independent dependency chains and the 4-cycle FMA, MUFU and
  * shuffle latencies of one tile are covered by the other (ncu: "wait"/"short scoreboard" stalls dominated the one-tile loop). */
 #ifndef B200NB_TILE_ILP
-#define B200NB_TILE_ILP 2
+#define B200NB_TILE_ILP 1 /* measured (profiles/r1/g_sweep_one_entry_per_warp.txt): 1 tile in flight at 32 warps/SM beats 2 at 20 */
 #endif
 template<int EEL, bool GEOM, int NT>
 __device__ __forceinline__ void tile_pairs_multi(const IData& I, const JAtom (&J)[NT], const NbParamsDev& P, const KConst& K,
@@ -379,7 +379,7 @@ __device__ __forceinline__ void reduce_store_j_multi(const float2 (&tx)[NT], con
 #define B200NB_FORCE_WARPS 1 /* warps (= list entries) per CTA: small CTAs refill an SM's warp slots at entry granularity */
 #endif
 #ifndef B200NB_FORCE_MIN_BLOCKS
-#define B200NB_FORCE_MIN_BLOCKS (20 / B200NB_FORCE_WARPS) /* 20 resident warps per SM = 96 registers per thread */
+#define B200NB_FORCE_MIN_BLOCKS (32 / B200NB_FORCE_WARPS) /* 32 resident warps per SM = 64 registers per thread */
 #endif
 template<int EEL, bool GEOM, bool VF>
 __global__ void __launch_bounds__(32 * B200NB_FORCE_WARPS, B200NB_FORCE_MIN_BLOCKS)

@@ -147,6 +147,11 @@ class TorchDistTransport:
     def barrier(self):
         self.dist.barrier(self.group)
 
+    def allgather_object(self, obj):
+        out = [None] * self.nranks
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
 
 class LoopbackTransport:
     """All ranks live in one process as threads (single-GPU parity tests): a queue per (src, dst) pair."""
@@ -157,6 +162,7 @@ class LoopbackTransport:
         self.q = {(s, d): queue.Queue() for s in range(nranks) for d in range(nranks)}
         import threading
         self._bar = threading.Barrier(nranks)
+        self._objs = [None] * nranks
 
     def endpoint(self, rank):
         return _LoopbackEndpoint(self, rank)
@@ -187,6 +193,13 @@ class _LoopbackEndpoint:
     def barrier(self):
         self.hub._bar.wait()
 
+    def allgather_object(self, obj):
+        self.hub._objs[self.rank] = obj
+        self.hub._bar.wait()
+        out = list(self.hub._objs)
+        self.hub._bar.wait()
+        return out
+
 
 # ---------------------------------------------------------------------------------------------------------
 # one rank of the decomposed calculation
@@ -196,11 +209,17 @@ class DomainRank:
     device buffers of the halo exchange, and the per-step schedule of do_force() (mdlib/sim_util.cpp:1388-1902
     restricted to the nonbonded path):
 
-        x home -> grid order | pack halo x -> send/recv -> halo x -> grid order | clear | local kernel |
-        non-local kernel | forces -> atom order | halo f send/recv -> unpack-add (+ shift force on the edge)
+        x home -> grid order + clear | push halo x | local kernel | wait halo x -> grid order | non-local kernel |
+        push halo f | wait halo f, add (+ shift force on the edge), forces -> atom order
+
+    Per step everything is ONE library call (b200nb_dd_step): the halos move through peer-memory windows written by
+    the neighbours' kernels over NVLink (CUDA IPC), flags instead of host synchronisation, no collective.  The
+    transport (NCCL send/recv, or the in-process loopback of the tests) is used at set-up (window handles) and on
+    pair-search steps, where the halo composition changes.  `use_windows=False` keeps the transport on the per-step
+    path as well (the first version of this file; kept for comparison runs).
     """
 
-    def __init__(self, system, options, transport, rank=None, nranks=None, device=0):
+    def __init__(self, system, options, transport, rank=None, nranks=None, device=0, use_windows=True):
         import torch
         self.torch = torch
         self.t = transport
@@ -232,7 +251,26 @@ class DomainRank:
             self.x[:p.nhome].copy_(torch.from_numpy(np.ascontiguousarray(system.x[p.home])))
         self.nb.synchronize()
         self.fshift_halo = np.zeros(3, np.float64)
+        self.use_windows = bool(use_windows) and self.nranks > 1
+        if self.use_windows:
+            self._open_windows()
         self.search(first=True)
+
+    # -- peer-memory halo windows: created once, sized with slack for later search steps -----------------------------------
+    def _open_windows(self):
+        import os
+        p = self.plan
+        max_halo = int(1.5 * p.nhalo) + 4096
+        max_send = int(1.5 * len(p.send_local)) + 4096
+        handle, ptr = self.nb.dd_create_window(max_halo, max_send)
+        info = self.t.allgather_object(dict(pid=os.getpid(), handle=handle, ptr=ptr, max_halo=max_halo))
+        for side, peer in ((0, p.left), (1, p.right)):
+            pi = info[peer]
+            if pi["pid"] == os.getpid():
+                self.nb.dd_open_peer(side, window_ptr=pi["ptr"], peer_max_halo=pi["max_halo"])
+            else:
+                self.nb.dd_open_peer(side, ipc_handle=pi["handle"], peer_max_halo=pi["max_halo"])
+        self.t.barrier()
 
     # -- pair search step: put_on_grid (home, then halo) + constructPairlist: mdlib/sim_util.cpp:1316-1366, 1454 ------
     def search(self, first=False):
@@ -248,6 +286,10 @@ class DomainRank:
             hu = np.array([upper[0] + self.rlist, box[1], box[2]], np.float32)
             self.nb.put_on_grid(self.x.data_ptr(), hl, hu, 1, p.nhome, self.nlocal, on_device=True)
         self.nb.build_pairlist()
+        if self.use_windows:
+            edge = SHIFT_PLUS_X if self.rank == 0 else -1
+            self.nb.dd_set_plan(p.nhome, p.nhalo, p.send_local, p.send_shift, edge)
+            self.t.barrier()  # every rank has its plan before anybody steps
 
     # -- dd_move_x ------------------------------------------------------------------------------------------------------
     def _halo_x(self):
@@ -276,6 +318,9 @@ class DomainRank:
     def step(self, flags=0):
         """One nonbonded step on coordinates already in self.x[:nhome] (device). Leaves forces in self.f[:nhome]."""
         p = self.plan
+        if self.use_windows:
+            self.nb.dd_step(self.x.data_ptr(), self.f.data_ptr(), flags)
+            return
         self.nb.set_x(self.x.data_ptr(), on_device=True, atom_begin=0, atom_end=p.nhome)
         self.nb.clear_outputs()
         self.nb.launch_force(0, flags)
@@ -296,16 +341,22 @@ class DomainRank:
         if f_home_host is None:
             f_home_host = torch.empty((p.nhome, 3), dtype=torch.float32).pin_memory()
         fh = f_home_host if isinstance(f_home_host, torch.Tensor) else torch.from_numpy(f_home_host)
-        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            self.x[:p.nhome].copy_(xh, non_blocking=True)
-            self.step(flags)
-            fh.copy_(self.f[:p.nhome], non_blocking=True)
+        if self.use_windows and xh.is_pinned() and fh.is_pinned():
+            # the kernels read the pinned coordinates and write the pinned forces in place (no staging copy)
+            self.nb.dd_step(xh.data_ptr(), fh.data_ptr(), flags)
+        else:
+            with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+                self.x[:p.nhome].copy_(xh, non_blocking=True)
+                self.step(flags)
+                fh.copy_(self.f[:p.nhome], non_blocking=True)
         self.nb.synchronize()
+        if self.use_windows:
+            self.nb.dd_status()
         fs = np.zeros((_lib.SHIFTS, 3), np.float32)
         elj = eel = 0.0
         if flags:
             fs, elj, eel = self.nb.get_outputs()
-            if self.rank == 0 and self.nranks > 1:
+            if self.rank == 0 and self.nranks > 1 and not self.use_windows:
                 fs[SHIFT_PLUS_X] += self.fshift_halo.astype(np.float32)
         return fh, fs, elj, eel
 

@@ -17,7 +17,8 @@ EXPORTS = [
     "b200nb_create", "b200nb_destroy", "b200nb_last_error", "b200nb_stream", "b200nb_set_stream", "b200nb_synchronize",
     "b200nb_set_params", "b200nb_set_atoms", "b200nb_set_box", "b200nb_put_on_grid", "b200nb_build_pairlist",
     "b200nb_set_x", "b200nb_clear_outputs", "b200nb_launch_force", "b200nb_launch_prune", "b200nb_get_f",
-    "b200nb_get_outputs", "b200nb_compute", "b200nb_step", "b200nb_halo_pack_x", "b200nb_halo_unpack_f", "b200nb_get_stats",
+    "b200nb_get_outputs", "b200nb_compute", "b200nb_step", "b200nb_dd_create_window", "b200nb_dd_open_peer", "b200nb_dd_set_plan",
+    "b200nb_dd_step", "b200nb_dd_status", "b200nb_halo_pack_x", "b200nb_halo_unpack_f", "b200nb_get_stats",
     "b200nb_get_grid_order", "b200nb_get_tiles", "b200nb_get_pairs", "b200nb_time_force_kernel", "b200nb_time_step",
 ]
 
@@ -80,6 +81,11 @@ def load_library():
     L.b200nb_get_outputs.argtypes = [vp, vp, vp]
     L.b200nb_compute.argtypes = [vp, vp, ci, vp, vp, vp]
     L.b200nb_step.argtypes = [vp, vp, ci, vp]
+    L.b200nb_dd_create_window.argtypes = [vp, ci, ci, vp, C.POINTER(vp)]
+    L.b200nb_dd_open_peer.argtypes = [vp, ci, vp, vp, ci]
+    L.b200nb_dd_set_plan.argtypes = [vp, ci, ci, vp, ci, vp, ci]
+    L.b200nb_dd_step.argtypes = [vp, vp, vp, ci]
+    L.b200nb_dd_status.argtypes = [vp]
     L.b200nb_halo_pack_x.argtypes = [vp, vp, vp, ci, vp, vp]
     L.b200nb_halo_unpack_f.argtypes = [vp, vp, vp, ci, vp]
     L.b200nb_get_stats.argtypes = [vp, C.POINTER(_Stats)]
@@ -242,6 +248,35 @@ class NbnxmGpu:
     def step(self, x_dev, f_dev, flags=0):
         """Device-resident step (x_dev, f_dev: device addresses of natoms*3 floats); asynchronous."""
         self._check(self._L.b200nb_step(self._h, _ptr(x_dev), flags, _ptr(f_dev)), "step")
+
+    # ---- domain-decomposed step over peer-memory halo windows ----
+    def dd_create_window(self, max_halo, max_send):
+        """Returns (64-byte CUDA IPC handle, device pointer) of this rank's halo window."""
+        handle = C.create_string_buffer(64)
+        ptr = C.c_void_p()
+        self._check(self._L.b200nb_dd_create_window(self._h, int(max_halo), int(max_send), handle, C.byref(ptr)),
+                    "dd_create_window")
+        return handle.raw, int(ptr.value)
+
+    def dd_open_peer(self, side, ipc_handle=None, window_ptr=None, peer_max_halo=0):
+        hb = C.create_string_buffer(ipc_handle, 64) if ipc_handle is not None else None
+        self._check(self._L.b200nb_dd_open_peer(self._h, int(side), hb, C.c_void_p(window_ptr) if window_ptr else None,
+                                                int(peer_max_halo)), "dd_open_peer")
+
+    def dd_set_plan(self, nhome, nhalo, send_idx, shift, edge_shift=-1):
+        si = np.ascontiguousarray(send_idx, dtype=np.int32)
+        sh = np.ascontiguousarray(shift, dtype=np.float32)
+        self._check(self._L.b200nb_dd_set_plan(self._h, int(nhome), int(nhalo), _ptr(si) if si.size else None, int(si.size),
+                                               _ptr(sh), int(edge_shift)), "dd_set_plan")
+
+    def dd_step(self, x_home, f_home, flags=0):
+        """x_home / f_home: addresses (device or pinned host) of nhome*3 floats; asynchronous."""
+        rc = self._L.b200nb_dd_step(self._h, x_home, f_home, flags)
+        if rc != 0:
+            self._check(rc, "dd_step")
+
+    def dd_status(self):
+        self._check(self._L.b200nb_dd_status(self._h), "dd_status")
 
     def halo_pack_x(self, x_dev, index_dev, n, shift, out_dev):
         s = np.ascontiguousarray(shift, dtype=np.float32)

@@ -150,6 +150,31 @@ int b200nb_halo_pack_x(b200nb_t* h, const float* x_dev, const int* index_dev, in
                        float* out_dev);
 int b200nb_halo_unpack_f(b200nb_t* h, float* f_dev, const int* index_dev, int n, const float* in_dev);
 
+/* ---- domain-decomposed step over peer-memory halo windows ---------------------------------------------------
+ * Replaces dd_move_x / dd_move_f (domdec/domdec.cpp:260-460) and GpuHaloExchange (domdec/gpuhaloexchange_impl.cu:133-444)
+ * on the per-step path for a 1-D (x-slab) decomposition with one pulse.  Each rank creates ONE window in its device memory
+ * and hands its CUDA IPC handle to both neighbours; the neighbours' kernels store halo coordinates / halo forces straight
+ * into it over NVLink and raise a flag, the owner's kernels wait on the flag (a one-thread wait kernel, bounded to 10 s).  No host synchronisation and no
+ * library collective inside a step.  b200nb_halo_pack_x / _unpack_f above remain for callers that move the data themselves
+ * (the pair-search step, where the halo composition changes, goes through them). */
+/* ipc_handle_out: 64 bytes (cudaIpcMemHandle_t) for peers in other processes; window_dev_out: the device pointer, for peers
+ * in this process.  max_halo / max_send bound the plans that may be set later. */
+int b200nb_dd_create_window(b200nb_t* h, int max_halo, int max_send, void* ipc_handle_out, void** window_dev_out);
+/* side 0 = the -x neighbour (gets our halo coordinates), side 1 = the +x neighbour (gets the forces on its atoms);
+ * give either the peer's IPC handle or, inside one process, its window pointer; peer_max_halo = the peer's max_halo. */
+int b200nb_dd_open_peer(b200nb_t* h, int side, const void* ipc_handle, void* same_process_window, int peer_max_halo);
+/* Plan of the current search interval: local atoms [0, nhome) home, [nhome, natoms) halo in the +x neighbour's send order;
+ * send_idx_host[nsend]: home atoms sent to the -x neighbour with `shift` added (dd_move_x's box shift, domdec.cpp:300-318);
+ * edge_shift_index: shift-force slot that also receives the returned forces (domdec.cpp:426-458) or -1. */
+int b200nb_dd_set_plan(b200nb_t* h, int nhome, int nhalo, const int* send_idx_host, int nsend, const float shift[3],
+                       int edge_shift_index);
+/* One decomposed step, asynchronous on the context's stream: 9 launches (x -> grid + clear; push halo x; local kernel; wait;
+ * halo x -> grid; non-local kernel; push halo f; wait; add + un-sort).  x_home in, f_home out: nhome*3 floats, device or
+ * pinned host memory.  Every neighbour must call it the same number of times. */
+int b200nb_dd_step(b200nb_t* h, const float* x_home, float* f_home, int flags);
+/* after b200nb_synchronize: B200NB_ERR_STATE if a halo flag timed out in any step since the last call */
+int b200nb_dd_status(b200nb_t* h);
+
 /* ---- introspection used by the parity tests and the bench ------------------------------------------------ */
 typedef struct
 {

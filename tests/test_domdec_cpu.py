@@ -123,7 +123,12 @@ def _worker(rank, world, port, q):
         exp[plan.send_local] = plan.home[plan.send_local]
         ok_f = bool(np.array_equal(f[:plan.nhome, 0].numpy(), exp))
         tot = t.allreduce_sum(torch.tensor([float(plan.nhome)]))
-        q.put((rank, ok_x, ok_f, int(tot.item()) == s.n, plan.nhalo))
+        # window set-up exchange of DomainRank._open_windows: every rank learns both neighbours' (pid, handle, size);
+        # what a rank will receive as halo must fit what its +x neighbour says it sends, and vice versa
+        info = t.allgather_object(dict(pid=os.getpid(), rank=rank, nsend=len(plan.send_local), nhalo=plan.nhalo))
+        ok_w = (info[plan.right]["nsend"] == plan.nhalo and info[plan.left]["nhalo"] == len(plan.send_local)
+                and [i["rank"] for i in info] == list(range(world)) and len({i["pid"] for i in info}) == world)
+        q.put((rank, ok_x, ok_f and ok_w, int(tot.item()) == s.n, plan.nhalo))
     finally:
         dist.destroy_process_group()
 

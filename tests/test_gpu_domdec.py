@@ -35,15 +35,21 @@ def canonical(pairs_global, tx_dd):
     return (i << 34) | (j << 6) | idx
 
 
-def run_ranks(s, opt, nranks, flags):
+def run_ranks(s, opt, nranks, flags, use_windows=True, nsteps=1):
     hub = LoopbackTransport(nranks)
     out = [None] * nranks
     err = []
 
     def work(r):
         try:
-            d = DomainRank(s, opt, hub.endpoint(r), rank=r, nranks=nranks, device=0)
-            f, fs, elj, eel = d.compute(np.ascontiguousarray(s.x[d.plan.home]), flags)
+            d = DomainRank(s, opt, hub.endpoint(r), rank=r, nranks=nranks, device=0, use_windows=use_windows)
+            assert d.use_windows == use_windows
+            import torch
+            xh = np.ascontiguousarray(s.x[d.plan.home])
+            if r % 2 == 0:
+                xh = torch.from_numpy(xh).pin_memory()  # even ranks: pinned host buffers, read / written in place by the kernels
+            for _ in range(nsteps):  # repeated steps reuse the windows: flags advance, buffers are overwritten
+                f, fs, elj, eel = d.compute(xh, flags)
             pr = d.nb.pairs(RC)
             p = d.plan
             loc = p.local
@@ -70,15 +76,20 @@ def run_ranks(s, opt, nranks, flags):
     return out
 
 
-@pytest.mark.parametrize("name,nranks,coulomb", [("water_24k", 2, g.CoulombType.Pme), ("water_24k", 3, g.CoulombType.ReactionField),
-                                                 ("water_24k", 6, g.CoulombType.Pme), ("water_96k", 4, g.CoulombType.Pme)])
-def test_domain_decomposition_matches_single_domain(built, name, nranks, coulomb):
+@pytest.mark.parametrize("name,nranks,coulomb,windows", [("water_24k", 2, g.CoulombType.Pme, True),
+                                                         ("water_24k", 3, g.CoulombType.ReactionField, True),
+                                                         ("water_24k", 6, g.CoulombType.Pme, True),
+                                                         ("water_96k", 4, g.CoulombType.Pme, True),
+                                                         ("water_24k", 3, g.CoulombType.Pme, False)])
+def test_domain_decomposition_matches_single_domain(built, name, nranks, coulomb, windows):
+    """windows=True: halos move through the peer-memory windows of b200nb_dd_step (the product path);
+    windows=False: through the transport's send/recv with the separate pack / unpack kernels."""
     s = g.systems.named(name)
     # reaction field with epsilon_rf = infinity (benchmark/bench_setup.cpp:152-155): the force vanishes at the cut-off, so
     # a pair flipped by the rounding of the periodic-edge shift (below) cannot show up in the forces
     opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coulomb, computeVirialAndEnergy=True, epsilonRf=0.0)
     flags = nb.FLAG_ENERGY | nb.FLAG_VIRIAL
-    res = run_ranks(s, opt, nranks, flags)
+    res = run_ranks(s, opt, nranks, flags, use_windows=windows, nsteps=3 if windows else 1)
     if coulomb == g.CoulombType.Pme:
         kw = dict(eeltype=oracle.EEL_EWALD, beta=float(np.float32(g.systems.ewald_beta(RC))))
     else:
