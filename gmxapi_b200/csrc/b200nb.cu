@@ -116,6 +116,13 @@ extern "C" void b200nb_destroy(b200nb_t* h)
     }
     for (int side = 0; side < 2; side++)
         if (h->dd.peer[side] && h->dd.peer_is_ipc[side]) cudaIpcCloseMemHandle(h->dd.peer[side]);
+    if (h->dd.stream_nl)
+    {
+        cudaStreamSynchronize(h->dd.stream_nl);
+        cudaStreamDestroy(h->dd.stream_nl);
+        cudaEventDestroy(h->dd.ev_begin);
+        cudaEventDestroy(h->dd.ev_nl_done);
+    }
     cudaFree(h->dd.window);
     cudaFree(h->dd.d_count);
     cudaFree(h->dd.d_send_idx);
@@ -1933,6 +1940,13 @@ extern "C" int b200nb_dd_create_window(b200nb_t* h, int max_halo, int max_send, 
     NB_CUDA(h, cudaMemset(D.window, 0, D.window_bytes));
     NB_CUDA(h, cudaMalloc((void**)&D.d_count, sizeof(int) * 2));
     NB_CUDA(h, cudaMemset(D.d_count, 0, sizeof(int) * 2));
+    {
+        int lo = 0, hi = 0;
+        NB_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi)); /* hi = numerically lowest = highest priority */
+        NB_CUDA(h, cudaStreamCreateWithPriority(&D.stream_nl, cudaStreamNonBlocking, hi));
+        NB_CUDA(h, cudaEventCreateWithFlags(&D.ev_begin, cudaEventDisableTiming));
+        NB_CUDA(h, cudaEventCreateWithFlags(&D.ev_nl_done, cudaEventDisableTiming));
+    }
     if (ipc_handle_out)
     {
         cudaIpcMemHandle_t hd;
@@ -2056,9 +2070,13 @@ extern "C" int b200nb_dd_step(b200nb_t* h, const float* x_home, float* f_home, i
     else
         k_step_begin<false><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf);
     LAUNCH_CHECK(h);
+    /* halo chain on the high-priority non-local stream, local kernel on the main stream */
+    cudaStream_t snl = D.stream_nl;
+    NB_CUDA(h, cudaEventRecord(D.ev_begin, h->stream));
+    NB_CUDA(h, cudaStreamWaitEvent(snl, D.ev_begin, 0));
     if (D.peer[0])
     {
-        k_dd_push_x<<<(unsigned)std::max(1, (D.nsend + 255) / 256), 256, 0, h->stream>>>(
+        k_dd_push_x<<<(unsigned)std::max(1, (D.nsend + 255) / 256), 256, 0, snl>>>(
                 reinterpret_cast<const float4*>(h->d_xq), h->d_slot_of_atom, D.d_send_idx, D.nsend, D.shift[0], D.shift[1], D.shift[2],
                 reinterpret_cast<float*>(D.peer[0] + 256), reinterpret_cast<int*>(D.peer[0]), seq, D.d_count);
         LAUNCH_CHECK(h);
@@ -2067,17 +2085,23 @@ extern "C" int b200nb_dd_step(b200nb_t* h, const float* x_home, float* f_home, i
     if ((rc = nb_launch_force_kernel(h, 0, flags))) return rc;
     if (D.peer[1])
     {
-        k_dd_wait<<<1, 1, 0, h->stream>>>(flag_x, seq, err);
+        k_dd_wait<<<1, 1, 0, snl>>>(flag_x, seq, err);
         LAUNCH_CHECK(h);
-        k_dd_recv_x<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, h->stream>>>(reinterpret_cast<const float*>(D.window + D.off_recv_x),
-                                                                                       h->d_slot_of_atom, D.nhome, D.nhalo, h->d_xq);
+        k_dd_recv_x<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, snl>>>(reinterpret_cast<const float*>(D.window + D.off_recv_x),
+                                                                                 h->d_slot_of_atom, D.nhome, D.nhalo, h->d_xq);
         LAUNCH_CHECK(h);
-        if ((rc = nb_launch_force_kernel(h, 1, flags))) return rc;
-        k_dd_push_f<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, h->stream>>>(
+        cudaStream_t keep = h->stream;
+        h->stream         = snl; /* the non-local kernel goes to the non-local stream */
+        rc                = nb_launch_force_kernel(h, 1, flags);
+        h->stream         = keep;
+        if (rc) return rc;
+        k_dd_push_f<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, snl>>>(
                 h->d_f, h->d_slot_of_atom, D.nhome, D.nhalo, reinterpret_cast<float*>(D.peer[1] + D.peer_off_recv_f[1]),
                 reinterpret_cast<int*>(D.peer[1] + 64), seq, D.d_count + 1);
         LAUNCH_CHECK(h);
     }
+    NB_CUDA(h, cudaEventRecord(D.ev_nl_done, snl));
+    NB_CUDA(h, cudaStreamWaitEvent(h->stream, D.ev_nl_done, 0));
     const unsigned nb1 = (unsigned)std::max(1, (n + 255) / 256);
     if (D.peer[0])
     {
@@ -2107,7 +2131,7 @@ extern "C" int b200nb_dd_status(b200nb_t* h)
     if (e)
     {
         cudaMemset(D.window + 128, 0, sizeof(int));
-        return nb_fail(h, B200NB_ERR_STATE, "dd_step: a halo exchange flag did not arrive within 2 s (peer stalled or not stepping)");
+        return nb_fail(h, B200NB_ERR_STATE, "dd_step: a halo exchange flag did not arrive within 10 s (peer stalled or not stepping)");
     }
     return 0;
 }

@@ -115,6 +115,10 @@ struct DdState
     int            seq = 0;
     int*           d_count = nullptr; /* 2 last-block counters */
     bool           have_plan = false;
+    /* the halo chain (push x, wait, halo x -> grid, non-local kernel, push f) runs on its own high-priority stream beside
+     * the local kernel, the reference's local / non-local stream split (cuda/nbnxm_cuda_data_mgmt.cu:260-291) */
+    cudaStream_t   stream_nl = nullptr;
+    cudaEvent_t    ev_begin = nullptr, ev_nl_done = nullptr;
 };
 
 struct b200nb_context

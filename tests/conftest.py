@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# The single-GPU domain-decomposition tests run up to 6 ranks x 2 streams in ONE process; with CUDA's default of 8 hardware
+# queues, streams alias and a flag-wait kernel could sit in front of the push kernel it waits for.  Production runs one
+# process per GPU (2 streams).  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
