@@ -116,6 +116,8 @@ extern "C" void b200nb_destroy(b200nb_t* h)
     }
     for (int side = 0; side < 2; side++)
         if (h->dd.peer[side] && h->dd.peer_is_ipc[side]) cudaIpcCloseMemHandle(h->dd.peer[side]);
+    for (auto& G : h->graph)
+        if (G.exec) cudaGraphExecDestroy(G.exec);
     if (h->dd.stream_nl)
     {
         cudaStreamSynchronize(h->dd.stream_nl);
@@ -1322,6 +1324,7 @@ extern "C" int b200nb_build_pairlist(b200nb_t* h)
         if (launch_pack(h, loc, 0, 1)) return B200NB_ERR_CUDA;
     NB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->have_list = true;
+    h->generation++;
     return 0;
 }
 
@@ -1502,18 +1505,85 @@ __global__ void k_flush(float* p, size_t n)
  * Both buffer kernels move the atom-order arrays as coalesced 16-byte vectors through shared memory, so x / f may be
  * device memory or PINNED HOST memory mapped into the device address space: in the host case the kernels read and write
  * it over PCIe themselves (no separate cudaMemcpyAsync, no staging buffer, two fewer dependent launches per step). */
+#define NB_DD_SPIN_LIMIT_NS 10000000000ll /* a flag that does not arrive within 10 s raises the window's err word */
+
+/* flags of the peer-memory halo windows (DdState, b200nb_internal.h): system-scope release / acquire */
+__device__ __forceinline__ int ld_acquire_sys(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ long long globaltimer_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+/* thread 0 of the CTA waits until *flag >= *seq (the step number, device-resident so that a captured CUDA graph of the step
+ * can be replayed), then the CTA proceeds.  Bounded: a peer that never arrives raises *err instead of hanging the GPU. */
+__device__ __forceinline__ void wait_flag(const int* flag, const int* seq, int* err)
+{
+    if (threadIdx.x == 0)
+    {
+        const int       want = *reinterpret_cast<const volatile int*>(seq);
+        const long long t0   = globaltimer_ns();
+        while (ld_acquire_sys(flag) < want)
+        {
+            __nanosleep(64);
+            if (globaltimer_ns() - t0 > NB_DD_SPIN_LIMIT_NS)
+            {
+                atomicExch(err, 1);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+/* after this CTA's stores to the peer: the last CTA of the grid publishes the step number in the peer's flag */
+__device__ __forceinline__ void publish_flag(int* counter, int* peer_flag, const int* seq)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        if (atomicAdd(counter, 1) == (int)gridDim.x - 1)
+        {
+            *counter = 0;
+            __threadfence_system();
+            st_release_sys(peer_flag, *reinterpret_cast<const volatile int*>(seq));
+        }
+    }
+}
+
+/* what k_step_begin does on top of its single-domain work when the step is domain-decomposed */
+struct DdBegin
+{
+    int*       seq;        /* step counter, incremented here */
+    const int* send_pos;   /* per home atom: position in the send list or -1 */
+    float      sx, sy, sz; /* shift added to the coordinates we send (box on the periodic edge) */
+    float*     peer_recv_x;
+    int*       peer_flag;
+    int*       counter;
+};
+
 struct PrefetchRange
 {
     const char* p[4];
     size_t      bytes[4];
 };
-template<bool VEC>
+template<bool VEC, bool DD>
 __global__ void __launch_bounds__(256)
 k_step_begin(const float* __restrict__ x, const int* __restrict__ slot_of_atom, int a0, int a1, float* __restrict__ xq,
-             float4* __restrict__ f, int nclear, float* __restrict__ fshift, double* __restrict__ energy, PrefetchRange pf)
+             float4* __restrict__ f, int nclear, float* __restrict__ fshift, double* __restrict__ energy, PrefetchRange pf, DdBegin dd)
 {
     __shared__ __align__(16) float sx[768];
     const int tid = threadIdx.x, t = blockIdx.x * 256 + tid;
+    if (DD && t == 0) *dd.seq = *dd.seq + 1; /* published to the other CTAs by the fence + counter in publish_flag */
     /* pull the read-only inputs of the force kernel that is about to run (packed list, LJ parameters) into L2 while this
      * kernel streams the coordinates: its prologue is a chain of dependent loads, ~3x shorter on L2 hits than from HBM */
 #pragma unroll
@@ -1525,17 +1595,19 @@ k_step_begin(const float* __restrict__ x, const int* __restrict__ slot_of_atom, 
     if (t < NB_OUT_COPIES * 2) energy[t] = 0.0;
     const int base = a0 + blockIdx.x * 256;
     const int nb   = min(256, a1 - base);
-    if (nb <= 0) return;
-    const float* src = x + 3 * (size_t)base;
-    const int    nfl = nb * 3;
-    if (VEC)
+    if (nb > 0)
     {
-        if (tid * 4 + 3 < nfl) *reinterpret_cast<float4*>(&sx[tid * 4]) = reinterpret_cast<const float4*>(src)[tid];
+        const float* src = x + 3 * (size_t)base;
+        const int    nfl = nb * 3;
+        if (VEC)
+        {
+            if (tid * 4 + 3 < nfl) *reinterpret_cast<float4*>(&sx[tid * 4]) = reinterpret_cast<const float4*>(src)[tid];
+            else
+                for (int k = tid * 4; k < nfl && k < tid * 4 + 4; k++) sx[k] = src[k];
+        }
         else
-            for (int k = tid * 4; k < nfl && k < tid * 4 + 4; k++) sx[k] = src[k];
+            for (int k = tid; k < nfl; k += 256) sx[k] = src[k];
     }
-    else
-        for (int k = tid; k < nfl; k += 256) sx[k] = src[k];
     __syncthreads();
     if (tid < nb)
     {
@@ -1543,7 +1615,20 @@ k_step_begin(const float* __restrict__ x, const int* __restrict__ slot_of_atom, 
         xb[0]     = sx[3 * tid];
         xb[1]     = sx[3 * tid + 1];
         xb[2]     = sx[3 * tid + 2];
+        if (DD)
+        {
+            /* dd_move_x, sending side (packSendBufKernel, gpuhaloexchange_impl.cu:77-100) fused with the transfer: atoms within
+             * rlist of our lower face go straight into the -x neighbour's window, shifted on the periodic edge */
+            const int p = dd.send_pos[base + tid];
+            if (p >= 0)
+            {
+                dd.peer_recv_x[3 * p]     = sx[3 * tid] + dd.sx;
+                dd.peer_recv_x[3 * p + 1] = sx[3 * tid + 1] + dd.sy;
+                dd.peer_recv_x[3 * p + 2] = sx[3 * tid + 2] + dd.sz;
+            }
+        }
     }
+    if (DD && dd.peer_flag) publish_flag(dd.counter, dd.peer_flag, dd.seq);
 }
 
 template<bool VEC>
@@ -1594,9 +1679,9 @@ static int launch_step(b200nb_context* h, const float* x_dev, int flags, float* 
         pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
     }
     if ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0)
-        k_step_begin<true><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf);
+        k_step_begin<true, false><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, DdBegin{});
     else
-        k_step_begin<false><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf);
+        k_step_begin<false, false><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, DdBegin{});
     LAUNCH_CHECK(h);
     int rc;
     if (ev_force0) NB_CUDA(h, cudaEventRecord(ev_force0, h->stream));
@@ -1608,6 +1693,8 @@ static int launch_step(b200nb_context* h, const float* x_dev, int flags, float* 
     return 0;
 }
 
+static int run_step_graph(b200nb_context* h, int which, const float* x, float* f, int flags);
+
 /* device-resident step (the reference's GPU buffer-ops path, mdlib/sim_util.cpp:1043-1108): asynchronous on the stream */
 extern "C" int b200nb_step(b200nb_t* h, const float* x_dev, int flags, float* f_dev)
 {
@@ -1615,7 +1702,7 @@ extern "C" int b200nb_step(b200nb_t* h, const float* x_dev, int flags, float* f_
     if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "step: no pair list");
     if (h->grid[1].valid) return nb_fail(h, B200NB_ERR_STATE, "step: single-domain call on a context with a halo grid");
     cudaSetDevice(h->device);
-    return launch_step(h, x_dev, flags, f_dev);
+    return run_step_graph(h, 0, x_dev, f_dev, flags);
 }
 
 /* Times `niter` device-resident steps with CUDA events on the context's stream: the whole step and, inside it, the
@@ -1698,7 +1785,7 @@ extern "C" int b200nb_compute(b200nb_t* h, const float* x_host, int flags, float
     if (!fd) fd = mapped_host_pointer(h->h_pinned + off_out / 2);
     if (!xd || !fd) return nb_fail(h, B200NB_ERR_CUDA, "compute: pinned host memory is not mapped into the device address space");
     int rc;
-    if ((rc = launch_step(h, xd, flags, fd))) return rc;
+    if ((rc = run_step_graph(h, 0, xd, fd, flags))) return rc;
     float*  fs_pin = reinterpret_cast<float*>(h->h_pinned + off_out);
     double* e_pin  = reinterpret_cast<double*>(h->h_pinned + off_out + 640);
     if (want_out)
@@ -1768,77 +1855,12 @@ extern "C" int b200nb_halo_unpack_f(b200nb_t* h, float* f_dev, const int* index_
 /* ------------------------------------------------------------------------------------------------------ */
 /* domain-decomposed step over peer-memory halo windows (DdState, b200nb_internal.h)                      */
 /* ------------------------------------------------------------------------------------------------------ */
-#define NB_DD_SPIN_LIMIT_NS 10000000000ll /* a flag that does not arrive within 10 s raises the window's err word */
-
-__device__ __forceinline__ int ld_acquire_sys(const int* p)
-{
-    int v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(int* p, int v)
-{
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ long long globaltimer_ns()
-{
-    long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-/* Waits until *flag >= seq: a one-thread kernel, so that a late peer costs one idle warp slot and never SM capacity the
- * peer's own kernels might need when several ranks share a GPU (the single-GPU parity tests); the kernel boundary orders the
- * consumer's loads after the flag. */
-__global__ void k_dd_wait(const int* __restrict__ flag, int seq, int* __restrict__ err)
-{
-    const long long t0 = globaltimer_ns();
-    while (ld_acquire_sys(flag) < seq)
-    {
-        __nanosleep(100);
-        if (globaltimer_ns() - t0 > NB_DD_SPIN_LIMIT_NS)
-        {
-            atomicExch(err, 1);
-            break;
-        }
-    }
-}
-/* after this CTA's stores to the peer: the last CTA of the grid publishes the flag */
-__device__ __forceinline__ void publish_flag(int* counter, int* peer_flag, int seq)
-{
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        if (atomicAdd(counter, 1) == (int)gridDim.x - 1)
-        {
-            *counter = 0;
-            __threadfence_system();
-            st_release_sys(peer_flag, seq);
-        }
-    }
-}
-
-/* dd_move_x, sending side: packSendBufKernel (gpuhaloexchange_impl.cu:77-100) fused with the transfer: the coordinates of
- * the atoms within rlist of our lower face (+ box shift on the periodic edge) go straight into the -x neighbour's window */
-__global__ void __launch_bounds__(256)
-k_dd_push_x(const float4* __restrict__ xq, const int* __restrict__ slot_of_atom, const int* __restrict__ send_idx, int nsend, float sx,
-            float sy, float sz, float* __restrict__ peer_recv_x, int* __restrict__ peer_flag, int seq, int* __restrict__ counter)
-{
-    const int k = blockIdx.x * 256 + threadIdx.x;
-    if (k < nsend)
-    {
-        const float4 v      = xq[slot_of_atom[send_idx[k]]];
-        peer_recv_x[3 * k]     = v.x + sx;
-        peer_recv_x[3 * k + 1] = v.y + sy;
-        peer_recv_x[3 * k + 2] = v.z + sz;
-    }
-    publish_flag(counter, peer_flag, seq);
-}
-
 /* dd_move_x, receiving side, fused with nbnxn_gpu_x_to_nbat_x for the halo grid: window -> grid layout */
 __global__ void __launch_bounds__(256)
-k_dd_recv_x(const float* __restrict__ recv_x, const int* __restrict__ slot_of_atom, int nhome, int nhalo, float* __restrict__ xq)
+k_dd_recv_x(const int* __restrict__ flag, const int* __restrict__ seq, int* __restrict__ err, const float* __restrict__ recv_x,
+            const int* __restrict__ slot_of_atom, int nhome, int nhalo, float* __restrict__ xq)
 {
+    wait_flag(flag, seq, err);
     const int k = blockIdx.x * 256 + threadIdx.x;
     if (k >= nhalo) return;
     float* xb = xq + 4 * (size_t)slot_of_atom[nhome + k];
@@ -1850,7 +1872,7 @@ k_dd_recv_x(const float* __restrict__ recv_x, const int* __restrict__ slot_of_at
 /* dd_move_f, sending side: the forces we computed on the halo atoms go into their owner's (+x neighbour's) window */
 __global__ void __launch_bounds__(256)
 k_dd_push_f(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom, int nhome, int nhalo, float* __restrict__ peer_recv_f,
-            int* __restrict__ peer_flag, int seq, int* __restrict__ counter)
+            int* __restrict__ peer_flag, const int* __restrict__ seq, int* __restrict__ counter)
 {
     const int k = blockIdx.x * 256 + threadIdx.x;
     if (k < nhalo)
@@ -1869,12 +1891,14 @@ k_dd_push_f(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom,
 template<bool VEC>
 __global__ void __launch_bounds__(256)
 k_dd_step_end(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom, int nhome, const int* __restrict__ send_pos,
-              const float* __restrict__ recv_f, float* __restrict__ f, float* __restrict__ fshift_edge)
+              const int* __restrict__ flag, const int* __restrict__ seq, int* __restrict__ err, const float* __restrict__ recv_f,
+              float* __restrict__ f, float* __restrict__ fshift_edge)
 {
     __shared__ __align__(16) float sf[768];
     const int tid  = threadIdx.x;
     const int base = blockIdx.x * 256;
     const int nb   = min(256, nhome - base);
+    if (flag) wait_flag(flag, seq, err); /* the forces on the atoms we sent have landed in our window */
     if (nb <= 0) return;
     float ex = 0.f, ey = 0.f, ez = 0.f;
     if (tid < nb)
@@ -1938,8 +1962,9 @@ extern "C" int b200nb_dd_create_window(b200nb_t* h, int max_halo, int max_send, 
     D.window_bytes = D.off_recv_f + align256(sizeof(float) * 3 * (size_t)max_send);
     NB_CUDA(h, cudaMalloc((void**)&D.window, D.window_bytes));
     NB_CUDA(h, cudaMemset(D.window, 0, D.window_bytes));
-    NB_CUDA(h, cudaMalloc((void**)&D.d_count, sizeof(int) * 2));
-    NB_CUDA(h, cudaMemset(D.d_count, 0, sizeof(int) * 2));
+    NB_CUDA(h, cudaMalloc((void**)&D.d_count, sizeof(int) * 4));
+    NB_CUDA(h, cudaMemset(D.d_count, 0, sizeof(int) * 4));
+    D.d_seq = D.d_count + 2; /* the step counter the flags carry */
     {
         int lo = 0, hi = 0;
         NB_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi)); /* hi = numerically lowest = highest priority */
@@ -2016,13 +2041,127 @@ extern "C" int b200nb_dd_set_plan(b200nb_t* h, int nhome, int nhalo, const int* 
     for (int d = 0; d < 3; d++) D.shift[d] = shift ? shift[d] : 0.f;
     D.edge_shift = edge_shift_index;
     D.have_plan  = true;
+    h->generation++;
+    return 0;
+}
+
+/* the launches of one decomposed step; x_home / f_home are device-visible addresses */
+static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home, int flags)
+{
+    DdState&  D      = h->dd;
+    int*      flag_x = reinterpret_cast<int*>(D.window);
+    int*      flag_f = reinterpret_cast<int*>(D.window + 64);
+    int*      err    = reinterpret_cast<int*>(D.window + 128);
+    const int n = D.nhome, nclear = h->npad + NB_DUMMY_SLOTS;
+    const unsigned nb0 = (unsigned)((std::max(std::max(n, nclear), NB_OUT_COPIES * NB_FSHIFT_PITCH) + 255) / 256);
+    PrefetchRange pf{};
+    {
+        const PackedList& P = h->packed[0];
+        pf.p[0]     = reinterpret_cast<const char*>(P.entries);
+        pf.bytes[0] = sizeof(Entry) * (size_t)P.nentries;
+        pf.p[1]     = reinterpret_cast<const char*>(P.ja);
+        pf.bytes[1] = sizeof(int) * 8 * (size_t)P.nentries * P.pitch;
+        pf.p[2]     = reinterpret_cast<const char*>(P.mask);
+        pf.bytes[2] = sizeof(uint64_t) * (size_t)P.nentries * P.pitch;
+        pf.p[3]     = reinterpret_cast<const char*>(h->comb_geom ? (const void*)h->d_lj : (const void*)h->d_atype);
+        pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
+    }
+    DdBegin B{};
+    B.seq      = D.d_seq;
+    B.send_pos = D.d_send_pos;
+    B.sx = D.shift[0], B.sy = D.shift[1], B.sz = D.shift[2];
+    B.peer_recv_x = D.peer[0] ? reinterpret_cast<float*>(D.peer[0] + 256) : nullptr;
+    B.peer_flag   = D.peer[0] ? reinterpret_cast<int*>(D.peer[0]) : nullptr;
+    B.counter     = D.d_count;
+    /* 1. home x -> grid layout, outputs cleared, halo x pushed into the -x neighbour's window */
+    if ((reinterpret_cast<uintptr_t>(x_home) & 15) == 0)
+        k_step_begin<true, true><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, B);
+    else
+        k_step_begin<false, true><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, B);
+    LAUNCH_CHECK(h);
+    /* 2. the halo chain on the high-priority non-local stream, the local kernel on the main stream */
+    cudaStream_t snl = D.stream_nl;
+    NB_CUDA(h, cudaEventRecord(D.ev_begin, h->stream));
+    NB_CUDA(h, cudaStreamWaitEvent(snl, D.ev_begin, 0));
+    int rc;
+    if ((rc = nb_launch_force_kernel(h, 0, flags))) return rc;
+    if (D.peer[1])
+    {
+        k_dd_recv_x<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, snl>>>(flag_x, D.d_seq, err,
+                                                                                 reinterpret_cast<const float*>(D.window + D.off_recv_x),
+                                                                                 h->d_slot_of_atom, D.nhome, D.nhalo, h->d_xq);
+        LAUNCH_CHECK(h);
+        cudaStream_t keep = h->stream;
+        h->stream         = snl; /* the non-local kernel goes to the non-local stream */
+        rc                = nb_launch_force_kernel(h, 1, flags);
+        h->stream         = keep;
+        if (rc) return rc;
+        k_dd_push_f<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, snl>>>(
+                h->d_f, h->d_slot_of_atom, D.nhome, D.nhalo, reinterpret_cast<float*>(D.peer[1] + D.peer_off_recv_f[1]),
+                reinterpret_cast<int*>(D.peer[1] + 64), D.d_seq, D.d_count + 1);
+        LAUNCH_CHECK(h);
+    }
+    NB_CUDA(h, cudaEventRecord(D.ev_nl_done, snl));
+    NB_CUDA(h, cudaStreamWaitEvent(h->stream, D.ev_nl_done, 0));
+    /* 3. wait for the forces on the atoms we sent, add them, forces -> atom order */
+    const unsigned nb1 = (unsigned)std::max(1, (n + 255) / 256);
+    const int*     wf  = D.peer[0] ? flag_f : nullptr;
+    float* fse = (D.edge_shift >= 0 && (flags & B200NB_FLAG_VIRIAL)) ? h->d_fshift + 3 * D.edge_shift : nullptr;
+    if ((reinterpret_cast<uintptr_t>(f_home) & 15) == 0)
+        k_dd_step_end<true><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.peer[0] ? D.d_send_pos : nullptr, wf, D.d_seq, err,
+                                                       reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, fse);
+    else
+        k_dd_step_end<false><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.peer[0] ? D.d_send_pos : nullptr, wf, D.d_seq, err,
+                                                        reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, fse);
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+/* Replays (capturing it first if needed) the CUDA graph of one step: the launches depend only on the buffers, the flags and
+ * the current list / plan (`generation`), so a step costs ONE graph launch: no per-kernel launch gaps on the critical path.
+ * Falls back to direct launches when the stream cannot be captured (e.g. the caller is itself capturing). */
+static int run_step_graph(b200nb_context* h, int which, const float* x, float* f, int flags)
+{
+    StepGraph& G = h->graph[which];
+    auto direct = [&]() { return which == 0 ? launch_step(h, x, flags, f) : launch_dd_step(h, x, f, flags); };
+    if (!h->use_graphs) return direct();
+    if (!G.exec || G.x != x || G.f != f || G.flags != flags || G.generation != h->generation || G.stream != h->stream)
+    {
+        if (G.exec) cudaGraphExecDestroy(G.exec);
+        G.exec = nullptr;
+        const long long l0 = h->nlaunches;
+        cudaGraph_t     graph = nullptr;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        {
+            cudaGetLastError();
+            h->use_graphs = false;
+            return direct();
+        }
+        const int   rc = direct();
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (rc || ce != cudaSuccess || !graph || cudaGraphInstantiate(&G.exec, graph, 0) != cudaSuccess)
+        {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            G.exec        = nullptr;
+            h->use_graphs = false;
+            h->nlaunches  = l0;
+            return rc ? rc : direct();
+        }
+        cudaGraphDestroy(graph);
+        G.nkernels   = (int)(h->nlaunches - l0);
+        h->nlaunches = l0;
+        G.x = x, G.f = f, G.flags = flags, G.generation = h->generation, G.stream = h->stream;
+    }
+    NB_CUDA(h, cudaGraphLaunch(G.exec, h->stream));
+    h->nlaunches += G.nkernels;
     return 0;
 }
 
 /* One step of the decomposed calculation, asynchronous on the context's stream (the nonbonded part of do_force,
- * mdlib/sim_util.cpp:1388-1902): home x -> grid layout + clear | push halo x to the -x neighbour | local kernel |
- * wait for our halo x, -> grid layout | non-local kernel | push halo forces to the +x neighbour | wait for the forces on
- * the atoms we sent, add, un-sort.  x_home / f_home: nhome*3 floats, device or pinned host memory. */
+ * mdlib/sim_util.cpp:1388-1902): home x -> grid layout + clear + push halo x to the -x neighbour | local kernel || wait for
+ * our halo x, -> grid layout | non-local kernel | push halo forces to the +x neighbour || wait for the forces on the atoms we
+ * sent, add, un-sort.  x_home / f_home: nhome*3 floats, device or pinned host memory. */
 extern "C" int b200nb_dd_step(b200nb_t* h, const float* x_home, float* f_home, int flags)
 {
     if (!h || !x_home || !f_home) return nb_fail(h, B200NB_ERR_ARG, "dd_step: bad argument");
@@ -2045,78 +2184,7 @@ extern "C" int b200nb_dd_step(b200nb_t* h, const float* x_home, float* f_home, i
         h->map_x_dev  = static_cast<float*>(ax.devicePointer);
         h->map_f_dev  = static_cast<float*>(af.devicePointer);
     }
-    x_home = h->map_x_dev;
-    f_home = h->map_f_dev;
-    const int seq = ++D.seq;
-    int*      flag_x = reinterpret_cast<int*>(D.window);
-    int*      flag_f = reinterpret_cast<int*>(D.window + 64);
-    int*      err    = reinterpret_cast<int*>(D.window + 128);
-    const int n = D.nhome, nclear = h->npad + NB_DUMMY_SLOTS;
-    const unsigned nb0 = (unsigned)((std::max(std::max(n, nclear), NB_OUT_COPIES * NB_FSHIFT_PITCH) + 255) / 256);
-    PrefetchRange pf{};
-    {
-        const PackedList& P = h->packed[0];
-        pf.p[0]     = reinterpret_cast<const char*>(P.entries);
-        pf.bytes[0] = sizeof(Entry) * (size_t)P.nentries;
-        pf.p[1]     = reinterpret_cast<const char*>(P.ja);
-        pf.bytes[1] = sizeof(int) * 8 * (size_t)P.nentries * P.pitch;
-        pf.p[2]     = reinterpret_cast<const char*>(P.mask);
-        pf.bytes[2] = sizeof(uint64_t) * (size_t)P.nentries * P.pitch;
-        pf.p[3]     = reinterpret_cast<const char*>(h->comb_geom ? (const void*)h->d_lj : (const void*)h->d_atype);
-        pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
-    }
-    if ((reinterpret_cast<uintptr_t>(x_home) & 15) == 0)
-        k_step_begin<true><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf);
-    else
-        k_step_begin<false><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf);
-    LAUNCH_CHECK(h);
-    /* halo chain on the high-priority non-local stream, local kernel on the main stream */
-    cudaStream_t snl = D.stream_nl;
-    NB_CUDA(h, cudaEventRecord(D.ev_begin, h->stream));
-    NB_CUDA(h, cudaStreamWaitEvent(snl, D.ev_begin, 0));
-    if (D.peer[0])
-    {
-        k_dd_push_x<<<(unsigned)std::max(1, (D.nsend + 255) / 256), 256, 0, snl>>>(
-                reinterpret_cast<const float4*>(h->d_xq), h->d_slot_of_atom, D.d_send_idx, D.nsend, D.shift[0], D.shift[1], D.shift[2],
-                reinterpret_cast<float*>(D.peer[0] + 256), reinterpret_cast<int*>(D.peer[0]), seq, D.d_count);
-        LAUNCH_CHECK(h);
-    }
-    int rc;
-    if ((rc = nb_launch_force_kernel(h, 0, flags))) return rc;
-    if (D.peer[1])
-    {
-        k_dd_wait<<<1, 1, 0, snl>>>(flag_x, seq, err);
-        LAUNCH_CHECK(h);
-        k_dd_recv_x<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, snl>>>(reinterpret_cast<const float*>(D.window + D.off_recv_x),
-                                                                                 h->d_slot_of_atom, D.nhome, D.nhalo, h->d_xq);
-        LAUNCH_CHECK(h);
-        cudaStream_t keep = h->stream;
-        h->stream         = snl; /* the non-local kernel goes to the non-local stream */
-        rc                = nb_launch_force_kernel(h, 1, flags);
-        h->stream         = keep;
-        if (rc) return rc;
-        k_dd_push_f<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, snl>>>(
-                h->d_f, h->d_slot_of_atom, D.nhome, D.nhalo, reinterpret_cast<float*>(D.peer[1] + D.peer_off_recv_f[1]),
-                reinterpret_cast<int*>(D.peer[1] + 64), seq, D.d_count + 1);
-        LAUNCH_CHECK(h);
-    }
-    NB_CUDA(h, cudaEventRecord(D.ev_nl_done, snl));
-    NB_CUDA(h, cudaStreamWaitEvent(h->stream, D.ev_nl_done, 0));
-    const unsigned nb1 = (unsigned)std::max(1, (n + 255) / 256);
-    if (D.peer[0])
-    {
-        k_dd_wait<<<1, 1, 0, h->stream>>>(flag_f, seq, err);
-        LAUNCH_CHECK(h);
-    }
-    float* fse = (D.edge_shift >= 0 && (flags & B200NB_FLAG_VIRIAL)) ? h->d_fshift + 3 * D.edge_shift : nullptr;
-    if ((reinterpret_cast<uintptr_t>(f_home) & 15) == 0)
-        k_dd_step_end<true><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.peer[0] ? D.d_send_pos : nullptr,
-                                                       reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, fse);
-    else
-        k_dd_step_end<false><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.peer[0] ? D.d_send_pos : nullptr,
-                                                        reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, fse);
-    LAUNCH_CHECK(h);
-    return 0;
+    return run_step_graph(h, 1, h->map_x_dev, h->map_f_dev, flags);
 }
 
 /* after synchronising: B200NB_ERR_STATE when a halo flag did not arrive in time during any step since the last call */

@@ -112,13 +112,24 @@ struct DdState
     size_t         cap_send = 0, cap_home = 0;
     float          shift[3] = { 0, 0, 0 };
     int            edge_shift = -1; /* shift index the returned forces also count for (periodic edge), or -1 */
-    int            seq = 0;
     int*           d_count = nullptr; /* 2 last-block counters */
+    int*           d_seq = nullptr;   /* device-resident step counter: the value the flags carry (graph-replayable) */
     bool           have_plan = false;
     /* the halo chain (push x, wait, halo x -> grid, non-local kernel, push f) runs on its own high-priority stream beside
      * the local kernel, the reference's local / non-local stream split (cuda/nbnxm_cuda_data_mgmt.cu:260-291) */
     cudaStream_t   stream_nl = nullptr;
     cudaEvent_t    ev_begin = nullptr, ev_nl_done = nullptr;
+};
+
+/* a captured step: the launches of b200nb_step / b200nb_dd_step for one set of buffers */
+struct StepGraph
+{
+    cudaGraphExec_t exec = nullptr;
+    const float*    x = nullptr;
+    float*          f = nullptr;
+    int             flags = -1, nkernels = 0;
+    long long       generation = -1;
+    cudaStream_t    stream = nullptr;
 };
 
 struct b200nb_context
@@ -184,6 +195,9 @@ struct b200nb_context
     bool     have_list = false;
     PackedList packed[2];
     DdState    dd;
+    StepGraph  graph[2];       /* [0] single-domain step, [1] decomposed step */
+    long long  generation = 0; /* bumped whenever a list or halo plan is rebuilt: invalidates the captured graphs */
+    bool       use_graphs = true;
     int        dummy_slot = 0; /* first of the NB_DUMMY_SLOTS far-away filler slots appended after the grids */
 
     float* d_flush = nullptr;
