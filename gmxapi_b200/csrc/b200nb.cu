@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "b200nb_internal.h"
@@ -1968,6 +1969,8 @@ extern "C" int b200nb_dd_create_window(b200nb_t* h, int max_halo, int max_send, 
     {
         int lo = 0, hi = 0;
         NB_CUDA(h, cudaDeviceGetStreamPriorityRange(&lo, &hi)); /* hi = numerically lowest = highest priority */
+        if (getenv("B200NB_DD_PRIO") && atoi(getenv("B200NB_DD_PRIO")) == 0) hi = lo; /* A/B switch for profiles/ */
+        D.prio_high = hi;
         NB_CUDA(h, cudaStreamCreateWithPriority(&D.stream_nl, cudaStreamNonBlocking, hi));
         NB_CUDA(h, cudaEventCreateWithFlags(&D.ev_begin, cudaEventDisableTiming));
         NB_CUDA(h, cudaEventCreateWithFlags(&D.ev_nl_done, cudaEventDisableTiming));
@@ -2045,6 +2048,19 @@ extern "C" int b200nb_dd_set_plan(b200nb_t* h, int nhome, int nhalo, const int* 
     return 0;
 }
 
+/* While a step is being captured: remember the graph node the last launch on the non-local stream created, so that its
+ * priority can be set explicitly afterwards (a captured kernel node does not inherit the priority of the stream it was
+ * captured from: measured, the non-local chain then queues behind the local kernel). */
+static void tag_nonlocal_node(b200nb_context* h)
+{
+    if (!h->capturing) return;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    const cudaGraphNode_t*  deps = nullptr;
+    size_t                  nd = 0;
+    if (cudaStreamGetCaptureInfo_v2(h->dd.stream_nl, &st, nullptr, nullptr, &deps, &nd) == cudaSuccess && st == cudaStreamCaptureStatusActive)
+        for (size_t k = 0; k < nd; k++) h->nl_nodes.push_back(deps[k]);
+}
+
 /* the launches of one decomposed step; x_home / f_home are device-visible addresses */
 static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home, int flags)
 {
@@ -2091,15 +2107,18 @@ static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home,
                                                                                  reinterpret_cast<const float*>(D.window + D.off_recv_x),
                                                                                  h->d_slot_of_atom, D.nhome, D.nhalo, h->d_xq);
         LAUNCH_CHECK(h);
+        tag_nonlocal_node(h);
         cudaStream_t keep = h->stream;
         h->stream         = snl; /* the non-local kernel goes to the non-local stream */
         rc                = nb_launch_force_kernel(h, 1, flags);
         h->stream         = keep;
         if (rc) return rc;
+        tag_nonlocal_node(h);
         k_dd_push_f<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, snl>>>(
                 h->d_f, h->d_slot_of_atom, D.nhome, D.nhalo, reinterpret_cast<float*>(D.peer[1] + D.peer_off_recv_f[1]),
                 reinterpret_cast<int*>(D.peer[1] + 64), D.d_seq, D.d_count + 1);
         LAUNCH_CHECK(h);
+        tag_nonlocal_node(h);
     }
     NB_CUDA(h, cudaEventRecord(D.ev_nl_done, snl));
     NB_CUDA(h, cudaStreamWaitEvent(h->stream, D.ev_nl_done, 0));
@@ -2124,6 +2143,8 @@ static int run_step_graph(b200nb_context* h, int which, const float* x, float* f
 {
     StepGraph& G = h->graph[which];
     auto direct = [&]() { return which == 0 ? launch_step(h, x, flags, f) : launch_dd_step(h, x, f, flags); };
+    if (const char* e = getenv("B200NB_GRAPHS")) /* A/B switch for profiles/: 0 = direct launches */
+        if (atoi(e) == 0) h->use_graphs = false;
     if (!h->use_graphs) return direct();
     if (!G.exec || G.x != x || G.f != f || G.flags != flags || G.generation != h->generation || G.stream != h->stream)
     {
@@ -2137,9 +2158,26 @@ static int run_step_graph(b200nb_context* h, int which, const float* x, float* f
             h->use_graphs = false;
             return direct();
         }
+        h->nl_nodes.clear();
+        h->capturing   = true;
         const int   rc = direct();
+        h->capturing   = false;
         cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-        if (rc || ce != cudaSuccess || !graph || cudaGraphInstantiate(&G.exec, graph, 0) != cudaSuccess)
+        if (ce == cudaSuccess && graph)
+        {
+            cudaKernelNodeAttrValue v{};
+            v.priority = h->dd.prio_high;
+            for (cudaGraphNode_t nd : h->nl_nodes)
+            {
+                cudaGraphNodeType ty;
+                if (cudaGraphNodeGetType(nd, &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel)
+                    cudaGraphKernelNodeSetAttribute(nd, cudaKernelNodeAttributePriority, &v);
+            }
+            cudaGetLastError();
+        }
+        /* UseNodePriority: run with the per-node priorities (the non-local chain's) instead of the launch stream's for all */
+        if (rc || ce != cudaSuccess || !graph
+            || cudaGraphInstantiateWithFlags(&G.exec, graph, which == 1 ? cudaGraphInstantiateFlagUseNodePriority : 0) != cudaSuccess)
         {
             cudaGetLastError();
             if (graph) cudaGraphDestroy(graph);

@@ -117,6 +117,7 @@ struct DdState
     bool           have_plan = false;
     /* the halo chain (push x, wait, halo x -> grid, non-local kernel, push f) runs on its own high-priority stream beside
      * the local kernel, the reference's local / non-local stream split (cuda/nbnxm_cuda_data_mgmt.cu:260-291) */
+    int            prio_high = 0;
     cudaStream_t   stream_nl = nullptr;
     cudaEvent_t    ev_begin = nullptr, ev_nl_done = nullptr;
 };
@@ -198,6 +199,8 @@ struct b200nb_context
     StepGraph  graph[2];       /* [0] single-domain step, [1] decomposed step */
     long long  generation = 0; /* bumped whenever a list or halo plan is rebuilt: invalidates the captured graphs */
     bool       use_graphs = true;
+    bool       capturing = false;
+    std::vector<cudaGraphNode_t> nl_nodes; /* kernel nodes captured from the non-local stream (get an explicit priority) */
     int        dummy_slot = 0; /* first of the NB_DUMMY_SLOTS far-away filler slots appended after the grids */
 
     float* d_flush = nullptr;
