@@ -79,8 +79,9 @@ extern "C" int b200nb_create(b200nb_t** out, int device)
     cudaMalloc((void**)&h->d_fshift_sum, sizeof(float) * NB_FSHIFT_PITCH);
     cudaMalloc((void**)&h->d_energy_sum, sizeof(double) * 2);
     cudaMalloc((void**)&h->d_scratch, sizeof(int) * 64);
-    cudaMalloc((void**)&h->d_kconst, sizeof(float) * 8);
+    cudaMalloc((void**)&h->d_kconst, sizeof(float) * 12);
     cudaMalloc((void**)&h->d_counter, sizeof(long long) * 8);
+    cudaMalloc((void**)&h->d_hist, sizeof(int) * 80);
     cudaMemsetAsync(h->d_fshift, 0, sizeof(float) * NB_OUT_COPIES * NB_FSHIFT_PITCH, h->stream);
     cudaMemsetAsync(h->d_energy, 0, sizeof(double) * NB_OUT_COPIES * 2, h->stream);
     *out = h;
@@ -104,7 +105,7 @@ extern "C" void b200nb_destroy(b200nb_t* h)
                      h->d_x,          h->d_fout,     h->d_col_of_atom, h->d_col_count, h->d_col_cell0, h->d_col_fill,
                      h->d_atom_index, h->d_slot_of_atom, h->d_xq,   h->d_lj,           h->d_atype,     h->d_bb,
                      h->d_cellz,      h->d_f,        h->d_fshift,   h->d_energy,       h->d_scratch,   h->d_counter,
-                     h->d_fshift_sum, h->d_energy_sum,
+                     h->d_fshift_sum, h->d_energy_sum, h->d_hist,
                      h->d_cnt_tiles,  h->d_cnt_entries, h->d_flush };
     for (void* p : ptrs) cudaFree(p);
     for (int l = 0; l < 2; l++)
@@ -112,6 +113,8 @@ extern "C" void b200nb_destroy(b200nb_t* h)
         if (!h->inner_is_outer) free_list(h->inner[l]);
         free_list(h->outer[l]);
         cudaFree(h->packed[l].entries);
+        cudaFree(h->packed[l].dest);
+        cudaFree(h->packed[l].sizes);
         cudaFree(h->packed[l].ja);
         cudaFree(h->packed[l].mask);
     }
@@ -239,8 +242,12 @@ extern "C" int b200nb_set_params(b200nb_t* h, const b200nb_params_t* p)
     d.self_q2       = (p->epsfac != 0.0f) ? d.self_sub / p->epsfac : 0.0f;
     {
         /* leading coefficients of pmeForceCorrection (simd/simd_math.h:1609-1650) and the loop-invariant scalars */
-        const float kc[8] = { d.rc2, d.beta, d.beta2, 0.0011193462567257629232f, 0.014866955030185295499f,
-                              -1.7357322914161492954e-8f, 1.4703624142580877519e-6f, 0.0f };
+        /* the denominator coefficients FD4..FD0 are stored divided by beta, so that the kernel's 1/denominator already carries
+         * the factor beta of beta * pmecorrF (reaction field: beta = 0, coefficients unused) */
+        const float ib    = d.beta != 0.0f ? 1.0f / d.beta : 0.0f;
+        const float kc[12] = { d.rc2, d.beta, d.beta2, 0.0011193462567257629232f * ib, 0.014866955030185295499f * ib,
+                               -1.7357322914161492954e-8f, 1.4703624142580877519e-6f, 0.11583842382862377919f * ib,
+                               0.50736591960530292870f * ib, 1.0f * ib, 0.0f, 0.0f };
         NB_CUDA(h, cudaMemcpy(h->d_kconst, kc, sizeof(kc), cudaMemcpyHostToDevice));
     }
     d.ntypes        = ntf;
@@ -1062,7 +1069,7 @@ k_prune(const Entry* __restrict__ oe, const int* __restrict__ ocj, const uint64_
 __global__ void __launch_bounds__(128)
 k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t* __restrict__ imask, long long nentries, int part,
        int nparts, const float* __restrict__ xq, const float* __restrict__ shift_vec, float rlist2, int intra, int dummy_slot, int pitch,
-       Entry* __restrict__ pe, int* __restrict__ pja, uint64_t* __restrict__ pmask)
+       const int* __restrict__ dest, int* __restrict__ sizes, Entry* __restrict__ pe, int* __restrict__ pja, uint64_t* __restrict__ pmask)
 {
     __shared__ int      s_ja[4][32 * 8];
     __shared__ unsigned s_m0[4][32], s_m1[4][32];
@@ -1114,8 +1121,15 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
         if (pass == 0) nm = n;
     }
     __syncwarp();
-    const int       ntp = (n + 7) >> 3, nmt = (nm + 7) >> 3;
-    const long long t0  = e * pitch; /* entry e owns packed tiles [e*pitch, (e+1)*pitch) */
+    const int ntp = (n + 7) >> 3, nmt = (nm + 7) >> 3;
+    if (sizes)
+    {
+        /* first pass of a full pack: only the packed size, from which the size-sorted positions `dest` are made */
+        if (lane == 0) sizes[e] = ntp;
+        return;
+    }
+    const long long d  = dest ? dest[e] : e; /* position of this entry in the packed list (largest entries first) */
+    const long long t0 = d * pitch;          /* packed entry d owns tiles [d*pitch, (d+1)*pitch) */
     for (int k = lane; k < ntp * 8; k += 32) pja[(size_t)t0 * 8 + k] = s_ja[w][k];
     if (lane < ntp) pmask[t0 + lane] = lane < nmt ? (((uint64_t)s_m1[w][lane] << 32) | s_m0[w][lane]) : ~0ull;
     if (lane == 0)
@@ -1125,8 +1139,40 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
         o.shift_nmask = shift | (nmt << 8) | (has_self << 24);
         o.start       = (int)t0;
         o.end         = (int)t0 + ntp;
-        pe[e]         = o;
+        pe[d]         = o;
     }
+}
+
+/* Positions of the packed entries: descending packed size (counting sort on <= 33 values; the role of sort_sci,
+ * nbnxm/pairlist.cpp:3827-3873).  The force kernel runs one entry per single-warp CTA and CTAs start in index order, so the
+ * big entries start first and the last wave holds only the smallest ones: the tail of the kernel shrinks from one full entry
+ * to one short entry.  hist: 2 x 40 ints (histogram, cursors). */
+__global__ void k_order_hist(const int* __restrict__ sizes, int n, int* __restrict__ hist)
+{
+    __shared__ int sh[40];
+    if (threadIdx.x < 40) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) atomicAdd(&sh[min(sizes[e], 39)], 1);
+    __syncthreads();
+    if (threadIdx.x < 40 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void k_order_scan(int* __restrict__ hist)
+{
+    if (threadIdx.x == 0)
+    {
+        int run = 0;
+        for (int c = 39; c >= 0; c--) /* largest first */
+        {
+            hist[40 + c] = run;
+            run += hist[c];
+        }
+    }
+}
+__global__ void k_order_assign(const int* __restrict__ sizes, int n, int* __restrict__ hist, int* __restrict__ dest)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) dest[e] = atomicAdd(&hist[40 + min(sizes[e], 39)], 1);
 }
 
 static int ensure_packed(b200nb_context* h, PackedList& P, size_t cap_tiles, size_t cap_entries)
@@ -1144,8 +1190,13 @@ static int ensure_packed(b200nb_context* h, PackedList& P, size_t cap_tiles, siz
     if (cap_entries > P.cap_entries || !P.entries)
     {
         cudaFree(P.entries);
+        cudaFree(P.dest);
+        cudaFree(P.sizes);
         P.entries = nullptr;
+        P.dest = P.sizes = nullptr;
         NB_CUDA(h, cudaMalloc((void**)&P.entries, std::max<size_t>(cap_entries, 1) * sizeof(Entry)));
+        NB_CUDA(h, cudaMalloc((void**)&P.dest, std::max<size_t>(cap_entries, 1) * sizeof(int)));
+        NB_CUDA(h, cudaMalloc((void**)&P.sizes, std::max<size_t>(cap_entries, 1) * sizeof(int)));
         P.cap_entries = cap_entries;
     }
     return 0;
@@ -1163,9 +1214,26 @@ static int launch_pack(b200nb_context* h, int loc, int part, int nparts)
     if (ensure_packed(h, P, I.cap_entries * P.pitch, I.cap_entries)) return B200NB_ERR_CUDA;
     long long nw = (I.nentries - part + nparts - 1) / nparts;
     if (nw <= 0) return 0;
-    const float r2 = h->inner_is_outer ? h->dp.rlist_outer2 : h->dp.rlist_inner2;
-    k_pack<<<(unsigned)((nw + 3) / 4), 128, 0, h->stream>>>(I.entries, I.cj, I.mask, I.nentries, part, nparts, h->d_xq, h->d_shift_vec, r2,
-                                                           loc == 0, h->dummy_slot, P.pitch, P.entries, P.ja, P.mask);
+    const float    r2   = h->inner_is_outer ? h->dp.rlist_outer2 : h->dp.rlist_inner2;
+    const unsigned nblk = (unsigned)((nw + 3) / 4);
+    if (nparts == 1)
+    {
+        /* full pack: sizes first, then the size-sorted positions, then the pack proper.  Rolling parts (nparts > 1) keep the
+         * positions of the last full pack: their entries only shrink a little, the order stays nearly sorted. */
+        const int n = (int)I.nentries;
+        k_pack<<<nblk, 128, 0, h->stream>>>(I.entries, I.cj, I.mask, I.nentries, 0, 1, h->d_xq, h->d_shift_vec, r2, loc == 0, h->dummy_slot,
+                                            P.pitch, nullptr, P.sizes, P.entries, P.ja, P.mask);
+        LAUNCH_CHECK(h);
+        NB_CUDA(h, cudaMemsetAsync(h->d_hist, 0, sizeof(int) * 80, h->stream));
+        k_order_hist<<<(n + 255) / 256, 256, 0, h->stream>>>(P.sizes, n, h->d_hist);
+        LAUNCH_CHECK(h);
+        k_order_scan<<<1, 32, 0, h->stream>>>(h->d_hist);
+        LAUNCH_CHECK(h);
+        k_order_assign<<<(n + 255) / 256, 256, 0, h->stream>>>(P.sizes, n, h->d_hist, P.dest);
+        LAUNCH_CHECK(h);
+    }
+    k_pack<<<nblk, 128, 0, h->stream>>>(I.entries, I.cj, I.mask, I.nentries, part, nparts, h->d_xq, h->d_shift_vec, r2, loc == 0,
+                                        h->dummy_slot, P.pitch, P.dest, nullptr, P.entries, P.ja, P.mask);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -1584,6 +1652,9 @@ k_step_begin(const float* __restrict__ x, const int* __restrict__ slot_of_atom, 
 {
     __shared__ __align__(16) float sx[768];
     const int tid = threadIdx.x, t = blockIdx.x * 256 + tid;
+    /* let the force kernel behind us start launching: its prologue only reads the list (it waits for this grid's completion,
+     * griddepcontrol.wait, before it touches xq or f) */
+    asm volatile("griddepcontrol.launch_dependents;");
     if (DD && t == 0) *dd.seq = *dd.seq + 1; /* published to the other CTAs by the fence + counter in publish_flag */
     /* pull the read-only inputs of the force kernel that is about to run (packed list, LJ parameters) into L2 while this
      * kernel streams the coordinates: its prologue is a chain of dependent loads, ~3x shorter on L2 hits than from HBM */
@@ -2145,6 +2216,8 @@ static int run_step_graph(b200nb_context* h, int which, const float* x, float* f
     auto direct = [&]() { return which == 0 ? launch_step(h, x, flags, f) : launch_dd_step(h, x, f, flags); };
     if (const char* e = getenv("B200NB_GRAPHS")) /* A/B switch for profiles/: 0 = direct launches */
         if (atoi(e) == 0) h->use_graphs = false;
+    if (const char* e = getenv("B200NB_PDL")) /* A/B switch: 0 = no programmatic dependent launch of the force kernel */
+        h->use_pdl = atoi(e) != 0;
     if (!h->use_graphs) return direct();
     if (!G.exec || G.x != x || G.f != f || G.flags != flags || G.generation != h->generation || G.stream != h->stream)
     {

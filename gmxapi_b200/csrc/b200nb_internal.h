@@ -84,6 +84,8 @@ struct PackedList
     Entry*    entries = nullptr;
     int*      ja      = nullptr; /* 8 slots per packed tile */
     uint64_t* mask    = nullptr;
+    int*      dest    = nullptr; /* per entry of the pruned list: its position here (entries are stored largest first) */
+    int*      sizes   = nullptr; /* packed tile count per entry of the pruned list (scratch of the ordering) */
     long long nentries = 0;
     int       pitch = 0; /* tiles reserved per entry (= max_tiles_per_entry): entry e owns tiles [e*pitch, (e+1)*pitch), so
                             the force kernel can fetch an entry's j indices without first reading the entry itself */
@@ -148,7 +150,7 @@ struct b200nb_context
     bool              comb_geom = false;
     int               max_tiles = 16;
     float*            d_nbfp = nullptr; /* float2 per type pair */
-    float*            d_kconst = nullptr; /* 8 floats: rc2, beta, beta2, FD4, FD3, FN6, FN5, 0 (force.cu KConst) */
+    float*            d_kconst = nullptr; /* 12 floats: rc2, beta, beta2, FD4/b, FD3/b, FN6, FN5, FD2/b, FD1/b, FD0/b, 0, 0 (force.cu KConst) */
 
     int    natoms = 0;
     int*   d_type = nullptr;
@@ -186,6 +188,7 @@ struct b200nb_context
     double*  d_energy_sum = nullptr; /* 2 */
     int*     d_scratch = nullptr; /* small ints: totals, flags, counters */
     long long* d_counter = nullptr;
+    int*     d_hist = nullptr; /* 80 ints: histogram + cursors of the entry ordering */
 
     int*  d_cnt_tiles = nullptr; /* per i-cluster counts / offsets for the two-pass search */
     int*  d_cnt_entries = nullptr;
@@ -199,6 +202,7 @@ struct b200nb_context
     StepGraph  graph[2];       /* [0] single-domain step, [1] decomposed step */
     long long  generation = 0; /* bumped whenever a list or halo plan is rebuilt: invalidates the captured graphs */
     bool       use_graphs = true;
+    bool       use_pdl = true; /* launch the force kernel with programmatic stream serialization (see force.cu) */
     bool       capturing = false;
     std::vector<cudaGraphNode_t> nl_nodes; /* kernel nodes captured from the non-local stream (get an explicit priority) */
     int        dummy_slot = 0; /* first of the NB_DUMMY_SLOTS far-away filler slots appended after the grids */

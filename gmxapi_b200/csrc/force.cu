@@ -93,10 +93,11 @@ __device__ __forceinline__ void load_j(JAtom& J, const unsigned char* s_lane, in
 }
 
 /* simd/simd_math.h:1609-1650 pmeForceCorrection: denominator and numerator */
-__device__ __forceinline__ float2 pme_force_den(float2 z2, float2 z4, float fd4, float fd3)
+/* all five coefficients arrive divided by beta (KConst), so 1/den is already beta / denominator: saves the multiplication by
+ * beta per pair at the cost of three more loop-invariant registers */
+__device__ __forceinline__ float2 pme_force_den(float2 z2, float2 z4, float fd4, float fd3, float fd2, float fd1, float fd0)
 {
-    const float2 FD4 = dup(fd4), FD3 = dup(fd3),
-                 FD2 = dup(0.11583842382862377919f), FD1 = dup(0.50736591960530292870f), FD0 = dup(1.0f);
+    const float2 FD4 = dup(fd4), FD3 = dup(fd3), FD2 = dup(fd2), FD1 = dup(fd1), FD0 = dup(fd0);
     float2 d0 = fma2(FD4, z4, FD2), d1 = fma2(FD3, z4, FD1);
     d0        = fma2(d0, z4, FD0);
     return fma2(d1, z2, d0);
@@ -140,7 +141,7 @@ __device__ __forceinline__ float2 pme_pot_corr2(float2 z2)
  * immediates inside the pair loop (7 issue slots per tile in the first version). */
 struct KConst
 {
-    float rc2, beta, beta2, fd4, fd3, fn6, fn5;
+    float rc2, beta2, fd4, fd3, fd2, fd1, fd0, fn6, fn5; /* fd*: pmeForceCorrection denominator coefficients / beta */
 };
 struct IData
 {
@@ -208,9 +209,9 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
     {
         const float2 z2 = mul2(dup(K.beta2), r2);
         const float2 z4 = mul2(z2, z2);
-        const float2 den = pme_force_den(z2, z4, K.fd4, K.fd3);
+        const float2 den = pme_force_den(z2, z4, K.fd4, K.fd3, K.fd2, K.fd1, K.fd0);
         const float2 num = pme_force_num(z2, z4, K.fn6, K.fn5);
-        const float2 t   = mul2(mul2(num, dup(K.beta)), make_float2(rcp_approx(den.x), rcp_approx(den.y))); /* beta * pmecorrF(z2) */
+        const float2 t   = mul2(num, make_float2(rcp_approx(den.x), rcp_approx(den.y))); /* beta * pmecorrF(z2) */
         fsum             = fma2(qq, fma2(t, z2, rinv_ex), fsum);
         if (VF)
         {
@@ -251,7 +252,8 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
 #endif
 template<int EEL, bool GEOM, int NT>
 __device__ __forceinline__ void tile_pairs_multi(const IData& I, const JAtom (&J)[NT], const NbParamsDev& P, const KConst& K,
-                                                 const float2* __restrict__ nbfp, float2 (&tx)[NT], float2 (&ty)[NT], float2 (&tz)[NT])
+                                                 const float2* __restrict__ nbfp, float2& fix, float2& fiy, float2& fiz, float (&sx)[NT],
+                                                 float (&sy)[NT], float (&sz)[NT])
 {
     const float2 m1 = dup(-1.0f);
     float2       dx[NT], dy[NT], dz[NT], r2[NT], rinv[NT], rinvsq[NT], rinv6[NT], c6n[NT], c12[NT], fsum[NT], qq[NT];
@@ -294,11 +296,11 @@ __device__ __forceinline__ void tile_pairs_multi(const IData& I, const JAtom (&J
 #pragma unroll
         for (int u = 0; u < NT; u++) z4[u] = mul2(z2[u], z2[u]);
 #pragma unroll
-        for (int u = 0; u < NT; u++) den[u] = pme_force_den(z2[u], z4[u], K.fd4, K.fd3);
+        for (int u = 0; u < NT; u++) den[u] = pme_force_den(z2[u], z4[u], K.fd4, K.fd3, K.fd2, K.fd1, K.fd0);
 #pragma unroll
         for (int u = 0; u < NT; u++) den[u] = make_float2(rcp_approx(den[u].x), rcp_approx(den[u].y));
 #pragma unroll
-        for (int u = 0; u < NT; u++) num[u] = mul2(pme_force_num(z2[u], z4[u], K.fn6, K.fn5), dup(K.beta));
+        for (int u = 0; u < NT; u++) num[u] = pme_force_num(z2[u], z4[u], K.fn6, K.fn5);
     }
 #pragma unroll
     for (int u = 0; u < NT; u++) rinvsq[u] = mul2(rinv[u], rinv[u]);
@@ -318,9 +320,15 @@ __device__ __forceinline__ void tile_pairs_multi(const IData& I, const JAtom (&J
         float2 fscal = mul2(rinvsq[u], fsum[u]);
         fscal.x      = (r2[u].x < K.rc2) ? fscal.x : 0.0f;
         fscal.y      = (r2[u].y < K.rc2) ? fscal.y : 0.0f;
-        tx[u]        = mul2(fscal, dx[u]);
-        ty[u]        = mul2(fscal, dy[u]);
-        tz[u]        = mul2(fscal, dz[u]);
+        /* force on the two i-atoms: one packed FMA per component into the entry's accumulators; force on the j-atom: minus
+         * the sum over the lane's two pairs, one scalar FMUL + FFMA per component (4 FMA-pipe cycles per component instead
+         * of the 5 of packed multiply, packed add, scalar add) */
+        fix   = fma2(fscal, dx[u], fix);
+        fiy   = fma2(fscal, dy[u], fiy);
+        fiz   = fma2(fscal, dz[u], fiz);
+        sx[u] = __fmaf_rn(-fscal.y, dx[u].y, -(fscal.x * dx[u].x));
+        sy[u] = __fmaf_rn(-fscal.y, dy[u].y, -(fscal.x * dy[u].x));
+        sz[u] = __fmaf_rn(-fscal.y, dz[u].y, -(fscal.x * dz[u].x));
     }
 }
 
@@ -348,13 +356,11 @@ __device__ __forceinline__ void reduce_store_j(const float2 tx, const float2 ty,
 }
 
 template<int NT>
-__device__ __forceinline__ void reduce_store_j_multi(const float2 (&tx)[NT], const float2 (&ty)[NT], const float2 (&tz)[NT], const LaneClass& C,
+__device__ __forceinline__ void reduce_store_j_multi(const float (&sx)[NT], const float (&sy)[NT], const float (&sz)[NT], const LaneClass& C,
                                                      const int (&jslot)[NT])
 {
     const unsigned full = 0xffffffffu;
-    float          sx[NT], sy[NT], sz[NT], k0[NT], k1[NT], v[NT];
-#pragma unroll
-    for (int u = 0; u < NT; u++) sx[u] = -tx[u].x - tx[u].y, sy[u] = -ty[u].x - ty[u].y, sz[u] = -tz[u].x - tz[u].y;
+    float          k0[NT], k1[NT], v[NT];
 #pragma unroll
     for (int u = 0; u < NT; u++) k0[u] = __shfl_xor_sync(full, C.b4 ? sx[u] : sz[u], 16);
 #pragma unroll
@@ -400,9 +406,14 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
     const int4 ev    = __ldg(reinterpret_cast<const int4*>(entries) + e);
     KConst K;
     {
-        const float4 k0 = __ldg(reinterpret_cast<const float4*>(kconst)), k1 = __ldg(reinterpret_cast<const float4*>(kconst) + 1);
-        K.rc2 = k0.x, K.beta = k0.y, K.beta2 = k0.z, K.fd4 = k0.w, K.fd3 = k1.x, K.fn6 = k1.y, K.fn5 = k1.z;
+        const float4 k0 = __ldg(reinterpret_cast<const float4*>(kconst)), k1 = __ldg(reinterpret_cast<const float4*>(kconst) + 1),
+                     k2 = __ldg(reinterpret_cast<const float4*>(kconst) + 2);
+        K.rc2 = k0.x, K.beta2 = k0.z, K.fd4 = k0.w, K.fd3 = k1.x, K.fn6 = k1.y, K.fn5 = k1.z, K.fd2 = k1.w, K.fd1 = k2.x, K.fd0 = k2.y;
     }
+    /* Programmatic dependent launch: this grid may have started while the preceding kernel of the stream (k_step_begin:
+     * coordinates -> grid layout, output clear) was still running; everything above reads only the list.  From here on the
+     * kernel touches xq and f, so wait for the predecessor's completion (a no-op for a normally serialised launch). */
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int  start = ev.z, end = ev.w;
     const bool self  = VF && NB_ENTRY_SELF(ev.y);
     if (start >= end && !self) return;
@@ -504,24 +515,17 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
         constexpr int NT = B200NB_TILE_ILP;
         for (; t + NT <= ntile; t += NT)
         {
-            JAtom  J[NT];
-            int    js[NT];
-            float2 tx[NT], ty[NT], tz[NT];
+            JAtom J[NT];
+            int   js[NT];
+            float sx[NT], sy[NT], sz[NT];
 #pragma unroll
             for (int u = 0; u < NT; u++)
             {
                 load_j(J[u], s_lane, t + u);
                 js[u] = J[u].slot;
             }
-            tile_pairs_multi<EEL, GEOM, NT>(I, J, P, K, nbfp, tx, ty, tz);
-#pragma unroll
-            for (int u = 0; u < NT; u++)
-            {
-                fix = add2(fix, tx[u]);
-                fiy = add2(fiy, ty[u]);
-                fiz = add2(fiz, tz[u]);
-            }
-            reduce_store_j_multi<NT>(tx, ty, tz, C, js);
+            tile_pairs_multi<EEL, GEOM, NT>(I, J, P, K, nbfp, fix, fiy, fiz, sx, sy, sz);
+            reduce_store_j_multi<NT>(sx, sy, sz, C, js);
         }
     }
     for (; t < ntile; t++)
@@ -594,10 +598,20 @@ int launch(b200nb_context* h, const PackedList& L, int intra)
     const unsigned nblk = (unsigned)((L.nentries + B200NB_FORCE_WARPS - 1) / B200NB_FORCE_WARPS);
     const int      maxt = h->max_tiles;
     const size_t   smem = (size_t)B200NB_FORCE_WARPS * maxt * NB_TILE_SMEM;
-    k_force<EEL, GEOM, VF><<<nblk, 32 * B200NB_FORCE_WARPS, smem, h->stream>>>(
-            L.entries, L.nentries, L.ja, L.mask, reinterpret_cast<const float4*>(h->d_xq), reinterpret_cast<const float2*>(h->d_lj),
-            h->d_atype, reinterpret_cast<const float2*>(h->d_nbfp), h->d_shift_vec, h->d_f, h->d_fshift, h->d_energy, h->dp, intra, maxt,
-            h->d_kconst);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim          = dim3(nblk);
+    cfg.blockDim         = dim3(32 * B200NB_FORCE_WARPS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream           = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1; /* overlap our list loads with the tail of the preceding kernel */
+    cfg.attrs    = at;
+    cfg.numAttrs = h->use_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k_force<EEL, GEOM, VF>, (const Entry*)L.entries, (long long)L.nentries, (const int*)L.ja, (const uint64_t*)L.mask,
+                       reinterpret_cast<const float4*>(h->d_xq), reinterpret_cast<const float2*>(h->d_lj), (const int*)h->d_atype,
+                       reinterpret_cast<const float2*>(h->d_nbfp), (const float*)h->d_shift_vec, h->d_f, h->d_fshift, h->d_energy, h->dp,
+                       intra, maxt, (const float*)h->d_kconst);
     h->nlaunches++;
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return nb_fail(h, B200NB_ERR_CUDA, std::string("force kernel launch: ") + cudaGetErrorString(err));
