@@ -26,6 +26,10 @@ int nb_fail(b200nb_context* h, int code, const std::string& msg)
     return code;
 }
 
+#ifndef B200NB_HOST_DMA_DEFAULT
+#define B200NB_HOST_DMA_DEFAULT 0 /* b200nb_compute: 0 = the step kernels read / write pinned host buffers in place (measured faster) */
+#endif
+
 #define LAUNCH_CHECK(h)                 \
     do                                  \
     {                                   \
@@ -1286,10 +1290,11 @@ extern "C" int b200nb_build_pairlist(b200nb_t* h)
      * (the reference handles that with shp[XX]=2, pairlist.cpp:3185-3188; outside our scope) */
     for (int d = 0; d < 3; d++)
         if (h->pbc[d] && h->box[d] < 2 * rl) return nb_fail(h, B200NB_ERR_ARG, "build_pairlist: box smaller than 2*rlist along a periodic dimension");
-    /* list balancing granularity (the role of get_nsubpair_target, pairlist.cpp:2485-2587): small systems need many short
-     * entries to fill 148 SMs x 32 warps, large ones amortise the per-entry prologue over more tiles
-     * (profiles/r1/g_sweep_one_entry_per_warp.txt: 24 k atoms best at 16, 192 k atoms at 24) */
-    if (h->hp.max_tiles_per_entry <= 0) h->max_tiles = (h->grid[0].atom_end - h->grid[0].atom_begin) >= 100000 ? 24 : 16;
+    /* list balancing granularity (the role of get_nsubpair_target, pairlist.cpp:2485-2587): with the packed entries stored
+     * largest-first, 24 cluster pairs (about 15 packed tiles) per entry is best from 24 k to 192 k atoms
+     * (profiles/r1/r_sweep_sorted_entries.txt); shorter entries pay the per-entry prologue more often, longer ones leave a
+     * longer tail on small systems */
+    if (h->hp.max_tiles_per_entry <= 0) h->max_tiles = 24;
     const bool want_inner = h->dp.rlist_inner2 < h->dp.rlist_outer2;
     if (!want_inner && !h->inner_is_outer)
     {
@@ -1857,7 +1862,19 @@ extern "C" int b200nb_compute(b200nb_t* h, const float* x_host, int flags, float
     if (!fd) fd = mapped_host_pointer(h->h_pinned + off_out / 2);
     if (!xd || !fd) return nb_fail(h, B200NB_ERR_CUDA, "compute: pinned host memory is not mapped into the device address space");
     int rc;
-    if ((rc = run_step_graph(h, 0, xd, fd, flags))) return rc;
+    if (h->host_dma < 0)
+    {
+        const char* e = getenv("B200NB_HOST_DMA"); /* A/B switch: 1 = copy engines + staging, 0 = kernels access the host buffers */
+        h->host_dma   = e ? (atoi(e) != 0) : B200NB_HOST_DMA_DEFAULT;
+    }
+    if (h->host_dma)
+    {
+        /* the copy engines need the host pointers themselves (pinned: the caller's, or our scratch) */
+        const float* xh = h->map_x_dev ? x_host : reinterpret_cast<const float*>(h->h_pinned);
+        float*       fh = h->map_f_dev ? f_host : reinterpret_cast<float*>(h->h_pinned + off_out / 2);
+        if ((rc = run_step_graph(h, 2, xh, fh, flags))) return rc;
+    }
+    else if ((rc = run_step_graph(h, 0, xd, fd, flags))) return rc;
     float*  fs_pin = reinterpret_cast<float*>(h->h_pinned + off_out);
     double* e_pin  = reinterpret_cast<double*>(h->h_pinned + off_out + 640);
     if (want_out)
@@ -2213,7 +2230,17 @@ static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home,
 static int run_step_graph(b200nb_context* h, int which, const float* x, float* f, int flags)
 {
     StepGraph& G = h->graph[which];
-    auto direct = [&]() { return which == 0 ? launch_step(h, x, flags, f) : launch_dd_step(h, x, f, flags); };
+    auto direct = [&]() -> int {
+        if (which == 0) return launch_step(h, x, flags, f);
+        if (which == 1) return launch_dd_step(h, x, f, flags);
+        /* which == 2: host step through the copy engines: x / f are PINNED HOST buffers, staged through d_x / d_fout */
+        const size_t bytes = sizeof(float) * 3 * (size_t)h->natoms;
+        NB_CUDA(h, cudaMemcpyAsync(h->d_x, x, bytes, cudaMemcpyHostToDevice, h->stream));
+        int rc = launch_step(h, h->d_x, flags, h->d_fout);
+        if (rc) return rc;
+        NB_CUDA(h, cudaMemcpyAsync(f, h->d_fout, bytes, cudaMemcpyDeviceToHost, h->stream));
+        return 0;
+    };
     if (const char* e = getenv("B200NB_GRAPHS")) /* A/B switch for profiles/: 0 = direct launches */
         if (atoi(e) == 0) h->use_graphs = false;
     if (const char* e = getenv("B200NB_PDL")) /* A/B switch: 0 = no programmatic dependent launch of the force kernel */

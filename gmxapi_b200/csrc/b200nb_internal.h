@@ -199,7 +199,8 @@ struct b200nb_context
     bool     have_list = false;
     PackedList packed[2];
     DdState    dd;
-    StepGraph  graph[2];       /* [0] single-domain step, [1] decomposed step */
+    StepGraph  graph[3];       /* [0] single-domain step, [1] decomposed step, [2] host step through the copy engines */
+    int        host_dma = -1;  /* b200nb_compute: 1 = cudaMemcpyAsync staging, 0 = zero-copy kernels, -1 = not decided yet */
     long long  generation = 0; /* bumped whenever a list or halo plan is rebuilt: invalidates the captured graphs */
     bool       use_graphs = true;
     bool       use_pdl = true; /* launch the force kernel with programmatic stream serialization (see force.cu) */
