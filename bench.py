@@ -138,7 +138,8 @@ def run_reference(args):
     from oracle import gmxref, oracle
     import gmxapi_b200 as g
     nx, ny, nz = g.systems.NAMED[args.workload]
-    s = g.systems.water_box(nx * max(args.gpus, 1), ny, nz)  # the same box the GPU arm decomposes over args.gpus ranks
+    mult = max(args.gpus, 1) if args.scaling == "weak" else 1
+    s = g.systems.water_box(nx * mult, ny, nz)  # the same box the GPU arm decomposes over args.gpus ranks
     cores = host_cores()
     npairs = len(oracle.pair_set(s.x, s.box, RC, s.excl_off, s.excl_idx))
     kind = "reference" if gmxref.available() else "port"
@@ -148,9 +149,9 @@ def run_reference(args):
     t, tk, n = time_reference(s, args.eel, cores, args.steps, args.warmup, budget_s=60.0)
     val = npairs / t
     out = {"metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
-           "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "impl": "reference",
-           "config": {"workload": args.workload if args.gpus <= 1 else "%d x %s along x" % (args.gpus, args.workload),
+           "config": {"workload": args.workload if mult <= 1 else "%d x %s along x" % (args.gpus, args.workload),
                       "atoms": int(s.n), "useful_pairs_per_step": npairs, "rc": RC,
                       "interaction": "LJ + " + ("Ewald real space (analytical)" if args.eel == "ewald" else "reaction field"),
                       "flavor": "force only"},
@@ -302,7 +303,7 @@ def run_multi_gpu(args, rank, world, local_rank):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peaks = measured_peaks()
     nx, ny, nz = g.systems.NAMED[args.workload]
-    s = g.systems.water_box(nx * world, ny, nz)
+    s = g.systems.water_box(nx * world if args.scaling == "weak" else nx, ny, nz)
     coul = g.CoulombType.Pme if args.eel == "ewald" else g.CoulombType.ReactionField
     opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coul, computeVirialAndEnergy=False, device=local_rank, epsilonRf=0.0,
                             maxTilesPerEntry=args.max_tiles)
@@ -367,9 +368,10 @@ def run_multi_gpu(args, rank, world, local_rank):
         halo_bytes = nhalo_tot * 12
         out = {
             "metric": METRIC, "value": npairs / (step_ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%d x %s along x" % (world, args.workload), "atoms": int(natoms),
+            "config": {"workload": ("%d x %s along x" % (world, args.workload)) if args.scaling == "weak"
+                       else "%s over %d x-slabs" % (args.workload, world), "atoms": int(natoms),
                        "useful_pairs_per_step": int(npairs), "computed_pairs_per_step": int(ntiles * 64), "rc": RC, "rlist": RC,
                        "interaction": "LJ + " + ("Ewald real space (analytical)" if args.eel == "ewald" else "reaction field"),
                        "flavor": "force only", "l2": "L2 flushed (256 MiB write) between timed steps" if not args.no_flush else "not flushed",
@@ -401,6 +403,8 @@ def main():
     ap.add_argument("--workload", default="water_24k")
     ap.add_argument("--eel", default="ewald", choices=["ewald", "rf"])
     ap.add_argument("--max-tiles", type=int, default=0, help="cluster pairs per list entry (0 = library default)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = N copies of the workload along x (default), strong = the workload itself over N slabs")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

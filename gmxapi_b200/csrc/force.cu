@@ -49,13 +49,21 @@ __device__ __forceinline__ float2 dup(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float rcp_approx(float x)
 {
     float r;
+#ifdef B200NB_DIAG_NO_MUFU /* diagnostic build only (wrong results): an FMA in place of the special-function unit */
+    r = __fmaf_rn(x, 0.001f, 1.0f);
+#else
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+#endif
     return r;
 }
 __device__ __forceinline__ float rsqrt_approx(float x)
 {
     float r;
+#ifdef B200NB_DIAG_NO_MUFU
+    r = __fmaf_rn(x, -0.5f, 1.5f);
+#else
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+#endif
     return r;
 }
 
@@ -525,7 +533,9 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
                 js[u] = J[u].slot;
             }
             tile_pairs_multi<EEL, GEOM, NT>(I, J, P, K, nbfp, fix, fiy, fiz, sx, sy, sz);
+#ifndef B200NB_DIAG_NO_JFORCE /* diagnostic build only: no j-forces at all (wrong results), isolates the pair arithmetic */
             reduce_store_j_multi<NT>(sx, sy, sz, C, js);
+#endif
         }
     }
     for (; t < ntile; t++)
