@@ -256,8 +256,37 @@ extern "C" int b200nb_set_params(b200nb_t* h, const b200nb_params_t* p)
     }
     d.ntypes        = ntf;
     d.eeltype       = p->eeltype;
+    d.vdw_modifier  = B200NB_VDW_POTSHIFT;
+    d.rvdw2         = d.rc2;
+    d.rvdw_switch   = 0.0f;
+    d.disp_c2 = d.disp_c3 = d.rep_c2 = d.rep_c3 = 0.0f;
+    d.sw_c3 = d.sw_c4 = d.sw_c5 = 0.0f;
     h->have_params  = true;
     h->have_list    = false;
+    return 0;
+}
+
+extern "C" int b200nb_set_vdw(b200nb_t* h, const b200nb_vdw_t* v)
+{
+    if (!h || !v) return B200NB_ERR_ARG;
+    if (!h->have_params) return nb_fail(h, B200NB_ERR_STATE, "set_vdw: set_params first");
+    if (v->vdw_modifier < B200NB_VDW_POTSHIFT || v->vdw_modifier > B200NB_VDW_POTSWITCH)
+        return nb_fail(h, B200NB_ERR_ARG, "set_vdw: unknown modifier");
+    const float rvdw = v->rvdw > 0.0f ? v->rvdw : h->hp.rc;
+    if (rvdw > h->hp.rc) return nb_fail(h, B200NB_ERR_ARG, "set_vdw: rvdw > rc (the list radius follows the Coulomb cut-off)");
+    /* the reference's Verlet scheme allows rvdw != rcoulomb only with PME electrostatics (kerneldispatch.cpp:175-200:
+     * twin-range variants exist for the Ewald kernels alone) */
+    if (rvdw < h->hp.rc && h->dp.eeltype != B200NB_EEL_EWALD)
+        return nb_fail(h, B200NB_ERR_ARG, "set_vdw: rvdw < rcoulomb needs Ewald electrostatics");
+    if (v->vdw_modifier != B200NB_VDW_POTSHIFT && !(v->rvdw_switch >= 0.0f && v->rvdw_switch < rvdw))
+        return nb_fail(h, B200NB_ERR_ARG, "set_vdw: rvdw_switch must lie in [0, rvdw)");
+    NbParamsDev& d = h->dp;
+    d.vdw_modifier = v->vdw_modifier;
+    d.rvdw2        = rvdw * rvdw;
+    d.rvdw_switch  = v->rvdw_switch;
+    d.disp_c2 = v->disp_c2, d.disp_c3 = v->disp_c3, d.rep_c2 = v->rep_c2, d.rep_c3 = v->rep_c3;
+    d.sw_c3 = v->sw_c3, d.sw_c4 = v->sw_c4, d.sw_c5 = v->sw_c5;
+    h->generation++; /* captured step graphs carry the kernel parameters by value */
     return 0;
 }
 

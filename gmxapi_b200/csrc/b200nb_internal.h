@@ -61,6 +61,11 @@ struct NbParamsDev
     float self_q2;  /* self_sub / epsfac (0 when epsfac is 0) */
     int   ntypes;   /* including the filler type */
     int   eeltype;
+    /* LJ modifiers / twin-range cut-off (b200nb_set_vdw; interaction_const_t rvdw, rvdw_switch, *_shift, vdw_switch) */
+    int   vdw_modifier;
+    float rvdw2, rvdw_switch;
+    float disp_c2, disp_c3, rep_c2, rep_c3;
+    float sw_c3, sw_c4, sw_c5;
 };
 
 struct PairList

@@ -160,7 +160,7 @@ struct IData
 };
 
 /* One tile: lane computes pairs (i0, jl) [.x] and (i1, jl) [.y].  Returns the force ON THE i-ATOMS in (tx,ty,tz). */
-template<int EEL, bool GEOM, bool VF, bool MASKED>
+template<int EEL, bool GEOM, bool VF, bool MASKED, bool GEN>
 __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const NbParamsDev& P, const KConst& K, const float2* __restrict__ nbfp,
                                            float inter0, float inter1, bool ok0, bool ok1, float2& tx, float2& ty, float2& tz,
                                            float& evdw, float& ecoul)
@@ -201,7 +201,61 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
     if (MASKED) rinv6 = mul2(rinv6, inter);
     float2 fsum; /* F*r summed over LJ and Coulomb */
     float2 frlj6, frlj12;
-    if (VF)
+    float2 vlj = dup(0.0f);
+    if (GEN)
+    {
+        /* LJ with a force or potential switch and / or a VdW cut-off shorter than the Coulomb one: the arithmetic of
+         * kernels_reference/kernel_ref_inner.h:152-262 (cuda/nbnxm_cuda_kernel_utils.cuh calculate_force_switch_F[_E],
+         * calculate_potential_switch_F[_E]; VDW_CUTOFF_CHECK nbnxm_cuda_kernel.cuh:540-548).  c6n = -6 C6. */
+        frlj6  = mul2(c6n, rinv6);
+        frlj12 = mul2(mul2(c12, rinv6), rinv6);
+        fsum   = add2(frlj12, frlj6);
+        const bool need_v = VF || P.vdw_modifier == B200NB_VDW_POTSWITCH;
+        if (need_v)
+        {
+            const float2 v6  = mul2(dup(1.0f / 6.0f), fma2(c6n, dup(P.disp_cpot), frlj6));
+            const float2 v12 = mul2(dup(1.0f / 12.0f), fma2(c12, dup(P.rep_cpot), frlj12));
+            vlj              = add2(v12, v6);
+        }
+        if (P.vdw_modifier != B200NB_VDW_POTSHIFT)
+        {
+            const float2 r   = mul2(r2, rinv);
+            float2       rsw = add2(r, dup(-P.rvdw_switch));
+            rsw              = make_float2(fmaxf(rsw.x, 0.0f), fmaxf(rsw.y, 0.0f));
+            const float2 rsw2 = mul2(rsw, rsw);
+            if (P.vdw_modifier == B200NB_VDW_FORCESWITCH)
+            {
+                const float2 a = fma2(c6n, fma2(dup(P.disp_c3), rsw, dup(P.disp_c2)), mul2(c12, fma2(dup(P.rep_c3), rsw, dup(P.rep_c2))));
+                fsum           = fma2(a, mul2(rsw2, r), fsum);
+                if (VF)
+                {
+                    const float2 b = fma2(c6n, fma2(dup(-0.25f * P.disp_c3), rsw, dup(-P.disp_c2 * (1.0f / 3.0f))),
+                                          mul2(c12, fma2(dup(-0.25f * P.rep_c3), rsw, dup(-P.rep_c2 * (1.0f / 3.0f)))));
+                    vlj            = fma2(b, mul2(rsw2, rsw), vlj);
+                }
+                if (MASKED) vlj = mul2(vlj, inter);
+            }
+            else
+            {
+                if (MASKED) vlj = mul2(vlj, inter);
+                const float2 sw  = fma2(fma2(fma2(dup(P.sw_c5), rsw, dup(P.sw_c4)), rsw, dup(P.sw_c3)), mul2(rsw2, rsw), dup(1.0f));
+                const float2 dsw = mul2(fma2(fma2(dup(5.0f * P.sw_c5), rsw, dup(4.0f * P.sw_c4)), rsw, dup(3.0f * P.sw_c3)), rsw2);
+                fsum             = fma2(mul2(dsw, vlj), mul2(r, dup(-1.0f)), mul2(sw, fsum));
+                vlj              = mul2(sw, vlj);
+            }
+        }
+        else if (MASKED)
+        {
+            vlj = mul2(vlj, inter);
+        }
+        /* VdW cut-off shorter than the Coulomb cut-off (PME load balancing grows rcoulomb, rvdw stays) */
+        const bool va = r2.x < P.rvdw2, vb = r2.y < P.rvdw2;
+        fsum.x = va ? fsum.x : 0.0f;
+        fsum.y = vb ? fsum.y : 0.0f;
+        vlj.x  = va ? vlj.x : 0.0f;
+        vlj.y  = vb ? vlj.y : 0.0f;
+    }
+    else if (VF)
     {
         frlj6  = mul2(c6n, rinv6);               /* -6 C6 r^-6 */
         frlj12 = mul2(mul2(c12, rinv6), rinv6);  /* 12 C12 r^-12 */
@@ -242,11 +296,14 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
     tz           = mul2(fscal, dz);
     if (VF)
     {
-        /* kernels_simd_2xmm/kernel_inner.h:612-626: V = (FrLJ12 + c12*cpot12)/12 - (FrLJ6 + c6*cpot6)/6 */
-        float2 v6  = mul2(dup(1.0f / 6.0f), fma2(c6n, dup(P.disp_cpot), frlj6)); /* = -(FrLJ6 + c6 cpot6)/6 */
-        float2 v12 = mul2(dup(1.0f / 12.0f), fma2(c12, dup(P.rep_cpot), frlj12));
-        float2 vlj = add2(v12, v6);
-        if (MASKED) vlj = mul2(vlj, inter);
+        if (!GEN)
+        {
+            /* kernels_simd_2xmm/kernel_inner.h:612-626: V = (FrLJ12 + c12*cpot12)/12 - (FrLJ6 + c6*cpot6)/6 */
+            float2 v6  = mul2(dup(1.0f / 6.0f), fma2(c6n, dup(P.disp_cpot), frlj6)); /* = -(FrLJ6 + c6 cpot6)/6 */
+            float2 v12 = mul2(dup(1.0f / 12.0f), fma2(c12, dup(P.rep_cpot), frlj12));
+            vlj        = add2(v12, v6);
+            if (MASKED) vlj = mul2(vlj, inter);
+        }
         evdw += (wa ? vlj.x : 0.0f) + (wb ? vlj.y : 0.0f);
         ecoul += (wa ? vcoul.x : 0.0f) + (wb ? vcoul.y : 0.0f);
     }
@@ -255,6 +312,12 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
 /* Two plain (unmasked, force-only) tiles evaluated in lock step: every step of the arithmetic is written for both tiles
  * before the next step, so the instruction stream carries two independent dependency chains and the 4-cycle FMA, MUFU and
  * shuffle latencies of one tile are covered by the other (ncu: "wait"/"short scoreboard" stalls dominated the one-tile loop). */
+#ifndef B200NB_RING
+#define B200NB_RING 1
+#endif
+#ifndef NB_CHUNK
+#define NB_CHUNK 8 /* packed tiles per ring buffer (multiple of 4: one staging round covers 32 j-atoms) */
+#endif
 #ifndef B200NB_TILE_ILP
 #define B200NB_TILE_ILP 1 /* measured (profiles/r1/g_sweep_one_entry_per_warp.txt): 1 tile in flight at 32 warps/SM beats 2 at 20 */
 #endif
@@ -395,7 +458,7 @@ __device__ __forceinline__ void reduce_store_j_multi(const float (&sx)[NT], cons
 #ifndef B200NB_FORCE_MIN_BLOCKS
 #define B200NB_FORCE_MIN_BLOCKS (32 / B200NB_FORCE_WARPS) /* 32 resident warps per SM = 64 registers per thread */
 #endif
-template<int EEL, bool GEOM, bool VF>
+template<int EEL, bool GEOM, bool VF, bool GEN>
 __global__ void __launch_bounds__(32 * B200NB_FORCE_WARPS, B200NB_FORCE_MIN_BLOCKS)
 k_force(const Entry* __restrict__ entries, long long nentries, const int* __restrict__ pja, const uint64_t* __restrict__ tmask,
         const float4* __restrict__ xq, const float2* __restrict__ lj, const int* __restrict__ atype, const float2* __restrict__ nbfp,
@@ -404,6 +467,160 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
 {
     const long long e = (long long)blockIdx.x * B200NB_FORCE_WARPS + (threadIdx.x >> 5);
     if (e >= nentries) return;
+    const int lane = threadIdx.x & 31;
+#if B200NB_RING
+    /* Entry e owns the packed tiles [e*maxt, (e+1)*maxt) (maxt = the list's pitch).  Its j data go through a two-buffer ring of
+     * NB_CHUNK tiles in shared memory: chunk c+1 is gathered with cp.async while chunk c is being computed, so the shared
+     * memory per warp is constant (2 x NB_CHUNK x 256 B) whatever the entry's length, and entries can hold a whole
+     * (i-cluster, shift) list.  The kernel is issue-bound (profiles/r1/v_*): what an entry costs is its instruction count,
+     * not the latency of these loads -- long entries pay the prologue / epilogue instructions less often. */
+    const int* const ja = pja + (size_t)e * maxt * 8;
+    const int4       ev = __ldg(reinterpret_cast<const int4*>(entries) + e);
+    KConst K;
+    {
+        const float4 k0 = __ldg(reinterpret_cast<const float4*>(kconst)), k1 = __ldg(reinterpret_cast<const float4*>(kconst) + 1),
+                     k2 = __ldg(reinterpret_cast<const float4*>(kconst) + 2);
+        K.rc2 = k0.x, K.beta2 = k0.z, K.fd4 = k0.w, K.fd3 = k1.x, K.fn6 = k1.y, K.fn5 = k1.z, K.fd2 = k1.w, K.fd1 = k2.x, K.fd0 = k2.y;
+    }
+    /* Programmatic dependent launch: everything above reads only the list; from here on the kernel touches xq and f, so wait
+     * for the completion of the preceding kernel of the stream (k_step_begin) -- a no-op for a normally serialised launch. */
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int  start = ev.z, end = ev.w;
+    const bool self  = VF && NB_ENTRY_SELF(ev.y);
+    if (start >= end && !self) return;
+    const int jl = lane & 7, ih = lane >> 3;
+    const int ci = ev.x, shift = NB_ENTRY_SHIFT(ev.y), nmask = NB_ENTRY_NMASK(ev.y);
+    const int ntile = end - start;
+    const unsigned full = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int CHUNK_BYTES = NB_CHUNK * NB_TILE_SMEM;
+    unsigned char* const sj = smem_raw + (threadIdx.x >> 5) * (2 * CHUNK_BYTES);
+    const unsigned       s0 = (unsigned)__cvta_generic_to_shared(sj) + (lane >> 3) * NB_TILE_SMEM + (lane & 7) * 16;
+    auto stage = [&](int c) {
+        /* each lane gathers one j-atom per round: 16 B xyzq, 8 B LJ pair (or 4 B type), and keeps the slot index beside them */
+        const unsigned sb = s0 + (c & 1) * CHUNK_BYTES;
+#pragma unroll
+        for (int r = 0; r < NB_CHUNK / 4; r++)
+        {
+            const int a = c * (NB_CHUNK * 8) + 32 * r + lane;
+            if (a < ntile * 8)
+            {
+                const int      slot = __ldg(ja + a);
+                const unsigned dx   = sb + r * 4 * NB_TILE_SMEM;
+                cp_async16(dx, xq + slot);
+                if (GEOM) cp_async8(dx + 128, lj + slot);
+                else cp_async4(dx + 128, atype + slot);
+                asm volatile("st.shared.s32 [%0], %1;" ::"r"(dx + 136), "r"(slot) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0);
+    LaneClass C;
+    C.b4     = (lane & 16) != 0;
+    C.b3     = (lane & 8) != 0;
+    C.b3or4  = C.b3 || C.b4;
+    C.b3only = C.b3 && !C.b4;
+    C.f_lane = reinterpret_cast<char*>(f) + 4 * (2 * (int)C.b4 + (int)C.b3);
+    IData I;
+    {
+        const float4 a = __ldg(xq + (size_t)ci * 8 + 2 * ih), b = __ldg(xq + (size_t)ci * 8 + 2 * ih + 1);
+        const float  sx = __ldg(shift_vec + 3 * shift), sy = __ldg(shift_vec + 3 * shift + 1), sz = __ldg(shift_vec + 3 * shift + 2);
+        /* the reference adds the shift to the i-atom before the subtraction: kernel_outer.h:482-489 */
+        I.x = make_float2(__fadd_rn(a.x, sx), __fadd_rn(b.x, sx));
+        I.y = make_float2(__fadd_rn(a.y, sy), __fadd_rn(b.y, sy));
+        I.z = make_float2(__fadd_rn(a.z, sz), __fadd_rn(b.z, sz));
+        I.q = make_float2(P.epsfac * a.w, P.epsfac * b.w);
+        if (GEOM)
+        {
+            const float4 l = __ldg(reinterpret_cast<const float4*>(lj + (size_t)ci * 8 + 2 * ih));
+            I.c6n          = make_float2(-l.x, -l.z);
+            I.c12          = make_float2(l.y, l.w);
+            I.t0 = I.t1 = 0;
+        }
+        else
+        {
+            const int2 t = __ldg(reinterpret_cast<const int2*>(atype + (size_t)ci * 8 + 2 * ih));
+            I.t0         = t.x * P.ntypes;
+            I.t1         = t.y * P.ntypes;
+            I.c6n = I.c12 = dup(0.0f);
+        }
+    }
+    float2 fix = dup(0.f), fiy = dup(0.f), fiz = dup(0.f);
+    float  evdw = 0.f, ecoul = 0.f;
+    if (self && jl < 2)
+    {
+        /* Coulomb self term, once per i-atom: kernel_outer.h:408-452 (fillers carry q = 0) */
+        const float qi = (jl == 0 ? I.q.x : I.q.y);
+        ecoul -= qi * qi * P.self_q2;
+    }
+    const uint2* const emask = reinterpret_cast<const uint2*>(tmask) + (size_t)e * maxt;
+    const int          nchunk = (ntile + NB_CHUNK - 1) / NB_CHUNK;
+    int                t      = 0;
+    for (int c = 0; c < nchunk; c++)
+    {
+        if (c + 1 < nchunk) stage(c + 1);
+        else asm volatile("cp.async.commit_group;" ::: "memory"); /* keeps "all but the newest group" = chunk c landed */
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        /* load_j addresses tile t at s_lane + t*256: bias the base so that tile c*NB_CHUNK falls on this chunk's buffer */
+        const unsigned char* const s_lane = sj + (c & 1) * CHUNK_BYTES + jl * 16 - c * CHUNK_BYTES;
+        const int                  tend   = min(ntile, (c + 1) * NB_CHUNK);
+
+        /* ---- tiles with exclusion masks (sorted to the front of the entry) ---- */
+        for (const int tm = min(nmask, tend); t < tm; t++)
+        {
+            JAtom J;
+            load_j(J, s_lane, t);
+            const uint2 m = __ldg(emask + t);
+            /* mask word w, bit `lane`: pair (i-atom 2*ih + w, j-slot jl) interacts */
+            const float in0 = (float)((m.x >> lane) & 1u), in1 = (float)((m.y >> lane) & 1u);
+            bool        ok0 = true, ok1 = true;
+            if (intra && shift == B200NB_CENTRAL && (J.slot >> 3) == ci)
+            {
+                /* j-atom of the i-cluster itself: only j > i (nbnxm/pairlist.cpp:880-904, kernel_gpu_ref.cpp:223-226) */
+                ok0 = (J.slot & 7) > 2 * ih;
+                ok1 = (J.slot & 7) > 2 * ih + 1;
+            }
+            float2 tx, ty, tz;
+            tile_pairs<EEL, GEOM, VF, true, GEN>(I, J, P, K, nbfp, in0, in1, ok0, ok1, tx, ty, tz, evdw, ecoul);
+            fix = add2(fix, tx);
+            fiy = add2(fiy, ty);
+            fiz = add2(fiz, tz);
+            reduce_store_j(tx, ty, tz, C, J.slot);
+        }
+
+        /* ---- plain tiles ---- */
+        if (!VF && !GEN)
+        {
+            for (; t < tend; t++)
+            {
+                JAtom J[1];
+                int   js[1];
+                float sx[1], sy[1], sz[1];
+                load_j(J[0], s_lane, t);
+                js[0] = J[0].slot;
+                tile_pairs_multi<EEL, GEOM, 1>(I, J, P, K, nbfp, fix, fiy, fiz, sx, sy, sz);
+#ifndef B200NB_DIAG_NO_JFORCE /* diagnostic build only: no j-forces at all (wrong results), isolates the pair arithmetic */
+                reduce_store_j_multi<1>(sx, sy, sz, C, js);
+#endif
+            }
+        }
+        for (; t < tend; t++)
+        {
+            JAtom J;
+            load_j(J, s_lane, t);
+            float2 tx, ty, tz;
+            tile_pairs<EEL, GEOM, VF, false, GEN>(I, J, P, K, nbfp, 1.f, 1.f, true, true, tx, ty, tz, evdw, ecoul);
+            fix = add2(fix, tx);
+            fiy = add2(fiy, ty);
+            fiz = add2(fiz, tz);
+            reduce_store_j(tx, ty, tz, C, J.slot);
+        }
+        __syncwarp(); /* every lane is done with this buffer before the next iteration's gather overwrites it */
+    }
+
+#else /* !B200NB_RING: the whole entry staged at once (entries <= 32 tiles, maxt x 256 B of shared memory per warp) */
     const int lane = threadIdx.x & 31;
     /* Level-1 loads, all independent: entry e owns the packed tiles [e*maxt, (e+1)*maxt), so its first 64 j-slot indices and
      * its masks are fetched together with the entry itself (values beyond the entry's tile count are never used). */
@@ -510,7 +727,7 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
             ok1 = (J.slot & 7) > 2 * ih + 1;
         }
         float2 tx, ty, tz;
-        tile_pairs<EEL, GEOM, VF, true>(I, J, P, K, nbfp, in0, in1, ok0, ok1, tx, ty, tz, evdw, ecoul);
+        tile_pairs<EEL, GEOM, VF, true, GEN>(I, J, P, K, nbfp, in0, in1, ok0, ok1, tx, ty, tz, evdw, ecoul);
         fix = add2(fix, tx);
         fiy = add2(fiy, ty);
         fiz = add2(fiz, tz);
@@ -518,7 +735,7 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
     }
 
     /* ---- plain tiles ---- */
-    if (!VF)
+    if (!VF && !GEN)
     {
         constexpr int NT = B200NB_TILE_ILP;
         for (; t + NT <= ntile; t += NT)
@@ -543,13 +760,14 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
         JAtom J;
         load_j(J, s_lane, t);
         float2 tx, ty, tz;
-        tile_pairs<EEL, GEOM, VF, false>(I, J, P, K, nbfp, 1.f, 1.f, true, true, tx, ty, tz, evdw, ecoul);
+        tile_pairs<EEL, GEOM, VF, false, GEN>(I, J, P, K, nbfp, 1.f, 1.f, true, true, tx, ty, tz, evdw, ecoul);
         fix = add2(fix, tx);
         fiy = add2(fiy, ty);
         fiz = add2(fiz, tz);
         reduce_store_j(tx, ty, tz, C, J.slot);
     }
 
+#endif /* B200NB_RING */
     /* ---- i-forces: reduce over the 8 j-lanes (bits 0-2). Stage 1 is transposed: even lanes keep atom i0, odd lanes i1. */
     const bool     odd  = lane & 1;
     float          kx = odd ? fix.y : fix.x, ky = odd ? fiy.y : fiy.x, kz = odd ? fiz.y : fiz.x;
@@ -602,12 +820,16 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
     }
 }
 
-template<int EEL, bool GEOM, bool VF>
+template<int EEL, bool GEOM, bool VF, bool GEN>
 int launch(b200nb_context* h, const PackedList& L, int intra)
 {
     const unsigned nblk = (unsigned)((L.nentries + B200NB_FORCE_WARPS - 1) / B200NB_FORCE_WARPS);
     const int      maxt = h->max_tiles;
-    const size_t   smem = (size_t)B200NB_FORCE_WARPS * maxt * NB_TILE_SMEM;
+#if B200NB_RING
+    const size_t smem = (size_t)B200NB_FORCE_WARPS * 2 * NB_CHUNK * NB_TILE_SMEM;
+#else
+    const size_t smem = (size_t)B200NB_FORCE_WARPS * maxt * NB_TILE_SMEM;
+#endif
     cudaLaunchConfig_t cfg{};
     cfg.gridDim          = dim3(nblk);
     cfg.blockDim         = dim3(32 * B200NB_FORCE_WARPS);
@@ -618,7 +840,7 @@ int launch(b200nb_context* h, const PackedList& L, int intra)
     at[0].val.programmaticStreamSerializationAllowed = 1; /* overlap our list loads with the tail of the preceding kernel */
     cfg.attrs    = at;
     cfg.numAttrs = h->use_pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, k_force<EEL, GEOM, VF>, (const Entry*)L.entries, (long long)L.nentries, (const int*)L.ja, (const uint64_t*)L.mask,
+    cudaLaunchKernelEx(&cfg, k_force<EEL, GEOM, VF, GEN>, (const Entry*)L.entries, (long long)L.nentries, (const int*)L.ja, (const uint64_t*)L.mask,
                        reinterpret_cast<const float4*>(h->d_xq), reinterpret_cast<const float2*>(h->d_lj), (const int*)h->d_atype,
                        reinterpret_cast<const float2*>(h->d_nbfp), (const float*)h->d_shift_vec, h->d_f, h->d_fshift, h->d_energy, h->dp,
                        intra, maxt, (const float*)h->d_kconst);
@@ -637,11 +859,13 @@ int nb_launch_force_kernel(b200nb_context* h, int loc, int flags)
     const bool vf    = (flags & (B200NB_FLAG_ENERGY | B200NB_FLAG_VIRIAL)) != 0;
     const bool ewald = h->dp.eeltype == B200NB_EEL_EWALD;
     const int  intra = (loc == 0);
-    if (ewald)
-    {
-        if (h->comb_geom) return vf ? launch<1, true, true>(h, L, intra) : launch<1, true, false>(h, L, intra);
-        return vf ? launch<1, false, true>(h, L, intra) : launch<1, false, false>(h, L, intra);
-    }
-    if (h->comb_geom) return vf ? launch<0, true, true>(h, L, intra) : launch<0, true, false>(h, L, intra);
-    return vf ? launch<0, false, true>(h, L, intra) : launch<0, false, false>(h, L, intra);
+    /* the plain kernels cover LJ cut-off + potential shift with rvdw == rcoulomb (every BASELINE configuration); the
+     * general ones add the force / potential switch and the twin-range check (cuda/nbnxm_cuda.cu:165-282 kernel table) */
+    const bool gen = h->dp.vdw_modifier != B200NB_VDW_POTSHIFT || h->dp.rvdw2 < h->dp.rc2;
+#define NB_PICK(E, G)                                                                                           \
+    (gen ? (vf ? launch<E, G, true, true>(h, L, intra) : launch<E, G, false, true>(h, L, intra))               \
+         : (vf ? launch<E, G, true, false>(h, L, intra) : launch<E, G, false, false>(h, L, intra)))
+    if (ewald) return h->comb_geom ? NB_PICK(1, true) : NB_PICK(1, false);
+    return h->comb_geom ? NB_PICK(0, true) : NB_PICK(0, false);
+#undef NB_PICK
 }

@@ -15,7 +15,7 @@ FLAG_ENERGY, FLAG_VIRIAL = 1, 2
 
 EXPORTS = [
     "b200nb_create", "b200nb_destroy", "b200nb_last_error", "b200nb_stream", "b200nb_set_stream", "b200nb_synchronize",
-    "b200nb_set_params", "b200nb_set_atoms", "b200nb_set_box", "b200nb_put_on_grid", "b200nb_build_pairlist",
+    "b200nb_set_params", "b200nb_set_vdw", "b200nb_set_atoms", "b200nb_set_box", "b200nb_put_on_grid", "b200nb_build_pairlist",
     "b200nb_set_x", "b200nb_clear_outputs", "b200nb_launch_force", "b200nb_launch_prune", "b200nb_get_f",
     "b200nb_get_outputs", "b200nb_compute", "b200nb_step", "b200nb_dd_create_window", "b200nb_dd_open_peer", "b200nb_dd_set_plan",
     "b200nb_dd_step", "b200nb_dd_status", "b200nb_halo_pack_x", "b200nb_halo_unpack_f", "b200nb_get_stats",
@@ -32,6 +32,37 @@ class _Params(C.Structure):
                 ("rlist_inner", C.c_float), ("eeltype", C.c_int), ("epsfac", C.c_float), ("k_rf", C.c_float),
                 ("c_rf", C.c_float), ("ewald_beta", C.c_float), ("sh_ewald", C.c_float), ("disp_cpot", C.c_float),
                 ("rep_cpot", C.c_float), ("comb_rule", C.c_int), ("max_tiles_per_entry", C.c_int)]
+
+
+class _Vdw(C.Structure):  # b200nb_vdw_t
+    _fields_ = [("vdw_modifier", C.c_int), ("rvdw", C.c_float), ("rvdw_switch", C.c_float), ("disp_c2", C.c_float),
+                ("disp_c3", C.c_float), ("rep_c2", C.c_float), ("rep_c3", C.c_float), ("sw_c3", C.c_float),
+                ("sw_c4", C.c_float), ("sw_c5", C.c_float)]
+
+
+VDW_POTSHIFT, VDW_FORCESWITCH, VDW_POTSWITCH = 0, 1, 2
+
+
+def vdw_modifier_constants(modifier, rvdw, rvdw_switch):
+    """The LJ modifier constants of interaction_const_t as init_interaction_const derives them
+    (mdlib/forcerec.cpp:850-874; force_switch_constants :787-801, potential_switch_constants :803-816), rounded to
+    float where the reference stores a `real`."""
+    f32 = lambda v: float(np.float32(v))
+    d = dict(disp_cpot=0.0, rep_cpot=0.0, disp_c2=0.0, disp_c3=0.0, rep_c2=0.0, rep_c3=0.0, sw_c3=0.0, sw_c4=0.0, sw_c5=0.0)
+    rc, rsw = float(rvdw), float(rvdw_switch)
+    if modifier == VDW_POTSHIFT:
+        d["disp_cpot"], d["rep_cpot"] = -1.0 / rc ** 6, -1.0 / rc ** 12
+    elif modifier == VDW_FORCESWITCH:
+        for name, pw in (("disp", 6.0), ("rep", 12.0)):
+            c2 = f32(((pw + 1) * rsw - (pw + 4) * rc) / (rc ** (pw + 2) * (rc - rsw) ** 2))
+            c3 = f32(-((pw + 1) * rsw - (pw + 3) * rc) / (rc ** (pw + 2) * (rc - rsw) ** 3))
+            d[name + "_c2"], d[name + "_c3"] = c2, c3
+            d[name + "_cpot"] = f32(-rc ** (-pw) + pw * c2 / 3 * (rc - rsw) ** 3 + pw * c3 / 4 * (rc - rsw) ** 4)
+    elif modifier == VDW_POTSWITCH:
+        d["sw_c3"], d["sw_c4"], d["sw_c5"] = f32(-10 / (rc - rsw) ** 3), f32(15 / (rc - rsw) ** 4), f32(-6 / (rc - rsw) ** 5)
+    else:
+        raise B200NBError("unknown vdw modifier %r" % (modifier,))
+    return d
 
 
 class _Stats(C.Structure):
@@ -69,6 +100,7 @@ def load_library():
     L.b200nb_synchronize.argtypes = [vp]
     L.b200nb_set_stream.argtypes = [vp, vp]
     L.b200nb_set_params.argtypes = [vp, C.POINTER(_Params)]
+    L.b200nb_set_vdw.argtypes = [vp, C.POINTER(_Vdw)]
     L.b200nb_set_atoms.argtypes = [vp, ci, vp, vp, vp, vp]
     L.b200nb_set_box.argtypes = [vp, vp, vp]
     L.b200nb_put_on_grid.argtypes = [vp, ci, vp, vp, ci, ci, cf, vp, ci]
@@ -162,6 +194,14 @@ class NbnxmGpu:
                     -1.0 / rc ** 6 if disp_cpot is None else disp_cpot,
                     -1.0 / rc ** 12 if rep_cpot is None else rep_cpot, comb_rule, max_tiles_per_entry)
         self._check(self._L.b200nb_set_params(self._h, C.byref(p)), "set_params")
+
+    def set_vdw(self, vdw_modifier=VDW_POTSHIFT, rvdw=0.0, rvdw_switch=0.0, constants=None):
+        """b200nb_set_vdw: LJ force / potential switch and VdW cut-off (<= rc).  `constants`: the c2/c3/c3..c5 values
+        (vdw_modifier_constants); the matching potential shifts belong in set_params(disp_cpot=, rep_cpot=)."""
+        k = constants or {}
+        v = _Vdw(int(vdw_modifier), float(rvdw), float(rvdw_switch), k.get("disp_c2", 0.0), k.get("disp_c3", 0.0),
+                 k.get("rep_c2", 0.0), k.get("rep_c3", 0.0), k.get("sw_c3", 0.0), k.get("sw_c4", 0.0), k.get("sw_c5", 0.0))
+        self._check(self._L.b200nb_set_vdw(self._h, C.byref(v)), "set_vdw")
 
     def set_atoms(self, types, q, excl_off=None, excl_idx=None):
         types = np.ascontiguousarray(types, dtype=np.int32)

@@ -26,6 +26,12 @@ class CoulombType(enum.Enum):  # api/nblib/kerneloptions.h:72-79
     ReactionField = 2
 
 
+class VdwModifier(enum.Enum):  # interaction_const_t::vdw_modifier (eintmodPOTSHIFT / FORCESWITCH / POTSWITCH)
+    PotentialShift = 0
+    ForceSwitch = 1
+    PotentialSwitch = 2
+
+
 @dataclass
 class NBKernelOptions:
     useGpu: bool = True
@@ -37,6 +43,11 @@ class NBKernelOptions:
     rlistInner: float = 0.0
     maxTilesPerEntry: int = 0  # list balancing granularity (split_sci_entry, pairlist.cpp:2077-2194); 0 = library default
     epsilonRf: float = 1.0  # interaction_const_t::epsilon_rf as gmxsetup.cpp:251-253 leaves it; 0 = infinity
+    # LJ modifier and VdW cut-off (the reference's nblib fixes potential shift and rvdw = rcoulomb, gmxsetup.cpp:231-240;
+    # mdrun reaches the others through the .mdp options vdw-modifier, rvdw, rvdw-switch)
+    vdwModifier: VdwModifier = VdwModifier.PotentialShift
+    vdwCutoff: float = 0.0  # rvdw <= pairlistCutoff (= rcoulomb); 0 = the same
+    vdwSwitch: float = 0.0  # rvdw-switch
     device: int = 0
 
 
@@ -93,8 +104,15 @@ class ForceCalculator:
         rc = float(options.pairlistCutoff)
         self.nb = _lib.NbnxmGpu(options.device)
         kw = interaction_kwargs(options)
+        rvdw = float(options.vdwCutoff) or rc
+        if rvdw > rc:
+            raise InputException("vdwCutoff must not exceed pairlistCutoff")
+        vk = _lib.vdw_modifier_constants(options.vdwModifier.value, rvdw, options.vdwSwitch)
         self.nb.set_params(state.nonbondedParameters, rc, rlist_outer=options.rlistOuter or rc,
-                           rlist_inner=options.rlistInner or 0.0, max_tiles_per_entry=options.maxTilesPerEntry, **kw)
+                           rlist_inner=options.rlistInner or 0.0, max_tiles_per_entry=options.maxTilesPerEntry,
+                           disp_cpot=vk["disp_cpot"], rep_cpot=vk["rep_cpot"], **kw)
+        if options.vdwModifier != VdwModifier.PotentialShift or rvdw < rc:
+            self.nb.set_vdw(options.vdwModifier.value, rvdw, options.vdwSwitch, vk)
         self.nb.set_atoms(state.types, state.charges, state.excl_off, state.excl_idx)
         self._set_particles_on_grid(state.coordinates, state.box)
         self.nb.build_pairlist()  # constructPairList, gmxsetup.cpp:299-303

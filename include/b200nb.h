@@ -45,6 +45,13 @@ enum
 
 enum
 {
+    B200NB_VDW_POTSHIFT    = 0, /* eintmodPOTSHIFT / eintmodNONE: plain cut-off, constant potential shift (disp_cpot, rep_cpot) */
+    B200NB_VDW_FORCESWITCH = 1, /* eintmodFORCESWITCH: vdwktLJFORCESWITCH (nbnxm/kerneldispatch.cpp:208-216, cuda evdwSwitch kernels) */
+    B200NB_VDW_POTSWITCH   = 2  /* eintmodPOTSWITCH */
+};
+
+enum
+{
     B200NB_FLAG_ENERGY = 1, /* StepWorkload::computeEnergy */
     B200NB_FLAG_VIRIAL = 2  /* StepWorkload::computeVirial: accumulate the 45 shift forces */
 };
@@ -70,6 +77,21 @@ typedef struct
     int          max_tiles_per_entry; /* list balancing granularity (pairlist.cpp:2077-2194 split_sci_entry); 0 = default */
 } b200nb_params_t;
 
+/* Van der Waals modifier and VdW cut-off: the part of interaction_const_t (mdtypes/interaction_const.h:107-172) that
+ * init_interaction_const derives in mdlib/forcerec.cpp:850-874 (force_switch_constants :787-801, potential_switch_constants
+ * :803-816) and NBParamGpu carries as dispersion_shift / repulsion_shift / vdw_switch / rvdw_switch / rvdw_sq
+ * (nbnxm/gpu_types_common.h:63-124).  Optional: without it the library evaluates LJ cut-off + potential shift, rvdw = rc. */
+typedef struct
+{
+    int   vdw_modifier; /* B200NB_VDW_* */
+    float rvdw;         /* <= rc (= rcoulomb).  rvdw < rc is the twin-range case PME load balancing produces
+                           (gpu_pme_loadbal_update_param, nbnxm_gpu_data_mgmt.cpp:188-205); 0 means rc */
+    float rvdw_switch;  /* start of the switching range */
+    float disp_c2, disp_c3, rep_c2, rep_c3; /* shift_consts_t::c2, c3 of dispersion_shift / repulsion_shift (force switch); the
+                                               matching cpot values go in b200nb_params_t::disp_cpot / rep_cpot */
+    float sw_c3, sw_c4, sw_c5;              /* switch_consts_t vdw_switch (potential switch) */
+} b200nb_vdw_t;
+
 typedef struct b200nb_context b200nb_t;
 
 /* ---- lifetime: Nbnxm::gpu_init / gpu_free (cuda/nbnxm_cuda_data_mgmt.cu:242,395) ------------------------ */
@@ -86,6 +108,9 @@ int   b200nb_synchronize(b200nb_t* h);
 
 /* ---- parameters: init_nbparam / gpu_pme_loadbal_update_param (nbnxm_gpu_data_mgmt.cpp:225) -------------- */
 int b200nb_set_params(b200nb_t* h, const b200nb_params_t* p);
+/* LJ modifier / VdW cut-off; call after b200nb_set_params (which resets them to potential shift, rvdw = rc).  Only the
+ * force kernel changes: the pair list is built for rlist >= rc either way. */
+int b200nb_set_vdw(b200nb_t* h, const b200nb_vdw_t* v);
 
 /* ---- atoms: nbnxn_atomdata_set (atomdata.cpp:955-977) + the exclusion ListOfLists handed to
  * constructPairlist (nbnxm.h:263).  Exclusions are CSR over LOCAL atom indices, each atom's list contains

@@ -29,7 +29,10 @@ class _Params(C.Structure):
                 ("k_rf", C.c_float), ("c_rf", C.c_float), ("ewaldcoeff", C.c_float),
                 ("sh_ewald", C.c_float), ("disp_cpot", C.c_float), ("rep_cpot", C.c_float),
                 ("kernel", C.c_int), ("comb_rule", C.c_int), ("nthreads", C.c_int),
-                ("exact_atom_flags", C.c_int), ("put_in_box", C.c_int), ("min_ilist_count", C.c_int)]
+                ("exact_atom_flags", C.c_int), ("put_in_box", C.c_int), ("min_ilist_count", C.c_int),
+                ("rvdw", C.c_float), ("vdw_modifier", C.c_int), ("rvdw_switch", C.c_float),
+                ("disp_c2", C.c_float), ("disp_c3", C.c_float), ("rep_c2", C.c_float), ("rep_c3", C.c_float),
+                ("sw_c3", C.c_float), ("sw_c4", C.c_float), ("sw_c5", C.c_float)]
 
 
 _lib = None
@@ -83,7 +86,8 @@ class RefNbnxm:
     def __init__(self, x, box, types, q, nbfp, excl_off, excl_idx, rc, rlist=None, eeltype=EEL_CUT,
                  epsfac=138.935458, k_rf=0.0, c_rf=0.0, ewaldcoeff=0.0, sh_ewald=0.0,
                  disp_cpot=None, rep_cpot=None, kernel=None, comb_rule=0, nthreads=1,
-                 exact_atom_flags=0, put_in_box=0, rlist_inner=0.0, min_ilist_count=0):
+                 exact_atom_flags=0, put_in_box=0, rlist_inner=0.0, min_ilist_count=0,
+                 rvdw=0.0, vdw_modifier=0, rvdw_switch=0.0, modifier_constants=None):
         L = lib()
         self.n = int(len(types))
         self._x = np.ascontiguousarray(x, dtype=np.float32).reshape(self.n, 3)
@@ -98,13 +102,20 @@ class RefNbnxm:
                     self._eo.ctypes.data, self._ei.ctypes.data)
         if kernel is None:
             kernel = default_simd_kernel()
+        # modifier_constants: dict from oracle.vdw_modifier_constants (the values init_interaction_const would store)
+        k = modifier_constants or {}
+        rv = rvdw if rvdw > 0 else rc
         if disp_cpot is None:
-            disp_cpot = -1.0 / rc ** 6
+            disp_cpot = k.get("disp_cpot", -1.0 / rv ** 6)
         if rep_cpot is None:
-            rep_cpot = -1.0 / rc ** 12
+            rep_cpot = k.get("rep_cpot", -1.0 / rv ** 12)
+        if vdw_modifier != 0 and not k:
+            raise ValueError("vdw_modifier needs modifier_constants")
         p = _Params(rc, rlist if rlist else rc, rlist_inner, 0, eeltype, epsfac, k_rf, c_rf, ewaldcoeff,
                     sh_ewald, disp_cpot, rep_cpot, kernel, comb_rule, nthreads, exact_atom_flags,
-                    put_in_box, min_ilist_count)
+                    put_in_box, min_ilist_count, rvdw, vdw_modifier, rvdw_switch,
+                    k.get("disp_c2", 0.0), k.get("disp_c3", 0.0), k.get("rep_c2", 0.0), k.get("rep_c3", 0.0),
+                    k.get("sw_c3", 0.0), k.get("sw_c4", 0.0), k.get("sw_c5", 0.0))
         self.rc = rc
         self.h = L.gmxref_create(C.byref(s), C.byref(p))
         if not self.h:

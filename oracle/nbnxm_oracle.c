@@ -45,7 +45,37 @@ typedef struct
     float rep_cpot;   /* repulsion_shift.cpot */
     int   ntypes;
     const float* nbfp; /* ntypes*ntypes*2: 6*C6, 12*C12 (nbnxm/atomdata.cpp:498-506) */
+    /* Van der Waals modifiers and the twin-range cut-off (interaction_const_t, mdtypes/interaction_const.h:107-172) */
+    float rvdw;        /* <= rc; 0 means rc.  rvdw < rc: VDW_CUTOFF_CHECK, kernel_ref_inner.h:252-262 */
+    int   vdw_modifier; /* ORC_VDW_* */
+    float rvdw_switch;
+    float disp_c2, disp_c3, rep_c2, rep_c3; /* dispersion_shift / repulsion_shift .c2 .c3 (force switch) */
+    float sw_c3, sw_c4, sw_c5;              /* vdw_switch (potential switch) */
 } orc_params;
+
+enum { ORC_VDW_POTSHIFT = 0, ORC_VDW_FORCESWITCH = 1, ORC_VDW_POTSWITCH = 2 };
+
+/* mdlib/forcerec.cpp:787-801 force_switch_constants for a potential r^-p: out = {c2, c3, cpot} */
+void orc_force_switch_constants(double pw, double rsw, double rc, float out[3])
+{
+    const double c2 = ((pw + 1) * rsw - (pw + 4) * rc) / (pow(rc, pw + 2) * (rc - rsw) * (rc - rsw));
+    const double c3 = -((pw + 1) * rsw - (pw + 3) * rc) / (pow(rc, pw + 2) * (rc - rsw) * (rc - rsw) * (rc - rsw));
+    /* the reference evaluates these in `real` = float: round the stored coefficients the same way */
+    const float c2f = (float)c2, c3f = (float)c3;
+    const double d  = rc - rsw;
+    out[0]          = c2f;
+    out[1]          = c3f;
+    out[2]          = (float)(-pow(rc, -pw) + pw * c2f / 3 * d * d * d + pw * c3f / 4 * d * d * d * d);
+}
+
+/* mdlib/forcerec.cpp:803-816 potential_switch_constants: out = {c3, c4, c5} */
+void orc_potential_switch_constants(double rsw, double rc, float out[3])
+{
+    const double d = rc - rsw;
+    out[0]         = (float)(-10 / (d * d * d));
+    out[1]         = (float)(15 / (d * d * d * d));
+    out[2]         = (float)(-6 / (d * d * d * d * d));
+}
 
 static int shift_index(int tx, int ty, int tz)
 {
@@ -606,12 +636,47 @@ static void force_cb(void* vctx, int ai, int aj, int is, float rsq)
     const float c6 = p->nbfp[(ti * p->ntypes + tj) * 2], c12 = p->nbfp[(ti * p->ntypes + tj) * 2 + 1];
     const float rinvsix = rinvsq * rinvsq * rinvsq * interact;
     const float frlj6 = c6 * rinvsix, frlj12 = c12 * rinvsix * rinvsix;
-    const float frlj  = frlj12 - frlj6;
+    float       frlj  = frlj12 - frlj6;
+    /* kernel_ref_inner.h:157-164: the LJ energy is also needed by the potential switch */
+    float vlj = (1.0f / 12.0f) * fmaf(c12, p->rep_cpot, frlj12) - (1.0f / 6.0f) * fmaf(c6, p->disp_cpot, frlj6);
+    if (p->vdw_modifier != ORC_VDW_POTSHIFT)
+    {
+        /* kernel_ref_inner.h:166-172: force or potential switching from rvdw_switch */
+        const float r   = rsq * rinv;
+        float       rsw = r - p->rvdw_switch;
+        rsw             = (rsw >= 0.0f ? rsw : 0.0f);
+        if (p->vdw_modifier == ORC_VDW_FORCESWITCH)
+        {
+            /* kernel_ref_inner.h:173-182 */
+            frlj += -c6 * (p->disp_c2 + p->disp_c3 * rsw) * rsw * rsw * r + c12 * (p->rep_c2 + p->rep_c3 * rsw) * rsw * rsw * r;
+            vlj += -c6 * (-p->disp_c2 / 3 - p->disp_c3 / 4 * rsw) * rsw * rsw * rsw
+                   + c12 * (-p->rep_c2 / 3 - p->rep_c3 / 4 * rsw) * rsw * rsw * rsw;
+            vlj = vlj * interact; /* :184-191 masking after force switching */
+        }
+        else
+        {
+            /* kernel_ref_inner.h:184-205: mask, then sw = 1 + c3 rsw^3 + c4 rsw^4 + c5 rsw^5, dsw = its derivative */
+            vlj = vlj * interact;
+            const float sw  = 1.0f + (p->sw_c3 + (p->sw_c4 + p->sw_c5 * rsw) * rsw) * rsw * rsw * rsw;
+            const float dsw = (3 * p->sw_c3 + (4 * p->sw_c4 + 5 * p->sw_c5 * rsw) * rsw) * rsw * rsw;
+            frlj            = frlj * sw - r * vlj * dsw;
+            vlj *= sw;
+        }
+    }
+    else
+    {
+        vlj = vlj * interact;
+    }
+    if (p->rvdw > 0.0f && p->rvdw < p->rc)
+    {
+        /* kernel_ref_inner.h:252-262 VDW_CUTOFF_CHECK: VdW cut-off shorter than the Coulomb cut-off */
+        const float skip = (rsq < p->rvdw * p->rvdw) ? 1.0f : 0.0f;
+        frlj *= skip;
+        vlj *= skip;
+    }
     if (c->want_energy)
     {
-        float v6  = (1.0f / 6.0f) * fmaf(c6, p->disp_cpot, frlj6);
-        float v12 = (1.0f / 12.0f) * fmaf(c12, p->rep_cpot, frlj12);
-        c->evdw += (double)((v12 - v6) * interact);
+        c->evdw += (double)vlj;
         c->ecoul += (double)vcoul;
     }
     const float fscal = rinvsq * (frcoul + frlj);

@@ -18,7 +18,32 @@ CENTRAL, SHIFTS = 22, 45
 class _Params(C.Structure):
     _fields_ = [("rc", C.c_float), ("eeltype", C.c_int), ("epsfac", C.c_float), ("k_rf", C.c_float),
                 ("c_rf", C.c_float), ("beta", C.c_float), ("sh_ewald", C.c_float),
-                ("disp_cpot", C.c_float), ("rep_cpot", C.c_float), ("ntypes", C.c_int), ("nbfp", C.c_void_p)]
+                ("disp_cpot", C.c_float), ("rep_cpot", C.c_float), ("ntypes", C.c_int), ("nbfp", C.c_void_p),
+                ("rvdw", C.c_float), ("vdw_modifier", C.c_int), ("rvdw_switch", C.c_float),
+                ("disp_c2", C.c_float), ("disp_c3", C.c_float), ("rep_c2", C.c_float), ("rep_c3", C.c_float),
+                ("sw_c3", C.c_float), ("sw_c4", C.c_float), ("sw_c5", C.c_float)]
+
+
+VDW_POTSHIFT, VDW_FORCESWITCH, VDW_POTSWITCH = 0, 1, 2
+
+
+def vdw_modifier_constants(modifier, rvdw, rvdw_switch):
+    """interaction_const_t's LJ modifier constants as init_interaction_const makes them (mdlib/forcerec.cpp:850-874):
+    dict(disp_cpot, rep_cpot, disp_c2, disp_c3, rep_c2, rep_c3, sw_c3, sw_c4, sw_c5)."""
+    d = dict(disp_cpot=0.0, rep_cpot=0.0, disp_c2=0.0, disp_c3=0.0, rep_c2=0.0, rep_c3=0.0, sw_c3=0.0, sw_c4=0.0, sw_c5=0.0)
+    if modifier == VDW_POTSHIFT:
+        d["disp_cpot"], d["rep_cpot"] = -1.0 / rvdw ** 6, -1.0 / rvdw ** 12
+    elif modifier == VDW_FORCESWITCH:
+        o = (C.c_float * 3)()
+        lib().orc_force_switch_constants(C.c_double(6.0), C.c_double(rvdw_switch), C.c_double(rvdw), o)
+        d["disp_c2"], d["disp_c3"], d["disp_cpot"] = float(o[0]), float(o[1]), float(o[2])
+        lib().orc_force_switch_constants(C.c_double(12.0), C.c_double(rvdw_switch), C.c_double(rvdw), o)
+        d["rep_c2"], d["rep_c3"], d["rep_cpot"] = float(o[0]), float(o[1]), float(o[2])
+    else:
+        o = (C.c_float * 3)()
+        lib().orc_potential_switch_constants(C.c_double(rvdw_switch), C.c_double(rvdw), o)
+        d["sw_c3"], d["sw_c4"], d["sw_c5"] = float(o[0]), float(o[1]), float(o[2])
+    return d
 
 
 _lib = None
@@ -142,19 +167,25 @@ def prune_tiles(tiles, atom_index, x, box, rlist_inner):
 
 
 def forces(x, box, q, types, nbfp, rc, excl_off=None, excl_idx=None, eeltype=EEL_CUT, epsfac=138.935458,
-           k_rf=0.0, c_rf=0.0, beta=0.0, sh_ewald=0.0, disp_cpot=None, rep_cpot=None, energy=True):
-    """Returns (f[n,3] float64, fshift[45,3] float64, evdw, ecoul, npairs)."""
+           k_rf=0.0, c_rf=0.0, beta=0.0, sh_ewald=0.0, disp_cpot=None, rep_cpot=None, energy=True,
+           rvdw=0.0, vdw_modifier=VDW_POTSHIFT, rvdw_switch=0.0):
+    """Returns (f[n,3] float64, fshift[45,3] float64, evdw, ecoul, npairs).  rvdw < rc: twin-range cut-off (Ewald only in
+    the reference); vdw_modifier: VDW_POTSHIFT / VDW_FORCESWITCH / VDW_POTSWITCH from rvdw_switch to rvdw."""
     x = _f32(x)
     n = x.shape[0]
     q = _f32(q)
     types = _i32(types)
     nbfp = _f32(nbfp).ravel()
     ntypes = int(round((nbfp.size // 2) ** 0.5))
+    rv = rvdw if rvdw > 0 else rc
+    k = vdw_modifier_constants(vdw_modifier, rv, rvdw_switch)
     if disp_cpot is None:
-        disp_cpot = -1.0 / rc ** 6
+        disp_cpot = k["disp_cpot"]
     if rep_cpot is None:
-        rep_cpot = -1.0 / rc ** 12
-    p = _Params(rc, eeltype, epsfac, k_rf, c_rf, beta, sh_ewald, disp_cpot, rep_cpot, ntypes, nbfp.ctypes.data)
+        rep_cpot = k["rep_cpot"]
+    p = _Params(rc, eeltype, epsfac, k_rf, c_rf, beta, sh_ewald, disp_cpot, rep_cpot, ntypes, nbfp.ctypes.data,
+                rvdw, vdw_modifier, rvdw_switch, k["disp_c2"], k["disp_c3"], k["rep_c2"], k["rep_c3"],
+                k["sw_c3"], k["sw_c4"], k["sw_c5"])
     b = (C.c_float * 3)(*[float(v) for v in box])
     eo = _i32(excl_off) if excl_off is not None else None
     ei = _i32(excl_idx) if excl_idx is not None else None

@@ -176,6 +176,26 @@ void* gmxref_create(const gmxref_system* s, const gmxref_params* p)
     ic.rcoulomb              = p->rc;
     ic.dispersion_shift.cpot = p->disp_cpot;
     ic.repulsion_shift.cpot  = p->rep_cpot;
+    /* the derived constants come from the caller exactly as init_interaction_const (mdlib/forcerec.cpp:850-874) stores
+     * them; that function is static in forcerec.cpp, so the test side restates its three formulas */
+    if (p->rvdw > 0) ic.rvdw = p->rvdw;
+    if (p->vdw_modifier == 1)
+    {
+        ic.vdw_modifier        = eintmodFORCESWITCH;
+        ic.rvdw_switch         = p->rvdw_switch;
+        ic.dispersion_shift.c2 = p->disp_c2;
+        ic.dispersion_shift.c3 = p->disp_c3;
+        ic.repulsion_shift.c2  = p->rep_c2;
+        ic.repulsion_shift.c3  = p->rep_c3;
+    }
+    else if (p->vdw_modifier == 2)
+    {
+        ic.vdw_modifier  = eintmodPOTSWITCH;
+        ic.rvdw_switch   = p->rvdw_switch;
+        ic.vdw_switch.c3 = p->sw_c3;
+        ic.vdw_switch.c4 = p->sw_c4;
+        ic.vdw_switch.c5 = p->sw_c5;
+    }
     ic.epsilon_r             = 1;
     ic.epsfac                = p->epsfac;
     ic.k_rf                  = p->k_rf;

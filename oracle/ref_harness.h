@@ -36,6 +36,12 @@ typedef struct
     int   exact_atom_flags; /* 0: all atoms flagged VdW+Q (bench default) */
     int   put_in_box;
     int   min_ilist_count;  /* GPU list balancing target, 0 = none */
+    /* LJ modifier and twin-range cut-off (interaction_const_t::vdw_modifier, rvdw, rvdw_switch) */
+    float rvdw;             /* 0: = rc; < rc: VdW cut-off check (Ewald kernels only, kerneldispatch.cpp:175-200) */
+    int   vdw_modifier;     /* 0 potential shift (disp_cpot / rep_cpot above), 1 force switch, 2 potential switch */
+    float rvdw_switch;
+    float disp_c2, disp_c3, rep_c2, rep_c3; /* shift_consts_t::c2, c3 as force_switch_constants makes them (forcerec.cpp:787-801) */
+    float sw_c3, sw_c4, sw_c5;              /* switch_consts_t (forcerec.cpp:803-816) */
 } gmxref_params;
 
 int    gmxref_simd_width(void);

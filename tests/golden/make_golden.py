@@ -9,6 +9,10 @@ and oracle/_ref exist; the fixtures then travel to the GPU box, the reference tr
       f (n,3) f32, fshift (45,3) f32, e_lj, e_el   -- CPU SIMD kernel (2xMM on AVX-512), the parity target
       npairs, pairs_sha256                           -- in-range non-excluded pair set at rc (canonical keys)
       grid_sha256, grid_dims                         -- GPU-geometry (8x8x8) grid atom order
+ 3. ref_water_3k_vdw_<flavour>.npz: the reference's CPU SIMD kernels with an LJ force switch, an LJ potential switch
+    and / or a VdW cut-off shorter than the Coulomb cut-off (Ewald electrostatics), once with the water charges and
+    once with all charges zero (f_lj: Lennard-Jones forces alone, so that the modifier arithmetic is not hidden
+    under the 100x larger Coulomb forces).
 """
 import hashlib
 import json
@@ -69,5 +73,36 @@ def main():
             print(sysname, eel, len(keys), elj, eel_)
 
 
+VDW_FLAVOURS = {  # name: (vdw_modifier, rvdw, rvdw_switch)
+    "twin": (0, 0.8, 0.0),
+    "fswitch": (1, 0.9, 0.75),
+    "pswitch": (2, 0.9, 0.75),
+    "fswitch_twin": (1, 0.8, 0.65),
+}
+
+
+def vdw_flavours():
+    import gmxapi_b200.systems as S
+    from oracle import gmxref, oracle
+    beta = float(np.float32(S.ewald_beta(RC)))
+    s = S.named("water_3k")
+    for name, (mod, rvdw, rsw) in VDW_FLAVOURS.items():
+        k = oracle.vdw_modifier_constants(mod, rvdw, rsw)
+        out = dict(beta=np.float64(beta), vdw_modifier=np.int64(mod), rvdw=np.float64(rvdw), rvdw_switch=np.float64(rsw))
+        for tag, q in (("", s.q), ("_lj", np.zeros_like(s.q))):
+            r = gmxref.RefNbnxm(s.x, s.box, s.types, q, s.nbfp, s.excl_off, s.excl_idx, rc=RC, nthreads=4,
+                                eeltype=gmxref.EEL_EWALD_ANA, ewaldcoeff=beta, rvdw=rvdw if rvdw < RC else 0.0,
+                                vdw_modifier=mod, rvdw_switch=rsw, modifier_constants=k)
+            f, fs, elj, eel_ = r.compute()
+            r.close()
+            out["f" + tag], out["fshift" + tag] = f, fs
+            out["e_lj" + tag], out["e_el" + tag] = np.float64(elj), np.float64(eel_)
+        np.savez_compressed(os.path.join(HERE, "ref_water_3k_vdw_%s.npz" % name), **out)
+        print(name, out["e_lj"], out["e_el"], out["e_lj_lj"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "vdw":
+        vdw_flavours()
+        sys.exit(0)
     main()

@@ -93,6 +93,46 @@ def test_pairs_forces_energies(built, name, coulomb):
     assert abs(eel - eco) <= 2e-4 * abs(eco)
 
 
+@pytest.mark.parametrize("flavour,mod,rvdw,rsw", [("twin", g.VdwModifier.PotentialShift, 0.8, 0.0),
+                                                  ("fswitch", g.VdwModifier.ForceSwitch, 0.9, 0.75),
+                                                  ("pswitch", g.VdwModifier.PotentialSwitch, 0.9, 0.75),
+                                                  ("fswitch_twin", g.VdwModifier.ForceSwitch, 0.8, 0.65)])
+def test_vdw_flavours(built, flavour, mod, rvdw, rsw):
+    """LJ force switch, potential switch and the twin-range VdW cut-off (the general kernels, b200nb_set_vdw) against the
+    oracle and against the committed outputs of the reference's SIMD kernels; once with the water charges, once with all
+    charges zero so that the Lennard-Jones arithmetic is what the force tolerance measures."""
+    import os
+    gd = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_water_3k_vdw_%s.npz" % flavour))
+    s = g.systems.named("water_3k")
+    beta = float(np.float32(g.systems.ewald_beta(RC)))
+    for tag, q in (("", s.q), ("_lj", np.zeros_like(s.q))):
+        for energy in (True, False):
+            opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, computeVirialAndEnergy=energy,
+                                    vdwModifier=mod, vdwCutoff=rvdw, vdwSwitch=rsw)
+            fc = g.ForceCalculator(g.SimulationState(s.x, s.box, s.types, q, s.nbfp, s.excl_off, s.excl_idx), opt)
+            f = fc.compute()
+            fo, fso, evo, eco, _ = oracle.forces(s.x, s.box, q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx,
+                                                 eeltype=oracle.EEL_EWALD, beta=beta, vdw_modifier=mod.value,
+                                                 rvdw=rvdw, rvdw_switch=rsw)
+            assert relrms(f, fo) < FORCE_TOL
+            assert relrms(f, gd["f" + tag].astype(np.float64)) < FORCE_TOL
+            if energy:
+                elj, eel = fc.energies
+                assert abs(elj - evo) <= 2e-4 * abs(evo)
+                assert abs(elj - float(gd["e_lj" + tag])) <= 2e-4 * abs(float(gd["e_lj" + tag]))
+                if tag == "":
+                    assert abs(eel - eco) <= 2e-4 * abs(eco)
+                m = np.ones(45, bool)
+                m[nb.CENTRAL] = False
+                fs = fc.shiftForces.astype(np.float64)
+                assert np.abs(fs[m] - fso[m]).max() <= VIRIAL_TOL * np.abs(fso[m]).max()
+            fc.nb.close()
+    # rvdw < rcoulomb without Ewald is refused, as in the reference's Verlet scheme
+    with pytest.raises(nb.B200NBError):
+        g.ForceCalculator(g.SimulationState.from_system(s),
+                          g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.ReactionField, vdwCutoff=0.8))
+
+
 def test_tile_list_is_exact(built):
     """The device list holds exactly the cluster pairs with >= 1 atom pair inside rlist (what the reference list
     converges to after pruning), in the half-list convention."""
