@@ -85,7 +85,7 @@ extern "C" int b200nb_create(b200nb_t** out, int device)
     cudaMalloc((void**)&h->d_scratch, sizeof(int) * 64);
     cudaMalloc((void**)&h->d_kconst, sizeof(float) * 12);
     cudaMalloc((void**)&h->d_counter, sizeof(long long) * 8);
-    cudaMalloc((void**)&h->d_hist, sizeof(int) * 80);
+    cudaMalloc((void**)&h->d_hist, sizeof(int) * 2 * NB_ORDER_BINS);
     cudaMemsetAsync(h->d_fshift, 0, sizeof(float) * NB_OUT_COPIES * NB_FSHIFT_PITCH, h->stream);
     cudaMemsetAsync(h->d_energy, 0, sizeof(double) * NB_OUT_COPIES * 2, h->stream);
     *out = h;
@@ -221,8 +221,8 @@ extern "C" int b200nb_set_params(b200nb_t* h, const b200nb_params_t* p)
             geom          = within(c6 * c6, c6ii * c6jj) && within(c12 * c12, c12ii * c12jj);
         }
     h->comb_geom = (p->comb_rule == 1) || (p->comb_rule == 0 && geom);
-    /* <= 32: force.cu keeps an entry's masks in one warp register; 0 = chosen from the system size in build_pairlist */
-    h->max_tiles = p->max_tiles_per_entry > 0 ? std::min(p->max_tiles_per_entry, 32) : 16;
+    /* 0 = chosen from the system size in build_pairlist */
+    h->max_tiles = p->max_tiles_per_entry > 0 ? std::min(p->max_tiles_per_entry, NB_MAX_ENTRY_TILES) : 16;
     if (alloc_exact(h, &h->d_nbfp, (size_t)ntf * ntf * 2)) return B200NB_ERR_CUDA;
     NB_CUDA(h, cudaMemcpyAsync(h->d_nbfp, h->nbfp_host.data(), sizeof(float) * ntf * ntf * 2, cudaMemcpyHostToDevice, h->stream));
     NB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -962,7 +962,9 @@ k_search(SearchArgs A, const float* __restrict__ xq, const float* __restrict__ b
                     /* close this (ci, shift) group: pairlist.cpp:2167-2194 closeIEntry + split_sci_entry */
                     const int n = n_mask + n_plain;
                     if (n == 0) continue;
+                    /* equal parts instead of full parts plus a short remainder: the same number of entries, none of them tiny */
                     const int nchunks = (n + A.max_tiles - 1) / A.max_tiles;
+                    const int csize   = (n + nchunks - 1) / nchunks;
                     if (A.pass == 1)
                     {
                         __syncwarp();
@@ -977,10 +979,10 @@ k_search(SearchArgs A, const float* __restrict__ xq, const float* __restrict__ b
                         {
                             Entry e;
                             e.ci          = ci;
-                            int nm        = min(max(n_mask - k * A.max_tiles, 0), A.max_tiles);
+                            int nm        = min(max(n_mask - k * csize, 0), csize);
                             e.shift_nmask = shift | (nm << 8);
-                            e.start       = tile_cursor + k * A.max_tiles;
-                            e.end         = tile_cursor + min((k + 1) * A.max_tiles, n);
+                            e.start       = tile_cursor + k * csize;
+                            e.end         = tile_cursor + min((k + 1) * csize, n);
                             entries[entry_cursor + k] = e;
                         }
                         __syncwarp();
@@ -1104,8 +1106,8 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
        int nparts, const float* __restrict__ xq, const float* __restrict__ shift_vec, float rlist2, int intra, int dummy_slot, int pitch,
        const int* __restrict__ dest, int* __restrict__ sizes, Entry* __restrict__ pe, int* __restrict__ pja, uint64_t* __restrict__ pmask)
 {
-    __shared__ int      s_ja[4][32 * 8];
-    __shared__ unsigned s_m0[4][32], s_m1[4][32];
+    __shared__ int      s_ja[4][NB_MAX_ENTRY_TILES * 8];
+    __shared__ unsigned s_m0[4][NB_MAX_ENTRY_TILES], s_m1[4][NB_MAX_ENTRY_TILES];
     const int       w   = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * 4 + w;
     const long long e   = wid * nparts + part;
@@ -1113,10 +1115,13 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
     const int   lane = threadIdx.x & 31, jl = lane & 7, ih = lane >> 3;
     const Entry en   = ie[e];
     const int   shift = NB_ENTRY_SHIFT(en.shift_nmask), nmask = NB_ENTRY_NMASK(en.shift_nmask);
-    const int   ntile = min(en.end - en.start, 32);
+    const int   ntile = min(en.end - en.start, NB_MAX_ENTRY_TILES);
     for (int k = lane; k < ntile * 8; k += 32) s_ja[w][k] = dummy_slot + (int)(e & (NB_DUMMY_SLOTS / 8 - 1)) * 8 + (k & 7);
-    s_m0[w][lane] = 0u;
-    s_m1[w][lane] = 0u;
+    for (int k = lane; k < NB_MAX_ENTRY_TILES; k += 32)
+    {
+        s_m0[w][k] = 0u;
+        s_m1[w][k] = 0u;
+    }
     __syncwarp();
     const float4 xa = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + 2 * ih];
     const float4 xb = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + 2 * ih + 1];
@@ -1164,7 +1169,7 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
     const long long d  = dest ? dest[e] : e; /* position of this entry in the packed list (largest entries first) */
     const long long t0 = d * pitch;          /* packed entry d owns tiles [d*pitch, (d+1)*pitch) */
     for (int k = lane; k < ntp * 8; k += 32) pja[(size_t)t0 * 8 + k] = s_ja[w][k];
-    if (lane < ntp) pmask[t0 + lane] = lane < nmt ? (((uint64_t)s_m1[w][lane] << 32) | s_m0[w][lane]) : ~0ull;
+    for (int k = lane; k < ntp; k += 32) pmask[t0 + k] = k < nmt ? (((uint64_t)s_m1[w][k] << 32) | s_m0[w][k]) : ~0ull;
     if (lane == 0)
     {
         Entry o;
@@ -1179,25 +1184,25 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
 /* Positions of the packed entries: descending packed size (counting sort on <= 33 values; the role of sort_sci,
  * nbnxm/pairlist.cpp:3827-3873).  The force kernel runs one entry per single-warp CTA and CTAs start in index order, so the
  * big entries start first and the last wave holds only the smallest ones: the tail of the kernel shrinks from one full entry
- * to one short entry.  hist: 2 x 40 ints (histogram, cursors). */
+ * to one short entry.  hist: 2 x NB_ORDER_BINS ints (histogram, cursors). */
 __global__ void k_order_hist(const int* __restrict__ sizes, int n, int* __restrict__ hist)
 {
-    __shared__ int sh[40];
-    if (threadIdx.x < 40) sh[threadIdx.x] = 0;
+    __shared__ int sh[NB_ORDER_BINS];
+    if (threadIdx.x < NB_ORDER_BINS) sh[threadIdx.x] = 0;
     __syncthreads();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) atomicAdd(&sh[min(sizes[e], 39)], 1);
+    if (e < n) atomicAdd(&sh[min(sizes[e], NB_ORDER_BINS - 1)], 1);
     __syncthreads();
-    if (threadIdx.x < 40 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+    if (threadIdx.x < NB_ORDER_BINS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 __global__ void k_order_scan(int* __restrict__ hist)
 {
     if (threadIdx.x == 0)
     {
         int run = 0;
-        for (int c = 39; c >= 0; c--) /* largest first */
+        for (int c = NB_ORDER_BINS - 1; c >= 0; c--) /* largest first */
         {
-            hist[40 + c] = run;
+            hist[NB_ORDER_BINS + c] = run;
             run += hist[c];
         }
     }
@@ -1205,7 +1210,7 @@ __global__ void k_order_scan(int* __restrict__ hist)
 __global__ void k_order_assign(const int* __restrict__ sizes, int n, int* __restrict__ hist, int* __restrict__ dest)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) dest[e] = atomicAdd(&hist[40 + min(sizes[e], 39)], 1);
+    if (e < n) dest[e] = atomicAdd(&hist[NB_ORDER_BINS + min(sizes[e], NB_ORDER_BINS - 1)], 1);
 }
 
 static int ensure_packed(b200nb_context* h, PackedList& P, size_t cap_tiles, size_t cap_entries)
@@ -1257,7 +1262,7 @@ static int launch_pack(b200nb_context* h, int loc, int part, int nparts)
         k_pack<<<nblk, 128, 0, h->stream>>>(I.entries, I.cj, I.mask, I.nentries, 0, 1, h->d_xq, h->d_shift_vec, r2, loc == 0, h->dummy_slot,
                                             P.pitch, nullptr, P.sizes, P.entries, P.ja, P.mask);
         LAUNCH_CHECK(h);
-        NB_CUDA(h, cudaMemsetAsync(h->d_hist, 0, sizeof(int) * 80, h->stream));
+        NB_CUDA(h, cudaMemsetAsync(h->d_hist, 0, sizeof(int) * 2 * NB_ORDER_BINS, h->stream));
         k_order_hist<<<(n + 255) / 256, 256, 0, h->stream>>>(P.sizes, n, h->d_hist);
         LAUNCH_CHECK(h);
         k_order_scan<<<1, 32, 0, h->stream>>>(h->d_hist);
@@ -1319,11 +1324,13 @@ extern "C" int b200nb_build_pairlist(b200nb_t* h)
      * (the reference handles that with shp[XX]=2, pairlist.cpp:3185-3188; outside our scope) */
     for (int d = 0; d < 3; d++)
         if (h->pbc[d] && h->box[d] < 2 * rl) return nb_fail(h, B200NB_ERR_ARG, "build_pairlist: box smaller than 2*rlist along a periodic dimension");
-    /* list balancing granularity (the role of get_nsubpair_target, pairlist.cpp:2485-2587): with the packed entries stored
-     * largest-first, 24 cluster pairs (about 15 packed tiles) per entry is best from 24 k to 192 k atoms
-     * (profiles/r1/r_sweep_sorted_entries.txt); shorter entries pay the per-entry prologue more often, longer ones leave a
-     * longer tail on small systems */
-    if (h->hp.max_tiles_per_entry <= 0) h->max_tiles = 24;
+    /* list balancing granularity (the role of get_nsubpair_target, pairlist.cpp:2485-2587).  The force kernel is issue-bound
+     * and an entry costs about 560 issue cycles on top of its tiles (prologue, masked first tile, i-force reduction;
+     * profiles/r1/v_sweep_pair_loop_diagnostics.txt), so entries should be as long as the need for parallelism allows:
+     * up to 48 k atoms 24 cluster pairs per entry keep ~2 entries per resident warp (r_sweep_sorted_entries.txt); larger
+     * systems have entries to spare and take whole (i-cluster, shift) lists, up to NB_MAX_ENTRY_TILES */
+    if (h->hp.max_tiles_per_entry <= 0)
+        h->max_tiles = h->natoms <= 48000 ? 24 : std::min(NB_MAX_ENTRY_TILES, (int)(24.0 * h->natoms / 48000.0));
     const bool want_inner = h->dp.rlist_inner2 < h->dp.rlist_outer2;
     if (!want_inner && !h->inner_is_outer)
     {
@@ -1674,6 +1681,11 @@ struct DdBegin
     int*       counter;
 };
 
+/* The L2 prefetch of the packed list pays on small systems, where the force kernel is a few waves long and its first
+ * loads would otherwise come from HBM; a list of tens of MB belongs to a kernel that hides that latency by itself, and
+ * streaming it twice per step would only cost bandwidth and time in k_step_begin. */
+static inline size_t nb_list_prefetch_bytes(size_t bytes) { return bytes <= ((size_t)12 << 20) ? bytes : 0; }
+
 struct PrefetchRange
 {
     const char* p[4];
@@ -1778,9 +1790,9 @@ static int launch_step(b200nb_context* h, const float* x_dev, int flags, float* 
         pf.p[0]     = reinterpret_cast<const char*>(P.entries);
         pf.bytes[0] = sizeof(Entry) * (size_t)P.nentries;
         pf.p[1]     = reinterpret_cast<const char*>(P.ja);
-        pf.bytes[1] = sizeof(int) * 8 * (size_t)P.nentries * P.pitch;
+        pf.bytes[1] = nb_list_prefetch_bytes(sizeof(int) * 8 * (size_t)P.nentries * P.pitch);
         pf.p[2]     = reinterpret_cast<const char*>(P.mask);
-        pf.bytes[2] = sizeof(uint64_t) * (size_t)P.nentries * P.pitch;
+        pf.bytes[2] = nb_list_prefetch_bytes(sizeof(uint64_t) * (size_t)P.nentries * P.pitch);
         pf.p[3]     = reinterpret_cast<const char*>(h->comb_geom ? (const void*)h->d_lj : (const void*)h->d_atype);
         pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
     }
@@ -2193,9 +2205,9 @@ static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home,
         pf.p[0]     = reinterpret_cast<const char*>(P.entries);
         pf.bytes[0] = sizeof(Entry) * (size_t)P.nentries;
         pf.p[1]     = reinterpret_cast<const char*>(P.ja);
-        pf.bytes[1] = sizeof(int) * 8 * (size_t)P.nentries * P.pitch;
+        pf.bytes[1] = nb_list_prefetch_bytes(sizeof(int) * 8 * (size_t)P.nentries * P.pitch);
         pf.p[2]     = reinterpret_cast<const char*>(P.mask);
-        pf.bytes[2] = sizeof(uint64_t) * (size_t)P.nentries * P.pitch;
+        pf.bytes[2] = nb_list_prefetch_bytes(sizeof(uint64_t) * (size_t)P.nentries * P.pitch);
         pf.p[3]     = reinterpret_cast<const char*>(h->comb_geom ? (const void*)h->d_lj : (const void*)h->d_atype);
         pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
     }

@@ -13,6 +13,8 @@
 #define NB_CL 8      /* atoms per cluster */
 #define NB_CELL 64   /* atoms per grid cell = 8 clusters (nbnxm/pairlistparams.h:69-77) */
 #define NB_MIN_RSQ 3.82e-07f /* nbnxm/pairlist.h:146 c_nbnxnMinDistanceSquared */
+#define NB_MAX_ENTRY_TILES 64 /* cluster pairs (and so packed tiles) per list entry at most: k_pack staging, ordering bins */
+#define NB_ORDER_BINS (NB_MAX_ENTRY_TILES + 8)
 #define NB_MAX_GROUP_TILES 512 /* staging capacity of one (i-cluster, shift) group in the search */
 #define NB_OUT_COPIES 32   /* replicas of the shift-force / energy accumulators: per-entry atomics spread over them */
 #define NB_FSHIFT_PITCH 136 /* floats per shift-force replica (45*3 rounded up) */

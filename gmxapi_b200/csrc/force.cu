@@ -621,7 +621,6 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
     }
 
 #else /* !B200NB_RING: the whole entry staged at once (entries <= 32 tiles, maxt x 256 B of shared memory per warp) */
-    const int lane = threadIdx.x & 31;
     /* Level-1 loads, all independent: entry e owns the packed tiles [e*maxt, (e+1)*maxt), so its first 64 j-slot indices and
      * its masks are fetched together with the entry itself (values beyond the entry's tile count are never used). */
     const int* const ja   = pja + (size_t)e * maxt * 8;
@@ -823,8 +822,15 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
 template<int EEL, bool GEOM, bool VF, bool GEN>
 int launch(b200nb_context* h, const PackedList& L, int intra)
 {
+    /* One entry per single-warp CTA; CTAs start in index order, i.e. largest entries first.  A persistent variant (resident
+     * warps walking the sorted list in boustrophedon order, equal tiles per warp) was measured and is 10-18 % slower: warps
+     * that start equal entries together also wait for their prologue loads together
+     * (profiles/r1/y_sweep_persistent_boustrophedon.txt). */
     const unsigned nblk = (unsigned)((L.nentries + B200NB_FORCE_WARPS - 1) / B200NB_FORCE_WARPS);
-    const int      maxt = h->max_tiles;
+    const int      maxt = L.pitch;
+#if !B200NB_RING
+    if (maxt > 32) return nb_fail(h, B200NB_ERR_ARG, "force kernel (whole-entry staging build): entries longer than 32 tiles");
+#endif
 #if B200NB_RING
     const size_t smem = (size_t)B200NB_FORCE_WARPS * 2 * NB_CHUNK * NB_TILE_SMEM;
 #else
