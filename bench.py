@@ -14,9 +14,11 @@ with the output clear, cluster-pair force kernel (LJ + Ewald real space, force o
            the HBM view beside it;
   cpu_baseline: the reference's own CPU SIMD nbnxm path (oracle/_ref, compiled from the reference sources)
            on this host's cores, bounded sample.
-N > 1: atoms are split into N slabs along x (spatial domain decomposition), one rank per GPU, halo
-coordinates / forces exchanged every step over NCCL (see gmxapi_b200/domdec.py); weak scaling: the box holds
-N copies of the N=1 workload along x, one slab per rank.
+N > 1: atoms are split into N slabs along x (spatial domain decomposition), one rank per GPU; halo coordinates and
+forces go straight into the neighbours' peer-memory windows over NVLink from inside the step's kernels
+(b200nb_dd_step, gmxapi_b200/domdec.py; torch.distributed / NCCL only carries set-up data).  Weak scaling (default):
+the box holds N copies of the N=1 workload along x, one slab per rank; --scaling strong: the named workload itself
+over N slabs (BASELINE configs[3]: --workload water_1M --scaling strong).
 """
 import argparse
 import json
@@ -93,6 +95,15 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: %s" % self.err], "samples": 0}
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
                 "samples": len(self.sm)}
+
+
+def ncu_traffic(workload, eel):
+    """DRAM bytes of one force-kernel launch from the committed ncu capture of this workload (profiles/r1/traffic.json), or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1", "traffic.json")))
+        return int(d[workload]["bytes"]) if eel == "ewald" else None
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def workload_system(name):
@@ -281,7 +292,7 @@ def run_gpu(args):
                                   % (peaks["sm_max_mhz"], peaks["source"]),
                      "useful_pairs_per_s_kernel": npairs / (k_ms * 1e-3),
                      "computed_pairs_per_s_kernel": ntiles * 64 / (k_ms * 1e-3),
-                     "traffic": None,
+                     "traffic": ncu_traffic(args.workload, args.eel),
                      "hbm": {"algorithmic_bytes": int(alg_bytes), "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
                              "peak_gbs": peaks["hbm_gbs"], "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}},
         "cpu_baseline": cpu,
@@ -294,8 +305,8 @@ def run_gpu(args):
 
 
 def run_multi_gpu(args, rank, world, local_rank):
-    """N ranks, one per GPU: slab decomposition along x of a box holding N copies of the N=1 workload (weak
-    scaling), halo coordinates / forces exchanged every step over NCCL (gmxapi_b200/domdec.py)."""
+    """N ranks, one per GPU: slab decomposition along x of a box holding N copies of the N=1 workload (weak scaling) or of
+    the workload itself (strong), halos through peer-memory windows (gmxapi_b200/domdec.py)."""
     import torch
     import torch.distributed as dist
     import gmxapi_b200 as g

@@ -25,7 +25,7 @@ in-process loopback used by the single-GPU parity tests.
 import numpy as np
 
 from . import lib as _lib
-from .nblib import InputException, interaction_kwargs
+from .nblib import InputException, configure_interactions
 
 SHIFT_PLUS_X = 5 * (3 * 1 + 1) + 1 + 2  # XYZ2IS(+1, 0, 0), pbcutil/ishift.h:50
 
@@ -72,6 +72,25 @@ class DomainPlan:
         self.nhome, self.nhalo = len(self.home), len(self.halo)
         self.local = np.concatenate([self.home, self.halo]).astype(np.int32)
 
+    @classmethod
+    def from_parts(cls, box, nranks, rank, rlist, home, send_local, halo):
+        """A plan assembled from what the ranks exchanged at a repartitioning step (migrate_atoms) instead of from the
+        global coordinates."""
+        p = cls.__new__(cls)
+        p.nranks, p.rank, p.rlist = nranks, rank, float(rlist)
+        p.box = np.asarray(box, dtype=np.float32).reshape(3)
+        p.bounds = cls.boundaries(p.box, nranks)
+        p.lo, p.hi = float(p.bounds[rank]), float(p.bounds[rank + 1])
+        p.left, p.right = (rank - 1) % nranks, (rank + 1) % nranks
+        p.home = np.ascontiguousarray(home, dtype=np.int32)
+        p.send_local = np.ascontiguousarray(send_local, dtype=np.int32)
+        p.halo = np.ascontiguousarray(halo, dtype=np.int32)
+        p.send_shift = np.array([p.box[0] if (rank == 0 and nranks > 1) else 0.0, 0.0, 0.0], np.float32)
+        p.recv_from_periodic = nranks > 1 and p.right == 0
+        p.nhome, p.nhalo = len(p.home), len(p.halo)
+        p.local = np.concatenate([p.home, p.halo]).astype(np.int32)
+        return p
+
     @staticmethod
     def boundaries(box, nranks):
         return (np.arange(nranks + 1, dtype=np.float64) * (float(box[0]) / nranks)).astype(np.float32)
@@ -115,6 +134,92 @@ class DomainPlan:
         if self.recv_from_periodic:
             h[:, 0] += self.box[0]
         return h
+
+
+# ---------------------------------------------------------------------------------------------------------
+# repartitioning: atoms that left their slab change owner (dd_partition_system, domdec/partition.cpp: dd_redistribute_cg
+# domdec/redistribute.cpp moves them to the neighbour cell, setup_dd_communication rebuilds the halo send lists, and
+# GpuHaloExchange::reinitHalo (domdec/gpuhaloexchange_impl.cu:133-213) takes the new index maps)
+# ---------------------------------------------------------------------------------------------------------
+def wrap_into_box(x, box):
+    """put_atoms_in_box for a rectangular box (pbcutil/pbc.cpp): x - floor(x / box) * box, in float32 like the reference."""
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 3).copy()
+    box = np.asarray(box, dtype=np.float32).reshape(3)
+    for d in range(3):
+        while True:
+            lo = x[:, d] < 0
+            hi = x[:, d] >= box[d]
+            if not (lo.any() or hi.any()):
+                break
+            x[lo, d] += box[d]
+            x[hi, d] -= box[d]
+    return x
+
+
+def migrate_atoms(t, box, nranks, rank, rlist, home, x_home, to_tensor=None):
+    """One repartitioning step of the x-slab decomposition, collective over the ranks of transport `t`.
+
+    home / x_home: the global indices and CURRENT coordinates of the atoms this rank owned so far.  Atoms whose wrapped
+    x coordinate now lies in a neighbour's slab are handed to that neighbour (one slab at most: the reference makes the
+    same assumption per repartitioning, redistribute.cpp "moved more than one cell"); then every rank tells its -x
+    neighbour which of its atoms lie within rlist of its lower face (the new halo).  Returns
+    (home_new ascending, x_home_new, send_local, halo) -- exactly what DomainPlan computes from global coordinates.
+    `to_tensor`: numpy int32 array -> tensor the transport can move (CUDA for NCCL, CPU for gloo / loopback)."""
+    import torch
+    if to_tensor is None:
+        to_tensor = torch.from_numpy
+    box = np.asarray(box, dtype=np.float32).reshape(3)
+    home = np.ascontiguousarray(home, dtype=np.int32)
+    x = wrap_into_box(x_home, box)
+    left, right = (rank - 1) % nranks, (rank + 1) % nranks
+    if nranks == 1:
+        order = np.argsort(home, kind="stable")
+        return home[order], x[order], np.zeros(0, np.int32), np.zeros(0, np.int32)
+    owner = DomainPlan.owner_of(x, box, nranks)
+    stay = owner == rank
+    go_l = (owner == left) & ~stay
+    go_r = (owner == right) & ~stay & ~go_l if left != right else np.zeros_like(stay)
+    if left == right:
+        # two ranks: both faces lead to the same neighbour; everything that leaves goes "left" (the receiver does not care)
+        go_l = ~stay
+    if not np.all(stay | go_l | go_r):
+        raise InputException("an atom moved more than one domain between two repartitioning steps")
+
+    def pack(mask):
+        m = np.nonzero(mask)[0]
+        buf = np.empty((len(m), 4), np.int32)
+        buf[:, 0] = home[m]
+        buf[:, 1:] = x[m].view(np.int32)
+        return buf
+
+    out_l, out_r = pack(go_l), pack(go_r)
+    counts = t.allgather_object(dict(to_left=len(out_l), to_right=len(out_r)))
+    # what arrives from the right neighbour is what it sends to ITS left, and vice versa
+    in_r = np.empty((counts[right]["to_left"], 4), np.int32)
+    in_l = np.empty((counts[left]["to_right"], 4), np.int32)
+
+    def exchange(send_np, dst, recv_np, src):
+        send = to_tensor(np.ascontiguousarray(send_np)) if len(send_np) else None
+        recv = to_tensor(recv_np) if len(recv_np) else None
+        t.sendrecv(send, dst, recv, src)
+        if recv is not None:
+            recv_np[...] = recv.cpu().numpy()
+
+    exchange(out_l, left, in_r, right)
+    exchange(out_r, right, in_l, left)
+    arrived = np.concatenate([in_r, in_l]) if (len(in_r) or len(in_l)) else np.zeros((0, 4), np.int32)
+    ids = np.concatenate([home[stay], arrived[:, 0]]).astype(np.int32)
+    xs = np.concatenate([x[stay], arrived[:, 1:].copy().view(np.float32)]).astype(np.float32)
+    order = np.argsort(ids, kind="stable")
+    home_new, x_new = ids[order], np.ascontiguousarray(xs[order])
+    bounds = DomainPlan.boundaries(box, nranks)
+    if len(home_new) and not np.array_equal(DomainPlan.owner_of(x_new, box, nranks), np.full(len(home_new), rank, np.int32)):
+        raise InputException("repartitioning left an atom outside its new owner's slab")
+    send_local = DomainPlan._send_list(x_new, np.arange(len(home_new)), bounds[rank], rlist)
+    nsend = t.allgather_object(int(len(send_local)))
+    halo = np.empty(nsend[right], np.int32)
+    exchange(home_new[send_local], left, halo, right)
+    return home_new, x_new, send_local, halo
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -236,11 +341,22 @@ class DomainRank:
         self.nb.set_stream(self.stream.cuda_stream)
         if hasattr(transport, "sync"):
             transport.sync = self.nb.synchronize
-        self.nb.set_params(system.nbfp, rc, rlist_outer=self.rlist, rlist_inner=options.rlistInner or 0.0,
-                           max_tiles_per_entry=options.maxTilesPerEntry, **interaction_kwargs(options))
-        types, q, eo, ei = p.local_topology(system.types, system.q, system.excl_off, system.excl_idx)
-        self.nb.set_atoms(types, q, eo, ei)
+        configure_interactions(self.nb, system.nbfp, options, self.rlist)
+        # the topology is global and replicated on every rank (as the reference keeps gmx_mtop_t); ownership is what moves
+        self.topology = (np.asarray(system.types), np.asarray(system.q), np.asarray(system.excl_off), np.asarray(system.excl_idx))
         self.nb.set_box(system.box, pbc=(0 if self.nranks > 1 else 1, 1, 1))
+        self.fshift_halo = np.zeros(3, np.float64)
+        self.use_windows = bool(use_windows) and self.nranks > 1
+        self.max_halo = self.max_send = 0
+        self._setup_local(np.ascontiguousarray(system.x[p.home]), first=True)
+
+    def _setup_local(self, x_home, first=False):
+        """(Re)build everything that depends on which atoms this rank owns and receives: local topology, device buffers,
+        grids, pair list, halo plan."""
+        torch = self.torch
+        p = self.plan
+        types, q, eo, ei = p.local_topology(*self.topology)
+        self.nb.set_atoms(types, q, eo, ei)
         self.nlocal = p.nhome + p.nhalo
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self.x = torch.zeros((self.nlocal, 3), dtype=torch.float32, device=self.device)
@@ -248,13 +364,32 @@ class DomainRank:
             self.send_idx = torch.from_numpy(p.send_local).to(self.device)
             self.send_buf = torch.zeros((len(p.send_local), 3), dtype=torch.float32, device=self.device)
             self.recv_f = torch.zeros((len(p.send_local), 3), dtype=torch.float32, device=self.device)
-            self.x[:p.nhome].copy_(torch.from_numpy(np.ascontiguousarray(system.x[p.home])))
+            self.x[:p.nhome].copy_(torch.from_numpy(np.ascontiguousarray(x_home, dtype=np.float32)))
         self.nb.synchronize()
-        self.fshift_halo = np.zeros(3, np.float64)
-        self.use_windows = bool(use_windows) and self.nranks > 1
         if self.use_windows:
-            self._open_windows()
-        self.search(first=True)
+            if first:
+                self._open_windows()
+            elif p.nhalo > self.max_halo or len(p.send_local) > self.max_send:
+                raise InputException("repartition: halo of %d / %d atoms exceeds the window capacity %d / %d"
+                                     % (p.nhalo, len(p.send_local), self.max_halo, self.max_send))
+        self.search(first=first)
+
+    def repartition(self):
+        """Pair-search step WITH atom migration (dd_partition_system, domdec/partition.cpp): atoms whose current
+        coordinates (self.x[:nhome], on the device) left this rank's slab change owner, coordinates are wrapped into the
+        box, the halo send lists are rebuilt from the new ownership, then grids and pair list are rebuilt.  Collective:
+        every rank calls it at the same step.  Returns the new plan (plan.home = global indices now owned, ascending;
+        a caller integrating the equations of motion moves its velocities etc. with the same map)."""
+        torch = self.torch
+        p = self.plan
+        self.nb.synchronize()
+        x_home = self.x[:p.nhome].cpu().numpy()
+        to_dev = lambda a: torch.from_numpy(a).to(self.device)
+        home, x_new, send_local, halo = migrate_atoms(self.t, p.box, self.nranks, self.rank, self.rlist, p.home, x_home,
+                                                      to_tensor=to_dev)
+        self.plan = DomainPlan.from_parts(p.box, self.nranks, self.rank, self.rlist, home, send_local, halo)
+        self._setup_local(x_new)
+        return self.plan
 
     # -- peer-memory halo windows: created once, sized with slack for later search steps -----------------------------------
     def _open_windows(self):
@@ -262,6 +397,7 @@ class DomainRank:
         p = self.plan
         max_halo = int(1.5 * p.nhalo) + 4096
         max_send = int(1.5 * len(p.send_local)) + 4096
+        self.max_halo, self.max_send = max_halo, max_send
         handle, ptr = self.nb.dd_create_window(max_halo, max_send)
         info = self.t.allgather_object(dict(pid=os.getpid(), handle=handle, ptr=ptr, max_halo=max_halo))
         for side, peer in ((0, p.left), (1, p.right)):

@@ -72,6 +72,22 @@ def interaction_kwargs(options):
     return kw
 
 
+def configure_interactions(nb, nonbonded_parameters, options, rlist_outer=None):
+    """b200nb_set_params (+ b200nb_set_vdw) from NBKernelOptions: what setupInteractionConst and gpu_init make of the
+    interaction constants (api/nblib/gmxsetup.cpp:226-284, nbnxm/nbnxm_gpu_data_mgmt.cpp:166-245)."""
+    rc = float(options.pairlistCutoff)
+    kw = interaction_kwargs(options)
+    rvdw = float(options.vdwCutoff) or rc
+    if rvdw > rc:
+        raise InputException("vdwCutoff must not exceed pairlistCutoff")
+    vk = _lib.vdw_modifier_constants(options.vdwModifier.value, rvdw, options.vdwSwitch)
+    nb.set_params(nonbonded_parameters, rc, rlist_outer=rlist_outer or options.rlistOuter or rc,
+                  rlist_inner=options.rlistInner or 0.0, max_tiles_per_entry=options.maxTilesPerEntry,
+                  disp_cpot=vk["disp_cpot"], rep_cpot=vk["rep_cpot"], **kw)
+    if options.vdwModifier != VdwModifier.PotentialShift or rvdw < rc:
+        nb.set_vdw(options.vdwModifier.value, rvdw, options.vdwSwitch, vk)
+
+
 class SimulationState:
     def __init__(self, coordinates, box, types, charges, nonbondedParameters, excl_off=None, excl_idx=None):
         self.coordinates = np.ascontiguousarray(coordinates, dtype=np.float32).reshape(-1, 3)
@@ -103,16 +119,7 @@ class ForceCalculator:
         self.state = state
         rc = float(options.pairlistCutoff)
         self.nb = _lib.NbnxmGpu(options.device)
-        kw = interaction_kwargs(options)
-        rvdw = float(options.vdwCutoff) or rc
-        if rvdw > rc:
-            raise InputException("vdwCutoff must not exceed pairlistCutoff")
-        vk = _lib.vdw_modifier_constants(options.vdwModifier.value, rvdw, options.vdwSwitch)
-        self.nb.set_params(state.nonbondedParameters, rc, rlist_outer=options.rlistOuter or rc,
-                           rlist_inner=options.rlistInner or 0.0, max_tiles_per_entry=options.maxTilesPerEntry,
-                           disp_cpot=vk["disp_cpot"], rep_cpot=vk["rep_cpot"], **kw)
-        if options.vdwModifier != VdwModifier.PotentialShift or rvdw < rc:
-            self.nb.set_vdw(options.vdwModifier.value, rvdw, options.vdwSwitch, vk)
+        configure_interactions(self.nb, state.nonbondedParameters, options)
         self.nb.set_atoms(state.types, state.charges, state.excl_off, state.excl_idx)
         self._set_particles_on_grid(state.coordinates, state.box)
         self.nb.build_pairlist()  # constructPairList, gmxsetup.cpp:299-303

@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from gmxapi_b200 import systems as S
-from gmxapi_b200.domdec import DomainPlan, TorchDistTransport
+from gmxapi_b200.domdec import DomainPlan, TorchDistTransport, migrate_atoms, wrap_into_box
 
 RLIST = 0.9
 
@@ -147,3 +147,65 @@ def test_halo_exchange_gloo(world):
         assert p.exitcode == 0
     for rank, ok_x, ok_f, ok_n, nhalo in res:
         assert ok_x and ok_f and ok_n and nhalo > 0, (rank, ok_x, ok_f, ok_n, nhalo)
+
+
+def _moved(s, seed=11, amp=0.35):
+    """the same displaced coordinates on every rank: up to `amp` nm along each axis, so atoms cross slab faces and box edges"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return (s.x + rng.uniform(-amp, amp, s.x.shape)).astype(np.float32)
+
+
+def _migrate_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        s = S.water_box(12, 6, 6, seed=5)
+        t = TorchDistTransport()
+        plan0 = DomainPlan(s.x, s.box, world, rank, RLIST)
+        x1 = _moved(s)
+        home, xh, send_local, halo = migrate_atoms(t, s.box, world, rank, RLIST, plan0.home, x1[plan0.home])
+        x1w = wrap_into_box(x1, s.box)
+        exp = DomainPlan(x1w, s.box, world, rank, RLIST)  # what a plan made from the global coordinates says
+        ok = (np.array_equal(home, exp.home) and np.array_equal(xh, x1w[exp.home]) and np.array_equal(send_local, exp.send_local)
+              and np.array_equal(halo, exp.halo))
+        plan1 = DomainPlan.from_parts(s.box, world, rank, RLIST, home, send_local, halo)
+        ok = ok and np.array_equal(plan1.local, exp.local) and plan1.recv_from_periodic == exp.recv_from_periodic \
+            and np.array_equal(plan1.send_shift, exp.send_shift)
+        moved = int(len(np.setdiff1d(home, plan0.home)))
+        # a second repartitioning without motion changes nothing
+        h2, x2, s2, l2 = migrate_atoms(t, s.box, world, rank, RLIST, home, xh)
+        ok = ok and np.array_equal(h2, home) and np.array_equal(x2, xh) and np.array_equal(s2, send_local) and np.array_equal(l2, halo)
+        tot = t.allreduce_sum(torch.tensor([float(len(home))]))
+        q.put((rank, bool(ok), moved, int(tot.item()) == s.n))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_repartition_migrates_atoms_gloo(world):
+    """DD repartitioning (dd_partition_system): after the atoms moved, exchanging leavers with the two neighbours and the
+    new halo lists gives every rank exactly the plan it would compute from the global coordinates."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_migrate_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, moved, ok_n in res:
+        assert ok and ok_n and moved > 0, (rank, ok, moved, ok_n)
+
+
+def test_migrate_rejects_long_jumps():
+    """an atom that crosses more than one slab between two repartitioning steps is an error, as in the reference"""
+    from gmxapi_b200.domdec import LoopbackTransport
+    from gmxapi_b200.nblib import InputException
+    s = S.water_box(16, 6, 6, seed=5)  # 4.97 nm: 4 slabs of 1.24 nm
+    plan = DomainPlan(s.x, s.box, 4, 0, RLIST)
+    x = s.x[plan.home].copy()
+    x[0, 0] = 3.0  # two slabs away
+    with pytest.raises(InputException):
+        migrate_atoms(LoopbackTransport(4).endpoint(0), s.box, 4, 0, RLIST, plan.home, x)

@@ -35,7 +35,7 @@ def canonical(pairs_global, tx_dd):
     return (i << 34) | (j << 6) | idx
 
 
-def run_ranks(s, opt, nranks, flags, use_windows=True, nsteps=1):
+def run_ranks(s, opt, nranks, flags, use_windows=True, nsteps=1, moved_x=None):
     hub = LoopbackTransport(nranks)
     out = [None] * nranks
     err = []
@@ -50,6 +50,18 @@ def run_ranks(s, opt, nranks, flags, use_windows=True, nsteps=1):
                 xh = torch.from_numpy(xh).pin_memory()  # even ranks: pinned host buffers, read / written in place by the kernels
             for _ in range(nsteps):  # repeated steps reuse the windows: flags advance, buffers are overwritten
                 f, fs, elj, eel = d.compute(xh, flags)
+            if moved_x is not None:
+                # the atoms moved (integration is the caller's business): new coordinates of the atoms this rank owns go to
+                # the device, then a repartitioning search step, then a step on the new decomposition
+                old_home = d.plan.home.copy()
+                d.x[:d.plan.nhome].copy_(torch.from_numpy(np.ascontiguousarray(moved_x[old_home])))
+                plan = d.repartition()
+                assert len(np.setdiff1d(plan.home, old_home)) > 0, "nothing migrated: the test does not test"
+                from gmxapi_b200.domdec import wrap_into_box
+                xh = np.ascontiguousarray(wrap_into_box(moved_x, s.box)[plan.home])
+                assert np.array_equal(d.x[:plan.nhome].cpu().numpy(), xh)
+                for _ in range(2):
+                    f, fs, elj, eel = d.compute(xh, flags)
             pr = d.nb.pairs(RC)
             p = d.plan
             loc = p.local
@@ -128,3 +140,33 @@ def test_domain_decomposition_matches_single_domain(built, name, nranks, coulomb
     vir_g = -0.5 * (x.T @ f + sv.T @ fs)
     vir_o = -0.5 * (x.T @ fo + sv.T @ fso)
     assert np.abs(vir_g - vir_o).max() <= 1e-5 * np.abs(vir_o).max()
+
+
+@pytest.mark.parametrize("nranks,windows", [(3, True), (2, True), (3, False)])
+def test_repartition_after_motion(built, nranks, windows):
+    """DD repartitioning (dd_partition_system): after the atoms moved -- here by a rigid translation across slab faces and
+    the box edge plus a little noise -- DomainRank.repartition() migrates them, rebuilds halo plan, grids and lists, and the
+    decomposed forces / pair set again equal the single-domain oracle on the new coordinates."""
+    from gmxapi_b200.domdec import wrap_into_box
+    s = g.systems.named("water_24k")
+    rng = np.random.Generator(np.random.PCG64(23))
+    x1 = (s.x + np.array([0.43, 0.31, -0.27], np.float32) + rng.uniform(-0.01, 0.01, s.x.shape)).astype(np.float32)
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, computeVirialAndEnergy=True)
+    flags = nb.FLAG_ENERGY | nb.FLAG_VIRIAL
+    res = run_ranks(s, opt, nranks, flags, use_windows=windows, nsteps=1, moved_x=x1)
+    x1w = wrap_into_box(x1, s.box)
+    fo, fso, evo, eco, npairs = oracle.forces(x1w, s.box, s.q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx,
+                                              eeltype=oracle.EEL_EWALD, beta=float(np.float32(g.systems.ewald_beta(RC))))
+    owned = np.concatenate([r["home"] for r in res])
+    assert np.array_equal(np.sort(owned), np.arange(s.n))
+    keys = np.sort(np.concatenate([r["keys"] for r in res]))
+    ok = oracle.canonical_pairs(oracle.pair_set(x1w, s.box, RC, s.excl_off, s.excl_idx))
+    diff = np.setxor1d(keys, ok)  # only pairs within rounding of rc^2 across the periodic x edge may differ (see above)
+    assert len(diff) <= 2
+    f = np.zeros((s.n, 3), np.float64)
+    for r in res:
+        f[r["home"]] = r["f"]
+    assert np.sqrt(((f - fo) ** 2).sum() / (fo ** 2).sum()) < 1e-5
+    elj, eel = sum(r["elj"] for r in res), sum(r["eel"] for r in res)
+    assert abs(elj - evo) <= 2e-4 * abs(evo)
+    assert abs(eel - eco) <= 2e-4 * abs(eco)
