@@ -97,13 +97,14 @@ class ClockSampler:
                 "samples": len(self.sm)}
 
 
-def ncu_traffic(workload, eel):
-    """DRAM bytes of one force-kernel launch from the committed ncu capture of this workload (profiles/r1/traffic.json), or None."""
+def ncu_capture(workload, eel):
+    """What the committed `ncu --set full` capture of this workload's force kernel says (profiles/r1/traffic.json): DRAM bytes
+    of one launch and the measured FP32-pipe / issue utilisation; {} when there is no capture for the workload."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "r1", "traffic.json")))
-        return int(d[workload]["bytes"]) if eel == "ewald" else None
+        return dict(d[workload]) if eel == "ewald" else {}
     except Exception:  # noqa: BLE001
-        return None
+        return {}
 
 
 def workload_system(name):
@@ -292,7 +293,8 @@ def run_gpu(args):
                                   % (peaks["sm_max_mhz"], peaks["source"]),
                      "useful_pairs_per_s_kernel": npairs / (k_ms * 1e-3),
                      "computed_pairs_per_s_kernel": ntiles * 64 / (k_ms * 1e-3),
-                     "traffic": ncu_traffic(args.workload, args.eel),
+                     "traffic": ncu_capture(args.workload, args.eel).get("bytes"),
+                     "ncu": {k: v for k, v in ncu_capture(args.workload, args.eel).items() if k != "bytes"} or None,
                      "hbm": {"algorithmic_bytes": int(alg_bytes), "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
                              "peak_gbs": peaks["hbm_gbs"], "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}},
         "cpu_baseline": cpu,
@@ -335,10 +337,14 @@ def run_multi_gpu(args, rank, world, local_rank):
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     l0 = h.stats()["nlaunches"]
+    align = torch.zeros(1, dtype=torch.float32, device=dev)
     for k in range(args.steps):
-        if flush is not None:
-            with torch.cuda.stream(stream):
+        with torch.cuda.stream(stream):
+            if flush is not None:
                 flush.fill_(k & 0xff)
+            # the 256 MiB flush takes ~43 us +- a few on every rank: without re-aligning the ranks after it, each timed step
+            # would also measure how much later the neighbour finished its flush.  Outside the timed region.
+            dist.all_reduce(align)
         ev[k][0].record(stream)
         d.step(0)
         ev[k][1].record(stream)

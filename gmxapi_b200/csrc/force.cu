@@ -6,14 +6,16 @@
  *   arithmetic parity target = the CPU SIMD kernels nbnxm/kernels_simd_2xmm/kernel_inner.h:226-880 and
  *   kernel_outer.h:395-452 (self terms), simd/simd_math.h:1609-1722 (Ewald correction polynomials).
  *
- * Design (not a port of the reference CUDA kernel), sized with profiles/tools/microbench.cu: on sm_100 the FP32
- * pipe retires 128 lane-FMAs/clk/SM whether issued as scalar FFMA or packed FFMA2, but a packed instruction takes
- * ONE issue slot for two lanes' work; ALU-pipe instructions (FSEL, FMNMX, LOP3, IADD3) run at half that rate, SHFL
- * at ~0.44 warp-instructions/clk/SMSP, MUFU at 16 lanes/clk/SM.  So the kernel is written to be FMA-pipe-bound:
+ * Design (not a port of the reference CUDA kernel), sized with profiles/tools/microbench.cu and the diagnostic builds of
+ * profiles/r1/v_sweep_pair_loop_diagnostics.txt: on sm_100 the FP32 pipe retires 128 lane-FMAs/clk/SM whether issued as
+ * scalar FFMA or packed FFMA2; a packed instruction costs its sub-partition two issue cycles and every other instruction
+ * one, and that -- instruction issue with the FP32 pipe as its largest client -- is what bounds this kernel, not latency.
+ * ALU-pipe instructions (FSEL, FMNMX, LOP3, IADD3) run at half rate on their own pipe, SHFL at ~0.44 warp-instructions/
+ * clk/SMSP, MUFU at 16 lanes/clk/SM.  So the kernel is written to spend its issue slots on FP32 math:
  *  - one warp per list entry = one 8-atom i-cluster + shift against a run of PACKED tiles of 8 j-atom slots each
  *    (PackedList, b200nb_internal.h: j-atoms with no pair inside the list radius were dropped when the list was packed);
- *  - lane = jl + 8*ih holds the j-atom in slot jl of the tile and the TWO i-atoms (2*ih, 2*ih+1) as packed float2 registers for the whole
- *    entry: all pair arithmetic is packed (fma.rn.f32x2 -> FFMA2/FMUL2/FADD2), the j operands enter as the
+ *  - lane = jl + 8*ih holds the j-atom in slot jl of the tile and the TWO i-atoms (2*ih, 2*ih+1) as packed float2 registers
+ *    for the whole entry: all pair arithmetic is packed (fma.rn.f32x2 -> FFMA2/FMUL2/FADD2), the j operands enter as the
  *    scalar-broadcast operand form of those instructions, so a tile costs two 16-byte shared-memory loads (xyzq;
  *    LJ pair + the j-atom's slot index; the 4 lanes sharing a j-atom hit the same address) and no register shuffling;
  *  - j-forces: in-lane add of the two pairs, 2-stage reduce-scatter (3 shuffles) over the 4 lanes sharing the j-atom,
@@ -22,17 +24,21 @@
  *  - tiles that carry exclusion masks are sorted to the front of an entry (b200nb.cu k_search) and run through a
  *    separate code path; the unmasked path has no mask logic and no r^2 clamp;
  *  - LJ is evaluated as (c12*r^-6 - c6)*r^-6, the Ewald correction polynomials keep their coefficients as
- *    instruction immediates (folding beta^3 into them would cost seven registers); out-of-range lanes are discarded by select, so garbage there cannot poison a sum;
+ *    instruction immediates (folding beta^3 into them would cost seven registers); out-of-range lanes are discarded by
+ *    select, so garbage there cannot poison a sum;
  *  - r^2 is evaluated with the reference's operand roles and operation order so the in-range pair set is
  *    bit-identical (see nb_rsq in b200nb_internal.h);
- *  - the j-atom data of a whole entry (<= 32 tiles x 256 B) is staged in shared memory with cp.async (LDGSTS): each lane
- *    reads one j-slot index of the entry (coalesced) and gathers that atom's 16-byte xyzq and 8-byte LJ pair,
- *    before the pair loop starts: the first version loaded j data with LDG one
- *    tile ahead and spent its time in long-scoreboard stalls (L1 hit rate 35 %: consecutive entries belong to the same
- *    i-cluster and share no j data; profiles/r1).  The i-cluster lives in registers, which beats shared memory.
- *    TMA (cp.async.bulk) was considered and not used: the stream is a gather of 128-byte lines by cluster index, so a
- *    bulk copy would move one line per instruction issued by one elected lane plus mbarrier traffic, while LDGSTS moves
- *    512 B per warp instruction with per-lane addresses and needs only wait_group + syncwarp.
+ *  - the j-atom data go through a two-buffer ring of NB_CHUNK tiles in shared memory, filled with cp.async (LDGSTS): each
+ *    lane reads one j-slot index (coalesced) and gathers that atom's 16-byte xyzq and 8-byte LJ pair while the previous
+ *    chunk is being computed; the pair loop never touches L2, and a warp needs 4 KB whatever the length of its entry.
+ *    (The first version loaded j data with LDG one tile ahead and spent its time in long-scoreboard stalls; the second
+ *    staged a whole entry at once, which tied the entry length to the shared memory per warp.)  The i-cluster lives in
+ *    registers, which beats shared memory.
+ *    TMA (cp.async.bulk) was considered and not used: the stream is a gather of 16-byte atoms by slot index, so a bulk copy
+ *    would move one atom per instruction issued by one elected lane plus mbarrier traffic, while LDGSTS moves 512 B per
+ *    warp instruction with per-lane addresses and needs only wait_group + syncwarp;
+ *  - LJ force switch / potential switch / VdW cut-off below the Coulomb cut-off are a second set of instantiations (GEN):
+ *    the plain kernels, which every BASELINE configuration uses, pay nothing for them.
  */
 #include <cstdio>
 
@@ -312,9 +318,6 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
 /* Two plain (unmasked, force-only) tiles evaluated in lock step: every step of the arithmetic is written for both tiles
  * before the next step, so the instruction stream carries two independent dependency chains and the 4-cycle FMA, MUFU and
  * shuffle latencies of one tile are covered by the other (ncu: "wait"/"short scoreboard" stalls dominated the one-tile loop). */
-#ifndef B200NB_RING
-#define B200NB_RING 1
-#endif
 #ifndef NB_CHUNK
 #define NB_CHUNK 8 /* packed tiles per ring buffer (multiple of 4: one staging round covers 32 j-atoms) */
 #endif
@@ -468,7 +471,6 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
     const long long e = (long long)blockIdx.x * B200NB_FORCE_WARPS + (threadIdx.x >> 5);
     if (e >= nentries) return;
     const int lane = threadIdx.x & 31;
-#if B200NB_RING
     /* Entry e owns the packed tiles [e*maxt, (e+1)*maxt) (maxt = the list's pitch).  Its j data go through a two-buffer ring of
      * NB_CHUNK tiles in shared memory: chunk c+1 is gathered with cp.async while chunk c is being computed, so the shared
      * memory per warp is constant (2 x NB_CHUNK x 256 B) whatever the entry's length, and entries can hold a whole
@@ -620,153 +622,6 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
         __syncwarp(); /* every lane is done with this buffer before the next iteration's gather overwrites it */
     }
 
-#else /* !B200NB_RING: the whole entry staged at once (entries <= 32 tiles, maxt x 256 B of shared memory per warp) */
-    /* Level-1 loads, all independent: entry e owns the packed tiles [e*maxt, (e+1)*maxt), so its first 64 j-slot indices and
-     * its masks are fetched together with the entry itself (values beyond the entry's tile count are never used). */
-    const int* const ja   = pja + (size_t)e * maxt * 8;
-    const int        jsp0 = __ldg(ja + min(lane, maxt * 8 - 1)), jsp1 = __ldg(ja + min(lane + 32, maxt * 8 - 1));
-    uint2            mreg = make_uint2(~0u, ~0u);
-    if (lane < maxt) mreg = __ldg(reinterpret_cast<const uint2*>(tmask) + e * maxt + lane);
-    const int4 ev    = __ldg(reinterpret_cast<const int4*>(entries) + e);
-    KConst K;
-    {
-        const float4 k0 = __ldg(reinterpret_cast<const float4*>(kconst)), k1 = __ldg(reinterpret_cast<const float4*>(kconst) + 1),
-                     k2 = __ldg(reinterpret_cast<const float4*>(kconst) + 2);
-        K.rc2 = k0.x, K.beta2 = k0.z, K.fd4 = k0.w, K.fd3 = k1.x, K.fn6 = k1.y, K.fn5 = k1.z, K.fd2 = k1.w, K.fd1 = k2.x, K.fd0 = k2.y;
-    }
-    /* Programmatic dependent launch: this grid may have started while the preceding kernel of the stream (k_step_begin:
-     * coordinates -> grid layout, output clear) was still running; everything above reads only the list.  From here on the
-     * kernel touches xq and f, so wait for the predecessor's completion (a no-op for a normally serialised launch). */
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int  start = ev.z, end = ev.w;
-    const bool self  = VF && NB_ENTRY_SELF(ev.y);
-    if (start >= end && !self) return;
-    const int jl = lane & 7, ih = lane >> 3;
-    const int ci = ev.x, shift = NB_ENTRY_SHIFT(ev.y), nmask = NB_ENTRY_NMASK(ev.y);
-    const int ntile = end - start;
-    const unsigned full = 0xffffffffu;
-    if (lane >= nmask) mreg = make_uint2(~0u, ~0u);
-
-    /* ---- level 2: stage the j data of all tiles: each lane gathers one j-atom per round ---- */
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char* const sj = smem_raw + (threadIdx.x >> 5) * (maxt * NB_TILE_SMEM);
-    {
-        const unsigned s0 = (unsigned)__cvta_generic_to_shared(sj);
-        for (int a0 = 0; a0 < ntile * 8; a0 += 32)
-        {
-            const int a = a0 + lane;
-            if (a < ntile * 8)
-            {
-                const int      slot = a0 == 0 ? jsp0 : (a0 == 32 ? jsp1 : __ldg(ja + a));
-                const unsigned dx   = s0 + (a >> 3) * NB_TILE_SMEM + (a & 7) * 16;
-                cp_async16(dx, xq + slot);
-                if (GEOM) cp_async8(dx + 128, lj + slot);
-                else cp_async4(dx + 128, atype + slot);
-                asm volatile("st.shared.s32 [%0], %1;" ::"r"(dx + 136), "r"(slot) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    LaneClass C;
-    C.b4     = (lane & 16) != 0;
-    C.b3     = (lane & 8) != 0;
-    C.b3or4  = C.b3 || C.b4;
-    C.b3only = C.b3 && !C.b4;
-    C.f_lane = reinterpret_cast<char*>(f) + 4 * (2 * (int)C.b4 + (int)C.b3);
-    IData I;
-    {
-        const float4 a = __ldg(xq + (size_t)ci * 8 + 2 * ih), b = __ldg(xq + (size_t)ci * 8 + 2 * ih + 1);
-        const float  sx = __ldg(shift_vec + 3 * shift), sy = __ldg(shift_vec + 3 * shift + 1), sz = __ldg(shift_vec + 3 * shift + 2);
-        /* the reference adds the shift to the i-atom before the subtraction: kernel_outer.h:482-489 */
-        I.x = make_float2(__fadd_rn(a.x, sx), __fadd_rn(b.x, sx));
-        I.y = make_float2(__fadd_rn(a.y, sy), __fadd_rn(b.y, sy));
-        I.z = make_float2(__fadd_rn(a.z, sz), __fadd_rn(b.z, sz));
-        I.q = make_float2(P.epsfac * a.w, P.epsfac * b.w);
-        if (GEOM)
-        {
-            const float4 l = __ldg(reinterpret_cast<const float4*>(lj + (size_t)ci * 8 + 2 * ih));
-            I.c6n          = make_float2(-l.x, -l.z);
-            I.c12          = make_float2(l.y, l.w);
-            I.t0 = I.t1 = 0;
-        }
-        else
-        {
-            const int2 t = __ldg(reinterpret_cast<const int2*>(atype + (size_t)ci * 8 + 2 * ih));
-            I.t0         = t.x * P.ntypes;
-            I.t1         = t.y * P.ntypes;
-            I.c6n = I.c12 = dup(0.0f);
-        }
-    }
-    float2 fix = dup(0.f), fiy = dup(0.f), fiz = dup(0.f);
-    float  evdw = 0.f, ecoul = 0.f;
-    if (self && jl < 2)
-    {
-        /* Coulomb self term, once per i-atom: kernel_outer.h:408-452 (fillers carry q = 0) */
-        const float qi = (jl == 0 ? I.q.x : I.q.y);
-        ecoul -= qi * qi * P.self_q2;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    const unsigned char* const s_lane = sj + jl * 16;
-    int t = 0;
-
-    /* ---- tiles with exclusion masks (sorted to the front of the entry) ---- */
-    for (; t < nmask; t++)
-    {
-        JAtom J;
-        load_j(J, s_lane, t);
-        const unsigned mx = __shfl_sync(full, mreg.x, t), my = __shfl_sync(full, mreg.y, t);
-        /* mask word w, bit `lane`: pair (i-atom 2*ih + w, j-slot jl) interacts */
-        const float in0 = (float)((mx >> lane) & 1u), in1 = (float)((my >> lane) & 1u);
-        bool        ok0 = true, ok1 = true;
-        if (intra && shift == B200NB_CENTRAL && (J.slot >> 3) == ci)
-        {
-            /* j-atom of the i-cluster itself: only j > i (nbnxm/pairlist.cpp:880-904, kernel_gpu_ref.cpp:223-226) */
-            ok0 = (J.slot & 7) > 2 * ih;
-            ok1 = (J.slot & 7) > 2 * ih + 1;
-        }
-        float2 tx, ty, tz;
-        tile_pairs<EEL, GEOM, VF, true, GEN>(I, J, P, K, nbfp, in0, in1, ok0, ok1, tx, ty, tz, evdw, ecoul);
-        fix = add2(fix, tx);
-        fiy = add2(fiy, ty);
-        fiz = add2(fiz, tz);
-        reduce_store_j(tx, ty, tz, C, J.slot);
-    }
-
-    /* ---- plain tiles ---- */
-    if (!VF && !GEN)
-    {
-        constexpr int NT = B200NB_TILE_ILP;
-        for (; t + NT <= ntile; t += NT)
-        {
-            JAtom J[NT];
-            int   js[NT];
-            float sx[NT], sy[NT], sz[NT];
-#pragma unroll
-            for (int u = 0; u < NT; u++)
-            {
-                load_j(J[u], s_lane, t + u);
-                js[u] = J[u].slot;
-            }
-            tile_pairs_multi<EEL, GEOM, NT>(I, J, P, K, nbfp, fix, fiy, fiz, sx, sy, sz);
-#ifndef B200NB_DIAG_NO_JFORCE /* diagnostic build only: no j-forces at all (wrong results), isolates the pair arithmetic */
-            reduce_store_j_multi<NT>(sx, sy, sz, C, js);
-#endif
-        }
-    }
-    for (; t < ntile; t++)
-    {
-        JAtom J;
-        load_j(J, s_lane, t);
-        float2 tx, ty, tz;
-        tile_pairs<EEL, GEOM, VF, false, GEN>(I, J, P, K, nbfp, 1.f, 1.f, true, true, tx, ty, tz, evdw, ecoul);
-        fix = add2(fix, tx);
-        fiy = add2(fiy, ty);
-        fiz = add2(fiz, tz);
-        reduce_store_j(tx, ty, tz, C, J.slot);
-    }
-
-#endif /* B200NB_RING */
     /* ---- i-forces: reduce over the 8 j-lanes (bits 0-2). Stage 1 is transposed: even lanes keep atom i0, odd lanes i1. */
     const bool     odd  = lane & 1;
     float          kx = odd ? fix.y : fix.x, ky = odd ? fiy.y : fiy.x, kz = odd ? fiz.y : fiz.x;
@@ -828,14 +683,7 @@ int launch(b200nb_context* h, const PackedList& L, int intra)
      * (profiles/r1/y_sweep_persistent_boustrophedon.txt). */
     const unsigned nblk = (unsigned)((L.nentries + B200NB_FORCE_WARPS - 1) / B200NB_FORCE_WARPS);
     const int      maxt = L.pitch;
-#if !B200NB_RING
-    if (maxt > 32) return nb_fail(h, B200NB_ERR_ARG, "force kernel (whole-entry staging build): entries longer than 32 tiles");
-#endif
-#if B200NB_RING
-    const size_t smem = (size_t)B200NB_FORCE_WARPS * 2 * NB_CHUNK * NB_TILE_SMEM;
-#else
-    const size_t smem = (size_t)B200NB_FORCE_WARPS * maxt * NB_TILE_SMEM;
-#endif
+    const size_t smem = (size_t)B200NB_FORCE_WARPS * 2 * NB_CHUNK * NB_TILE_SMEM; /* the two ring buffers of each warp */
     cudaLaunchConfig_t cfg{};
     cfg.gridDim          = dim3(nblk);
     cfg.blockDim         = dim3(32 * B200NB_FORCE_WARPS);
