@@ -7,7 +7,7 @@ a GPU fails loudly -- there is no CPU fallback.
 """
 from . import systems  # noqa: F401
 from .lib import B200NBError, NbnxmGpu, load_library, library_path  # noqa: F401
-from .nblib import (CoulombType, ForceCalculator, NBKernelOptions, SimulationState, VdwModifier)  # noqa: F401
+from .nblib import (CoulombType, ForceCalculator, LjPme, NBKernelOptions, SimulationState, VdwModifier)  # noqa: F401
 
 __all__ = ["systems", "B200NBError", "NbnxmGpu", "load_library", "library_path", "CoulombType", "ForceCalculator",
-           "NBKernelOptions", "SimulationState", "VdwModifier"]
+           "NBKernelOptions", "SimulationState", "VdwModifier", "LjPme"]

@@ -105,7 +105,7 @@ extern "C" void b200nb_destroy(b200nb_t* h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    void* ptrs[] = { h->d_kconst, h->d_nbfp,       h->d_type,     h->d_q,        h->d_excl_off,     h->d_excl_idx,  h->d_shift_vec,
+    void* ptrs[] = { h->d_kconst, h->d_nbfp_comb, h->d_nbfp,       h->d_type,     h->d_q,        h->d_excl_off,     h->d_excl_idx,  h->d_shift_vec,
                      h->d_x,          h->d_fout,     h->d_col_of_atom, h->d_col_count, h->d_col_cell0, h->d_col_fill,
                      h->d_atom_index, h->d_slot_of_atom, h->d_xq,   h->d_lj,           h->d_atype,     h->d_bb,
                      h->d_cellz,      h->d_f,        h->d_fshift,   h->d_energy,       h->d_scratch,   h->d_counter,
@@ -261,6 +261,8 @@ extern "C" int b200nb_set_params(b200nb_t* h, const b200nb_params_t* p)
     d.rvdw_switch   = 0.0f;
     d.disp_c2 = d.disp_c3 = d.rep_c2 = d.rep_c3 = 0.0f;
     d.sw_c3 = d.sw_c4 = d.sw_c5 = 0.0f;
+    d.ljpme      = 0;
+    d.lje_coeff2 = d.lje_coeff6_6 = d.sh_lj_ewald = 0.0f;
     h->have_params  = true;
     h->have_list    = false;
     return 0;
@@ -280,7 +282,37 @@ extern "C" int b200nb_set_vdw(b200nb_t* h, const b200nb_vdw_t* v)
         return nb_fail(h, B200NB_ERR_ARG, "set_vdw: rvdw < rcoulomb needs Ewald electrostatics");
     if (v->vdw_modifier != B200NB_VDW_POTSHIFT && !(v->rvdw_switch >= 0.0f && v->rvdw_switch < rvdw))
         return nb_fail(h, B200NB_ERR_ARG, "set_vdw: rvdw_switch must lie in [0, rvdw)");
+    if (v->ljpme_comb_rule < 0 || v->ljpme_comb_rule > 2) return nb_fail(h, B200NB_ERR_ARG, "set_vdw: unknown LJ-PME combination rule");
+    if (v->ljpme_comb_rule && v->vdw_modifier != B200NB_VDW_POTSHIFT)
+        return nb_fail(h, B200NB_ERR_ARG, "set_vdw: LJ-PME goes with the potential-shift modifier only");
     NbParamsDev& d = h->dp;
+    d.ljpme        = v->ljpme_comb_rule;
+    if (d.ljpme)
+    {
+        /* nbfp_comb as set_lj_parameter_data stores it (atomdata.cpp:291-322): geometric {sqrt(6 C6_ii), sqrt(12 C12_ii)},
+         * Lorentz-Berthelot {0.5 (C12/C6)^(1/6), sqrt(C6^2 / C12)} (zero for types without LJ); the filler type gets zeros */
+        const int          ntf = d.ntypes;
+        std::vector<float> comb((size_t)ntf * 2, 0.0f);
+        for (int i = 0; i < ntf; i++)
+        {
+            const float c6 = h->nbfp_host[((size_t)i * ntf + i) * 2], c12 = h->nbfp_host[((size_t)i * ntf + i) * 2 + 1];
+            if (d.ljpme == 1)
+            {
+                comb[2 * i]     = std::sqrt(c6);
+                comb[2 * i + 1] = std::sqrt(c12);
+            }
+            else if (c6 > 0 && c12 > 0)
+            {
+                comb[2 * i]     = 0.5f * std::pow(c12 / c6, 1.0f / 6.0f);
+                comb[2 * i + 1] = std::sqrt(c6 * c6 / c12);
+            }
+        }
+        if (alloc_exact(h, &h->d_nbfp_comb, (size_t)ntf * 2)) return B200NB_ERR_CUDA;
+        NB_CUDA(h, cudaMemcpy(h->d_nbfp_comb, comb.data(), sizeof(float) * ntf * 2, cudaMemcpyHostToDevice));
+        d.lje_coeff2   = v->ewaldcoeff_lj * v->ewaldcoeff_lj;
+        d.lje_coeff6_6 = d.lje_coeff2 * d.lje_coeff2 * d.lje_coeff2 / 6.0f;
+        d.sh_lj_ewald  = v->sh_lj_ewald;
+    }
     d.vdw_modifier = v->vdw_modifier;
     d.rvdw2        = rvdw * rvdw;
     d.rvdw_switch  = v->rvdw_switch;

@@ -68,6 +68,8 @@ struct NbParamsDev
     float rvdw2, rvdw_switch;
     float disp_c2, disp_c3, rep_c2, rep_c3;
     float sw_c3, sw_c4, sw_c5;
+    int   ljpme; /* 0 none, 1 geometric, 2 Lorentz-Berthelot grid combination rule */
+    float lje_coeff2, lje_coeff6_6, sh_lj_ewald;
 };
 
 struct PairList
@@ -157,6 +159,7 @@ struct b200nb_context
     bool              comb_geom = false;
     int               max_tiles = 16;
     float*            d_nbfp = nullptr; /* float2 per type pair */
+    float*            d_nbfp_comb = nullptr; /* LJ-PME: float2 per type, NBParamGpu::nbfp_comb */
     float*            d_kconst = nullptr; /* 12 floats: rc2, beta, beta2, FD4/b, FD3/b, FN6, FN5, FD2/b, FD1/b, FD0/b, 0, 0 (force.cu KConst) */
 
     int    natoms = 0;

@@ -73,6 +73,13 @@ __device__ __forceinline__ float rsqrt_approx(float x)
     return r;
 }
 
+__device__ __forceinline__ float exp_approx(float x) /* e^x through MUFU.EX2; relative error ~1e-7 for the |x| <= 12 used here */
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
+
 struct JAtom
 {
     float4 xq;
@@ -163,12 +170,13 @@ struct IData
     float2 q;        /* epsfac * q_i */
     float2 c6n, c12; /* GEOM: -sqrt(6 C6_i), sqrt(12 C12_i) */
     int    t0, t1;   /* table path: type_i * ntypes */
+    float2 g0, g1;   /* LJ-PME (GEN kernels): nbfp_comb of the two i-atoms' types */
 };
 
 /* One tile: lane computes pairs (i0, jl) [.x] and (i1, jl) [.y].  Returns the force ON THE i-ATOMS in (tx,ty,tz). */
 template<int EEL, bool GEOM, bool VF, bool MASKED, bool GEN>
 __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const NbParamsDev& P, const KConst& K, const float2* __restrict__ nbfp,
-                                           float inter0, float inter1, bool ok0, bool ok1, float2& tx, float2& ty, float2& tz,
+                                           const float2* __restrict__ nbfp_comb, float inter0, float inter1, bool ok0, bool ok1, float2& tx, float2& ty, float2& tz,
                                            float& evdw, float& ecoul)
 {
     const float2 m1 = dup(-1.0f);
@@ -253,6 +261,35 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
         else if (MASKED)
         {
             vlj = mul2(vlj, inter);
+        }
+        if (!GEOM && P.ljpme)
+        {
+            /* LJ-PME: subtract the grid part of the dispersion (kernel_ref_inner.h:207-250; cuda calculate_lj_ewald_comb_geom_F[_E],
+             * calculate_lj_ewald_comb_LB_F_E).  r^-6 here is NOT masked by the exclusions: excluded pairs inside the cut-off
+             * keep this correction, exactly like the Coulomb exclusion correction. */
+            const float2 gj = __ldg(nbfp_comb + __float_as_int(J.lj.x));
+            float2       c6grid;
+            if (P.ljpme == 1)
+            {
+                c6grid = make_float2(I.g0.x * gj.x, I.g1.x * gj.x);
+            }
+            else
+            {
+                const float2 sg = make_float2(I.g0.x + gj.x, I.g1.x + gj.x);
+                const float2 s2 = mul2(sg, sg);
+                c6grid          = mul2(make_float2(I.g0.y * gj.y, I.g1.y * gj.y), mul2(mul2(s2, s2), s2));
+            }
+            const float2 rinv6nm = mul2(mul2(rinvsq, rinvsq), rinvsq);
+            const float2 cr2     = mul2(dup(P.lje_coeff2), r2);
+            const float2 nex     = make_float2(-exp_approx(-cr2.x), -exp_approx(-cr2.y)); /* -exp(-cr2) */
+            const float2 poly    = fma2(fma2(dup(0.5f), cr2, dup(1.0f)), cr2, dup(1.0f));
+            fsum                 = fma2(c6grid, fma2(nex, fma2(rinv6nm, poly, dup(P.lje_coeff6_6)), rinv6nm), fsum);
+            if (VF)
+            {
+                float2 sh = dup(P.sh_lj_ewald);
+                if (MASKED) sh = mul2(sh, inter);
+                vlj = fma2(mul2(c6grid, dup(1.0f / 6.0f)), fma2(rinv6nm, fma2(nex, poly, dup(1.0f)), sh), vlj);
+            }
         }
         /* VdW cut-off shorter than the Coulomb cut-off (PME load balancing grows rcoulomb, rvdw stays) */
         const bool va = r2.x < P.rvdw2, vb = r2.y < P.rvdw2;
@@ -466,7 +503,8 @@ __global__ void __launch_bounds__(32 * B200NB_FORCE_WARPS, B200NB_FORCE_MIN_BLOC
 k_force(const Entry* __restrict__ entries, long long nentries, const int* __restrict__ pja, const uint64_t* __restrict__ tmask,
         const float4* __restrict__ xq, const float2* __restrict__ lj, const int* __restrict__ atype, const float2* __restrict__ nbfp,
         const float* __restrict__ shift_vec, float4* __restrict__ f, float* __restrict__ fshift, double* __restrict__ energy,
-        const __grid_constant__ NbParamsDev P, const int intra, const int maxt, const float* __restrict__ kconst)
+        const __grid_constant__ NbParamsDev P, const int intra, const int maxt, const float* __restrict__ kconst,
+        const float2* __restrict__ nbfp_comb)
 {
     const long long e = (long long)blockIdx.x * B200NB_FORCE_WARPS + (threadIdx.x >> 5);
     if (e >= nentries) return;
@@ -546,6 +584,11 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
             I.t0         = t.x * P.ntypes;
             I.t1         = t.y * P.ntypes;
             I.c6n = I.c12 = dup(0.0f);
+            if (GEN && P.ljpme)
+            {
+                I.g0 = __ldg(nbfp_comb + t.x);
+                I.g1 = __ldg(nbfp_comb + t.y);
+            }
         }
     }
     float2 fix = dup(0.f), fiy = dup(0.f), fiz = dup(0.f);
@@ -555,6 +598,12 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
         /* Coulomb self term, once per i-atom: kernel_outer.h:408-452 (fillers carry q = 0) */
         const float qi = (jl == 0 ? I.q.x : I.q.y);
         ecoul -= qi * qi * P.self_q2;
+        if (GEN && !GEOM && P.ljpme)
+        {
+            /* LJ Ewald self interaction, kernel_ref_outer.h:316-321: 0.5 * (6 C6_ii) / 6 * coeff^6 / 6 */
+            const int ti = (jl == 0 ? I.t0 : I.t1);
+            evdw += 0.5f * __ldg(nbfp + ti + ti / P.ntypes).x * (1.0f / 6.0f) * P.lje_coeff6_6;
+        }
     }
     const uint2* const emask = reinterpret_cast<const uint2*>(tmask) + (size_t)e * maxt;
     const int          nchunk = (ntile + NB_CHUNK - 1) / NB_CHUNK;
@@ -585,7 +634,7 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
                 ok1 = (J.slot & 7) > 2 * ih + 1;
             }
             float2 tx, ty, tz;
-            tile_pairs<EEL, GEOM, VF, true, GEN>(I, J, P, K, nbfp, in0, in1, ok0, ok1, tx, ty, tz, evdw, ecoul);
+            tile_pairs<EEL, GEOM, VF, true, GEN>(I, J, P, K, nbfp, nbfp_comb, in0, in1, ok0, ok1, tx, ty, tz, evdw, ecoul);
             fix = add2(fix, tx);
             fiy = add2(fiy, ty);
             fiz = add2(fiz, tz);
@@ -613,7 +662,7 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
             JAtom J;
             load_j(J, s_lane, t);
             float2 tx, ty, tz;
-            tile_pairs<EEL, GEOM, VF, false, GEN>(I, J, P, K, nbfp, 1.f, 1.f, true, true, tx, ty, tz, evdw, ecoul);
+            tile_pairs<EEL, GEOM, VF, false, GEN>(I, J, P, K, nbfp, nbfp_comb, 1.f, 1.f, true, true, tx, ty, tz, evdw, ecoul);
             fix = add2(fix, tx);
             fiy = add2(fiy, ty);
             fiz = add2(fiz, tz);
@@ -697,7 +746,7 @@ int launch(b200nb_context* h, const PackedList& L, int intra)
     cudaLaunchKernelEx(&cfg, k_force<EEL, GEOM, VF, GEN>, (const Entry*)L.entries, (long long)L.nentries, (const int*)L.ja, (const uint64_t*)L.mask,
                        reinterpret_cast<const float4*>(h->d_xq), reinterpret_cast<const float2*>(h->d_lj), (const int*)h->d_atype,
                        reinterpret_cast<const float2*>(h->d_nbfp), (const float*)h->d_shift_vec, h->d_f, h->d_fshift, h->d_energy, h->dp,
-                       intra, maxt, (const float*)h->d_kconst);
+                       intra, maxt, (const float*)h->d_kconst, reinterpret_cast<const float2*>(h->d_nbfp_comb));
     h->nlaunches++;
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return nb_fail(h, B200NB_ERR_CUDA, std::string("force kernel launch: ") + cudaGetErrorString(err));
@@ -715,11 +764,13 @@ int nb_launch_force_kernel(b200nb_context* h, int loc, int flags)
     const int  intra = (loc == 0);
     /* the plain kernels cover LJ cut-off + potential shift with rvdw == rcoulomb (every BASELINE configuration); the
      * general ones add the force / potential switch and the twin-range check (cuda/nbnxm_cuda.cu:165-282 kernel table) */
-    const bool gen = h->dp.vdw_modifier != B200NB_VDW_POTSHIFT || h->dp.rvdw2 < h->dp.rc2;
+    const bool gen = h->dp.vdw_modifier != B200NB_VDW_POTSHIFT || h->dp.rvdw2 < h->dp.rc2 || h->dp.ljpme != 0;
+    /* LJ-PME reads its per-type grid parameters through the atom types, which only the type-table kernels stage */
+    const bool geom = h->comb_geom && h->dp.ljpme == 0;
 #define NB_PICK(E, G)                                                                                           \
     (gen ? (vf ? launch<E, G, true, true>(h, L, intra) : launch<E, G, false, true>(h, L, intra))               \
          : (vf ? launch<E, G, true, false>(h, L, intra) : launch<E, G, false, false>(h, L, intra)))
-    if (ewald) return h->comb_geom ? NB_PICK(1, true) : NB_PICK(1, false);
-    return h->comb_geom ? NB_PICK(0, true) : NB_PICK(0, false);
+    if (ewald) return geom ? NB_PICK(1, true) : NB_PICK(1, false);
+    return geom ? NB_PICK(0, true) : NB_PICK(0, false);
 #undef NB_PICK
 }

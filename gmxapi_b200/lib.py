@@ -37,10 +37,19 @@ class _Params(C.Structure):
 class _Vdw(C.Structure):  # b200nb_vdw_t
     _fields_ = [("vdw_modifier", C.c_int), ("rvdw", C.c_float), ("rvdw_switch", C.c_float), ("disp_c2", C.c_float),
                 ("disp_c3", C.c_float), ("rep_c2", C.c_float), ("rep_c3", C.c_float), ("sw_c3", C.c_float),
-                ("sw_c4", C.c_float), ("sw_c5", C.c_float)]
+                ("sw_c4", C.c_float), ("sw_c5", C.c_float), ("ljpme_comb_rule", C.c_int), ("ewaldcoeff_lj", C.c_float),
+                ("sh_lj_ewald", C.c_float)]
 
 
 VDW_POTSHIFT, VDW_FORCESWITCH, VDW_POTSWITCH = 0, 1, 2
+LJPME_NONE, LJPME_GEOM, LJPME_LB = 0, 1, 2
+
+
+def lj_ewald_shift(ewaldcoeff_lj, rvdw):
+    """interaction_const_t::sh_lj_ewald for a potential-shift modifier (mdlib/forcerec.cpp:709-713)."""
+    import math
+    crc2 = (float(ewaldcoeff_lj) * float(rvdw)) ** 2
+    return (math.exp(-crc2) * (1 + crc2 + 0.5 * crc2 * crc2) - 1) / float(rvdw) ** 6
 
 
 def vdw_modifier_constants(modifier, rvdw, rvdw_switch):
@@ -195,12 +204,14 @@ class NbnxmGpu:
                     -1.0 / rc ** 12 if rep_cpot is None else rep_cpot, comb_rule, max_tiles_per_entry)
         self._check(self._L.b200nb_set_params(self._h, C.byref(p)), "set_params")
 
-    def set_vdw(self, vdw_modifier=VDW_POTSHIFT, rvdw=0.0, rvdw_switch=0.0, constants=None):
-        """b200nb_set_vdw: LJ force / potential switch and VdW cut-off (<= rc).  `constants`: the c2/c3/c3..c5 values
-        (vdw_modifier_constants); the matching potential shifts belong in set_params(disp_cpot=, rep_cpot=)."""
+    def set_vdw(self, vdw_modifier=VDW_POTSHIFT, rvdw=0.0, rvdw_switch=0.0, constants=None, ljpme=LJPME_NONE,
+                ewaldcoeff_lj=0.0, sh_lj_ewald=0.0):
+        """b200nb_set_vdw: LJ force / potential switch, VdW cut-off (<= rc) and the LJ-PME grid correction.  `constants`: the
+        c2/c3/c3..c5 values (vdw_modifier_constants); the matching potential shifts belong in set_params(disp_cpot=, rep_cpot=)."""
         k = constants or {}
         v = _Vdw(int(vdw_modifier), float(rvdw), float(rvdw_switch), k.get("disp_c2", 0.0), k.get("disp_c3", 0.0),
-                 k.get("rep_c2", 0.0), k.get("rep_c3", 0.0), k.get("sw_c3", 0.0), k.get("sw_c4", 0.0), k.get("sw_c5", 0.0))
+                 k.get("rep_c2", 0.0), k.get("rep_c3", 0.0), k.get("sw_c3", 0.0), k.get("sw_c4", 0.0), k.get("sw_c5", 0.0),
+                 int(ljpme), float(ewaldcoeff_lj), float(sh_lj_ewald))
         self._check(self._L.b200nb_set_vdw(self._h, C.byref(v)), "set_vdw")
 
     def set_atoms(self, types, q, excl_off=None, excl_idx=None):

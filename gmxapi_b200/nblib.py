@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import lib as _lib
-from .systems import ONE_4PI_EPS0, ewald_beta, rf_constants
+from .systems import ONE_4PI_EPS0, ewald_beta, ewald_beta_lj, rf_constants
 
 
 class CoulombType(enum.Enum):  # api/nblib/kerneloptions.h:72-79
@@ -30,6 +30,12 @@ class VdwModifier(enum.Enum):  # interaction_const_t::vdw_modifier (eintmodPOTSH
     PotentialShift = 0
     ForceSwitch = 1
     PotentialSwitch = 2
+
+
+class LjPme(enum.Enum):  # vdwtype = evdwPME with ljpme_combination_rule (eljpmeGEOM / eljpmeLB); the real-space part only
+    Off = 0
+    Geometric = 1
+    LorentzBerthelot = 2
 
 
 @dataclass
@@ -48,6 +54,8 @@ class NBKernelOptions:
     vdwModifier: VdwModifier = VdwModifier.PotentialShift
     vdwCutoff: float = 0.0  # rvdw <= pairlistCutoff (= rcoulomb); 0 = the same
     vdwSwitch: float = 0.0  # rvdw-switch
+    ljPme: LjPme = LjPme.Off  # subtract the LJ-PME grid part in real space (the mesh part is not this library's business)
+    ljPmeEwaldCoeff: float = 0.0  # ewaldcoeff_lj; 0 = calc_ewaldcoeff_lj(rvdw, 1e-3)
     device: int = 0
 
 
@@ -84,7 +92,13 @@ def configure_interactions(nb, nonbonded_parameters, options, rlist_outer=None):
     nb.set_params(nonbonded_parameters, rc, rlist_outer=rlist_outer or options.rlistOuter or rc,
                   rlist_inner=options.rlistInner or 0.0, max_tiles_per_entry=options.maxTilesPerEntry,
                   disp_cpot=vk["disp_cpot"], rep_cpot=vk["rep_cpot"], **kw)
-    if options.vdwModifier != VdwModifier.PotentialShift or rvdw < rc:
+    if options.ljPme != LjPme.Off:
+        if options.vdwModifier != VdwModifier.PotentialShift:
+            raise InputException("LJ-PME goes with the potential-shift modifier only")
+        bl = float(np.float32(options.ljPmeEwaldCoeff or ewald_beta_lj(rvdw, 1e-3)))
+        nb.set_vdw(options.vdwModifier.value, rvdw, options.vdwSwitch, vk, ljpme=options.ljPme.value, ewaldcoeff_lj=bl,
+                   sh_lj_ewald=_lib.lj_ewald_shift(bl, rvdw))
+    elif options.vdwModifier != VdwModifier.PotentialShift or rvdw < rc:
         nb.set_vdw(options.vdwModifier.value, rvdw, options.vdwSwitch, vk)
 
 

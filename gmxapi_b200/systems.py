@@ -59,6 +59,22 @@ def water_box(nx, ny, nz, seed=20261017, jitter=0.02):
     return System(x, box32, types, q, nbfp, excl_off, excl_idx, mol_id, "water_%dx%dx%d" % (nx, ny, nz))
 
 
+def nbfp_two_lj_types(sigma_h=0.12, eps_h=0.19):
+    """A second nonbonded-parameter table for the water boxes in which the hydrogens carry Lennard-Jones parameters too
+    (a TIP-like sigma / epsilon pair) and the O-H cross term follows Lorentz-Berthelot: two LJ types whose geometric and
+    Lorentz-Berthelot combinations differ, for the tests of the combination-rule dependent paths (type table, LJ-PME)."""
+    c6 = {0: C6_O, 1: 4 * eps_h * sigma_h ** 6}
+    c12 = {0: C12_O, 1: 4 * eps_h * sigma_h ** 12}
+    sig = {t: (c12[t] / c6[t]) ** (1.0 / 6.0) for t in (0, 1)}
+    eps = {t: c6[t] ** 2 / (4 * c12[t]) for t in (0, 1)}
+    nbfp = np.zeros((2, 2, 2), np.float32)
+    for a in (0, 1):
+        for b in (0, 1):
+            s_ab, e_ab = 0.5 * (sig[a] + sig[b]), (eps[a] * eps[b]) ** 0.5
+            nbfp[a, b] = (6.0 * 4 * e_ab * s_ab ** 6, 12.0 * 4 * e_ab * s_ab ** 12)
+    return nbfp
+
+
 NAMED = {
     "water_3k": (10, 10, 10),
     "water_24k": (20, 20, 20),      # BASELINE.json configs[1]
@@ -99,6 +115,32 @@ def ewald_beta(rc, rtol=1e-5):
     for _ in range(n):
         beta = (low + high) / 2
         if erfc(beta * rc) > rtol:
+            low = beta
+        else:
+            high = beta
+    return beta
+
+
+def ewald_beta_lj(rc, rtol=1e-3):
+    """calc_ewaldcoeff_lj (src/gromacs/ewald/ewald_utils.cpp:76-115): bisection on exp(-x^2)(1 + x^2 + x^4/2) = rtol, x = beta*rc
+    (ewald-rtol-lj defaults to 1e-3)."""
+    from math import exp
+
+    def fn(beta):
+        x2 = (beta * rc) ** 2
+        return exp(-x2) * (1 + x2 + x2 * x2 / 2.0)
+
+    beta = 5.0
+    i = 0
+    while True:
+        i += 1
+        beta *= 2
+        if not fn(beta) > rtol:
+            break
+    low, high = 0.0, beta
+    for _ in range(i + 60):
+        beta = (low + high) / 2
+        if fn(beta) > rtol:
             low = beta
         else:
             high = beta

@@ -90,6 +90,13 @@ typedef struct
     float disp_c2, disp_c3, rep_c2, rep_c3; /* shift_consts_t::c2, c3 of dispersion_shift / repulsion_shift (force switch); the
                                                matching cpot values go in b200nb_params_t::disp_cpot / rep_cpot */
     float sw_c3, sw_c4, sw_c5;              /* switch_consts_t vdw_switch (potential switch) */
+    /* LJ-PME (vdwtype = evdwPME): the real-space kernel subtracts the grid part of the dispersion (evdwTypeEWALDGEOM / EWALDLB
+     * kernels, cuda/nbnxm_cuda_kernel_utils.cuh calculate_lj_ewald_comb_*; kernels_reference/kernel_ref_inner.h:207-250).  The
+     * per-type grid parameters are derived from the diagonal of nbfp as set_lj_parameter_data does (atomdata.cpp:291-322).
+     * Needs vdw_modifier = B200NB_VDW_POTSHIFT; the reciprocal-space part is outside this library. */
+    int   ljpme_comb_rule; /* 0 = no LJ-PME, 1 = geometric (eljpmeGEOM), 2 = Lorentz-Berthelot (eljpmeLB) */
+    float ewaldcoeff_lj;   /* interaction_const_t::ewaldcoeff_lj */
+    float sh_lj_ewald;     /* interaction_const_t::sh_lj_ewald (mdlib/forcerec.cpp:709-717) */
 } b200nb_vdw_t;
 
 typedef struct b200nb_context b200nb_t;

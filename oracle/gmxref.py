@@ -32,7 +32,8 @@ class _Params(C.Structure):
                 ("exact_atom_flags", C.c_int), ("put_in_box", C.c_int), ("min_ilist_count", C.c_int),
                 ("rvdw", C.c_float), ("vdw_modifier", C.c_int), ("rvdw_switch", C.c_float),
                 ("disp_c2", C.c_float), ("disp_c3", C.c_float), ("rep_c2", C.c_float), ("rep_c3", C.c_float),
-                ("sw_c3", C.c_float), ("sw_c4", C.c_float), ("sw_c5", C.c_float)]
+                ("sw_c3", C.c_float), ("sw_c4", C.c_float), ("sw_c5", C.c_float),
+                ("ljpme", C.c_int), ("ewaldcoeff_lj", C.c_float), ("sh_lj_ewald", C.c_float)]
 
 
 _lib = None
@@ -87,7 +88,8 @@ class RefNbnxm:
                  epsfac=138.935458, k_rf=0.0, c_rf=0.0, ewaldcoeff=0.0, sh_ewald=0.0,
                  disp_cpot=None, rep_cpot=None, kernel=None, comb_rule=0, nthreads=1,
                  exact_atom_flags=0, put_in_box=0, rlist_inner=0.0, min_ilist_count=0,
-                 rvdw=0.0, vdw_modifier=0, rvdw_switch=0.0, modifier_constants=None):
+                 rvdw=0.0, vdw_modifier=0, rvdw_switch=0.0, modifier_constants=None, ljpme=0, ewaldcoeff_lj=0.0,
+                 sh_lj_ewald=0.0):
         L = lib()
         self.n = int(len(types))
         self._x = np.ascontiguousarray(x, dtype=np.float32).reshape(self.n, 3)
@@ -115,7 +117,7 @@ class RefNbnxm:
                     sh_ewald, disp_cpot, rep_cpot, kernel, comb_rule, nthreads, exact_atom_flags,
                     put_in_box, min_ilist_count, rvdw, vdw_modifier, rvdw_switch,
                     k.get("disp_c2", 0.0), k.get("disp_c3", 0.0), k.get("rep_c2", 0.0), k.get("rep_c3", 0.0),
-                    k.get("sw_c3", 0.0), k.get("sw_c4", 0.0), k.get("sw_c5", 0.0))
+                    k.get("sw_c3", 0.0), k.get("sw_c4", 0.0), k.get("sw_c5", 0.0), ljpme, ewaldcoeff_lj, sh_lj_ewald)
         self.rc = rc
         self.h = L.gmxref_create(C.byref(s), C.byref(p))
         if not self.h:

@@ -51,6 +51,10 @@ typedef struct
     float rvdw_switch;
     float disp_c2, disp_c3, rep_c2, rep_c3; /* dispersion_shift / repulsion_shift .c2 .c3 (force switch) */
     float sw_c3, sw_c4, sw_c5;              /* vdw_switch (potential switch) */
+    /* LJ-PME real-space grid correction (vdwtype = evdwPME; kernel_ref_inner.h:207-250, kernel_ref_outer.h:182-189,316-321) */
+    int   ljpme;          /* 0 none, 1 geometric (eljpmeGEOM), 2 Lorentz-Berthelot (eljpmeLB) grid combination rule */
+    float ewaldcoeff_lj;  /* interaction_const_t::ewaldcoeff_lj */
+    float sh_lj_ewald;    /* interaction_const_t::sh_lj_ewald (mdlib/forcerec.cpp:709-717) */
 } orc_params;
 
 enum { ORC_VDW_POTSHIFT = 0, ORC_VDW_FORCESWITCH = 1, ORC_VDW_POTSWITCH = 2 };
@@ -667,6 +671,35 @@ static void force_cb(void* vctx, int ai, int aj, int is, float rsq)
     {
         vlj = vlj * interact;
     }
+    if (p->ljpme)
+    {
+        /* kernel_ref_inner.h:207-250: subtract the grid (mesh) part of the dispersion from the real-space LJ; the per-type
+         * grid parameters are nbfp_comb as set_lj_parameter_data stores them (nbnxm/atomdata.cpp:291-322) */
+        const float c6ii = p->nbfp[(ti * p->ntypes + ti) * 2], c12ii = p->nbfp[(ti * p->ntypes + ti) * 2 + 1];
+        const float c6jj = p->nbfp[(tj * p->ntypes + tj) * 2], c12jj = p->nbfp[(tj * p->ntypes + tj) * 2 + 1];
+        float       c6grid;
+        if (p->ljpme == 1)
+        {
+            c6grid = sqrtf(c6ii) * sqrtf(c6jj);
+        }
+        else
+        {
+            const float si = (c6ii > 0 && c12ii > 0) ? 0.5f * powf(c12ii / c6ii, 1.0f / 6.0f) : 0.0f;
+            const float ei = (c6ii > 0 && c12ii > 0) ? sqrtf(c6ii * c6ii / c12ii) : 0.0f;
+            const float sj = (c6jj > 0 && c12jj > 0) ? 0.5f * powf(c12jj / c6jj, 1.0f / 6.0f) : 0.0f;
+            const float ej = (c6jj > 0 && c12jj > 0) ? sqrtf(c6jj * c6jj / c12jj) : 0.0f;
+            const float sigma = si + sj, sigma2 = sigma * sigma;
+            c6grid            = ei * ej * sigma2 * sigma2 * sigma2;
+        }
+        const float lje_coeff2   = p->ewaldcoeff_lj * p->ewaldcoeff_lj;
+        const float lje_coeff6_6 = lje_coeff2 * lje_coeff2 * lje_coeff2 / 6.0f;
+        const float rinvsix_nm   = rinvsq * rinvsq * rinvsq; /* without the exclusion mask */
+        const float cr2          = lje_coeff2 * rsq;
+        const float expmcr2      = expf(-cr2);
+        const float poly         = 1 + cr2 + 0.5f * cr2 * cr2;
+        frlj += c6grid * (rinvsix_nm - expmcr2 * (rinvsix_nm * poly + lje_coeff6_6));
+        vlj += c6grid / 6 * (rinvsix_nm * (1 - expmcr2 * poly) + p->sh_lj_ewald * interact);
+    }
     if (p->rvdw > 0.0f && p->rvdw < p->rc)
     {
         /* kernel_ref_inner.h:252-262 VDW_CUTOFF_CHECK: VdW cut-off shorter than the Coulomb cut-off */
@@ -719,6 +752,12 @@ long long orc_forces(int n, const float* x, const float box[3], const float* q, 
         double sub = (p->eeltype == ORC_EEL_EWALD) ? 0.5 * p->beta * 1.12837916709551257390 /* M_2_SQRTPI */
                                                    : 0.5 * p->c_rf;
         for (int a = 0; a < n; a++) c.ecoul -= (double)p->epsfac * q[a] * q[a] * sub;
+        if (p->ljpme)
+        {
+            /* kernel_ref_outer.h:316-321: LJ Ewald self interaction, 0.5 * (6 C6_ii) / 6 * coeff^6 / 6 per atom */
+            const double c2 = (double)p->ewaldcoeff_lj * p->ewaldcoeff_lj, c6_6 = c2 * c2 * c2 / 6.0;
+            for (int a = 0; a < n; a++) c.evdw += 0.5 * (double)p->nbfp[(type[a] * p->ntypes + type[a]) * 2] / 6.0 * c6_6;
+        }
     }
     energies[0] = c.evdw;
     energies[1] = c.ecoul;

@@ -21,10 +21,21 @@ class _Params(C.Structure):
                 ("disp_cpot", C.c_float), ("rep_cpot", C.c_float), ("ntypes", C.c_int), ("nbfp", C.c_void_p),
                 ("rvdw", C.c_float), ("vdw_modifier", C.c_int), ("rvdw_switch", C.c_float),
                 ("disp_c2", C.c_float), ("disp_c3", C.c_float), ("rep_c2", C.c_float), ("rep_c3", C.c_float),
-                ("sw_c3", C.c_float), ("sw_c4", C.c_float), ("sw_c5", C.c_float)]
+                ("sw_c3", C.c_float), ("sw_c4", C.c_float), ("sw_c5", C.c_float),
+                ("ljpme", C.c_int), ("ewaldcoeff_lj", C.c_float), ("sh_lj_ewald", C.c_float)]
 
 
 VDW_POTSHIFT, VDW_FORCESWITCH, VDW_POTSWITCH = 0, 1, 2
+
+
+LJPME_NONE, LJPME_GEOM, LJPME_LB = 0, 1, 2
+
+
+def lj_ewald_shift(ewaldcoeff_lj, rvdw):
+    """interaction_const_t::sh_lj_ewald with a potential-shift modifier (mdlib/forcerec.cpp:709-713)."""
+    import math
+    crc2 = (ewaldcoeff_lj * rvdw) ** 2
+    return (math.exp(-crc2) * (1 + crc2 + 0.5 * crc2 * crc2) - 1) / rvdw ** 6
 
 
 def vdw_modifier_constants(modifier, rvdw, rvdw_switch):
@@ -168,7 +179,7 @@ def prune_tiles(tiles, atom_index, x, box, rlist_inner):
 
 def forces(x, box, q, types, nbfp, rc, excl_off=None, excl_idx=None, eeltype=EEL_CUT, epsfac=138.935458,
            k_rf=0.0, c_rf=0.0, beta=0.0, sh_ewald=0.0, disp_cpot=None, rep_cpot=None, energy=True,
-           rvdw=0.0, vdw_modifier=VDW_POTSHIFT, rvdw_switch=0.0):
+           rvdw=0.0, vdw_modifier=VDW_POTSHIFT, rvdw_switch=0.0, ljpme=0, ewaldcoeff_lj=0.0, sh_lj_ewald=None):
     """Returns (f[n,3] float64, fshift[45,3] float64, evdw, ecoul, npairs).  rvdw < rc: twin-range cut-off (Ewald only in
     the reference); vdw_modifier: VDW_POTSHIFT / VDW_FORCESWITCH / VDW_POTSWITCH from rvdw_switch to rvdw."""
     x = _f32(x)
@@ -185,7 +196,8 @@ def forces(x, box, q, types, nbfp, rc, excl_off=None, excl_idx=None, eeltype=EEL
         rep_cpot = k["rep_cpot"]
     p = _Params(rc, eeltype, epsfac, k_rf, c_rf, beta, sh_ewald, disp_cpot, rep_cpot, ntypes, nbfp.ctypes.data,
                 rvdw, vdw_modifier, rvdw_switch, k["disp_c2"], k["disp_c3"], k["rep_c2"], k["rep_c3"],
-                k["sw_c3"], k["sw_c4"], k["sw_c5"])
+                k["sw_c3"], k["sw_c4"], k["sw_c5"], ljpme, ewaldcoeff_lj,
+                lj_ewald_shift(ewaldcoeff_lj, rv) if (sh_lj_ewald is None and ljpme) else (sh_lj_ewald or 0.0))
     b = (C.c_float * 3)(*[float(v) for v in box])
     eo = _i32(excl_off) if excl_off is not None else None
     ei = _i32(excl_idx) if excl_idx is not None else None

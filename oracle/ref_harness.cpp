@@ -196,6 +196,13 @@ void* gmxref_create(const gmxref_system* s, const gmxref_params* p)
         ic.vdw_switch.c4 = p->sw_c4;
         ic.vdw_switch.c5 = p->sw_c5;
     }
+    if (p->ljpme)
+    {
+        ic.vdwtype        = evdwPME;
+        ic.ljpme_comb_rule = (p->ljpme == 1) ? eljpmeGEOM : eljpmeLB;
+        ic.ewaldcoeff_lj  = p->ewaldcoeff_lj;
+        ic.sh_lj_ewald    = p->sh_lj_ewald;
+    }
     ic.epsilon_r             = 1;
     ic.epsfac                = p->epsfac;
     ic.k_rf                  = p->k_rf;

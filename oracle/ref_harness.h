@@ -42,6 +42,10 @@ typedef struct
     float rvdw_switch;
     float disp_c2, disp_c3, rep_c2, rep_c3; /* shift_consts_t::c2, c3 as force_switch_constants makes them (forcerec.cpp:787-801) */
     float sw_c3, sw_c4, sw_c5;              /* switch_consts_t (forcerec.cpp:803-816) */
+    /* LJ-PME: vdwtype = evdwPME with ljpme_comb_rule GEOM (1) or LB (2; plain-C kernel only, kerneldispatch.cpp:219-233);
+     * the caller also passes comb_rule = 1 / 2 for the atom-data initialisation (nbnxm_setup.cpp:399-410) */
+    int   ljpme;
+    float ewaldcoeff_lj, sh_lj_ewald;
 } gmxref_params;
 
 int    gmxref_simd_width(void);

@@ -101,7 +101,35 @@ def vdw_flavours():
         print(name, out["e_lj"], out["e_el"], out["e_lj_lj"])
 
 
+def ljpme_flavours():
+    """ref_water_3k_ljpme_{geom,lb}.npz: LJ-PME real-space kernels of the reference (SIMD for the geometric grid rule, plain C
+    for Lorentz-Berthelot: the only kernel that has it) on the 3 k water box with LJ on the hydrogens too
+    (systems.nbfp_two_lj_types), with the water charges and with all charges zero."""
+    import gmxapi_b200.systems as S
+    from oracle import gmxref, oracle
+    beta = float(np.float32(S.ewald_beta(RC)))
+    bl = float(np.float32(S.ewald_beta_lj(RC)))
+    sh = oracle.lj_ewald_shift(bl, RC)
+    s = S.named("water_3k")
+    nbfp = S.nbfp_two_lj_types()
+    for name, ljpme, kern in (("geom", 1, None), ("lb", 2, gmxref.KERNEL_PLAINC)):
+        out = dict(beta=np.float64(beta), ewaldcoeff_lj=np.float64(bl), sh_lj_ewald=np.float64(sh), ljpme=np.int64(ljpme), nbfp=nbfp)
+        for tag, q in (("", s.q), ("_lj", np.zeros_like(s.q))):
+            r = gmxref.RefNbnxm(s.x, s.box, s.types, q, nbfp, s.excl_off, s.excl_idx, rc=RC, nthreads=4, kernel=kern,
+                                eeltype=gmxref.EEL_EWALD_ANA, ewaldcoeff=beta, comb_rule=ljpme, ljpme=ljpme,
+                                ewaldcoeff_lj=bl, sh_lj_ewald=sh)
+            f, fs, elj, eel_ = r.compute()
+            r.close()
+            out["f" + tag], out["fshift" + tag] = f, fs
+            out["e_lj" + tag], out["e_el" + tag] = np.float64(elj), np.float64(eel_)
+        np.savez_compressed(os.path.join(HERE, "ref_water_3k_ljpme_%s.npz" % name), **out)
+        print(name, out["e_lj"], out["e_el"], out["e_lj_lj"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ljpme":
+        ljpme_flavours()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "vdw":
         vdw_flavours()
         sys.exit(0)

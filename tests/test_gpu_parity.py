@@ -133,6 +133,52 @@ def test_vdw_flavours(built, flavour, mod, rvdw, rsw):
                           g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.ReactionField, vdwCutoff=0.8))
 
 
+@pytest.mark.parametrize("rule,ljpme", [("geom", g.LjPme.Geometric), ("lb", g.LjPme.LorentzBerthelot)])
+def test_ljpme_grid_correction(built, rule, ljpme):
+    """LJ-PME real-space kernels (grid part of the dispersion subtracted; geometric and Lorentz-Berthelot grid rule) against
+    the oracle and the committed outputs of the reference kernels, with the water charges and with all charges zero; the
+    system has LJ on the hydrogens too, so the two rules differ (4e-4 of the forces) and the type-table kernels run."""
+    import os
+    gd = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_water_3k_ljpme_%s.npz" % rule))
+    s = g.systems.named("water_3k")
+    nbfp = g.systems.nbfp_two_lj_types()
+    beta = float(np.float32(g.systems.ewald_beta(RC)))
+    bl = float(gd["ewaldcoeff_lj"])
+    for tag, q in (("", s.q), ("_lj", np.zeros_like(s.q))):
+        for energy in (True, False):
+            opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, computeVirialAndEnergy=energy, ljPme=ljpme)
+            fc = g.ForceCalculator(g.SimulationState(s.x, s.box, s.types, q, nbfp, s.excl_off, s.excl_idx), opt)
+            assert not fc.nb.stats()["comb_geometric"]  # Lorentz-Berthelot cross terms: the type table
+            f = fc.compute()
+            fo, fso, evo, eco, _ = oracle.forces(s.x, s.box, q, s.types, nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_EWALD,
+                                                 beta=beta, ljpme=ljpme.value, ewaldcoeff_lj=bl)
+            assert relrms(f, fo) < FORCE_TOL
+            assert relrms(f, gd["f" + tag].astype(np.float64)) < FORCE_TOL
+            if energy:
+                elj, eel = fc.energies
+                assert abs(elj - evo) <= 2e-4 * abs(evo)
+                assert abs(elj - float(gd["e_lj" + tag])) <= 2e-4 * abs(float(gd["e_lj" + tag]))
+                if tag == "":
+                    assert abs(eel - eco) <= 2e-4 * abs(eco)
+                m = np.ones(45, bool)
+                m[nb.CENTRAL] = False
+                fs = fc.shiftForces.astype(np.float64)
+                assert np.abs(fs[m] - fso[m]).max() <= VIRIAL_TOL * np.abs(fso[m]).max()
+            fc.nb.close()
+    # geometric LJ parameters (plain water) with LJ-PME: the library switches to the type-table kernels by itself
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, computeVirialAndEnergy=True, ljPme=ljpme)
+    fc = g.ForceCalculator(g.SimulationState.from_system(s), opt)
+    assert fc.nb.stats()["comb_geometric"]
+    f = fc.compute()
+    fo, _, evo, _, _ = oracle.forces(s.x, s.box, s.q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_EWALD, beta=beta,
+                                     ljpme=ljpme.value, ewaldcoeff_lj=float(np.float32(g.systems.ewald_beta_lj(RC))))
+    assert relrms(f, fo) < FORCE_TOL and abs(fc.energies[0] - evo) <= 2e-4 * abs(evo)
+    # LJ-PME with a switch modifier is refused, as in the reference (vdwtype PME implies potential shift)
+    with pytest.raises(g.nblib.InputException):
+        g.ForceCalculator(g.SimulationState.from_system(s), g.NBKernelOptions(pairlistCutoff=RC, ljPme=ljpme, vdwSwitch=0.7,
+                                                                               vdwModifier=g.VdwModifier.ForceSwitch))
+
+
 def test_tile_list_is_exact(built):
     """The device list holds exactly the cluster pairs with >= 1 atom pair inside rlist (what the reference list
     converges to after pruning), in the half-list convention."""
