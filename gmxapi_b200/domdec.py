@@ -1,6 +1,6 @@
 """Spatial domain decomposition of the nonbonded path over the GPUs of one box: one rank per GPU, atoms
 partitioned into slabs along x, halo coordinates sent before and halo forces returned after the non-local
-kernel, every step.
+kernel, every step; at pair-search steps atoms that left their slab migrate to the neighbour (repartitioning).
 
 Reference behaviour mirrored (paths relative to /root/reference/src/gromacs):
   zones / eighth shell      domdec/domdec.cpp:133-146: with one decomposed dimension there are two zones, home (0)
@@ -13,7 +13,10 @@ Reference behaviour mirrored (paths relative to /root/reference/src/gromacs):
                             the sender's home forces; on the periodic edge their sum also goes into the shift
                             force of the +x shift (:426-458)
   GPU halo                  domdec/gpuhaloexchange_impl.cu:77-131 pack / unpack kernels (ours: b200nb_halo_pack_x,
-                            b200nb_halo_unpack_f), :403-444 the transfer (ours: NCCL send/recv over NVLink)
+                            b200nb_halo_unpack_f), :403-444 the transfer (ours: stores into the neighbour's peer-memory
+                            window from inside the step's kernels, b200nb_dd_step; transport send/recv at search steps)
+  repartitioning            domdec/partition.cpp dd_partition_system, domdec/redistribute.cpp dd_redistribute_cg
+                            (ours: migrate_atoms + DomainRank.repartition)
   non-local gridding        nbnxm.cpp:77-95 nbnxn_put_on_grid_nonlocal (ours: grid 1 of the C ABI)
 
 The decomposition PLAN (who owns which atom, which atoms are sent) is a pure function of the coordinates at
