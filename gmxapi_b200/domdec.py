@@ -248,6 +248,16 @@ class TorchDistTransport:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()  # CUDA: orders the current stream after the transfer, does not block the host
 
+    def exchange(self, sends, recvs):
+        """Several messages at once (domdec_nd: one per half-shell neighbour): sends = [(tensor, dst)], recvs = [(tensor, src)];
+        messages between the same two ranks are matched in list order."""
+        dist = self.dist
+        ops = [dist.P2POp(dist.isend, t, dst, self.group) for t, dst in sends if t is not None and t.numel()]
+        ops += [dist.P2POp(dist.irecv, t, src, self.group) for t, src in recvs if t is not None and t.numel()]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
     def allreduce_sum(self, t):
         self.dist.all_reduce(t, group=self.group)
         return t
@@ -294,6 +304,25 @@ class _LoopbackEndpoint:
             if self.sync:
                 self.sync()  # the copy must have run before `buf` returns to the sender's stream pool and is rewritten
             del buf
+
+    def exchange(self, sends, recvs):
+        """all sends are queued first (the queues are unbounded), then the receives are taken in list order"""
+        live = [(t, dst) for t, dst in sends if t is not None and t.numel()]
+        if live and self.sync:
+            self.sync()
+        for t, dst in live:
+            self.hub.q[(self.rank, dst)].put(t.clone())
+        if live and self.sync:
+            self.sync()
+        got = False
+        for t, src in recvs:
+            if t is not None and t.numel():
+                buf = self.hub.q[(src, self.rank)].get(timeout=120)
+                t.copy_(buf)
+                got = True
+                del buf
+        if got and self.sync:
+            self.sync()
 
     def allreduce_sum(self, t):
         raise NotImplementedError

@@ -1,0 +1,320 @@
+"""Domain decomposition of the nonbonded path in one, two or three dimensions (e.g. 2 x 2 x 2 ranks for the 8 GPUs of a box).
+
+The slab decomposition of `domdec.py` (eighth shell with one decomposed dimension, halos through peer-memory windows) is
+the fast path; this module is the general one.  It assigns pairs with the HALF-SHELL rule instead of the reference's eighth
+shell (domdec/domdec.cpp:133-146): rank A imports the atoms near its boundary from the 13 (3-D), 4 (2-D) or 1 (1-D)
+neighbours B = A + o whose offset o is lexicographically positive (first non-zero component +1) and computes
+home x home (half list) and home x halo (full list) -- every pair of atoms of two different domains is then computed exactly
+once, on the rank that sees the other domain at a positive offset, and there are NO halo x halo pairs, so the two grids
+(home, halo) and the two list kinds the library has are all that is needed.  The price is a halo about twice the eighth
+shell's, and direct exchanges with every neighbour instead of three forwarding pulses -- which is how an NVSwitch box wants
+it anyway (every GPU reaches every other at full bandwidth).
+
+Reference behaviour mirrored (paths relative to /root/reference/src/gromacs):
+  dd_move_x / dd_move_f        domdec/domdec.cpp:260-460: coordinates of boundary atoms out (shifted by the box vector when they
+                               cross a periodic edge, :300-318), forces on them back and added, their sum into the shift force
+                               of that shift for the virial (:426-458)
+  non-local gridding / search  nbnxm.cpp:77-95, pairlist.cpp:3876-3916: halo atoms are gridded as the second grid, periodic
+                               images are switched off along decomposed dimensions
+  pack / unpack                domdec/gpuhaloexchange_impl.cu:77-131 (ours: b200nb_halo_pack_x / b200nb_halo_unpack_f)
+The per-step exchange runs through the transport (NCCL send/recv between GPUs, the in-process loopback in the single-GPU
+tests), not through the peer-memory windows: this path is about capability (2 x 2 x 2), the slab path about speed.
+"""
+import itertools
+
+import numpy as np
+
+from . import lib as _lib
+from .nblib import InputException, configure_interactions
+
+
+def shift_index(k):
+    """XYZ2IS, pbcutil/ishift.h:50"""
+    return 5 * (3 * (int(k[2]) + 1) + (int(k[1]) + 1)) + int(k[0]) + 2
+
+
+def half_shell_offsets(grid):
+    """Offsets o in {-1,0,1}^3, non-zero only along decomposed dimensions, whose first non-zero component is +1."""
+    rng = [(-1, 0, 1) if n > 1 else (0,) for n in grid]
+    out = []
+    for o in itertools.product(*rng):
+        nz = [c for c in o if c != 0]
+        if nz and nz[0] > 0:
+            out.append(tuple(o))
+    return out
+
+
+class DomainPlanND:
+    """Rank `rank` of a grid of nx x ny x nz domains (rank = (ix * ny + iy) * nz + iz), equal widths.
+
+    home    global indices owned, ascending
+    recv    list of dict(rank, offset, shift[3], ids): what arrives from neighbour `rank` seen at `offset`; `shift` (in box
+            vectors, -1/0/+1 per dimension) is what the SENDER adds so the atoms appear next to this domain
+    send    list of dict(rank, offset, shift[3], local): positions in `home` of the atoms this rank sends to `rank`, which sees
+            this domain at `offset`
+    halo    concatenation of the recv ids, in recv order (a global index can appear once only: domains of width >= 2 rlist
+            along a dimension with two ranks, see below)
+    """
+
+    def __init__(self, x, box, grid, rank, rlist):
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 3)
+        self.box = np.asarray(box, dtype=np.float32).reshape(3)
+        self.grid = tuple(int(g) for g in grid)
+        self.nranks = int(np.prod(self.grid))
+        if len(self.grid) != 3 or min(self.grid) < 1 or not (0 <= rank < self.nranks):
+            raise InputException("bad grid / rank")
+        self.rank, self.rlist = int(rank), float(rlist)
+        self.width = self.box.astype(np.float64) / np.array(self.grid)
+        for d in range(3):
+            if self.grid[d] > 1 and self.width[d] < rlist:
+                raise InputException("domain width %.3f < list radius %.3f along dimension %d" % (self.width[d], rlist, d))
+            if self.grid[d] == 2 and self.width[d] < 2 * rlist:
+                # both faces lead to the same neighbour: an atom within rlist of both would be imported as two images
+                raise InputException("two domains along dimension %d need a width of at least 2 x the list radius" % d)
+        self.coords = self.coords_of(self.rank, self.grid)
+        self.lo = np.array([self.bound(d, self.coords[d]) for d in range(3)], np.float32)
+        self.hi = np.array([self.bound(d, self.coords[d] + 1) for d in range(3)], np.float32)
+        owner = self.owner_of(x, self.box, self.grid)
+        self.home = np.nonzero(owner == self.rank)[0].astype(np.int32)
+        self.offsets = half_shell_offsets(self.grid)
+        self.recv, self.send = [], []
+        for o in self.offsets:
+            # what I receive from the neighbour at +o: its atoms near the boundary it shares with me
+            nb, shift = self.neighbour(self.coords, o, +1)
+            nb_home = np.nonzero(owner == nb)[0].astype(np.int32)
+            sel = self.boundary_atoms(x[nb_home], self.coords_of(nb, self.grid), o)
+            self.recv.append(dict(rank=nb, offset=o, shift=shift, ids=nb_home[sel]))
+            # what I send to the rank that sees me at +o
+            dst, _ = self.neighbour(self.coords, o, -1)
+            _, sshift = self.neighbour(self.coords_of(dst, self.grid), o, +1)
+            self.send.append(dict(rank=dst, offset=o, shift=sshift,
+                                  local=self.boundary_atoms(x[self.home], self.coords, o).astype(np.int32)))
+        self.halo = (np.concatenate([r["ids"] for r in self.recv]) if self.recv else np.zeros(0, np.int32)).astype(np.int32)
+        if len(np.unique(self.halo)) != len(self.halo):
+            raise InputException("an atom would be imported twice (domain too thin for its number of ranks)")
+        self.nhome, self.nhalo = len(self.home), len(self.halo)
+        self.local = np.concatenate([self.home, self.halo]).astype(np.int32)
+
+    # -- geometry ---------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def coords_of(rank, grid):
+        iz = rank % grid[2]
+        iy = (rank // grid[2]) % grid[1]
+        ix = rank // (grid[1] * grid[2])
+        return (ix, iy, iz)
+
+    @staticmethod
+    def rank_of(coords, grid):
+        return (coords[0] * grid[1] + coords[1]) * grid[2] + coords[2]
+
+    def bound(self, d, i):
+        return np.float32(i * (float(self.box[d]) / self.grid[d]))
+
+    @staticmethod
+    def owner_of(x, box, grid):
+        idx = []
+        for d in range(3):
+            b = (np.arange(grid[d] + 1, dtype=np.float64) * (float(box[d]) / grid[d])).astype(np.float32)
+            idx.append(np.clip(np.searchsorted(b, x[:, d], side="right") - 1, 0, grid[d] - 1))
+        return ((idx[0] * grid[1] + idx[1]) * grid[2] + idx[2]).astype(np.int32)
+
+    def neighbour(self, coords, o, sign):
+        """Rank at coords + sign*o (periodic) and the shift, in box vectors, under which ITS atoms appear next to `coords`."""
+        c, shift = [], []
+        for d in range(3):
+            v = coords[d] + sign * o[d]
+            k = 0
+            if v >= self.grid[d]:
+                v -= self.grid[d]
+                k = +1
+            elif v < 0:
+                v += self.grid[d]
+                k = -1
+            c.append(v)
+            shift.append(k)
+        return self.rank_of(c, self.grid), np.array(shift, np.int32)
+
+    def boundary_atoms(self, xs, coords, o):
+        """Positions (in xs) of the atoms of domain `coords` that a domain seeing it at offset +o needs: within rlist of the
+        lower face along dimensions with o = +1, of the upper face where o = -1 (slab criteria: a superset of the sphere)."""
+        m = np.ones(len(xs), bool)
+        r = np.float32(self.rlist)
+        for d in range(3):
+            if o[d] == +1:
+                m &= xs[:, d] - self.bound(d, coords[d]) < r
+            elif o[d] == -1:
+                m &= self.bound(d, coords[d] + 1) - xs[:, d] <= r
+        return np.nonzero(m)[0]
+
+    # -- derived data -------------------------------------------------------------------------------------------------------
+    def halo_x(self, x):
+        """What the halo coordinates must be after the coordinate exchange (expected values for the tests)."""
+        x = np.asarray(x, np.float32)
+        parts = [x[r["ids"]] + (r["shift"].astype(np.float32) * self.box) for r in self.recv]
+        return np.concatenate(parts).astype(np.float32) if parts else np.zeros((0, 3), np.float32)
+
+    def local_topology(self, types, q, excl_off, excl_idx):
+        """types / charges / exclusions of home + halo atoms, exclusions renumbered to local indices (as DomainPlan)."""
+        from .domdec import DomainPlan
+        return DomainPlan.local_topology(self, types, q, excl_off, excl_idx)
+
+    def halo_bounds(self):
+        """Bounding region of the halo grid: the domain grown by rlist on the faces a half-shell neighbour can sit behind."""
+        lo, hi = self.lo.copy(), self.hi.copy()
+        for d in range(3):
+            if any(o[d] == +1 for o in self.offsets):
+                hi[d] += np.float32(self.rlist)
+            if any(o[d] == -1 for o in self.offsets):
+                lo[d] -= np.float32(self.rlist)
+        return lo, hi
+
+
+class DomainRankND:
+    """One rank of the 1-D / 2-D / 3-D decomposed calculation: schedule of do_force() restricted to the nonbonded path,
+
+        x home -> grid | local kernel | halo x from every half-shell neighbour | halo x -> grid | non-local kernel |
+        halo f back to the owners, added (+ shift forces for images across a periodic edge) | forces -> atom order
+
+    with the halo traffic on the transport (see the module docstring)."""
+
+    def __init__(self, system, options, transport, grid, rank=None, device=0):
+        import torch
+        self.torch = torch
+        self.t = transport
+        self.rank = transport.rank if rank is None else rank
+        self.options = options
+        rc = float(options.pairlistCutoff)
+        self.rlist = float(options.rlistOuter or rc)
+        self.plan = p = DomainPlanND(system.x, system.box, grid, self.rank, self.rlist)
+        self.nranks = p.nranks
+        self.nb = _lib.NbnxmGpu(device)
+        self.device = torch.device("cuda", device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.nb.set_stream(self.stream.cuda_stream)
+        if hasattr(transport, "sync"):
+            transport.sync = self.nb.synchronize
+        configure_interactions(self.nb, system.nbfp, options, self.rlist)
+        types, q, eo, ei = p.local_topology(system.types, system.q, system.excl_off, system.excl_idx)
+        self.nb.set_atoms(types, q, eo, ei)
+        # periodic images only along dimensions that are not decomposed: across the others the images arrive as halo atoms
+        self.nb.set_box(system.box, pbc=tuple(1 if g == 1 else 0 for g in p.grid))
+        self.nlocal = p.nhome + p.nhalo
+        box = p.box
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self.x = torch.zeros((self.nlocal, 3), dtype=torch.float32, device=self.device)
+            self.f = torch.zeros((self.nlocal, 3), dtype=torch.float32, device=self.device)
+            self.x[:p.nhome].copy_(torch.from_numpy(np.ascontiguousarray(system.x[p.home])))
+            self.send_idx = [torch.from_numpy(s["local"]).to(self.device) for s in p.send]
+            self.send_buf = [torch.zeros((len(s["local"]), 3), dtype=torch.float32, device=self.device) for s in p.send]
+            self.recv_f = [torch.zeros((len(s["local"]), 3), dtype=torch.float32, device=self.device) for s in p.send]
+        self.send_shift = [(s["shift"].astype(np.float32) * box).astype(np.float32) for s in p.send]
+        off = p.nhome
+        self.recv_range = []
+        for r in p.recv:
+            self.recv_range.append((off, off + len(r["ids"])))
+            off += len(r["ids"])
+        self.nb.synchronize()
+        self.fshift_halo = np.zeros((_lib.SHIFTS, 3), np.float64)
+        self.search()
+
+    def search(self):
+        p = self.plan
+        self._halo_x()
+        self.nb.synchronize()
+        lower = np.where(np.array(p.grid) > 1, p.lo, 0.0).astype(np.float32)
+        upper = np.where(np.array(p.grid) > 1, p.hi, p.box).astype(np.float32)
+        self.nb.put_on_grid(self.x.data_ptr(), lower, upper, 0, 0, p.nhome, on_device=True)
+        if p.nhalo:
+            hl, hu = p.halo_bounds()
+            hl = np.where(np.array(p.grid) > 1, hl, 0.0).astype(np.float32)
+            hu = np.where(np.array(p.grid) > 1, hu, p.box).astype(np.float32)
+            self.nb.put_on_grid(self.x.data_ptr(), hl, hu, 1, p.nhome, self.nlocal, on_device=True)
+        self.nb.build_pairlist()
+
+    def _exchange(self, sends, recvs):
+        """all messages of one halo phase at once; messages between the same two ranks keep the half-shell offset order on
+        both sides, so they match without tags"""
+        if hasattr(self.t, "exchange"):
+            self.t.exchange(sends, recvs)
+        else:
+            raise InputException("the transport has no exchange(): use domdec.TorchDistTransport or LoopbackTransport")
+
+    def _halo_x(self):
+        p = self.plan
+        if not p.recv:
+            return
+        torch = self.torch
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            sends, recvs = [], []
+            for k, s in enumerate(p.send):
+                n = len(s["local"])
+                if n:
+                    self.nb.halo_pack_x(self.x.data_ptr(), self.send_idx[k].data_ptr(), n, self.send_shift[k], self.send_buf[k].data_ptr())
+                sends.append((self.send_buf[k], s["rank"]))
+            for k, r in enumerate(p.recv):
+                a, b = self.recv_range[k]
+                recvs.append((self.x[a:b], r["rank"]))
+            self._exchange(sends, recvs)
+
+    def _halo_f(self, virial):
+        p = self.plan
+        if not p.recv:
+            return
+        torch = self.torch
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            sends, recvs = [], []
+            for k, r in enumerate(p.recv):
+                a, b = self.recv_range[k]
+                sends.append((self.f[a:b], r["rank"]))
+            for k, s in enumerate(p.send):
+                recvs.append((self.recv_f[k], s["rank"]))
+            self._exchange(sends, recvs)
+            self.fshift_halo[:] = 0
+            for k, s in enumerate(p.send):
+                n = len(s["local"])
+                if not n:
+                    continue
+                self.nb.halo_unpack_f(self.f.data_ptr(), self.send_idx[k].data_ptr(), n, self.recv_f[k].data_ptr())
+                if virial and np.any(s["shift"] != 0):
+                    # domdec/domdec.cpp:426-458: forces on images that crossed a periodic edge also enter the shift forces
+                    self.fshift_halo[shift_index(s["shift"])] += self.recv_f[k].sum(0, dtype=torch.float64).cpu().numpy()
+
+    def step(self, flags=0):
+        """One nonbonded step on the coordinates in self.x[:nhome] (device); leaves forces in self.f[:nhome]."""
+        p = self.plan
+        self.nb.set_x(self.x.data_ptr(), on_device=True, atom_begin=0, atom_end=p.nhome)
+        self.nb.clear_outputs()
+        self.nb.launch_force(0, flags)
+        self._halo_x()
+        if p.nhalo:
+            self.nb.set_x(self.x.data_ptr(), on_device=True, atom_begin=p.nhome, atom_end=self.nlocal)
+            self.nb.launch_force(1, flags)
+        self.nb.get_f(self.f.data_ptr(), on_device=True)
+        self._halo_f(bool(flags & _lib.FLAG_VIRIAL))
+
+    def compute(self, x_home_host, flags=0):
+        """Host coordinates of the home atoms in, (f_home, fshift[45,3], e_lj, e_el) out: this rank's share of the sums."""
+        torch = self.torch
+        p = self.plan
+        xh = x_home_host if isinstance(x_home_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_home_host, np.float32))
+        fh = torch.empty((p.nhome, 3), dtype=torch.float32).pin_memory()
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self.x[:p.nhome].copy_(xh, non_blocking=True)
+            self.step(flags)
+            fh.copy_(self.f[:p.nhome], non_blocking=True)
+        self.nb.synchronize()
+        fs = np.zeros((_lib.SHIFTS, 3), np.float32)
+        elj = eel = 0.0
+        if flags:
+            fs, elj, eel = self.nb.get_outputs()
+            fs = fs + self.fshift_halo.astype(np.float32)
+        return fh, fs, elj, eel
+
+    def pair_count(self, r):
+        return self.nb.pair_count(r)
+
+    def close(self):
+        self.nb.synchronize()
+        self.nb.close()
+        self.x = self.f = None
+        self.send_idx = self.send_buf = self.recv_f = None

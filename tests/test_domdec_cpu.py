@@ -11,6 +11,7 @@ import torch.multiprocessing as mp
 
 from gmxapi_b200 import systems as S
 from gmxapi_b200.domdec import DomainPlan, TorchDistTransport, migrate_atoms, wrap_into_box
+from gmxapi_b200.domdec_nd import DomainPlanND, half_shell_offsets
 
 RLIST = 0.9
 
@@ -209,3 +210,123 @@ def test_migrate_rejects_long_jumps():
     x[0, 0] = 3.0  # two slabs away
     with pytest.raises(InputException):
         migrate_atoms(LoopbackTransport(4).endpoint(0), s.box, 4, 0, RLIST, plan.home, x)
+
+
+# ---- 1-D / 2-D / 3-D decomposition with the half-shell rule (gmxapi_b200/domdec_nd.py) -------------------------------------
+
+def test_half_shell_offsets():
+    assert half_shell_offsets((1, 1, 1)) == []
+    assert half_shell_offsets((3, 1, 1)) == [(1, 0, 0)]
+    assert len(half_shell_offsets((2, 2, 1))) == 4 and len(half_shell_offsets((2, 2, 2))) == 13
+    for grid in ((2, 2, 1), (2, 2, 2), (1, 3, 2)):
+        offs = half_shell_offsets(grid)
+        assert all(tuple(-c for c in o) not in offs for o in offs)  # of o and -o exactly one is in the half shell
+        allo = [o for o in np.ndindex(3, 3, 3)]
+        assert len(offs) * 2 + 1 == len([o for o in allo if all(grid[d] > 1 or o[d] == 1 for d in range(3))])
+
+
+@pytest.mark.parametrize("grid", [(2, 2, 1), (2, 2, 2), (3, 2, 1), (1, 2, 3), (4, 1, 1)])
+def test_plan_nd_partitions_atoms_and_pairs(grid):
+    """Half-shell rule: every atom has one owner, no atom is imported twice, and the union over ranks of home x home and
+    home x halo pairs within rlist is every pair of the fully periodic system exactly once."""
+    r = 0.45  # small list radius so that small boxes satisfy width >= 2 r with two ranks
+    s = S.water_box(8, 6, 6, seed=9)  # 2.49 x 1.86 x 1.86 nm
+    x, box = s.x, s.box
+    nr = int(np.prod(grid))
+    plans = [DomainPlanND(x, box, grid, k, r) for k in range(nr)]
+    assert np.array_equal(np.sort(np.concatenate([p.home for p in plans])), np.arange(s.n))
+    # reference: all pairs within r, minimum image in every dimension
+    d = x[:, None, :].astype(np.float64) - x[None, :, :].astype(np.float64)
+    d -= np.round(d / box) * box
+    ref = np.argwhere(np.triu((d ** 2).sum(-1) < r * r, 1))
+    ref_keys = np.sort(ref[:, 0].astype(np.int64) * s.n + ref[:, 1])
+    got = []
+    for p in plans:
+        assert len(p.send) == len(p.recv) == len(half_shell_offsets(grid))
+        xh = x[p.home].astype(np.float64)
+        # along dimensions that are NOT decomposed the kernel applies the periodic images itself: minimum image there
+        per = np.array([g == 1 for g in grid])
+
+        def pairs(xa, xb, same):
+            dd = xa[:, None, :] - xb[None, :, :]
+            dd -= np.where(per, np.round(dd / box) * box, 0.0)
+            m = (dd ** 2).sum(-1) < r * r
+            if same:
+                m = np.triu(m, 1)
+            return np.argwhere(m)
+        hh = pairs(xh, xh, True)
+        got.append(np.stack([p.home[hh[:, 0]], p.home[hh[:, 1]]], 1))
+        if p.nhalo:
+            hj = pairs(xh, p.halo_x(x).astype(np.float64), False)
+            got.append(np.stack([p.home[hj[:, 0]], p.halo[hj[:, 1]]], 1))
+    got = np.concatenate(got)
+    lo, hi = np.minimum(got[:, 0], got[:, 1]), np.maximum(got[:, 0], got[:, 1])
+    keys = np.sort(lo.astype(np.int64) * s.n + hi)
+    assert len(keys) == len(np.unique(keys)), "a pair is computed twice"
+    assert np.array_equal(keys, ref_keys)
+    # what a rank sends is what its peer expects, message by message, in the same order
+    for p in plans:
+        for k, sd in enumerate(p.send):
+            q = plans[sd["rank"]]
+            assert q.recv[k]["rank"] == p.rank and np.array_equal(q.recv[k]["ids"], p.home[sd["local"]])
+            assert np.array_equal(q.recv[k]["shift"], sd["shift"])
+
+
+def test_plan_nd_rejects_thin_domains():
+    from gmxapi_b200.nblib import InputException
+    s = S.water_box(8, 6, 6, seed=9)
+    with pytest.raises(InputException):
+        DomainPlanND(s.x, s.box, (2, 2, 1), 0, 0.9)  # 0.93 nm wide in y with two ranks: < 2 x 0.9
+
+
+def _nd_worker(rank, world, port, q, grid):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        s = S.water_box(8, 6, 6, seed=9)
+        r = 0.45
+        plan = DomainPlanND(s.x, s.box, grid, rank, r)
+        t = TorchDistTransport()
+        # coordinates out: pack (restated with torch on the CPU for this host-logic test), exchange, compare with the plan
+        x = torch.from_numpy(s.x[plan.local].copy())
+        x[plan.nhome:] = float("nan")
+        sends = [(x[:plan.nhome][torch.from_numpy(sd["local"]).long()] + torch.from_numpy(sd["shift"].astype(np.float32) * s.box), sd["rank"])
+                 for sd in plan.send]
+        recvs, off = [], plan.nhome
+        for rv in plan.recv:
+            recvs.append((x[off:off + len(rv["ids"])], rv["rank"]))
+            off += len(rv["ids"])
+        t.exchange([(a.contiguous(), d) for a, d in sends], recvs)
+        ok_x = bool(np.array_equal(x[plan.nhome:].numpy(), plan.halo_x(s.x)))
+        # forces back: every halo atom carries its global index; the owner must get exactly one contribution per sent atom
+        f = torch.zeros((plan.nhome + plan.nhalo, 3))
+        f[plan.nhome:] = torch.from_numpy(plan.halo.astype(np.float32))[:, None]
+        back = [torch.zeros((len(sd["local"]), 3)) for sd in plan.send]
+        fs, off = [], plan.nhome
+        for rv in plan.recv:
+            fs.append((f[off:off + len(rv["ids"])].contiguous(), rv["rank"]))
+            off += len(rv["ids"])
+        t.exchange(fs, [(b, sd["rank"]) for b, sd in zip(back, plan.send)])
+        ok_f = all(np.array_equal(b[:, 0].numpy(), plan.home[sd["local"]].astype(np.float32)) for b, sd in zip(back, plan.send))
+        q.put((rank, ok_x, bool(ok_f), plan.nhalo))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("grid", [(2, 2, 1), (2, 2, 2)])
+def test_halo_exchange_nd_gloo(grid):
+    """2 x 2 and 2 x 2 x 2 ranks over gloo: with two ranks along a dimension a neighbour is reached through both faces, so
+    several messages travel between the same two ranks and must match in order."""
+    world = int(np.prod(grid))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nd_worker, args=(r, world, port, q, grid)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_x, ok_f, nhalo in res:
+        assert ok_x and ok_f and nhalo > 0, (rank, ok_x, ok_f, nhalo)

@@ -170,3 +170,123 @@ def test_repartition_after_motion(built, nranks, windows):
     elj, eel = sum(r["elj"] for r in res), sum(r["eel"] for r in res)
     assert abs(elj - evo) <= 2e-4 * abs(evo)
     assert abs(eel - eco) <= 2e-4 * abs(eco)
+
+
+# ---- 2-D / 3-D decomposition, half-shell rule (gmxapi_b200/domdec_nd.py) ----------------------------------------------------
+_ND_CACHE = {}
+
+
+def run_ranks_nd(grid):
+    """all ranks of a grid as threads on this GPU (loopback transport); cached: two tests look at the same run"""
+    if grid in _ND_CACHE:
+        return _ND_CACHE[grid]
+    from gmxapi_b200.domdec_nd import DomainRankND
+    s = g.systems.named("water_24k")
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, computeVirialAndEnergy=True)
+    flags = nb.FLAG_ENERGY | nb.FLAG_VIRIAL
+    nranks = int(np.prod(grid))
+    hub = LoopbackTransport(nranks)
+    out = [None] * nranks
+    err = []
+
+    def work(r):
+        try:
+            d = DomainRankND(s, opt, hub.endpoint(r), grid, rank=r, device=0)
+            p = d.plan
+            xh = np.ascontiguousarray(s.x[p.home])
+            for _ in range(2):
+                f, fs, elj, eel = d.compute(xh, flags)
+            pr = d.nb.pairs(RC)
+            loc = p.local
+            # shift (in box vectors) each halo atom was sent with; home atoms: none
+            ksh = np.zeros((len(loc), 3), np.int64)
+            off = p.nhome
+            for rv in p.recv:
+                ksh[off:off + len(rv["ids"])] = rv["shift"]
+                off += len(rv["ids"])
+            out[r] = dict(home=p.home, f=f.numpy().copy(), fs=fs, elj=elj, eel=eel, nhalo=p.nhalo,
+                          pairs=np.stack([loc[pr[:, 0]], loc[pr[:, 1]], pr[:, 2]], 1), jshift=ksh[pr[:, 1]])
+            hub.endpoint(r).barrier()
+            d.close()
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            err.append((r, repr(e), traceback.format_exc()))
+            try:
+                hub._bar.abort()
+            except Exception:
+                pass
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert not err, err
+    _ND_CACHE[grid] = (s, out)
+    return s, out
+
+
+def canonical_nd(pairs, jshift):
+    """(i, j, kernel shift) + the box-vector shift the j-atom was imported with -> half-list convention keys"""
+    p = np.asarray(pairs, np.int64).reshape(-1, 3)
+    sidx = p[:, 2]
+    t = np.stack([(sidx % 5) - 2, (sidx // 5) % 3 - 1, sidx // 15 - 1], 1) - np.asarray(jshift, np.int64)  # shift of i relative to j
+    idx = 5 * (3 * (t[:, 2] + 1) + (t[:, 1] + 1)) + t[:, 0] + 2
+    swap = (idx > CENTRAL) | ((idx == CENTRAL) & (p[:, 0] > p[:, 1]))
+    i = np.where(swap, p[:, 1], p[:, 0])
+    j = np.where(swap, p[:, 0], p[:, 1])
+    t = np.where(swap[:, None], -t, t)
+    idx = 5 * (3 * (t[:, 2] + 1) + (t[:, 1] + 1)) + t[:, 0] + 2
+    return (i << 34) | (j << 6) | idx
+
+
+ND_GRIDS = [(2, 2, 1), (2, 2, 2), (3, 2, 1)]
+
+
+@pytest.mark.parametrize("grid", ND_GRIDS)
+def test_decomposition_nd_matches_single_domain(built, grid):
+    """2 x 2, 2 x 2 x 2 and 3 x 2 ranks (half-shell rule, direct exchanges with every neighbour): pair set, forces and
+    energies of the decomposed calculation equal the single-domain oracle."""
+    s, res = run_ranks_nd(grid)
+    fo, fso, evo, eco, npairs = oracle.forces(s.x, s.box, s.q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_EWALD,
+                                              beta=float(np.float32(g.systems.ewald_beta(RC))))
+    assert np.array_equal(np.sort(np.concatenate([r["home"] for r in res])), np.arange(s.n))
+    keys = np.sort(np.concatenate([canonical_nd(r["pairs"], r["jshift"]) for r in res]))
+    ok = oracle.canonical_pairs(oracle.pair_set(s.x, s.box, RC, s.excl_off, s.excl_idx))
+    # images across a periodic edge arrive as x_j + box rounded to float32 (as dd_move_x sends them), where the single domain
+    # evaluates (x_i - box) - x_j: only a pair within rounding of rc^2 may flip (see the slab test above)
+    diff = np.setxor1d(keys, ok)
+    assert len(diff) <= 6
+    sv = oracle.shift_vectors(s.box).astype(np.float64)
+    for k in diff:
+        i, j, sh = int(k >> 34), int((k >> 6) & ((1 << 28) - 1)), int(k & 63)
+        assert sh != CENTRAL
+        r2 = ((s.x[i].astype(np.float64) + sv[sh] - s.x[j].astype(np.float64)) ** 2).sum()
+        assert abs(r2 - RC * RC) < 5e-6
+    assert len(keys) == len(np.unique(keys))
+    f = np.zeros((s.n, 3), np.float64)
+    for r in res:
+        assert r["nhalo"] > 0
+        f[r["home"]] = r["f"]
+    assert np.sqrt(((f - fo) ** 2).sum() / (fo ** 2).sum()) < 1e-5
+    elj, eel = sum(r["elj"] for r in res), sum(r["eel"] for r in res)
+    assert abs(elj - evo) <= 2e-4 * abs(evo)
+    assert abs(eel - eco) <= 2e-4 * abs(eco)
+
+
+@pytest.mark.parametrize("grid", ND_GRIDS)
+def test_decomposition_nd_virial(built, grid):
+    """the virial -1/2 [ sum_a x_a (x) f_a + sum_s shift_vec[s] (x) fshift[s] ] is decomposition-invariant: forces on images
+    that crossed a periodic edge enter the shift forces of the shift they were sent with (domdec.cpp:426-458)"""
+    s, res = run_ranks_nd(grid)
+    fo, fso, _, _, _ = oracle.forces(s.x, s.box, s.q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_EWALD,
+                                     beta=float(np.float32(g.systems.ewald_beta(RC))))
+    sv = oracle.shift_vectors(s.box).astype(np.float64)
+    f = np.zeros((s.n, 3), np.float64)
+    for r in res:
+        f[r["home"]] = r["f"]
+    fs = sum(r["fs"].astype(np.float64) for r in res)
+    x = s.x.astype(np.float64)
+    vir_g = -0.5 * (x.T @ f + sv.T @ fs)
+    vir_o = -0.5 * (x.T @ fo + sv.T @ fso)
+    assert np.abs(vir_g - vir_o).max() <= 1e-5 * np.abs(vir_o).max()
