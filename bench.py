@@ -320,7 +320,17 @@ def run_multi_gpu(args, rank, world, local_rank):
     coul = g.CoulombType.Pme if args.eel == "ewald" else g.CoulombType.ReactionField
     opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coul, computeVirialAndEnergy=False, device=local_rank, epsilonRf=0.0,
                             maxTilesPerEntry=args.max_tiles)
-    d = domdec.DomainRank(s, opt, domdec.TorchDistTransport(), device=local_rank)
+    if args.dd_grid:
+        # 2-D / 3-D decomposition (half-shell rule, halos through NCCL send/recv: gmxapi_b200/domdec_nd.py); --scaling strong only
+        from gmxapi_b200 import domdec_nd
+        grid = tuple(int(v) for v in args.dd_grid.lower().split("x"))
+        if len(grid) != 3 or int(np.prod(grid)) != world:
+            raise SystemExit("--dd-grid NXxNYxNZ must multiply to --gpus")
+        if args.scaling != "strong":
+            raise SystemExit("--dd-grid goes with --scaling strong")
+        d = domdec_nd.DomainRankND(s, opt, domdec.TorchDistTransport(), grid, device=local_rank)
+    else:
+        d = domdec.DomainRank(s, opt, domdec.TorchDistTransport(), device=local_rank)
     h, stream = d.nb, d.stream
     dev = torch.device("cuda", local_rank)
     cnt = torch.tensor([d.pair_count(RC), d.plan.nhome, d.plan.nhalo, h.stats()["ntiles_packed"]], dtype=torch.float64, device=dev)
@@ -388,11 +398,13 @@ def run_multi_gpu(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": ("%d x %s along x" % (world, args.workload)) if args.scaling == "weak"
-                       else "%s over %d x-slabs" % (args.workload, world), "atoms": int(natoms),
+                       else ("%s over %s domains" % (args.workload, args.dd_grid) if args.dd_grid
+                             else "%s over %d x-slabs" % (args.workload, world)), "atoms": int(natoms),
                        "useful_pairs_per_step": int(npairs), "computed_pairs_per_step": int(ntiles * 64), "rc": RC, "rlist": RC,
                        "interaction": "LJ + " + ("Ewald real space (analytical)" if args.eel == "ewald" else "reaction field"),
                        "flavor": "force only", "l2": "L2 flushed (256 MiB write) between timed steps" if not args.no_flush else "not flushed",
-                       "parallelism": "dd%dx1x1" % world, "halo_atoms_total": int(nhalo_tot),
+                       "parallelism": ("dd%s half-shell, NCCL halos" % args.dd_grid) if args.dd_grid else "dd%dx1x1" % world,
+                       "halo_atoms_total": int(nhalo_tot),
                        "halo_bytes_per_step_each_way": int(halo_bytes)},
             "roofline": {"bound": "fp32", "kernel": "k_force (local + non-local), slowest rank", "achieved": achieved, "peak": fp32_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp32_peak, "kernel_ms": k_ms, "flops_per_useful_pair": flops,
@@ -422,6 +434,7 @@ def main():
     ap.add_argument("--max-tiles", type=int, default=0, help="cluster pairs per list entry (0 = library default)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = N copies of the workload along x (default), strong = the workload itself over N slabs")
+    ap.add_argument("--dd-grid", default="", help="N > 1: decompose as NXxNYxNZ ranks (e.g. 2x2x2) instead of x slabs")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -292,12 +292,14 @@ class DomainRankND:
         self.nb.get_f(self.f.data_ptr(), on_device=True)
         self._halo_f(bool(flags & _lib.FLAG_VIRIAL))
 
-    def compute(self, x_home_host, flags=0):
+    def compute(self, x_home_host, flags=0, f_home_host=None):
         """Host coordinates of the home atoms in, (f_home, fshift[45,3], e_lj, e_el) out: this rank's share of the sums."""
         torch = self.torch
         p = self.plan
         xh = x_home_host if isinstance(x_home_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_home_host, np.float32))
-        fh = torch.empty((p.nhome, 3), dtype=torch.float32).pin_memory()
+        if f_home_host is None:
+            f_home_host = torch.empty((p.nhome, 3), dtype=torch.float32).pin_memory()
+        fh = f_home_host if isinstance(f_home_host, torch.Tensor) else torch.from_numpy(f_home_host)
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self.x[:p.nhome].copy_(xh, non_blocking=True)
             self.step(flags)
