@@ -168,8 +168,9 @@ def run_reference(args):
                       "interaction": "LJ + " + ("Ewald real space (analytical)" if args.eel == "ewald" else "reaction field"),
                       "flavor": "force only"},
            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": kind,
-                            "sample": "%d full steps (x convert + 2xMM SIMD kernel + f reduce) of %s, %d OpenMP threads; "
-                                      "kernel-only %.3f ms" % (n, args.workload, cores, tk * 1e3)},
+                            "sample": "%d full steps (x convert + 2xMM SIMD kernel + f reduce) of %s (%d atoms), %d OpenMP threads; "
+                                      "kernel-only %.3f ms" % (n, args.workload if mult <= 1 else "%d x %s" % (args.gpus, args.workload),
+                                                               int(s.n), cores, tk * 1e3)},
            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
