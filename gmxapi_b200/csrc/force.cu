@@ -352,15 +352,13 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
     }
 }
 
-/* Two plain (unmasked, force-only) tiles evaluated in lock step: every step of the arithmetic is written for both tiles
- * before the next step, so the instruction stream carries two independent dependency chains and the 4-cycle FMA, MUFU and
- * shuffle latencies of one tile are covered by the other (ncu: "wait"/"short scoreboard" stalls dominated the one-tile loop). */
 #ifndef NB_CHUNK
 #define NB_CHUNK 8 /* packed tiles per ring buffer (multiple of 4: one staging round covers 32 j-atoms) */
 #endif
-#ifndef B200NB_TILE_ILP
-#define B200NB_TILE_ILP 1 /* measured (profiles/r1/g_sweep_one_entry_per_warp.txt): 1 tile in flight at 32 warps/SM beats 2 at 20 */
-#endif
+/* NT plain (unmasked, force-only) tiles evaluated in lock step: every step of the arithmetic is written for all NT tiles
+ * before the next step, so the instruction stream carries NT independent dependency chains.  The kernel uses NT = 1: one
+ * tile in flight at 32 warps/SM beat two at 20 (profiles/r1/g_sweep_one_entry_per_warp.txt); the generality is kept because
+ * the statement order below (not the tile count) is what makes ptxas emit the packed sequence this file is tuned around. */
 template<int EEL, bool GEOM, int NT>
 __device__ __forceinline__ void tile_pairs_multi(const IData& I, const JAtom (&J)[NT], const NbParamsDev& P, const KConst& K,
                                                  const float2* __restrict__ nbfp, float2& fix, float2& fiy, float2& fiz, float (&sx)[NT],
