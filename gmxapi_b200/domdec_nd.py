@@ -58,6 +58,37 @@ class DomainPlanND:
 
     def __init__(self, x, box, grid, rank, rlist):
         x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 3)
+        self._geometry(box, grid, rank, rlist)
+        owner = self.owner_of(x, self.box, self.grid)
+        self.home = np.nonzero(owner == self.rank)[0].astype(np.int32)
+        self.recv, self.send = [], []
+        for o in self.offsets:
+            # what I receive from the neighbour at +o: its atoms near the boundary it shares with me
+            nb, shift, dst, sshift = self._peers(o)
+            nb_home = np.nonzero(owner == nb)[0].astype(np.int32)
+            sel = self.boundary_atoms(x[nb_home], self.coords_of(nb, self.grid), o)
+            self.recv.append(dict(rank=nb, offset=o, shift=shift, ids=nb_home[sel]))
+            # what I send to the rank that sees me at +o
+            self.send.append(dict(rank=dst, offset=o, shift=sshift,
+                                  local=self.boundary_atoms(x[self.home], self.coords, o).astype(np.int32)))
+        self._finish()
+
+    @classmethod
+    def from_parts(cls, box, grid, rank, rlist, home, send_locals, recv_ids):
+        """A plan assembled from what the ranks exchanged at a repartitioning step (migrate_atoms_nd): the new home set and,
+        per half-shell offset, the positions sent and the global indices received."""
+        p = cls.__new__(cls)
+        p._geometry(box, grid, rank, rlist)
+        p.home = np.ascontiguousarray(home, dtype=np.int32)
+        p.recv, p.send = [], []
+        for k, o in enumerate(p.offsets):
+            nb, shift, dst, sshift = p._peers(o)
+            p.recv.append(dict(rank=nb, offset=o, shift=shift, ids=np.ascontiguousarray(recv_ids[k], dtype=np.int32)))
+            p.send.append(dict(rank=dst, offset=o, shift=sshift, local=np.ascontiguousarray(send_locals[k], dtype=np.int32)))
+        p._finish()
+        return p
+
+    def _geometry(self, box, grid, rank, rlist):
         self.box = np.asarray(box, dtype=np.float32).reshape(3)
         self.grid = tuple(int(g) for g in grid)
         self.nranks = int(np.prod(self.grid))
@@ -74,21 +105,16 @@ class DomainPlanND:
         self.coords = self.coords_of(self.rank, self.grid)
         self.lo = np.array([self.bound(d, self.coords[d]) for d in range(3)], np.float32)
         self.hi = np.array([self.bound(d, self.coords[d] + 1) for d in range(3)], np.float32)
-        owner = self.owner_of(x, self.box, self.grid)
-        self.home = np.nonzero(owner == self.rank)[0].astype(np.int32)
         self.offsets = half_shell_offsets(self.grid)
-        self.recv, self.send = [], []
-        for o in self.offsets:
-            # what I receive from the neighbour at +o: its atoms near the boundary it shares with me
-            nb, shift = self.neighbour(self.coords, o, +1)
-            nb_home = np.nonzero(owner == nb)[0].astype(np.int32)
-            sel = self.boundary_atoms(x[nb_home], self.coords_of(nb, self.grid), o)
-            self.recv.append(dict(rank=nb, offset=o, shift=shift, ids=nb_home[sel]))
-            # what I send to the rank that sees me at +o
-            dst, _ = self.neighbour(self.coords, o, -1)
-            _, sshift = self.neighbour(self.coords_of(dst, self.grid), o, +1)
-            self.send.append(dict(rank=dst, offset=o, shift=sshift,
-                                  local=self.boundary_atoms(x[self.home], self.coords, o).astype(np.int32)))
+
+    def _peers(self, o):
+        """(rank I receive from at +o, shift of its atoms; rank that sees me at +o, shift of my atoms there)"""
+        nb, shift = self.neighbour(self.coords, o, +1)
+        dst, _ = self.neighbour(self.coords, o, -1)
+        _, sshift = self.neighbour(self.coords_of(dst, self.grid), o, +1)
+        return nb, shift, dst, sshift
+
+    def _finish(self):
         self.halo = (np.concatenate([r["ids"] for r in self.recv]) if self.recv else np.zeros(0, np.int32)).astype(np.int32)
         if len(np.unique(self.halo)) != len(self.halo):
             raise InputException("an atom would be imported twice (domain too thin for its number of ranks)")
@@ -169,6 +195,72 @@ class DomainPlanND:
         return lo, hi
 
 
+def migrate_atoms_nd(t, box, grid, rank, rlist, home, x_home, to_tensor=None):
+    """One repartitioning step of the N-D decomposition (dd_partition_system, domdec/partition.cpp; dd_redistribute_cg,
+    domdec/redistribute.cpp), collective over the ranks of transport `t`: coordinates are wrapped into the box, atoms whose
+    coordinates now lie in another domain go to its owner (at most one domain away per dimension, as in the reference), and
+    every rank tells each rank that sees it at a half-shell offset which of its atoms lie near the shared boundary.
+    Returns (home ascending, x_home, send_locals[k], recv_ids[k]) with k running over half_shell_offsets(grid) -- the pieces of
+    DomainPlanND.from_parts, equal to what DomainPlanND computes from the global coordinates."""
+    import torch
+    from .domdec import wrap_into_box
+    if to_tensor is None:
+        to_tensor = torch.from_numpy
+    geo = DomainPlanND.__new__(DomainPlanND)
+    geo._geometry(box, grid, rank, rlist)
+    home = np.ascontiguousarray(home, dtype=np.int32)
+    x = wrap_into_box(x_home, geo.box)
+    owner = DomainPlanND.owner_of(x, geo.box, geo.grid)
+    stay = owner == rank
+    # destination must be a neighbour domain: per dimension the same cell or the next one (periodically)
+    for d in range(3):
+        n = geo.grid[d]
+        cd = np.array([DomainPlanND.coords_of(int(o), geo.grid)[d] for o in np.unique(owner)])
+        dist = np.minimum((cd - geo.coords[d]) % n, (geo.coords[d] - cd) % n)
+        if np.any(dist > 1):
+            raise InputException("an atom moved more than one domain between two repartitioning steps")
+
+    def pack(mask):
+        m = np.nonzero(mask)[0]
+        buf = np.empty((len(m), 4), np.int32)
+        buf[:, 0] = home[m]
+        buf[:, 1:] = x[m].view(np.int32)
+        return buf
+
+    dests = [int(r) for r in np.unique(owner[~stay])]
+    out = {r: pack(owner == r) for r in dests}
+    counts = t.allgather_object({r: len(b) for r, b in out.items()})
+    srcs = [r for r in range(geo.nranks) if r != rank and counts[r].get(rank, 0) > 0]
+    inb = {r: np.empty((counts[r][rank], 4), np.int32) for r in srcs}
+
+    def exchange(send_list, recv_list):
+        sends = [(to_tensor(np.ascontiguousarray(a)), dst) for a, dst in send_list if len(a)]
+        recvs = [(to_tensor(a), src) for a, src in recv_list if len(a)]
+        t.exchange(sends, recvs)
+        k = 0
+        for a, src in recv_list:
+            if len(a):
+                a[...] = recvs[k][0].cpu().numpy()
+                k += 1
+
+    exchange([(out[r], r) for r in sorted(out)], [(inb[r], r) for r in sorted(inb)])
+    arrived = np.concatenate([inb[r] for r in sorted(inb)]) if inb else np.zeros((0, 4), np.int32)
+    ids = np.concatenate([home[stay], arrived[:, 0]]).astype(np.int32)
+    xs = np.concatenate([x[stay], arrived[:, 1:].copy().view(np.float32)]).astype(np.float32)
+    order = np.argsort(ids, kind="stable")
+    home_new, x_new = ids[order], np.ascontiguousarray(xs[order])
+    if len(home_new) and not np.all(DomainPlanND.owner_of(x_new, geo.box, geo.grid) == rank):
+        raise InputException("repartitioning left an atom outside its new owner's domain")
+    # the new halo: per half-shell offset, my boundary atoms go to the rank that sees me there; sizes first
+    send_locals = [geo.boundary_atoms(x_new, geo.coords, o).astype(np.int32) for o in geo.offsets]
+    peers = [geo._peers(o) for o in geo.offsets]
+    nsend = t.allgather_object([int(len(sl)) for sl in send_locals])
+    recv_ids = [np.empty(nsend[nb][k], np.int32) for k, (nb, _, _, _) in enumerate(peers)]
+    exchange([(home_new[sl], dst) for sl, (_, _, dst, _) in zip(send_locals, peers)],
+             [(buf, nb) for buf, (nb, _, _, _) in zip(recv_ids, peers)])
+    return home_new, x_new, send_locals, recv_ids
+
+
 class DomainRankND:
     """One rank of the 1-D / 2-D / 3-D decomposed calculation: schedule of do_force() restricted to the nonbonded path,
 
@@ -194,16 +286,25 @@ class DomainRankND:
         if hasattr(transport, "sync"):
             transport.sync = self.nb.synchronize
         configure_interactions(self.nb, system.nbfp, options, self.rlist)
-        types, q, eo, ei = p.local_topology(system.types, system.q, system.excl_off, system.excl_idx)
-        self.nb.set_atoms(types, q, eo, ei)
+        # the topology is global and replicated on every rank; ownership is what moves (repartition)
+        self.topology = (np.asarray(system.types), np.asarray(system.q), np.asarray(system.excl_off), np.asarray(system.excl_idx))
         # periodic images only along dimensions that are not decomposed: across the others the images arrive as halo atoms
         self.nb.set_box(system.box, pbc=tuple(1 if g == 1 else 0 for g in p.grid))
+        self.fshift_halo = np.zeros((_lib.SHIFTS, 3), np.float64)
+        self._setup_local(np.ascontiguousarray(system.x[p.home]))
+
+    def _setup_local(self, x_home):
+        """(re)build everything that depends on which atoms this rank owns and receives"""
+        torch = self.torch
+        p = self.plan
+        types, q, eo, ei = p.local_topology(*self.topology)
+        self.nb.set_atoms(types, q, eo, ei)
         self.nlocal = p.nhome + p.nhalo
         box = p.box
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self.x = torch.zeros((self.nlocal, 3), dtype=torch.float32, device=self.device)
             self.f = torch.zeros((self.nlocal, 3), dtype=torch.float32, device=self.device)
-            self.x[:p.nhome].copy_(torch.from_numpy(np.ascontiguousarray(system.x[p.home])))
+            self.x[:p.nhome].copy_(torch.from_numpy(np.ascontiguousarray(x_home, dtype=np.float32)))
             self.send_idx = [torch.from_numpy(s["local"]).to(self.device) for s in p.send]
             self.send_buf = [torch.zeros((len(s["local"]), 3), dtype=torch.float32, device=self.device) for s in p.send]
             self.recv_f = [torch.zeros((len(s["local"]), 3), dtype=torch.float32, device=self.device) for s in p.send]
@@ -214,8 +315,21 @@ class DomainRankND:
             self.recv_range.append((off, off + len(r["ids"])))
             off += len(r["ids"])
         self.nb.synchronize()
-        self.fshift_halo = np.zeros((_lib.SHIFTS, 3), np.float64)
         self.search()
+
+    def repartition(self):
+        """Pair-search step with atom migration: the current coordinates of the home atoms (self.x[:nhome], on the device)
+        decide the new owners; halo lists, grids and pair list are rebuilt.  Collective.  Returns the new plan."""
+        torch = self.torch
+        p = self.plan
+        self.nb.synchronize()
+        x_home = self.x[:p.nhome].cpu().numpy()
+        to_dev = lambda a: torch.from_numpy(a).to(self.device)
+        home, x_new, send_locals, recv_ids = migrate_atoms_nd(self.t, p.box, p.grid, self.rank, self.rlist, p.home, x_home,
+                                                              to_tensor=to_dev)
+        self.plan = DomainPlanND.from_parts(p.box, p.grid, self.rank, self.rlist, home, send_locals, recv_ids)
+        self._setup_local(x_new)
+        return self.plan
 
     def search(self):
         p = self.plan

@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 
 from gmxapi_b200 import systems as S
 from gmxapi_b200.domdec import DomainPlan, TorchDistTransport, migrate_atoms, wrap_into_box
-from gmxapi_b200.domdec_nd import DomainPlanND, half_shell_offsets
+from gmxapi_b200.domdec_nd import DomainPlanND, half_shell_offsets, migrate_atoms_nd
 
 RLIST = 0.9
 
@@ -330,3 +330,49 @@ def test_halo_exchange_nd_gloo(grid):
         assert p.exitcode == 0
     for rank, ok_x, ok_f, nhalo in res:
         assert ok_x and ok_f and nhalo > 0, (rank, ok_x, ok_f, nhalo)
+
+
+def _migrate_nd_worker(rank, world, port, q, grid):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        s = S.water_box(8, 6, 6, seed=9)
+        r = 0.45
+        t = TorchDistTransport()
+        plan0 = DomainPlanND(s.x, s.box, grid, rank, r)
+        x1 = _moved(s, seed=13, amp=0.3)  # the same displaced coordinates on every rank; atoms cross faces, edges and the box
+        home, xh, send_locals, recv_ids = migrate_atoms_nd(t, s.box, grid, rank, r, plan0.home, x1[plan0.home])
+        x1w = wrap_into_box(x1, s.box)
+        exp = DomainPlanND(x1w, s.box, grid, rank, r)  # what a plan made from the global coordinates says
+        ok = np.array_equal(home, exp.home) and np.array_equal(xh, x1w[exp.home])
+        ok = ok and all(np.array_equal(a, b["local"]) for a, b in zip(send_locals, exp.send))
+        ok = ok and all(np.array_equal(a, b["ids"]) for a, b in zip(recv_ids, exp.recv))
+        plan1 = DomainPlanND.from_parts(s.box, grid, rank, r, home, send_locals, recv_ids)
+        ok = ok and np.array_equal(plan1.local, exp.local) and np.array_equal(plan1.halo_x(x1w), exp.halo_x(x1w))
+        ok = ok and all(a["rank"] == b["rank"] and np.array_equal(a["shift"], b["shift"]) for a, b in zip(plan1.send + plan1.recv, exp.send + exp.recv))
+        moved = int(len(np.setdiff1d(home, plan0.home)))
+        h2, x2, s2, r2 = migrate_atoms_nd(t, s.box, grid, rank, r, home, xh)  # no motion: nothing changes
+        ok = ok and np.array_equal(h2, home) and np.array_equal(x2, xh) and all(np.array_equal(a, b) for a, b in zip(s2 + r2, send_locals + recv_ids))
+        tot = t.allreduce_sum(torch.tensor([float(len(home))]))
+        q.put((rank, bool(ok), moved, int(tot.item()) == s.n))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("grid", [(2, 2, 1), (2, 2, 2)])
+def test_repartition_nd_migrates_atoms_gloo(grid):
+    """repartitioning of the N-D decomposition: leavers go to up to 26 neighbour domains, the half-shell halo lists are
+    rebuilt by exchange -- every rank ends with exactly the plan the global coordinates give"""
+    world = int(np.prod(grid))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_migrate_nd_worker, args=(r, world, port, q, grid)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, moved, ok_n in res:
+        assert ok and ok_n and moved > 0, (rank, ok, moved, ok_n)

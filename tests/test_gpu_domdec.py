@@ -290,3 +290,56 @@ def test_decomposition_nd_virial(built, grid):
     vir_g = -0.5 * (x.T @ f + sv.T @ fs)
     vir_o = -0.5 * (x.T @ fo + sv.T @ fso)
     assert np.abs(vir_g - vir_o).max() <= 1e-5 * np.abs(vir_o).max()
+
+
+def test_repartition_nd_after_motion(built):
+    """repartitioning of the 2 x 2 decomposition after a rigid translation across faces, an edge and the box boundary"""
+    from gmxapi_b200.domdec import wrap_into_box
+    from gmxapi_b200.domdec_nd import DomainRankND
+    grid = (2, 2, 1)
+    s = g.systems.named("water_24k")
+    rng = np.random.Generator(np.random.PCG64(29))
+    x1 = (s.x + np.array([0.43, -0.37, 0.21], np.float32) + rng.uniform(-0.01, 0.01, s.x.shape)).astype(np.float32)
+    x1w = wrap_into_box(x1, s.box)
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, computeVirialAndEnergy=True)
+    flags = nb.FLAG_ENERGY | nb.FLAG_VIRIAL
+    nranks = int(np.prod(grid))
+    hub = LoopbackTransport(nranks)
+    out, err = [None] * nranks, []
+
+    def work(r):
+        try:
+            import torch
+            d = DomainRankND(s, opt, hub.endpoint(r), grid, rank=r, device=0)
+            d.compute(np.ascontiguousarray(s.x[d.plan.home]), flags)
+            old_home = d.plan.home.copy()
+            d.x[:d.plan.nhome].copy_(torch.from_numpy(np.ascontiguousarray(x1[old_home])))
+            plan = d.repartition()
+            assert len(np.setdiff1d(plan.home, old_home)) > 0
+            f, fs, elj, eel = d.compute(np.ascontiguousarray(x1w[plan.home]), flags)
+            out[r] = dict(home=plan.home, f=f.numpy().copy(), elj=elj, eel=eel)
+            hub.endpoint(r).barrier()
+            d.close()
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            err.append((r, repr(e), traceback.format_exc()))
+            try:
+                hub._bar.abort()
+            except Exception:
+                pass
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert not err, err
+    fo, _, evo, eco, _ = oracle.forces(x1w, s.box, s.q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_EWALD,
+                                       beta=float(np.float32(g.systems.ewald_beta(RC))))
+    assert np.array_equal(np.sort(np.concatenate([r["home"] for r in out])), np.arange(s.n))
+    f = np.zeros((s.n, 3), np.float64)
+    for r in out:
+        f[r["home"]] = r["f"]
+    assert np.sqrt(((f - fo) ** 2).sum() / (fo ** 2).sum()) < 1e-5
+    assert abs(sum(r["elj"] for r in out) - evo) <= 2e-4 * abs(evo)
+    assert abs(sum(r["eel"] for r in out) - eco) <= 2e-4 * abs(eco)
