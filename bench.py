@@ -124,6 +124,16 @@ def ref_instance(s, eel, nthreads):
                            nthreads=nthreads, **kw)
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:  # noqa: BLE001
+        pass
+    return "unknown CPU"
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -168,9 +178,9 @@ def run_reference(args):
                       "interaction": "LJ + " + ("Ewald real space (analytical)" if args.eel == "ewald" else "reaction field"),
                       "flavor": "force only"},
            "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": kind,
-                            "sample": "%d full steps (x convert + 2xMM SIMD kernel + f reduce) of %s (%d atoms), %d OpenMP threads; "
+                            "sample": "%d full steps (x convert + 2xMM SIMD kernel + f reduce) of %s (%d atoms), %d OpenMP threads of %s; "
                                       "kernel-only %.3f ms" % (n, args.workload if mult <= 1 else "%d x %s" % (args.gpus, args.workload),
-                                                               int(s.n), cores, tk * 1e3)},
+                                                               int(s.n), cores, cpu_model(), tk * 1e3)},
            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -264,8 +274,8 @@ def run_gpu(args):
             cores = host_cores()
             t, tk, n = time_reference(s, args.eel, cores, 2000, 3, budget_s=15.0)
             cpu = {"value": npairs / t, "unit": "pairs/s", "cores": cores, "kind": "reference",
-                   "sample": "%d full steps of %s on %d OpenMP threads (x convert + 2xMM SIMD kernel + f reduce), "
-                             "%.3f ms/step; kernel alone %.3f ms" % (n, args.workload, cores, t * 1e3, tk * 1e3)}
+                   "sample": "%d full steps of %s on %d OpenMP threads of %s (x convert + 2xMM SIMD kernel + f reduce), "
+                             "%.3f ms/step; kernel alone %.3f ms" % (n, args.workload, cores, cpu_model(), t * 1e3, tk * 1e3)}
         except Exception as e:  # the checker library is optional for the GPU numbers
             cpu = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
 
