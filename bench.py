@@ -50,8 +50,9 @@ class ClockSampler:
     2 ms from a background thread: the timed loops of the small workloads last only milliseconds, far below the start-up
     time of an `nvidia-smi -lms` child process."""
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, power=False):
         self.index, self.sm, self.mx, self.reasons, self.err = index, [], [], set(), None
+        self.power, self.watts = power, []
         self._stop = threading.Event()
         self._t = None
 
@@ -78,6 +79,8 @@ class ClockSampler:
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
                 self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                if self.power:
+                    self.watts.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
                 for bit, name in names.items():
                     if r & bit:
@@ -93,8 +96,63 @@ class ClockSampler:
             self._t.join(timeout=2)
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: %s" % self.err], "samples": 0}
-        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
-                "samples": len(self.sm)}
+        out = {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
+               "samples": len(self.sm)}
+        if self.power and self.watts:
+            out.update(sm_mhz_min=float(np.min(self.sm)), power_w_median=float(np.median(self.watts)), power_w_max=float(np.max(self.watts)))
+        return out
+
+
+def sustained_block(h, s, npairs, seconds=2.0, flops_per_pair=66, device=0):
+    """the burst figure (`value`: 20-200 flushed steps, a few ms of GPU time) says nothing about the SM clock
+    a seconds-long MD run of this FP32-bound kernel holds.  Here: >= `seconds` of back-to-back device-resident steps (CUDA graph
+    replays, no L2 flush, no host synchronisation inside a batch), NVML sampled every 2 ms on a side thread: median SM clock,
+    throttle reasons, power; pairs/s over the whole interval (CUDA events) and the FP32 peak AT THE MEASURED MEDIAN CLOCK."""
+    import torch
+    dev = torch.device("cuda", device)
+    x_dev = torch.from_numpy(s.x).to(dev).contiguous()
+    f_dev = torch.zeros_like(x_dev)
+    stream = torch.cuda.Stream(device=dev)
+    h.set_stream(stream.cuda_stream)
+    xp, fp = x_dev.data_ptr(), f_dev.data_ptr()
+    for _ in range(20):
+        h.step(xp, fp, 0)
+    h.synchronize()
+    # batch size: ~20 ms of queued work per host synchronisation
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(50):
+        h.step(xp, fp, 0)
+    e1.record(stream)
+    h.synchronize()
+    t1 = e0.elapsed_time(e1) / 50.0  # ms per step
+    batch = max(10, int(20.0 / max(t1, 1e-3)))
+    sampler = ClockSampler(device, power=True)
+    sampler.start()
+    n = 0
+    t_wall = time.perf_counter()
+    e0.record(stream)
+    prev = None
+    while time.perf_counter() - t_wall < seconds:
+        for _ in range(batch):
+            h.step(xp, fp, 0)
+        n += batch
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        if prev is not None:
+            prev.synchronize()  # at most two batches queued: the GPU never runs dry, the host never runs away
+        prev = ev
+    e1.record(stream)
+    h.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    mhz = clocks.get("sm_mhz") or 0.0
+    peak = 148 * 128 * 2 * mhz * 1e6 / 1e12 if mhz else None
+    pps = npairs * n / (ms * 1e-3)
+    return {"seconds": ms * 1e-3, "steps": n, "ms_per_step": ms / n, "pairs_per_s": pps, "clocks": clocks,
+            "fp32_peak_at_median_clock_tflops": peak,
+            "step_algorithmic_frac_at_median_clock": (pps * flops_per_pair / 1e12 / peak) if peak else None,
+            "note": "back-to-back graph replays of the device-resident step, L2 warm, two batches of %d steps in flight" % batch}
 
 
 def ncu_capture(workload, eel):

@@ -122,7 +122,7 @@ extern "C" void b200nb_destroy(b200nb_t* h)
         cudaFree(h->packed[l].ja);
         cudaFree(h->packed[l].mask);
     }
-    for (int side = 0; side < 2; side++)
+    for (int side = 0; side < NB_DD_MAX_PEERS; side++)
         if (h->dd.peer[side] && h->dd.peer_is_ipc[side]) cudaIpcCloseMemHandle(h->dd.peer[side]);
     for (auto& G : h->graph)
         if (G.exec) cudaGraphExecDestroy(G.exec);
@@ -135,8 +135,11 @@ extern "C" void b200nb_destroy(b200nb_t* h)
     }
     cudaFree(h->dd.window);
     cudaFree(h->dd.d_count);
-    cudaFree(h->dd.d_send_idx);
-    cudaFree(h->dd.d_send_pos);
+    cudaFree(h->dd.d_send_atom);
+    cudaFree(h->dd.d_send_link);
+    cudaFree(h->dd.d_ent_off);
+    cudaFree(h->dd.d_ent_idx);
+    cudaFree(h->dd.d_halo_link);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -379,6 +382,19 @@ extern "C" int b200nb_set_box(b200nb_t* h, const float box[3], const int pbc_dim
                 h->h_shift_vec[3 * n + 2] = m * box[2];
             }
     NB_CUDA(h, cudaMemcpy(h->d_shift_vec, h->h_shift_vec, sizeof(h->h_shift_vec), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+/* gpu_upload_shiftvec (cuda/nbnxm_cuda_data_mgmt.cu:283-295): the 45 shift vectors as the caller computed them (nbat->shift_vec =
+ * calc_shifts(box)), for callers that grid and search themselves (b200nb_upload_pairlist): any box shape the reference's
+ * list was built for.  b200nb_set_box remains the call for the device search (rectangular boxes). */
+extern "C" int b200nb_set_shift_vec(b200nb_t* h, const float* shift_vec_host)
+{
+    if (!h || !shift_vec_host) return nb_fail(h, B200NB_ERR_ARG, "set_shift_vec: bad argument");
+    cudaSetDevice(h->device);
+    memcpy(h->h_shift_vec, shift_vec_host, sizeof(h->h_shift_vec));
+    NB_CUDA(h, cudaMemcpyAsync(h->d_shift_vec, h->h_shift_vec, sizeof(h->h_shift_vec), cudaMemcpyHostToDevice, h->stream));
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -670,6 +686,12 @@ extern "C" int b200nb_put_on_grid(b200nb_t* h, int gi, const float lower[3], con
     if (atom_begin < 0 || atom_end > h->natoms || atom_begin > atom_end) return nb_fail(h, B200NB_ERR_ARG, "put_on_grid: bad atom range");
     if (gi == 1 && !h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "put_on_grid: grid 0 must be set before grid 1");
     cudaSetDevice(h->device);
+    if (h->grid_uploaded)
+    {
+        /* back from the reference-built grid (b200nb_set_grid_atoms): its slot arrays lack the search data, reallocate all */
+        h->grid_uploaded = false;
+        h->cap_pad       = 0;
+    }
     const int n = atom_end - atom_begin;
     for (int d = 0; d < 3; d++)
         if (!(upper[d] > lower[d])) return nb_fail(h, B200NB_ERR_ARG, "put_on_grid: upper <= lower");
@@ -1127,10 +1149,13 @@ k_prune(const Entry* __restrict__ oe, const int* __restrict__ ocj, const uint64_
 }
 
 /* Re-pack entries of the cluster-pair list at j-atom granularity for the force kernel (PackedList, b200nb_internal.h).
- * One warp per entry, lane = jl + 8*ih as everywhere.  A j-atom is kept iff one of its pairs with the entry's 8 i-atoms has
+ * One warp per entry, lane = jl + 8*ih as in the search.  A j-atom is kept iff one of its pairs with the entry's 8 i-atoms has
  * r^2 < rlist2 and is not removed by the j > i rule of the self tile; kept j-atoms that have an excluded pair (or belong to
- * the self tile) are placed first so that only the leading tiles need masks.  Excluded pairs inside the cut-off must stay:
- * the kernels evaluate their Ewald / reaction-field exclusion correction (kernel_inner.h:330-360).
+ * the self tile) are placed first so that only the leading STEPS (16 j-atoms = 2 packed tiles, what the force kernel consumes
+ * per iteration) need masks.  Mask format of a step: 4 words; bit (j16 + 16*half) of word k says pair (i-atom 4*half + k,
+ * j-atom j16 of the step) interacts -- the force kernel's lane j16 + 16*half reads its own bit of each word.
+ * Excluded pairs inside the cut-off must stay: the kernels evaluate their Ewald / reaction-field exclusion correction
+ * (kernel_inner.h:330-360).  The j list of an entry is padded to a whole number of steps with far-away dummy atoms.
  * The reference has no such step: its GPU list stays at 8x8 cluster-pair granularity with per-pair masks
  * (nbnxm/pairlist.h:190-225); this is the same pruning idea as nbnxn_kernel_prune_cuda taken down to single j-atoms. */
 __global__ void __launch_bounds__(128)
@@ -1138,8 +1163,8 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
        int nparts, const float* __restrict__ xq, const float* __restrict__ shift_vec, float rlist2, int intra, int dummy_slot, int pitch,
        const int* __restrict__ dest, int* __restrict__ sizes, Entry* __restrict__ pe, int* __restrict__ pja, uint64_t* __restrict__ pmask)
 {
-    __shared__ int      s_ja[4][NB_MAX_ENTRY_TILES * 8];
-    __shared__ unsigned s_m0[4][NB_MAX_ENTRY_TILES], s_m1[4][NB_MAX_ENTRY_TILES];
+    __shared__ int      s_ja[4][NB_MAX_ENTRY_TILES * 8 + 16];
+    __shared__ unsigned s_m[4][NB_MAX_ENTRY_TILES * 2 + 4]; /* 4 words per step of 16 j-atoms */
     const int       w   = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * 4 + w;
     const long long e   = wid * nparts + part;
@@ -1148,17 +1173,15 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
     const Entry en   = ie[e];
     const int   shift = NB_ENTRY_SHIFT(en.shift_nmask), nmask = NB_ENTRY_NMASK(en.shift_nmask);
     const int   ntile = min(en.end - en.start, NB_MAX_ENTRY_TILES);
-    for (int k = lane; k < ntile * 8; k += 32) s_ja[w][k] = dummy_slot + (int)(e & (NB_DUMMY_SLOTS / 8 - 1)) * 8 + (k & 7);
-    for (int k = lane; k < NB_MAX_ENTRY_TILES; k += 32)
-    {
-        s_m0[w][k] = 0u;
-        s_m1[w][k] = 0u;
-    }
+    for (int k = lane; k < ntile * 8 + 16; k += 32) s_ja[w][k] = dummy_slot + (int)(e & (NB_DUMMY_SLOTS / 16 - 1)) * 16 + (k & 15);
+    for (int k = lane; k < NB_MAX_ENTRY_TILES * 2 + 4; k += 32) s_m[w][k] = 0u;
     __syncwarp();
     const float4 xa = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + 2 * ih];
     const float4 xb = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + 2 * ih + 1];
     const float  sx = shift_vec[3 * shift], sy = shift_vec[3 * shift + 1], sz = shift_vec[3 * shift + 2];
     const float  xi0 = xa.x + sx, yi0 = xa.y + sy, zi0 = xa.z + sz, xi1 = xb.x + sx, yi1 = xb.y + sy, zi1 = xb.z + sz;
+    /* where this lane's two pairs (i-atoms 2*ih, 2*ih+1) live in the step masks */
+    const int mword = 2 * (ih & 1), mhalf = 16 * (ih >> 1);
     int n = 0, nm = 0, has_self = 0;
     for (int pass = 0; pass < 2; pass++)
     {
@@ -1182,16 +1205,17 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
             {
                 const int pos = n + __popc(sel & ((1u << jl) - 1u));
                 if (ih == 0) s_ja[w][pos] = cj * 8 + jl;
-                const int dl = (pos & 7) + 8 * ih;
-                atomicOr(&s_m0[w][pos >> 3], ba << dl);
-                atomicOr(&s_m1[w][pos >> 3], bb << dl);
+                const int bit = (pos & 15) + mhalf;
+                atomicOr(&s_m[w][(pos >> 4) * 4 + mword], ba << bit);
+                atomicOr(&s_m[w][(pos >> 4) * 4 + mword + 1], bb << bit);
             }
             n += __popc(sel);
         }
         if (pass == 0) nm = n;
     }
     __syncwarp();
-    const int ntp = (n + 7) >> 3, nmt = (nm + 7) >> 3;
+    const int nsp = (n + 15) >> 4, nms = (nm + 15) >> 4; /* steps, masked steps */
+    const int ntp = 2 * nsp;                             /* packed tiles of 8 j-atoms */
     if (sizes)
     {
         /* first pass of a full pack: only the packed size, from which the size-sorted positions `dest` are made */
@@ -1201,12 +1225,13 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
     const long long d  = dest ? dest[e] : e; /* position of this entry in the packed list (largest entries first) */
     const long long t0 = d * pitch;          /* packed entry d owns tiles [d*pitch, (d+1)*pitch) */
     for (int k = lane; k < ntp * 8; k += 32) pja[(size_t)t0 * 8 + k] = s_ja[w][k];
-    for (int k = lane; k < ntp; k += 32) pmask[t0 + k] = k < nmt ? (((uint64_t)s_m1[w][k] << 32) | s_m0[w][k]) : ~0ull;
+    unsigned* const pm = reinterpret_cast<unsigned*>(pmask + t0);
+    for (int k = lane; k < nsp * 4; k += 32) pm[k] = k < nms * 4 ? s_m[w][k] : ~0u;
     if (lane == 0)
     {
         Entry o;
         o.ci          = en.ci;
-        o.shift_nmask = shift | (nmt << 8) | (has_self << 24);
+        o.shift_nmask = shift | (nms << 8) | (has_self << 24); /* packed list: the mask count is in STEPS */
         o.start       = (int)t0;
         o.end         = (int)t0 + ntp;
         pe[d]         = o;
@@ -1278,7 +1303,7 @@ static int launch_pack(b200nb_context* h, int loc, int part, int nparts)
     const PairList& I = h->inner[loc];
     PackedList&     P = h->packed[loc];
     P.nentries        = I.nentries;
-    P.pitch           = h->max_tiles;
+    P.pitch           = (h->max_tiles + 1) & ~1; /* whole steps of 16 j-atoms = 2 tiles */
     if (I.nentries == 0) return 0;
     if ((size_t)I.nentries * P.pitch > 2000000000ull) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: packed list exceeds 2^31 tiles");
     if (ensure_packed(h, P, I.cap_entries * P.pitch, I.cap_entries)) return B200NB_ERR_CUDA;
@@ -1346,6 +1371,26 @@ static int launch_prune(b200nb_context* h, int loc, int part, int nparts)
     return 0;
 }
 
+/* the far-away dummy atoms the packed list pads its last tiles with: NB_DUMMY_SLOTS slots past the grids */
+static int write_dummy_atoms(b200nb_context* h)
+{
+    if ((size_t)h->npad + NB_DUMMY_SLOTS > h->cap_pad) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: no room for the dummy atoms");
+    h->dummy_slot = h->npad;
+    std::vector<float> dxq(4 * NB_DUMMY_SLOTS), dlj(2 * NB_DUMMY_SLOTS, 0.0f);
+    std::vector<int>   dty(NB_DUMMY_SLOTS, h->dp.ntypes - 1);
+    for (int k = 0; k < NB_DUMMY_SLOTS; k++)
+    {
+        dxq[4 * k] = dxq[4 * k + 1] = -3.0e6f;
+        dxq[4 * k + 2]              = -3.0e6f - 64.0f * k;
+        dxq[4 * k + 3]              = 0.0f;
+    }
+    NB_CUDA(h, cudaMemcpyAsync(h->d_xq + 4 * (size_t)h->npad, dxq.data(), sizeof(float) * dxq.size(), cudaMemcpyHostToDevice, h->stream));
+    NB_CUDA(h, cudaMemcpyAsync(h->d_lj + 2 * (size_t)h->npad, dlj.data(), sizeof(float) * dlj.size(), cudaMemcpyHostToDevice, h->stream));
+    NB_CUDA(h, cudaMemcpyAsync(h->d_atype + (size_t)h->npad, dty.data(), sizeof(int) * dty.size(), cudaMemcpyHostToDevice, h->stream));
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 extern "C" int b200nb_build_pairlist(b200nb_t* h)
 {
     if (!h) return B200NB_ERR_ARG;
@@ -1389,7 +1434,11 @@ extern "C" int b200nb_build_pairlist(b200nb_t* h)
         L.ntiles = L.nentries = 0;
         if (loc == 1 && !h->grid[1].valid)
         {
+            /* no halo grid (any more): the non-local lists of an earlier search must not survive -- the packed one would be
+             * re-packed against the new gridding and run by b200nb_launch_force(-1) / b200nb_dd_step */
             if (want_inner) h->inner[1].ntiles = h->inner[1].nentries = 0;
+            else h->inner[1] = L;
+            h->packed[1].nentries = 0;
             continue;
         }
         SearchArgs A;
@@ -1445,28 +1494,258 @@ extern "C" int b200nb_build_pairlist(b200nb_t* h)
             h->inner[loc] = L;
         }
     }
-    {
-        /* the far-away dummy atoms the packed list pads its last tiles with: NB_DUMMY_SLOTS slots past the grids */
-        if ((size_t)h->npad + NB_DUMMY_SLOTS > h->cap_pad) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: no room for the dummy atoms");
-        h->dummy_slot = h->npad;
-        std::vector<float> dxq(4 * NB_DUMMY_SLOTS), dlj(2 * NB_DUMMY_SLOTS, 0.0f);
-        std::vector<int>   dty(NB_DUMMY_SLOTS, h->dp.ntypes - 1);
-        for (int k = 0; k < NB_DUMMY_SLOTS; k++)
-        {
-            dxq[4 * k] = dxq[4 * k + 1] = -3.0e6f;
-            dxq[4 * k + 2]              = -3.0e6f - 64.0f * k;
-            dxq[4 * k + 3]              = 0.0f;
-        }
-        NB_CUDA(h, cudaMemcpyAsync(h->d_xq + 4 * (size_t)h->npad, dxq.data(), sizeof(float) * dxq.size(), cudaMemcpyHostToDevice, h->stream));
-        NB_CUDA(h, cudaMemcpyAsync(h->d_lj + 2 * (size_t)h->npad, dlj.data(), sizeof(float) * dlj.size(), cudaMemcpyHostToDevice, h->stream));
-        NB_CUDA(h, cudaMemcpyAsync(h->d_atype + (size_t)h->npad, dty.data(), sizeof(int) * dty.size(), cudaMemcpyHostToDevice, h->stream));
-        NB_CUDA(h, cudaStreamSynchronize(h->stream));
-    }
+    if (int rc = write_dummy_atoms(h)) return rc;
     for (int loc = 0; loc < 2; loc++)
         if (launch_pack(h, loc, 0, 1)) return B200NB_ERR_CUDA;
     NB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->have_list = true;
     h->generation++;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* reference-built grid and pair list (the drop-in path behind Nbnxm::gpu_*, shim/nbnxm_b200.cpp)          */
+/* ------------------------------------------------------------------------------------------------------ */
+/* With mdrun / nblib in front, gridding and pair search stay where the reference does them for its CUDA backend -- on the
+ * CPU (nbnxn_put_on_grid, PairlistSet::constructPairlists) -- and the backend receives the finished products: the atom
+ * data in grid order (gpu_init_atomdata, nbnxm_gpu_data_mgmt.cpp) and the 8x8x8 super-cluster list (gpu_init_pairlist,
+ * nbnxm_gpu_data_mgmt.cpp:251-311).  These entry points take exactly those, so the reference needs no patched call site. */
+
+/* gpu_init_atomdata: nslots = nbat->numAtoms() (a multiple of 8), xq_host = nbat->x() in nbatXYZQ format (4 floats per slot,
+ * atomdata.cpp:659-662), type_host = nbat->params().type (filler slots carry the extra zero-parameter type ntypes, atomdata.cpp:456) */
+extern "C" int b200nb_set_grid_atoms(b200nb_t* h, int nslots, const float* xq_host, const int* type_host)
+{
+    if (!h || nslots < 8 || (nslots & 7) || !xq_host || !type_host) return nb_fail(h, B200NB_ERR_ARG, "set_grid_atoms: bad argument");
+    if (!h->have_params) return nb_fail(h, B200NB_ERR_STATE, "set_grid_atoms: set_params first");
+    cudaSetDevice(h->device);
+    const int ntf = h->dp.ntypes;
+    std::vector<float> ljv((size_t)nslots * 2);
+    for (int s = 0; s < nslots; s++)
+    {
+        const int t = type_host[s];
+        if (t < 0 || t >= ntf) return nb_fail(h, B200NB_ERR_ARG, "set_grid_atoms: atom type out of range");
+        ljv[2 * (size_t)s]     = std::sqrt(h->nbfp_host[((size_t)t * ntf + t) * 2]);
+        ljv[2 * (size_t)s + 1] = std::sqrt(h->nbfp_host[((size_t)t * ntf + t) * 2 + 1]);
+    }
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if ((size_t)nslots + NB_DUMMY_SLOTS > h->cap_pad)
+    {
+        const size_t cap = ((size_t)(nslots * 1.15) + NB_DUMMY_SLOTS + 1024 + 63) / 64 * 64;
+        cudaFree(h->d_xq), cudaFree(h->d_lj), cudaFree(h->d_atype), cudaFree(h->d_f), cudaFree(h->d_atom_index);
+        h->d_xq = h->d_lj = nullptr, h->d_atype = h->d_atom_index = nullptr, h->d_f = nullptr;
+        h->cap_pad = 0;
+        NB_CUDA(h, cudaMalloc((void**)&h->d_xq, cap * 4 * sizeof(float)));
+        NB_CUDA(h, cudaMalloc((void**)&h->d_lj, cap * 2 * sizeof(float)));
+        NB_CUDA(h, cudaMalloc((void**)&h->d_atype, cap * sizeof(int)));
+        NB_CUDA(h, cudaMalloc((void**)&h->d_atom_index, cap * sizeof(int)));
+        NB_CUDA(h, cudaMalloc((void**)&h->d_f, cap * sizeof(float4)));
+        NB_CUDA(h, cudaMemset(h->d_f, 0, cap * sizeof(float4)));
+        h->cap_pad = cap;
+    }
+    if (alloc_exact(h, &h->d_fout, (size_t)nslots * 3)) return B200NB_ERR_CUDA;
+    h->npad          = nslots;
+    h->natoms        = 0; /* no atom-order view in this mode: b200nb_step / b200nb_compute / get_f refuse to run */
+    h->grid_uploaded = true;
+    h->grid[0].valid = h->grid[1].valid = 0;
+    {
+        /* The reference parks all filler atoms of a grid at ONE far-away point (atomdata.cpp:146) and relies on its kernels
+         * clamping r^2 (pairlist.h:146); our unmasked pair path has no clamp, so fillers get the unique far-away positions our
+         * own gridding gives them (k_column_sort): no two at zero distance, none within reach of a real atom. */
+        std::vector<float> xqv(xq_host, xq_host + 4 * (size_t)nslots);
+        for (int s = 0; s < nslots; s++)
+            if (type_host[s] == ntf - 1)
+            {
+                xqv[4 * (size_t)s]     = -1.0e6f - 8.0f * (float)(s & 0xfffff);
+                xqv[4 * (size_t)s + 1] = -1.0e6f - 64.0f * (float)(s >> 20);
+                xqv[4 * (size_t)s + 2] = -1.0e6f;
+                xqv[4 * (size_t)s + 3] = 0.0f;
+            }
+        NB_CUDA(h, cudaMemcpy(h->d_xq, xqv.data(), sizeof(float) * 4 * (size_t)nslots, cudaMemcpyHostToDevice));
+    }
+    if (alloc_exact(h, &h->d_x, (size_t)nslots * 4)) return B200NB_ERR_CUDA; /* staging of b200nb_copy_xq_grid */
+    NB_CUDA(h, cudaMemcpy(h->d_lj, ljv.data(), sizeof(float) * 2 * (size_t)nslots, cudaMemcpyHostToDevice));
+    NB_CUDA(h, cudaMemcpy(h->d_atype, type_host, sizeof(int) * (size_t)nslots, cudaMemcpyHostToDevice));
+    {
+        /* slot -> "atom" for the introspection calls (b200nb_get_pairs reports SLOT indices in this mode): -1 marks fillers */
+        std::vector<int> ai((size_t)nslots);
+        for (int s = 0; s < nslots; s++) ai[s] = type_host[s] == ntf - 1 ? -1 : s;
+        NB_CUDA(h, cudaMemcpy(h->d_atom_index, ai.data(), sizeof(int) * (size_t)nslots, cudaMemcpyHostToDevice));
+    }
+    h->have_list = false;
+    h->generation++;
+    return write_dummy_atoms(h);
+}
+
+/* gpu_init_pairlist (nbnxm_gpu_data_mgmt.cpp:251-311): takes the reference's NbnxnPairlistGpu (pairlist.h:267-299) and turns it
+ * into our (i-cluster, shift) entries: every set bit (jm*8 + im) of a cj4's imask is one 8x8 cluster pair (ci = sci*8 + im,
+ * cj = cj4.cj[jm]); its atom-pair interaction bits are excl[imei[jc/4].excl_ind].pair[(jc&3)*8 + ic] >> (jm*8 + im)
+ * (kernel_gpu_ref.cpp:223-240), re-indexed to our lane order.  Cluster pairs with a cleared bit go to the front of their entry
+ * (the format k_pack expects), entries are cut at max_tiles_per_entry.  The conversion runs on the host, like the search that
+ * produced the list; from here on (prune, re-pack, force) everything is on the device. */
+extern "C" int b200nb_upload_pairlist(b200nb_t* h, int locality, const b200nb_sci_t* sci, int nsci, const b200nb_cj4_t* cj4, int ncj4,
+                                      const b200nb_excl_t* excl, int nexcl)
+{
+    if (!h || locality < 0 || locality > 1 || nsci < 0 || ncj4 < 0 || nexcl < 1 || (nsci && !sci) || (ncj4 && !cj4) || !excl)
+        return nb_fail(h, B200NB_ERR_ARG, "upload_pairlist: bad argument");
+    if (!h->grid_uploaded) return nb_fail(h, B200NB_ERR_STATE, "upload_pairlist: set_grid_atoms first");
+    cudaSetDevice(h->device);
+    const int ncl = h->npad / 8;
+    if (h->hp.max_tiles_per_entry <= 0)
+        h->max_tiles = h->npad <= 48000 ? 24 : std::min(NB_MAX_ENTRY_TILES, (int)(24.0 * h->npad / 48000.0));
+    const int maxt = h->max_tiles;
+    struct Tile
+    {
+        int      cj;
+        uint64_t mask;
+    };
+    std::vector<Entry>    ent;
+    std::vector<int>      cjv;
+    std::vector<uint64_t> mv;
+    std::vector<Tile>     masked[8], plain[8];
+    for (int s = 0; s < nsci; s++)
+    {
+        const b200nb_sci_t& S = sci[s];
+        const int           shift = S.shift & 255; /* NBNXN_CI_SHIFT: the flags above bit 7 are CPU-list only */
+        if (S.cj4_ind_start < 0 || S.cj4_ind_end > ncj4 || S.cj4_ind_start > S.cj4_ind_end || shift >= B200NB_SHIFTS || S.sci < 0
+            || S.sci * 8 + 7 >= ncl)
+            return nb_fail(h, B200NB_ERR_ARG, "upload_pairlist: sci entry out of range");
+        for (int im = 0; im < 8; im++) masked[im].clear(), plain[im].clear();
+        for (int c = S.cj4_ind_start; c < S.cj4_ind_end; c++)
+        {
+            const b200nb_cj4_t& C = cj4[c];
+            const unsigned      im_all = C.imei[0].imask;
+            if (!im_all) continue;
+            if (C.imei[0].excl_ind < 0 || C.imei[0].excl_ind >= nexcl || C.imei[1].excl_ind < 0 || C.imei[1].excl_ind >= nexcl)
+                return nb_fail(h, B200NB_ERR_ARG, "upload_pairlist: exclusion index out of range");
+            const unsigned* e0 = excl[C.imei[0].excl_ind].pair;
+            const unsigned* e1 = excl[C.imei[1].excl_ind].pair;
+            for (int jm = 0; jm < 4; jm++)
+                for (int im = 0; im < 8; im++)
+                {
+                    const int bit = jm * 8 + im;
+                    if (!((im_all >> bit) & 1u)) continue;
+                    if (C.cj[jm] < 0 || C.cj[jm] >= ncl) return nb_fail(h, B200NB_ERR_ARG, "upload_pairlist: j-cluster out of range");
+                    uint64_t m = 0;
+                    for (int jc = 0; jc < 8; jc++)
+                    {
+                        const unsigned* e = jc < 4 ? e0 : e1;
+                        for (int ic = 0; ic < 8; ic++)
+                            if ((e[(jc & 3) * 8 + ic] >> bit) & 1u) m |= 1ull << (32 * (ic & 1) + jc + 8 * (ic >> 1));
+                    }
+                    (m == ~0ull ? plain[im] : masked[im]).push_back(Tile{ C.cj[jm], m });
+                }
+        }
+        for (int im = 0; im < 8; im++)
+        {
+            const size_t nm = masked[im].size(), nt = nm + plain[im].size();
+            for (size_t t0 = 0; t0 < nt; t0 += (size_t)maxt)
+            {
+                const size_t t1 = std::min(nt, t0 + (size_t)maxt);
+                Entry        E;
+                E.ci          = S.sci * 8 + im;
+                E.shift_nmask = shift | ((int)(t0 < nm ? std::min(nm, t1) - t0 : 0) << 8);
+                E.start       = (int)cjv.size();
+                for (size_t t = t0; t < t1; t++)
+                {
+                    const Tile& T = t < nm ? masked[im][t] : plain[im][t - nm];
+                    cjv.push_back(T.cj);
+                    mv.push_back(T.mask);
+                }
+                E.end = (int)cjv.size();
+                ent.push_back(E);
+            }
+        }
+    }
+    const bool want_inner = h->dp.rlist_inner2 < h->dp.rlist_outer2;
+    if (want_inner != !h->inner_is_outer)
+    {
+        /* switching between "inner list = outer list" (aliases) and a separate pruned list: as b200nb_build_pairlist */
+        if (!want_inner) for (int l = 0; l < 2; l++) free_list(h->inner[l]);
+        else for (int l = 0; l < 2; l++) h->inner[l] = PairList();
+        h->inner_is_outer = !want_inner;
+    }
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    PairList& L = h->outer[locality];
+    if (ensure_list(h, L, cjv.size(), ent.size())) return B200NB_ERR_CUDA;
+    L.ntiles   = (long long)cjv.size();
+    L.nentries = (long long)ent.size();
+    if (!ent.empty())
+    {
+        NB_CUDA(h, cudaMemcpy(L.entries, ent.data(), sizeof(Entry) * ent.size(), cudaMemcpyHostToDevice));
+        NB_CUDA(h, cudaMemcpy(L.cj, cjv.data(), sizeof(int) * cjv.size(), cudaMemcpyHostToDevice));
+        NB_CUDA(h, cudaMemcpy(L.mask, mv.data(), sizeof(uint64_t) * mv.size(), cudaMemcpyHostToDevice));
+    }
+    if (want_inner)
+    {
+        PairList& I = h->inner[locality];
+        if (ensure_list(h, I, cjv.size(), ent.size())) return B200NB_ERR_CUDA;
+        I.ntiles   = L.ntiles;
+        I.nentries = L.nentries;
+        if (launch_prune(h, locality, 0, 1)) return B200NB_ERR_CUDA; /* fresh-list prune (cuda/nbnxm_cuda.cu:510-517) */
+    }
+    else
+        h->inner[locality] = L;
+    if (locality == 0 && !h->have_list)
+    {
+        /* a context that never had a non-local list: its packed list is empty, not stale */
+        h->outer[1].ntiles = h->outer[1].nentries = 0;
+        if (h->inner_is_outer) h->inner[1] = h->outer[1];
+        else h->inner[1].ntiles = h->inner[1].nentries = 0;
+        h->packed[1].nentries = 0;
+    }
+    if (launch_pack(h, locality, 0, 1)) return B200NB_ERR_CUDA;
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->have_list = true;
+    h->generation++;
+    return 0;
+}
+
+/* new coordinates of the real atoms of a reference-built grid; filler slots keep the positions set_grid_atoms gave them */
+__global__ void k_xq_grid_update(const float4* __restrict__ in, const int* __restrict__ atype, int filler, int s0, int s1, float4* __restrict__ xq)
+{
+    const int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < s1 && atype[s] != filler) xq[s] = in[s];
+}
+
+/* gpu_copy_xq_to_gpu (cuda/nbnxm_cuda.cu:395-465): slots [slot_begin, slot_end) of nbat->x(), asynchronous on the stream */
+extern "C" int b200nb_copy_xq_grid(b200nb_t* h, const float* xq_host, int slot_begin, int slot_end)
+{
+    if (!h || !xq_host || slot_begin < 0 || slot_end < slot_begin) return nb_fail(h, B200NB_ERR_ARG, "copy_xq_grid: bad argument");
+    if (!h->grid_uploaded || slot_end > h->npad) return nb_fail(h, B200NB_ERR_STATE, "copy_xq_grid: set_grid_atoms first / range beyond the grid");
+    cudaSetDevice(h->device);
+    const int n = slot_end - slot_begin;
+    if (n == 0) return 0;
+    NB_CUDA(h, cudaMemcpyAsync(h->d_x + 4 * (size_t)slot_begin, xq_host + 4 * (size_t)slot_begin, sizeof(float) * 4 * (size_t)n,
+                               cudaMemcpyHostToDevice, h->stream));
+    k_xq_grid_update<<<(n + 255) / 256, 256, 0, h->stream>>>(reinterpret_cast<const float4*>(h->d_x), h->d_atype, h->dp.ntypes - 1, slot_begin,
+                                                             slot_end, reinterpret_cast<float4*>(h->d_xq));
+    LAUNCH_CHECK(h);
+    return 0;
+}
+
+__global__ void k_f_grid_to_f3(const float4* __restrict__ fg, int s0, int s1, float* __restrict__ out)
+{
+    const int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= s1) return;
+    const float4 v = fg[s];
+    out[3 * (size_t)s]     = v.x;
+    out[3 * (size_t)s + 1] = v.y;
+    out[3 * (size_t)s + 2] = v.z;
+}
+
+/* gpu_launch_cpyback (cuda/nbnxm_cuda.cu:720-814), force part: grid-ordered forces of slots [slot_begin, slot_end) into
+ * nbat->out[0].f (3 floats per slot), asynchronous on the stream -- b200nb_synchronize before reading */
+extern "C" int b200nb_get_f_grid(b200nb_t* h, float* f_host, int slot_begin, int slot_end)
+{
+    if (!h || !f_host || slot_begin < 0 || slot_end < slot_begin) return nb_fail(h, B200NB_ERR_ARG, "get_f_grid: bad argument");
+    if (!h->grid_uploaded || slot_end > h->npad) return nb_fail(h, B200NB_ERR_STATE, "get_f_grid: set_grid_atoms first / range beyond the grid");
+    cudaSetDevice(h->device);
+    const int n = slot_end - slot_begin;
+    if (n == 0) return 0;
+    k_f_grid_to_f3<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_f, slot_begin, slot_end, h->d_fout);
+    LAUNCH_CHECK(h);
+    NB_CUDA(h, cudaMemcpyAsync(f_host + 3 * (size_t)slot_begin, h->d_fout + 3 * (size_t)slot_begin, sizeof(float) * 3 * (size_t)n,
+                               cudaMemcpyDeviceToHost, h->stream));
     return 0;
 }
 
@@ -1545,7 +1824,7 @@ extern "C" int b200nb_set_x(b200nb_t* h, const float* x, int x_on_device, int a0
 extern "C" int b200nb_clear_outputs(b200nb_t* h)
 {
     if (!h) return B200NB_ERR_ARG;
-    if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "clear_outputs: put_on_grid first");
+    if (!h->grid[0].valid && !h->grid_uploaded) return nb_fail(h, B200NB_ERR_STATE, "clear_outputs: put_on_grid first");
     cudaSetDevice(h->device);
     NB_CUDA(h, cudaMemsetAsync(h->d_f, 0, sizeof(float4) * (size_t)h->npad, h->stream));
     NB_CUDA(h, cudaMemsetAsync(h->d_fshift, 0, sizeof(float) * NB_OUT_COPIES * NB_FSHIFT_PITCH, h->stream));
@@ -1666,12 +1945,14 @@ __device__ __forceinline__ long long globaltimer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-/* thread 0 of the CTA waits until *flag >= *seq (the step number, device-resident so that a captured CUDA graph of the step
- * can be replayed), then the CTA proceeds.  Bounded: a peer that never arrives raises *err instead of hanging the GPU. */
-__device__ __forceinline__ void wait_flag(const int* flag, const int* seq, int* err)
+/* Threads k < n of the CTA each wait until their flag (32 bytes apart, starting at `flags`) has reached *seq (the step number,
+ * device-resident so that a captured CUDA graph of the step can be replayed) -- only the links with active[k] != 0 -- then the
+ * CTA proceeds.  Bounded: a peer that never arrives raises *err instead of hanging the GPU. */
+__device__ __forceinline__ void wait_flags(const unsigned char* flags, int n, const int* active_begin, const int* seq, int* err)
 {
-    if (threadIdx.x == 0)
+    if ((int)threadIdx.x < n && active_begin[threadIdx.x + 1] > active_begin[threadIdx.x])
     {
+        const int*      flag = reinterpret_cast<const int*>(flags + 32 * threadIdx.x);
         const int       want = *reinterpret_cast<const volatile int*>(seq);
         const long long t0   = globaltimer_ns();
         while (ld_acquire_sys(flag) < want)
@@ -1686,30 +1967,34 @@ __device__ __forceinline__ void wait_flag(const int* flag, const int* seq, int* 
     }
     __syncthreads();
 }
-/* after this CTA's stores to the peer: the last CTA of the grid publishes the step number in the peer's flag */
-__device__ __forceinline__ void publish_flag(int* counter, int* peer_flag, const int* seq)
+/* after this CTA's stores to the peers: the last CTA of the grid publishes the step number in the peers' flags, one thread
+ * per link with traffic */
+__device__ __forceinline__ void publish_flags(int* counter, int* const* peer_flags, int n, const int* active_begin, const int* seq)
 {
+    __shared__ int s_last;
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0)
     {
-        if (atomicAdd(counter, 1) == (int)gridDim.x - 1)
-        {
-            *counter = 0;
-            __threadfence_system();
-            st_release_sys(peer_flag, *reinterpret_cast<const volatile int*>(seq));
-        }
+        const int last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
+        if (last) *counter = 0;
+        s_last = last;
+    }
+    __syncthreads();
+    if (s_last && (int)threadIdx.x < n && active_begin[threadIdx.x + 1] > active_begin[threadIdx.x])
+    {
+        __threadfence_system();
+        st_release_sys(peer_flags[threadIdx.x], *reinterpret_cast<const volatile int*>(seq));
     }
 }
 
 /* what k_step_begin does on top of its single-domain work when the step is domain-decomposed */
 struct DdBegin
 {
-    int*       seq;        /* step counter, incremented here */
-    const int* send_pos;   /* per home atom: position in the send list or -1 */
-    float      sx, sy, sz; /* shift added to the coordinates we send (box on the periodic edge) */
-    float*     peer_recv_x;
-    int*       peer_flag;
+    int*       seq;       /* step counter, incremented here */
+    const int* send_atom; /* per send entry: home atom */
+    const int* send_link; /* per send entry: link */
+    int        nsend;
     int*       counter;
 };
 
@@ -1726,7 +2011,8 @@ struct PrefetchRange
 template<bool VEC, bool DD>
 __global__ void __launch_bounds__(256)
 k_step_begin(const float* __restrict__ x, const int* __restrict__ slot_of_atom, int a0, int a1, float* __restrict__ xq,
-             float4* __restrict__ f, int nclear, float* __restrict__ fshift, double* __restrict__ energy, PrefetchRange pf, DdBegin dd)
+             float4* __restrict__ f, int nclear, float* __restrict__ fshift, double* __restrict__ energy, PrefetchRange pf, DdBegin dd,
+             const __grid_constant__ DdLinksDev L)
 {
     __shared__ __align__(16) float sx[768];
     const int tid = threadIdx.x, t = blockIdx.x * 256 + tid;
@@ -1765,20 +2051,21 @@ k_step_begin(const float* __restrict__ x, const int* __restrict__ slot_of_atom, 
         xb[0]     = sx[3 * tid];
         xb[1]     = sx[3 * tid + 1];
         xb[2]     = sx[3 * tid + 2];
-        if (DD)
-        {
-            /* dd_move_x, sending side (packSendBufKernel, gpuhaloexchange_impl.cu:77-100) fused with the transfer: atoms within
-             * rlist of our lower face go straight into the -x neighbour's window, shifted on the periodic edge */
-            const int p = dd.send_pos[base + tid];
-            if (p >= 0)
-            {
-                dd.peer_recv_x[3 * p]     = sx[3 * tid] + dd.sx;
-                dd.peer_recv_x[3 * p + 1] = sx[3 * tid + 1] + dd.sy;
-                dd.peer_recv_x[3 * p + 2] = sx[3 * tid + 2] + dd.sz;
-            }
-        }
     }
-    if (DD && dd.peer_flag) publish_flag(dd.counter, dd.peer_flag, dd.seq);
+    if (DD)
+    {
+        /* dd_move_x, sending side (packSendBufKernel, gpuhaloexchange_impl.cu:77-100) fused with the transfer: every send entry
+         * (home atom, link) goes straight into the destination's window, shifted when the link crosses a periodic edge */
+        for (int e = t; e < dd.nsend; e += (int)gridDim.x * 256)
+        {
+            const int    a = dd.send_atom[e], l = dd.send_link[e];
+            float* const d = L.peer_recv_x[l] + 3 * (size_t)(e - L.send_off[l]);
+            d[0]           = x[3 * (size_t)a] + L.shift[l][0];
+            d[1]           = x[3 * (size_t)a + 1] + L.shift[l][1];
+            d[2]           = x[3 * (size_t)a + 2] + L.shift[l][2];
+        }
+        publish_flags(dd.counter, L.peer_flag_x, L.nlinks, L.send_off, dd.seq);
+    }
 }
 
 template<bool VEC>
@@ -1829,9 +2116,9 @@ static int launch_step(b200nb_context* h, const float* x_dev, int flags, float* 
         pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
     }
     if ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0)
-        k_step_begin<true, false><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, DdBegin{});
+        k_step_begin<true, false><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, DdBegin{}, DdLinksDev{});
     else
-        k_step_begin<false, false><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, DdBegin{});
+        k_step_begin<false, false><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, DdBegin{}, DdLinksDev{});
     LAUNCH_CHECK(h);
     int rc;
     if (ev_force0) NB_CUDA(h, cudaEventRecord(ev_force0, h->stream));
@@ -2017,12 +2304,13 @@ extern "C" int b200nb_halo_unpack_f(b200nb_t* h, float* f_dev, const int* index_
 /* ------------------------------------------------------------------------------------------------------ */
 /* domain-decomposed step over peer-memory halo windows (DdState, b200nb_internal.h)                      */
 /* ------------------------------------------------------------------------------------------------------ */
-/* dd_move_x, receiving side, fused with nbnxn_gpu_x_to_nbat_x for the halo grid: window -> grid layout */
+/* dd_move_x, receiving side, fused with nbnxn_gpu_x_to_nbat_x for the halo grid: window -> grid layout, after the
+ * coordinates of every link have landed */
 __global__ void __launch_bounds__(256)
-k_dd_recv_x(const int* __restrict__ flag, const int* __restrict__ seq, int* __restrict__ err, const float* __restrict__ recv_x,
-            const int* __restrict__ slot_of_atom, int nhome, int nhalo, float* __restrict__ xq)
+k_dd_recv_x(const unsigned char* __restrict__ window, const int* __restrict__ seq, const float* __restrict__ recv_x,
+            const int* __restrict__ slot_of_atom, int nhome, int nhalo, float* __restrict__ xq, const __grid_constant__ DdLinksDev L)
 {
-    wait_flag(flag, seq, err);
+    wait_flags(window + NB_DD_FLAG_X(0), L.nlinks, L.halo_off, seq, reinterpret_cast<int*>(const_cast<unsigned char*>(window) + NB_DD_ERR));
     const int k = blockIdx.x * 256 + threadIdx.x;
     if (k >= nhalo) return;
     float* xb = xq + 4 * (size_t)slot_of_atom[nhome + k];
@@ -2031,70 +2319,62 @@ k_dd_recv_x(const int* __restrict__ flag, const int* __restrict__ seq, int* __re
     xb[2]     = __ldcg(recv_x + 3 * k + 2);
 }
 
-/* dd_move_f, sending side: the forces we computed on the halo atoms go into their owner's (+x neighbour's) window */
+/* dd_move_f, sending side: the forces we computed on the halo atoms go into their owners' windows; forces on atoms that
+ * arrived across a periodic edge also enter the shift force of that shift (domdec/domdec.cpp:426-458: the reference adds
+ * them on the owner's side; the virial sums the shift forces over all ranks, so the side does not matter) */
 __global__ void __launch_bounds__(256)
-k_dd_push_f(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom, int nhome, int nhalo, float* __restrict__ peer_recv_f,
-            int* __restrict__ peer_flag, const int* __restrict__ seq, int* __restrict__ counter)
+k_dd_push_f(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom, int nhome, int nhalo, const unsigned char* __restrict__ halo_link,
+            const int* __restrict__ seq, int* __restrict__ counter, float* __restrict__ fshift, const __grid_constant__ DdLinksDev L)
 {
     const int k = blockIdx.x * 256 + threadIdx.x;
     if (k < nhalo)
     {
-        const float4 v      = fg[slot_of_atom[nhome + k]];
-        peer_recv_f[3 * k]     = v.x;
-        peer_recv_f[3 * k + 1] = v.y;
-        peer_recv_f[3 * k + 2] = v.z;
+        const float4 v = fg[slot_of_atom[nhome + k]];
+        const int    l = halo_link[k];
+        float* const d = L.peer_recv_f[l] + 3 * (size_t)(k - L.halo_off[l]);
+        d[0]           = v.x;
+        d[1]           = v.y;
+        d[2]           = v.z;
+        if (fshift && L.fshift_index[l] >= 0)
+        {
+            float* fs = fshift + (blockIdx.x & (NB_OUT_COPIES - 1)) * NB_FSHIFT_PITCH + 3 * L.fshift_index[l];
+            atomicAdd(fs, v.x);
+            atomicAdd(fs + 1, v.y);
+            atomicAdd(fs + 2, v.z);
+        }
     }
-    publish_flag(counter, peer_flag, seq);
+    publish_flags(counter, L.peer_flag_f, L.nlinks, L.halo_off, seq);
 }
 
 /* dd_move_f, receiving side (unpackRecvBufKernel<accumulate>, gpuhaloexchange_impl.cu:108-131) fused with the force
- * un-sort (reduceKernel): f_home[a] = f_grid[slot[a]] + returned halo force of a; on the periodic edge the returned forces
- * also enter the shift forces (domdec/domdec.cpp:426-458) */
+ * un-sort (reduceKernel): f_home[a] = f_grid[slot[a]] + the forces returned for every send entry that carried a */
 template<bool VEC>
 __global__ void __launch_bounds__(256)
-k_dd_step_end(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom, int nhome, const int* __restrict__ send_pos,
-              const int* __restrict__ flag, const int* __restrict__ seq, int* __restrict__ err, const float* __restrict__ recv_f,
-              float* __restrict__ f, float* __restrict__ fshift_edge)
+k_dd_step_end(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom, int nhome, const int* __restrict__ ent_off,
+              const int* __restrict__ ent_idx, const unsigned char* __restrict__ window, const int* __restrict__ seq,
+              const float* __restrict__ recv_f, float* __restrict__ f, const __grid_constant__ DdLinksDev L)
 {
     __shared__ __align__(16) float sf[768];
     const int tid  = threadIdx.x;
     const int base = blockIdx.x * 256;
     const int nb   = min(256, nhome - base);
-    if (flag) wait_flag(flag, seq, err); /* the forces on the atoms we sent have landed in our window */
+    /* the forces on the atoms we sent have landed in our window */
+    wait_flags(window + NB_DD_FLAG_F(0), L.nlinks, L.send_off, seq, reinterpret_cast<int*>(const_cast<unsigned char*>(window) + NB_DD_ERR));
     if (nb <= 0) return;
-    float ex = 0.f, ey = 0.f, ez = 0.f;
     if (tid < nb)
     {
-        float4    v = fg[slot_of_atom[base + tid]];
-        const int p = send_pos ? send_pos[base + tid] : -1;
-        if (p >= 0)
+        float4    v  = fg[slot_of_atom[base + tid]];
+        const int e0 = ent_off[base + tid], e1 = ent_off[base + tid + 1];
+        for (int k = e0; k < e1; k++)
         {
-            ex = __ldcg(recv_f + 3 * p);
-            ey = __ldcg(recv_f + 3 * p + 1);
-            ez = __ldcg(recv_f + 3 * p + 2);
-            v.x += ex;
-            v.y += ey;
-            v.z += ez;
+            const int e = ent_idx[k];
+            v.x += __ldcg(recv_f + 3 * (size_t)e);
+            v.y += __ldcg(recv_f + 3 * (size_t)e + 1);
+            v.z += __ldcg(recv_f + 3 * (size_t)e + 2);
         }
         sf[3 * tid]     = v.x;
         sf[3 * tid + 1] = v.y;
         sf[3 * tid + 2] = v.z;
-    }
-    if (fshift_edge)
-    {
-        for (int o = 16; o > 0; o >>= 1)
-        {
-            ex += __shfl_xor_sync(0xffffffffu, ex, o);
-            ey += __shfl_xor_sync(0xffffffffu, ey, o);
-            ez += __shfl_xor_sync(0xffffffffu, ez, o);
-        }
-        if ((tid & 31) == 0 && (ex != 0.f || ey != 0.f || ez != 0.f))
-        {
-            float* fs = fshift_edge + (blockIdx.x & (NB_OUT_COPIES - 1)) * NB_FSHIFT_PITCH;
-            atomicAdd(fs, ex);
-            atomicAdd(fs + 1, ey);
-            atomicAdd(fs + 2, ez);
-        }
     }
     __syncthreads();
     float*    dst = f + 3 * (size_t)base;
@@ -2119,8 +2399,8 @@ extern "C" int b200nb_dd_create_window(b200nb_t* h, int max_halo, int max_send, 
     if (D.window) return nb_fail(h, B200NB_ERR_STATE, "dd_create_window: window exists (peers hold its handle)");
     D.max_halo     = max_halo;
     D.max_send     = max_send;
-    D.off_recv_x   = 256;
-    D.off_recv_f   = 256 + align256(sizeof(float) * 3 * (size_t)max_halo);
+    D.off_recv_x   = NB_DD_DATA;
+    D.off_recv_f   = NB_DD_DATA + align256(sizeof(float) * 3 * (size_t)max_halo);
     D.window_bytes = D.off_recv_f + align256(sizeof(float) * 3 * (size_t)max_send);
     NB_CUDA(h, cudaMalloc((void**)&D.window, D.window_bytes));
     NB_CUDA(h, cudaMemset(D.window, 0, D.window_bytes));
@@ -2146,21 +2426,23 @@ extern "C" int b200nb_dd_create_window(b200nb_t* h, int max_halo, int max_send, 
     return 0;
 }
 
-/* side 0: the -x neighbour (receives our halo coordinates), side 1: the +x neighbour (receives the forces on its atoms).
- * Either an IPC handle from another process, or the window's device pointer when the peer lives in this process.
- * peer_max_halo: the max_halo the peer created its window with (fixes where its recv_f block starts). */
-extern "C" int b200nb_dd_open_peer(b200nb_t* h, int side, const void* ipc_handle, void* same_process_window, int peer_max_halo)
+/* Opens a neighbour's window as peer `peer` (0 .. NB_DD_MAX_PEERS-1; with b200nb_dd_set_plan: 0 = the -x neighbour, which
+ * receives our halo coordinates, 1 = the +x neighbour, which receives the forces on its atoms).  Either an IPC handle from
+ * another process, or the window's device pointer when the peer lives in this process.  A neighbour reached over several
+ * links is opened ONCE (a CUDA IPC handle maps once per process).  peer_max_halo: the max_halo the peer created its window
+ * with (fixes where its recv_f block starts). */
+extern "C" int b200nb_dd_open_peer(b200nb_t* h, int peer, const void* ipc_handle, void* same_process_window, int peer_max_halo)
 {
-    if (!h || side < 0 || side > 1 || (!ipc_handle && !same_process_window) || peer_max_halo < 0)
+    if (!h || peer < 0 || peer >= NB_DD_MAX_PEERS || (!ipc_handle && !same_process_window) || peer_max_halo < 0)
         return nb_fail(h, B200NB_ERR_ARG, "dd_open_peer: bad argument");
     cudaSetDevice(h->device);
     DdState& D = h->dd;
-    if (D.peer[side] && D.peer_is_ipc[side]) cudaIpcCloseMemHandle(D.peer[side]);
-    D.peer[side] = nullptr;
+    if (D.peer[peer] && D.peer_is_ipc[peer]) cudaIpcCloseMemHandle(D.peer[peer]);
+    D.peer[peer] = nullptr;
     if (same_process_window)
     {
-        D.peer[side]        = static_cast<unsigned char*>(same_process_window);
-        D.peer_is_ipc[side] = false;
+        D.peer[peer]        = static_cast<unsigned char*>(same_process_window);
+        D.peer_is_ipc[peer] = false;
     }
     else
     {
@@ -2168,45 +2450,129 @@ extern "C" int b200nb_dd_open_peer(b200nb_t* h, int side, const void* ipc_handle
         memcpy(&hd, ipc_handle, sizeof(hd));
         void* p = nullptr;
         NB_CUDA(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
-        D.peer[side]        = static_cast<unsigned char*>(p);
-        D.peer_is_ipc[side] = true;
+        D.peer[peer]        = static_cast<unsigned char*>(p);
+        D.peer_is_ipc[peer] = true;
     }
-    D.peer_off_recv_f[side] = 256 + align256(sizeof(float) * 3 * (size_t)peer_max_halo);
+    D.peer_off_recv_f[peer] = NB_DD_DATA + align256(sizeof(float) * 3 * (size_t)peer_max_halo);
+    h->generation++;
     return 0;
 }
 
-/* The halo plan of the current pair-search interval: local atoms [0, nhome) are home, [nhome, nhome + nhalo) halo (in the
- * order the +x neighbour sends them); send_idx_host: the nsend home atoms we send to the -x neighbour, shift added to them;
- * edge_shift_index: shift-force slot the returned forces also count for when they crossed the periodic edge, else -1. */
-extern "C" int b200nb_dd_set_plan(b200nb_t* h, int nhome, int nhalo, const int* send_idx_host, int nsend, const float shift[3],
-                                  int edge_shift_index)
+/* The halo plan of the current pair-search interval, general form: local atoms [0, nhome) are home, [nhome, nhome + nhalo) halo,
+ * in link order (all atoms received over link 0, then link 1, ...).  See b200nb_dd_link_t in b200nb.h. */
+extern "C" int b200nb_dd_set_links(b200nb_t* h, int nhome, int nhalo, int nlinks, const b200nb_dd_link_t* links)
 {
-    if (!h || nhome < 0 || nhalo < 0 || nsend < 0 || (nsend && !send_idx_host)) return nb_fail(h, B200NB_ERR_ARG, "dd_set_plan: bad argument");
+    if (!h || nhome < 0 || nhalo < 0 || nlinks < 0 || nlinks > NB_DD_MAX_LINKS || (nlinks && !links))
+        return nb_fail(h, B200NB_ERR_ARG, "dd_set_links: bad argument");
     cudaSetDevice(h->device);
     DdState& D = h->dd;
-    if (!D.window) return nb_fail(h, B200NB_ERR_STATE, "dd_set_plan: create the window first");
-    if (nhalo > D.max_halo || nsend > D.max_send) return nb_fail(h, B200NB_ERR_CAPACITY, "dd_set_plan: halo larger than the window");
-    if (nhome + nhalo != h->natoms) return nb_fail(h, B200NB_ERR_ARG, "dd_set_plan: nhome + nhalo != natoms");
-    if (ensure(h, &D.d_send_idx, &D.cap_send, (size_t)std::max(nsend, 1)) || ensure(h, &D.d_send_pos, &D.cap_home, (size_t)std::max(nhome, 1)))
-        return B200NB_ERR_CUDA;
-    std::vector<int> pos((size_t)std::max(nhome, 1), -1);
-    for (int k = 0; k < nsend; k++)
+    if (!D.window) return nb_fail(h, B200NB_ERR_STATE, "dd_set_links: create the window first");
+    if (nhome + nhalo != h->natoms) return nb_fail(h, B200NB_ERR_ARG, "dd_set_links: nhome + nhalo != natoms");
+    DdLinksDev L{};
+    L.nlinks = nlinks;
+    long long nsend = 0, nrecv = 0;
+    for (int k = 0; k < nlinks; k++)
     {
-        const int a = send_idx_host[k];
-        if (a < 0 || a >= nhome || pos[a] >= 0) return nb_fail(h, B200NB_ERR_ARG, "dd_set_plan: send index out of range or repeated");
-        pos[a] = k;
+        const b200nb_dd_link_t& K = links[k];
+        if (K.nsend < 0 || K.nrecv < 0 || (K.nsend && !K.send_idx_host)) return nb_fail(h, B200NB_ERR_ARG, "dd_set_links: bad link");
+        if (K.nsend && (K.send_peer < 0 || K.send_peer >= NB_DD_MAX_PEERS || !D.peer[K.send_peer]))
+            return nb_fail(h, B200NB_ERR_STATE, "dd_set_links: the destination window of a link is not open");
+        if (K.nrecv && (K.recv_peer < 0 || K.recv_peer >= NB_DD_MAX_PEERS || !D.peer[K.recv_peer]))
+            return nb_fail(h, B200NB_ERR_STATE, "dd_set_links: the source window of a link is not open");
+        if (K.peer_halo_offset < 0 || K.peer_entry_offset < 0 || K.fshift_index >= B200NB_SHIFTS)
+            return nb_fail(h, B200NB_ERR_ARG, "dd_set_links: bad offset / shift index");
+        L.send_off[k] = (int)nsend;
+        L.halo_off[k] = (int)nrecv;
+        nsend += K.nsend;
+        nrecv += K.nrecv;
+        for (int d = 0; d < 3; d++) L.shift[k][d] = K.shift[d];
+        L.fshift_index[k] = K.nrecv ? K.fshift_index : -1;
+        if (K.nsend)
+        {
+            unsigned char* w = D.peer[K.send_peer];
+            L.peer_recv_x[k] = reinterpret_cast<float*>(w + NB_DD_DATA) + 3 * (size_t)K.peer_halo_offset;
+            L.peer_flag_x[k] = reinterpret_cast<int*>(w + NB_DD_FLAG_X(k));
+        }
+        if (K.nrecv)
+        {
+            unsigned char* w = D.peer[K.recv_peer];
+            L.peer_recv_f[k] = reinterpret_cast<float*>(w + D.peer_off_recv_f[K.recv_peer]) + 3 * (size_t)K.peer_entry_offset;
+            L.peer_flag_f[k] = reinterpret_cast<int*>(w + NB_DD_FLAG_F(k));
+        }
     }
+    for (int k = nlinks; k <= NB_DD_MAX_LINKS; k++) L.send_off[k] = (int)nsend, L.halo_off[k] = (int)nrecv;
+    if (nrecv != nhalo) return nb_fail(h, B200NB_ERR_ARG, "dd_set_links: the links' receive counts do not add up to nhalo");
+    if (nhalo > D.max_halo || nsend > D.max_send) return nb_fail(h, B200NB_ERR_CAPACITY, "dd_set_links: halo larger than the window");
+    /* per entry: atom and link; per home atom: the entries that carry it (CSR); per halo atom: its link */
+    std::vector<int>           atom((size_t)std::max<long long>(nsend, 1)), link((size_t)std::max<long long>(nsend, 1));
+    std::vector<int>           off((size_t)nhome + 2, 0), idx((size_t)std::max<long long>(nsend, 1));
+    std::vector<unsigned char> hl((size_t)std::max(nhalo, 1));
+    for (int k = 0, e = 0; k < nlinks; k++)
+        for (int p = 0; p < links[k].nsend; p++, e++)
+        {
+            const int a = links[k].send_idx_host[p];
+            if (a < 0 || a >= nhome) return nb_fail(h, B200NB_ERR_ARG, "dd_set_links: send index out of range");
+            atom[e] = a;
+            link[e] = k;
+            off[a + 1]++;
+        }
+    for (int a = 0; a < nhome; a++) off[a + 1] += off[a];
+    {
+        std::vector<int> cur(off.begin(), off.end() - 1);
+        for (int e = 0; e < (int)nsend; e++) idx[cur[atom[e]]++] = e;
+    }
+    for (int k = 0; k < nlinks; k++)
+        for (int p = 0; p < links[k].nrecv; p++) hl[(size_t)L.halo_off[k] + p] = (unsigned char)k;
+    auto grow = [&](void** ptr, size_t* cap, size_t need, size_t elem) -> int {
+        if (*ptr && need <= *cap) return 0;
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        *cap = need + need / 4 + 64;
+        return cudaMalloc(ptr, *cap * elem) != cudaSuccess;
+    };
     NB_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (nsend) NB_CUDA(h, cudaMemcpy(D.d_send_idx, send_idx_host, sizeof(int) * nsend, cudaMemcpyHostToDevice));
-    NB_CUDA(h, cudaMemcpy(D.d_send_pos, pos.data(), sizeof(int) * std::max(nhome, 1), cudaMemcpyHostToDevice));
+    size_t c1 = D.cap_send, c2 = D.cap_send, c3 = D.cap_send;
+    if (grow((void**)&D.d_send_atom, &c1, (size_t)nsend + 1, sizeof(int)) || grow((void**)&D.d_send_link, &c2, (size_t)nsend + 1, sizeof(int))
+        || grow((void**)&D.d_ent_idx, &c3, (size_t)nsend + 1, sizeof(int)))
+        return nb_fail(h, B200NB_ERR_CUDA, "dd_set_links: device allocation failed");
+    D.cap_send = c1;
+    if (grow((void**)&D.d_ent_off, &D.cap_home, (size_t)nhome + 2, sizeof(int)) || grow((void**)&D.d_halo_link, &D.cap_halo, (size_t)nhalo + 1, 1))
+        return nb_fail(h, B200NB_ERR_CUDA, "dd_set_links: device allocation failed");
+    if (nsend)
+    {
+        NB_CUDA(h, cudaMemcpy(D.d_send_atom, atom.data(), sizeof(int) * nsend, cudaMemcpyHostToDevice));
+        NB_CUDA(h, cudaMemcpy(D.d_send_link, link.data(), sizeof(int) * nsend, cudaMemcpyHostToDevice));
+        NB_CUDA(h, cudaMemcpy(D.d_ent_idx, idx.data(), sizeof(int) * nsend, cudaMemcpyHostToDevice));
+    }
+    NB_CUDA(h, cudaMemcpy(D.d_ent_off, off.data(), sizeof(int) * ((size_t)nhome + 1), cudaMemcpyHostToDevice));
+    if (nhalo) NB_CUDA(h, cudaMemcpy(D.d_halo_link, hl.data(), (size_t)nhalo, cudaMemcpyHostToDevice));
+    D.links = L;
     D.nhome = nhome;
     D.nhalo = nhalo;
-    D.nsend = nsend;
-    for (int d = 0; d < 3; d++) D.shift[d] = shift ? shift[d] : 0.f;
-    D.edge_shift = edge_shift_index;
-    D.have_plan  = true;
+    D.nsend = (int)nsend;
+    D.have_plan = true;
     h->generation++;
     return 0;
+}
+
+/* The 1-D (x-slab) form of b200nb_dd_set_links: one link; peer 0 = the -x neighbour (gets our halo coordinates), peer 1 = the +x
+ * neighbour (owns our halo atoms).  send_idx_host: the nsend home atoms we send, `shift` added to them; halo_fshift_index: shift-
+ * force slot that also receives the forces WE compute on our halo atoms when those arrived across the periodic edge, else -1. */
+extern "C" int b200nb_dd_set_plan(b200nb_t* h, int nhome, int nhalo, const int* send_idx_host, int nsend, const float shift[3],
+                                  int halo_fshift_index)
+{
+    if (!h || nsend < 0 || nhalo < 0) return nb_fail(h, B200NB_ERR_ARG, "dd_set_plan: bad argument");
+    b200nb_dd_link_t K{};
+    K.send_peer     = 0;
+    K.nsend         = nsend;
+    K.send_idx_host = send_idx_host;
+    for (int d = 0; d < 3; d++) K.shift[d] = shift ? shift[d] : 0.f;
+    K.peer_halo_offset  = 0;
+    K.recv_peer         = 1;
+    K.nrecv             = nhalo;
+    K.peer_entry_offset = 0;
+    K.fshift_index      = halo_fshift_index;
+    return b200nb_dd_set_links(h, nhome, nhalo, 1, &K);
 }
 
 /* While a step is being captured: remember the graph node the last launch on the non-local stream created, so that its
@@ -2225,10 +2591,7 @@ static void tag_nonlocal_node(b200nb_context* h)
 /* the launches of one decomposed step; x_home / f_home are device-visible addresses */
 static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home, int flags)
 {
-    DdState&  D      = h->dd;
-    int*      flag_x = reinterpret_cast<int*>(D.window);
-    int*      flag_f = reinterpret_cast<int*>(D.window + 64);
-    int*      err    = reinterpret_cast<int*>(D.window + 128);
+    DdState&  D = h->dd;
     const int n = D.nhome, nclear = h->npad + NB_DUMMY_SLOTS;
     const unsigned nb0 = (unsigned)((std::max(std::max(n, nclear), NB_OUT_COPIES * NB_FSHIFT_PITCH) + 255) / 256);
     PrefetchRange pf{};
@@ -2244,17 +2607,16 @@ static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home,
         pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
     }
     DdBegin B{};
-    B.seq      = D.d_seq;
-    B.send_pos = D.d_send_pos;
-    B.sx = D.shift[0], B.sy = D.shift[1], B.sz = D.shift[2];
-    B.peer_recv_x = D.peer[0] ? reinterpret_cast<float*>(D.peer[0] + 256) : nullptr;
-    B.peer_flag   = D.peer[0] ? reinterpret_cast<int*>(D.peer[0]) : nullptr;
-    B.counter     = D.d_count;
-    /* 1. home x -> grid layout, outputs cleared, halo x pushed into the -x neighbour's window */
+    B.seq       = D.d_seq;
+    B.send_atom = D.d_send_atom;
+    B.send_link = D.d_send_link;
+    B.nsend     = D.nsend;
+    B.counter   = D.d_count;
+    /* 1. home x -> grid layout, outputs cleared, halo x pushed into the neighbours' windows */
     if ((reinterpret_cast<uintptr_t>(x_home) & 15) == 0)
-        k_step_begin<true, true><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, B);
+        k_step_begin<true, true><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, B, D.links);
     else
-        k_step_begin<false, true><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, B);
+        k_step_begin<false, true><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, B, D.links);
     LAUNCH_CHECK(h);
     /* 2. the halo chain on the high-priority non-local stream, the local kernel on the main stream */
     cudaStream_t snl = D.stream_nl;
@@ -2262,11 +2624,10 @@ static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home,
     NB_CUDA(h, cudaStreamWaitEvent(snl, D.ev_begin, 0));
     int rc;
     if ((rc = nb_launch_force_kernel(h, 0, flags))) return rc;
-    if (D.peer[1])
+    if (D.nhalo)
     {
-        k_dd_recv_x<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, snl>>>(flag_x, D.d_seq, err,
-                                                                                 reinterpret_cast<const float*>(D.window + D.off_recv_x),
-                                                                                 h->d_slot_of_atom, D.nhome, D.nhalo, h->d_xq);
+        k_dd_recv_x<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, snl>>>(D.window, D.d_seq, reinterpret_cast<const float*>(D.window + D.off_recv_x),
+                                                                                 h->d_slot_of_atom, D.nhome, D.nhalo, h->d_xq, D.links);
         LAUNCH_CHECK(h);
         tag_nonlocal_node(h);
         cudaStream_t keep = h->stream;
@@ -2275,9 +2636,8 @@ static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home,
         h->stream         = keep;
         if (rc) return rc;
         tag_nonlocal_node(h);
-        k_dd_push_f<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, snl>>>(
-                h->d_f, h->d_slot_of_atom, D.nhome, D.nhalo, reinterpret_cast<float*>(D.peer[1] + D.peer_off_recv_f[1]),
-                reinterpret_cast<int*>(D.peer[1] + 64), D.d_seq, D.d_count + 1);
+        k_dd_push_f<<<(unsigned)std::max(1, (D.nhalo + 255) / 256), 256, 0, snl>>>(h->d_f, h->d_slot_of_atom, D.nhome, D.nhalo, D.d_halo_link, D.d_seq,
+                                                                                 D.d_count + 1, (flags & B200NB_FLAG_VIRIAL) ? h->d_fshift : nullptr, D.links);
         LAUNCH_CHECK(h);
         tag_nonlocal_node(h);
     }
@@ -2285,14 +2645,12 @@ static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home,
     NB_CUDA(h, cudaStreamWaitEvent(h->stream, D.ev_nl_done, 0));
     /* 3. wait for the forces on the atoms we sent, add them, forces -> atom order */
     const unsigned nb1 = (unsigned)std::max(1, (n + 255) / 256);
-    const int*     wf  = D.peer[0] ? flag_f : nullptr;
-    float* fse = (D.edge_shift >= 0 && (flags & B200NB_FLAG_VIRIAL)) ? h->d_fshift + 3 * D.edge_shift : nullptr;
     if ((reinterpret_cast<uintptr_t>(f_home) & 15) == 0)
-        k_dd_step_end<true><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.peer[0] ? D.d_send_pos : nullptr, wf, D.d_seq, err,
-                                                       reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, fse);
+        k_dd_step_end<true><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.d_ent_off, D.d_ent_idx, D.window, D.d_seq,
+                                                       reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, D.links);
     else
-        k_dd_step_end<false><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.peer[0] ? D.d_send_pos : nullptr, wf, D.d_seq, err,
-                                                        reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, fse);
+        k_dd_step_end<false><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.d_ent_off, D.d_ent_idx, D.window, D.d_seq,
+                                                        reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, D.links);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -2378,7 +2736,6 @@ extern "C" int b200nb_dd_step(b200nb_t* h, const float* x_home, float* f_home, i
     if (!h || !x_home || !f_home) return nb_fail(h, B200NB_ERR_ARG, "dd_step: bad argument");
     DdState& D = h->dd;
     if (!h->have_list || !D.have_plan) return nb_fail(h, B200NB_ERR_STATE, "dd_step: needs a pair list and a halo plan");
-    if ((D.nsend && !D.peer[0]) || (D.nhalo && !D.peer[1])) return nb_fail(h, B200NB_ERR_STATE, "dd_step: peer windows not opened");
     cudaSetDevice(h->device);
     if (h->map_x_host != x_home || h->map_f_host != f_home)
     {
@@ -2406,10 +2763,10 @@ extern "C" int b200nb_dd_status(b200nb_t* h)
     if (!D.window) return 0;
     cudaSetDevice(h->device);
     int e = 0;
-    NB_CUDA(h, cudaMemcpy(&e, D.window + 128, sizeof(int), cudaMemcpyDeviceToHost));
+    NB_CUDA(h, cudaMemcpy(&e, D.window + NB_DD_ERR, sizeof(int), cudaMemcpyDeviceToHost));
     if (e)
     {
-        cudaMemset(D.window + 128, 0, sizeof(int));
+        cudaMemset(D.window + NB_DD_ERR, 0, sizeof(int));
         return nb_fail(h, B200NB_ERR_STATE, "dd_step: a halo exchange flag did not arrive within 10 s (peer stalled or not stepping)");
     }
     return 0;
@@ -2517,7 +2874,8 @@ extern "C" long long b200nb_get_tiles(b200nb_t* h, int outer, int* tiles_host, l
 }
 
 /* every interacting atom pair of the PACKED list (what the force kernel consumes): mask bit set, not on/below the
- * diagonal of the i-cluster's own atoms, both atoms real, r^2 < r2 -- the same predicate the force kernel applies */
+ * diagonal of the i-cluster's own atoms, both atoms real, r^2 < r2 -- the same predicate, step and lane mapping the force
+ * kernel applies (lane = j16 + 16*half: j-atom j16 of the step against i-atoms 4*half .. 4*half+3) */
 __global__ void __launch_bounds__(128)
 k_pairs(const Entry* __restrict__ ent, const int* __restrict__ pja, const uint64_t* __restrict__ tmask, long long nentries,
         const float* __restrict__ xq, const float* __restrict__ shift_vec, const int* __restrict__ atom_index, int nslots, float r2,
@@ -2525,24 +2883,26 @@ k_pairs(const Entry* __restrict__ ent, const int* __restrict__ pja, const uint64
 {
     const long long e = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (e >= nentries) return;
-    const int   lane = threadIdx.x & 31, jl = lane & 7, ih = lane >> 3;
+    const int   lane = threadIdx.x & 31, j16 = lane & 15, half = lane >> 4;
     const Entry en   = ent[e];
     const int   shift = NB_ENTRY_SHIFT(en.shift_nmask), nmask = NB_ENTRY_NMASK(en.shift_nmask);
     const float sx = shift_vec[3 * shift], sy = shift_vec[3 * shift + 1], sz = shift_vec[3 * shift + 2];
-    for (int t = en.start; t < en.end; t++)
+    const int   nstep = (en.end - en.start) >> 1;
+    for (int s = 0; s < nstep; s++)
     {
-        const int      js   = pja[(size_t)t * 8 + jl];
-        const uint64_t mask = (t - en.start < nmask) ? tmask[t] : ~0ull;
-        const bool     diag = intra && shift == B200NB_CENTRAL && (js >> 3) == en.ci;
-        const float4   xj   = reinterpret_cast<const float4*>(xq)[js];
-        const int      aj   = js < nslots ? atom_index[js] : -1;
-        for (int w = 0; w < 2; w++)
+        const int       js   = pja[(size_t)en.start * 8 + s * 16 + j16];
+        const unsigned* mw   = reinterpret_cast<const unsigned*>(tmask + en.start) + 4 * s;
+        const bool      diag = intra && shift == B200NB_CENTRAL && (js >> 3) == en.ci;
+        const float4    xj   = reinterpret_cast<const float4*>(xq)[js];
+        const int       aj   = js < nslots ? atom_index[js] : -1;
+        for (int k = 0; k < 4; k++)
         {
-            const int    i  = 2 * ih + w;
-            const float4 xi = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + i];
-            const float  r  = nb_rsq(xi.x + sx, xi.y + sy, xi.z + sz, xj.x, xj.y, xj.z);
-            const int    ai = atom_index[en.ci * 8 + i];
-            bool ok = (r < r2) && ((mask >> (32 * w + lane)) & 1ull) && ai >= 0 && aj >= 0 && !(diag && (js & 7) <= i);
+            const int      i  = 4 * half + k;
+            const unsigned m  = s < nmask ? mw[k] : ~0u;
+            const float4   xi = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + i];
+            const float    r  = nb_rsq(xi.x + sx, xi.y + sy, xi.z + sz, xj.x, xj.y, xj.z);
+            const int      ai = atom_index[en.ci * 8 + i];
+            bool ok = (r < r2) && ((m >> lane) & 1u) && ai >= 0 && aj >= 0 && !(diag && (js & 7) <= i);
             if (ok)
             {
                 unsigned long long pos = atomicAdd(counter, 1ull);

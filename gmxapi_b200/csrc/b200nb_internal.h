@@ -101,32 +101,57 @@ struct PackedList
     size_t    cap_tiles = 0, cap_entries = 0;
 };
 
-/* Peer-memory halo exchange of the domain-decomposed step (b200nb_dd_*): each rank owns a WINDOW in its device memory,
- *   [flag_x @0][flag_f @64][err @128] ... [recv_x: 3 floats per halo atom @256][recv_f: 3 floats per sent atom],
+/* Peer-memory halo exchange of the domain-decomposed step (b200nb_dd_*).  A rank exchanges halos over up to NB_DD_MAX_LINKS
+ * LINKS; link k of every rank belongs to the same neighbour offset (1-D: the one +x neighbour; N-D half shell: the 13 / 4
+ * lexicographically positive offsets, gmxapi_b200/domdec_nd.py), so "my receive link k" and "my source's send link k" are the
+ * two ends of one connection and share the flag index k.  Each rank owns a WINDOW in its device memory,
+ *   [flag_x[k] @ 32*k][flag_f[k] @ 512 + 32*k][err @ 1024] ... [recv_x: 3 floats per halo atom @ 2048][recv_f: 3 floats per send entry],
  * that its neighbours write directly over NVLink (CUDA IPC mapping, or the plain device pointer inside one process):
- * the rank that owns the halo atoms stores their coordinates into recv_x and then raises flag_x to the step number; the
- * rank that computed forces on them stores those into the owner's recv_f and raises flag_f.  Consumer kernels spin on the
- * flag in their own memory (bounded; a time-out raises err).  One exchange each way per step, no host involvement, no NCCL
- * call on the per-step path (the reference pushes with cudaMemcpyAsync + event handshakes, gpuhaloexchange_impl.cu:403-444). */
+ * the owner of halo atoms stores their coordinates into the receiver's recv_x (at the link's halo offset) and raises the
+ * receiver's flag_x[k] to the step number; the rank that computed forces on them stores those into the owner's recv_f (at the
+ * link's send-entry offset) and raises the owner's flag_f[k].  Consumer kernels spin on the flags in their own memory (bounded;
+ * a time-out raises err).  One exchange each way per step, no host involvement, no NCCL call on the per-step path (the reference
+ * pushes with cudaMemcpyAsync + event handshakes, gpuhaloexchange_impl.cu:403-444, one pulse per dimension, domdec.cpp:260-460). */
+#define NB_DD_MAX_LINKS 16
+#define NB_DD_MAX_PEERS 16
+#define NB_DD_FLAG_X(k) (32 * (k))
+#define NB_DD_FLAG_F(k) (512 + 32 * (k))
+#define NB_DD_ERR 1024
+#define NB_DD_DATA 2048
+/* what the step's kernels need to know about the links (kernel parameter, by value) */
+struct DdLinksDev
+{
+    int    nlinks;
+    int    send_off[NB_DD_MAX_LINKS + 1]; /* send entries of link k: [send_off[k], send_off[k+1]) */
+    int    halo_off[NB_DD_MAX_LINKS + 1]; /* halo atoms (0-based after the home atoms) received over link k */
+    float  shift[NB_DD_MAX_LINKS][3];     /* added to the coordinates sent over link k (dd_move_x's box shift, domdec.cpp:300-318) */
+    int    fshift_index[NB_DD_MAX_LINKS]; /* receive link k: shift-force slot that also gets the forces on its halo atoms, or -1 */
+    float* peer_recv_x[NB_DD_MAX_LINKS];  /* send link k: where its coordinates land in the destination's window */
+    int*   peer_flag_x[NB_DD_MAX_LINKS];
+    float* peer_recv_f[NB_DD_MAX_LINKS];  /* receive link k: where the forces on its halo atoms go in the source's window */
+    int*   peer_flag_f[NB_DD_MAX_LINKS];
+};
 struct DdState
 {
     unsigned char* window = nullptr;
     size_t         window_bytes = 0;
     int            max_halo = 0, max_send = 0;
-    size_t         off_recv_x = 256, off_recv_f = 0;
-    unsigned char* peer[2] = { nullptr, nullptr }; /* [0]: -x neighbour's window (we push x there), [1]: +x neighbour's (we push f) */
-    bool           peer_is_ipc[2] = { false, false };
-    size_t         peer_off_recv_f[2] = { 0, 0 };
-    int            nhome = 0, nhalo = 0, nsend = 0;
-    int*           d_send_idx = nullptr; /* home atoms we send, local indices */
-    int*           d_send_pos = nullptr; /* per home atom: its position in the send list or -1 */
-    size_t         cap_send = 0, cap_home = 0;
-    float          shift[3] = { 0, 0, 0 };
-    int            edge_shift = -1; /* shift index the returned forces also count for (periodic edge), or -1 */
+    size_t         off_recv_x = NB_DD_DATA, off_recv_f = 0;
+    unsigned char* peer[NB_DD_MAX_PEERS] = {}; /* opened neighbour windows */
+    bool           peer_is_ipc[NB_DD_MAX_PEERS] = {};
+    size_t         peer_off_recv_f[NB_DD_MAX_PEERS] = {};
+    int            nhome = 0, nhalo = 0, nsend = 0; /* nsend = send entries over all links (an atom can go to several) */
+    DdLinksDev     links{};
+    int*           d_send_atom = nullptr; /* per send entry: the home atom */
+    int*           d_send_link = nullptr; /* per send entry: its link */
+    int*           d_ent_off = nullptr;   /* per home atom: CSR into d_ent_idx, the send entries that carry it (force return) */
+    int*           d_ent_idx = nullptr;
+    unsigned char* d_halo_link = nullptr; /* per halo atom: the link it came over */
+    size_t         cap_send = 0, cap_home = 0, cap_halo = 0;
     int*           d_count = nullptr; /* 2 last-block counters */
     int*           d_seq = nullptr;   /* device-resident step counter: the value the flags carry (graph-replayable) */
     bool           have_plan = false;
-    /* the halo chain (push x, wait, halo x -> grid, non-local kernel, push f) runs on its own high-priority stream beside
+    /* the halo chain (wait, halo x -> grid, non-local kernel, push f) runs on its own high-priority stream beside
      * the local kernel, the reference's local / non-local stream split (cuda/nbnxm_cuda_data_mgmt.cu:260-291) */
     int            prio_high = 0;
     cudaStream_t   stream_nl = nullptr;
@@ -176,6 +201,7 @@ struct b200nb_context
     float  h_shift_vec[B200NB_SHIFTS * 3];
 
     GridDesc grid[2]{};
+    bool     grid_uploaded = false; /* slot arrays come from b200nb_set_grid_atoms (reference-built grid), no atom-order view */
     int      ncol_total = 0, ncells_total = 0, npad = 0;
     size_t   cap_atoms = 0, cap_pad = 0, cap_cols = 0;
     float*   d_x = nullptr;          /* natoms*3, original order (staging) */

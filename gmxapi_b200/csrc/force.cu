@@ -6,39 +6,39 @@
  *   arithmetic parity target = the CPU SIMD kernels nbnxm/kernels_simd_2xmm/kernel_inner.h:226-880 and
  *   kernel_outer.h:395-452 (self terms), simd/simd_math.h:1609-1722 (Ewald correction polynomials).
  *
- * Design (not a port of the reference CUDA kernel), sized with profiles/tools/microbench.cu and the diagnostic builds of
- * profiles/r1/v_sweep_pair_loop_diagnostics.txt: on sm_100 the FP32 pipe retires 128 lane-FMAs/clk/SM whether issued as
- * scalar FFMA or packed FFMA2; a packed instruction costs its sub-partition two issue cycles and every other instruction
- * one, and that -- instruction issue with the FP32 pipe as its largest client -- is what bounds this kernel, not latency.
- * ALU-pipe instructions (FSEL, FMNMX, LOP3, IADD3) run at half rate on their own pipe, SHFL at ~0.44 warp-instructions/
- * clk/SMSP, MUFU at 16 lanes/clk/SM.  So the kernel is written to spend its issue slots on FP32 math:
- *  - one warp per list entry = one 8-atom i-cluster + shift against a run of PACKED tiles of 8 j-atom slots each
- *    (PackedList, b200nb_internal.h: j-atoms with no pair inside the list radius were dropped when the list was packed);
- *  - lane = jl + 8*ih holds the j-atom in slot jl of the tile and the TWO i-atoms (2*ih, 2*ih+1) as packed float2 registers
- *    for the whole entry: all pair arithmetic is packed (fma.rn.f32x2 -> FFMA2/FMUL2/FADD2), the j operands enter as the
- *    scalar-broadcast operand form of those instructions, so a tile costs two 16-byte shared-memory loads (xyzq;
- *    LJ pair + the j-atom's slot index; the 4 lanes sharing a j-atom hit the same address) and no register shuffling;
- *  - j-forces: in-lane add of the two pairs, 2-stage reduce-scatter (3 shuffles) over the 4 lanes sharing the j-atom,
- *    then one scalar red.global.add.f32 per lane: 32 lanes cover the float4 force slots of the tile's 8 j-atoms;
- *  - i-forces stay in registers; per entry one transposed butterfly over the 8 j-lanes and one 16-byte red per atom;
- *  - tiles that carry exclusion masks are sorted to the front of an entry (b200nb.cu k_search) and run through a
- *    separate code path; the unmasked path has no mask logic and no r^2 clamp;
+ * Design (not a port of the reference CUDA kernel), sized with profiles/tools/microbench.cu, the diagnostic builds of
+ * profiles/r1/v_sweep_pair_loop_diagnostics.txt and the round-1 ncu source page (profiles/r1/z_ncu_source_regions_*): on
+ * sm_100 the FP32 pipe retires 128 lane-FMAs/clk/SM whether issued as scalar FFMA or packed FFMA2; a packed instruction
+ * keeps the pipe busy for two cycles, everything else competes for the remaining issue slots.  The round-1 kernel
+ * (2 i-atoms x 1 j-atom per lane, 8 j-atoms per tile) spent only 35 of its 68 pair-loop instructions on packed FP32
+ * math: the rest was the j-force reduce-scatter over the 4 lanes sharing a j-atom (3 shuffles, 8 selects, 6 scalar FMAs,
+ * one red per lane and tile) and, outside the loop, the cp.async staging ring (15 % of all instructions).  This kernel
+ * removes both:
+ *  - one warp per list entry = one 8-atom i-cluster + shift against a run of PACKED j-atoms (PackedList,
+ *    b200nb_internal.h), consumed 16 at a time (a "step" = 2 packed tiles);
+ *  - lane = jl + 16*ih owns ONE j-atom of the step (jl) and FOUR i-atoms (4*ih .. 4*ih+3) as two packed float2 pairs
+ *    held in registers for the whole entry.  All pair arithmetic is packed (fma.rn.f32x2 -> FFMA2/FMUL2), the j operands
+ *    enter in the scalar-broadcast operand form.  The j-atom's data (16-byte xyzq, 8-byte LJ pair) are loaded straight
+ *    into the lane's registers with one LDG.128 + one LDG.64, one step AHEAD of their use (the slot index two steps
+ *    ahead), so a step's loads have 4 pair evaluations (~200 instructions per warp, x the resident warps) to land:
+ *    no shared memory, no cp.async, no staging code;
+ *  - j-forces: accumulated in the lane over its 4 pairs with the same packed FMAs that feed the i accumulators, then ONE
+ *    exchange with the other half-warp per step (2 shuffles) and one red per lane (half 0: red.v2 {x,y}, half 1: red z):
+ *    per 64 pairs 1 shuffle + 0.5 red instead of 3 shuffles + 1 red + 14 ALU / scalar-FMA instructions;
+ *  - i-forces stay in registers (12 floats per lane); per entry one transposed butterfly over the 16 lanes of the half
+ *    (15 shuffles) and one 16-byte red per i-atom;
+ *  - steps that carry exclusion masks are sorted to the front of an entry (k_pack) and run through a separate code
+ *    path; the unmasked path has no mask logic and no r^2 clamp;
  *  - LJ is evaluated as (c12*r^-6 - c6)*r^-6, the Ewald correction polynomials keep their coefficients as
- *    instruction immediates (folding beta^3 into them would cost seven registers); out-of-range lanes are discarded by
- *    select, so garbage there cannot poison a sum;
+ *    instruction immediates; out-of-range lanes are discarded by select, so garbage there cannot poison a sum;
  *  - r^2 is evaluated with the reference's operand roles and operation order so the in-range pair set is
  *    bit-identical (see nb_rsq in b200nb_internal.h);
- *  - the j-atom data go through a two-buffer ring of NB_CHUNK tiles in shared memory, filled with cp.async (LDGSTS): each
- *    lane reads one j-slot index (coalesced) and gathers that atom's 16-byte xyzq and 8-byte LJ pair while the previous
- *    chunk is being computed; the pair loop never touches L2, and a warp needs 4 KB whatever the length of its entry.
- *    (The first version loaded j data with LDG one tile ahead and spent its time in long-scoreboard stalls; the second
- *    staged a whole entry at once, which tied the entry length to the shared memory per warp.)  The i-cluster lives in
- *    registers, which beats shared memory.
- *    TMA (cp.async.bulk) was considered and not used: the stream is a gather of 16-byte atoms by slot index, so a bulk copy
- *    would move one atom per instruction issued by one elected lane plus mbarrier traffic, while LDGSTS moves 512 B per
- *    warp instruction with per-lane addresses and needs only wait_group + syncwarp;
- *  - LJ force switch / potential switch / VdW cut-off below the Coulomb cut-off are a second set of instantiations (GEN):
- *    the plain kernels, which every BASELINE configuration uses, pay nothing for them.
+ *  - TMA (cp.async.bulk / tile::gather4) is not used: the j stream is a gather of single 16-byte atoms by slot index
+ *    whose consumer is ONE lane; a per-lane LDG.128 delivers it into that lane's registers with no barrier, no shared
+ *    memory round trip and no elected-thread issue; gather4 moves rows of a 2-D tensor into shared memory, from where
+ *    every lane would have to fetch its own row again;
+ *  - LJ force switch / potential switch / VdW cut-off below the Coulomb cut-off / LJ-PME are a second set of
+ *    instantiations (GEN): the plain kernels, which every BASELINE configuration uses, pay nothing for them.
  */
 #include <cstdio>
 
@@ -83,34 +83,60 @@ __device__ __forceinline__ float exp_approx(float x) /* e^x through MUFU.EX2; re
 struct JAtom
 {
     float4 xq;
-    float2 lj; /* GEOM: sqrt(6 C6), sqrt(12 C12); table: atom type in lj.x (as int bits) */
+    float2 lj;   /* GEOM: sqrt(6 C6), sqrt(12 C12); table: atom type in lj.x (as int bits) */
     int    slot; /* grid slot of the j-atom: index into xq / f */
 };
 
-/* The j-atom data of a whole entry is staged in shared memory with cp.async (LDGSTS) before the pair loop, so the
- * loop itself never waits on L2.  Per warp and packed tile 256 B: [8 x float4 xyzq][8 x {lj.x, lj.y, slot, -}]; the 8
- * lanes of a quarter-warp read 128 contiguous bytes (no bank conflicts), the 4 quarter-warps the same ones (broadcast). */
-#define NB_TILE_SMEM 256
-__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async8(unsigned smem_addr, const void* gptr)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async4(unsigned smem_addr, const void* gptr)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
+#define NB_JSTEP 16 /* j-atoms per step = 2 packed tiles: lanes jl and jl + 16 share j-atom jl */
+#ifndef NB_RING
+#define NB_RING 4 /* stages of the per-warp j-atom ring in shared memory: a step's gather is issued NB_RING - 1 steps ahead */
+#endif
 
-/* s_lane = this warp's staging area + jl*16 */
-__device__ __forceinline__ void load_j(JAtom& J, const unsigned char* s_lane, int t)
+/* The j-atom stream.  Every lane owns one 32-byte record per ring stage in shared memory, {x, y, z, q | lj.x, lj.y, slot, -},
+ * filled by the lane itself with cp.async (16 bytes of xq, 8 bytes of LJ parameters or 4 bytes of atom type) straight from
+ * global memory and read back by the same lane NB_RING - 1 steps later: no register holds data in flight (with the gather
+ * loaded into registers ptxas, at the 128-register cap, sank the loads to the end of the step, right in front of their first
+ * use: 41 % of the stall samples of profiles/r2/a_ncu_source_k_force_water192k.txt), no cross-lane hand-over, so no barrier --
+ * a lane only waits for its own copies (cp.async.wait_group). */
+__device__ __forceinline__ void cp_async_16(unsigned dst, const void* src)
 {
-    J.xq           = *reinterpret_cast<const float4*>(s_lane + t * NB_TILE_SMEM);
-    const float4 a = *reinterpret_cast<const float4*>(s_lane + t * NB_TILE_SMEM + 128);
-    J.lj           = make_float2(a.x, a.y);
-    J.slot         = __float_as_int(a.z);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(unsigned dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(unsigned dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+/* starts the gather of the j-atom in grid slot `slot` into the lane's record at shared address `rec` (read-only path: xq / lj /
+ * atype are written by the kernel BEFORE this one in the stream, never during it) */
+template<bool GEOM>
+__device__ __forceinline__ void gather_j(unsigned rec, int slot, const int* next_index, const float4* __restrict__ xq,
+                                         const float2* __restrict__ lj, const int* __restrict__ atype)
+{
+    cp_async_16(rec, xq + slot);
+    if (GEOM) cp_async_8(rec + 512, lj + slot);
+    else cp_async_4(rec + 512, atype + slot);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(rec + 520), "r"(slot) : "memory");
+    /* the record's fourth word carries the slot index of the step NB_RING - 1 steps after this one: it lands with the record and
+     * is exactly what the gather issued when this record is consumed needs (the index stream rides the same ring, so no global
+     * load result is ever waited for inside the step loop) */
+    if (next_index) cp_async_4(rec + 524, next_index);
+}
+/* returns the slot index stored in the record's fourth word */
+__device__ __forceinline__ int read_j(JAtom& J, unsigned rec)
+{
+    float sl, nx;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(J.xq.x), "=f"(J.xq.y), "=f"(J.xq.z), "=f"(J.xq.w) : "r"(rec) : "memory");
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(J.lj.x), "=f"(J.lj.y), "=f"(sl), "=f"(nx) : "r"(rec + 512) : "memory");
+    J.slot = __float_as_int(sl);
+    return __float_as_int(nx);
 }
 
 /* simd/simd_math.h:1609-1650 pmeForceCorrection: denominator and numerator */
@@ -166,26 +192,27 @@ struct KConst
 };
 struct IData
 {
-    float2 x, y, z;  /* the two i-atoms of this lane, shift already added */
+    float2 x, y, z;  /* two i-atoms of this lane, shift already added */
     float2 q;        /* epsfac * q_i */
     float2 c6n, c12; /* GEOM: -sqrt(6 C6_i), sqrt(12 C12_i) */
     int    t0, t1;   /* table path: type_i * ntypes */
     float2 g0, g1;   /* LJ-PME (GEN kernels): nbfp_comb of the two i-atoms' types */
 };
 
-/* One tile: lane computes pairs (i0, jl) [.x] and (i1, jl) [.y].  Returns the force ON THE i-ATOMS in (tx,ty,tz). */
+/* Two pairs: (i0, j) in .x and (i1, j) in .y.  Returns F/r (zero outside the cut-off or for a switched-off pair) and the
+ * distance vector xi - xj; adds the pair energies to evdw / ecoul when VF. */
 template<int EEL, bool GEOM, bool VF, bool MASKED, bool GEN>
-__device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const NbParamsDev& P, const KConst& K, const float2* __restrict__ nbfp,
-                                           const float2* __restrict__ nbfp_comb, float inter0, float inter1, bool ok0, bool ok1, float2& tx, float2& ty, float2& tz,
-                                           float& evdw, float& ecoul)
+__device__ __forceinline__ float2 pair_fscal(const IData& I, const JAtom& J, const NbParamsDev& P, const KConst& K,
+                                             const float2* __restrict__ nbfp, const float2* __restrict__ nbfp_comb, float inter0, float inter1,
+                                             bool ok0, bool ok1, float2& dx, float2& dy, float2& dz, float& evdw, float& ecoul)
 {
     const float2 m1 = dup(-1.0f);
-    const float2 dx = fma2(dup(J.xq.x), m1, I.x); /* xi - xj: the product is exact */
-    const float2 dy = fma2(dup(J.xq.y), m1, I.y);
-    const float2 dz = fma2(dup(J.xq.z), m1, I.z);
-    float2       r2 = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
-    bool         wa = r2.x < K.rc2, wb = r2.y < K.rc2;
-    float2       inter;
+    dx              = fma2(dup(J.xq.x), m1, I.x); /* xi - xj: the product is exact */
+    dy              = fma2(dup(J.xq.y), m1, I.y);
+    dz              = fma2(dup(J.xq.z), m1, I.z);
+    float2 r2       = fma2(dz, dz, fma2(dx, dx, mul2(dy, dy)));
+    bool   wa = r2.x < K.rc2, wb = r2.y < K.rc2;
+    float2 inter;
     if (MASKED)
     {
         wa    = wa && ok0;
@@ -193,12 +220,8 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
         inter = make_float2(inter0, inter1);
         r2    = make_float2(fmaxf(r2.x, NB_MIN_RSQ), fmaxf(r2.y, NB_MIN_RSQ));
     }
-    const float2 rinv   = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
-    const float2 rinvsq = mul2(rinv, rinv);
-    float2       rinv_ex = rinv;
-    if (MASKED) rinv_ex = mul2(rinv, inter);
-
-    float2 c6n, c12;
+    const float2 rinv    = make_float2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+    float2       c6n, c12;
     if (GEOM)
     {
         c6n = mul2(I.c6n, dup(J.lj.x));
@@ -211,6 +234,21 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
         c6n             = make_float2(-pa.x, -pb.x);
         c12             = make_float2(pa.y, pb.y);
     }
+    const float2 qq = mul2(I.q, dup(J.xq.w));
+    /* Ewald correction polynomials first: their reciprocal (MUFU) then overlaps the LJ arithmetic */
+    float2 z2 = dup(0.0f), ewt = dup(0.0f);
+    if (EEL == 1)
+    {
+        z2               = mul2(dup(K.beta2), r2);
+        const float2 z4  = mul2(z2, z2);
+        const float2 den = pme_force_den(z2, z4, K.fd4, K.fd3, K.fd2, K.fd1, K.fd0);
+        const float2 rd  = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+        const float2 num = pme_force_num(z2, z4, K.fn6, K.fn5);
+        ewt              = mul2(num, rd); /* beta * pmecorrF(z2) */
+    }
+    const float2 rinvsq  = mul2(rinv, rinv);
+    float2       rinv_ex = rinv;
+    if (MASKED) rinv_ex = mul2(rinv, inter);
     float2 rinv6 = mul2(mul2(rinvsq, rinvsq), rinvsq);
     if (MASKED) rinv6 = mul2(rinv6, inter);
     float2 fsum; /* F*r summed over LJ and Coulomb */
@@ -308,16 +346,10 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
     {
         fsum = mul2(fma2(c12, rinv6, c6n), rinv6);
     }
-    const float2 qq = mul2(I.q, dup(J.xq.w));
-    float2       vcoul = dup(0.0f);
+    float2 vcoul = dup(0.0f);
     if (EEL == 1)
     {
-        const float2 z2 = mul2(dup(K.beta2), r2);
-        const float2 z4 = mul2(z2, z2);
-        const float2 den = pme_force_den(z2, z4, K.fd4, K.fd3, K.fd2, K.fd1, K.fd0);
-        const float2 num = pme_force_num(z2, z4, K.fn6, K.fn5);
-        const float2 t   = mul2(num, make_float2(rcp_approx(den.x), rcp_approx(den.y))); /* beta * pmecorrF(z2) */
-        fsum             = fma2(qq, fma2(t, z2, rinv_ex), fsum);
+        fsum = fma2(qq, fma2(ewt, z2, rinv_ex), fsum);
         if (VF)
         {
             float2 vsub = mul2(dup(P.beta), pme_pot_corr2(z2));
@@ -334,9 +366,6 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
     float2 fscal = mul2(rinvsq, fsum);
     fscal.x      = wa ? fscal.x : 0.0f;
     fscal.y      = wb ? fscal.y : 0.0f;
-    tx           = mul2(fscal, dx);
-    ty           = mul2(fscal, dy);
-    tz           = mul2(fscal, dz);
     if (VF)
     {
         if (!GEN)
@@ -350,154 +379,42 @@ __device__ __forceinline__ void tile_pairs(const IData& I, const JAtom& J, const
         evdw += (wa ? vlj.x : 0.0f) + (wb ? vlj.y : 0.0f);
         ecoul += (wa ? vcoul.x : 0.0f) + (wb ? vcoul.y : 0.0f);
     }
+    return fscal;
 }
 
-#ifndef NB_CHUNK
-#define NB_CHUNK 8 /* packed tiles per ring buffer (multiple of 4: one staging round covers 32 j-atoms) */
-#endif
-/* NT plain (unmasked, force-only) tiles evaluated in lock step: every step of the arithmetic is written for all NT tiles
- * before the next step, so the instruction stream carries NT independent dependency chains.  The kernel uses NT = 1: one
- * tile in flight at 32 warps/SM beat two at 20 (profiles/r1/g_sweep_one_entry_per_warp.txt); the generality is kept because
- * the statement order below (not the tile count) is what makes ptxas emit the packed sequence this file is tuned around. */
-template<int EEL, bool GEOM, int NT>
-__device__ __forceinline__ void tile_pairs_multi(const IData& I, const JAtom (&J)[NT], const NbParamsDev& P, const KConst& K,
-                                                 const float2* __restrict__ nbfp, float2& fix, float2& fiy, float2& fiz, float (&sx)[NT],
-                                                 float (&sy)[NT], float (&sz)[NT])
-{
-    const float2 m1 = dup(-1.0f);
-    float2       dx[NT], dy[NT], dz[NT], r2[NT], rinv[NT], rinvsq[NT], rinv6[NT], c6n[NT], c12[NT], fsum[NT], qq[NT];
-#pragma unroll
-    for (int u = 0; u < NT; u++) dx[u] = fma2(dup(J[u].xq.x), m1, I.x);
-#pragma unroll
-    for (int u = 0; u < NT; u++) dy[u] = fma2(dup(J[u].xq.y), m1, I.y);
-#pragma unroll
-    for (int u = 0; u < NT; u++) dz[u] = fma2(dup(J[u].xq.z), m1, I.z);
-#pragma unroll
-    for (int u = 0; u < NT; u++) r2[u] = mul2(dy[u], dy[u]);
-#pragma unroll
-    for (int u = 0; u < NT; u++) r2[u] = fma2(dx[u], dx[u], r2[u]);
-#pragma unroll
-    for (int u = 0; u < NT; u++) r2[u] = fma2(dz[u], dz[u], r2[u]);
-#pragma unroll
-    for (int u = 0; u < NT; u++) rinv[u] = make_float2(rsqrt_approx(r2[u].x), rsqrt_approx(r2[u].y));
-#pragma unroll
-    for (int u = 0; u < NT; u++)
-    {
-        if (GEOM)
-        {
-            c6n[u] = mul2(I.c6n, dup(J[u].lj.x));
-            c12[u] = mul2(I.c12, dup(J[u].lj.y));
-        }
-        else
-        {
-            const int    tj = __float_as_int(J[u].lj.x);
-            const float2 pa = __ldg(nbfp + I.t0 + tj), pb = __ldg(nbfp + I.t1 + tj);
-            c6n[u]          = make_float2(-pa.x, -pb.x);
-            c12[u]          = make_float2(pa.y, pb.y);
-        }
-        qq[u] = mul2(I.q, dup(J[u].xq.w));
-    }
-    float2 z2[NT], z4[NT], den[NT], num[NT];
-    if (EEL == 1)
-    {
-#pragma unroll
-        for (int u = 0; u < NT; u++) z2[u] = mul2(dup(K.beta2), r2[u]);
-#pragma unroll
-        for (int u = 0; u < NT; u++) z4[u] = mul2(z2[u], z2[u]);
-#pragma unroll
-        for (int u = 0; u < NT; u++) den[u] = pme_force_den(z2[u], z4[u], K.fd4, K.fd3, K.fd2, K.fd1, K.fd0);
-#pragma unroll
-        for (int u = 0; u < NT; u++) den[u] = make_float2(rcp_approx(den[u].x), rcp_approx(den[u].y));
-#pragma unroll
-        for (int u = 0; u < NT; u++) num[u] = pme_force_num(z2[u], z4[u], K.fn6, K.fn5);
-    }
-#pragma unroll
-    for (int u = 0; u < NT; u++) rinvsq[u] = mul2(rinv[u], rinv[u]);
-#pragma unroll
-    for (int u = 0; u < NT; u++) rinv6[u] = mul2(mul2(rinvsq[u], rinvsq[u]), rinvsq[u]);
-#pragma unroll
-    for (int u = 0; u < NT; u++) fsum[u] = mul2(fma2(c12[u], rinv6[u], c6n[u]), rinv6[u]);
-#pragma unroll
-    for (int u = 0; u < NT; u++)
-    {
-        if (EEL == 1) fsum[u] = fma2(qq[u], fma2(mul2(num[u], den[u]), z2[u], rinv[u]), fsum[u]);
-        else fsum[u] = fma2(qq[u], fma2(r2[u], dup(-P.two_k_rf), rinv[u]), fsum[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < NT; u++)
-    {
-        float2 fscal = mul2(rinvsq[u], fsum[u]);
-        fscal.x      = (r2[u].x < K.rc2) ? fscal.x : 0.0f;
-        fscal.y      = (r2[u].y < K.rc2) ? fscal.y : 0.0f;
-        /* force on the two i-atoms: one packed FMA per component into the entry's accumulators; force on the j-atom: minus
-         * the sum over the lane's two pairs, one scalar FMUL + FFMA per component (4 FMA-pipe cycles per component instead
-         * of the 5 of packed multiply, packed add, scalar add) */
-        fix   = fma2(fscal, dx[u], fix);
-        fiy   = fma2(fscal, dy[u], fiy);
-        fiz   = fma2(fscal, dz[u], fiz);
-        sx[u] = __fmaf_rn(-fscal.y, dx[u].y, -(fscal.x * dx[u].x));
-        sy[u] = __fmaf_rn(-fscal.y, dy[u].y, -(fscal.x * dy[u].x));
-        sz[u] = __fmaf_rn(-fscal.y, dz[u].y, -(fscal.x * dz[u].x));
-    }
-}
-
-/* j-force: both pairs of the lane act on the same j-atom: sum them (negated: the force on j is minus the force on i), then
- * a 2-stage reduce-scatter over the 4 lanes (bits 4 and 3) that share the j-atom leaves lane class (b4,b3) = (0,0) with the
- * x total, (0,1) y, (1,0) z and (1,1) a second copy of z; every lane then issues ONE scalar red.global.add.f32 to float
- * slot 2*b4+b3 of f[cj*8+jl] -- the copy lands in the float4's pad slot, which nothing reads.  3 shuffles, 4 selects, no
- * divergent branch (a predicated 16-byte red by 8 lanes compiled to BSSY/BRA/BSYNC plus a convergence check before the
- * next shuffle: 7 more instructions per tile). */
-struct LaneClass
-{
-    bool  b4, b3, b3or4, b3only;
-    char* f_lane; /* f + component slot (2*b4+b3) * 4 bytes */
-};
-__device__ __forceinline__ void reduce_store_j(const float2 tx, const float2 ty, const float2 tz, const LaneClass& C, int jslot)
+/* j-force of a step: the lane's packed accumulators hold, per component, the sums over its even (.x) and odd (.y) i-atoms
+ * of F/r * d (the force ON THE i-ATOMS); the force on the j-atom is minus their sum plus the other half-warp's share.
+ * One exchange: half 0 hands over z and gets x, both get each other's y; then one red.v2 per lane into the j-atom's float4
+ * force slot: 2 shuffles + 1 red per 128 pairs. */
+__device__ __forceinline__ void reduce_store_j(const float2 fjx, const float2 fjy, const float2 fjz, const bool upper, float4* __restrict__ f,
+                                               const int jslot)
 {
     const unsigned full = 0xffffffffu;
-    const float sx = -tx.x - tx.y, sy = -ty.x - ty.y, sz = -tz.x - tz.y;
-    float k0 = C.b4 ? sz : sx;
-    k0 += __shfl_xor_sync(full, C.b4 ? sx : sz, 16);   /* b4=0: x of both halves, b4=1: z of both halves */
-    const float k1 = sy + __shfl_xor_sync(full, sy, 16); /* y of both halves (used by the b4=0 lanes) */
-    float v = C.b3only ? k1 : k0;
-    v += __shfl_xor_sync(full, C.b3or4 ? k0 : k1, 8);
-    atomicAdd(reinterpret_cast<float*>(C.f_lane + (size_t)(unsigned)jslot * 16u), v);
-}
-
-template<int NT>
-__device__ __forceinline__ void reduce_store_j_multi(const float (&sx)[NT], const float (&sy)[NT], const float (&sz)[NT], const LaneClass& C,
-                                                     const int (&jslot)[NT])
-{
-    const unsigned full = 0xffffffffu;
-    float          k0[NT], k1[NT], v[NT];
-#pragma unroll
-    for (int u = 0; u < NT; u++) k0[u] = __shfl_xor_sync(full, C.b4 ? sx[u] : sz[u], 16);
-#pragma unroll
-    for (int u = 0; u < NT; u++) k1[u] = __shfl_xor_sync(full, sy[u], 16);
-#pragma unroll
-    for (int u = 0; u < NT; u++) k0[u] += C.b4 ? sz[u] : sx[u], k1[u] += sy[u];
-#pragma unroll
-    for (int u = 0; u < NT; u++) v[u] = __shfl_xor_sync(full, C.b3or4 ? k0[u] : k1[u], 8);
-#pragma unroll
-    for (int u = 0; u < NT; u++) v[u] += C.b3only ? k1[u] : k0[u];
-#pragma unroll
-    for (int u = 0; u < NT; u++)
-    {
+    const float    sx = -fjx.x - fjx.y, sy = -fjy.x - fjy.y, sz = -fjz.x - fjz.y;
+    const float    rcv = __shfl_xor_sync(full, upper ? sx : sz, 16);
+    const float    rcy = __shfl_xor_sync(full, sy, 16);
+    /* every lane issues the SAME instruction: half 0 adds {x, y} to the slot's first two floats, half 1 {z, 0} to the last two
+     * (the pad float of the float4 slot is never read).  Two predicated reds compiled to two divergent branches with
+     * BSSY / BSYNC around each: 6 more instructions per step. */
+    float* const fp = reinterpret_cast<float*>(f + jslot) + (upper ? 2 : 0);
+    const float  a  = (upper ? sz : sx) + rcv, b = upper ? 0.0f : sy + rcy;
 #ifdef B200NB_DIAG_NO_RED /* diagnostic build only: drops the j-force scatter (wrong results) to measure its cost */
-        if (v[u] == 12345.678f)
+    if (rcv == 12345.678f)
 #endif
-            atomicAdd(reinterpret_cast<float*>(C.f_lane + (size_t)(unsigned)jslot[u] * 16u), v[u]);
-    }
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(fp), "f"(a), "f"(b) : "memory");
 }
 
 #ifndef B200NB_FORCE_WARPS
 #define B200NB_FORCE_WARPS 1 /* warps (= list entries) per CTA: small CTAs refill an SM's warp slots at entry granularity */
 #endif
 #ifndef B200NB_FORCE_MIN_BLOCKS
-#define B200NB_FORCE_MIN_BLOCKS (32 / B200NB_FORCE_WARPS) /* 32 resident warps per SM = 64 registers per thread */
+/* resident warps per SM the register allocation aims at: 20 (<= 96 registers) for the force-only kernels -- with the j-atom
+ * stream in the shared-memory ring they fit without spills, and 20 warps beat 16 by 8 % (profiles/r2/c_sweep_ring.txt); the
+ * energy / modifier kernels need up to 128 registers */
+#define B200NB_FORCE_MIN_BLOCKS(VF, GEN) (((VF) || (GEN) ? 16 : 20) / B200NB_FORCE_WARPS)
 #endif
 template<int EEL, bool GEOM, bool VF, bool GEN>
-__global__ void __launch_bounds__(32 * B200NB_FORCE_WARPS, B200NB_FORCE_MIN_BLOCKS)
+__global__ void __launch_bounds__(32 * B200NB_FORCE_WARPS, B200NB_FORCE_MIN_BLOCKS(VF, GEN))
 k_force(const Entry* __restrict__ entries, long long nentries, const int* __restrict__ pja, const uint64_t* __restrict__ tmask,
         const float4* __restrict__ xq, const float2* __restrict__ lj, const int* __restrict__ atype, const float2* __restrict__ nbfp,
         const float* __restrict__ shift_vec, float4* __restrict__ f, float* __restrict__ fshift, double* __restrict__ energy,
@@ -506,12 +423,8 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
 {
     const long long e = (long long)blockIdx.x * B200NB_FORCE_WARPS + (threadIdx.x >> 5);
     if (e >= nentries) return;
-    const int lane = threadIdx.x & 31;
-    /* Entry e owns the packed tiles [e*maxt, (e+1)*maxt) (maxt = the list's pitch).  Its j data go through a two-buffer ring of
-     * NB_CHUNK tiles in shared memory: chunk c+1 is gathered with cp.async while chunk c is being computed, so the shared
-     * memory per warp is constant (2 x NB_CHUNK x 256 B) whatever the entry's length, and entries can hold a whole
-     * (i-cluster, shift) list.  The kernel is issue-bound (profiles/r1/v_*): what an entry costs is its instruction count,
-     * not the latency of these loads -- long entries pay the prologue / epilogue instructions less often. */
+    const int lane = threadIdx.x & 31, jl = lane & (NB_JSTEP - 1), ih = lane >> 4;
+    /* Entry e owns the packed tiles [e*maxt, (e+1)*maxt) (maxt = the list's pitch), i.e. j slots ja[0 .. 8*ntile), ntile even */
     const int* const ja = pja + (size_t)e * maxt * 8;
     const int4       ev = __ldg(reinterpret_cast<const int4*>(entries) + e);
     KConst K;
@@ -520,179 +433,189 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
                      k2 = __ldg(reinterpret_cast<const float4*>(kconst) + 2);
         K.rc2 = k0.x, K.beta2 = k0.z, K.fd4 = k0.w, K.fd3 = k1.x, K.fn6 = k1.y, K.fn5 = k1.z, K.fd2 = k1.w, K.fd1 = k2.x, K.fd0 = k2.y;
     }
+    const int nstep = (ev.w - ev.z) >> 1;
+    /* the j slots of the first NB_RING steps: list data only, so they may be fetched before the dependency wait below */
+    int slot_first[NB_RING - 1];
+#pragma unroll
+    for (int k = 0; k < NB_RING - 1; k++) slot_first[k] = k < nstep ? __ldg(ja + k * NB_JSTEP + jl) : 0;
     /* Programmatic dependent launch: everything above reads only the list; from here on the kernel touches xq and f, so wait
      * for the completion of the preceding kernel of the stream (k_step_begin) -- a no-op for a normally serialised launch. */
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int  start = ev.z, end = ev.w;
-    const bool self  = VF && NB_ENTRY_SELF(ev.y);
-    if (start >= end && !self) return;
-    const int jl = lane & 7, ih = lane >> 3;
-    const int ci = ev.x, shift = NB_ENTRY_SHIFT(ev.y), nmask = NB_ENTRY_NMASK(ev.y);
-    const int ntile = end - start;
+    const bool self = VF && NB_ENTRY_SELF(ev.y);
+    if (nstep == 0 && !self) return;
+    const int      ci = ev.x, shift = NB_ENTRY_SHIFT(ev.y), nmask = NB_ENTRY_NMASK(ev.y);
     const unsigned full = 0xffffffffu;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int CHUNK_BYTES = NB_CHUNK * NB_TILE_SMEM;
-    unsigned char* const sj = smem_raw + (threadIdx.x >> 5) * (2 * CHUNK_BYTES);
-    const unsigned       s0 = (unsigned)__cvta_generic_to_shared(sj) + (lane >> 3) * NB_TILE_SMEM + (lane & 7) * 16;
-    auto stage = [&](int c) {
-        /* each lane gathers one j-atom per round: 16 B xyzq, 8 B LJ pair (or 4 B type), and keeps the slot index beside them */
-        const unsigned sb = s0 + (c & 1) * CHUNK_BYTES;
+    const bool     upper = ih != 0;
+    /* the ring: NB_RING stages of 1 KB per warp; one commit group per step, empty past the end of the entry */
+    __shared__ __align__(16) float4 s_ring[B200NB_FORCE_WARPS][NB_RING][64];
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(&s_ring[threadIdx.x >> 5][0][0]) + 16u * lane;
 #pragma unroll
-        for (int r = 0; r < NB_CHUNK / 4; r++)
-        {
-            const int a = c * (NB_CHUNK * 8) + 32 * r + lane;
-            if (a < ntile * 8)
-            {
-                const int      slot = __ldg(ja + a);
-                const unsigned dx   = sb + r * 4 * NB_TILE_SMEM;
-                cp_async16(dx, xq + slot);
-                if (GEOM) cp_async8(dx + 128, lj + slot);
-                else cp_async4(dx + 128, atype + slot);
-                asm volatile("st.shared.s32 [%0], %1;" ::"r"(dx + 136), "r"(slot) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    stage(0);
-    LaneClass C;
-    C.b4     = (lane & 16) != 0;
-    C.b3     = (lane & 8) != 0;
-    C.b3or4  = C.b3 || C.b4;
-    C.b3only = C.b3 && !C.b4;
-    C.f_lane = reinterpret_cast<char*>(f) + 4 * (2 * (int)C.b4 + (int)C.b3);
-    IData I;
+    for (int k = 0; k < NB_RING - 1; k++)
     {
-        const float4 a = __ldg(xq + (size_t)ci * 8 + 2 * ih), b = __ldg(xq + (size_t)ci * 8 + 2 * ih + 1);
-        const float  sx = __ldg(shift_vec + 3 * shift), sy = __ldg(shift_vec + 3 * shift + 1), sz = __ldg(shift_vec + 3 * shift + 2);
-        /* the reference adds the shift to the i-atom before the subtraction: kernel_outer.h:482-489 */
-        I.x = make_float2(__fadd_rn(a.x, sx), __fadd_rn(b.x, sx));
-        I.y = make_float2(__fadd_rn(a.y, sy), __fadd_rn(b.y, sy));
-        I.z = make_float2(__fadd_rn(a.z, sz), __fadd_rn(b.z, sz));
-        I.q = make_float2(P.epsfac * a.w, P.epsfac * b.w);
-        if (GEOM)
+        if (k < nstep) gather_j<GEOM>(ring + 1024u * k, slot_first[k], k + NB_RING - 1 < nstep ? ja + (k + NB_RING - 1) * NB_JSTEP + jl : nullptr, xq, lj, atype);
+        cp_async_commit();
+    }
+    IData I[2];
+    {
+        const float sx = __ldg(shift_vec + 3 * shift), sy = __ldg(shift_vec + 3 * shift + 1), sz = __ldg(shift_vec + 3 * shift + 2);
+#pragma unroll
+        for (int p = 0; p < 2; p++)
         {
-            const float4 l = __ldg(reinterpret_cast<const float4*>(lj + (size_t)ci * 8 + 2 * ih));
-            I.c6n          = make_float2(-l.x, -l.z);
-            I.c12          = make_float2(l.y, l.w);
-            I.t0 = I.t1 = 0;
-        }
-        else
-        {
-            const int2 t = __ldg(reinterpret_cast<const int2*>(atype + (size_t)ci * 8 + 2 * ih));
-            I.t0         = t.x * P.ntypes;
-            I.t1         = t.y * P.ntypes;
-            I.c6n = I.c12 = dup(0.0f);
-            if (GEN && P.ljpme)
+            const size_t ia = (size_t)ci * 8 + 4 * ih + 2 * p;
+            const float4 a = __ldg(xq + ia), b = __ldg(xq + ia + 1);
+            /* the reference adds the shift to the i-atom before the subtraction: kernel_outer.h:482-489 */
+            I[p].x = make_float2(__fadd_rn(a.x, sx), __fadd_rn(b.x, sx));
+            I[p].y = make_float2(__fadd_rn(a.y, sy), __fadd_rn(b.y, sy));
+            I[p].z = make_float2(__fadd_rn(a.z, sz), __fadd_rn(b.z, sz));
+            I[p].q = make_float2(P.epsfac * a.w, P.epsfac * b.w);
+            I[p].g0 = I[p].g1 = dup(0.0f);
+            if (GEOM)
             {
-                I.g0 = __ldg(nbfp_comb + t.x);
-                I.g1 = __ldg(nbfp_comb + t.y);
+                const float4 l = __ldg(reinterpret_cast<const float4*>(lj + ia));
+                I[p].c6n       = make_float2(-l.x, -l.z);
+                I[p].c12       = make_float2(l.y, l.w);
+                I[p].t0 = I[p].t1 = 0;
+            }
+            else
+            {
+                const int2 t = __ldg(reinterpret_cast<const int2*>(atype + ia));
+                I[p].t0      = t.x * P.ntypes;
+                I[p].t1      = t.y * P.ntypes;
+                I[p].c6n = I[p].c12 = dup(0.0f);
+                if (GEN && P.ljpme)
+                {
+                    I[p].g0 = __ldg(nbfp_comb + t.x);
+                    I[p].g1 = __ldg(nbfp_comb + t.y);
+                }
             }
         }
     }
-    float2 fix = dup(0.f), fiy = dup(0.f), fiz = dup(0.f);
+#define NB_LOAD_I(IP, p) const IData& IP = I[p];
+    float2 fix[2] = { dup(0.f), dup(0.f) }, fiy[2] = { dup(0.f), dup(0.f) }, fiz[2] = { dup(0.f), dup(0.f) };
     float  evdw = 0.f, ecoul = 0.f;
-    if (self && jl < 2)
+    if (self && jl < 4)
     {
-        /* Coulomb self term, once per i-atom: kernel_outer.h:408-452 (fillers carry q = 0) */
-        const float qi = (jl == 0 ? I.q.x : I.q.y);
+        /* Coulomb self term, once per i-atom (lane jl of each half takes i-atom 4*ih + jl): kernel_outer.h:408-452
+         * (fillers carry q = 0) */
+        const float2 qp = (jl & 2) ? I[1].q : I[0].q;
+        const float  qi = (jl & 1) ? qp.y : qp.x;
         ecoul -= qi * qi * P.self_q2;
         if (GEN && !GEOM && P.ljpme)
         {
             /* LJ Ewald self interaction, kernel_ref_outer.h:316-321: 0.5 * (6 C6_ii) / 6 * coeff^6 / 6 */
-            const int ti = (jl == 0 ? I.t0 : I.t1);
+            const int ta = (jl & 2) ? I[1].t0 : I[0].t0, tb = (jl & 2) ? I[1].t1 : I[0].t1;
+            const int ti = (jl & 1) ? tb : ta;
             evdw += 0.5f * __ldg(nbfp + ti + ti / P.ntypes).x * (1.0f / 6.0f) * P.lje_coeff6_6;
         }
     }
-    const uint2* const emask = reinterpret_cast<const uint2*>(tmask) + (size_t)e * maxt;
-    const int          nchunk = (ntile + NB_CHUNK - 1) / NB_CHUNK;
-    int                t      = 0;
-    for (int c = 0; c < nchunk; c++)
+    /* masks of the leading steps: 4 words per step, bit `lane` of word k = pair (i-atom 4*ih + k, j-atom jl) interacts */
+    const uint4* const emask = reinterpret_cast<const uint4*>(tmask + (size_t)e * maxt);
+    int                s     = 0;
+    const int*         jp    = ja + 2 * (NB_RING - 1) * NB_JSTEP + jl; /* slot index of step s + 2 (NB_RING - 1) */
+    unsigned           st_use = 0, st_fill = (NB_RING - 1) * 1024u;     /* ring offsets of step s and of step s + NB_RING - 1 */
+    /* Top of step s: the gathers of steps s .. s + NB_RING - 2 are in flight (one commit group each).  next_j() waits for the
+     * group of step s, reads its record (the j-atom and the slot index of step s + NB_RING - 1) and starts the gather of step
+     * s + NB_RING - 1 into the stage step s - 1 just released, together with the fetch of the slot index of step
+     * s + 2 (NB_RING - 1) into that record. */
+    auto next_j = [&](JAtom& J) {
+        cp_async_wait<NB_RING - 2>();
+        const int slot_next = read_j(J, ring + st_use);
+        if (s + NB_RING - 1 < nstep) gather_j<GEOM>(ring + st_fill, slot_next, s + 2 * (NB_RING - 1) < nstep ? jp : nullptr, xq, lj, atype);
+        cp_async_commit();
+        jp += NB_JSTEP;
+        st_use  = (st_use + 1024u) & (NB_RING * 1024u - 1);
+        st_fill = (st_fill + 1024u) & (NB_RING * 1024u - 1);
+    };
+
+    /* ---- steps with exclusion masks (sorted to the front of the entry; one or two per entry) ---- */
+    for (const int sm = min(nmask, nstep); s < sm; s++)
     {
-        if (c + 1 < nchunk) stage(c + 1);
-        else asm volatile("cp.async.commit_group;" ::: "memory"); /* keeps "all but the newest group" = chunk c landed */
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncwarp();
-        /* load_j addresses tile t at s_lane + t*256: bias the base so that tile c*NB_CHUNK falls on this chunk's buffer */
-        const unsigned char* const s_lane = sj + (c & 1) * CHUNK_BYTES + jl * 16 - c * CHUNK_BYTES;
-        const int                  tend   = min(ntile, (c + 1) * NB_CHUNK);
-
-        /* ---- tiles with exclusion masks (sorted to the front of the entry) ---- */
-        for (const int tm = min(nmask, tend); t < tm; t++)
+        JAtom J;
+        next_j(J);
+        const uint4 m = __ldg(emask + s);
+        /* j-atom of the i-cluster itself: only j > i (nbnxm/pairlist.cpp:880-904, kernel_gpu_ref.cpp:223-226) */
+        const bool diag = intra && shift == B200NB_CENTRAL && (J.slot >> 3) == ci;
+        const int  jin  = J.slot & 7;
+        float2     fjx = dup(0.f), fjy = dup(0.f), fjz = dup(0.f);
+#pragma unroll
+        for (int p = 0; p < 2; p++)
         {
-            JAtom J;
-            load_j(J, s_lane, t);
-            const uint2 m = __ldg(emask + t);
-            /* mask word w, bit `lane`: pair (i-atom 2*ih + w, j-slot jl) interacts */
-            const float in0 = (float)((m.x >> lane) & 1u), in1 = (float)((m.y >> lane) & 1u);
-            bool        ok0 = true, ok1 = true;
-            if (intra && shift == B200NB_CENTRAL && (J.slot >> 3) == ci)
-            {
-                /* j-atom of the i-cluster itself: only j > i (nbnxm/pairlist.cpp:880-904, kernel_gpu_ref.cpp:223-226) */
-                ok0 = (J.slot & 7) > 2 * ih;
-                ok1 = (J.slot & 7) > 2 * ih + 1;
-            }
-            float2 tx, ty, tz;
-            tile_pairs<EEL, GEOM, VF, true, GEN>(I, J, P, K, nbfp, nbfp_comb, in0, in1, ok0, ok1, tx, ty, tz, evdw, ecoul);
-            fix = add2(fix, tx);
-            fiy = add2(fiy, ty);
-            fiz = add2(fiz, tz);
-            reduce_store_j(tx, ty, tz, C, J.slot);
+            const unsigned w0 = p ? m.z : m.x, w1 = p ? m.w : m.y;
+            const float    in0 = (float)((w0 >> lane) & 1u), in1 = (float)((w1 >> lane) & 1u);
+            const bool     ok0 = !diag || jin > 4 * ih + 2 * p, ok1 = !diag || jin > 4 * ih + 2 * p + 1;
+            float2         dx, dy, dz;
+            NB_LOAD_I(Ip, p)
+            const float2   fs = pair_fscal<EEL, GEOM, VF, true, GEN>(Ip, J, P, K, nbfp, nbfp_comb, in0, in1, ok0, ok1, dx, dy, dz, evdw, ecoul);
+            fix[p] = fma2(fs, dx, fix[p]);
+            fiy[p] = fma2(fs, dy, fiy[p]);
+            fiz[p] = fma2(fs, dz, fiz[p]);
+            fjx    = fma2(fs, dx, fjx);
+            fjy    = fma2(fs, dy, fjy);
+            fjz    = fma2(fs, dz, fjz);
         }
-
-        /* ---- plain tiles ---- */
-        if (!VF && !GEN)
-        {
-            for (; t < tend; t++)
-            {
-                JAtom J[1];
-                int   js[1];
-                float sx[1], sy[1], sz[1];
-                load_j(J[0], s_lane, t);
-                js[0] = J[0].slot;
-                tile_pairs_multi<EEL, GEOM, 1>(I, J, P, K, nbfp, fix, fiy, fiz, sx, sy, sz);
-#ifndef B200NB_DIAG_NO_JFORCE /* diagnostic build only: no j-forces at all (wrong results), isolates the pair arithmetic */
-                reduce_store_j_multi<1>(sx, sy, sz, C, js);
-#endif
-            }
-        }
-        for (; t < tend; t++)
-        {
-            JAtom J;
-            load_j(J, s_lane, t);
-            float2 tx, ty, tz;
-            tile_pairs<EEL, GEOM, VF, false, GEN>(I, J, P, K, nbfp, nbfp_comb, 1.f, 1.f, true, true, tx, ty, tz, evdw, ecoul);
-            fix = add2(fix, tx);
-            fiy = add2(fiy, ty);
-            fiz = add2(fiz, tz);
-            reduce_store_j(tx, ty, tz, C, J.slot);
-        }
-        __syncwarp(); /* every lane is done with this buffer before the next iteration's gather overwrites it */
+        reduce_store_j(fjx, fjy, fjz, upper, f, J.slot);
     }
-
-    /* ---- i-forces: reduce over the 8 j-lanes (bits 0-2). Stage 1 is transposed: even lanes keep atom i0, odd lanes i1. */
-    const bool     odd  = lane & 1;
-    float          kx = odd ? fix.y : fix.x, ky = odd ? fiy.y : fiy.x, kz = odd ? fiz.y : fiz.x;
-    const float    sx = odd ? fix.x : fix.y, sy = odd ? fiy.x : fiy.y, sz = odd ? fiz.x : fiz.y;
-    kx += __shfl_xor_sync(full, sx, 1);
-    ky += __shfl_xor_sync(full, sy, 1);
-    kz += __shfl_xor_sync(full, sz, 1);
+    /* ---- plain steps ---- */
+    for (; s < nstep; s++)
+    {
+        JAtom J;
+        next_j(J);
+        float2 fjx = dup(0.f), fjy = dup(0.f), fjz = dup(0.f);
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+        {
+            float2       dx, dy, dz;
+            NB_LOAD_I(Ip, p)
+            const float2 fs = pair_fscal<EEL, GEOM, VF, false, GEN>(Ip, J, P, K, nbfp, nbfp_comb, 1.f, 1.f, true, true, dx, dy, dz, evdw, ecoul);
+            fix[p] = fma2(fs, dx, fix[p]);
+            fiy[p] = fma2(fs, dy, fiy[p]);
+            fiz[p] = fma2(fs, dz, fiz[p]);
+#ifndef B200NB_DIAG_NO_JFORCE /* diagnostic build only: no j-forces at all (wrong results), isolates the pair arithmetic */
+            fjx = fma2(fs, dx, fjx);
+            fjy = fma2(fs, dy, fjy);
+            fjz = fma2(fs, dz, fjz);
+#endif
+        }
+#ifndef B200NB_DIAG_NO_JFORCE
+        reduce_store_j(fjx, fjy, fjz, upper, f, J.slot);
+#endif
+    }
+    /* ---- i-forces: 12 floats per lane (2 pairs x 2 atoms x 3) summed over the 16 j-lanes of this half (lane bits 0-3),
+     * transposed so that every exchange halves what is still carried: bit 3 picks the pair, bit 2 the atom of the pair ---- */
+    const bool b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+    float      r0, r1, r2, r3, r4, r5;
+#define NB_STAGE_A(out, v0, v1)                                          \
+    {                                                                    \
+        const float keep_ = b3 ? (v1) : (v0), send_ = b3 ? (v0) : (v1);  \
+        out               = keep_ + __shfl_xor_sync(full, send_, 8);     \
+    }
+    NB_STAGE_A(r0, fix[0].x, fix[1].x)
+    NB_STAGE_A(r1, fix[0].y, fix[1].y)
+    NB_STAGE_A(r2, fiy[0].x, fiy[1].x)
+    NB_STAGE_A(r3, fiy[0].y, fiy[1].y)
+    NB_STAGE_A(r4, fiz[0].x, fiz[1].x)
+    NB_STAGE_A(r5, fiz[0].y, fiz[1].y)
+#undef NB_STAGE_A
+    float kx = (b2 ? r1 : r0) + __shfl_xor_sync(full, b2 ? r0 : r1, 4);
+    float ky = (b2 ? r3 : r2) + __shfl_xor_sync(full, b2 ? r2 : r3, 4);
+    float kz = (b2 ? r5 : r4) + __shfl_xor_sync(full, b2 ? r4 : r5, 4);
     kx += __shfl_xor_sync(full, kx, 2);
     ky += __shfl_xor_sync(full, ky, 2);
     kz += __shfl_xor_sync(full, kz, 2);
-    kx += __shfl_xor_sync(full, kx, 4);
-    ky += __shfl_xor_sync(full, ky, 4);
-    kz += __shfl_xor_sync(full, kz, 4);
-    /* lanes with jl in {0,1} hold the total force on i-atom 2*ih + jl */
-    if (jl < 2 && ntile > 0) atomicAdd(f + ((size_t)ci * 8 + 2 * ih + jl), make_float4(kx, ky, kz, 0.f));
+    kx += __shfl_xor_sync(full, kx, 1);
+    ky += __shfl_xor_sync(full, ky, 1);
+    kz += __shfl_xor_sync(full, kz, 1);
+    /* the lanes with bits 0-1 clear hold the total force on i-atom 4*ih + 2*b3 + b2 */
+    if ((lane & 3) == 0 && nstep > 0) atomicAdd(f + ((size_t)ci * 8 + 4 * ih + 2 * (int)b3 + (int)b2), make_float4(kx, ky, kz, 0.f));
     if (VF)
     {
         /* shift force = sum of the i-forces of this entry (kernel_outer.h:620-640; the CUDA kernel skips the central
          * shift, nbnxm_cuda_kernel.cuh:624-628) */
         if (shift != B200NB_CENTRAL)
         {
-            kx += __shfl_xor_sync(full, kx, 1);
-            ky += __shfl_xor_sync(full, ky, 1);
-            kz += __shfl_xor_sync(full, kz, 1);
+            kx += __shfl_xor_sync(full, kx, 4);
+            ky += __shfl_xor_sync(full, ky, 4);
+            kz += __shfl_xor_sync(full, kz, 4);
             kx += __shfl_xor_sync(full, kx, 8);
             ky += __shfl_xor_sync(full, ky, 8);
             kz += __shfl_xor_sync(full, kz, 8);
@@ -730,11 +653,10 @@ int launch(b200nb_context* h, const PackedList& L, int intra)
      * (profiles/r1/y_sweep_persistent_boustrophedon.txt). */
     const unsigned nblk = (unsigned)((L.nentries + B200NB_FORCE_WARPS - 1) / B200NB_FORCE_WARPS);
     const int      maxt = L.pitch;
-    const size_t smem = (size_t)B200NB_FORCE_WARPS * 2 * NB_CHUNK * NB_TILE_SMEM; /* the two ring buffers of each warp */
     cudaLaunchConfig_t cfg{};
     cfg.gridDim          = dim3(nblk);
     cfg.blockDim         = dim3(32 * B200NB_FORCE_WARPS);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = 0;
     cfg.stream           = h->stream;
     cudaLaunchAttribute at[1];
     at[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -455,7 +455,9 @@ class DomainRank:
             self.nb.put_on_grid(self.x.data_ptr(), hl, hu, 1, p.nhome, self.nlocal, on_device=True)
         self.nb.build_pairlist()
         if self.use_windows:
-            edge = SHIFT_PLUS_X if self.rank == 0 else -1
+            # the forces this rank computes on halo atoms that arrived across the periodic edge (the last slab's halo is
+            # rank 0's lower boundary, shifted by +box) also enter the +x shift force (domdec/domdec.cpp:426-458)
+            edge = SHIFT_PLUS_X if p.recv_from_periodic else -1
             self.nb.dd_set_plan(p.nhome, p.nhalo, p.send_local, p.send_shift, edge)
             self.t.barrier()  # every rank has its plan before anybody steps
 

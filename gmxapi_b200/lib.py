@@ -17,9 +17,10 @@ EXPORTS = [
     "b200nb_create", "b200nb_destroy", "b200nb_last_error", "b200nb_stream", "b200nb_set_stream", "b200nb_synchronize",
     "b200nb_set_params", "b200nb_set_vdw", "b200nb_set_atoms", "b200nb_set_box", "b200nb_put_on_grid", "b200nb_build_pairlist",
     "b200nb_set_x", "b200nb_clear_outputs", "b200nb_launch_force", "b200nb_launch_prune", "b200nb_get_f",
-    "b200nb_get_outputs", "b200nb_compute", "b200nb_step", "b200nb_dd_create_window", "b200nb_dd_open_peer", "b200nb_dd_set_plan",
+    "b200nb_get_outputs", "b200nb_compute", "b200nb_step", "b200nb_dd_create_window", "b200nb_dd_open_peer", "b200nb_dd_set_plan", "b200nb_dd_set_links",
     "b200nb_dd_step", "b200nb_dd_status", "b200nb_halo_pack_x", "b200nb_halo_unpack_f", "b200nb_get_stats",
     "b200nb_get_grid_order", "b200nb_get_tiles", "b200nb_get_pairs", "b200nb_time_force_kernel", "b200nb_time_step",
+    "b200nb_set_grid_atoms", "b200nb_upload_pairlist", "b200nb_copy_xq_grid", "b200nb_get_f_grid", "b200nb_set_shift_vec",
 ]
 
 
@@ -39,6 +40,12 @@ class _Vdw(C.Structure):  # b200nb_vdw_t
                 ("disp_c3", C.c_float), ("rep_c2", C.c_float), ("rep_c3", C.c_float), ("sw_c3", C.c_float),
                 ("sw_c4", C.c_float), ("sw_c5", C.c_float), ("ljpme_comb_rule", C.c_int), ("ewaldcoeff_lj", C.c_float),
                 ("sh_lj_ewald", C.c_float)]
+
+
+class _DdLink(C.Structure):  # b200nb_dd_link_t
+    _fields_ = [("send_peer", C.c_int), ("nsend", C.c_int), ("send_idx_host", C.c_void_p), ("shift", C.c_float * 3),
+                ("peer_halo_offset", C.c_int), ("recv_peer", C.c_int), ("nrecv", C.c_int), ("peer_entry_offset", C.c_int),
+                ("fshift_index", C.c_int)]
 
 
 VDW_POTSHIFT, VDW_FORCESWITCH, VDW_POTSWITCH = 0, 1, 2
@@ -125,6 +132,7 @@ def load_library():
     L.b200nb_dd_create_window.argtypes = [vp, ci, ci, vp, C.POINTER(vp)]
     L.b200nb_dd_open_peer.argtypes = [vp, ci, vp, vp, ci]
     L.b200nb_dd_set_plan.argtypes = [vp, ci, ci, vp, ci, vp, ci]
+    L.b200nb_dd_set_links.argtypes = [vp, ci, ci, ci, C.POINTER(_DdLink)]
     L.b200nb_dd_step.argtypes = [vp, vp, vp, ci]
     L.b200nb_dd_status.argtypes = [vp]
     L.b200nb_halo_pack_x.argtypes = [vp, vp, vp, ci, vp, vp]
@@ -137,6 +145,11 @@ def load_library():
     L.b200nb_get_pairs.restype = cll
     L.b200nb_time_force_kernel.argtypes = [vp, ci, ci, ci, ci, ci, C.POINTER(cf)]
     L.b200nb_time_step.argtypes = [vp, vp, vp, ci, ci, ci, ci, C.POINTER(cf), C.POINTER(cf)]
+    L.b200nb_set_grid_atoms.argtypes = [vp, ci, vp, vp]
+    L.b200nb_upload_pairlist.argtypes = [vp, ci, vp, ci, vp, ci, vp, ci]
+    L.b200nb_copy_xq_grid.argtypes = [vp, vp, ci, ci]
+    L.b200nb_get_f_grid.argtypes = [vp, vp, ci, ci]
+    L.b200nb_set_shift_vec.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -314,11 +327,30 @@ class NbnxmGpu:
         self._check(self._L.b200nb_dd_open_peer(self._h, int(side), hb, C.c_void_p(window_ptr) if window_ptr else None,
                                                 int(peer_max_halo)), "dd_open_peer")
 
-    def dd_set_plan(self, nhome, nhalo, send_idx, shift, edge_shift=-1):
+    def dd_set_plan(self, nhome, nhalo, send_idx, shift, halo_fshift_index=-1):
+        """1-D plan: one link (send to peer 0, receive from peer 1); halo_fshift_index: shift-force slot that also gets the
+        forces computed here on the halo atoms when those arrived across the periodic edge, else -1."""
         si = np.ascontiguousarray(send_idx, dtype=np.int32)
         sh = np.ascontiguousarray(shift, dtype=np.float32)
         self._check(self._L.b200nb_dd_set_plan(self._h, int(nhome), int(nhalo), _ptr(si) if si.size else None, int(si.size),
-                                               _ptr(sh), int(edge_shift)), "dd_set_plan")
+                                               _ptr(sh), int(halo_fshift_index)), "dd_set_plan")
+
+    def dd_set_links(self, nhome, nhalo, links):
+        """General plan (b200nb_dd_set_links).  links: list of dicts with keys send_peer, send_idx (int32 array), shift[3],
+        peer_halo_offset, recv_peer, nrecv, peer_entry_offset, fshift_index."""
+        arr = (_DdLink * max(len(links), 1))()
+        keep = []
+        for k, l in enumerate(links):
+            si = np.ascontiguousarray(l["send_idx"], dtype=np.int32)
+            keep.append(si)
+            arr[k].send_peer, arr[k].nsend = int(l["send_peer"]), int(si.size)
+            arr[k].send_idx_host = si.ctypes.data if si.size else None
+            for d in range(3):
+                arr[k].shift[d] = float(l["shift"][d])
+            arr[k].peer_halo_offset = int(l["peer_halo_offset"])
+            arr[k].recv_peer, arr[k].nrecv = int(l["recv_peer"]), int(l["nrecv"])
+            arr[k].peer_entry_offset, arr[k].fshift_index = int(l["peer_entry_offset"]), int(l["fshift_index"])
+        self._check(self._L.b200nb_dd_set_links(self._h, int(nhome), int(nhalo), len(links), arr), "dd_set_links")
 
     def dd_step(self, x_home, f_home, flags=0):
         """x_home / f_home: addresses (device or pinned host) of nhome*3 floats; asynchronous."""
@@ -373,6 +405,33 @@ class NbnxmGpu:
         if n < 0:
             self._check(int(n), "get_pairs")
         return int(n)
+
+    # -- reference-built grid and list (what the Nbnxm::gpu_* shim calls) -----------------------------------------------
+    def set_grid_atoms(self, xq_grid, type_grid):
+        """nbat->x() (nslots x 4) and nbat->params().type (nslots) in grid order (gpu_init_atomdata)."""
+        xq = np.ascontiguousarray(xq_grid, dtype=np.float32).reshape(-1, 4)
+        ty = np.ascontiguousarray(type_grid, dtype=np.int32)
+        self._nslots = len(ty)
+        self._check(self._L.b200nb_set_grid_atoms(self._h, len(ty), _ptr(xq), _ptr(ty)), "set_grid_atoms")
+
+    def upload_pairlist(self, locality, sci, cj4, excl):
+        """NbnxnPairlistGpu arrays as int32 / uint32 numpy arrays: sci (n, 4), cj4 (n, 8), excl (n, 32) (gpu_init_pairlist)."""
+        sci = np.ascontiguousarray(sci, dtype=np.int32).reshape(-1, 4)
+        cj4 = np.ascontiguousarray(cj4, dtype=np.int32).reshape(-1, 8)
+        excl = np.ascontiguousarray(excl, dtype=np.uint32).reshape(-1, 32)
+        self._check(self._L.b200nb_upload_pairlist(self._h, int(locality), _ptr(sci) if len(sci) else None, len(sci),
+                                                   _ptr(cj4) if len(cj4) else None, len(cj4), _ptr(excl), len(excl)), "upload_pairlist")
+
+    def copy_xq_grid(self, xq_grid, slot_begin=0, slot_end=None):
+        xq = np.ascontiguousarray(xq_grid, dtype=np.float32).reshape(-1, 4)
+        self._check(self._L.b200nb_copy_xq_grid(self._h, _ptr(xq), slot_begin, len(xq) if slot_end is None else slot_end), "copy_xq_grid")
+        self.synchronize()  # xq may be a temporary
+
+    def get_f_grid(self):
+        f = np.zeros((self._nslots, 3), np.float32)
+        self._check(self._L.b200nb_get_f_grid(self._h, _ptr(f), 0, self._nslots), "get_f_grid")
+        self.synchronize()
+        return f
 
     def time_step(self, x_dev, f_dev, flags=0, nwarm=3, niter=20, flush_l2=True):
         """(ms per device-resident step, ms of the force kernel inside it), CUDA-event timed on the context's stream."""

@@ -144,6 +144,44 @@ int b200nb_put_on_grid(b200nb_t* h, int grid_index, const float lower[3], const 
  * (cuda/nbnxm_cuda.cu:510-517).  Grid 0 x grid 0 is a half list, grid 0 x grid 1 a full list. */
 int b200nb_build_pairlist(b200nb_t* h);
 
+/* ---- reference-built grid and list: the drop-in path behind Nbnxm::gpu_* (shim/nbnxm_b200.cpp) ---------------------
+ * With mdrun / nblib in front, gridding and pair search stay on the CPU, where the reference does them for its own CUDA
+ * backend, and the backend receives their products.  These four calls take exactly what the reference hands to
+ * gpu_init_atomdata / gpu_init_pairlist / gpu_copy_xq_to_gpu / gpu_launch_cpyback, so no reference call site changes.
+ * In this mode the context has no atom-order view: use b200nb_launch_force / _launch_prune / _clear_outputs / _get_outputs
+ * with the calls below; b200nb_step, b200nb_compute, b200nb_set_x and b200nb_get_f need b200nb_put_on_grid instead. */
+typedef struct
+{
+    int sci, shift, cj4_ind_start, cj4_ind_end;
+} b200nb_sci_t; /* = nbnxn_sci_t, nbnxm/pairlist.h:174-188 */
+typedef struct
+{
+    int cj[4];
+    struct
+    {
+        unsigned int imask;
+        int          excl_ind;
+    } imei[2];
+} b200nb_cj4_t; /* = nbnxn_cj4_t, nbnxm/pairlist.h:190-205 */
+typedef struct
+{
+    unsigned int pair[32];
+} b200nb_excl_t; /* = nbnxn_excl_t, nbnxm/pairlist.h:208-225 */
+/* gpu_init_atomdata (nbnxm_gpu_data_mgmt.cpp; cuda/nbnxm_cuda_data_mgmt.cu:297-348): nslots = nbat->numAtoms(), xq_host =
+ * nbat->x() (nbatXYZQ: 4 floats per slot), type_host = nbat->params().type (fillers carry the zero-parameter type `ntypes`). */
+int b200nb_set_grid_atoms(b200nb_t* h, int nslots, const float* xq_host, const int* type_host);
+/* gpu_init_pairlist (nbnxm_gpu_data_mgmt.cpp:251-311): the NbnxnPairlistGpu of one locality (sci, cj4, excl arrays as they
+ * are); followed on the device by the fresh-list prune to rlist_inner and the re-packing for the force kernel. */
+int b200nb_upload_pairlist(b200nb_t* h, int locality, const b200nb_sci_t* sci, int nsci, const b200nb_cj4_t* cj4, int ncj4,
+                           const b200nb_excl_t* excl, int nexcl);
+/* gpu_upload_shiftvec (cuda/nbnxm_cuda_data_mgmt.cu:283-295): nbat->shift_vec, 45 x 3 floats, as calc_shifts(box) made them. */
+int b200nb_set_shift_vec(b200nb_t* h, const float* shift_vec_host);
+/* gpu_copy_xq_to_gpu (cuda/nbnxm_cuda.cu:395-465): slots [slot_begin, slot_end) of nbat->x(); asynchronous on the stream. */
+int b200nb_copy_xq_grid(b200nb_t* h, const float* xq_host, int slot_begin, int slot_end);
+/* gpu_launch_cpyback, force part (cuda/nbnxm_cuda.cu:720-814): grid-ordered forces of slots [slot_begin, slot_end) into
+ * nbat->out[0].f (3 floats per slot, overwritten); asynchronous on the stream: b200nb_synchronize before reading. */
+int b200nb_get_f_grid(b200nb_t* h, float* f_host, int slot_begin, int slot_end);
+
 /* ---- per step ------------------------------------------------------------------------------------------- */
 /* gpu_copy_xq_to_gpu + nbnxn_gpu_x_to_nbat_x (cuda/nbnxm_cuda.cu:395,829): new coordinates (original
  * order, natoms*3) -> grid-ordered device layout.  atom range [atom_begin, atom_end) lets the caller
@@ -184,25 +222,46 @@ int b200nb_halo_unpack_f(b200nb_t* h, float* f_dev, const int* index_dev, int n,
 
 /* ---- domain-decomposed step over peer-memory halo windows ---------------------------------------------------
  * Replaces dd_move_x / dd_move_f (domdec/domdec.cpp:260-460) and GpuHaloExchange (domdec/gpuhaloexchange_impl.cu:133-444)
- * on the per-step path for a 1-D (x-slab) decomposition with one pulse.  Each rank creates ONE window in its device memory
- * and hands its CUDA IPC handle to both neighbours; the neighbours' kernels store halo coordinates / halo forces straight
- * into it over NVLink and raise a flag, the owner's kernels wait on the flag (a one-thread wait kernel, bounded to 10 s).  No host synchronisation and no
- * library collective inside a step.  b200nb_halo_pack_x / _unpack_f above remain for callers that move the data themselves
- * (the pair-search step, where the halo composition changes, goes through them). */
+ * on the per-step path, for a 1-D (x-slab) decomposition (b200nb_dd_set_plan) and for 2-D / 3-D decompositions with up to 16
+ * halo LINKS per rank (b200nb_dd_set_links; e.g. the 13 half-shell neighbours of a 2 x 2 x 2 grid).  Each rank creates ONE
+ * window in its device memory and hands its CUDA IPC handle to its neighbours; the neighbours' kernels store halo coordinates /
+ * halo forces straight into it over NVLink and raise a per-link flag, the owner's kernels wait on the flags (bounded to 10 s).
+ * No host synchronisation and no library collective inside a step.  b200nb_halo_pack_x / _unpack_f above remain for callers
+ * that move the data themselves (the pair-search step, where the halo composition changes, goes through them). */
 /* ipc_handle_out: 64 bytes (cudaIpcMemHandle_t) for peers in other processes; window_dev_out: the device pointer, for peers
- * in this process.  max_halo / max_send bound the plans that may be set later. */
+ * in this process.  max_halo bounds the halo atoms, max_send the send entries (atom, link) of the plans that may be set later. */
 int b200nb_dd_create_window(b200nb_t* h, int max_halo, int max_send, void* ipc_handle_out, void** window_dev_out);
-/* side 0 = the -x neighbour (gets our halo coordinates), side 1 = the +x neighbour (gets the forces on its atoms);
- * give either the peer's IPC handle or, inside one process, its window pointer; peer_max_halo = the peer's max_halo. */
-int b200nb_dd_open_peer(b200nb_t* h, int side, const void* ipc_handle, void* same_process_window, int peer_max_halo);
-/* Plan of the current search interval: local atoms [0, nhome) home, [nhome, natoms) halo in the +x neighbour's send order;
- * send_idx_host[nsend]: home atoms sent to the -x neighbour with `shift` added (dd_move_x's box shift, domdec.cpp:300-318);
- * edge_shift_index: shift-force slot that also receives the returned forces (domdec.cpp:426-458) or -1. */
+/* Opens a neighbour's window as peer number `peer` (0..15).  Give either the peer's IPC handle or, inside one process, its
+ * window pointer; peer_max_halo = the peer's max_halo.  A neighbour reached over several links is opened once.
+ * With b200nb_dd_set_plan: peer 0 = the -x neighbour (gets our halo coordinates), peer 1 = the +x neighbour. */
+int b200nb_dd_open_peer(b200nb_t* h, int peer, const void* ipc_handle, void* same_process_window, int peer_max_halo);
+/* One halo link = one (neighbour offset) connection; link k of every rank belongs to the same offset, so this rank's receive
+ * side of link k and its source's send side of link k are the two ends of one connection (they share flag index k). */
+typedef struct
+{
+    /* send side: nsend of our home atoms go to peer `send_peer`, `shift` added (dd_move_x's box shift, domdec.cpp:300-318);
+     * they become halo atoms peer_halo_offset .. peer_halo_offset + nsend - 1 of the destination */
+    int        send_peer, nsend;
+    const int* send_idx_host;
+    float      shift[3];
+    int        peer_halo_offset;
+    /* receive side: nrecv halo atoms arrive from peer `recv_peer` (they follow the halo atoms of the links before this one);
+     * the forces we compute on them return to the source's send entries peer_entry_offset .. + nrecv - 1 (= the number of
+     * entries the source sends over its links before this one); fshift_index: shift-force slot that also receives those
+     * forces when the atoms arrived across a periodic edge (domdec.cpp:426-458), else -1 */
+    int recv_peer, nrecv, peer_entry_offset, fshift_index;
+} b200nb_dd_link_t;
+/* Plan of the current search interval: local atoms [0, nhome) home, [nhome, nhome + nhalo) halo in link order. */
+int b200nb_dd_set_links(b200nb_t* h, int nhome, int nhalo, int nlinks, const b200nb_dd_link_t* links);
+/* The 1-D form: one link, sending to peer 0, receiving from peer 1.  send_idx_host[nsend]: home atoms sent to the -x neighbour
+ * with `shift` added; halo_fshift_index: shift-force slot that also receives the forces computed HERE on the halo atoms when
+ * those arrived across the periodic edge (the last slab), or -1. */
 int b200nb_dd_set_plan(b200nb_t* h, int nhome, int nhalo, const int* send_idx_host, int nsend, const float shift[3],
-                       int edge_shift_index);
-/* One decomposed step, asynchronous on the context's stream: 9 launches (x -> grid + clear; push halo x; local kernel; wait;
- * halo x -> grid; non-local kernel; push halo f; wait; add + un-sort).  x_home in, f_home out: nhome*3 floats, device or
- * pinned host memory.  Every neighbour must call it the same number of times. */
+                       int halo_fshift_index);
+/* One decomposed step, asynchronous on the context's stream, replayed as one CUDA graph of 6 kernels: home x -> grid + clear +
+ * push of the halo x into the neighbours' windows | local kernel || wait, halo x -> grid | non-local kernel | push of the halo
+ * forces || wait, add, un-sort.  x_home in, f_home out: nhome*3 floats, device or pinned host memory.  Every neighbour must
+ * call it the same number of times. */
 int b200nb_dd_step(b200nb_t* h, const float* x_home, float* f_home, int flags);
 /* after b200nb_synchronize: B200NB_ERR_STATE if a halo flag timed out in any step since the last call */
 int b200nb_dd_status(b200nb_t* h);

@@ -69,6 +69,8 @@ def lib():
         L.gmxref_ewald_coeff.argtypes = [C.c_float, C.c_float]
         L.gmxref_simd_rsq.restype = C.c_float
         L.gmxref_simd_rsq.argtypes = [C.c_float] * 6
+        L.gmxref_gpu_list.argtypes = [C.c_void_p] * 10
+        L.gmxref_grid_forces.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -178,6 +180,29 @@ class RefNbnxm:
         ci, cj = C.c_int(), C.c_int()
         lib().gmxref_list_stats(self.h, C.byref(a), C.byref(b), C.byref(ci), C.byref(cj))
         return dict(cluster_pairs=a.value, atom_pairs_computed=b.value, na_ci=ci.value, na_cj=cj.value)
+
+    def gpu_list(self):
+        """The reference-built 8x8x8 list and grid-ordered atom data (GPUREF instances): dict(sci (n,4) int32, cj4 (n,8) int32,
+        excl (n,32) uint32, xq (nslots,4) float32, type (nslots,) int32): the arguments of gpu_init_pairlist / gpu_init_atomdata."""
+        L = lib()
+        n = [C.c_int() for _ in range(4)]
+        if L.gmxref_gpu_list(self.h, *[C.byref(v) for v in n], None, None, None, None, None):
+            raise RuntimeError("gpu_list needs a GPUREF_8X8X8 instance")
+        nsci, ncj4, nexcl, nslots = [v.value for v in n]
+        out = dict(sci=np.zeros((nsci, 4), np.int32), cj4=np.zeros((ncj4, 8), np.int32), excl=np.zeros((nexcl, 32), np.uint32),
+                   xq=np.zeros((nslots, 4), np.float32), type=np.zeros(nslots, np.int32))
+        rc = L.gmxref_gpu_list(self.h, *[C.byref(v) for v in n], *[out[k].ctypes.data_as(C.c_void_p) for k in ("sci", "cj4", "excl", "xq", "type")])
+        if rc:
+            raise RuntimeError("gmxref_gpu_list failed: %d" % rc)
+        return out
+
+    def grid_forces(self):
+        """nbat->out[0].f of the last compute(), grid order (nslots, 3)."""
+        n = self.grid_dims()[4]
+        f = np.zeros((n, 3), np.float32)
+        if lib().gmxref_grid_forces(self.h, f.ctypes.data_as(C.c_void_p), n) != n:
+            raise RuntimeError("gmxref_grid_forces failed")
+        return f
 
     def pair_count(self, rc=None):
         return int(lib().gmxref_pair_set(self.h, rc or self.rc, None, 0))

@@ -641,4 +641,41 @@ long long gmxref_pair_set(void* h, float rc, int* pairs, long long cap)
     return n;
 }
 
+/* The reference-built 8x8x8 list and grid-ordered atom data, as Nbnxm::gpu_init_pairlist / gpu_init_atomdata receive them
+ * (nbnxm_gpu_data_mgmt.cpp:251-311): the inputs of b200nb_upload_pairlist / b200nb_set_grid_atoms in the parity tests of the
+ * drop-in path.  Only for GMXREF_KERNEL_GPUREF_8X8X8 instances.  Sizes first (all pointers NULL), then the data. */
+int gmxref_gpu_list(void* h, int* nsci, int* ncj4, int* nexcl, int* nslots, int* sci, int* cj4, unsigned* excl, float* xq, int* type)
+{
+    auto* inst = static_cast<Instance*>(h);
+    if (inst->kernelType != Nbnxm::KernelType::Cpu8x8x8_PlainC) return 1;
+    const NbnxnPairlistGpu* l    = inst->nbv->pairlistSets().pairlistSet(gmx::InteractionLocality::Local).gpuList();
+    const nbnxn_atomdata_t& nbat = *inst->nbv->nbat;
+    *nsci   = static_cast<int>(l->sci.size());
+    *ncj4   = static_cast<int>(l->cj4.size());
+    *nexcl  = static_cast<int>(l->excl.size());
+    *nslots = nbat.numAtoms();
+    static_assert(sizeof(nbnxn_sci_t) == 16 && sizeof(nbnxn_cj4_t) == 32 && sizeof(nbnxn_excl_t) == 128, "list element layout");
+    if (sci) std::memcpy(sci, l->sci.data(), l->sci.size() * sizeof(nbnxn_sci_t));
+    if (cj4) std::memcpy(cj4, l->cj4.data(), l->cj4.size() * sizeof(nbnxn_cj4_t));
+    if (excl) std::memcpy(excl, l->excl.data(), l->excl.size() * sizeof(nbnxn_excl_t));
+    if (xq)
+    {
+        if (nbat.XFormat != nbatXYZQ) return 2;
+        std::memcpy(xq, nbat.x().data(), static_cast<size_t>(nbat.numAtoms()) * 4 * sizeof(float));
+    }
+    if (type) std::memcpy(type, nbat.params().type.data(), static_cast<size_t>(nbat.numAtoms()) * sizeof(int));
+    return 0;
+}
+
+/* forces of the last gmxref_compute in GRID order (nbat->out[0].f, 3 floats per slot): what gpu_launch_cpyback delivers */
+int gmxref_grid_forces(void* h, float* f, int cap_slots)
+{
+    auto*                   inst = static_cast<Instance*>(h);
+    const nbnxn_atomdata_t& nbat = *inst->nbv->nbat;
+    const int               n    = nbat.numAtoms();
+    if (n > cap_slots) return -1;
+    std::memcpy(f, nbat.out[0].f.data(), static_cast<size_t>(n) * 3 * sizeof(float));
+    return n;
+}
+
 } // extern "C"

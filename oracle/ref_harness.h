@@ -63,6 +63,8 @@ int    gmxref_grid_order(void* h, int* out, int cap);
 void   gmxref_grid_dims(void* h, int* ncx, int* ncy, float* cellx, float* celly, int* natomsPadded);
 void   gmxref_list_stats(void* h, long long* nClusterPairs, long long* nAtomPairsComputed, int* na_ci, int* na_cj);
 long long gmxref_pair_set(void* h, float rc, int* pairs, long long cap);
+int    gmxref_gpu_list(void* h, int* nsci, int* ncj4, int* nexcl, int* nslots, int* sci, int* cj4, unsigned* excl, float* xq, int* type);
+int    gmxref_grid_forces(void* h, float* f, int cap_slots);
 
 #ifdef __cplusplus
 }
