@@ -1,7 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- nonbonded pair-interactions/s and ms/step of the B200 nbnxm path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--scaling strong|weak] [--impl reference]
+
+Default workload for EVERY N (1, 2, 4, 8): water_1M, the 1.03 M-atom water box of BASELINE.json configs[3], strong scaling --
+the configuration the north_star's 8-GPU target is defined on; at N = 1 the line also carries a `secondary` block for
+water_24k (configs[1]).  --workload ref_water_24k / ref_water_96k / ref_water_1M use the reference's own benchmark water
+(liquid structure, nbnxm/benchmark/bench_coords.h) instead of the jittered lattice; --scaling weak puts N copies of the
+workload side by side along x.
 
 A step = one pass of the hot path over one set of coordinates: coordinates -> grid-ordered device layout fused
 with the output clear, cluster-pair force kernel (LJ + Ewald real space, force only), force un-sort: 3 launches.
@@ -12,13 +18,15 @@ with the output clear, cluster-pair force kernel (LJ + Ewald real space, force o
            pinned HOST buffers (H2D of x and D2H of f inside the timed region);
   roofline: the force kernel alone against the FP32 FMA roofline (the path is FP32-bound), with
            the HBM view beside it;
+  search : what the metric above does not contain -- steady-state re-gridding + pair search + packing, the rolling prune,
+           and the step amortised over a pair-list lifetime (nstlist = 100) with dynamic pruning;
+  sustained: >= 2 s of back-to-back steps with NVML sampled every 2 ms: the SM clock an MD run of this kernel holds;
   cpu_baseline: the reference's own CPU SIMD nbnxm path (oracle/_ref, compiled from the reference sources)
            on this host's cores, bounded sample.
 N > 1: atoms are split into N slabs along x (spatial domain decomposition), one rank per GPU; halo coordinates and
 forces go straight into the neighbours' peer-memory windows over NVLink from inside the step's kernels
-(b200nb_dd_step, gmxapi_b200/domdec.py; torch.distributed / NCCL only carries set-up data).  Weak scaling (default):
-the box holds N copies of the N=1 workload along x, one slab per rank; --scaling strong: the named workload itself
-over N slabs (BASELINE configs[3]: --workload water_1M --scaling strong).
+(b200nb_dd_step, gmxapi_b200/domdec.py; torch.distributed / NCCL only carries set-up data); --dd-grid 2x2x2 decomposes in
+three dimensions instead.  Outside the timed region the decomposed forces are checked against a single-domain run.
 """
 import argparse
 import json
@@ -156,18 +164,33 @@ def sustained_block(h, s, npairs, seconds=2.0, flops_per_pair=66, device=0):
 
 
 def ncu_capture(workload, eel):
-    """What the committed `ncu --set full` capture of this workload's force kernel says (profiles/r1/traffic.json): DRAM bytes
-    of one launch and the measured FP32-pipe / issue utilisation; {} when there is no capture for the workload."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1", "traffic.json")))
-        return dict(d[workload]) if eel == "ewald" else {}
-    except Exception:  # noqa: BLE001
-        return {}
+    """What the committed `ncu --set full` capture of this workload's force kernel says (profiles/r2/traffic.json, written by
+    profiles/tools/ncu_traffic.py from the captures of the round): DRAM bytes of one launch and the measured FP32-pipe / issue
+    utilisation; {} when there is no capture for the workload."""
+    for rnd in ("r2", "r1"):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", rnd, "traffic.json")))
+            if eel == "ewald" and workload in d:
+                return dict(d[workload])
+        except Exception:  # noqa: BLE001
+            pass
+    return {}
 
 
-def workload_system(name):
+def workload_system(name, copies_along_x=1):
+    """The named box, or `copies_along_x` of it side by side (weak scaling)."""
     import gmxapi_b200 as g
-    return g.systems.named(name)
+    gen, (nx, ny, nz) = g.systems.tiles_of(name)
+    return gen(nx * copies_along_x, ny, nz)
+
+
+def common_config(workload, s, npairs, eel, scaling, n_gpus):
+    """The part of `config` both arms print identically (the driver compares the two dicts)."""
+    return {"workload": workload if (scaling == "strong" or n_gpus <= 1) else "%d x %s along x" % (n_gpus, workload),
+            "atoms": int(s.n), "useful_pairs_per_step": int(npairs), "rc": RC, "rlist": RC,
+            "interaction": "LJ + " + ("Ewald real space (analytical)" if eel == "ewald" else "reaction field"),
+            "flavor": "force only", "scaling": scaling if n_gpus > 1 else "single GPU",
+            "l2_between_steps": "GPU arm: flushed (256 MiB write) between timed steps; CPU arm: not applicable"}
 
 
 def ref_instance(s, eel, nthreads):
@@ -193,10 +216,20 @@ def cpu_model():
 
 
 def host_cores():
+    """PHYSICAL cores this process may run on (BASELINE.md section 2 quotes physical cores): logical CPUs of the affinity mask
+    grouped by their hyper-thread siblings; the reference arm runs one OpenMP thread per physical core."""
     try:
-        return len(os.sched_getaffinity(0))
-    except Exception:
-        return os.cpu_count() or 1
+        cpus = sorted(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        cpus = list(range(os.cpu_count() or 1))
+    cores = set()
+    for c in cpus:
+        try:
+            sib = open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c).read().strip()
+        except Exception:  # noqa: BLE001
+            sib = str(c)
+        cores.add(sib)
+    return max(1, len(cores))
 
 
 def time_reference(s, eel, nthreads, steps, warmup, budget_s=20.0):
@@ -215,50 +248,105 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import gmxref, oracle
-    import gmxapi_b200 as g
-    nx, ny, nz = g.systems.NAMED[args.workload]
+    from oracle import gmxref
     mult = max(args.gpus, 1) if args.scaling == "weak" else 1
-    s = g.systems.water_box(nx * mult, ny, nz)  # the same box the GPU arm decomposes over args.gpus ranks
+    s = workload_system(args.workload, mult)  # the same box the GPU arm decomposes over args.gpus ranks
     cores = host_cores()
-    npairs = len(oracle.pair_set(s.x, s.box, RC, s.excl_off, s.excl_idx))
-    kind = "reference" if gmxref.available() else "port"
     if not gmxref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgmxref_nbnxm.so missing"}))
         return
+    r = ref_instance(s, args.eel, cores)
+    npairs = r.pair_count()
+    r.close()
     t, tk, n = time_reference(s, args.eel, cores, args.steps, args.warmup, budget_s=60.0)
     val = npairs / t
     out = {"metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
            "data": "synthetic", "impl": "reference",
-           "config": {"workload": args.workload if mult <= 1 else "%d x %s along x" % (args.gpus, args.workload),
-                      "atoms": int(s.n), "useful_pairs_per_step": npairs, "rc": RC,
-                      "interaction": "LJ + " + ("Ewald real space (analytical)" if args.eel == "ewald" else "reaction field"),
-                      "flavor": "force only"},
-           "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": kind,
-                            "sample": "%d full steps (x convert + 2xMM SIMD kernel + f reduce) of %s (%d atoms), %d OpenMP threads of %s; "
-                                      "kernel-only %.3f ms" % (n, args.workload if mult <= 1 else "%d x %s" % (args.gpus, args.workload),
-                                                               int(s.n), cores, cpu_model(), tk * 1e3)},
+           "config": common_config(args.workload, s, npairs, args.eel, args.scaling, args.gpus),
+           "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "reference",
+                            "sample": "%d full steps (x convert + 2xMM SIMD kernel + f reduce) of %s (%d atoms), one OpenMP thread on each of "
+                                      "the %d physical cores of %s; kernel-only %.3f ms" % (n, args.workload if mult <= 1 else "%d x %s" % (args.gpus, args.workload),
+                                                                                             int(s.n), cores, cpu_model(), tk * 1e3)},
            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
 
-def run_gpu(args):
+def time_search(h, s, x_dev, reps=3):
+    """Steady-state pair-search step: re-gridding + search + (fresh prune) + packing of a context that has searched before, with
+    the coordinates already on the device (b200nb_put_on_grid + b200nb_build_pairlist).  CUDA events on the context's stream
+    around both calls (the host stalls of the calls sit between the events, so they are inside) and the host wall clock."""
+    import torch
+    stream = torch.cuda.ExternalStream(int(h.stream))
+    ev_ms, wall_ms = [], []
+    lo, hi = np.zeros(3, np.float32), np.asarray(s.box, np.float32)
+    for _ in range(reps + 1):
+        h.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        h.put_on_grid(x_dev.data_ptr(), lo, hi, on_device=True)
+        h.build_pairlist()
+        e1.record(stream)
+        h.synchronize()
+        wall_ms.append((time.perf_counter() - t0) * 1e3)
+        ev_ms.append(e0.elapsed_time(e1))
+    return float(np.mean(ev_ms[1:])), float(np.mean(wall_ms[1:]))  # the first repetition may still grow buffers
+
+
+def search_block(args, s, coul, local_rank, step_ms, k_ms, h_static, x_dev):
+    """What `value` leaves out: the pair-search step and the rolling prune, and the step amortised over a
+    pair-list lifetime.  Scenario (reference defaults for a GPU run, pairlist_tuning.cpp:398-572, pairlistsets.h:100-114):
+    nstlist = 100, outer list at rc + 0.15 nm, dynamically pruned to rc + 0.05 nm, rolling prune of one of nstlistPrune / 2 = 5
+    parts every second step."""
     import torch
     import gmxapi_b200 as g
-    from gmxapi_b200 import lib as nb
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        return run_multi_gpu(args, rank, world, local_rank)
+    nstlist, nprune = 100, 10
+    rlo, rli = RC + 0.15, RC + 0.05
+    static_ev, static_wall = time_search(h_static, s, x_dev)
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coul, computeVirialAndEnergy=False, device=local_rank, epsilonRf=0.0,
+                            rlistOuter=rlo, rlistInner=rli)
+    fc = g.ForceCalculator(g.SimulationState.from_system(s), opt)
+    h = fc.nb
+    f_dev = torch.zeros_like(x_dev)
+    dyn_ev, dyn_wall = time_search(h, s, x_dev)
+    stream = torch.cuda.ExternalStream(int(h.stream))
+    nparts = nprune // 2
+    for part in range(nparts):
+        h.launch_prune(0, part, nparts)
+    h.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 4
+    e0.record(stream)
+    for _ in range(reps):
+        for part in range(nparts):
+            h.launch_prune(0, part, nparts)  # k_prune + k_pack of that part
+    e1.record(stream)
+    h.synchronize()
+    prune_part_ms = e0.elapsed_time(e1) / (reps * nparts)
+    dyn_step_ms, dyn_k_ms = h.time_step(x_dev.data_ptr(), f_dev.data_ptr(), 0, 3, max(10, min(args.steps, 50)), flush_l2=not args.no_flush)
+    st = h.stats()
+    fc.nb.close()
+    amort = dyn_step_ms + 0.5 * prune_part_ms + dyn_ev / nstlist
+    return {"search_ms": static_ev, "search_wall_ms": static_wall, "search_over_force_kernel": static_ev / k_ms,
+            "search_note": "steady-state b200nb_put_on_grid + b200nb_build_pairlist, coordinates on the device, rlist = rc (the list `value` runs on)",
+            "scenario": {"nstlist": nstlist, "nstlist_prune": nprune, "rolling_parts": nparts, "rlist_outer": rlo, "rlist_inner": rli},
+            "search_ms_dynamic": dyn_ev, "search_wall_ms_dynamic": dyn_wall,
+            "prune_ms": prune_part_ms, "prune_note": "one rolling part (k_prune + re-pack of 1/%d of the entries), every second step" % nparts,
+            "ms_per_step_pruned_list": dyn_step_ms, "force_kernel_ms_pruned_list": dyn_k_ms,
+            "computed_pairs_per_step_pruned_list": int(st["ntiles_packed"] * 64),
+            "ms_per_step_amortised": amort,
+            "amortised_overhead_frac": (amort - dyn_step_ms) / dyn_step_ms,
+            "amortised_vs_static_step": amort / step_ms}
 
+
+def measure_single(args, workload, local_rank, full):
+    """One GPU, one workload: device-resident step (flushed), force kernel alone, end to end through the public API; with
+    `full` also the search / prune / amortised block, the sustained block and the CPU baseline."""
+    import torch
+    import gmxapi_b200 as g
     peaks = measured_peaks()
-    s = workload_system(args.workload)
+    s = workload_system(workload)
     coul = g.CoulombType.Pme if args.eel == "ewald" else g.CoulombType.ReactionField
     opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coul, computeVirialAndEnergy=False, device=local_rank, epsilonRf=0.0,
                             maxTilesPerEntry=args.max_tiles)
@@ -277,8 +365,8 @@ def run_gpu(args):
     f_dev = torch.zeros_like(x_dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if not args.no_flush else None
     torch.cuda.synchronize()
-
     xp, fp = x_dev.data_ptr(), f_dev.data_ptr()
+    steps = args.steps
 
     def step():
         h.step(xp, fp, 0)  # 3 launches: x -> grid layout + output clear, force kernel, f -> atom order
@@ -289,9 +377,9 @@ def run_gpu(args):
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     l0 = h.stats()["nlaunches"]
-    for k in range(args.steps):
+    for k in range(steps):
         if flush is not None:
             with torch.cuda.stream(stream):
                 flush.fill_(k & 0xff)
@@ -304,8 +392,8 @@ def run_gpu(args):
     step_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
 
     # ---- force kernel alone (roofline): CUDA events around its launch inside the same step, on the kernels' stream ----
-    _, k_ms = h.time_step(xp, fp, 0, 3, max(10, min(args.steps, 100)), flush_l2=not args.no_flush)
-    k_ms_cold = h.time_force_kernel(-1, 0, 3, max(10, min(args.steps, 50)), flush_l2=not args.no_flush)
+    _, k_ms = h.time_step(xp, fp, 0, 3, max(10, min(steps, 100)), flush_l2=not args.no_flush)
+    k_ms_cold = h.time_force_kernel(-1, 0, 3, max(10, min(steps, 50)), flush_l2=not args.no_flush)
     clocks = sampler.stop()
 
     # ---- end to end through the public API with pinned host buffers -----------------------------------------
@@ -316,26 +404,14 @@ def run_gpu(args):
         fc.compute(xh, fh)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         fc.compute(xh, fh)  # synchronous: returns after the D2H of the forces completed
     torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
     f_host = fh.copy()
 
     # ---- parity spot-check of what was timed (cheap, not in any timed region) -------------------------------
     assert np.allclose(f_dev.cpu().numpy(), f_host, rtol=1e-3, atol=1e-2 * np.abs(f_host).mean())
-
-    # ---- CPU baseline: the reference's own SIMD path on this host --------------------------------------------
-    cpu = None
-    if not args.no_cpu:
-        try:
-            cores = host_cores()
-            t, tk, n = time_reference(s, args.eel, cores, 2000, 3, budget_s=15.0)
-            cpu = {"value": npairs / t, "unit": "pairs/s", "cores": cores, "kind": "reference",
-                   "sample": "%d full steps of %s on %d OpenMP threads of %s (x convert + 2xMM SIMD kernel + f reduce), "
-                             "%.3f ms/step; kernel alone %.3f ms" % (n, args.workload, cores, cpu_model(), t * 1e3, tk * 1e3)}
-        except Exception as e:  # the checker library is optional for the GPU numbers
-            cpu = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
 
     flops = FLOPS_PER_PAIR[args.eel]
     fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
@@ -343,16 +419,14 @@ def run_gpu(args):
     npad, ntiles = st["natoms_padded"], st["ntiles_packed"]
     # xq 16 + lj 8 read once, f 16 read-modify-written (32) per slot; 32 B of j-slot indices per packed tile; 16 B per entry
     alg_bytes = npad * (16 + 8 + 32) + ntiles * 32 + st["nentries"] * 16
+    cap = ncu_capture(workload, args.eel)
     out = {
-        "metric": METRIC, "value": npairs / (step_ms * 1e-3), "unit": "pairs/s", "n_gpus": 1, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "atoms": int(s.n), "useful_pairs_per_step": int(npairs),
-                   "computed_pairs_per_step": int(ntiles * 64),
-                   "cluster_pair_lanes_before_packing": int(st["ntiles_inner"] * 64), "rc": RC, "rlist": RC,
-                   "interaction": "LJ + " + ("Ewald real space (analytical)" if args.eel == "ewald" else "reaction field"),
-                   "flavor": "force only", "l2": "inputs < L2; L2 flushed (256 MiB write) between timed steps"
-                   if not args.no_flush else "not flushed", "setup_s": t_setup, "parallelism": "1 GPU"},
+        "value": npairs / (step_ms * 1e-3), "ms_per_step": step_ms,
+        "config": common_config(workload, s, npairs, args.eel, "strong", 1),
+        "details": {"computed_pairs_per_step": int(ntiles * 64), "useful_lane_fraction": npairs / float(ntiles * 64),
+                    "cluster_pair_lanes_before_packing": int(st["ntiles_inner"] * 64), "list_entries": int(st["nentries"]),
+                    "setup_s": t_setup, "parallelism": "1 GPU",
+                    "l2": "inputs < L2; L2 flushed (256 MiB write) between timed steps" if not args.no_flush else "not flushed"},
         "roofline": {"bound": "fp32", "kernel": "k_force<Ewald,geometric LJ,F>" if args.eel == "ewald" else "k_force<RF,geometric LJ,F>",
                      "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                      "kernel_ms": k_ms, "kernel_ms_alone_after_l2_flush": k_ms_cold, "flops_per_useful_pair": flops,
@@ -362,16 +436,63 @@ def run_gpu(args):
                                   % (peaks["sm_max_mhz"], peaks["source"]),
                      "useful_pairs_per_s_kernel": npairs / (k_ms * 1e-3),
                      "computed_pairs_per_s_kernel": ntiles * 64 / (k_ms * 1e-3),
-                     "traffic": ncu_capture(args.workload, args.eel).get("bytes"),
-                     "ncu": {k: v for k, v in ncu_capture(args.workload, args.eel).items() if k != "bytes"} or None,
+                     "traffic": cap.get("bytes"),
+                     "ncu": {k: v for k, v in cap.items() if k != "bytes"} or None,
                      "hbm": {"algorithmic_bytes": int(alg_bytes), "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
                              "peak_gbs": peaks["hbm_gbs"], "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}},
-        "cpu_baseline": cpu,
         "e2e": {"value": npairs / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(s.n * 12), "d2h_bytes_per_step": int(s.n * 12)},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if full:
+        del flush
+        if not args.no_search:
+            out["search"] = search_block(args, s, coul, local_rank, step_ms, k_ms, h, x_dev)
+        if not args.no_sustained:
+            # after the re-searches above the context holds a freshly built list of the same coordinates
+            out["sustained"] = sustained_block(h, s, npairs, seconds=args.sustained_seconds, flops_per_pair=flops, device=local_rank)
+        # ---- CPU baseline: the reference's own SIMD path on this host ----------------------------------------
+        cpu = None
+        if not args.no_cpu:
+            try:
+                cores = host_cores()
+                t, tk, n = time_reference(s, args.eel, cores, 2000, 3, budget_s=15.0)
+                cpu = {"value": npairs / t, "unit": "pairs/s", "cores": cores, "kind": "reference",
+                       "sample": "%d full steps of %s, one OpenMP thread on each of the %d physical cores of %s (x convert + 2xMM SIMD kernel + "
+                                 "f reduce), %.3f ms/step; kernel alone %.3f ms" % (n, workload, cores, cpu_model(), t * 1e3, tk * 1e3)}
+            except Exception as e:  # the checker library is optional for the GPU numbers
+                cpu = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "reference", "sample": "unavailable: %r" % (e,)}
+        out["cpu_baseline"] = cpu
+    fc.nb.close()
+    return out
+
+
+def run_gpu(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        return run_multi_gpu(args, rank, world, local_rank)
+    m = measure_single(args, args.workload, local_rank, full=True)
+    out = {"metric": METRIC, "value": m["value"], "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic"}
+    out.update({k: m[k] for k in ("config", "details", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks") if k in m})
+    for k in ("search", "sustained"):
+        if k in m:
+            out[k] = m[k]
+    if args.secondary and args.secondary != args.workload:
+        # BASELINE.json configs[1] beside the default configs[3]: same measurements, fewer steps of bookkeeping
+        m2 = measure_single(args, args.secondary, local_rank, full=False)
+        out["secondary"] = {"metric": METRIC, "unit": "pairs/s", "value": m2["value"], "ms_per_step": m2["ms_per_step"], "config": m2["config"],
+                            "details": m2["details"], "roofline": m2["roofline"], "e2e": m2["e2e"], "gpu_launches": m2["gpu_launches"],
+                            "clocks": m2["clocks"]}
     print(json.dumps(out))
 
 
@@ -384,8 +505,7 @@ def run_multi_gpu(args, rank, world, local_rank):
     from gmxapi_b200 import domdec
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peaks = measured_peaks()
-    nx, ny, nz = g.systems.NAMED[args.workload]
-    s = g.systems.water_box(nx * world if args.scaling == "weak" else nx, ny, nz)
+    s = workload_system(args.workload, world if args.scaling == "weak" else 1)
     coul = g.CoulombType.Pme if args.eel == "ewald" else g.CoulombType.ReactionField
     opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=coul, computeVirialAndEnergy=False, device=local_rank, epsilonRf=0.0,
                             maxTilesPerEntry=args.max_tiles)
@@ -457,6 +577,29 @@ def run_multi_gpu(args, rank, world, local_rank):
     e2e_ms = float(te.item())
     lt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
     dist.all_reduce(lt)
+
+    # ---- parity of the path that was just timed (outside every timed region): the decomposed forces, gathered from the ranks'
+    # pinned output buffers of the last e2e step, against a single-domain run of the same box on rank 0's GPU ----
+    parity = None
+    if not args.no_parity:
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object((np.asarray(d.plan.home), f_pin.numpy().copy()), parts, dst=0)
+        if rank == 0:
+            f_dd = np.zeros((s.n, 3), np.float32)
+            seen = np.zeros(s.n, np.int32)
+            for home, fh in parts:
+                f_dd[home] = fh
+                seen[home] += 1
+            assert np.all(seen == 1), "every atom must be home on exactly one rank"
+            fc1 = g.ForceCalculator(g.SimulationState.from_system(s), opt)
+            f_one = fc1.compute()
+            n_one = fc1.nb.pair_count(RC)
+            fc1.nb.close()
+            rel = float(np.sqrt(((f_dd.astype(np.float64) - f_one) ** 2).sum() / (f_one.astype(np.float64) ** 2).sum()))
+            parity = {"force_rel_rms_vs_single_domain": rel, "pairs_decomposed": int(npairs), "pairs_single_domain": int(n_one),
+                      "checked": "forces of the last end-to-end step of every rank, gathered; pair counts summed over ranks"}
+            if not (rel <= 1e-5 and n_one == npairs):
+                raise SystemExit("decomposed run disagrees with the single-domain run: %r" % (parity,))
     if rank == 0:
         flops = FLOPS_PER_PAIR[args.eel]
         fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12 * world
@@ -466,15 +609,15 @@ def run_multi_gpu(args, rank, world, local_rank):
             "metric": METRIC, "value": npairs / (step_ms * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": ("%d x %s along x" % (world, args.workload)) if args.scaling == "weak"
-                       else ("%s over %s domains" % (args.workload, args.dd_grid) if args.dd_grid
-                             else "%s over %d x-slabs" % (args.workload, world)), "atoms": int(natoms),
-                       "useful_pairs_per_step": int(npairs), "computed_pairs_per_step": int(ntiles * 64), "rc": RC, "rlist": RC,
-                       "interaction": "LJ + " + ("Ewald real space (analytical)" if args.eel == "ewald" else "reaction field"),
-                       "flavor": "force only", "l2": "L2 flushed (256 MiB write) between timed steps" if not args.no_flush else "not flushed",
-                       "parallelism": ("dd%s half-shell, NCCL halos" % args.dd_grid) if args.dd_grid else "dd%dx1x1" % world,
-                       "halo_atoms_total": int(nhalo_tot),
-                       "halo_bytes_per_step_each_way": int(halo_bytes)},
+            "config": common_config(args.workload, s, npairs, args.eel, args.scaling, world),
+            "details": {"computed_pairs_per_step": int(ntiles * 64),
+                        "decomposition": ("%s over %s domains, half shell" % (args.workload, args.dd_grid)) if args.dd_grid
+                        else "%d x-slabs" % world,
+                        "parallelism": ("dd%s" % args.dd_grid) if args.dd_grid else "dd%dx1x1" % world,
+                        "halo": "peer-memory windows over NVLink, written and awaited inside the step's kernels",
+                        "l2": "L2 flushed (256 MiB write) between timed steps" if not args.no_flush else "not flushed",
+                        "halo_atoms_total": int(nhalo_tot), "halo_bytes_per_step_each_way": int(halo_bytes)},
+            "parity": parity,
             "roofline": {"bound": "fp32", "kernel": "k_force (local + non-local), slowest rank", "achieved": achieved, "peak": fp32_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp32_peak, "kernel_ms": k_ms, "flops_per_useful_pair": flops,
                          "peak_note": "%d GPUs x 148 SMs x 128 FP32 lanes x 2 x %.0f MHz" % (world, peaks["sm_max_mhz"]), "traffic": None},
@@ -495,17 +638,23 @@ def run_multi_gpu(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="water_24k")
+    ap.add_argument("--workload", default="water_1M", help="water_24k / water_96k / water_192k / water_1M / water_1.5M (jittered lattice) or "
+                    "ref_water_24k / ref_water_96k / ref_water_192k / ref_water_1M (the reference's benchmark water)")
+    ap.add_argument("--secondary", default="water_24k", help="N = 1: a second workload reported in the `secondary` block ('' = none)")
     ap.add_argument("--eel", default="ewald", choices=["ewald", "rf"])
     ap.add_argument("--max-tiles", type=int, default=0, help="cluster pairs per list entry (0 = library default)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = N copies of the workload along x (default), strong = the workload itself over N slabs")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong = the workload itself over N domains (default), weak = N copies of the workload along x")
     ap.add_argument("--dd-grid", default="", help="N > 1: decompose as NXxNYxNZ ranks (e.g. 2x2x2) instead of x slabs")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-search", action="store_true", help="skip the search / prune / amortised block")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the sustained-clock block")
+    ap.add_argument("--sustained-seconds", type=float, default=2.5)
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the check against a single-domain run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

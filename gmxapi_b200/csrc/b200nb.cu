@@ -847,7 +847,8 @@ struct SearchArgs
     float    box[3];
     float    rlist2, rlist;
     int      max_tiles;
-    int      pass;       /* 0 count, 1 fill */
+    int      pass;       /* 0 count, 1 fill at the scanned offsets, 2 single pass: space claimed with atomics, bounded by cap_* */
+    long long cap_tiles, cap_entries;
 };
 
 __device__ __forceinline__ float bb_dist2(const float* ilo, const float* ihi, const float* jb)
@@ -875,7 +876,7 @@ k_search(SearchArgs A, const float* __restrict__ xq, const float* __restrict__ b
          const int* __restrict__ col_cell0, const int* __restrict__ atom_index, const int* __restrict__ excl_off,
          const int* __restrict__ excl_idx, const float* __restrict__ shift_vec, int* __restrict__ cnt_tiles,
          int* __restrict__ cnt_entries, Entry* __restrict__ entries, int* __restrict__ tile_cj, uint64_t* __restrict__ tile_mask,
-         int* __restrict__ err_flag)
+         int* __restrict__ err_flag, unsigned long long* __restrict__ claim)
 {
     __shared__ int      s_cj[4][NB_MAX_GROUP_TILES];
     __shared__ uint64_t s_mask[4][NB_MAX_GROUP_TILES];
@@ -1019,7 +1020,25 @@ k_search(SearchArgs A, const float* __restrict__ xq, const float* __restrict__ b
                     /* equal parts instead of full parts plus a short remainder: the same number of entries, none of them tiny */
                     const int nchunks = (n + A.max_tiles - 1) / A.max_tiles;
                     const int csize   = (n + nchunks - 1) / nchunks;
-                    if (A.pass == 1)
+                    bool write = A.pass == 1;
+                    if (A.pass == 2)
+                    {
+                        /* single pass: this group's room in the list is claimed here; a list that outgrew the buffers of the
+                         * previous search raises err_flag bit 1 and the host repeats the search with the two-pass scheme */
+                        unsigned long long t0 = 0, e0 = 0;
+                        if (lane == 0)
+                        {
+                            t0 = atomicAdd(claim, (unsigned long long)n);
+                            e0 = atomicAdd(claim + 1, (unsigned long long)nchunks);
+                        }
+                        t0           = __shfl_sync(0xffffffffu, t0, 0);
+                        e0           = __shfl_sync(0xffffffffu, e0, 0);
+                        tile_cursor  = (int)t0;
+                        entry_cursor = (int)e0;
+                        write        = (long long)(t0 + n) <= A.cap_tiles && (long long)(e0 + nchunks) <= A.cap_entries;
+                        if (!write && lane == 0) atomicOr(err_flag, 2);
+                    }
+                    if (write)
                     {
                         __syncwarp();
                         for (int k = lane; k < n; k += 32)
@@ -1148,32 +1167,36 @@ k_prune(const Entry* __restrict__ oe, const int* __restrict__ ocj, const uint64_
     }
 }
 
-/* Re-pack entries of the cluster-pair list at j-atom granularity for the force kernel (PackedList, b200nb_internal.h).
- * One warp per entry, lane = jl + 8*ih as in the search.  A j-atom is kept iff one of its pairs with the entry's 8 i-atoms has
- * r^2 < rlist2 and is not removed by the j > i rule of the self tile; kept j-atoms that have an excluded pair (or belong to
- * the self tile) are placed first so that only the leading STEPS (16 j-atoms = 2 packed tiles, what the force kernel consumes
- * per iteration) need masks.  Mask format of a step: 4 words; bit (j16 + 16*half) of word k says pair (i-atom 4*half + k,
- * j-atom j16 of the step) interacts -- the force kernel's lane j16 + 16*half reads its own bit of each word.
+/* Prune + re-pack: entries of the OUTER cluster-pair list at j-atom granularity for the force kernel (PackedList,
+ * b200nb_internal.h).  One warp per entry, lane = jl + 8*ih as in the search; ONE pass over the entry's cluster pairs.  A j-atom
+ * is kept iff one of its pairs with the entry's 8 i-atoms has r^2 < rlist2 (the inner, dynamic-pruning radius) and is not
+ * removed by the j > i rule of the self tile -- which subsumes the cluster-pair prune of nbnxn_kernel_prune_cuda
+ * (cuda/nbnxm_cuda_kernel_pruneonly.cuh:104-277): a cluster pair without a pair in range contributes no j-atom, so no separate
+ * prune kernel and no pruned cluster-pair list are needed on the per-step path (rolling pruning = this kernel on one part of
+ * the outer list).  Kept j-atoms that have an excluded pair (or belong to the self tile) go to a front buffer, the others to a
+ * back buffer, and are written out front first so that only the leading STEPS (16 j-atoms = 2 packed tiles, what the force kernel
+ * consumes per iteration) need masks.  Mask format of a step: 4 words; bit (j16 + 16*half) of word k says pair (i-atom
+ * 4*half + k, j-atom j16 of the step) interacts -- the force kernel's lane j16 + 16*half reads its own bit of each word.
  * Excluded pairs inside the cut-off must stay: the kernels evaluate their Ewald / reaction-field exclusion correction
  * (kernel_inner.h:330-360).  The j list of an entry is padded to a whole number of steps with far-away dummy atoms.
  * The reference has no such step: its GPU list stays at 8x8 cluster-pair granularity with per-pair masks
- * (nbnxm/pairlist.h:190-225); this is the same pruning idea as nbnxn_kernel_prune_cuda taken down to single j-atoms. */
+ * (nbnxm/pairlist.h:190-225). */
 __global__ void __launch_bounds__(128)
 k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t* __restrict__ imask, long long nentries, int part,
        int nparts, const float* __restrict__ xq, const float* __restrict__ shift_vec, float rlist2, int intra, int dummy_slot, int pitch,
-       const int* __restrict__ dest, int* __restrict__ sizes, Entry* __restrict__ pe, int* __restrict__ pja, uint64_t* __restrict__ pmask)
+       const int* __restrict__ dest, Entry* __restrict__ pe, int* __restrict__ pja, uint64_t* __restrict__ pmask)
 {
-    __shared__ int      s_ja[4][NB_MAX_ENTRY_TILES * 8 + 16];
-    __shared__ unsigned s_m[4][NB_MAX_ENTRY_TILES * 2 + 4]; /* 4 words per step of 16 j-atoms */
+    __shared__ int      s_ja[4][NB_MAX_ENTRY_TILES * 8 + 16]; /* front: j-atoms that need masks */
+    __shared__ int      s_jb[4][NB_MAX_ENTRY_TILES * 8];      /* back: the others */
+    __shared__ unsigned s_m[4][NB_MAX_ENTRY_TILES * 2 + 4];   /* 4 words per step of 16 j-atoms */
     const int       w   = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * 4 + w;
-    const long long e   = wid * nparts + part;
+    const long long e   = wid * nparts + part; /* rolling parts interleave entries: pruneonly.cuh:165-166 */
     if (e >= nentries) return;
     const int   lane = threadIdx.x & 31, jl = lane & 7, ih = lane >> 3;
     const Entry en   = ie[e];
     const int   shift = NB_ENTRY_SHIFT(en.shift_nmask), nmask = NB_ENTRY_NMASK(en.shift_nmask);
     const int   ntile = min(en.end - en.start, NB_MAX_ENTRY_TILES);
-    for (int k = lane; k < ntile * 8 + 16; k += 32) s_ja[w][k] = dummy_slot + (int)(e & (NB_DUMMY_SLOTS / 16 - 1)) * 16 + (k & 15);
     for (int k = lane; k < NB_MAX_ENTRY_TILES * 2 + 4; k += 32) s_m[w][k] = 0u;
     __syncwarp();
     const float4 xa = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + 2 * ih];
@@ -1182,49 +1205,63 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
     const float  xi0 = xa.x + sx, yi0 = xa.y + sy, zi0 = xa.z + sz, xi1 = xb.x + sx, yi1 = xb.y + sy, zi1 = xb.z + sz;
     /* where this lane's two pairs (i-atoms 2*ih, 2*ih+1) live in the step masks */
     const int mword = 2 * (ih & 1), mhalf = 16 * (ih >> 1);
-    int n = 0, nm = 0, has_self = 0;
-    for (int pass = 0; pass < 2; pass++)
+    int na = 0, nb = 0, has_self = 0;
+    /* the cluster index of the next tile is fetched one tile ahead: its coordinates load does not wait for it */
+    int cj_next = ntile > 0 ? icj[en.start] : 0;
+    for (int t = 0; t < ntile; t++)
     {
-        const int tend = pass == 0 ? nmask : ntile;
-        for (int t = 0; t < tend; t++)
+        const int cj = cj_next;
+        if (t + 1 < ntile) cj_next = icj[en.start + t + 1];
+        const float4   xj   = reinterpret_cast<const float4*>(xq)[(size_t)cj * 8 + jl];
+        const bool     diag = intra && shift == B200NB_CENTRAL && cj == en.ci;
+        if (diag) has_self = 1;
+        const bool     ina  = nb_rsq(xi0, yi0, zi0, xj.x, xj.y, xj.z) < rlist2 && !(diag && jl <= 2 * ih);
+        const bool     inb  = nb_rsq(xi1, yi1, zi1, xj.x, xj.y, xj.z) < rlist2 && !(diag && jl <= 2 * ih + 1);
+        unsigned       kb   = __ballot_sync(0xffffffffu, ina || inb);
+        kb                  = (kb | (kb >> 8) | (kb >> 16) | (kb >> 24)) & 0xffu;
+        if (!kb) continue; /* the cluster-pair prune: nothing of this tile within the radius */
+        unsigned ba = 1u, bb = 1u, sb = 0u;
+        if (t < nmask || diag)
         {
-            const int      cj   = icj[en.start + t];
-            const uint64_t m    = (t < nmask) ? imask[en.start + t] : ~0ull;
-            const bool     diag = intra && shift == B200NB_CENTRAL && cj == en.ci;
-            if (diag) has_self = 1;
-            const float4   xj   = reinterpret_cast<const float4*>(xq)[(size_t)cj * 8 + jl];
-            const bool     ina  = nb_rsq(xi0, yi0, zi0, xj.x, xj.y, xj.z) < rlist2 && !(diag && jl <= 2 * ih);
-            const bool     inb  = nb_rsq(xi1, yi1, zi1, xj.x, xj.y, xj.z) < rlist2 && !(diag && jl <= 2 * ih + 1);
-            const unsigned ba = (unsigned)(m >> lane) & 1u, bb = (unsigned)(m >> (32 + lane)) & 1u;
-            unsigned       kb = __ballot_sync(0xffffffffu, ina || inb);
-            unsigned       sb = __ballot_sync(0xffffffffu, !(ba && bb) || diag);
-            kb                = (kb | (kb >> 8) | (kb >> 16) | (kb >> 24)) & 0xffu;
-            sb                = (sb | (sb >> 8) | (sb >> 16) | (sb >> 24)) & 0xffu;
-            const unsigned sel = pass == 0 ? (kb & sb) : (kb & ~sb);
-            if ((sel >> jl) & 1u)
-            {
-                const int pos = n + __popc(sel & ((1u << jl) - 1u));
-                if (ih == 0) s_ja[w][pos] = cj * 8 + jl;
-                const int bit = (pos & 15) + mhalf;
-                atomicOr(&s_m[w][(pos >> 4) * 4 + mword], ba << bit);
-                atomicOr(&s_m[w][(pos >> 4) * 4 + mword + 1], bb << bit);
-            }
-            n += __popc(sel);
+            const uint64_t m = (t < nmask) ? imask[en.start + t] : ~0ull;
+            ba               = (unsigned)(m >> lane) & 1u;
+            bb               = (unsigned)(m >> (32 + lane)) & 1u;
+            sb               = __ballot_sync(0xffffffffu, !(ba && bb) || diag);
+            sb               = (sb | (sb >> 8) | (sb >> 16) | (sb >> 24)) & 0xffu;
         }
-        if (pass == 0) nm = n;
+        const unsigned sela = kb & sb, selb = kb & ~sb;
+        if ((sela >> jl) & 1u)
+        {
+            const int pos = na + __popc(sela & ((1u << jl) - 1u));
+            if (ih == 0) s_ja[w][pos] = cj * 8 + jl;
+            const int bit = (pos & 15) + mhalf;
+            atomicOr(&s_m[w][(pos >> 4) * 4 + mword], ba << bit);
+            atomicOr(&s_m[w][(pos >> 4) * 4 + mword + 1], bb << bit);
+        }
+        if (ih == 0 && ((selb >> jl) & 1u)) s_jb[w][nb + __popc(selb & ((1u << jl) - 1u))] = cj * 8 + jl;
+        na += __popc(sela);
+        nb += __popc(selb);
     }
     __syncwarp();
-    const int nsp = (n + 15) >> 4, nms = (nm + 15) >> 4; /* steps, masked steps */
+    const int n   = na + nb;
+    const int nsp = (n + 15) >> 4, nms = (na + 15) >> 4; /* steps, masked steps */
     const int ntp = 2 * nsp;                             /* packed tiles of 8 j-atoms */
-    if (sizes)
+    /* the unmasked j-atoms (and the padding) that share the last masked step interact with all 8 i-atoms */
+    if (na & 15)
     {
-        /* first pass of a full pack: only the packed size, from which the size-sorted positions `dest` are made */
-        if (lane == 0) sizes[e] = ntp;
-        return;
+        const int p = (na & ~15) + (lane & 15); /* position of this lane's j-atom in that step */
+        if (p >= na && lane < 16)
+        {
+            unsigned* const mw = &s_m[w][(p >> 4) * 4];
+            const unsigned  b2 = (1u << (p & 15)) | (1u << ((p & 15) + 16));
+            atomicOr(mw, b2), atomicOr(mw + 1, b2), atomicOr(mw + 2, b2), atomicOr(mw + 3, b2);
+        }
     }
+    __syncwarp();
     const long long d  = dest ? dest[e] : e; /* position of this entry in the packed list (largest entries first) */
     const long long t0 = d * pitch;          /* packed entry d owns tiles [d*pitch, (d+1)*pitch) */
-    for (int k = lane; k < ntp * 8; k += 32) pja[(size_t)t0 * 8 + k] = s_ja[w][k];
+    const int       dummy0 = dummy_slot + (int)(e & (NB_DUMMY_SLOTS / 16 - 1)) * 16;
+    for (int k = lane; k < ntp * 8; k += 32) pja[(size_t)t0 * 8 + k] = k < na ? s_ja[w][k] : (k < n ? s_jb[w][k - na] : dummy0 + (k & 15));
     unsigned* const pm = reinterpret_cast<unsigned*>(pmask + t0);
     for (int k = lane; k < nsp * 4; k += 32) pm[k] = k < nms * 4 ? s_m[w][k] : ~0u;
     if (lane == 0)
@@ -1236,6 +1273,14 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
         o.end         = (int)t0 + ntp;
         pe[d]         = o;
     }
+}
+
+/* ordering key of the packed entries: the cluster pairs of the outer entry (the packed size follows it closely and costs a
+ * whole packing pass to know exactly) */
+__global__ void k_entry_sizes(const Entry* __restrict__ e, int n, int* __restrict__ sizes)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sizes[i] = e[i].end - e[i].start;
 }
 
 /* Positions of the packed entries: descending packed size (counting sort on <= 33 values; the role of sort_sci,
@@ -1297,10 +1342,10 @@ static int ensure_packed(b200nb_context* h, PackedList& P, size_t cap_tiles, siz
     return 0;
 }
 
-/* packs part `part` of `nparts` of the inner list of locality loc */
+/* prunes + packs part `part` of `nparts` of the outer list of locality loc (radius: the inner list radius) */
 static int launch_pack(b200nb_context* h, int loc, int part, int nparts)
 {
-    const PairList& I = h->inner[loc];
+    const PairList& I = h->outer[loc];
     PackedList&     P = h->packed[loc];
     P.nentries        = I.nentries;
     P.pitch           = (h->max_tiles + 1) & ~1; /* whole steps of 16 j-atoms = 2 tiles */
@@ -1313,11 +1358,10 @@ static int launch_pack(b200nb_context* h, int loc, int part, int nparts)
     const unsigned nblk = (unsigned)((nw + 3) / 4);
     if (nparts == 1)
     {
-        /* full pack: sizes first, then the size-sorted positions, then the pack proper.  Rolling parts (nparts > 1) keep the
-         * positions of the last full pack: their entries only shrink a little, the order stays nearly sorted. */
+        /* full pack: the size-sorted positions first.  Rolling parts (nparts > 1) keep the positions of the last full pack:
+         * their entries only shrink or grow a little, the order stays nearly sorted. */
         const int n = (int)I.nentries;
-        k_pack<<<nblk, 128, 0, h->stream>>>(I.entries, I.cj, I.mask, I.nentries, 0, 1, h->d_xq, h->d_shift_vec, r2, loc == 0, h->dummy_slot,
-                                            P.pitch, nullptr, P.sizes, P.entries, P.ja, P.mask);
+        k_entry_sizes<<<(n + 255) / 256, 256, 0, h->stream>>>(I.entries, n, P.sizes);
         LAUNCH_CHECK(h);
         NB_CUDA(h, cudaMemsetAsync(h->d_hist, 0, sizeof(int) * 2 * NB_ORDER_BINS, h->stream));
         k_order_hist<<<(n + 255) / 256, 256, 0, h->stream>>>(P.sizes, n, h->d_hist);
@@ -1328,8 +1372,9 @@ static int launch_pack(b200nb_context* h, int loc, int part, int nparts)
         LAUNCH_CHECK(h);
     }
     k_pack<<<nblk, 128, 0, h->stream>>>(I.entries, I.cj, I.mask, I.nentries, part, nparts, h->d_xq, h->d_shift_vec, r2, loc == 0,
-                                        h->dummy_slot, P.pitch, P.dest, nullptr, P.entries, P.ja, P.mask);
+                                        h->dummy_slot, P.pitch, P.dest, P.entries, P.ja, P.mask);
     LAUNCH_CHECK(h);
+    h->inner_stale[loc] = true; /* the pruned CLUSTER-PAIR list (introspection only) no longer matches the packed one */
     return 0;
 }
 
@@ -1371,11 +1416,29 @@ static int launch_prune(b200nb_context* h, int loc, int part, int nparts)
     return 0;
 }
 
-/* the far-away dummy atoms the packed list pads its last tiles with: NB_DUMMY_SLOTS slots past the grids */
+/* the pruned cluster-pair list, for b200nb_get_tiles / b200nb_get_stats only: the per-step path goes outer list -> packed list */
+static int refresh_inner_list(b200nb_context* h)
+{
+    if (h->inner_is_outer) return 0;
+    for (int loc = 0; loc < 2; loc++)
+        if (h->inner_stale[loc])
+        {
+            if (launch_prune(h, loc, 0, 1)) return B200NB_ERR_CUDA;
+            h->inner_stale[loc] = false;
+        }
+    return 0;
+}
+
+/* the far-away dummy atoms the packed list pads its last tiles with: the LAST NB_DUMMY_SLOTS slots of the slot arrays, written
+ * once per allocation (a pair-search step neither moves nor rewrites them) */
 static int write_dummy_atoms(b200nb_context* h)
 {
     if ((size_t)h->npad + NB_DUMMY_SLOTS > h->cap_pad) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: no room for the dummy atoms");
-    h->dummy_slot = h->npad;
+    const int slot = (int)h->cap_pad - NB_DUMMY_SLOTS;
+    if (h->dummy_slot == slot && h->dummy_cap == h->cap_pad && h->dummy_ntypes == h->dp.ntypes) return 0;
+    h->dummy_slot   = slot;
+    h->dummy_cap    = h->cap_pad;
+    h->dummy_ntypes = h->dp.ntypes;
     std::vector<float> dxq(4 * NB_DUMMY_SLOTS), dlj(2 * NB_DUMMY_SLOTS, 0.0f);
     std::vector<int>   dty(NB_DUMMY_SLOTS, h->dp.ntypes - 1);
     for (int k = 0; k < NB_DUMMY_SLOTS; k++)
@@ -1384,10 +1447,10 @@ static int write_dummy_atoms(b200nb_context* h)
         dxq[4 * k + 2]              = -3.0e6f - 64.0f * k;
         dxq[4 * k + 3]              = 0.0f;
     }
-    NB_CUDA(h, cudaMemcpyAsync(h->d_xq + 4 * (size_t)h->npad, dxq.data(), sizeof(float) * dxq.size(), cudaMemcpyHostToDevice, h->stream));
-    NB_CUDA(h, cudaMemcpyAsync(h->d_lj + 2 * (size_t)h->npad, dlj.data(), sizeof(float) * dlj.size(), cudaMemcpyHostToDevice, h->stream));
-    NB_CUDA(h, cudaMemcpyAsync(h->d_atype + (size_t)h->npad, dty.data(), sizeof(int) * dty.size(), cudaMemcpyHostToDevice, h->stream));
-    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    NB_CUDA(h, cudaMemcpyAsync(h->d_xq + 4 * (size_t)slot, dxq.data(), sizeof(float) * dxq.size(), cudaMemcpyHostToDevice, h->stream));
+    NB_CUDA(h, cudaMemcpyAsync(h->d_lj + 2 * (size_t)slot, dlj.data(), sizeof(float) * dlj.size(), cudaMemcpyHostToDevice, h->stream));
+    NB_CUDA(h, cudaMemcpyAsync(h->d_atype + (size_t)slot, dty.data(), sizeof(int) * dty.size(), cudaMemcpyHostToDevice, h->stream));
+    NB_CUDA(h, cudaStreamSynchronize(h->stream)); /* the host vectors go out of scope */
     return 0;
 }
 
@@ -1396,6 +1459,7 @@ extern "C" int b200nb_build_pairlist(b200nb_t* h)
     if (!h) return B200NB_ERR_ARG;
     if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "build_pairlist: put_on_grid first");
     cudaSetDevice(h->device);
+    if (const char* e = getenv("B200NB_SEARCH_TWO_PASS")) h->search_two_pass = atoi(e) != 0; /* A/B switch for profiles/ */
     const float rl = h->hp.rlist_outer;
     /* a periodic dimension must hold at least two list radii, else one pair has several images in range
      * (the reference handles that with shp[XX]=2, pairlist.cpp:3185-3188; outside our scope) */
@@ -1455,39 +1519,64 @@ extern "C" int b200nb_build_pairlist(b200nb_t* h)
         A.max_tiles = h->max_tiles;
         NB_CUDA(h, cudaMemsetAsync(h->d_scratch + 8, 0, sizeof(int), h->stream));
         const unsigned nblk = (unsigned)((ncl_i + 3) / 4);
-        A.pass              = 0;
-        k_search<<<nblk, 128, 0, h->stream>>>(A, h->d_xq, h->d_bb, h->d_cellz, h->d_col_cell0, h->d_atom_index, h->d_excl_off,
-                                              h->d_excl_idx, h->d_shift_vec, h->d_cnt_tiles, h->d_cnt_entries, nullptr, nullptr,
-                                              nullptr, h->d_scratch + 8);
-        LAUNCH_CHECK(h);
-        k_scan2<<<1, 1024, 0, h->stream>>>(h->d_cnt_tiles, h->d_cnt_entries, ncl_i, h->d_counter);
-        LAUNCH_CHECK(h);
-        long long tot[2];
-        int       flag = 0;
-        NB_CUDA(h, cudaMemcpyAsync(tot, h->d_counter, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
-        NB_CUDA(h, cudaMemcpyAsync(&flag, h->d_scratch + 8, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        NB_CUDA(h, cudaStreamSynchronize(h->stream));
-        if (flag) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: more than 512 cluster pairs for one i-cluster and shift");
-        if (tot[0] > 2000000000LL) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: pair list exceeds 2^31 cluster pairs");
-        if (ensure_list(h, L, (size_t)tot[0], (size_t)tot[1])) return B200NB_ERR_CUDA;
-        L.ntiles   = tot[0];
-        L.nentries = tot[1];
-        if (tot[0] > 0)
+        long long      tot[2] = { 0, 0 };
+        int            flag = 0;
+        bool           done = false;
+        unsigned long long* const claim = reinterpret_cast<unsigned long long*>(h->d_counter);
+        if (L.cap_tiles > 0 && L.cap_entries > 0 && L.entries && !h->search_two_pass)
         {
-            A.pass = 1;
+            /* steady state: ONE pass into the buffers the previous search left (they hold 10 % more than it needed; a pair list
+             * changes by well under 1 % between searches), room claimed with two atomics per (i-cluster, shift) group */
+            A.pass        = 2;
+            A.cap_tiles   = (long long)L.cap_tiles;
+            A.cap_entries = (long long)L.cap_entries;
+            NB_CUDA(h, cudaMemsetAsync(h->d_counter, 0, 2 * sizeof(long long), h->stream));
             k_search<<<nblk, 128, 0, h->stream>>>(A, h->d_xq, h->d_bb, h->d_cellz, h->d_col_cell0, h->d_atom_index, h->d_excl_off,
                                                   h->d_excl_idx, h->d_shift_vec, h->d_cnt_tiles, h->d_cnt_entries, L.entries, L.cj,
-                                                  L.mask, h->d_scratch + 8);
+                                                  L.mask, h->d_scratch + 8, claim);
             LAUNCH_CHECK(h);
+            NB_CUDA(h, cudaMemcpyAsync(tot, h->d_counter, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+            NB_CUDA(h, cudaMemcpyAsync(&flag, h->d_scratch + 8, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            NB_CUDA(h, cudaStreamSynchronize(h->stream));
+            if (flag & 1) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: more than 512 cluster pairs for one i-cluster and shift");
+            done = !(flag & 2);
+            if (!done) NB_CUDA(h, cudaMemsetAsync(h->d_scratch + 8, 0, sizeof(int), h->stream));
         }
+        if (!done)
+        {
+            A.pass = 0;
+            k_search<<<nblk, 128, 0, h->stream>>>(A, h->d_xq, h->d_bb, h->d_cellz, h->d_col_cell0, h->d_atom_index, h->d_excl_off,
+                                                  h->d_excl_idx, h->d_shift_vec, h->d_cnt_tiles, h->d_cnt_entries, nullptr, nullptr,
+                                                  nullptr, h->d_scratch + 8, claim);
+            LAUNCH_CHECK(h);
+            k_scan2<<<1, 1024, 0, h->stream>>>(h->d_cnt_tiles, h->d_cnt_entries, ncl_i, h->d_counter);
+            LAUNCH_CHECK(h);
+            NB_CUDA(h, cudaMemcpyAsync(tot, h->d_counter, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+            NB_CUDA(h, cudaMemcpyAsync(&flag, h->d_scratch + 8, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            NB_CUDA(h, cudaStreamSynchronize(h->stream));
+            if (flag) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: more than 512 cluster pairs for one i-cluster and shift");
+            if (tot[0] > 2000000000LL) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: pair list exceeds 2^31 cluster pairs");
+            if (ensure_list(h, L, (size_t)tot[0], (size_t)tot[1])) return B200NB_ERR_CUDA;
+            if (tot[0] > 0)
+            {
+                A.pass = 1;
+                k_search<<<nblk, 128, 0, h->stream>>>(A, h->d_xq, h->d_bb, h->d_cellz, h->d_col_cell0, h->d_atom_index, h->d_excl_off,
+                                                      h->d_excl_idx, h->d_shift_vec, h->d_cnt_tiles, h->d_cnt_entries, L.entries, L.cj,
+                                                      L.mask, h->d_scratch + 8, claim);
+                LAUNCH_CHECK(h);
+            }
+        }
+        L.ntiles   = tot[0];
+        L.nentries = tot[1];
         if (want_inner)
         {
             PairList& I = h->inner[loc];
             if (ensure_list(h, I, (size_t)tot[0], (size_t)tot[1])) return B200NB_ERR_CUDA;
             I.ntiles   = tot[0]; /* upper bound; exact count via get_stats */
             I.nentries = tot[1];
-            /* fresh-list prune of the whole list (cuda/nbnxm_cuda.cu:510-517) */
-            if (launch_prune(h, loc, 0, 1)) return B200NB_ERR_CUDA;
+            /* the fresh-list prune (cuda/nbnxm_cuda.cu:510-517) is part of the packing below (k_pack prunes while it packs);
+             * the pruned cluster-pair list itself is only materialised for introspection (refresh_inner_list) */
+            h->inner_stale[loc] = true;
         }
         else
         {
@@ -1497,7 +1586,7 @@ extern "C" int b200nb_build_pairlist(b200nb_t* h)
     if (int rc = write_dummy_atoms(h)) return rc;
     for (int loc = 0; loc < 2; loc++)
         if (launch_pack(h, loc, 0, 1)) return B200NB_ERR_CUDA;
-    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    /* no synchronisation here: everything that follows (steps, prunes, introspection) is ordered on the stream */
     h->have_list = true;
     h->generation++;
     return 0;
@@ -1681,7 +1770,7 @@ extern "C" int b200nb_upload_pairlist(b200nb_t* h, int locality, const b200nb_sc
         if (ensure_list(h, I, cjv.size(), ent.size())) return B200NB_ERR_CUDA;
         I.ntiles   = L.ntiles;
         I.nentries = L.nentries;
-        if (launch_prune(h, locality, 0, 1)) return B200NB_ERR_CUDA; /* fresh-list prune (cuda/nbnxm_cuda.cu:510-517) */
+        h->inner_stale[locality] = true; /* fresh-list prune (cuda/nbnxm_cuda.cu:510-517): done by the packing below */
     }
     else
         h->inner[locality] = L;
@@ -1757,7 +1846,7 @@ extern "C" int b200nb_launch_prune(b200nb_t* h, int locality, int part, int num_
     for (int loc = 0; loc < 2; loc++)
         if (locality < 0 || locality == loc)
         {
-            if (launch_prune(h, loc, part, num_parts)) return B200NB_ERR_CUDA;
+            /* k_pack prunes the part's entries of the outer list to the inner radius while re-packing them */
             if (!h->inner_is_outer && launch_pack(h, loc, part, num_parts)) return B200NB_ERR_CUDA;
         }
     return 0;
@@ -2101,7 +2190,7 @@ static int launch_step(b200nb_context* h, const float* x_dev, int flags, float* 
                        cudaEvent_t ev_force1 = nullptr)
 {
     const int n      = h->natoms;
-    const int nclear = h->npad + NB_DUMMY_SLOTS; /* + the dummy atoms of the packed list */
+    const int nclear = (int)h->cap_pad; /* grid slots + slack + the dummy atoms of the packed list at the end */
     const unsigned nb0 = (unsigned)((std::max(std::max(n, nclear), NB_OUT_COPIES * NB_FSHIFT_PITCH) + 255) / 256), nb1 = (unsigned)((n + 255) / 256);
     PrefetchRange pf{};
     {
@@ -2592,7 +2681,7 @@ static void tag_nonlocal_node(b200nb_context* h)
 static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home, int flags)
 {
     DdState&  D = h->dd;
-    const int n = D.nhome, nclear = h->npad + NB_DUMMY_SLOTS;
+    const int n = D.nhome, nclear = (int)h->cap_pad;
     const unsigned nb0 = (unsigned)((std::max(std::max(n, nclear), NB_OUT_COPIES * NB_FSHIFT_PITCH) + 255) / 256);
     PrefetchRange pf{};
     {
@@ -2797,6 +2886,8 @@ extern "C" int b200nb_get_stats(b200nb_t* h, b200nb_stats_t* out)
     out->comb_geometric = h->comb_geom ? 1 : 0;
     if (h->have_list)
     {
+        if (refresh_inner_list(h)) return B200NB_ERR_CUDA;
+        out->nentries_nonlocal = h->packed[1].nentries;
         for (int l = 0; l < 2; l++)
         {
             out->ntiles_outer += h->outer[l].ntiles;
@@ -2848,6 +2939,7 @@ extern "C" long long b200nb_get_tiles(b200nb_t* h, int outer, int* tiles_host, l
     if (!h) return B200NB_ERR_ARG;
     if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "get_tiles: no pair list");
     cudaSetDevice(h->device);
+    if (!outer && refresh_inner_list(h)) return B200NB_ERR_CUDA;
     cudaStreamSynchronize(h->stream);
     long long n = 0;
     for (int l = 0; l < 2; l++)

@@ -232,7 +232,9 @@ struct b200nb_context
 
     PairList outer[2], inner[2];
     bool     inner_is_outer = true;
+    bool     inner_stale[2] = { false, false }; /* inner[] (pruned cluster pairs, introspection only) is behind the packed list */
     bool     have_list = false;
+    bool     search_two_pass = false; /* B200NB_SEARCH_TWO_PASS=1: always count, scan, fill (A/B switch; the first search always does) */
     PackedList packed[2];
     DdState    dd;
     StepGraph  graph[3];       /* [0] single-domain step, [1] decomposed step, [2] host step through the copy engines */
@@ -242,7 +244,9 @@ struct b200nb_context
     bool       use_pdl = true; /* launch the force kernel with programmatic stream serialization (see force.cu) */
     bool       capturing = false;
     std::vector<cudaGraphNode_t> nl_nodes; /* kernel nodes captured from the non-local stream (get an explicit priority) */
-    int        dummy_slot = 0; /* first of the NB_DUMMY_SLOTS far-away filler slots appended after the grids */
+    int        dummy_slot = -1; /* first of the NB_DUMMY_SLOTS far-away filler slots: the tail of the slot arrays */
+    size_t     dummy_cap = 0;   /* cap_pad / type count the dummies were written for */
+    int        dummy_ntypes = 0;
 
     float* d_flush = nullptr;
     size_t flush_bytes = 0;

@@ -84,7 +84,8 @@ def vdw_modifier_constants(modifier, rvdw, rvdw_switch):
 class _Stats(C.Structure):
     _fields_ = [("natoms", C.c_int), ("natoms_padded", C.c_int), ("nclusters", C.c_int), ("ncx", C.c_int),
                 ("ncy", C.c_int), ("ntiles_outer", C.c_longlong), ("ntiles_inner", C.c_longlong),
-                ("nentries", C.c_longlong), ("comb_geometric", C.c_int), ("nlaunches", C.c_longlong), ("ntiles_packed", C.c_longlong)]
+                ("nentries", C.c_longlong), ("comb_geometric", C.c_int), ("nlaunches", C.c_longlong), ("ntiles_packed", C.c_longlong),
+                ("nentries_nonlocal", C.c_longlong)]
 
 
 _lib = None

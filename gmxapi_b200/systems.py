@@ -85,7 +85,50 @@ NAMED = {
 }
 
 
+# The reference's own benchmark water: BenchmarkSystem(S) stacks coordinates1000 (1000 SPC/E molecules, liquid structure,
+# 3.10736 nm box) 2 x 2 x ... times (nbnxm/benchmark/bench_system.cpp:90-151); tiles per dimension here
+REF_NAMED = {
+    "ref_water_3k": (1, 1, 1),
+    "ref_water_24k": (2, 2, 2),     # BenchmarkSystem(8):  BASELINE.json configs[1] as SURVEY 8(d) defines it
+    "ref_water_96k": (4, 4, 2),     # BenchmarkSystem(32): configs[2]
+    "ref_water_192k": (4, 4, 4),
+    "ref_water_1M": (7, 7, 7),      # configs[3]: 1.029 M atoms (the reference's tiler only does powers of two)
+}
+
+
+def ref_water_box(tx, ty, tz):
+    """generateCoordinates + BenchmarkSystem (bench_system.cpp:90-195): the base tile shifted by whole boxes, x outermost and z
+    innermost, put in the box; O type 0 / H type 1, SPC/E charges, intramolecular exclusions."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "ref_water_1000.npz"))
+    base, edge = d["x"].astype(np.float32), np.float32(d["box_edge"])
+    sh = np.stack(np.meshgrid(np.arange(tx), np.arange(ty), np.arange(tz), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    x = (base[None, :, :] + (sh * edge)[:, None, :]).reshape(-1, 3).astype(np.float32)
+    box = (np.array([tx, ty, tz], np.float32) * edge).astype(np.float32)
+    x = np.where(x >= box, x - box, x)
+    x = np.where(x < 0, x + box, x).astype(np.float32)  # put_atoms_in_box, bench_system.cpp:157
+    n = x.shape[0]
+    nmol = n // 3
+    types = np.tile(np.array([0, 1, 1], np.int32), nmol)
+    q = np.tile(np.array([Q_O, Q_H, Q_H], np.float32), nmol)
+    nbfp = np.zeros((2, 2, 2), np.float32)
+    nbfp[0, 0] = (6.0 * C6_O, 12.0 * C12_O)
+    first = (np.arange(n) // 3) * 3
+    excl_idx = (first[:, None] + np.arange(3)[None, :]).astype(np.int32).ravel()
+    excl_off = (np.arange(n + 1) * 3).astype(np.int32)
+    return System(x, box, types, q, nbfp, excl_off, excl_idx, (np.arange(n) // 3).astype(np.int32), "ref_water_%dx%dx%d" % (tx, ty, tz))
+
+
+def tiles_of(name):
+    """(generator, (nx, ny, nz)) of a named workload: molecules per dimension (lattice water) or tiles (reference water)."""
+    if name in REF_NAMED:
+        return ref_water_box, REF_NAMED[name]
+    return water_box, NAMED[name]
+
+
 def named(name, seed=20261017):
+    if name in REF_NAMED:
+        return ref_water_box(*REF_NAMED[name])
     return water_box(*NAMED[name], seed=seed)
 
 

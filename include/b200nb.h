@@ -277,6 +277,7 @@ typedef struct
     int       comb_geometric;  /* 1 if the geometric-rule kernel is used */
     long long nlaunches;       /* kernels launched by this context so far */
     long long ntiles_packed;   /* 8-j-atom x 8-i-atom tiles the force kernel evaluates (the pruned list re-packed per j-atom) */
+    long long nentries_nonlocal; /* entries of the packed non-local (home x halo) list the next non-local launch runs */
 } b200nb_stats_t;
 int b200nb_get_stats(b200nb_t* h, b200nb_stats_t* out);
 /* slot -> original atom (-1 filler), natoms_padded ints: GridSet::atomIndices() */

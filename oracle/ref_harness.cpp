@@ -29,6 +29,7 @@
 #include "gromacs/mdlib/gmx_omp_nthreads.h"
 #include "gromacs/mdtypes/enerdata.h"
 #include "gromacs/mdtypes/forcerec.h"
+#include "gromacs/nbnxm/benchmark/bench_coords.h"
 #include "gromacs/mdtypes/interaction_const.h"
 #include "gromacs/mdtypes/simulation_workload.h"
 #include "gromacs/nbnxm/atomdata.h"
@@ -665,6 +666,18 @@ int gmxref_gpu_list(void* h, int* nsci, int* ncj4, int* nexcl, int* nslots, int*
     }
     if (type) std::memcpy(type, nbat.params().type.data(), static_cast<size_t>(nbat.numAtoms()) * sizeof(int));
     return 0;
+}
+
+/* The reference's benchmark water (benchmark/bench_coords.h:47-49: 1000 SPC/E molecules equilibrated at 300 K, 1 bar, cubic box
+ * 3.10736 nm), the base tile of BenchmarkSystem (bench_system.cpp:90-151).  out: 3000 x 3 floats; returns the atom count. */
+int gmxref_bench_coordinates1000(float* out, int cap_atoms, float* box_edge)
+{
+    const int n = static_cast<int>(coordinates1000.size());
+    *box_edge   = box1000[XX][XX];
+    if (out == nullptr || cap_atoms < n) return n;
+    for (int i = 0; i < n; i++)
+        for (int d = 0; d < DIM; d++) out[3 * i + d] = coordinates1000[i][d];
+    return n;
 }
 
 /* forces of the last gmxref_compute in GRID order (nbat->out[0].f, 3 floats per slot): what gpu_launch_cpyback delivers */

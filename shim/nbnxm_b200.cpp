@@ -40,7 +40,6 @@
 #include "gromacs/pbcutil/ishift.h"
 #include "gromacs/timing/gpu_timing.h"
 #include "gromacs/utility/arrayref.h"
-#include "gromacs/utility/exceptions.h"
 #include "gromacs/utility/fatalerror.h"
 
 #include "b200nb.h"
@@ -62,6 +61,13 @@ struct NbnxmGpu
     int  rollingNumParts[2] = { 0, 0 };
     bool haveFreshList[2]   = { false, false };
     bool haveList[2]        = { false, false };
+    /* nblib builds the pair list BEFORE it sets the atom properties (api/nblib/gmxsetup.cpp:316-320; mdrun does it the other way
+     * round, mdlib/sim_util.cpp:1327-1366): a list that arrives before the atom data of its grid is kept until gpu_init_atomdata */
+    bool                      haveAtomData = false;
+    bool                      pending[2]   = { false, false };
+    std::vector<nbnxn_sci_t>  pendingSci[2];
+    std::vector<nbnxn_cj4_t>  pendingCj4[2];
+    std::vector<nbnxn_excl_t> pendingExcl[2];
     /* staged outputs of the step in flight (NBStagingData, nbnxm/gpu_types_common.h:126-136) */
     bool                      didEnergy = false, didVirial = false;
     gmx_wallclock_gpu_nbnxn_t timings{};
@@ -72,10 +78,10 @@ namespace
 
 void check(NbnxmGpu* nb, int rc, const char* what)
 {
-    /* the reference reports GPU failures through gmx_fatal / exceptions, never through return codes */
+    /* the reference reports GPU failures through gmx_fatal (CU_RET_ERR, cuda/nbnxm_cuda.cu), never through return codes */
     if (rc != B200NB_OK)
     {
-        GMX_THROW(gmx::InternalError(std::string("b200nb ") + what + ": " + (nb && nb->h ? b200nb_last_error(nb->h) : "no context")));
+        gmx_fatal(FARGS, "B200 nonbonded backend, %s: %s", what, nb && nb->h ? b200nb_last_error(nb->h) : "no context");
     }
 }
 
@@ -168,6 +174,18 @@ void setParameters(NbnxmGpu* nb, const interaction_const_t* ic, const PairlistPa
     }
 }
 
+void uploadList(NbnxmGpu* nb, int l, const nbnxn_sci_t* sci, size_t nsci, const nbnxn_cj4_t* cj4, size_t ncj4, const nbnxn_excl_t* excl, size_t nexcl)
+{
+    check(nb,
+          b200nb_upload_pairlist(nb->h, l, reinterpret_cast<const b200nb_sci_t*>(sci), static_cast<int>(nsci),
+                                 reinterpret_cast<const b200nb_cj4_t*>(cj4), static_cast<int>(ncj4),
+                                 reinterpret_cast<const b200nb_excl_t*>(excl), static_cast<int>(nexcl)),
+          "upload_pairlist");
+    nb->haveList[l]      = true;
+    nb->haveFreshList[l] = true; /* the library prunes a fresh list at upload: nothing left for the first prune-only call */
+    nb->rollingPart[l]   = 0;
+}
+
 void slotRange(const NbnxmGpu* nb, gmx::AtomLocality aloc, int* begin, int* end)
 {
     /* getGpuAtomRange, nbnxm/gpu_common_utils.h: local = [0, natoms_local), non-local = the rest */
@@ -236,6 +254,17 @@ void gpu_init_atomdata(NbnxmGpu* nb, const nbnxn_atomdata_t* nbat)
     check(nb, b200nb_set_grid_atoms(nb->h, nb->numSlots, nbat->x().data(), nbat->params().type.data()), "set_grid_atoms");
     check(nb, b200nb_set_shift_vec(nb->h, reinterpret_cast<const float*>(nbat->shift_vec.data())), "set_shift_vec");
     nb->haveList[0] = nb->haveList[1] = false;
+    nb->haveAtomData                  = true;
+    for (int l = 0; l < 2; l++)
+    {
+        if (nb->pending[l])
+        {
+            uploadList(nb, l, nb->pendingSci[l].data(), nb->pendingSci[l].size(), nb->pendingCj4[l].data(), nb->pendingCj4[l].size(),
+                       nb->pendingExcl[l].data(), nb->pendingExcl[l].size());
+            nb->pending[l] = false;
+            nb->pendingSci[l].clear(), nb->pendingCj4[l].clear(), nb->pendingExcl[l].clear();
+        }
+    }
 }
 
 void gpu_upload_shiftvec(NbnxmGpu* nb, const nbnxn_atomdata_t* nbatom)
@@ -246,14 +275,16 @@ void gpu_upload_shiftvec(NbnxmGpu* nb, const nbnxn_atomdata_t* nbatom)
 void gpu_init_pairlist(NbnxmGpu* nb, const NbnxnPairlistGpu* h_nblist, gmx::InteractionLocality iloc)
 {
     const int l = locIndex(iloc);
-    check(nb,
-          b200nb_upload_pairlist(nb->h, l, reinterpret_cast<const b200nb_sci_t*>(h_nblist->sci.data()), static_cast<int>(h_nblist->sci.size()),
-                                 reinterpret_cast<const b200nb_cj4_t*>(h_nblist->cj4.data()), static_cast<int>(h_nblist->cj4.size()),
-                                 reinterpret_cast<const b200nb_excl_t*>(h_nblist->excl.data()), static_cast<int>(h_nblist->excl.size())),
-          "upload_pairlist");
-    nb->haveList[l]      = true;
-    nb->haveFreshList[l] = true; /* the library prunes a fresh list at upload: nothing left for the first prune-only call */
-    nb->rollingPart[l]   = 0;
+    if (!nb->haveAtomData)
+    {
+        nb->pendingSci[l].assign(h_nblist->sci.begin(), h_nblist->sci.end());
+        nb->pendingCj4[l].assign(h_nblist->cj4.begin(), h_nblist->cj4.end());
+        nb->pendingExcl[l].assign(h_nblist->excl.begin(), h_nblist->excl.end());
+        nb->pending[l] = true;
+        return;
+    }
+    uploadList(nb, l, h_nblist->sci.data(), h_nblist->sci.size(), h_nblist->cj4.data(), h_nblist->cj4.size(), h_nblist->excl.data(),
+               h_nblist->excl.size());
 }
 
 void gpu_copy_xq_to_gpu(NbnxmGpu* nb, const nbnxn_atomdata_t* nbdata, gmx::AtomLocality aloc)

@@ -13,6 +13,7 @@ from oracle import oracle
 
 pytestmark = pytest.mark.gpu
 RC = 0.9
+ENERGY_TOL = 2e-5  # relative, against the oracle's double-precision sums (the reference's own FP32 sums sit 1e-5 .. 2e-4 from those)
 CENTRAL = 22
 
 
@@ -132,8 +133,8 @@ def test_domain_decomposition_matches_single_domain(built, name, nranks, coulomb
     assert np.sqrt(((f - fo) ** 2).sum() / (fo ** 2).sum()) < 1e-5
     # energies
     elj, eel = sum(r["elj"] for r in res), sum(r["eel"] for r in res)
-    assert abs(elj - evo) <= 2e-4 * abs(evo)
-    assert abs(eel - eco) <= 2e-4 * abs(eco)
+    assert abs(elj - evo) <= ENERGY_TOL * abs(evo)
+    assert abs(eel - eco) <= ENERGY_TOL * abs(eco)
     # virial: -1/2 [ sum_a x_a (x) f_a + sum_s shift_vec[s] (x) fshift[s] ], decomposition-invariant
     fs = sum(r["fs"].astype(np.float64) for r in res)
     x = s.x.astype(np.float64)
@@ -168,8 +169,8 @@ def test_repartition_after_motion(built, nranks, windows):
         f[r["home"]] = r["f"]
     assert np.sqrt(((f - fo) ** 2).sum() / (fo ** 2).sum()) < 1e-5
     elj, eel = sum(r["elj"] for r in res), sum(r["eel"] for r in res)
-    assert abs(elj - evo) <= 2e-4 * abs(evo)
-    assert abs(eel - eco) <= 2e-4 * abs(eco)
+    assert abs(elj - evo) <= ENERGY_TOL * abs(evo)
+    assert abs(eel - eco) <= ENERGY_TOL * abs(eco)
 
 
 # ---- 2-D / 3-D decomposition, half-shell rule (gmxapi_b200/domdec_nd.py) ----------------------------------------------------
@@ -270,8 +271,8 @@ def test_decomposition_nd_matches_single_domain(built, grid):
         f[r["home"]] = r["f"]
     assert np.sqrt(((f - fo) ** 2).sum() / (fo ** 2).sum()) < 1e-5
     elj, eel = sum(r["elj"] for r in res), sum(r["eel"] for r in res)
-    assert abs(elj - evo) <= 2e-4 * abs(evo)
-    assert abs(eel - eco) <= 2e-4 * abs(eco)
+    assert abs(elj - evo) <= ENERGY_TOL * abs(evo)
+    assert abs(eel - eco) <= ENERGY_TOL * abs(eco)
 
 
 @pytest.mark.parametrize("grid", ND_GRIDS)
@@ -341,5 +342,5 @@ def test_repartition_nd_after_motion(built):
     for r in out:
         f[r["home"]] = r["f"]
     assert np.sqrt(((f - fo) ** 2).sum() / (fo ** 2).sum()) < 1e-5
-    assert abs(sum(r["elj"] for r in out) - evo) <= 2e-4 * abs(evo)
-    assert abs(sum(r["eel"] for r in out) - eco) <= 2e-4 * abs(eco)
+    assert abs(sum(r["elj"] for r in out) - evo) <= ENERGY_TOL * abs(evo)
+    assert abs(sum(r["eel"] for r in out) - eco) <= ENERGY_TOL * abs(eco)

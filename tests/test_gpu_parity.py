@@ -13,6 +13,7 @@ from oracle import oracle
 pytestmark = pytest.mark.gpu
 
 RC = 0.9
+ENERGY_TOL = 2e-5  # relative, against the oracle's double-precision sums (the reference's own FP32 sums sit 1e-5 .. 2e-4 from those)
 FORCE_TOL = 1e-5  # relative RMS, north_star
 VIRIAL_TOL = 1e-5
 
@@ -84,13 +85,12 @@ def test_pairs_forces_energies(built, name, coulomb):
     vo = oracle.virial_from_fshift(s.box, fso)
     vg = oracle.virial_from_fshift(s.box, np.where(m[:, None], fs, 0.0))
     assert np.abs(vg - vo).max() <= VIRIAL_TOL * np.abs(vo).max()
-    # 4. energies. E_lj and E_el are sums of ~1e6 terms of both signs whose magnitudes sum to >1e3 x the
-    # total; single-precision pair arithmetic (ours AND the reference's: its own SIMD vs plain-C kernels
-    # differ by 1e-4 relative on E_el, tests/test_oracle_vs_reference.py) bounds the achievable agreement.
-    # We require 1e-5 of the magnitude sum and 2e-4 of the total.
+    # 4. energies, against the oracle's DOUBLE-precision sums of the same single-precision pair terms.  The kernel keeps per-warp
+    # single-precision partial sums and adds those in double, which holds 2e-5 of the total; the reference's own all-FP32 sums
+    # sit 1e-5 .. 1.8e-4 from the double sum, hence the looser 2e-4 where the expected value is a reference output.
     elj, eel = fc.energies
-    assert abs(elj - evo) <= 2e-4 * abs(evo)
-    assert abs(eel - eco) <= 2e-4 * abs(eco)
+    assert abs(elj - evo) <= ENERGY_TOL * abs(evo)
+    assert abs(eel - eco) <= ENERGY_TOL * abs(eco)
 
 
 @pytest.mark.parametrize("flavour,mod,rvdw,rsw", [("twin", g.VdwModifier.PotentialShift, 0.8, 0.0),
@@ -118,10 +118,12 @@ def test_vdw_flavours(built, flavour, mod, rvdw, rsw):
             assert relrms(f, gd["f" + tag].astype(np.float64)) < FORCE_TOL
             if energy:
                 elj, eel = fc.energies
-                assert abs(elj - evo) <= 2e-4 * abs(evo)
+                # the switched LJ energy of this box is a near-cancelling sum (8 kJ/mol against 113 with the plain cut-off): the
+                # bar is ENERGY_TOL of the larger of the two, i.e. the same absolute error as for the plain potential
+                assert abs(elj - evo) <= ENERGY_TOL * max(abs(evo), 113.0)
                 assert abs(elj - float(gd["e_lj" + tag])) <= 2e-4 * abs(float(gd["e_lj" + tag]))
                 if tag == "":
-                    assert abs(eel - eco) <= 2e-4 * abs(eco)
+                    assert abs(eel - eco) <= ENERGY_TOL * abs(eco)
                 m = np.ones(45, bool)
                 m[nb.CENTRAL] = False
                 fs = fc.shiftForces.astype(np.float64)
@@ -156,10 +158,10 @@ def test_ljpme_grid_correction(built, rule, ljpme):
             assert relrms(f, gd["f" + tag].astype(np.float64)) < FORCE_TOL
             if energy:
                 elj, eel = fc.energies
-                assert abs(elj - evo) <= 2e-4 * abs(evo)
+                assert abs(elj - evo) <= ENERGY_TOL * abs(evo)
                 assert abs(elj - float(gd["e_lj" + tag])) <= 2e-4 * abs(float(gd["e_lj" + tag]))
                 if tag == "":
-                    assert abs(eel - eco) <= 2e-4 * abs(eco)
+                    assert abs(eel - eco) <= ENERGY_TOL * abs(eco)
                 m = np.ones(45, bool)
                 m[nb.CENTRAL] = False
                 fs = fc.shiftForces.astype(np.float64)
@@ -172,7 +174,7 @@ def test_ljpme_grid_correction(built, rule, ljpme):
     f = fc.compute()
     fo, _, evo, _, _ = oracle.forces(s.x, s.box, s.q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_EWALD, beta=beta,
                                      ljpme=ljpme.value, ewaldcoeff_lj=float(np.float32(g.systems.ewald_beta_lj(RC))))
-    assert relrms(f, fo) < FORCE_TOL and abs(fc.energies[0] - evo) <= 2e-4 * abs(evo)
+    assert relrms(f, fo) < FORCE_TOL and abs(fc.energies[0] - evo) <= ENERGY_TOL * abs(evo)
     # LJ-PME with a switch modifier is refused, as in the reference (vdwtype PME implies potential shift)
     with pytest.raises(g.nblib.InputException):
         g.ForceCalculator(g.SimulationState.from_system(s), g.NBKernelOptions(pairlistCutoff=RC, ljPme=ljpme, vdwSwitch=0.7,
