@@ -207,6 +207,7 @@ struct b200nb_context
     float*   d_x = nullptr;          /* natoms*3, original order (staging) */
     float*   d_fout = nullptr;       /* natoms*3 staging for D2H */
     int*     d_col_of_atom = nullptr;
+    int*     d_pos_in_col = nullptr;  /* rank of the atom inside its column (from the counting atomic) */
     int*     d_col_count = nullptr;
     int*     d_col_cell0 = nullptr;
     int*     d_col_fill = nullptr;
@@ -241,6 +242,8 @@ struct b200nb_context
     int        host_dma = -1;  /* b200nb_compute: 1 = cudaMemcpyAsync staging, 0 = zero-copy kernels, -1 = not decided yet */
     long long  generation = 0; /* bumped whenever a list or halo plan is rebuilt: invalidates the captured graphs */
     bool       use_graphs = true;
+    int        persistent = -1; /* force kernel: 1 = resident warps walking the list (k_force_p), 0 = one CTA per entry, -1 = unset */
+    int        num_sms = 148;
     bool       use_pdl = true; /* launch the force kernel with programmatic stream serialization (see force.cu) */
     bool       capturing = false;
     std::vector<cudaGraphNode_t> nl_nodes; /* kernel nodes captured from the non-local stream (get an explicit priority) */

@@ -40,7 +40,9 @@
  *  - LJ force switch / potential switch / VdW cut-off below the Coulomb cut-off / LJ-PME are a second set of
  *    instantiations (GEN): the plain kernels, which every BASELINE configuration uses, pay nothing for them.
  */
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "b200nb_internal.h"
 
@@ -644,17 +646,330 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
     }
 }
 
+/* ------------------------------------------------------------------------------------------------------------------------
+ * EXPERIMENT, kept selectable (B200NB_PERSISTENT=1), parity-tested, not the default: see launch() for the measurement.
+ * The persistent form of the kernel above: one warp per CTA as before, but only as many CTAs as the GPU keeps resident
+ * (148 SMs x the resident warps of the build), each walking the entries w, w + G, w + 2G, ... of the size-sorted list (G = grid
+ * size: every warp gets the same mix of sizes).  What an entry costs on top of its steps in k_force -- a chain of dependent
+ * loads (entry -> i-atoms; slot indices -> first gathers), the ring filling up and draining: a third of the warp-time at
+ * 192 k atoms, profiles/r2/d_ncu_source_k_force_water192k.txt -- is taken off the critical path:
+ *  - the j-atom ring never drains: the gather cursor runs NB_RING - 1 steps ahead of the use cursor ACROSS entry boundaries;
+ *  - everything the gather cursor needs of an entry arrives in shared memory before it gets there, by cp.async issued one or
+ *    two entries earlier: the 16-byte entry header (two entries ahead), the entry's slot indices (one entry ahead);
+ *  - the i-atoms (coordinates, LJ parameters) and the masks of the entry's leading steps are requested when the gather cursor
+ *    enters the entry, NB_RING - 1 steps before the use cursor does, and wait in shared memory;
+ *  - an entry without steps (everything pruned away) runs one step on far-away dummy atoms, so that every entry advances both
+ *    cursors and the bookkeeping has no special cases.
+ * Completion is tracked with the one-commit-group-per-step scheme of k_force; the only extra waits are a full drain when the
+ * previous entry was shorter than the ring (its successors' data may still be in flight) and one __syncwarp per entry (the
+ * staged data are written by other lanes of the warp). */
+#define NB_P_MAXSTEPS (NB_MAX_ENTRY_TILES / 2) /* steps (16 j-atoms) per entry at most */
+struct PStage /* shared memory of one persistent warp */
+{
+    float4 ring[NB_RING][64];          /* j-atom records, as in k_force */
+    int    idx[2][NB_P_MAXSTEPS * 16]; /* slot indices of the entry the gather cursor is in / the next one */
+    int4   hdr[8];                     /* entry headers, by entry ordinal & 7 */
+    float4 ixq[4][8];                  /* i-atoms of the entries between the two cursors, by ordinal & 3 */
+    float2 ilj[4][8];                  /* their LJ parameters (geometric rule) or atom type in .x (type table) */
+    uint4  msk[4][4];                  /* masks of their first 4 steps */
+};
+
+template<int EEL, bool GEOM, bool VF, bool GEN>
+__global__ void __launch_bounds__(32, B200NB_FORCE_MIN_BLOCKS(VF, GEN))
+k_force_p(const Entry* __restrict__ entries, long long nentries, const int* __restrict__ pja, const uint64_t* __restrict__ tmask,
+          const float4* __restrict__ xq, const float2* __restrict__ lj, const int* __restrict__ atype, const float2* __restrict__ nbfp,
+          const float* __restrict__ shift_vec, float4* __restrict__ f, float* __restrict__ fshift, double* __restrict__ energy,
+          const __grid_constant__ NbParamsDev P, const int intra, const int maxt, const float* __restrict__ kconst,
+          const float2* __restrict__ nbfp_comb, const int dummy_slot)
+{
+    __shared__ __align__(16) PStage S;
+    const long long w = blockIdx.x, G = gridDim.x;
+    if (w >= nentries) return;
+    const int      n_my = (int)((nentries - w + G - 1) / G); /* entries of this warp: ordinals 0 .. n_my - 1 */
+    const int      lane = threadIdx.x & 31, jl = lane & (NB_JSTEP - 1), ih = lane >> 4;
+    const unsigned full = 0xffffffffu;
+    const bool     upper = ih != 0;
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(&S.ring[0][0]) + 16u * lane;
+    KConst K;
+    {
+        const float4 k0 = __ldg(reinterpret_cast<const float4*>(kconst)), k1 = __ldg(reinterpret_cast<const float4*>(kconst) + 1),
+                     k2 = __ldg(reinterpret_cast<const float4*>(kconst) + 2);
+        K.rc2 = k0.x, K.beta2 = k0.z, K.fd4 = k0.w, K.fd3 = k1.x, K.fn6 = k1.y, K.fn5 = k1.z, K.fd2 = k1.w, K.fd1 = k2.x, K.fd0 = k2.y;
+    }
+    auto entry_of = [&](int k) { return w + (long long)k * G; };
+    /* ---- staging requests (cp.async; they join the commit group that is open when they are issued) ---- */
+    auto req_header = [&](int k) {
+        if (k < n_my && lane == 0) cp_async_16((unsigned)__cvta_generic_to_shared(&S.hdr[k & 7]), entries + entry_of(k));
+    };
+    auto req_indices = [&](int k) { /* needs hdr(k) */
+        if (k >= n_my) return;
+        const int4 hv     = S.hdr[k & 7];
+        const int  nchunk = ((hv.w - hv.z) >> 1) * 4; /* 16-byte chunks: 64 bytes per step */
+        const int* src    = pja + (size_t)entry_of(k) * maxt * 8;
+        for (int c = lane; c < nchunk; c += 32) cp_async_16((unsigned)__cvta_generic_to_shared(&S.idx[k & 1][4 * c]), src + 4 * c);
+    };
+    auto req_iatoms = [&](int k, const int4 hv) { /* i-atoms and leading masks of entry k */
+        const size_t ia = (size_t)hv.x * 8;
+        if (lane < 8) cp_async_16((unsigned)__cvta_generic_to_shared(&S.ixq[k & 3][lane]), xq + ia + lane);
+        else if (lane < 16)
+        {
+            if (GEOM) cp_async_8((unsigned)__cvta_generic_to_shared(&S.ilj[k & 3][lane - 8]), lj + ia + lane - 8);
+            else cp_async_4((unsigned)__cvta_generic_to_shared(&S.ilj[k & 3][lane - 8]), atype + ia + lane - 8);
+        }
+        else if (lane < 20 && lane - 16 < min(NB_ENTRY_NMASK(hv.y), 4))
+            cp_async_16((unsigned)__cvta_generic_to_shared(&S.msk[k & 3][lane - 16]), tmask + (size_t)entry_of(k) * maxt + 2 * (lane - 16));
+    };
+
+    /* ---- list-only staging before the dependency wait: the first three headers, then the first entry's indices ---- */
+    req_header(0), req_header(1), req_header(2);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    req_indices(0);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    /* ---- the gather cursor ---- */
+    int      kg = -1, sg = 0, nstep_g = 0, ngath_g = 0; /* entry ordinal, step in it, its (effective) steps, gathers issued in it */
+    unsigned st_fill = 0;
+    bool     prologue = true;
+    auto gather_step = [&]() { /* issues the gather of the next step of the stream (if any) and closes one commit group */
+        if (kg < n_my && sg >= nstep_g)
+        {
+            /* enter the next entry: its header and indices, and the header after it, were requested at least one entry ago; they
+             * are known complete if that entry ran >= NB_RING - 1 steps through the per-step waits of the main loop */
+            const int k = kg + 1;
+            if (k < n_my)
+            {
+                if (prologue || ngath_g < NB_RING - 1) cp_async_wait<0>();
+                __syncwarp();
+                const int4 hv = S.hdr[k & 7];
+                req_iatoms(k, hv);
+                req_indices(k + 1);
+                req_header(k + 3);
+                nstep_g = max((hv.w - hv.z) >> 1, 1); /* an empty entry runs one step on dummy atoms */
+                sg      = 0;
+                ngath_g = 0;
+            }
+            kg = k;
+        }
+        if (kg < n_my)
+        {
+            const int4 hv   = S.hdr[kg & 7];
+            const int  slot = sg < ((hv.w - hv.z) >> 1) ? S.idx[kg & 1][sg * NB_JSTEP + jl] : dummy_slot + jl;
+            gather_j<GEOM>(ring + st_fill, slot, nullptr, xq, lj, atype);
+            st_fill = (st_fill + 1024u) & (NB_RING * 1024u - 1);
+            sg++;
+            ngath_g++;
+        }
+        cp_async_commit();
+    };
+    /* req_header(k + 3) above keeps three headers ahead; the first three were requested before the loop, so ordinal 3 onward */
+#pragma unroll 1
+    for (int k = 0; k < NB_RING - 1; k++) gather_step();
+    prologue = false;
+
+    /* ---- the use cursor ---- */
+    IData    I[2];
+    float2   fix[2], fiy[2], fiz[2];
+    float    evdw = 0.f, ecoul = 0.f;
+    int      ci = 0, shift = 0, nmask = 0, nstep = 0, su = 0;
+    long long e = 0;
+    unsigned st_use = 0;
+#pragma unroll 1
+    for (int ku = 0; ku < n_my; ku++)
+    {
+        /* -- entry prologue: the group of the entry's first step (and with it its i-atoms and masks) is complete after this wait -- */
+        cp_async_wait<NB_RING - 2>();
+        __syncwarp();
+        {
+            const int4 hv = S.hdr[ku & 7];
+            e             = entry_of(ku);
+            ci = hv.x, shift = NB_ENTRY_SHIFT(hv.y), nmask = NB_ENTRY_NMASK(hv.y);
+            nstep              = (hv.w - hv.z) >> 1;
+            const bool  self   = VF && NB_ENTRY_SELF(hv.y);
+            const float sx = __ldg(shift_vec + 3 * shift), sy = __ldg(shift_vec + 3 * shift + 1), sz = __ldg(shift_vec + 3 * shift + 2);
+#pragma unroll
+            for (int p = 0; p < 2; p++)
+            {
+                const int    i0 = 4 * ih + 2 * p;
+                const float4 a = S.ixq[ku & 3][i0], b = S.ixq[ku & 3][i0 + 1];
+                /* the reference adds the shift to the i-atom before the subtraction: kernel_outer.h:482-489 */
+                I[p].x = make_float2(__fadd_rn(a.x, sx), __fadd_rn(b.x, sx));
+                I[p].y = make_float2(__fadd_rn(a.y, sy), __fadd_rn(b.y, sy));
+                I[p].z = make_float2(__fadd_rn(a.z, sz), __fadd_rn(b.z, sz));
+                I[p].q = make_float2(P.epsfac * a.w, P.epsfac * b.w);
+                I[p].g0 = I[p].g1 = dup(0.0f);
+                const float2 la = S.ilj[ku & 3][i0], lb = S.ilj[ku & 3][i0 + 1];
+                if (GEOM)
+                {
+                    I[p].c6n       = make_float2(-la.x, -lb.x);
+                    I[p].c12       = make_float2(la.y, lb.y);
+                    I[p].t0 = I[p].t1 = 0;
+                }
+                else
+                {
+                    const int ta = __float_as_int(la.x), tb = __float_as_int(lb.x);
+                    I[p].t0      = ta * P.ntypes;
+                    I[p].t1      = tb * P.ntypes;
+                    I[p].c6n = I[p].c12 = dup(0.0f);
+                    if (GEN && P.ljpme)
+                    {
+                        I[p].g0 = __ldg(nbfp_comb + ta);
+                        I[p].g1 = __ldg(nbfp_comb + tb);
+                    }
+                }
+                fix[p] = fiy[p] = fiz[p] = dup(0.f);
+            }
+            if (VF)
+            {
+                evdw = ecoul = 0.f;
+                if (self && jl < 4)
+                {
+                    /* Coulomb self term, once per i-atom (lane jl of each half takes i-atom 4*ih + jl): kernel_outer.h:408-452 */
+                    const float2 qp = (jl & 2) ? I[1].q : I[0].q;
+                    const float  qi = (jl & 1) ? qp.y : qp.x;
+                    ecoul -= qi * qi * P.self_q2;
+                    if (GEN && !GEOM && P.ljpme)
+                    {
+                        const int ta = (jl & 2) ? I[1].t0 : I[0].t0, tb = (jl & 2) ? I[1].t1 : I[0].t1;
+                        const int ti = (jl & 1) ? tb : ta;
+                        evdw += 0.5f * __ldg(nbfp + ti + ti / P.ntypes).x * (1.0f / 6.0f) * P.lje_coeff6_6;
+                    }
+                }
+            }
+        }
+        const uint4* const emask = reinterpret_cast<const uint4*>(tmask + (size_t)e * maxt);
+        const int          nrun  = max(nstep, 1);
+#pragma unroll 1
+        for (su = 0; su < nrun; su++)
+        {
+            if (su > 0) cp_async_wait<NB_RING - 2>();
+            JAtom J;
+            read_j(J, ring + st_use);
+            st_use = (st_use + 1024u) & (NB_RING * 1024u - 1);
+            gather_step();
+            float2 fjx = dup(0.f), fjy = dup(0.f), fjz = dup(0.f);
+            if (su < nmask)
+            {
+                const uint4 m = su < 4 ? S.msk[ku & 3][su] : __ldg(emask + su);
+                /* j-atom of the i-cluster itself: only j > i (nbnxm/pairlist.cpp:880-904, kernel_gpu_ref.cpp:223-226) */
+                const bool diag = intra && shift == B200NB_CENTRAL && (J.slot >> 3) == ci;
+                const int  jin  = J.slot & 7;
+#pragma unroll
+                for (int p = 0; p < 2; p++)
+                {
+                    const unsigned w0 = p ? m.z : m.x, w1 = p ? m.w : m.y;
+                    const float    in0 = (float)((w0 >> lane) & 1u), in1 = (float)((w1 >> lane) & 1u);
+                    const bool     ok0 = !diag || jin > 4 * ih + 2 * p, ok1 = !diag || jin > 4 * ih + 2 * p + 1;
+                    float2         dx, dy, dz;
+                    const float2   fs = pair_fscal<EEL, GEOM, VF, true, GEN>(I[p], J, P, K, nbfp, nbfp_comb, in0, in1, ok0, ok1, dx, dy, dz, evdw, ecoul);
+                    fix[p] = fma2(fs, dx, fix[p]);
+                    fiy[p] = fma2(fs, dy, fiy[p]);
+                    fiz[p] = fma2(fs, dz, fiz[p]);
+                    fjx    = fma2(fs, dx, fjx);
+                    fjy    = fma2(fs, dy, fjy);
+                    fjz    = fma2(fs, dz, fjz);
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int p = 0; p < 2; p++)
+                {
+                    float2       dx, dy, dz;
+                    const float2 fs = pair_fscal<EEL, GEOM, VF, false, GEN>(I[p], J, P, K, nbfp, nbfp_comb, 1.f, 1.f, true, true, dx, dy, dz, evdw, ecoul);
+                    fix[p] = fma2(fs, dx, fix[p]);
+                    fiy[p] = fma2(fs, dy, fiy[p]);
+                    fiz[p] = fma2(fs, dz, fiz[p]);
+                    fjx    = fma2(fs, dx, fjx);
+                    fjy    = fma2(fs, dy, fjy);
+                    fjz    = fma2(fs, dz, fjz);
+                }
+            }
+            reduce_store_j(fjx, fjy, fjz, upper, f, J.slot);
+        }
+        /* -- entry epilogue: i-forces (12 floats per lane) summed over the 16 j-lanes of the half, as in k_force -- */
+        const bool b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+        float      r0, r1, r2, r3, r4, r5;
+#define NB_STAGE_A(out, v0, v1)                                          \
+    {                                                                    \
+        const float keep_ = b3 ? (v1) : (v0), send_ = b3 ? (v0) : (v1);  \
+        out               = keep_ + __shfl_xor_sync(full, send_, 8);     \
+    }
+        NB_STAGE_A(r0, fix[0].x, fix[1].x)
+        NB_STAGE_A(r1, fix[0].y, fix[1].y)
+        NB_STAGE_A(r2, fiy[0].x, fiy[1].x)
+        NB_STAGE_A(r3, fiy[0].y, fiy[1].y)
+        NB_STAGE_A(r4, fiz[0].x, fiz[1].x)
+        NB_STAGE_A(r5, fiz[0].y, fiz[1].y)
+#undef NB_STAGE_A
+        float kx = (b2 ? r1 : r0) + __shfl_xor_sync(full, b2 ? r0 : r1, 4);
+        float ky = (b2 ? r3 : r2) + __shfl_xor_sync(full, b2 ? r2 : r3, 4);
+        float kz = (b2 ? r5 : r4) + __shfl_xor_sync(full, b2 ? r4 : r5, 4);
+        kx += __shfl_xor_sync(full, kx, 2);
+        ky += __shfl_xor_sync(full, ky, 2);
+        kz += __shfl_xor_sync(full, kz, 2);
+        kx += __shfl_xor_sync(full, kx, 1);
+        ky += __shfl_xor_sync(full, ky, 1);
+        kz += __shfl_xor_sync(full, kz, 1);
+        if ((lane & 3) == 0 && nstep > 0) atomicAdd(f + ((size_t)ci * 8 + 4 * ih + 2 * (int)b3 + (int)b2), make_float4(kx, ky, kz, 0.f));
+        if (VF)
+        {
+            if (shift != B200NB_CENTRAL)
+            {
+                kx += __shfl_xor_sync(full, kx, 4);
+                ky += __shfl_xor_sync(full, ky, 4);
+                kz += __shfl_xor_sync(full, kz, 4);
+                kx += __shfl_xor_sync(full, kx, 8);
+                ky += __shfl_xor_sync(full, ky, 8);
+                kz += __shfl_xor_sync(full, kz, 8);
+                kx += __shfl_xor_sync(full, kx, 16);
+                ky += __shfl_xor_sync(full, ky, 16);
+                kz += __shfl_xor_sync(full, kz, 16);
+                if (lane == 0)
+                {
+                    float* fs = fshift + (int)(e & (NB_OUT_COPIES - 1)) * NB_FSHIFT_PITCH + 3 * shift;
+                    atomicAdd(fs, kx);
+                    atomicAdd(fs + 1, ky);
+                    atomicAdd(fs + 2, kz);
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                evdw += __shfl_xor_sync(full, evdw, o);
+                ecoul += __shfl_xor_sync(full, ecoul, o);
+            }
+            if (lane == 0)
+            {
+                double* en = energy + 2 * (int)(e & (NB_OUT_COPIES - 1));
+                atomicAdd(en, (double)evdw);
+                atomicAdd(en + 1, (double)ecoul);
+            }
+        }
+    }
+}
+
 template<int EEL, bool GEOM, bool VF, bool GEN>
 int launch(b200nb_context* h, const PackedList& L, int intra)
 {
-    /* One entry per single-warp CTA; CTAs start in index order, i.e. largest entries first.  A persistent variant (resident
-     * warps walking the sorted list in boustrophedon order, equal tiles per warp) was measured and is 10-18 % slower: warps
-     * that start equal entries together also wait for their prologue loads together
-     * (profiles/r1/y_sweep_persistent_boustrophedon.txt). */
-    const unsigned nblk = (unsigned)((L.nentries + B200NB_FORCE_WARPS - 1) / B200NB_FORCE_WARPS);
-    const int      maxt = L.pitch;
+    const int maxt = L.pitch;
+    if (h->persistent < 0)
+    {
+        /* B200NB_PERSISTENT=1 selects k_force_p.  Measured (profiles/r2/k_sweep_persistent.txt, k_ncu_k_force_p_water192k.txt): it
+         * does what it was built for -- long-scoreboard stalls per issue fall from 1.81 to 0.12 -- but its bookkeeping costs 41
+         * more instructions per step (172 against 131) and the issue rate stays where it was (0.62 per cycle: the kernel is
+         * issue-bound on its FFMA2-heavy mix, not latency-bound), so it is 20-30 % SLOWER: 127 us against 97 us at 192 k atoms.
+         * Default: one CTA per entry. */
+        const char* e = getenv("B200NB_PERSISTENT");
+        h->persistent = e ? (atoi(e) != 0) : 0;
+        int nsm       = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+        h->num_sms = nsm;
+    }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim          = dim3(nblk);
     cfg.blockDim         = dim3(32 * B200NB_FORCE_WARPS);
     cfg.dynamicSmemBytes = 0;
     cfg.stream           = h->stream;
@@ -663,10 +978,33 @@ int launch(b200nb_context* h, const PackedList& L, int intra)
     at[0].val.programmaticStreamSerializationAllowed = 1; /* overlap our list loads with the tail of the preceding kernel */
     cfg.attrs    = at;
     cfg.numAttrs = h->use_pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, k_force<EEL, GEOM, VF, GEN>, (const Entry*)L.entries, (long long)L.nentries, (const int*)L.ja, (const uint64_t*)L.mask,
-                       reinterpret_cast<const float4*>(h->d_xq), reinterpret_cast<const float2*>(h->d_lj), (const int*)h->d_atype,
-                       reinterpret_cast<const float2*>(h->d_nbfp), (const float*)h->d_shift_vec, h->d_f, h->d_fshift, h->d_energy, h->dp,
-                       intra, maxt, (const float*)h->d_kconst, reinterpret_cast<const float2*>(h->d_nbfp_comb));
+    if (h->persistent)
+    {
+        /* as many single-warp CTAs as stay resident; warp w walks the entries w, w + G, ... of the size-sorted list */
+        static bool carveout_set = false;
+        if (!carveout_set)
+        {
+            cudaFuncSetAttribute(k_force_p<EEL, GEOM, VF, GEN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carveout_set = true;
+        }
+        const long long resident = (long long)h->num_sms * B200NB_FORCE_MIN_BLOCKS(VF, GEN);
+        cfg.gridDim              = dim3((unsigned)std::min<long long>(L.nentries, resident));
+        cudaLaunchKernelEx(&cfg, k_force_p<EEL, GEOM, VF, GEN>, (const Entry*)L.entries, (long long)L.nentries, (const int*)L.ja,
+                           (const uint64_t*)L.mask, reinterpret_cast<const float4*>(h->d_xq), reinterpret_cast<const float2*>(h->d_lj),
+                           (const int*)h->d_atype, reinterpret_cast<const float2*>(h->d_nbfp), (const float*)h->d_shift_vec, h->d_f,
+                           h->d_fshift, h->d_energy, h->dp, intra, maxt, (const float*)h->d_kconst,
+                           reinterpret_cast<const float2*>(h->d_nbfp_comb), h->dummy_slot);
+    }
+    else
+    {
+        /* one entry per single-warp CTA; CTAs start in index order, i.e. largest entries first */
+        cfg.gridDim = dim3((unsigned)((L.nentries + B200NB_FORCE_WARPS - 1) / B200NB_FORCE_WARPS));
+        cudaLaunchKernelEx(&cfg, k_force<EEL, GEOM, VF, GEN>, (const Entry*)L.entries, (long long)L.nentries, (const int*)L.ja,
+                           (const uint64_t*)L.mask, reinterpret_cast<const float4*>(h->d_xq), reinterpret_cast<const float2*>(h->d_lj),
+                           (const int*)h->d_atype, reinterpret_cast<const float2*>(h->d_nbfp), (const float*)h->d_shift_vec, h->d_f,
+                           h->d_fshift, h->d_energy, h->dp, intra, maxt, (const float*)h->d_kconst,
+                           reinterpret_cast<const float2*>(h->d_nbfp_comb));
+    }
     h->nlaunches++;
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return nb_fail(h, B200NB_ERR_CUDA, std::string("force kernel launch: ") + cudaGetErrorString(err));

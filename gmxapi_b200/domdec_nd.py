@@ -17,8 +17,10 @@ Reference behaviour mirrored (paths relative to /root/reference/src/gromacs):
   non-local gridding / search  nbnxm.cpp:77-95, pairlist.cpp:3876-3916: halo atoms are gridded as the second grid, periodic
                                images are switched off along decomposed dimensions
   pack / unpack                domdec/gpuhaloexchange_impl.cu:77-131 (ours: b200nb_halo_pack_x / b200nb_halo_unpack_f)
-The per-step exchange runs through the transport (NCCL send/recv between GPUs, the in-process loopback in the single-GPU
-tests), not through the peer-memory windows: this path is about capability (2 x 2 x 2), the slab path about speed.
+The per-step exchange runs through the same peer-memory windows as the slab path (b200nb_dd_set_links: one LINK per half-shell
+offset, up to 13; the kernels of the step write the halo coordinates / forces straight into the neighbours' windows over NVLink
+and wait on per-link flags); `use_windows=False` keeps the transport (NCCL send/recv, or the in-process loopback) on the
+per-step path with separate pack / unpack kernels.  The pair-search steps always use the transport.
 """
 import itertools
 
@@ -269,7 +271,7 @@ class DomainRankND:
 
     with the halo traffic on the transport (see the module docstring)."""
 
-    def __init__(self, system, options, transport, grid, rank=None, device=0):
+    def __init__(self, system, options, transport, grid, rank=None, device=0, use_windows=True):
         import torch
         self.torch = torch
         self.t = transport
@@ -279,6 +281,8 @@ class DomainRankND:
         self.rlist = float(options.rlistOuter or rc)
         self.plan = p = DomainPlanND(system.x, system.box, grid, self.rank, self.rlist)
         self.nranks = p.nranks
+        self.use_windows = bool(use_windows) and self.nranks > 1 and len(p.offsets) <= _lib.DD_MAX_LINKS
+        self._windows_open = False
         self.nb = _lib.NbnxmGpu(device)
         self.device = torch.device("cuda", device)
         self.stream = torch.cuda.Stream(device=self.device)
@@ -315,7 +319,54 @@ class DomainRankND:
             self.recv_range.append((off, off + len(r["ids"])))
             off += len(r["ids"])
         self.nb.synchronize()
+        if self.use_windows and not self._windows_open:
+            self._open_windows()
         self.search()
+
+    # -- peer-memory halo windows: one per rank, opened once by every neighbour (CUDA IPC across processes) ---------------------
+    def _open_windows(self):
+        import os
+        p = self.plan
+        nsend = sum(len(s["local"]) for s in p.send)
+        self.max_halo, self.max_send = int(1.5 * p.nhalo) + 4096, int(1.5 * nsend) + 4096
+        handle, ptr = self.nb.dd_create_window(self.max_halo, self.max_send)
+        info = self.t.allgather_object(dict(pid=os.getpid(), handle=handle, ptr=ptr, max_halo=self.max_halo))
+        # every rank I exchange with over some link, each opened once; peer number = position in this list
+        self.peers = sorted({s["rank"] for s in p.send} | {r["rank"] for r in p.recv})
+        if len(self.peers) > _lib.DD_MAX_PEERS:
+            raise InputException("more than %d neighbour ranks" % _lib.DD_MAX_PEERS)
+        for k, peer in enumerate(self.peers):
+            pi = info[peer]
+            if pi["pid"] == os.getpid():
+                self.nb.dd_open_peer(k, window_ptr=pi["ptr"], peer_max_halo=pi["max_halo"])
+            else:
+                self.nb.dd_open_peer(k, ipc_handle=pi["handle"], peer_max_halo=pi["max_halo"])
+        self._windows_open = True
+        self.t.barrier()
+
+    def _set_links(self):
+        """The halo plan of this search interval as links (b200nb_dd_set_links): link k = half-shell offset k on every rank."""
+        p = self.plan
+        nsend = [len(s["local"]) for s in p.send]
+        nrecv = [len(r["ids"]) for r in p.recv]
+        if p.nhalo > self.max_halo or sum(nsend) > self.max_send:
+            raise InputException("repartition: halo of %d / %d atoms exceeds the window capacity %d / %d"
+                                 % (p.nhalo, sum(nsend), self.max_halo, self.max_send))
+        counts = self.t.allgather_object(dict(nsend=nsend, nrecv=nrecv))
+        links = []
+        for k, (s, r) in enumerate(zip(p.send, p.recv)):
+            dst, src = s["rank"], r["rank"]
+            links.append(dict(send_peer=self.peers.index(dst), send_idx=s["local"], shift=self.send_shift[k],
+                              # my atoms become halo atoms of `dst` after everything it receives over its links before k
+                              peer_halo_offset=int(sum(counts[dst]["nrecv"][:k])),
+                              recv_peer=self.peers.index(src), nrecv=nrecv[k],
+                              # the forces on them return to the send entries of `src`, behind those of its links before k
+                              peer_entry_offset=int(sum(counts[src]["nsend"][:k])),
+                              # images across a periodic edge: the forces on them also enter that shift's shift force
+                              # (domdec/domdec.cpp:426-458)
+                              fshift_index=shift_index(r["shift"]) if np.any(r["shift"] != 0) else -1))
+        self.nb.dd_set_links(p.nhome, p.nhalo, links)
+        self.t.barrier()  # every rank has its plan before anybody steps
 
     def repartition(self):
         """Pair-search step with atom migration: the current coordinates of the home atoms (self.x[:nhome], on the device)
@@ -344,6 +395,8 @@ class DomainRankND:
             hu = np.where(np.array(p.grid) > 1, hu, p.box).astype(np.float32)
             self.nb.put_on_grid(self.x.data_ptr(), hl, hu, 1, p.nhome, self.nlocal, on_device=True)
         self.nb.build_pairlist()
+        if self.use_windows:
+            self._set_links()
 
     def _exchange(self, sends, recvs):
         """all messages of one halo phase at once; messages between the same two ranks keep the half-shell offset order on
@@ -396,6 +449,9 @@ class DomainRankND:
     def step(self, flags=0):
         """One nonbonded step on the coordinates in self.x[:nhome] (device); leaves forces in self.f[:nhome]."""
         p = self.plan
+        if self.use_windows:
+            self.nb.dd_step(self.x.data_ptr(), self.f.data_ptr(), flags)
+            return
         self.nb.set_x(self.x.data_ptr(), on_device=True, atom_begin=0, atom_end=p.nhome)
         self.nb.clear_outputs()
         self.nb.launch_force(0, flags)
@@ -414,16 +470,23 @@ class DomainRankND:
         if f_home_host is None:
             f_home_host = torch.empty((p.nhome, 3), dtype=torch.float32).pin_memory()
         fh = f_home_host if isinstance(f_home_host, torch.Tensor) else torch.from_numpy(f_home_host)
-        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            self.x[:p.nhome].copy_(xh, non_blocking=True)
-            self.step(flags)
-            fh.copy_(self.f[:p.nhome], non_blocking=True)
+        if self.use_windows and xh.is_pinned() and fh.is_pinned():
+            # the kernels read the pinned coordinates and write the pinned forces in place (no staging copy)
+            self.nb.dd_step(xh.data_ptr(), fh.data_ptr(), flags)
+        else:
+            with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+                self.x[:p.nhome].copy_(xh, non_blocking=True)
+                self.step(flags)
+                fh.copy_(self.f[:p.nhome], non_blocking=True)
         self.nb.synchronize()
+        if self.use_windows:
+            self.nb.dd_status()
         fs = np.zeros((_lib.SHIFTS, 3), np.float32)
         elj = eel = 0.0
         if flags:
             fs, elj, eel = self.nb.get_outputs()
-            fs = fs + self.fshift_halo.astype(np.float32)
+            if not self.use_windows:
+                fs = fs + self.fshift_halo.astype(np.float32)
         return fh, fs, elj, eel
 
     def pair_count(self, r):

@@ -48,6 +48,7 @@ class _DdLink(C.Structure):  # b200nb_dd_link_t
                 ("fshift_index", C.c_int)]
 
 
+DD_MAX_LINKS, DD_MAX_PEERS = 16, 16  # NB_DD_MAX_LINKS / NB_DD_MAX_PEERS (b200nb_internal.h)
 VDW_POTSHIFT, VDW_FORCESWITCH, VDW_POTSWITCH = 0, 1, 2
 LJPME_NONE, LJPME_GEOM, LJPME_LB = 0, 1, 2
 

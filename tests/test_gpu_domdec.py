@@ -177,10 +177,12 @@ def test_repartition_after_motion(built, nranks, windows):
 _ND_CACHE = {}
 
 
-def run_ranks_nd(grid):
-    """all ranks of a grid as threads on this GPU (loopback transport); cached: two tests look at the same run"""
-    if grid in _ND_CACHE:
-        return _ND_CACHE[grid]
+def run_ranks_nd(grid, use_windows=True):
+    """all ranks of a grid as threads on this GPU (loopback transport); cached: two tests look at the same run.
+    use_windows: per-step halos through the peer-memory windows (b200nb_dd_set_links, the product path) or the transport"""
+    key = (grid, use_windows)
+    if key in _ND_CACHE:
+        return _ND_CACHE[key]
     from gmxapi_b200.domdec_nd import DomainRankND
     s = g.systems.named("water_24k")
     opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, computeVirialAndEnergy=True)
@@ -192,10 +194,14 @@ def run_ranks_nd(grid):
 
     def work(r):
         try:
-            d = DomainRankND(s, opt, hub.endpoint(r), grid, rank=r, device=0)
+            d = DomainRankND(s, opt, hub.endpoint(r), grid, rank=r, device=0, use_windows=use_windows)
+            assert d.use_windows == use_windows
             p = d.plan
             xh = np.ascontiguousarray(s.x[p.home])
-            for _ in range(2):
+            if use_windows and r % 2 == 0:
+                import torch
+                xh = torch.from_numpy(xh).pin_memory()  # even ranks: the kernels read / write pinned host buffers in place
+            for _ in range(3 if use_windows else 2):  # repeated steps reuse the windows: flags advance
                 f, fs, elj, eel = d.compute(xh, flags)
             pr = d.nb.pairs(RC)
             loc = p.local
@@ -223,7 +229,7 @@ def run_ranks_nd(grid):
     for t in th:
         t.join(timeout=300)
     assert not err, err
-    _ND_CACHE[grid] = (s, out)
+    _ND_CACHE[key] = (s, out)
     return s, out
 
 
@@ -241,14 +247,15 @@ def canonical_nd(pairs, jshift):
     return (i << 34) | (j << 6) | idx
 
 
-ND_GRIDS = [(2, 2, 1), (2, 2, 2), (3, 2, 1)]
+# (grid, per-step halos through the peer-memory windows?): the window path is the product path, the transport path stays covered
+ND_GRIDS = [((2, 2, 1), True), ((2, 2, 2), True), ((3, 2, 1), True), ((2, 2, 1), False)]
 
 
-@pytest.mark.parametrize("grid", ND_GRIDS)
-def test_decomposition_nd_matches_single_domain(built, grid):
+@pytest.mark.parametrize("grid,windows", ND_GRIDS)
+def test_decomposition_nd_matches_single_domain(built, grid, windows):
     """2 x 2, 2 x 2 x 2 and 3 x 2 ranks (half-shell rule, direct exchanges with every neighbour): pair set, forces and
     energies of the decomposed calculation equal the single-domain oracle."""
-    s, res = run_ranks_nd(grid)
+    s, res = run_ranks_nd(grid, windows)
     fo, fso, evo, eco, npairs = oracle.forces(s.x, s.box, s.q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_EWALD,
                                               beta=float(np.float32(g.systems.ewald_beta(RC))))
     assert np.array_equal(np.sort(np.concatenate([r["home"] for r in res])), np.arange(s.n))
@@ -275,11 +282,11 @@ def test_decomposition_nd_matches_single_domain(built, grid):
     assert abs(eel - eco) <= ENERGY_TOL * abs(eco)
 
 
-@pytest.mark.parametrize("grid", ND_GRIDS)
-def test_decomposition_nd_virial(built, grid):
+@pytest.mark.parametrize("grid,windows", ND_GRIDS)
+def test_decomposition_nd_virial(built, grid, windows):
     """the virial -1/2 [ sum_a x_a (x) f_a + sum_s shift_vec[s] (x) fshift[s] ] is decomposition-invariant: forces on images
     that crossed a periodic edge enter the shift forces of the shift they were sent with (domdec.cpp:426-458)"""
-    s, res = run_ranks_nd(grid)
+    s, res = run_ranks_nd(grid, windows)
     fo, fso, _, _, _ = oracle.forces(s.x, s.box, s.q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_EWALD,
                                      beta=float(np.float32(g.systems.ewald_beta(RC))))
     sv = oracle.shift_vectors(s.box).astype(np.float64)
