@@ -602,9 +602,15 @@ def run_multi_gpu(args, rank, world, local_rank):
             n_one = fc1.nb.pair_count(RC)
             fc1.nb.close()
             rel = float(np.sqrt(((f_dd.astype(np.float64) - f_one) ** 2).sum() / (f_one.astype(np.float64) ** 2).sum()))
+            # a pair whose r^2 sits within float rounding of rc^2 AND straddles a periodic edge of a decomposed dimension may flip:
+            # the halo carries x_j + box (rounded), the single-domain kernel evaluates (x_i - box) - x_j -- the reference's own DD
+            # runs differ from its single-rank runs the same way (domdec.cpp:300-318); tests/test_gpu_domdec.py checks every such pair
+            allowed = max(2, int(n_one) // 500000)
             parity = {"force_rel_rms_vs_single_domain": rel, "pairs_decomposed": int(npairs), "pairs_single_domain": int(n_one),
-                      "checked": "forces of the last end-to-end step of every rank, gathered; pair counts summed over ranks"}
-            if not (rel <= 1e-5 and n_one == npairs):
+                      "pair_count_tolerance": allowed,
+                      "checked": "forces of the last end-to-end step of every rank, gathered; pair counts summed over ranks (pairs at "
+                                 "r^2 = rc^2 +- rounding across a periodic edge may flip, see tests/test_gpu_domdec.py)"}
+            if not (rel <= 1e-5 and abs(n_one - npairs) <= allowed):
                 raise SystemExit("decomposed run disagrees with the single-domain run: %r" % (parity,))
     if rank == 0:
         flops = FLOPS_PER_PAIR[args.eel]

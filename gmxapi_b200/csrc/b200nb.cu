@@ -105,7 +105,7 @@ extern "C" void b200nb_destroy(b200nb_t* h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    void* ptrs[] = { h->d_kconst, h->d_nbfp_comb, h->d_nbfp,       h->d_type,     h->d_q,        h->d_excl_off,     h->d_excl_idx,  h->d_shift_vec,
+    void* ptrs[] = { h->d_ewald_tab, h->d_kconst, h->d_nbfp_comb, h->d_nbfp,       h->d_type,     h->d_q,        h->d_excl_off,     h->d_excl_idx,  h->d_shift_vec,
                      h->d_x,          h->d_fout,     h->d_col_of_atom, h->d_pos_in_col, h->d_col_count, h->d_col_cell0, h->d_col_fill,
                      h->d_atom_index, h->d_slot_of_atom, h->d_xq,   h->d_lj,           h->d_atype,     h->d_bb,
                      h->d_cellz,      h->d_f,        h->d_fshift,   h->d_energy,       h->d_scratch,   h->d_counter,
@@ -266,6 +266,8 @@ extern "C" int b200nb_set_params(b200nb_t* h, const b200nb_params_t* p)
     d.sw_c3 = d.sw_c4 = d.sw_c5 = 0.0f;
     d.ljpme      = 0;
     d.lje_coeff2 = d.lje_coeff6_6 = d.sh_lj_ewald = 0.0f;
+    d.ewald_tab  = nullptr; /* analytical Ewald correction until b200nb_set_ewald_table */
+    d.tab_scale = d.tab_max = 0.0f;
     h->have_params  = true;
     h->have_list    = false;
     return 0;
@@ -321,6 +323,38 @@ extern "C" int b200nb_set_vdw(b200nb_t* h, const b200nb_vdw_t* v)
     d.rvdw_switch  = v->rvdw_switch;
     d.disp_c2 = v->disp_c2, d.disp_c3 = v->disp_c3, d.rep_c2 = v->rep_c2, d.rep_c3 = v->rep_c3;
     d.sw_c3 = v->sw_c3, d.sw_c4 = v->sw_c4, d.sw_c5 = v->sw_c5;
+    h->generation++; /* captured step graphs carry the kernel parameters by value */
+    return 0;
+}
+
+/* init_ewald_coulomb_force_table (nbnxm_gpu_data_mgmt.cpp:71-83): the reference's tabulated Ewald force correction,
+ * EwaldCorrectionTables::tableF with its scale (tables/forcetable.cpp generateEwaldCorrectionTables).  With a table set, the plain
+ * Ewald kernels interpolate it (EL_EWALD_TAB) instead of evaluating the analytical correction; n = 0 returns to the analytical form. */
+extern "C" int b200nb_set_ewald_table(b200nb_t* h, const float* table_f_host, int n, float scale)
+{
+    if (!h || n < 0 || (n > 0 && (!table_f_host || n < 2 || !(scale > 0)))) return nb_fail(h, B200NB_ERR_ARG, "set_ewald_table: bad argument");
+    if (!h->have_params) return nb_fail(h, B200NB_ERR_STATE, "set_ewald_table: set_params first");
+    cudaSetDevice(h->device);
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (n == 0)
+    {
+        h->dp.ewald_tab = nullptr;
+        h->generation++;
+        return 0;
+    }
+    if (h->dp.eeltype != B200NB_EEL_EWALD) return nb_fail(h, B200NB_ERR_ARG, "set_ewald_table: the interaction is not Ewald");
+    std::vector<float> t(2 * (size_t)n);
+    for (int i = 0; i < n; i++)
+    {
+        t[2 * i]     = table_f_host[i];
+        t[2 * i + 1] = i + 1 < n ? table_f_host[i + 1] - table_f_host[i] : 0.0f;
+    }
+    if (alloc_exact(h, &h->d_ewald_tab, t.size())) return B200NB_ERR_CUDA;
+    NB_CUDA(h, cudaMemcpy(h->d_ewald_tab, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice));
+    h->dp.ewald_tab = reinterpret_cast<const float2*>(h->d_ewald_tab);
+    h->dp.tab_scale = scale;
+    h->dp.tab_max   = (float)(n - 2) + 0.999f; /* the last interval: lanes beyond the table (outside the cut-off) read inside it */
+    if (h->hp.rc * scale > (float)(n - 1)) return nb_fail(h, B200NB_ERR_ARG, "set_ewald_table: the table ends before the cut-off");
     h->generation++; /* captured step graphs carry the kernel parameters by value */
     return 0;
 }
@@ -2384,13 +2418,12 @@ extern "C" int b200nb_compute(b200nb_t* h, const float* x_host, int flags, float
     if (h->grid[1].valid) return nb_fail(h, B200NB_ERR_STATE, "compute: single-domain call on a context with a halo grid");
     cudaSetDevice(h->device);
     const size_t bytes = sizeof(float) * 3 * (size_t)h->natoms;
-    if (h->map_x_host != x_host || h->map_f_host != f_host)
-    {
-        h->map_x_host = x_host;
-        h->map_f_host = f_host;
-        h->map_x_dev  = mapped_host_pointer(x_host);
-        h->map_f_dev  = mapped_host_pointer(f_host);
-    }
+    /* the device-visible aliases are looked up on every call (a pointer-attribute query costs well under a microsecond): a buffer
+     * the caller freed or unregistered, and whose address came back as different memory, must not be reached through a stale alias */
+    h->map_x_host = x_host;
+    h->map_f_host = f_host;
+    h->map_x_dev  = mapped_host_pointer(x_host);
+    h->map_f_dev  = mapped_host_pointer(f_host);
     const bool want_out = fshift_host || energies_host;
     /* pinned scratch: [x staging][f staging][fshift 135 floats][energies 2 doubles] */
     const size_t off_out = 2 * ((bytes + 255) & ~(size_t)255);
@@ -2921,9 +2954,9 @@ extern "C" int b200nb_dd_step(b200nb_t* h, const float* x_home, float* f_home, i
     DdState& D = h->dd;
     if (!h->have_list || !D.have_plan) return nb_fail(h, B200NB_ERR_STATE, "dd_step: needs a pair list and a halo plan");
     cudaSetDevice(h->device);
-    if (h->map_x_host != x_home || h->map_f_host != f_home)
     {
-        /* pinned host buffers are used in place through their device-visible address; device pointers pass through */
+        /* pinned host buffers are used in place through their device-visible address; device pointers pass through.  Queried on
+         * every call: see b200nb_compute */
         cudaPointerAttributes ax, af;
         if (cudaPointerGetAttributes(&ax, x_home) != cudaSuccess || cudaPointerGetAttributes(&af, f_home) != cudaSuccess
             || !ax.devicePointer || !af.devicePointer)

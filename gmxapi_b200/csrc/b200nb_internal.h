@@ -70,6 +70,9 @@ struct NbParamsDev
     float sw_c3, sw_c4, sw_c5;
     int   ljpme; /* 0 none, 1 geometric, 2 Lorentz-Berthelot grid combination rule */
     float lje_coeff2, lje_coeff6_6, sh_lj_ewald;
+    /* tabulated Ewald force correction (b200nb_set_ewald_table): {F[i], F[i+1] - F[i]} per table point, null = analytical */
+    const float2* ewald_tab;
+    float         tab_scale, tab_max;
 };
 
 struct PairList
@@ -185,6 +188,7 @@ struct b200nb_context
     int               max_tiles = 16;
     float*            d_nbfp = nullptr; /* float2 per type pair */
     float*            d_nbfp_comb = nullptr; /* LJ-PME: float2 per type, NBParamGpu::nbfp_comb */
+    float*            d_ewald_tab = nullptr; /* float2 per table point */
     float*            d_kconst = nullptr; /* 12 floats: rc2, beta, beta2, FD4/b, FD3/b, FN6, FN5, FD2/b, FD1/b, FD0/b, 0, 0 (force.cu KConst) */
 
     int    natoms = 0;

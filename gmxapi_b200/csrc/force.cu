@@ -248,6 +248,21 @@ __device__ __forceinline__ float2 pair_fscal(const IData& I, const JAtom& J, con
         const float2 num = pme_force_num(z2, z4, K.fn6, K.fn5);
         ewt              = mul2(num, rd); /* beta * pmecorrF(z2) */
     }
+    if (EEL == 2)
+    {
+        /* tabulated Ewald correction (the reference's EL_EWALD_TAB kernels: interpolate_coulomb_force_r,
+         * cuda/nbnxm_cuda_kernel_utils.cuh:380-391; kernel_gpu_ref.cpp:262-272): F(r) interpolated linearly between the points of
+         * interaction_const_t::coulombEwaldTables->tableF; the table holds {F[i], F[i+1] - F[i]} so one 8-byte load serves a pair.
+         * ewt becomes -F_table(r) * r, to be added to int_bit / r like the analytical term. */
+        if (VF) z2 = mul2(dup(K.beta2), r2);
+        const float2 r  = mul2(r2, rinv);
+        float2       rt = mul2(r, dup(P.tab_scale));
+        rt              = make_float2(fminf(rt.x, P.tab_max), fminf(rt.y, P.tab_max)); /* lanes beyond the cut-off stay inside the table */
+        const int    i0 = (int)rt.x, i1 = (int)rt.y;
+        const float2 t0 = __ldg(P.ewald_tab + i0), t1 = __ldg(P.ewald_tab + i1);
+        const float2 ft = make_float2(__fmaf_rn(rt.x - (float)i0, t0.y, t0.x), __fmaf_rn(rt.y - (float)i1, t1.y, t1.x));
+        ewt             = mul2(mul2(ft, r), m1);
+    }
     const float2 rinvsq  = mul2(rinv, rinv);
     float2       rinv_ex = rinv;
     if (MASKED) rinv_ex = mul2(rinv, inter);
@@ -349,9 +364,10 @@ __device__ __forceinline__ float2 pair_fscal(const IData& I, const JAtom& J, con
         fsum = mul2(fma2(c12, rinv6, c6n), rinv6);
     }
     float2 vcoul = dup(0.0f);
-    if (EEL == 1)
+    if (EEL >= 1)
     {
-        fsum = fma2(qq, fma2(ewt, z2, rinv_ex), fsum);
+        if (EEL == 1) fsum = fma2(qq, fma2(ewt, z2, rinv_ex), fsum);
+        else fsum = fma2(qq, add2(ewt, rinv_ex), fsum);
         if (VF)
         {
             float2 vsub = mul2(dup(P.beta), pme_pot_corr2(z2));
@@ -1028,6 +1044,11 @@ int nb_launch_force_kernel(b200nb_context* h, int loc, int flags)
 #define NB_PICK(E, G)                                                                                           \
     (gen ? (vf ? launch<E, G, true, true>(h, L, intra) : launch<E, G, false, true>(h, L, intra))               \
          : (vf ? launch<E, G, true, false>(h, L, intra) : launch<E, G, false, false>(h, L, intra)))
+    /* tabulated Ewald correction (b200nb_set_ewald_table; the reference's EL_EWALD_TAB choice, nbnxm_gpu_data_mgmt.cpp:118-154):
+     * plain kernels only -- the reference's CUDA backend has no tabulated kernel with LJ-PME either way round that matters here */
+#define NB_PICK_PLAIN(E, G) (vf ? launch<E, G, true, false>(h, L, intra) : launch<E, G, false, false>(h, L, intra))
+    if (ewald && h->dp.ewald_tab != nullptr && !gen) return geom ? NB_PICK_PLAIN(2, true) : NB_PICK_PLAIN(2, false);
+#undef NB_PICK_PLAIN
     if (ewald) return geom ? NB_PICK(1, true) : NB_PICK(1, false);
     return geom ? NB_PICK(0, true) : NB_PICK(0, false);
 #undef NB_PICK

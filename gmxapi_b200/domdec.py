@@ -415,7 +415,12 @@ class DomainRank:
         torch = self.torch
         p = self.plan
         self.nb.synchronize()
-        x_home = self.x[:p.nhome].cpu().numpy()
+        xc = getattr(self, "_x_host_current", None)
+        if xc is not None and len(xc) == p.nhome:
+            x_home = xc.numpy().copy()  # the last step ran on the caller's pinned buffer: those are the current coordinates
+        else:
+            x_home = self.x[:p.nhome].cpu().numpy()
+        self._x_host_current = None
         to_dev = lambda a: torch.from_numpy(a).to(self.device)
         home, x_new, send_local, halo = migrate_atoms(self.t, p.box, self.nranks, self.rank, self.rlist, p.home, x_home,
                                                       to_tensor=to_dev)
@@ -512,9 +517,12 @@ class DomainRank:
             f_home_host = torch.empty((p.nhome, 3), dtype=torch.float32).pin_memory()
         fh = f_home_host if isinstance(f_home_host, torch.Tensor) else torch.from_numpy(f_home_host)
         if self.use_windows and xh.is_pinned() and fh.is_pinned():
-            # the kernels read the pinned coordinates and write the pinned forces in place (no staging copy)
+            # the kernels read the pinned coordinates and write the pinned forces in place (no staging copy); repartition()
+            # takes the current coordinates from this buffer (self.x is not refreshed on this path)
             self.nb.dd_step(xh.data_ptr(), fh.data_ptr(), flags)
+            self._x_host_current = xh
         else:
+            self._x_host_current = None
             with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
                 self.x[:p.nhome].copy_(xh, non_blocking=True)
                 self.step(flags)

@@ -20,7 +20,7 @@ EXPORTS = [
     "b200nb_get_outputs", "b200nb_compute", "b200nb_step", "b200nb_dd_create_window", "b200nb_dd_open_peer", "b200nb_dd_set_plan", "b200nb_dd_set_links",
     "b200nb_dd_step", "b200nb_dd_status", "b200nb_halo_pack_x", "b200nb_halo_unpack_f", "b200nb_get_stats",
     "b200nb_get_grid_order", "b200nb_get_tiles", "b200nb_get_pairs", "b200nb_time_force_kernel", "b200nb_time_step",
-    "b200nb_set_grid_atoms", "b200nb_upload_pairlist", "b200nb_copy_xq_grid", "b200nb_get_f_grid", "b200nb_set_shift_vec",
+    "b200nb_set_grid_atoms", "b200nb_upload_pairlist", "b200nb_copy_xq_grid", "b200nb_get_f_grid", "b200nb_set_shift_vec", "b200nb_set_ewald_table",
 ]
 
 
@@ -152,6 +152,7 @@ def load_library():
     L.b200nb_copy_xq_grid.argtypes = [vp, vp, ci, ci]
     L.b200nb_get_f_grid.argtypes = [vp, vp, ci, ci]
     L.b200nb_set_shift_vec.argtypes = [vp, vp]
+    L.b200nb_set_ewald_table.argtypes = [vp, vp, ci, cf]
     _lib = L
     return L
 
@@ -218,6 +219,14 @@ class NbnxmGpu:
                     -1.0 / rc ** 6 if disp_cpot is None else disp_cpot,
                     -1.0 / rc ** 12 if rep_cpot is None else rep_cpot, comb_rule, max_tiles_per_entry)
         self._check(self._L.b200nb_set_params(self._h, C.byref(p)), "set_params")
+
+    def set_ewald_table(self, table_f, scale):
+        """Tabulated Ewald force correction (EwaldCorrectionTables::tableF, tableScale); table_f=None returns to the analytical one."""
+        if table_f is None:
+            self._check(self._L.b200nb_set_ewald_table(self._h, None, 0, 0.0), "set_ewald_table")
+            return
+        t = np.ascontiguousarray(table_f, dtype=np.float32)
+        self._check(self._L.b200nb_set_ewald_table(self._h, _ptr(t), len(t), float(scale)), "set_ewald_table")
 
     def set_vdw(self, vdw_modifier=VDW_POTSHIFT, rvdw=0.0, rvdw_switch=0.0, constants=None, ljpme=LJPME_NONE,
                 ewaldcoeff_lj=0.0, sh_lj_ewald=0.0):

@@ -56,6 +56,11 @@ class NBKernelOptions:
     vdwSwitch: float = 0.0  # rvdw-switch
     ljPme: LjPme = LjPme.Off  # subtract the LJ-PME grid part in real space (the mesh part is not this library's business)
     ljPmeEwaldCoeff: float = 0.0  # ewaldcoeff_lj; 0 = calc_ewaldcoeff_lj(rvdw, 1e-3)
+    # NBKernelOptions::useTabulatedEwaldCorr (api/nblib/kerneloptions.h): the tabulated instead of the analytical Ewald correction
+    # (the reference's EL_EWALD_TAB GPU kernels).  The table is F(r) = erf(beta r)/r^2 - 2 beta/sqrt(pi) exp(-beta^2 r^2)/r at
+    # 2000 points per nm; a caller that has the reference's own table (interaction_const_t::coulombEwaldTables) passes that one to
+    # NbnxmGpu.set_ewald_table instead.
+    useTabulatedEwaldCorr: bool = False
     device: int = 0
 
 
@@ -80,6 +85,18 @@ def interaction_kwargs(options):
     return kw
 
 
+def ewald_force_table(beta, rc, scale=2000.0):
+    """(tableF, scale): the Ewald correction force -(d/dr)(erf(beta r)/r) at r = i / scale, i = 0 .. rc*scale + 2 (the quantity
+    EwaldCorrectionTables::tableF holds, tables/forcetable.cpp; F(0) = 0)."""
+    from math import erf
+    n = int(rc * scale) + 3
+    r = np.arange(n, dtype=np.float64) / scale
+    f = np.zeros(n, np.float64)
+    rr = r[1:]
+    f[1:] = np.array([erf(beta * v) for v in rr]) / rr ** 2 - 2.0 * beta / np.sqrt(np.pi) * np.exp(-(beta * rr) ** 2) / rr
+    return f.astype(np.float32), float(scale)
+
+
 def configure_interactions(nb, nonbonded_parameters, options, rlist_outer=None):
     """b200nb_set_params (+ b200nb_set_vdw) from NBKernelOptions: what setupInteractionConst and gpu_init make of the
     interaction constants (api/nblib/gmxsetup.cpp:226-284, nbnxm/nbnxm_gpu_data_mgmt.cpp:166-245)."""
@@ -100,6 +117,8 @@ def configure_interactions(nb, nonbonded_parameters, options, rlist_outer=None):
                    sh_lj_ewald=_lib.lj_ewald_shift(bl, rvdw))
     elif options.vdwModifier != VdwModifier.PotentialShift or rvdw < rc:
         nb.set_vdw(options.vdwModifier.value, rvdw, options.vdwSwitch, vk)
+    if options.useTabulatedEwaldCorr and options.coulombType == CoulombType.Pme:
+        nb.set_ewald_table(*ewald_force_table(kw["ewald_beta"], rc))
 
 
 class SimulationState:

@@ -119,6 +119,12 @@ int b200nb_set_params(b200nb_t* h, const b200nb_params_t* p);
  * force kernel changes: the pair list is built for rlist >= rc either way. */
 int b200nb_set_vdw(b200nb_t* h, const b200nb_vdw_t* v);
 
+/* Tabulated Ewald force correction (the reference's EL_EWALD_TAB kernels; chosen there by nbnxn_gpu_pick_ewald_kernel_type,
+ * nbnxm_gpu_data_mgmt.cpp:118-154; table upload init_ewald_coulomb_force_table :71-83): table_f_host = n points of
+ * interaction_const_t::coulombEwaldTables->tableF, scale = its tableScale (points per nm).  Call after b200nb_set_params with
+ * Ewald electrostatics; n = 0 returns to the analytical correction (the default).  Applies to the plain LJ kernels. */
+int b200nb_set_ewald_table(b200nb_t* h, const float* table_f_host, int n, float scale);
+
 /* ---- atoms: nbnxn_atomdata_set (atomdata.cpp:955-977) + the exclusion ListOfLists handed to
  * constructPairlist (nbnxm.h:263).  Exclusions are CSR over LOCAL atom indices, each atom's list contains
  * itself (bench_system.cpp:192-195).  natoms counts every atom this rank holds (home + halo). */

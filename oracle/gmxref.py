@@ -71,6 +71,7 @@ def lib():
         L.gmxref_simd_rsq.argtypes = [C.c_float] * 6
         L.gmxref_gpu_list.argtypes = [C.c_void_p] * 10
         L.gmxref_grid_forces.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.gmxref_ewald_table.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -195,6 +196,14 @@ class RefNbnxm:
         if rc:
             raise RuntimeError("gmxref_gpu_list failed: %d" % rc)
         return out
+
+    def ewald_table(self):
+        """(tableF float32 array, scale): the reference's tabulated Ewald force correction of this instance."""
+        sc = C.c_float()
+        n = lib().gmxref_ewald_table(self.h, None, 0, C.byref(sc))
+        t = np.zeros(n, np.float32)
+        lib().gmxref_ewald_table(self.h, t.ctypes.data_as(C.c_void_p), n, C.byref(sc))
+        return t, float(sc.value)
 
     def grid_forces(self):
         """nbat->out[0].f of the last compute(), grid order (nslots, 3)."""

@@ -680,6 +680,21 @@ int gmxref_bench_coordinates1000(float* out, int cap_atoms, float* box_edge)
     return n;
 }
 
+/* The Ewald correction force table of this instance (interaction_const_t::coulombEwaldTables: tableF and its scale), what
+ * init_ewald_coulomb_force_table uploads for the reference's tabulated GPU kernels (nbnxm_gpu_data_mgmt.cpp:71-83).
+ * Returns the number of table points (0: no Ewald tables); writes at most cap. */
+int gmxref_ewald_table(void* h, float* table_f, int cap, float* scale)
+{
+    auto* inst = static_cast<Instance*>(h);
+    if (!inst->ic.coulombEwaldTables) return 0;
+    const auto& t = *inst->ic.coulombEwaldTables;
+    const int   n = static_cast<int>(t.tableF.size());
+    *scale        = t.scale;
+    if (table_f)
+        for (int i = 0; i < n && i < cap; i++) table_f[i] = t.tableF[i];
+    return n;
+}
+
 /* forces of the last gmxref_compute in GRID order (nbat->out[0].f, 3 floats per slot): what gpu_launch_cpyback delivers */
 int gmxref_grid_forces(void* h, float* f, int cap_slots)
 {

@@ -65,6 +65,7 @@ void   gmxref_list_stats(void* h, long long* nClusterPairs, long long* nAtomPair
 long long gmxref_pair_set(void* h, float rc, int* pairs, long long cap);
 int    gmxref_gpu_list(void* h, int* nsci, int* ncj4, int* nexcl, int* nslots, int* sci, int* cj4, unsigned* excl, float* xq, int* type);
 int    gmxref_grid_forces(void* h, float* f, int cap_slots);
+int    gmxref_ewald_table(void* h, float* table_f, int cap, float* scale);
 int    gmxref_bench_coordinates1000(float* out, int cap_atoms, float* box_edge);
 
 #ifdef __cplusplus

@@ -2,8 +2,9 @@
 # Builds shim/_build/libgmx_nbnxm_b200.so: the reference's nbnxm module with its GPU sub-interface ENABLED (GMX_GPU_CUDA=1,
 # so the Nbnxm::gpu_* calls in nbnxm.cpp / pairlist.cpp / kerneldispatch.cpp / prunekerneldispatch.cpp are real external
 # calls, not the empty stubs of a CPU build) + nblib's ForceCalculator with the GPU hook of shim/nblib_gmxsetup_gpu.patch + shim/nblib_gmxcalculator_gpu.patch + our
-# implementation of that sub-interface (shim/nbnxm_b200.cpp) on libb200nb.so; and shim/_build/nblib_gpu_test, the reference's
-# nblib force tests (api/nblib/tests/nbkernelsystem.cpp:69-202) run with NBKernelOptions::useGpu = true.
+# implementation of that sub-interface (shim/nbnxm_b200.cpp) on libb200nb.so; shim/_build/nblib_gpu_test, the reference's
+# nblib force tests (api/nblib/tests/nbkernelsystem.cpp:69-202) run with NBKernelOptions::useGpu = true; and
+# shim/_build/nbnxm_bench_gpu, the reference's nonbonded-benchmark protocol (nbnxm/benchmark/bench_setup.cpp) with the GPU backend.
 # Reference sources are compiled where they lie under /root/reference (never copied into the repo; the two nblib files the
 # patch touches are patched in shim/_build/src/, which is git-ignored).  No cmake: g++ on the files directly, as
 # oracle/build_ref.sh does for the CPU build, whose objects (GPU-independent files) are reused.
@@ -65,4 +66,7 @@ $CXX -shared -fopenmp -o "$OUT/libgmx_nbnxm_b200.so" $OBJ/*.o $CPUOBJ -Wl,-z,def
   -Wl,-rpath,'$ORIGIN/../../gmxapi_b200' -L"${CUDA_HOME:-/usr/local/cuda}/lib64" -lcudart -lm
 $CXX $FLAGS -o "$OUT/nblib_gpu_test" "$HERE/nblib_gpu_test.cpp" "$N/tests/testsystems.cpp" -L"$OUT" -lgmx_nbnxm_b200 -Wl,-rpath,'$ORIGIN' -L"$ROOT/gmxapi_b200" -lb200nb \
   -Wl,-rpath,'$ORIGIN/../../gmxapi_b200' -fopenmp
-echo "built $OUT/libgmx_nbnxm_b200.so and $OUT/nblib_gpu_test"
+# the reference's benchmark protocol with the GPU backend, on the reference's own BenchmarkSystem (bench_system.cpp from the tree)
+$CXX $FLAGS -o "$OUT/nbnxm_bench_gpu" "$HERE/nbnxm_bench_gpu.cpp" "$R/gromacs/nbnxm/benchmark/bench_system.cpp" -L"$OUT" -lgmx_nbnxm_b200 \
+  -Wl,-rpath,'$ORIGIN' -L"$ROOT/gmxapi_b200" -lb200nb -Wl,-rpath,'$ORIGIN/../../gmxapi_b200' -fopenmp
+echo "built $OUT/libgmx_nbnxm_b200.so, $OUT/nblib_gpu_test and $OUT/nbnxm_bench_gpu"

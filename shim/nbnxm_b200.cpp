@@ -61,6 +61,7 @@ struct NbnxmGpu
     int  rollingNumParts[2] = { 0, 0 };
     bool haveFreshList[2]   = { false, false };
     bool haveList[2]        = { false, false };
+    bool ewaldTabulated     = false;
     /* nblib builds the pair list BEFORE it sets the atom properties (api/nblib/gmxsetup.cpp:316-320; mdrun does it the other way
      * round, mdlib/sim_util.cpp:1327-1366): a list that arrives before the atom data of its grid is kept until gpu_init_atomdata */
     bool                      haveAtomData = false;
@@ -138,6 +139,14 @@ void setParameters(NbnxmGpu* nb, const interaction_const_t* ic, const PairlistPa
     p.comb_rule           = nbatParams.comb_rule == ljcrGEOM ? 1 : 2;
     p.max_tiles_per_entry = 0;
     check(nb, b200nb_set_params(nb->h, &p), "set_params");
+    /* nbnxn_gpu_pick_ewald_kernel_type (nbnxm_gpu_data_mgmt.cpp:118-154): analytical by default on current GPUs, tabulated on request */
+    nb->ewaldTabulated = p.eeltype == B200NB_EEL_EWALD && ic->coulombEwaldTables != nullptr && !ic->coulombEwaldTables->tableF.empty()
+                         && (getenv("GMX_GPU_NB_TAB_EWALD") != nullptr || getenv("GMX_CUDA_NB_TAB_EWALD") != nullptr);
+    if (nb->ewaldTabulated)
+    {
+        const EwaldCorrectionTables& t = *ic->coulombEwaldTables;
+        check(nb, b200nb_set_ewald_table(nb->h, t.tableF.data(), static_cast<int>(t.tableF.size()), t.scale), "set_ewald_table");
+    }
 
     const bool ljPme = ic->vdwtype == evdwPME;
     if (ic->vdwtype != evdwCUT && !ljPme)
@@ -408,9 +417,9 @@ int gpu_min_ci_balanced(NbnxmGpu* /* nb */)
     return 0;
 }
 
-bool gpu_is_kernel_ewald_analytical(const NbnxmGpu* /* nb */)
+bool gpu_is_kernel_ewald_analytical(const NbnxmGpu* nb)
 {
-    return true;
+    return !nb->ewaldTabulated;
 }
 
 void setupGpuShortRangeWork(NbnxmGpu* /* nb */, const gmx::GpuBonded* /* gpuBonded */, gmx::InteractionLocality /* iLocality */) {}

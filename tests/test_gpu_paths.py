@@ -112,6 +112,38 @@ def test_rebuild_without_halo_grid_drops_the_nonlocal_list(built):
     h.close()
 
 
+def test_tabulated_ewald(built):
+    """the EL_EWALD_TAB flavour (b200nb_set_ewald_table): with the REFERENCE's own table against the reference's GPU-layout kernel,
+    which interpolates the same table (kernel_gpu_ref.cpp:262-272), where oracle/_ref is on this box; with the analytic table of
+    the Python mirror against the oracle's analytical Ewald (interpolation error of a 2000-point-per-nm table: < 2e-6)"""
+    from oracle import gmxref
+    s = g.systems.named("water_3k")
+    beta = float(np.float32(g.systems.ewald_beta(RC)))
+    fo, fso, evo, eco, _ = oracle.forces(s.x, s.box, s.q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_EWALD, beta=beta)
+    fc = g.ForceCalculator(g.SimulationState.from_system(s), g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme,
+                                                                                computeVirialAndEnergy=True))
+    f_ana = fc.compute().copy()
+    for energy in (True, False):
+        ft = g.ForceCalculator(g.SimulationState.from_system(s), g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme,
+                                                                                    computeVirialAndEnergy=energy, useTabulatedEwaldCorr=True))
+        f_tab = ft.compute().copy()
+        assert not np.array_equal(f_tab, f_ana)  # the other kernel ran
+        assert relrms(f_tab, fo) < 1e-5
+        if energy:
+            assert abs(ft.energies[1] - eco) <= 2e-5 * abs(eco)  # energies use the analytical form in the tabulated kernels too
+    if gmxref.available():
+        r = gmxref.RefNbnxm(s.x, s.box, s.types, s.q, s.nbfp, s.excl_off, s.excl_idx, rc=RC, eeltype=gmxref.EEL_EWALD_TAB, ewaldcoeff=beta,
+                            kernel=gmxref.KERNEL_GPUREF, nthreads=1)
+        f_ref = r.compute(energy=False, virial=False)[0]
+        table, scale = r.ewald_table()
+        fc.nb.set_ewald_table(table, scale)
+        f_tab = fc.compute()
+        assert relrms(f_tab, f_ref) < 3e-6  # same table, same interpolation: closer than to the analytical form
+        fc.nb.set_ewald_table(None, 0.0)
+        assert relrms(fc.compute(), f_ana) < 1e-6  # and back
+        r.close()
+
+
 @pytest.mark.parametrize("name", ["ref_water_3k", "ref_water_24k"])
 def test_reference_liquid_water(built, name):
     """BenchmarkSystem's own coordinates (nbnxm/benchmark/bench_coords.h through gmxapi_b200/data/ref_water_1000.npz): liquid

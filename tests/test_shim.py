@@ -14,6 +14,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "shim", "_build", "libgmx_nbnxm_b200.so")
 EXE = os.path.join(ROOT, "shim", "_build", "nblib_gpu_test")
+BENCH = os.path.join(ROOT, "shim", "_build", "nbnxm_bench_gpu")
 needs_shim = pytest.mark.skipif(not (os.path.exists(LIB) and os.path.exists(EXE)),
                                 reason="shim/_build not built (needs the reference tree: shim/build_shim.sh)")
 
@@ -87,3 +88,31 @@ def test_reference_nblib_force_tests_with_use_gpu():
     for key in ("spc_methanol_rf", "spc_methanol_pme"):
         gpu, cpu = np.array(d[key]["gpu"], np.float64), np.array(d[key]["cpu"], np.float64)
         assert np.sqrt(((gpu - cpu) ** 2).sum() / (cpu ** 2).sum()) < 1e-5, key
+
+
+def run_bench(args, cpu_only):
+    env = dict(os.environ, OMP_PROC_BIND="spread", OMP_PLACES="cores")
+    if cpu_only:
+        env["NBNXM_BENCH_CPU_ONLY"] = "1"
+    r = subprocess.run([BENCH] + [str(a) for a in args], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stdout[-800:], r.stderr[-2000:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@needs_shim
+def test_benchmark_driver_cpu_leg():
+    d = run_bench([1, "rf", 2, 2], cpu_only=True)
+    assert d["atoms"] == 3000 and d["cpu_ms_per_step"] > 0
+
+
+@pytest.mark.gpu
+@needs_shim
+@pytest.mark.parametrize("size,eel", [(32, "pme"), (8, "rf")])
+def test_reference_benchmark_protocol_with_gpu_backend(size, eel):
+    """BASELINE configs[2] (BenchmarkSystem(32), 96 000 atoms) and configs[1] through C++: the reference's nonbonded-benchmark
+    set-up and step (nbnxm/benchmark/bench_setup.cpp:170-343) with KernelType::Gpu8x8x8 -- unmodified nbnxm module, reference-built
+    grid and pair list, Nbnxm::gpu_* shim, B200 kernels -- against the reference's CPU SIMD kernel in the same process."""
+    d = run_bench([size, eel, 20], cpu_only=False)
+    assert d["atoms"] == 3000 * size
+    assert d["force_rel_rms_gpu_vs_cpu"] < 1e-5
+    assert d["gpu_ms_per_step"] < d["cpu_ms_per_step"]
