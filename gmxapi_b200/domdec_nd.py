@@ -368,15 +368,21 @@ class DomainRankND:
         self.nb.dd_set_links(p.nhome, p.nhalo, links)
         self.t.barrier()  # every rank has its plan before anybody steps
 
-    def repartition(self):
+    def repartition(self, x_home=None):
         """Pair-search step with atom migration: the current coordinates of the home atoms (self.x[:nhome], on the device)
         decide the new owners; halo lists, grids and pair list are rebuilt.  Collective.  Returns the new plan."""
         torch = self.torch
         p = self.plan
         self.nb.synchronize()
+        # the current coordinates of the home atoms: the caller's (x_home, e.g. after an integration step), else those of the
+        # last step -- the caller's pinned buffer when the step ran on it in place, self.x otherwise
         xc = getattr(self, "_x_host_current", None)
-        if xc is not None and len(xc) == p.nhome:
-            x_home = xc.numpy().copy()  # the last step ran on the caller's pinned buffer: those are the current coordinates
+        if x_home is not None:
+            x_home = np.ascontiguousarray(x_home.numpy() if hasattr(x_home, "numpy") else x_home, dtype=np.float32).reshape(-1, 3)
+            if len(x_home) != p.nhome:
+                raise InputException("repartition: x_home must hold the %d home atoms" % p.nhome)
+        elif xc is not None and len(xc) == p.nhome:
+            x_home = xc.numpy().copy()
         else:
             x_home = self.x[:p.nhome].cpu().numpy()
         self._x_host_current = None

@@ -105,7 +105,7 @@ std::unique_ptr<nonbonded_verlet_t> setupNbnxm(const gmx::BenchmarkSystem& syste
     auto pairSearch = std::make_unique<PairSearch>(PbcType::Xyz, false, nullptr, nullptr, pairlistParams.pairlistType, false, numThreads, pinPolicy);
     auto atomData   = std::make_unique<nbnxn_atomdata_t>(pinPolicy);
     nbnxn_atomdata_init(gmx::MDLogger(), atomData.get(), kernelSetup.kernelType, 0 /* geometric rule */, system.numAtomTypes,
-                        system.nonbondedParameters, 1, numThreads);
+                        system.nonbondedParameters, 1, useGpu ? 1 : numThreads); /* one output buffer with a GPU: nbnxm_setup.cpp:431-433 */
     NbnxmGpu* gpuNbv = nullptr;
     if (useGpu)
     {

@@ -55,8 +55,7 @@ def run_ranks(s, opt, nranks, flags, use_windows=True, nsteps=1, moved_x=None):
                 # the atoms moved (integration is the caller's business): new coordinates of the atoms this rank owns go to
                 # the device, then a repartitioning search step, then a step on the new decomposition
                 old_home = d.plan.home.copy()
-                d.x[:d.plan.nhome].copy_(torch.from_numpy(np.ascontiguousarray(moved_x[old_home])))
-                plan = d.repartition()
+                plan = d.repartition(x_home=moved_x[old_home])
                 assert len(np.setdiff1d(plan.home, old_home)) > 0, "nothing migrated: the test does not test"
                 from gmxapi_b200.domdec import wrap_into_box
                 xh = np.ascontiguousarray(wrap_into_box(moved_x, s.box)[plan.home])
@@ -321,8 +320,7 @@ def test_repartition_nd_after_motion(built):
             d = DomainRankND(s, opt, hub.endpoint(r), grid, rank=r, device=0)
             d.compute(np.ascontiguousarray(s.x[d.plan.home]), flags)
             old_home = d.plan.home.copy()
-            d.x[:d.plan.nhome].copy_(torch.from_numpy(np.ascontiguousarray(x1[old_home])))
-            plan = d.repartition()
+            plan = d.repartition(x_home=x1[old_home])
             assert len(np.setdiff1d(plan.home, old_home)) > 0
             f, fs, elj, eel = d.compute(np.ascontiguousarray(x1w[plan.home]), flags)
             out[r] = dict(home=plan.home, f=f.numpy().copy(), elj=elj, eel=eel)
