@@ -117,6 +117,7 @@ extern "C" void b200nb_destroy(b200nb_t* h)
         if (!h->inner_is_outer) free_list(h->inner[l]);
         free_list(h->outer[l]);
         cudaFree(h->packed[l].entries);
+        cudaFree(h->packed[l].staged);
         cudaFree(h->packed[l].dest);
         cudaFree(h->packed[l].sizes);
         cudaFree(h->packed[l].ja);
@@ -1264,27 +1265,28 @@ k_prune(const Entry* __restrict__ oe, const int* __restrict__ ocj, const uint64_
 }
 
 /* Prune + re-pack: entries of the OUTER cluster-pair list at j-atom granularity for the force kernel (PackedList,
- * b200nb_internal.h).  One warp per entry, lane = jl + 8*ih as in the search; ONE pass over the entry's cluster pairs.  A j-atom
- * is kept iff one of its pairs with the entry's 8 i-atoms has r^2 < rlist2 (the inner, dynamic-pruning radius) and is not
- * removed by the j > i rule of the self tile -- which subsumes the cluster-pair prune of nbnxn_kernel_prune_cuda
- * (cuda/nbnxm_cuda_kernel_pruneonly.cuh:104-277): a cluster pair without a pair in range contributes no j-atom, so no separate
- * prune kernel and no pruned cluster-pair list are needed on the per-step path (rolling pruning = this kernel on one part of
- * the outer list).  Kept j-atoms that have an excluded pair (or belong to the self tile) go to a front buffer, the others to a
- * back buffer, and are written out front first so that only the leading STEPS (16 j-atoms = 2 packed tiles, what the force kernel
- * consumes per iteration) need masks.  Mask format of a step: 4 words; bit (j16 + 16*half) of word k says pair (i-atom
- * 4*half + k, j-atom j16 of the step) interacts -- the force kernel's lane j16 + 16*half reads its own bit of each word.
- * Excluded pairs inside the cut-off must stay: the kernels evaluate their Ewald / reaction-field exclusion correction
- * (kernel_inner.h:330-360).  The j list of an entry is padded to a whole number of steps with far-away dummy atoms.
+ * b200nb_internal.h), TWO half-entries per entry: one for the i-atoms 0-3 of the i-cluster, one for 4-7.  One warp per entry, lane =
+ * jl + 8*ih as in the search; ONE pass over the entry's cluster pairs.  A j-atom is kept for a half iff one of its pairs with the
+ * half's 4 i-atoms has r^2 < rlist2 (the inner, dynamic-pruning radius) and is not removed by the j > i rule of the self tile
+ * -- which subsumes the cluster-pair prune of nbnxn_kernel_prune_cuda (cuda/nbnxm_cuda_kernel_pruneonly.cuh:104-277): a cluster
+ * pair without a pair in range contributes no j-atom, so no separate prune kernel and no pruned cluster-pair list are needed on
+ * the per-step path (rolling pruning = this kernel on one part of the outer list).  Kept j-atoms that have an excluded pair with
+ * the half (or belong to the self tile) go to a front buffer, the others to a back buffer, and are written out front first so
+ * that only the leading STEPS (16 j-atoms, what a half-warp of the force kernel consumes per iteration) need masks.  Mask of a
+ * step: 64 bits, bit 16*k + j says pair (i-atom 4*half + k, j-atom j of the step) interacts.  Excluded pairs inside the cut-off
+ * must stay: the kernels evaluate their Ewald / reaction-field exclusion correction (kernel_inner.h:330-360).  The j list of a
+ * half-entry is padded to a whole number of steps with far-away dummy atoms.
  * The reference has no such step: its GPU list stays at 8x8 cluster-pair granularity with per-pair masks
  * (nbnxm/pairlist.h:190-225). */
+#define NB_PACK_FRONT (NB_MAX_ENTRY_TILES * 8 + 16)
 __global__ void __launch_bounds__(128)
 k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t* __restrict__ imask, long long nentries, int part,
        int nparts, const float* __restrict__ xq, const float* __restrict__ shift_vec, float rlist2, int intra, int dummy_slot, int pitch,
-       const int* __restrict__ dest, Entry* __restrict__ pe, int* __restrict__ pja, uint64_t* __restrict__ pmask)
+       Entry* __restrict__ staged, int* __restrict__ sizes, int* __restrict__ pja, uint64_t* __restrict__ pmask)
 {
-    __shared__ int      s_ja[4][NB_MAX_ENTRY_TILES * 8 + 16]; /* front: j-atoms that need masks */
-    __shared__ int      s_jb[4][NB_MAX_ENTRY_TILES * 8];      /* back: the others */
-    __shared__ unsigned s_m[4][NB_MAX_ENTRY_TILES * 2 + 4];   /* 4 words per step of 16 j-atoms */
+    __shared__ int      s_ja[4][2][NB_PACK_FRONT];            /* front, per half: j-atoms that need masks */
+    __shared__ int      s_jb[4][2][NB_MAX_ENTRY_TILES * 8];   /* back: the others */
+    __shared__ unsigned s_m[4][2][NB_MAX_ENTRY_TILES + 4];    /* 2 words per step of 16 j-atoms */
     __shared__ float4   s_xi[4][8];                           /* the entry's i-atoms, shifted */
     const int       w   = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * 4 + w;
@@ -1294,15 +1296,16 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
     const Entry en   = ie[e];
     const int   shift = NB_ENTRY_SHIFT(en.shift_nmask), nmask = NB_ENTRY_NMASK(en.shift_nmask);
     const int   ntile = min(en.end - en.start, NB_MAX_ENTRY_TILES);
-    for (int k = lane; k < NB_MAX_ENTRY_TILES * 2 + 4; k += 32) s_m[w][k] = 0u;
+    for (int k = lane; k < 2 * (NB_MAX_ENTRY_TILES + 4); k += 32) (&s_m[w][0][0])[k] = 0u;
     __syncwarp();
     const float4 xa = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + 2 * ih];
     const float4 xb = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + 2 * ih + 1];
     const float  sx = shift_vec[3 * shift], sy = shift_vec[3 * shift + 1], sz = shift_vec[3 * shift + 2];
     const float  xi0 = xa.x + sx, yi0 = xa.y + sy, zi0 = xa.z + sz, xi1 = xb.x + sx, yi1 = xb.y + sy, zi1 = xb.z + sz;
-    /* where this lane's two pairs (i-atoms 2*ih, 2*ih+1) live in the step masks */
-    const int mword = 2 * (ih & 1), mhalf = 16 * (ih >> 1);
-    int na = 0, nb = 0, has_self = 0;
+    /* this lane's two pairs (i-atoms 2*ih, 2*ih+1) belong to half ih >> 1, where they are i-atoms k = 2*(ih & 1) and k + 1:
+     * word (ih & 1) of the step mask, bits j and 16 + j */
+    const int hf = ih >> 1, mword = ih & 1;
+    int na0 = 0, na1 = 0, nb0 = 0, nb1 = 0, has_self = 0;
     /* ---- cluster pairs that carry a mask (exclusions, the self tile): sorted to the front of the entry by the search, a few per
      * entry.  Lane = jl + 8*ih looks at j-atom jl against i-atoms 2*ih, 2*ih + 1: the layout of the tile masks. ---- */
     const int nmt = min(nmask, ntile);
@@ -1314,30 +1317,28 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
         if (diag) has_self = 1;
         const bool     ina  = nb_rsq(xi0, yi0, zi0, xj.x, xj.y, xj.z) < rlist2 && !(diag && jl <= 2 * ih);
         const bool     inb  = nb_rsq(xi1, yi1, zi1, xj.x, xj.y, xj.z) < rlist2 && !(diag && jl <= 2 * ih + 1);
-        unsigned       kb   = __ballot_sync(0xffffffffu, ina || inb);
-        kb                  = (kb | (kb >> 8) | (kb >> 16) | (kb >> 24)) & 0xffu;
-        if (!kb) continue; /* the cluster-pair prune: nothing of this tile within the radius */
+        const unsigned kb   = __ballot_sync(0xffffffffu, ina || inb);
+        const unsigned kb0 = (kb | (kb >> 8)) & 0xffu, kb1 = ((kb >> 16) | (kb >> 24)) & 0xffu;
+        if (!(kb0 | kb1)) continue; /* the cluster-pair prune: nothing of this tile within the radius */
         const uint64_t m  = imask[en.start + t];
         const unsigned ba = (unsigned)(m >> lane) & 1u, bb = (unsigned)(m >> (32 + lane)) & 1u;
-        unsigned       sb = __ballot_sync(0xffffffffu, !(ba && bb) || diag);
-        sb                = (sb | (sb >> 8) | (sb >> 16) | (sb >> 24)) & 0xffu;
-        const unsigned sela = kb & sb, selb = kb & ~sb;
+        const unsigned sb = __ballot_sync(0xffffffffu, !(ba && bb) || diag);
+        const unsigned sb0 = (sb | (sb >> 8)) & 0xffu, sb1 = ((sb >> 16) | (sb >> 24)) & 0xffu;
+        const unsigned sela0 = kb0 & sb0, selb0 = kb0 & ~sb0, sela1 = kb1 & sb1, selb1 = kb1 & ~sb1;
+        const unsigned sela = hf ? sela1 : sela0, selb = hf ? selb1 : selb0, below = (1u << jl) - 1u;
         if ((sela >> jl) & 1u)
         {
-            const int pos = na + __popc(sela & ((1u << jl) - 1u));
-            if (ih == 0) s_ja[w][pos] = cj * 8 + jl;
-            const int bit = (pos & 15) + mhalf;
-            atomicOr(&s_m[w][(pos >> 4) * 4 + mword], ba << bit);
-            atomicOr(&s_m[w][(pos >> 4) * 4 + mword + 1], bb << bit);
+            const int pos = (hf ? na1 : na0) + __popc(sela & below);
+            if (mword == 0) s_ja[w][hf][pos] = cj * 8 + jl;
+            atomicOr(&s_m[w][hf][(pos >> 4) * 2 + mword], (ba << (pos & 15)) | (bb << (16 + (pos & 15))));
         }
-        if (ih == 0 && ((selb >> jl) & 1u)) s_jb[w][nb + __popc(selb & ((1u << jl) - 1u))] = cj * 8 + jl;
-        na += __popc(sela);
-        nb += __popc(selb);
+        if (mword == 0 && ((selb >> jl) & 1u)) s_jb[w][hf][(hf ? nb1 : nb0) + __popc(selb & below)] = cj * 8 + jl;
+        na0 += __popc(sela0), na1 += __popc(sela1);
+        nb0 += __popc(selb0), nb1 += __popc(selb1);
     }
     /* ---- the rest (all pairs interact, never the self tile): FOUR cluster pairs per iteration, lane = jl + 8*q tests j-atom jl
-     * of pair t + q against all 8 i-atoms (shifted coordinates broadcast from shared memory): one ballot and one compaction per
-     * 32 j-atoms instead of per 8, ~20 instead of ~45 instructions per cluster pair.  Cluster indices are fetched two groups
-     * ahead, coordinates one group ahead. ---- */
+     * of pair t + q against the 8 i-atoms (shifted coordinates broadcast from shared memory), 0-3 and 4-7 separately: two ballots
+     * and two compactions per 32 j-atoms.  Cluster indices are fetched two groups ahead, coordinates one group ahead. ---- */
     {
         if (lane < 8)
         {
@@ -1345,12 +1346,13 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
             s_xi[w][lane]  = make_float4(v.x + sx, v.y + sy, v.z + sz, 0.f);
         }
         __syncwarp();
-        const int    q      = lane >> 3;
-        const int    tbase  = en.start + nmt + q;
-        const int    nplain = ntile - nmt;
-        const float4 far    = make_float4(3.0e30f, 3.0e30f, 3.0e30f, 0.f);
-        int          cj_cur = q < nplain ? icj[tbase] : -1, cj_next = q + 4 < nplain ? icj[tbase + 4] : -1;
-        float4       xj_cur = cj_cur >= 0 ? reinterpret_cast<const float4*>(xq)[(size_t)cj_cur * 8 + jl] : far;
+        const int      q      = lane >> 3;
+        const int      tbase  = en.start + nmt + q;
+        const int      nplain = ntile - nmt;
+        const float4   far    = make_float4(3.0e30f, 3.0e30f, 3.0e30f, 0.f);
+        const unsigned lt     = (1u << lane) - 1u;
+        int            cj_cur = q < nplain ? icj[tbase] : -1, cj_next = q + 4 < nplain ? icj[tbase + 4] : -1;
+        float4         xj_cur = cj_cur >= 0 ? reinterpret_cast<const float4*>(xq)[(size_t)cj_cur * 8 + jl] : far;
         for (int g = 0; g < nplain; g += 4)
         {
             const int    cj = cj_cur;
@@ -1358,64 +1360,65 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
             cj_cur          = cj_next;
             xj_cur          = cj_cur >= 0 ? reinterpret_cast<const float4*>(xq)[(size_t)cj_cur * 8 + jl] : far;
             cj_next         = g + 8 + q < nplain ? icj[tbase + g + 8] : -1;
-            bool in = false;
+            bool in0 = false, in1 = false;
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < 4; i++)
             {
-                const float4 xi = s_xi[w][i];
-                in              = in || nb_rsq(xi.x, xi.y, xi.z, xj.x, xj.y, xj.z) < rlist2;
+                const float4 xl = s_xi[w][i], xu = s_xi[w][i + 4];
+                in0             = in0 || nb_rsq(xl.x, xl.y, xl.z, xj.x, xj.y, xj.z) < rlist2;
+                in1             = in1 || nb_rsq(xu.x, xu.y, xu.z, xj.x, xj.y, xj.z) < rlist2;
             }
-            in                = in && cj >= 0;
-            const unsigned kb = __ballot_sync(0xffffffffu, in);
-            if (in) s_jb[w][nb + __popc(kb & ((1u << lane) - 1u))] = cj * 8 + jl;
-            nb += __popc(kb);
+            in0                = in0 && cj >= 0;
+            in1                = in1 && cj >= 0;
+            const unsigned kb0 = __ballot_sync(0xffffffffu, in0), kb1 = __ballot_sync(0xffffffffu, in1);
+            if (in0) s_jb[w][0][nb0 + __popc(kb0 & lt)] = cj * 8 + jl;
+            if (in1) s_jb[w][1][nb1 + __popc(kb1 & lt)] = cj * 8 + jl;
+            nb0 += __popc(kb0);
+            nb1 += __popc(kb1);
         }
     }
     __syncwarp();
-    const int n   = na + nb;
-    const int nsp = (n + 15) >> 4, nms = (na + 15) >> 4; /* steps, masked steps */
-    const int ntp = 2 * nsp;                             /* packed tiles of 8 j-atoms */
-    /* the unmasked j-atoms (and the padding) that share the last masked step interact with all 8 i-atoms */
-    if (na & 15)
+    /* the unmasked j-atoms (and the padding) that share the last masked step of a half interact with all 4 i-atoms: lanes 0-15
+     * complete half 0's step, lanes 16-31 half 1's */
     {
-        const int p = (na & ~15) + (lane & 15); /* position of this lane's j-atom in that step */
-        if (p >= na && lane < 16)
+        const int hh = lane >> 4, nah = hh ? na1 : na0;
+        const int p  = (nah & ~15) + (lane & 15); /* position of this lane's j-atom in that step */
+        if ((nah & 15) && p >= nah)
         {
-            unsigned* const mw = &s_m[w][(p >> 4) * 4];
-            const unsigned  b2 = (1u << (p & 15)) | (1u << ((p & 15) + 16));
-            atomicOr(mw, b2), atomicOr(mw + 1, b2), atomicOr(mw + 2, b2), atomicOr(mw + 3, b2);
+            const unsigned b2 = (1u << (p & 15)) | (1u << ((p & 15) + 16));
+            atomicOr(&s_m[w][hh][(p >> 4) * 2], b2), atomicOr(&s_m[w][hh][(p >> 4) * 2 + 1], b2);
         }
     }
     __syncwarp();
-    const long long d  = dest ? dest[e] : e; /* position of this entry in the packed list (largest entries first) */
-    const long long t0 = d * pitch;          /* packed entry d owns tiles [d*pitch, (d+1)*pitch) */
-    const int       dummy0 = dummy_slot + (int)(e & (NB_DUMMY_SLOTS / 16 - 1)) * 16;
-    for (int k = lane; k < ntp * 8; k += 32) pja[(size_t)t0 * 8 + k] = k < na ? s_ja[w][k] : (k < n ? s_jb[w][k - na] : dummy0 + (k & 15));
-    unsigned* const pm = reinterpret_cast<unsigned*>(pmask + t0);
-    for (int k = lane; k < nsp * 4; k += 32) pm[k] = k < nms * 4 ? s_m[w][k] : ~0u;
-    if (lane == 0)
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++)
     {
-        Entry o;
-        o.ci          = en.ci;
-        o.shift_nmask = shift | (nms << 8) | (has_self << 24); /* packed list: the mask count is in STEPS */
-        o.start       = (int)t0;
-        o.end         = (int)t0 + ntp;
-        pe[d]         = o;
+        const int       na = hh ? na1 : na0, n = na + (hh ? nb1 : nb0);
+        const int       nsp = (n + 15) >> 4, nms = (na + 15) >> 4; /* steps, masked steps */
+        const long long p   = 2 * e + hh;                          /* half-entry in packing order */
+        const long long s0  = p * (pitch >> 1);                    /* it owns the steps [s0, s0 + pitch/2) */
+        const int       dummy0 = dummy_slot + (int)(p & (NB_DUMMY_SLOTS / 16 - 1)) * 16;
+        for (int k = lane; k < nsp * 16; k += 32) pja[(size_t)s0 * 16 + k] = k < na ? s_ja[w][hh][k] : (k < n ? s_jb[w][hh][k - na] : dummy0 + (k & 15));
+        unsigned* const pm = reinterpret_cast<unsigned*>(pmask + s0);
+        for (int k = lane; k < nsp * 2; k += 32) pm[k] = k < nms * 2 ? s_m[w][hh][k] : ~0u;
+        if (lane == 0)
+        {
+            Entry o;
+            o.ci          = en.ci;
+            o.shift_nmask = shift | (nms << 8) | (has_self << 24) | (hh << 25); /* packed list: the mask count is in STEPS */
+            o.start       = (int)s0;
+            o.end         = (int)s0 + nsp;
+            staged[p]     = o;
+            sizes[p]      = nsp;
+        }
     }
 }
 
-/* ordering key of the packed entries: the cluster pairs of the outer entry (the packed size follows it closely and costs a
- * whole packing pass to know exactly) */
-__global__ void k_entry_sizes(const Entry* __restrict__ e, int n, int* __restrict__ sizes)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) sizes[i] = e[i].end - e[i].start;
-}
-
-/* Positions of the packed entries: descending packed size (counting sort on <= 33 values; the role of sort_sci,
- * nbnxm/pairlist.cpp:3827-3873).  The force kernel runs one entry per single-warp CTA and CTAs start in index order, so the
- * big entries start first and the last wave holds only the smallest ones: the tail of the kernel shrinks from one full entry
- * to one short entry.  hist: 2 x NB_ORDER_BINS ints (histogram, cursors). */
+/* Positions of the packed half-entries: descending step count (counting sort on <= 33 values; the role of sort_sci,
+ * nbnxm/pairlist.cpp:3827-3873).  The force kernel runs two consecutive half-entries per single-warp CTA and CTAs start in index
+ * order, so (i) the two halves of a warp run the same number of steps, (ii) the big ones start first and the last wave holds
+ * only the smallest: the tail of the kernel shrinks from one full entry to one short entry.  hist: 2 x NB_ORDER_BINS ints
+ * (histogram, cursors). */
 __global__ void k_order_hist(const int* __restrict__ sizes, int n, int* __restrict__ hist)
 {
     __shared__ int sh[NB_ORDER_BINS];
@@ -1443,29 +1446,56 @@ __global__ void k_order_assign(const int* __restrict__ sizes, int n, int* __rest
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < n) dest[e] = atomicAdd(&hist[NB_ORDER_BINS + min(sizes[e], NB_ORDER_BINS - 1)], 1);
 }
+/* headers from packing order into execution order.  After a rolling part the positions of the last full pack are kept: the
+ * part's half-entries only shrink or grow a little, the order stays nearly sorted. */
+__global__ void k_place_headers(const Entry* __restrict__ staged, const int* __restrict__ dest, int n, Entry* __restrict__ entries)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) reinterpret_cast<int4*>(entries)[dest[e]] = reinterpret_cast<const int4*>(staged)[e];
+}
+
+/* The two half-entries a warp of the force kernel runs side by side (positions 2w and 2w + 1 of the execution order) are walked
+ * in lockstep for the longer one's steps: the shorter one gets the difference as steps of far-away dummy atoms behind its own
+ * (its row has pitch/2 >= the longer one's steps of room).  Differences are rare (the order is by step count) and short. */
+__global__ void k_pad_partner(const Entry* __restrict__ entries, int nwarps, int* __restrict__ pja, int dummy_slot)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwarps) return;
+    const int4 a = reinterpret_cast<const int4*>(entries)[2 * w], b = reinterpret_cast<const int4*>(entries)[2 * w + 1];
+    const int  na = a.w - a.z, nb = b.w - b.z;
+    if (na == nb) return;
+    const int   s0 = na < nb ? a.z : b.z, ns = min(na, nb), nl = max(na, nb);
+    const int   d0 = dummy_slot + (int)((2 * w + (na < nb ? 0 : 1)) & (NB_DUMMY_SLOTS / 16 - 1)) * 16;
+    for (int s = ns; s < nl; s++)
+        for (int j = 0; j < 16; j++) pja[(size_t)(s0 + s) * 16 + j] = d0 + j;
+}
 
 static int ensure_packed(b200nb_context* h, PackedList& P, size_t cap_tiles, size_t cap_entries)
 {
+    /* cap_tiles = outer entries x pitch: per outer entry 2 half-entries x pitch/2 steps x (16 slots, one 64-bit mask) */
     if (cap_tiles > P.cap_tiles || !P.ja)
     {
         cudaFree(P.ja);
         cudaFree(P.mask);
         P.ja = nullptr;
         P.mask = nullptr;
-        NB_CUDA(h, cudaMalloc((void**)&P.ja, std::max<size_t>(cap_tiles, 1) * 8 * sizeof(int)));
+        NB_CUDA(h, cudaMalloc((void**)&P.ja, std::max<size_t>(cap_tiles, 1) * 16 * sizeof(int)));
         NB_CUDA(h, cudaMalloc((void**)&P.mask, std::max<size_t>(cap_tiles, 1) * sizeof(uint64_t)));
         P.cap_tiles = cap_tiles;
     }
     if (cap_entries > P.cap_entries || !P.entries)
     {
         cudaFree(P.entries);
+        cudaFree(P.staged);
         cudaFree(P.dest);
         cudaFree(P.sizes);
-        P.entries = nullptr;
+        P.entries = P.staged = nullptr;
         P.dest = P.sizes = nullptr;
-        NB_CUDA(h, cudaMalloc((void**)&P.entries, std::max<size_t>(cap_entries, 1) * sizeof(Entry)));
-        NB_CUDA(h, cudaMalloc((void**)&P.dest, std::max<size_t>(cap_entries, 1) * sizeof(int)));
-        NB_CUDA(h, cudaMalloc((void**)&P.sizes, std::max<size_t>(cap_entries, 1) * sizeof(int)));
+        const size_t nh = 2 * std::max<size_t>(cap_entries, 1);
+        NB_CUDA(h, cudaMalloc((void**)&P.entries, nh * sizeof(Entry)));
+        NB_CUDA(h, cudaMalloc((void**)&P.staged, nh * sizeof(Entry)));
+        NB_CUDA(h, cudaMalloc((void**)&P.dest, nh * sizeof(int)));
+        NB_CUDA(h, cudaMalloc((void**)&P.sizes, nh * sizeof(int)));
         P.cap_entries = cap_entries;
     }
     return 0;
@@ -1476,22 +1506,23 @@ static int launch_pack(b200nb_context* h, int loc, int part, int nparts)
 {
     const PairList& I = h->outer[loc];
     PackedList&     P = h->packed[loc];
-    P.nentries        = I.nentries;
+    P.nentries        = 2 * I.nentries;
     P.pitch           = (h->max_tiles + 1) & ~1; /* whole steps of 16 j-atoms = 2 tiles */
     if (I.nentries == 0) return 0;
-    if ((size_t)I.nentries * P.pitch > 2000000000ull) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: packed list exceeds 2^31 tiles");
+    if ((size_t)I.nentries * P.pitch > 2000000000ull) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: packed list exceeds 2^31 steps");
     if (ensure_packed(h, P, I.cap_entries * P.pitch, I.cap_entries)) return B200NB_ERR_CUDA;
     long long nw = (I.nentries - part + nparts - 1) / nparts;
     if (nw <= 0) return 0;
     const float    r2   = h->inner_is_outer ? h->dp.rlist_outer2 : h->dp.rlist_inner2;
     const unsigned nblk = (unsigned)((nw + 3) / 4);
+    k_pack<<<nblk, 128, 0, h->stream>>>(I.entries, I.cj, I.mask, I.nentries, part, nparts, h->d_xq, h->d_shift_vec, r2, loc == 0,
+                                        h->dummy_slot, P.pitch, P.staged, P.sizes, P.ja, P.mask);
+    LAUNCH_CHECK(h);
+    const int n = (int)P.nentries;
     if (nparts == 1)
     {
-        /* full pack: the size-sorted positions first.  Rolling parts (nparts > 1) keep the positions of the last full pack:
-         * their entries only shrink or grow a little, the order stays nearly sorted. */
-        const int n = (int)I.nentries;
-        k_entry_sizes<<<(n + 255) / 256, 256, 0, h->stream>>>(I.entries, n, P.sizes);
-        LAUNCH_CHECK(h);
+        /* full pack: execution order by the packed step counts.  Rolling parts (nparts > 1) keep the positions of the last
+         * full pack. */
         NB_CUDA(h, cudaMemsetAsync(h->d_hist, 0, sizeof(int) * 2 * NB_ORDER_BINS, h->stream));
         k_order_hist<<<(n + 255) / 256, 256, 0, h->stream>>>(P.sizes, n, h->d_hist);
         LAUNCH_CHECK(h);
@@ -1500,8 +1531,9 @@ static int launch_pack(b200nb_context* h, int loc, int part, int nparts)
         k_order_assign<<<(n + 255) / 256, 256, 0, h->stream>>>(P.sizes, n, h->d_hist, P.dest);
         LAUNCH_CHECK(h);
     }
-    k_pack<<<nblk, 128, 0, h->stream>>>(I.entries, I.cj, I.mask, I.nentries, part, nparts, h->d_xq, h->d_shift_vec, r2, loc == 0,
-                                        h->dummy_slot, P.pitch, P.dest, P.entries, P.ja, P.mask);
+    k_place_headers<<<(n + 255) / 256, 256, 0, h->stream>>>(P.staged, P.dest, n, P.entries);
+    LAUNCH_CHECK(h);
+    k_pad_partner<<<(n / 2 + 255) / 256, 256, 0, h->stream>>>(P.entries, n / 2, P.ja, h->dummy_slot);
     LAUNCH_CHECK(h);
     h->inner_stale[loc] = true; /* the pruned CLUSTER-PAIR list (introspection only) no longer matches the packed one */
     return 0;
@@ -2329,7 +2361,7 @@ static int launch_step(b200nb_context* h, const float* x_dev, int flags, float* 
         pf.p[1]     = reinterpret_cast<const char*>(P.ja);
         pf.bytes[1] = nb_list_prefetch_bytes(sizeof(int) * 8 * (size_t)P.nentries * P.pitch);
         pf.p[2]     = reinterpret_cast<const char*>(P.mask);
-        pf.bytes[2] = nb_list_prefetch_bytes(sizeof(uint64_t) * (size_t)P.nentries * P.pitch);
+        pf.bytes[2] = nb_list_prefetch_bytes(sizeof(uint64_t) * (size_t)P.nentries * (P.pitch / 2));
         pf.p[3]     = reinterpret_cast<const char*>(h->comb_geom ? (const void*)h->d_lj : (const void*)h->d_atype);
         pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
     }
@@ -2819,7 +2851,7 @@ static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home,
         pf.p[1]     = reinterpret_cast<const char*>(P.ja);
         pf.bytes[1] = nb_list_prefetch_bytes(sizeof(int) * 8 * (size_t)P.nentries * P.pitch);
         pf.p[2]     = reinterpret_cast<const char*>(P.mask);
-        pf.bytes[2] = nb_list_prefetch_bytes(sizeof(uint64_t) * (size_t)P.nentries * P.pitch);
+        pf.bytes[2] = nb_list_prefetch_bytes(sizeof(uint64_t) * (size_t)P.nentries * (P.pitch / 2));
         pf.p[3]     = reinterpret_cast<const char*>(h->comb_geom ? (const void*)h->d_lj : (const void*)h->d_atype);
         pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
     }
@@ -2992,6 +3024,17 @@ extern "C" int b200nb_dd_status(b200nb_t* h)
 /* ------------------------------------------------------------------------------------------------------ */
 /* introspection                                                                                           */
 /* ------------------------------------------------------------------------------------------------------ */
+/* what the force kernel computes on the packed list, in tiles of 8 x 8 pair lanes: a warp runs the half-entries 2w and 2w + 1
+ * in lockstep for the longer one's steps, 128 pair lanes (= 2 tiles) per step */
+__global__ void k_count_packed(const Entry* __restrict__ e, long long nwarps, long long* out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long v = 0;
+    if (i < nwarps) v = 2 * max(e[2 * i].end - e[2 * i].start, e[2 * i + 1].end - e[2 * i + 1].start);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd((unsigned long long*)out, (unsigned long long)v);
+}
+
 __global__ void k_count_tiles(const Entry* __restrict__ e, long long n, long long* out)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -3040,8 +3083,8 @@ extern "C" int b200nb_get_stats(b200nb_t* h, b200nb_stats_t* out)
             {
                 long long v = 0;
                 NB_CUDA(h, cudaMemsetAsync(h->d_counter + 4, 0, sizeof(long long), h->stream));
-                k_count_tiles<<<(unsigned)((h->packed[l].nentries + 255) / 256), 256, 0, h->stream>>>(h->packed[l].entries,
-                                                                                                    h->packed[l].nentries, h->d_counter + 4);
+                k_count_packed<<<(unsigned)((h->packed[l].nentries / 2 + 255) / 256), 256, 0, h->stream>>>(h->packed[l].entries,
+                                                                                                         h->packed[l].nentries / 2, h->d_counter + 4);
                 LAUNCH_CHECK(h);
                 NB_CUDA(h, cudaMemcpyAsync(&v, h->d_counter + 4, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
                 NB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -3094,8 +3137,8 @@ extern "C" long long b200nb_get_tiles(b200nb_t* h, int outer, int* tiles_host, l
 }
 
 /* every interacting atom pair of the PACKED list (what the force kernel consumes): mask bit set, not on/below the
- * diagonal of the i-cluster's own atoms, both atoms real, r^2 < r2 -- the same predicate, step and lane mapping the force
- * kernel applies (lane = j16 + 16*half: j-atom j16 of the step against i-atoms 4*half .. 4*half+3) */
+ * diagonal of the i-cluster's own atoms, both atoms real, r^2 < r2 -- the same predicate and step layout the force kernel
+ * applies.  One warp per half-entry: lane = j16 + 16*kp looks at j-atom j16 of the step against the i-atoms 4*half + 2*kp, + 1 */
 __global__ void __launch_bounds__(128)
 k_pairs(const Entry* __restrict__ ent, const int* __restrict__ pja, const uint64_t* __restrict__ tmask, long long nentries,
         const float* __restrict__ xq, const float* __restrict__ shift_vec, const int* __restrict__ atom_index, int nslots, float r2,
@@ -3103,26 +3146,25 @@ k_pairs(const Entry* __restrict__ ent, const int* __restrict__ pja, const uint64
 {
     const long long e = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (e >= nentries) return;
-    const int   lane = threadIdx.x & 31, j16 = lane & 15, half = lane >> 4;
+    const int   lane = threadIdx.x & 31, j16 = lane & 15, kp = lane >> 4;
     const Entry en   = ent[e];
-    const int   shift = NB_ENTRY_SHIFT(en.shift_nmask), nmask = NB_ENTRY_NMASK(en.shift_nmask);
+    const int   shift = NB_ENTRY_SHIFT(en.shift_nmask), nmask = NB_ENTRY_NMASK(en.shift_nmask), half = NB_ENTRY_HALF(en.shift_nmask);
     const float sx = shift_vec[3 * shift], sy = shift_vec[3 * shift + 1], sz = shift_vec[3 * shift + 2];
-    const int   nstep = (en.end - en.start) >> 1;
+    const int   nstep = en.end - en.start;
     for (int s = 0; s < nstep; s++)
     {
-        const int       js   = pja[(size_t)en.start * 8 + s * 16 + j16];
-        const unsigned* mw   = reinterpret_cast<const unsigned*>(tmask + en.start) + 4 * s;
-        const bool      diag = intra && shift == B200NB_CENTRAL && (js >> 3) == en.ci;
-        const float4    xj   = reinterpret_cast<const float4*>(xq)[js];
-        const int       aj   = js < nslots ? atom_index[js] : -1;
-        for (int k = 0; k < 4; k++)
+        const int      js   = pja[(size_t)(en.start + s) * 16 + j16];
+        const uint64_t m    = s < nmask ? tmask[en.start + s] : ~(uint64_t)0;
+        const bool     diag = intra && shift == B200NB_CENTRAL && (js >> 3) == en.ci;
+        const float4   xj   = reinterpret_cast<const float4*>(xq)[js];
+        const int      aj   = js < nslots ? atom_index[js] : -1;
+        for (int kk = 0; kk < 2; kk++)
         {
-            const int      i  = 4 * half + k;
-            const unsigned m  = s < nmask ? mw[k] : ~0u;
-            const float4   xi = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + i];
-            const float    r  = nb_rsq(xi.x + sx, xi.y + sy, xi.z + sz, xj.x, xj.y, xj.z);
-            const int      ai = atom_index[en.ci * 8 + i];
-            bool ok = (r < r2) && ((m >> lane) & 1u) && ai >= 0 && aj >= 0 && !(diag && (js & 7) <= i);
+            const int    k  = 2 * kp + kk, i = 4 * half + k;
+            const float4 xi = reinterpret_cast<const float4*>(xq)[(size_t)en.ci * 8 + i];
+            const float  r  = nb_rsq(xi.x + sx, xi.y + sy, xi.z + sz, xj.x, xj.y, xj.z);
+            const int    ai = atom_index[en.ci * 8 + i];
+            bool ok = (r < r2) && ((m >> (16 * k + j16)) & 1u) && ai >= 0 && aj >= 0 && !(diag && (js & 7) <= i);
             if (ok)
             {
                 unsigned long long pos = atomicAdd(counter, 1ull);

@@ -45,13 +45,15 @@ struct GridDesc
 struct Entry
 {
     int ci;
-    int shift_nmask; /* bits 0-7 shift index, bits 8-23 number of leading tiles that carry a mask, bit 24 (packed list
-                        only): the entry holds the i-cluster's self tile (Coulomb self term, kernel_outer.h:408-452) */
-    int start, end;  /* tile range */
+    int shift_nmask; /* bits 0-7 shift index, bits 8-23 number of leading tiles that carry a mask; packed list only: bit 24 the
+                        entry holds the i-cluster's self tile (Coulomb self term, kernel_outer.h:408-452), bit 25 which half of
+                        the i-cluster (i-atoms 4*half .. 4*half + 3) the half-entry is for */
+    int start, end;  /* tile range (cluster-pair lists); STEP range (packed list: 16 j slots and one 64-bit mask per step) */
 };
 #define NB_ENTRY_SHIFT(v) ((v)&255)
 #define NB_ENTRY_NMASK(v) (((v) >> 8) & 0xffff)
 #define NB_ENTRY_SELF(v) (((v) >> 24) & 1)
+#define NB_ENTRY_HALF(v) (((v) >> 25) & 1)
 
 struct NbParamsDev
 {
@@ -84,23 +86,28 @@ struct PairList
     size_t    cap_tiles = 0, cap_entries = 0;
 };
 
-/* The list the force kernel consumes: every entry of the (pruned) cluster-pair list re-packed at j-ATOM granularity.
- * A packed tile is 8 j-atom slots (any clusters) against the entry's 8-atom i-cluster; a j-atom is kept only when at
- * least one of its 8 pairs is inside the list radius, which raises the share of in-range lanes from 35 % (8x8 cluster
- * pairs) to 55 % at rlist = rc = 0.9 nm.  j-atoms with an excluded / self pair come first (`nmask` leading tiles carry
- * masks in the same two-word lane format as the cluster-pair list); the tail of the last tile points at far-away
- * dummy atoms, NB_DUMMY_SLOTS of them shared round-robin by the entries (the kernel's zero-valued force reductions
- * for padding lanes then never pile up on one address: same-address reductions serialise in L2). */
+/* The list the force kernel consumes: every entry of the (pruned) cluster-pair list re-packed at j-ATOM granularity, once
+ * per HALF of its i-cluster.  A half-entry is four i-atoms (4*half .. 4*half + 3 of cluster ci) + shift against a run of
+ * j-atom slots (any clusters), 16 per STEP; a j-atom is kept only when at least one of its 4 pairs with the i-quad is inside
+ * the list radius, which raises the share of in-range lanes from 35 % (8x8 cluster pairs) over 54 % (8 i-atoms per j-atom) to
+ * ~63 % at rlist = rc = 0.9 nm.  j-atoms with an excluded / self pair come first (`nmask` leading steps carry a 64-bit mask: bit
+ * 16*k + j = pair (i-atom 4*half + k, j-atom j of the step) interacts); the tail of the last step points at far-away dummy
+ * atoms, NB_DUMMY_SLOTS of them shared round-robin by the entries (the kernel's zero-valued force reductions for padding lanes
+ * then never pile up on one address: same-address reductions serialise in L2).
+ * Half-entry p = 2*e + half of outer entry e is PACKED into the steps [p*pitch/2, (p+1)*pitch/2) of ja / mask (`staged` holds its
+ * header); `entries` holds the same headers sorted by descending step count, and the force kernel gives the half-entries 2w and
+ * 2w + 1 of that order to the two halves of warp w: equal step counts up to the warps that straddle a size boundary, where
+ * k_pad_partner extends the shorter one's j slots with dummy atoms to the longer one's steps. */
 struct PackedList
 {
-    Entry*    entries = nullptr;
-    int*      ja      = nullptr; /* 8 slots per packed tile */
-    uint64_t* mask    = nullptr;
-    int*      dest    = nullptr; /* per entry of the pruned list: its position here (entries are stored largest first) */
-    int*      sizes   = nullptr; /* packed tile count per entry of the pruned list (scratch of the ordering) */
-    long long nentries = 0;
-    int       pitch = 0; /* tiles reserved per entry (= max_tiles_per_entry): entry e owns tiles [e*pitch, (e+1)*pitch), so
-                            the force kernel can fetch an entry's j indices without first reading the entry itself */
+    Entry*    entries = nullptr; /* headers in execution order (largest first) */
+    Entry*    staged  = nullptr; /* headers in packing order */
+    int*      ja      = nullptr; /* 16 slots per step */
+    uint64_t* mask    = nullptr; /* one per step */
+    int*      dest    = nullptr; /* per half-entry in packing order: its position in `entries` */
+    int*      sizes   = nullptr; /* per half-entry in packing order: its steps (the ordering key) */
+    long long nentries = 0;      /* HALF-entries: 2 x the entries of the outer list */
+    int       pitch = 0;         /* tiles of 8 j slots reserved per half-entry (= max_tiles_per_entry, even): pitch/2 steps */
     size_t    cap_tiles = 0, cap_entries = 0;
 };
 
@@ -246,8 +253,6 @@ struct b200nb_context
     int        host_dma = -1;  /* b200nb_compute: 1 = cudaMemcpyAsync staging, 0 = zero-copy kernels, -1 = not decided yet */
     long long  generation = 0; /* bumped whenever a list or halo plan is rebuilt: invalidates the captured graphs */
     bool       use_graphs = true;
-    int        persistent = -1; /* force kernel: 1 = resident warps walking the list (k_force_p), 0 = one CTA per entry, -1 = unset */
-    int        num_sms = 148;
     bool       use_pdl = true; /* launch the force kernel with programmatic stream serialization (see force.cu) */
     bool       capturing = false;
     std::vector<cudaGraphNode_t> nl_nodes; /* kernel nodes captured from the non-local stream (get an explicit priority) */

@@ -7,38 +7,40 @@
  *   kernel_outer.h:395-452 (self terms), simd/simd_math.h:1609-1722 (Ewald correction polynomials).
  *
  * Design (not a port of the reference CUDA kernel), sized with profiles/tools/microbench.cu, the diagnostic builds of
- * profiles/r1/v_sweep_pair_loop_diagnostics.txt and the round-1 ncu source page (profiles/r1/z_ncu_source_regions_*): on
- * sm_100 the FP32 pipe retires 128 lane-FMAs/clk/SM whether issued as scalar FFMA or packed FFMA2; a packed instruction
- * keeps the pipe busy for two cycles, everything else competes for the remaining issue slots.  The round-1 kernel
- * (2 i-atoms x 1 j-atom per lane, 8 j-atoms per tile) spent only 35 of its 68 pair-loop instructions on packed FP32
- * math: the rest was the j-force reduce-scatter over the 4 lanes sharing a j-atom (3 shuffles, 8 selects, 6 scalar FMAs,
- * one red per lane and tile) and, outside the loop, the cp.async staging ring (15 % of all instructions).  This kernel
- * removes both:
- *  - one warp per list entry = one 8-atom i-cluster + shift against a run of PACKED j-atoms (PackedList,
- *    b200nb_internal.h), consumed 16 at a time (a "step" = 2 packed tiles);
- *  - lane = jl + 16*ih owns ONE j-atom of the step (jl) and FOUR i-atoms (4*ih .. 4*ih+3) as two packed float2 pairs
+ * profiles/r1/v_sweep_pair_loop_diagnostics.txt and the ncu source pages under profiles/: on sm_100 the FP32 pipe retires
+ * 128 lane-FMAs/clk/SM whether issued as scalar FFMA or packed FFMA2; a packed instruction keeps the pipe busy for two
+ * cycles, everything else competes for the remaining issue slots.
+ *  - the unit of the list is a HALF-ENTRY: four i-atoms (one half of an 8-atom i-cluster) + shift against a run of PACKED
+ *    j-atoms (PackedList, b200nb_internal.h) -- the j-atoms that have at least one of their FOUR pairs inside the list radius.
+ *    Packing per i-quad instead of per i-cluster raises the share of in-range lanes from 54 % to ~63 %: the one lever that
+ *    removes FP32 work instead of overhead;
+ *  - one warp runs TWO half-entries side by side, lanes 0-15 the first, lanes 16-31 the second; they are neighbours in the
+ *    size-sorted list, so they have the same number of steps (a step = 16 j-atoms per half-entry) up to the few warps that
+ *    straddle a size boundary; a half that runs out first continues on far-away dummy atoms;
+ *  - lane = jl + 16*ih owns ONE j-atom per step (jl of its half-entry's list) and FOUR i-atoms as two packed float2 pairs
  *    held in registers for the whole entry.  All pair arithmetic is packed (fma.rn.f32x2 -> FFMA2/FMUL2), the j operands
- *    enter in the scalar-broadcast operand form.  The j-atom's data (16-byte xyzq, 8-byte LJ pair) are loaded straight
- *    into the lane's registers with one LDG.128 + one LDG.64, one step AHEAD of their use (the slot index two steps
- *    ahead), so a step's loads have 4 pair evaluations (~200 instructions per warp, x the resident warps) to land:
- *    no shared memory, no cp.async, no staging code;
- *  - j-forces: accumulated in the lane over its 4 pairs with the same packed FMAs that feed the i accumulators, then ONE
- *    exchange with the other half-warp per step (2 shuffles) and one red per lane (half 0: red.v2 {x,y}, half 1: red z):
- *    per 64 pairs 1 shuffle + 0.5 red instead of 3 shuffles + 1 red + 14 ALU / scalar-FMA instructions;
- *  - i-forces stay in registers (12 floats per lane); per entry one transposed butterfly over the 16 lanes of the half
+ *    enter in the scalar-broadcast operand form;
+ *  - the j-atom's data (16-byte xyzq, 8-byte LJ pair, slot index) stream through a per-lane cp.async ring in shared memory
+ *    (see gather_j): no register holds data in flight, no cross-lane hand-over, no barrier;
+ *  - j-forces: accumulated in the lane over its 4 pairs with the same packed FMAs that feed the i accumulators and
+ *    reduced by the lane itself (red.v2 {x, y} + red {z}): the two halves of a warp hold different j-atoms, so there is no
+ *    exchange (the cluster-granular layout needed 2 shuffles + 5 selects / negations per step to share a j-atom between halves);
+ *  - i-forces stay in registers (12 floats per lane); per half-entry one transposed butterfly over its 16 lanes
  *    (15 shuffles) and one 16-byte red per i-atom;
- *  - steps that carry exclusion masks are sorted to the front of an entry (k_pack) and run through a separate code
+ *  - steps that carry exclusion masks are sorted to the front of a half-entry (k_pack) and run through a separate code
  *    path; the unmasked path has no mask logic and no r^2 clamp;
  *  - LJ is evaluated as (c12*r^-6 - c6)*r^-6, the Ewald correction polynomials keep their coefficients as
  *    instruction immediates; out-of-range lanes are discarded by select, so garbage there cannot poison a sum;
  *  - r^2 is evaluated with the reference's operand roles and operation order so the in-range pair set is
  *    bit-identical (see nb_rsq in b200nb_internal.h);
  *  - TMA (cp.async.bulk / tile::gather4) is not used: the j stream is a gather of single 16-byte atoms by slot index
- *    whose consumer is ONE lane; a per-lane LDG.128 delivers it into that lane's registers with no barrier, no shared
- *    memory round trip and no elected-thread issue; gather4 moves rows of a 2-D tensor into shared memory, from where
- *    every lane would have to fetch its own row again;
+ *    whose consumer is ONE lane; a per-lane cp.async delivers it into that lane's record with no barrier and no
+ *    elected-thread issue; gather4 moves rows of a 2-D tensor into shared memory for a whole CTA and needs an mbarrier
+ *    round trip per stage;
  *  - LJ force switch / potential switch / VdW cut-off below the Coulomb cut-off / LJ-PME are a second set of
  *    instantiations (GEN): the plain kernels, which every BASELINE configuration uses, pay nothing for them.
+ * Measured and dropped (profiles/r2/k_*): a persistent form with cross-entry pipelining (k_force_p) --
+ * it removed the per-entry latency and was 25-30 % slower by its extra bookkeeping instructions.
  */
 #include <algorithm>
 #include <cstdio>
@@ -89,7 +91,7 @@ struct JAtom
     int    slot; /* grid slot of the j-atom: index into xq / f */
 };
 
-#define NB_JSTEP 16 /* j-atoms per step = 2 packed tiles: lanes jl and jl + 16 share j-atom jl */
+#define NB_JSTEP 16 /* j-atoms per step of a half-entry: lane jl + 16*ih holds j-atom jl of the step of half-entry ih of the warp */
 #ifndef NB_RING
 #define NB_RING 4 /* stages of the per-warp j-atom ring in shared memory: a step's gather is issued NB_RING - 1 steps ahead */
 #endif
@@ -401,25 +403,25 @@ __device__ __forceinline__ float2 pair_fscal(const IData& I, const JAtom& J, con
 }
 
 /* j-force of a step: the lane's packed accumulators hold, per component, the sums over its even (.x) and odd (.y) i-atoms
- * of F/r * d (the force ON THE i-ATOMS); the force on the j-atom is minus their sum plus the other half-warp's share.
- * One exchange: half 0 hands over z and gets x, both get each other's y; then one red.v2 per lane into the j-atom's float4
- * force slot: 2 shuffles + 1 red per 128 pairs. */
-__device__ __forceinline__ void reduce_store_j(const float2 fjx, const float2 fjy, const float2 fjz, const bool upper, float4* __restrict__ f,
-                                               const int jslot)
+ * of F/r * d (the force ON THE i-ATOMS); the force on the lane's j-atom is minus their sum.  Every lane has its own j-atom, so
+ * it reduces all three components itself with ONE 16-byte red into the j-atom's float4 force slot.  Measured
+ * (profiles/r2/q_sweep_half_entries.txt): red.v2 {x, y} + red {z} saves the fourth, useless add in L2 but doubles the L2 requests
+ * and is 12 % slower at 1 M atoms (B200NB_JRED_SPLIT builds it). */
+__device__ __forceinline__ void reduce_store_j(const float2 fjx, const float2 fjy, const float2 fjz, float4* __restrict__ f, const int jslot)
 {
-    const unsigned full = 0xffffffffu;
-    const float    sx = -fjx.x - fjx.y, sy = -fjy.x - fjy.y, sz = -fjz.x - fjz.y;
-    const float    rcv = __shfl_xor_sync(full, upper ? sx : sz, 16);
-    const float    rcy = __shfl_xor_sync(full, sy, 16);
-    /* every lane issues the SAME instruction: half 0 adds {x, y} to the slot's first two floats, half 1 {z, 0} to the last two
-     * (the pad float of the float4 slot is never read).  Two predicated reds compiled to two divergent branches with
-     * BSSY / BSYNC around each: 6 more instructions per step. */
-    float* const fp = reinterpret_cast<float*>(f + jslot) + (upper ? 2 : 0);
-    const float  a  = (upper ? sz : sx) + rcv, b = upper ? 0.0f : sy + rcy;
+    const float  sx = -fjx.x - fjx.y, sy = -fjy.x - fjy.y, sz = -fjz.x - fjz.y;
+    float* const fp = reinterpret_cast<float*>(f + jslot);
 #ifdef B200NB_DIAG_NO_RED /* diagnostic build only: drops the j-force scatter (wrong results) to measure its cost */
-    if (rcv == 12345.678f)
+    if (sx == 12345.678f)
 #endif
-        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(fp), "f"(a), "f"(b) : "memory");
+    {
+#ifndef B200NB_JRED_SPLIT
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(fp), "f"(sx), "f"(sy), "f"(sz), "f"(0.0f) : "memory");
+#else
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(fp), "f"(sx), "f"(sy) : "memory");
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(fp + 2), "f"(sz) : "memory");
+#endif
+    }
 }
 
 #ifndef B200NB_FORCE_WARPS
@@ -433,44 +435,54 @@ __device__ __forceinline__ void reduce_store_j(const float2 fjx, const float2 fj
 #endif
 template<int EEL, bool GEOM, bool VF, bool GEN>
 __global__ void __launch_bounds__(32 * B200NB_FORCE_WARPS, B200NB_FORCE_MIN_BLOCKS(VF, GEN))
-k_force(const Entry* __restrict__ entries, long long nentries, const int* __restrict__ pja, const uint64_t* __restrict__ tmask,
+k_force(const Entry* __restrict__ entries, long long nwarps, const int* __restrict__ pja, const uint64_t* __restrict__ tmask,
         const float4* __restrict__ xq, const float2* __restrict__ lj, const int* __restrict__ atype, const float2* __restrict__ nbfp,
         const float* __restrict__ shift_vec, float4* __restrict__ f, float* __restrict__ fshift, double* __restrict__ energy,
-        const __grid_constant__ NbParamsDev P, const int intra, const int maxt, const float* __restrict__ kconst,
+        const __grid_constant__ NbParamsDev P, const int intra, const float* __restrict__ kconst,
         const float2* __restrict__ nbfp_comb)
 {
-    const long long e = (long long)blockIdx.x * B200NB_FORCE_WARPS + (threadIdx.x >> 5);
-    if (e >= nentries) return;
-    const int lane = threadIdx.x & 31, jl = lane & (NB_JSTEP - 1), ih = lane >> 4;
-    /* Entry e owns the packed tiles [e*maxt, (e+1)*maxt) (maxt = the list's pitch), i.e. j slots ja[0 .. 8*ntile), ntile even */
-    const int* const ja = pja + (size_t)e * maxt * 8;
-    const int4       ev = __ldg(reinterpret_cast<const int4*>(entries) + e);
+    const long long w = (long long)blockIdx.x * B200NB_FORCE_WARPS + (threadIdx.x >> 5);
+    if (w >= nwarps) return;
+    const int      lane = threadIdx.x & 31, jl = lane & (NB_JSTEP - 1), ih = lane >> 4;
+    const unsigned full = 0xffffffffu;
+    /* Warp w runs the half-entries 2w (lanes 0-15) and 2w + 1 (lanes 16-31) of the size-sorted list.  Both headers are loaded
+     * by every lane (two broadcast loads from warp-uniform addresses), so that the step counts bounding the loops are provably
+     * warp-uniform for the compiler (uniform datapath, no divergence bookkeeping around the loop bodies); everything else that
+     * derives from a header is a per-HALF value picked by ih. */
+    const int4 evA = __ldg(reinterpret_cast<const int4*>(entries) + 2 * w), evB = __ldg(reinterpret_cast<const int4*>(entries) + 2 * w + 1);
+    const int4 ev  = ih ? evB : evA;
     KConst K;
     {
         const float4 k0 = __ldg(reinterpret_cast<const float4*>(kconst)), k1 = __ldg(reinterpret_cast<const float4*>(kconst) + 1),
                      k2 = __ldg(reinterpret_cast<const float4*>(kconst) + 2);
         K.rc2 = k0.x, K.beta2 = k0.z, K.fd4 = k0.w, K.fd3 = k1.x, K.fn6 = k1.y, K.fn5 = k1.z, K.fd2 = k1.w, K.fd1 = k2.x, K.fd0 = k2.y;
     }
-    const int nstep = (ev.w - ev.z) >> 1;
-    /* the j slots of the first NB_RING steps: list data only, so they may be fetched before the dependency wait below */
+    /* the half-entry owns the steps [ev.z, ev.w) of the j-slot array (16 slots per step) and of the mask array (64 bits per step) */
+    const int nstep_my = ev.w - ev.z;
+    const int nstep    = max(evA.w - evA.z, evB.w - evB.z);
+    /* this lane's slot of step k is ja[16 k].  A half-entry that is shorter than the one sharing its warp runs the difference on
+     * far-away dummy atoms: k_pad_partner (b200nb.cu) has written their slots behind its own steps, so the loops below need no
+     * per-half bounds -- only the mask fetch and the outputs look at nstep_my */
+    const int* const ja = pja + (size_t)ev.z * NB_JSTEP + jl;
+    /* the j slots of the first NB_RING - 1 steps: list data only, so they may be fetched before the dependency wait below */
     int slot_first[NB_RING - 1];
 #pragma unroll
-    for (int k = 0; k < NB_RING - 1; k++) slot_first[k] = k < nstep ? __ldg(ja + k * NB_JSTEP + jl) : 0;
+    for (int k = 0; k < NB_RING - 1; k++) slot_first[k] = k < nstep ? __ldg(ja + k * NB_JSTEP) : 0;
     /* Programmatic dependent launch: everything above reads only the list; from here on the kernel touches xq and f, so wait
      * for the completion of the preceding kernel of the stream (k_step_begin) -- a no-op for a normally serialised launch. */
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const bool self = VF && NB_ENTRY_SELF(ev.y);
-    if (nstep == 0 && !self) return;
-    const int      ci = ev.x, shift = NB_ENTRY_SHIFT(ev.y), nmask = NB_ENTRY_NMASK(ev.y);
-    const unsigned full = 0xffffffffu;
-    const bool     upper = ih != 0;
+    if (nstep == 0 && !(VF && (NB_ENTRY_SELF(evA.y) || NB_ENTRY_SELF(evB.y)))) return;
+    const int  ci = ev.x, shift = NB_ENTRY_SHIFT(ev.y), half = NB_ENTRY_HALF(ev.y);
+    const int  nmask_my = min(NB_ENTRY_NMASK(ev.y), nstep_my);
+    const int  nmask    = max(min(NB_ENTRY_NMASK(evA.y), evA.w - evA.z), min(NB_ENTRY_NMASK(evB.y), evB.w - evB.z));
     /* the ring: NB_RING stages of 1 KB per warp; one commit group per step, empty past the end of the entry */
     __shared__ __align__(16) float4 s_ring[B200NB_FORCE_WARPS][NB_RING][64];
     const unsigned ring = (unsigned)__cvta_generic_to_shared(&s_ring[threadIdx.x >> 5][0][0]) + 16u * lane;
 #pragma unroll
     for (int k = 0; k < NB_RING - 1; k++)
     {
-        if (k < nstep) gather_j<GEOM>(ring + 1024u * k, slot_first[k], k + NB_RING - 1 < nstep ? ja + (k + NB_RING - 1) * NB_JSTEP + jl : nullptr, xq, lj, atype);
+        if (k < nstep) gather_j<GEOM>(ring + 1024u * k, slot_first[k], k + NB_RING - 1 < nstep ? ja + (k + NB_RING - 1) * NB_JSTEP : nullptr, xq, lj, atype);
         cp_async_commit();
     }
     IData I[2];
@@ -479,7 +491,7 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
 #pragma unroll
         for (int p = 0; p < 2; p++)
         {
-            const size_t ia = (size_t)ci * 8 + 4 * ih + 2 * p;
+            const size_t ia = (size_t)ci * 8 + 4 * half + 2 * p;
             const float4 a = __ldg(xq + ia), b = __ldg(xq + ia + 1);
             /* the reference adds the shift to the i-atom before the subtraction: kernel_outer.h:482-489 */
             I[p].x = make_float2(__fadd_rn(a.x, sx), __fadd_rn(b.x, sx));
@@ -513,7 +525,7 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
     float  evdw = 0.f, ecoul = 0.f;
     if (self && jl < 4)
     {
-        /* Coulomb self term, once per i-atom (lane jl of each half takes i-atom 4*ih + jl): kernel_outer.h:408-452
+        /* Coulomb self term, once per i-atom (lane jl of the half-entry takes i-atom 4*half + jl): kernel_outer.h:408-452
          * (fillers carry q = 0) */
         const float2 qp = (jl & 2) ? I[1].q : I[0].q;
         const float  qi = (jl & 1) ? qp.y : qp.x;
@@ -526,11 +538,11 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
             evdw += 0.5f * __ldg(nbfp + ti + ti / P.ntypes).x * (1.0f / 6.0f) * P.lje_coeff6_6;
         }
     }
-    /* masks of the leading steps: 4 words per step, bit `lane` of word k = pair (i-atom 4*ih + k, j-atom jl) interacts */
-    const uint4* const emask = reinterpret_cast<const uint4*>(tmask + (size_t)e * maxt);
+    /* masks of the leading steps: 64 bits per step, bit 16*k + jl = pair (i-atom 4*half + k, j-atom jl) interacts */
+    const uint2* const emask = reinterpret_cast<const uint2*>(tmask) + ev.z;
     int                s     = 0;
-    const int*         jp    = ja + 2 * (NB_RING - 1) * NB_JSTEP + jl; /* slot index of step s + 2 (NB_RING - 1) */
-    unsigned           st_use = 0, st_fill = (NB_RING - 1) * 1024u;     /* ring offsets of step s and of step s + NB_RING - 1 */
+    const int*         jp    = ja + 2 * (NB_RING - 1) * NB_JSTEP; /* slot index of step s + 2 (NB_RING - 1) */
+    unsigned           st_use = 0, st_fill = (NB_RING - 1) * 1024u; /* ring offsets of step s and of step s + NB_RING - 1 */
     /* Top of step s: the gathers of steps s .. s + NB_RING - 2 are in flight (one commit group each).  next_j() waits for the
      * group of step s, reads its record (the j-atom and the slot index of step s + NB_RING - 1) and starts the gather of step
      * s + NB_RING - 1 into the stage step s - 1 just released, together with the fetch of the slot index of step
@@ -545,12 +557,13 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
         st_fill = (st_fill + 1024u) & (NB_RING * 1024u - 1);
     };
 
-    /* ---- steps with exclusion masks (sorted to the front of the entry; one or two per entry) ---- */
-    for (const int sm = min(nmask, nstep); s < sm; s++)
+    /* ---- steps with exclusion masks (sorted to the front of a half-entry; one or two per half-entry) ---- */
+    for (; s < nmask; s++)
     {
         JAtom J;
         next_j(J);
-        const uint4 m = __ldg(emask + s);
+        uint2 m = make_uint2(~0u, ~0u);
+        if (s < nmask_my) m = __ldg(emask + s);
         /* j-atom of the i-cluster itself: only j > i (nbnxm/pairlist.cpp:880-904, kernel_gpu_ref.cpp:223-226) */
         const bool diag = intra && shift == B200NB_CENTRAL && (J.slot >> 3) == ci;
         const int  jin  = J.slot & 7;
@@ -558,9 +571,9 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
 #pragma unroll
         for (int p = 0; p < 2; p++)
         {
-            const unsigned w0 = p ? m.z : m.x, w1 = p ? m.w : m.y;
-            const float    in0 = (float)((w0 >> lane) & 1u), in1 = (float)((w1 >> lane) & 1u);
-            const bool     ok0 = !diag || jin > 4 * ih + 2 * p, ok1 = !diag || jin > 4 * ih + 2 * p + 1;
+            const unsigned wd  = p ? m.y : m.x;
+            const float    in0 = (float)((wd >> jl) & 1u), in1 = (float)((wd >> (16 + jl)) & 1u);
+            const bool     ok0 = !diag || jin > 4 * half + 2 * p, ok1 = !diag || jin > 4 * half + 2 * p + 1;
             float2         dx, dy, dz;
             NB_LOAD_I(Ip, p)
             const float2   fs = pair_fscal<EEL, GEOM, VF, true, GEN>(Ip, J, P, K, nbfp, nbfp_comb, in0, in1, ok0, ok1, dx, dy, dz, evdw, ecoul);
@@ -571,7 +584,7 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
             fjy    = fma2(fs, dy, fjy);
             fjz    = fma2(fs, dz, fjz);
         }
-        reduce_store_j(fjx, fjy, fjz, upper, f, J.slot);
+        reduce_store_j(fjx, fjy, fjz, f, J.slot);
     }
     /* ---- plain steps ---- */
     for (; s < nstep; s++)
@@ -595,7 +608,7 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
 #endif
         }
 #ifndef B200NB_DIAG_NO_JFORCE
-        reduce_store_j(fjx, fjy, fjz, upper, f, J.slot);
+        reduce_store_j(fjx, fjy, fjz, f, J.slot);
 #endif
     }
     /* ---- i-forces: 12 floats per lane (2 pairs x 2 atoms x 3) summed over the 16 j-lanes of this half (lane bits 0-3),
@@ -623,30 +636,24 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
     kx += __shfl_xor_sync(full, kx, 1);
     ky += __shfl_xor_sync(full, ky, 1);
     kz += __shfl_xor_sync(full, kz, 1);
-    /* the lanes with bits 0-1 clear hold the total force on i-atom 4*ih + 2*b3 + b2 */
-    if ((lane & 3) == 0 && nstep > 0) atomicAdd(f + ((size_t)ci * 8 + 4 * ih + 2 * (int)b3 + (int)b2), make_float4(kx, ky, kz, 0.f));
+    /* the lanes with bits 0-1 clear hold the total force on i-atom 4*half + 2*b3 + b2 of their half-entry */
+    if ((lane & 3) == 0 && nstep_my > 0) atomicAdd(f + ((size_t)ci * 8 + 4 * half + 2 * (int)b3 + (int)b2), make_float4(kx, ky, kz, 0.f));
     if (VF)
     {
-        /* shift force = sum of the i-forces of this entry (kernel_outer.h:620-640; the CUDA kernel skips the central
-         * shift, nbnxm_cuda_kernel.cuh:624-628) */
-        if (shift != B200NB_CENTRAL)
+        /* shift force = sum of the i-forces of a half-entry (kernel_outer.h:620-640; the CUDA kernel skips the central
+         * shift, nbnxm_cuda_kernel.cuh:624-628): summed over the 16 lanes of the half, the two halves may carry different shifts */
+        kx += __shfl_xor_sync(full, kx, 4);
+        ky += __shfl_xor_sync(full, ky, 4);
+        kz += __shfl_xor_sync(full, kz, 4);
+        kx += __shfl_xor_sync(full, kx, 8);
+        ky += __shfl_xor_sync(full, ky, 8);
+        kz += __shfl_xor_sync(full, kz, 8);
+        if (jl == 0 && shift != B200NB_CENTRAL && nstep_my > 0)
         {
-            kx += __shfl_xor_sync(full, kx, 4);
-            ky += __shfl_xor_sync(full, ky, 4);
-            kz += __shfl_xor_sync(full, kz, 4);
-            kx += __shfl_xor_sync(full, kx, 8);
-            ky += __shfl_xor_sync(full, ky, 8);
-            kz += __shfl_xor_sync(full, kz, 8);
-            kx += __shfl_xor_sync(full, kx, 16);
-            ky += __shfl_xor_sync(full, ky, 16);
-            kz += __shfl_xor_sync(full, kz, 16);
-            if (lane == 0)
-            {
-                float* fs = fshift + (int)(e & (NB_OUT_COPIES - 1)) * NB_FSHIFT_PITCH + 3 * shift;
-                atomicAdd(fs, kx);
-                atomicAdd(fs + 1, ky);
-                atomicAdd(fs + 2, kz);
-            }
+            float* fs = fshift + (int)(w & (NB_OUT_COPIES - 1)) * NB_FSHIFT_PITCH + 3 * shift;
+            atomicAdd(fs, kx);
+            atomicAdd(fs + 1, ky);
+            atomicAdd(fs + 2, kz);
         }
         for (int o = 16; o > 0; o >>= 1)
         {
@@ -655,315 +662,9 @@ k_force(const Entry* __restrict__ entries, long long nentries, const int* __rest
         }
         if (lane == 0)
         {
-            double* en = energy + 2 * (int)(e & (NB_OUT_COPIES - 1));
+            double* en = energy + 2 * (int)(w & (NB_OUT_COPIES - 1));
             atomicAdd(en, (double)evdw);
             atomicAdd(en + 1, (double)ecoul);
-        }
-    }
-}
-
-/* ------------------------------------------------------------------------------------------------------------------------
- * EXPERIMENT, kept selectable (B200NB_PERSISTENT=1), parity-tested, not the default: see launch() for the measurement.
- * The persistent form of the kernel above: one warp per CTA as before, but only as many CTAs as the GPU keeps resident
- * (148 SMs x the resident warps of the build), each walking the entries w, w + G, w + 2G, ... of the size-sorted list (G = grid
- * size: every warp gets the same mix of sizes).  What an entry costs on top of its steps in k_force -- a chain of dependent
- * loads (entry -> i-atoms; slot indices -> first gathers), the ring filling up and draining: a third of the warp-time at
- * 192 k atoms, profiles/r2/d_ncu_source_k_force_water192k.txt -- is taken off the critical path:
- *  - the j-atom ring never drains: the gather cursor runs NB_RING - 1 steps ahead of the use cursor ACROSS entry boundaries;
- *  - everything the gather cursor needs of an entry arrives in shared memory before it gets there, by cp.async issued one or
- *    two entries earlier: the 16-byte entry header (two entries ahead), the entry's slot indices (one entry ahead);
- *  - the i-atoms (coordinates, LJ parameters) and the masks of the entry's leading steps are requested when the gather cursor
- *    enters the entry, NB_RING - 1 steps before the use cursor does, and wait in shared memory;
- *  - an entry without steps (everything pruned away) runs one step on far-away dummy atoms, so that every entry advances both
- *    cursors and the bookkeeping has no special cases.
- * Completion is tracked with the one-commit-group-per-step scheme of k_force; the only extra waits are a full drain when the
- * previous entry was shorter than the ring (its successors' data may still be in flight) and one __syncwarp per entry (the
- * staged data are written by other lanes of the warp). */
-#define NB_P_MAXSTEPS (NB_MAX_ENTRY_TILES / 2) /* steps (16 j-atoms) per entry at most */
-struct PStage /* shared memory of one persistent warp */
-{
-    float4 ring[NB_RING][64];          /* j-atom records, as in k_force */
-    int    idx[2][NB_P_MAXSTEPS * 16]; /* slot indices of the entry the gather cursor is in / the next one */
-    int4   hdr[8];                     /* entry headers, by entry ordinal & 7 */
-    float4 ixq[4][8];                  /* i-atoms of the entries between the two cursors, by ordinal & 3 */
-    float2 ilj[4][8];                  /* their LJ parameters (geometric rule) or atom type in .x (type table) */
-    uint4  msk[4][4];                  /* masks of their first 4 steps */
-};
-
-template<int EEL, bool GEOM, bool VF, bool GEN>
-__global__ void __launch_bounds__(32, B200NB_FORCE_MIN_BLOCKS(VF, GEN))
-k_force_p(const Entry* __restrict__ entries, long long nentries, const int* __restrict__ pja, const uint64_t* __restrict__ tmask,
-          const float4* __restrict__ xq, const float2* __restrict__ lj, const int* __restrict__ atype, const float2* __restrict__ nbfp,
-          const float* __restrict__ shift_vec, float4* __restrict__ f, float* __restrict__ fshift, double* __restrict__ energy,
-          const __grid_constant__ NbParamsDev P, const int intra, const int maxt, const float* __restrict__ kconst,
-          const float2* __restrict__ nbfp_comb, const int dummy_slot)
-{
-    __shared__ __align__(16) PStage S;
-    const long long w = blockIdx.x, G = gridDim.x;
-    if (w >= nentries) return;
-    const int      n_my = (int)((nentries - w + G - 1) / G); /* entries of this warp: ordinals 0 .. n_my - 1 */
-    const int      lane = threadIdx.x & 31, jl = lane & (NB_JSTEP - 1), ih = lane >> 4;
-    const unsigned full = 0xffffffffu;
-    const bool     upper = ih != 0;
-    const unsigned ring = (unsigned)__cvta_generic_to_shared(&S.ring[0][0]) + 16u * lane;
-    KConst K;
-    {
-        const float4 k0 = __ldg(reinterpret_cast<const float4*>(kconst)), k1 = __ldg(reinterpret_cast<const float4*>(kconst) + 1),
-                     k2 = __ldg(reinterpret_cast<const float4*>(kconst) + 2);
-        K.rc2 = k0.x, K.beta2 = k0.z, K.fd4 = k0.w, K.fd3 = k1.x, K.fn6 = k1.y, K.fn5 = k1.z, K.fd2 = k1.w, K.fd1 = k2.x, K.fd0 = k2.y;
-    }
-    auto entry_of = [&](int k) { return w + (long long)k * G; };
-    /* ---- staging requests (cp.async; they join the commit group that is open when they are issued) ---- */
-    auto req_header = [&](int k) {
-        if (k < n_my && lane == 0) cp_async_16((unsigned)__cvta_generic_to_shared(&S.hdr[k & 7]), entries + entry_of(k));
-    };
-    auto req_indices = [&](int k) { /* needs hdr(k) */
-        if (k >= n_my) return;
-        const int4 hv     = S.hdr[k & 7];
-        const int  nchunk = ((hv.w - hv.z) >> 1) * 4; /* 16-byte chunks: 64 bytes per step */
-        const int* src    = pja + (size_t)entry_of(k) * maxt * 8;
-        for (int c = lane; c < nchunk; c += 32) cp_async_16((unsigned)__cvta_generic_to_shared(&S.idx[k & 1][4 * c]), src + 4 * c);
-    };
-    auto req_iatoms = [&](int k, const int4 hv) { /* i-atoms and leading masks of entry k */
-        const size_t ia = (size_t)hv.x * 8;
-        if (lane < 8) cp_async_16((unsigned)__cvta_generic_to_shared(&S.ixq[k & 3][lane]), xq + ia + lane);
-        else if (lane < 16)
-        {
-            if (GEOM) cp_async_8((unsigned)__cvta_generic_to_shared(&S.ilj[k & 3][lane - 8]), lj + ia + lane - 8);
-            else cp_async_4((unsigned)__cvta_generic_to_shared(&S.ilj[k & 3][lane - 8]), atype + ia + lane - 8);
-        }
-        else if (lane < 20 && lane - 16 < min(NB_ENTRY_NMASK(hv.y), 4))
-            cp_async_16((unsigned)__cvta_generic_to_shared(&S.msk[k & 3][lane - 16]), tmask + (size_t)entry_of(k) * maxt + 2 * (lane - 16));
-    };
-
-    /* ---- list-only staging before the dependency wait: the first three headers, then the first entry's indices ---- */
-    req_header(0), req_header(1), req_header(2);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncwarp();
-    req_indices(0);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncwarp();
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-
-    /* ---- the gather cursor ---- */
-    int      kg = -1, sg = 0, nstep_g = 0, ngath_g = 0; /* entry ordinal, step in it, its (effective) steps, gathers issued in it */
-    unsigned st_fill = 0;
-    bool     prologue = true;
-    auto gather_step = [&]() { /* issues the gather of the next step of the stream (if any) and closes one commit group */
-        if (kg < n_my && sg >= nstep_g)
-        {
-            /* enter the next entry: its header and indices, and the header after it, were requested at least one entry ago; they
-             * are known complete if that entry ran >= NB_RING - 1 steps through the per-step waits of the main loop */
-            const int k = kg + 1;
-            if (k < n_my)
-            {
-                if (prologue || ngath_g < NB_RING - 1) cp_async_wait<0>();
-                __syncwarp();
-                const int4 hv = S.hdr[k & 7];
-                req_iatoms(k, hv);
-                req_indices(k + 1);
-                req_header(k + 3);
-                nstep_g = max((hv.w - hv.z) >> 1, 1); /* an empty entry runs one step on dummy atoms */
-                sg      = 0;
-                ngath_g = 0;
-            }
-            kg = k;
-        }
-        if (kg < n_my)
-        {
-            const int4 hv   = S.hdr[kg & 7];
-            const int  slot = sg < ((hv.w - hv.z) >> 1) ? S.idx[kg & 1][sg * NB_JSTEP + jl] : dummy_slot + jl;
-            gather_j<GEOM>(ring + st_fill, slot, nullptr, xq, lj, atype);
-            st_fill = (st_fill + 1024u) & (NB_RING * 1024u - 1);
-            sg++;
-            ngath_g++;
-        }
-        cp_async_commit();
-    };
-    /* req_header(k + 3) above keeps three headers ahead; the first three were requested before the loop, so ordinal 3 onward */
-#pragma unroll 1
-    for (int k = 0; k < NB_RING - 1; k++) gather_step();
-    prologue = false;
-
-    /* ---- the use cursor ---- */
-    IData    I[2];
-    float2   fix[2], fiy[2], fiz[2];
-    float    evdw = 0.f, ecoul = 0.f;
-    int      ci = 0, shift = 0, nmask = 0, nstep = 0, su = 0;
-    long long e = 0;
-    unsigned st_use = 0;
-#pragma unroll 1
-    for (int ku = 0; ku < n_my; ku++)
-    {
-        /* -- entry prologue: the group of the entry's first step (and with it its i-atoms and masks) is complete after this wait -- */
-        cp_async_wait<NB_RING - 2>();
-        __syncwarp();
-        {
-            const int4 hv = S.hdr[ku & 7];
-            e             = entry_of(ku);
-            ci = hv.x, shift = NB_ENTRY_SHIFT(hv.y), nmask = NB_ENTRY_NMASK(hv.y);
-            nstep              = (hv.w - hv.z) >> 1;
-            const bool  self   = VF && NB_ENTRY_SELF(hv.y);
-            const float sx = __ldg(shift_vec + 3 * shift), sy = __ldg(shift_vec + 3 * shift + 1), sz = __ldg(shift_vec + 3 * shift + 2);
-#pragma unroll
-            for (int p = 0; p < 2; p++)
-            {
-                const int    i0 = 4 * ih + 2 * p;
-                const float4 a = S.ixq[ku & 3][i0], b = S.ixq[ku & 3][i0 + 1];
-                /* the reference adds the shift to the i-atom before the subtraction: kernel_outer.h:482-489 */
-                I[p].x = make_float2(__fadd_rn(a.x, sx), __fadd_rn(b.x, sx));
-                I[p].y = make_float2(__fadd_rn(a.y, sy), __fadd_rn(b.y, sy));
-                I[p].z = make_float2(__fadd_rn(a.z, sz), __fadd_rn(b.z, sz));
-                I[p].q = make_float2(P.epsfac * a.w, P.epsfac * b.w);
-                I[p].g0 = I[p].g1 = dup(0.0f);
-                const float2 la = S.ilj[ku & 3][i0], lb = S.ilj[ku & 3][i0 + 1];
-                if (GEOM)
-                {
-                    I[p].c6n       = make_float2(-la.x, -lb.x);
-                    I[p].c12       = make_float2(la.y, lb.y);
-                    I[p].t0 = I[p].t1 = 0;
-                }
-                else
-                {
-                    const int ta = __float_as_int(la.x), tb = __float_as_int(lb.x);
-                    I[p].t0      = ta * P.ntypes;
-                    I[p].t1      = tb * P.ntypes;
-                    I[p].c6n = I[p].c12 = dup(0.0f);
-                    if (GEN && P.ljpme)
-                    {
-                        I[p].g0 = __ldg(nbfp_comb + ta);
-                        I[p].g1 = __ldg(nbfp_comb + tb);
-                    }
-                }
-                fix[p] = fiy[p] = fiz[p] = dup(0.f);
-            }
-            if (VF)
-            {
-                evdw = ecoul = 0.f;
-                if (self && jl < 4)
-                {
-                    /* Coulomb self term, once per i-atom (lane jl of each half takes i-atom 4*ih + jl): kernel_outer.h:408-452 */
-                    const float2 qp = (jl & 2) ? I[1].q : I[0].q;
-                    const float  qi = (jl & 1) ? qp.y : qp.x;
-                    ecoul -= qi * qi * P.self_q2;
-                    if (GEN && !GEOM && P.ljpme)
-                    {
-                        const int ta = (jl & 2) ? I[1].t0 : I[0].t0, tb = (jl & 2) ? I[1].t1 : I[0].t1;
-                        const int ti = (jl & 1) ? tb : ta;
-                        evdw += 0.5f * __ldg(nbfp + ti + ti / P.ntypes).x * (1.0f / 6.0f) * P.lje_coeff6_6;
-                    }
-                }
-            }
-        }
-        const uint4* const emask = reinterpret_cast<const uint4*>(tmask + (size_t)e * maxt);
-        const int          nrun  = max(nstep, 1);
-#pragma unroll 1
-        for (su = 0; su < nrun; su++)
-        {
-            if (su > 0) cp_async_wait<NB_RING - 2>();
-            JAtom J;
-            read_j(J, ring + st_use);
-            st_use = (st_use + 1024u) & (NB_RING * 1024u - 1);
-            gather_step();
-            float2 fjx = dup(0.f), fjy = dup(0.f), fjz = dup(0.f);
-            if (su < nmask)
-            {
-                const uint4 m = su < 4 ? S.msk[ku & 3][su] : __ldg(emask + su);
-                /* j-atom of the i-cluster itself: only j > i (nbnxm/pairlist.cpp:880-904, kernel_gpu_ref.cpp:223-226) */
-                const bool diag = intra && shift == B200NB_CENTRAL && (J.slot >> 3) == ci;
-                const int  jin  = J.slot & 7;
-#pragma unroll
-                for (int p = 0; p < 2; p++)
-                {
-                    const unsigned w0 = p ? m.z : m.x, w1 = p ? m.w : m.y;
-                    const float    in0 = (float)((w0 >> lane) & 1u), in1 = (float)((w1 >> lane) & 1u);
-                    const bool     ok0 = !diag || jin > 4 * ih + 2 * p, ok1 = !diag || jin > 4 * ih + 2 * p + 1;
-                    float2         dx, dy, dz;
-                    const float2   fs = pair_fscal<EEL, GEOM, VF, true, GEN>(I[p], J, P, K, nbfp, nbfp_comb, in0, in1, ok0, ok1, dx, dy, dz, evdw, ecoul);
-                    fix[p] = fma2(fs, dx, fix[p]);
-                    fiy[p] = fma2(fs, dy, fiy[p]);
-                    fiz[p] = fma2(fs, dz, fiz[p]);
-                    fjx    = fma2(fs, dx, fjx);
-                    fjy    = fma2(fs, dy, fjy);
-                    fjz    = fma2(fs, dz, fjz);
-                }
-            }
-            else
-            {
-#pragma unroll
-                for (int p = 0; p < 2; p++)
-                {
-                    float2       dx, dy, dz;
-                    const float2 fs = pair_fscal<EEL, GEOM, VF, false, GEN>(I[p], J, P, K, nbfp, nbfp_comb, 1.f, 1.f, true, true, dx, dy, dz, evdw, ecoul);
-                    fix[p] = fma2(fs, dx, fix[p]);
-                    fiy[p] = fma2(fs, dy, fiy[p]);
-                    fiz[p] = fma2(fs, dz, fiz[p]);
-                    fjx    = fma2(fs, dx, fjx);
-                    fjy    = fma2(fs, dy, fjy);
-                    fjz    = fma2(fs, dz, fjz);
-                }
-            }
-            reduce_store_j(fjx, fjy, fjz, upper, f, J.slot);
-        }
-        /* -- entry epilogue: i-forces (12 floats per lane) summed over the 16 j-lanes of the half, as in k_force -- */
-        const bool b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
-        float      r0, r1, r2, r3, r4, r5;
-#define NB_STAGE_A(out, v0, v1)                                          \
-    {                                                                    \
-        const float keep_ = b3 ? (v1) : (v0), send_ = b3 ? (v0) : (v1);  \
-        out               = keep_ + __shfl_xor_sync(full, send_, 8);     \
-    }
-        NB_STAGE_A(r0, fix[0].x, fix[1].x)
-        NB_STAGE_A(r1, fix[0].y, fix[1].y)
-        NB_STAGE_A(r2, fiy[0].x, fiy[1].x)
-        NB_STAGE_A(r3, fiy[0].y, fiy[1].y)
-        NB_STAGE_A(r4, fiz[0].x, fiz[1].x)
-        NB_STAGE_A(r5, fiz[0].y, fiz[1].y)
-#undef NB_STAGE_A
-        float kx = (b2 ? r1 : r0) + __shfl_xor_sync(full, b2 ? r0 : r1, 4);
-        float ky = (b2 ? r3 : r2) + __shfl_xor_sync(full, b2 ? r2 : r3, 4);
-        float kz = (b2 ? r5 : r4) + __shfl_xor_sync(full, b2 ? r4 : r5, 4);
-        kx += __shfl_xor_sync(full, kx, 2);
-        ky += __shfl_xor_sync(full, ky, 2);
-        kz += __shfl_xor_sync(full, kz, 2);
-        kx += __shfl_xor_sync(full, kx, 1);
-        ky += __shfl_xor_sync(full, ky, 1);
-        kz += __shfl_xor_sync(full, kz, 1);
-        if ((lane & 3) == 0 && nstep > 0) atomicAdd(f + ((size_t)ci * 8 + 4 * ih + 2 * (int)b3 + (int)b2), make_float4(kx, ky, kz, 0.f));
-        if (VF)
-        {
-            if (shift != B200NB_CENTRAL)
-            {
-                kx += __shfl_xor_sync(full, kx, 4);
-                ky += __shfl_xor_sync(full, ky, 4);
-                kz += __shfl_xor_sync(full, kz, 4);
-                kx += __shfl_xor_sync(full, kx, 8);
-                ky += __shfl_xor_sync(full, ky, 8);
-                kz += __shfl_xor_sync(full, kz, 8);
-                kx += __shfl_xor_sync(full, kx, 16);
-                ky += __shfl_xor_sync(full, ky, 16);
-                kz += __shfl_xor_sync(full, kz, 16);
-                if (lane == 0)
-                {
-                    float* fs = fshift + (int)(e & (NB_OUT_COPIES - 1)) * NB_FSHIFT_PITCH + 3 * shift;
-                    atomicAdd(fs, kx);
-                    atomicAdd(fs + 1, ky);
-                    atomicAdd(fs + 2, kz);
-                }
-            }
-            for (int o = 16; o > 0; o >>= 1)
-            {
-                evdw += __shfl_xor_sync(full, evdw, o);
-                ecoul += __shfl_xor_sync(full, ecoul, o);
-            }
-            if (lane == 0)
-            {
-                double* en = energy + 2 * (int)(e & (NB_OUT_COPIES - 1));
-                atomicAdd(en, (double)evdw);
-                atomicAdd(en + 1, (double)ecoul);
-            }
         }
     }
 }
@@ -971,20 +672,6 @@ k_force_p(const Entry* __restrict__ entries, long long nentries, const int* __re
 template<int EEL, bool GEOM, bool VF, bool GEN>
 int launch(b200nb_context* h, const PackedList& L, int intra)
 {
-    const int maxt = L.pitch;
-    if (h->persistent < 0)
-    {
-        /* B200NB_PERSISTENT=1 selects k_force_p.  Measured (profiles/r2/k_sweep_persistent.txt, k_ncu_k_force_p_water192k.txt): it
-         * does what it was built for -- long-scoreboard stalls per issue fall from 1.81 to 0.12 -- but its bookkeeping costs 41
-         * more instructions per step (172 against 131) and the issue rate stays where it was (0.62 per cycle: the kernel is
-         * issue-bound on its FFMA2-heavy mix, not latency-bound), so it is 20-30 % SLOWER: 127 us against 97 us at 192 k atoms.
-         * Default: one CTA per entry. */
-        const char* e = getenv("B200NB_PERSISTENT");
-        h->persistent = e ? (atoi(e) != 0) : 0;
-        int nsm       = 148;
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-        h->num_sms = nsm;
-    }
     cudaLaunchConfig_t cfg{};
     cfg.blockDim         = dim3(32 * B200NB_FORCE_WARPS);
     cfg.dynamicSmemBytes = 0;
@@ -994,33 +681,13 @@ int launch(b200nb_context* h, const PackedList& L, int intra)
     at[0].val.programmaticStreamSerializationAllowed = 1; /* overlap our list loads with the tail of the preceding kernel */
     cfg.attrs    = at;
     cfg.numAttrs = h->use_pdl ? 1 : 0;
-    if (h->persistent)
-    {
-        /* as many single-warp CTAs as stay resident; warp w walks the entries w, w + G, ... of the size-sorted list */
-        static bool carveout_set = false;
-        if (!carveout_set)
-        {
-            cudaFuncSetAttribute(k_force_p<EEL, GEOM, VF, GEN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            carveout_set = true;
-        }
-        const long long resident = (long long)h->num_sms * B200NB_FORCE_MIN_BLOCKS(VF, GEN);
-        cfg.gridDim              = dim3((unsigned)std::min<long long>(L.nentries, resident));
-        cudaLaunchKernelEx(&cfg, k_force_p<EEL, GEOM, VF, GEN>, (const Entry*)L.entries, (long long)L.nentries, (const int*)L.ja,
-                           (const uint64_t*)L.mask, reinterpret_cast<const float4*>(h->d_xq), reinterpret_cast<const float2*>(h->d_lj),
-                           (const int*)h->d_atype, reinterpret_cast<const float2*>(h->d_nbfp), (const float*)h->d_shift_vec, h->d_f,
-                           h->d_fshift, h->d_energy, h->dp, intra, maxt, (const float*)h->d_kconst,
-                           reinterpret_cast<const float2*>(h->d_nbfp_comb), h->dummy_slot);
-    }
-    else
-    {
-        /* one entry per single-warp CTA; CTAs start in index order, i.e. largest entries first */
-        cfg.gridDim = dim3((unsigned)((L.nentries + B200NB_FORCE_WARPS - 1) / B200NB_FORCE_WARPS));
-        cudaLaunchKernelEx(&cfg, k_force<EEL, GEOM, VF, GEN>, (const Entry*)L.entries, (long long)L.nentries, (const int*)L.ja,
-                           (const uint64_t*)L.mask, reinterpret_cast<const float4*>(h->d_xq), reinterpret_cast<const float2*>(h->d_lj),
-                           (const int*)h->d_atype, reinterpret_cast<const float2*>(h->d_nbfp), (const float*)h->d_shift_vec, h->d_f,
-                           h->d_fshift, h->d_energy, h->dp, intra, maxt, (const float*)h->d_kconst,
-                           reinterpret_cast<const float2*>(h->d_nbfp_comb));
-    }
+    /* two half-entries per single-warp CTA; CTAs start in index order, i.e. largest half-entries first */
+    const long long nwarps = L.nentries / 2;
+    cfg.gridDim            = dim3((unsigned)((nwarps + B200NB_FORCE_WARPS - 1) / B200NB_FORCE_WARPS));
+    cudaLaunchKernelEx(&cfg, k_force<EEL, GEOM, VF, GEN>, (const Entry*)L.entries, nwarps, (const int*)L.ja, (const uint64_t*)L.mask,
+                       reinterpret_cast<const float4*>(h->d_xq), reinterpret_cast<const float2*>(h->d_lj), (const int*)h->d_atype,
+                       reinterpret_cast<const float2*>(h->d_nbfp), (const float*)h->d_shift_vec, h->d_f, h->d_fshift, h->d_energy, h->dp,
+                       intra, (const float*)h->d_kconst, reinterpret_cast<const float2*>(h->d_nbfp_comb));
     h->nlaunches++;
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return nb_fail(h, B200NB_ERR_CUDA, std::string("force kernel launch: ") + cudaGetErrorString(err));
