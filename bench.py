@@ -421,8 +421,9 @@ def measure_single(args, workload, local_rank, full):
     fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
     achieved = npairs * flops / (k_ms * 1e-3) / 1e12
     npad, ntiles = st["natoms_padded"], st["ntiles_packed"]
-    # xq 16 + lj 8 read once, f 16 read-modify-written (32) per slot; 32 B of j-slot indices per packed tile; 16 B per entry
-    alg_bytes = npad * (16 + 8 + 32) + ntiles * 32 + st["nentries"] * 16
+    # xq 16 + lj 8 read once, f 16 read-modify-written (32) per slot; 64 B of j-slot indices per packed tile (a warp step = 2 tiles
+    # = 16 slots for each of its two half-entries); two 16 B half-entry headers per entry of the cluster-pair list
+    alg_bytes = npad * (16 + 8 + 32) + ntiles * 64 + st["nentries"] * 32
     cap = ncu_capture(workload, args.eel)
     out = {
         "value": npairs / (step_ms * 1e-3), "ms_per_step": step_ms,

@@ -18,7 +18,17 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h> /* header-only: ranges cost a null-pointer check when no profiler is attached */
+
 #include "b200nb_internal.h"
+
+/* NVTX range around an API call, the role of the reference's wallcycle / NVTX markers around its nonbonded calls
+ * (timing/wallcycle.cpp, utility/nvtx ranges in cuda builds): shows the search, prune and step calls on a profiler timeline */
+struct NvtxRange
+{
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 int nb_fail(b200nb_context* h, int code, const std::string& msg)
 {
@@ -141,6 +151,7 @@ extern "C" void b200nb_destroy(b200nb_t* h)
     cudaFree(h->dd.d_ent_off);
     cudaFree(h->dd.d_ent_idx);
     cudaFree(h->dd.d_halo_link);
+    cudaFree(h->dd.d_gtype), cudaFree(h->dd.d_gq), cudaFree(h->dd.d_geoff), cudaFree(h->dd.d_geidx), cudaFree(h->dd.d_g2l), cudaFree(h->dd.d_part_scratch);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -392,6 +403,25 @@ extern "C" int b200nb_set_atoms(b200nb_t* h, int natoms, const int* type_host, c
     if (alloc_exact(h, &h->d_x, (size_t)natoms * 3) || alloc_exact(h, &h->d_fout, (size_t)natoms * 3)
         || alloc_exact(h, &h->d_col_of_atom, (size_t)natoms) || alloc_exact(h, &h->d_slot_of_atom, (size_t)natoms)
         || alloc_exact(h, &h->d_pos_in_col, (size_t)natoms))
+        return B200NB_ERR_CUDA;
+    h->grid[0].valid = h->grid[1].valid = 0;
+    h->have_list                        = false;
+    return 0;
+}
+
+/* b200nb_set_atoms for arrays that are BUILT ON THE DEVICE (b200nb_dd_set_local_atoms, dd_partition.cu): the same allocations,
+ * the caller's kernels fill d_type / d_q / d_excl_off / d_excl_idx.  nexcl < 0: everything but the exclusion indices (their count
+ * is not known yet); nexcl >= 0: the exclusion indices. */
+int nb_install_atoms_dev(b200nb_context* h, int natoms, int nexcl)
+{
+    if (nexcl >= 0) return alloc_exact(h, &h->d_excl_idx, (size_t)nexcl) ? B200NB_ERR_CUDA : 0;
+    if (!h->have_params) return nb_fail(h, B200NB_ERR_STATE, "set_atoms: set_params first");
+    h->natoms = natoms;
+    h->h_type.clear(); /* no host copies on this path */
+    h->h_q.clear();
+    if (alloc_exact(h, &h->d_type, (size_t)natoms) || alloc_exact(h, &h->d_q, (size_t)natoms) || alloc_exact(h, &h->d_excl_off, (size_t)natoms + 1)
+        || alloc_exact(h, &h->d_x, (size_t)natoms * 3) || alloc_exact(h, &h->d_fout, (size_t)natoms * 3) || alloc_exact(h, &h->d_col_of_atom, (size_t)natoms)
+        || alloc_exact(h, &h->d_slot_of_atom, (size_t)natoms) || alloc_exact(h, &h->d_pos_in_col, (size_t)natoms))
         return B200NB_ERR_CUDA;
     h->grid[0].valid = h->grid[1].valid = 0;
     h->have_list                        = false;
@@ -736,6 +766,7 @@ static void grid_dimensions(GridDesc& g, int natoms, const float lower[3], const
 extern "C" int b200nb_put_on_grid(b200nb_t* h, int gi, const float lower[3], const float upper[3], int atom_begin, int atom_end,
                                   float density, const float* x, int x_on_device)
 {
+    NvtxRange nvtx_("b200nb_put_on_grid");
     if (!h || gi < 0 || gi > 1 || !lower || !upper || !x) return nb_fail(h, B200NB_ERR_ARG, "put_on_grid: bad argument");
     if (!h->natoms) return nb_fail(h, B200NB_ERR_STATE, "put_on_grid: set_atoms first");
     if (atom_begin < 0 || atom_end > h->natoms || atom_begin > atom_end) return nb_fail(h, B200NB_ERR_ARG, "put_on_grid: bad atom range");
@@ -885,7 +916,7 @@ extern "C" int b200nb_put_on_grid(b200nb_t* h, int gi, const float lower[3], con
     if (gi == 0)
     {
         double s = 0;
-        for (int a = atom_begin; a < atom_end; a++) s += (double)h->h_q[a] * h->h_q[a];
+        for (int a = atom_begin; a < atom_end && a < (int)h->h_q.size(); a++) s += (double)h->h_q[a] * h->h_q[a]; /* informational only */
         h->sum_q2 = s;
     }
     return 0;
@@ -1282,7 +1313,8 @@ k_prune(const Entry* __restrict__ oe, const int* __restrict__ ocj, const uint64_
 __global__ void __launch_bounds__(128)
 k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t* __restrict__ imask, long long nentries, int part,
        int nparts, const float* __restrict__ xq, const float* __restrict__ shift_vec, float rlist2, int intra, int dummy_slot, int pitch,
-       Entry* __restrict__ staged, int* __restrict__ sizes, int* __restrict__ pja, uint64_t* __restrict__ pmask)
+       Entry* __restrict__ staged, int* __restrict__ sizes, int* __restrict__ pja, uint64_t* __restrict__ pmask,
+       const int* __restrict__ dest, Entry* __restrict__ placed)
 {
     __shared__ int      s_ja[4][2][NB_PACK_FRONT];            /* front, per half: j-atoms that need masks */
     __shared__ int      s_jb[4][2][NB_MAX_ENTRY_TILES * 8];   /* back: the others */
@@ -1396,9 +1428,10 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
         const int       na = hh ? na1 : na0, n = na + (hh ? nb1 : nb0);
         const int       nsp = (n + 15) >> 4, nms = (na + 15) >> 4; /* steps, masked steps */
         const long long p   = 2 * e + hh;                          /* half-entry in packing order */
-        const long long s0  = p * (pitch >> 1);                    /* it owns the steps [s0, s0 + pitch/2) */
+        const long long s0  = p * ((pitch >> 1) + NB_PACK_TAIL);   /* its row: pitch/2 steps + the tail of dummy atoms */
         const int       dummy0 = dummy_slot + (int)(p & (NB_DUMMY_SLOTS / 16 - 1)) * 16;
-        for (int k = lane; k < nsp * 16; k += 32) pja[(size_t)s0 * 16 + k] = k < na ? s_ja[w][hh][k] : (k < n ? s_jb[w][hh][k - na] : dummy0 + (k & 15));
+        for (int k = lane; k < (nsp + NB_PACK_TAIL) * 16; k += 32)
+            pja[(size_t)s0 * 16 + k] = k < na ? s_ja[w][hh][k] : (k < n ? s_jb[w][hh][k - na] : dummy0 + (k & 15));
         unsigned* const pm = reinterpret_cast<unsigned*>(pmask + s0);
         for (int k = lane; k < nsp * 2; k += 32) pm[k] = k < nms * 2 ? s_m[w][hh][k] : ~0u;
         if (lane == 0)
@@ -1410,6 +1443,7 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
             o.end         = (int)s0 + nsp;
             staged[p]     = o;
             sizes[p]      = nsp;
+            if (dest) placed[dest[p]] = o; /* rolling part: the execution order of the last full pack stands */
         }
     }
 }
@@ -1456,23 +1490,34 @@ __global__ void k_place_headers(const Entry* __restrict__ staged, const int* __r
 
 /* The two half-entries a warp of the force kernel runs side by side (positions 2w and 2w + 1 of the execution order) are walked
  * in lockstep for the longer one's steps: the shorter one gets the difference as steps of far-away dummy atoms behind its own
- * (its row has pitch/2 >= the longer one's steps of room).  Differences are rare (the order is by step count) and short. */
-__global__ void k_pad_partner(const Entry* __restrict__ entries, int nwarps, int* __restrict__ pja, int dummy_slot)
+ * (its row has pitch/2 >= the longer one's steps of room, plus the tail every row ends in).  Differences are rare (the order is by step count) and short. */
+__global__ void k_pad_partner(const Entry* __restrict__ entries, int nwarps, int* __restrict__ pja, int dummy_slot, const int* __restrict__ dest,
+                              int part, int nparts)
 {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    /* full pack: one thread per warp of the force kernel.  Rolling part: one thread per half-entry of the part (those of the outer
+     * entries part, part + nparts, ...), which looks after the warp its half-entry runs in; two threads may then treat the same
+     * warp and write the same values */
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dest)
+    {
+        const long long p = 2 * ((long long)(w >> 1) * nparts + part) + (w & 1);
+        if (p >= 2LL * nwarps) return;
+        w = dest[p] >> 1;
+    }
     if (w >= nwarps) return;
     const int4 a = reinterpret_cast<const int4*>(entries)[2 * w], b = reinterpret_cast<const int4*>(entries)[2 * w + 1];
     const int  na = a.w - a.z, nb = b.w - b.z;
     if (na == nb) return;
     const int   s0 = na < nb ? a.z : b.z, ns = min(na, nb), nl = max(na, nb);
     const int   d0 = dummy_slot + (int)((2 * w + (na < nb ? 0 : 1)) & (NB_DUMMY_SLOTS / 16 - 1)) * 16;
-    for (int s = ns; s < nl; s++)
+    for (int s = ns; s < nl + NB_PACK_TAIL; s++)
         for (int j = 0; j < 16; j++) pja[(size_t)(s0 + s) * 16 + j] = d0 + j;
 }
 
 static int ensure_packed(b200nb_context* h, PackedList& P, size_t cap_tiles, size_t cap_entries)
 {
-    /* cap_tiles = outer entries x pitch: per outer entry 2 half-entries x pitch/2 steps x (16 slots, one 64-bit mask) */
+    /* cap_tiles = outer entries x (pitch + 2 NB_PACK_TAIL): per outer entry 2 rows of pitch/2 + NB_PACK_TAIL steps x (16 slots, one
+     * 64-bit mask) */
     if (cap_tiles > P.cap_tiles || !P.ja)
     {
         cudaFree(P.ja);
@@ -1508,21 +1553,22 @@ static int launch_pack(b200nb_context* h, int loc, int part, int nparts)
     PackedList&     P = h->packed[loc];
     P.nentries        = 2 * I.nentries;
     P.pitch           = (h->max_tiles + 1) & ~1; /* whole steps of 16 j-atoms = 2 tiles */
+    P.row             = P.pitch / 2 + NB_PACK_TAIL;
     if (I.nentries == 0) return 0;
-    if ((size_t)I.nentries * P.pitch > 2000000000ull) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: packed list exceeds 2^31 steps");
-    if (ensure_packed(h, P, I.cap_entries * P.pitch, I.cap_entries)) return B200NB_ERR_CUDA;
+    if ((size_t)I.nentries * 2 * P.row > 2000000000ull) return nb_fail(h, B200NB_ERR_CAPACITY, "build_pairlist: packed list exceeds 2^31 steps");
+    if (ensure_packed(h, P, I.cap_entries * 2 * P.row, I.cap_entries)) return B200NB_ERR_CUDA;
     long long nw = (I.nentries - part + nparts - 1) / nparts;
     if (nw <= 0) return 0;
     const float    r2   = h->inner_is_outer ? h->dp.rlist_outer2 : h->dp.rlist_inner2;
     const unsigned nblk = (unsigned)((nw + 3) / 4);
+    const bool rolling = nparts > 1; /* keeps the positions of the last full pack: the part's half-entries only shrink or grow a little */
     k_pack<<<nblk, 128, 0, h->stream>>>(I.entries, I.cj, I.mask, I.nentries, part, nparts, h->d_xq, h->d_shift_vec, r2, loc == 0,
-                                        h->dummy_slot, P.pitch, P.staged, P.sizes, P.ja, P.mask);
+                                        h->dummy_slot, P.pitch, P.staged, P.sizes, P.ja, P.mask, rolling ? P.dest : nullptr, P.entries);
     LAUNCH_CHECK(h);
     const int n = (int)P.nentries;
-    if (nparts == 1)
+    if (!rolling)
     {
-        /* full pack: execution order by the packed step counts.  Rolling parts (nparts > 1) keep the positions of the last
-         * full pack. */
+        /* full pack: execution order by the packed step counts */
         NB_CUDA(h, cudaMemsetAsync(h->d_hist, 0, sizeof(int) * 2 * NB_ORDER_BINS, h->stream));
         k_order_hist<<<(n + 255) / 256, 256, 0, h->stream>>>(P.sizes, n, h->d_hist);
         LAUNCH_CHECK(h);
@@ -1530,11 +1576,16 @@ static int launch_pack(b200nb_context* h, int loc, int part, int nparts)
         LAUNCH_CHECK(h);
         k_order_assign<<<(n + 255) / 256, 256, 0, h->stream>>>(P.sizes, n, h->d_hist, P.dest);
         LAUNCH_CHECK(h);
+        k_place_headers<<<(n + 255) / 256, 256, 0, h->stream>>>(P.staged, P.dest, n, P.entries);
+        LAUNCH_CHECK(h);
+        k_pad_partner<<<(n / 2 + 255) / 256, 256, 0, h->stream>>>(P.entries, n / 2, P.ja, h->dummy_slot, nullptr, 0, 1);
+        LAUNCH_CHECK(h);
     }
-    k_place_headers<<<(n + 255) / 256, 256, 0, h->stream>>>(P.staged, P.dest, n, P.entries);
-    LAUNCH_CHECK(h);
-    k_pad_partner<<<(n / 2 + 255) / 256, 256, 0, h->stream>>>(P.entries, n / 2, P.ja, h->dummy_slot);
-    LAUNCH_CHECK(h);
+    else
+    {
+        k_pad_partner<<<(unsigned)((2 * nw + 255) / 256), 256, 0, h->stream>>>(P.entries, n / 2, P.ja, h->dummy_slot, P.dest, part, nparts);
+        LAUNCH_CHECK(h);
+    }
     h->inner_stale[loc] = true; /* the pruned CLUSTER-PAIR list (introspection only) no longer matches the packed one */
     return 0;
 }
@@ -1617,6 +1668,7 @@ static int write_dummy_atoms(b200nb_context* h)
 
 extern "C" int b200nb_build_pairlist(b200nb_t* h)
 {
+    NvtxRange nvtx_("b200nb_build_pairlist");
     if (!h) return B200NB_ERR_ARG;
     if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "build_pairlist: put_on_grid first");
     cudaSetDevice(h->device);
@@ -1835,6 +1887,7 @@ extern "C" int b200nb_set_grid_atoms(b200nb_t* h, int nslots, const float* xq_ho
 extern "C" int b200nb_upload_pairlist(b200nb_t* h, int locality, const b200nb_sci_t* sci, int nsci, const b200nb_cj4_t* cj4, int ncj4,
                                       const b200nb_excl_t* excl, int nexcl)
 {
+    NvtxRange nvtx_("b200nb_upload_pairlist");
     if (!h || locality < 0 || locality > 1 || nsci < 0 || ncj4 < 0 || nexcl < 1 || (nsci && !sci) || (ncj4 && !cj4) || !excl)
         return nb_fail(h, B200NB_ERR_ARG, "upload_pairlist: bad argument");
     if (!h->grid_uploaded) return nb_fail(h, B200NB_ERR_STATE, "upload_pairlist: set_grid_atoms first");
@@ -2001,6 +2054,7 @@ extern "C" int b200nb_get_f_grid(b200nb_t* h, float* f_host, int slot_begin, int
 
 extern "C" int b200nb_launch_prune(b200nb_t* h, int locality, int part, int num_parts)
 {
+    NvtxRange nvtx_("b200nb_launch_prune");
     if (!h || num_parts < 1 || part < 0 || part >= num_parts) return nb_fail(h, B200NB_ERR_ARG, "launch_prune: bad argument");
     if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "launch_prune: no pair list");
     cudaSetDevice(h->device);
@@ -2051,6 +2105,7 @@ __global__ void k_f_from_grid(const float4* __restrict__ fg, const int* __restri
 
 extern "C" int b200nb_set_x(b200nb_t* h, const float* x, int x_on_device, int a0, int a1)
 {
+    NvtxRange nvtx_("b200nb_set_x");
     if (!h || !x) return nb_fail(h, B200NB_ERR_ARG, "set_x: bad argument");
     if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "set_x: put_on_grid first");
     if (a0 < 0 || a1 > h->natoms || a0 > a1) return nb_fail(h, B200NB_ERR_ARG, "set_x: bad atom range");
@@ -2084,6 +2139,7 @@ extern "C" int b200nb_clear_outputs(b200nb_t* h)
 
 extern "C" int b200nb_launch_force(b200nb_t* h, int locality, int flags)
 {
+    NvtxRange nvtx_("b200nb_launch_force");
     if (!h) return B200NB_ERR_ARG;
     if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "launch_force: no pair list");
     cudaSetDevice(h->device);
@@ -2098,6 +2154,7 @@ extern "C" int b200nb_launch_force(b200nb_t* h, int locality, int flags)
 
 extern "C" int b200nb_get_f(b200nb_t* h, float* f, int f_on_device, int accumulate, int a0, int a1)
 {
+    NvtxRange nvtx_("b200nb_get_f");
     if (!h || !f) return nb_fail(h, B200NB_ERR_ARG, "get_f: bad argument");
     if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "get_f: put_on_grid first");
     if (a0 < 0 || a1 > h->natoms || a0 > a1) return nb_fail(h, B200NB_ERR_ARG, "get_f: bad atom range");
@@ -2359,9 +2416,9 @@ static int launch_step(b200nb_context* h, const float* x_dev, int flags, float* 
         pf.p[0]     = reinterpret_cast<const char*>(P.entries);
         pf.bytes[0] = sizeof(Entry) * (size_t)P.nentries;
         pf.p[1]     = reinterpret_cast<const char*>(P.ja);
-        pf.bytes[1] = nb_list_prefetch_bytes(sizeof(int) * 8 * (size_t)P.nentries * P.pitch);
+        pf.bytes[1] = nb_list_prefetch_bytes(sizeof(int) * 16 * (size_t)P.nentries * P.row);
         pf.p[2]     = reinterpret_cast<const char*>(P.mask);
-        pf.bytes[2] = nb_list_prefetch_bytes(sizeof(uint64_t) * (size_t)P.nentries * (P.pitch / 2));
+        pf.bytes[2] = nb_list_prefetch_bytes(sizeof(uint64_t) * (size_t)P.nentries * P.row);
         pf.p[3]     = reinterpret_cast<const char*>(h->comb_geom ? (const void*)h->d_lj : (const void*)h->d_atype);
         pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
     }
@@ -2385,6 +2442,7 @@ static int run_step_graph(b200nb_context* h, int which, const float* x, float* f
 /* device-resident step (the reference's GPU buffer-ops path, mdlib/sim_util.cpp:1043-1108): asynchronous on the stream */
 extern "C" int b200nb_step(b200nb_t* h, const float* x_dev, int flags, float* f_dev)
 {
+    NvtxRange nvtx_("b200nb_step");
     if (!h || !x_dev || !f_dev) return nb_fail(h, B200NB_ERR_ARG, "step: bad argument");
     if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "step: no pair list");
     if (h->grid[1].valid) return nb_fail(h, B200NB_ERR_STATE, "step: single-domain call on a context with a halo grid");
@@ -2445,6 +2503,7 @@ static float* mapped_host_pointer(const void* p)
 
 extern "C" int b200nb_compute(b200nb_t* h, const float* x_host, int flags, float* f_host, float* fshift_host, double* energies_host)
 {
+    NvtxRange nvtx_("b200nb_compute");
     if (!h || !x_host || !f_host) return nb_fail(h, B200NB_ERR_ARG, "compute: bad argument");
     if (!h->have_list) return nb_fail(h, B200NB_ERR_STATE, "compute: no pair list");
     if (h->grid[1].valid) return nb_fail(h, B200NB_ERR_STATE, "compute: single-domain call on a context with a halo grid");
@@ -2711,6 +2770,7 @@ extern "C" int b200nb_dd_open_peer(b200nb_t* h, int peer, const void* ipc_handle
  * in link order (all atoms received over link 0, then link 1, ...).  See b200nb_dd_link_t in b200nb.h. */
 extern "C" int b200nb_dd_set_links(b200nb_t* h, int nhome, int nhalo, int nlinks, const b200nb_dd_link_t* links)
 {
+    NvtxRange nvtx_("b200nb_dd_set_links");
     if (!h || nhome < 0 || nhalo < 0 || nlinks < 0 || nlinks > NB_DD_MAX_LINKS || (nlinks && !links))
         return nb_fail(h, B200NB_ERR_ARG, "dd_set_links: bad argument");
     cudaSetDevice(h->device);
@@ -2849,9 +2909,9 @@ static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home,
         pf.p[0]     = reinterpret_cast<const char*>(P.entries);
         pf.bytes[0] = sizeof(Entry) * (size_t)P.nentries;
         pf.p[1]     = reinterpret_cast<const char*>(P.ja);
-        pf.bytes[1] = nb_list_prefetch_bytes(sizeof(int) * 8 * (size_t)P.nentries * P.pitch);
+        pf.bytes[1] = nb_list_prefetch_bytes(sizeof(int) * 16 * (size_t)P.nentries * P.row);
         pf.p[2]     = reinterpret_cast<const char*>(P.mask);
-        pf.bytes[2] = nb_list_prefetch_bytes(sizeof(uint64_t) * (size_t)P.nentries * (P.pitch / 2));
+        pf.bytes[2] = nb_list_prefetch_bytes(sizeof(uint64_t) * (size_t)P.nentries * P.row);
         pf.p[3]     = reinterpret_cast<const char*>(h->comb_geom ? (const void*)h->d_lj : (const void*)h->d_atype);
         pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
     }
@@ -2982,6 +3042,7 @@ static int run_step_graph(b200nb_context* h, int which, const float* x, float* f
  * sent, add, un-sort.  x_home / f_home: nhome*3 floats, device or pinned host memory. */
 extern "C" int b200nb_dd_step(b200nb_t* h, const float* x_home, float* f_home, int flags)
 {
+    NvtxRange nvtx_("b200nb_dd_step");
     if (!h || !x_home || !f_home) return nb_fail(h, B200NB_ERR_ARG, "dd_step: bad argument");
     DdState& D = h->dd;
     if (!h->have_list || !D.have_plan) return nb_fail(h, B200NB_ERR_STATE, "dd_step: needs a pair list and a halo plan");
@@ -3091,6 +3152,27 @@ extern "C" int b200nb_get_stats(b200nb_t* h, b200nb_stats_t* out)
                 out->ntiles_packed += v;
             }
     out->nlaunches = h->nlaunches;
+    return 0;
+}
+
+/* one line about the context for logs: the role of the reference's "Using a ... Verlet scheme / GPU info" setup lines
+ * (nbnxm_setup.cpp:180-260, mdrunutility/printhardware) */
+extern "C" int b200nb_describe(b200nb_t* h, char* buf, int cap)
+{
+    if (!h || !buf || cap < 1) return B200NB_ERR_ARG;
+    cudaDeviceProp pr{};
+    cudaGetDeviceProperties(&pr, h->device);
+    const char* eel = h->dp.eeltype == B200NB_EEL_EWALD ? (h->dp.ewald_tab ? "Ewald(tab)" : "Ewald(analytical)") : (h->dp.k_rf != 0.f ? "RF" : "cut-off");
+    const long long ne0 = h->packed[0].nentries, ne1 = h->packed[1].nentries;
+    snprintf(buf, (size_t)cap,
+             "b200nb: %s (sm_%d%d, %d SMs) device %d | %d atoms in %d slots, grid %d x %d columns | rc %.3g rlist %.3g/%.3g | LJ %s + %s | "
+             "list: %lld + %lld cluster pairs -> %lld + %lld half-entries, <= %d cluster pairs per entry | force kernel: 2 half-entries per "
+             "warp, 1 warp per CTA, %s | %s%s",
+             pr.name, pr.major, pr.minor, pr.multiProcessorCount, h->device, h->natoms, h->npad, h->grid[0].ncx, h->grid[0].ncy,
+             h->have_params ? sqrtf(h->dp.rc2) : 0.f, h->have_params ? sqrtf(h->dp.rlist_outer2) : 0.f, h->have_params ? sqrtf(h->dp.rlist_inner2) : 0.f,
+             h->comb_geom ? "geometric" : "type table", eel, h->outer[0].ntiles, h->outer[1].ntiles, ne0, ne1, h->max_tiles,
+             h->use_pdl ? "programmatic dependent launch" : "serialized launch", h->use_graphs ? "step = 1 CUDA graph" : "direct launches",
+             h->dd.have_plan ? " | halo over peer-memory windows" : "");
     return 0;
 }
 

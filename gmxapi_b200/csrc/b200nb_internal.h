@@ -18,6 +18,8 @@
 #define NB_MAX_GROUP_TILES 512 /* staging capacity of one (i-cluster, shift) group in the search */
 #define NB_OUT_COPIES 32   /* replicas of the shift-force / energy accumulators: per-entry atomics spread over them */
 #define NB_FSHIFT_PITCH 136 /* floats per shift-force replica (45*3 rounded up) */
+#define NB_PACK_TAIL 2    /* steps of dummy atoms behind the last step of every row of the packed list: the force kernel's gather runs
+                             one step ahead of the arithmetic and its slot fetch two, without bounds checks */
 #define NB_DUMMY_SLOTS 512 /* far-away filler atoms appended after the grids: padding targets of the packed list */
 
 /* Device atom layout, grid (slot) order, slot = cluster*8 + k:
@@ -94,8 +96,8 @@ struct PairList
  * 16*k + j = pair (i-atom 4*half + k, j-atom j of the step) interacts); the tail of the last step points at far-away dummy
  * atoms, NB_DUMMY_SLOTS of them shared round-robin by the entries (the kernel's zero-valued force reductions for padding lanes
  * then never pile up on one address: same-address reductions serialise in L2).
- * Half-entry p = 2*e + half of outer entry e is PACKED into the steps [p*pitch/2, (p+1)*pitch/2) of ja / mask (`staged` holds its
- * header); `entries` holds the same headers sorted by descending step count, and the force kernel gives the half-entries 2w and
+ * Half-entry p = 2*e + half of outer entry e is PACKED into row p of ja / mask, the steps [p*row, (p+1)*row) with row = pitch/2 +
+ * NB_PACK_TAIL (`staged` holds its header); `entries` holds the same headers sorted by descending step count, and the force kernel gives the half-entries 2w and
  * 2w + 1 of that order to the two halves of warp w: equal step counts up to the warps that straddle a size boundary, where
  * k_pad_partner extends the shorter one's j slots with dummy atoms to the longer one's steps. */
 struct PackedList
@@ -108,6 +110,7 @@ struct PackedList
     int*      sizes   = nullptr; /* per half-entry in packing order: its steps (the ordering key) */
     long long nentries = 0;      /* HALF-entries: 2 x the entries of the outer list */
     int       pitch = 0;         /* tiles of 8 j slots reserved per half-entry (= max_tiles_per_entry, even): pitch/2 steps */
+    int       row = 0;           /* steps per row: pitch/2 + NB_PACK_TAIL */
     size_t    cap_tiles = 0, cap_entries = 0;
 };
 
@@ -158,6 +161,12 @@ struct DdState
     int*           d_ent_idx = nullptr;
     unsigned char* d_halo_link = nullptr; /* per halo atom: the link it came over */
     size_t         cap_send = 0, cap_home = 0, cap_halo = 0;
+    /* device-side repartitioning (dd_partition.cu): the replicated global topology, the ga2la look-up, scratch */
+    int            nglobal = 0;
+    int *          d_gtype = nullptr, *d_geoff = nullptr, *d_geidx = nullptr, *d_g2l = nullptr;
+    float*         d_gq = nullptr;
+    int*           d_part_scratch = nullptr;
+    size_t         cap_part_scratch = 0;
     int*           d_count = nullptr; /* 2 last-block counters */
     int*           d_seq = nullptr;   /* device-resident step counter: the value the flags carry (graph-replayable) */
     bool           have_plan = false;

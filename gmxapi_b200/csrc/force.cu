@@ -20,8 +20,13 @@
  *  - lane = jl + 16*ih owns ONE j-atom per step (jl of its half-entry's list) and FOUR i-atoms as two packed float2 pairs
  *    held in registers for the whole entry.  All pair arithmetic is packed (fma.rn.f32x2 -> FFMA2/FMUL2), the j operands
  *    enter in the scalar-broadcast operand form;
- *  - the j-atom's data (16-byte xyzq, 8-byte LJ pair, slot index) stream through a per-lane cp.async ring in shared memory
- *    (see gather_j): no register holds data in flight, no cross-lane hand-over, no barrier;
+ *  - the j-atom's data (16-byte xyzq, 8-byte LJ pair) are gathered straight into the lane's registers ONE STEP AHEAD of their use,
+ *    the slot index two steps ahead: two loads + one index load per step, no shared memory.  What makes this work is where the
+ *    loads sit: at the top of the step, pinned there by the (deferred) j-force red of the previous step (see load_j).  The
+ *    round-2 kernels before this one staged the stream through a 4-stage per-lane cp.async ring in shared memory (three steps
+ *    of lead): ncu showed the L1TEX data pipe at 86 % with it (cp.async fills, record reads, the slot hand-over) and the
+ *    register form is 2-5 % faster at every size (profiles/r2/s_sweep_register_gather.txt); prefetch instructions (CCTL) for a
+ *    longer lead cost 10-15 % and were dropped (u_, w_sweep_*.txt);
  *  - j-forces: accumulated in the lane over its 4 pairs with the same packed FMAs that feed the i accumulators and
  *    reduced by the lane itself (red.v2 {x, y} + red {z}): the two halves of a warp hold different j-atoms, so there is no
  *    exchange (the cluster-granular layout needed 2 shuffles + 5 selects / negations per step to share a j-atom between halves);
@@ -34,9 +39,9 @@
  *  - r^2 is evaluated with the reference's operand roles and operation order so the in-range pair set is
  *    bit-identical (see nb_rsq in b200nb_internal.h);
  *  - TMA (cp.async.bulk / tile::gather4) is not used: the j stream is a gather of single 16-byte atoms by slot index
- *    whose consumer is ONE lane; a per-lane cp.async delivers it into that lane's record with no barrier and no
- *    elected-thread issue; gather4 moves rows of a 2-D tensor into shared memory for a whole CTA and needs an mbarrier
- *    round trip per stage;
+ *    whose consumer is ONE lane; a per-lane load delivers it into that lane's registers with no barrier, no shared memory
+ *    and no elected-thread issue; gather4 moves rows of a 2-D tensor into shared memory for a whole CTA and needs an mbarrier
+ *    round trip per stage plus a shared-memory read per lane;
  *  - LJ force switch / potential switch / VdW cut-off below the Coulomb cut-off / LJ-PME are a second set of
  *    instantiations (GEN): the plain kernels, which every BASELINE configuration uses, pay nothing for them.
  * Measured and dropped (profiles/r2/k_*): a persistent form with cross-entry pipelining (k_force_p) --
@@ -92,55 +97,34 @@ struct JAtom
 };
 
 #define NB_JSTEP 16 /* j-atoms per step of a half-entry: lane jl + 16*ih holds j-atom jl of the step of half-entry ih of the warp */
-#ifndef NB_RING
-#define NB_RING 4 /* stages of the per-warp j-atom ring in shared memory: a step's gather is issued NB_RING - 1 steps ahead */
-#endif
-
-/* The j-atom stream.  Every lane owns one 32-byte record per ring stage in shared memory, {x, y, z, q | lj.x, lj.y, slot, -},
- * filled by the lane itself with cp.async (16 bytes of xq, 8 bytes of LJ parameters or 4 bytes of atom type) straight from
- * global memory and read back by the same lane NB_RING - 1 steps later: no register holds data in flight (with the gather
- * loaded into registers ptxas, at the 128-register cap, sank the loads to the end of the step, right in front of their first
- * use: 41 % of the stall samples of profiles/r2/a_ncu_source_k_force_water192k.txt), no cross-lane hand-over, so no barrier --
- * a lane only waits for its own copies (cp.async.wait_group). */
-__device__ __forceinline__ void cp_async_16(unsigned dst, const void* src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_8(unsigned dst, const void* src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_4(unsigned dst, const void* src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template<int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-/* starts the gather of the j-atom in grid slot `slot` into the lane's record at shared address `rec` (read-only path: xq / lj /
- * atype are written by the kernel BEFORE this one in the stream, never during it) */
+/* The j-atom gather into registers.  Plain (weak) global loads in volatile asm with a memory clobber, NOT the read-only path:
+ * the loads of step s + 1 are issued at the TOP of step s, in front of the red that flushes the j-forces of step s - 1, and a
+ * weak load may not be moved across a later reduction to an address ptxas cannot tell apart -- which pins the loads a whole
+ * step ahead of their first use.  (An ld.global.nc placed there was sunk by ptxas to the end of the step, right in front of
+ * its consumer: 41 % of the stall samples of profiles/r2/a_ncu_source_k_force_water192k.txt.) */
 template<bool GEOM>
-__device__ __forceinline__ void gather_j(unsigned rec, int slot, const int* next_index, const float4* __restrict__ xq,
-                                         const float2* __restrict__ lj, const int* __restrict__ atype)
+__device__ __forceinline__ void load_j(JAtom& J, int slot, const float4* __restrict__ xq, const float2* __restrict__ lj, const int* __restrict__ atype)
 {
-    cp_async_16(rec, xq + slot);
-    if (GEOM) cp_async_8(rec + 512, lj + slot);
-    else cp_async_4(rec + 512, atype + slot);
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(rec + 520), "r"(slot) : "memory");
-    /* the record's fourth word carries the slot index of the step NB_RING - 1 steps after this one: it lands with the record and
-     * is exactly what the gather issued when this record is consumed needs (the index stream rides the same ring, so no global
-     * load result is ever waited for inside the step loop) */
-    if (next_index) cp_async_4(rec + 524, next_index);
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(J.xq.x), "=f"(J.xq.y), "=f"(J.xq.z), "=f"(J.xq.w) : "l"(xq + slot) : "memory");
+#ifdef B200NB_DIAG_NO_LJ /* diagnostic build only (wrong results): what the second gather instruction of a step costs */
+    if (GEOM) J.lj = make_float2(0.05f, 0.003f);
+    else
+#endif
+    if (GEOM) asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(J.lj.x), "=f"(J.lj.y) : "l"(lj + slot) : "memory");
+    else asm volatile("ld.global.f32 %0, [%1];" : "=f"(J.lj.x) : "l"(atype + slot) : "memory");
+    J.slot = slot;
 }
-/* returns the slot index stored in the record's fourth word */
-__device__ __forceinline__ int read_j(JAtom& J, unsigned rec)
+__device__ __forceinline__ int load_index(const int* p)
 {
-    float sl, nx;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(J.xq.x), "=f"(J.xq.y), "=f"(J.xq.z), "=f"(J.xq.w) : "r"(rec) : "memory");
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(J.lj.x), "=f"(J.lj.y), "=f"(sl), "=f"(nx) : "r"(rec + 512) : "memory");
-    J.slot = __float_as_int(sl);
-    return __float_as_int(nx);
+    int v;
+#ifdef B200NB_INDEX_EVICT_FIRST /* experiment: the slot-index stream (read once) marked evict-first in L2, so that it does not push out xq / f */
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+#else
+    asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#endif
+    return v;
 }
 
 /* simd/simd_math.h:1609-1650 pmeForceCorrection: denominator and numerator */
@@ -407,9 +391,8 @@ __device__ __forceinline__ float2 pair_fscal(const IData& I, const JAtom& J, con
  * it reduces all three components itself with ONE 16-byte red into the j-atom's float4 force slot.  Measured
  * (profiles/r2/q_sweep_half_entries.txt): red.v2 {x, y} + red {z} saves the fourth, useless add in L2 but doubles the L2 requests
  * and is 12 % slower at 1 M atoms (B200NB_JRED_SPLIT builds it). */
-__device__ __forceinline__ void reduce_store_j(const float2 fjx, const float2 fjy, const float2 fjz, float4* __restrict__ f, const int jslot)
+__device__ __forceinline__ void red_j(const float sx, const float sy, const float sz, float4* __restrict__ f, const int jslot)
 {
-    const float  sx = -fjx.x - fjx.y, sy = -fjy.x - fjy.y, sz = -fjz.x - fjz.y;
     float* const fp = reinterpret_cast<float*>(f + jslot);
 #ifdef B200NB_DIAG_NO_RED /* diagnostic build only: drops the j-force scatter (wrong results) to measure its cost */
     if (sx == 12345.678f)
@@ -423,16 +406,15 @@ __device__ __forceinline__ void reduce_store_j(const float2 fjx, const float2 fj
 #endif
     }
 }
-
 #ifndef B200NB_FORCE_WARPS
 #define B200NB_FORCE_WARPS 1 /* warps (= list entries) per CTA: small CTAs refill an SM's warp slots at entry granularity */
 #endif
-#ifndef B200NB_FORCE_MIN_BLOCKS
-/* resident warps per SM the register allocation aims at: 20 (<= 96 registers) for the force-only kernels -- with the j-atom
- * stream in the shared-memory ring they fit without spills, and 20 warps beat 16 by 8 % (profiles/r2/c_sweep_ring.txt); the
- * energy / modifier kernels need up to 128 registers */
-#define B200NB_FORCE_MIN_BLOCKS(VF, GEN) (((VF) || (GEN) ? 16 : 20) / B200NB_FORCE_WARPS)
+#ifndef B200NB_MB_PLAIN
+#define B200NB_MB_PLAIN 20
 #endif
+/* resident warps per SM the register allocation aims at: 20 (<= 96 registers) for the force-only kernels, 16 for the energy /
+ * modifier kernels, which need up to 128 registers */
+#define B200NB_FORCE_MIN_BLOCKS(VF, GEN) (((VF) || (GEN) ? 16 : B200NB_MB_PLAIN) / B200NB_FORCE_WARPS)
 template<int EEL, bool GEOM, bool VF, bool GEN>
 __global__ void __launch_bounds__(32 * B200NB_FORCE_WARPS, B200NB_FORCE_MIN_BLOCKS(VF, GEN))
 k_force(const Entry* __restrict__ entries, long long nwarps, const int* __restrict__ pja, const uint64_t* __restrict__ tmask,
@@ -464,10 +446,8 @@ k_force(const Entry* __restrict__ entries, long long nwarps, const int* __restri
      * far-away dummy atoms: k_pad_partner (b200nb.cu) has written their slots behind its own steps, so the loops below need no
      * per-half bounds -- only the mask fetch and the outputs look at nstep_my */
     const int* const ja = pja + (size_t)ev.z * NB_JSTEP + jl;
-    /* the j slots of the first NB_RING - 1 steps: list data only, so they may be fetched before the dependency wait below */
-    int slot_first[NB_RING - 1];
-#pragma unroll
-    for (int k = 0; k < NB_RING - 1; k++) slot_first[k] = k < nstep ? __ldg(ja + k * NB_JSTEP) : 0;
+    /* the j slots of the first two steps: list data only, so they may be fetched before the dependency wait below */
+    int slot_n = __ldg(ja), slot_nn = __ldg(ja + NB_JSTEP); /* always valid: a row ends in NB_PACK_TAIL steps of dummy atoms */
     /* Programmatic dependent launch: everything above reads only the list; from here on the kernel touches xq and f, so wait
      * for the completion of the preceding kernel of the stream (k_step_begin) -- a no-op for a normally serialised launch. */
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -476,15 +456,9 @@ k_force(const Entry* __restrict__ entries, long long nwarps, const int* __restri
     const int  ci = ev.x, shift = NB_ENTRY_SHIFT(ev.y), half = NB_ENTRY_HALF(ev.y);
     const int  nmask_my = min(NB_ENTRY_NMASK(ev.y), nstep_my);
     const int  nmask    = max(min(NB_ENTRY_NMASK(evA.y), evA.w - evA.z), min(NB_ENTRY_NMASK(evB.y), evB.w - evB.z));
-    /* the ring: NB_RING stages of 1 KB per warp; one commit group per step, empty past the end of the entry */
-    __shared__ __align__(16) float4 s_ring[B200NB_FORCE_WARPS][NB_RING][64];
-    const unsigned ring = (unsigned)__cvta_generic_to_shared(&s_ring[threadIdx.x >> 5][0][0]) + 16u * lane;
-#pragma unroll
-    for (int k = 0; k < NB_RING - 1; k++)
-    {
-        if (k < nstep) gather_j<GEOM>(ring + 1024u * k, slot_first[k], k + NB_RING - 1 < nstep ? ja + (k + NB_RING - 1) * NB_JSTEP : nullptr, xq, lj, atype);
-        cp_async_commit();
-    }
+    JAtom Jn; /* the j-atom of the NEXT step, in flight */
+    Jn.xq = make_float4(0.f, 0.f, 0.f, 0.f), Jn.lj = dup(0.f), Jn.slot = 0;
+    load_j<GEOM>(Jn, slot_n, xq, lj, atype);
     IData I[2];
     {
         const float sx = __ldg(shift_vec + 3 * shift), sy = __ldg(shift_vec + 3 * shift + 1), sz = __ldg(shift_vec + 3 * shift + 2);
@@ -541,21 +515,22 @@ k_force(const Entry* __restrict__ entries, long long nwarps, const int* __restri
     /* masks of the leading steps: 64 bits per step, bit 16*k + jl = pair (i-atom 4*half + k, j-atom jl) interacts */
     const uint2* const emask = reinterpret_cast<const uint2*>(tmask) + ev.z;
     int                s     = 0;
-    const int*         jp    = ja + 2 * (NB_RING - 1) * NB_JSTEP; /* slot index of step s + 2 (NB_RING - 1) */
-    unsigned           st_use = 0, st_fill = (NB_RING - 1) * 1024u; /* ring offsets of step s and of step s + NB_RING - 1 */
-    /* Top of step s: the gathers of steps s .. s + NB_RING - 2 are in flight (one commit group each).  next_j() waits for the
-     * group of step s, reads its record (the j-atom and the slot index of step s + NB_RING - 1) and starts the gather of step
-     * s + NB_RING - 1 into the stage step s - 1 just released, together with the fetch of the slot index of step
-     * s + 2 (NB_RING - 1) into that record. */
+    /* Top of step s: the registers Jn hold (or are about to receive) the j-atom of step s, slot_nn the slot of step s + 1.
+     * next_j() hands Jn over as the current j-atom, issues the gather of step s + 1 and the fetch of the slot of step s + 2, and
+     * then flushes the j-force of step s - 1 (pending in pjx .. pslot): that red is what keeps the loads above it. */
+    const int* jp = ja + 2 * NB_JSTEP; /* slot index of step s + 2 */
+    float      pjx = 0.f, pjy = 0.f, pjz = 0.f;
+    int        pslot = slot_n; /* the first flush adds zeros to the first j-atom's slot */
     auto next_j = [&](JAtom& J) {
-        cp_async_wait<NB_RING - 2>();
-        const int slot_next = read_j(J, ring + st_use);
-        if (s + NB_RING - 1 < nstep) gather_j<GEOM>(ring + st_fill, slot_next, s + 2 * (NB_RING - 1) < nstep ? jp : nullptr, xq, lj, atype);
-        cp_async_commit();
+        J = Jn;
+        /* unconditional: past the last step these fetch the dummy atoms that end every row (NB_PACK_TAIL), so that the loop has
+         * no predicates and the registers of Jn are simply renamed from step to step */
+        load_j<GEOM>(Jn, slot_nn, xq, lj, atype);
+        slot_nn = load_index(jp);
         jp += NB_JSTEP;
-        st_use  = (st_use + 1024u) & (NB_RING * 1024u - 1);
-        st_fill = (st_fill + 1024u) & (NB_RING * 1024u - 1);
+        red_j(pjx, pjy, pjz, f, pslot);
     };
+#define NB_STORE_J(fjx, fjy, fjz, slot) pjx = -(fjx).x - (fjx).y, pjy = -(fjy).x - (fjy).y, pjz = -(fjz).x - (fjz).y, pslot = (slot)
 
     /* ---- steps with exclusion masks (sorted to the front of a half-entry; one or two per half-entry) ---- */
     for (; s < nmask; s++)
@@ -584,9 +559,10 @@ k_force(const Entry* __restrict__ entries, long long nwarps, const int* __restri
             fjy    = fma2(fs, dy, fjy);
             fjz    = fma2(fs, dz, fjz);
         }
-        reduce_store_j(fjx, fjy, fjz, f, J.slot);
+        NB_STORE_J(fjx, fjy, fjz, J.slot);
     }
     /* ---- plain steps ---- */
+#pragma unroll 2
     for (; s < nstep; s++)
     {
         JAtom J;
@@ -608,9 +584,11 @@ k_force(const Entry* __restrict__ entries, long long nwarps, const int* __restri
 #endif
         }
 #ifndef B200NB_DIAG_NO_JFORCE
-        reduce_store_j(fjx, fjy, fjz, f, J.slot);
+        NB_STORE_J(fjx, fjy, fjz, J.slot);
 #endif
     }
+    if (nstep > 0) red_j(pjx, pjy, pjz, f, pslot); /* the j-force of the last step */
+#undef NB_STORE_J
     /* ---- i-forces: 12 floats per lane (2 pairs x 2 atoms x 3) summed over the 16 j-lanes of this half (lane bits 0-3),
      * transposed so that every exchange halves what is still carried: bit 3 picks the pair, bit 2 the atom of the pair ---- */
     const bool b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;

@@ -139,6 +139,41 @@ class DomainPlan:
         return h
 
 
+class DevicePlan(DomainPlan):
+    """The plan of a repartitioning step that ran on the GPU: the global indices of the home and halo atoms live on the device
+    (home_dev, halo_dev); home / halo / local are downloaded when somebody asks (a caller that keeps per-atom state of its own
+    permutes it with plan.home; the per-step path never needs them)."""
+
+    def __init__(self, box, nranks, rank, rlist, home_dev, send_local, halo_dev):
+        self.nranks, self.rank, self.rlist = nranks, rank, float(rlist)
+        self.box = np.asarray(box, dtype=np.float32).reshape(3)
+        self.bounds = self.boundaries(self.box, nranks)
+        self.lo, self.hi = float(self.bounds[rank]), float(self.bounds[rank + 1])
+        self.left, self.right = (rank - 1) % nranks, (rank + 1) % nranks
+        self.home_dev, self.halo_dev = home_dev, halo_dev
+        self.send_local = np.ascontiguousarray(send_local, dtype=np.int32)
+        self.send_shift = np.array([self.box[0] if (rank == 0 and nranks > 1) else 0.0, 0.0, 0.0], np.float32)
+        self.recv_from_periodic = nranks > 1 and self.right == 0
+        self.nhome, self.nhalo = int(home_dev.shape[0]), int(halo_dev.shape[0])
+        self._home = self._halo = None
+
+    @property
+    def home(self):
+        if self._home is None:
+            self._home = self.home_dev.cpu().numpy().astype(np.int32)
+        return self._home
+
+    @property
+    def halo(self):
+        if self._halo is None:
+            self._halo = self.halo_dev.cpu().numpy().astype(np.int32)
+        return self._halo
+
+    @property
+    def local(self):
+        return np.concatenate([self.home, self.halo]).astype(np.int32)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # repartitioning: atoms that left their slab change owner (dd_partition_system, domdec/partition.cpp: dd_redistribute_cg
 # domdec/redistribute.cpp moves them to the neighbour cell, setup_dd_communication rebuilds the halo send lists, and
@@ -382,13 +417,15 @@ class DomainRank:
         self.max_halo = self.max_send = 0
         self._setup_local(np.ascontiguousarray(system.x[p.home]), first=True)
 
-    def _setup_local(self, x_home, first=False):
+    def _setup_local(self, x_home, first=False, atoms_installed=False):
         """(Re)build everything that depends on which atoms this rank owns and receives: local topology, device buffers,
-        grids, pair list, halo plan."""
+        grids, pair list, halo plan.  atoms_installed: the local topology is already in the context (built on the device by
+        b200nb_dd_set_local_atoms) and x_home is a device tensor."""
         torch = self.torch
         p = self.plan
-        types, q, eo, ei = p.local_topology(*self.topology)
-        self.nb.set_atoms(types, q, eo, ei)
+        if not atoms_installed:
+            types, q, eo, ei = p.local_topology(*self.topology)
+            self.nb.set_atoms(types, q, eo, ei)
         self.nlocal = p.nhome + p.nhalo
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self.x = torch.zeros((self.nlocal, 3), dtype=torch.float32, device=self.device)
@@ -396,7 +433,10 @@ class DomainRank:
             self.send_idx = torch.from_numpy(p.send_local).to(self.device)
             self.send_buf = torch.zeros((len(p.send_local), 3), dtype=torch.float32, device=self.device)
             self.recv_f = torch.zeros((len(p.send_local), 3), dtype=torch.float32, device=self.device)
-            self.x[:p.nhome].copy_(torch.from_numpy(np.ascontiguousarray(x_home, dtype=np.float32)))
+            if isinstance(x_home, torch.Tensor):
+                self.x[:p.nhome].copy_(x_home)
+            else:
+                self.x[:p.nhome].copy_(torch.from_numpy(np.ascontiguousarray(x_home, dtype=np.float32)))
         self.nb.synchronize()
         if self.use_windows:
             if first:
@@ -406,7 +446,7 @@ class DomainRank:
                                      % (p.nhalo, len(p.send_local), self.max_halo, self.max_send))
         self.search(first=first)
 
-    def repartition(self, x_home=None):
+    def repartition(self, x_home=None, on_device=True):
         """Pair-search step WITH atom migration (dd_partition_system, domdec/partition.cpp): atoms whose current
         coordinates (self.x[:nhome], on the device) left this rank's slab change owner, coordinates are wrapped into the
         box, the halo send lists are rebuilt from the new ownership, then grids and pair list are rebuilt.  Collective:
@@ -415,6 +455,9 @@ class DomainRank:
         torch = self.torch
         p = self.plan
         self.nb.synchronize()
+        if on_device:
+            return self._repartition_device(x_home)
+        # ---- host variant (numpy; what the gloo tests of the plan logic run, and the cross-check of the device variant) ----
         # the current coordinates of the home atoms: the caller's (x_home, e.g. after an integration step), else those of the
         # last step -- the caller's pinned buffer when the step ran on it in place, self.x otherwise
         xc = getattr(self, "_x_host_current", None)
@@ -432,6 +475,90 @@ class DomainRank:
                                                       to_tensor=to_dev)
         self.plan = DomainPlan.from_parts(p.box, self.nranks, self.rank, self.rlist, home, send_local, halo)
         self._setup_local(x_new)
+        return self.plan
+
+    def _repartition_device(self, x_home):
+        """repartition() with the coordinate-dependent work on the GPU (csrc/dd_partition.cu): wrap + ownership, stable compaction
+        of stayers / leavers, message packing, merge of stayers and arrivals into the new home set, halo selection, local
+        topology with exclusions renumbered through a device-resident global -> local look-up.  Coordinates stay on the device;
+        the host sees the counts (a dozen ints) and the send list that b200nb_dd_set_plan takes.  Messages between the ranks
+        travel as device tensors through the transport (NCCL send/recv; the loopback of the single-GPU tests)."""
+        torch = self.torch
+        p, nb, t = self.plan, self.nb, self.t
+        dev = self.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev), torch.cuda.stream(self.stream):
+            if not getattr(self, "_global_topology_on_device", False):
+                nb.dd_set_global_topology(*self.topology)
+                self._global_topology_on_device = True
+            xc = getattr(self, "_x_host_current", None)
+            if x_home is not None:
+                xt = x_home if isinstance(x_home, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_home, dtype=np.float32))
+                if tuple(xt.shape) != (p.nhome, 3):
+                    raise InputException("repartition: x_home must hold the %d home atoms" % p.nhome)
+                x = xt.to(dev, dtype=torch.float32, copy=True).contiguous()
+            elif xc is not None and len(xc) == p.nhome:
+                x = xc.to(dev, copy=True)
+            else:
+                x = self.x[:p.nhome].clone()
+            self._x_host_current = None
+            gid = getattr(p, "home_dev", None)
+            if gid is None:
+                gid = torch.from_numpy(np.ascontiguousarray(p.home, dtype=np.int32)).to(dev)
+            n = p.nhome
+            bounds = DomainPlan.boundaries(p.box, self.nranks)
+            code = torch.empty(max(n, 1), **i32)
+            idx = torch.empty(max(n, 1), **i32)
+            nb.dd_wrap_classify(x.data_ptr(), n, p.box, bounds, self.nranks, self.rank, code.data_ptr())
+            nstay, nl, nr, nlost = nb.dd_partition_indices(code.data_ptr(), n, 4, idx.data_ptr())
+            if self.nranks == 1:
+                nstay, nl, nr, nlost = n, 0, 0, 0
+            if nlost:
+                raise InputException("an atom moved more than one domain between two repartitioning steps")
+            out_l = torch.empty((nl, 4), **i32)
+            out_r = torch.empty((nr, 4), **i32)
+            nb.dd_pack_atoms(idx.data_ptr() + 4 * nstay, nl, gid.data_ptr(), x.data_ptr(), out_l.data_ptr())
+            nb.dd_pack_atoms(idx.data_ptr() + 4 * (nstay + nl), nr, gid.data_ptr(), x.data_ptr(), out_r.data_ptr())
+            if self.nranks > 1:
+                counts = t.allgather_object(dict(to_left=nl, to_right=nr))
+                # what arrives from the right neighbour is what it sends to ITS left, and vice versa
+                in_r = torch.empty((counts[p.right]["to_left"], 4), **i32)
+                in_l = torch.empty((counts[p.left]["to_right"], 4), **i32)
+                t.sendrecv(out_l, p.left, in_r, p.right)
+                t.sendrecv(out_r, p.right, in_l, p.left)
+                arrived = torch.cat([in_r, in_l]).contiguous()
+            else:
+                arrived = torch.empty((0, 4), **i32)
+            m = int(arrived.shape[0])
+            n_new = nstay + m
+            gid_new = torch.empty(max(n_new, 1), **i32)[:n_new]
+            x_new = torch.empty((max(n_new, 1), 3), dtype=torch.float32, device=dev)[:n_new]
+            nb.dd_merge_home(idx.data_ptr(), nstay, gid.data_ptr(), x.data_ptr(), arrived.data_ptr() if m else 0, m,
+                             gid_new.data_ptr(), x_new.data_ptr())
+            # every atom of the new home set must lie in this rank's slab (the host variant's owner_of check), and the halo of the
+            # -x neighbour = the home atoms within rlist of the lower face: one more classification + partition each
+            code2 = torch.empty(max(n_new, 1), **i32)
+            idx2 = torch.empty(max(n_new, 1), **i32)
+            if self.nranks > 1:
+                nb.dd_wrap_classify(x_new.data_ptr(), n_new, p.box, bounds, self.nranks, self.rank, code2.data_ptr())
+                if nb.dd_partition_indices(code2.data_ptr(), n_new, 4, idx2.data_ptr())[0] != n_new:
+                    raise InputException("repartitioning left an atom outside its new owner's slab")
+                nb.dd_select_lower_face(x_new.data_ptr(), n_new, float(bounds[self.rank]), self.rlist, code2.data_ptr())
+                nkeep, nsend = nb.dd_partition_indices(code2.data_ptr(), n_new, 2, idx2.data_ptr())
+                send_local_dev = idx2[nkeep:nkeep + nsend]
+                send_gid = torch.empty(max(nsend, 1), **i32)[:nsend]
+                nb.dd_gather_int(idx2.data_ptr() + 4 * nkeep, nsend, gid_new.data_ptr(), send_gid.data_ptr())
+                nsends = t.allgather_object(int(nsend))
+                halo_gid = torch.empty(max(nsends[p.right], 1), **i32)[:nsends[p.right]]
+                t.sendrecv(send_gid, p.left, halo_gid, p.right)
+                send_local = send_local_dev.cpu().numpy().astype(np.int32)  # b200nb_dd_set_plan takes it from the host: a few thousand ints
+            else:
+                halo_gid = torch.empty(0, **i32)
+                send_local = np.zeros(0, np.int32)
+            local_gid = torch.cat([gid_new, halo_gid]).contiguous()
+            nb.dd_set_local_atoms(local_gid.data_ptr(), int(local_gid.shape[0]))
+        self.plan = DevicePlan(p.box, self.nranks, self.rank, self.rlist, gid_new, send_local, halo_gid)
+        self._setup_local(x_new, atoms_installed=True)
         return self.plan
 
     # -- peer-memory halo windows: created once, sized with slack for later search steps -----------------------------------

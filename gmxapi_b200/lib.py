@@ -20,7 +20,9 @@ EXPORTS = [
     "b200nb_get_outputs", "b200nb_compute", "b200nb_step", "b200nb_dd_create_window", "b200nb_dd_open_peer", "b200nb_dd_set_plan", "b200nb_dd_set_links",
     "b200nb_dd_step", "b200nb_dd_status", "b200nb_halo_pack_x", "b200nb_halo_unpack_f", "b200nb_get_stats",
     "b200nb_get_grid_order", "b200nb_get_tiles", "b200nb_get_pairs", "b200nb_time_force_kernel", "b200nb_time_step",
-    "b200nb_set_grid_atoms", "b200nb_upload_pairlist", "b200nb_copy_xq_grid", "b200nb_get_f_grid", "b200nb_set_shift_vec", "b200nb_set_ewald_table",
+    "b200nb_set_grid_atoms", "b200nb_upload_pairlist", "b200nb_copy_xq_grid", "b200nb_get_f_grid", "b200nb_set_shift_vec", "b200nb_set_ewald_table", "b200nb_describe",
+    "b200nb_dd_wrap_classify", "b200nb_dd_select_lower_face", "b200nb_dd_partition_indices", "b200nb_dd_pack_atoms", "b200nb_dd_merge_home",
+    "b200nb_dd_gather_int", "b200nb_dd_set_global_topology", "b200nb_dd_set_local_atoms",
 ]
 
 
@@ -153,6 +155,15 @@ def load_library():
     L.b200nb_get_f_grid.argtypes = [vp, vp, ci, ci]
     L.b200nb_set_shift_vec.argtypes = [vp, vp]
     L.b200nb_set_ewald_table.argtypes = [vp, vp, ci, cf]
+    L.b200nb_describe.argtypes = [vp, C.c_char_p, ci]
+    L.b200nb_dd_wrap_classify.argtypes = [vp, vp, ci, vp, vp, ci, ci, vp]
+    L.b200nb_dd_select_lower_face.argtypes = [vp, vp, ci, cf, cf, vp]
+    L.b200nb_dd_partition_indices.argtypes = [vp, vp, ci, ci, vp, vp]
+    L.b200nb_dd_pack_atoms.argtypes = [vp, vp, ci, vp, vp, vp]
+    L.b200nb_dd_merge_home.argtypes = [vp, vp, ci, vp, vp, vp, ci, vp, vp]
+    L.b200nb_dd_gather_int.argtypes = [vp, vp, ci, vp, vp]
+    L.b200nb_dd_set_global_topology.argtypes = [vp, ci, vp, vp, vp, vp]
+    L.b200nb_dd_set_local_atoms.argtypes = [vp, vp, ci]
     _lib = L
     return L
 
@@ -346,6 +357,46 @@ class NbnxmGpu:
         self._check(self._L.b200nb_dd_set_plan(self._h, int(nhome), int(nhalo), _ptr(si) if si.size else None, int(si.size),
                                                _ptr(sh), int(halo_fshift_index)), "dd_set_plan")
 
+    # -- repartitioning on the device (b200nb_dd_* of csrc/dd_partition.cu); pointers are device addresses (ints) ----------------
+    def dd_wrap_classify(self, x_dev, n, box, bounds, nranks, rank, code_dev):
+        b = np.ascontiguousarray(box, dtype=np.float32)
+        bd = np.ascontiguousarray(bounds, dtype=np.float32)
+        self._check(self._L.b200nb_dd_wrap_classify(self._h, _ptr(x_dev), int(n), _ptr(b), _ptr(bd), int(nranks), int(rank), _ptr(code_dev)),
+                    "dd_wrap_classify")
+
+    def dd_select_lower_face(self, x_dev, n, lo, rlist, code_dev):
+        self._check(self._L.b200nb_dd_select_lower_face(self._h, _ptr(x_dev), int(n), float(lo), float(rlist), _ptr(code_dev)),
+                    "dd_select_lower_face")
+
+    def dd_partition_indices(self, code_dev, n, ncodes, idx_dev):
+        """Stable partition of 0 .. n-1 by code; returns the counts per code (list of ncodes ints)."""
+        cnt = np.zeros(4, np.int32)
+        self._check(self._L.b200nb_dd_partition_indices(self._h, _ptr(code_dev), int(n), int(ncodes), _ptr(idx_dev), _ptr(cnt)),
+                    "dd_partition_indices")
+        return [int(v) for v in cnt[:ncodes]]
+
+    def dd_pack_atoms(self, idx_dev, m, gid_dev, x_dev, out4_dev):
+        self._check(self._L.b200nb_dd_pack_atoms(self._h, _ptr(idx_dev), int(m), _ptr(gid_dev), _ptr(x_dev), _ptr(out4_dev)), "dd_pack_atoms")
+
+    def dd_merge_home(self, stay_idx_dev, nstay, gid_dev, x_dev, arrived4_dev, narrived, gid_out_dev, x_out_dev):
+        self._check(self._L.b200nb_dd_merge_home(self._h, _ptr(stay_idx_dev), int(nstay), _ptr(gid_dev), _ptr(x_dev), _ptr(arrived4_dev),
+                                                 int(narrived), _ptr(gid_out_dev), _ptr(x_out_dev)), "dd_merge_home")
+
+    def dd_gather_int(self, idx_dev, m, in_dev, out_dev):
+        self._check(self._L.b200nb_dd_gather_int(self._h, _ptr(idx_dev), int(m), _ptr(in_dev), _ptr(out_dev)), "dd_gather_int")
+
+    def dd_set_global_topology(self, types, q, excl_off=None, excl_idx=None):
+        types = np.ascontiguousarray(types, dtype=np.int32)
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        eo = np.ascontiguousarray(excl_off, dtype=np.int32) if excl_off is not None else None
+        ei = np.ascontiguousarray(excl_idx, dtype=np.int32) if excl_idx is not None else None
+        self._check(self._L.b200nb_dd_set_global_topology(self._h, int(types.shape[0]), _ptr(types), _ptr(q), _ptr(eo), _ptr(ei)),
+                    "dd_set_global_topology")
+
+    def dd_set_local_atoms(self, local_gid_dev, nlocal):
+        self.natoms = int(nlocal)
+        self._check(self._L.b200nb_dd_set_local_atoms(self._h, _ptr(local_gid_dev), int(nlocal)), "dd_set_local_atoms")
+
     def dd_set_links(self, nhome, nhalo, links):
         """General plan (b200nb_dd_set_links).  links: list of dicts with keys send_peer, send_idx (int32 array), shift[3],
         peer_halo_offset, recv_peer, nrecv, peer_entry_offset, fshift_index."""
@@ -380,6 +431,12 @@ class NbnxmGpu:
     def halo_unpack_f(self, f_dev, index_dev, n, in_dev):
         self._check(self._L.b200nb_halo_unpack_f(self._h, _ptr(f_dev), _ptr(index_dev), n, _ptr(in_dev)),
                     "halo_unpack_f")
+
+    def describe(self):
+        """One line about this context (device, atoms, grid, kernel flavour, list sizes) for logs."""
+        buf = C.create_string_buffer(1024)
+        self._check(self._L.b200nb_describe(self._h, buf, 1024), "describe")
+        return buf.value.decode()
 
     def stats(self):
         s = _Stats()

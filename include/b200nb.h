@@ -272,6 +272,35 @@ int b200nb_dd_step(b200nb_t* h, const float* x_home, float* f_home, int flags);
 /* after b200nb_synchronize: B200NB_ERR_STATE if a halo flag timed out in any step since the last call */
 int b200nb_dd_status(b200nb_t* h);
 
+/* ---- repartitioning on the device (the coordinate-dependent work of dd_partition_system; gmxapi_b200/csrc/dd_partition.cu) ----
+ * Replaces CPU code of the reference: domdec/redistribute.cpp:505-760 (dd_redistribute_cg: which atoms left, where to, compaction,
+ * packing per direction), pbcutil/pbc.cpp put_atoms_in_box, domdec/partition.cpp:2058-2440 + domdec/domdec.cpp setup_dd_communication
+ * (send lists = home atoms within the cut-off of a face), domdec/localtopology.cpp make_exclusions_zone + ga2la (exclusions of the local
+ * atoms in local indices).  All pointers named *_dev are device memory of this context's GPU; coordinates stay on the device, the
+ * host sees counts.  Messages between ranks (leavers, halo indices) are the caller's: search-step traffic of a few thousand atoms. */
+/* x-slab decomposition: wraps the home atoms into the box (in place) and classifies each: 0 stays, 1 goes to the -x neighbour,
+ * 2 to the +x neighbour, 3 moved more than one domain (the caller treats a non-zero count of 3 as fatal, like the reference).
+ * bounds_host: nranks + 1 slab boundaries, float32(k * box_x / nranks). */
+int b200nb_dd_wrap_classify(b200nb_t* h, float* x_dev, int n, const float box[3], const float* bounds_host, int nranks, int rank, int* code_dev);
+/* code 1 for the home atoms within rlist of the slab's lower face (x - lo < rlist in float32: the halo of the -x neighbour), else 0 */
+int b200nb_dd_select_lower_face(b200nb_t* h, const float* x_dev, int n, float lo, float rlist, int* code_dev);
+/* stable partition of the indices 0 .. n-1 by code (0 .. ncodes-1, ncodes <= 4): idx_dev = the indices with code 0 in ascending
+ * order, then those with code 1, ...; counts_host[k] = how many have code k (synchronises the stream for these few ints) */
+int b200nb_dd_partition_indices(b200nb_t* h, const int* code_dev, int n, int ncodes, int* idx_dev, int* counts_host);
+/* the message for a neighbour: per listed atom 4 ints {global index, x, y, z bit patterns} */
+int b200nb_dd_pack_atoms(b200nb_t* h, const int* idx_dev, int m, const int* gid_dev, const float* x_dev, int* out4_dev);
+/* the new home set in ascending global index: the stayers (listed by stay_idx_dev, ascending already) merged with the arrived
+ * messages (any order); writes nstay + narrived global indices and coordinates */
+int b200nb_dd_merge_home(b200nb_t* h, const int* stay_idx_dev, int nstay, const int* gid_dev, const float* x_dev, const int* arrived4_dev,
+                         int narrived, int* gid_out_dev, float* x_out_dev);
+int b200nb_dd_gather_int(b200nb_t* h, const int* idx_dev, int m, const int* in_dev, int* out_dev);
+/* the replicated global topology (types, charges, exclusions as CSR over global atom indices), uploaded once */
+int b200nb_dd_set_global_topology(b200nb_t* h, int nglobal, const int* type_host, const float* q_host, const int* excl_off_host,
+                                  const int* excl_idx_host);
+/* b200nb_set_atoms for home + halo atoms given by their global indices ON THE DEVICE: types and charges gathered, exclusions
+ * renumbered to local indices (partners that are not local are dropped: they cannot be in range on this rank) */
+int b200nb_dd_set_local_atoms(b200nb_t* h, const int* local_gid_dev, int nlocal);
+
 /* ---- introspection used by the parity tests and the bench ------------------------------------------------ */
 typedef struct
 {
@@ -282,10 +311,13 @@ typedef struct
     long long nentries;        /* work units */
     int       comb_geometric;  /* 1 if the geometric-rule kernel is used */
     long long nlaunches;       /* kernels launched by this context so far */
-    long long ntiles_packed;   /* 8-j-atom x 8-i-atom tiles the force kernel evaluates (the pruned list re-packed per j-atom) */
-    long long nentries_nonlocal; /* entries of the packed non-local (home x halo) list the next non-local launch runs */
+    long long ntiles_packed;   /* what the force kernel evaluates on the packed list, in units of 64 pair lanes (2 per warp step) */
+    long long nentries_nonlocal; /* half-entries of the packed non-local (home x halo) list the next non-local launch runs */
 } b200nb_stats_t;
 int b200nb_get_stats(b200nb_t* h, b200nb_stats_t* out);
+/* one line describing the context (device, atoms, grid, cut-offs, kernel flavour, list sizes, launch mode) for the caller's log:
+ * the reference prints its set-up the same way (nbnxm/nbnxm_setup.cpp:180-260 "Using a ... Verlet scheme", hardware report) */
+int b200nb_describe(b200nb_t* h, char* buf, int cap);
 /* slot -> original atom (-1 filler), natoms_padded ints: GridSet::atomIndices() */
 int b200nb_get_grid_order(b200nb_t* h, int* atom_index_host, int cap);
 /* the cluster pairs of the inner (or outer) list as (ci, shift, cj) triples */

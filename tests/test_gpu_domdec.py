@@ -36,7 +36,7 @@ def canonical(pairs_global, tx_dd):
     return (i << 34) | (j << 6) | idx
 
 
-def run_ranks(s, opt, nranks, flags, use_windows=True, nsteps=1, moved_x=None):
+def run_ranks(s, opt, nranks, flags, use_windows=True, nsteps=1, moved_x=None, repart_on_device=True):
     hub = LoopbackTransport(nranks)
     out = [None] * nranks
     err = []
@@ -55,7 +55,7 @@ def run_ranks(s, opt, nranks, flags, use_windows=True, nsteps=1, moved_x=None):
                 # the atoms moved (integration is the caller's business): new coordinates of the atoms this rank owns go to
                 # the device, then a repartitioning search step, then a step on the new decomposition
                 old_home = d.plan.home.copy()
-                plan = d.repartition(x_home=moved_x[old_home])
+                plan = d.repartition(x_home=moved_x[old_home], on_device=repart_on_device)
                 assert len(np.setdiff1d(plan.home, old_home)) > 0, "nothing migrated: the test does not test"
                 from gmxapi_b200.domdec import wrap_into_box
                 xh = np.ascontiguousarray(wrap_into_box(moved_x, s.box)[plan.home])
@@ -69,7 +69,8 @@ def run_ranks(s, opt, nranks, flags, use_windows=True, nsteps=1, moved_x=None):
             is_halo = pr[:, 1] >= p.nhome
             gl = np.stack([loc[pr[:, 0]], loc[pr[:, 1]], pr[:, 2]], 1)
             keys = np.concatenate([canonical(gl[~is_halo], 0), canonical(gl[is_halo], -1 if halo_periodic else 0)])
-            out[r] = dict(home=p.home, f=f.numpy().copy(), fs=fs, elj=elj, eel=eel, keys=keys, nhalo=p.nhalo)
+            out[r] = dict(home=p.home, f=f.numpy().copy(), fs=fs, elj=elj, eel=eel, keys=keys, nhalo=p.nhalo, halo=p.halo.copy(),
+                          send_local=p.send_local.copy(), npairs=len(pr))
             hub.endpoint(r).barrier()
             d.close()
         except Exception as e:  # noqa: BLE001
@@ -170,6 +171,29 @@ def test_repartition_after_motion(built, nranks, windows):
     elj, eel = sum(r["elj"] for r in res), sum(r["eel"] for r in res)
     assert abs(elj - evo) <= ENERGY_TOL * abs(evo)
     assert abs(eel - eco) <= ENERGY_TOL * abs(eco)
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_device_repartition_equals_host_repartition(built, nranks):
+    """The repartitioning kernels (csrc/dd_partition.cu: wrap + ownership, stable compaction, message packing, merge into the new
+    home set, halo selection, local topology on the device) against the numpy restatement of the same step (migrate_atoms +
+    DomainPlan.local_topology): identical home sets, send lists and halos on every rank, identical pair counts (the exclusions
+    went through the device-side global -> local renumbering) and forces equal up to summation order."""
+    s = g.systems.named("water_24k")
+    rng = np.random.Generator(np.random.PCG64(29))
+    x1 = (s.x + np.array([-0.52, 0.2, 0.35], np.float32) + rng.uniform(-0.01, 0.01, s.x.shape)).astype(np.float32)
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, computeVirialAndEnergy=True)
+    flags = nb.FLAG_ENERGY | nb.FLAG_VIRIAL
+    dev = run_ranks(s, opt, nranks, flags, moved_x=x1, repart_on_device=True)
+    host = run_ranks(s, opt, nranks, flags, moved_x=x1, repart_on_device=False)
+    for a, b in zip(dev, host):
+        assert np.array_equal(a["home"], b["home"])
+        assert np.array_equal(a["send_local"], b["send_local"])
+        assert np.array_equal(a["halo"], b["halo"])
+        assert a["npairs"] == b["npairs"]
+        assert np.array_equal(np.sort(a["keys"]), np.sort(b["keys"]))
+        assert np.abs(a["f"] - b["f"]).max() <= 1e-4 * np.abs(b["f"]).max()
+        assert abs(a["eel"] - b["eel"]) <= 1e-6 * abs(b["eel"])
 
 
 # ---- 2-D / 3-D decomposition, half-shell rule (gmxapi_b200/domdec_nd.py) ----------------------------------------------------

@@ -162,3 +162,15 @@ def test_reference_liquid_water(built, name):
     assert relrms(f, fo) < 1e-5
     elj, eel = fc.energies
     assert abs(elj - evo) <= 2e-5 * abs(evo) and abs(eel - eco) <= 2e-5 * abs(eco)
+
+
+@pytest.mark.gpu
+def test_describe_names_the_setup(built):
+    """b200nb_describe: the one-line set-up summary (device, atoms, grid, flavour, list sizes) a caller logs."""
+    import gmxapi_b200 as g
+    s = g.systems.named("water_3k")
+    fc = g.ForceCalculator(g.SimulationState.from_system(s), g.NBKernelOptions(pairlistCutoff=0.9, coulombType=g.CoulombType.Pme))
+    line = fc.nb.describe()
+    assert "3000 atoms" in line and "Ewald(analytical)" in line and "half-entries" in line and "sm_100" in line, line
+    st = fc.nb.stats()
+    assert "%d + 0 cluster pairs" % st["ntiles_outer"] in line, line
