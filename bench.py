@@ -510,6 +510,8 @@ def run_multi_gpu(args, rank, world, local_rank):
     import torch.distributed as dist
     import gmxapi_b200 as g
     from gmxapi_b200 import domdec
+    # stdout carries exactly one JSON line: whatever NCCL has to say (its version line under NCCL_DEBUG=VERSION / INFO) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peaks = measured_peaks()
     s = workload_system(args.workload, world if args.scaling == "weak" else 1)
