@@ -510,8 +510,11 @@ def run_multi_gpu(args, rank, world, local_rank):
     import torch.distributed as dist
     import gmxapi_b200 as g
     from gmxapi_b200 import domdec
-    # stdout carries exactly one JSON line: whatever NCCL has to say (its version line under NCCL_DEBUG=VERSION / INFO) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line: while the job runs, file descriptor 1 points at stderr, so that whatever the libraries
+    # underneath print (NCCL's version line under NCCL_DEBUG=VERSION / WARN / INFO) cannot end up in front of it
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peaks = measured_peaks()
     s = workload_system(args.workload, world if args.scaling == "weak" else 1)
@@ -642,7 +645,10 @@ def run_multi_gpu(args, rank, world, local_rank):
             "gpu_launches": int(lt.item()),
             "clocks": clocks,
         }
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
         print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     dist.barrier()
     d.close()
     del flush, x_pin, f_pin

@@ -141,7 +141,14 @@ extern "C" void b200nb_destroy(b200nb_t* h)
     {
         cudaStreamSynchronize(h->dd.stream_nl);
         cudaStreamDestroy(h->dd.stream_nl);
+        if (h->dd.stream_px)
+        {
+            cudaStreamSynchronize(h->dd.stream_px);
+            cudaStreamDestroy(h->dd.stream_px);
+        }
         cudaEventDestroy(h->dd.ev_begin);
+        cudaEventDestroy(h->dd.ev_start);
+        if (h->dd.ev_px_done) cudaEventDestroy(h->dd.ev_px_done);
         cudaEventDestroy(h->dd.ev_nl_done);
     }
     cudaFree(h->dd.window);
@@ -958,7 +965,10 @@ __device__ __forceinline__ float bb_dist2(const float* ilo, const float* ihi, co
  * the reference's bounding-box search, pairlist.cpp:1090-1244, followed by its list pruning,
  * nbnxm_cuda_kernel_pruneonly.cuh), so the list is the tightest superset of the in-range pairs.
  * Exclusion masks (pairlist.cpp:1874-1972): bit `lane` of mask word w is 1 when atoms (2*ih+w, jl) interact. */
-__global__ void __launch_bounds__(128, 6)
+#ifndef NB_SEARCH_BLOCKS
+#define NB_SEARCH_BLOCKS 6 /* resident CTAs of 4 warps per SM */
+#endif
+__global__ void __launch_bounds__(128, NB_SEARCH_BLOCKS)
 k_search(SearchArgs A, const float* __restrict__ xq, const float* __restrict__ bb, const float* __restrict__ cellz,
          const int* __restrict__ col_cell0, const int* __restrict__ atom_index, const int* __restrict__ excl_off,
          const int* __restrict__ excl_idx, const float* __restrict__ shift_vec, int* __restrict__ cnt_tiles,
@@ -1475,10 +1485,24 @@ __global__ void k_order_scan(int* __restrict__ hist)
         }
     }
 }
-__global__ void k_order_assign(const int* __restrict__ sizes, int n, int* __restrict__ hist, int* __restrict__ dest)
+/* a block counts its half-entries per bin in shared memory, claims room in every bin it uses with ONE global atomic per bin, and
+ * hands out the positions from there (one global atomic per half-entry on ~30 addresses took 80 us at 1 M atoms) */
+__global__ void __launch_bounds__(256) k_order_assign(const int* __restrict__ sizes, int n, int* __restrict__ hist, int* __restrict__ dest)
 {
+    __shared__ int cnt[NB_ORDER_BINS], base[NB_ORDER_BINS];
+    if (threadIdx.x < NB_ORDER_BINS) cnt[threadIdx.x] = 0;
+    __syncthreads();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) dest[e] = atomicAdd(&hist[NB_ORDER_BINS + min(sizes[e], NB_ORDER_BINS - 1)], 1);
+    int       bin = 0, local = 0;
+    if (e < n)
+    {
+        bin   = min(sizes[e], NB_ORDER_BINS - 1);
+        local = atomicAdd(&cnt[bin], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < NB_ORDER_BINS && cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(&hist[NB_ORDER_BINS + threadIdx.x], cnt[threadIdx.x]);
+    __syncthreads();
+    if (e < n) dest[e] = base[bin] + local;
 }
 /* headers from packing order into execution order.  After a rolling part the positions of the last full pack are kept: the
  * part's half-entries only shrink or grow a little, the order stays nearly sorted. */
@@ -2260,7 +2284,7 @@ __device__ __forceinline__ void wait_flags(const unsigned char* flags, int n, co
     if ((int)threadIdx.x < n && active_begin[threadIdx.x + 1] > active_begin[threadIdx.x])
     {
         const int*      flag = reinterpret_cast<const int*>(flags + 32 * threadIdx.x);
-        const int       want = *reinterpret_cast<const volatile int*>(seq);
+        const int       want = *reinterpret_cast<const volatile int*>(seq) + 1; /* the step in progress: see k_dd_step_end */
         const long long t0   = globaltimer_ns();
         while (ld_acquire_sys(flag) < want)
         {
@@ -2291,14 +2315,14 @@ __device__ __forceinline__ void publish_flags(int* counter, int* const* peer_fla
     if (s_last && (int)threadIdx.x < n && active_begin[threadIdx.x + 1] > active_begin[threadIdx.x])
     {
         __threadfence_system();
-        st_release_sys(peer_flags[threadIdx.x], *reinterpret_cast<const volatile int*>(seq));
+        st_release_sys(peer_flags[threadIdx.x], *reinterpret_cast<const volatile int*>(seq) + 1);
     }
 }
 
 /* what k_step_begin does on top of its single-domain work when the step is domain-decomposed */
 struct DdBegin
 {
-    int*       seq;       /* step counter, incremented here */
+    int*       seq;       /* step counter (advanced by k_dd_step_end) */
     const int* send_atom; /* per send entry: home atom */
     const int* send_link; /* per send entry: link */
     int        nsend;
@@ -2315,18 +2339,16 @@ struct PrefetchRange
     const char* p[4];
     size_t      bytes[4];
 };
-template<bool VEC, bool DD>
+template<bool VEC>
 __global__ void __launch_bounds__(256)
 k_step_begin(const float* __restrict__ x, const int* __restrict__ slot_of_atom, int a0, int a1, float* __restrict__ xq,
-             float4* __restrict__ f, int nclear, float* __restrict__ fshift, double* __restrict__ energy, PrefetchRange pf, DdBegin dd,
-             const __grid_constant__ DdLinksDev L)
+             float4* __restrict__ f, int nclear, float* __restrict__ fshift, double* __restrict__ energy, PrefetchRange pf)
 {
     __shared__ __align__(16) float sx[768];
     const int tid = threadIdx.x, t = blockIdx.x * 256 + tid;
     /* let the force kernel behind us start launching: its prologue only reads the list (it waits for this grid's completion,
      * griddepcontrol.wait, before it touches xq or f) */
     asm volatile("griddepcontrol.launch_dependents;");
-    if (DD && t == 0) *dd.seq = *dd.seq + 1; /* published to the other CTAs by the fence + counter in publish_flag */
     /* pull the read-only inputs of the force kernel that is about to run (packed list, LJ parameters) into L2 while this
      * kernel streams the coordinates: its prologue is a chain of dependent loads, ~3x shorter on L2 hits than from HBM */
 #pragma unroll
@@ -2359,20 +2381,26 @@ k_step_begin(const float* __restrict__ x, const int* __restrict__ slot_of_atom, 
         xb[1]     = sx[3 * tid + 1];
         xb[2]     = sx[3 * tid + 2];
     }
-    if (DD)
+}
+
+/* dd_move_x, sending side (packSendBufKernel, gpuhaloexchange_impl.cu:77-100) fused with the transfer: every send entry (home
+ * atom, link) goes straight from the caller's coordinates into the destination's window, shifted when the link crosses a
+ * periodic edge, then the flags.  Its own kernel at the head of the NON-LOCAL stream: it needs nothing but x, so it runs beside
+ * k_step_begin, and the system-scope fences of the flag protocol (an NVLink round trip) stay off the path to the local force
+ * kernel (fused into k_step_begin they delayed it by ~4 us at 128 k atoms per GPU). */
+__global__ void __launch_bounds__(256)
+k_dd_push_x(const float* __restrict__ x, DdBegin dd, const __grid_constant__ DdLinksDev L)
+{
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    for (int e = t; e < dd.nsend; e += (int)gridDim.x * 256)
     {
-        /* dd_move_x, sending side (packSendBufKernel, gpuhaloexchange_impl.cu:77-100) fused with the transfer: every send entry
-         * (home atom, link) goes straight into the destination's window, shifted when the link crosses a periodic edge */
-        for (int e = t; e < dd.nsend; e += (int)gridDim.x * 256)
-        {
-            const int    a = dd.send_atom[e], l = dd.send_link[e];
-            float* const d = L.peer_recv_x[l] + 3 * (size_t)(e - L.send_off[l]);
-            d[0]           = x[3 * (size_t)a] + L.shift[l][0];
-            d[1]           = x[3 * (size_t)a + 1] + L.shift[l][1];
-            d[2]           = x[3 * (size_t)a + 2] + L.shift[l][2];
-        }
-        publish_flags(dd.counter, L.peer_flag_x, L.nlinks, L.send_off, dd.seq);
+        const int    a = dd.send_atom[e], l = dd.send_link[e];
+        float* const d = L.peer_recv_x[l] + 3 * (size_t)(e - L.send_off[l]);
+        d[0]           = x[3 * (size_t)a] + L.shift[l][0];
+        d[1]           = x[3 * (size_t)a + 1] + L.shift[l][1];
+        d[2]           = x[3 * (size_t)a + 2] + L.shift[l][2];
     }
+    publish_flags(dd.counter, L.peer_flag_x, L.nlinks, L.send_off, dd.seq);
 }
 
 template<bool VEC>
@@ -2423,9 +2451,9 @@ static int launch_step(b200nb_context* h, const float* x_dev, int flags, float* 
         pf.bytes[3] = (h->comb_geom ? 8 : 4) * (size_t)h->npad;
     }
     if ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0)
-        k_step_begin<true, false><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, DdBegin{}, DdLinksDev{});
+        k_step_begin<true><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf);
     else
-        k_step_begin<false, false><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, DdBegin{}, DdLinksDev{});
+        k_step_begin<false><<<nb0, 256, 0, h->stream>>>(x_dev, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf);
     LAUNCH_CHECK(h);
     int rc;
     if (ev_force0) NB_CUDA(h, cudaEventRecord(ev_force0, h->stream));
@@ -2659,7 +2687,7 @@ k_dd_push_f(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom,
 template<bool VEC>
 __global__ void __launch_bounds__(256)
 k_dd_step_end(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom, int nhome, const int* __restrict__ ent_off,
-              const int* __restrict__ ent_idx, const unsigned char* __restrict__ window, const int* __restrict__ seq,
+              const int* __restrict__ ent_idx, const unsigned char* __restrict__ window, int* __restrict__ seq, int* __restrict__ counter,
               const float* __restrict__ recv_f, float* __restrict__ f, const __grid_constant__ DdLinksDev L)
 {
     __shared__ __align__(16) float sf[768];
@@ -2668,6 +2696,18 @@ k_dd_step_end(const float4* __restrict__ fg, const int* __restrict__ slot_of_ato
     const int nb   = min(256, nhome - base);
     /* the forces on the atoms we sent have landed in our window */
     wait_flags(window + NB_DD_FLAG_F(0), L.nlinks, L.send_off, seq, reinterpret_cast<int*>(const_cast<unsigned char*>(window) + NB_DD_ERR));
+    /* The step counter: during step s the device-resident counter holds s - 1 and every kernel of the step uses counter + 1 (the
+     * value the flags carry), whichever branch of the graph it runs on; this kernel is the last of the step, and the last of its
+     * CTAs to get here -- every CTA has read the counter in wait_flags by then -- advances it for the next replay. */
+    if (tid == 0)
+    {
+        __threadfence();
+        if (atomicAdd(counter, 1) == (int)gridDim.x - 1)
+        {
+            *counter = 0;
+            *seq     = *seq + 1;
+        }
+    }
     if (nb <= 0) return;
     if (tid < nb)
     {
@@ -2721,7 +2761,11 @@ extern "C" int b200nb_dd_create_window(b200nb_t* h, int max_halo, int max_send, 
         if (getenv("B200NB_DD_PRIO") && atoi(getenv("B200NB_DD_PRIO")) == 0) hi = lo; /* A/B switch for profiles/ */
         D.prio_high = hi;
         NB_CUDA(h, cudaStreamCreateWithPriority(&D.stream_nl, cudaStreamNonBlocking, hi));
+        NB_CUDA(h, cudaStreamCreateWithPriority(&D.stream_px, cudaStreamNonBlocking, hi));
+        if (const char* e = getenv("B200NB_DD_PUSH_INLINE")) D.push_inline = atoi(e) != 0;
+        NB_CUDA(h, cudaEventCreateWithFlags(&D.ev_px_done, cudaEventDisableTiming));
         NB_CUDA(h, cudaEventCreateWithFlags(&D.ev_begin, cudaEventDisableTiming));
+        NB_CUDA(h, cudaEventCreateWithFlags(&D.ev_start, cudaEventDisableTiming));
         NB_CUDA(h, cudaEventCreateWithFlags(&D.ev_nl_done, cudaEventDisableTiming));
     }
     if (ipc_handle_out)
@@ -2887,13 +2931,14 @@ extern "C" int b200nb_dd_set_plan(b200nb_t* h, int nhome, int nhalo, const int* 
 /* While a step is being captured: remember the graph node the last launch on the non-local stream created, so that its
  * priority can be set explicitly afterwards (a captured kernel node does not inherit the priority of the stream it was
  * captured from: measured, the non-local chain then queues behind the local kernel). */
-static void tag_nonlocal_node(b200nb_context* h)
+static void tag_nonlocal_node(b200nb_context* h, cudaStream_t stream = nullptr)
 {
     if (!h->capturing) return;
+    if (!stream) stream = h->dd.stream_nl;
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     const cudaGraphNode_t*  deps = nullptr;
     size_t                  nd = 0;
-    if (cudaStreamGetCaptureInfo_v2(h->dd.stream_nl, &st, nullptr, nullptr, &deps, &nd) == cudaSuccess && st == cudaStreamCaptureStatusActive)
+    if (cudaStreamGetCaptureInfo_v2(stream, &st, nullptr, nullptr, &deps, &nd) == cudaSuccess && st == cudaStreamCaptureStatusActive)
         for (size_t k = 0; k < nd; k++) h->nl_nodes.push_back(deps[k]);
 }
 
@@ -2921,14 +2966,34 @@ static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home,
     B.send_link = D.d_send_link;
     B.nsend     = D.nsend;
     B.counter   = D.d_count;
-    /* 1. home x -> grid layout, outputs cleared, halo x pushed into the neighbours' windows */
-    if ((reinterpret_cast<uintptr_t>(x_home) & 15) == 0)
-        k_step_begin<true, true><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, B, D.links);
-    else
-        k_step_begin<false, true><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf, B, D.links);
-    LAUNCH_CHECK(h);
-    /* 2. the halo chain on the high-priority non-local stream, the local kernel on the main stream */
+    /* 1. the halo x goes out first, on a branch of its own (high priority): it needs only the caller's coordinates, nothing in
+     * this step waits for it (the consumers are the neighbours), and it never waits itself -- so it can share a hardware queue
+     * with anything without holding it up */
     cudaStream_t snl = D.stream_nl;
+    const unsigned npx = (unsigned)std::max(1, std::min((D.nsend + 255) / 256, 2 * 148));
+    if (D.push_inline)
+    {
+        /* B200NB_DD_PUSH_INLINE=1: the push in front of k_step_begin on the main stream.  For MANY ranks as threads of one
+         * process on one GPU (tests): their graphs' branches share that device's hardware queues, and a push queued behind
+         * another rank's flag wait would never run.  One process per GPU (production) has its queues to itself. */
+        k_dd_push_x<<<npx, 256, 0, h->stream>>>(x_home, B, D.links);
+        LAUNCH_CHECK(h);
+    }
+    else
+    {
+        NB_CUDA(h, cudaEventRecord(D.ev_start, h->stream));
+        NB_CUDA(h, cudaStreamWaitEvent(D.stream_px, D.ev_start, 0));
+        k_dd_push_x<<<npx, 256, 0, D.stream_px>>>(x_home, B, D.links);
+        LAUNCH_CHECK(h);
+        tag_nonlocal_node(h, D.stream_px);
+        NB_CUDA(h, cudaEventRecord(D.ev_px_done, D.stream_px));
+    }
+    /* 2. home x -> grid layout, outputs cleared; then the local kernel on the main stream, the halo chain on the non-local one */
+    if ((reinterpret_cast<uintptr_t>(x_home) & 15) == 0)
+        k_step_begin<true><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf);
+    else
+        k_step_begin<false><<<nb0, 256, 0, h->stream>>>(x_home, h->d_slot_of_atom, 0, n, h->d_xq, h->d_f, nclear, h->d_fshift, h->d_energy, pf);
+    LAUNCH_CHECK(h);
     NB_CUDA(h, cudaEventRecord(D.ev_begin, h->stream));
     NB_CUDA(h, cudaStreamWaitEvent(snl, D.ev_begin, 0));
     int rc;
@@ -2952,13 +3017,14 @@ static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home,
     }
     NB_CUDA(h, cudaEventRecord(D.ev_nl_done, snl));
     NB_CUDA(h, cudaStreamWaitEvent(h->stream, D.ev_nl_done, 0));
+    if (!D.push_inline) NB_CUDA(h, cudaStreamWaitEvent(h->stream, D.ev_px_done, 0));
     /* 3. wait for the forces on the atoms we sent, add them, forces -> atom order */
     const unsigned nb1 = (unsigned)std::max(1, (n + 255) / 256);
     if ((reinterpret_cast<uintptr_t>(f_home) & 15) == 0)
-        k_dd_step_end<true><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.d_ent_off, D.d_ent_idx, D.window, D.d_seq,
+        k_dd_step_end<true><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.d_ent_off, D.d_ent_idx, D.window, D.d_seq, D.d_count + 3,
                                                        reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, D.links);
     else
-        k_dd_step_end<false><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.d_ent_off, D.d_ent_idx, D.window, D.d_seq,
+        k_dd_step_end<false><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.d_ent_off, D.d_ent_idx, D.window, D.d_seq, D.d_count + 3,
                                                         reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, D.links);
     LAUNCH_CHECK(h);
     return 0;

@@ -173,8 +173,9 @@ struct DdState
     /* the halo chain (wait, halo x -> grid, non-local kernel, push f) runs on its own high-priority stream beside
      * the local kernel, the reference's local / non-local stream split (cuda/nbnxm_cuda_data_mgmt.cu:260-291) */
     int            prio_high = 0;
-    cudaStream_t   stream_nl = nullptr;
-    cudaEvent_t    ev_begin = nullptr, ev_nl_done = nullptr;
+    cudaStream_t   stream_nl = nullptr, stream_px = nullptr; /* stream_px: the halo x push, a branch of its own */
+    bool           push_inline = false; /* B200NB_DD_PUSH_INLINE=1: halo x push on the main stream (many ranks sharing one GPU) */
+    cudaEvent_t    ev_start = nullptr, ev_begin = nullptr, ev_nl_done = nullptr, ev_px_done = nullptr;
 };
 
 /* a captured step: the launches of b200nb_step / b200nb_dd_step for one set of buffers */

@@ -264,9 +264,9 @@ int b200nb_dd_set_links(b200nb_t* h, int nhome, int nhalo, int nlinks, const b20
  * those arrived across the periodic edge (the last slab), or -1. */
 int b200nb_dd_set_plan(b200nb_t* h, int nhome, int nhalo, const int* send_idx_host, int nsend, const float shift[3],
                        int halo_fshift_index);
-/* One decomposed step, asynchronous on the context's stream, replayed as one CUDA graph of 6 kernels: home x -> grid + clear +
- * push of the halo x into the neighbours' windows | local kernel || wait, halo x -> grid | non-local kernel | push of the halo
- * forces || wait, add, un-sort.  x_home in, f_home out: nhome*3 floats, device or pinned host memory.  Every neighbour must
+/* One decomposed step, asynchronous on the context's stream, replayed as one CUDA graph of 7 kernels on two branches:
+ * home x -> grid + clear | local kernel || push of the halo x into the neighbours' windows | wait, halo x -> grid | non-local
+ * kernel | push of the halo forces || wait, add, un-sort.  x_home in, f_home out: nhome*3 floats, device or pinned host memory.  Every neighbour must
  * call it the same number of times. */
 int b200nb_dd_step(b200nb_t* h, const float* x_home, float* f_home, int flags);
 /* after b200nb_synchronize: B200NB_ERR_STATE if a halo flag timed out in any step since the last call */

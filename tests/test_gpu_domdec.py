@@ -1,6 +1,7 @@
 """GPU parity of the domain-decomposed path on ONE GPU: the ranks are threads of this process, each with its own
 NbnxmGpu context, exchanging halos through the in-process loopback transport (the multi-GPU run uses the same
 DomainRank code over NCCL).  Global forces / pair set / energies / virial must equal the single-domain oracle."""
+import os
 import threading
 
 import numpy as np
@@ -94,9 +95,14 @@ def run_ranks(s, opt, nranks, flags, use_windows=True, nsteps=1, moved_x=None, r
                                                          ("water_24k", 6, g.CoulombType.Pme, True),
                                                          ("water_96k", 4, g.CoulombType.Pme, True),
                                                          ("water_24k", 3, g.CoulombType.Pme, False)])
-def test_domain_decomposition_matches_single_domain(built, name, nranks, coulomb, windows):
+def test_domain_decomposition_matches_single_domain(built, name, nranks, coulomb, windows, monkeypatch):
     """windows=True: halos move through the peer-memory windows of b200nb_dd_step (the product path);
     windows=False: through the transport's send/recv with the separate pack / unpack kernels."""
+    if nranks > 3:
+        # more than three ranks as threads on ONE GPU: the branches of their step graphs share that device's hardware queues, and a
+        # halo push on a branch of its own could queue behind another rank's flag wait; such runs push from the main stream (the
+        # separate branch is what 2 and 3 ranks here, the two-process IPC test and every bench.py run with N > 1 exercise)
+        monkeypatch.setenv("B200NB_DD_PUSH_INLINE", "1")
     s = g.systems.named(name)
     # reaction field with epsilon_rf = infinity (benchmark/bench_setup.cpp:152-155): the force vanishes at the cut-off, so
     # a pair flipped by the rounding of the periodic-edge shift (below) cannot show up in the forces
@@ -246,11 +252,20 @@ def run_ranks_nd(grid, use_windows=True):
             except Exception:
                 pass
 
-    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
-    for t in th:
-        t.start()
-    for t in th:
-        t.join(timeout=300)
+    # four and more ranks as threads on ONE GPU: halo push from the main stream (see test_domain_decomposition_matches_single_domain)
+    old = os.environ.get("B200NB_DD_PUSH_INLINE")
+    os.environ["B200NB_DD_PUSH_INLINE"] = "1" if nranks > 3 else "0"
+    try:
+        th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(timeout=300)
+    finally:
+        if old is None:
+            os.environ.pop("B200NB_DD_PUSH_INLINE", None)
+        else:
+            os.environ["B200NB_DD_PUSH_INLINE"] = old
     assert not err, err
     _ND_CACHE[key] = (s, out)
     return s, out
@@ -323,8 +338,9 @@ def test_decomposition_nd_virial(built, grid, windows):
     assert np.abs(vir_g - vir_o).max() <= 1e-5 * np.abs(vir_o).max()
 
 
-def test_repartition_nd_after_motion(built):
+def test_repartition_nd_after_motion(built, monkeypatch):
     """repartitioning of the 2 x 2 decomposition after a rigid translation across faces, an edge and the box boundary"""
+    monkeypatch.setenv("B200NB_DD_PUSH_INLINE", "1")  # four ranks as threads on one GPU: see run_ranks_nd
     from gmxapi_b200.domdec import wrap_into_box
     from gmxapi_b200.domdec_nd import DomainRankND
     grid = (2, 2, 1)
