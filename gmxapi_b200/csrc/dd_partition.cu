@@ -22,7 +22,7 @@
 #include "b200nb_internal.h"
 
 #define PART_BLOCK 256
-#define PART_MAX_CODES 4
+#define PART_MAX_CODES 32 /* the 27 neighbour offsets of an N-D grid + 'moved more than one domain' */
 
 namespace
 {
@@ -64,6 +64,68 @@ __global__ void k_select_lower_face(const float* __restrict__ x, int n, float lo
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a < n) code[a] = __fsub_rn(x[3 * a], lo) < rlist ? 1 : 0;
+}
+
+/* N-D grids (gmxapi_b200/domdec_nd.py): per dimension the owner cell of the wrapped coordinate, as the offset -1 / 0 / +1 from
+ * this rank's cell (periodic; with two cells along a dimension the other one is offset +1); code = 9 (ox+1) + 3 (oy+1) + (oz+1),
+ * 13 = stays, 27 = moved more than one domain.  Cell boundaries are float32(i * box_d / n_d), owner = searchsorted(bounds, x,
+ * "right") - 1 clipped: DomainPlanND.owner_of, bit for bit. */
+struct NdGeom
+{
+    float box[3];
+    int   grid[3], coords[3];
+};
+__device__ __forceinline__ int owner_cell(float v, float b, int n)
+{
+    if (n == 1) return 0;
+    const double w = (double)b / n;
+    int          o = max(0, min((int)(v * ((float)n / b)), n - 1));
+    while (o > 0 && v < (float)(o * w)) o--;
+    while (o < n - 1 && v >= (float)((o + 1) * w)) o++;
+    return o;
+}
+__global__ void k_wrap_classify_nd(float* __restrict__ x, int n, NdGeom G, int* __restrict__ code)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    int c = 0;
+    bool lost = false;
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+    {
+        const float v = wrap1(x[3 * a + d], G.box[d]);
+        x[3 * a + d]  = v;
+        const int nd = G.grid[d], o = owner_cell(v, G.box[d], nd);
+        int       off = 0;
+        if (o != G.coords[d])
+        {
+            const int fwd = (o - G.coords[d] + nd) % nd, bwd = (G.coords[d] - o + nd) % nd;
+            if (fwd == 1) off = 1; /* also the only other cell of a two-cell dimension */
+            else if (bwd == 1) off = -1;
+            else lost = true;
+        }
+        c = 3 * c + (off + 1);
+    }
+    code[a] = lost ? 27 : c;
+}
+/* boundary atoms of this domain for the rank that sees it at half-shell offset o (DomainPlanND.boundary_atoms): within rlist of
+ * the lower face along dimensions with o = +1 (x - lo < r), of the upper face where o = -1 (hi - x <= r), float32 */
+__global__ void k_select_boundary(const float* __restrict__ x, int n, float lo0, float lo1, float lo2, float hi0, float hi1, float hi2, int o0, int o1,
+                                  int o2, float rlist, int* __restrict__ code)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const float lo[3] = { lo0, lo1, lo2 }, hi[3] = { hi0, hi1, hi2 };
+    const int   o[3]  = { o0, o1, o2 };
+    bool        m     = true;
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+    {
+        const float v = x[3 * a + d];
+        if (o[d] == 1) m = m && (__fsub_rn(v, lo[d]) < rlist);
+        else if (o[d] == -1) m = m && (__fsub_rn(hi[d], v) <= rlist);
+    }
+    code[a] = m ? 1 : 0;
 }
 
 /* ---- stable multi-way partition of the indices 0..n-1 by code: counts per block, scan over the blocks, scatter ---- */
@@ -327,6 +389,34 @@ extern "C" int b200nb_dd_select_lower_face(b200nb_t* h, const float* x_dev, int 
     return 0;
 }
 
+extern "C" int b200nb_dd_wrap_classify_nd(b200nb_t* h, float* x_dev, int n, const float box[3], const int grid[3], const int coords[3], int* code_dev)
+{
+    if (!h || !x_dev || !code_dev || !box || !grid || !coords || n < 0) return nb_fail(h, B200NB_ERR_ARG, "dd_wrap_classify_nd: bad argument");
+    NdGeom G;
+    for (int d = 0; d < 3; d++)
+    {
+        if (grid[d] < 1 || coords[d] < 0 || coords[d] >= grid[d] || !(box[d] > 0)) return nb_fail(h, B200NB_ERR_ARG, "dd_wrap_classify_nd: bad grid");
+        G.box[d] = box[d], G.grid[d] = grid[d], G.coords[d] = coords[d];
+    }
+    if (n == 0) return 0;
+    cudaSetDevice(h->device);
+    k_wrap_classify_nd<<<(n + 255) / 256, 256, 0, h->stream>>>(x_dev, n, G, code_dev);
+    PART_LAUNCH_CHECK(h);
+    return 0;
+}
+
+extern "C" int b200nb_dd_select_boundary(b200nb_t* h, const float* x_dev, int n, const float lo[3], const float hi[3], const int offset[3], float rlist,
+                                         int* code_dev)
+{
+    if (!h || !x_dev || !code_dev || !lo || !hi || !offset || n < 0) return nb_fail(h, B200NB_ERR_ARG, "dd_select_boundary: bad argument");
+    if (n == 0) return 0;
+    cudaSetDevice(h->device);
+    k_select_boundary<<<(n + 255) / 256, 256, 0, h->stream>>>(x_dev, n, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], offset[0], offset[1], offset[2], rlist,
+                                                             code_dev);
+    PART_LAUNCH_CHECK(h);
+    return 0;
+}
+
 extern "C" int b200nb_dd_partition_indices(b200nb_t* h, const int* code_dev, int n, int ncodes, int* idx_dev, int* counts_host)
 {
     if (!h || !code_dev || !idx_dev || !counts_host || n < 0 || ncodes < 1 || ncodes > PART_MAX_CODES)
@@ -340,7 +430,7 @@ extern "C" int b200nb_dd_partition_indices(b200nb_t* h, const int* code_dev, int
     int* d_tot = d_blk + (size_t)PART_MAX_CODES * nblk;
     k_part_count<<<nblk, PART_BLOCK, 0, h->stream>>>(code_dev, n, ncodes, d_blk);
     PART_LAUNCH_CHECK(h);
-    k_part_scan<<<1, 32, 0, h->stream>>>(d_blk, nblk, ncodes, d_tot);
+    k_part_scan<<<1, PART_MAX_CODES, 0, h->stream>>>(d_blk, nblk, ncodes, d_tot);
     PART_LAUNCH_CHECK(h);
     k_part_scatter<<<nblk, PART_BLOCK, 0, h->stream>>>(code_dev, n, ncodes, d_blk, d_tot, idx_dev);
     PART_LAUNCH_CHECK(h);

@@ -297,18 +297,23 @@ class DomainRankND:
         self.fshift_halo = np.zeros((_lib.SHIFTS, 3), np.float64)
         self._setup_local(np.ascontiguousarray(system.x[p.home]))
 
-    def _setup_local(self, x_home):
-        """(re)build everything that depends on which atoms this rank owns and receives"""
+    def _setup_local(self, x_home, atoms_installed=False):
+        """(re)build everything that depends on which atoms this rank owns and receives.  atoms_installed: the local topology is
+        already in the context (built on the device by b200nb_dd_set_local_atoms) and x_home is a device tensor."""
         torch = self.torch
         p = self.plan
-        types, q, eo, ei = p.local_topology(*self.topology)
-        self.nb.set_atoms(types, q, eo, ei)
+        if not atoms_installed:
+            types, q, eo, ei = p.local_topology(*self.topology)
+            self.nb.set_atoms(types, q, eo, ei)
         self.nlocal = p.nhome + p.nhalo
         box = p.box
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self.x = torch.zeros((self.nlocal, 3), dtype=torch.float32, device=self.device)
             self.f = torch.zeros((self.nlocal, 3), dtype=torch.float32, device=self.device)
-            self.x[:p.nhome].copy_(torch.from_numpy(np.ascontiguousarray(x_home, dtype=np.float32)))
+            if isinstance(x_home, torch.Tensor):
+                self.x[:p.nhome].copy_(x_home)
+            else:
+                self.x[:p.nhome].copy_(torch.from_numpy(np.ascontiguousarray(x_home, dtype=np.float32)))
             self.send_idx = [torch.from_numpy(s["local"]).to(self.device) for s in p.send]
             self.send_buf = [torch.zeros((len(s["local"]), 3), dtype=torch.float32, device=self.device) for s in p.send]
             self.recv_f = [torch.zeros((len(s["local"]), 3), dtype=torch.float32, device=self.device) for s in p.send]
@@ -368,12 +373,16 @@ class DomainRankND:
         self.nb.dd_set_links(p.nhome, p.nhalo, links)
         self.t.barrier()  # every rank has its plan before anybody steps
 
-    def repartition(self, x_home=None):
+    def repartition(self, x_home=None, on_device=True):
         """Pair-search step with atom migration: the current coordinates of the home atoms (self.x[:nhome], on the device)
-        decide the new owners; halo lists, grids and pair list are rebuilt.  Collective.  Returns the new plan."""
+        decide the new owners; halo lists, grids and pair list are rebuilt.  Collective.  Returns the new plan.
+        on_device: the decisions are taken by the kernels of csrc/dd_partition.cu (coordinates stay on the GPU); False: the numpy
+        restatement of the same step (migrate_atoms_nd), what the gloo tests run and the kernels are checked against."""
         torch = self.torch
         p = self.plan
         self.nb.synchronize()
+        if on_device:
+            return self._repartition_device(x_home)
         # the current coordinates of the home atoms: the caller's (x_home, e.g. after an integration step), else those of the
         # last step -- the caller's pinned buffer when the step ran on it in place, self.x otherwise
         xc = getattr(self, "_x_host_current", None)
@@ -391,6 +400,92 @@ class DomainRankND:
                                                               to_tensor=to_dev)
         self.plan = DomainPlanND.from_parts(p.box, p.grid, self.rank, self.rlist, home, send_locals, recv_ids)
         self._setup_local(x_new)
+        return self.plan
+
+    def _repartition_device(self, x_home):
+        """repartition() with the coordinate-dependent work on the GPU: wrap + new owner cell per atom as one of the 27 neighbour
+        offsets (k_wrap_classify_nd), stable 28-way partition into stayers and leavers per offset, messages per destination rank,
+        merge into the new home set, per half-shell offset the boundary atoms the neighbour there needs (k_select_boundary +
+        partition), local topology through the device-resident global -> local look-up.  The host sees counts and the index
+        lists of the plan (global indices of home / halo atoms, send lists): bookkeeping, no coordinates."""
+        torch = self.torch
+        p, nb, t = self.plan, self.nb, self.t
+        dev = self.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev), torch.cuda.stream(self.stream):
+            if not getattr(self, "_global_topology_on_device", False):
+                nb.dd_set_global_topology(*self.topology)
+                self._global_topology_on_device = True
+            xc = getattr(self, "_x_host_current", None)
+            if x_home is not None:
+                xt = x_home if isinstance(x_home, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x_home, dtype=np.float32))
+                if tuple(xt.shape) != (p.nhome, 3):
+                    raise InputException("repartition: x_home must hold the %d home atoms" % p.nhome)
+                x = xt.to(dev, dtype=torch.float32, copy=True).contiguous()
+            elif xc is not None and len(xc) == p.nhome:
+                x = xc.to(dev, copy=True)
+            else:
+                x = self.x[:p.nhome].clone()
+            self._x_host_current = None
+            gid = torch.from_numpy(np.ascontiguousarray(p.home, dtype=np.int32)).to(dev)
+            n = p.nhome
+            code = torch.empty(max(n, 1), **i32)
+            idx = torch.empty(max(n, 1), **i32)
+            nb.dd_wrap_classify_nd(x.data_ptr(), n, p.box, p.grid, p.coords, code.data_ptr())
+            cnt = nb.dd_partition_indices(code.data_ptr(), n, 28, idx.data_ptr())
+            if cnt[27]:
+                raise InputException("an atom moved more than one domain between two repartitioning steps")
+            start = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+            nstay = cnt[13]
+            # messages per destination RANK: the offsets that lead to the same rank (two cells along a dimension) are concatenated
+            out = {}
+            for c in range(27):
+                if c == 13 or cnt[c] == 0:
+                    continue
+                o = (c // 9 - 1, (c // 3) % 3 - 1, c % 3 - 1)
+                dst, _ = p.neighbour(p.coords, o, +1)
+                buf = torch.empty((cnt[c], 4), **i32)
+                nb.dd_pack_atoms(idx.data_ptr() + 4 * int(start[c]), cnt[c], gid.data_ptr(), x.data_ptr(), buf.data_ptr())
+                out.setdefault(int(dst), []).append(buf)
+            out = {r: (torch.cat(b).contiguous() if len(b) > 1 else b[0]) for r, b in out.items()}
+            counts = t.allgather_object({r: int(b.shape[0]) for r, b in out.items()})
+            srcs = [r for r in range(p.nranks) if r != self.rank and counts[r].get(self.rank, 0) > 0]
+            inb = {r: torch.empty((counts[r][self.rank], 4), **i32) for r in srcs}
+            t.exchange([(out[r], r) for r in sorted(out)], [(inb[r], r) for r in sorted(inb)])
+            arrived = torch.cat([inb[r] for r in sorted(inb)]).contiguous() if inb else torch.empty((0, 4), **i32)
+            m = int(arrived.shape[0])
+            n_new = nstay + m
+            gid_new = torch.empty(max(n_new, 1), **i32)[:n_new]
+            x_new = torch.empty((max(n_new, 1), 3), dtype=torch.float32, device=dev)[:n_new]
+            nb.dd_merge_home(idx.data_ptr() + 4 * int(start[13]), nstay, gid.data_ptr(), x.data_ptr(), arrived.data_ptr() if m else 0, m,
+                             gid_new.data_ptr(), x_new.data_ptr())
+            code2 = torch.empty(max(n_new, 1), **i32)
+            idx2 = torch.empty(max(n_new, 1), **i32)
+            nb.dd_wrap_classify_nd(x_new.data_ptr(), n_new, p.box, p.grid, p.coords, code2.data_ptr())
+            if nb.dd_partition_indices(code2.data_ptr(), n_new, 28, idx2.data_ptr())[13] != n_new:
+                raise InputException("repartitioning left an atom outside its new owner's domain")
+            # the new halo: per half-shell offset, my boundary atoms go to the rank that sees me there; sizes first
+            send_locals, send_gids = [], []
+            for o in p.offsets:
+                nb.dd_select_boundary(x_new.data_ptr(), n_new, p.lo, p.hi, o, self.rlist, code2.data_ptr())
+                nkeep, nsend = nb.dd_partition_indices(code2.data_ptr(), n_new, 2, idx2.data_ptr())
+                sl = idx2[nkeep:nkeep + nsend].clone()
+                sg = torch.empty(max(nsend, 1), **i32)[:nsend]
+                nb.dd_gather_int(sl.data_ptr() if nsend else 0, nsend, gid_new.data_ptr(), sg.data_ptr() if nsend else 0)
+                send_locals.append(sl)
+                send_gids.append(sg)
+            peers = [p._peers(o) for o in p.offsets]
+            nsends = t.allgather_object([int(sl.shape[0]) for sl in send_locals])
+            recv_ids = [torch.empty(max(nsends[nbr][k], 1), **i32)[:nsends[nbr][k]] for k, (nbr, _, _, _) in enumerate(peers)]
+            t.exchange([(sg, dst) for sg, (_, _, dst, _) in zip(send_gids, peers)], [(buf, nbr) for buf, (nbr, _, _, _) in zip(recv_ids, peers)])
+            local_gid = torch.cat([gid_new] + recv_ids).contiguous()
+            nb.dd_set_local_atoms(local_gid.data_ptr(), int(local_gid.shape[0]))
+            nb.synchronize()
+            home_h = gid_new.cpu().numpy()
+            send_h = [sl.cpu().numpy() for sl in send_locals]
+            recv_h = [r.cpu().numpy() for r in recv_ids]
+        self.plan = DomainPlanND.from_parts(p.box, p.grid, self.rank, self.rlist, home_h, send_h, recv_h)
+        self._setup_local(x_new, atoms_installed=True)
         return self.plan
 
     def search(self):

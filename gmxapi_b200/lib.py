@@ -22,7 +22,8 @@ EXPORTS = [
     "b200nb_get_grid_order", "b200nb_get_tiles", "b200nb_get_pairs", "b200nb_time_force_kernel", "b200nb_time_step",
     "b200nb_set_grid_atoms", "b200nb_upload_pairlist", "b200nb_copy_xq_grid", "b200nb_get_f_grid", "b200nb_set_shift_vec", "b200nb_set_ewald_table", "b200nb_describe",
     "b200nb_dd_wrap_classify", "b200nb_dd_select_lower_face", "b200nb_dd_partition_indices", "b200nb_dd_pack_atoms", "b200nb_dd_merge_home",
-    "b200nb_dd_gather_int", "b200nb_dd_set_global_topology", "b200nb_dd_set_local_atoms",
+    "b200nb_dd_gather_int", "b200nb_dd_set_global_topology", "b200nb_dd_set_local_atoms", "b200nb_dd_wrap_classify_nd",
+    "b200nb_dd_select_boundary",
 ]
 
 
@@ -164,6 +165,8 @@ def load_library():
     L.b200nb_dd_gather_int.argtypes = [vp, vp, ci, vp, vp]
     L.b200nb_dd_set_global_topology.argtypes = [vp, ci, vp, vp, vp, vp]
     L.b200nb_dd_set_local_atoms.argtypes = [vp, vp, ci]
+    L.b200nb_dd_wrap_classify_nd.argtypes = [vp, vp, ci, vp, vp, vp, vp]
+    L.b200nb_dd_select_boundary.argtypes = [vp, vp, ci, vp, vp, vp, cf, vp]
     _lib = L
     return L
 
@@ -364,13 +367,27 @@ class NbnxmGpu:
         self._check(self._L.b200nb_dd_wrap_classify(self._h, _ptr(x_dev), int(n), _ptr(b), _ptr(bd), int(nranks), int(rank), _ptr(code_dev)),
                     "dd_wrap_classify")
 
+    def dd_wrap_classify_nd(self, x_dev, n, box, grid, coords, code_dev):
+        b = np.ascontiguousarray(box, dtype=np.float32)
+        g = np.ascontiguousarray(grid, dtype=np.int32)
+        c = np.ascontiguousarray(coords, dtype=np.int32)
+        self._check(self._L.b200nb_dd_wrap_classify_nd(self._h, _ptr(x_dev), int(n), _ptr(b), _ptr(g), _ptr(c), _ptr(code_dev)),
+                    "dd_wrap_classify_nd")
+
+    def dd_select_boundary(self, x_dev, n, lo, hi, offset, rlist, code_dev):
+        lo = np.ascontiguousarray(lo, dtype=np.float32)
+        hi = np.ascontiguousarray(hi, dtype=np.float32)
+        o = np.ascontiguousarray(offset, dtype=np.int32)
+        self._check(self._L.b200nb_dd_select_boundary(self._h, _ptr(x_dev), int(n), _ptr(lo), _ptr(hi), _ptr(o), float(rlist), _ptr(code_dev)),
+                    "dd_select_boundary")
+
     def dd_select_lower_face(self, x_dev, n, lo, rlist, code_dev):
         self._check(self._L.b200nb_dd_select_lower_face(self._h, _ptr(x_dev), int(n), float(lo), float(rlist), _ptr(code_dev)),
                     "dd_select_lower_face")
 
     def dd_partition_indices(self, code_dev, n, ncodes, idx_dev):
         """Stable partition of 0 .. n-1 by code; returns the counts per code (list of ncodes ints)."""
-        cnt = np.zeros(4, np.int32)
+        cnt = np.zeros(32, np.int32)
         self._check(self._L.b200nb_dd_partition_indices(self._h, _ptr(code_dev), int(n), int(ncodes), _ptr(idx_dev), _ptr(cnt)),
                     "dd_partition_indices")
         return [int(v) for v in cnt[:ncodes]]

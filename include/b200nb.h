@@ -282,9 +282,17 @@ int b200nb_dd_status(b200nb_t* h);
  * 2 to the +x neighbour, 3 moved more than one domain (the caller treats a non-zero count of 3 as fatal, like the reference).
  * bounds_host: nranks + 1 slab boundaries, float32(k * box_x / nranks). */
 int b200nb_dd_wrap_classify(b200nb_t* h, float* x_dev, int n, const float box[3], const float* bounds_host, int nranks, int rank, int* code_dev);
+/* the same for an N-D grid of domains (grid[3] cells, this rank at coords[3]): code = 9 (ox+1) + 3 (oy+1) + (oz+1) with the offset
+ * -1 / 0 / +1 of the atom's new cell from this rank's per dimension (13 = stays; the other cell of a two-cell dimension is +1),
+ * 27 = moved more than one domain */
+int b200nb_dd_wrap_classify_nd(b200nb_t* h, float* x_dev, int n, const float box[3], const int grid[3], const int coords[3], int* code_dev);
+/* code 1 for the home atoms the rank seeing this domain at half-shell offset[3] needs: within rlist of the lower face where
+ * offset = +1 (x - lo < rlist), of the upper face where offset = -1 (hi - x <= rlist); else 0 */
+int b200nb_dd_select_boundary(b200nb_t* h, const float* x_dev, int n, const float lo[3], const float hi[3], const int offset[3], float rlist,
+                              int* code_dev);
 /* code 1 for the home atoms within rlist of the slab's lower face (x - lo < rlist in float32: the halo of the -x neighbour), else 0 */
 int b200nb_dd_select_lower_face(b200nb_t* h, const float* x_dev, int n, float lo, float rlist, int* code_dev);
-/* stable partition of the indices 0 .. n-1 by code (0 .. ncodes-1, ncodes <= 4): idx_dev = the indices with code 0 in ascending
+/* stable partition of the indices 0 .. n-1 by code (0 .. ncodes-1, ncodes <= 32): idx_dev = the indices with code 0 in ascending
  * order, then those with code 1, ...; counts_host[k] = how many have code k (synchronises the stream for these few ints) */
 int b200nb_dd_partition_indices(b200nb_t* h, const int* code_dev, int n, int ncodes, int* idx_dev, int* counts_host);
 /* the message for a neighbour: per listed atom 4 ints {global index, x, y, z bit patterns} */

@@ -7,6 +7,12 @@ import pytest
 # queues, streams alias and a flag-wait kernel could sit in front of the push kernel it waits for.  Production runs one
 # process per GPU (2 streams).  Must be set before the CUDA context exists.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# Same cause, second measure: ranks that are THREADS of one process put the branches of all their step graphs on the hardware queues
+# of one device, where a halo push on a graph branch of its own (the product path) can end up queued behind another rank's flag
+# wait -- a dependency cycle that one process per GPU cannot have.  The in-process tests therefore push from the main stream;
+# the separate branch is what tests/test_gpu_domdec_ipc.py (two processes) and every multi-GPU bench.py run (forces checked
+# against a single-domain run) exercise.
+os.environ.setdefault("B200NB_DD_PUSH_INLINE", "1")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

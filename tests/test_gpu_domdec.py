@@ -95,14 +95,9 @@ def run_ranks(s, opt, nranks, flags, use_windows=True, nsteps=1, moved_x=None, r
                                                          ("water_24k", 6, g.CoulombType.Pme, True),
                                                          ("water_96k", 4, g.CoulombType.Pme, True),
                                                          ("water_24k", 3, g.CoulombType.Pme, False)])
-def test_domain_decomposition_matches_single_domain(built, name, nranks, coulomb, windows, monkeypatch):
+def test_domain_decomposition_matches_single_domain(built, name, nranks, coulomb, windows):
     """windows=True: halos move through the peer-memory windows of b200nb_dd_step (the product path);
     windows=False: through the transport's send/recv with the separate pack / unpack kernels."""
-    if nranks > 3:
-        # more than three ranks as threads on ONE GPU: the branches of their step graphs share that device's hardware queues, and a
-        # halo push on a branch of its own could queue behind another rank's flag wait; such runs push from the main stream (the
-        # separate branch is what 2 and 3 ranks here, the two-process IPC test and every bench.py run with N > 1 exercise)
-        monkeypatch.setenv("B200NB_DD_PUSH_INLINE", "1")
     s = g.systems.named(name)
     # reaction field with epsilon_rf = infinity (benchmark/bench_setup.cpp:152-155): the force vanishes at the cut-off, so
     # a pair flipped by the rounding of the periodic-edge shift (below) cannot show up in the forces
@@ -252,20 +247,11 @@ def run_ranks_nd(grid, use_windows=True):
             except Exception:
                 pass
 
-    # four and more ranks as threads on ONE GPU: halo push from the main stream (see test_domain_decomposition_matches_single_domain)
-    old = os.environ.get("B200NB_DD_PUSH_INLINE")
-    os.environ["B200NB_DD_PUSH_INLINE"] = "1" if nranks > 3 else "0"
-    try:
-        th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join(timeout=300)
-    finally:
-        if old is None:
-            os.environ.pop("B200NB_DD_PUSH_INLINE", None)
-        else:
-            os.environ["B200NB_DD_PUSH_INLINE"] = old
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
     assert not err, err
     _ND_CACHE[key] = (s, out)
     return s, out
@@ -338,12 +324,13 @@ def test_decomposition_nd_virial(built, grid, windows):
     assert np.abs(vir_g - vir_o).max() <= 1e-5 * np.abs(vir_o).max()
 
 
-def test_repartition_nd_after_motion(built, monkeypatch):
-    """repartitioning of the 2 x 2 decomposition after a rigid translation across faces, an edge and the box boundary"""
-    monkeypatch.setenv("B200NB_DD_PUSH_INLINE", "1")  # four ranks as threads on one GPU: see run_ranks_nd
+@pytest.mark.parametrize("grid", [(2, 2, 1), (3, 1, 2)])
+def test_repartition_nd_after_motion(built, grid):
+    """repartitioning of a 2 x 2 and a 3 x 1 x 2 decomposition after a rigid translation across faces, an edge and the box boundary: on the
+    device (csrc/dd_partition.cu: 28-way partition by neighbour offset, per-offset boundary selection, device-side local topology)
+    and through the numpy restatement of the same step -- identical plans, forces against the single-domain oracle"""
     from gmxapi_b200.domdec import wrap_into_box
     from gmxapi_b200.domdec_nd import DomainRankND
-    grid = (2, 2, 1)
     s = g.systems.named("water_24k")
     rng = np.random.Generator(np.random.PCG64(29))
     x1 = (s.x + np.array([0.43, -0.37, 0.21], np.float32) + rng.uniform(-0.01, 0.01, s.x.shape)).astype(np.float32)
@@ -351,35 +338,46 @@ def test_repartition_nd_after_motion(built, monkeypatch):
     opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, computeVirialAndEnergy=True)
     flags = nb.FLAG_ENERGY | nb.FLAG_VIRIAL
     nranks = int(np.prod(grid))
-    hub = LoopbackTransport(nranks)
-    out, err = [None] * nranks, []
 
-    def work(r):
-        try:
-            import torch
-            d = DomainRankND(s, opt, hub.endpoint(r), grid, rank=r, device=0)
-            d.compute(np.ascontiguousarray(s.x[d.plan.home]), flags)
-            old_home = d.plan.home.copy()
-            plan = d.repartition(x_home=x1[old_home])
-            assert len(np.setdiff1d(plan.home, old_home)) > 0
-            f, fs, elj, eel = d.compute(np.ascontiguousarray(x1w[plan.home]), flags)
-            out[r] = dict(home=plan.home, f=f.numpy().copy(), elj=elj, eel=eel)
-            hub.endpoint(r).barrier()
-            d.close()
-        except Exception as e:  # noqa: BLE001
-            import traceback
-            err.append((r, repr(e), traceback.format_exc()))
+    def run(on_device):
+        hub = LoopbackTransport(nranks)
+        out, err = [None] * nranks, []
+
+        def work(r):
             try:
-                hub._bar.abort()
-            except Exception:
-                pass
+                d = DomainRankND(s, opt, hub.endpoint(r), grid, rank=r, device=0)
+                d.compute(np.ascontiguousarray(s.x[d.plan.home]), flags)
+                old_home = d.plan.home.copy()
+                plan = d.repartition(x_home=x1[old_home], on_device=on_device)
+                assert len(np.setdiff1d(plan.home, old_home)) > 0
+                assert np.array_equal(d.x[:plan.nhome].cpu().numpy(), x1w[plan.home])
+                f, fs, elj, eel = d.compute(np.ascontiguousarray(x1w[plan.home]), flags)
+                out[r] = dict(home=plan.home, f=f.numpy().copy(), elj=elj, eel=eel, halo=plan.halo.copy(),
+                              send=[sd["local"].copy() for sd in plan.send], npairs=d.pair_count(RC))
+                hub.endpoint(r).barrier()
+                d.close()
+            except Exception as e:  # noqa: BLE001
+                import traceback
+                err.append((r, repr(e), traceback.format_exc()))
+                try:
+                    hub._bar.abort()
+                except Exception:
+                    pass
 
-    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
-    for t in th:
-        t.start()
-    for t in th:
-        t.join(timeout=300)
-    assert not err, err
+        th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(timeout=300)
+        assert not err, err
+        return out
+
+    out = run(True)
+    host = run(False)
+    for a, b in zip(out, host):
+        assert np.array_equal(a["home"], b["home"]) and np.array_equal(a["halo"], b["halo"]) and a["npairs"] == b["npairs"]
+        assert len(a["send"]) == len(b["send"]) and all(np.array_equal(u, v) for u, v in zip(a["send"], b["send"]))
+        assert np.abs(a["f"] - b["f"]).max() <= 1e-4 * np.abs(b["f"]).max()
     fo, _, evo, eco, _ = oracle.forces(x1w, s.box, s.q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_EWALD,
                                        beta=float(np.float32(g.systems.ewald_beta(RC))))
     assert np.array_equal(np.sort(np.concatenate([r["home"] for r in out])), np.arange(s.n))

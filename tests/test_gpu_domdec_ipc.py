@@ -27,7 +27,7 @@ def free_port():
 @pytest.mark.parametrize("nranks", [2, 3])
 def test_decomposed_step_over_cuda_ipc_windows(built, tmp_path, nranks):
     workload, port = "water_24k", free_port()
-    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", B200NB_DD_PUSH_INLINE="0")  # two processes: the product path
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dd_ipc_worker.py"), str(r), str(nranks), port, workload,
                                str(tmp_path / ("rank%d.npz" % r))], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
              for r in range(nranks)]
