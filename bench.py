@@ -430,7 +430,7 @@ def measure_single(args, workload, local_rank, full):
         "config": common_config(workload, s, npairs, args.eel, "strong", 1),
         "details": {"computed_pairs_per_step": int(ntiles * 64), "useful_lane_fraction": npairs / float(ntiles * 64),
                     "cluster_pair_lanes_before_packing": int(st["ntiles_inner"] * 64), "list_entries": int(st["nentries"]),
-                    "setup_s": t_setup, "parallelism": "1 GPU",
+                    "setup_s": t_setup, "parallelism": "1 GPU", "setup": fc.nb.describe(),
                     "l2": "inputs < L2; L2 flushed (256 MiB write) between timed steps" if not args.no_flush else "not flushed"},
         "roofline": {"bound": "fp32", "kernel": "k_force<Ewald,geometric LJ,F>" if args.eel == "ewald" else "k_force<RF,geometric LJ,F>",
                      "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
