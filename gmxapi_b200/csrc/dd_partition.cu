@@ -206,37 +206,50 @@ __global__ void k_pack_atoms(const int* __restrict__ idx, int m, const int* __re
 }
 
 /* The new home set = stayers (already ascending in global index: the home set is kept sorted and the partition is stable)
- * merged with the arrivals (a few thousand, any order): every atom computes its own position -- a stayer its rank among the
- * stayers plus the arrivals with a smaller global index (counted directly: arrivals are few), an arrival its rank among the
- * arrivals plus the stayers with a smaller index (binary search). */
-__global__ void k_merge_home(const int* __restrict__ stay_idx, int ns, const int* __restrict__ gid, const float* __restrict__ x, const int* __restrict__ arr4,
+ * merged with the arrivals (a few thousand, any order).  First the arrivals are put in order by ranking (every arrival counts
+ * the arrivals with a smaller index: they are few); then every atom computes its own position with one binary search -- a stayer
+ * its rank among the stayers plus the arrivals with a smaller global index, an arrival its rank among the arrivals plus the
+ * stayers with a smaller index. */
+__global__ void k_rank_arrivals(const int* __restrict__ arr4, int m, int* __restrict__ sorted4)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const int g = arr4[4 * j];
+    int       r = 0;
+    for (int i = 0; i < m; i++) r += arr4[4 * i] < g || (arr4[4 * i] == g && i < j);
+    reinterpret_cast<int4*>(sorted4)[r] = reinterpret_cast<const int4*>(arr4)[j];
+}
+__global__ void k_merge_home(const int* __restrict__ stay_idx, int ns, const int* __restrict__ gid, const float* __restrict__ x, const int* __restrict__ sorted4,
                              int m, int* __restrict__ gid_out, float* __restrict__ x_out)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < ns)
     {
         const int a = stay_idx[t], g = gid[a];
-        int       before = 0;
-        for (int j = 0; j < m; j++) before += arr4[4 * j] < g;
-        const int p   = t + before;
+        int       lo = 0, hi = m; /* arrivals with a smaller global index */
+        while (lo < hi)
+        {
+            const int mid = (lo + hi) >> 1;
+            if (sorted4[4 * mid] < g) lo = mid + 1;
+            else hi = mid;
+        }
+        const int p   = t + lo;
         gid_out[p]    = g;
         x_out[3 * p]  = x[3 * a], x_out[3 * p + 1] = x[3 * a + 1], x_out[3 * p + 2] = x[3 * a + 2];
     }
     else if (t < ns + m)
     {
-        const int j = t - ns, g = arr4[4 * j];
-        int       before = 0;
-        for (int i = 0; i < m; i++) before += arr4[4 * i] < g || (arr4[4 * i] == g && i < j);
-        int lo = 0, hi = ns; /* stayers with a smaller global index */
+        const int j = t - ns, g = sorted4[4 * j];
+        int       lo = 0, hi = ns; /* stayers with a smaller global index */
         while (lo < hi)
         {
             const int mid = (lo + hi) >> 1;
             if (gid[stay_idx[mid]] < g) lo = mid + 1;
             else hi = mid;
         }
-        const int p  = before + lo;
+        const int p  = j + lo;
         gid_out[p]   = g;
-        x_out[3 * p] = __int_as_float(arr4[4 * j + 1]), x_out[3 * p + 1] = __int_as_float(arr4[4 * j + 2]), x_out[3 * p + 2] = __int_as_float(arr4[4 * j + 3]);
+        x_out[3 * p] = __int_as_float(sorted4[4 * j + 1]), x_out[3 * p + 1] = __int_as_float(sorted4[4 * j + 2]), x_out[3 * p + 2] = __int_as_float(sorted4[4 * j + 3]);
     }
 }
 
@@ -458,7 +471,14 @@ extern "C" int b200nb_dd_merge_home(b200nb_t* h, const int* stay_idx_dev, int ns
     const int n = nstay + narrived;
     if (n == 0) return 0;
     cudaSetDevice(h->device);
-    k_merge_home<<<(n + 255) / 256, 256, 0, h->stream>>>(stay_idx_dev, nstay, gid_dev, x_dev, arrived4_dev, narrived, gid_out_dev, x_out_dev);
+    if (ensure_scratch(h, 4 * (size_t)narrived + 16)) return B200NB_ERR_CUDA;
+    int* sorted4 = reinterpret_cast<int*>((reinterpret_cast<uintptr_t>(h->dd.d_part_scratch) + 15) & ~(uintptr_t)15);
+    if (narrived)
+    {
+        k_rank_arrivals<<<(narrived + 255) / 256, 256, 0, h->stream>>>(arrived4_dev, narrived, sorted4);
+        PART_LAUNCH_CHECK(h);
+    }
+    k_merge_home<<<(n + 255) / 256, 256, 0, h->stream>>>(stay_idx_dev, nstay, gid_dev, x_dev, sorted4, narrived, gid_out_dev, x_out_dev);
     PART_LAUNCH_CHECK(h);
     return 0;
 }
