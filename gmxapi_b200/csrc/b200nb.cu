@@ -128,6 +128,7 @@ extern "C" void b200nb_destroy(b200nb_t* h)
         free_list(h->outer[l]);
         cudaFree(h->packed[l].entries);
         cudaFree(h->packed[l].staged);
+        cudaFree(h->packed[l].order_blk);
         cudaFree(h->packed[l].dest);
         cudaFree(h->packed[l].sizes);
         cudaFree(h->packed[l].ja);
@@ -1458,51 +1459,85 @@ k_pack(const Entry* __restrict__ ie, const int* __restrict__ icj, const uint64_t
     }
 }
 
-/* Positions of the packed half-entries: descending step count (counting sort on <= 33 values; the role of sort_sci,
- * nbnxm/pairlist.cpp:3827-3873).  The force kernel runs two consecutive half-entries per single-warp CTA and CTAs start in index
- * order, so (i) the two halves of a warp run the same number of steps, (ii) the big ones start first and the last wave holds
- * only the smallest: the tail of the kernel shrinks from one full entry to one short entry.  hist: 2 x NB_ORDER_BINS ints
- * (histogram, cursors). */
-__global__ void k_order_hist(const int* __restrict__ sizes, int n, int* __restrict__ hist)
+/* Positions of the packed half-entries: descending step count, and -- STABLE -- packing order within a step count (counting
+ * sort on <= 33 values; the role of sort_sci, nbnxm/pairlist.cpp:3827-3873).  The force kernel runs two consecutive half-entries
+ * per single-warp CTA and CTAs start in index order, so (i) the two halves of a warp run the same number of steps, (ii) the big
+ * ones start first and the last wave holds only the smallest: the tail of the kernel shrinks from one full entry to one short
+ * entry, (iii) the packing order is the grid order of the i-clusters, so the two half-entries of a warp, and the warps that run
+ * at the same time, belong to neighbouring i-clusters and share most of their j-atoms: their gathers and their j-force
+ * reductions hit the same lines.  blkcnt: NB_ORDER_BINS x nblk ints (per bin and block of 256 half-entries: count, then offset
+ * inside the bin); base: NB_ORDER_BINS ints (where each bin starts). */
+__global__ void __launch_bounds__(256) k_order_count(const int* __restrict__ sizes, int n, int* __restrict__ blkcnt)
 {
-    __shared__ int sh[NB_ORDER_BINS];
-    if (threadIdx.x < NB_ORDER_BINS) sh[threadIdx.x] = 0;
-    __syncthreads();
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) atomicAdd(&sh[min(sizes[e], NB_ORDER_BINS - 1)], 1);
-    __syncthreads();
-    if (threadIdx.x < NB_ORDER_BINS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
-}
-__global__ void k_order_scan(int* __restrict__ hist)
-{
-    if (threadIdx.x == 0)
-    {
-        int run = 0;
-        for (int c = NB_ORDER_BINS - 1; c >= 0; c--) /* largest first */
-        {
-            hist[NB_ORDER_BINS + c] = run;
-            run += hist[c];
-        }
-    }
-}
-/* a block counts its half-entries per bin in shared memory, claims room in every bin it uses with ONE global atomic per bin, and
- * hands out the positions from there (one global atomic per half-entry on ~30 addresses took 80 us at 1 M atoms) */
-__global__ void __launch_bounds__(256) k_order_assign(const int* __restrict__ sizes, int n, int* __restrict__ hist, int* __restrict__ dest)
-{
-    __shared__ int cnt[NB_ORDER_BINS], base[NB_ORDER_BINS];
+    __shared__ int cnt[NB_ORDER_BINS];
     if (threadIdx.x < NB_ORDER_BINS) cnt[threadIdx.x] = 0;
     __syncthreads();
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    int       bin = 0, local = 0;
-    if (e < n)
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e < n) atomicAdd(&cnt[min(sizes[e], NB_ORDER_BINS - 1)], 1);
+    __syncthreads();
+    if (threadIdx.x < NB_ORDER_BINS) blkcnt[threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];
+}
+/* one CTA per bin: exclusive scan of the bin's row of block counts (256 blocks per round, warp scans), row total -> tot[bin] */
+__global__ void __launch_bounds__(256) k_order_scan_rows(int* __restrict__ blkcnt, int nblk, int* __restrict__ tot)
+{
+    __shared__ int ws[8];
+    __shared__ int carry;
+    int* const row = blkcnt + (size_t)blockIdx.x * nblk;
+    const int  lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nblk; b0 += 256)
     {
-        bin   = min(sizes[e], NB_ORDER_BINS - 1);
-        local = atomicAdd(&cnt[bin], 1);
+        const int b = b0 + threadIdx.x;
+        const int v = b < nblk ? row[b] : 0;
+        int       s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int u = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += u;
+        }
+        if (lane == 31) ws[w] = s;
+        __syncthreads();
+        int before = carry;
+        for (int k = 0; k < w; k++) before += ws[k];
+        if (b < nblk) row[b] = before + s - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = before + s;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) tot[blockIdx.x] = carry;
+}
+/* where each bin starts: after all bins of more steps (largest first) */
+__global__ void __launch_bounds__(NB_ORDER_BINS) k_order_base(const int* __restrict__ tot, int* __restrict__ base)
+{
+    __shared__ int t[NB_ORDER_BINS];
+    const int c = threadIdx.x;
+    t[c]        = tot[c];
     __syncthreads();
-    if (threadIdx.x < NB_ORDER_BINS && cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(&hist[NB_ORDER_BINS + threadIdx.x], cnt[threadIdx.x]);
+    int before = 0;
+    for (int k = c + 1; k < NB_ORDER_BINS; k++) before += t[k];
+    base[c] = before;
+}
+__global__ void __launch_bounds__(256) k_order_assign(const int* __restrict__ sizes, int n, const int* __restrict__ blkcnt, const int* __restrict__ base,
+                                                      int* __restrict__ dest)
+{
+    __shared__ int wcnt[8][NB_ORDER_BINS];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < 8 * NB_ORDER_BINS; k += 256) (&wcnt[0][0])[k] = 0;
     __syncthreads();
-    if (e < n) dest[e] = base[bin] + local;
+    const int e   = blockIdx.x * 256 + threadIdx.x;
+    const int bin = e < n ? min(sizes[e], NB_ORDER_BINS - 1) : -1 - lane; /* idle lanes: a bin of their own each */
+    const unsigned same = __match_any_sync(0xffffffffu, bin);
+    const int      rank = __popc(same & ((1u << lane) - 1u));
+    if (bin >= 0 && rank == 0) wcnt[w][bin] = __popc(same);
+    __syncthreads();
+    if (bin >= 0)
+    {
+        int before = 0;
+        for (int k = 0; k < w; k++) before += wcnt[k][bin];
+        dest[e] = base[bin] + blkcnt[bin * gridDim.x + blockIdx.x] + before + rank;
+    }
 }
 /* headers from packing order into execution order.  After a rolling part the positions of the last full pack are kept: the
  * part's half-entries only shrink or grow a little, the order stays nearly sorted. */
@@ -1565,6 +1600,9 @@ static int ensure_packed(b200nb_context* h, PackedList& P, size_t cap_tiles, siz
         NB_CUDA(h, cudaMalloc((void**)&P.staged, nh * sizeof(Entry)));
         NB_CUDA(h, cudaMalloc((void**)&P.dest, nh * sizeof(int)));
         NB_CUDA(h, cudaMalloc((void**)&P.sizes, nh * sizeof(int)));
+        cudaFree(P.order_blk);
+        P.order_blk = nullptr;
+        NB_CUDA(h, cudaMalloc((void**)&P.order_blk, ((nh + 255) / 256 + 1) * NB_ORDER_BINS * sizeof(int)));
         P.cap_entries = cap_entries;
     }
     return 0;
@@ -1593,12 +1631,14 @@ static int launch_pack(b200nb_context* h, int loc, int part, int nparts)
     if (!rolling)
     {
         /* full pack: execution order by the packed step counts */
-        NB_CUDA(h, cudaMemsetAsync(h->d_hist, 0, sizeof(int) * 2 * NB_ORDER_BINS, h->stream));
-        k_order_hist<<<(n + 255) / 256, 256, 0, h->stream>>>(P.sizes, n, h->d_hist);
+        const int nblk = (n + 255) / 256;
+        k_order_count<<<nblk, 256, 0, h->stream>>>(P.sizes, n, P.order_blk);
         LAUNCH_CHECK(h);
-        k_order_scan<<<1, 32, 0, h->stream>>>(h->d_hist);
+        k_order_scan_rows<<<NB_ORDER_BINS, 256, 0, h->stream>>>(P.order_blk, nblk, h->d_hist + NB_ORDER_BINS);
         LAUNCH_CHECK(h);
-        k_order_assign<<<(n + 255) / 256, 256, 0, h->stream>>>(P.sizes, n, h->d_hist, P.dest);
+        k_order_base<<<1, NB_ORDER_BINS, 0, h->stream>>>(h->d_hist + NB_ORDER_BINS, h->d_hist);
+        LAUNCH_CHECK(h);
+        k_order_assign<<<nblk, 256, 0, h->stream>>>(P.sizes, n, P.order_blk, h->d_hist, P.dest);
         LAUNCH_CHECK(h);
         k_place_headers<<<(n + 255) / 256, 256, 0, h->stream>>>(P.staged, P.dest, n, P.entries);
         LAUNCH_CHECK(h);

@@ -108,6 +108,7 @@ struct PackedList
     uint64_t* mask    = nullptr; /* one per step */
     int*      dest    = nullptr; /* per half-entry in packing order: its position in `entries` */
     int*      sizes   = nullptr; /* per half-entry in packing order: its steps (the ordering key) */
+    int*      order_blk = nullptr; /* scratch of the stable ordering: NB_ORDER_BINS x blocks of 256 half-entries */
     long long nentries = 0;      /* HALF-entries: 2 x the entries of the outer list */
     int       pitch = 0;         /* tiles of 8 j slots reserved per half-entry (= max_tiles_per_entry, even): pitch/2 steps */
     int       row = 0;           /* steps per row: pitch/2 + NB_PACK_TAIL */
