@@ -1,4 +1,4 @@
-/* b200nb force kernels: Lennard-Jones + {reaction-field / plain cut-off, Ewald real space (analytical)}
+/* b200nb force kernels: Lennard-Jones + {reaction-field / plain cut-off, Ewald real space (analytical or tabulated)}
  * cluster-pair force and energy with shift-force reduction, hand-written for sm_100a.
  *
  * Replaces (paths relative to /root/reference/src/gromacs):
@@ -12,7 +12,7 @@
  * cycles, everything else competes for the remaining issue slots.
  *  - the unit of the list is a HALF-ENTRY: four i-atoms (one half of an 8-atom i-cluster) + shift against a run of PACKED
  *    j-atoms (PackedList, b200nb_internal.h) -- the j-atoms that have at least one of their FOUR pairs inside the list radius.
- *    Packing per i-quad instead of per i-cluster raises the share of in-range lanes from 54 % to ~63 %: the one lever that
+ *    Packing per i-quad instead of per i-cluster raises the share of in-range lanes from 54 % to 65 %: the one lever that
  *    removes FP32 work instead of overhead;
  *  - one warp runs TWO half-entries side by side, lanes 0-15 the first, lanes 16-31 the second; they are neighbours in the
  *    size-sorted list, so they have the same number of steps (a step = 16 j-atoms per half-entry) up to the few warps that
@@ -28,8 +28,8 @@
  *    register form is 2-5 % faster at every size (profiles/r2/s_sweep_register_gather.txt); prefetch instructions (CCTL) for a
  *    longer lead cost 10-15 % and were dropped (u_, w_sweep_*.txt);
  *  - j-forces: accumulated in the lane over its 4 pairs with the same packed FMAs that feed the i accumulators and
- *    reduced by the lane itself (red.v2 {x, y} + red {z}): the two halves of a warp hold different j-atoms, so there is no
- *    exchange (the cluster-granular layout needed 2 shuffles + 5 selects / negations per step to share a j-atom between halves);
+ *    reduced by the lane itself with one 16-byte red (see red_j): the two halves of a warp hold different j-atoms, so there is
+ *    no exchange (the cluster-granular layout needed 2 shuffles + 5 selects / negations per step to share a j-atom between halves);
  *  - i-forces stay in registers (12 floats per lane); per half-entry one transposed butterfly over its 16 lanes
  *    (15 shuffles) and one 16-byte red per i-atom;
  *  - steps that carry exclusion masks are sorted to the front of a half-entry (k_pack) and run through a separate code
@@ -389,8 +389,9 @@ __device__ __forceinline__ float2 pair_fscal(const IData& I, const JAtom& J, con
 /* j-force of a step: the lane's packed accumulators hold, per component, the sums over its even (.x) and odd (.y) i-atoms
  * of F/r * d (the force ON THE i-ATOMS); the force on the lane's j-atom is minus their sum.  Every lane has its own j-atom, so
  * it reduces all three components itself with ONE 16-byte red into the j-atom's float4 force slot.  Measured
- * (profiles/r2/q_sweep_half_entries.txt): red.v2 {x, y} + red {z} saves the fourth, useless add in L2 but doubles the L2 requests
- * and is 12 % slower at 1 M atoms (B200NB_JRED_SPLIT builds it). */
+ * (profiles/r2/q_sweep_half_entries.txt, zl_sweep_jred_split_register_gather.txt): red.v2 {x, y} + red {z} saves the fourth, useless
+ * add in L2 but doubles the requests on the SM -> L2 reduction path, which saturates at ~240 G lane-level reductions/s: 487 us
+ * instead of 403 us at 1 M atoms, for Ewald and reaction field alike (B200NB_JRED_SPLIT builds it). */
 __device__ __forceinline__ void red_j(const float sx, const float sy, const float sz, float4* __restrict__ f, const int jslot)
 {
     float* const fp = reinterpret_cast<float*>(f + jslot);
