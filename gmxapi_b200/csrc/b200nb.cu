@@ -1520,7 +1520,7 @@ __global__ void __launch_bounds__(NB_ORDER_BINS) k_order_base(const int* __restr
     base[c] = before;
 }
 __global__ void __launch_bounds__(256) k_order_assign(const int* __restrict__ sizes, int n, const int* __restrict__ blkcnt, const int* __restrict__ base,
-                                                      int* __restrict__ dest, int interleave)
+                                                      int* __restrict__ dest)
 {
     __shared__ int wcnt[8][NB_ORDER_BINS];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1536,17 +1536,7 @@ __global__ void __launch_bounds__(256) k_order_assign(const int* __restrict__ si
     {
         int before = 0;
         for (int k = 0; k < w; k++) before += wcnt[k][bin];
-        int d = base[bin] + blkcnt[bin * gridDim.x + blockIdx.x] + before + rank;
-        if (interleave)
-        {
-            /* experiment (B200NB_ORDER_INTERLEAVE=1): the warps (pairs of positions) of the longer half of the list on the even
-             * warp slots, those of the shorter half on the odd ones, so that a wave of CTAs is not a convoy of equally long
-             * entries that start and end together */
-            const int m = n >> 1, w = d >> 1, hm = (m + 1) >> 1;
-            const int wp = w < hm ? 2 * w : 2 * (w - hm) + 1;
-            d            = 2 * wp + (d & 1);
-        }
-        dest[e] = d;
+        dest[e] = base[bin] + blkcnt[bin * gridDim.x + blockIdx.x] + before + rank;
     }
 }
 /* headers from packing order into execution order.  After a rolling part the positions of the last full pack are kept: the
@@ -1648,8 +1638,7 @@ static int launch_pack(b200nb_context* h, int loc, int part, int nparts)
         LAUNCH_CHECK(h);
         k_order_base<<<1, NB_ORDER_BINS, 0, h->stream>>>(h->d_hist + NB_ORDER_BINS, h->d_hist);
         LAUNCH_CHECK(h);
-        static const int interleave = getenv("B200NB_ORDER_INTERLEAVE") ? atoi(getenv("B200NB_ORDER_INTERLEAVE")) : 0;
-        k_order_assign<<<nblk, 256, 0, h->stream>>>(P.sizes, n, P.order_blk, h->d_hist, P.dest, interleave);
+        k_order_assign<<<nblk, 256, 0, h->stream>>>(P.sizes, n, P.order_blk, h->d_hist, P.dest);
         LAUNCH_CHECK(h);
         k_place_headers<<<(n + 255) / 256, 256, 0, h->stream>>>(P.staged, P.dest, n, P.entries);
         LAUNCH_CHECK(h);
