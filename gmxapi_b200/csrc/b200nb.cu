@@ -442,8 +442,9 @@ extern "C" int b200nb_set_box(b200nb_t* h, const float box[3], const int pbc_dim
     cudaSetDevice(h->device);
     for (int d = 0; d < 3; d++)
     {
-        h->box[d] = box[d];
-        h->pbc[d] = pbc_dims ? pbc_dims[d] : 1;
+        h->box[d]     = box[d];
+        h->box_off[d] = 0.f;
+        h->pbc[d]     = pbc_dims ? pbc_dims[d] : 1;
     }
     /* pbcutil/pbc.cpp:1187-1202 calc_shifts, rectangular box */
     int n = 0;
@@ -455,6 +456,32 @@ extern "C" int b200nb_set_box(b200nb_t* h, const float box[3], const int pbc_dim
                 h->h_shift_vec[3 * n + 1] = l * box[1];
                 h->h_shift_vec[3 * n + 2] = m * box[2];
             }
+    NB_CUDA(h, cudaMemcpy(h->d_shift_vec, h->h_shift_vec, sizeof(h->h_shift_vec), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+/* Triclinic cell: the lower-triangular GROMACS box matrix, rows a = (a_x, 0, 0), b = (b_x, b_y, 0), c = (c_x, c_y, c_z), within the
+ * reference's limits (pbcutil/pbc.cpp check_box: |b_x|, |c_x| <= a_x / 2, |c_y| <= b_y / 2, margin 1.001).  Atoms are expected where
+ * put_atoms_in_box leaves them: in the brick [0, a_x) x [0, b_y) x [0, c_z), which is what b200nb_put_on_grid covers; the cell's
+ * shape enters through the 45 shift vectors k a + l b + m c (calc_shifts, pbc.cpp:1187-1202) and the x-shift range of 2
+ * (nbnxm/pairlist.cpp:3181-3188).  All three dimensions periodic; not combined with domain decomposition. */
+extern "C" int b200nb_set_box_triclinic(b200nb_t* h, const float box9[9])
+{
+    if (!h || !box9) return nb_fail(h, B200NB_ERR_ARG, "set_box_triclinic: bad argument");
+    if (box9[1] != 0.f || box9[2] != 0.f || box9[5] != 0.f) return nb_fail(h, B200NB_ERR_ARG, "set_box_triclinic: the box matrix must be lower triangular");
+    if (!(box9[0] > 0.f && box9[4] > 0.f && box9[8] > 0.f)) return nb_fail(h, B200NB_ERR_ARG, "set_box_triclinic: non-positive diagonal");
+    const float margin = 1.001f;
+    if (fabsf(box9[3]) > 0.5f * margin * box9[0] || fabsf(box9[6]) > 0.5f * margin * box9[0] || fabsf(box9[7]) > 0.5f * margin * box9[4])
+        return nb_fail(h, B200NB_ERR_ARG, "set_box_triclinic: off-diagonal elements exceed half the diagonal (pbcutil/pbc.cpp check_box)");
+    cudaSetDevice(h->device);
+    h->box[0] = box9[0], h->box[1] = box9[4], h->box[2] = box9[8];
+    h->box_off[0] = box9[3], h->box_off[1] = box9[6], h->box_off[2] = box9[7];
+    h->pbc[0] = h->pbc[1] = h->pbc[2] = 1;
+    int n = 0;
+    for (int m = -1; m <= 1; m++)
+        for (int l = -1; l <= 1; l++)
+            for (int k = -2; k <= 2; k++, n++)
+                for (int d = 0; d < 3; d++) h->h_shift_vec[3 * n + d] = k * box9[d] + l * box9[3 + d] + m * box9[6 + d];
     NB_CUDA(h, cudaMemcpy(h->d_shift_vec, h->h_shift_vec, sizeof(h->h_shift_vec), cudaMemcpyHostToDevice));
     return 0;
 }
@@ -1740,8 +1767,20 @@ extern "C" int b200nb_build_pairlist(b200nb_t* h)
     const float rl = h->hp.rlist_outer;
     /* a periodic dimension must hold at least two list radii, else one pair has several images in range
      * (the reference handles that with shp[XX]=2, pairlist.cpp:3185-3188; outside our scope) */
-    for (int d = 0; d < 3; d++)
-        if (h->pbc[d] && h->box[d] < 2 * rl) return nb_fail(h, B200NB_ERR_ARG, "build_pairlist: box smaller than 2*rlist along a periodic dimension");
+    const bool triclinic = h->box_off[0] != 0.f || h->box_off[1] != 0.f || h->box_off[2] != 0.f;
+    if (triclinic)
+    {
+        /* pbcutil/pbc.cpp:179-208 max_cutoff2: half the shortest box vector, and the smallest diagonal element (b_y less |c_y|) */
+        const float* o   = h->box_off;
+        const float  a2  = h->box[0] * h->box[0], b2 = o[0] * o[0] + h->box[1] * h->box[1], c2 = o[1] * o[1] + o[2] * o[2] + h->box[2] * h->box[2];
+        const float  mss = std::min(h->box[0], std::min(h->box[1] - fabsf(o[2]), h->box[2]));
+        if (rl * rl > std::min(0.25f * std::min(a2, std::min(b2, c2)), mss * mss))
+            return nb_fail(h, B200NB_ERR_ARG, "build_pairlist: list radius exceeds what the triclinic cell allows (max_cutoff2)");
+        if (h->grid[1].valid) return nb_fail(h, B200NB_ERR_ARG, "build_pairlist: triclinic cells are not combined with a halo grid");
+    }
+    else
+        for (int d = 0; d < 3; d++)
+            if (h->pbc[d] && h->box[d] < 2 * rl) return nb_fail(h, B200NB_ERR_ARG, "build_pairlist: box smaller than 2*rlist along a periodic dimension");
     /* list balancing granularity (the role of get_nsubpair_target, pairlist.cpp:2485-2587).  The force kernel is issue-bound
      * and an entry costs about 560 issue cycles on top of its tiles (prologue, masked first tile, i-force reduction;
      * profiles/r1/v_sweep_pair_loop_diagnostics.txt), so entries should be as long as the need for parallelism allows:
@@ -1788,7 +1827,9 @@ extern "C" int b200nb_build_pairlist(b200nb_t* h)
         A.intra = (loc == 0);
         for (int d = 0; d < 3; d++)
         {
-            A.shp[d] = h->pbc[d] ? 1 : 0;
+            /* triclinic cells: images two box vectors away along x can be in range (nbnxm/pairlist.cpp:3181-3188 takes 2 when
+             * a_x - |b_x| - |c_x| is below the cell-to-cell list range; always taking it costs a few empty shift iterations) */
+            A.shp[d] = h->pbc[d] ? ((d == 0 && triclinic) ? 2 : 1) : 0;
             A.box[d] = h->box[d];
         }
         A.rlist     = rl;
@@ -2781,6 +2822,8 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 extern "C" int b200nb_dd_create_window(b200nb_t* h, int max_halo, int max_send, void* ipc_handle_out, void** window_dev_out)
 {
+    if (h && (h->box_off[0] != 0.f || h->box_off[1] != 0.f || h->box_off[2] != 0.f))
+        return nb_fail(h, B200NB_ERR_ARG, "dd_create_window: domain decomposition of a triclinic cell is not supported");
     if (!h || max_halo < 0 || max_send < 0) return nb_fail(h, B200NB_ERR_ARG, "dd_create_window: bad argument");
     cudaSetDevice(h->device);
     DdState& D = h->dd;

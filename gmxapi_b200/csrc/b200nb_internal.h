@@ -217,7 +217,8 @@ struct b200nb_context
     std::vector<float> h_q;
     double             sum_q2 = 0;
 
-    float box[3] = { 0, 0, 0 };
+    float box[3] = { 0, 0, 0 };     /* diagonal of the box matrix */
+    float box_off[3] = { 0, 0, 0 }; /* triclinic cell: box[YY][XX], box[ZZ][XX], box[ZZ][YY] (b200nb_set_box_triclinic) */
     int   pbc[3] = { 1, 1, 1 };
     float* d_shift_vec = nullptr; /* 45*3 */
     float  h_shift_vec[B200NB_SHIFTS * 3];

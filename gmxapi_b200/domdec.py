@@ -393,6 +393,8 @@ class DomainRank:
 
     def __init__(self, system, options, transport, rank=None, nranks=None, device=0, use_windows=True):
         import torch
+        if np.any(np.asarray(getattr(system, "box_offdiag", np.zeros(3))) != 0):
+            raise InputException("domain decomposition of a triclinic cell is not supported")
         self.torch = torch
         self.t = transport
         self.rank = transport.rank if rank is None else rank

@@ -23,7 +23,7 @@ EXPORTS = [
     "b200nb_set_grid_atoms", "b200nb_upload_pairlist", "b200nb_copy_xq_grid", "b200nb_get_f_grid", "b200nb_set_shift_vec", "b200nb_set_ewald_table", "b200nb_describe",
     "b200nb_dd_wrap_classify", "b200nb_dd_select_lower_face", "b200nb_dd_partition_indices", "b200nb_dd_pack_atoms", "b200nb_dd_merge_home",
     "b200nb_dd_gather_int", "b200nb_dd_set_global_topology", "b200nb_dd_set_local_atoms", "b200nb_dd_wrap_classify_nd",
-    "b200nb_dd_select_boundary",
+    "b200nb_dd_select_boundary", "b200nb_set_box_triclinic",
 ]
 
 
@@ -124,6 +124,7 @@ def load_library():
     L.b200nb_set_vdw.argtypes = [vp, C.POINTER(_Vdw)]
     L.b200nb_set_atoms.argtypes = [vp, ci, vp, vp, vp, vp]
     L.b200nb_set_box.argtypes = [vp, vp, vp]
+    L.b200nb_set_box_triclinic.argtypes = [vp, vp]
     L.b200nb_put_on_grid.argtypes = [vp, ci, vp, vp, ci, ci, cf, vp, ci]
     L.b200nb_build_pairlist.argtypes = [vp]
     L.b200nb_set_x.argtypes = [vp, vp, ci, ci, ci]
@@ -262,7 +263,14 @@ class NbnxmGpu:
                     "set_atoms")
 
     def set_box(self, box, pbc=(1, 1, 1)):
+        """box: 3 edge lengths (rectangular) or the 3 x 3 lower-triangular box matrix of a triclinic cell (fully periodic)"""
         b = np.ascontiguousarray(box, dtype=np.float32)
+        if b.size == 9:
+            m = b.reshape(3, 3)
+            if m[1, 0] != 0 or m[2, 0] != 0 or m[2, 1] != 0:
+                self._check(self._L.b200nb_set_box_triclinic(self._h, _ptr(np.ascontiguousarray(m.ravel()))), "set_box_triclinic")
+                return
+            b = np.ascontiguousarray(np.diag(m))
         p = np.ascontiguousarray(pbc, dtype=np.int32)
         self._check(self._L.b200nb_set_box(self._h, _ptr(b), _ptr(p)), "set_box")
 

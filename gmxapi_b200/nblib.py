@@ -124,7 +124,8 @@ def configure_interactions(nb, nonbonded_parameters, options, rlist_outer=None):
 class SimulationState:
     def __init__(self, coordinates, box, types, charges, nonbondedParameters, excl_off=None, excl_idx=None):
         self.coordinates = np.ascontiguousarray(coordinates, dtype=np.float32).reshape(-1, 3)
-        self.box = np.ascontiguousarray(box, dtype=np.float32).reshape(3)
+        box = np.ascontiguousarray(box, dtype=np.float32)
+        self.box = box.reshape(3, 3) if box.size == 9 else box.reshape(3)  # edge lengths, or the triclinic box matrix (rows a, b, c)
         self.types = np.ascontiguousarray(types, dtype=np.int32)
         self.charges = np.ascontiguousarray(charges, dtype=np.float32)
         self.nonbondedParameters = np.ascontiguousarray(nonbondedParameters, dtype=np.float32)
@@ -141,7 +142,8 @@ class SimulationState:
 
     @classmethod
     def from_system(cls, s):
-        return cls(s.x, s.box, s.types, s.q, s.nbfp, s.excl_off, s.excl_idx)
+        box = s.box_matrix if np.any(getattr(s, "box_offdiag", np.zeros(3)) != 0) else s.box
+        return cls(s.x, box, s.types, s.q, s.nbfp, s.excl_off, s.excl_idx)
 
 
 class ForceCalculator:
@@ -159,11 +161,12 @@ class ForceCalculator:
 
     def _set_particles_on_grid(self, coordinates, box):
         # GmxForceCalculator::setParticlesOnGrid, api/nblib/gmxcalculator.cpp:85-103
-        box = np.ascontiguousarray(box, dtype=np.float32).reshape(3)
-        if not np.all(box > 0):
+        box = np.ascontiguousarray(box, dtype=np.float32)
+        diag = np.ascontiguousarray(np.diag(box.reshape(3, 3))) if box.size == 9 else box.reshape(3)
+        if not np.all(diag > 0):
             raise InputException("box must be positive")
-        self.nb.set_box(box)
-        self.nb.put_on_grid(coordinates, np.zeros(3, np.float32), box)
+        self.nb.set_box(box)  # 3 edge lengths, or a 3 x 3 triclinic box matrix: the grid covers the brick spanned by its diagonal
+        self.nb.put_on_grid(coordinates, np.zeros(3, np.float32), diag)
 
     def compute(self, coordinates=None, forces=None):
         """Returns forces[n,3] (float32). With computeVirialAndEnergy also keeps .energies / .shiftForces."""

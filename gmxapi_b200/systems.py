@@ -22,6 +22,14 @@ class System:
         self.x, self.box, self.types, self.q, self.nbfp = x, box, types, q, nbfp
         self.excl_off, self.excl_idx, self.mol_id, self.name = excl_off, excl_idx, mol_id, name
         self.n = x.shape[0]
+        # triclinic cells: `box` is the diagonal of the lower-triangular box matrix, box_offdiag = box[YY][XX], box[ZZ][XX],
+        # box[ZZ][YY] (all zero: rectangular)
+        self.box_offdiag = np.zeros(3, np.float32)
+
+    @property
+    def box_matrix(self):
+        b, o = self.box, self.box_offdiag
+        return np.array([[b[0], 0, 0], [o[0], b[1], 0], [o[1], o[2], b[2]]], np.float32)
 
 
 def water_box(nx, ny, nz, seed=20261017, jitter=0.02):
@@ -57,6 +65,38 @@ def water_box(nx, ny, nz, seed=20261017, jitter=0.02):
     excl_off = (np.arange(n + 1) * 3).astype(np.int32)
     mol_id = (np.arange(n) // 3).astype(np.int32)
     return System(x, box32, types, q, nbfp, excl_off, excl_idx, mol_id, "water_%dx%dx%d" % (nx, ny, nz))
+
+
+def put_atoms_in_triclinic_box(x, box_matrix):
+    """put_atoms_in_box for a triclinic cell (pbcutil/pbc.cpp): from z down to x, whole box vectors are added / subtracted until
+    0 <= x[d] < box[d][d] -- the atoms end up in the brick spanned by the diagonal, which is what the nbnxm grid covers."""
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 3).copy()
+    m = np.asarray(box_matrix, dtype=np.float32).reshape(3, 3)
+    for d in (2, 1, 0):
+        while True:
+            lo = x[:, d] < 0
+            hi = x[:, d] >= m[d, d]
+            if not (lo.any() or hi.any()):
+                break
+            x[lo] += m[d]
+            x[hi] -= m[d]
+    return x
+
+
+def sheared(system, offdiag_frac=(0.25, -0.2, 0.3)):
+    """The same molecules in a TRICLINIC cell of the same volume: box vectors a = (L_x, 0, 0), b = (f0 L_x, L_y, 0),
+    c = (f1 L_x, f2 L_y, L_z) (within the reference's limits |b_x|, |c_x| <= a_x / 2, |c_y| <= b_y / 2), every atom carried
+    along by the shear (fractional coordinates kept), then put into the brick the grid covers.  Molecules are deformed a little;
+    the nonbonded parity tests do not care."""
+    b = system.box.astype(np.float64)
+    off = np.array([offdiag_frac[0] * b[0], offdiag_frac[1] * b[0], offdiag_frac[2] * b[1]], np.float32)
+    m = np.array([[b[0], 0, 0], [off[0], b[1], 0], [off[1], off[2], b[2]]], np.float64)
+    frac = system.x.astype(np.float64) / b
+    x = put_atoms_in_triclinic_box((frac @ m).astype(np.float32), m.astype(np.float32))
+    out = System(x, system.box.copy(), system.types, system.q, system.nbfp, system.excl_off, system.excl_idx, system.mol_id,
+                 system.name + "_triclinic")
+    out.box_offdiag = off
+    return out
 
 
 def nbfp_two_lj_types(sigma_h=0.12, eps_h=0.19):

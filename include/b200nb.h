@@ -135,6 +135,11 @@ int b200nb_set_atoms(b200nb_t* h, int natoms, const int* type_host, const float*
  * pbc_dims[d] = 0 switches periodic images off along d (a dimension decomposed over ranks,
  * pairlist.cpp:3168-3176). */
 int b200nb_set_box(b200nb_t* h, const float box[3], const int pbc_dims[3]);
+/* the same for a TRICLINIC cell: box9 = the lower-triangular box matrix of the reference, rows a, b, c (`matrix box`,
+ * pbcutil/pbc.cpp; limits of check_box apply); atoms in the brick put_atoms_in_box leaves them in.  The shift vectors follow
+ * calc_shifts (pbc.cpp:1187-1202), the x-shift range nbnxm/pairlist.cpp:3181-3188, the largest list radius max_cutoff2
+ * (pbc.cpp:179-208).  Fully periodic, single domain. */
+int b200nb_set_box_triclinic(b200nb_t* h, const float box9[9]);
 
 /* ---- gridding: nbnxn_put_on_grid (nbnxm.cpp:58-75 -> gridset.cpp:135-241 -> grid.cpp:103-1445).
  * Grid 0 = home atoms, grid 1 = halo atoms (nbnxn_put_on_grid_nonlocal, nbnxm.cpp:77-95).  Atoms

@@ -33,7 +33,8 @@ class _Params(C.Structure):
                 ("rvdw", C.c_float), ("vdw_modifier", C.c_int), ("rvdw_switch", C.c_float),
                 ("disp_c2", C.c_float), ("disp_c3", C.c_float), ("rep_c2", C.c_float), ("rep_c3", C.c_float),
                 ("sw_c3", C.c_float), ("sw_c4", C.c_float), ("sw_c5", C.c_float),
-                ("ljpme", C.c_int), ("ewaldcoeff_lj", C.c_float), ("sh_lj_ewald", C.c_float)]
+                ("ljpme", C.c_int), ("ewaldcoeff_lj", C.c_float), ("sh_lj_ewald", C.c_float),
+                ("box_offdiag", C.c_float * 3)]
 
 
 _lib = None
@@ -92,7 +93,8 @@ class RefNbnxm:
                  disp_cpot=None, rep_cpot=None, kernel=None, comb_rule=0, nthreads=1,
                  exact_atom_flags=0, put_in_box=0, rlist_inner=0.0, min_ilist_count=0,
                  rvdw=0.0, vdw_modifier=0, rvdw_switch=0.0, modifier_constants=None, ljpme=0, ewaldcoeff_lj=0.0,
-                 sh_lj_ewald=0.0):
+                 sh_lj_ewald=0.0, box_offdiag=(0.0, 0.0, 0.0)):
+        """box: the diagonal of the box matrix; box_offdiag: box[YY][XX], box[ZZ][XX], box[ZZ][YY] of a triclinic cell"""
         L = lib()
         self.n = int(len(types))
         self._x = np.ascontiguousarray(x, dtype=np.float32).reshape(self.n, 3)
@@ -120,7 +122,8 @@ class RefNbnxm:
                     sh_ewald, disp_cpot, rep_cpot, kernel, comb_rule, nthreads, exact_atom_flags,
                     put_in_box, min_ilist_count, rvdw, vdw_modifier, rvdw_switch,
                     k.get("disp_c2", 0.0), k.get("disp_c3", 0.0), k.get("rep_c2", 0.0), k.get("rep_c3", 0.0),
-                    k.get("sw_c3", 0.0), k.get("sw_c4", 0.0), k.get("sw_c5", 0.0), ljpme, ewaldcoeff_lj, sh_lj_ewald)
+                    k.get("sw_c3", 0.0), k.get("sw_c4", 0.0), k.get("sw_c5", 0.0), ljpme, ewaldcoeff_lj, sh_lj_ewald,
+                    (C.c_float * 3)(*[float(v) for v in box_offdiag]))
         self.rc = rc
         self.h = L.gmxref_create(C.byref(s), C.byref(p))
         if not self.h:

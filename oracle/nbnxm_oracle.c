@@ -86,18 +86,26 @@ static int shift_index(int tx, int ty, int tz)
     return 5 * (3 * (tz + 1) + (ty + 1)) + tx + 2; /* pbcutil/ishift.h:50 XYZ2IS */
 }
 
-/* pbcutil/pbc.cpp:1187-1202 calc_shifts for a rectangular box */
+/* Triclinic cells: the functions below take the DIAGONAL of the box matrix (box[3] = {a_x, b_y, c_z}); the off-diagonal elements
+ * of a lower-triangular GROMACS box, {b_x, c_x, c_y} = box[YY][XX], box[ZZ][XX], box[ZZ][YY], are a mode of the oracle set with
+ * orc_set_triclinic (all zero = rectangular, the default).  Atoms are expected in the brick [0, a_x) x [0, b_y) x [0, c_z), where
+ * put_atoms_in_box leaves them (pbcutil/pbc.cpp). */
+static float g_tric[3] = { 0.f, 0.f, 0.f };
+void orc_set_triclinic(const float offdiag[3])
+{
+    for (int d = 0; d < 3; d++) g_tric[d] = offdiag ? offdiag[d] : 0.f;
+}
+static int orc_is_triclinic(void) { return g_tric[0] != 0.f || g_tric[1] != 0.f || g_tric[2] != 0.f; }
+
+/* pbcutil/pbc.cpp:1187-1202 calc_shifts: shift_vec[n] = k a + l b + m c, in float like the reference */
 void orc_shift_vectors(const float box[3], float* shift_vec /* 45*3 */)
 {
-    int n = 0;
+    const float a[3] = { box[0], 0.f, 0.f }, b[3] = { g_tric[0], box[1], 0.f }, c[3] = { g_tric[1], g_tric[2], box[2] };
+    int         n = 0;
     for (int m = -1; m <= 1; m++)
         for (int l = -1; l <= 1; l++)
             for (int k = -2; k <= 2; k++, n++)
-            {
-                shift_vec[3 * n + 0] = k * box[0];
-                shift_vec[3 * n + 1] = l * box[1];
-                shift_vec[3 * n + 2] = m * box[2];
-            }
+                for (int d = 0; d < 3; d++) shift_vec[3 * n + d] = k * a[d] + l * b[d] + m * c[d];
 }
 
 /* r^2 with the reference's operand roles and operation order (see header). */
@@ -325,6 +333,22 @@ static void for_each_pair(int n, const float* x, const float box[3], float rmax,
 {
     float sv[ORC_SHIFTS * 3];
     orc_shift_vectors(box, sv);
+    if (orc_is_triclinic())
+    {
+        /* triclinic cell: brute force over all atom pairs and all 23 shifts with index <= CENTRAL (nbnxm/pairlist.cpp:3339-3342:
+         * the i-atom carries the shift; CENTRAL: each pair once) -- small systems only */
+        const float r2m = rmax * rmax;
+        for (int is = 0; is <= ORC_CENTRAL; is++)
+            for (int a = 0; a < n; a++)
+                for (int b = (is == ORC_CENTRAL ? a + 1 : 0); b < n; b++)
+                {
+                    if (a == b) continue;
+                    const float r2 = orc_rsq(x[3 * a], x[3 * a + 1], x[3 * a + 2], sv[3 * is], sv[3 * is + 1], sv[3 * is + 2], x[3 * b],
+                                             x[3 * b + 1], x[3 * b + 2]);
+                    if (r2 < r2m) cb(ctx, a, b, is, r2);
+                }
+        return;
+    }
     cell_list cl;
     /* cells at least rmax*(1+eps) wide so that +-1 neighbour cells suffice */
     cl_build(&cl, n, x, box, rmax * 1.0001f + 1e-6f);

@@ -97,6 +97,15 @@ def rsq(xi, shift, xj):
     return float(lib().orc_rsq(*[C.c_float(float(v)) for v in (*xi, *shift, *xj)]))
 
 
+def set_triclinic(offdiag=None):
+    """Triclinic mode of the oracle: the off-diagonal box elements box[YY][XX], box[ZZ][XX], box[ZZ][YY] (None / zeros:
+    rectangular).  A mode, not an argument: every function keeps taking the box DIAGONAL.  Pair enumeration becomes brute force."""
+    if offdiag is None:
+        lib().orc_set_triclinic(C.c_void_p(0))
+    else:
+        lib().orc_set_triclinic((C.c_float * 3)(*[float(v) for v in offdiag]))
+
+
 def shift_vectors(box):
     sv = np.zeros((SHIFTS, 3), np.float32)
     b = (C.c_float * 3)(*[float(v) for v in box])

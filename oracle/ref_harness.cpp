@@ -237,6 +237,9 @@ void* gmxref_create(const gmxref_system* s, const gmxref_params* p)
     inst->box[XX][XX] = s->box[0];
     inst->box[YY][YY] = s->box[1];
     inst->box[ZZ][ZZ] = s->box[2];
+    inst->box[YY][XX] = p->box_offdiag[0];
+    inst->box[ZZ][XX] = p->box_offdiag[1];
+    inst->box[ZZ][YY] = p->box_offdiag[2];
     calc_shifts(inst->box, inst->shiftVec);
     inst->fr            = static_cast<t_forcerec*>(std::calloc(1, sizeof(t_forcerec)));
     inst->fr->shift_vec = inst->shiftVec;

@@ -46,6 +46,9 @@ typedef struct
      * the caller also passes comb_rule = 1 / 2 for the atom-data initialisation (nbnxm_setup.cpp:399-410) */
     int   ljpme;
     float ewaldcoeff_lj, sh_lj_ewald;
+    /* triclinic cell: the off-diagonal elements box[YY][XX], box[ZZ][XX], box[ZZ][YY] of the lower-triangular box matrix
+     * (gmxref_system::box is its diagonal); all zero = rectangular */
+    float box_offdiag[3];
 } gmxref_params;
 
 int    gmxref_simd_width(void);

@@ -9,6 +9,7 @@ and oracle/_ref exist; the fixtures then travel to the GPU box, the reference tr
       f (n,3) f32, fshift (45,3) f32, e_lj, e_el   -- CPU SIMD kernel (2xMM on AVX-512), the parity target
       npairs, pairs_sha256                           -- in-range non-excluded pair set at rc (canonical keys)
       grid_sha256, grid_dims                         -- GPU-geometry (8x8x8) grid atom order
+ 2b. ref_water_3k_triclinic_{ewald,rf}.npz: the same for the 3 k box sheared into a triclinic cell (`make_golden.py triclinic`).
  3. ref_water_3k_vdw_<flavour>.npz: the reference's CPU SIMD kernels with an LJ force switch, an LJ potential switch
     and / or a VdW cut-off shorter than the Coulomb cut-off (Ewald electrostatics), once with the water charges and
     once with all charges zero (f_lj: Lennard-Jones forces alone, so that the modifier arithmetic is not hidden
@@ -126,11 +127,33 @@ def ljpme_flavours():
         print(name, out["e_lj"], out["e_el"], out["e_lj_lj"])
 
 
+def triclinic():
+    """ref_water_3k_triclinic_{ewald,rf}.npz: the reference on the 3 k water box sheared into a triclinic cell
+    (gmxapi_b200.systems.sheared: box[YY][XX] = 0.25 L, box[ZZ][XX] = -0.2 L, box[ZZ][YY] = 0.3 L)."""
+    import gmxapi_b200.systems as S
+    from oracle import gmxref, oracle
+    beta = float(np.float32(S.ewald_beta(RC)))
+    k_rf, c_rf = S.rf_constants(RC)
+    s = S.sheared(S.named("water_3k"))
+    for eel, kw in (("ewald", dict(eeltype=gmxref.EEL_EWALD_ANA, ewaldcoeff=beta)), ("rf", dict(eeltype=gmxref.EEL_RF, k_rf=k_rf, c_rf=c_rf))):
+        r = gmxref.RefNbnxm(s.x, s.box, s.types, s.q, s.nbfp, s.excl_off, s.excl_idx, rc=RC, nthreads=4, box_offdiag=s.box_offdiag, **kw)
+        f, fs, elj, eel_ = r.compute()
+        keys = oracle.canonical_pairs(r.pair_set())
+        r.close()
+        out = dict(f=f, fshift=fs, e_lj=np.float64(elj), e_el=np.float64(eel_), npairs=np.int64(len(keys)), pairs_sha256=np.array(sha(keys)),
+                   beta=np.float64(beta), box=s.box, box_offdiag=s.box_offdiag, x_sha256=np.array(sha(s.x)), seed=np.int64(20261017))
+        np.savez_compressed(os.path.join(HERE, "ref_water_3k_triclinic_%s.npz" % eel), **out)
+        print("triclinic", eel, len(keys), elj, eel_)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ljpme":
         ljpme_flavours()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "vdw":
         vdw_flavours()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "triclinic":
+        triclinic()
         sys.exit(0)
     main()

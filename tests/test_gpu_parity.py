@@ -93,6 +93,46 @@ def test_pairs_forces_energies(built, name, coulomb):
     assert abs(eel - eco) <= ENERGY_TOL * abs(eco)
 
 
+@pytest.mark.parametrize("coulomb,rlo,rli", [(g.CoulombType.Pme, 0.0, 0.0), (g.CoulombType.ReactionField, 0.0, 0.0),
+                                             (g.CoulombType.Pme, 1.05, 0.95)])
+def test_triclinic_cell(built, coulomb, rlo, rli):
+    """A triclinic cell (b200nb_set_box_triclinic: the 3 k water box sheared, box[YY][XX] = 0.25 L, box[ZZ][XX] = -0.2 L,
+    box[ZZ][YY] = 0.3 L): shift vectors k a + l b + m c, x-shift range 2.  Pair set bit-exact, forces, shift forces / virial and
+    energies against the triclinic mode of the oracle, and the forces against the reference's own output on the same cell
+    (tests/golden/ref_water_3k_triclinic_*.npz); once with a list buffer and dynamic pruning."""
+    import os
+    s = g.systems.sheared(g.systems.named("water_3k"))
+    fc = make(s, coulomb, rlo=rlo, rli=rli)
+    f = fc.compute()
+    oracle.set_triclinic(s.box_offdiag)
+    try:
+        fo, fso, evo, eco, npairs = oracle.forces(s.x, s.box, s.q, s.types, s.nbfp, RC, s.excl_off, s.excl_idx, **oracle_kwargs(coulomb))
+        op = oracle.canonical_pairs(oracle.pair_set(s.x, s.box, RC, s.excl_off, s.excl_idx))
+        sv = oracle.shift_vectors(s.box).astype(np.float64)
+    finally:
+        oracle.set_triclinic(None)
+    gp = oracle.canonical_pairs(fc.nb.pairs(RC))
+    assert len(gp) == len(op) == npairs and np.array_equal(gp, op)
+    assert relrms(f, fo) < FORCE_TOL
+    m = np.ones(45, bool)
+    m[nb.CENTRAL] = False
+    fs = fc.shiftForces.astype(np.float64)
+    assert np.abs(fs[m] - fso[m]).max() <= VIRIAL_TOL * np.abs(fso[m]).max()
+    vo, vg = -0.5 * sv.T @ fso, -0.5 * sv.T @ np.where(m[:, None], fs, 0.0)
+    assert np.abs(vo).max() > 0 and np.abs(vg - vo).max() <= VIRIAL_TOL * np.abs(vo).max()
+    elj, eel = fc.energies
+    assert abs(elj - evo) <= ENERGY_TOL * abs(evo) and abs(eel - eco) <= ENERGY_TOL * abs(eco)
+    if coulomb == g.CoulombType.Pme:  # the reaction-field fixture was made with epsilon_rf = infinity, this run uses 1
+        gd = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_water_3k_triclinic_ewald.npz"))
+        assert len(gp) == int(gd["npairs"]) and relrms(f, gd["f"].astype(np.float64)) < FORCE_TOL
+    # a list radius the cell cannot hold is refused (max_cutoff2), as is a box matrix outside the reference's limits
+    with pytest.raises(nb.B200NBError):
+        make(s, coulomb, rc=1.6)
+    with pytest.raises(nb.B200NBError):
+        fc.nb.set_box(np.array([[3.0, 0, 0], [1.6, 3.0, 0], [0, 0, 3.0]], np.float32))
+    fc.nb.close()
+
+
 @pytest.mark.parametrize("flavour,mod,rvdw,rsw", [("twin", g.VdwModifier.PotentialShift, 0.8, 0.0),
                                                   ("fswitch", g.VdwModifier.ForceSwitch, 0.9, 0.75),
                                                   ("pswitch", g.VdwModifier.PotentialSwitch, 0.9, 0.75),
