@@ -159,6 +159,7 @@ extern "C" void b200nb_destroy(b200nb_t* h)
     cudaFree(h->dd.d_ent_off);
     cudaFree(h->dd.d_ent_idx);
     cudaFree(h->dd.d_halo_link);
+    if (h->dd.h_err) cudaFreeHost(h->dd.h_err);
     cudaFree(h->dd.d_gtype), cudaFree(h->dd.d_gq), cudaFree(h->dd.d_geoff), cudaFree(h->dd.d_geidx), cudaFree(h->dd.d_g2l), cudaFree(h->dd.d_part_scratch);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -2769,7 +2770,7 @@ template<bool VEC>
 __global__ void __launch_bounds__(256)
 k_dd_step_end(const float4* __restrict__ fg, const int* __restrict__ slot_of_atom, int nhome, const int* __restrict__ ent_off,
               const int* __restrict__ ent_idx, const unsigned char* __restrict__ window, int* __restrict__ seq, int* __restrict__ counter,
-              const float* __restrict__ recv_f, float* __restrict__ f, const __grid_constant__ DdLinksDev L)
+              int* __restrict__ host_err, const float* __restrict__ recv_f, float* __restrict__ f, const __grid_constant__ DdLinksDev L)
 {
     __shared__ __align__(16) float sf[768];
     const int tid  = threadIdx.x;
@@ -2787,6 +2788,10 @@ k_dd_step_end(const float4* __restrict__ fg, const int* __restrict__ slot_of_ato
         {
             *counter = 0;
             *seq     = *seq + 1;
+            /* the time-out flag of this step's flag waits, mirrored into mapped host memory: b200nb_dd_status reads it there
+             * without a device call (a 4-byte cudaMemcpy per step cost ~8 us of every end-to-end step) */
+            const int e = *reinterpret_cast<const volatile int*>(window + NB_DD_ERR);
+            if (e) *reinterpret_cast<volatile int*>(host_err) = e;
         }
     }
     if (nb <= 0) return;
@@ -2845,6 +2850,9 @@ extern "C" int b200nb_dd_create_window(b200nb_t* h, int max_halo, int max_send, 
         D.prio_high = hi;
         NB_CUDA(h, cudaStreamCreateWithPriority(&D.stream_nl, cudaStreamNonBlocking, hi));
         NB_CUDA(h, cudaStreamCreateWithPriority(&D.stream_px, cudaStreamNonBlocking, hi));
+        NB_CUDA(h, cudaHostAlloc((void**)&D.h_err, 64, cudaHostAllocMapped));
+        *D.h_err = 0;
+        NB_CUDA(h, cudaHostGetDevicePointer((void**)&D.d_host_err, D.h_err, 0));
         if (const char* e = getenv("B200NB_DD_PUSH_INLINE")) D.push_inline = atoi(e) != 0;
         NB_CUDA(h, cudaEventCreateWithFlags(&D.ev_px_done, cudaEventDisableTiming));
         NB_CUDA(h, cudaEventCreateWithFlags(&D.ev_begin, cudaEventDisableTiming));
@@ -3105,10 +3113,10 @@ static int launch_dd_step(b200nb_context* h, const float* x_home, float* f_home,
     const unsigned nb1 = (unsigned)std::max(1, (n + 255) / 256);
     if ((reinterpret_cast<uintptr_t>(f_home) & 15) == 0)
         k_dd_step_end<true><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.d_ent_off, D.d_ent_idx, D.window, D.d_seq, D.d_count + 3,
-                                                       reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, D.links);
+                                                       D.d_host_err, reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, D.links);
     else
         k_dd_step_end<false><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, n, D.d_ent_off, D.d_ent_idx, D.window, D.d_seq, D.d_count + 3,
-                                                        reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, D.links);
+                                                        D.d_host_err, reinterpret_cast<const float*>(D.window + D.off_recv_f), f_home, D.links);
     LAUNCH_CHECK(h);
     return 0;
 }
@@ -3221,10 +3229,11 @@ extern "C" int b200nb_dd_status(b200nb_t* h)
     DdState& D = h->dd;
     if (!D.window) return 0;
     cudaSetDevice(h->device);
-    int e = 0;
-    NB_CUDA(h, cudaMemcpy(&e, D.window + NB_DD_ERR, sizeof(int), cudaMemcpyDeviceToHost));
+    /* the last kernel of every decomposed step mirrors the window's time-out flag into mapped host memory */
+    const int e = D.h_err ? *reinterpret_cast<volatile int*>(D.h_err) : 0;
     if (e)
     {
+        *reinterpret_cast<volatile int*>(D.h_err) = 0;
         cudaMemset(D.window + NB_DD_ERR, 0, sizeof(int));
         return nb_fail(h, B200NB_ERR_STATE, "dd_step: a halo exchange flag did not arrive within 10 s (peer stalled or not stepping)");
     }

@@ -169,6 +169,7 @@ struct DdState
     int*           d_part_scratch = nullptr;
     size_t         cap_part_scratch = 0;
     int*           d_count = nullptr; /* 2 last-block counters */
+    int *          h_err = nullptr, *d_host_err = nullptr; /* mapped host mirror of the window's time-out flag (b200nb_dd_status) */
     int*           d_seq = nullptr;   /* device-resident step counter: the value the flags carry (graph-replayable) */
     bool           have_plan = false;
     /* the halo chain (wait, halo x -> grid, non-local kernel, push f) runs on its own high-priority stream beside
