@@ -93,15 +93,20 @@ def test_pairs_forces_energies(built, name, coulomb):
     assert abs(eel - eco) <= ENERGY_TOL * abs(eco)
 
 
-@pytest.mark.parametrize("coulomb,rlo,rli", [(g.CoulombType.Pme, 0.0, 0.0), (g.CoulombType.ReactionField, 0.0, 0.0),
-                                             (g.CoulombType.Pme, 1.05, 0.95)])
-def test_triclinic_cell(built, coulomb, rlo, rli):
+DEFAULT_SHEAR = (0.25, -0.2, 0.3)
+
+
+@pytest.mark.parametrize("coulomb,rlo,rli,shear", [(g.CoulombType.Pme, 0.0, 0.0, DEFAULT_SHEAR), (g.CoulombType.ReactionField, 0.0, 0.0, DEFAULT_SHEAR),
+                                                   (g.CoulombType.Pme, 1.05, 0.95, DEFAULT_SHEAR),
+                                                   # at the limits of check_box: 1169 pairs sit two box vectors away along x
+                                                   (g.CoulombType.Pme, 0.0, 0.0, (0.5, 0.5, -0.5))])
+def test_triclinic_cell(built, coulomb, rlo, rli, shear):
     """A triclinic cell (b200nb_set_box_triclinic: the 3 k water box sheared, box[YY][XX] = 0.25 L, box[ZZ][XX] = -0.2 L,
     box[ZZ][YY] = 0.3 L): shift vectors k a + l b + m c, x-shift range 2.  Pair set bit-exact, forces, shift forces / virial and
     energies against the triclinic mode of the oracle, and the forces against the reference's own output on the same cell
     (tests/golden/ref_water_3k_triclinic_*.npz); once with a list buffer and dynamic pruning."""
     import os
-    s = g.systems.sheared(g.systems.named("water_3k"))
+    s = g.systems.sheared(g.systems.named("water_3k"), shear)
     fc = make(s, coulomb, rlo=rlo, rli=rli)
     f = fc.compute()
     oracle.set_triclinic(s.box_offdiag)
@@ -113,6 +118,8 @@ def test_triclinic_cell(built, coulomb, rlo, rli):
         oracle.set_triclinic(None)
     gp = oracle.canonical_pairs(fc.nb.pairs(RC))
     assert len(gp) == len(op) == npairs and np.array_equal(gp, op)
+    if shear != DEFAULT_SHEAR:
+        assert np.any(np.isin(gp & 63, [0, 4, 5, 9, 10, 14, 15, 19, 20]))  # shifts with |t_x| = 2 and index <= CENTRAL are in use
     assert relrms(f, fo) < FORCE_TOL
     m = np.ones(45, bool)
     m[nb.CENTRAL] = False
@@ -122,7 +129,7 @@ def test_triclinic_cell(built, coulomb, rlo, rli):
     assert np.abs(vo).max() > 0 and np.abs(vg - vo).max() <= VIRIAL_TOL * np.abs(vo).max()
     elj, eel = fc.energies
     assert abs(elj - evo) <= ENERGY_TOL * abs(evo) and abs(eel - eco) <= ENERGY_TOL * abs(eco)
-    if coulomb == g.CoulombType.Pme:  # the reaction-field fixture was made with epsilon_rf = infinity, this run uses 1
+    if coulomb == g.CoulombType.Pme and shear == DEFAULT_SHEAR:  # (the reaction-field fixture has epsilon_rf = infinity, this run 1)
         gd = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_water_3k_triclinic_ewald.npz"))
         assert len(gp) == int(gd["npairs"]) and relrms(f, gd["f"].astype(np.float64)) < FORCE_TOL
     # a list radius the cell cannot hold is refused (max_cutoff2), as is a box matrix outside the reference's limits
