@@ -180,6 +180,17 @@ struct DdState
     cudaEvent_t    ev_start = nullptr, ev_begin = nullptr, ev_nl_done = nullptr, ev_px_done = nullptr;
 };
 
+/* perturbed (free-energy) pairs: fep.cu */
+struct FepState
+{
+    int          natoms = 0, nri = 0;
+    int *        d_typeA = nullptr, *d_typeB = nullptr;
+    float *      d_qA = nullptr, *d_qB = nullptr;
+    int *        d_iinr = nullptr, *d_shift = nullptr, *d_jindex = nullptr, *d_jjnr = nullptr; /* t_nblist, mdtypes/nblist.h:117-137 */
+    signed char* d_excl = nullptr;
+    double*      d_out = nullptr; /* Vc, Vv, dvdl_coul, dvdl_vdw */
+};
+
 /* a captured step: the launches of b200nb_step / b200nb_dd_step for one set of buffers */
 struct StepGraph
 {
@@ -262,6 +273,7 @@ struct b200nb_context
     bool     search_two_pass = false; /* B200NB_SEARCH_TWO_PASS=1: always count, scan, fill (A/B switch; the first search always does) */
     PackedList packed[2];
     DdState    dd;
+    FepState   fep;
     StepGraph  graph[3];       /* [0] single-domain step, [1] decomposed step, [2] host step through the copy engines */
     int        host_dma = -1;  /* b200nb_compute: 1 = cudaMemcpyAsync staging, 0 = zero-copy kernels, -1 = not decided yet */
     long long  generation = 0; /* bumped whenever a list or halo plan is rebuilt: invalidates the captured graphs */
@@ -293,6 +305,8 @@ int nb_fail(b200nb_context* h, int code, const std::string& msg);
 
 /* force.cu */
 int nb_launch_force_kernel(b200nb_context* h, int locality, int flags);
+/* fep.cu */
+void nb_fep_free(b200nb_context* h);
 
 
 /* ---- device helpers shared by search / prune / pair extraction ---- */

@@ -24,6 +24,7 @@ EXPORTS = [
     "b200nb_dd_wrap_classify", "b200nb_dd_select_lower_face", "b200nb_dd_partition_indices", "b200nb_dd_pack_atoms", "b200nb_dd_merge_home",
     "b200nb_dd_gather_int", "b200nb_dd_set_global_topology", "b200nb_dd_set_local_atoms", "b200nb_dd_wrap_classify_nd",
     "b200nb_dd_select_boundary", "b200nb_set_box_triclinic",
+    "b200nb_fep_set_atoms", "b200nb_fep_upload_list", "b200nb_fep_launch", "b200nb_fep_get_outputs",
 ]
 
 
@@ -100,6 +101,11 @@ def library_path():
     return os.environ.get("B200NB_LIBRARY") or os.path.join(_HERE, "libb200nb.so")
 
 
+class _FepParams(C.Structure):
+    _fields_ = [("lambda_coul", C.c_float), ("lambda_vdw", C.c_float), ("sc_alpha", C.c_float), ("sc_power", C.c_int),
+                ("sc_sigma", C.c_float), ("sc_sigma_min", C.c_float), ("sc_coul", C.c_int)]
+
+
 def load_library():
     """Loads libb200nb.so; raises if it has not been built (no fallback)."""
     global _lib
@@ -125,6 +131,10 @@ def load_library():
     L.b200nb_set_atoms.argtypes = [vp, ci, vp, vp, vp, vp]
     L.b200nb_set_box.argtypes = [vp, vp, vp]
     L.b200nb_set_box_triclinic.argtypes = [vp, vp]
+    L.b200nb_fep_set_atoms.argtypes = [vp, vp, vp, vp, vp]
+    L.b200nb_fep_upload_list.argtypes = [vp, ci, vp, vp, vp, vp, vp]
+    L.b200nb_fep_launch.argtypes = [vp, C.POINTER(_FepParams)]
+    L.b200nb_fep_get_outputs.argtypes = [vp, vp]
     L.b200nb_put_on_grid.argtypes = [vp, ci, vp, vp, ci, ci, cf, vp, ci]
     L.b200nb_build_pairlist.argtypes = [vp]
     L.b200nb_set_x.argtypes = [vp, vp, ci, ci, ci]
@@ -367,6 +377,30 @@ class NbnxmGpu:
         sh = np.ascontiguousarray(shift, dtype=np.float32)
         self._check(self._L.b200nb_dd_set_plan(self._h, int(nhome), int(nhalo), _ptr(si) if si.size else None, int(si.size),
                                                _ptr(sh), int(halo_fshift_index)), "dd_set_plan")
+
+    # -- perturbed (free-energy) pairs: csrc/fep.cu -------------------------------------------------------------------------------
+    def fep_set_atoms(self, typeA, typeB, qA, qB):
+        """A / B state of every atom (t_mdatoms::typeA / typeB / chargeA / chargeB), atom order"""
+        tA, tB = np.ascontiguousarray(typeA, dtype=np.int32), np.ascontiguousarray(typeB, dtype=np.int32)
+        cA, cB = np.ascontiguousarray(qA, dtype=np.float32), np.ascontiguousarray(qB, dtype=np.float32)
+        self._check(self._L.b200nb_fep_set_atoms(self._h, _ptr(tA), _ptr(tB), _ptr(cA), _ptr(cB)), "fep_set_atoms")
+
+    def fep_upload_list(self, iinr, shift, jindex, jjnr, excl_fep):
+        """the perturbed pair list in t_nblist form (mdtypes/nblist.h): i-entries {iinr, shift, jindex}, jjnr, excl_fep"""
+        ii, sh = np.ascontiguousarray(iinr, dtype=np.int32), np.ascontiguousarray(shift, dtype=np.int32)
+        ji, jj = np.ascontiguousarray(jindex, dtype=np.int32), np.ascontiguousarray(jjnr, dtype=np.int32)
+        ex = np.ascontiguousarray(excl_fep, dtype=np.int8)
+        self._check(self._L.b200nb_fep_upload_list(self._h, int(len(ii)), _ptr(ii), _ptr(sh), _ptr(ji), _ptr(jj), _ptr(ex)), "fep_upload_list")
+
+    def fep_launch(self, lambda_coul, lambda_vdw, sc_alpha=0.5, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=False):
+        p = _FepParams(lambda_coul, lambda_vdw, sc_alpha, int(sc_power), sc_sigma, sc_sigma_min, int(bool(sc_coul)))
+        self._check(self._L.b200nb_fep_launch(self._h, C.byref(p)), "fep_launch")
+
+    def fep_outputs(self):
+        """(Vc, Vv, dV/dlambda_coul, dV/dlambda_vdw) of the launches since the last call"""
+        out = np.zeros(4, np.float64)
+        self._check(self._L.b200nb_fep_get_outputs(self._h, _ptr(out)), "fep_get_outputs")
+        return tuple(float(v) for v in out)
 
     # -- repartitioning on the device (b200nb_dd_* of csrc/dd_partition.cu); pointers are device addresses (ints) ----------------
     def dd_wrap_classify(self, x_dev, n, box, bounds, nranks, rank, code_dev):

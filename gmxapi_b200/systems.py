@@ -99,6 +99,35 @@ def sheared(system, offdiag_frac=(0.25, -0.2, 0.3)):
     return out
 
 
+def perturbed_water(name="water_3k", nmol=20, seed=7, q_scale_b=0.25):
+    """A water box with `nmol` perturbed molecules for the free-energy tests: in state B their charges are scaled by q_scale_b and
+    the oxygen's Lennard-Jones interaction is switched off (type 1: a disappearing particle, what soft-core exists for).
+    Returns (system, perturbed[n] bool, typeA, typeB, qA, qB, types_masked, q_masked) -- the masked arrays are what the cluster-pair
+    path gets (nbnxn_atomdata_mask_fep, nbnxm/atomdata.cpp: perturbed atoms carry zero charge and no LJ there)."""
+    s = named(name)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    mols = rng.choice(s.n // 3, nmol, replace=False)
+    pert = np.zeros(s.n, bool)
+    for m in mols:
+        pert[3 * m:3 * m + 3] = True
+    qA, qB = s.q.copy(), s.q.copy()
+    qB[pert] *= np.float32(q_scale_b)
+    tA, tB = s.types.copy(), s.types.copy()
+    tB[pert] = 1
+    tm, qm = s.types.copy(), s.q.copy()
+    tm[pert] = 1
+    qm[pert] = 0
+    return s, pert, tA, tB, qA, qB, tm, qm
+
+
+FEP_CASES = {  # name: parameters of the reference's soft-core (t_lambda) and the two lambdas
+    "sc1": dict(lambda_coul=0.3, lambda_vdw=0.6, sc_alpha=0.5, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=False),
+    "nosc": dict(lambda_coul=0.4, lambda_vdw=0.4, sc_alpha=0.0, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=False),
+    "sc2coul": dict(lambda_coul=0.5, lambda_vdw=0.5, sc_alpha=0.7, sc_power=2, sc_sigma=0.3, sc_sigma_min=0.25, sc_coul=True),
+    "sc1coul": dict(lambda_coul=0.2, lambda_vdw=0.9, sc_alpha=0.5, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=True),
+}
+
+
 def nbfp_two_lj_types(sigma_h=0.12, eps_h=0.19):
     """A second nonbonded-parameter table for the water boxes in which the hydrogens carry Lennard-Jones parameters too
     (a TIP-like sigma / epsilon pair) and the O-H cross term follows Lorentz-Berthelot: two LJ types whose geometric and

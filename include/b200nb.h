@@ -315,6 +315,32 @@ int b200nb_dd_set_global_topology(b200nb_t* h, int nglobal, const int* type_host
 int b200nb_dd_set_local_atoms(b200nb_t* h, const int* local_gid_dev, int nlocal);
 
 /* ---- introspection used by the parity tests and the bench ------------------------------------------------ */
+/* ---- perturbed (free-energy) pairs (gmxapi_b200/csrc/fep.cu) ----
+ * Replaces CPU code of the reference: the free-energy kernel gmxlib/nonbonded/nb_free_energy.cpp:203-860, which the reference runs
+ * on the host beside its GPU kernels (nonbonded_verlet_t::dispatchFreeEnergyKernel, nbnxm/kerneldispatch.cpp:486-588).  Built so
+ * far: reaction-field / plain cut-off electrostatics, cut-off LJ with potential shift, soft-core (r-power 6, lambda power 1 or 2)
+ * or none; Ewald, LJ-PME and the potential switch return B200NB_ERR_ARG.  As in the reference (nbnxn_atomdata_mask_fep) the caller
+ * gives the perturbed atoms zero charge and a type without LJ in b200nb_set_atoms, so the cluster-pair kernels skip them, and
+ * hands over the perturbed pair list in t_nblist form (mdtypes/nblist.h:117-137; what nbnxm/pairlist.cpp:1699-1872 make_fep_list
+ * builds: every pair within the list radius with a perturbed atom, excl_fep = 0 for excluded pairs and for a perturbed atom listed
+ * with itself).  b200nb_fep_launch goes between b200nb_clear_outputs / b200nb_launch_force and b200nb_get_f: it adds into the same
+ * forces and shift forces. */
+typedef struct
+{
+    float lambda_coul, lambda_vdw; /* nb_kernel_data_t::lambda[efptCOUL], [efptVDW] */
+    float sc_alpha;                /* t_lambda::sc_alpha; 0 = no soft-core */
+    int   sc_power;                /* t_lambda::sc_power: 1 or 2 */
+    float sc_sigma, sc_sigma_min;  /* t_lambda::sc_sigma, sc_sigma_min (nm) */
+    int   sc_coul;                 /* t_lambda::bScCoul: soft-core on Coulomb as well */
+} b200nb_fep_params_t;
+/* A / B state of every atom (atom order, b200nb_set_atoms' natoms): t_mdatoms::typeA/typeB/chargeA/chargeB */
+int b200nb_fep_set_atoms(b200nb_t* h, const int* typeA_host, const int* typeB_host, const float* qA_host, const float* qB_host);
+int b200nb_fep_upload_list(b200nb_t* h, int nri, const int* iinr, const int* shift, const int* jindex, const int* jjnr,
+                           const signed char* excl_fep);
+int b200nb_fep_launch(b200nb_t* h, const b200nb_fep_params_t* p);
+/* Vc, Vv, dV/dlambda_coul, dV/dlambda_vdw summed over the launches since the last call (read and reset) */
+int b200nb_fep_get_outputs(b200nb_t* h, double out4_host[4]);
+
 typedef struct
 {
     int       natoms, natoms_padded, nclusters;

@@ -23,7 +23,8 @@ SRCS=$(ls $R/gromacs/nbnxm/*.cpp $R/gromacs/nbnxm/kernels_reference/*.cpp \
           $R/gromacs/nbnxm/kernels_simd_2xmm/*.cpp $R/gromacs/nbnxm/kernels_simd_4xm/*.cpp | grep -v nbnxm_gpu_data_mgmt)
 for f in pbcutil/pbc.cpp mdlib/enerdata_utils.cpp utility/alignedallocator.cpp gpu_utils/hostallocator.cpp \
          math/functions.cpp utility/smalloc.cpp utility/stringutil.cpp tables/forcetable.cpp \
-         ewald/ewald_utils.cpp math/utilities.cpp utility/logger.cpp; do
+         ewald/ewald_utils.cpp math/utilities.cpp utility/logger.cpp \
+         gmxlib/nonbonded/nb_free_energy.cpp mdtypes/interaction_const.cpp; do
   SRCS="$SRCS $R/gromacs/$f"
 done
 SRCS="$SRCS $HERE/ref_harness.cpp $HERE/ref_stubs.cpp"

@@ -225,3 +225,35 @@ class RefNbnxm:
         out = np.zeros((max(n, 1), 3), np.int32)
         lib().gmxref_pair_set(self.h, rc or self.rc, out.ctypes.data, n)
         return out[:n]
+
+
+class _FepParams(C.Structure):
+    _fields_ = [("rc", C.c_float), ("epsfac", C.c_float), ("k_rf", C.c_float), ("c_rf", C.c_float), ("disp_cpot", C.c_float),
+                ("rep_cpot", C.c_float), ("lambda_coul", C.c_float), ("lambda_vdw", C.c_float), ("sc_alpha", C.c_float),
+                ("sc_power", C.c_int), ("sc_sigma", C.c_float), ("sc_sigma_min", C.c_float), ("sc_coul", C.c_int)]
+
+
+def fep_kernel(x, shift_vec, nbfp, typeA, typeB, qA, qB, iinr, shift, jindex, jjnr, excl_fep, rc, lambda_coul, lambda_vdw,
+               epsfac=138.935458, k_rf=0.0, c_rf=0.0, sc_alpha=0.5, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=False):
+    """The reference's gmx_nb_free_energy_kernel (gmxlib/nonbonded/nb_free_energy.cpp) on a perturbed pair list in t_nblist form.
+    Returns f[n,3], fshift[45,3], (Vc, Vv, dvdl_coul, dvdl_vdw)."""
+    L = lib()
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 3)
+    n = x.shape[0]
+    sv = np.ascontiguousarray(shift_vec, dtype=np.float32).reshape(45, 3)
+    nb = np.ascontiguousarray(nbfp, dtype=np.float32).ravel()
+    ntypes = int(round((nb.size // 2) ** 0.5))
+    arr = lambda a, t: np.ascontiguousarray(a, dtype=t)
+    tA, tB, cA, cB = arr(typeA, np.int32), arr(typeB, np.int32), arr(qA, np.float32), arr(qB, np.float32)
+    ii, sh, ji, jj = arr(iinr, np.int32), arr(shift, np.int32), arr(jindex, np.int32), arr(jjnr, np.int32)
+    ex = arr(excl_fep, np.int8)
+    p = _FepParams(rc, epsfac, k_rf, c_rf, -1.0 / rc ** 6, -1.0 / rc ** 12, lambda_coul, lambda_vdw, sc_alpha, sc_power, sc_sigma,
+                   sc_sigma_min, int(bool(sc_coul)))
+    f = np.zeros((n, 3), np.float32)
+    fs = np.zeros((45, 3), np.float32)
+    out = np.zeros(4, np.float32)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    L.gmxref_fep_kernel.restype = C.c_int
+    L.gmxref_fep_kernel(C.c_int(n), vp(x), vp(sv), C.c_int(ntypes), vp(nb), vp(tA), vp(tB), vp(cA), vp(cB), C.c_int(len(ii)), vp(ii), vp(sh),
+                        vp(ji), vp(jj), vp(ex), C.byref(p), vp(f), vp(fs), vp(out))
+    return f, fs, tuple(float(v) for v in out)

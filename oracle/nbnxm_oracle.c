@@ -799,3 +799,199 @@ void orc_virial_from_fshift(const float box[3], const double* fshift, double* vi
         for (int a = 0; a < 3; a++)
             for (int b = 0; b < 3; b++) vir[3 * a + b] += -0.5 * (double)sv[3 * s + a] * fshift[3 * s + b];
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Perturbed (free-energy) pairs: gmxlib/nonbonded/nb_free_energy.cpp:203-860 restated for the flavours
+ * our FEP kernel covers -- reaction-field / plain cut-off electrostatics, cut-off LJ with potential shift,
+ * soft-core with r-power 6 (lambda power 1 or 2) or none -- on a pair list in t_nblist form (mdtypes/nblist.h:117-137):
+ * nri i-entries {iinr, shift, jindex[nri+1]}, jjnr, excl_fep (1: the pair interacts, 0: excluded, only its
+ * reaction-field correction is evaluated; an atom listed with itself counts half).
+ * Arithmetic in float like the reference's ScalarDataTypes instantiation (GMX_DOUBLE = 0), sums in float in
+ * the reference's order of accumulation; out4 = {Vc, Vv, dvdl_coul, dvdl_vdw}.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct
+{
+    float rc, epsfac, k_rf, c_rf, disp_cpot, rep_cpot;
+    float lambda_coul, lambda_vdw;
+    float alpha_coul, alpha_vdw; /* interaction_const_t::SoftCoreParameters: alphaCoulomb = bScCoul ? sc_alpha : 0 */
+    int   lam_power;
+    float sigma6_def, sigma6_min;
+} orc_fep_params;
+
+void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntype, const float* nbfp, const int* typeA, const int* typeB,
+                    const float* chargeA, const float* chargeB, int nri, const int* iinr, const int* shift, const int* jindex, const int* jjnr,
+                    const signed char* excl_fep, const orc_fep_params* p, float* f, float* fshift, float* out4)
+{
+    const float facel = p->epsfac, krf = p->k_rf, crf = p->c_rf, rcoulomb = p->rc, rvdw = p->rc;
+    const float alpha_coul = p->alpha_coul, alpha_vdw = p->alpha_vdw, sigma6_def = p->sigma6_def, sigma6_min = p->sigma6_min;
+    const float lam_power = (float)p->lam_power;
+    const int   useSoftCore = !(alpha_coul == 0.f && alpha_vdw == 0.f);                             /* :946-958 */
+    const int   scDiffer = useSoftCore && !(p->lambda_coul == p->lambda_vdw && alpha_coul == alpha_vdw); /* :980-992 */
+    const float rcutoff_max2 = rcoulomb * rcoulomb;
+    float LFC[2] = { 1.f - p->lambda_coul, p->lambda_coul }, LFV[2] = { 1.f - p->lambda_vdw, p->lambda_vdw }, DLF[2] = { -1.f, 1.f };
+    float lfac_coul[2], dlfac_coul[2], lfac_vdw[2], dlfac_vdw[2];
+    for (int i = 0; i < 2; i++) /* :363-370 */
+    {
+        lfac_coul[i]  = (p->lam_power == 2 ? (1 - LFC[i]) * (1 - LFC[i]) : (1 - LFC[i]));
+        dlfac_coul[i] = DLF[i] * lam_power / 6.0f * (p->lam_power == 2 ? (1 - LFC[i]) : 1);
+        lfac_vdw[i]   = (p->lam_power == 2 ? (1 - LFV[i]) * (1 - LFV[i]) : (1 - LFV[i]));
+        dlfac_vdw[i]  = DLF[i] * lam_power / 6.0f * (p->lam_power == 2 ? (1 - LFV[i]) : 1);
+    }
+    for (int k = 0; k < 3 * natoms; k++) f[k] = 0.f;
+    for (int k = 0; k < 3 * ORC_SHIFTS; k++) fshift[k] = 0.f;
+    float dvdl_coul = 0.f, dvdl_vdw = 0.f, Vc = 0.f, Vv = 0.f;
+    for (int n = 0; n < nri; n++)
+    {
+        int         npair_within_cutoff = 0;
+        const int   is3 = 3 * shift[n], ii = iinr[n];
+        const float ix = shift_vec[is3] + x[3 * ii], iy = shift_vec[is3 + 1] + x[3 * ii + 1], iz = shift_vec[is3 + 2] + x[3 * ii + 2];
+        const float iqA = facel * chargeA[ii], iqB = facel * chargeB[ii];
+        const int   ntiA = 2 * ntype * typeA[ii], ntiB = 2 * ntype * typeB[ii];
+        float       vctot = 0, vvtot = 0, fix = 0, fiy = 0, fiz = 0;
+        for (int k = jindex[n]; k < jindex[n + 1]; k++)
+        {
+            const int   jnr = jjnr[k];
+            const float dx = ix - x[3 * jnr], dy = iy - x[3 * jnr + 1], dz = iz - x[3 * jnr + 2];
+            const float rsq = dx * dx + dy * dy + dz * dz;
+            const int   included = excl_fep == 0 || excl_fep[k];
+            if (rsq >= rcutoff_max2 && included) continue; /* :421-434 */
+            npair_within_cutoff++;
+            float rinv = 0.f, r = 0.f, rp, rpm2;
+            if (rsq > 0)
+            {
+                rinv = 1.0f / sqrtf(rsq);
+                r    = rsq * rinv;
+            }
+            if (useSoftCore)
+            {
+                rpm2 = rsq * rsq;
+                rp   = rpm2 * rsq;
+            }
+            else
+            {
+                rpm2 = rinv * rinv;
+                rp   = 1;
+            }
+            float Fscal = 0;
+            float qq[2] = { iqA * chargeA[jnr], iqB * chargeB[jnr] };
+            int   tj[2] = { ntiA + 2 * typeA[jnr], ntiB + 2 * typeB[jnr] };
+            if (included)
+            {
+                float c6[2], c12[2], sigma6[2] = { 0, 0 }, alpha_vdw_eff = 0, alpha_coul_eff = 0;
+                float FscalC[2], FscalV[2], Vcoul[2], Vvdw[2];
+                for (int i = 0; i < 2; i++)
+                {
+                    c6[i]  = nbfp[tj[i]];
+                    c12[i] = nbfp[tj[i] + 1];
+                    if (useSoftCore)
+                    {
+                        if (c6[i] > 0 && c12[i] > 0)
+                        {
+                            sigma6[i] = 0.5f * c12[i] / c6[i];
+                            if (sigma6[i] < sigma6_min) sigma6[i] = sigma6_min;
+                        }
+                        else sigma6[i] = sigma6_def;
+                    }
+                }
+                if (useSoftCore && !(c12[0] > 0 && c12[1] > 0)) /* :498-509: soft-core only if an end state has no repulsion */
+                {
+                    alpha_vdw_eff  = alpha_vdw;
+                    alpha_coul_eff = alpha_coul;
+                }
+                for (int i = 0; i < 2; i++)
+                {
+                    FscalC[i] = FscalV[i] = Vcoul[i] = Vvdw[i] = 0;
+                    float rinvC, rinvV, rC, rV, rpinvC, rpinvV;
+                    if (qq[i] != 0 || c6[i] != 0 || c12[i] != 0)
+                    {
+                        if (useSoftCore)
+                        {
+                            rpinvC = 1.0f / (alpha_coul_eff * lfac_coul[i] * sigma6[i] + rp);
+                            rC     = 1.0f / sqrtf(cbrtf(rpinvC)); /* pthRoot: invPthRoot = invsqrt(cbrt(.)), the effective r */
+                            rinvC  = 1.0f / rC;
+                            if (scDiffer)
+                            {
+                                rpinvV = 1.0f / (alpha_vdw_eff * lfac_vdw[i] * sigma6[i] + rp);
+                                rV     = 1.0f / sqrtf(cbrtf(rpinvV));
+                                rinvV  = 1.0f / rV;
+                            }
+                            else
+                            {
+                                rpinvV = rpinvC;
+                                rinvV  = rinvC;
+                                rV     = rC;
+                            }
+                        }
+                        else
+                        {
+                            rpinvC = rpinvV = 1;
+                            rinvC = rinvV = rinv;
+                            rC = rV = r;
+                        }
+                        if (qq[i] != 0 && rC < rcoulomb) /* :565-581, reaction field */
+                        {
+                            Vcoul[i]  = qq[i] * (rinvC + krf * rC * rC - crf);
+                            FscalC[i] = qq[i] * (rinvC - 2.0f * krf * rC * rC);
+                        }
+                        if ((c6[i] != 0 || c12[i] != 0) && rV < rvdw) /* :588-607 */
+                        {
+                            float rinv6;
+                            if (useSoftCore) rinv6 = rpinvV;
+                            else
+                            {
+                                rinv6 = rinvV * rinvV;
+                                rinv6 = rinv6 * rinv6 * rinv6;
+                            }
+                            const float Vvdw6 = c6[i] * rinv6, Vvdw12 = c12[i] * rinv6 * rinv6;
+                            Vvdw[i]   = (Vvdw12 + c12[i] * p->rep_cpot) * (1.0f / 12.0f) - (Vvdw6 + c6[i] * p->disp_cpot) * (1.0f / 6.0f);
+                            FscalV[i] = Vvdw12 - Vvdw6;
+                        }
+                        FscalC[i] *= rpinvC;
+                        FscalV[i] *= rpinvV;
+                    }
+                }
+                for (int i = 0; i < 2; i++) /* :644-667 */
+                {
+                    vctot += LFC[i] * Vcoul[i];
+                    vvtot += LFV[i] * Vvdw[i];
+                    Fscal += LFC[i] * FscalC[i] * rpm2;
+                    Fscal += LFV[i] * FscalV[i] * rpm2;
+                    if (useSoftCore)
+                    {
+                        dvdl_coul += Vcoul[i] * DLF[i] + LFC[i] * alpha_coul_eff * dlfac_coul[i] * FscalC[i] * sigma6[i];
+                        dvdl_vdw += Vvdw[i] * DLF[i] + LFV[i] * alpha_vdw_eff * dlfac_vdw[i] * FscalV[i] * sigma6[i];
+                    }
+                    else
+                    {
+                        dvdl_coul += Vcoul[i] * DLF[i];
+                        dvdl_vdw += Vvdw[i] * DLF[i];
+                    }
+                }
+            }
+            else /* :669-691: excluded pair, reaction-field correction only (icoul is always REACTIONFIELD here: eelCUT or RF) */
+            {
+                const float FF = -2.0f * krf;
+                float       VV = krf * rsq - crf;
+                if (ii == jnr) VV *= 0.5f;
+                for (int i = 0; i < 2; i++)
+                {
+                    vctot += LFC[i] * qq[i] * VV;
+                    Fscal += LFC[i] * qq[i] * FF;
+                    dvdl_coul += DLF[i] * qq[i] * VV;
+                }
+            }
+            const float tx = Fscal * dx, ty = Fscal * dy, tz = Fscal * dz;
+            fix += tx, fiy += ty, fiz += tz;
+            f[3 * jnr] -= tx, f[3 * jnr + 1] -= ty, f[3 * jnr + 2] -= tz;
+        }
+        if (npair_within_cutoff > 0)
+        {
+            f[3 * ii] += fix, f[3 * ii + 1] += fiy, f[3 * ii + 2] += fiz;
+            fshift[is3] += fix, fshift[is3 + 1] += fiy, fshift[is3 + 2] += fiz;
+            Vc += vctot;
+            Vv += vvtot;
+        }
+    }
+    out4[0] = Vc, out4[1] = Vv, out4[2] = dvdl_coul, out4[3] = dvdl_vdw;
+}

@@ -224,3 +224,63 @@ def virial_from_fshift(box, fshift):
     vir = np.zeros(9, np.float64)
     lib().orc_virial_from_fshift(b, _p(fs), _p(vir))
     return vir.reshape(3, 3)
+
+
+class _FepParams(C.Structure):
+    _fields_ = [("rc", C.c_float), ("epsfac", C.c_float), ("k_rf", C.c_float), ("c_rf", C.c_float), ("disp_cpot", C.c_float),
+                ("rep_cpot", C.c_float), ("lambda_coul", C.c_float), ("lambda_vdw", C.c_float), ("alpha_coul", C.c_float),
+                ("alpha_vdw", C.c_float), ("lam_power", C.c_int), ("sigma6_def", C.c_float), ("sigma6_min", C.c_float)]
+
+
+def fep_kernel(x, shift_vec, nbfp, typeA, typeB, qA, qB, iinr, shift, jindex, jjnr, excl_fep, rc, lambda_coul, lambda_vdw,
+               epsfac=138.935458, k_rf=0.0, c_rf=0.0, sc_alpha=0.5, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=False):
+    """Plain-C restatement of the reference's free-energy kernel (orc_fep_kernel) on a perturbed pair list in t_nblist form; the
+    soft-core parameters are the inputrec's (sc_alpha, sc_power, sc_sigma, sc_sigma_min, sc_coul), processed like
+    interaction_const_t::SoftCoreParameters (mdtypes/interaction_const.cpp).  Returns f, fshift, (Vc, Vv, dvdl_coul, dvdl_vdw)."""
+    x = _f32(x).reshape(-1, 3)
+    n = x.shape[0]
+    sv = _f32(shift_vec).reshape(45, 3)
+    nb = _f32(nbfp).ravel()
+    ntypes = int(round((nb.size // 2) ** 0.5))
+    tA, tB, cA, cB = _i32(typeA), _i32(typeB), _f32(qA), _f32(qB)
+    ii, sh, ji, jj = _i32(iinr), _i32(shift), _i32(jindex), _i32(jjnr)
+    ex = np.ascontiguousarray(excl_fep, dtype=np.int8)
+    p = _FepParams(rc, epsfac, k_rf, c_rf, -1.0 / rc ** 6, -1.0 / rc ** 12, lambda_coul, lambda_vdw,
+                   sc_alpha if sc_coul else 0.0, sc_alpha, sc_power, sc_sigma ** 6, (sc_sigma_min ** 6) if sc_coul else 0.0)
+    f = np.zeros((n, 3), np.float32)
+    fs = np.zeros((45, 3), np.float32)
+    out = np.zeros(4, np.float32)
+    lib().orc_fep_kernel(C.c_int(n), _p(x), _p(sv), C.c_int(ntypes), _p(nb), _p(tA), _p(tB), _p(cA), _p(cB), C.c_int(len(ii)), _p(ii),
+                         _p(sh), _p(ji), _p(jj), _p(ex), C.byref(p), _p(f), _p(fs), _p(out))
+    return f, fs, tuple(float(v) for v in out)
+
+
+def fep_pair_list(x, box, rlist, perturbed, excl_off, excl_idx):
+    """The perturbed pair list the reference's make_fep_list (nbnxm/pairlist.cpp:1699-1872) would hand to the free-energy kernel:
+    every atom pair within rlist with at least one perturbed atom -- excluded pairs included, flagged 0 -- and every perturbed atom
+    with itself (flag 0: its reaction-field self term), grouped by (i-atom, shift) in t_nblist form.  Returns iinr, shift, jindex,
+    jjnr, excl_fep."""
+    x = _f32(x)
+    n = x.shape[0]
+    pert = np.asarray(perturbed, bool)
+    pairs = pair_set(x, box, rlist)  # no exclusions given: every pair in range
+    pairs = pairs[pert[pairs[:, 0]] | pert[pairs[:, 1]]]
+    flag = np.ones(len(pairs), np.int8)
+    eo, ei = np.asarray(excl_off), np.asarray(excl_idx)
+    exset = set()
+    for a in np.nonzero(pert)[0]:
+        for b in ei[eo[a]:eo[a + 1]]:
+            exset.add((int(a), int(b)))
+            exset.add((int(b), int(a)))
+    for k, (i, j, sft) in enumerate(pairs):
+        if sft == CENTRAL and (int(i), int(j)) in exset:
+            flag[k] = 0
+    selfp = np.nonzero(pert)[0].astype(np.int32)
+    pairs = np.concatenate([pairs, np.stack([selfp, selfp, np.full(len(selfp), CENTRAL, np.int32)], 1)])
+    flag = np.concatenate([flag, np.zeros(len(selfp), np.int8)])
+    order = np.lexsort((pairs[:, 1], pairs[:, 2], pairs[:, 0]))
+    pairs, flag = pairs[order], flag[order]
+    key = pairs[:, 0].astype(np.int64) * 64 + pairs[:, 2]
+    uk, start = np.unique(key, return_index=True)
+    return ((uk // 64).astype(np.int32), (uk % 64).astype(np.int32), np.append(start, len(pairs)).astype(np.int32),
+            np.ascontiguousarray(pairs[:, 1], dtype=np.int32), flag)

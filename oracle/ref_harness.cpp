@@ -710,3 +710,94 @@ int gmxref_grid_forces(void* h, float* f, int cap_slots)
 }
 
 } // extern "C"
+
+
+/* ---- the reference's free-energy kernel on a caller-built perturbed pair list ---------------------------------------------------------- */
+#include "gromacs/gmxlib/nonbonded/nb_free_energy.h"
+#include "gromacs/gmxlib/nonbonded/nonbonded.h"
+#include "gromacs/mdtypes/forceoutput.h"
+#include "gromacs/mdtypes/inputrec.h"
+#include "gromacs/mdtypes/mdatom.h"
+#include "gromacs/mdtypes/nblist.h"
+#include "gromacs/utility/arrayref.h"
+
+int gmxref_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntypes, const float* nbfp, const int* typeA, const int* typeB,
+                      const float* qA, const float* qB, int nri, const int* iinr, const int* shift, const int* jindex, const int* jjnr,
+                      const char* excl_fep, const gmxref_fep_params* p, float* f, float* fshift, float* out4)
+{
+    /* interaction constants as init_interaction_const would store them (mdlib/forcerec.cpp:850-874) */
+    interaction_const_t ic;
+    ic.eeltype          = (p->k_rf != 0.0f) ? eelRF : eelCUT;
+    ic.coulomb_modifier = eintmodNONE;
+    ic.vdwtype          = evdwCUT;
+    ic.vdw_modifier     = eintmodPOTSHIFT;
+    ic.rcoulomb = ic.rvdw = p->rc;
+    ic.epsfac             = p->epsfac;
+    ic.k_rf               = p->k_rf;
+    ic.c_rf               = p->c_rf;
+    ic.dispersion_shift.cpot = p->disp_cpot;
+    ic.repulsion_shift.cpot  = p->rep_cpot;
+    t_lambda fepvals{};
+    fepvals.sc_alpha     = p->sc_alpha;
+    fepvals.sc_power     = p->sc_power;
+    fepvals.sc_r_power   = 6.0;
+    fepvals.sc_sigma     = p->sc_sigma;
+    fepvals.sc_sigma_min = p->sc_sigma_min;
+    fepvals.bScCoul      = p->sc_coul != 0;
+    ic.softCoreParameters = std::make_unique<interaction_const_t::SoftCoreParameters>(fepvals);
+
+    std::vector<gmx::RVec> shiftVec(SHIFTS);
+    for (int s = 0; s < SHIFTS; s++) shiftVec[s] = { shift_vec[3 * s], shift_vec[3 * s + 1], shift_vec[3 * s + 2] };
+    t_forcerec* fr = static_cast<t_forcerec*>(std::calloc(1, sizeof(t_forcerec)));
+    fr->ic         = &ic;
+    fr->shift_vec  = as_rvec_array(shiftVec.data());
+    fr->ntype      = ntypes;
+    new (&fr->nbfp) std::vector<real>(nbfp, nbfp + 2 * ntypes * ntypes);
+    fr->use_simd_kernels = FALSE;
+
+    std::vector<real> cA(qA, qA + natoms), cB(qB, qB + natoms);
+    std::vector<int>  tA(typeA, typeA + natoms), tB(typeB, typeB + natoms);
+    t_mdatoms md{};
+    md.chargeA = cA.data();
+    md.chargeB = cB.data();
+    md.typeA   = tA.data();
+    md.typeB   = tB.data();
+
+    std::vector<int>  vi(iinr, iinr + nri), vs(shift, shift + nri), vg(nri, 0), vj(jindex, jindex + nri + 1), vjj(jjnr, jjnr + jindex[nri]);
+    std::vector<char> ve(excl_fep, excl_fep + jindex[nri]);
+    t_nblist nl{};
+    nl.nri = nl.maxnri = nri;
+    nl.nrj = nl.maxnrj = jindex[nri];
+    nl.iinr     = vi.data();
+    nl.gid      = vg.data();
+    nl.shift    = vs.data();
+    nl.jindex   = vj.data();
+    nl.jjnr     = vjj.data();
+    nl.excl_fep = ve.data();
+
+    gmx::PaddedVector<gmx::RVec> xx(natoms), ff(natoms, { 0, 0, 0 });
+    for (int a = 0; a < natoms; a++) xx[a] = { x[3 * a], x[3 * a + 1], x[3 * a + 2] };
+    std::vector<gmx::RVec>     fsh(SHIFTS, { 0, 0, 0 });
+    gmx::ForceWithShiftForces forces(ff.arrayRefWithPadding(), true, fsh);
+
+    real lambda[efptNR] = { 0 }, dvdl[efptNR] = { 0 }, vc = 0, vv = 0;
+    lambda[efptCOUL]    = p->lambda_coul;
+    lambda[efptVDW]     = p->lambda_vdw;
+    nb_kernel_data_t kd{};
+    kd.flags          = GMX_NONBONDED_DO_FORCE | GMX_NONBONDED_DO_SHIFTFORCE | GMX_NONBONDED_DO_POTENTIAL | GMX_NONBONDED_DO_SR;
+    kd.lambda         = lambda;
+    kd.dvdl           = dvdl;
+    kd.energygrp_elec = &vc;
+    kd.energygrp_vdw  = &vv;
+    t_nrnb nrnb{};
+    gmx_nb_free_energy_kernel(&nl, as_rvec_array(xx.data()), &forces, fr, &md, &kd, &nrnb);
+
+    for (int a = 0; a < natoms; a++)
+        for (int d = 0; d < 3; d++) f[3 * a + d] = ff[a][d];
+    for (int s = 0; s < SHIFTS; s++)
+        for (int d = 0; d < 3; d++) fshift[3 * s + d] = fsh[s][d];
+    out4[0] = vc, out4[1] = vv, out4[2] = dvdl[efptCOUL], out4[3] = dvdl[efptVDW];
+    fr->nbfp.~vector();
+    std::free(fr);
+    return 0;
+}

@@ -136,11 +136,7 @@ namespace gmx
 {
 int nonbondedMtsFactor(const t_inputrec&) { unreachable("nonbondedMtsFactor"); }
 } // namespace gmx
-void gmx_nb_free_energy_kernel(const t_nblist*, rvec*, gmx::ForceWithShiftForces*, const t_forcerec*,
-                               const t_mdatoms*, nb_kernel_data_t*, t_nrnb*)
-{
-    unreachable("gmx_nb_free_energy_kernel");
-}
+/* gmx_nb_free_energy_kernel: the real one is compiled in (gmxlib/nonbonded/nb_free_energy.cpp, oracle/build_ref.sh) */
 bool haveFepPerturbedNBInteractions(const gmx_mtop_t&) { unreachable("haveFepPerturbedNBInteractions"); }
 int  inputrec2nboundeddim(const t_inputrec*) { unreachable("inputrec2nboundeddim"); }
 void shift_self(const t_graph&, const matrix, rvec*) { unreachable("shift_self"); }

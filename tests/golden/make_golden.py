@@ -10,6 +10,7 @@ and oracle/_ref exist; the fixtures then travel to the GPU box, the reference tr
       npairs, pairs_sha256                           -- in-range non-excluded pair set at rc (canonical keys)
       grid_sha256, grid_dims                         -- GPU-geometry (8x8x8) grid atom order
  2b. ref_water_3k_triclinic_{ewald,rf}.npz: the same for the 3 k box sheared into a triclinic cell (`make_golden.py triclinic`).
+ 2c. ref_water_3k_fep_rf.npz: the reference's free-energy kernel on a perturbed pair list (`make_golden.py fep`).
  3. ref_water_3k_vdw_<flavour>.npz: the reference's CPU SIMD kernels with an LJ force switch, an LJ potential switch
     and / or a VdW cut-off shorter than the Coulomb cut-off (Ewald electrostatics), once with the water charges and
     once with all charges zero (f_lj: Lennard-Jones forces alone, so that the modifier arithmetic is not hidden
@@ -146,6 +147,23 @@ def triclinic():
         print("triclinic", eel, len(keys), elj, eel_)
 
 
+def fep():
+    """ref_water_3k_fep_rf.npz: the reference's free-energy kernel (gmxlib/nonbonded/nb_free_energy.cpp, compiled into oracle/_ref) on the
+    perturbed pair list of gmxapi_b200.systems.perturbed_water, reaction field, for the soft-core settings of systems.FEP_CASES."""
+    import gmxapi_b200.systems as S
+    from oracle import gmxref, oracle
+    s, pert, tA, tB, qA, qB, tm, qm = S.perturbed_water()
+    lst = oracle.fep_pair_list(s.x, s.box, RC, pert, s.excl_off, s.excl_idx)
+    sv = oracle.shift_vectors(s.box)
+    k_rf, c_rf = S.rf_constants(RC, eps_rf=1.0)
+    out = dict(list_sha256=np.array(sha(np.concatenate([a.astype(np.int64).ravel() for a in lst]))), npairs=np.int64(len(lst[3])), nri=np.int64(len(lst[0])))
+    for name, kw in S.FEP_CASES.items():
+        f, fs, o4 = gmxref.fep_kernel(s.x, sv, s.nbfp, tA, tB, qA, qB, *lst, RC, k_rf=k_rf, c_rf=c_rf, **kw)
+        out["f_" + name], out["fshift_" + name], out["out4_" + name] = f, fs, np.array(o4, np.float64)
+        print("fep", name, o4)
+    np.savez_compressed(os.path.join(HERE, "ref_water_3k_fep_rf.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ljpme":
         ljpme_flavours()
@@ -155,5 +173,8 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "triclinic":
         triclinic()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fep":
+        fep()
         sys.exit(0)
     main()

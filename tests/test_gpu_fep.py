@@ -1,0 +1,87 @@
+"""-m gpu: the perturbed-pair (free-energy) kernel, gmxapi_b200/csrc/fep.cu, through the C ABI, against the restatement of the
+reference's gmx_nb_free_energy_kernel (oracle/nbnxm_oracle.c orc_fep_kernel, pinned to the reference kernel itself in
+tests/test_oracle_cpu.py) and against the committed outputs of the reference kernel (tests/golden/ref_water_3k_fep_rf.npz).
+Tolerances: forces 1e-5 relative RMS (north_star), energies and dV/dlambda 2e-5 of the largest of the four sums."""
+import os
+
+import numpy as np
+import pytest
+
+import gmxapi_b200 as g
+from gmxapi_b200 import lib as nb
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+RC = 0.9
+
+
+def relrms(a, b):
+    return float(np.sqrt(((a - b) ** 2).sum() / (b ** 2).sum()))
+
+
+@pytest.mark.parametrize("case", ["sc1", "nosc", "sc2coul", "sc1coul"])
+def test_fep_kernel_matches_oracle_and_reference(built, case):
+    """20 perturbed water molecules in the 3 k box, reaction field.  The cluster-pair path runs on the MASKED atom data (perturbed atoms
+    without charge and LJ, as nbnxn_atomdata_mask_fep leaves them), the free-energy kernel on the perturbed pair list; their sum is the
+    force field of the lambda state.  Checked: the sum against oracle(masked system) + oracle(FEP list); the FEP part alone against
+    the reference kernel's committed output; Vc, Vv, dV/dlambda."""
+    S = g.systems
+    s, pert, tA, tB, qA, qB, tm, qm = S.perturbed_water()
+    kw = S.FEP_CASES[case]
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.ReactionField, computeVirialAndEnergy=True)
+    masked = g.SimulationState(s.x, s.box, tm, qm, s.nbfp, s.excl_off, s.excl_idx)
+    fc = g.ForceCalculator(masked, opt)
+    h = fc.nb
+    lst = oracle.fep_pair_list(s.x, s.box, RC, pert, s.excl_off, s.excl_idx)
+    h.fep_set_atoms(tA, tB, qA, qB)
+    h.fep_upload_list(*lst)
+    flags = nb.FLAG_ENERGY | nb.FLAG_VIRIAL
+    # the cluster-pair kernels alone, then with the free-energy kernel between launch and read-back
+    h.set_x(s.x)
+    h.clear_outputs()
+    h.launch_force(-1, flags)
+    f_plain = h.get_f().copy()
+    fs_plain = h.get_outputs()[0].astype(np.float64)
+    h.set_x(s.x)
+    h.clear_outputs()
+    h.launch_force(-1, flags)
+    h.fep_launch(**kw)
+    f_sum = h.get_f().copy()
+    fs_sum = h.get_outputs()[0].astype(np.float64)
+    out4 = np.array(h.fep_outputs())
+    # expected
+    k, c = S.rf_constants(RC, eps_rf=1.0)
+    sv = oracle.shift_vectors(s.box)
+    fo_fep, fso_fep, o4 = oracle.fep_kernel(s.x, sv, s.nbfp, tA, tB, qA, qB, *lst, RC, k_rf=k, c_rf=c, **kw)
+    fo_plain = oracle.forces(s.x, s.box, qm, tm, s.nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_RF, k_rf=k, c_rf=c)[0]
+    assert relrms(f_plain, fo_plain) < 1e-5
+    f_fep = f_sum.astype(np.float64) - f_plain
+    assert relrms(f_fep, fo_fep.astype(np.float64)) < 1e-5
+    assert relrms(f_sum, fo_plain + fo_fep) < 1e-5
+    gd = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_water_3k_fep_rf.npz"))
+    assert relrms(f_fep, gd["f_" + case].astype(np.float64)) < 1e-5
+    m = np.ones(45, bool)
+    m[nb.CENTRAL] = False
+    fs_fep = fs_sum - fs_plain
+    ref_fs = gd["fshift_" + case].astype(np.float64)
+    assert np.abs(fs_fep[m] - ref_fs[m]).max() <= 2e-5 * np.abs(ref_fs[m]).max()
+    o4r = gd["out4_" + case]
+    assert np.abs(out4 - np.array(o4)).max() <= 2e-5 * np.abs(np.array(o4)).max()
+    assert np.abs(out4 - o4r).max() <= 2e-5 * np.abs(o4r).max()
+    # read and reset: nothing launched since
+    assert h.fep_outputs() == (0.0, 0.0, 0.0, 0.0)
+    fc.nb.close()
+
+
+def test_fep_refuses_what_is_not_built(built):
+    S = g.systems
+    s, pert, tA, tB, qA, qB, tm, qm = S.perturbed_water()
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme)
+    fc = g.ForceCalculator(g.SimulationState(s.x, s.box, tm, qm, s.nbfp, s.excl_off, s.excl_idx), opt)
+    fc.nb.fep_set_atoms(tA, tB, qA, qB)
+    fc.nb.fep_upload_list(*oracle.fep_pair_list(s.x, s.box, RC, pert, s.excl_off, s.excl_idx))
+    with pytest.raises(nb.B200NBError):
+        fc.nb.fep_launch(0.5, 0.5)  # Ewald electrostatics: the tabulated long-range subtraction is not built
+    with pytest.raises(nb.B200NBError):
+        fc.nb.fep_upload_list([0], [22], [0, 1], [s.n + 5], [1])  # j-atom out of range
+    fc.nb.close()
