@@ -3,8 +3,9 @@
  * Replaces CPU code of the reference: gmxlib/nonbonded/nb_free_energy.cpp:203-860 (nb_free_energy_kernel, the scalar instantiation:
  * the reference has no SIMD or GPU form of it and runs it on the host beside the GPU nonbonded kernels, mdlib/sim_util.cpp
  * do_nb_verlet -> nonbonded_verlet_t::dispatchFreeEnergyKernel, nbnxm/kerneldispatch.cpp:486-588), for the flavours built so far:
- * reaction-field / plain cut-off electrostatics, cut-off LJ with potential shift, soft-core with r-power 6 (lambda power 1 or 2) or
- * none.  Ewald electrostatics (the tabulated long-range subtraction, :693-737), LJ-PME and the LJ potential switch are refused.
+ * reaction-field / plain cut-off or Ewald electrostatics (the long-range part subtracted unsoftened, :693-737, evaluated directly
+ * instead of from the reference's spline table), cut-off LJ with potential shift, soft-core with r-power 6 (lambda power 1 or 2) or
+ * none.  LJ-PME and the LJ potential switch are refused.
  * The pair list comes from the caller in t_nblist form (mdtypes/nblist.h:117-137; b200nb_fep_upload_list) -- what
  * nbnxm/pairlist.cpp:1699-1872 make_fep_list produces: every pair within the list radius with a perturbed atom, excluded pairs
  * flagged, perturbed atoms listed with themselves; building it on the device from the cluster-pair search is the next step.
@@ -30,6 +31,8 @@ struct FepDev
     float lfac_coul[2], dlfac_coul[2], lfac_vdw[2], dlfac_vdw[2];
     float alpha_coul, alpha_vdw, sigma6_def, sigma6_min;
     int   soft_core, sc_differ, ntypes;
+    int   ewald;
+    float beta, sh_ewald;
 };
 
 /* r^(1/6) of 1 / (alpha sigma^6 + r^6) and its inverse: pthRoot, nb_free_energy.cpp:81-87 */
@@ -129,10 +132,18 @@ k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, cons
                         rinvC = rinvV = rinv;
                         rC = rV = r;
                     }
-                    if (qq[i] != 0 && rC < P.rc) /* reaction field: :565-581 */
+                    if (qq[i] != 0 && (P.ewald ? r < P.rc : rC < P.rc)) /* :565-581 */
                     {
-                        Vcoul  = qq[i] * (rinvC + P.k_rf * rC * rC - P.c_rf);
-                        FscalC = qq[i] * (rinvC - 2.0f * P.k_rf * rC * rC);
+                        if (P.ewald) /* plain (soft-cored) 1/r; the long-range part is subtracted below, unsoftened */
+                        {
+                            Vcoul  = qq[i] * (rinvC - P.sh_ewald);
+                            FscalC = qq[i] * rinvC;
+                        }
+                        else
+                        {
+                            Vcoul  = qq[i] * (rinvC + P.k_rf * rC * rC - P.c_rf);
+                            FscalC = qq[i] * (rinvC - 2.0f * P.k_rf * rC * rC);
+                        }
                     }
                     if ((c6[i] != 0 || c12[i] != 0) && rV < P.rc) /* :588-607 */
                     {
@@ -163,7 +174,7 @@ k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, cons
                 }
             }
         }
-        else /* excluded pair: its reaction-field correction, no soft-core; an atom listed with itself counts half: :669-691 */
+        else if (!P.ewald) /* excluded pair: its reaction-field correction, no soft-core; an atom listed with itself counts half: :669-691 */
         {
             const float FF = -2.0f * P.k_rf;
             float       VV = P.k_rf * rsq - P.c_rf;
@@ -174,6 +185,32 @@ k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, cons
                 vctot += P.LFC[i] * qq[i] * VV;
                 Fscal += P.LFC[i] * qq[i] * FF;
                 dvdl_coul += DLF[i] * qq[i] * VV;
+            }
+        }
+        if (P.ewald && (r < P.rc || !included))
+        {
+            /* :693-737: the reciprocal-space part of the pair, erf(beta r) / r, subtracted unsoftened (also for excluded pairs and for
+             * a perturbed atom with itself, half).  The reference interpolates it from its cubic-spline table; evaluated directly
+             * here (the parity tests against the reference kernel measure the difference: forces 1-3e-6) */
+            float v_lr, f_lr;
+            if (rsq > 0)
+            {
+                const float br = P.beta * r;
+                v_lr           = erff(br) * rinv;
+                f_lr           = (v_lr - 1.1283791670955126f * P.beta * expf(-br * br)) * rinv * rinv; /* -(dv/dr) / r */
+            }
+            else
+            {
+                v_lr = 1.1283791670955126f * P.beta;
+                f_lr = 0.f;
+            }
+            if (ii == jnr) v_lr *= 0.5f;
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+            {
+                vctot -= P.LFC[i] * qq[i] * v_lr;
+                Fscal -= P.LFC[i] * qq[i] * f_lr;
+                dvdl_coul -= (DLF[i] * qq[i]) * v_lr;
             }
         }
         const float tx = Fscal * dx, ty = Fscal * dy, tz = Fscal * dz;
@@ -269,7 +306,6 @@ extern "C" int b200nb_fep_launch(b200nb_t* h, const b200nb_fep_params_t* p)
     FepState& F = h->fep;
     if (F.natoms != h->natoms || !F.d_out) return nb_fail(h, B200NB_ERR_STATE, "fep_launch: fep_set_atoms for the current atoms first");
     if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "fep_launch: put_on_grid first");
-    if (h->dp.eeltype == B200NB_EEL_EWALD) return nb_fail(h, B200NB_ERR_ARG, "fep_launch: Ewald electrostatics is not built for perturbed pairs (reaction field / cut-off only)");
     if (h->dp.vdw_modifier != B200NB_VDW_POTSHIFT || h->dp.rvdw2 < h->dp.rc2 || h->dp.ljpme != 0)
         return nb_fail(h, B200NB_ERR_ARG, "fep_launch: only cut-off LJ with potential shift and rvdw = rcoulomb is built for perturbed pairs");
     if (p->sc_power != 1 && p->sc_power != 2) return nb_fail(h, B200NB_ERR_ARG, "fep_launch: sc_power must be 1 or 2");
@@ -278,6 +314,7 @@ extern "C" int b200nb_fep_launch(b200nb_t* h, const b200nb_fep_params_t* p)
     FepDev D{};
     D.rc = h->hp.rc, D.rc2 = h->dp.rc2, D.epsfac = h->dp.epsfac, D.k_rf = h->dp.k_rf, D.c_rf = h->dp.c_rf, D.disp_cpot = h->dp.disp_cpot, D.rep_cpot = h->dp.rep_cpot;
     D.ntypes = h->dp.ntypes;
+    D.ewald = h->dp.eeltype == B200NB_EEL_EWALD, D.beta = h->dp.beta, D.sh_ewald = h->dp.sh_ewald;
     /* interaction_const_t::SoftCoreParameters (mdtypes/interaction_const.cpp:47-56) */
     D.alpha_vdw  = p->sc_alpha;
     D.alpha_coul = p->sc_coul ? p->sc_alpha : 0.f;

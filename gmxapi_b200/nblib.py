@@ -61,6 +61,9 @@ class NBKernelOptions:
     # 2000 points per nm; a caller that has the reference's own table (interaction_const_t::coulombEwaldTables) passes that one to
     # NbnxmGpu.set_ewald_table instead.
     useTabulatedEwaldCorr: bool = False
+    # interaction_const_t::sh_ewald = erfc(beta rc) / rc, the Coulomb potential shift mdrun applies with coulomb-modifier =
+    # potential-shift (initCoulombEwaldParameters, mdtypes/interaction_const.cpp); the reference's nblib leaves it 0
+    ewaldPotentialShift: bool = False
     device: int = 0
 
 
@@ -73,7 +76,11 @@ def interaction_kwargs(options):
     rc = float(options.pairlistCutoff)
     kw = dict(epsfac=ONE_4PI_EPS0)
     if options.coulombType == CoulombType.Pme:
-        kw.update(eeltype=_lib.EEL_EWALD, ewald_beta=float(np.float32(ewald_beta(rc, 1e-5))))
+        beta = float(np.float32(ewald_beta(rc, 1e-5)))
+        kw.update(eeltype=_lib.EEL_EWALD, ewald_beta=beta)
+        if options.ewaldPotentialShift:
+            from math import erfc
+            kw.update(sh_ewald=float(np.float32(erfc(beta * rc) / rc)))
     elif options.coulombType == CoulombType.Cutoff:
         k, c = rf_constants(rc, eps_rf=1.0)
         kw.update(eeltype=_lib.EEL_CUT, k_rf=k, c_rf=c)

@@ -230,11 +230,13 @@ class RefNbnxm:
 class _FepParams(C.Structure):
     _fields_ = [("rc", C.c_float), ("epsfac", C.c_float), ("k_rf", C.c_float), ("c_rf", C.c_float), ("disp_cpot", C.c_float),
                 ("rep_cpot", C.c_float), ("lambda_coul", C.c_float), ("lambda_vdw", C.c_float), ("sc_alpha", C.c_float),
-                ("sc_power", C.c_int), ("sc_sigma", C.c_float), ("sc_sigma_min", C.c_float), ("sc_coul", C.c_int)]
+                ("sc_power", C.c_int), ("sc_sigma", C.c_float), ("sc_sigma_min", C.c_float), ("sc_coul", C.c_int),
+                ("ewaldcoeff", C.c_float), ("sh_ewald", C.c_float)]
 
 
 def fep_kernel(x, shift_vec, nbfp, typeA, typeB, qA, qB, iinr, shift, jindex, jjnr, excl_fep, rc, lambda_coul, lambda_vdw,
-               epsfac=138.935458, k_rf=0.0, c_rf=0.0, sc_alpha=0.5, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=False):
+               epsfac=138.935458, k_rf=0.0, c_rf=0.0, sc_alpha=0.5, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=False,
+               ewaldcoeff=0.0, sh_ewald=0.0):
     """The reference's gmx_nb_free_energy_kernel (gmxlib/nonbonded/nb_free_energy.cpp) on a perturbed pair list in t_nblist form.
     Returns f[n,3], fshift[45,3], (Vc, Vv, dvdl_coul, dvdl_vdw)."""
     L = lib()
@@ -248,7 +250,7 @@ def fep_kernel(x, shift_vec, nbfp, typeA, typeB, qA, qB, iinr, shift, jindex, jj
     ii, sh, ji, jj = arr(iinr, np.int32), arr(shift, np.int32), arr(jindex, np.int32), arr(jjnr, np.int32)
     ex = arr(excl_fep, np.int8)
     p = _FepParams(rc, epsfac, k_rf, c_rf, -1.0 / rc ** 6, -1.0 / rc ** 12, lambda_coul, lambda_vdw, sc_alpha, sc_power, sc_sigma,
-                   sc_sigma_min, int(bool(sc_coul)))
+                   sc_sigma_min, int(bool(sc_coul)), ewaldcoeff, sh_ewald)
     f = np.zeros((n, 3), np.float32)
     fs = np.zeros((45, 3), np.float32)
     out = np.zeros(4, np.float32)

@@ -803,7 +803,7 @@ void orc_virial_from_fshift(const float box[3], const double* fshift, double* vi
 
 /* ------------------------------------------------------------------------------------------------
  * Perturbed (free-energy) pairs: gmxlib/nonbonded/nb_free_energy.cpp:203-860 restated for the flavours
- * our FEP kernel covers -- reaction-field / plain cut-off electrostatics, cut-off LJ with potential shift,
+ * our FEP kernel covers -- reaction-field / plain cut-off or Ewald electrostatics, cut-off LJ with potential shift,
  * soft-core with r-power 6 (lambda power 1 or 2) or none -- on a pair list in t_nblist form (mdtypes/nblist.h:117-137):
  * nri i-entries {iinr, shift, jindex[nri+1]}, jjnr, excl_fep (1: the pair interacts, 0: excluded, only its
  * reaction-field correction is evaluated; an atom listed with itself counts half).
@@ -817,6 +817,7 @@ typedef struct
     float alpha_coul, alpha_vdw; /* interaction_const_t::SoftCoreParameters: alphaCoulomb = bScCoul ? sc_alpha : 0 */
     int   lam_power;
     float sigma6_def, sigma6_min;
+    float beta, sh_ewald; /* beta > 0: Ewald electrostatics */
 } orc_fep_params;
 
 void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntype, const float* nbfp, const int* typeA, const int* typeB,
@@ -828,6 +829,7 @@ void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntyp
     const float lam_power = (float)p->lam_power;
     const int   useSoftCore = !(alpha_coul == 0.f && alpha_vdw == 0.f);                             /* :946-958 */
     const int   scDiffer = useSoftCore && !(p->lambda_coul == p->lambda_vdw && alpha_coul == alpha_vdw); /* :980-992 */
+    const int   ewald = p->beta > 0.f;
     const float rcutoff_max2 = rcoulomb * rcoulomb;
     float LFC[2] = { 1.f - p->lambda_coul, p->lambda_coul }, LFV[2] = { 1.f - p->lambda_vdw, p->lambda_vdw }, DLF[2] = { -1.f, 1.f };
     float lfac_coul[2], dlfac_coul[2], lfac_vdw[2], dlfac_vdw[2];
@@ -929,10 +931,18 @@ void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntyp
                             rinvC = rinvV = rinv;
                             rC = rV = r;
                         }
-                        if (qq[i] != 0 && rC < rcoulomb) /* :565-581, reaction field */
+                        if (qq[i] != 0 && (ewald ? r < rcoulomb : rC < rcoulomb)) /* :565-581 */
                         {
-                            Vcoul[i]  = qq[i] * (rinvC + krf * rC * rC - crf);
-                            FscalC[i] = qq[i] * (rinvC - 2.0f * krf * rC * rC);
+                            if (ewald) /* plain (soft-cored) 1/r: the long-range part is subtracted below */
+                            {
+                                Vcoul[i]  = qq[i] * (rinvC - p->sh_ewald);
+                                FscalC[i] = qq[i] * rinvC;
+                            }
+                            else
+                            {
+                                Vcoul[i]  = qq[i] * (rinvC + krf * rC * rC - crf);
+                                FscalC[i] = qq[i] * (rinvC - 2.0f * krf * rC * rC);
+                            }
                         }
                         if ((c6[i] != 0 || c12[i] != 0) && rV < rvdw) /* :588-607 */
                         {
@@ -969,7 +979,7 @@ void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntyp
                     }
                 }
             }
-            else /* :669-691: excluded pair, reaction-field correction only (icoul is always REACTIONFIELD here: eelCUT or RF) */
+            else if (!ewald) /* :669-691: excluded pair, reaction-field correction only (eelCUT or RF) */
             {
                 const float FF = -2.0f * krf;
                 float       VV = krf * rsq - crf;
@@ -979,6 +989,31 @@ void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntyp
                     vctot += LFC[i] * qq[i] * VV;
                     Fscal += LFC[i] * qq[i] * FF;
                     dvdl_coul += DLF[i] * qq[i] * VV;
+                }
+            }
+            if (ewald && (r < rcoulomb || !included))
+            {
+                /* :693-737: the reciprocal-space part of the pair, subtracted unsoftened.  The reference interpolates erf(beta r)/r
+                 * and its derivative from the cubic-spline table coulombEwaldTables (tableFDV0, spacing ~5e-4 nm); here they are
+                 * evaluated directly -- the test against the reference kernel measures the difference (forces 1e-6) */
+                float v_lr, f_lr;
+                if (rsq > 0)
+                {
+                    const double br = (double)p->beta * r, er = erf(br);
+                    v_lr = (float)(er / r);
+                    f_lr = (float)((er / r - 2.0 * p->beta / 1.7724538509055159 * exp(-br * br)) / ((double)r * r)); /* -(dv/dr) / r */
+                }
+                else
+                {
+                    v_lr = (float)(2.0 * p->beta / 1.7724538509055159);
+                    f_lr = 0.f;
+                }
+                if (ii == jnr) v_lr *= 0.5f;
+                for (int i = 0; i < 2; i++)
+                {
+                    vctot -= LFC[i] * qq[i] * v_lr;
+                    Fscal -= LFC[i] * qq[i] * f_lr;
+                    dvdl_coul -= (DLF[i] * qq[i]) * v_lr;
                 }
             }
             const float tx = Fscal * dx, ty = Fscal * dy, tz = Fscal * dz;

@@ -727,8 +727,8 @@ int gmxref_fep_kernel(int natoms, const float* x, const float* shift_vec, int nt
 {
     /* interaction constants as init_interaction_const would store them (mdlib/forcerec.cpp:850-874) */
     interaction_const_t ic;
-    ic.eeltype          = (p->k_rf != 0.0f) ? eelRF : eelCUT;
-    ic.coulomb_modifier = eintmodNONE;
+    ic.eeltype          = (p->ewaldcoeff > 0.0f) ? eelPME : ((p->k_rf != 0.0f) ? eelRF : eelCUT);
+    ic.coulomb_modifier = (p->ewaldcoeff > 0.0f) ? eintmodPOTSHIFT : eintmodNONE;
     ic.vdwtype          = evdwCUT;
     ic.vdw_modifier     = eintmodPOTSHIFT;
     ic.rcoulomb = ic.rvdw = p->rc;
@@ -737,6 +737,16 @@ int gmxref_fep_kernel(int natoms, const float* x, const float* shift_vec, int nt
     ic.c_rf               = p->c_rf;
     ic.dispersion_shift.cpot = p->disp_cpot;
     ic.repulsion_shift.cpot  = p->rep_cpot;
+    if (ic.eeltype == eelPME)
+    {
+        ic.ewaldcoeff_q       = p->ewaldcoeff;
+        ic.sh_ewald           = p->sh_ewald;
+        ic.coulombEwaldTables = std::make_unique<EwaldCorrectionTables>();
+        /* mdlib/forcerec.cpp:724-763 init_ewald_f_table, Coulomb only */
+        const real tableScale = ewald_spline3_table_scale(ic, true, false);
+        const int  tableSize  = static_cast<int>(ic.rcoulomb * tableScale) + 2;
+        *ic.coulombEwaldTables = generateEwaldCorrectionTables(tableSize, tableScale, ic.ewaldcoeff_q, v_q_ewald_lr);
+    }
     t_lambda fepvals{};
     fepvals.sc_alpha     = p->sc_alpha;
     fepvals.sc_power     = p->sc_power;

@@ -73,7 +73,7 @@ int    gmxref_bench_coordinates1000(float* out, int cap_atoms, float* box_edge);
 
 /* The reference's perturbed-pair (free-energy) kernel, gmxlib/nonbonded/nb_free_energy.cpp gmx_nb_free_energy_kernel, on a pair list
  * given by the caller in t_nblist form (nri i-entries {iinr, shift, jindex}, jjnr, excl_fep: 1 = the pair interacts, 0 = excluded).
- * Reaction-field / plain cut-off electrostatics and cut-off LJ with potential shift (the flavours our FEP kernel covers). */
+ * Reaction-field / plain cut-off or Ewald electrostatics and cut-off LJ with potential shift (the flavours our FEP kernel covers). */
 typedef struct
 {
     float rc;                 /* rcoulomb = rvdw */
@@ -84,6 +84,7 @@ typedef struct
     int   sc_power;           /* 1 or 2 */
     float sc_sigma, sc_sigma_min;
     int   sc_coul;            /* soft-core also on Coulomb (t_lambda::bScCoul) */
+    float ewaldcoeff, sh_ewald; /* ewaldcoeff > 0: Ewald electrostatics (eelPME; the kernel subtracts the tabulated long-range part) */
 } gmxref_fep_params;
 int gmxref_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntypes, const float* nbfp, const int* typeA, const int* typeB,
                       const float* qA, const float* qB, int nri, const int* iinr, const int* shift, const int* jindex, const int* jjnr,

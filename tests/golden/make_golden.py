@@ -162,6 +162,16 @@ def fep():
         out["f_" + name], out["fshift_" + name], out["out4_" + name] = f, fs, np.array(o4, np.float64)
         print("fep", name, o4)
     np.savez_compressed(os.path.join(HERE, "ref_water_3k_fep_rf.npz"), **out)
+    # the same with Ewald electrostatics: ref_water_3k_fep_ewald.npz
+    import math
+    beta = float(np.float32(S.ewald_beta(RC)))
+    sh = float(np.float32(math.erfc(beta * RC) / RC))
+    oute = dict(list_sha256=out["list_sha256"], beta=np.float64(beta), sh_ewald=np.float64(sh))
+    for name, kw in S.FEP_CASES.items():
+        f, fs, o4 = gmxref.fep_kernel(s.x, sv, s.nbfp, tA, tB, qA, qB, *lst, RC, ewaldcoeff=beta, sh_ewald=sh, **kw)
+        oute["f_" + name], oute["fshift_" + name], oute["out4_" + name] = f, fs, np.array(o4, np.float64)
+        print("fep ewald", name, o4)
+    np.savez_compressed(os.path.join(HERE, "ref_water_3k_fep_ewald.npz"), **oute)
 
 
 if __name__ == "__main__":

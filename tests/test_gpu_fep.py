@@ -19,8 +19,9 @@ def relrms(a, b):
     return float(np.sqrt(((a - b) ** 2).sum() / (b ** 2).sum()))
 
 
+@pytest.mark.parametrize("eel", ["rf", "ewald"])
 @pytest.mark.parametrize("case", ["sc1", "nosc", "sc2coul", "sc1coul"])
-def test_fep_kernel_matches_oracle_and_reference(built, case):
+def test_fep_kernel_matches_oracle_and_reference(built, case, eel):
     """20 perturbed water molecules in the 3 k box, reaction field.  The cluster-pair path runs on the MASKED atom data (perturbed atoms
     without charge and LJ, as nbnxn_atomdata_mask_fep leaves them), the free-energy kernel on the perturbed pair list; their sum is the
     force field of the lambda state.  Checked: the sum against oracle(masked system) + oracle(FEP list); the FEP part alone against
@@ -28,7 +29,9 @@ def test_fep_kernel_matches_oracle_and_reference(built, case):
     S = g.systems
     s, pert, tA, tB, qA, qB, tm, qm = S.perturbed_water()
     kw = S.FEP_CASES[case]
-    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.ReactionField, computeVirialAndEnergy=True)
+    ewald = eel == "ewald"
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme if ewald else g.CoulombType.ReactionField,
+                            computeVirialAndEnergy=True, ewaldPotentialShift=True)  # sh_ewald as mdrun sets it (and the fixture)
     masked = g.SimulationState(s.x, s.box, tm, qm, s.nbfp, s.excl_off, s.excl_idx)
     fc = g.ForceCalculator(masked, opt)
     h = fc.nb
@@ -50,15 +53,24 @@ def test_fep_kernel_matches_oracle_and_reference(built, case):
     fs_sum = h.get_outputs()[0].astype(np.float64)
     out4 = np.array(h.fep_outputs())
     # expected
+    import math
     k, c = S.rf_constants(RC, eps_rf=1.0)
+    beta = float(np.float32(S.ewald_beta(RC)))
     sv = oracle.shift_vectors(s.box)
-    fo_fep, fso_fep, o4 = oracle.fep_kernel(s.x, sv, s.nbfp, tA, tB, qA, qB, *lst, RC, k_rf=k, c_rf=c, **kw)
-    fo_plain = oracle.forces(s.x, s.box, qm, tm, s.nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_RF, k_rf=k, c_rf=c)[0]
+    if ewald:
+        fo_fep, fso_fep, o4 = oracle.fep_kernel(s.x, sv, s.nbfp, tA, tB, qA, qB, *lst, RC, ewaldcoeff=beta,
+                                                sh_ewald=float(np.float32(math.erfc(beta * RC) / RC)), **kw)
+        fo_plain = oracle.forces(s.x, s.box, qm, tm, s.nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_EWALD, beta=beta)[0]
+    else:
+        fo_fep, fso_fep, o4 = oracle.fep_kernel(s.x, sv, s.nbfp, tA, tB, qA, qB, *lst, RC, k_rf=k, c_rf=c, **kw)
+        fo_plain = oracle.forces(s.x, s.box, qm, tm, s.nbfp, RC, s.excl_off, s.excl_idx, eeltype=oracle.EEL_RF, k_rf=k, c_rf=c)[0]
     assert relrms(f_plain, fo_plain) < 1e-5
     f_fep = f_sum.astype(np.float64) - f_plain
     assert relrms(f_fep, fo_fep.astype(np.float64)) < 1e-5
     assert relrms(f_sum, fo_plain + fo_fep) < 1e-5
-    gd = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_water_3k_fep_rf.npz"))
+    gd = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_water_3k_fep_%s.npz" % eel))
+    if ewald:
+        assert abs(float(gd["sh_ewald"]) - math.erfc(beta * RC) / RC) < 1e-7 and abs(float(gd["beta"]) - beta) < 1e-6
     assert relrms(f_fep, gd["f_" + case].astype(np.float64)) < 1e-5
     m = np.ones(45, bool)
     m[nb.CENTRAL] = False
@@ -76,12 +88,14 @@ def test_fep_kernel_matches_oracle_and_reference(built, case):
 def test_fep_refuses_what_is_not_built(built):
     S = g.systems
     s, pert, tA, tB, qA, qB, tm, qm = S.perturbed_water()
-    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme)
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, vdwModifier=g.VdwModifier.PotentialSwitch, vdwSwitch=0.75)
     fc = g.ForceCalculator(g.SimulationState(s.x, s.box, tm, qm, s.nbfp, s.excl_off, s.excl_idx), opt)
     fc.nb.fep_set_atoms(tA, tB, qA, qB)
     fc.nb.fep_upload_list(*oracle.fep_pair_list(s.x, s.box, RC, pert, s.excl_off, s.excl_idx))
     with pytest.raises(nb.B200NBError):
-        fc.nb.fep_launch(0.5, 0.5)  # Ewald electrostatics: the tabulated long-range subtraction is not built
+        fc.nb.fep_launch(0.5, 0.5)  # LJ potential switch: not built for perturbed pairs
     with pytest.raises(nb.B200NBError):
         fc.nb.fep_upload_list([0], [22], [0, 1], [s.n + 5], [1])  # j-atom out of range
+    with pytest.raises(nb.B200NBError):
+        fc.nb.fep_launch(0.5, 0.5, sc_power=3)
     fc.nb.close()
