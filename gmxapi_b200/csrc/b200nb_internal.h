@@ -183,7 +183,9 @@ struct DdState
 /* perturbed (free-energy) pairs: fep.cu */
 struct FepState
 {
-    int          natoms = 0, nri = 0;
+    int          natoms = 0, nri = 0, nrj = 0, npert = 0;
+    int*           d_pert = nullptr;    /* the perturbed atoms, ascending */
+    unsigned char* d_is_pert = nullptr; /* per atom */
     int *        d_typeA = nullptr, *d_typeB = nullptr;
     float *      d_qA = nullptr, *d_qB = nullptr;
     int *        d_iinr = nullptr, *d_shift = nullptr, *d_jindex = nullptr, *d_jjnr = nullptr; /* t_nblist, mdtypes/nblist.h:117-137 */

@@ -8,7 +8,7 @@
  * none.  LJ-PME and the LJ potential switch are refused.
  * The pair list comes from the caller in t_nblist form (mdtypes/nblist.h:117-137; b200nb_fep_upload_list) -- what
  * nbnxm/pairlist.cpp:1699-1872 make_fep_list produces: every pair within the list radius with a perturbed atom, excluded pairs
- * flagged, perturbed atoms listed with themselves; building it on the device from the cluster-pair search is the next step.
+ * flagged, perturbed atoms listed with themselves -- or is built on the device from the gridded coordinates (b200nb_fep_build_list).
  * As in the reference the perturbed atoms carry zero charge and the filler LJ type in the normal atom data
  * (nbnxn_atomdata_mask_fep, nbnxm/atomdata.cpp), so the cluster-pair kernels compute nothing for them; this kernel adds the
  * forces of the perturbed pairs into the same grid-order force buffer and the same shift-force replicas.
@@ -247,6 +247,172 @@ k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, cons
     }
 }
 
+/* ---- the perturbed pair list, built on the device ----
+ * What nbnxm/pairlist.cpp:1699-1872 make_fep_list hands to the free-energy kernel: every atom pair within the list radius with at
+ * least one perturbed atom (excluded pairs stay in the list, flagged 0), every perturbed atom with itself (flag 0), grouped into
+ * i-entries of one i-atom and one shift.  The reference cuts these pairs out of its cluster-pair list while building it; here the
+ * cluster-pair path never sees them (perturbed atoms are masked in its atom data), so the list is a search of its own over the
+ * same grid: one warp per perturbed atom walks the cluster bounding boxes, lanes 8 x 4 test the atoms of four clusters at a time.
+ * A pair of two perturbed atoms is listed from the one with the lower index.  Two passes (count, fill) around one scan; the order
+ * of the j-atoms within an entry is the grid order, so the list and the sums over it are reproducible. */
+struct FepListArgs
+{
+    float box[3], inv_box[3];
+    int   pbc[3];
+    float rlist2;
+    int   nclusters;
+};
+
+template<bool FILL>
+__global__ void __launch_bounds__(128)
+k_fep_list(int npert, const int* __restrict__ pert, const unsigned char* __restrict__ is_pert, const float4* __restrict__ xq,
+           const int* __restrict__ slot_of_atom, const int* __restrict__ atom_index, const float* __restrict__ bb,
+           const int* __restrict__ excl_off, const int* __restrict__ excl_idx, const float* __restrict__ shift_vec, const FepListArgs A,
+           int* __restrict__ cnt, const int* __restrict__ off, const int* __restrict__ eidx, int* __restrict__ iinr, int* __restrict__ shift,
+           int* __restrict__ jindex, int* __restrict__ jjnr, signed char* __restrict__ excl_fep)
+{
+    __shared__ int s_cnt[4][B200NB_SHIFTS + 3];
+    __shared__ int s_q[4][32];
+    const int      w = threadIdx.x >> 5, lane = threadIdx.x & 31, ip = blockIdx.x * 4 + w;
+    if (ip >= npert) return; /* warp-uniform; only warp-level synchronisation below */
+    const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+    const int      p  = pert[ip];
+    const float4   xp = xq[slot_of_atom[p]];
+    const float    xpv[3] = { xp.x, xp.y, xp.z };
+    int            pe0 = 0, pe1 = 0;
+    if (excl_off) pe0 = excl_off[p], pe1 = excl_off[p + 1];
+    for (int k = lane; k < B200NB_SHIFTS; k += 32) s_cnt[w][k] = 0;
+    __syncwarp();
+    for (int c0 = 0; c0 < A.nclusters; c0 += 32)
+    {
+        const int c   = c0 + lane;
+        bool      hit = false;
+        if (c < A.nclusters)
+        {
+            const float* b = bb + (size_t)c * 6;
+            if (b[0] <= b[3]) /* not an all-filler cluster */
+            {
+                float d2 = 0.f;
+#pragma unroll
+                for (int d = 0; d < 3; d++)
+                {
+                    const float half = 0.5f * (b[3 + d] - b[d]);
+                    float       dc   = xpv[d] - 0.5f * (b[3 + d] + b[d]);
+                    if (A.pbc[d]) dc -= A.box[d] * rintf(dc * A.inv_box[d]);
+                    const float t = fabsf(dc) - half - 1e-4f; /* margin: the atom test below decides */
+                    if (t > 0.f) d2 += t * t;
+                }
+                hit = d2 < A.rlist2;
+            }
+        }
+        const unsigned m = __ballot_sync(full, hit);
+        if (hit) s_q[w][__popc(m & lt)] = c;
+        const int nq = __popc(m);
+        __syncwarp();
+        for (int q0 = 0; q0 < nq; q0 += 4)
+        {
+            const int qi = q0 + (lane >> 3);
+            bool      ok = false;
+            int       j = -1, s = B200NB_CENTRAL;
+            if (qi < nq)
+            {
+                const int sj = s_q[w][qi] * 8 + (lane & 7);
+                j            = atom_index[sj];
+                if (j >= 0 && !(j != p && is_pert[j] && j < p))
+                {
+                    const float4 xj    = xq[sj];
+                    const float  dv[3] = { xp.x - xj.x, xp.y - xj.y, xp.z - xj.z };
+                    int          t[3]  = { 0, 0, 0 };
+#pragma unroll
+                    for (int d = 0; d < 3; d++)
+                        if (A.pbc[d]) t[d] = -(int)rintf(dv[d] * A.inv_box[d]);
+                    if (t[0] >= -2 && t[0] <= 2 && t[1] >= -1 && t[1] <= 1 && t[2] >= -1 && t[2] <= 1)
+                    {
+                        s = 5 * (3 * (t[2] + 1) + (t[1] + 1)) + t[0] + 2; /* pbcutil/ishift.h:50 */
+                        const float r2 = nb_rsq(xp.x + shift_vec[3 * s], xp.y + shift_vec[3 * s + 1], xp.z + shift_vec[3 * s + 2], xj.x, xj.y, xj.z);
+                        ok = r2 < A.rlist2 && (j != p || s == B200NB_CENTRAL);
+                    }
+                }
+            }
+            const unsigned act = __ballot_sync(full, ok);
+            if (ok)
+            {
+                const unsigned same = __match_any_sync(act, s);
+                const int      rank = __popc(same & lt), base = s_cnt[w][s];
+                __syncwarp(act);
+                if (rank == 0) s_cnt[w][s] = base + __popc(same);
+                if (FILL)
+                {
+                    /* excluded: within the central image and on either atom's exclusion list (or the atom itself) */
+                    signed char flag = 1;
+                    if (j == p) flag = 0;
+                    else if (s == B200NB_CENTRAL && excl_off)
+                    {
+                        for (int e = pe0; e < pe1; e++)
+                            if (excl_idx[e] == j) flag = 0;
+                        for (int e = excl_off[j]; e < excl_off[j + 1]; e++)
+                            if (excl_idx[e] == p) flag = 0;
+                    }
+                    const int k = off[ip * B200NB_SHIFTS + s] + base + rank;
+                    jjnr[k]     = j;
+                    excl_fep[k] = flag;
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+    for (int k = lane; k < B200NB_SHIFTS; k += 32)
+    {
+        const int n = s_cnt[w][k];
+        if (!FILL) cnt[ip * B200NB_SHIFTS + k] = n;
+        else if (n > 0)
+        {
+            const int e = eidx[ip * B200NB_SHIFTS + k];
+            iinr[e] = p, shift[e] = k, jindex[e] = off[ip * B200NB_SHIFTS + k];
+        }
+    }
+}
+
+/* exclusive scans of the counts and of (count > 0) over m slots, one block; totals[0] = pairs, totals[1] = non-empty entries */
+__global__ void __launch_bounds__(1024) k_fep_scan(int m, const int* __restrict__ cnt, int* __restrict__ off, int* __restrict__ eidx, int* __restrict__ totals)
+{
+    __shared__ int s_a[32], s_b[32], s_carry[2];
+    const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry[0] = s_carry[1] = 0;
+    __syncthreads();
+    for (int k0 = 0; k0 < m; k0 += 1024)
+    {
+        const int k = k0 + threadIdx.x;
+        const int a = k < m ? cnt[k] : 0, b = a > 0;
+        int       ia = a, ib = b;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) ia += ta, ib += tb;
+        }
+        if (lane == 31) s_a[w] = ia, s_b[w] = ib;
+        __syncthreads();
+        if (w == 0)
+        {
+            int va = s_a[lane], vb = s_b[lane];
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int ta = __shfl_up_sync(0xffffffffu, va, o), tb = __shfl_up_sync(0xffffffffu, vb, o);
+                if (lane >= o) va += ta, vb += tb;
+            }
+            s_a[lane] = va, s_b[lane] = vb;
+        }
+        __syncthreads();
+        const int ca = s_carry[0] + (w ? s_a[w - 1] : 0), cb = s_carry[1] + (w ? s_b[w - 1] : 0);
+        if (k < m) off[k] = ca + ia - a, eidx[k] = cb + ib - b;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry[0] += s_a[31], s_carry[1] += s_b[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[0] = s_carry[0], totals[1] = s_carry[1];
+}
+
 template<typename T>
 int upload(b200nb_context* h, T** dst, const T* src, size_t n)
 {
@@ -272,6 +438,13 @@ extern "C" int b200nb_fep_set_atoms(b200nb_t* h, const int* typeA_host, const in
         || upload(h, &F.d_qB, qB_host, h->natoms))
         return B200NB_ERR_CUDA;
     F.natoms = h->natoms;
+    /* the perturbed atoms: charge or type differs between the end states (t_mdatoms::bPerturbed without the mass) */
+    std::vector<int>           pert;
+    std::vector<unsigned char> is_pert(h->natoms, 0);
+    for (int a = 0; a < h->natoms; a++)
+        if (typeA_host[a] != typeB_host[a] || qA_host[a] != qB_host[a]) pert.push_back(a), is_pert[a] = 1;
+    if (upload(h, &F.d_pert, pert.data(), pert.size()) || upload(h, &F.d_is_pert, is_pert.data(), is_pert.size())) return B200NB_ERR_CUDA;
+    F.npert = (int)pert.size();
     if (!F.d_out)
     {
         NB_CUDA(h, cudaMalloc((void**)&F.d_out, sizeof(double) * 4));
@@ -296,7 +469,92 @@ extern "C" int b200nb_fep_upload_list(b200nb_t* h, int nri, const int* iinr, con
     if (upload(h, &F.d_iinr, iinr, nri) || upload(h, &F.d_shift, shift, nri) || upload(h, &F.d_jindex, jindex, (size_t)nri + (nri ? 1 : 0))
         || upload(h, &F.d_jjnr, jjnr, nrj) || upload(h, &F.d_excl, excl_fep, nrj))
         return B200NB_ERR_CUDA;
-    F.nri = nri;
+    F.nri = nri, F.nrj = nrj;
+    return 0;
+}
+
+extern "C" int b200nb_fep_build_list(b200nb_t* h, int* nri_out, int* nrj_out)
+{
+    if (!h) return B200NB_ERR_ARG;
+    FepState& F = h->fep;
+    if (F.natoms != h->natoms || F.natoms < 1) return nb_fail(h, B200NB_ERR_STATE, "fep_build_list: fep_set_atoms for the current atoms first");
+    if (!h->grid[0].valid || !h->have_params) return nb_fail(h, B200NB_ERR_STATE, "fep_build_list: set_params and put_on_grid first");
+    if (h->box_off[0] != 0.f || h->box_off[1] != 0.f || h->box_off[2] != 0.f)
+        return nb_fail(h, B200NB_ERR_ARG, "fep_build_list: triclinic cells are not built for the device-side perturbed pair list (upload the list)");
+    if (h->dd.window) return nb_fail(h, B200NB_ERR_ARG, "fep_build_list: not built for decomposed runs");
+    cudaSetDevice(h->device);
+    FepListArgs A{};
+    for (int d = 0; d < 3; d++)
+    {
+        A.box[d] = h->box[d], A.inv_box[d] = h->box[d] > 0.f ? 1.0f / h->box[d] : 0.f, A.pbc[d] = h->pbc[d] && h->box[d] > 0.f;
+        if (A.pbc[d] && h->box[d] < 2.0f * h->hp.rlist_outer)
+            return nb_fail(h, B200NB_ERR_ARG, "fep_build_list: a periodic dimension narrower than twice the list radius");
+    }
+    A.rlist2    = h->dp.rlist_outer2;
+    A.nclusters = h->npad / 8;
+    F.nri       = 0;
+    if (nri_out) *nri_out = 0;
+    if (nrj_out) *nrj_out = 0;
+    if (F.npert == 0) return 0;
+    const size_t m = (size_t)F.npert * B200NB_SHIFTS;
+    int *        d_cnt = nullptr, *d_off = nullptr, *d_eidx = nullptr, *d_tot = nullptr;
+    NB_CUDA(h, cudaMalloc((void**)&d_cnt, sizeof(int) * (3 * m + 2)));
+    d_off = d_cnt + m, d_eidx = d_off + m, d_tot = d_eidx + m;
+    const unsigned nblk = (unsigned)((F.npert + 3) / 4);
+    const float4*  xq   = reinterpret_cast<const float4*>(h->d_xq);
+    k_fep_list<false><<<nblk, 128, 0, h->stream>>>(F.npert, F.d_pert, F.d_is_pert, xq, h->d_slot_of_atom, h->d_atom_index, h->d_bb, h->d_excl_off, h->d_excl_idx,
+                                                   h->d_shift_vec, A, d_cnt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    k_fep_scan<<<1, 1024, 0, h->stream>>>((int)m, d_cnt, d_off, d_eidx, d_tot);
+    int tot[2] = { 0, 0 };
+    cudaError_t e = cudaMemcpyAsync(tot, d_tot, sizeof(tot), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess)
+    {
+        cudaFree(d_cnt);
+        NB_CUDA(h, e);
+    }
+    const int nrj = tot[0], nri = tot[1];
+    cudaFree(F.d_iinr), cudaFree(F.d_shift), cudaFree(F.d_jindex), cudaFree(F.d_jjnr), cudaFree(F.d_excl);
+    F.d_iinr = F.d_shift = F.d_jindex = F.d_jjnr = nullptr, F.d_excl = nullptr;
+    if (cudaMalloc((void**)&F.d_iinr, sizeof(int) * std::max(nri, 1)) != cudaSuccess || cudaMalloc((void**)&F.d_shift, sizeof(int) * std::max(nri, 1)) != cudaSuccess
+        || cudaMalloc((void**)&F.d_jindex, sizeof(int) * (nri + 1)) != cudaSuccess || cudaMalloc((void**)&F.d_jjnr, sizeof(int) * std::max(nrj, 1)) != cudaSuccess
+        || cudaMalloc((void**)&F.d_excl, std::max(nrj, 1)) != cudaSuccess)
+    {
+        cudaFree(d_cnt);
+        return nb_fail(h, B200NB_ERR_CUDA, "fep_build_list: out of device memory");
+    }
+    k_fep_list<true><<<nblk, 128, 0, h->stream>>>(F.npert, F.d_pert, F.d_is_pert, xq, h->d_slot_of_atom, h->d_atom_index, h->d_bb, h->d_excl_off, h->d_excl_idx,
+                                                  h->d_shift_vec, A, nullptr, d_off, d_eidx, F.d_iinr, F.d_shift, F.d_jindex, F.d_jjnr, F.d_excl);
+    e = cudaMemcpyAsync(F.d_jindex + nri, &d_tot[0], sizeof(int), cudaMemcpyDeviceToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(d_cnt);
+    NB_CUDA(h, e);
+    h->nlaunches += 3;
+    F.nri = nri, F.nrj = nrj;
+    if (nri_out) *nri_out = nri;
+    if (nrj_out) *nrj_out = nrj;
+    return 0;
+}
+
+extern "C" int b200nb_fep_get_list(b200nb_t* h, int* iinr_host, int* shift_host, int* jindex_host, int* jjnr_host, signed char* excl_fep_host)
+{
+    if (!h || !iinr_host || !shift_host || !jindex_host || !jjnr_host || !excl_fep_host) return nb_fail(h, B200NB_ERR_ARG, "fep_get_list: bad argument");
+    FepState& F = h->fep;
+    cudaSetDevice(h->device);
+    if (F.nri == 0)
+    {
+        jindex_host[0] = 0;
+        return 0;
+    }
+    NB_CUDA(h, cudaMemcpy(iinr_host, F.d_iinr, sizeof(int) * F.nri, cudaMemcpyDeviceToHost));
+    NB_CUDA(h, cudaMemcpy(shift_host, F.d_shift, sizeof(int) * F.nri, cudaMemcpyDeviceToHost));
+    NB_CUDA(h, cudaMemcpy(jindex_host, F.d_jindex, sizeof(int) * (F.nri + 1), cudaMemcpyDeviceToHost));
+    if (F.nrj > 0)
+    {
+        NB_CUDA(h, cudaMemcpy(jjnr_host, F.d_jjnr, sizeof(int) * F.nrj, cudaMemcpyDeviceToHost));
+        NB_CUDA(h, cudaMemcpy(excl_fep_host, F.d_excl, F.nrj, cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 
@@ -356,6 +614,6 @@ void nb_fep_free(b200nb_context* h)
 {
     FepState& F = h->fep;
     cudaFree(F.d_typeA), cudaFree(F.d_typeB), cudaFree(F.d_qA), cudaFree(F.d_qB), cudaFree(F.d_iinr), cudaFree(F.d_shift), cudaFree(F.d_jindex);
-    cudaFree(F.d_jjnr), cudaFree(F.d_excl), cudaFree(F.d_out);
+    cudaFree(F.d_jjnr), cudaFree(F.d_excl), cudaFree(F.d_out), cudaFree(F.d_pert), cudaFree(F.d_is_pert);
     F = FepState{};
 }

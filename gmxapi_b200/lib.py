@@ -25,6 +25,7 @@ EXPORTS = [
     "b200nb_dd_gather_int", "b200nb_dd_set_global_topology", "b200nb_dd_set_local_atoms", "b200nb_dd_wrap_classify_nd",
     "b200nb_dd_select_boundary", "b200nb_set_box_triclinic",
     "b200nb_fep_set_atoms", "b200nb_fep_upload_list", "b200nb_fep_launch", "b200nb_fep_get_outputs",
+    "b200nb_fep_build_list", "b200nb_fep_get_list",
 ]
 
 
@@ -134,6 +135,8 @@ def load_library():
     L.b200nb_fep_set_atoms.argtypes = [vp, vp, vp, vp, vp]
     L.b200nb_fep_upload_list.argtypes = [vp, ci, vp, vp, vp, vp, vp]
     L.b200nb_fep_launch.argtypes = [vp, C.POINTER(_FepParams)]
+    L.b200nb_fep_build_list.argtypes = [vp, vp, vp]
+    L.b200nb_fep_get_list.argtypes = [vp, vp, vp, vp, vp, vp]
     L.b200nb_fep_get_outputs.argtypes = [vp, vp]
     L.b200nb_put_on_grid.argtypes = [vp, ci, vp, vp, ci, ci, cf, vp, ci]
     L.b200nb_build_pairlist.argtypes = [vp]
@@ -391,6 +394,21 @@ class NbnxmGpu:
         ji, jj = np.ascontiguousarray(jindex, dtype=np.int32), np.ascontiguousarray(jjnr, dtype=np.int32)
         ex = np.ascontiguousarray(excl_fep, dtype=np.int8)
         self._check(self._L.b200nb_fep_upload_list(self._h, int(len(ii)), _ptr(ii), _ptr(sh), _ptr(ji), _ptr(jj), _ptr(ex)), "fep_upload_list")
+
+    def fep_build_list(self):
+        """the perturbed pair list from the gridded coordinates, on the device (make_fep_list's output); returns (nri, nrj)"""
+        nri, nrj = C.c_int(0), C.c_int(0)
+        self._check(self._L.b200nb_fep_build_list(self._h, C.byref(nri), C.byref(nrj)), "fep_build_list")
+        self._fep_sizes = (nri.value, nrj.value)
+        return self._fep_sizes
+
+    def fep_list(self):
+        """the list fep_build_list made, on the host: iinr, shift, jindex, jjnr, excl_fep"""
+        nri, nrj = self._fep_sizes
+        ii, sh, ji = np.zeros(nri, np.int32), np.zeros(nri, np.int32), np.zeros(nri + 1, np.int32)
+        jj, ex = np.zeros(nrj, np.int32), np.zeros(nrj, np.int8)
+        self._check(self._L.b200nb_fep_get_list(self._h, _ptr(ii), _ptr(sh), _ptr(ji), _ptr(jj), _ptr(ex)), "fep_get_list")
+        return ii, sh, ji, jj, ex
 
     def fep_launch(self, lambda_coul, lambda_vdw, sc_alpha=0.5, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=False):
         p = _FepParams(lambda_coul, lambda_vdw, sc_alpha, int(sc_power), sc_sigma, sc_sigma_min, int(bool(sc_coul)))

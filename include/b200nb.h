@@ -338,6 +338,15 @@ typedef struct
 int b200nb_fep_set_atoms(b200nb_t* h, const int* typeA_host, const int* typeB_host, const float* qA_host, const float* qB_host);
 int b200nb_fep_upload_list(b200nb_t* h, int nri, const int* iinr, const int* shift, const int* jindex, const int* jjnr,
                            const signed char* excl_fep);
+/* The same list built on the device from the gridded coordinates (after b200nb_put_on_grid, at every search step): the pairs
+ * nbnxm/pairlist.cpp:1699-1872 make_fep_list cuts out of the cluster-pair list, here a search of its own over the cluster bounding
+ * boxes (the cluster-pair path never sees the perturbed atoms' interactions: their charge and LJ are masked).  Perturbed atoms =
+ * those whose A and B type or charge differ in b200nb_fep_set_atoms.  A pair of two perturbed atoms is listed from the lower atom
+ * index; j-atoms within an entry in grid order.  Rectangular cells, one domain; nri / nrj: entries and pairs (may be NULL). */
+int b200nb_fep_build_list(b200nb_t* h, int* nri_out, int* nrj_out);
+/* the current list (built or uploaded) back on the host, arrays sized from the nri / nrj of the build: iinr[nri], shift[nri],
+ * jindex[nri + 1], jjnr[nrj], excl_fep[nrj] */
+int b200nb_fep_get_list(b200nb_t* h, int* iinr_host, int* shift_host, int* jindex_host, int* jjnr_host, signed char* excl_fep_host);
 int b200nb_fep_launch(b200nb_t* h, const b200nb_fep_params_t* p);
 /* Vc, Vv, dV/dlambda_coul, dV/dlambda_vdw summed over the launches since the last call (read and reset) */
 int b200nb_fep_get_outputs(b200nb_t* h, double out4_host[4]);

@@ -85,6 +85,56 @@ def test_fep_kernel_matches_oracle_and_reference(built, case, eel):
     fc.nb.close()
 
 
+def _canonical(lst):
+    """the pairs of a t_nblist as sorted keys (lower atom, higher atom, shift seen from the lower atom, flag)"""
+    ii, sh, ji, jj, ex = [np.asarray(a) for a in lst]
+    n = np.diff(ji)
+    i, s, j = np.repeat(ii, n).astype(np.int64), np.repeat(sh, n).astype(np.int64), jj.astype(np.int64)
+    swap = i > j
+    a, b, s = np.where(swap, j, i), np.where(swap, i, j), np.where(swap, 44 - s, s)
+    return np.sort((((a << 24) | b) << 8 | s) * 2 + ex.astype(np.int64))
+
+
+@pytest.mark.parametrize("name,nmol,rlist", [("water_3k", 20, 0.9), ("water_3k", 20, 1.0), ("water_24k", 60, 1.0)])
+def test_fep_list_built_on_the_device(built, name, nmol, rlist):
+    """b200nb_fep_build_list against the oracle's list (make_fep_list's pair set): the same pairs, shifts and exclusion flags --
+    bit-exact as a set; a pair may be listed from the other atom, with the opposite shift -- and the kernel on the built list
+    against the kernel on the uploaded one: forces, energies, dV/dlambda, virial."""
+    S = g.systems
+    s, pert, tA, tB, qA, qB, tm, qm = S.perturbed_water(name, nmol=nmol)
+    opt = g.NBKernelOptions(pairlistCutoff=RC, rlistOuter=rlist, coulombType=g.CoulombType.Pme, computeVirialAndEnergy=True)
+    fc = g.ForceCalculator(g.SimulationState(s.x, s.box, tm, qm, s.nbfp, s.excl_off, s.excl_idx), opt)
+    h = fc.nb
+    h.fep_set_atoms(tA, tB, qA, qB)
+    want = oracle.fep_pair_list(s.x, s.box, rlist, pert, s.excl_off, s.excl_idx)
+    nri, nrj = h.fep_build_list()
+    got = h.fep_list()
+    assert nrj == len(want[3]) and got[2][-1] == nrj and nri == len(got[0])
+    assert np.array_equal(_canonical(got), _canonical(want))
+    assert len(np.unique(got[0].astype(np.int64) * 64 + got[1])) == nri and (np.diff(got[2]) > 0).all()  # one entry per (i, shift)
+    assert set(np.unique(got[0])) <= set(np.nonzero(pert)[0])  # i-atoms are perturbed atoms
+    sv = oracle.shift_vectors(s.box).astype(np.float64)
+    res = []
+    for lst in (None, want):
+        if lst is not None:
+            h.fep_upload_list(*lst)
+        h.set_x(s.x)
+        h.clear_outputs()
+        h.fep_launch(**S.FEP_CASES["sc1coul"])
+        f = h.get_f().astype(np.float64)
+        fs = h.get_outputs()[0].astype(np.float64)
+        res.append((f, np.einsum("sa,sb->ab", sv, fs), np.array(h.fep_outputs())))
+    (f0, v0, o0), (f1, v1, o1) = res
+    assert relrms(f0, f1) < 2e-6
+    assert np.abs(v0 - v1).max() <= 2e-5 * np.abs(v1).max()
+    assert np.abs(o0 - o1).max() <= 2e-5 * np.abs(o1).max()
+    # twice the same list: reproducible order
+    h.fep_build_list()
+    again = h.fep_list()
+    assert all(np.array_equal(a, b) for a, b in zip(got, again))
+    fc.nb.close()
+
+
 def test_fep_refuses_what_is_not_built(built):
     S = g.systems
     s, pert, tA, tB, qA, qB, tm, qm = S.perturbed_water()
