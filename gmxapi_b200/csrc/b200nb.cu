@@ -115,6 +115,7 @@ extern "C" void b200nb_destroy(b200nb_t* h)
     if (!h) return;
     cudaSetDevice(h->device);
     nb_fep_free(h);
+    nb_bonded_free(h);
     cudaStreamSynchronize(h->stream);
     void* ptrs[] = { h->d_ewald_tab, h->d_kconst, h->d_nbfp_comb, h->d_nbfp,       h->d_type,     h->d_q,        h->d_excl_off,     h->d_excl_idx,  h->d_shift_vec,
                      h->d_x,          h->d_fout,     h->d_col_of_atom, h->d_pos_in_col, h->d_col_count, h->d_col_cell0, h->d_col_fill,

@@ -193,6 +193,16 @@ struct FepState
     double*      d_out = nullptr; /* Vc, Vv, dvdl_coul, dvdl_vdw */
 };
 
+/* listed interactions on the device (bonded.cu): lists in atom order, 6 floats per parameter set */
+struct BondedState
+{
+    int     natoms = 0;
+    int     count[B200NB_BONDED_KINDS] = {};
+    int*    d_iatoms[B200NB_BONDED_KINDS] = {};
+    float*  d_params[B200NB_BONDED_KINDS] = {};
+    double* d_energy = nullptr; /* per kind + Coulomb-14 */
+};
+
 /* a captured step: the launches of b200nb_step / b200nb_dd_step for one set of buffers */
 struct StepGraph
 {
@@ -276,6 +286,7 @@ struct b200nb_context
     PackedList packed[2];
     DdState    dd;
     FepState   fep;
+    BondedState bonded;
     StepGraph  graph[3];       /* [0] single-domain step, [1] decomposed step, [2] host step through the copy engines */
     int        host_dma = -1;  /* b200nb_compute: 1 = cudaMemcpyAsync staging, 0 = zero-copy kernels, -1 = not decided yet */
     long long  generation = 0; /* bumped whenever a list or halo plan is rebuilt: invalidates the captured graphs */
@@ -309,6 +320,8 @@ int nb_fail(b200nb_context* h, int code, const std::string& msg);
 int nb_launch_force_kernel(b200nb_context* h, int locality, int flags);
 /* fep.cu */
 void nb_fep_free(b200nb_context* h);
+/* bonded.cu */
+void nb_bonded_free(b200nb_context* h);
 
 
 /* ---- device helpers shared by search / prune / pair extraction ---- */

@@ -26,6 +26,7 @@ EXPORTS = [
     "b200nb_dd_select_boundary", "b200nb_set_box_triclinic",
     "b200nb_fep_set_atoms", "b200nb_fep_upload_list", "b200nb_fep_launch", "b200nb_fep_get_outputs",
     "b200nb_fep_build_list", "b200nb_fep_get_list",
+    "b200nb_bonded_set_list", "b200nb_bonded_launch", "b200nb_bonded_get_energies",
 ]
 
 
@@ -136,6 +137,9 @@ def load_library():
     L.b200nb_fep_upload_list.argtypes = [vp, ci, vp, vp, vp, vp, vp]
     L.b200nb_fep_launch.argtypes = [vp, C.POINTER(_FepParams)]
     L.b200nb_fep_build_list.argtypes = [vp, vp, vp]
+    L.b200nb_bonded_set_list.argtypes = [vp, ci, ci, vp, ci, vp]
+    L.b200nb_bonded_launch.argtypes = [vp, ci, C.c_float]
+    L.b200nb_bonded_get_energies.argtypes = [vp, vp]
     L.b200nb_fep_get_list.argtypes = [vp, vp, vp, vp, vp, vp]
     L.b200nb_fep_get_outputs.argtypes = [vp, vp]
     L.b200nb_put_on_grid.argtypes = [vp, ci, vp, vp, ci, ci, cf, vp, ci]
@@ -183,6 +187,10 @@ def load_library():
     L.b200nb_dd_select_boundary.argtypes = [vp, vp, ci, vp, vp, vp, cf, vp]
     _lib = L
     return L
+
+
+BONDED_KINDS = ("bonds", "angles", "urey_bradley", "pdihs", "rbdihs", "idihs", "pidihs", "lj14")  # B200NB_BONDED_*
+BONDED_NRAL = (2, 3, 3, 4, 4, 4, 4, 2)
 
 
 def _ptr(a):
@@ -409,6 +417,23 @@ class NbnxmGpu:
         jj, ex = np.zeros(nrj, np.int32), np.zeros(nrj, np.int8)
         self._check(self._L.b200nb_fep_get_list(self._h, _ptr(ii), _ptr(sh), _ptr(ji), _ptr(jj), _ptr(ex)), "fep_get_list")
         return ii, sh, ji, jj, ex
+
+    # -- listed ("bonded") interactions: csrc/bonded.cu --------------------------------------------------------------------------
+    def bonded_set_list(self, kind, iatoms, params6):
+        """one interaction type of gmx::GpuBonded: iatoms[nbonds, nral + 1] = {parameter index, atoms}, params6[nparams, 6]"""
+        k = BONDED_KINDS.index(kind) if isinstance(kind, str) else int(kind)
+        ia = np.ascontiguousarray(iatoms, dtype=np.int32).reshape(-1, BONDED_NRAL[k] + 1)
+        p6 = np.ascontiguousarray(params6, dtype=np.float32).reshape(-1, 6)
+        self._check(self._L.b200nb_bonded_set_list(self._h, k, len(ia), _ptr(ia), len(p6), _ptr(p6)), "bonded_set_list")
+
+    def bonded_launch(self, flags=0, epsfac_fudge=138.935458 * 0.5):
+        self._check(self._L.b200nb_bonded_launch(self._h, int(flags), float(epsfac_fudge)), "bonded_launch")
+
+    def bonded_energies(self):
+        """{kind: energy} + "coul14", summed over the launches since the last call (read and reset)"""
+        out = np.zeros(len(BONDED_KINDS) + 1, np.float64)
+        self._check(self._L.b200nb_bonded_get_energies(self._h, _ptr(out)), "bonded_get_energies")
+        return dict(zip(BONDED_KINDS + ("coul14",), (float(v) for v in out)))
 
     def fep_launch(self, lambda_coul, lambda_vdw, sc_alpha=0.5, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=False):
         p = _FepParams(lambda_coul, lambda_vdw, sc_alpha, int(sc_power), sc_sigma, sc_sigma_min, int(bool(sc_coul)))

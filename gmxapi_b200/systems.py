@@ -289,3 +289,84 @@ def spc_methanol():
     excl_off = (np.arange(n + 1) * 3).astype(np.int32)
     return System(x, np.array([3.01] * 3, np.float32), types, q, nbfp, excl_off, excl_idx,
                   (np.arange(n) // 3).astype(np.int32), "spc_methanol")
+
+
+def bonded_chains(nchains=40, length=24, box=(3.1, 2.9, 3.3), seed=13, box_matrix=None):
+    """Flexible chains for the listed-interaction ("bonded") tests: `nchains` random-walk chains of `length` atoms (bond length
+    ~0.15 nm, bend and torsion angles well away from 0 / 180 degrees), wrapped atom by atom into a rectangular periodic box so
+    that many interactions straddle a face (`box_matrix`: the same chains wrapped into that triclinic cell instead; `box` is then
+    its diagonal).  Returns a dict: x[n,3], q[n], box[3], and per interaction type of the reference's
+    GPU bonded module (listed_forces/gpubonded.h:84-85) `iatoms` = {parameter index, atoms...} rows and `params` = rows of 6
+    floats (the t_iparams fields the type reads):
+      bonds {r0, k} | angles {theta0 deg, k} | urey_bradley {theta0, ktheta, r13, kUB} | pdihs, pidihs {phi0 deg, k, multiplicity}
+      | rbdihs {C0..C5} | idihs {xi0 deg, k} | lj14 {c6, c12}."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    box = np.asarray(box, np.float32)
+    M = np.diag(box).astype(np.float64) if box_matrix is None else np.asarray(box_matrix, np.float64)
+    box = np.diag(M).astype(np.float32)
+
+    def min_image_norm(d):
+        for dim in (2, 1, 0):
+            d = d - np.rint(d[:, dim] / M[dim, dim])[:, None] * M[dim]
+        return np.sqrt((d * d).sum(1))
+
+    xs = []  # finished chains; no two atoms that are not bonded neighbours closer than 0.2 nm (a liquid, not overlapping walks)
+
+    def clear_of(q, others):
+        return len(others) == 0 or min_image_norm(np.asarray(others) - q).min() >= 0.2
+
+    while len(xs) < nchains:
+        done = np.concatenate(xs) if xs else np.zeros((0, 3))
+        p = [rng.uniform(0, box)]
+        if not clear_of(p[0], done):
+            continue
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        while len(p) < length:
+            for _ in range(40):
+                # turn the direction by 50-80 degrees around a random axis: bend angles 100-130 degrees, torsions anywhere
+                axis = np.cross(d, rng.normal(size=3))
+                axis /= np.linalg.norm(axis)
+                ang = np.deg2rad(rng.uniform(50, 80))
+                dn = d * np.cos(ang) + np.cross(axis, d) * np.sin(ang) + axis * np.dot(axis, d) * (1 - np.cos(ang))
+                q = p[-1] + dn * rng.uniform(0.13, 0.17)
+                if clear_of(q, done) and clear_of(q, p[:-3]):
+                    p.append(q)
+                    d = dn
+                    break
+            else:
+                break  # dead end: start this chain again
+        if len(p) == length:
+            xs.append(np.array(p))
+    x = put_atoms_in_triclinic_box(np.concatenate(xs).astype(np.float32), M.astype(np.float32))
+    n = nchains * length
+    q = rng.uniform(-0.6, 0.6, n).astype(np.float32)
+    first = np.arange(nchains) * length
+
+    def rows(nat, ntypes, step=1):
+        out = []
+        for c in first:
+            for a in range(0, length - nat + 1, step):
+                out.append([rng.integers(ntypes)] + [c + a + k for k in range(nat)])
+        return np.array(out, np.int32)
+
+    def p6(*cols):
+        m = np.zeros((len(cols[0]), 6), np.float32)
+        for k, c in enumerate(cols):
+            m[:, k] = c
+        return m
+
+    s = dict(x=x, q=q, box=box, n=n)
+    s["bonds"] = dict(iatoms=rows(2, 3), params=p6([0.14, 0.15, 0.16], [2.5e5, 3.0e5, 2.0e5]))
+    s["angles"] = dict(iatoms=rows(3, 3), params=p6([109.5, 120.0, 114.0], [400.0, 520.0, 350.0]))
+    s["urey_bradley"] = dict(iatoms=rows(3, 2, step=2), params=p6([110.0, 118.0], [300.0, 420.0], [0.24, 0.26], [2.0e4, 3.0e4]))
+    s["pdihs"] = dict(iatoms=rows(4, 4), params=p6([0.0, 180.0, 60.0, 35.0], [4.0, 6.5, 1.2, 9.0], [3, 2, 1, 4]))
+    s["rbdihs"] = dict(iatoms=rows(4, 2, step=2), params=np.array([[9.28, 12.16, -13.12, -3.06, 26.24, -31.5],
+                                                                     [2.0, -1.5, 0.7, 3.3, -0.4, 0.9]], np.float32))
+    imp = rows(4, 2, step=3)
+    imp[:, 1:] = imp[:, [2, 1, 3, 4]]  # centre atom first, as an improper lists them
+    s["idihs"] = dict(iatoms=imp, params=p6([35.3, -20.0], [167.0, 334.0]))
+    pimp = rows(4, 2, step=5)
+    s["pidihs"] = dict(iatoms=pimp, params=p6([180.0, 0.0], [4.6, 43.9], [2, 2]))
+    s["lj14"] = dict(iatoms=rows(4, 3)[:, [0, 1, 4]].copy(), params=p6([2.3e-3, 1.1e-3, 0.0], [2.5e-6, 9.0e-7, 4.0e-7]))
+    return s

@@ -351,6 +351,36 @@ int b200nb_fep_launch(b200nb_t* h, const b200nb_fep_params_t* p);
 /* Vc, Vv, dV/dlambda_coul, dV/dlambda_vdw summed over the launches since the last call (read and reset) */
 int b200nb_fep_get_outputs(b200nb_t* h, double out4_host[4]);
 
+/* ---- listed ("bonded") interactions on the nonbonded buffers (gmxapi_b200/csrc/bonded.cu) ----
+ * Replaces gmx::GpuBonded (listed_forces/gpubonded.h:99-172) for the types it covers (fTypesOnGpu, gpubonded.h:84-85):
+ * updateInteractionListsAndDeviceBuffers (gpubonded_impl.cu:178-310) -> b200nb_bonded_set_list, once per topology: the lists
+ *   stay in atom order on the device and are mapped to the grid order inside the kernel, so search steps need no update;
+ * launchKernel (gpubondedkernels.cu:823-861, exec_kernel_gpu :721-821) -> b200nb_bonded_launch, between b200nb_launch_force /
+ *   b200nb_clear_outputs and b200nb_get_f: one fused kernel, a thread per interaction, forces added into the nonbonded force
+ *   buffer, shift forces into the nonbonded replicas (flags & B200NB_FLAG_VIRIAL), energies per type (B200NB_FLAG_ENERGY);
+ * launchEnergyTransfer / waitAccumulateEnergyTerms / clearEnergies (gpubonded_impl.cu:330-380) -> b200nb_bonded_get_energies.
+ * iatoms: t_ilist rows {parameter index, atoms...} (topology/idef.h); params6: 6 floats per parameter set, the t_iparams fields
+ * the type reads: bonds harmonic {rA, krA}; angles harmonic {thetaA deg, kA}; Urey-Bradley u_b {thetaA, kthetaA, r13A, kUBA};
+ * proper and periodic improper dihedrals pdihs {phiA deg, cpA, mult}; Ryckaert-Bellemans rbdihs.rbcA[0..5]; improper dihedrals
+ * harmonic {rA deg, krA}; 1-4 pairs lj14 {c6A, c12A} with the charges of b200nb_set_atoms.  One domain; any cell shape. */
+enum
+{
+    B200NB_BONDED_BONDS = 0,    /* F_BONDS */
+    B200NB_BONDED_ANGLES,       /* F_ANGLES */
+    B200NB_BONDED_UREY_BRADLEY, /* F_UREY_BRADLEY */
+    B200NB_BONDED_PDIHS,        /* F_PDIHS */
+    B200NB_BONDED_RBDIHS,       /* F_RBDIHS */
+    B200NB_BONDED_IDIHS,        /* F_IDIHS */
+    B200NB_BONDED_PIDIHS,       /* F_PIDIHS */
+    B200NB_BONDED_LJ14,         /* F_LJ14 (+ F_COUL14) */
+    B200NB_BONDED_KINDS
+};
+int b200nb_bonded_set_list(b200nb_t* h, int kind, int nbonds, const int* iatoms_host, int nparams, const float* params6_host);
+/* epsfac_fudge: BondedCudaKernelParameters::electrostaticsScaleFactor = epsfac * fudgeQQ (gpubonded_impl.cu:105) */
+int b200nb_bonded_launch(b200nb_t* h, int flags, float epsfac_fudge);
+/* energies per kind, [B200NB_BONDED_KINDS] = the Coulomb part of the 1-4 pairs; summed over the launches since the last call */
+int b200nb_bonded_get_energies(b200nb_t* h, double energies_host[B200NB_BONDED_KINDS + 1]);
+
 typedef struct
 {
     int       natoms, natoms_padded, nclusters;

@@ -24,7 +24,8 @@ SRCS=$(ls $R/gromacs/nbnxm/*.cpp $R/gromacs/nbnxm/kernels_reference/*.cpp \
 for f in pbcutil/pbc.cpp mdlib/enerdata_utils.cpp utility/alignedallocator.cpp gpu_utils/hostallocator.cpp \
          math/functions.cpp utility/smalloc.cpp utility/stringutil.cpp tables/forcetable.cpp \
          ewald/ewald_utils.cpp math/utilities.cpp utility/logger.cpp \
-         gmxlib/nonbonded/nb_free_energy.cpp mdtypes/interaction_const.cpp; do
+         gmxlib/nonbonded/nb_free_energy.cpp mdtypes/interaction_const.cpp \
+         listed_forces/bonded.cpp listed_forces/pairs.cpp listed_forces/restcbt.cpp pbcutil/pbc_simd.cpp topology/ifunc.cpp; do
   SRCS="$SRCS $R/gromacs/$f"
 done
 SRCS="$SRCS $HERE/ref_harness.cpp $HERE/ref_stubs.cpp"

@@ -259,3 +259,29 @@ def fep_kernel(x, shift_vec, nbfp, typeA, typeB, qA, qB, iinr, shift, jindex, jj
     L.gmxref_fep_kernel(C.c_int(n), vp(x), vp(sv), C.c_int(ntypes), vp(nb), vp(tA), vp(tB), vp(cA), vp(cB), C.c_int(len(ii)), vp(ii), vp(sh),
                         vp(ji), vp(jj), vp(ex), C.byref(p), vp(f), vp(fs), vp(out))
     return f, fs, tuple(float(v) for v in out)
+
+
+def bonded(kind, iatoms, params6, x, q, box_matrix, epsfac_fudge=138.935458 * 0.5, virial_energy=True):
+    """The reference's CPU functions for the listed interactions its GPU bonded module covers (gmxref_bonded: bonded.cpp
+    calculateSimpleBond, pairs.cpp do_pairs).  Arguments as oracle.bonded.  Returns f[n,3], fshift[45,3] (float32), energy; for
+    lj14 forces only (the reference's analytical path has no energy / virial: its general path uses spline tables)."""
+    from .oracle import BONDED_KINDS, BONDED_NRAL
+    k = BONDED_KINDS.index(kind) if isinstance(kind, str) else int(kind)
+    ia = np.ascontiguousarray(iatoms, dtype=np.int32).reshape(-1, BONDED_NRAL[k] + 1)
+    p6 = np.ascontiguousarray(params6, dtype=np.float32).reshape(-1, 6)
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, 3)
+    n = x.shape[0]
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    b = np.ascontiguousarray(box_matrix, dtype=np.float32).reshape(9)
+    f = np.zeros((n, 3), np.float32)
+    fs = np.zeros((45, 3), np.float32)
+    e = np.zeros(2, np.float64)
+    L = lib()
+    L.gmxref_bonded.restype = C.c_int
+    vp = C.c_void_p
+    L.gmxref_bonded.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, vp, vp, vp]
+    rc = L.gmxref_bonded(k, len(ia), ia.ctypes.data, len(p6), p6.ctypes.data, n, x.ctypes.data, q.ctypes.data, b.ctypes.data,
+                         float(epsfac_fudge), int(bool(virial_energy)), f.ctypes.data, fs.ctypes.data, e.ctypes.data)
+    if rc != 0:
+        raise ValueError("gmxref_bonded failed (%d)" % rc)
+    return f, fs, float(e[0])

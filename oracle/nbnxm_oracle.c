@@ -1030,3 +1030,196 @@ void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntyp
     }
     out4[0] = Vc, out4[1] = Vv, out4[2] = dvdl_coul, out4[3] = dvdl_vdw;
 }
+
+/* ---- listed ("bonded") interactions: the types the reference runs on the GPU (listed_forces/gpubonded.h:84-85) ----
+ * TEST INFRASTRUCTURE.  Restates listed_forces/gpubondedkernels.cu (bonds :93-141, angles :164-232, Urey-Bradley :234-335,
+ * dih_angle / do_dih_fup :337-436, proper :438-481, Ryckaert-Bellemans :483-585, improper :600-656, 1-4 pairs :658-718) and the
+ * minimum-image rule of pbcutil/pbc_aiuc_cuda.cuh:60-125: displacement and image decision in float, everything after it in double,
+ * sums in double.  Pinned to the reference's CPU functions for the same types (bonded.cpp / pairs.cpp through oracle/_ref,
+ * tests/test_oracle_cpu.py).  kind / iatoms / params6 as gmxref_bonded (oracle/ref_harness.h).  Shift forces as the reference's
+ * kernels book them: the force on an atom goes to the shift of its image relative to the interaction's reference atom. */
+#define ORC_CENTRAL 22
+static int orc_pbc_dx(const float* b, const float* x1, const float* x2, double* dr)
+{
+    float d0 = x1[0] - x2[0], d1 = x1[1] - x2[1], d2 = x1[2] - x2[2];
+    float shz = 0.f, shy = 0.f, shx = 0.f;
+    if (b[8] > 0.f)
+    {
+        shz = rintf(d2 * (1.0f / b[8]));
+        d0 -= shz * b[6], d1 -= shz * b[7], d2 -= shz * b[8];
+    }
+    if (b[4] > 0.f)
+    {
+        shy = rintf(d1 * (1.0f / b[4]));
+        d0 -= shy * b[3], d1 -= shy * b[4];
+    }
+    if (b[0] > 0.f)
+    {
+        shx = rintf(d0 * (1.0f / b[0]));
+        d0 -= shx * b[0];
+    }
+    dr[0] = d0, dr[1] = d1, dr[2] = d2;
+    return 5 * (3 * (-(int)shz + 1) + (-(int)shy + 1)) + (-(int)shx + 2); /* pbcutil/ishift.h:50 */
+}
+static double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static void   cross3(const double* a, const double* b, double* c)
+{
+    c[0] = a[1] * b[2] - a[2] * b[1], c[1] = a[2] * b[0] - a[0] * b[2], c[2] = a[0] * b[1] - a[1] * b[0];
+}
+static void add_f(double* f, double* fshift, int a, int s, const double* v, double sign)
+{
+    for (int d = 0; d < 3; d++)
+    {
+        f[3 * a + d] += sign * v[d];
+        fshift[3 * s + d] += sign * v[d];
+    }
+}
+/* forces of a torsion from dV/dphi: gpubondedkernels.cu:378-436 */
+static void orc_dih_forces(const float* box9, const float* x, const int* a, double ddphi, const double* r_ij, const double* r_kj,
+                           const double* r_kl, const double* m, const double* n, int t1, int t2, double* f, double* fshift)
+{
+    const double iprm = dot3(m, m), iprn = dot3(n, n), nrkj2 = dot3(r_kj, r_kj);
+    const double toler = nrkj2 * 1.1920928955078125e-07; /* GMX_REAL_EPS, mixed precision */
+    if (!(iprm > toler && iprn > toler)) return;
+    const double nrkj = sqrt(nrkj2);
+    double       f_i[3], f_l[3], f_j[3], f_k[3];
+    const double ca = -ddphi * nrkj / iprm, cb = ddphi * nrkj / iprn;
+    const double p = dot3(r_ij, r_kj) / nrkj2, q = dot3(r_kl, r_kj) / nrkj2;
+    for (int d = 0; d < 3; d++)
+    {
+        f_i[d]         = ca * m[d];
+        f_l[d]         = cb * n[d];
+        const double s = p * f_i[d] - q * f_l[d];
+        f_j[d]         = f_i[d] - s;
+        f_k[d]         = f_l[d] + s;
+    }
+    double    dx_jl[3];
+    const int t3 = orc_pbc_dx(box9, x + 3 * a[3], x + 3 * a[1], dx_jl);
+    add_f(f, fshift, a[0], t1, f_i, 1.0);
+    add_f(f, fshift, a[1], ORC_CENTRAL, f_j, -1.0);
+    add_f(f, fshift, a[2], t2, f_k, -1.0);
+    add_f(f, fshift, a[3], t3, f_l, 1.0);
+}
+
+int orc_bonded(int kind, int nbonds, const int* iatoms, const float* params6, int natoms, const float* x, const float* q,
+               const float* box9, float epsfac_fudge, double* f, double* fshift, double* energy2)
+{
+    static const int nral[8] = { 2, 3, 3, 4, 4, 4, 4, 2 };
+    const double     deg2rad = 3.14159265358979323846 / 180.0, pi = 3.14159265358979323846;
+    if (kind < 0 || kind > 7) return -1;
+    const int stride = nral[kind] + 1;
+    for (int i = 0; i < nbonds; i++)
+    {
+        const int*   ia = iatoms + (size_t)stride * i;
+        const float* p  = params6 + 6 * ia[0];
+        const int*   a  = ia + 1;
+        for (int k = 0; k < nral[kind]; k++)
+            if (a[k] < 0 || a[k] >= natoms) return -2;
+        if (kind == 0 || kind == 7)
+        {
+            double    dx[3];
+            const int ki  = orc_pbc_dx(box9, x + 3 * a[0], x + 3 * a[1], dx);
+            const double r2 = dot3(dx, dx);
+            double       fs;
+            if (kind == 0)
+            {
+                const double r = sqrt(r2), dr = r - p[0];
+                energy2[0] += 0.5 * p[1] * dr * dr;
+                if (r2 == 0.0) continue;
+                fs = -p[1] * dr / r;
+            }
+            else
+            {
+                const double rinv2 = 1.0 / r2, rinv6 = rinv2 * rinv2 * rinv2, velec = (double)epsfac_fudge * q[a[0]] * q[a[1]] * sqrt(rinv2);
+                fs = ((12.0 * p[1] * rinv6 - 6.0 * p[0]) * rinv6 + velec) * rinv2;
+                energy2[0] += (p[1] * rinv6 - p[0]) * rinv6;
+                energy2[1] += velec;
+            }
+            double fij[3] = { fs * dx[0], fs * dx[1], fs * dx[2] };
+            add_f(f, fshift, a[0], ki, fij, 1.0);
+            add_f(f, fshift, a[1], ORC_CENTRAL, fij, -1.0);
+        }
+        else if (kind == 1 || kind == 2)
+        {
+            double    r_ij[3], r_kj[3];
+            const int t1 = orc_pbc_dx(box9, x + 3 * a[0], x + 3 * a[1], r_ij), t2 = orc_pbc_dx(box9, x + 3 * a[2], x + 3 * a[1], r_kj);
+            const double nij2 = dot3(r_ij, r_ij), nkj2 = dot3(r_kj, r_kj);
+            double       c = dot3(r_ij, r_kj) / sqrt(nij2 * nkj2);
+            c              = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
+            const double th = acos(c), dth = th - p[0] * deg2rad;
+            energy2[0] += 0.5 * p[1] * dth * dth;
+            const double c2 = c * c;
+            if (c2 < 1.0)
+            {
+                const double st = -p[1] * dth / sqrt(1.0 - c2), sth = st * c;
+                const double cik = st / sqrt(nij2 * nkj2), cii = sth / nij2, ckk = sth / nkj2;
+                double       f_i[3], f_k[3], f_j[3];
+                for (int d = 0; d < 3; d++)
+                {
+                    f_i[d] = -(cik * r_kj[d] - cii * r_ij[d]);
+                    f_k[d] = -(cik * r_ij[d] - ckk * r_kj[d]);
+                    f_j[d] = -f_i[d] - f_k[d];
+                }
+                add_f(f, fshift, a[0], t1, f_i, 1.0);
+                add_f(f, fshift, a[1], ORC_CENTRAL, f_j, 1.0);
+                add_f(f, fshift, a[2], t2, f_k, 1.0);
+            }
+            if (kind == 2) /* the 1-3 bond of Urey-Bradley */
+            {
+                double    r_ik[3];
+                const int ki  = orc_pbc_dx(box9, x + 3 * a[0], x + 3 * a[2], r_ik);
+                const double r2 = dot3(r_ik, r_ik), r = sqrt(r2), dr = r - p[2];
+                energy2[0] += 0.5 * p[3] * dr * dr;
+                if (r2 != 0.0)
+                {
+                    const double fs = -p[3] * dr / r;
+                    double       fik[3] = { fs * r_ik[0], fs * r_ik[1], fs * r_ik[2] };
+                    add_f(f, fshift, a[0], ki, fik, 1.0);
+                    add_f(f, fshift, a[2], ORC_CENTRAL, fik, -1.0);
+                }
+            }
+        }
+        else
+        {
+            double    r_ij[3], r_kj[3], r_kl[3], m[3], n[3], mxn[3];
+            const int t1 = orc_pbc_dx(box9, x + 3 * a[0], x + 3 * a[1], r_ij), t2 = orc_pbc_dx(box9, x + 3 * a[2], x + 3 * a[1], r_kj);
+            (void)orc_pbc_dx(box9, x + 3 * a[2], x + 3 * a[3], r_kl);
+            cross3(r_ij, r_kj, m);
+            cross3(r_kj, r_kl, n);
+            cross3(m, n, mxn);
+            double phi = atan2(sqrt(dot3(mxn, mxn)), dot3(m, n)); /* gmx_angle */
+            if (dot3(r_ij, n) < 0.0) phi = -phi;
+            double ddphi;
+            if (kind == 3 || kind == 6)
+            {
+                const double mult = (double)(int)p[2], mdphi = mult * phi - p[0] * deg2rad;
+                energy2[0] += p[1] * (1.0 + cos(mdphi));
+                ddphi = -p[1] * mult * sin(mdphi);
+            }
+            else if (kind == 4)
+            {
+                phi += phi < 0.0 ? pi : -pi; /* polymer convention */
+                const double cp = cos(phi), sp = sin(phi);
+                double       v = p[0], dd = 0.0, cf = 1.0;
+                for (int k = 1; k < 6; k++)
+                {
+                    dd += k * p[k] * cf;
+                    cf *= cp;
+                    v += cf * p[k];
+                }
+                energy2[0] += v;
+                ddphi = -dd * sp;
+            }
+            else
+            {
+                double dp = phi - p[0] * deg2rad;
+                if (dp >= pi) dp -= 2.0 * pi;
+                else if (dp < -pi) dp += 2.0 * pi;
+                energy2[0] += 0.5 * p[1] * dp * dp;
+                ddphi = p[1] * dp;
+            }
+            orc_dih_forces(box9, x, a, ddphi, r_ij, r_kj, r_kl, m, n, t1, t2, f, fshift);
+        }
+    }
+    return 0;
+}

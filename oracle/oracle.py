@@ -287,3 +287,30 @@ def fep_pair_list(x, box, rlist, perturbed, excl_off, excl_idx):
     uk, start = np.unique(key, return_index=True)
     return ((uk // 64).astype(np.int32), (uk % 64).astype(np.int32), np.append(start, len(pairs)).astype(np.int32),
             np.ascontiguousarray(pairs[:, 1], dtype=np.int32), flag)
+
+
+BONDED_KINDS = ("bonds", "angles", "urey_bradley", "pdihs", "rbdihs", "idihs", "pidihs", "lj14")
+BONDED_NRAL = (2, 3, 3, 4, 4, 4, 4, 2)
+
+
+def bonded(kind, iatoms, params6, x, q, box_matrix, epsfac_fudge=138.935458 * 0.5):
+    """Plain-C restatement (orc_bonded) of the reference's GPU bonded kernels for one interaction type (`kind`: index into
+    BONDED_KINDS).  iatoms[nbonds, nral + 1] = {parameter index, atoms}; params6[ntypes, 6]; box_matrix 3x3 lower-triangular.
+    Returns f[n,3], fshift[45,3] (float64), (energy, Coulomb-14 energy for lj14)."""
+    k = BONDED_KINDS.index(kind) if isinstance(kind, str) else int(kind)
+    ia = _i32(iatoms).reshape(-1, BONDED_NRAL[k] + 1)
+    p6 = _f32(params6).reshape(-1, 6)
+    x = _f32(x).reshape(-1, 3)
+    n = x.shape[0]
+    q = _f32(q)
+    b = _f32(box_matrix).reshape(9)
+    f = np.zeros((n, 3), np.float64)
+    fs = np.zeros((45, 3), np.float64)
+    e = np.zeros(2, np.float64)
+    L = lib()
+    L.orc_bonded.restype = C.c_int
+    rc = L.orc_bonded(C.c_int(k), C.c_int(len(ia)), _p(ia), _p(p6), C.c_int(n), _p(x), _p(q), _p(b), C.c_float(epsfac_fudge), _p(f), _p(fs),
+                      _p(e))
+    if rc != 0:
+        raise ValueError("orc_bonded: bad input (%d)" % rc)
+    return f, fs, (float(e[0]), float(e[1]))

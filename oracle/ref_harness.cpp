@@ -811,3 +811,101 @@ int gmxref_fep_kernel(int natoms, const float* x, const float* shift_vec, int nt
     std::free(fr);
     return 0;
 }
+
+/* ---- listed ("bonded") interactions the reference's GPU bonded module covers (listed_forces/gpubonded.h:84-85 fTypesOnGpu):
+ * the reference's CPU functions for the same types (listed_forces/bonded.cpp calculateSimpleBond, pairs.cpp do_pairs), compiled
+ * from the tree.  TEST INFRASTRUCTURE: pins oracle/nbnxm_oracle.c orc_bonded. ---- */
+#include "gromacs/listed_forces/bonded.h"
+#include "gromacs/listed_forces/pairs.h"
+#include "gromacs/topology/idef.h"
+#include "gromacs/topology/ifunc.h"
+
+extern "C" int gmxref_bonded(int kind, int nbonds, const int* iatoms, int nparams, const float* params6, int natoms, const float* x,
+                             const float* q, const float* box9, float epsfac_fudge, int want_virial_energy, float* f, float* fshift,
+                             double* energy2)
+{
+    static const int ftypes[GMXREF_BONDED_KINDS] = { F_BONDS, F_ANGLES, F_UREY_BRADLEY, F_PDIHS, F_RBDIHS, F_IDIHS, F_PIDIHS, F_LJ14 };
+    if (kind < 0 || kind >= GMXREF_BONDED_KINDS) return -1;
+    const int                ftype = ftypes[kind];
+    const int                nral  = interaction_function[ftype].nratoms;
+    std::vector<t_iparams>   ip(nparams);
+    for (int t = 0; t < nparams; t++)
+    {
+        const float* p = params6 + 6 * t;
+        std::memset(&ip[t], 0, sizeof(t_iparams));
+        switch (ftype)
+        {
+            case F_BONDS:
+            case F_ANGLES:
+            case F_IDIHS:
+                ip[t].harmonic.rA = ip[t].harmonic.rB = p[0];
+                ip[t].harmonic.krA = ip[t].harmonic.krB = p[1];
+                break;
+            case F_UREY_BRADLEY:
+                ip[t].u_b.thetaA = ip[t].u_b.thetaB = p[0];
+                ip[t].u_b.kthetaA = ip[t].u_b.kthetaB = p[1];
+                ip[t].u_b.r13A = ip[t].u_b.r13B = p[2];
+                ip[t].u_b.kUBA = ip[t].u_b.kUBB = p[3];
+                break;
+            case F_PDIHS:
+            case F_PIDIHS:
+                ip[t].pdihs.phiA = ip[t].pdihs.phiB = p[0];
+                ip[t].pdihs.cpA = ip[t].pdihs.cpB = p[1];
+                ip[t].pdihs.mult                  = (int)p[2];
+                break;
+            case F_RBDIHS:
+                for (int k = 0; k < 6; k++) ip[t].rbdihs.rbcA[k] = ip[t].rbdihs.rbcB[k] = p[k];
+                break;
+            case F_LJ14:
+                ip[t].lj14.c6A = ip[t].lj14.c6B = p[0];
+                ip[t].lj14.c12A = ip[t].lj14.c12B = p[1];
+                break;
+        }
+    }
+    matrix box;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) box[i][j] = box9[3 * i + j];
+    t_pbc pbc;
+    set_pbc(&pbc, PbcType::Xyz, box);
+    std::vector<gmx::RVec> xv(natoms);
+    for (int a = 0; a < natoms; a++) xv[a] = { x[3 * a], x[3 * a + 1], x[3 * a + 2] };
+    std::vector<real> f4((size_t)natoms * 4, 0.0f);
+    std::vector<real> fs(SHIFTS * 3, 0.0f);
+    std::vector<int>  glob(natoms);
+    for (int a = 0; a < natoms; a++) glob[a] = a;
+    t_mdatoms         md{};
+    std::vector<real> qa(q, q + natoms);
+    md.chargeA = qa.data();
+    md.chargeB = qa.data();
+    energy2[0] = energy2[1] = 0.0;
+    real dvdl               = 0;
+    if (ftype == F_LJ14)
+    {
+        /* the plain analytical code path (pairs.cpp:636-676: no tables) -- forces only; the reference computes 1-4 energies and
+         * the virial from its spline tables on the CPU and analytically on the GPU (gpubondedkernels.cu:658-718) */
+        interaction_const_t ic;
+        ic.vdwtype = evdwCUT;
+        ic.eeltype = eelCUT;
+        ic.epsfac  = epsfac_fudge;
+        t_forcerec* fr = static_cast<t_forcerec*>(std::calloc(1, sizeof(t_forcerec)));
+        fr->ic               = &ic;
+        fr->fudgeQQ          = 1.0f;
+        fr->use_simd_kernels = FALSE;
+        gmx::StepWorkload stepWork;
+        real              lambda[efptNR] = { 0 };
+        real              dvdl4[efptNR]  = { 0 };
+        do_pairs(F_LJ14, nbonds * (nral + 1), iatoms, ip.data(), as_rvec_array(xv.data()), reinterpret_cast<rvec4*>(f4.data()),
+                 reinterpret_cast<rvec*>(fs.data()), &pbc, lambda, dvdl4, &md, fr, false, stepWork, nullptr, glob.data());
+        std::free(fr);
+    }
+    else
+    {
+        const BondedKernelFlavor flavor = want_virial_energy ? BondedKernelFlavor::ForcesAndVirialAndEnergy : BondedKernelFlavor::ForcesNoSimd;
+        energy2[0] = calculateSimpleBond(ftype, nbonds * (nral + 1), iatoms, ip.data(), as_rvec_array(xv.data()), reinterpret_cast<rvec4*>(f4.data()),
+                                         reinterpret_cast<rvec*>(fs.data()), &pbc, 0.0f, &dvdl, &md, nullptr, glob.data(), flavor);
+    }
+    for (int a = 0; a < natoms; a++)
+        for (int d = 0; d < 3; d++) f[3 * a + d] = f4[4 * a + d];
+    for (int k = 0; k < SHIFTS * 3; k++) fshift[k] = fs[k];
+    return 0;
+}

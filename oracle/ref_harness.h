@@ -90,6 +90,16 @@ int gmxref_fep_kernel(int natoms, const float* x, const float* shift_vec, int nt
                       const float* qA, const float* qB, int nri, const int* iinr, const int* shift, const int* jindex, const int* jjnr,
                       const char* excl_fep, const gmxref_fep_params* p, float* f, float* fshift, float* out4);
 
+/* The reference's CPU functions for the listed interactions its GPU bonded module covers (listed_forces/bonded.cpp
+ * calculateSimpleBond; pairs.cpp do_pairs, analytical force-only path for LJ14).  kind: 0 bonds, 1 angles, 2 Urey-Bradley, 3 proper
+ * dihedrals, 4 Ryckaert-Bellemans, 5 improper (harmonic) dihedrals, 6 periodic improper dihedrals, 7 LJ-14 pairs.  iatoms: per
+ * interaction {parameter index, atoms...} (t_ilist); params6: 6 floats per parameter set ({r0, k}; {theta0, k}; {theta0, ktheta,
+ * r13, kUB}; {phi0, k, multiplicity}; {C0..C5}; {xi0, k}; as 3; {c6, c12}).  f[natoms*3], fshift[45*3] are overwritten. */
+#define GMXREF_BONDED_KINDS 8
+int gmxref_bonded(int kind, int nbonds, const int* iatoms, int nparams, const float* params6, int natoms, const float* x,
+                  const float* q, const float* box9, float epsfac_fudge, int want_virial_energy, float* f, float* fshift,
+                  double* energy2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,6 +145,22 @@ void pr_ivecs(FILE*, int, const char*, const ivec*, int, gmx_bool) {}
 void pr_rvecs(FILE*, int, const char*, const rvec*, int) {}
 t_graph mk_graph_moltype(const gmx_moltype_t&) { unreachable("mk_graph_moltype"); }
 
+/* listed_forces/bonded.cpp references the restraint functions of subsystems we do not compile; never reached for the types the
+ * harness drives (gmxref_bonded) */
+union t_iparams;
+struct t_pbc;
+typedef real rvec4[4]; /* topology/ifunc.h:55 */
+struct t_fcdata;
+int  glatnr(const int* global_atom_index, int i) { return global_atom_index ? global_atom_index[i] + 1 : i + 1; }
+real orires(int, const int*, const t_iparams*, const rvec*, rvec4*, rvec*, const t_pbc*, real, real*, const t_mdatoms*, t_fcdata*, int*)
+{
+    unreachable("orires");
+}
+real ta_disres(int, const int*, const t_iparams*, const rvec*, rvec4*, rvec*, const t_pbc*, real, real*, const t_mdatoms*, t_fcdata*, int*)
+{
+    unreachable("ta_disres");
+}
+
 #include <omp.h>
 #include <exception>
 #include <vector>

@@ -174,7 +174,32 @@ def fep():
     np.savez_compressed(os.path.join(HERE, "ref_water_3k_fep_ewald.npz"), **oute)
 
 
+BONDED_TRICLINIC = ((3.1, 0.0, 0.0), (0.6, 2.9, 0.0), (-0.5, 0.7, 3.3))
+
+
+def bonded():
+    """ref_bonded_chains.npz: the reference's CPU functions (listed_forces/bonded.cpp calculateSimpleBond, pairs.cpp do_pairs,
+    compiled into oracle/_ref) for the interaction types its GPU bonded module covers, on gmxapi_b200.systems.bonded_chains in the
+    rectangular box and wrapped into a triclinic one."""
+    import gmxapi_b200.systems as S
+    from oracle import gmxref, oracle
+    out = dict(box_triclinic=np.array(BONDED_TRICLINIC, np.float32))
+    for tag, bm in (("rect", None), ("tric", BONDED_TRICLINIC)):
+        s = S.bonded_chains(box_matrix=bm)
+        B, x = (np.diag(s["box"]) if bm is None else np.array(bm)).astype(np.float32), s["x"]
+        out["x_sha256_" + tag] = np.array(sha(x))
+        for kind in oracle.BONDED_KINDS:
+            d = s[kind]
+            f, fs, e = gmxref.bonded(kind, d["iatoms"], d["params"], x, s["q"], B)
+            out["f_%s_%s" % (tag, kind)], out["fshift_%s_%s" % (tag, kind)], out["e_%s_%s" % (tag, kind)] = f, fs, np.float64(e)
+            print("bonded", tag, kind, len(d["iatoms"]), e)
+    np.savez_compressed(os.path.join(HERE, "ref_bonded_chains.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "bonded":
+        bonded()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ljpme":
         ljpme_flavours()
         sys.exit(0)
