@@ -2543,6 +2543,10 @@ static int launch_step(b200nb_context* h, const float* x_dev, int flags, float* 
     if (ev_force0) NB_CUDA(h, cudaEventRecord(ev_force0, h->stream));
     if ((rc = b200nb_launch_force(h, -1, flags))) return rc;
     if (ev_force1) NB_CUDA(h, cudaEventRecord(ev_force1, h->stream));
+    /* listed interactions and perturbed pairs, when made part of the step (b200nb_bonded_in_step, b200nb_fep_in_step): into the
+     * same grid-order forces, before the un-sort */
+    if ((rc = nb_bonded_enqueue_in_step(h, flags))) return rc;
+    if ((rc = nb_fep_enqueue_in_step(h))) return rc;
     if ((reinterpret_cast<uintptr_t>(f_dev) & 15) == 0) k_step_end<true><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, 0, n, f_dev);
     else k_step_end<false><<<nb1, 256, 0, h->stream>>>(h->d_f, h->d_slot_of_atom, 0, n, f_dev);
     LAUNCH_CHECK(h);

@@ -191,6 +191,8 @@ struct FepState
     int *        d_iinr = nullptr, *d_shift = nullptr, *d_jindex = nullptr, *d_jjnr = nullptr; /* t_nblist, mdtypes/nblist.h:117-137 */
     signed char* d_excl = nullptr;
     double*      d_out = nullptr; /* Vc, Vv, dvdl_coul, dvdl_vdw */
+    bool                in_step = false; /* launched by b200nb_step / b200nb_compute, inside the captured graph */
+    b200nb_fep_params_t step_params{};
 };
 
 /* listed interactions on the device (bonded.cu): lists in atom order, 6 floats per parameter set */
@@ -201,6 +203,8 @@ struct BondedState
     int*    d_iatoms[B200NB_BONDED_KINDS] = {};
     float*  d_params[B200NB_BONDED_KINDS] = {};
     double* d_energy = nullptr; /* per kind + Coulomb-14 */
+    bool    in_step = false;    /* launched by b200nb_step / b200nb_compute, inside the captured graph */
+    float   scale14 = 0.f;
 };
 
 /* a captured step: the launches of b200nb_step / b200nb_dd_step for one set of buffers */
@@ -320,8 +324,10 @@ int nb_fail(b200nb_context* h, int code, const std::string& msg);
 int nb_launch_force_kernel(b200nb_context* h, int locality, int flags);
 /* fep.cu */
 void nb_fep_free(b200nb_context* h);
+int  nb_fep_enqueue_in_step(b200nb_context* h);
 /* bonded.cu */
 void nb_bonded_free(b200nb_context* h);
+int  nb_bonded_enqueue_in_step(b200nb_context* h, int flags);
 
 
 /* ---- device helpers shared by search / prune / pair extraction ---- */

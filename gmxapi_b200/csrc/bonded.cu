@@ -272,6 +272,7 @@ extern "C" int b200nb_bonded_set_list(b200nb_t* h, int kind, int nbonds, const i
         S.count[kind] = nbonds;
     }
     S.natoms = h->natoms;
+    h->generation++; /* a captured step that includes the bonded kernel carries the list pointers by value */
     if (!S.d_energy)
     {
         NB_CUDA(h, cudaMalloc((void**)&S.d_energy, sizeof(double) * (B200NB_BONDED_KINDS + 1)));
@@ -328,6 +329,24 @@ extern "C" int b200nb_bonded_get_energies(b200nb_t* h, double energies_host[B200
     NB_CUDA(h, cudaMemsetAsync(S.d_energy, 0, sizeof(double) * (B200NB_BONDED_KINDS + 1), h->stream)); /* read and reset */
     NB_CUDA(h, cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+/* The bonded kernel as part of b200nb_step / b200nb_compute: launched between the force kernel and the un-sort, inside the
+ * captured step graph (the reference launches its bonded kernel on the nonbonded stream between the nonbonded kernel and the
+ * force copy-back in the same way, mdlib/sim_util.cpp:1467-1478). */
+extern "C" int b200nb_bonded_in_step(b200nb_t* h, int enable, float epsfac_fudge)
+{
+    if (!h) return B200NB_ERR_ARG;
+    h->bonded.in_step = enable != 0;
+    h->bonded.scale14 = epsfac_fudge;
+    h->generation++;
+    return 0;
+}
+
+int nb_bonded_enqueue_in_step(b200nb_context* h, int flags)
+{
+    if (!h->bonded.in_step) return 0;
+    return b200nb_bonded_launch(h, flags, h->bonded.scale14);
 }
 
 void nb_bonded_free(b200nb_context* h)

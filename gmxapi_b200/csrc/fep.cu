@@ -445,6 +445,7 @@ extern "C" int b200nb_fep_set_atoms(b200nb_t* h, const int* typeA_host, const in
         if (typeA_host[a] != typeB_host[a] || qA_host[a] != qB_host[a]) pert.push_back(a), is_pert[a] = 1;
     if (upload(h, &F.d_pert, pert.data(), pert.size()) || upload(h, &F.d_is_pert, is_pert.data(), is_pert.size())) return B200NB_ERR_CUDA;
     F.npert = (int)pert.size();
+    h->generation++;
     if (!F.d_out)
     {
         NB_CUDA(h, cudaMalloc((void**)&F.d_out, sizeof(double) * 4));
@@ -470,6 +471,7 @@ extern "C" int b200nb_fep_upload_list(b200nb_t* h, int nri, const int* iinr, con
         || upload(h, &F.d_jjnr, jjnr, nrj) || upload(h, &F.d_excl, excl_fep, nrj))
         return B200NB_ERR_CUDA;
     F.nri = nri, F.nrj = nrj;
+    h->generation++; /* captured steps that include the free-energy kernel carry the list pointers by value */
     return 0;
 }
 
@@ -532,6 +534,7 @@ extern "C" int b200nb_fep_build_list(b200nb_t* h, int* nri_out, int* nrj_out)
     NB_CUDA(h, e);
     h->nlaunches += 3;
     F.nri = nri, F.nrj = nrj;
+    h->generation++;
     if (nri_out) *nri_out = nri;
     if (nrj_out) *nrj_out = nrj;
     return 0;
@@ -608,6 +611,23 @@ extern "C" int b200nb_fep_get_outputs(b200nb_t* h, double out4_host[4])
     NB_CUDA(h, cudaMemsetAsync(F.d_out, 0, sizeof(double) * 4, h->stream)); /* read and reset: the sums of the launches since the last read */
     NB_CUDA(h, cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+/* The free-energy kernel as part of b200nb_step / b200nb_compute (inside the captured step graph, after the force kernel);
+ * p == NULL takes it out again.  The list is the one current at capture: build or upload it before the next step. */
+extern "C" int b200nb_fep_in_step(b200nb_t* h, const b200nb_fep_params_t* p)
+{
+    if (!h) return B200NB_ERR_ARG;
+    h->fep.in_step = p != nullptr;
+    if (p) h->fep.step_params = *p;
+    h->generation++;
+    return 0;
+}
+
+int nb_fep_enqueue_in_step(b200nb_context* h)
+{
+    if (!h->fep.in_step) return 0;
+    return b200nb_fep_launch(h, &h->fep.step_params);
 }
 
 void nb_fep_free(b200nb_context* h)

@@ -26,7 +26,7 @@ EXPORTS = [
     "b200nb_dd_select_boundary", "b200nb_set_box_triclinic",
     "b200nb_fep_set_atoms", "b200nb_fep_upload_list", "b200nb_fep_launch", "b200nb_fep_get_outputs",
     "b200nb_fep_build_list", "b200nb_fep_get_list",
-    "b200nb_bonded_set_list", "b200nb_bonded_launch", "b200nb_bonded_get_energies",
+    "b200nb_bonded_set_list", "b200nb_bonded_launch", "b200nb_bonded_get_energies", "b200nb_bonded_in_step", "b200nb_fep_in_step",
 ]
 
 
@@ -140,6 +140,8 @@ def load_library():
     L.b200nb_bonded_set_list.argtypes = [vp, ci, ci, vp, ci, vp]
     L.b200nb_bonded_launch.argtypes = [vp, ci, C.c_float]
     L.b200nb_bonded_get_energies.argtypes = [vp, vp]
+    L.b200nb_bonded_in_step.argtypes = [vp, ci, C.c_float]
+    L.b200nb_fep_in_step.argtypes = [vp, C.POINTER(_FepParams)]
     L.b200nb_fep_get_list.argtypes = [vp, vp, vp, vp, vp, vp]
     L.b200nb_fep_get_outputs.argtypes = [vp, vp]
     L.b200nb_put_on_grid.argtypes = [vp, ci, vp, vp, ci, ci, cf, vp, ci]
@@ -429,6 +431,10 @@ class NbnxmGpu:
     def bonded_launch(self, flags=0, epsfac_fudge=138.935458 * 0.5):
         self._check(self._L.b200nb_bonded_launch(self._h, int(flags), float(epsfac_fudge)), "bonded_launch")
 
+    def bonded_in_step(self, enable=True, epsfac_fudge=138.935458 * 0.5):
+        """make the bonded kernel part of step() / compute() (inside the captured step graph)"""
+        self._check(self._L.b200nb_bonded_in_step(self._h, int(bool(enable)), float(epsfac_fudge)), "bonded_in_step")
+
     def bonded_energies(self):
         """{kind: energy} + "coul14", summed over the launches since the last call (read and reset)"""
         out = np.zeros(len(BONDED_KINDS) + 1, np.float64)
@@ -438,6 +444,14 @@ class NbnxmGpu:
     def fep_launch(self, lambda_coul, lambda_vdw, sc_alpha=0.5, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=False):
         p = _FepParams(lambda_coul, lambda_vdw, sc_alpha, int(sc_power), sc_sigma, sc_sigma_min, int(bool(sc_coul)))
         self._check(self._L.b200nb_fep_launch(self._h, C.byref(p)), "fep_launch")
+
+    def fep_in_step(self, lambda_coul=None, lambda_vdw=None, sc_alpha=0.5, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=False):
+        """make the free-energy kernel part of step() / compute() with these parameters (lambda_coul=None: take it out again)"""
+        if lambda_coul is None:
+            self._check(self._L.b200nb_fep_in_step(self._h, None), "fep_in_step")
+            return
+        p = _FepParams(lambda_coul, lambda_vdw, sc_alpha, int(sc_power), sc_sigma, sc_sigma_min, int(bool(sc_coul)))
+        self._check(self._L.b200nb_fep_in_step(self._h, C.byref(p)), "fep_in_step")
 
     def fep_outputs(self):
         """(Vc, Vv, dV/dlambda_coul, dV/dlambda_vdw) of the launches since the last call"""

@@ -350,6 +350,9 @@ int b200nb_fep_get_list(b200nb_t* h, int* iinr_host, int* shift_host, int* jinde
 int b200nb_fep_launch(b200nb_t* h, const b200nb_fep_params_t* p);
 /* Vc, Vv, dV/dlambda_coul, dV/dlambda_vdw summed over the launches since the last call (read and reset) */
 int b200nb_fep_get_outputs(b200nb_t* h, double out4_host[4]);
+/* p != NULL: every b200nb_step / b200nb_compute launches the free-energy kernel with these parameters on the current list, inside
+ * the captured step graph; NULL takes it out again */
+int b200nb_fep_in_step(b200nb_t* h, const b200nb_fep_params_t* p);
 
 /* ---- listed ("bonded") interactions on the nonbonded buffers (gmxapi_b200/csrc/bonded.cu) ----
  * Replaces gmx::GpuBonded (listed_forces/gpubonded.h:99-172) for the types it covers (fTypesOnGpu, gpubonded.h:84-85):
@@ -380,6 +383,9 @@ int b200nb_bonded_set_list(b200nb_t* h, int kind, int nbonds, const int* iatoms_
 int b200nb_bonded_launch(b200nb_t* h, int flags, float epsfac_fudge);
 /* energies per kind, [B200NB_BONDED_KINDS] = the Coulomb part of the 1-4 pairs; summed over the launches since the last call */
 int b200nb_bonded_get_energies(b200nb_t* h, double energies_host[B200NB_BONDED_KINDS + 1]);
+/* enable != 0: every b200nb_step / b200nb_compute launches the bonded kernel between the force kernel and the un-sort, inside
+ * the captured step graph (the reference puts its bonded kernel on the nonbonded stream the same way, mdlib/sim_util.cpp:1467-1478) */
+int b200nb_bonded_in_step(b200nb_t* h, int enable, float epsfac_fudge);
 
 typedef struct
 {

@@ -96,6 +96,25 @@ def test_bonded_kernel_matches_oracle_and_reference(built, cell):
     fs = h.get_outputs()[0].astype(np.float64)
     assert relrms(h.get_f().astype(np.float64), f_all) < 1e-5
     assert np.abs(fs[m] - fs_all[m]).max() <= 2e-5 * np.abs(fs_all).max()
+    # as part of the step: ForceCalculator.compute() = one captured graph with the bonded kernel between force kernel and un-sort
+    f_plain = fc.compute(s["x"]).astype(np.float64)
+    fs_plain = fc.shiftForces.astype(np.float64)
+    assert relrms(f_plain, f_nb) < 1e-6
+    h.bonded_energies()
+    h.bonded_in_step(True, SCALE14)
+    for rep in range(3):  # the replayed graph gives the same forces every time
+        f_step = fc.compute(s["x"]).astype(np.float64)
+        assert relrms(f_step - f_plain, f_all) < 1e-5, rep
+        assert np.abs((fc.shiftForces.astype(np.float64) - fs_plain)[m] - fs_all[m]).max() <= 2e-5 * np.abs(fs_all).max()
+    e = h.bonded_energies()  # summed over the three steps
+    eo = oracle.bonded("bonds", s["bonds"]["iatoms"], s["bonds"]["params"], s["x"], s["q"], B, SCALE14)[2][0]
+    assert abs(e["bonds"] - 3 * eo) <= 2e-5 * 3 * abs(eo)
+    h.bonded_set_list("lj14", np.zeros((0, 3), np.int32), np.zeros((0, 6), np.float32))  # a changed list re-captures the step
+    f_step = fc.compute(s["x"]).astype(np.float64)
+    f14 = oracle.bonded("lj14", s["lj14"]["iatoms"], s["lj14"]["params"], s["x"], s["q"], B, SCALE14)[0]
+    assert relrms(f_step - f_plain, f_all - f14) < 1e-5
+    h.bonded_in_step(False)
+    assert relrms(fc.compute(s["x"]).astype(np.float64), f_plain) < 1e-6
     fc.nb.close()
 
 

@@ -128,6 +128,16 @@ def test_fep_list_built_on_the_device(built, name, nmol, rlist):
     assert relrms(f0, f1) < 2e-6
     assert np.abs(v0 - v1).max() <= 2e-5 * np.abs(v1).max()
     assert np.abs(o0 - o1).max() <= 2e-5 * np.abs(o1).max()
+    # as part of the step: compute() = cluster-pair kernel + free-energy kernel in one captured graph
+    f_plain = fc.compute(s.x).astype(np.float64)
+    h.fep_build_list()
+    h.fep_outputs()
+    h.fep_in_step(**S.FEP_CASES["sc1coul"])
+    for rep in range(2):
+        assert relrms(fc.compute(s.x).astype(np.float64) - f_plain, f0) < 1e-5 * max(1.0, np.abs(f_plain).max() / np.abs(f0).max())
+    assert np.abs(np.array(h.fep_outputs()) - 2 * o0).max() <= 2e-5 * 2 * np.abs(o0).max()
+    h.fep_in_step(None)
+    assert relrms(fc.compute(s.x).astype(np.float64), f_plain) < 1e-6
     # twice the same list: reproducible order
     h.fep_build_list()
     again = h.fep_list()
