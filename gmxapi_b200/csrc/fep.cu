@@ -258,10 +258,28 @@ k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, cons
 struct FepListArgs
 {
     float box[3], inv_box[3];
+    float off[3]; /* triclinic cell: box[YY][XX], box[ZZ][XX], box[ZZ][YY] */
+    int   triclinic;
     int   pbc[3];
     float rlist2;
     int   nclusters;
 };
+
+/* d reduced to the image with |d_k| <= box_kk / 2, z then y then x (pbcutil/pbc_aiuc_cuda.cuh:60-125); t = the shift of the first
+ * point's image (-sh).  Within the list radius (at most half the smallest diagonal element: build_pairlist's max_cutoff2 check)
+ * that image is the only one in range. */
+__device__ __forceinline__ void fep_reduce(const FepListArgs& A, float* d, int* t)
+{
+    float sh = A.pbc[2] ? rintf(d[2] * A.inv_box[2]) : 0.f;
+    d[0] -= sh * A.off[1], d[1] -= sh * A.off[2], d[2] -= sh * A.box[2];
+    t[2] = -(int)sh;
+    sh   = A.pbc[1] ? rintf(d[1] * A.inv_box[1]) : 0.f;
+    d[0] -= sh * A.off[0], d[1] -= sh * A.box[1];
+    t[1] = -(int)sh;
+    sh   = A.pbc[0] ? rintf(d[0] * A.inv_box[0]) : 0.f;
+    d[0] -= sh * A.box[0];
+    t[0] = -(int)sh;
+}
 
 template<bool FILL>
 __global__ void __launch_bounds__(128)
@@ -292,16 +310,27 @@ k_fep_list(int npert, const int* __restrict__ pert, const unsigned char* __restr
             const float* b = bb + (size_t)c * 6;
             if (b[0] <= b[3]) /* not an all-filler cluster */
             {
-                float d2 = 0.f;
+                float dc[3], half[3], d2 = 0.f;
+                int   tc[3];
+                bool  ambiguous = false;
 #pragma unroll
                 for (int d = 0; d < 3; d++)
                 {
-                    const float half = 0.5f * (b[3 + d] - b[d]);
-                    float       dc   = xpv[d] - 0.5f * (b[3 + d] + b[d]);
-                    if (A.pbc[d]) dc -= A.box[d] * rintf(dc * A.inv_box[d]);
-                    const float t = fabsf(dc) - half - 1e-4f; /* margin: the atom test below decides */
-                    if (t > 0.f) d2 += t * t;
+                    half[d] = 0.5f * (b[3 + d] - b[d]) + 1e-4f; /* margin: the atom test below decides */
+                    dc[d]   = xpv[d] - 0.5f * (b[3 + d] + b[d]);
                 }
+                fep_reduce(A, dc, tc);
+#pragma unroll
+                for (int d = 0; d < 3; d++)
+                {
+                    const float t = fabsf(dc[d]) - half[d];
+                    if (t > 0.f) d2 += t * t;
+                    /* a box that reaches across the half-cell plane: its atoms can reduce with another lattice vector than its
+                     * centre.  Rectangular cells: that image is only nearer, the test stays conservative.  Triclinic: the other
+                     * image moves the lower components too -- take the cluster */
+                    ambiguous = ambiguous || (A.pbc[d] && fabsf(dc[d]) + half[d] > 0.5f * A.box[d]);
+                }
+                if (A.triclinic && ambiguous) d2 = 0.f;
                 hit = d2 < A.rlist2;
             }
         }
@@ -321,11 +350,9 @@ k_fep_list(int npert, const int* __restrict__ pert, const unsigned char* __restr
                 if (j >= 0 && !(j != p && is_pert[j] && j < p))
                 {
                     const float4 xj    = xq[sj];
-                    const float  dv[3] = { xp.x - xj.x, xp.y - xj.y, xp.z - xj.z };
-                    int          t[3]  = { 0, 0, 0 };
-#pragma unroll
-                    for (int d = 0; d < 3; d++)
-                        if (A.pbc[d]) t[d] = -(int)rintf(dv[d] * A.inv_box[d]);
+                    float        dv[3] = { xp.x - xj.x, xp.y - xj.y, xp.z - xj.z };
+                    int          t[3];
+                    fep_reduce(A, dv, t);
                     if (t[0] >= -2 && t[0] <= 2 && t[1] >= -1 && t[1] <= 1 && t[2] >= -1 && t[2] <= 1)
                     {
                         s = 5 * (3 * (t[2] + 1) + (t[1] + 1)) + t[0] + 2; /* pbcutil/ishift.h:50 */
@@ -481,17 +508,19 @@ extern "C" int b200nb_fep_build_list(b200nb_t* h, int* nri_out, int* nrj_out)
     FepState& F = h->fep;
     if (F.natoms != h->natoms || F.natoms < 1) return nb_fail(h, B200NB_ERR_STATE, "fep_build_list: fep_set_atoms for the current atoms first");
     if (!h->grid[0].valid || !h->have_params) return nb_fail(h, B200NB_ERR_STATE, "fep_build_list: set_params and put_on_grid first");
-    if (h->box_off[0] != 0.f || h->box_off[1] != 0.f || h->box_off[2] != 0.f)
-        return nb_fail(h, B200NB_ERR_ARG, "fep_build_list: triclinic cells are not built for the device-side perturbed pair list (upload the list)");
     if (h->dd.window) return nb_fail(h, B200NB_ERR_ARG, "fep_build_list: not built for decomposed runs");
     cudaSetDevice(h->device);
     FepListArgs A{};
     for (int d = 0; d < 3; d++)
     {
         A.box[d] = h->box[d], A.inv_box[d] = h->box[d] > 0.f ? 1.0f / h->box[d] : 0.f, A.pbc[d] = h->pbc[d] && h->box[d] > 0.f;
+        A.off[d] = h->box_off[d];
         if (A.pbc[d] && h->box[d] < 2.0f * h->hp.rlist_outer)
             return nb_fail(h, B200NB_ERR_ARG, "fep_build_list: a periodic dimension narrower than twice the list radius");
     }
+    A.triclinic = A.off[0] != 0.f || A.off[1] != 0.f || A.off[2] != 0.f;
+    /* (every diagonal element >= 2 rlist, checked above, is what makes the reduced image the only one in range: |d| < rlist
+     * bounds every component by half its diagonal element) */
     A.rlist2    = h->dp.rlist_outer2;
     A.nclusters = h->npad / 8;
     F.nri       = 0;

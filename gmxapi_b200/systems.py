@@ -104,7 +104,7 @@ def perturbed_water(name="water_3k", nmol=20, seed=7, q_scale_b=0.25):
     the oxygen's Lennard-Jones interaction is switched off (type 1: a disappearing particle, what soft-core exists for).
     Returns (system, perturbed[n] bool, typeA, typeB, qA, qB, types_masked, q_masked) -- the masked arrays are what the cluster-pair
     path gets (nbnxn_atomdata_mask_fep, nbnxm/atomdata.cpp: perturbed atoms carry zero charge and no LJ there)."""
-    s = named(name)
+    s = name if isinstance(name, System) else named(name)
     rng = np.random.Generator(np.random.PCG64(seed))
     mols = rng.choice(s.n // 3, nmol, replace=False)
     pert = np.zeros(s.n, bool)

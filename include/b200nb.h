@@ -342,7 +342,7 @@ int b200nb_fep_upload_list(b200nb_t* h, int nri, const int* iinr, const int* shi
  * nbnxm/pairlist.cpp:1699-1872 make_fep_list cuts out of the cluster-pair list, here a search of its own over the cluster bounding
  * boxes (the cluster-pair path never sees the perturbed atoms' interactions: their charge and LJ are masked).  Perturbed atoms =
  * those whose A and B type or charge differ in b200nb_fep_set_atoms.  A pair of two perturbed atoms is listed from the lower atom
- * index; j-atoms within an entry in grid order.  Rectangular cells, one domain; nri / nrj: entries and pairs (may be NULL). */
+ * index; j-atoms within an entry in grid order.  Rectangular and triclinic cells, one domain; nri / nrj: entries and pairs (may be NULL). */
 int b200nb_fep_build_list(b200nb_t* h, int* nri_out, int* nrj_out);
 /* the current list (built or uploaded) back on the host, arrays sized from the nri / nrj of the build: iinr[nri], shift[nri],
  * jindex[nri + 1], jjnr[nrj], excl_fep[nrj] */

@@ -95,25 +95,35 @@ def _canonical(lst):
     return np.sort((((a << 24) | b) << 8 | s) * 2 + ex.astype(np.int64))
 
 
-@pytest.mark.parametrize("name,nmol,rlist", [("water_3k", 20, 0.9), ("water_3k", 20, 1.0), ("water_24k", 60, 1.0)])
+@pytest.mark.parametrize("name,nmol,rlist", [("water_3k", 20, 0.9), ("water_3k", 20, 1.0), ("water_24k", 60, 1.0),
+                                             ("water_3k_sheared", 30, 1.0), ("water_3k_sheared_hard", 30, 0.9)])
 def test_fep_list_built_on_the_device(built, name, nmol, rlist):
     """b200nb_fep_build_list against the oracle's list (make_fep_list's pair set): the same pairs, shifts and exclusion flags --
     bit-exact as a set; a pair may be listed from the other atom, with the opposite shift -- and the kernel on the built list
     against the kernel on the uploaded one: forces, energies, dV/dlambda, virial."""
     S = g.systems
-    s, pert, tA, tB, qA, qB, tm, qm = S.perturbed_water(name, nmol=nmol)
+    if name.startswith("water_3k_sheared"):  # triclinic cells: a moderate shear and one at the limits of check_box
+        base = S.sheared(S.named("water_3k"), (0.5, 0.5, -0.5) if name.endswith("hard") else (0.25, -0.2, 0.3))
+    else:
+        base = S.named(name)
+    s, pert, tA, tB, qA, qB, tm, qm = S.perturbed_water(base, nmol=nmol)
+    triclinic = bool(np.any(s.box_offdiag != 0))
     opt = g.NBKernelOptions(pairlistCutoff=RC, rlistOuter=rlist, coulombType=g.CoulombType.Pme, computeVirialAndEnergy=True)
-    fc = g.ForceCalculator(g.SimulationState(s.x, s.box, tm, qm, s.nbfp, s.excl_off, s.excl_idx), opt)
+    fc = g.ForceCalculator(g.SimulationState(s.x, s.box_matrix if triclinic else s.box, tm, qm, s.nbfp, s.excl_off, s.excl_idx), opt)
     h = fc.nb
     h.fep_set_atoms(tA, tB, qA, qB)
-    want = oracle.fep_pair_list(s.x, s.box, rlist, pert, s.excl_off, s.excl_idx)
+    oracle.set_triclinic(s.box_offdiag if triclinic else None)
+    try:
+        want = oracle.fep_pair_list(s.x, s.box, rlist, pert, s.excl_off, s.excl_idx)
+        sv = oracle.shift_vectors(s.box).astype(np.float64)
+    finally:
+        oracle.set_triclinic(None)
     nri, nrj = h.fep_build_list()
     got = h.fep_list()
     assert nrj == len(want[3]) and got[2][-1] == nrj and nri == len(got[0])
     assert np.array_equal(_canonical(got), _canonical(want))
     assert len(np.unique(got[0].astype(np.int64) * 64 + got[1])) == nri and (np.diff(got[2]) > 0).all()  # one entry per (i, shift)
     assert set(np.unique(got[0])) <= set(np.nonzero(pert)[0])  # i-atoms are perturbed atoms
-    sv = oracle.shift_vectors(s.box).astype(np.float64)
     res = []
     for lst in (None, want):
         if lst is not None:
