@@ -205,6 +205,9 @@ struct BondedState
     double* d_energy = nullptr; /* per kind + Coulomb-14 */
     bool    in_step = false;    /* launched by b200nb_step / b200nb_compute, inside the captured graph */
     float   scale14 = 0.f;
+    bool    have_pbc = false;   /* b200nb_bonded_set_pbc: the cell of the image search, when it is not the context's */
+    float   box9[9] = {};
+    int     npbcdim = 3;
 };
 
 /* a captured step: the launches of b200nb_step / b200nb_dd_step for one set of buffers */

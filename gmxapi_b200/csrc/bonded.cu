@@ -13,6 +13,7 @@
  * cluster-pair kernels).
  * Minimum image as pbcutil/pbc_aiuc_cuda.cuh:60-125 (z, y, x in turn, general triclinic). */
 #include <cstdio>
+#include <cstring>
 #include <vector>
 
 #include "b200nb_internal.h"
@@ -120,7 +121,7 @@ k_bonded(const __grid_constant__ BondedDev B, const float4* __restrict__ xq, con
         float4       x4[4];
         for (int k = 0; k < nral; k++)
         {
-            s[k]  = slot_of_atom[ia[1 + k]];
+            s[k]  = slot_of_atom ? slot_of_atom[ia[1 + k]] : ia[1 + k];
             x4[k] = xq[s[k]];
         }
         if (kind == B200NB_BONDED_BONDS)
@@ -250,14 +251,18 @@ extern "C" int b200nb_bonded_set_list(b200nb_t* h, int kind, int nbonds, const i
     if (!h) return B200NB_ERR_ARG;
     if (kind < 0 || kind >= B200NB_BONDED_KINDS || nbonds < 0 || nparams < 0 || (nbonds && (!iatoms_host || !params6_host || nparams < 1)))
         return nb_fail(h, B200NB_ERR_ARG, "bonded_set_list: bad argument");
-    if (h->natoms < 1) return nb_fail(h, B200NB_ERR_STATE, "bonded_set_list: set_atoms first");
+    /* atom indices, or -- on a context whose atoms came in grid order (b200nb_set_grid_atoms: the reference-built grid of the
+     * Nbnxm::gpu_* shim, no atom-order view) -- grid slots: the caller converts its lists with the grid's atom order at every
+     * search step, as gpubonded_impl.cu:178-310 does */
+    const int limit = h->natoms > 0 ? h->natoms : h->npad;
+    if (limit < 1) return nb_fail(h, B200NB_ERR_STATE, "bonded_set_list: set_atoms (or set_grid_atoms) first");
     const int nral = (kind == B200NB_BONDED_BONDS || kind == B200NB_BONDED_LJ14) ? 2 : (kind <= B200NB_BONDED_UREY_BRADLEY ? 3 : 4);
     for (int i = 0; i < nbonds; i++)
     {
         const int* ia = iatoms_host + (size_t)(nral + 1) * i;
         if (ia[0] < 0 || ia[0] >= nparams) return nb_fail(h, B200NB_ERR_ARG, "bonded_set_list: parameter index out of range");
         for (int k = 1; k <= nral; k++)
-            if (ia[k] < 0 || ia[k] >= h->natoms) return nb_fail(h, B200NB_ERR_ARG, "bonded_set_list: atom index out of range");
+            if (ia[k] < 0 || ia[k] >= limit) return nb_fail(h, B200NB_ERR_ARG, "bonded_set_list: atom index out of range");
     }
     cudaSetDevice(h->device);
     BondedState& S = h->bonded;
@@ -287,7 +292,7 @@ extern "C" int b200nb_bonded_launch(b200nb_t* h, int flags, float epsfac_fudge)
     BondedState& S = h->bonded;
     if (!S.d_energy) return 0; /* no lists: haveInteractions() == false */
     if (S.natoms != h->natoms) return nb_fail(h, B200NB_ERR_STATE, "bonded_launch: lists were set for another set of atoms");
-    if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "bonded_launch: put_on_grid first");
+    if (h->natoms > 0 && !h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "bonded_launch: put_on_grid first");
     if (h->dd.window) return nb_fail(h, B200NB_ERR_ARG, "bonded_launch: not built for decomposed runs");
     cudaSetDevice(h->device);
     BondedDev B{};
@@ -302,17 +307,29 @@ extern "C" int b200nb_bonded_launch(b200nb_t* h, int flags, float epsfac_fudge)
     }
     B.first[B200NB_BONDED_KINDS] = nthreads;
     if (nthreads == 0) return 0;
-    const float bx = h->pbc[0] ? h->box[0] : 0.f, by = h->pbc[1] ? h->box[1] : 0.f, bz = h->pbc[2] ? h->box[2] : 0.f;
+    /* setPbcAiuc, pbcutil/pbc_aiuc.h:99-131: the first npbcdim dimensions are periodic */
+    float bx, by, bz, yx, zx, zy;
+    if (S.have_pbc)
+    {
+        bx = S.npbcdim > 0 ? S.box9[0] : 0.f, by = S.npbcdim > 1 ? S.box9[4] : 0.f, bz = S.npbcdim > 2 ? S.box9[8] : 0.f;
+        yx = S.box9[3], zx = S.box9[6], zy = S.box9[7];
+    }
+    else
+    {
+        bx = h->pbc[0] ? h->box[0] : 0.f, by = h->pbc[1] ? h->box[1] : 0.f, bz = h->pbc[2] ? h->box[2] : 0.f;
+        yx = h->box_off[0], zx = h->box_off[1], zy = h->box_off[2];
+    }
     B.pbc.xx = bx, B.pbc.inv_xx = bx > 0.f ? 1.0f / bx : 0.f;
-    B.pbc.yy = by, B.pbc.inv_yy = by > 0.f ? 1.0f / by : 0.f, B.pbc.yx = by > 0.f ? h->box_off[0] : 0.f;
-    B.pbc.zz = bz, B.pbc.inv_zz = bz > 0.f ? 1.0f / bz : 0.f, B.pbc.zx = bz > 0.f ? h->box_off[1] : 0.f, B.pbc.zy = bz > 0.f ? h->box_off[2] : 0.f;
+    B.pbc.yy = by, B.pbc.inv_yy = by > 0.f ? 1.0f / by : 0.f, B.pbc.yx = by > 0.f ? yx : 0.f;
+    B.pbc.zz = bz, B.pbc.inv_zz = bz > 0.f ? 1.0f / bz : 0.f, B.pbc.zx = bz > 0.f ? zx : 0.f, B.pbc.zy = bz > 0.f ? zy : 0.f;
     B.scale14 = epsfac_fudge;
     const unsigned nblk = (unsigned)((nthreads + 127) / 128);
     const float4*  xq   = reinterpret_cast<const float4*>(h->d_xq);
+    const int*     slot_map = h->natoms > 0 ? h->d_slot_of_atom : nullptr; /* grid-order atoms: the lists hold slots already */
     if (flags & (B200NB_FLAG_ENERGY | B200NB_FLAG_VIRIAL))
-        k_bonded<true><<<nblk, 128, 0, h->stream>>>(B, xq, h->d_slot_of_atom, h->d_f, h->d_fshift, S.d_energy);
+        k_bonded<true><<<nblk, 128, 0, h->stream>>>(B, xq, slot_map, h->d_f, h->d_fshift, S.d_energy);
     else
-        k_bonded<false><<<nblk, 128, 0, h->stream>>>(B, xq, h->d_slot_of_atom, h->d_f, h->d_fshift, S.d_energy);
+        k_bonded<false><<<nblk, 128, 0, h->stream>>>(B, xq, slot_map, h->d_f, h->d_fshift, S.d_energy);
     h->nlaunches++;
     NB_CUDA(h, cudaGetLastError());
     return 0;
@@ -328,6 +345,19 @@ extern "C" int b200nb_bonded_get_energies(b200nb_t* h, double energies_host[B200
     NB_CUDA(h, cudaMemcpyAsync(energies_host, S.d_energy, sizeof(double) * (B200NB_BONDED_KINDS + 1), cudaMemcpyDeviceToHost, h->stream));
     NB_CUDA(h, cudaMemsetAsync(S.d_energy, 0, sizeof(double) * (B200NB_BONDED_KINDS + 1), h->stream)); /* read and reset */
     NB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+/* GpuBonded::setPbc (gpubonded_impl.cu:312-316 -> setPbcAiuc): the cell of the image search, for callers whose context was not
+ * given the box (the Nbnxm::gpu_* interface passes shift vectors only); box9 = NULL returns to the context's cell. */
+extern "C" int b200nb_bonded_set_pbc(b200nb_t* h, const float box9[9], int npbcdim)
+{
+    if (!h || npbcdim < 0 || npbcdim > 3) return nb_fail(h, B200NB_ERR_ARG, "bonded_set_pbc: bad argument");
+    BondedState& S = h->bonded;
+    const bool   changed = (box9 != nullptr) != S.have_pbc || (box9 && (memcmp(S.box9, box9, sizeof(S.box9)) != 0 || S.npbcdim != npbcdim));
+    S.have_pbc = box9 != nullptr;
+    if (box9) memcpy(S.box9, box9, sizeof(S.box9)), S.npbcdim = npbcdim;
+    if (changed) h->generation++; /* the cell is a kernel parameter of a captured step */
     return 0;
 }
 

@@ -26,7 +26,7 @@ EXPORTS = [
     "b200nb_dd_select_boundary", "b200nb_set_box_triclinic",
     "b200nb_fep_set_atoms", "b200nb_fep_upload_list", "b200nb_fep_launch", "b200nb_fep_get_outputs",
     "b200nb_fep_build_list", "b200nb_fep_get_list",
-    "b200nb_bonded_set_list", "b200nb_bonded_launch", "b200nb_bonded_get_energies", "b200nb_bonded_in_step", "b200nb_fep_in_step",
+    "b200nb_bonded_set_list", "b200nb_bonded_launch", "b200nb_bonded_get_energies", "b200nb_bonded_in_step", "b200nb_fep_in_step", "b200nb_bonded_set_pbc",
 ]
 
 
@@ -141,6 +141,7 @@ def load_library():
     L.b200nb_bonded_launch.argtypes = [vp, ci, C.c_float]
     L.b200nb_bonded_get_energies.argtypes = [vp, vp]
     L.b200nb_bonded_in_step.argtypes = [vp, ci, C.c_float]
+    L.b200nb_bonded_set_pbc.argtypes = [vp, vp, ci]
     L.b200nb_fep_in_step.argtypes = [vp, C.POINTER(_FepParams)]
     L.b200nb_fep_get_list.argtypes = [vp, vp, vp, vp, vp, vp]
     L.b200nb_fep_get_outputs.argtypes = [vp, vp]
@@ -430,6 +431,11 @@ class NbnxmGpu:
 
     def bonded_launch(self, flags=0, epsfac_fudge=138.935458 * 0.5):
         self._check(self._L.b200nb_bonded_launch(self._h, int(flags), float(epsfac_fudge)), "bonded_launch")
+
+    def bonded_set_pbc(self, box_matrix=None, npbcdim=3):
+        """GpuBonded::setPbc: the cell of the bonded image search when it is not the context's (None: the context's)"""
+        b = None if box_matrix is None else np.ascontiguousarray(box_matrix, dtype=np.float32).reshape(9)
+        self._check(self._L.b200nb_bonded_set_pbc(self._h, _ptr(b), int(npbcdim)), "bonded_set_pbc")
 
     def bonded_in_step(self, enable=True, epsfac_fudge=138.935458 * 0.5):
         """make the bonded kernel part of step() / compute() (inside the captured step graph)"""

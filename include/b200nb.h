@@ -365,7 +365,9 @@ int b200nb_fep_in_step(b200nb_t* h, const b200nb_fep_params_t* p);
  * iatoms: t_ilist rows {parameter index, atoms...} (topology/idef.h); params6: 6 floats per parameter set, the t_iparams fields
  * the type reads: bonds harmonic {rA, krA}; angles harmonic {thetaA deg, kA}; Urey-Bradley u_b {thetaA, kthetaA, r13A, kUBA};
  * proper and periodic improper dihedrals pdihs {phiA deg, cpA, mult}; Ryckaert-Bellemans rbdihs.rbcA[0..5]; improper dihedrals
- * harmonic {rA deg, krA}; 1-4 pairs lj14 {c6A, c12A} with the charges of b200nb_set_atoms.  One domain; any cell shape. */
+ * harmonic {rA deg, krA}; 1-4 pairs lj14 {c6A, c12A} with the charges of b200nb_set_atoms.  One domain; any cell shape.
+ * On a context whose atoms were given in grid order (b200nb_set_grid_atoms: a reference-built grid, no atom-order view) the atom
+ * indices of iatoms are GRID SLOTS and the caller converts its lists at every search step, as the reference does. */
 enum
 {
     B200NB_BONDED_BONDS = 0,    /* F_BONDS */
@@ -379,6 +381,10 @@ enum
     B200NB_BONDED_KINDS
 };
 int b200nb_bonded_set_list(b200nb_t* h, int kind, int nbonds, const int* iatoms_host, int nparams, const float* params6_host);
+/* GpuBonded::setPbc (gpubonded_impl.cu:312-316): the cell of the image search -- box9 the row-major GROMACS box matrix, the first
+ * npbcdim dimensions periodic (setPbcAiuc) -- for callers whose context was not given the box (the Nbnxm::gpu_* interface passes
+ * shift vectors only); NULL: the cell of b200nb_set_box / b200nb_set_box_triclinic (the default) */
+int b200nb_bonded_set_pbc(b200nb_t* h, const float box9[9], int npbcdim);
 /* epsfac_fudge: BondedCudaKernelParameters::electrostaticsScaleFactor = epsfac * fudgeQQ (gpubonded_impl.cu:105) */
 int b200nb_bonded_launch(b200nb_t* h, int flags, float epsfac_fudge);
 /* energies per kind, [B200NB_BONDED_KINDS] = the Coulomb part of the 1-4 pairs; summed over the launches since the last call */

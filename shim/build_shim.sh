@@ -2,7 +2,8 @@
 # Builds shim/_build/libgmx_nbnxm_b200.so: the reference's nbnxm module with its GPU sub-interface ENABLED (GMX_GPU_CUDA=1,
 # so the Nbnxm::gpu_* calls in nbnxm.cpp / pairlist.cpp / kerneldispatch.cpp / prunekerneldispatch.cpp are real external
 # calls, not the empty stubs of a CPU build) + nblib's ForceCalculator with the GPU hook of shim/nblib_gmxsetup_gpu.patch + shim/nblib_gmxcalculator_gpu.patch + our
-# implementation of that sub-interface (shim/nbnxm_b200.cpp) on libb200nb.so; shim/_build/nblib_gpu_test, the reference's
+# implementation of that sub-interface (shim/nbnxm_b200.cpp) and of gmx::GpuBonded (shim/gpubonded_b200.cpp) on libb200nb.so;
+# shim/_build/nblib_gpu_test, the reference's
 # nblib force tests (api/nblib/tests/nbkernelsystem.cpp:69-202) run with NBKernelOptions::useGpu = true; and
 # shim/_build/nbnxm_bench_gpu, the reference's nonbonded-benchmark protocol (nbnxm/benchmark/bench_setup.cpp) with the GPU backend.
 # Reference sources are compiled where they lie under /root/reference (never copied into the repo; the two nblib files the
@@ -50,7 +51,7 @@ for f in box.cpp forcecalculator.cpp integrator.cpp interactions.cpp molecules.c
 done
 SRCS="$SRCS $OUT/src/gmxsetup.cpp $OUT/src/gmxcalculator.cpp"
 # 3. ours
-SRCS="$SRCS $HERE/nbnxm_b200.cpp $HERE/gmx_link_stubs.cpp"
+SRCS="$SRCS $HERE/nbnxm_b200.cpp $HERE/gpubonded_b200.cpp $HERE/gmx_link_stubs.cpp"
 compile_one() {
   src="$1"; obj="$OBJ/$(echo "$src" | sed "s#$R/gromacs/##; s#$N/#nblib_#; s#$OUT/src/#nblib_#; s#$HERE/#shim_#; s#/#_#g; s#\.cpp\$#.o#")"
   if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$OUT/cfg/config.h" -nt "$obj" ] || [ "$ROOT/include/b200nb.h" -nt "$obj" ]; then
@@ -69,4 +70,7 @@ $CXX $FLAGS -o "$OUT/nblib_gpu_test" "$HERE/nblib_gpu_test.cpp" "$N/tests/testsy
 # the reference's benchmark protocol with the GPU backend, on the reference's own BenchmarkSystem (bench_system.cpp from the tree)
 $CXX $FLAGS -o "$OUT/nbnxm_bench_gpu" "$HERE/nbnxm_bench_gpu.cpp" "$R/gromacs/nbnxm/benchmark/bench_system.cpp" -L"$OUT" -lgmx_nbnxm_b200 \
   -Wl,-rpath,'$ORIGIN' -L"$ROOT/gmxapi_b200" -lb200nb -Wl,-rpath,'$ORIGIN/../../gmxapi_b200' -fopenmp
-echo "built $OUT/libgmx_nbnxm_b200.so, $OUT/nblib_gpu_test and $OUT/nbnxm_bench_gpu"
+# gmx::GpuBonded on libb200nb (gpubonded_b200.cpp, in the library) driven as do_force() drives it, against the reference's CPU functions
+$CXX $FLAGS -o "$OUT/gpubonded_test" "$HERE/gpubonded_test.cpp" "$R/gromacs/nbnxm/benchmark/bench_system.cpp" -L"$OUT" -lgmx_nbnxm_b200 \
+  -Wl,-rpath,'$ORIGIN' -L"$ROOT/gmxapi_b200" -lb200nb -Wl,-rpath,'$ORIGIN/../../gmxapi_b200' -fopenmp
+echo "built $OUT/libgmx_nbnxm_b200.so, $OUT/nblib_gpu_test, $OUT/nbnxm_bench_gpu and $OUT/gpubonded_test"

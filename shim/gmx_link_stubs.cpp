@@ -149,3 +149,13 @@ bool checkNumericValues(const std::vector<Vec3>& values)
     return true;
 }
 } // namespace nblib
+
+/* topology/idef.cpp holds the InteractionDefinitions constructor next to the parameter printers (which drag in the text writer
+ * and the pr_* helpers); the listed-forces test (shim/gpubonded_test.cpp) needs only the constructor: it binds the parameter
+ * tables of the force field (idef.h:372-400) */
+#include "gromacs/topology/forcefieldparameters.h"
+#include "gromacs/topology/idef.h"
+InteractionDefinitions::InteractionDefinitions(const gmx_ffparams_t& ffparams) :
+    iparams(ffparams.iparams), functype(ffparams.functype), cmap_grid(ffparams.cmap_grid)
+{
+}

@@ -437,9 +437,12 @@ const DeviceStream* gpu_get_command_stream(NbnxmGpu* /* nb */, gmx::InteractionL
 {
     return nullptr;
 }
-void* gpu_get_xq(NbnxmGpu* /* nb */)
+void* gpu_get_xq(NbnxmGpu* nb)
 {
-    return nullptr;
+    /* mdrun passes this pointer (and gpu_get_f / gpu_get_fshift) on to gmx::GpuBonded::updateInteractionListsAndDeviceBuffers
+     * (mdlib/sim_util.cpp:1340-1356) and never looks inside: our GpuBonded (shim/gpubonded_b200.cpp) takes it as the b200nb
+     * context, whose xq / f / fshift buffers the bonded kernel of the same library works on */
+    return nb ? static_cast<void*>(nb->h) : nullptr;
 }
 DeviceBuffer<gmx::RVec> gpu_get_f(NbnxmGpu* /* nb */)
 {

@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "shim", "_build", "libgmx_nbnxm_b200.so")
 EXE = os.path.join(ROOT, "shim", "_build", "nblib_gpu_test")
 BENCH = os.path.join(ROOT, "shim", "_build", "nbnxm_bench_gpu")
+BONDED = os.path.join(ROOT, "shim", "_build", "gpubonded_test")
 needs_shim = pytest.mark.skipif(not (os.path.exists(LIB) and os.path.exists(EXE)),
                                 reason="shim/_build not built (needs the reference tree: shim/build_shim.sh)")
 
@@ -116,3 +117,39 @@ def test_reference_benchmark_protocol_with_gpu_backend(size, eel):
     assert d["atoms"] == 3000 * size
     assert d["force_rel_rms_gpu_vs_cpu"] < 1e-5
     assert d["gpu_ms_per_step"] < d["cpu_ms_per_step"]
+
+
+def run_bonded(cpu_only):
+    env = dict(os.environ)
+    if cpu_only:
+        env["GPUBONDED_TEST_CPU_ONLY"] = "1"
+    r = subprocess.run([BONDED], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-800:], r.stderr[-2000:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@needs_shim
+def test_gpubonded_class_is_defined_and_cpu_leg_runs():
+    """gmx::GpuBonded (listed_forces/gpubonded.h:99-172) is defined by the shim library on the C ABI, and the test program's CPU
+    leg (the reference's calculateSimpleBond / do_pairs on the listed interactions laid over the benchmark water) runs."""
+    out = subprocess.run(["nm", "-D", "-C", "--defined-only", LIB], capture_output=True, text=True).stdout
+    for fn in ("GpuBonded(gmx_ffparams_t const&", "updateInteractionListsAndDeviceBuffers(", "setPbcAndlaunchKernel(", "launchKernel(",
+               "launchEnergyTransfer(", "waitAccumulateEnergyTerms(", "clearEnergies(", "haveInteractions("):
+        assert "gmx::GpuBonded::" + fn in out, fn
+    und = subprocess.run(["nm", "-u", os.path.join(ROOT, "shim", "_build", "obj", "shim_gpubonded_b200.o")], capture_output=True, text=True).stdout
+    assert "b200nb_bonded_set_list" in und and "b200nb_bonded_launch" in und and "cuda" not in und.lower()
+    d = run_bonded(cpu_only=True)
+    assert d["atoms"] == 3000 and d["bonds"] == 2000 and d["cpu_force_sumsq"] > 0 and d["cpu_e_bonds"] > 1e4
+
+
+@pytest.mark.gpu
+@needs_shim
+def test_reference_gpubonded_interface_on_b200nb():
+    """gmx::GpuBonded driven the way do_force() drives it -- updateInteractionListsAndDeviceBuffers with Nbnxm::gpu_get_xq,
+    setPbcAndlaunchKernel between gpu_copy_xq_to_gpu and the nonbonded kernel, launchEnergyTransfer, waitAccumulateEnergyTerms --
+    through the unmodified nbnxm module and the shim, against the reference's CPU functions in the same process: all eight
+    interaction types, forces (energy / virial and force-only flavours), energies per type, shift forces."""
+    d = run_bonded(cpu_only=False)
+    assert d["force_rel_rms_gpu_vs_cpu"] < 1e-5 and d["force_only_rel_rms_gpu_vs_cpu"] < 1e-5
+    assert d["energy_max_rel_err"] < 2e-5 and d["fshift_max_abs_diff"] <= 2e-5 * d["fshift_max"]
+    assert d["lj14"] != 0 and d["coul14"] != 0
