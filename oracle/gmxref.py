@@ -34,7 +34,7 @@ class _Params(C.Structure):
                 ("disp_c2", C.c_float), ("disp_c3", C.c_float), ("rep_c2", C.c_float), ("rep_c3", C.c_float),
                 ("sw_c3", C.c_float), ("sw_c4", C.c_float), ("sw_c5", C.c_float),
                 ("ljpme", C.c_int), ("ewaldcoeff_lj", C.c_float), ("sh_lj_ewald", C.c_float),
-                ("box_offdiag", C.c_float * 3)]
+                ("box_offdiag", C.c_float * 3), ("perturbed", C.c_void_p)]
 
 
 _lib = None
@@ -93,9 +93,10 @@ class RefNbnxm:
                  disp_cpot=None, rep_cpot=None, kernel=None, comb_rule=0, nthreads=1,
                  exact_atom_flags=0, put_in_box=0, rlist_inner=0.0, min_ilist_count=0,
                  rvdw=0.0, vdw_modifier=0, rvdw_switch=0.0, modifier_constants=None, ljpme=0, ewaldcoeff_lj=0.0,
-                 sh_lj_ewald=0.0, box_offdiag=(0.0, 0.0, 0.0)):
+                 sh_lj_ewald=0.0, box_offdiag=(0.0, 0.0, 0.0), perturbed=None):
         """box: the diagonal of the box matrix; box_offdiag: box[YY][XX], box[ZZ][XX], box[ZZ][YY] of a triclinic cell"""
         L = lib()
+        pert = None if perturbed is None else np.ascontiguousarray(perturbed, dtype=np.uint8)  # read during gmxref_create only
         self.n = int(len(types))
         self._x = np.ascontiguousarray(x, dtype=np.float32).reshape(self.n, 3)
         self._types = np.ascontiguousarray(types, dtype=np.int32)
@@ -123,7 +124,8 @@ class RefNbnxm:
                     put_in_box, min_ilist_count, rvdw, vdw_modifier, rvdw_switch,
                     k.get("disp_c2", 0.0), k.get("disp_c3", 0.0), k.get("rep_c2", 0.0), k.get("rep_c3", 0.0),
                     k.get("sw_c3", 0.0), k.get("sw_c4", 0.0), k.get("sw_c5", 0.0), ljpme, ewaldcoeff_lj, sh_lj_ewald,
-                    (C.c_float * 3)(*[float(v) for v in box_offdiag]))
+                    (C.c_float * 3)(*[float(v) for v in box_offdiag]),
+                    None if perturbed is None else pert.ctypes.data)
         self.rc = rc
         self.h = L.gmxref_create(C.byref(s), C.byref(p))
         if not self.h:
@@ -232,6 +234,24 @@ class _FepParams(C.Structure):
                 ("rep_cpot", C.c_float), ("lambda_coul", C.c_float), ("lambda_vdw", C.c_float), ("sc_alpha", C.c_float),
                 ("sc_power", C.c_int), ("sc_sigma", C.c_float), ("sc_sigma_min", C.c_float), ("sc_coul", C.c_int),
                 ("ewaldcoeff", C.c_float), ("sh_ewald", C.c_float)]
+
+
+def fep_list(ref):
+    """The perturbed pair lists the reference's own search built for a Reference(..., perturbed=flags): nbnxm/pairlist.cpp
+    make_fep_list through PairlistSet::fepLists(), concatenated over the search threads.  Returns iinr, shift, jindex, jjnr,
+    excl_fep."""
+    L = lib()
+    nri, nrj = C.c_int(0), C.c_int(0)
+    vp = C.c_void_p
+    L.gmxref_fep_list.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L.gmxref_fep_list(ref.h, C.addressof(nri), C.addressof(nrj), 0, 0, None, None, None, None, None)
+    ii, sh, ji = np.zeros(nri.value, np.int32), np.zeros(nri.value, np.int32), np.zeros(nri.value + 1, np.int32)
+    jj, ex = np.zeros(max(nrj.value, 1), np.int32), np.zeros(max(nrj.value, 1), np.int8)
+    rc = L.gmxref_fep_list(ref.h, C.addressof(nri), C.addressof(nrj), len(ii), len(jj), ii.ctypes.data, sh.ctypes.data, ji.ctypes.data,
+                           jj.ctypes.data, ex.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("gmxref_fep_list failed")
+    return ii, sh, ji, jj[:nrj.value], ex[:nrj.value]
 
 
 def fep_kernel(x, shift_vec, nbfp, typeA, typeB, qA, qB, iinr, shift, jindex, jjnr, excl_fep, rc, lambda_coul, lambda_vdw,

@@ -314,3 +314,28 @@ def bonded(kind, iatoms, params6, x, q, box_matrix, epsfac_fudge=138.935458 * 0.
     if rc != 0:
         raise ValueError("orc_bonded: bad input (%d)" % rc)
     return f, fs, (float(e[0]), float(e[1]))
+
+
+def fep_list_canonical(lst, keep=None):
+    """Sorted keys of the pairs of a perturbed pair list in t_nblist form, independent of which atom is listed as i and of how the
+    entries are split: (lower atom, higher atom, shift seen from the lower atom, exclusion flag)."""
+    ii, sh, ji, jj, ex = [np.asarray(a) for a in lst]
+    n = np.diff(ji)
+    i, s, j, e = np.repeat(ii, n).astype(np.int64), np.repeat(sh, n).astype(np.int64), jj.astype(np.int64), ex.astype(np.int64)
+    if keep is not None:
+        i, s, j, e = i[keep], s[keep], j[keep], e[keep]
+    swap = i > j
+    a, b, s = np.where(swap, j, i), np.where(swap, i, j), np.where(swap, SHIFTS - 1 - s, s)
+    return np.sort((((a << 24) | b) << 8 | s) * 2 + e)
+
+
+def fep_list_within(lst, x, box, rlist):
+    """Mask of the pairs of a t_nblist within rlist (float32, x_i + shift - x_j as the reference's make_fep_list evaluates it,
+    nbnxm/pairlist.cpp:1811-1824): the reference keeps pairs up to rlist + a cluster-size dependent buffer in its lists."""
+    ii, sh, ji, jj, ex = [np.asarray(a) for a in lst]
+    n = np.diff(ji)
+    i, sft = np.repeat(ii, n), np.repeat(sh, n)
+    x = _f32(x)
+    d = x[jj] - (x[i] + shift_vectors(box)[sft]).astype(np.float32)
+    r2 = ((d[:, 0] * d[:, 0]).astype(np.float32) + (d[:, 1] * d[:, 1]).astype(np.float32)).astype(np.float32) + (d[:, 2] * d[:, 2]).astype(np.float32)
+    return r2.astype(np.float32) < np.float32(np.float32(rlist) * np.float32(rlist))

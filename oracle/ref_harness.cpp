@@ -275,6 +275,10 @@ void* gmxref_create(const gmxref_system* s, const gmxref_params* p)
         {
             SET_CGINFO_HAS_Q(inst->atomInfo[a]);
         }
+        if (p->perturbed && p->perturbed[a])
+        {
+            SET_CGINFO_FEP(inst->atomInfo[a]);
+        }
         const int n0 = s->excl_off[a], n1 = s->excl_off[a + 1];
         inst->excls.pushBackListOfSize(n1 - n0);
         gmx::ArrayRef<int> e = inst->excls.back();
@@ -289,7 +293,8 @@ void* gmxref_create(const gmxref_system* s, const gmxref_params* p)
     }
 
     const auto pin = gmx::PinningPolicy::CannotBePinned;
-    PairlistParams pairlistParams(kernelType, false, p->rlist, false);
+    const bool     haveFep = p->perturbed != nullptr;
+    PairlistParams pairlistParams(kernelType, haveFep, p->rlist, false);
     if (p->rlist_inner > 0 && p->rlist_inner < p->rlist)
     {
         /* dynamic pruning set up as pairlist_tuning.cpp:506-572 would */
@@ -301,7 +306,7 @@ void* gmxref_create(const gmxref_system* s, const gmxref_params* p)
     }
     auto pairlistSets = std::make_unique<PairlistSets>(pairlistParams, false, p->min_ilist_count);
     auto pairSearch   = std::make_unique<PairSearch>(PbcType::Xyz, false, nullptr, nullptr,
-                                                   pairlistParams.pairlistType, false, nth, pin);
+                                                   pairlistParams.pairlistType, haveFep, nth, pin);
     auto atomData     = std::make_unique<nbnxn_atomdata_t>(pin);
     inst->nbv = std::make_unique<nonbonded_verlet_t>(std::move(pairlistSets), std::move(pairSearch),
                                                      std::move(atomData), kernelSetup, nullptr, nullptr);
@@ -907,5 +912,29 @@ extern "C" int gmxref_bonded(int kind, int nbonds, const int* iatoms, int nparam
     for (int a = 0; a < natoms; a++)
         for (int d = 0; d < 3; d++) f[3 * a + d] = f4[4 * a + d];
     for (int k = 0; k < SHIFTS * 3; k++) fshift[k] = fs[k];
+    return 0;
+}
+
+
+extern "C" int gmxref_fep_list(void* h, int* nri, int* nrj, int cap_nri, int cap_nrj, int* iinr, int* shift, int* jindex, int* jjnr, char* excl_fep)
+{
+    auto*      inst  = static_cast<Instance*>(h);
+    const auto lists = inst->nbv->pairlistSets().pairlistSet(gmx::InteractionLocality::Local).fepLists();
+    int        ni = 0, nj = 0;
+    for (const auto& l : lists) ni += l->nri, nj += l->nrj;
+    *nri = ni, *nrj = nj;
+    if (cap_nri == 0 && cap_nrj == 0) return 0;
+    if (cap_nri < ni || cap_nrj < nj) return -1;
+    int ki = 0, kj = 0;
+    for (const auto& l : lists)
+    {
+        for (int n = 0; n < l->nri; n++)
+        {
+            iinr[ki] = l->iinr[n], shift[ki] = l->shift[n], jindex[ki] = kj;
+            for (int k = l->jindex[n]; k < l->jindex[n + 1]; k++) jjnr[kj] = l->jjnr[k], excl_fep[kj] = l->excl_fep[k], kj++;
+            ki++;
+        }
+    }
+    jindex[ki] = kj;
     return 0;
 }

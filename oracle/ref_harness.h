@@ -49,6 +49,9 @@ typedef struct
     /* triclinic cell: the off-diagonal elements box[YY][XX], box[ZZ][XX], box[ZZ][YY] of the lower-triangular box matrix
      * (gmxref_system::box is its diagonal); all zero = rectangular */
     float box_offdiag[3];
+    /* free-energy perturbation: per atom 1 = perturbed (atom info bit SET_CGINFO_FEP; the search then builds the perturbed pair
+     * lists, nbnxm/pairlist.cpp make_fep_list, and takes those pairs out of the cluster-pair list); NULL = none */
+    const unsigned char* perturbed;
 } gmxref_params;
 
 int    gmxref_simd_width(void);
@@ -70,6 +73,10 @@ int    gmxref_gpu_list(void* h, int* nsci, int* ncj4, int* nexcl, int* nslots, i
 int    gmxref_grid_forces(void* h, float* f, int cap_slots);
 int    gmxref_ewald_table(void* h, float* table_f, int cap, float* scale);
 int    gmxref_bench_coordinates1000(float* out, int cap_atoms, float* box_edge);
+
+/* The perturbed pair lists the reference's search built (gmxref_params::perturbed; PairlistSet::fepLists(), one t_nblist per search
+ * thread), concatenated: call with cap_nri = cap_nrj = 0 for the sizes, then with arrays (jindex: nri + 1). */
+int gmxref_fep_list(void* h, int* nri, int* nrj, int cap_nri, int cap_nrj, int* iinr, int* shift, int* jindex, int* jjnr, char* excl_fep);
 
 /* The reference's perturbed-pair (free-energy) kernel, gmxlib/nonbonded/nb_free_energy.cpp gmx_nb_free_energy_kernel, on a pair list
  * given by the caller in t_nblist form (nri i-entries {iinr, shift, jindex}, jjnr, excl_fep: 1 = the pair interacts, 0 = excluded).

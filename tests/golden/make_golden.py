@@ -157,6 +157,16 @@ def fep():
     sv = oracle.shift_vectors(s.box)
     k_rf, c_rf = S.rf_constants(RC, eps_rf=1.0)
     out = dict(list_sha256=np.array(sha(np.concatenate([a.astype(np.int64).ravel() for a in lst]))), npairs=np.int64(len(lst[3])), nri=np.int64(len(lst[0])))
+    # the reference's OWN perturbed pair lists (nbnxm/pairlist.cpp make_fep_list on the GPU-layout list, through the search of
+    # oracle/_ref with the perturbed atoms flagged), restricted to the pairs within rlist (the reference keeps a buffer beyond it):
+    # hash and count of the canonical pair keys, for rlist = rc and rlist > rc
+    for rl in (0.9, 1.0):
+        r = gmxref.RefNbnxm(s.x, s.box, tm, qm, s.nbfp, s.excl_off, s.excl_idx, RC, rlist=rl, eeltype=gmxref.EEL_RF, k_rf=k_rf, c_rf=c_rf,
+                            kernel=gmxref.KERNEL_GPUREF, perturbed=pert.astype(np.uint8), nthreads=1)
+        ref = gmxref.fep_list(r)
+        keys = oracle.fep_list_canonical(ref, oracle.fep_list_within(ref, s.x, s.box, rl))
+        out["ref_list_sha256_%.1f" % rl], out["ref_list_npairs_%.1f" % rl], out["ref_list_npairs_all_%.1f" % rl] = np.array(sha(keys)), np.int64(len(keys)), np.int64(len(ref[3]))
+        print("reference fep list rlist", rl, len(ref[3]), "pairs,", len(keys), "within rlist")
     for name, kw in S.FEP_CASES.items():
         f, fs, o4 = gmxref.fep_kernel(s.x, sv, s.nbfp, tA, tB, qA, qB, *lst, RC, k_rf=k_rf, c_rf=c_rf, **kw)
         out["f_" + name], out["fshift_" + name], out["out4_" + name] = f, fs, np.array(o4, np.float64)
