@@ -5,7 +5,8 @@
  * do_nb_verlet -> nonbonded_verlet_t::dispatchFreeEnergyKernel, nbnxm/kerneldispatch.cpp:486-588), for the flavours built so far:
  * reaction-field / plain cut-off or Ewald electrostatics (the long-range part subtracted unsoftened, :693-737, evaluated directly
  * instead of from the reference's spline table), cut-off LJ with potential shift, soft-core with r-power 6 (lambda power 1 or 2) or
- * none.  LJ-PME and the LJ potential switch are refused.
+ * none, LJ potential shift or potential switch.  LJ-PME and the LJ force switch (which the reference's kernel does not have
+ * either) are refused.
  * The pair list comes from the caller in t_nblist form (mdtypes/nblist.h:117-137; b200nb_fep_upload_list) -- what
  * nbnxm/pairlist.cpp:1699-1872 make_fep_list produces: every pair within the list radius with a perturbed atom, excluded pairs
  * flagged, perturbed atoms listed with themselves -- or is built on the device from the gridded coordinates (b200nb_fep_build_list).
@@ -33,6 +34,8 @@ struct FepDev
     int   soft_core, sc_differ, ntypes;
     int   ewald;
     float beta, sh_ewald;
+    int   pot_switch; /* LJ potential switch from rvdw_switch to rc (interaction_const_t::vdw_switch) */
+    float rvdw_switch, sw_c3, sw_c4, sw_c5;
 };
 
 /* r^(1/6) of 1 / (alpha sigma^6 + r^6) and its inverse: pthRoot, nb_free_energy.cpp:81-87 */
@@ -157,6 +160,14 @@ k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, cons
                         const float v6 = c6[i] * rinv6, v12 = c12[i] * rinv6 * rinv6;
                         Vvdw   = (v12 + c12[i] * P.rep_cpot) * (1.0f / 12.0f) - (v6 + c6[i] * P.disp_cpot) * (1.0f / 6.0f);
                         FscalV = v12 - v6;
+                        if (P.pot_switch) /* :613-625, on the (soft-cored) distance */
+                        {
+                            const float d = fmaxf(rV - P.rvdw_switch, 0.f), d2 = d * d;
+                            const float sw  = 1.0f + d2 * d * (P.sw_c3 + d * (P.sw_c4 + d * P.sw_c5));
+                            const float dsw = d2 * (3.0f * P.sw_c3 + d * (4.0f * P.sw_c4 + d * 5.0f * P.sw_c5));
+                            FscalV = FscalV * sw - rV * Vvdw * dsw;
+                            Vvdw *= sw;
+                        }
                     }
                     FscalC *= rpinvC;
                     FscalV *= rpinvV;
@@ -596,8 +607,8 @@ extern "C" int b200nb_fep_launch(b200nb_t* h, const b200nb_fep_params_t* p)
     FepState& F = h->fep;
     if (F.natoms != h->natoms || !F.d_out) return nb_fail(h, B200NB_ERR_STATE, "fep_launch: fep_set_atoms for the current atoms first");
     if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "fep_launch: put_on_grid first");
-    if (h->dp.vdw_modifier != B200NB_VDW_POTSHIFT || h->dp.rvdw2 < h->dp.rc2 || h->dp.ljpme != 0)
-        return nb_fail(h, B200NB_ERR_ARG, "fep_launch: only cut-off LJ with potential shift and rvdw = rcoulomb is built for perturbed pairs");
+    if (h->dp.vdw_modifier == B200NB_VDW_FORCESWITCH || h->dp.rvdw2 < h->dp.rc2 || h->dp.ljpme != 0)
+        return nb_fail(h, B200NB_ERR_ARG, "fep_launch: cut-off LJ with potential shift or potential switch and rvdw = rcoulomb is what is built for perturbed pairs");
     if (p->sc_power != 1 && p->sc_power != 2) return nb_fail(h, B200NB_ERR_ARG, "fep_launch: sc_power must be 1 or 2");
     if (F.nri == 0) return 0;
     cudaSetDevice(h->device);
@@ -605,6 +616,8 @@ extern "C" int b200nb_fep_launch(b200nb_t* h, const b200nb_fep_params_t* p)
     D.rc = h->hp.rc, D.rc2 = h->dp.rc2, D.epsfac = h->dp.epsfac, D.k_rf = h->dp.k_rf, D.c_rf = h->dp.c_rf, D.disp_cpot = h->dp.disp_cpot, D.rep_cpot = h->dp.rep_cpot;
     D.ntypes = h->dp.ntypes;
     D.ewald = h->dp.eeltype == B200NB_EEL_EWALD, D.beta = h->dp.beta, D.sh_ewald = h->dp.sh_ewald;
+    D.pot_switch = h->dp.vdw_modifier == B200NB_VDW_POTSWITCH, D.rvdw_switch = h->dp.rvdw_switch;
+    D.sw_c3 = h->dp.sw_c3, D.sw_c4 = h->dp.sw_c4, D.sw_c5 = h->dp.sw_c5;
     /* interaction_const_t::SoftCoreParameters (mdtypes/interaction_const.cpp:47-56) */
     D.alpha_vdw  = p->sc_alpha;
     D.alpha_coul = p->sc_coul ? p->sc_alpha : 0.f;

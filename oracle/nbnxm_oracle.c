@@ -818,6 +818,7 @@ typedef struct
     int   lam_power;
     float sigma6_def, sigma6_min;
     float beta, sh_ewald; /* beta > 0: Ewald electrostatics */
+    float rvdw_switch;    /* > 0: LJ potential switch from rvdw_switch to rc (eintmodPOTSWITCH; disp_cpot = rep_cpot = 0 then) */
 } orc_fep_params;
 
 void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntype, const float* nbfp, const int* typeA, const int* typeB,
@@ -956,6 +957,19 @@ void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntyp
                             const float Vvdw6 = c6[i] * rinv6, Vvdw12 = c12[i] * rinv6 * rinv6;
                             Vvdw[i]   = (Vvdw12 + c12[i] * p->rep_cpot) * (1.0f / 12.0f) - (Vvdw6 + c6[i] * p->disp_cpot) * (1.0f / 6.0f);
                             FscalV[i] = Vvdw12 - Vvdw6;
+                            if (p->rvdw_switch > 0.f) /* :613-625 potential switch on the (soft-cored) distance; constants :273-285 */
+                            {
+                                const float dsw_ = rvdw - p->rvdw_switch;
+                                const float swV3 = -10.0f / (dsw_ * dsw_ * dsw_), swV4 = 15.0f / (dsw_ * dsw_ * dsw_ * dsw_),
+                                            swV5 = -6.0f / (dsw_ * dsw_ * dsw_ * dsw_ * dsw_);
+                                float d = rV - p->rvdw_switch;
+                                d       = d > 0.f ? d : 0.f;
+                                const float d2 = d * d;
+                                const float sw = 1.0f + d2 * d * (swV3 + d * (swV4 + d * swV5));
+                                const float dsw = d2 * (3.0f * swV3 + d * (4.0f * swV4 + d * 5.0f * swV5));
+                                FscalV[i] = FscalV[i] * sw - rV * Vvdw[i] * dsw; /* rV < rvdw holds here */
+                                Vvdw[i]   = Vvdw[i] * sw;
+                            }
                         }
                         FscalC[i] *= rpinvC;
                         FscalV[i] *= rpinvV;

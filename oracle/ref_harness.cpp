@@ -735,7 +735,8 @@ int gmxref_fep_kernel(int natoms, const float* x, const float* shift_vec, int nt
     ic.eeltype          = (p->ewaldcoeff > 0.0f) ? eelPME : ((p->k_rf != 0.0f) ? eelRF : eelCUT);
     ic.coulomb_modifier = (p->ewaldcoeff > 0.0f) ? eintmodPOTSHIFT : eintmodNONE;
     ic.vdwtype          = evdwCUT;
-    ic.vdw_modifier     = eintmodPOTSHIFT;
+    ic.vdw_modifier     = p->rvdw_switch > 0.0f ? eintmodPOTSWITCH : eintmodPOTSHIFT;
+    ic.rvdw_switch      = p->rvdw_switch;
     ic.rcoulomb = ic.rvdw = p->rc;
     ic.epsfac             = p->epsfac;
     ic.k_rf               = p->k_rf;

@@ -171,6 +171,11 @@ def fep():
         f, fs, o4 = gmxref.fep_kernel(s.x, sv, s.nbfp, tA, tB, qA, qB, *lst, RC, k_rf=k_rf, c_rf=c_rf, **kw)
         out["f_" + name], out["fshift_" + name], out["out4_" + name] = f, fs, np.array(o4, np.float64)
         print("fep", name, o4)
+    # LJ potential switch 0.75 -> 0.9 (eintmodPOTSWITCH: on the soft-cored distance, nb_free_energy.cpp:613-625)
+    for name, kw in S.FEP_CASES.items():
+        f, fs, o4 = gmxref.fep_kernel(s.x, sv, s.nbfp, tA, tB, qA, qB, *lst, RC, k_rf=k_rf, c_rf=c_rf, rvdw_switch=0.75, **kw)
+        out["f_pswitch_" + name], out["fshift_pswitch_" + name], out["out4_pswitch_" + name] = f, fs, np.array(o4, np.float64)
+        print("fep pswitch", name, o4)
     np.savez_compressed(os.path.join(HERE, "ref_water_3k_fep_rf.npz"), **out)
     # the same with Ewald electrostatics: ref_water_3k_fep_ewald.npz
     import math

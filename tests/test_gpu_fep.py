@@ -155,15 +155,45 @@ def test_fep_list_built_on_the_device(built, name, nmol, rlist):
     fc.nb.close()
 
 
+@pytest.mark.parametrize("case", ["sc1", "nosc", "sc2coul"])
+def test_fep_kernel_potential_switch(built, case):
+    """LJ potential switch 0.75 -> 0.9 nm in the free-energy kernel (applied on the soft-cored distance, nb_free_energy.cpp:613-625)
+    against the oracle and the committed output of the reference kernel; reaction field."""
+    S = g.systems
+    s, pert, tA, tB, qA, qB, tm, qm = S.perturbed_water()
+    kw = S.FEP_CASES[case]
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.ReactionField, computeVirialAndEnergy=True,
+                            vdwModifier=g.VdwModifier.PotentialSwitch, vdwSwitch=0.75)
+    fc = g.ForceCalculator(g.SimulationState(s.x, s.box, tm, qm, s.nbfp, s.excl_off, s.excl_idx), opt)
+    h = fc.nb
+    lst = oracle.fep_pair_list(s.x, s.box, RC, pert, s.excl_off, s.excl_idx)
+    h.fep_set_atoms(tA, tB, qA, qB)
+    h.fep_upload_list(*lst)
+    h.set_x(s.x)
+    h.clear_outputs()
+    h.fep_launch(**kw)
+    f = h.get_f().astype(np.float64)
+    out4 = np.array(h.fep_outputs())
+    k, c = S.rf_constants(RC, eps_rf=1.0)
+    fo, fso, o4 = oracle.fep_kernel(s.x, oracle.shift_vectors(s.box), s.nbfp, tA, tB, qA, qB, *lst, RC, k_rf=k, c_rf=c, rvdw_switch=0.75, **kw)
+    gd = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_water_3k_fep_rf.npz"))
+    assert relrms(f, fo.astype(np.float64)) < 1e-5 and relrms(f, gd["f_pswitch_" + case].astype(np.float64)) < 1e-5
+    assert relrms(f, gd["f_" + case].astype(np.float64)) > 2e-5  # not the unswitched forces
+    o4r = gd["out4_pswitch_" + case]
+    assert np.abs(out4 - np.array(o4)).max() <= 2e-5 * np.abs(np.array(o4)).max()
+    assert np.abs(out4 - o4r).max() <= 2e-5 * np.abs(o4r).max()
+    fc.nb.close()
+
+
 def test_fep_refuses_what_is_not_built(built):
     S = g.systems
     s, pert, tA, tB, qA, qB, tm, qm = S.perturbed_water()
-    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, vdwModifier=g.VdwModifier.PotentialSwitch, vdwSwitch=0.75)
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, vdwModifier=g.VdwModifier.ForceSwitch, vdwSwitch=0.75)
     fc = g.ForceCalculator(g.SimulationState(s.x, s.box, tm, qm, s.nbfp, s.excl_off, s.excl_idx), opt)
     fc.nb.fep_set_atoms(tA, tB, qA, qB)
     fc.nb.fep_upload_list(*oracle.fep_pair_list(s.x, s.box, RC, pert, s.excl_off, s.excl_idx))
     with pytest.raises(nb.B200NBError):
-        fc.nb.fep_launch(0.5, 0.5)  # LJ potential switch: not built for perturbed pairs
+        fc.nb.fep_launch(0.5, 0.5)  # LJ force switch: not in the reference's free-energy kernel, not built here
     with pytest.raises(nb.B200NBError):
         fc.nb.fep_upload_list([0], [22], [0, 1], [s.n + 5], [1])  # j-atom out of range
     with pytest.raises(nb.B200NBError):
