@@ -193,6 +193,10 @@ struct FepState
     double*      d_out = nullptr; /* Vc, Vv, dvdl_coul, dvdl_vdw */
     bool                in_step = false; /* launched by b200nb_step / b200nb_compute, inside the captured graph */
     b200nb_fep_params_t step_params{};
+    /* capacities of the list arrays and the count / offset scratch of b200nb_fep_build_list: grown with head-room, kept across
+     * search steps (no cudaMalloc / cudaFree in a steady-state rebuild) */
+    size_t cap_nri = 0, cap_nrj = 0, cap_scratch = 0;
+    int*   d_scratch = nullptr;
 };
 
 /* listed interactions on the device (bonded.cu): lists in atom order, 6 floats per parameter set */
@@ -202,6 +206,7 @@ struct BondedState
     int     count[B200NB_BONDED_KINDS] = {};
     int*    d_iatoms[B200NB_BONDED_KINDS] = {};
     float*  d_params[B200NB_BONDED_KINDS] = {};
+    size_t  cap_iatoms[B200NB_BONDED_KINDS] = {}, cap_params[B200NB_BONDED_KINDS] = {}; /* elements; kept across updates */
     double* d_energy = nullptr; /* per kind + Coulomb-14 */
     bool    in_step = false;    /* launched by b200nb_step / b200nb_compute, inside the captured graph */
     float   scale14 = 0.f;

@@ -266,14 +266,29 @@ extern "C" int b200nb_bonded_set_list(b200nb_t* h, int kind, int nbonds, const i
     }
     cudaSetDevice(h->device);
     BondedState& S = h->bonded;
-    cudaFree(S.d_iatoms[kind]), cudaFree(S.d_params[kind]);
-    S.d_iatoms[kind] = nullptr, S.d_params[kind] = nullptr, S.count[kind] = 0;
+    S.count[kind] = 0;
     if (nbonds > 0)
     {
-        NB_CUDA(h, cudaMalloc((void**)&S.d_iatoms[kind], sizeof(int) * (size_t)(nral + 1) * nbonds));
-        NB_CUDA(h, cudaMalloc((void**)&S.d_params[kind], sizeof(float) * 6 * (size_t)nparams));
-        NB_CUDA(h, cudaMemcpy(S.d_iatoms[kind], iatoms_host, sizeof(int) * (size_t)(nral + 1) * nbonds, cudaMemcpyHostToDevice));
-        NB_CUDA(h, cudaMemcpy(S.d_params[kind], params6_host, sizeof(float) * 6 * (size_t)nparams, cudaMemcpyHostToDevice));
+        /* the arrays are kept and only grown (with head-room): callers that convert their lists at every search step -- the
+         * Nbnxm::gpu_* shim -- update all eight types each time */
+        const size_t ni = (size_t)(nral + 1) * nbonds, np = 6 * (size_t)nparams;
+        if (ni > S.cap_iatoms[kind])
+        {
+            cudaFree(S.d_iatoms[kind]);
+            S.d_iatoms[kind] = nullptr, S.cap_iatoms[kind] = 0;
+            NB_CUDA(h, cudaMalloc((void**)&S.d_iatoms[kind], sizeof(int) * (ni + ni / 8 + 64)));
+            S.cap_iatoms[kind] = ni + ni / 8 + 64;
+        }
+        if (np > S.cap_params[kind])
+        {
+            cudaFree(S.d_params[kind]);
+            S.d_params[kind] = nullptr, S.cap_params[kind] = 0;
+            NB_CUDA(h, cudaMalloc((void**)&S.d_params[kind], sizeof(float) * np));
+            S.cap_params[kind] = np;
+        }
+        NB_CUDA(h, cudaMemcpyAsync(S.d_iatoms[kind], iatoms_host, sizeof(int) * ni, cudaMemcpyHostToDevice, h->stream));
+        NB_CUDA(h, cudaMemcpyAsync(S.d_params[kind], params6_host, sizeof(float) * np, cudaMemcpyHostToDevice, h->stream));
+        NB_CUDA(h, cudaStreamSynchronize(h->stream)); /* the host arrays are the caller's */
         S.count[kind] = nbonds;
     }
     S.natoms = h->natoms;

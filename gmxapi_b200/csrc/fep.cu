@@ -509,6 +509,7 @@ extern "C" int b200nb_fep_upload_list(b200nb_t* h, int nri, const int* iinr, con
         || upload(h, &F.d_jjnr, jjnr, nrj) || upload(h, &F.d_excl, excl_fep, nrj))
         return B200NB_ERR_CUDA;
     F.nri = nri, F.nrj = nrj;
+    F.cap_nri = F.cap_nrj = 0; /* exact-size arrays: a later b200nb_fep_build_list allocates its own */
     h->generation++; /* captured steps that include the free-energy kernel carry the list pointers by value */
     return 0;
 }
@@ -539,39 +540,39 @@ extern "C" int b200nb_fep_build_list(b200nb_t* h, int* nri_out, int* nrj_out)
     if (nrj_out) *nrj_out = 0;
     if (F.npert == 0) return 0;
     const size_t m = (size_t)F.npert * B200NB_SHIFTS;
-    int *        d_cnt = nullptr, *d_off = nullptr, *d_eidx = nullptr, *d_tot = nullptr;
-    NB_CUDA(h, cudaMalloc((void**)&d_cnt, sizeof(int) * (3 * m + 2)));
-    d_off = d_cnt + m, d_eidx = d_off + m, d_tot = d_eidx + m;
+    if (3 * m + 2 > F.cap_scratch)
+    {
+        cudaFree(F.d_scratch);
+        F.d_scratch = nullptr, F.cap_scratch = 0;
+        NB_CUDA(h, cudaMalloc((void**)&F.d_scratch, sizeof(int) * (3 * m + 2)));
+        F.cap_scratch = 3 * m + 2;
+    }
+    int *d_cnt = F.d_scratch, *d_off = d_cnt + m, *d_eidx = d_off + m, *d_tot = d_eidx + m;
     const unsigned nblk = (unsigned)((F.npert + 3) / 4);
     const float4*  xq   = reinterpret_cast<const float4*>(h->d_xq);
     k_fep_list<false><<<nblk, 128, 0, h->stream>>>(F.npert, F.d_pert, F.d_is_pert, xq, h->d_slot_of_atom, h->d_atom_index, h->d_bb, h->d_excl_off, h->d_excl_idx,
                                                    h->d_shift_vec, A, d_cnt, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     k_fep_scan<<<1, 1024, 0, h->stream>>>((int)m, d_cnt, d_off, d_eidx, d_tot);
     int tot[2] = { 0, 0 };
-    cudaError_t e = cudaMemcpyAsync(tot, d_tot, sizeof(tot), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess)
-    {
-        cudaFree(d_cnt);
-        NB_CUDA(h, e);
-    }
+    NB_CUDA(h, cudaMemcpyAsync(tot, d_tot, sizeof(tot), cudaMemcpyDeviceToHost, h->stream));
+    NB_CUDA(h, cudaStreamSynchronize(h->stream)); /* the one host round trip of a rebuild: the list's sizes */
     const int nrj = tot[0], nri = tot[1];
-    cudaFree(F.d_iinr), cudaFree(F.d_shift), cudaFree(F.d_jindex), cudaFree(F.d_jjnr), cudaFree(F.d_excl);
-    F.d_iinr = F.d_shift = F.d_jindex = F.d_jjnr = nullptr, F.d_excl = nullptr;
-    if (cudaMalloc((void**)&F.d_iinr, sizeof(int) * std::max(nri, 1)) != cudaSuccess || cudaMalloc((void**)&F.d_shift, sizeof(int) * std::max(nri, 1)) != cudaSuccess
-        || cudaMalloc((void**)&F.d_jindex, sizeof(int) * (nri + 1)) != cudaSuccess || cudaMalloc((void**)&F.d_jjnr, sizeof(int) * std::max(nrj, 1)) != cudaSuccess
-        || cudaMalloc((void**)&F.d_excl, std::max(nrj, 1)) != cudaSuccess)
+    if ((size_t)nri + 1 > F.cap_nri || (size_t)nrj > F.cap_nrj || !F.d_iinr)
     {
-        cudaFree(d_cnt);
-        return nb_fail(h, B200NB_ERR_CUDA, "fep_build_list: out of device memory");
+        /* the list outgrew its arrays (or was uploaded with exact sizes): new ones with 20 % head-room */
+        cudaFree(F.d_iinr), cudaFree(F.d_shift), cudaFree(F.d_jindex), cudaFree(F.d_jjnr), cudaFree(F.d_excl);
+        F.d_iinr = F.d_shift = F.d_jindex = F.d_jjnr = nullptr, F.d_excl = nullptr, F.cap_nri = F.cap_nrj = 0;
+        const size_t ci = (size_t)(1.2 * nri) + 64, cj = (size_t)(1.2 * nrj) + 256;
+        if (cudaMalloc((void**)&F.d_iinr, sizeof(int) * ci) != cudaSuccess || cudaMalloc((void**)&F.d_shift, sizeof(int) * ci) != cudaSuccess
+            || cudaMalloc((void**)&F.d_jindex, sizeof(int) * ci) != cudaSuccess || cudaMalloc((void**)&F.d_jjnr, sizeof(int) * cj) != cudaSuccess
+            || cudaMalloc((void**)&F.d_excl, cj) != cudaSuccess)
+            return nb_fail(h, B200NB_ERR_CUDA, "fep_build_list: out of device memory");
+        F.cap_nri = ci, F.cap_nrj = cj;
     }
     k_fep_list<true><<<nblk, 128, 0, h->stream>>>(F.npert, F.d_pert, F.d_is_pert, xq, h->d_slot_of_atom, h->d_atom_index, h->d_bb, h->d_excl_off, h->d_excl_idx,
                                                   h->d_shift_vec, A, nullptr, d_off, d_eidx, F.d_iinr, F.d_shift, F.d_jindex, F.d_jjnr, F.d_excl);
-    e = cudaMemcpyAsync(F.d_jindex + nri, &d_tot[0], sizeof(int), cudaMemcpyDeviceToDevice, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(d_cnt);
-    NB_CUDA(h, e);
+    NB_CUDA(h, cudaMemcpyAsync(F.d_jindex + nri, &d_tot[0], sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+    NB_CUDA(h, cudaGetLastError());
     h->nlaunches += 3;
     F.nri = nri, F.nrj = nrj;
     h->generation++;
@@ -590,14 +591,16 @@ extern "C" int b200nb_fep_get_list(b200nb_t* h, int* iinr_host, int* shift_host,
         jindex_host[0] = 0;
         return 0;
     }
-    NB_CUDA(h, cudaMemcpy(iinr_host, F.d_iinr, sizeof(int) * F.nri, cudaMemcpyDeviceToHost));
-    NB_CUDA(h, cudaMemcpy(shift_host, F.d_shift, sizeof(int) * F.nri, cudaMemcpyDeviceToHost));
-    NB_CUDA(h, cudaMemcpy(jindex_host, F.d_jindex, sizeof(int) * (F.nri + 1), cudaMemcpyDeviceToHost));
+    /* on the context's stream, behind the fill pass of b200nb_fep_build_list (which returns without waiting for it) */
+    NB_CUDA(h, cudaMemcpyAsync(iinr_host, F.d_iinr, sizeof(int) * F.nri, cudaMemcpyDeviceToHost, h->stream));
+    NB_CUDA(h, cudaMemcpyAsync(shift_host, F.d_shift, sizeof(int) * F.nri, cudaMemcpyDeviceToHost, h->stream));
+    NB_CUDA(h, cudaMemcpyAsync(jindex_host, F.d_jindex, sizeof(int) * (F.nri + 1), cudaMemcpyDeviceToHost, h->stream));
     if (F.nrj > 0)
     {
-        NB_CUDA(h, cudaMemcpy(jjnr_host, F.d_jjnr, sizeof(int) * F.nrj, cudaMemcpyDeviceToHost));
-        NB_CUDA(h, cudaMemcpy(excl_fep_host, F.d_excl, F.nrj, cudaMemcpyDeviceToHost));
+        NB_CUDA(h, cudaMemcpyAsync(jjnr_host, F.d_jjnr, sizeof(int) * F.nrj, cudaMemcpyDeviceToHost, h->stream));
+        NB_CUDA(h, cudaMemcpyAsync(excl_fep_host, F.d_excl, F.nrj, cudaMemcpyDeviceToHost, h->stream));
     }
+    NB_CUDA(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -676,6 +679,6 @@ void nb_fep_free(b200nb_context* h)
 {
     FepState& F = h->fep;
     cudaFree(F.d_typeA), cudaFree(F.d_typeB), cudaFree(F.d_qA), cudaFree(F.d_qB), cudaFree(F.d_iinr), cudaFree(F.d_shift), cudaFree(F.d_jindex);
-    cudaFree(F.d_jjnr), cudaFree(F.d_excl), cudaFree(F.d_out), cudaFree(F.d_pert), cudaFree(F.d_is_pert);
+    cudaFree(F.d_jjnr), cudaFree(F.d_excl), cudaFree(F.d_out), cudaFree(F.d_pert), cudaFree(F.d_is_pert), cudaFree(F.d_scratch);
     F = FepState{};
 }
