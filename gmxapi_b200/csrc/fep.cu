@@ -5,8 +5,8 @@
  * do_nb_verlet -> nonbonded_verlet_t::dispatchFreeEnergyKernel, nbnxm/kerneldispatch.cpp:486-588), for the flavours built so far:
  * reaction-field / plain cut-off or Ewald electrostatics (the long-range part subtracted unsoftened, :693-737, evaluated directly
  * instead of from the reference's spline table), cut-off LJ with potential shift, soft-core with r-power 6 (lambda power 1 or 2) or
- * none, LJ potential shift or potential switch.  LJ-PME and the LJ force switch (which the reference's kernel does not have
- * either) are refused.
+ * none, LJ potential shift or potential switch, LJ-PME (potential shift; the grid part subtracted unsoftened, :725-770, evaluated
+ * directly as well).  The LJ force switch (which the reference's kernel does not have either) is refused.
  * The pair list comes from the caller in t_nblist form (mdtypes/nblist.h:117-137; b200nb_fep_upload_list) -- what
  * nbnxm/pairlist.cpp:1699-1872 make_fep_list produces: every pair within the list radius with a perturbed atom, excluded pairs
  * flagged, perturbed atoms listed with themselves -- or is built on the device from the gridded coordinates (b200nb_fep_build_list).
@@ -36,7 +36,18 @@ struct FepDev
     float beta, sh_ewald;
     int   pot_switch; /* LJ potential switch from rvdw_switch to rc (interaction_const_t::vdw_switch) */
     float rvdw_switch, sw_c3, sw_c4, sw_c5;
+    int   ljpme; /* 0 none, 1 geometric, 2 Lorentz-Berthelot grid combination rule (vdwtype = evdwPME) */
+    float lje_coeff2, sh_lj_ewald; /* ewaldcoeff_lj^2, interaction_const_t::sh_lj_ewald */
 };
+
+/* the grid C6 of a type pair, times six like nbfp's C6 (fr->ljpme_c6grid, mdlib/forcerec.cpp:157-195), from the per-type
+ * nbfp_comb entries the cluster-pair kernels use (b200nb_set_vdw) */
+__device__ __forceinline__ float grid_c6(int rule, float2 gi, float2 gj)
+{
+    if (rule == 1) return gi.x * gj.x;
+    const float sg = gi.x + gj.x, s2 = sg * sg;
+    return gi.y * gj.y * (s2 * s2 * s2);
+}
 
 /* r^(1/6) of 1 / (alpha sigma^6 + r^6) and its inverse: pthRoot, nb_free_energy.cpp:81-87 */
 __device__ __forceinline__ void sixth_root(float rpinv, float& rinv_eff, float& r_eff)
@@ -49,7 +60,7 @@ __global__ void __launch_bounds__(128)
 k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, const int* __restrict__ jindex, const int* __restrict__ jjnr,
       const signed char* __restrict__ excl_fep, const float4* __restrict__ xq, const int* __restrict__ slot_of_atom, const float* __restrict__ shift_vec,
       const int* __restrict__ typeA, const int* __restrict__ typeB, const float* __restrict__ qA, const float* __restrict__ qB,
-      const float2* __restrict__ nbfp, const __grid_constant__ FepDev P, float4* __restrict__ f, float* __restrict__ fshift, double* __restrict__ out4)
+      const float2* __restrict__ nbfp, const float2* __restrict__ nbfp_comb, const __grid_constant__ FepDev P, float4* __restrict__ f, float* __restrict__ fshift, double* __restrict__ out4)
 {
     const int n = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= nri) return;
@@ -59,6 +70,8 @@ k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, cons
     const float  ix = shift_vec[3 * is] + xi.x, iy = shift_vec[3 * is + 1] + xi.y, iz = shift_vec[3 * is + 2] + xi.z;
     const float  iqA = P.epsfac * qA[ii], iqB = P.epsfac * qB[ii];
     const int    tiA = typeA[ii] * P.ntypes, tiB = typeB[ii] * P.ntypes;
+    float2       giA = make_float2(0.f, 0.f), giB = giA;
+    if (P.ljpme) giA = nbfp_comb[typeA[ii]], giB = nbfp_comb[typeB[ii]];
     const float  DLF[2] = { -1.f, 1.f };
     float        vctot = 0, vvtot = 0, fix = 0, fiy = 0, fiz = 0, dvdl_coul = 0, dvdl_vdw = 0;
     int          nwithin = 0;
@@ -89,6 +102,12 @@ k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, cons
         }
         float       Fscal = 0.f;
         const float qq[2] = { iqA * qA[jnr], iqB * qB[jnr] };
+        float       c6grid[2] = { 0.f, 0.f }; /* nbfp_grid[tj[i]], :609, :764 */
+        if (P.ljpme)
+        {
+            c6grid[0] = grid_c6(P.ljpme, giA, nbfp_comb[typeA[jnr]]);
+            c6grid[1] = grid_c6(P.ljpme, giB, nbfp_comb[typeB[jnr]]);
+        }
         if (included)
         {
             const float2 pa = nbfp[tiA + typeA[jnr]], pb = nbfp[tiB + typeB[jnr]];
@@ -148,7 +167,7 @@ k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, cons
                             FscalC = qq[i] * (rinvC - 2.0f * P.k_rf * rC * rC);
                         }
                     }
-                    if ((c6[i] != 0 || c12[i] != 0) && rV < P.rc) /* :588-607 */
+                    if ((c6[i] != 0 || c12[i] != 0) && (P.ljpme ? r < P.rc : rV < P.rc)) /* :586-611 */
                     {
                         float rinv6;
                         if (P.soft_core) rinv6 = rpinvV;
@@ -160,6 +179,7 @@ k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, cons
                         const float v6 = c6[i] * rinv6, v12 = c12[i] * rinv6 * rinv6;
                         Vvdw   = (v12 + c12[i] * P.rep_cpot) * (1.0f / 12.0f) - (v6 + c6[i] * P.disp_cpot) * (1.0f / 6.0f);
                         FscalV = v12 - v6;
+                        if (P.ljpme) Vvdw += c6grid[i] * P.sh_lj_ewald * (1.0f / 6.0f); /* the grid potential at the cut-off */
                         if (P.pot_switch) /* :613-625, on the (soft-cored) distance */
                         {
                             const float d = fmaxf(rV - P.rvdw_switch, 0.f), d2 = d * d;
@@ -222,6 +242,48 @@ k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, cons
                 vctot -= P.LFC[i] * qq[i] * v_lr;
                 Fscal -= P.LFC[i] * qq[i] * f_lr;
                 dvdl_coul -= (DLF[i] * qq[i]) * v_lr;
+            }
+        }
+        if (P.ljpme && r < P.rc)
+        {
+            /* :725-770: the grid (reciprocal-space) part of the dispersion, g(x) / r^6 with g = 1 - exp(-x) (1 + x + x^2 / 2),
+             * x = (ewaldcoeff_lj r)^2 (tables/forcetable.cpp v_lj_ewald_lr), taken off unsoftened -- for excluded pairs and a
+             * perturbed atom with itself (half) too.  The reference interpolates it and its derivative from the cubic-spline table
+             * vdwEwaldTables (it avoids the closed form because that cancels for small r, :738-741); evaluated directly here, by
+             * the series g = exp(-x) x^3 / 6 (1 + x/4 + x^2/20 + ...) below x = 1, which has no 1 / r^6 in it at all */
+            const float b2 = P.lje_coeff2, x = b2 * rsq, ex = expf(-x), b6 = b2 * b2 * b2;
+            float       v_lr, f_lr; /* v, -(dv/dr) / r */
+            if (rsq > 0)
+            {
+                const float rinv2 = rinv * rinv;
+                if (x < 1.0f)
+                {
+                    const float ser = x * (1.0f / 4 + x * (1.0f / 20 + x * (1.0f / 120 + x * (1.0f / 840 + x * (1.0f / 6720
+                                      + x * (1.0f / 60480 + x * (1.0f / 604800 + x * (1.0f / 6652800 + x * (1.0f / 79833600)))))))));
+                    v_lr = b6 * ex * (1.0f + ser) * (1.0f / 6.0f);
+                    f_lr = b6 * ex * ser * rinv2;
+                }
+                else
+                {
+                    const float g = 1.0f - ex * (1.0f + x + 0.5f * x * x), rinv6 = rinv2 * rinv2 * rinv2;
+                    v_lr = g * rinv6;
+                    f_lr = (6.0f * g * rinv6 - b6 * ex) * rinv2;
+                }
+            }
+            else
+            {
+                v_lr = b6 * (1.0f / 6.0f);
+                f_lr = 0.f;
+            }
+            const float FF = f_lr * (1.0f / 6.0f);
+            float       VV = v_lr * (1.0f / 6.0f);
+            if (ii == jnr) VV *= 0.5f;
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+            {
+                vvtot += P.LFV[i] * c6grid[i] * VV;
+                Fscal += P.LFV[i] * c6grid[i] * FF;
+                dvdl_vdw += (DLF[i] * c6grid[i]) * VV;
             }
         }
         const float tx = Fscal * dx, ty = Fscal * dy, tz = Fscal * dz;
@@ -610,8 +672,9 @@ extern "C" int b200nb_fep_launch(b200nb_t* h, const b200nb_fep_params_t* p)
     FepState& F = h->fep;
     if (F.natoms != h->natoms || !F.d_out) return nb_fail(h, B200NB_ERR_STATE, "fep_launch: fep_set_atoms for the current atoms first");
     if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "fep_launch: put_on_grid first");
-    if (h->dp.vdw_modifier == B200NB_VDW_FORCESWITCH || h->dp.rvdw2 < h->dp.rc2 || h->dp.ljpme != 0)
-        return nb_fail(h, B200NB_ERR_ARG, "fep_launch: cut-off LJ with potential shift or potential switch and rvdw = rcoulomb is what is built for perturbed pairs");
+    if (h->dp.vdw_modifier == B200NB_VDW_FORCESWITCH || h->dp.rvdw2 < h->dp.rc2)
+        return nb_fail(h, B200NB_ERR_ARG, "fep_launch: LJ with potential shift or potential switch and rvdw = rcoulomb is what is built for perturbed pairs");
+    if (h->dp.ljpme && !h->d_nbfp_comb) return nb_fail(h, B200NB_ERR_STATE, "fep_launch: LJ-PME without its per-type grid parameters (b200nb_set_vdw)");
     if (p->sc_power != 1 && p->sc_power != 2) return nb_fail(h, B200NB_ERR_ARG, "fep_launch: sc_power must be 1 or 2");
     if (F.nri == 0) return 0;
     cudaSetDevice(h->device);
@@ -621,6 +684,7 @@ extern "C" int b200nb_fep_launch(b200nb_t* h, const b200nb_fep_params_t* p)
     D.ewald = h->dp.eeltype == B200NB_EEL_EWALD, D.beta = h->dp.beta, D.sh_ewald = h->dp.sh_ewald;
     D.pot_switch = h->dp.vdw_modifier == B200NB_VDW_POTSWITCH, D.rvdw_switch = h->dp.rvdw_switch;
     D.sw_c3 = h->dp.sw_c3, D.sw_c4 = h->dp.sw_c4, D.sw_c5 = h->dp.sw_c5;
+    D.ljpme = h->dp.ljpme, D.lje_coeff2 = h->dp.lje_coeff2, D.sh_lj_ewald = h->dp.sh_lj_ewald; /* set_vdw admits LJ-PME with the potential shift only */
     /* interaction_const_t::SoftCoreParameters (mdtypes/interaction_const.cpp:47-56) */
     D.alpha_vdw  = p->sc_alpha;
     D.alpha_coul = p->sc_coul ? p->sc_alpha : 0.f;
@@ -640,7 +704,8 @@ extern "C" int b200nb_fep_launch(b200nb_t* h, const b200nb_fep_params_t* p)
     }
     k_fep<<<(unsigned)((F.nri + 3) / 4), 128, 0, h->stream>>>(F.nri, F.d_iinr, F.d_shift, F.d_jindex, F.d_jjnr, F.d_excl, reinterpret_cast<const float4*>(h->d_xq),
                                                             h->d_slot_of_atom, h->d_shift_vec, F.d_typeA, F.d_typeB, F.d_qA, F.d_qB,
-                                                            reinterpret_cast<const float2*>(h->d_nbfp), D, h->d_f, h->d_fshift, F.d_out);
+                                                            reinterpret_cast<const float2*>(h->d_nbfp), reinterpret_cast<const float2*>(h->d_nbfp_comb), D,
+                                                            h->d_f, h->d_fshift, F.d_out);
     h->nlaunches++;
     NB_CUDA(h, cudaGetLastError());
     return 0;

@@ -144,6 +144,21 @@ def nbfp_two_lj_types(sigma_h=0.12, eps_h=0.19):
     return nbfp
 
 
+def perturbed_water_ljpme(nmol=20, seed=7, q_scale_b=0.25):
+    """perturbed_water for the LJ-PME tests of the free-energy kernel: the two-LJ-type table (so that the geometric and the
+    Lorentz-Berthelot grid rule differ) extended by a third type WITHOUT Lennard-Jones, which the perturbed atoms -- oxygens and
+    hydrogens, both with LJ in state A -- take in state B (disappearing particles: the soft-core is active, and their grid C6
+    vanishes in state B) and in the masked atom data of the cluster-pair path.  Returns (system, perturbed, typeA, typeB, qA, qB,
+    types_masked, q_masked, nbfp[3,3,2])."""
+    s, pert, tA, tB, qA, qB, tm, qm = perturbed_water(nmol=nmol, seed=seed, q_scale_b=q_scale_b)
+    nbfp = np.zeros((3, 3, 2), np.float32)
+    nbfp[:2, :2] = nbfp_two_lj_types()
+    tB, tm = tA.copy(), tA.copy()
+    tB[pert] = 2
+    tm[pert] = 2
+    return s, pert, tA, tB, qA, qB, tm, qm, nbfp
+
+
 NAMED = {
     "water_3k": (10, 10, 10),
     "water_24k": (20, 20, 20),      # BASELINE.json configs[1]

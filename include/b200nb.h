@@ -320,7 +320,9 @@ int b200nb_dd_set_local_atoms(b200nb_t* h, const int* local_gid_dev, int nlocal)
  * on the host beside its GPU kernels (nonbonded_verlet_t::dispatchFreeEnergyKernel, nbnxm/kerneldispatch.cpp:486-588).  Built so
  * far: Ewald (real-space part: plain soft-cored 1/r - sh_ewald, minus the unsoftened erf(beta r)/r, :693-737) / reaction-field /
  * plain cut-off electrostatics, cut-off LJ with potential shift or potential switch (:613-625, on the soft-cored distance),
- * soft-core (r-power 6, lambda power 1 or 2) or none; LJ-PME, the force switch (not in the reference's kernel either) and
+ * LJ-PME (b200nb_set_vdw's ljpme_comb_rule, both grid rules: cut-off on the plain distance, the grid potential at the cut-off and
+ * the grid part of the dispersion taken off unsoftened, :586-611 and :725-770, evaluated directly instead of from the reference's
+ * spline table), soft-core (r-power 6, lambda power 1 or 2) or none; the force switch (not in the reference's kernel either) and
  * rvdw < rcoulomb return B200NB_ERR_ARG.  As in the reference (nbnxn_atomdata_mask_fep) the caller
  * gives the perturbed atoms zero charge and a type without LJ in b200nb_set_atoms, so the cluster-pair kernels skip them, and
  * hands over the perturbed pair list in t_nblist form (mdtypes/nblist.h:117-137; what nbnxm/pairlist.cpp:1699-1872 make_fep_list

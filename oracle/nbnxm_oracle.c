@@ -819,6 +819,8 @@ typedef struct
     float sigma6_def, sigma6_min;
     float beta, sh_ewald; /* beta > 0: Ewald electrostatics */
     float rvdw_switch;    /* > 0: LJ potential switch from rvdw_switch to rc (eintmodPOTSWITCH; disp_cpot = rep_cpot = 0 then) */
+    int   ljpme;          /* 0: cut-off LJ; 1 / 2: LJ-PME with the geometric / Lorentz-Berthelot grid rule */
+    float beta_lj, sh_lj_ewald; /* interaction_const_t::ewaldcoeff_lj, sh_lj_ewald */
 } orc_fep_params;
 
 void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntype, const float* nbfp, const int* typeA, const int* typeB,
@@ -830,8 +832,29 @@ void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntyp
     const float lam_power = (float)p->lam_power;
     const int   useSoftCore = !(alpha_coul == 0.f && alpha_vdw == 0.f);                             /* :946-958 */
     const int   scDiffer = useSoftCore && !(p->lambda_coul == p->lambda_vdw && alpha_coul == alpha_vdw); /* :980-992 */
-    const int   ewald = p->beta > 0.f;
+    const int   ewald = p->beta > 0.f, ljpme = p->ljpme != 0;
     const float rcutoff_max2 = rcoulomb * rcoulomb;
+    /* LJ-PME: the grid C6 per type pair at the positions of C6 in nbfp (fr->ljpme_c6grid: mdlib/forcerec.cpp:157-195
+     * make_ljpme_c6grid, in real = float, from the types' own C6 / C12; nbfp holds 6 C6 and 12 C12) */
+    float* c6grid = 0;
+    if (ljpme)
+    {
+        c6grid = (float*)calloc(2 * (size_t)ntype * ntype, sizeof(float));
+        for (int i = 0; i < ntype; i++)
+            for (int j = 0; j < ntype; j++)
+            {
+                const float c6i = nbfp[2 * (i * ntype + i)] / 6.0f, c12i = nbfp[2 * (i * ntype + i) + 1] / 12.0f;
+                const float c6j = nbfp[2 * (j * ntype + j)] / 6.0f, c12j = nbfp[2 * (j * ntype + j) + 1] / 12.0f;
+                float       c6  = sqrtf(c6i * c6j);
+                if (p->ljpme == 2 && c6 != 0.f && c12i != 0.f && c12j != 0.f)
+                {
+                    const float sigmai = (float)pow((double)(c12i / c6i), 1.0 / 6.0), sigmaj = (float)pow((double)(c12j / c6j), 1.0 / 6.0);
+                    const float epsi = c6i * c6i / c12i, epsj = c6j * c6j / c12j, sm = 0.5f * (sigmai + sigmaj);
+                    c6 = sqrtf(epsi * epsj) * (sm * sm * sm * sm * sm * sm);
+                }
+                c6grid[2 * (ntype * i + j)] = c6 * 6.0f;
+            }
+    }
     float LFC[2] = { 1.f - p->lambda_coul, p->lambda_coul }, LFV[2] = { 1.f - p->lambda_vdw, p->lambda_vdw }, DLF[2] = { -1.f, 1.f };
     float lfac_coul[2], dlfac_coul[2], lfac_vdw[2], dlfac_vdw[2];
     for (int i = 0; i < 2; i++) /* :363-370 */
@@ -945,7 +968,7 @@ void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntyp
                                 FscalC[i] = qq[i] * (rinvC - 2.0f * krf * rC * rC);
                             }
                         }
-                        if ((c6[i] != 0 || c12[i] != 0) && rV < rvdw) /* :588-607 */
+                        if ((c6[i] != 0 || c12[i] != 0) && (ljpme ? r < rvdw : rV < rvdw)) /* :586-607 */
                         {
                             float rinv6;
                             if (useSoftCore) rinv6 = rpinvV;
@@ -957,6 +980,7 @@ void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntyp
                             const float Vvdw6 = c6[i] * rinv6, Vvdw12 = c12[i] * rinv6 * rinv6;
                             Vvdw[i]   = (Vvdw12 + c12[i] * p->rep_cpot) * (1.0f / 12.0f) - (Vvdw6 + c6[i] * p->disp_cpot) * (1.0f / 6.0f);
                             FscalV[i] = Vvdw12 - Vvdw6;
+                            if (ljpme) Vvdw[i] += c6grid[tj[i]] * p->sh_lj_ewald * (1.0f / 6.0f); /* :606-611: the grid potential at the cut-off */
                             if (p->rvdw_switch > 0.f) /* :613-625 potential switch on the (soft-cored) distance; constants :273-285 */
                             {
                                 const float dsw_ = rvdw - p->rvdw_switch;
@@ -1030,6 +1054,39 @@ void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntyp
                     dvdl_coul -= (DLF[i] * qq[i]) * v_lr;
                 }
             }
+            if (ljpme && r < rvdw)
+            {
+                /* :725-770: the grid (reciprocal-space) part of the dispersion, (1 - exp(-x)(1 + x + x^2/2)) / r^6 with x = (beta_lj r)^2
+                 * (tables/forcetable.cpp v_lj_ewald_lr), taken off unsoftened, for excluded pairs and the atom with itself (half) too.
+                 * The reference interpolates it and its derivative from the cubic-spline table vdwEwaldTables and divides by six; here
+                 * evaluated directly in double, by its series where the closed form cancels (x < 0.1) */
+                const double b2 = (double)p->beta_lj * p->beta_lj, xx = b2 * (double)r * r, ex = exp(-xx);
+                double       v_lr, f_lr;
+                if (rsq > 0)
+                {
+                    const double r2d = (double)r * r, r6d = r2d * r2d * r2d;
+                    const double ser = xx * (1.0 / 4 + xx * (1.0 / 20 + xx * (1.0 / 120 + xx * (1.0 / 840 + xx * (1.0 / 6720 + xx * (1.0 / 60480 + xx / 604800.0))))));
+                    const double g   = xx < 0.1 ? ex * xx * xx * xx / 6.0 * (1.0 + ser) : 1.0 - ex * (1.0 + xx + 0.5 * xx * xx);
+                    v_lr = g / r6d;
+                    /* -(dv/dr) / r = 6 g / r^8 - beta^6 exp(-x) / r^2 */
+                    f_lr = xx < 0.1 ? b2 * b2 * b2 * ex * ser / r2d : 6.0 * g / (r6d * r2d) - b2 * b2 * b2 * ex / r2d;
+                }
+                else
+                {
+                    v_lr = b2 * b2 * b2 / 6.0;
+                    f_lr = 0.0;
+                }
+                const float FF = (float)(f_lr / 6.0);
+                float       VV = (float)(v_lr / 6.0);
+                if (ii == jnr) VV *= 0.5f;
+                for (int i = 0; i < 2; i++)
+                {
+                    const float c6g = c6grid[tj[i]];
+                    vvtot += LFV[i] * c6g * VV;
+                    Fscal += LFV[i] * c6g * FF;
+                    dvdl_vdw += (DLF[i] * c6g) * VV;
+                }
+            }
             const float tx = Fscal * dx, ty = Fscal * dy, tz = Fscal * dz;
             fix += tx, fiy += ty, fiz += tz;
             f[3 * jnr] -= tx, f[3 * jnr + 1] -= ty, f[3 * jnr + 2] -= tz;
@@ -1043,6 +1100,7 @@ void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntyp
         }
     }
     out4[0] = Vc, out4[1] = Vv, out4[2] = dvdl_coul, out4[3] = dvdl_vdw;
+    free(c6grid);
 }
 
 /* ---- listed ("bonded") interactions: the types the reference runs on the GPU (listed_forces/gpubonded.h:84-85) ----

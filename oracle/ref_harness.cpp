@@ -743,15 +743,29 @@ int gmxref_fep_kernel(int natoms, const float* x, const float* shift_vec, int nt
     ic.c_rf               = p->c_rf;
     ic.dispersion_shift.cpot = p->disp_cpot;
     ic.repulsion_shift.cpot  = p->rep_cpot;
-    if (ic.eeltype == eelPME)
+    const bool ljpme = p->ljpme_comb_rule != 0;
+    if (ljpme)
     {
-        ic.ewaldcoeff_q       = p->ewaldcoeff;
-        ic.sh_ewald           = p->sh_ewald;
-        ic.coulombEwaldTables = std::make_unique<EwaldCorrectionTables>();
-        /* mdlib/forcerec.cpp:724-763 init_ewald_f_table, Coulomb only */
-        const real tableScale = ewald_spline3_table_scale(ic, true, false);
+        ic.vdwtype       = evdwPME;
+        ic.ewaldcoeff_lj = p->ewaldcoeff_lj;
+        ic.sh_lj_ewald   = p->sh_lj_ewald;
+    }
+    if (ic.eeltype == eelPME || ljpme)
+    {
+        /* mdlib/forcerec.cpp:724-763 init_ewald_f_table: one spacing for both tables, obeying both accuracy requirements */
+        if (ic.eeltype == eelPME) ic.ewaldcoeff_q = p->ewaldcoeff, ic.sh_ewald = p->sh_ewald;
+        const real tableScale = ewald_spline3_table_scale(ic, ic.eeltype == eelPME, ljpme);
         const int  tableSize  = static_cast<int>(ic.rcoulomb * tableScale) + 2;
-        *ic.coulombEwaldTables = generateEwaldCorrectionTables(tableSize, tableScale, ic.ewaldcoeff_q, v_q_ewald_lr);
+        if (ic.eeltype == eelPME)
+        {
+            ic.coulombEwaldTables  = std::make_unique<EwaldCorrectionTables>();
+            *ic.coulombEwaldTables = generateEwaldCorrectionTables(tableSize, tableScale, ic.ewaldcoeff_q, v_q_ewald_lr);
+        }
+        if (ljpme)
+        {
+            ic.vdwEwaldTables  = std::make_unique<EwaldCorrectionTables>();
+            *ic.vdwEwaldTables = generateEwaldCorrectionTables(tableSize, tableScale, ic.ewaldcoeff_lj, v_lj_ewald_lr);
+        }
     }
     t_lambda fepvals{};
     fepvals.sc_alpha     = p->sc_alpha;
@@ -770,6 +784,31 @@ int gmxref_fep_kernel(int natoms, const float* x, const float* shift_vec, int nt
     fr->ntype      = ntypes;
     new (&fr->nbfp) std::vector<real>(nbfp, nbfp + 2 * ntypes * ntypes);
     fr->use_simd_kernels = FALSE;
+    /* the grid C6 per type pair, at the positions of C6 in nbfp: make_ljpme_c6grid (static in mdlib/forcerec.cpp:157-195), from the
+     * diagonal of nbfp (which holds 6 C6 and 12 C12, forcerec.cpp mk_nbfp) */
+    std::vector<real> c6grid;
+    if (ljpme)
+    {
+        fr->ljpme_combination_rule = p->ljpme_comb_rule == 2 ? eljpmeLB : eljpmeGEOM;
+        c6grid.assign(2 * static_cast<size_t>(ntypes) * ntypes, 0);
+        for (int i = 0; i < ntypes; i++)
+        {
+            for (int j = 0; j < ntypes; j++)
+            {
+                const real c6i = nbfp[2 * (i * ntypes + i)] / 6.0, c12i = nbfp[2 * (i * ntypes + i) + 1] / 12.0;
+                const real c6j = nbfp[2 * (j * ntypes + j)] / 6.0, c12j = nbfp[2 * (j * ntypes + j) + 1] / 12.0;
+                real       c6  = std::sqrt(c6i * c6j);
+                if (fr->ljpme_combination_rule == eljpmeLB && !gmx_numzero(c6) && !gmx_numzero(c12i) && !gmx_numzero(c12j))
+                {
+                    const real sigmai = gmx::sixthroot(c12i / c6i), sigmaj = gmx::sixthroot(c12j / c6j);
+                    const real epsi = c6i * c6i / c12i, epsj = c6j * c6j / c12j;
+                    c6 = std::sqrt(epsi * epsj) * gmx::power6(0.5 * (sigmai + sigmaj));
+                }
+                c6grid[2 * (ntypes * i + j)] = c6 * 6.0;
+            }
+        }
+        fr->ljpme_c6grid = c6grid.data();
+    }
 
     std::vector<real> cA(qA, qA + natoms), cB(qB, qB + natoms);
     std::vector<int>  tA(typeA, typeA + natoms), tB(typeB, typeB + natoms);

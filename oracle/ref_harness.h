@@ -93,6 +93,8 @@ typedef struct
     int   sc_coul;            /* soft-core also on Coulomb (t_lambda::bScCoul) */
     float ewaldcoeff, sh_ewald; /* ewaldcoeff > 0: Ewald electrostatics (eelPME; the kernel subtracts the tabulated long-range part) */
     float rvdw_switch;          /* > 0: vdw_modifier = eintmodPOTSWITCH from rvdw_switch to rc (the caller passes disp_cpot = rep_cpot = 0) */
+    int   ljpme_comb_rule;      /* 0: cut-off LJ; 1 / 2: vdwtype = evdwPME with the geometric / Lorentz-Berthelot grid rule (eljpmeGEOM / eljpmeLB) */
+    float ewaldcoeff_lj, sh_lj_ewald; /* interaction_const_t::ewaldcoeff_lj, sh_lj_ewald */
 } gmxref_fep_params;
 int gmxref_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntypes, const float* nbfp, const int* typeA, const int* typeB,
                       const float* qA, const float* qB, int nri, const int* iinr, const int* shift, const int* jindex, const int* jjnr,

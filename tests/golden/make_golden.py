@@ -11,6 +11,7 @@ and oracle/_ref exist; the fixtures then travel to the GPU box, the reference tr
       grid_sha256, grid_dims                         -- GPU-geometry (8x8x8) grid atom order
  2b. ref_water_3k_triclinic_{ewald,rf}.npz: the same for the 3 k box sheared into a triclinic cell (`make_golden.py triclinic`).
  2c. ref_water_3k_fep_rf.npz: the reference's free-energy kernel on a perturbed pair list (`make_golden.py fep`).
+ 2d. ref_water_3k_fep_ljpme.npz: the same kernel with LJ-PME, both grid combination rules (`make_golden.py fep_ljpme`).
  3. ref_water_3k_vdw_<flavour>.npz: the reference's CPU SIMD kernels with an LJ force switch, an LJ potential switch
     and / or a VdW cut-off shorter than the Coulomb cut-off (Ewald electrostatics), once with the water charges and
     once with all charges zero (f_lj: Lennard-Jones forces alone, so that the modifier arithmetic is not hidden
@@ -189,6 +190,34 @@ def fep():
     np.savez_compressed(os.path.join(HERE, "ref_water_3k_fep_ewald.npz"), **oute)
 
 
+def fep_ljpme():
+    """ref_water_3k_fep_ljpme.npz: the reference's free-energy kernel with vdwtype = PME (the grid part of the dispersion subtracted
+    from its cubic-spline table, nb_free_energy.cpp:725-770; fr->ljpme_c6grid restated in oracle/ref_harness.cpp from the static
+    make_ljpme_c6grid) and Ewald electrostatics, both grid combination rules, on systems.perturbed_water_ljpme."""
+    import math
+    import gmxapi_b200.systems as S
+    from oracle import gmxref, oracle
+    s, pert, tA, tB, qA, qB, tm, qm, nbfp = S.perturbed_water_ljpme()
+    lst = oracle.fep_pair_list(s.x, s.box, RC, pert, s.excl_off, s.excl_idx)
+    sv = oracle.shift_vectors(s.box)
+    beta = float(np.float32(S.ewald_beta(RC)))
+    sh = float(np.float32(math.erfc(beta * RC) / RC))
+    bl = float(np.float32(S.ewald_beta_lj(RC)))
+    shlj = oracle.lj_ewald_shift(bl, RC)
+    out = dict(list_sha256=np.array(sha(np.concatenate([a.astype(np.int64).ravel() for a in lst]))), beta=np.float64(beta), sh_ewald=np.float64(sh),
+               ewaldcoeff_lj=np.float64(bl), sh_lj_ewald=np.float64(shlj), nbfp=nbfp)
+    for rule, tag in ((1, "geom"), (2, "lb")):
+        for name, kw in S.FEP_CASES.items():
+            f, fs, o4 = gmxref.fep_kernel(s.x, sv, nbfp, tA, tB, qA, qB, *lst, RC, ewaldcoeff=beta, sh_ewald=sh, ljpme=rule, ewaldcoeff_lj=bl,
+                                          sh_lj_ewald=shlj, **kw)
+            out["f_%s_%s" % (tag, name)], out["fshift_%s_%s" % (tag, name)], out["out4_%s_%s" % (tag, name)] = f, fs, np.array(o4, np.float64)
+            print("fep ljpme", tag, name, o4)
+    # the same pairs with cut-off LJ, for the size of the grid part
+    f, fs, o4 = gmxref.fep_kernel(s.x, sv, nbfp, tA, tB, qA, qB, *lst, RC, ewaldcoeff=beta, sh_ewald=sh, **S.FEP_CASES["sc1"])
+    out["f_cut_sc1"], out["out4_cut_sc1"] = f, np.array(o4, np.float64)
+    np.savez_compressed(os.path.join(HERE, "ref_water_3k_fep_ljpme.npz"), **out)
+
+
 BONDED_TRICLINIC = ((3.1, 0.0, 0.0), (0.6, 2.9, 0.0), (-0.5, 0.7, 3.3))
 
 
@@ -226,5 +255,8 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fep":
         fep()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fep_ljpme":
+        fep_ljpme()
         sys.exit(0)
     main()

@@ -185,6 +185,47 @@ def test_fep_kernel_potential_switch(built, case):
     fc.nb.close()
 
 
+@pytest.mark.parametrize("rule,ljpme", [("geom", g.LjPme.Geometric), ("lb", g.LjPme.LorentzBerthelot)])
+def test_fep_kernel_ljpme(built, rule, ljpme):
+    """LJ-PME in the free-energy kernel (nb_free_energy.cpp:586-611 and :725-770: cut-off on the plain distance, the grid potential
+    at the cut-off, the grid part of the dispersion taken off unsoftened -- also for excluded pairs and an atom with itself) with
+    Ewald electrostatics, both grid combination rules, against the oracle and the committed outputs of the reference kernel
+    (tests/golden/ref_water_3k_fep_ljpme.npz).  Oxygens and hydrogens carry LJ and disappear in state B."""
+    S = g.systems
+    s, pert, tA, tB, qA, qB, tm, qm, nbfp = S.perturbed_water_ljpme()
+    gd = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_water_3k_fep_ljpme.npz"))
+    beta, sh, bl, shlj = (float(gd[k]) for k in ("beta", "sh_ewald", "ewaldcoeff_lj", "sh_lj_ewald"))
+    opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, computeVirialAndEnergy=True, ewaldPotentialShift=True,
+                            ljPme=ljpme, ljPmeEwaldCoeff=bl)
+    fc = g.ForceCalculator(g.SimulationState(s.x, s.box, tm, qm, nbfp, s.excl_off, s.excl_idx), opt)
+    h = fc.nb
+    lst = oracle.fep_pair_list(s.x, s.box, RC, pert, s.excl_off, s.excl_idx)
+    h.fep_set_atoms(tA, tB, qA, qB)
+    h.fep_upload_list(*lst)
+    m = np.ones(45, bool)
+    m[nb.CENTRAL] = False
+    for case in ("sc1", "nosc", "sc2coul", "sc1coul"):
+        kw = S.FEP_CASES[case]
+        h.set_x(s.x)
+        h.clear_outputs()
+        h.fep_launch(**kw)
+        f = h.get_f().astype(np.float64)
+        fs = h.get_outputs()[0].astype(np.float64)
+        out4 = np.array(h.fep_outputs())
+        fo, fso, o4 = oracle.fep_kernel(s.x, oracle.shift_vectors(s.box), nbfp, tA, tB, qA, qB, *lst, RC, ewaldcoeff=beta, sh_ewald=sh,
+                                        ljpme=ljpme.value, ewaldcoeff_lj=bl, sh_lj_ewald=shlj, **kw)
+        tag = "_%s_%s" % (rule, case)
+        assert relrms(f, fo.astype(np.float64)) < 1e-5 and relrms(f, gd["f" + tag].astype(np.float64)) < 1e-5
+        fsr = gd["fshift" + tag].astype(np.float64)
+        assert np.abs(fs[m] - fsr[m]).max() <= 2e-5 * np.abs(fsr[m]).max()
+        o4r = gd["out4" + tag]
+        assert np.abs(out4 - np.array(o4)).max() <= 2e-5 * np.abs(np.array(o4)).max()
+        assert np.abs(out4 - o4r).max() <= 2e-5 * np.abs(o4r).max()
+        if case == "sc1":
+            assert relrms(f, gd["f_cut_sc1"].astype(np.float64)) > 1e-4  # not the cut-off LJ forces
+    fc.nb.close()
+
+
 def test_fep_refuses_what_is_not_built(built):
     S = g.systems
     s, pert, tA, tB, qA, qB, tm, qm = S.perturbed_water()
