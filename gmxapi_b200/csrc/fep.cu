@@ -5,7 +5,7 @@
  * do_nb_verlet -> nonbonded_verlet_t::dispatchFreeEnergyKernel, nbnxm/kerneldispatch.cpp:486-588), for the flavours built so far:
  * reaction-field / plain cut-off or Ewald electrostatics (the long-range part subtracted unsoftened, :693-737, evaluated directly
  * instead of from the reference's spline table), cut-off LJ with potential shift, soft-core with r-power 6 (lambda power 1 or 2) or
- * none, LJ potential shift or potential switch, LJ-PME (potential shift; the grid part subtracted unsoftened, :725-770, evaluated
+ * none, LJ potential shift or potential switch, rvdw <= rcoulomb, LJ-PME (potential shift; the grid part subtracted unsoftened, :725-770, evaluated
  * directly as well).  The LJ force switch (which the reference's kernel does not have either) is refused.
  * The pair list comes from the caller in t_nblist form (mdtypes/nblist.h:117-137; b200nb_fep_upload_list) -- what
  * nbnxm/pairlist.cpp:1699-1872 make_fep_list produces: every pair within the list radius with a perturbed atom, excluded pairs
@@ -28,6 +28,7 @@ namespace
 struct FepDev
 {
     float rc, rc2, epsfac, k_rf, c_rf, disp_cpot, rep_cpot;
+    float rvdw; /* <= rc = rcoulomb (shorter where PME load balancing grew rcoulomb); the list cut-off is the larger one, :300-301 */
     float LFC[2], LFV[2];
     float lfac_coul[2], dlfac_coul[2], lfac_vdw[2], dlfac_vdw[2];
     float alpha_coul, alpha_vdw, sigma6_def, sigma6_min;
@@ -167,7 +168,7 @@ k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, cons
                             FscalC = qq[i] * (rinvC - 2.0f * P.k_rf * rC * rC);
                         }
                     }
-                    if ((c6[i] != 0 || c12[i] != 0) && (P.ljpme ? r < P.rc : rV < P.rc)) /* :586-611 */
+                    if ((c6[i] != 0 || c12[i] != 0) && (P.ljpme ? r < P.rvdw : rV < P.rvdw)) /* :586-611 */
                     {
                         float rinv6;
                         if (P.soft_core) rinv6 = rpinvV;
@@ -244,7 +245,7 @@ k_fep(int nri, const int* __restrict__ iinr, const int* __restrict__ shift, cons
                 dvdl_coul -= (DLF[i] * qq[i]) * v_lr;
             }
         }
-        if (P.ljpme && r < P.rc)
+        if (P.ljpme && r < P.rvdw)
         {
             /* :725-770: the grid (reciprocal-space) part of the dispersion, g(x) / r^6 with g = 1 - exp(-x) (1 + x + x^2 / 2),
              * x = (ewaldcoeff_lj r)^2 (tables/forcetable.cpp v_lj_ewald_lr), taken off unsoftened -- for excluded pairs and a
@@ -672,8 +673,8 @@ extern "C" int b200nb_fep_launch(b200nb_t* h, const b200nb_fep_params_t* p)
     FepState& F = h->fep;
     if (F.natoms != h->natoms || !F.d_out) return nb_fail(h, B200NB_ERR_STATE, "fep_launch: fep_set_atoms for the current atoms first");
     if (!h->grid[0].valid) return nb_fail(h, B200NB_ERR_STATE, "fep_launch: put_on_grid first");
-    if (h->dp.vdw_modifier == B200NB_VDW_FORCESWITCH || h->dp.rvdw2 < h->dp.rc2)
-        return nb_fail(h, B200NB_ERR_ARG, "fep_launch: LJ with potential shift or potential switch and rvdw = rcoulomb is what is built for perturbed pairs");
+    if (h->dp.vdw_modifier == B200NB_VDW_FORCESWITCH)
+        return nb_fail(h, B200NB_ERR_ARG, "fep_launch: the LJ force switch is not built for perturbed pairs (the reference's free-energy kernel does not have it either)");
     if (h->dp.ljpme && !h->d_nbfp_comb) return nb_fail(h, B200NB_ERR_STATE, "fep_launch: LJ-PME without its per-type grid parameters (b200nb_set_vdw)");
     if (p->sc_power != 1 && p->sc_power != 2) return nb_fail(h, B200NB_ERR_ARG, "fep_launch: sc_power must be 1 or 2");
     if (F.nri == 0) return 0;
@@ -681,6 +682,7 @@ extern "C" int b200nb_fep_launch(b200nb_t* h, const b200nb_fep_params_t* p)
     FepDev D{};
     D.rc = h->hp.rc, D.rc2 = h->dp.rc2, D.epsfac = h->dp.epsfac, D.k_rf = h->dp.k_rf, D.c_rf = h->dp.c_rf, D.disp_cpot = h->dp.disp_cpot, D.rep_cpot = h->dp.rep_cpot;
     D.ntypes = h->dp.ntypes;
+    D.rvdw   = h->dp.rvdw2 < h->dp.rc2 ? sqrtf(h->dp.rvdw2) : h->hp.rc; /* b200nb_set_vdw keeps rvdw <= rc */
     D.ewald = h->dp.eeltype == B200NB_EEL_EWALD, D.beta = h->dp.beta, D.sh_ewald = h->dp.sh_ewald;
     D.pot_switch = h->dp.vdw_modifier == B200NB_VDW_POTSWITCH, D.rvdw_switch = h->dp.rvdw_switch;
     D.sw_c3 = h->dp.sw_c3, D.sw_c4 = h->dp.sw_c4, D.sw_c5 = h->dp.sw_c5;

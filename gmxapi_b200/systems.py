@@ -128,6 +128,10 @@ FEP_CASES = {  # name: parameters of the reference's soft-core (t_lambda) and th
 }
 
 
+FEP_TWIN = (  # tag, LJ-PME rule, rvdw_switch, soft-core case -- the rvdw = 0.8 < rcoulomb = 0.9 cases of the free-energy tests
+    ("cut_sc1", 0, 0.0, "sc1"), ("cut_sc2coul", 0, 0.0, "sc2coul"), ("pswitch_nosc", 0, 0.7, "nosc"), ("ljpme_geom_sc1coul", 1, 0.0, "sc1coul"))
+
+
 def nbfp_two_lj_types(sigma_h=0.12, eps_h=0.19):
     """A second nonbonded-parameter table for the water boxes in which the hydrogens carry Lennard-Jones parameters too
     (a TIP-like sigma / epsilon pair) and the O-H cross term follows Lorentz-Berthelot: two LJ types whose geometric and

@@ -322,8 +322,8 @@ int b200nb_dd_set_local_atoms(b200nb_t* h, const int* local_gid_dev, int nlocal)
  * plain cut-off electrostatics, cut-off LJ with potential shift or potential switch (:613-625, on the soft-cored distance),
  * LJ-PME (b200nb_set_vdw's ljpme_comb_rule, both grid rules: cut-off on the plain distance, the grid potential at the cut-off and
  * the grid part of the dispersion taken off unsoftened, :586-611 and :725-770, evaluated directly instead of from the reference's
- * spline table), soft-core (r-power 6, lambda power 1 or 2) or none; the force switch (not in the reference's kernel either) and
- * rvdw < rcoulomb return B200NB_ERR_ARG.  As in the reference (nbnxn_atomdata_mask_fep) the caller
+ * spline table), rvdw <= rcoulomb, soft-core (r-power 6, lambda power 1 or 2) or none; the force switch (not in the reference's
+ * kernel either) returns B200NB_ERR_ARG.  As in the reference (nbnxn_atomdata_mask_fep) the caller
  * gives the perturbed atoms zero charge and a type without LJ in b200nb_set_atoms, so the cluster-pair kernels skip them, and
  * hands over the perturbed pair list in t_nblist form (mdtypes/nblist.h:117-137; what nbnxm/pairlist.cpp:1699-1872 make_fep_list
  * builds: every pair within the list radius with a perturbed atom, excl_fep = 0 for excluded pairs and for a perturbed atom listed

@@ -234,7 +234,7 @@ class _FepParams(C.Structure):
                 ("rep_cpot", C.c_float), ("lambda_coul", C.c_float), ("lambda_vdw", C.c_float), ("sc_alpha", C.c_float),
                 ("sc_power", C.c_int), ("sc_sigma", C.c_float), ("sc_sigma_min", C.c_float), ("sc_coul", C.c_int),
                 ("ewaldcoeff", C.c_float), ("sh_ewald", C.c_float), ("rvdw_switch", C.c_float),
-                ("ljpme", C.c_int), ("ewaldcoeff_lj", C.c_float), ("sh_lj_ewald", C.c_float)]
+                ("ljpme", C.c_int), ("ewaldcoeff_lj", C.c_float), ("sh_lj_ewald", C.c_float), ("rvdw", C.c_float)]
 
 
 def fep_list(ref):
@@ -257,7 +257,7 @@ def fep_list(ref):
 
 def fep_kernel(x, shift_vec, nbfp, typeA, typeB, qA, qB, iinr, shift, jindex, jjnr, excl_fep, rc, lambda_coul, lambda_vdw,
                epsfac=138.935458, k_rf=0.0, c_rf=0.0, sc_alpha=0.5, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=False,
-               ewaldcoeff=0.0, sh_ewald=0.0, rvdw_switch=0.0, ljpme=0, ewaldcoeff_lj=0.0, sh_lj_ewald=0.0):
+               ewaldcoeff=0.0, sh_ewald=0.0, rvdw_switch=0.0, ljpme=0, ewaldcoeff_lj=0.0, sh_lj_ewald=0.0, rvdw=0.0):
     """The reference's gmx_nb_free_energy_kernel (gmxlib/nonbonded/nb_free_energy.cpp) on a perturbed pair list in t_nblist form.
     Returns f[n,3], fshift[45,3], (Vc, Vv, dvdl_coul, dvdl_vdw)."""
     L = lib()
@@ -270,9 +270,9 @@ def fep_kernel(x, shift_vec, nbfp, typeA, typeB, qA, qB, iinr, shift, jindex, jj
     tA, tB, cA, cB = arr(typeA, np.int32), arr(typeB, np.int32), arr(qA, np.float32), arr(qB, np.float32)
     ii, sh, ji, jj = arr(iinr, np.int32), arr(shift, np.int32), arr(jindex, np.int32), arr(jjnr, np.int32)
     ex = arr(excl_fep, np.int8)
-    cpot6, cpot12 = (0.0, 0.0) if rvdw_switch > 0 else (-1.0 / rc ** 6, -1.0 / rc ** 12)  # rvdw_switch > 0: LJ potential switch
+    cpot6, cpot12 = (0.0, 0.0) if rvdw_switch > 0 else (-1.0 / (rvdw or rc) ** 6, -1.0 / (rvdw or rc) ** 12)  # rvdw_switch > 0: LJ potential switch
     p = _FepParams(rc, epsfac, k_rf, c_rf, cpot6, cpot12, lambda_coul, lambda_vdw, sc_alpha, sc_power, sc_sigma,
-                   sc_sigma_min, int(bool(sc_coul)), ewaldcoeff, sh_ewald, rvdw_switch, int(ljpme), ewaldcoeff_lj, sh_lj_ewald)
+                   sc_sigma_min, int(bool(sc_coul)), ewaldcoeff, sh_ewald, rvdw_switch, int(ljpme), ewaldcoeff_lj, sh_lj_ewald, rvdw)
     f = np.zeros((n, 3), np.float32)
     fs = np.zeros((45, 3), np.float32)
     out = np.zeros(4, np.float32)

@@ -821,19 +821,20 @@ typedef struct
     float rvdw_switch;    /* > 0: LJ potential switch from rvdw_switch to rc (eintmodPOTSWITCH; disp_cpot = rep_cpot = 0 then) */
     int   ljpme;          /* 0: cut-off LJ; 1 / 2: LJ-PME with the geometric / Lorentz-Berthelot grid rule */
     float beta_lj, sh_lj_ewald; /* interaction_const_t::ewaldcoeff_lj, sh_lj_ewald */
+    float rvdw;           /* > 0: rvdw < rcoulomb = rc (disp_cpot / rep_cpot / sh_lj_ewald are for rvdw then) */
 } orc_fep_params;
 
 void orc_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntype, const float* nbfp, const int* typeA, const int* typeB,
                     const float* chargeA, const float* chargeB, int nri, const int* iinr, const int* shift, const int* jindex, const int* jjnr,
                     const signed char* excl_fep, const orc_fep_params* p, float* f, float* fshift, float* out4)
 {
-    const float facel = p->epsfac, krf = p->k_rf, crf = p->c_rf, rcoulomb = p->rc, rvdw = p->rc;
+    const float facel = p->epsfac, krf = p->k_rf, crf = p->c_rf, rcoulomb = p->rc, rvdw = p->rvdw > 0.f ? p->rvdw : p->rc;
     const float alpha_coul = p->alpha_coul, alpha_vdw = p->alpha_vdw, sigma6_def = p->sigma6_def, sigma6_min = p->sigma6_min;
     const float lam_power = (float)p->lam_power;
     const int   useSoftCore = !(alpha_coul == 0.f && alpha_vdw == 0.f);                             /* :946-958 */
     const int   scDiffer = useSoftCore && !(p->lambda_coul == p->lambda_vdw && alpha_coul == alpha_vdw); /* :980-992 */
     const int   ewald = p->beta > 0.f, ljpme = p->ljpme != 0;
-    const float rcutoff_max2 = rcoulomb * rcoulomb;
+    const float rcutoff_max2 = (rcoulomb > rvdw ? rcoulomb : rvdw) * (rcoulomb > rvdw ? rcoulomb : rvdw); /* :300-301 */
     /* LJ-PME: the grid C6 per type pair at the positions of C6 in nbfp (fr->ljpme_c6grid: mdlib/forcerec.cpp:157-195
      * make_ljpme_c6grid, in real = float, from the types' own C6 / C12; nbfp holds 6 C6 and 12 C12) */
     float* c6grid = 0;

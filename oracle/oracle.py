@@ -231,12 +231,12 @@ class _FepParams(C.Structure):
                 ("rep_cpot", C.c_float), ("lambda_coul", C.c_float), ("lambda_vdw", C.c_float), ("alpha_coul", C.c_float),
                 ("alpha_vdw", C.c_float), ("lam_power", C.c_int), ("sigma6_def", C.c_float), ("sigma6_min", C.c_float),
                 ("beta", C.c_float), ("sh_ewald", C.c_float), ("rvdw_switch", C.c_float),
-                ("ljpme", C.c_int), ("ewaldcoeff_lj", C.c_float), ("sh_lj_ewald", C.c_float)]
+                ("ljpme", C.c_int), ("ewaldcoeff_lj", C.c_float), ("sh_lj_ewald", C.c_float), ("rvdw", C.c_float)]
 
 
 def fep_kernel(x, shift_vec, nbfp, typeA, typeB, qA, qB, iinr, shift, jindex, jjnr, excl_fep, rc, lambda_coul, lambda_vdw,
                epsfac=138.935458, k_rf=0.0, c_rf=0.0, sc_alpha=0.5, sc_power=1, sc_sigma=0.3, sc_sigma_min=0.3, sc_coul=False,
-               ewaldcoeff=0.0, sh_ewald=0.0, rvdw_switch=0.0, ljpme=0, ewaldcoeff_lj=0.0, sh_lj_ewald=0.0):
+               ewaldcoeff=0.0, sh_ewald=0.0, rvdw_switch=0.0, ljpme=0, ewaldcoeff_lj=0.0, sh_lj_ewald=0.0, rvdw=0.0):
     """Plain-C restatement of the reference's free-energy kernel (orc_fep_kernel) on a perturbed pair list in t_nblist form; the
     soft-core parameters are the inputrec's (sc_alpha, sc_power, sc_sigma, sc_sigma_min, sc_coul), processed like
     interaction_const_t::SoftCoreParameters (mdtypes/interaction_const.cpp).  Returns f, fshift, (Vc, Vv, dvdl_coul, dvdl_vdw)."""
@@ -249,10 +249,10 @@ def fep_kernel(x, shift_vec, nbfp, typeA, typeB, qA, qB, iinr, shift, jindex, jj
     ii, sh, ji, jj = _i32(iinr), _i32(shift), _i32(jindex), _i32(jjnr)
     ex = np.ascontiguousarray(excl_fep, dtype=np.int8)
     # rvdw_switch > 0: LJ potential switch (no potential shift then, as interaction_const_t stores it)
-    cpot6, cpot12 = (0.0, 0.0) if rvdw_switch > 0 else (-1.0 / rc ** 6, -1.0 / rc ** 12)
+    cpot6, cpot12 = (0.0, 0.0) if rvdw_switch > 0 else (-1.0 / (rvdw or rc) ** 6, -1.0 / (rvdw or rc) ** 12)
     p = _FepParams(rc, epsfac, k_rf, c_rf, cpot6, cpot12, lambda_coul, lambda_vdw,
                    sc_alpha if sc_coul else 0.0, sc_alpha, sc_power, sc_sigma ** 6, (sc_sigma_min ** 6) if sc_coul else 0.0,
-                   ewaldcoeff, sh_ewald, rvdw_switch, int(ljpme), ewaldcoeff_lj, sh_lj_ewald)
+                   ewaldcoeff, sh_ewald, rvdw_switch, int(ljpme), ewaldcoeff_lj, sh_lj_ewald, rvdw)
     f = np.zeros((n, 3), np.float32)
     fs = np.zeros((45, 3), np.float32)
     out = np.zeros(4, np.float32)

@@ -738,6 +738,7 @@ int gmxref_fep_kernel(int natoms, const float* x, const float* shift_vec, int nt
     ic.vdw_modifier     = p->rvdw_switch > 0.0f ? eintmodPOTSWITCH : eintmodPOTSHIFT;
     ic.rvdw_switch      = p->rvdw_switch;
     ic.rcoulomb = ic.rvdw = p->rc;
+    if (p->rvdw > 0.0f) ic.rvdw = p->rvdw;
     ic.epsfac             = p->epsfac;
     ic.k_rf               = p->k_rf;
     ic.c_rf               = p->c_rf;

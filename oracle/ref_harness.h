@@ -95,6 +95,7 @@ typedef struct
     float rvdw_switch;          /* > 0: vdw_modifier = eintmodPOTSWITCH from rvdw_switch to rc (the caller passes disp_cpot = rep_cpot = 0) */
     int   ljpme_comb_rule;      /* 0: cut-off LJ; 1 / 2: vdwtype = evdwPME with the geometric / Lorentz-Berthelot grid rule (eljpmeGEOM / eljpmeLB) */
     float ewaldcoeff_lj, sh_lj_ewald; /* interaction_const_t::ewaldcoeff_lj, sh_lj_ewald */
+    float rvdw;                 /* > 0: rvdw < rcoulomb = rc (what PME load balancing leaves behind; disp_cpot / rep_cpot / sh_lj_ewald are for rvdw) */
 } gmxref_fep_params;
 int gmxref_fep_kernel(int natoms, const float* x, const float* shift_vec, int ntypes, const float* nbfp, const int* typeA, const int* typeB,
                       const float* qA, const float* qB, int nri, const int* iinr, const int* shift, const int* jindex, const int* jjnr,

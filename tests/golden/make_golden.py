@@ -12,6 +12,7 @@ and oracle/_ref exist; the fixtures then travel to the GPU box, the reference tr
  2b. ref_water_3k_triclinic_{ewald,rf}.npz: the same for the 3 k box sheared into a triclinic cell (`make_golden.py triclinic`).
  2c. ref_water_3k_fep_rf.npz: the reference's free-energy kernel on a perturbed pair list (`make_golden.py fep`).
  2d. ref_water_3k_fep_ljpme.npz: the same kernel with LJ-PME, both grid combination rules (`make_golden.py fep_ljpme`).
+ 2e. ref_water_3k_fep_twin.npz: the same kernel with rvdw < rcoulomb (`make_golden.py fep_twin`).
  3. ref_water_3k_vdw_<flavour>.npz: the reference's CPU SIMD kernels with an LJ force switch, an LJ potential switch
     and / or a VdW cut-off shorter than the Coulomb cut-off (Ewald electrostatics), once with the water charges and
     once with all charges zero (f_lj: Lennard-Jones forces alone, so that the modifier arithmetic is not hidden
@@ -218,6 +219,32 @@ def fep_ljpme():
     np.savez_compressed(os.path.join(HERE, "ref_water_3k_fep_ljpme.npz"), **out)
 
 
+def fep_twin():
+    """ref_water_3k_fep_twin.npz: the reference's free-energy kernel with rvdw = 0.8 < rcoulomb = 0.9 (what PME load balancing leaves
+    behind: nb_free_energy.cpp:300-301, :564-587 cut the two interactions separately) on systems.perturbed_water_ljpme."""
+    import math
+    import gmxapi_b200.systems as S
+    from oracle import gmxref, oracle
+    s, pert, tA, tB, qA, qB, tm, qm, nbfp = S.perturbed_water_ljpme()
+    lst = oracle.fep_pair_list(s.x, s.box, RC, pert, s.excl_off, s.excl_idx)
+    sv = oracle.shift_vectors(s.box)
+    rvdw = 0.8
+    beta = float(np.float32(S.ewald_beta(RC)))
+    sh = float(np.float32(math.erfc(beta * RC) / RC))
+    bl = float(np.float32(S.ewald_beta_lj(rvdw)))
+    shlj = oracle.lj_ewald_shift(bl, rvdw)
+    out = dict(list_sha256=np.array(sha(np.concatenate([a.astype(np.int64).ravel() for a in lst]))), beta=np.float64(beta), sh_ewald=np.float64(sh),
+               ewaldcoeff_lj=np.float64(bl), sh_lj_ewald=np.float64(shlj), rvdw=np.float64(rvdw))
+    for tag, rule, sw, case in S.FEP_TWIN:
+        kw = dict(S.FEP_CASES[case], ewaldcoeff=beta, sh_ewald=sh, rvdw=rvdw, rvdw_switch=sw)
+        if rule:
+            kw.update(ljpme=rule, ewaldcoeff_lj=bl, sh_lj_ewald=shlj)
+        f, fs, o4 = gmxref.fep_kernel(s.x, sv, nbfp, tA, tB, qA, qB, *lst, RC, **kw)
+        out["f_" + tag], out["fshift_" + tag], out["out4_" + tag] = f, fs, np.array(o4, np.float64)
+        print("fep twin", tag, o4)
+    np.savez_compressed(os.path.join(HERE, "ref_water_3k_fep_twin.npz"), **out)
+
+
 BONDED_TRICLINIC = ((3.1, 0.0, 0.0), (0.6, 2.9, 0.0), (-0.5, 0.7, 3.3))
 
 
@@ -258,5 +285,8 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fep_ljpme":
         fep_ljpme()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fep_twin":
+        fep_twin()
         sys.exit(0)
     main()

@@ -226,6 +226,40 @@ def test_fep_kernel_ljpme(built, rule, ljpme):
     fc.nb.close()
 
 
+def test_fep_kernel_twin_range(built):
+    """rvdw = 0.8 < rcoulomb = 0.9 in the free-energy kernel (nb_free_energy.cpp:300-301, :564-587: the list is cut at the larger
+    radius, each interaction at its own) for cut-off LJ, the potential switch 0.7 -> 0.8 and LJ-PME, Ewald electrostatics, against
+    the oracle and the committed outputs of the reference kernel (tests/golden/ref_water_3k_fep_twin.npz)."""
+    S = g.systems
+    s, pert, tA, tB, qA, qB, tm, qm, nbfp = S.perturbed_water_ljpme()
+    gd = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_water_3k_fep_twin.npz"))
+    beta, sh, bl, shlj, rvdw = (float(gd[k]) for k in ("beta", "sh_ewald", "ewaldcoeff_lj", "sh_lj_ewald", "rvdw"))
+    lst = oracle.fep_pair_list(s.x, s.box, RC, pert, s.excl_off, s.excl_idx)
+    for tag, rule, sw, case in S.FEP_TWIN:
+        kw = S.FEP_CASES[case]
+        opt = g.NBKernelOptions(pairlistCutoff=RC, coulombType=g.CoulombType.Pme, computeVirialAndEnergy=True, ewaldPotentialShift=True,
+                                vdwCutoff=rvdw, vdwSwitch=sw, vdwModifier=g.VdwModifier.PotentialSwitch if sw else g.VdwModifier.PotentialShift,
+                                ljPme=g.LjPme(rule), ljPmeEwaldCoeff=bl if rule else 0.0)
+        fc = g.ForceCalculator(g.SimulationState(s.x, s.box, tm, qm, nbfp, s.excl_off, s.excl_idx), opt)
+        h = fc.nb
+        h.fep_set_atoms(tA, tB, qA, qB)
+        h.fep_upload_list(*lst)
+        h.set_x(s.x)
+        h.clear_outputs()
+        h.fep_launch(**kw)
+        f = h.get_f().astype(np.float64)
+        out4 = np.array(h.fep_outputs())
+        okw = dict(kw, ewaldcoeff=beta, sh_ewald=sh, rvdw=rvdw, rvdw_switch=sw)
+        if rule:
+            okw.update(ljpme=rule, ewaldcoeff_lj=bl, sh_lj_ewald=shlj)
+        fo, fso, o4 = oracle.fep_kernel(s.x, oracle.shift_vectors(s.box), nbfp, tA, tB, qA, qB, *lst, RC, **okw)
+        assert relrms(f, fo.astype(np.float64)) < 1e-5 and relrms(f, gd["f_" + tag].astype(np.float64)) < 1e-5, tag
+        o4r = gd["out4_" + tag]
+        assert np.abs(out4 - np.array(o4)).max() <= 2e-5 * np.abs(np.array(o4)).max(), tag
+        assert np.abs(out4 - o4r).max() <= 2e-5 * np.abs(o4r).max(), tag
+        fc.nb.close()
+
+
 def test_fep_refuses_what_is_not_built(built):
     S = g.systems
     s, pert, tA, tB, qA, qB, tm, qm = S.perturbed_water()
