@@ -42,7 +42,9 @@ struct FepDev
 };
 
 /* the grid C6 of a type pair, times six like nbfp's C6 (fr->ljpme_c6grid, mdlib/forcerec.cpp:157-195), from the per-type
- * nbfp_comb entries the cluster-pair kernels use (b200nb_set_vdw) */
+ * nbfp_comb entries the cluster-pair kernels use (b200nb_set_vdw).  One corner differs from make_ljpme_c6grid: for a type with
+ * C6 > 0 and C12 = 0 the Lorentz-Berthelot rule has no sigma, the reference's table falls back to sqrt(C6_i C6_j) there while its
+ * cluster kernels' nbfp_comb (nbnxm/atomdata.cpp:303-321) -- and so this function -- give such a type no grid C6 at all */
 __device__ __forceinline__ float grid_c6(int rule, float2 gi, float2 gj)
 {
     if (rule == 1) return gi.x * gj.x;
