@@ -1,8 +1,8 @@
 /* b200nb: the perturbed-pair (free-energy) kernel on the device.
  *
  * Replaces CPU code of the reference: gmxlib/nonbonded/nb_free_energy.cpp:203-860 (nb_free_energy_kernel, the scalar instantiation:
- * the reference has no SIMD or GPU form of it and runs it on the host beside the GPU nonbonded kernels, mdlib/sim_util.cpp
- * do_nb_verlet -> nonbonded_verlet_t::dispatchFreeEnergyKernel, nbnxm/kerneldispatch.cpp:486-588), for the flavours built so far:
+ * the reference has no SIMD or GPU form of it and runs it on the host beside the GPU nonbonded kernels, mdlib/sim_util.cpp:1658
+ * do_force -> nonbonded_verlet_t::dispatchFreeEnergyKernel, nbnxm/kerneldispatch.cpp:458-567), for the flavours built so far:
  * reaction-field / plain cut-off or Ewald electrostatics (the long-range part subtracted unsoftened, :693-737, evaluated directly
  * instead of from the reference's spline table), cut-off LJ with potential shift, soft-core with r-power 6 (lambda power 1 or 2) or
  * none, LJ potential shift or potential switch, rvdw <= rcoulomb, LJ-PME (potential shift; the grid part subtracted unsoftened, :725-770, evaluated

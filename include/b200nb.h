@@ -317,7 +317,7 @@ int b200nb_dd_set_local_atoms(b200nb_t* h, const int* local_gid_dev, int nlocal)
 /* ---- introspection used by the parity tests and the bench ------------------------------------------------ */
 /* ---- perturbed (free-energy) pairs (gmxapi_b200/csrc/fep.cu) ----
  * Replaces CPU code of the reference: the free-energy kernel gmxlib/nonbonded/nb_free_energy.cpp:203-860, which the reference runs
- * on the host beside its GPU kernels (nonbonded_verlet_t::dispatchFreeEnergyKernel, nbnxm/kerneldispatch.cpp:486-588).  Built so
+ * on the host beside its GPU kernels (nonbonded_verlet_t::dispatchFreeEnergyKernel, nbnxm/kerneldispatch.cpp:458-567).  Built so
  * far: Ewald (real-space part: plain soft-cored 1/r - sh_ewald, minus the unsoftened erf(beta r)/r, :693-737) / reaction-field /
  * plain cut-off electrostatics, cut-off LJ with potential shift or potential switch (:613-625, on the soft-cored distance),
  * LJ-PME (b200nb_set_vdw's ljpme_comb_rule, both grid rules: cut-off on the plain distance, the grid potential at the cut-off and
